@@ -1,0 +1,342 @@
+"""ctypes binding of include/dropest_b200.h (the drop-in C ABI).  No torch types cross this boundary."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+MERGE_NONE, MERGE_REAL, MERGE_SIMPLE, MERGE_POISSON_REAL, MERGE_POISSON_SIMPLE, MERGE_ALL = range(6)
+BARCODES_CONST, BARCODES_INDROP = 0, 1
+UMI_MERGE_SIMPLE, UMI_MERGE_DIRECTIONAL = 0, 1
+CELLS_ALL, CELLS_REAL, CELLS_FILTERED = 0, 1, 2
+MATRIX_CM, MATRIX_CM_RAW = 0, 1
+NO_GENE = 0xFFFFFF
+ABI_VERSION = 1
+
+RECORD_DTYPE = np.dtype([("key", "<u8"), ("gene", "<u4"), ("read_idx", "<u4")])
+
+CELL_INFO_DTYPE = np.dtype(
+    [
+        ("barcode", "<u8"),
+        ("first_read_idx", "<u4"),
+        ("flags", "<u4"),
+        ("n_genes", "<i4"),
+        ("umis_stat", "<i4"),
+        ("reads_stat", "<i4"),
+        ("requested_genes_num", "<i4"),
+        ("requested_umis_num", "<i4"),
+        ("merge_target", "<i4"),
+    ]
+)
+assert CELL_INFO_DTYPE.itemsize == 40
+
+# exported symbols of include/dropest_b200.h (checked by tests/test_abi.py)
+EXPORTS = [
+    "dge_config_default", "dge_create", "dge_destroy", "dge_last_error", "dge_add_batch", "dge_add_batch_device",
+    "dge_set_initialized", "dge_merge_and_filter", "dge_set_stream", "dge_get_summary", "dge_get_timings", "dge_get_cells",
+    "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
+    "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
+    "dge_route_by_barcode_device",
+]
+
+
+class DgeError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dge error {code}: {msg}")
+        self.code = code
+
+
+class _Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("device", C.c_int32), ("cb_len", C.c_uint32), ("umi_len", C.c_uint32),
+        ("n_genes", C.c_uint32), ("merge_type", C.c_uint32), ("barcodes_type", C.c_uint32), ("umi_merge_type", C.c_uint32),
+        ("min_genes_before_merge", C.c_uint32), ("min_genes_after_merge", C.c_uint32),
+        ("max_cb_merge_edit_distance", C.c_uint32), ("max_umi_merge_edit_distance", C.c_uint32),
+        ("min_merge_fraction", C.c_double), ("max_merge_prob", C.c_double), ("max_real_merge_prob", C.c_double),
+        ("umi_merge_mult", C.c_double), ("query_mark_mask", C.c_uint32), ("max_cells", C.c_int32),
+        ("reads_output", C.c_uint32), ("reserved0", C.c_uint32), ("barcodes_file", C.c_char_p),
+        ("max_barcodes_hint", C.c_uint64),
+    ]
+
+
+class _Summary(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "n_reads", "total_cells_number", "real_cells_number", "filtered_cells_number", "n_genes_seen", "n_umigs",
+        "intergenic_reads", "has_exon_reads", "has_intron_reads", "has_not_annotated_reads", "cm_nnz", "cm_raw_nnz",
+        "n_merged", "n_excluded")]
+
+
+class _Timings(C.Structure):
+    _fields_ = [("ms_fill", C.c_float), ("ms_init", C.c_float), ("ms_merge", C.c_float), ("ms_finish", C.c_float),
+                ("ms_total", C.c_float), ("ms_dedup_kernel", C.c_float), ("n_kernel_launches", C.c_uint32),
+                ("n_dedup_launches", C.c_uint32)]
+
+
+class _SynthParams(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64), ("n_reads_total", C.c_uint64), ("n_cells", C.c_uint32), ("n_genes", C.c_uint32),
+        ("cb_len", C.c_uint32), ("umi_len", C.c_uint32), ("cell_cdf", C.c_void_p), ("cell_barcode", C.c_void_p),
+        ("cell_reads", C.c_void_p), ("gene_cdf", C.c_void_p), ("gene_weight", C.c_void_p), ("cb_error_ppm", C.c_uint32),
+        ("intergenic_ppm", C.c_uint32), ("intron_ppm", C.c_uint32), ("not_annotated_ppm", C.c_uint32),
+        ("reads_per_umi", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "lib", "libdropest_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA shared library.  Fails loudly when it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
+    lib.dge_config_default.argtypes = [C.POINTER(_Config)]
+    lib.dge_config_default.restype = None
+    lib.dge_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
+    lib.dge_destroy.argtypes = [C.c_void_p]
+    lib.dge_destroy.restype = None
+    lib.dge_last_error.argtypes = [C.c_void_p]
+    lib.dge_last_error.restype = C.c_char_p
+    lib.dge_add_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.dge_add_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.dge_set_initialized.argtypes = [C.c_void_p]
+    lib.dge_merge_and_filter.argtypes = [C.c_void_p]
+    lib.dge_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.dge_get_summary.argtypes = [C.c_void_p, C.POINTER(_Summary)]
+    lib.dge_get_timings.argtypes = [C.c_void_p, C.POINTER(_Timings)]
+    lib.dge_get_cells.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.dge_get_matrix.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.dge_get_gene_order.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.dge_get_merge_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.dge_get_umigs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.dge_edit_distance.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint]
+    lib.dge_edit_distance.restype = C.c_uint
+    lib.dge_hamming_distance.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    lib.dge_hamming_distance.restype = C.c_uint
+    lib.dge_whitelist_shape.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.dge_whitelist_token.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]
+    lib.dge_synth_generate_device.argtypes = [C.c_int, C.POINTER(_SynthParams), C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.dge_route_by_barcode_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+_CODE = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+
+def pack_seq(s: str) -> int:
+    v = 0
+    for ch in s:
+        v = (v << 2) | _CODE[ch]
+    return v
+
+
+def unpack_seq(v: int, length: int) -> str:
+    return "".join("ACGT"[(int(v) >> (2 * (length - 1 - i))) & 3] for i in range(length))
+
+
+def marks_to_mask(code: str = "eEBA") -> int:
+    """UMI::Mark::get_by_code (reference Estimation/UMI.cpp:123-154) -> bit mask over accumulated mark values."""
+    table = {"e": 2, "i": 4, "E": 3, "I": 5, "B": 6, "A": 7}
+    mask = 0
+    for ch in code:
+        if ch not in table:
+            raise ValueError(f"Unexpected gene match levels: {ch}")
+        mask |= 1 << table[ch]
+    return mask
+
+
+@dataclass
+class Config:
+    cb_len: int = 16
+    umi_len: int = 10
+    n_genes: int = 1
+    device: int = 0
+    merge_type: int = MERGE_NONE
+    barcodes_type: int = BARCODES_INDROP
+    barcodes_file: Optional[str] = None
+    umi_merge_type: int = UMI_MERGE_SIMPLE
+    min_genes_before_merge: int = 10
+    min_genes_after_merge: int = 10
+    max_cb_merge_edit_distance: int = 2
+    max_umi_merge_edit_distance: int = 1
+    min_merge_fraction: float = 0.2
+    max_merge_prob: float = 1e-4
+    max_real_merge_prob: float = 1e-7
+    umi_merge_mult: float = 2.0
+    marks: str = "eEBA"
+    max_cells: int = -1
+    reads_output: bool = False
+    max_barcodes_hint: int = 0
+    _keep: list = field(default_factory=list, repr=False)
+
+    def to_c(self) -> _Config:
+        lib = load_library()
+        c = _Config()
+        lib.dge_config_default(C.byref(c))
+        for name in ("cb_len", "umi_len", "n_genes", "device", "merge_type", "barcodes_type", "umi_merge_type",
+                     "min_genes_before_merge", "min_genes_after_merge", "max_cb_merge_edit_distance",
+                     "max_umi_merge_edit_distance", "min_merge_fraction", "max_merge_prob", "max_real_merge_prob",
+                     "umi_merge_mult", "max_cells", "max_barcodes_hint"):
+            setattr(c, name, getattr(self, name))
+        c.query_mark_mask = marks_to_mask(self.marks)
+        c.reads_output = 1 if self.reads_output else 0
+        if self.barcodes_file:
+            b = self.barcodes_file.encode()
+            self._keep.append(b)
+            c.barcodes_file = b
+        return c
+
+
+class Container:
+    """Python mirror of the reference's CellsDataContainer fill/query surface over the C ABI."""
+
+    def __init__(self, cfg: Config):
+        self._lib = load_library()
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        cc = cfg.to_c()
+        rc = self._lib.dge_create(C.byref(cc), C.byref(self._h))
+        if rc != 0:
+            raise DgeError(rc, self._lib.dge_last_error(None).decode())
+        self._keepalive = []
+
+    def close(self):
+        if self._h:
+            self._lib.dge_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise DgeError(rc, self._lib.dge_last_error(self._h).decode())
+
+    # ---- fill
+    def add_batch(self, recs: np.ndarray):
+        """Host records (numpy array of RECORD_DTYPE).  = n x CellsDataContainer::add_record."""
+        recs = np.ascontiguousarray(recs, dtype=RECORD_DTYPE)
+        self._check(self._lib.dge_add_batch(self._h, recs.ctypes.data, recs.shape[0]))
+
+    def add_batch_ptr(self, host_ptr: int, n: int):
+        self._check(self._lib.dge_add_batch(self._h, C.c_void_p(host_ptr), n))
+
+    def add_batch_device(self, dev_ptr: int, n: int, keepalive=None):
+        if keepalive is not None:
+            self._keepalive.append(keepalive)
+        self._check(self._lib.dge_add_batch_device(self._h, C.c_void_p(dev_ptr), n))
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.dge_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_initialized(self):
+        self._check(self._lib.dge_set_initialized(self._h))
+        self._keepalive.clear()
+
+    def merge_and_filter(self):
+        self._check(self._lib.dge_merge_and_filter(self._h))
+
+    # ---- query
+    def summary(self) -> dict:
+        s = _Summary()
+        self._check(self._lib.dge_get_summary(self._h, C.byref(s)))
+        return {n: int(getattr(s, n)) for n, _ in _Summary._fields_}
+
+    def timings(self) -> dict:
+        t = _Timings()
+        self._check(self._lib.dge_get_timings(self._h, C.byref(t)))
+        return {n: (float(getattr(t, n)) if n.startswith("ms") else int(getattr(t, n))) for n, _ in _Timings._fields_}
+
+    def cells(self, which: int) -> np.ndarray:
+        n = C.c_size_t(0)
+        self._check(self._lib.dge_get_cells(self._h, which, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=CELL_INFO_DTYPE)
+        if n.value:
+            self._check(self._lib.dge_get_cells(self._h, which, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def matrix(self, which: int):
+        """(indptr int64[n_cols+1], gene_ids int32[nnz], values int32[nnz])"""
+        nc, nnz = C.c_size_t(0), C.c_size_t(0)
+        self._check(self._lib.dge_get_matrix(self._h, which, None, None, None, C.byref(nc), C.byref(nnz)))
+        indptr = np.zeros(nc.value + 1, dtype=np.int64)
+        genes = np.zeros(nnz.value, dtype=np.int32)
+        vals = np.zeros(nnz.value, dtype=np.int32)
+        self._check(self._lib.dge_get_matrix(self._h, which, indptr.ctypes.data, genes.ctypes.data, vals.ctypes.data,
+                                             C.byref(nc), C.byref(nnz)))
+        return indptr, genes, vals
+
+    def gene_order(self) -> np.ndarray:
+        n = C.c_size_t(0)
+        self._check(self._lib.dge_get_gene_order(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.int32)
+        if n.value:
+            self._check(self._lib.dge_get_gene_order(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def merge_pairs(self):
+        n = C.c_size_t(0)
+        self._check(self._lib.dge_get_merge_pairs(self._h, None, None, 0, C.byref(n)))
+        a = np.zeros(n.value, dtype=np.uint64)
+        b = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            self._check(self._lib.dge_get_merge_pairs(self._h, a.ctypes.data, b.ctypes.data, n.value, C.byref(n)))
+        return a, b
+
+    def umigs(self, which: int) -> dict:
+        n = C.c_size_t(0)
+        self._check(self._lib.dge_get_umigs(self._h, which, None, None, None, None, None, 0, C.byref(n)))
+        m = n.value
+        out = {"cell": np.zeros(m, np.uint32), "gene": np.zeros(m, np.int32), "umi": np.zeros(m, np.uint32),
+               "count": np.zeros(m, np.uint32), "mark": np.zeros(m, np.uint8)}
+        if m:
+            self._check(self._lib.dge_get_umigs(self._h, which, out["cell"].ctypes.data, out["gene"].ctypes.data,
+                                                out["umi"].ctypes.data, out["count"].ctypes.data, out["mark"].ctypes.data,
+                                                m, C.byref(n)))
+        return out
+
+    def whitelist(self):
+        n_parts = C.c_uint32(0)
+        sizes = np.zeros(8, np.uint32)
+        lens = np.zeros(8, np.uint32)
+        self._check(self._lib.dge_whitelist_shape(self._h, C.byref(n_parts), sizes.ctypes.data, lens.ctypes.data, 8))
+        parts = []
+        buf = C.create_string_buffer(64)
+        for p in range(n_parts.value):
+            toks = []
+            for i in range(int(sizes[p])):
+                self._check(self._lib.dge_whitelist_token(self._h, p, i, buf, 64))
+                toks.append(buf.value.decode())
+            parts.append(toks)
+        return parts
+
+
+def edit_distance(a: str, b: str, skip_n: bool = True, max_ed: int = 10000) -> int:
+    return int(load_library().dge_edit_distance(a.encode(), b.encode(), 1 if skip_n else 0, max_ed))
+
+
+def hamming_distance(a: str, b: str, skip_n: bool = True) -> int:
+    return int(load_library().dge_hamming_distance(a.encode(), b.encode(), 1 if skip_n else 0))

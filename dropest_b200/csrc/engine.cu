@@ -1,0 +1,1203 @@
+// engine.cu -- orchestration of the device pipeline behind the C ABI in include/dropest_b200.h.
+//
+// Stage map (reference call stack SURVEY.md 3.1-3.3):
+//   dge_add_batch*        CellsDataContainer::add_record                 -> k_fill_compact (fill.cuh), one launch per batch
+//   dge_set_initialized   (rest of add_record work) + set_initialized    -> SortCombine (sortcombine.cuh) + segments.cuh + real/filtered cells
+//   dge_merge_and_filter  merge_and_filter: MergeStrategy::merge         -> merge.cuh kernels + host phase 2 (MergeStrategyBase.cpp:29-51)
+//                         UMI merge, update_cell_sizes, matrices         -> segments.cuh + k_matrix_*
+// There is no CPU implementation of the grouping here: without a CUDA device every entry point fails.
+#include "../../include/dropest_b200.h"
+#include "common.cuh"
+#include "fill.cuh"
+#include "merge.cuh"
+#include "scan.cuh"
+#include "segments.cuh"
+#include "sortcombine.cuh"
+#include "whitelist.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <unordered_map>
+#include <vector>
+
+using namespace dge;
+
+namespace
+{
+thread_local std::string g_create_error;
+
+struct HostCell
+{
+    uint64_t cb = 0;
+    uint32_t slot = 0, pc = 0, first_idx = 0, n_intergenic = 0;
+    int32_t n_genes = 0, umis_stat = 0, reads_stat = 0, req_genes = 0, req_umis = 0;
+    int32_t n_umis_distinct = 0;
+    bool merged = false, excluded = false, real = true;
+    int32_t target = -1; // index into `real`
+};
+
+struct KeyChunk
+{
+    DevBuf keys;
+    size_t capacity = 0;
+    size_t count = 0; // valid after counts were read back
+    unsigned long long *d_count = nullptr;
+};
+
+struct MatrixDev
+{
+    DevBuf indptr, gene, val, cols;
+    size_t n_cols = 0, nnz = 0;
+    bool built = false;
+};
+} // namespace
+
+struct dge_handle
+{
+    dge_config cfg{};
+    std::string barcodes_file;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int state = 0; // 0 filling, 1 initialized, 2 merged
+    bool device_ready = false;
+
+    KeyLayout kl{};
+    size_t table_cap = 0;
+    uint32_t min_after_eff = 0;
+
+    // fill-stage device state
+    DevBuf tab, gene_first, ctr, staging[2], ctr_counts;
+    std::vector<std::unique_ptr<KeyChunk>> chunks;
+    std::vector<DevBuf *> chunk_counts;
+    DevBuf chunk_count_pool;
+    size_t n_chunk_counters = 0;
+    uint64_t n_reads = 0;
+    int staging_turn = 0;
+    cudaEvent_t staging_ev[2] = {nullptr, nullptr};
+
+    // grouped state
+    DevBuf keys_all, ukey, uval, ukey2, uval2, overflow_flag;
+    DevBuf cg_key, cg_start, cg_req, cg_reads, cg_req_reads;
+    DevBuf pc_slot, pc_u_start, pc_cg_start, pc_reads, pc_req_genes, pc_req_umis, slot_pc;
+    DevBuf tile_a, tile_b, scan_scratch, flags, flags_off, rows_dev, misc;
+    uint32_t n_u = 0, n_cg = 0, n_pc = 0;
+    size_t n_keys = 0;
+    FillCounters counters{};
+    uint64_t total_cells = 0;
+
+    SortCombine sc;
+    SortCombineStats sc_stats;
+
+    // host state
+    std::vector<HostCell> real;            // cell-id (first-seen) order
+    std::vector<uint32_t> filtered;        // indices into real, ascending compare_cells
+    std::vector<int32_t> gene_order;       // gene ids in first-seen order
+    std::vector<std::pair<uint32_t, uint32_t>> merge_events; // (src real idx, dst real idx) in application order
+    uint64_t n_merged = 0, n_excluded = 0;
+    Whitelist wl;
+    bool wl_fast = false;
+    DevBuf wl_tokens[WL_MAX_PARTS];
+    WhitelistDev wl_dev{};
+
+    MatrixDev cm, cm_raw;
+    dge_timings timings{};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned launches = 0;
+
+    ~dge_handle()
+    {
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+        for (auto &e : staging_ev) if (e) cudaEventDestroy(e);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace
+{
+
+int fail(dge_handle *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+template <class F> int guarded(dge_handle *h, F &&f)
+{
+    try { return f(); }
+    catch (CudaError &e) { return fail(h, DGE_ERR_CUDA, e.what()); }
+    catch (std::bad_alloc &) { return fail(h, DGE_ERR_INTERNAL, "out of host memory"); }
+    catch (std::exception &e) { return fail(h, DGE_ERR_INTERNAL, e.what()); }
+}
+
+unsigned grid_for(size_t n, unsigned threads, unsigned max_blocks = 148 * 16)
+{
+    size_t g = div_up(n, size_t(threads));
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return unsigned(g);
+}
+
+template <class T> void d2h(std::vector<T> &dst, const void *src, size_t n, cudaStream_t st)
+{
+    dst.resize(n);
+    if (n) DGE_CUDA(cudaMemcpyAsync(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+}
+
+template <class T> T d2h_scalar(const void *src, cudaStream_t st)
+{
+    T v;
+    DGE_CUDA(cudaMemcpyAsync(&v, src, sizeof(T), cudaMemcpyDeviceToHost, st));
+    DGE_CUDA(cudaStreamSynchronize(st));
+    return v;
+}
+
+void ensure_device(dge_handle *h)
+{
+    DGE_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->device_ready) return;
+    if (!h->stream)
+    {
+        DGE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    for (auto &e : h->ev) DGE_CUDA(cudaEventCreate(&e));
+    for (auto &e : h->staging_ev) DGE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+
+    // key layout: [slot:tb | gene:gb | umi:ub | mark:3]
+    KeyLayout &kl = h->kl;
+    kl.ub = int(2 * h->cfg.umi_len);
+    kl.gb = std::max(1, ceil_log2_u64(h->cfg.n_genes));
+    const int tb_max = 61 - kl.gb - kl.ub;
+    int want = h->cfg.max_barcodes_hint ? ceil_log2_u64(2 * h->cfg.max_barcodes_hint) : 22;
+    kl.tb = std::min(std::min(tb_max, 28), std::max(10, want));
+    if (kl.tb < 10) throw std::runtime_error("key layout does not fit 64 bits: reduce n_genes or umi_len");
+    kl.kb = kl.tb + kl.gb + kl.ub + 3;
+    h->table_cap = size_t(1) << kl.tb;
+
+    h->tab.reserve(h->table_cap * sizeof(CellSlot));
+    k_table_init<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->tab.as<CellSlot>(), h->table_cap);
+    h->gene_first.reserve(size_t(h->cfg.n_genes) * 4);
+    k_fill_u32<<<grid_for(h->cfg.n_genes, 256), 256, 0, h->stream>>>(h->gene_first.as<uint32_t>(), h->cfg.n_genes, NONE32);
+    h->ctr.reserve(sizeof(FillCounters));
+    DGE_CUDA(cudaMemsetAsync(h->ctr.p, 0, sizeof(FillCounters), h->stream));
+    h->overflow_flag.reserve(sizeof(int));
+    DGE_CUDA(cudaMemsetAsync(h->overflow_flag.p, 0, sizeof(int), h->stream));
+    h->scan_scratch.reserve(((size_t(1) << 20) + 64) * 4); // enough for any scan of < 2^32 elements
+    h->chunk_count_pool.reserve(4096 * sizeof(unsigned long long));
+    DGE_CUDA(cudaMemsetAsync(h->chunk_count_pool.p, 0, 4096 * sizeof(unsigned long long), h->stream));
+    DGE_LAUNCH_CHECK();
+    h->launches += 2;
+    h->device_ready = true;
+}
+
+// One batch already resident on the device: barcode-table insert + key packing into a fresh chunk.
+void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n)
+{
+    if (n == 0) return;
+    if (h->n_chunk_counters >= 4096) throw std::runtime_error("too many batches (max 4096); use larger batches");
+    auto chunk = std::unique_ptr<KeyChunk>(new KeyChunk());
+    chunk->capacity = n;
+    chunk->keys.reserve(n * 8);
+    chunk->d_count = h->chunk_count_pool.as<unsigned long long>() + h->n_chunk_counters++;
+    // the kernel appends through FillCounters::n_keys; give every chunk its own cursor by pointing a private counter struct at it
+    // (we keep one FillCounters per handle and move the cursor: n_keys is reset per chunk and accumulated on the host later)
+    DGE_CUDA(cudaMemsetAsync(&h->ctr.as<FillCounters>()->n_keys, 0, sizeof(unsigned long long), h->stream));
+    unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(FILL_TILE)), 148 * 8));
+    k_fill_compact<<<grid, FILL_THREADS, 0, h->stream>>>(reinterpret_cast<const Rec16 *>(recs), n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes,
+                                                          h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(), h->ctr.as<FillCounters>(),
+                                                          /*l1_shift*/ 63, /*nb1*/ 0, nullptr);
+    DGE_LAUNCH_CHECK();
+    DGE_CUDA(cudaMemcpyAsync(chunk->d_count, &h->ctr.as<FillCounters>()->n_keys, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
+    ++h->launches;
+    h->chunks.push_back(std::move(chunk));
+    h->n_reads += n;
+}
+
+bool compare_cells(const HostCell &a, const HostCell &b)
+{
+    // CellsDataContainer::compare_cells (CellsDataContainer.cpp:329-344); barcode strings of equal length over ACGT compare
+    // like their 2-bit packings.
+    if (a.req_genes != b.req_genes) return a.req_genes < b.req_genes;
+    if (a.req_umis != b.req_umis) return a.req_umis < b.req_umis;
+    if (a.umis_stat != b.umis_stat) return a.umis_stat < b.umis_stat;
+    return a.cb < b.cb;
+}
+
+// update_filtered_gene_counts (CellsDataContainer.cpp:250-276)
+void update_filtered(dge_handle *h, uint32_t threshold, int cell_threshold)
+{
+    h->filtered.clear();
+    for (uint32_t i = 0; i < h->real.size(); ++i)
+    {
+        const HostCell &c = h->real[i];
+        if (!c.real) continue;
+        if (uint32_t(c.req_genes) >= threshold) h->filtered.push_back(i);
+    }
+    std::sort(h->filtered.begin(), h->filtered.end(), [&](uint32_t x, uint32_t y) { return compare_cells(h->real[x], h->real[y]); });
+    if (cell_threshold > 0 && size_t(cell_threshold) < h->filtered.size())
+        h->filtered.erase(h->filtered.begin(), h->filtered.end() - cell_threshold);
+}
+
+// (Re)build CG / PC tables from the current sorted U list.
+void build_segments(dge_handle *h)
+{
+    cudaStream_t st = h->stream;
+    const uint32_t n_u = h->n_u;
+    const int ub = h->kl.ub, gub = h->kl.gb + h->kl.ub;
+    const size_t nt = div_up(size_t(n_u), size_t(SEG_TILE));
+    h->tile_a.reserve((nt + 2) * 4); h->tile_b.reserve((nt + 2) * 4);
+    uint32_t *ta = h->tile_a.as<uint32_t>(), *tb = h->tile_b.as<uint32_t>();
+    if (nt == 0)
+    {
+        h->n_cg = h->n_pc = 0;
+        h->cg_start.reserve(8); h->pc_u_start.reserve(8); h->pc_cg_start.reserve(8);
+        DGE_CUDA(cudaMemsetAsync(h->cg_start.p, 0, 8, st));
+        DGE_CUDA(cudaMemsetAsync(h->pc_u_start.p, 0, 8, st));
+        DGE_CUDA(cudaMemsetAsync(h->pc_cg_start.p, 0, 8, st));
+        return;
+    }
+    k_seg_count<<<unsigned(nt), SEG_THREADS, 0, st>>>(h->ukey.as<uint64_t>(), n_u, ub, gub, ta, tb);
+    ++h->launches;
+    // two scans share the scratch: run sequentially on the stream, read totals in between
+    const uint32_t *tot_cg = device_exclusive_scan(ta, ta, nt, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+    h->n_cg = d2h_scalar<uint32_t>(tot_cg, st);
+    const uint32_t *tot_pc = device_exclusive_scan(tb, tb, nt, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+    h->n_pc = d2h_scalar<uint32_t>(tot_pc, st);
+
+    const size_t ncg = h->n_cg, npc = h->n_pc;
+    h->cg_key.reserve((ncg + 1) * 8); h->cg_start.reserve((ncg + 1) * 4);
+    h->cg_req.reserve((ncg + 1) * 4); h->cg_reads.reserve((ncg + 1) * 4);
+    if (h->cfg.reads_output) h->cg_req_reads.reserve((ncg + 1) * 4);
+    h->pc_slot.reserve((npc + 2) * 4); h->pc_u_start.reserve((npc + 2) * 4); h->pc_cg_start.reserve((npc + 2) * 4);
+    h->pc_reads.reserve((npc + 1) * 4); h->pc_req_genes.reserve((npc + 1) * 4); h->pc_req_umis.reserve((npc + 1) * 4);
+    k_seg_write<<<unsigned(nt), SEG_THREADS, 0, st>>>(h->ukey.as<uint64_t>(), n_u, ub, gub, ta, tb, h->cg_key.as<uint64_t>(),
+                                                       h->cg_start.as<uint32_t>(), h->pc_slot.as<uint32_t>(), h->pc_u_start.as<uint32_t>(),
+                                                       h->pc_cg_start.as<uint32_t>());
+    k_seg_sentinels<<<1, 1, 0, st>>>(n_u, h->n_cg, h->n_pc, h->cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), h->pc_cg_start.as<uint32_t>());
+    k_cg_reduce<<<grid_for(ncg, 256), 256, 0, st>>>(h->uval.as<uint32_t>(), h->cg_start.as<uint32_t>(), h->n_cg, h->cfg.query_mark_mask,
+                                                     h->cg_req.as<uint32_t>(), h->cg_reads.as<uint32_t>(),
+                                                     h->cfg.reads_output ? h->cg_req_reads.as<uint32_t>() : nullptr);
+    k_pc_reduce<<<grid_for(npc, 256), 256, 0, st>>>(h->cg_req.as<uint32_t>(), h->cg_reads.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(), h->n_pc,
+                                                     h->pc_reads.as<uint32_t>(), h->pc_req_genes.as<uint32_t>(), h->pc_req_umis.as<uint32_t>());
+    DGE_LAUNCH_CHECK();
+    h->launches += 4;
+}
+
+void build_slot_pc(dge_handle *h)
+{
+    h->slot_pc.reserve(h->table_cap * 4);
+    k_fill_u32<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->slot_pc.as<uint32_t>(), h->table_cap, NONE32);
+    if (h->n_pc)
+        k_build_slot_pc<<<grid_for(h->n_pc, 256), 256, 0, h->stream>>>(h->pc_slot.as<uint32_t>(), h->n_pc, h->slot_pc.as<uint32_t>());
+    DGE_LAUNCH_CHECK();
+    h->launches += 2;
+}
+
+void gather_rows(dge_handle *h, const std::vector<uint32_t> &pcs, std::vector<CellRow> &rows)
+{
+    rows.clear();
+    if (pcs.empty()) return;
+    h->misc.reserve(pcs.size() * 4);
+    h->rows_dev.reserve(pcs.size() * sizeof(CellRow));
+    DGE_CUDA(cudaMemcpyAsync(h->misc.p, pcs.data(), pcs.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    k_gather_rows_list<<<grid_for(pcs.size(), 256), 256, 0, h->stream>>>(h->misc.as<uint32_t>(), uint32_t(pcs.size()), h->tab.as<CellSlot>(),
+                                                                        h->pc_slot.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(),
+                                                                        h->pc_u_start.as<uint32_t>(), h->pc_reads.as<uint32_t>(),
+                                                                        h->pc_req_genes.as<uint32_t>(), h->pc_req_umis.as<uint32_t>(),
+                                                                        h->rows_dev.as<CellRow>());
+    DGE_LAUNCH_CHECK();
+    ++h->launches;
+    d2h(rows, h->rows_dev.p, pcs.size(), h->stream);
+    DGE_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+void do_set_initialized(dge_handle *h)
+{
+    ensure_device(h);
+    cudaStream_t st = h->stream;
+    DGE_CUDA(cudaEventRecord(h->ev[0], st));
+
+    // ---- collect compact keys of all batches into one array (chunks were produced at add time)
+    std::vector<unsigned long long> counts(h->n_chunk_counters);
+    if (!counts.empty())
+        DGE_CUDA(cudaMemcpyAsync(counts.data(), h->chunk_count_pool.p, counts.size() * 8, cudaMemcpyDeviceToHost, st));
+    DGE_CUDA(cudaMemcpyAsync(&h->counters, h->ctr.p, sizeof(FillCounters), cudaMemcpyDeviceToHost, st));
+    DGE_CUDA(cudaStreamSynchronize(st));
+    if (h->counters.table_overflow)
+        throw std::runtime_error("barcode table overflow: more distinct barcodes than the table holds; set max_barcodes_hint");
+    if (h->counters.bad_gene) throw std::runtime_error("record with gene id >= n_genes");
+    size_t n_keys = 0;
+    for (size_t c = 0; c < h->chunks.size(); ++c) { h->chunks[c]->count = size_t(counts[c]); n_keys += h->chunks[c]->count; }
+    if (n_keys >= 0xFFFFFFF0ull) throw std::runtime_error("more than 2^32 reads with genes on one device: shard across GPUs");
+    h->n_keys = n_keys;
+
+    const uint64_t *keys_in = nullptr;
+    if (h->chunks.size() == 1) keys_in = h->chunks[0]->keys.as<uint64_t>();
+    else if (h->chunks.size() > 1)
+    {
+        h->keys_all.reserve(n_keys * 8);
+        size_t off = 0;
+        for (auto &c : h->chunks)
+        {
+            if (c->count)
+                DGE_CUDA(cudaMemcpyAsync(h->keys_all.as<uint64_t>() + off, c->keys.p, c->count * 8, cudaMemcpyDeviceToDevice, st));
+            off += c->count;
+        }
+        keys_in = h->keys_all.as<uint64_t>();
+    }
+
+    // ---- group: distinct (cell, gene, UMI), sorted
+    h->ukey.reserve(std::max<size_t>(n_keys, 1) * 8);
+    h->uval.reserve(std::max<size_t>(n_keys, 1) * 4);
+    h->n_u = 0;
+    if (n_keys)
+    {
+        const int l1_bits = std::min(choose_l1_bits(n_keys), h->kl.kb - 3);
+        // the compact-key array doubles as the L2 scatter target / in-place dedup buffer
+        const uint32_t *n_u_ptr = h->sc.run(keys_in, nullptr, n_keys, h->kl.kb, l1_bits, nullptr, const_cast<uint64_t *>(keys_in),
+                                            h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), h->overflow_flag.as<int>(), st, &h->sc_stats);
+        h->n_u = d2h_scalar<uint32_t>(n_u_ptr, st);
+        h->sc.collect_timing();
+        int ovf = d2h_scalar<int>(h->overflow_flag.p, st);
+        if (ovf) throw std::runtime_error("sub-bucket hash table overflow in umig_dedup_sort");
+    }
+    for (auto &c : h->chunks) if (h->chunks.size() > 1) c->keys.release();
+
+    build_segments(h);
+    unsigned long long *d_total = reinterpret_cast<unsigned long long *>(h->ctr.as<FillCounters>());
+    (void)d_total;
+    h->misc.reserve(64);
+    DGE_CUDA(cudaMemsetAsync(h->misc.p, 0, 8, st));
+    k_count_occupied<<<grid_for(h->table_cap, 256), 256, 0, st>>>(h->tab.as<CellSlot>(), h->table_cap, h->misc.as<unsigned long long>());
+    ++h->launches;
+    h->total_cells = d2h_scalar<unsigned long long>(h->misc.p, st);
+    DGE_CUDA(cudaEventRecord(h->ev[1], st));
+
+    // ---- real cells -> host (Cell::is_real, Cell.cpp:125-128: n_genes >= min_genes_before_merge)
+    std::vector<CellRow> rows;
+    if (h->n_pc)
+    {
+        h->flags.reserve((size_t(h->n_pc) + 1) * 4); h->flags_off.reserve((size_t(h->n_pc) + 1) * 4);
+        k_real_flags<<<grid_for(h->n_pc, 256), 256, 0, st>>>(h->pc_cg_start.as<uint32_t>(), h->n_pc, h->cfg.min_genes_before_merge, h->flags.as<uint32_t>());
+        ++h->launches;
+        const uint32_t *tot = device_exclusive_scan(h->flags.as<uint32_t>(), h->flags_off.as<uint32_t>(), h->n_pc, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+        uint32_t n_real = d2h_scalar<uint32_t>(tot, st);
+        if (n_real)
+        {
+            h->rows_dev.reserve(size_t(n_real) * sizeof(CellRow));
+            k_gather_rows_flagged<<<grid_for(h->n_pc, 256), 256, 0, st>>>(h->flags.as<uint32_t>(), h->flags_off.as<uint32_t>(), h->n_pc, h->tab.as<CellSlot>(),
+                                                                          h->pc_slot.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(),
+                                                                          h->pc_reads.as<uint32_t>(), h->pc_req_genes.as<uint32_t>(),
+                                                                          h->pc_req_umis.as<uint32_t>(), h->rows_dev.as<CellRow>());
+            DGE_LAUNCH_CHECK();
+            ++h->launches;
+            d2h(rows, h->rows_dev.p, n_real, st);
+            DGE_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    // min_genes_before_merge == 0 makes every barcode real, including barcodes that only have intergenic reads
+    // (they own no UMI and are not in the PC table): pick them up from the barcode table.
+    std::vector<CellSlot> extra_slots;
+    if (h->cfg.min_genes_before_merge == 0 && h->total_cells > h->n_pc)
+    {
+        std::vector<CellSlot> tab_host;
+        d2h(tab_host, h->tab.p, h->table_cap, st);
+        std::vector<uint32_t> pc_slots;
+        d2h(pc_slots, h->pc_slot.p, h->n_pc, st);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        std::vector<char> present(h->table_cap, 0);
+        for (uint32_t s : pc_slots) present[s] = 1;
+        for (size_t s = 0; s < h->table_cap; ++s)
+            if (tab_host[s].cb != EMPTY64 && !present[s])
+            {
+                CellRow r{};
+                r.cb = tab_host[s].cb; r.slot = uint32_t(s); r.pc = NONE32; r.first_idx = tab_host[s].first_idx; r.n_intergenic = tab_host[s].n_intergenic;
+                rows.push_back(r);
+            }
+    }
+    std::sort(rows.begin(), rows.end(), [](const CellRow &a, const CellRow &b) { return a.first_idx < b.first_idx; });
+    h->real.clear();
+    h->real.reserve(rows.size());
+    for (auto const &r : rows)
+    {
+        HostCell c;
+        c.cb = r.cb; c.slot = r.slot; c.pc = r.pc; c.first_idx = r.first_idx; c.n_intergenic = r.n_intergenic;
+        c.n_genes = int32_t(r.n_genes); c.umis_stat = int32_t(r.n_umis); c.n_umis_distinct = int32_t(r.n_umis);
+        c.reads_stat = int32_t(r.n_reads); c.req_genes = int32_t(r.req_genes); c.req_umis = int32_t(r.req_umis);
+        c.target = int32_t(h->real.size());
+        h->real.push_back(c);
+    }
+    // gene first-seen order (StringIndexer::add, StringIndexer.cpp:10-18)
+    {
+        std::vector<uint32_t> gf;
+        d2h(gf, h->gene_first.p, h->cfg.n_genes, st);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        std::vector<std::pair<uint32_t, int32_t>> seen;
+        for (uint32_t g = 0; g < h->cfg.n_genes; ++g)
+            if (gf[g] != NONE32) seen.emplace_back(gf[g], int32_t(g));
+        std::sort(seen.begin(), seen.end());
+        h->gene_order.clear();
+        for (auto const &p : seen) h->gene_order.push_back(p.second);
+    }
+    update_filtered(h, 0, -1); // set_initialized: update_cell_sizes(query, 0, -1)  (CellsDataContainer.cpp:168)
+    DGE_CUDA(cudaEventRecord(h->ev[2], st));
+    DGE_CUDA(cudaStreamSynchronize(st));
+    h->state = 1;
+    cudaEventElapsedTime(&h->timings.ms_fill, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->timings.ms_init, h->ev[1], h->ev[2]);
+    h->timings.ms_total = h->timings.ms_fill + h->timings.ms_init;
+    h->timings.ms_dedup_kernel = h->sc_stats.dedup_ms;
+    h->timings.n_kernel_launches = h->launches + h->sc_stats.launches;
+    h->timings.n_dedup_launches = h->sc_stats.dedup_launches;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+void upload_whitelist(dge_handle *h)
+{
+    WhitelistDev &d = h->wl_dev;
+    d.n_parts = int(h->wl.parts.size());
+    int shift = int(2 * h->cfg.cb_len);
+    for (int k = 0; k < d.n_parts; ++k)
+    {
+        const auto &p = h->wl.parts[size_t(k)];
+        d.part_len[k] = int(p[0].size());
+        shift -= 2 * d.part_len[k];
+        d.part_shift[k] = shift;
+        d.part_size[k] = uint32_t(p.size());
+        std::vector<uint32_t> packed(p.size());
+        for (size_t t = 0; t < p.size(); ++t) { uint64_t v; pack_seq(p[t], v); packed[t] = uint32_t(v); }
+        h->wl_tokens[k].reserve(packed.size() * 4);
+        DGE_CUDA(cudaMemcpyAsync(h->wl_tokens[k].p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        DGE_CUDA(cudaStreamSynchronize(h->stream));
+        d.tokens[k] = h->wl_tokens[k].as<uint32_t>();
+    }
+}
+
+std::vector<uint32_t> run_intersections(dge_handle *h, const std::vector<PairJob> &jobs)
+{
+    std::vector<uint32_t> out;
+    if (jobs.empty()) return out;
+    DevBuf djobs, dout;
+    djobs.reserve(jobs.size() * sizeof(PairJob)); dout.reserve(jobs.size() * 4);
+    DGE_CUDA(cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(PairJob), cudaMemcpyHostToDevice, h->stream));
+    k_intersect<<<unsigned(jobs.size()), 128, 0, h->stream>>>(djobs.as<PairJob>(), uint32_t(jobs.size()), h->ukey.as<uint64_t>(),
+                                                              h->pc_u_start.as<uint32_t>(), h->pc_slot.as<uint32_t>(), h->kl.gb + h->kl.ub,
+                                                              dout.as<uint32_t>());
+    DGE_LAUNCH_CHECK();
+    ++h->launches;
+    d2h(out, dout.p, jobs.size(), h->stream);
+    DGE_CUDA(cudaStreamSynchronize(h->stream));
+    return out;
+}
+
+// RealBarcodesMergeStrategy::get_best_merge_target (RealBarcodesMergeStrategy.cpp:31-61) over an ORDERED neighbour list.
+long best_target_real(const dge_handle *h, uint32_t base, const std::vector<uint32_t> &nbs, const std::vector<uint32_t> &isect)
+{
+    if (nbs[0] == base) return long(base);
+    double max_frac = 0;
+    uint32_t best = nbs[0];
+    for (size_t k = 0; k < nbs.size(); ++k)
+    {
+        double frac = 0.5 * isect[k] * (1. / h->real[base].umis_stat + 1. / h->real[nbs[k]].umis_stat);
+        if (max_frac < frac) { max_frac = frac; best = nbs[k]; }
+    }
+    if (max_frac < h->cfg.min_merge_fraction) return -1;
+    return long(best);
+}
+
+// Phase 1 for RealBarcodesMergeStrategy: target (index into real, or -1) for every filtered cell.
+std::vector<long> phase1_real(dge_handle *h)
+{
+    cudaStream_t st = h->stream;
+    const size_t n = h->real.size();
+    std::vector<long> target(n, -2);
+    if (n == 0) return target;
+    std::unordered_map<uint64_t, uint32_t> by_cb;
+    by_cb.reserve(n * 2);
+    for (uint32_t i = 0; i < n; ++i) by_cb.emplace(h->real[i].cb, i);
+    std::vector<uint32_t> pc_to_real_keys;
+    std::unordered_map<uint32_t, uint32_t> by_pc;
+    by_pc.reserve(n * 2);
+    for (uint32_t i = 0; i < n; ++i) if (h->real[i].pc != NONE32) by_pc.emplace(h->real[i].pc, i);
+
+    std::vector<int> nb_count(n, NB_SLOW);
+    std::vector<uint32_t> nb_pc(n * WL_K, NONE32);
+    if (h->wl_fast)
+    {
+        upload_whitelist(h);
+        std::vector<uint64_t> cbs(n);
+        std::vector<uint32_t> umis(n);
+        for (size_t i = 0; i < n; ++i) { cbs[i] = h->real[i].cb; umis[i] = uint32_t(h->real[i].umis_stat); }
+        DevBuf dcb, dumis, dcount, dnb;
+        dcb.reserve(n * 8); dumis.reserve(n * 4); dcount.reserve(n * 4); dnb.reserve(n * WL_K * 4);
+        DGE_CUDA(cudaMemcpyAsync(dcb.p, cbs.data(), n * 8, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(cudaMemcpyAsync(dumis.p, umis.data(), n * 4, cudaMemcpyHostToDevice, st));
+        k_wl_class01<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(dcb.as<uint64_t>(), dumis.as<uint32_t>(), uint32_t(n), h->wl_dev, h->tab.as<CellSlot>(),
+                                                                            h->kl.tb, h->slot_pc.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(),
+                                                                            h->pc_u_start.as<uint32_t>(), h->cfg.min_genes_before_merge,
+                                                                            dcount.as<int>(), dnb.as<uint32_t>());
+        DGE_LAUNCH_CHECK();
+        ++h->launches;
+        d2h(nb_count, dcount.p, n, st);
+        d2h(nb_pc, dnb.p, n * WL_K, st);
+        DGE_CUDA(cudaStreamSynchronize(st));
+    }
+
+    // exact host path for the cells the fast path could not settle
+    auto exact_neighbours = [&](uint32_t i) {
+        const std::string cb = unpack_seq(h->real[i].cb, h->cfg.cb_len);
+        auto lookup = [&](const std::string &s) -> long {
+            uint64_t v;
+            if (!pack_seq(s, v)) return -1;
+            auto it = by_cb.find(v);
+            return it == by_cb.end() ? -1 : long(it->second);
+        };
+        // Any barcode known to the container but not real fails the size test below exactly like in the reference.
+        auto eligible = [&](long id) {
+            return uint32_t(h->real[size_t(id)].n_genes) >= h->cfg.min_genes_before_merge &&
+                   h->real[size_t(id)].umis_stat >= h->real[i].umis_stat;
+        };
+        std::vector<long> ids = h->wl.neighbours(cb, false, lookup, eligible);
+        return std::vector<uint32_t>(ids.begin(), ids.end());
+    };
+
+    std::vector<std::vector<uint32_t>> nbs(n);
+    std::vector<PairJob> jobs;
+    std::vector<std::pair<uint32_t, uint32_t>> job_owner; // (cell, k)
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        if (nb_count[i] == NB_SELF) { target[i] = long(i); continue; }
+        if (nb_count[i] == NB_SLOW) nbs[i] = exact_neighbours(i);
+        else
+            for (int k = 0; k < nb_count[i]; ++k) nbs[i].push_back(by_pc.at(nb_pc[size_t(i) * WL_K + size_t(k)]));
+        if (nbs[i].empty()) { target[i] = -1; continue; }
+        if (nbs[i][0] == i) { target[i] = long(i); continue; }
+        for (uint32_t k = 0; k < nbs[i].size(); ++k)
+        {
+            // a cell without UMIs (pc == NONE32) intersects nothing
+            if (h->real[i].pc == NONE32 || h->real[nbs[i][k]].pc == NONE32) continue;
+            jobs.push_back(PairJob{h->real[i].pc, h->real[nbs[i][k]].pc});
+            job_owner.emplace_back(i, k);
+        }
+    }
+    std::vector<uint32_t> isect_flat = run_intersections(h, jobs);
+    std::vector<std::vector<uint32_t>> isect(n);
+    for (uint32_t i = 0; i < n; ++i) isect[i].assign(nbs[i].size(), 0);
+    for (size_t j = 0; j < jobs.size(); ++j) isect[job_owner[j].first][job_owner[j].second] = isect_flat[j];
+
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        if (target[i] != -2) continue;
+        // The fast path reports the neighbour SET of the nearest class; the reference walks them in the order left by
+        // two unstable sorts.  That order only matters on exact ties of the best fraction: replay it then.
+        if (nb_count[i] > 1)
+        {
+            double best = -1; int n_best = 0;
+            for (size_t k = 0; k < nbs[i].size(); ++k)
+            {
+                double frac = 0.5 * isect[i][k] * (1. / h->real[i].umis_stat + 1. / h->real[nbs[i][k]].umis_stat);
+                if (frac > best) { best = frac; n_best = 1; } else if (frac == best) ++n_best;
+            }
+            if (n_best > 1 && !(best < h->cfg.min_merge_fraction))
+            {
+                std::vector<uint32_t> ordered = exact_neighbours(i);
+                std::vector<uint32_t> isect_ord(ordered.size(), 0);
+                for (size_t a = 0; a < ordered.size(); ++a)
+                    for (size_t b = 0; b < nbs[i].size(); ++b)
+                        if (nbs[i][b] == ordered[a]) isect_ord[a] = isect[i][b];
+                nbs[i] = ordered; isect[i] = isect_ord;
+            }
+        }
+        target[i] = best_target_real(h, i, nbs[i], isect[i]);
+    }
+    return target;
+}
+
+// Phase 2: MergeStrategyBase::merge_inited second loop + reassign (MergeStrategyBase.cpp:29-82), on real-cell indices.
+void phase2(dge_handle *h, const std::vector<long> &target)
+{
+    const size_t n = h->real.size();
+    std::vector<uint32_t> reassign(n);
+    std::iota(reassign.begin(), reassign.end(), 0u);
+    std::unordered_map<uint32_t, std::vector<uint32_t>> reassigned_to;
+    h->merge_events.clear();
+    h->n_merged = h->n_excluded = 0;
+    for (uint32_t base : h->filtered)
+    {
+        long t = target[base];
+        if (t < 0) { h->real[base].excluded = true; ++h->n_excluded; continue; }
+        if (uint32_t(t) != reassign[size_t(t)]) t = long(reassign[size_t(t)]);
+        if (uint32_t(t) == base) continue;
+        // merge_cells (CellsDataContainer.cpp:90-104): Stats::merge adds every counter (Stats.cpp:29-43)
+        HostCell &src = h->real[base];
+        HostCell &dst = h->real[size_t(t)];
+        dst.umis_stat += src.umis_stat; dst.reads_stat += src.reads_stat; dst.n_intergenic += src.n_intergenic;
+        src.merged = true;
+        h->merge_events.emplace_back(base, uint32_t(t));
+        ++h->n_merged;
+        // reassign
+        reassign[base] = uint32_t(t);
+        auto &to_t = reassigned_to[uint32_t(t)];
+        to_t.push_back(base);
+        auto it = reassigned_to.find(base);
+        if (it != reassigned_to.end())
+        {
+            std::vector<uint32_t> moved = it->second;
+            for (uint32_t r : moved) { reassign[r] = uint32_t(t); reassigned_to[uint32_t(t)].push_back(r); }
+            reassigned_to[base].clear();
+        }
+    }
+    for (uint32_t i = 0; i < n; ++i) h->real[i].target = int32_t(reassign[i]);
+}
+
+// Apply the recorded merges to the device lists.
+void apply_merges(dge_handle *h)
+{
+    if (h->merge_events.empty()) return;
+    cudaStream_t st = h->stream;
+    // absorbed sets: content of X after all events = own ∪ originals absorbed (sequential semantics of merge_cells)
+    std::unordered_map<uint32_t, std::vector<uint32_t>> absorbed;
+    for (auto const &e : h->merge_events)
+    {
+        std::vector<uint32_t> add{e.first};
+        auto it = absorbed.find(e.first);
+        if (it != absorbed.end()) add.insert(add.end(), it->second.begin(), it->second.end());
+        auto &dst = absorbed[e.second];
+        dst.insert(dst.end(), add.begin(), add.end());
+    }
+    std::vector<MoveJob> jobs;
+    uint64_t total = 0;
+    for (auto const &kv : absorbed)
+        for (uint32_t o : kv.second)
+        {
+            const HostCell &src = h->real[o];
+            if (src.pc == NONE32 || src.n_umis_distinct == 0) continue;
+            if (total + uint64_t(src.n_umis_distinct) >= 0xFFFFFFF0ull) throw std::runtime_error("merge volume exceeds 2^32 entries");
+            jobs.push_back(MoveJob{src.pc, h->real[kv.first].slot, uint32_t(total)});
+            total += uint64_t(src.n_umis_distinct);
+        }
+    if (jobs.empty()) return;
+    DevBuf djobs, mkeys, mvals, ekey, eval, keep, keep_off, xkey, xval;
+    djobs.reserve(jobs.size() * sizeof(MoveJob));
+    mkeys.reserve(total * 8); mvals.reserve(total * 4); ekey.reserve(total * 8); eval.reserve(total * 4);
+    DGE_CUDA(cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(MoveJob), cudaMemcpyHostToDevice, st));
+    const int gub = h->kl.gb + h->kl.ub;
+    k_gather_relabel<<<grid_for(jobs.size(), 1, 148 * 16), 256, 0, st>>>(djobs.as<MoveJob>(), uint32_t(jobs.size()), h->ukey.as<uint64_t>(),
+                                                                        h->uval.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), gub,
+                                                                        mkeys.as<uint64_t>(), mvals.as<uint32_t>());
+    DGE_LAUNCH_CHECK();
+    ++h->launches;
+    const int l1_bits = std::min(choose_l1_bits(total), h->kl.kb - 3);
+    const uint32_t *n_e_ptr = h->sc.run(mkeys.as<uint64_t>(), mvals.as<uint32_t>(), total, h->kl.kb, l1_bits, nullptr, mkeys.as<uint64_t>(),
+                                        ekey.as<uint64_t>(), eval.as<uint32_t>(), h->overflow_flag.as<int>(), st, &h->sc_stats);
+    const uint32_t n_e = d2h_scalar<uint32_t>(n_e_ptr, st);
+    h->sc.collect_timing();
+    if (d2h_scalar<int>(h->overflow_flag.p, st)) throw std::runtime_error("sub-bucket hash table overflow while merging cells");
+    keep.reserve(size_t(n_e + 1) * 4); keep_off.reserve(size_t(n_e + 1) * 4);
+    k_probe_merge<<<grid_for(n_e, 256), 256, 0, st>>>(ekey.as<uint64_t>(), eval.as<uint32_t>(), n_e, h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(),
+                                                       h->slot_pc.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), gub, keep.as<uint32_t>());
+    ++h->launches;
+    const uint32_t *n_x_ptr = device_exclusive_scan(keep.as<uint32_t>(), keep_off.as<uint32_t>(), n_e, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+    const uint32_t n_x = d2h_scalar<uint32_t>(n_x_ptr, st);
+    if (n_x)
+    {
+        if (uint64_t(h->n_u) + n_x >= 0xFFFFFFF0ull) throw std::runtime_error("too many distinct UMIs after merging");
+        xkey.reserve(size_t(n_x) * 8); xval.reserve(size_t(n_x) * 4);
+        k_compact_keep<<<grid_for(n_e, 256), 256, 0, st>>>(ekey.as<uint64_t>(), eval.as<uint32_t>(), n_e, keep.as<uint32_t>(), keep_off.as<uint32_t>(),
+                                                            xkey.as<uint64_t>(), xval.as<uint32_t>());
+        const size_t n_new = size_t(h->n_u) + n_x;
+        h->ukey2.reserve(n_new * 8); h->uval2.reserve(n_new * 4);
+        k_merge_rank<<<grid_for(n_new, 256), 256, 0, st>>>(h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), h->n_u, xkey.as<uint64_t>(), xval.as<uint32_t>(), n_x,
+                                                            h->ukey2.as<uint64_t>(), h->uval2.as<uint32_t>());
+        DGE_LAUNCH_CHECK();
+        h->launches += 2;
+        DGE_CUDA(cudaStreamSynchronize(st));
+        std::swap(h->ukey.p, h->ukey2.p); std::swap(h->ukey.bytes, h->ukey2.bytes);
+        std::swap(h->uval.p, h->uval2.p); std::swap(h->uval.bytes, h->uval2.bytes);
+        h->n_u = uint32_t(n_new);
+    }
+    DGE_CUDA(cudaStreamSynchronize(st));
+    build_segments(h);
+}
+
+void build_matrix(dge_handle *h, MatrixDev &m, const std::vector<uint32_t> &col_pcs, bool filtered)
+{
+    cudaStream_t st = h->stream;
+    m.n_cols = col_pcs.size();
+    m.nnz = 0;
+    m.built = true;
+    m.indptr.reserve((m.n_cols + 2) * 4);
+    if (m.n_cols == 0) { DGE_CUDA(cudaMemsetAsync(m.indptr.p, 0, 8, st)); return; }
+    m.cols.reserve(m.n_cols * 4);
+    DGE_CUDA(cudaMemcpyAsync(m.cols.p, col_pcs.data(), m.n_cols * 4, cudaMemcpyHostToDevice, st));
+    DevBuf nnz;
+    nnz.reserve((m.n_cols + 2) * 4);
+    k_matrix_col_nnz<<<grid_for(m.n_cols * 32, 256), 256, 0, st>>>(m.cols.as<uint32_t>(), uint32_t(m.n_cols), h->pc_cg_start.as<uint32_t>(),
+                                                                   h->cg_req.as<uint32_t>(), filtered ? 1 : 0, nnz.as<uint32_t>());
+    ++h->launches;
+    DGE_CUDA(cudaMemsetAsync(nnz.as<uint32_t>() + m.n_cols, 0, 4, st));
+    device_exclusive_scan(nnz.as<uint32_t>(), m.indptr.as<uint32_t>(), m.n_cols + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+    m.nnz = d2h_scalar<uint32_t>(m.indptr.as<uint32_t>() + m.n_cols, st);
+    m.gene.reserve(std::max<size_t>(m.nnz, 1) * 4); m.val.reserve(std::max<size_t>(m.nnz, 1) * 4);
+    const uint32_t *values;
+    int mode;
+    if (filtered) { values = h->cfg.reads_output ? h->cg_req_reads.as<uint32_t>() : h->cg_req.as<uint32_t>(); mode = 0; }
+    else if (h->cfg.reads_output) { values = h->cg_reads.as<uint32_t>(); mode = 2; }
+    else { values = nullptr; mode = 1; }
+    k_matrix_fill<<<grid_for(m.n_cols * 32, 256), 256, 0, st>>>(m.cols.as<uint32_t>(), uint32_t(m.n_cols), m.indptr.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(),
+                                                                h->cg_key.as<uint64_t>(), values, h->cg_start.as<uint32_t>(), mode,
+                                                                (1u << h->kl.gb) - 1, m.gene.as<int32_t>(), m.val.as<int32_t>());
+    DGE_LAUNCH_CHECK();
+    ++h->launches;
+}
+
+void do_merge_and_filter(dge_handle *h)
+{
+    DGE_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    DGE_CUDA(cudaEventRecord(h->ev[3], st));
+    build_slot_pc(h);
+
+    // ---- CB merge (MergeStrategyAbstract::merge, MergeStrategyAbstract.cpp:13-23)
+    if (h->cfg.merge_type == DGE_MERGE_REAL)
+    {
+        std::vector<long> target = phase1_real(h);
+        phase2(h, target);
+        apply_merges(h);
+    }
+    else if (h->cfg.merge_type != DGE_MERGE_NONE)
+        throw std::runtime_error("merge_type not implemented on the device path yet");
+    DGE_CUDA(cudaEventRecord(h->ev[4], st));
+
+    // ---- UMI merge: MergeUMIsStrategySimple only touches UMIs containing 'N' (MergeUMIsStrategySimple.cpp:21-59);
+    // 2-bit records cannot carry N, so there is nothing to repair here.
+    if (h->cfg.umi_merge_type != DGE_UMI_MERGE_SIMPLE) throw std::runtime_error("directional UMI merge not implemented on the device path yet");
+
+    // ---- update_cell_sizes (CellsDataContainer.cpp:111-125): requested sizes of every cell, real = !merged && !excluded && size >= min
+    if (!h->merge_events.empty())
+    {
+        std::vector<uint32_t> pcs, owners;
+        for (uint32_t i = 0; i < h->real.size(); ++i)
+            if (h->real[i].pc != NONE32) { pcs.push_back(h->real[i].pc); owners.push_back(i); }
+        std::vector<CellRow> rows;
+        gather_rows(h, pcs, rows);
+        for (size_t k = 0; k < rows.size(); ++k)
+        {
+            HostCell &c = h->real[owners[k]];
+            c.n_genes = int32_t(rows[k].n_genes); c.req_genes = int32_t(rows[k].req_genes); c.req_umis = int32_t(rows[k].req_umis);
+            c.n_umis_distinct = int32_t(rows[k].n_umis);
+        }
+    }
+    for (auto &c : h->real) c.real = !c.merged && !c.excluded && uint32_t(c.n_genes) >= h->cfg.min_genes_before_merge;
+    update_filtered(h, h->min_after_eff, h->cfg.max_cells);
+
+    // ---- matrices
+    std::vector<uint32_t> cols;
+    for (uint32_t i : h->filtered) cols.push_back(h->real[i].pc);
+    // a filtered cell always owns UMIs unless thresholds are 0; cells without UMIs contribute empty columns
+    std::vector<uint32_t> raw_cols;
+    for (auto const &c : h->real) if (c.real) raw_cols.push_back(c.pc);
+    for (auto &pc : cols) if (pc == NONE32) pc = h->n_pc;     // barcodes without UMIs: the empty sentinel cell
+    for (auto &pc : raw_cols) if (pc == NONE32) pc = h->n_pc;
+    build_matrix(h, h->cm, cols, true);
+    build_matrix(h, h->cm_raw, raw_cols, false);
+    DGE_CUDA(cudaEventRecord(h->ev[5], st));
+    DGE_CUDA(cudaStreamSynchronize(st));
+    h->state = 2;
+
+    auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]); return ms; };
+    h->timings.ms_fill = el(0, 1);
+    h->timings.ms_init = el(1, 2);
+    h->timings.ms_merge = el(3, 4);
+    h->timings.ms_finish = el(4, 5);
+    h->timings.ms_total = h->timings.ms_fill + h->timings.ms_init + h->timings.ms_merge + h->timings.ms_finish;
+    h->timings.ms_dedup_kernel = h->sc_stats.dedup_ms;
+    h->timings.n_kernel_launches = h->launches + h->sc_stats.launches;
+    h->timings.n_dedup_launches = h->sc_stats.dedup_launches;
+}
+
+// host copies for the query surface -----------------------------------------------------------------------------------
+struct AllCells
+{
+    std::vector<dge_cell_info> info; // first-seen order
+    std::vector<uint32_t> pc;        // present-cell index or NONE32
+};
+
+AllCells collect_all_cells(dge_handle *h)
+{
+    cudaStream_t st = h->stream;
+    std::vector<CellSlot> tab;
+    d2h(tab, h->tab.p, h->table_cap, st);
+    std::vector<uint32_t> pc_slot, pc_cg, pc_u, pc_reads, pc_rg, pc_ru;
+    d2h(pc_slot, h->pc_slot.p, h->n_pc, st);
+    d2h(pc_cg, h->pc_cg_start.p, size_t(h->n_pc) + 1, st);
+    d2h(pc_u, h->pc_u_start.p, size_t(h->n_pc) + 1, st);
+    d2h(pc_reads, h->pc_reads.p, h->n_pc, st);
+    d2h(pc_rg, h->pc_req_genes.p, h->n_pc, st);
+    d2h(pc_ru, h->pc_req_umis.p, h->n_pc, st);
+    DGE_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint32_t> slot_pc(h->table_cap, NONE32);
+    for (uint32_t i = 0; i < h->n_pc; ++i) slot_pc[pc_slot[i]] = i;
+    std::unordered_map<uint32_t, uint32_t> real_by_slot;
+    for (uint32_t i = 0; i < h->real.size(); ++i) real_by_slot.emplace(h->real[i].slot, i);
+    std::vector<std::pair<uint32_t, uint32_t>> order; // (first_idx, slot)
+    for (size_t s = 0; s < h->table_cap; ++s)
+        if (tab[s].cb != EMPTY64) order.emplace_back(tab[s].first_idx, uint32_t(s));
+    std::sort(order.begin(), order.end());
+    std::unordered_map<uint32_t, uint32_t> pos_of_slot;
+    pos_of_slot.reserve(order.size() * 2);
+    for (uint32_t p = 0; p < order.size(); ++p) pos_of_slot.emplace(order[p].second, p);
+    AllCells res;
+    res.info.resize(order.size());
+    res.pc.resize(order.size());
+    for (uint32_t p = 0; p < order.size(); ++p)
+    {
+        const uint32_t s = order[p].second;
+        dge_cell_info &ci = res.info[p];
+        ci.barcode = tab[s].cb; ci.first_read_idx = tab[s].first_idx;
+        const uint32_t pc = slot_pc[s];
+        res.pc[p] = pc;
+        ci.flags = 0; ci.merge_target = int32_t(p);
+        if (pc != NONE32)
+        {
+            ci.n_genes = int32_t(pc_cg[pc + 1] - pc_cg[pc]); ci.umis_stat = int32_t(pc_u[pc + 1] - pc_u[pc]);
+            ci.reads_stat = int32_t(pc_reads[pc]); ci.requested_genes_num = int32_t(pc_rg[pc]); ci.requested_umis_num = int32_t(pc_ru[pc]);
+        }
+        else ci.n_genes = ci.umis_stat = ci.reads_stat = ci.requested_genes_num = ci.requested_umis_num = 0;
+        auto it = real_by_slot.find(s);
+        if (it != real_by_slot.end())
+        {
+            const HostCell &c = h->real[it->second];
+            ci.flags = (c.real ? DGE_CELL_REAL : 0u) | (c.merged ? DGE_CELL_MERGED : 0u) | (c.excluded ? DGE_CELL_EXCLUDED : 0u);
+            ci.umis_stat = c.umis_stat; ci.reads_stat = c.reads_stat;
+            ci.merge_target = int32_t(pos_of_slot.at(h->real[size_t(c.target)].slot));
+        }
+    }
+    return res;
+}
+
+void fill_info(const dge_handle *h, const HostCell &c, dge_cell_info &ci)
+{
+    (void)h;
+    ci.barcode = c.cb; ci.first_read_idx = c.first_idx;
+    ci.flags = (c.real ? DGE_CELL_REAL : 0u) | (c.merged ? DGE_CELL_MERGED : 0u) | (c.excluded ? DGE_CELL_EXCLUDED : 0u);
+    ci.n_genes = c.n_genes; ci.umis_stat = c.umis_stat; ci.reads_stat = c.reads_stat;
+    ci.requested_genes_num = c.req_genes; ci.requested_umis_num = c.req_umis;
+    ci.merge_target = -1;
+}
+
+} // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+void dge_config_default(dge_config *cfg)
+{
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->abi_version = DGE_ABI_VERSION;
+    cfg->device = 0;
+    cfg->cb_len = 16; cfg->umi_len = 10; cfg->n_genes = 1;
+    cfg->merge_type = DGE_MERGE_NONE;
+    cfg->barcodes_type = DGE_BARCODES_INDROP; // MergeStrategyFactory.cpp:45 default "indrop"
+    cfg->umi_merge_type = DGE_UMI_MERGE_SIMPLE;
+    cfg->min_genes_before_merge = 10; cfg->min_genes_after_merge = 10;
+    cfg->max_cb_merge_edit_distance = 2; cfg->max_umi_merge_edit_distance = 1;
+    cfg->min_merge_fraction = 0.2; cfg->max_merge_prob = 1e-4; cfg->max_real_merge_prob = 1e-7; cfg->umi_merge_mult = 2;
+    cfg->query_mark_mask = 0xCC; // eEBA
+    cfg->max_cells = -1;
+}
+
+int dge_create(const dge_config *cfg, dge_handle **out)
+{
+    if (!cfg || !out) return fail(nullptr, DGE_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != DGE_ABI_VERSION) return fail(nullptr, DGE_ERR_INVALID, "abi_version mismatch");
+    if (cfg->cb_len == 0 || cfg->cb_len > 20) return fail(nullptr, DGE_ERR_INVALID, "cb_len must be in 1..20");
+    if (cfg->umi_len == 0 || cfg->umi_len > 12) return fail(nullptr, DGE_ERR_INVALID, "umi_len must be in 1..12");
+    if (cfg->n_genes == 0 || cfg->n_genes >= DGE_NO_GENE) return fail(nullptr, DGE_ERR_INVALID, "n_genes must be in 1..2^24-2");
+    if (cfg->merge_type > DGE_MERGE_ALL) return fail(nullptr, DGE_ERR_INVALID, "unknown merge_type");
+    if ((cfg->query_mark_mask & ~0xFEu) != 0) return fail(nullptr, DGE_ERR_INVALID, "query_mark_mask uses bits 1..7 only");
+    std::unique_ptr<dge_handle> h(new dge_handle());
+    h->cfg = *cfg;
+    if (cfg->barcodes_file) h->barcodes_file = cfg->barcodes_file;
+    h->cfg.barcodes_file = nullptr;
+    // MergeStrategyAbstract ctor: min_genes_after_merge = max(after, before)  (MergeStrategyAbstract.cpp:8-11)
+    h->min_after_eff = std::max(cfg->min_genes_after_merge, cfg->min_genes_before_merge);
+    const bool wants_wl = cfg->merge_type == DGE_MERGE_REAL || cfg->merge_type == DGE_MERGE_POISSON_REAL;
+    if (wants_wl)
+    {
+        if (h->barcodes_file.empty()) return fail(nullptr, DGE_ERR_INVALID, "merge_type needs barcodes_file");
+        try { h->wl.load(h->barcodes_file, cfg->barcodes_type == DGE_BARCODES_INDROP); }
+        catch (std::exception &e) { return fail(nullptr, DGE_ERR_IO, e.what()); }
+        h->wl_fast = h->wl.fast_path_ok(cfg->cb_len);
+    }
+    int n_dev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n_dev);
+    if (ce != cudaSuccess || n_dev <= 0)
+        return fail(nullptr, DGE_ERR_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, DGE_ERR_INVALID, "device ordinal out of range");
+    dge_handle *raw = h.get();
+    int rc = guarded(raw, [&] { ensure_device(raw); return int(DGE_OK); });
+    if (rc != DGE_OK) { g_create_error = raw->err; return rc; }
+    *out = h.release();
+    return DGE_OK;
+}
+
+void dge_destroy(dge_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    delete h;
+}
+
+const char *dge_last_error(const dge_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dge_set_stream(dge_handle *h, void *cuda_stream)
+{
+    if (!h) return DGE_ERR_INVALID;
+    if (h->n_reads) return fail(h, DGE_ERR_STATE, "dge_set_stream must precede the first batch");
+    return guarded(h, [&] {
+        DGE_CUDA(cudaSetDevice(h->cfg.device));
+        DGE_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->own_stream) cudaStreamDestroy(h->stream);
+        h->stream = static_cast<cudaStream_t>(cuda_stream);
+        h->own_stream = false;
+        return int(DGE_OK);
+    });
+}
+
+int dge_add_batch_device(dge_handle *h, const dge_record16 *recs, size_t n)
+{
+    if (!h || (!recs && n)) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state != 0) return fail(h, DGE_ERR_STATE, "Container is already initialized");
+    return guarded(h, [&] { ensure_device(h); fill_from_device(h, recs, n); return int(DGE_OK); });
+}
+
+int dge_add_batch(dge_handle *h, const dge_record16 *recs, size_t n)
+{
+    if (!h || (!recs && n)) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state != 0) return fail(h, DGE_ERR_STATE, "Container is already initialized");
+    return guarded(h, [&] {
+        ensure_device(h);
+        // double-buffered staging: copy slice k+1 while the fill kernel of slice k runs (single stream keeps order; the
+        // copy engine overlaps with the previous kernel when the host memory is pinned)
+        const size_t slice = size_t(32) << 20; // records per staging slice
+        for (size_t off = 0; off < n; off += slice)
+        {
+            const size_t m = std::min(slice, n - off);
+            DevBuf &stg = h->staging[h->staging_turn];
+            cudaEvent_t evt = h->staging_ev[h->staging_turn];
+            h->staging_turn ^= 1;
+            DGE_CUDA(cudaEventSynchronize(evt)); // the kernel that last read this staging buffer has finished
+            stg.reserve(m * sizeof(dge_record16));
+            DGE_CUDA(cudaMemcpyAsync(stg.p, recs + off, m * sizeof(dge_record16), cudaMemcpyHostToDevice, h->stream));
+            fill_from_device(h, stg.as<dge_record16>(), m);
+            DGE_CUDA(cudaEventRecord(evt, h->stream));
+        }
+        return int(DGE_OK);
+    });
+}
+
+int dge_set_initialized(dge_handle *h)
+{
+    if (!h) return DGE_ERR_INVALID;
+    if (h->state != 0) return fail(h, DGE_ERR_STATE, "Container is already initialized");
+    return guarded(h, [&] { do_set_initialized(h); return int(DGE_OK); });
+}
+
+int dge_merge_and_filter(dge_handle *h)
+{
+    if (!h) return DGE_ERR_INVALID;
+    if (h->state == 0) return fail(h, DGE_ERR_STATE, "You must initialize container");
+    if (h->state == 2) return fail(h, DGE_ERR_STATE, "merge_and_filter was already run");
+    return guarded(h, [&] { do_merge_and_filter(h); return int(DGE_OK); });
+}
+
+int dge_get_summary(dge_handle *h, dge_summary *out)
+{
+    if (!h || !out) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state == 0) return fail(h, DGE_ERR_STATE, "You must initialize container");
+    std::memset(out, 0, sizeof(*out));
+    out->n_reads = h->n_reads;
+    out->total_cells_number = h->total_cells;
+    for (auto const &c : h->real) out->real_cells_number += c.real;
+    out->filtered_cells_number = h->filtered.size();
+    out->n_genes_seen = h->gene_order.size();
+    out->n_umigs = h->n_u;
+    out->intergenic_reads = h->counters.intergenic;
+    out->has_exon_reads = h->counters.has_exon;
+    out->has_intron_reads = h->counters.has_intron;
+    out->has_not_annotated_reads = h->counters.has_not_annotated;
+    out->cm_nnz = h->cm.built ? h->cm.nnz : 0;
+    out->cm_raw_nnz = h->cm_raw.built ? h->cm_raw.nnz : 0;
+    out->n_merged = h->n_merged;
+    out->n_excluded = h->n_excluded;
+    return DGE_OK;
+}
+
+int dge_get_timings(dge_handle *h, dge_timings *out)
+{
+    if (!h || !out) return fail(h, DGE_ERR_INVALID, "null argument");
+    *out = h->timings;
+    return DGE_OK;
+}
+
+int dge_get_cells(dge_handle *h, int which, dge_cell_info *out, size_t capacity, size_t *n_out)
+{
+    if (!h || !n_out) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state == 0) return fail(h, DGE_ERR_STATE, "You must initialize container");
+    return guarded(h, [&] {
+        DGE_CUDA(cudaSetDevice(h->cfg.device));
+        if (which == DGE_CELLS_ALL)
+        {
+            AllCells all = collect_all_cells(h);
+            *n_out = all.info.size();
+            if (out && capacity >= all.info.size()) std::copy(all.info.begin(), all.info.end(), out);
+            return int(DGE_OK);
+        }
+        std::vector<uint32_t> ids;
+        if (which == DGE_CELLS_REAL) { for (uint32_t i = 0; i < h->real.size(); ++i) if (h->real[i].real) ids.push_back(i); }
+        else if (which == DGE_CELLS_FILTERED) ids = h->filtered;
+        else return fail(h, DGE_ERR_INVALID, "unknown cell class");
+        *n_out = ids.size();
+        if (out && capacity >= ids.size())
+        {
+            std::unordered_map<uint32_t, int32_t> pos;
+            for (size_t k = 0; k < ids.size(); ++k) pos.emplace(ids[k], int32_t(k));
+            for (size_t k = 0; k < ids.size(); ++k)
+            {
+                fill_info(h, h->real[ids[k]], out[k]);
+                auto it = pos.find(uint32_t(h->real[ids[k]].target));
+                out[k].merge_target = it == pos.end() ? -1 : it->second;
+            }
+        }
+        return int(DGE_OK);
+    });
+}
+
+int dge_get_matrix(dge_handle *h, int which, int64_t *indptr, int32_t *gene_ids, int32_t *values, size_t *n_cols, size_t *nnz)
+{
+    if (!h || !n_cols || !nnz) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state != 2) return fail(h, DGE_ERR_STATE, "matrices exist after merge_and_filter");
+    if (which != DGE_MATRIX_CM && which != DGE_MATRIX_CM_RAW) return fail(h, DGE_ERR_INVALID, "unknown matrix");
+    return guarded(h, [&] {
+        DGE_CUDA(cudaSetDevice(h->cfg.device));
+        MatrixDev &m = which == DGE_MATRIX_CM ? h->cm : h->cm_raw;
+        *n_cols = m.n_cols; *nnz = m.nnz;
+        std::vector<uint32_t> ip;
+        if (indptr)
+        {
+            d2h(ip, m.indptr.p, m.n_cols + 1, h->stream);
+            DGE_CUDA(cudaStreamSynchronize(h->stream));
+            for (size_t i = 0; i <= m.n_cols; ++i) indptr[i] = int64_t(ip[i]);
+        }
+        if (gene_ids && m.nnz) DGE_CUDA(cudaMemcpyAsync(gene_ids, m.gene.p, m.nnz * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (values && m.nnz) DGE_CUDA(cudaMemcpyAsync(values, m.val.p, m.nnz * 4, cudaMemcpyDeviceToHost, h->stream));
+        DGE_CUDA(cudaStreamSynchronize(h->stream));
+        return int(DGE_OK);
+    });
+}
+
+int dge_get_gene_order(dge_handle *h, int32_t *gene_ids, size_t capacity, size_t *n_out)
+{
+    if (!h || !n_out) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state == 0) return fail(h, DGE_ERR_STATE, "You must initialize container");
+    *n_out = h->gene_order.size();
+    if (gene_ids && capacity >= h->gene_order.size()) std::copy(h->gene_order.begin(), h->gene_order.end(), gene_ids);
+    return DGE_OK;
+}
+
+int dge_get_merge_pairs(dge_handle *h, uint64_t *from, uint64_t *to, size_t capacity, size_t *n_out)
+{
+    if (!h || !n_out) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state != 2) return fail(h, DGE_ERR_STATE, "merge targets exist after merge_and_filter");
+    size_t n = 0;
+    for (auto const &c : h->real) n += uint32_t(c.target) != uint32_t(&c - h->real.data());
+    *n_out = n;
+    if (from && to && capacity >= n)
+    {
+        size_t k = 0;
+        for (uint32_t i = 0; i < h->real.size(); ++i)
+            if (uint32_t(h->real[i].target) != i) { from[k] = h->real[i].cb; to[k] = h->real[size_t(h->real[i].target)].cb; ++k; }
+    }
+    return DGE_OK;
+}
+
+int dge_get_umigs(dge_handle *h, int which, uint32_t *cell_index, int32_t *gene_ids, uint32_t *umis, uint32_t *read_counts,
+                  uint8_t *marks, size_t capacity, size_t *n_out)
+{
+    if (!h || !n_out) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state == 0) return fail(h, DGE_ERR_STATE, "You must initialize container");
+    return guarded(h, [&] {
+        DGE_CUDA(cudaSetDevice(h->cfg.device));
+        std::vector<uint32_t> pcs;
+        if (which == DGE_CELLS_ALL) { AllCells all = collect_all_cells(h); pcs = all.pc; }
+        else if (which == DGE_CELLS_REAL) { for (auto const &c : h->real) if (c.real) pcs.push_back(c.pc); }
+        else if (which == DGE_CELLS_FILTERED) { for (uint32_t i : h->filtered) pcs.push_back(h->real[i].pc); }
+        else return fail(h, DGE_ERR_INVALID, "unknown cell class");
+        std::vector<uint32_t> pc_u;
+        d2h(pc_u, h->pc_u_start.p, size_t(h->n_pc) + 1, h->stream);
+        DGE_CUDA(cudaStreamSynchronize(h->stream));
+        size_t total = 0;
+        for (uint32_t pc : pcs) if (pc != NONE32) total += pc_u[pc + 1] - pc_u[pc];
+        *n_out = total;
+        if (capacity < total || total == 0) return int(DGE_OK);
+        std::vector<uint64_t> uk;
+        std::vector<uint32_t> uv;
+        d2h(uk, h->ukey.p, h->n_u, h->stream);
+        d2h(uv, h->uval.p, h->n_u, h->stream);
+        DGE_CUDA(cudaStreamSynchronize(h->stream));
+        size_t k = 0;
+        for (size_t ci = 0; ci < pcs.size(); ++ci)
+        {
+            if (pcs[ci] == NONE32) continue;
+            for (uint32_t i = pc_u[pcs[ci]]; i < pc_u[pcs[ci] + 1]; ++i, ++k)
+            {
+                if (cell_index) cell_index[k] = uint32_t(ci);
+                if (gene_ids) gene_ids[k] = int32_t(h->kl.gene_of_ukey(uk[i]));
+                if (umis) umis[k] = h->kl.umi_of_ukey(uk[i]);
+                if (read_counts) read_counts[k] = uv[i] & VAL_COUNT_MASK;
+                if (marks) marks[k] = uint8_t(uv[i] >> VAL_MARK_SHIFT);
+            }
+        }
+        return int(DGE_OK);
+    });
+}
+
+unsigned dge_edit_distance(const char *s1, const char *s2, int skip_n, unsigned max_ed) { return edit_distance_ref(s1, s2, skip_n != 0, max_ed); }
+
+unsigned dge_hamming_distance(const char *s1, const char *s2, int skip_n)
+{
+    if (std::strlen(s1) != std::strlen(s2)) return 0xFFFFFFFFu;
+    return hamming_distance_ref(s1, s2, skip_n != 0);
+}
+
+int dge_whitelist_shape(dge_handle *h, uint32_t *n_parts, uint32_t *part_sizes, uint32_t *part_lengths, size_t capacity)
+{
+    if (!h || !n_parts) return fail(h, DGE_ERR_INVALID, "null argument");
+    *n_parts = uint32_t(h->wl.parts.size());
+    for (size_t p = 0; p < h->wl.parts.size() && p < capacity; ++p)
+    {
+        if (part_sizes) part_sizes[p] = uint32_t(h->wl.parts[p].size());
+        if (part_lengths) part_lengths[p] = uint32_t(h->wl.parts[p][0].size());
+    }
+    return DGE_OK;
+}
+
+int dge_whitelist_token(dge_handle *h, uint32_t part, uint32_t index, char *out, size_t capacity)
+{
+    if (!h || !out) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (part >= h->wl.parts.size() || index >= h->wl.parts[part].size()) return fail(h, DGE_ERR_INVALID, "index out of range");
+    const std::string &t = h->wl.parts[part][index];
+    if (capacity < t.size() + 1) return fail(h, DGE_ERR_INVALID, "buffer too small");
+    std::memcpy(out, t.c_str(), t.size() + 1);
+    return DGE_OK;
+}
+
+} // extern "C"

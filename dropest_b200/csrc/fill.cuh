@@ -1,0 +1,159 @@
+// fill.cuh -- per-read front end: barcode table insert, first-seen tracking, intergenic short-circuit, 64-bit key packing.
+// Replaces, per read, CellsDataContainer::add_record (reference CellsDataContainer.cpp:59-88) up to the point where the
+// read is handed to Gene::add_umi; the grouping itself happens in sortcombine.cuh.
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+#include "sortcombine.cuh"
+
+namespace dge
+{
+
+struct Rec16 { unsigned long long key; uint32_t gene; uint32_t read_idx; };
+
+constexpr int FILL_THREADS = 256;
+constexpr int FILL_ITEMS = 8;
+constexpr int FILL_TILE = FILL_THREADS * FILL_ITEMS;
+
+struct FillCounters
+{
+    unsigned long long n_keys;       // reads with a gene (compact keys written)
+    unsigned long long intergenic;   // CellsDataContainer::_intergenic_reads
+    unsigned long long has_exon;     // _has_exon_reads
+    unsigned long long has_intron;   // _has_intron_reads
+    unsigned long long has_not_annotated;
+    int table_overflow;
+    int bad_gene;
+};
+
+__global__ void k_table_init(CellSlot *tab, size_t cap)
+{
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < cap; i += size_t(gridDim.x) * blockDim.x)
+    {
+        CellSlot s; s.cb = EMPTY64; s.first_idx = NONE32; s.n_intergenic = 0;
+        tab[i] = s;
+    }
+}
+
+__global__ void k_fill_u32(uint32_t *p, size_t n, uint32_t v)
+{
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = v;
+}
+
+// Insert-or-find; returns the slot index (= internal cell id) or NONE32 when the table is full.
+__device__ __forceinline__ uint32_t table_insert(CellSlot *tab, int tb, uint64_t cb)
+{
+    const uint32_t mask = (1u << tb) - 1;
+    uint32_t s = uint32_t(barcode_hash(cb) >> (64 - tb));
+    for (int probes = 0; probes < 8192; ++probes)
+    {
+        unsigned long long cur = tab[s].cb;
+        if (cur == EMPTY64)
+        {
+            cur = atomicCAS(&tab[s].cb, EMPTY64, (unsigned long long)cb);
+            if (cur == EMPTY64) return s;
+        }
+        if (cur == cb) return s;
+        s = (s + 1) & mask;
+    }
+    return NONE32;
+}
+
+__device__ __forceinline__ uint32_t table_find(const CellSlot *tab, int tb, uint64_t cb)
+{
+    const uint32_t mask = (1u << tb) - 1;
+    uint32_t s = uint32_t(barcode_hash(cb) >> (64 - tb));
+    for (int probes = 0; probes < 8192; ++probes)
+    {
+        unsigned long long cur = tab[s].cb;
+        if (cur == cb) return s;
+        if (cur == EMPTY64) return NONE32;
+        s = (s + 1) & mask;
+    }
+    return NONE32;
+}
+
+// records -> compact keys (dense, order irrelevant) + L1 histogram of the keys + global read counters.
+__global__ void __launch_bounds__(FILL_THREADS) k_fill_compact(const Rec16 *__restrict__ recs, size_t n, CellSlot *__restrict__ tab, KeyLayout kl,
+                                                               uint32_t n_genes, uint32_t *__restrict__ gene_first, uint64_t *__restrict__ out_keys,
+                                                               FillCounters *__restrict__ ctr, int l1_shift, int nb1, uint32_t *__restrict__ l1_hist)
+{
+    __shared__ uint32_t hist[SC_MAX_NB1];
+    __shared__ uint32_t ws[33];
+    __shared__ unsigned long long out_base_s;
+    for (int i = threadIdx.x; i < nb1; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+
+    uint32_t c_inter = 0, c_exon = 0, c_intron = 0, c_na = 0;
+    const size_t n_tiles = (n + FILL_TILE - 1) / FILL_TILE;
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    {
+        const size_t base = tile * FILL_TILE;
+        uint64_t keys[FILL_ITEMS];
+        uint32_t n_valid = 0;
+#pragma unroll
+        for (int j = 0; j < FILL_ITEMS; ++j)
+        {
+            const size_t i = base + size_t(j) * FILL_THREADS + threadIdx.x;
+            keys[j] = EMPTY64;
+            if (i >= n) continue;
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(recs) + i);
+            const uint64_t k = (uint64_t(raw.y) << 32) | raw.x;
+            const uint64_t cb = k >> 24;
+            const uint32_t umi = uint32_t(k) & 0xFFFFFFu;
+            const uint32_t gene = raw.z & 0xFFFFFFu;
+            const uint32_t mark = (raw.z >> 24) & 7u;
+            const uint32_t idx = raw.w;
+            const uint32_t slot = table_insert(tab, kl.tb, cb);
+            if (slot == NONE32) { ctr->table_overflow = 1; continue; }
+            if (idx < tab[slot].first_idx) atomicMin(&tab[slot].first_idx, idx);
+            if (gene == NO_GENE)
+            {
+                atomicAdd(&tab[slot].n_intergenic, 1u);
+                ++c_inter;
+                continue;
+            }
+            if (gene >= n_genes) { ctr->bad_gene = 1; continue; }
+            if (idx < gene_first[gene]) atomicMin(&gene_first[gene], idx);
+            c_exon += (mark >> 1) & 1u; c_intron += (mark >> 2) & 1u; c_na += mark & 1u;
+            keys[j] = kl.compose(slot, gene, umi, mark);
+            if (nb1) atomicAdd(&hist[keys[j] >> l1_shift], 1u);
+            ++n_valid;
+        }
+        uint32_t total;
+        uint32_t ex = block_exclusive_scan(n_valid, ws, &total);
+        if (threadIdx.x == 0) out_base_s = total ? atomicAdd(&ctr->n_keys, (unsigned long long)total) : 0ull;
+        __syncthreads();
+        unsigned long long pos = out_base_s + ex;
+#pragma unroll
+        for (int j = 0; j < FILL_ITEMS; ++j)
+            if (keys[j] != EMPTY64) out_keys[pos++] = keys[j];
+        __syncthreads();
+    }
+
+    // block-level reduction of the global counters
+    auto reduce_add = [&](uint32_t v, unsigned long long *dst) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, (unsigned long long)v);
+    };
+    reduce_add(c_inter, &ctr->intergenic);
+    reduce_add(c_exon, &ctr->has_exon);
+    reduce_add(c_intron, &ctr->has_intron);
+    reduce_add(c_na, &ctr->has_not_annotated);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb1; i += blockDim.x)
+        if (hist[i]) atomicAdd(&l1_hist[i], hist[i]);
+}
+
+__global__ void k_count_occupied(const CellSlot *__restrict__ tab, size_t cap, unsigned long long *out)
+{
+    uint32_t c = 0;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < cap; i += size_t(gridDim.x) * blockDim.x)
+        c += tab[i].cb != EMPTY64;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+} // namespace dge

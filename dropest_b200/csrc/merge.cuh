@@ -1,0 +1,357 @@
+// merge.cuh -- device kernels of the cell-barcode merge stage (reference Estimation/Merge/*).
+//   k_wl_class01   nearest-whitelist neighbours in distance classes 0 and 1 (RealBarcodesMergeStrategy::get_real_neighbour_cbs,
+//                  RealBarcodesMergeStrategy.cpp:63-109 + BarcodesParser.cpp:21-74) for equal-length, N-free whitelist parts, where
+//                  Levenshtein <= 1  <=>  Hamming <= 1.  Cells whose nearest eligible class is >= 2 are flagged for the exact path.
+//   k_intersect    |{(gene,umi)} of A  ∩  {(gene,umi)} of B|  (MergeStrategyBase::get_umigs_intersect_size, MergeStrategyBase.cpp:100-147)
+//   k_gather_relabel / k_probe_merge / k_merge_path : apply cell merges (CellsDataContainer::merge_cells, CellsDataContainer.cpp:90-104;
+//                  Gene::merge, Gene.cpp:26-36; UMI::merge, UMI.cpp:15-19: counts add, marks OR).
+#pragma once
+#include "common.cuh"
+#include "fill.cuh"
+
+namespace dge
+{
+
+constexpr int WL_MAX_PARTS = 4;
+constexpr int WL_K = 8;          // max neighbours reported by the fast path
+constexpr int NB_SELF = -1;      // base barcode is itself a whitelist barcode -> target = base
+constexpr int NB_SLOW = -2;      // needs the exact (distance class >= 2 / overflow) path
+
+struct WhitelistDev
+{
+    int n_parts;
+    int part_len[WL_MAX_PARTS];     // bases
+    int part_shift[WL_MAX_PARTS];   // bit offset of the part inside the packed barcode
+    uint32_t part_size[WL_MAX_PARTS];
+    const uint32_t *tokens[WL_MAX_PARTS]; // 2-bit packed tokens
+};
+
+__device__ __forceinline__ int hamming2bit(uint32_t a, uint32_t b)
+{
+    uint32_t x = a ^ b;
+    return __popc((x | (x >> 1)) & 0x55555555u);
+}
+
+// One warp per real cell.
+__global__ void __launch_bounds__(256) k_wl_class01(const uint64_t *__restrict__ cell_cb, const uint32_t *__restrict__ cell_umis, uint32_t n_cells,
+                                                    WhitelistDev wl, const CellSlot *__restrict__ tab, int tb,
+                                                    const uint32_t *__restrict__ slot_pc, const uint32_t *__restrict__ pc_cg_start,
+                                                    const uint32_t *__restrict__ pc_u_start, uint32_t min_genes,
+                                                    int *__restrict__ nb_count, uint32_t *__restrict__ nb_pc)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (cell >= n_cells) return;
+    const uint64_t cb = cell_cb[cell];
+    const uint32_t base_umis = cell_umis[cell];
+
+    // per part: count of exact tokens, and up to 32 distance-1 tokens kept as a per-lane register (one per lane) + overflow flag
+    int n_exact_parts = 0;
+    int missing_part = -1;          // the single part without an exact token (class 1 requires exactly one)
+    bool multi_exact = false;
+    uint32_t part_vals[WL_MAX_PARTS];
+    for (int k = 0; k < wl.n_parts; ++k)
+    {
+        const uint32_t pv = uint32_t(cb >> wl.part_shift[k]) & uint32_t((1ull << (2 * wl.part_len[k])) - 1);
+        part_vals[k] = pv;
+        int exact = 0;
+        for (uint32_t t = lane; t < wl.part_size[k]; t += 32) exact += wl.tokens[k][t] == pv;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) exact += __shfl_xor_sync(0xFFFFFFFFu, exact, d);
+        if (exact > 1) multi_exact = true;
+        if (exact >= 1) ++n_exact_parts; else missing_part = k;
+    }
+    if (multi_exact)
+    {   // duplicated tokens inside a part: leave the bookkeeping of duplicate leaves to the exact path
+        if (lane == 0) nb_count[cell] = NB_SLOW;
+        return;
+    }
+    if (n_exact_parts == wl.n_parts)
+    {
+        if (lane == 0) nb_count[cell] = NB_SELF;
+        return;
+    }
+    int found = 0;
+    bool overflow = false;
+    if (n_exact_parts == wl.n_parts - 1)
+    {
+        const int k = missing_part;
+        const uint64_t part_mask = ((1ull << (2 * wl.part_len[k])) - 1) << wl.part_shift[k];
+        for (uint32_t t0 = 0; t0 < wl.part_size[k]; t0 += 32)
+        {
+            const uint32_t t = t0 + lane;
+            bool eligible = false;
+            uint32_t pc = NONE32;
+            if (t < wl.part_size[k])
+            {
+                const uint32_t tok = wl.tokens[k][t];
+                if (hamming2bit(tok, part_vals[k]) == 1)
+                {
+                    const uint64_t cand = (cb & ~part_mask) | (uint64_t(tok) << wl.part_shift[k]);
+                    const uint32_t slot = table_find(tab, tb, cand);
+                    if (slot != NONE32)
+                    {
+                        pc = slot_pc[slot];
+                        if (pc != NONE32)
+                        {
+                            const uint32_t ng = pc_cg_start[pc + 1] - pc_cg_start[pc];
+                            const uint32_t nu = pc_u_start[pc + 1] - pc_u_start[pc];
+                            eligible = ng >= min_genes && nu >= base_umis;
+                        }
+                    }
+                }
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, eligible);
+            if (eligible)
+            {
+                const int pos = found + __popc(m & ((1u << lane) - 1));
+                if (pos < WL_K) nb_pc[size_t(cell) * WL_K + pos] = pc; else overflow = true;
+            }
+            found += __popc(m);
+        }
+        overflow = __any_sync(0xFFFFFFFFu, overflow);
+    }
+    if (lane == 0) nb_count[cell] = (found == 0 || overflow) ? NB_SLOW : found;
+}
+
+struct PairJob { uint32_t a_pc, b_pc; };
+
+// One block per pair: every (gene, umi) of A is searched in B's sorted range.
+__global__ void __launch_bounds__(128) k_intersect(const PairJob *__restrict__ jobs, uint32_t n_jobs, const uint64_t *__restrict__ ukey,
+                                                   const uint32_t *__restrict__ pc_u_start, const uint32_t *__restrict__ pc_slot, int gub,
+                                                   uint32_t *__restrict__ out)
+{
+    __shared__ uint32_t red[4];
+    const uint32_t job = blockIdx.x;
+    if (job >= n_jobs) return;
+    uint32_t a = jobs[job].a_pc, b = jobs[job].b_pc;
+    uint32_t as = pc_u_start[a], ae = pc_u_start[a + 1], bs = pc_u_start[b], be = pc_u_start[b + 1];
+    if (ae - as > be - bs) { uint32_t t; t = a; a = b; b = t; t = as; as = bs; bs = t; t = ae; ae = be; be = t; }
+    const uint64_t gu_mask = (1ull << gub) - 1;
+    const uint64_t b_prefix = uint64_t(pc_slot[b]) << gub;
+    uint32_t cnt = 0;
+    for (uint32_t i = as + threadIdx.x; i < ae; i += blockDim.x)
+    {
+        const uint64_t want = b_prefix | (ukey[i] & gu_mask);
+        uint32_t lo = bs, hi = be;
+        while (lo < hi)
+        {
+            uint32_t mid = (lo + hi) >> 1;
+            if (ukey[mid] < want) lo = mid + 1; else hi = mid;
+        }
+        cnt += lo < be && ukey[lo] == want;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xFFFFFFFFu, cnt, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) out[job] = red[0] + red[1] + red[2] + red[3];
+}
+
+// ---- applying merges -------------------------------------------------------------------------------------------------
+struct MoveJob { uint32_t src_pc, dst_slot, out_off; };   // out_off = exclusive prefix of the source sizes
+
+// copies the source cell's (gene, umi) list re-labelled to the destination slot, as sortcombine input ([ukey|000], val)
+__global__ void __launch_bounds__(256) k_gather_relabel(const MoveJob *__restrict__ jobs, uint32_t n_jobs, const uint64_t *__restrict__ ukey,
+                                                        const uint32_t *__restrict__ uval, const uint32_t *__restrict__ pc_u_start, int gub,
+                                                        uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
+{
+    const uint64_t gu_mask = (1ull << gub) - 1;
+    for (uint32_t j = blockIdx.x; j < n_jobs; j += gridDim.x)
+    {
+        const MoveJob job = jobs[j];
+        const uint32_t s = pc_u_start[job.src_pc], e = pc_u_start[job.src_pc + 1];
+        const uint64_t prefix = uint64_t(job.dst_slot) << gub;
+        for (uint32_t i = s + threadIdx.x; i < e; i += blockDim.x)
+        {
+            out_keys[job.out_off + (i - s)] = (prefix | (ukey[i] & gu_mask)) << 3;
+            out_vals[job.out_off + (i - s)] = uval[i];
+        }
+    }
+}
+
+// For every combined moved entry: if the destination already holds that (gene, umi) add into it, else keep it as an "extra".
+// keep[i] = 1 for extras.
+__global__ void __launch_bounds__(256) k_probe_merge(const uint64_t *__restrict__ ekey, const uint32_t *__restrict__ eval, uint32_t n_e,
+                                                     const uint64_t *__restrict__ ukey, uint32_t *__restrict__ uval,
+                                                     const uint32_t *__restrict__ slot_pc, const uint32_t *__restrict__ pc_u_start, int gub,
+                                                     uint32_t *__restrict__ keep)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_e; i += gridDim.x * blockDim.x)
+    {
+        const uint64_t want = ekey[i];
+        const uint32_t pc = slot_pc[uint32_t(want >> gub)];
+        uint32_t k = 1;
+        if (pc != NONE32)
+        {
+            uint32_t lo = pc_u_start[pc], hi = pc_u_start[pc + 1];
+            const uint32_t end = hi;
+            while (lo < hi)
+            {
+                uint32_t mid = (lo + hi) >> 1;
+                if (ukey[mid] < want) lo = mid + 1; else hi = mid;
+            }
+            if (lo < end && ukey[lo] == want)
+            {
+                const uint32_t v = eval[i];
+                uint32_t old = atomicAdd(&uval[lo], v & VAL_COUNT_MASK);
+                uint32_t mk = v & ~VAL_COUNT_MASK;
+                if ((old & mk) != mk) atomicOr(&uval[lo], mk);
+                k = 0;
+            }
+        }
+        keep[i] = k;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_compact_keep(const uint64_t *__restrict__ ekey, const uint32_t *__restrict__ eval, uint32_t n_e,
+                                                      const uint32_t *__restrict__ keep, const uint32_t *__restrict__ keep_off,
+                                                      uint64_t *__restrict__ okey, uint32_t *__restrict__ oval)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_e; i += gridDim.x * blockDim.x)
+        if (keep[i]) { okey[keep_off[i]] = ekey[i]; oval[keep_off[i]] = eval[i]; }
+}
+
+// Merge of two sorted key/value arrays with disjoint keys (A = current list, B = extras) by ranking:
+//   position of A[i] = i + lower_bound(B, A[i]);  position of B[j] = j + lower_bound(A, B[j]).
+__global__ void __launch_bounds__(256) k_merge_rank(const uint64_t *__restrict__ akey, const uint32_t *__restrict__ aval, uint32_t na,
+                                                    const uint64_t *__restrict__ bkey, const uint32_t *__restrict__ bval, uint32_t nb,
+                                                    uint64_t *__restrict__ okey, uint32_t *__restrict__ oval)
+{
+    const uint32_t total = na + nb;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
+    {
+        const bool from_a = t < na;
+        const uint32_t i = from_a ? t : t - na;
+        const uint64_t key = from_a ? akey[i] : bkey[i];
+        const uint64_t *other = from_a ? bkey : akey;
+        uint32_t lo = 0, hi = from_a ? nb : na;
+        while (lo < hi)
+        {
+            uint32_t mid = (lo + hi) >> 1;
+            if (other[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        okey[i + lo] = key;
+        oval[i + lo] = from_a ? aval[i] : bval[i];
+    }
+}
+
+// slot -> present-cell index (NONE32 when the barcode owns no UMI)
+__global__ void k_build_slot_pc(const uint32_t *__restrict__ pc_slot, uint32_t n_pc, uint32_t *__restrict__ slot_pc)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pc; i += gridDim.x * blockDim.x) slot_pc[pc_slot[i]] = i;
+}
+
+// ---- per-cell summaries for the host --------------------------------------------------------------------------------
+struct CellRow
+{
+    unsigned long long cb;
+    uint32_t slot, pc, first_idx, n_intergenic;
+    uint32_t n_genes, n_umis, n_reads, req_genes, req_umis;
+    uint32_t pad;
+};
+
+__global__ void k_real_flags(const uint32_t *__restrict__ pc_cg_start, uint32_t n_pc, uint32_t min_genes, uint32_t *__restrict__ flags)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pc; i += gridDim.x * blockDim.x)
+        flags[i] = (pc_cg_start[i + 1] - pc_cg_start[i]) >= min_genes;
+}
+
+__global__ void k_gather_rows_flagged(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ off, uint32_t n_pc,
+                                      const CellSlot *__restrict__ tab, const uint32_t *__restrict__ pc_slot,
+                                      const uint32_t *__restrict__ pc_cg_start, const uint32_t *__restrict__ pc_u_start,
+                                      const uint32_t *__restrict__ pc_reads, const uint32_t *__restrict__ pc_req_genes,
+                                      const uint32_t *__restrict__ pc_req_umis, CellRow *__restrict__ rows)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pc; i += gridDim.x * blockDim.x)
+    {
+        if (!flags[i]) continue;
+        CellRow r;
+        r.slot = pc_slot[i]; r.pc = i;
+        const CellSlot s = tab[r.slot];
+        r.cb = s.cb; r.first_idx = s.first_idx; r.n_intergenic = s.n_intergenic;
+        r.n_genes = pc_cg_start[i + 1] - pc_cg_start[i];
+        r.n_umis = pc_u_start[i + 1] - pc_u_start[i];
+        r.n_reads = pc_reads[i]; r.req_genes = pc_req_genes[i]; r.req_umis = pc_req_umis[i];
+        r.pad = 0;
+        rows[off[i]] = r;
+    }
+}
+
+// rows for an explicit list of present cells (after merges)
+__global__ void k_gather_rows_list(const uint32_t *__restrict__ pcs, uint32_t n, const CellSlot *__restrict__ tab,
+                                   const uint32_t *__restrict__ pc_slot, const uint32_t *__restrict__ pc_cg_start,
+                                   const uint32_t *__restrict__ pc_u_start, const uint32_t *__restrict__ pc_reads,
+                                   const uint32_t *__restrict__ pc_req_genes, const uint32_t *__restrict__ pc_req_umis,
+                                   CellRow *__restrict__ rows)
+{
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+    {
+        const uint32_t i = pcs[t];
+        CellRow r;
+        r.slot = pc_slot[i]; r.pc = i;
+        const CellSlot s = tab[r.slot];
+        r.cb = s.cb; r.first_idx = s.first_idx; r.n_intergenic = s.n_intergenic;
+        r.n_genes = pc_cg_start[i + 1] - pc_cg_start[i];
+        r.n_umis = pc_u_start[i + 1] - pc_u_start[i];
+        r.n_reads = pc_reads[i]; r.req_genes = pc_req_genes[i]; r.req_umis = pc_req_umis[i];
+        r.pad = 0;
+        rows[t] = r;
+    }
+}
+
+// ---- count matrices (ResultsPrinter.cpp:334-396) -----------------------------------------------------------------------
+// column sizes: number of (cell, gene) rows of the column's cell with a non-zero value
+__global__ void k_matrix_col_nnz(const uint32_t *__restrict__ col_pc, uint32_t n_cols, const uint32_t *__restrict__ pc_cg_start,
+                                 const uint32_t *__restrict__ cg_req, int filtered, uint32_t *__restrict__ col_nnz)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t c = warp_global; c < n_cols; c += n_warps)
+    {
+        const uint32_t pc = col_pc[c];
+        const uint32_t s = pc_cg_start[pc], e = pc_cg_start[pc + 1];
+        uint32_t cnt = 0;
+        if (filtered) { for (uint32_t i = s + lane; i < e; i += 32) cnt += cg_req[i] > 0; }
+        else cnt = lane == 0 ? e - s : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xFFFFFFFFu, cnt, d);
+        if (lane == 0) col_nnz[c] = cnt;
+    }
+}
+
+// fill: one warp per column, ordered compaction by ballot
+__global__ void k_matrix_fill(const uint32_t *__restrict__ col_pc, uint32_t n_cols, const uint32_t *__restrict__ col_off,
+                              const uint32_t *__restrict__ pc_cg_start, const uint64_t *__restrict__ cg_key,
+                              const uint32_t *__restrict__ values, const uint32_t *__restrict__ cg_start, int mode, uint32_t gene_mask,
+                              int32_t *__restrict__ out_gene, int32_t *__restrict__ out_val)
+{
+    // mode 0: value = values[i] (skip zeros); mode 1: value = cg_start[i+1]-cg_start[i] (all UMIs); mode 2: value = values[i], keep all
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t c = warp_global; c < n_cols; c += n_warps)
+    {
+        const uint32_t pc = col_pc[c];
+        const uint32_t s = pc_cg_start[pc], e = pc_cg_start[pc + 1];
+        uint32_t pos = col_off[c];
+        for (uint32_t i0 = s; i0 < e; i0 += 32)
+        {
+            const uint32_t i = i0 + lane;
+            uint32_t v = 0;
+            if (i < e) v = mode == 1 ? cg_start[i + 1] - cg_start[i] : values[i];
+            const bool keepit = i < e && (mode != 0 || v > 0);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, keepit);
+            if (keepit)
+            {
+                const uint32_t p = pos + __popc(m & ((1u << lane) - 1));
+                out_gene[p] = int32_t(uint32_t(cg_key[i]) & gene_mask);
+                out_val[p] = int32_t(v);
+            }
+            pos += __popc(m);
+        }
+    }
+}
+
+} // namespace dge

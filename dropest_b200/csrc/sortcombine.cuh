@@ -1,0 +1,514 @@
+// sortcombine.cuh -- device-wide "group identical keys, combine their values, emit sorted" for 64-bit keys.
+//
+// This is the engine under the per-read grouping (reference Gene::add_umi / UMI::add_read, Gene.cpp:17-24, UMI.cpp:21-34)
+// and under cell merges (Gene::merge, Gene.cpp:26-36).  Input: n keys laid out as [ukey : kb-3 | mark : 3] and optionally
+// n values (count | mark<<29).  Output: the DISTINCT ukeys in ascending order with combined values (counts added, marks ORed).
+//
+// Shape (two-level sample sort, then shared-memory hashing):
+//   L1  fixed-width radix partition on the top l1_bits of the key (exact histogram -> exclusive scan -> scatter)
+//   L2  per L1 bucket: sampled splitters (sorted in shared memory) -> exact sub-histogram -> scan -> scatter
+//   L3  per sub-bucket (~1.5 k records): stream through a shared-memory hash table (atomicCAS insert, atomicAdd/Or combine),
+//       compact, bitonic sort in shared memory, write back in place; then one scan + gather makes the output dense.
+// Range partitioning (not hashing) at L1/L2 is what makes the concatenated sub-bucket outputs globally sorted; sampling makes
+// sub-bucket sizes independent of how skewed cells / genes are.  Everything is HBM-bound integer work: no tensor cores.
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace dge
+{
+
+constexpr int SC_THREADS = 512;
+constexpr int SC_ITEMS = 16;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS; // 8192 keys per block tile
+constexpr int SC_MAX_NB1 = 4096;               // max L1 buckets
+constexpr int SC_MAX_P2 = 1024;                // max sub-buckets per L1 bucket
+constexpr int SC_TARGET = 1536;                // target records per sub-bucket
+constexpr int SC_SAMPLE = 8192;                // max sample size per L1 bucket
+constexpr int SC_HT = 4096;                    // shared-memory hash table slots per sub-bucket
+constexpr int SC_DEDUP_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool HAS_VAL> __device__ __forceinline__ void bitonic_sort_smem(uint64_t *k, uint32_t *v, int P)
+{
+    for (int size = 2; size <= P; size <<= 1)
+    {
+        for (int stride = size >> 1; stride > 0; stride >>= 1)
+        {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x)
+            {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool asc = (lo & size) == 0;
+                uint64_t a = k[lo], b = k[hi];
+                if ((a > b) == asc)
+                {
+                    k[lo] = b; k[hi] = a;
+                    if (HAS_VAL) { uint32_t va = v[lo]; v[lo] = v[hi]; v[hi] = va; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SC_THREADS) k_l1_hist(const uint64_t *__restrict__ keys, size_t n, int shift, int nb1, uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t h[SC_MAX_NB1];
+    for (int i = threadIdx.x; i < nb1; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+        atomicAdd(&h[keys[i] >> shift], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb1; i += blockDim.x)
+        if (h[i]) atomicAdd(&hist[i], h[i]);
+}
+
+// One tile of SC_TILE keys per block: rank inside the block with shared-memory atomics, reserve one run per (block, bucket)
+// with a single global atomicAdd, then write.
+template <bool HAS_VAL>
+__global__ void __launch_bounds__(SC_THREADS) k_l1_scatter(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, size_t n,
+                                                           int shift, int nb1, uint32_t *__restrict__ cursor,
+                                                           uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
+{
+    __shared__ uint32_t cnt[SC_MAX_NB1];
+    for (int i = threadIdx.x; i < nb1; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    const size_t base = size_t(blockIdx.x) * SC_TILE;
+    uint64_t k[SC_ITEMS];
+    uint32_t r[SC_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j)
+    {
+        size_t i = base + size_t(j) * SC_THREADS + threadIdx.x;
+        if (i < n)
+        {
+            k[j] = keys[i];
+            r[j] = atomicAdd(&cnt[k[j] >> shift], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb1; i += blockDim.x)
+    {
+        uint32_t c = cnt[i];
+        if (c) cnt[i] = atomicAdd(&cursor[i], c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j)
+    {
+        size_t i = base + size_t(j) * SC_THREADS + threadIdx.x;
+        if (i < n)
+        {
+            uint32_t pos = cnt[k[j] >> shift] + r[j];
+            out_keys[pos] = k[j];
+            if (HAS_VAL) out_vals[pos] = vals[i];
+        }
+    }
+}
+
+// Single block.  From the L1 offsets derive, per bucket, the number of sub-buckets p2 and of block tiles, and their
+// exclusive scans (sb_base, tile_base; entry [nb1] = totals).
+__global__ void __launch_bounds__(1024) k_l1_plan(const uint32_t *__restrict__ l1_off, int nb1, uint32_t *__restrict__ p2,
+                                                  uint32_t *__restrict__ sb_base, uint32_t *__restrict__ tile_base)
+{
+    __shared__ uint32_t ws[33];
+    __shared__ uint32_t carry[2];
+    if (threadIdx.x == 0) carry[0] = carry[1] = 0;
+    __syncthreads();
+    for (int base = 0; base < nb1; base += blockDim.x)
+    {
+        int b = base + threadIdx.x;
+        uint32_t nb = 0, np = 0, nt = 0;
+        if (b < nb1)
+        {
+            nb = l1_off[b + 1] - l1_off[b];
+            np = nb == 0 ? 0u : min(uint32_t(SC_MAX_P2), (nb + SC_TARGET - 1) / SC_TARGET);
+            nt = (nb + SC_TILE - 1) / SC_TILE;
+            p2[b] = np;
+        }
+        uint32_t tot_p, tot_t;
+        uint32_t ex_p = block_exclusive_scan(np, ws, &tot_p);
+        uint32_t ex_t = block_exclusive_scan(nt, ws, &tot_t);
+        if (b < nb1)
+        {
+            sb_base[b] = carry[0] + ex_p;
+            tile_base[b] = carry[1] + ex_t;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { carry[0] += tot_p; carry[1] += tot_t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { sb_base[nb1] = carry[0]; tile_base[nb1] = carry[1]; }
+}
+
+// One block per L1 bucket: strided sample of ukeys, bitonic sort in shared memory, pick p2-1 splitters.
+__global__ void __launch_bounds__(SC_THREADS) k_splitters(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ l1_off,
+                                                          const uint32_t *__restrict__ p2, uint64_t *__restrict__ splitters)
+{
+    extern __shared__ uint64_t samp[];
+    const int b = blockIdx.x;
+    const uint32_t np = p2[b];
+    if (np <= 1) return;
+    const uint32_t off = l1_off[b], nb = l1_off[b + 1] - off;
+    const uint32_t S = min(nb, uint32_t(SC_SAMPLE));
+    int P = 2;
+    while (uint32_t(P) < S) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+        samp[i] = uint32_t(i) < S ? (keys[off + uint32_t((uint64_t(i) * nb) / S)] >> 3) : EMPTY64;
+    bitonic_sort_smem<false>(samp, nullptr, P);
+    for (uint32_t j = 1 + threadIdx.x; j < np; j += blockDim.x)
+        splitters[size_t(b) * SC_MAX_P2 + (j - 1)] = samp[(uint64_t(j) * S) / np];
+}
+
+// number of splitters <= ukey  (splitters ascending, count = np-1)
+__device__ __forceinline__ uint32_t sub_bucket_of(const uint64_t *spl, uint32_t nspl, uint64_t ukey)
+{
+    uint32_t lo = 0, hi = nspl;
+    while (lo < hi)
+    {
+        uint32_t mid = (lo + hi) >> 1;
+        if (spl[mid] <= ukey) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void block_to_bucket_tile(const uint32_t *__restrict__ tile_base, int nb1, uint32_t blk, int *bucket, uint32_t *tile)
+{
+    // largest b with tile_base[b] <= blk  (tile_base non-decreasing; empty buckets repeat the value)
+    int lo = 0, hi = nb1;
+    while (lo < hi)
+    {
+        int mid = (lo + hi + 1) >> 1;
+        if (tile_base[mid] <= blk) lo = mid; else hi = mid - 1;
+    }
+    // skip to the last bucket sharing this base that actually owns tiles: buckets with zero tiles have tile_base[b+1]==tile_base[b]
+    *bucket = lo;
+    *tile = blk - tile_base[lo];
+}
+
+template <bool SCATTER, bool HAS_VAL>
+__global__ void __launch_bounds__(SC_THREADS) k_l2_pass(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                        const uint32_t *__restrict__ l1_off, int nb1, const uint32_t *__restrict__ p2,
+                                                        const uint32_t *__restrict__ sb_base, const uint32_t *__restrict__ tile_base,
+                                                        const uint64_t *__restrict__ splitters, uint32_t *__restrict__ sub_cnt_or_cursor,
+                                                        uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
+{
+    __shared__ uint64_t spl[SC_MAX_P2];
+    __shared__ uint32_t cnt[SC_MAX_P2];
+    const uint32_t blk = blockIdx.x;
+    if (blk >= tile_base[nb1]) return;
+    int b; uint32_t tile;
+    block_to_bucket_tile(tile_base, nb1, blk, &b, &tile);
+    const uint32_t np = p2[b];
+    const uint32_t off = l1_off[b], end = l1_off[b + 1];
+    const uint32_t t0 = off + tile * SC_TILE;
+    const uint32_t t1 = min(end, t0 + uint32_t(SC_TILE));
+    const uint32_t sb0 = sb_base[b];
+    for (uint32_t i = threadIdx.x; i < np; i += blockDim.x)
+    {
+        cnt[i] = 0;
+        if (i + 1 < np) spl[i] = splitters[size_t(b) * SC_MAX_P2 + i];
+    }
+    __syncthreads();
+    uint64_t k[SC_ITEMS];
+    uint32_t r[SC_ITEMS];
+    uint16_t sbk[SC_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j)
+    {
+        uint32_t i = t0 + uint32_t(j) * SC_THREADS + threadIdx.x;
+        if (i < t1)
+        {
+            k[j] = keys[i];
+            uint32_t s = np > 1 ? sub_bucket_of(spl, np - 1, k[j] >> 3) : 0u;
+            sbk[j] = uint16_t(s);
+            r[j] = atomicAdd(&cnt[s], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < np; i += blockDim.x)
+    {
+        uint32_t c = cnt[i];
+        if (c)
+        {
+            uint32_t old = atomicAdd(&sub_cnt_or_cursor[sb0 + i], c);
+            if (SCATTER) cnt[i] = old;
+        }
+    }
+    if (!SCATTER) return;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j)
+    {
+        uint32_t i = t0 + uint32_t(j) * SC_THREADS + threadIdx.x;
+        if (i < t1)
+        {
+            uint32_t pos = cnt[sbk[j]] + r[j];
+            out_keys[pos] = k[j];
+            if (HAS_VAL) out_vals[pos] = vals[i];
+        }
+    }
+}
+
+// One block per sub-bucket.  keys[s..e) -> distinct ukeys, ascending, written back IN PLACE at keys[s..s+m), values at
+// uvals[s..s+m); ucount[sb] = m.
+template <bool HAS_VAL>
+__global__ void __launch_bounds__(SC_DEDUP_THREADS) k_dedup_sort(uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals_in,
+                                                                 uint32_t *__restrict__ uvals, const uint32_t *__restrict__ sub_off,
+                                                                 const uint32_t *__restrict__ n_sub_ptr, uint32_t *__restrict__ ucount,
+                                                                 int *__restrict__ overflow)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned long long *ht_key = reinterpret_cast<unsigned long long *>(smem_raw);
+    uint64_t *list_key = reinterpret_cast<uint64_t *>(ht_key + SC_HT);
+    uint32_t *ht_val = reinterpret_cast<uint32_t *>(list_key + SC_HT);
+    uint32_t *list_val = ht_val + SC_HT;
+    __shared__ uint32_t m_s;
+
+    const uint32_t sb = blockIdx.x;
+    if (sb >= *n_sub_ptr) return;
+    const uint32_t s = sub_off[sb], e = sub_off[sb + 1];
+    if (e == s)
+    {
+        if (threadIdx.x == 0) ucount[sb] = 0;
+        return;
+    }
+    for (int i = threadIdx.x; i < SC_HT; i += blockDim.x) { ht_key[i] = EMPTY64; ht_val[i] = 0; }
+    if (threadIdx.x == 0) m_s = 0;
+    __syncthreads();
+
+    for (uint32_t i = s + threadIdx.x; i < e; i += blockDim.x)
+    {
+        const uint64_t key = keys[i];
+        const uint64_t uk = key >> 3;
+        const uint32_t v = HAS_VAL ? vals_in[i] : (1u | (uint32_t(key & 7) << VAL_MARK_SHIFT));
+        uint32_t slot = uint32_t((uk * 0x9E3779B97F4A7C15ull) >> 40) & (SC_HT - 1);
+        int probes = 0;
+        while (true)
+        {
+            unsigned long long cur = ht_key[slot];
+            if (cur == EMPTY64)
+            {
+                cur = atomicCAS(&ht_key[slot], EMPTY64, (unsigned long long)uk);
+                if (cur == EMPTY64) cur = uk;
+            }
+            if (cur == uk) break;
+            slot = (slot + 1) & (SC_HT - 1);
+            if (++probes >= SC_HT) { atomicExch(overflow, 1); slot = NONE32; break; }
+        }
+        if (slot != NONE32)
+        {
+            uint32_t old = atomicAdd(&ht_val[slot], v & VAL_COUNT_MASK);
+            uint32_t mk = v & ~VAL_COUNT_MASK;
+            if ((old & mk) != mk) atomicOr(&ht_val[slot], mk);
+        }
+    }
+    __syncthreads();
+
+    // compact occupied slots (order irrelevant: sorted next)
+    for (int i = threadIdx.x; i < SC_HT; i += blockDim.x)
+    {
+        unsigned long long kk = ht_key[i];
+        bool occ = kk != EMPTY64;
+        unsigned mask = __ballot_sync(0xFFFFFFFFu, occ);
+        uint32_t basepos = 0;
+        if ((threadIdx.x & 31) == 0 && mask) basepos = atomicAdd(&m_s, uint32_t(__popc(mask)));
+        basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
+        if (occ)
+        {
+            uint32_t pos = basepos + __popc(mask & ((1u << (threadIdx.x & 31)) - 1));
+            list_key[pos] = kk;
+            list_val[pos] = ht_val[i];
+        }
+    }
+    __syncthreads();
+    const uint32_t m = m_s;
+    int P = 2;
+    while (uint32_t(P) < m) P <<= 1;
+    for (int i = m + threadIdx.x; i < P; i += blockDim.x) { list_key[i] = EMPTY64; list_val[i] = 0; }
+    bitonic_sort_smem<true>(list_key, list_val, P);
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+    {
+        keys[s + i] = list_key[i];
+        uvals[s + i] = list_val[i];
+    }
+    if (threadIdx.x == 0) ucount[sb] = m;
+}
+
+__global__ void __launch_bounds__(256) k_compact_uniques(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ uvals,
+                                                         const uint32_t *__restrict__ sub_off, const uint32_t *__restrict__ u_off,
+                                                         const uint32_t *__restrict__ ucount, const uint32_t *__restrict__ n_sub_ptr,
+                                                         uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
+{
+    const uint32_t nsb = *n_sub_ptr;
+    for (uint32_t sb = blockIdx.x; sb < nsb; sb += gridDim.x)
+    {
+        const uint32_t m = ucount[sb], src = sub_off[sb], dst = u_off[sb];
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+        {
+            out_keys[dst + i] = keys[src + i];
+            out_vals[dst + i] = uvals[src + i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct SortCombineWorkspace
+{
+    DevBuf keysA, valsA, valsB, uvals_sparse, small, splitters, sub_cnt, sub_off, ucount, u_off, scan_scratch;
+};
+
+struct SortCombineStats
+{
+    unsigned launches = 0;
+    unsigned dedup_launches = 0;
+    float dedup_ms = 0;
+};
+
+inline int choose_l1_bits(size_t n)
+{
+    int b = ceil_log2_u64(div_up<uint64_t>(n ? n : 1, 200000));
+    if (b < 6) b = 6;
+    if (b > 12) b = 12;
+    return b;
+}
+
+// keys_in is CONSUMED (used as the L2 scatter target is NOT allowed: it is read-only here) -- buffers:
+//   keys_in --L1 scatter--> keysA --L2 scatter--> keys_tmp (caller-provided, n entries; may alias keys_in) --dedup in place-->
+//   gather --> out_keys/out_vals (caller-provided, capacity >= n_u; sized n by the caller or after reading the count).
+// l1_hist: optional precomputed L1 histogram (device, nb1 entries) -- the fill kernel fuses it.
+// Returns device pointer to n_u (uint32).  Sets *overflow_flag (device int) on table overflow.
+class SortCombine
+{
+public:
+    SortCombineWorkspace ws;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    ~SortCombine()
+    {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
+
+    static void configure()
+    {
+        static bool done = false;
+        if (done) return;
+        DGE_CUDA(cudaFuncSetAttribute(k_splitters, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SAMPLE * 8));
+        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_HT * 24));
+        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_HT * 24));
+        done = true;
+    }
+
+    // Layout of ws.small (uint32): [hist nb1+1][l1_off nb1+1][cursor nb1+1][p2 nb1+1][sb_base nb1+1][tile_base nb1+1]
+    const uint32_t *run(const uint64_t *keys_in, const uint32_t *vals_in, size_t n, int key_bits, int l1_bits,
+                        const uint32_t *l1_hist_pre, uint64_t *keys_tmp, uint64_t *out_keys, uint32_t *out_vals,
+                        int *overflow_flag, cudaStream_t st, SortCombineStats *stats)
+    {
+        configure();
+        if (!ev0) { DGE_CUDA(cudaEventCreate(&ev0)); DGE_CUDA(cudaEventCreate(&ev1)); }
+        const bool has_val = vals_in != nullptr;
+        const int nb1 = 1 << l1_bits;
+        const int shift = key_bits - l1_bits;
+        const size_t stride = size_t(nb1) + 1;
+        ws.small.reserve(stride * 6 * sizeof(uint32_t));
+        uint32_t *hist = ws.small.as<uint32_t>(), *l1_off = hist + stride, *cursor = l1_off + stride, *p2 = cursor + stride,
+                 *sb_base = p2 + stride, *tile_base = sb_base + stride;
+        const size_t nsb_bound = n / SC_TARGET + size_t(nb1) + 1;
+        const size_t tiles_bound = n / SC_TILE + size_t(nb1) + 1;
+        ws.keysA.reserve(n * 8);
+        if (has_val) { ws.valsA.reserve(n * 4); ws.valsB.reserve(n * 4); }
+        ws.uvals_sparse.reserve(n * 4);
+        ws.splitters.reserve(size_t(nb1) * SC_MAX_P2 * 8);
+        ws.sub_cnt.reserve((nsb_bound + 1) * 4);
+        ws.sub_off.reserve((nsb_bound + 1) * 4);
+        ws.ucount.reserve((nsb_bound + 1) * 4);
+        ws.u_off.reserve((nsb_bound + 1) * 4);
+        ws.scan_scratch.reserve(scan_scratch_elems(nsb_bound + 1) * 4);
+        unsigned &L = stats->launches;
+
+        // ---- L1
+        if (l1_hist_pre)
+            DGE_CUDA(cudaMemcpyAsync(hist, l1_hist_pre, nb1 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        else
+        {
+            DGE_CUDA(cudaMemsetAsync(hist, 0, stride * sizeof(uint32_t), st));
+            unsigned g = unsigned(std::min<size_t>(div_up(n, size_t(SC_THREADS * 8)), 148 * 8));
+            k_l1_hist<<<g ? g : 1, SC_THREADS, 0, st>>>(keys_in, n, shift, nb1, hist); ++L;
+        }
+        DGE_CUDA(cudaMemsetAsync(hist + nb1, 0, sizeof(uint32_t), st));
+        device_exclusive_scan(hist, l1_off, stride, ws.scan_scratch.as<uint32_t>(), st, &L);
+        DGE_CUDA(cudaMemcpyAsync(cursor, l1_off, stride * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        uint64_t *keysA = ws.keysA.as<uint64_t>();
+        const unsigned g_tiles = unsigned(div_up(n, size_t(SC_TILE)));
+        if (has_val)
+            k_l1_scatter<true><<<g_tiles, SC_THREADS, 0, st>>>(keys_in, vals_in, n, shift, nb1, cursor, keysA, ws.valsA.as<uint32_t>());
+        else
+            k_l1_scatter<false><<<g_tiles, SC_THREADS, 0, st>>>(keys_in, nullptr, n, shift, nb1, cursor, keysA, nullptr);
+        ++L;
+
+        // ---- L2
+        k_l1_plan<<<1, 1024, 0, st>>>(l1_off, nb1, p2, sb_base, tile_base); ++L;
+        k_splitters<<<nb1, SC_THREADS, SC_SAMPLE * 8, st>>>(keysA, l1_off, p2, ws.splitters.as<uint64_t>()); ++L;
+        uint32_t *sub_cnt = ws.sub_cnt.as<uint32_t>(), *sub_off = ws.sub_off.as<uint32_t>();
+        DGE_CUDA(cudaMemsetAsync(sub_cnt, 0, (nsb_bound + 1) * 4, st));
+        if (has_val)
+            k_l2_pass<false, true><<<unsigned(tiles_bound), SC_THREADS, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base,
+                                                                                  ws.splitters.as<uint64_t>(), sub_cnt, nullptr, nullptr);
+        else
+            k_l2_pass<false, false><<<unsigned(tiles_bound), SC_THREADS, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base,
+                                                                                   ws.splitters.as<uint64_t>(), sub_cnt, nullptr, nullptr);
+        ++L;
+        device_exclusive_scan(sub_cnt, sub_off, nsb_bound + 1, ws.scan_scratch.as<uint32_t>(), st, &L);
+        // cursors = copy of offsets (sub_cnt reused)
+        DGE_CUDA(cudaMemcpyAsync(sub_cnt, sub_off, (nsb_bound + 1) * 4, cudaMemcpyDeviceToDevice, st));
+        if (has_val)
+            k_l2_pass<true, true><<<unsigned(tiles_bound), SC_THREADS, 0, st>>>(keysA, ws.valsA.as<uint32_t>(), l1_off, nb1, p2, sb_base, tile_base,
+                                                                                 ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp, ws.valsB.as<uint32_t>());
+        else
+            k_l2_pass<true, false><<<unsigned(tiles_bound), SC_THREADS, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base,
+                                                                                  ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp, nullptr);
+        ++L;
+
+        // ---- L3: dedup + sort per sub-bucket
+        const uint32_t *n_sub_ptr = sb_base + nb1;
+        uint32_t *ucount = ws.ucount.as<uint32_t>(), *u_off = ws.u_off.as<uint32_t>();
+        DGE_CUDA(cudaMemsetAsync(ucount, 0, (nsb_bound + 1) * 4, st));
+        DGE_CUDA(cudaEventRecord(ev0, st));
+        if (has_val)
+            k_dedup_sort<true><<<unsigned(nsb_bound), SC_DEDUP_THREADS, SC_HT * 24, st>>>(keys_tmp, ws.valsB.as<uint32_t>(), ws.uvals_sparse.as<uint32_t>(),
+                                                                                           sub_off, n_sub_ptr, ucount, overflow_flag);
+        else
+            k_dedup_sort<false><<<unsigned(nsb_bound), SC_DEDUP_THREADS, SC_HT * 24, st>>>(keys_tmp, nullptr, ws.uvals_sparse.as<uint32_t>(),
+                                                                                            sub_off, n_sub_ptr, ucount, overflow_flag);
+        DGE_CUDA(cudaEventRecord(ev1, st));
+        ++L; ++stats->dedup_launches;
+        pending_dedup_event = true;
+        const uint32_t *n_u_ptr = device_exclusive_scan(ucount, u_off, nsb_bound + 1, ws.scan_scratch.as<uint32_t>(), st, &L);
+        k_compact_uniques<<<148 * 8, 256, 0, st>>>(keys_tmp, ws.uvals_sparse.as<uint32_t>(), sub_off, u_off, ucount, n_sub_ptr, out_keys, out_vals);
+        ++L;
+        DGE_LAUNCH_CHECK();
+        last_stats = stats;
+        return n_u_ptr;
+    }
+
+    // call after the stream has been synchronised
+    void collect_timing()
+    {
+        if (pending_dedup_event && last_stats)
+        {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) last_stats->dedup_ms += ms;
+        }
+        pending_dedup_event = false;
+    }
+
+private:
+    bool pending_dedup_event = false;
+    SortCombineStats *last_stats = nullptr;
+};
+
+} // namespace dge

@@ -1,0 +1,201 @@
+// synth.cu -- counter-based synthetic read generator and the barcode-hash router (multi-GPU partition step).
+// Record i is a pure function of (seed, i) and the tables, so host (dropest_b200/synth.py) and device produce the same
+// stream bit for bit; the oracle consumes the host copy, the device pipeline the device copy.
+#include "../../include/dropest_b200.h"
+#include "common.cuh"
+
+#include <vector>
+
+using namespace dge;
+
+namespace
+{
+
+__host__ __device__ inline uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+struct SynthDev
+{
+    uint64_t seed;
+    uint32_t n_cells, n_genes, cb_len, umi_len;
+    const uint64_t *cell_cdf, *cell_barcode, *cell_reads, *gene_cdf;
+    const uint32_t *gene_weight;
+    uint32_t cb_error_ppm, intergenic_ppm, intron_ppm, not_annotated_ppm, reads_per_umi;
+};
+
+// first index with cdf[idx] >= r  (cdf inclusive, last entry UINT64_MAX)
+__device__ __forceinline__ uint32_t cdf_search(const uint64_t *__restrict__ cdf, uint32_t n, uint64_t r)
+{
+    uint32_t lo = 0, hi = n - 1;
+    while (lo < hi)
+    {
+        uint32_t mid = (lo + hi) >> 1;
+        if (cdf[mid] < r) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) k_synth(SynthDev p, uint64_t first, uint64_t count, dge_record16 *__restrict__ out)
+{
+    for (uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < count; t += uint64_t(gridDim.x) * blockDim.x)
+    {
+        const uint64_t i = first + t;
+        const uint64_t base = splitmix64(p.seed ^ (i * 0xD6E8FEB86659FD93ull));
+        const uint64_t r0 = splitmix64(base + 0), r1 = splitmix64(base + 1), r2 = splitmix64(base + 2), r3 = splitmix64(base + 3),
+                       r4 = splitmix64(base + 4);
+        const uint32_t c = cdf_search(p.cell_cdf, p.n_cells, r0);
+        const uint32_t g = cdf_search(p.gene_cdf, p.n_genes, r1);
+        uint64_t pool = ((p.cell_reads[c] * uint64_t(p.gene_weight[g])) >> 32) / p.reads_per_umi;
+        if (pool < 1) pool = 1;
+        const uint64_t u_index = r2 % pool;
+        const uint32_t umi = uint32_t(splitmix64(splitmix64((uint64_t(c) << 32) | g) + u_index)) & uint32_t((1ull << (2 * p.umi_len)) - 1);
+        uint64_t cb = p.cell_barcode[c];
+        if (r3 % 1000000ull < p.cb_error_ppm)
+        {
+            const uint32_t pos = uint32_t(r4 % p.cb_len);
+            const uint32_t delta = 1 + uint32_t((r4 >> 8) % 3);
+            const uint32_t shift = 2 * (p.cb_len - 1 - pos);
+            const uint64_t old = (cb >> shift) & 3;
+            cb = (cb & ~(3ull << shift)) | (((old + delta) & 3) << shift);
+        }
+        const bool intergenic = ((r3 >> 20) % 1000000ull) < p.intergenic_ppm;
+        const uint64_t z = (r3 >> 40) % 1000000ull;
+        const uint32_t mark = z < p.intron_ppm ? DGE_MARK_INTRON : (z < uint64_t(p.intron_ppm) + p.not_annotated_ppm ? DGE_MARK_NOT_ANNOTATED : DGE_MARK_EXON);
+        dge_record16 r;
+        r.key = (cb << 24) | umi;
+        r.gene = (intergenic ? DGE_NO_GENE : g) | (mark << 24);
+        r.read_idx = uint32_t(i);
+        out[t] = r;
+    }
+}
+
+__host__ __device__ inline uint32_t rank_of(uint64_t cb, uint32_t n_ranks)
+{
+    return uint32_t(((barcode_hash(cb) >> 32) * uint64_t(n_ranks)) >> 32);
+}
+
+__global__ void __launch_bounds__(256) k_route_count(const dge_record16 *__restrict__ in, size_t n, uint32_t n_ranks, unsigned long long *__restrict__ counts)
+{
+    __shared__ uint32_t h[64];
+    if (threadIdx.x < 64) h[threadIdx.x] = 0;
+    __syncthreads();
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+        atomicAdd(&h[rank_of(in[i].key >> 24, n_ranks)], 1u);
+    __syncthreads();
+    if (threadIdx.x < n_ranks && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+constexpr int ROUTE_ITEMS = 8;
+__global__ void __launch_bounds__(256) k_route_scatter(const dge_record16 *__restrict__ in, size_t n, uint32_t n_ranks,
+                                                       unsigned long long *__restrict__ cursor, dge_record16 *__restrict__ out)
+{
+    __shared__ uint32_t cnt[64];
+    __shared__ unsigned long long basep[64];
+    if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t base = size_t(blockIdx.x) * 256 * ROUTE_ITEMS;
+    uint4 rec[ROUTE_ITEMS];
+    uint32_t rk[ROUTE_ITEMS], pos[ROUTE_ITEMS];
+#pragma unroll
+    for (int j = 0; j < ROUTE_ITEMS; ++j)
+    {
+        size_t i = base + size_t(j) * 256 + threadIdx.x;
+        if (i < n)
+        {
+            rec[j] = reinterpret_cast<const uint4 *>(in)[i];
+            uint64_t key = (uint64_t(rec[j].y) << 32) | rec[j].x;
+            rk[j] = rank_of(key >> 24, n_ranks);
+            pos[j] = atomicAdd(&cnt[rk[j]], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < n_ranks && cnt[threadIdx.x]) basep[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ROUTE_ITEMS; ++j)
+    {
+        size_t i = base + size_t(j) * 256 + threadIdx.x;
+        if (i < n) reinterpret_cast<uint4 *>(out)[basep[rk[j]] + pos[j]] = rec[j];
+    }
+}
+
+thread_local std::string g_err;
+
+} // namespace
+
+extern "C" {
+
+int dge_synth_generate_device(int device, const dge_synth_params *p, uint64_t first, uint64_t count, dge_record16 *out_device, void *cuda_stream)
+{
+    if (!p || (!out_device && count)) return DGE_ERR_INVALID;
+    if (p->n_cells == 0 || p->n_genes == 0 || p->reads_per_umi == 0 || p->cb_len == 0 || p->cb_len > 20 || p->umi_len == 0 || p->umi_len > 12)
+        return DGE_ERR_INVALID;
+    try
+    {
+        DGE_CUDA(cudaSetDevice(device));
+        cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+        DevBuf d_ccdf, d_cbc, d_creads, d_gcdf, d_gw;
+        d_ccdf.reserve(size_t(p->n_cells) * 8); d_cbc.reserve(size_t(p->n_cells) * 8); d_creads.reserve(size_t(p->n_cells) * 8);
+        d_gcdf.reserve(size_t(p->n_genes) * 8); d_gw.reserve(size_t(p->n_genes) * 4);
+        DGE_CUDA(cudaMemcpyAsync(d_ccdf.p, p->cell_cdf, size_t(p->n_cells) * 8, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(cudaMemcpyAsync(d_cbc.p, p->cell_barcode, size_t(p->n_cells) * 8, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(cudaMemcpyAsync(d_creads.p, p->cell_reads, size_t(p->n_cells) * 8, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(cudaMemcpyAsync(d_gcdf.p, p->gene_cdf, size_t(p->n_genes) * 8, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(cudaMemcpyAsync(d_gw.p, p->gene_weight, size_t(p->n_genes) * 4, cudaMemcpyHostToDevice, st));
+        SynthDev d;
+        d.seed = p->seed; d.n_cells = p->n_cells; d.n_genes = p->n_genes; d.cb_len = p->cb_len; d.umi_len = p->umi_len;
+        d.cell_cdf = d_ccdf.as<uint64_t>(); d.cell_barcode = d_cbc.as<uint64_t>(); d.cell_reads = d_creads.as<uint64_t>();
+        d.gene_cdf = d_gcdf.as<uint64_t>(); d.gene_weight = d_gw.as<uint32_t>();
+        d.cb_error_ppm = p->cb_error_ppm; d.intergenic_ppm = p->intergenic_ppm; d.intron_ppm = p->intron_ppm;
+        d.not_annotated_ppm = p->not_annotated_ppm; d.reads_per_umi = p->reads_per_umi;
+        if (count)
+        {
+            unsigned grid = unsigned(std::min<uint64_t>(div_up<uint64_t>(count, 256), 148 * 32));
+            k_synth<<<grid, 256, 0, st>>>(d, first, count, out_device);
+            DGE_LAUNCH_CHECK();
+        }
+        DGE_CUDA(cudaStreamSynchronize(st));
+        return DGE_OK;
+    }
+    catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_synth_generate_device: %s\n", e.what()); return DGE_ERR_CUDA; }
+}
+
+int dge_route_by_barcode_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, dge_record16 *out, uint64_t *counts, void *cuda_stream)
+{
+    if (!counts || n_ranks == 0 || n_ranks > 64 || (n && (!in || !out))) return DGE_ERR_INVALID;
+    try
+    {
+        DGE_CUDA(cudaSetDevice(device));
+        cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+        DevBuf d_counts;
+        d_counts.reserve(128 * 8);
+        DGE_CUDA(cudaMemsetAsync(d_counts.p, 0, 128 * 8, st));
+        unsigned long long *cnt = d_counts.as<unsigned long long>(), *cursor = cnt + 64;
+        std::vector<unsigned long long> hc(64, 0);
+        if (n)
+        {
+            unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(256 * 8)), 148 * 16));
+            k_route_count<<<grid, 256, 0, st>>>(in, n, n_ranks, cnt);
+            DGE_LAUNCH_CHECK();
+            DGE_CUDA(cudaMemcpyAsync(hc.data(), cnt, 64 * 8, cudaMemcpyDeviceToHost, st));
+            DGE_CUDA(cudaStreamSynchronize(st));
+            std::vector<unsigned long long> off(64, 0);
+            for (uint32_t r = 1; r < n_ranks; ++r) off[r] = off[r - 1] + hc[r - 1];
+            DGE_CUDA(cudaMemcpyAsync(cursor, off.data(), 64 * 8, cudaMemcpyHostToDevice, st));
+            k_route_scatter<<<unsigned(div_up(n, size_t(256 * ROUTE_ITEMS))), 256, 0, st>>>(in, n, n_ranks, cursor, out);
+            DGE_LAUNCH_CHECK();
+            DGE_CUDA(cudaStreamSynchronize(st));
+        }
+        for (uint32_t r = 0; r < n_ranks; ++r) counts[r] = hc[r];
+        return DGE_OK;
+    }
+    catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_route_by_barcode_device: %s\n", e.what()); return DGE_ERR_CUDA; }
+}
+
+} // extern "C"

@@ -1,0 +1,212 @@
+"""Synthetic read streams: table construction, the numpy mirror of csrc/synth.cu, and file output for the oracle.
+
+Record i depends only on (seed, i) and the tables built here, so the host stream (fed to the CPU oracle as strings) and the
+device stream (fed to the CUDA pipeline) are identical bit for bit -- tests/test_synth.py checks that.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .capi import NO_GENE, RECORD_DTYPE, _SynthParams, load_library, pack_seq
+
+U64 = np.uint64
+_M64 = (1 << 64) - 1
+
+
+def splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        x = (x + U64(0x9E3779B97F4A7C15)).astype(U64)
+        z = x
+        z = ((z ^ (z >> U64(30))) * U64(0xBF58476D1CE4E5B9)).astype(U64)
+        z = ((z ^ (z >> U64(27))) * U64(0x94D049BB133111EB)).astype(U64)
+        return (z ^ (z >> U64(31))).astype(U64)
+
+
+def mix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        x = x.astype(U64)
+        x = x ^ (x >> U64(33)); x = (x * U64(0xFF51AFD7ED558CCD)).astype(U64)
+        x = x ^ (x >> U64(33)); x = (x * U64(0xC4CEB9FE1A85EC53)).astype(U64)
+        return (x ^ (x >> U64(33))).astype(U64)
+
+
+def barcode_hash(cb: np.ndarray) -> np.ndarray:
+    """Host mirror of dge::barcode_hash (csrc/common.cuh)."""
+    with np.errstate(over="ignore"):
+        return mix64((cb.astype(U64) + U64(0x9E3779B97F4A7C15)).astype(U64))
+
+
+def rank_of(cb: np.ndarray, n_ranks: int) -> np.ndarray:
+    """Owner rank of a barcode: host mirror of rank_of in csrc/synth.cu (multi-GPU routing)."""
+    return (((barcode_hash(cb) >> U64(32)) * U64(n_ranks)) >> U64(32)).astype(np.uint32)
+
+
+def read_whitelist(path: str, indrop: bool = False) -> List[List[str]]:
+    """Whitelist parts as the reference stores them: every token reverse-complemented (BarcodesParser.cpp:117-144)."""
+    comp = {"A": "T", "T": "A", "G": "C", "C": "G", "N": "N"}
+    parts = []
+    with open(path) as f:
+        for line in f:
+            toks = line.split()
+            if not toks:
+                continue
+            parts.append(["".join(comp[c] for c in reversed(t)) for t in toks])
+            if indrop and len(parts) == 2:
+                break
+    return parts
+
+
+@dataclass
+class SynthSpec:
+    n_reads: int
+    n_cells: int
+    n_genes: int
+    cb_len: int = 16
+    umi_len: int = 12
+    seed: int = 42
+    cb_error_ppm: int = 20000      # 2 % of reads get one substituted barcode base
+    intergenic_ppm: int = 50000    # 5 % of reads have no gene
+    intron_ppm: int = 150000       # 15 % intronic
+    not_annotated_ppm: int = 50000  # 5 % not annotated, remaining 80 % exonic
+    reads_per_umi: int = 4
+    sigma: float = 1.0             # log-normal cell sizes
+    zipf: float = 1.0              # gene weights ~ rank^-zipf
+    whitelist_parts: Optional[Sequence[Sequence[str]]] = None  # product-form whitelist to draw true barcodes from
+
+
+class SynthTables:
+    """Sampling tables shared by host and device generators."""
+
+    def __init__(self, spec: SynthSpec):
+        self.spec = spec
+        rng = np.random.default_rng(spec.seed)
+        w = rng.lognormal(mean=0.0, sigma=spec.sigma, size=spec.n_cells)
+        w = w / w.sum()
+        cdf = np.cumsum(w)
+        cell_cdf = np.minimum(np.floor(cdf * float(2 ** 64)), float(2 ** 64 - 2 ** 11)).astype(U64)
+        cell_cdf[-1] = U64(_M64)
+        self.cell_cdf = np.ascontiguousarray(cell_cdf)
+        self.cell_reads = np.ascontiguousarray(np.maximum(1, np.round(w * spec.n_reads * (1 - spec.intergenic_ppm * 1e-6))).astype(U64))
+        gw = 1.0 / np.power(np.arange(1, spec.n_genes + 1, dtype=np.float64), spec.zipf)
+        gw = gw / gw.sum()
+        gcdf = np.cumsum(gw)
+        gene_cdf = np.minimum(np.floor(gcdf * float(2 ** 64)), float(2 ** 64 - 2 ** 11)).astype(U64)
+        gene_cdf[-1] = U64(_M64)
+        self.gene_cdf = np.ascontiguousarray(gene_cdf)
+        self.gene_weight = np.ascontiguousarray(np.minimum(np.floor(gw * float(2 ** 32)), float(2 ** 32 - 1)).astype(np.uint32))
+        # true barcodes: distinct whitelist combinations, or distinct random barcodes
+        if spec.whitelist_parts is not None:
+            parts = [np.array([pack_seq(t) for t in p], dtype=U64) for p in spec.whitelist_parts]
+            lens = [len(p[0]) for p in spec.whitelist_parts]
+            assert sum(lens) == spec.cb_len, "whitelist part lengths must add up to cb_len"
+            total = 1
+            for p in parts:
+                total *= len(p)
+            assert total >= spec.n_cells, "whitelist too small"
+            if total <= 50_000_000:
+                combo = rng.choice(total, size=spec.n_cells, replace=False)
+            else:
+                combo = np.unique(rng.integers(0, total, size=int(spec.n_cells * 1.2) + 16))
+                rng.shuffle(combo)
+                combo = combo[: spec.n_cells]
+                assert combo.shape[0] == spec.n_cells
+            cb = np.zeros(spec.n_cells, dtype=U64)
+            rem = combo.astype(np.int64)
+            idxs = []
+            for p in reversed(parts):
+                idxs.append(rem % len(p))
+                rem = rem // len(p)
+            idxs = list(reversed(idxs))
+            for p, ln, idx in zip(parts, lens, idxs):
+                cb = (cb << U64(2 * ln)) | p[idx]
+            self.cell_barcode = np.ascontiguousarray(cb)
+        else:
+            space = 1 << (2 * spec.cb_len)
+            cb = np.unique(rng.integers(0, space, size=int(spec.n_cells * 1.2) + 16, dtype=np.uint64))
+            rng.shuffle(cb)
+            assert cb.shape[0] >= spec.n_cells
+            self.cell_barcode = np.ascontiguousarray(cb[: spec.n_cells].astype(U64))
+
+    # ---- host generator (numpy mirror of k_synth) --------------------------------------------------------------
+    def generate_host(self, first: int, count: int) -> np.ndarray:
+        s = self.spec
+        with np.errstate(over="ignore"):
+            i = (np.arange(count, dtype=U64) + U64(first)).astype(U64)
+            base = splitmix64(U64(s.seed) ^ (i * U64(0xD6E8FEB86659FD93)).astype(U64))
+            r0, r1, r2, r3, r4 = (splitmix64((base + U64(k)).astype(U64)) for k in range(5))
+            c = np.searchsorted(self.cell_cdf, r0, side="left").astype(np.int64)
+            g = np.searchsorted(self.gene_cdf, r1, side="left").astype(np.int64)
+            pool = ((self.cell_reads[c] * self.gene_weight[g].astype(U64)) >> U64(32)) // U64(s.reads_per_umi)
+            pool = np.maximum(pool, U64(1))
+            u_index = r2 % pool
+            cg = (c.astype(U64) << U64(32)) | g.astype(U64)
+            umi = splitmix64((splitmix64(cg) + u_index).astype(U64)) & U64(0xFFFFFFFF)
+            umi = umi & U64((1 << (2 * s.umi_len)) - 1)
+            cb = self.cell_barcode[c].copy()
+            err = (r3 % U64(1000000)) < U64(s.cb_error_ppm)
+            pos = (r4 % U64(s.cb_len)).astype(np.int64)
+            delta = U64(1) + ((r4 >> U64(8)) % U64(3))
+            shift = (2 * (s.cb_len - 1 - pos)).astype(U64)
+            old = (cb >> shift) & U64(3)
+            new_cb = (cb & ~(U64(3) << shift)) | (((old + delta) & U64(3)) << shift)
+            cb = np.where(err, new_cb, cb)
+            intergenic = ((r3 >> U64(20)) % U64(1000000)) < U64(s.intergenic_ppm)
+            z = (r3 >> U64(40)) % U64(1000000)
+            mark = np.where(z < U64(s.intron_ppm), 4, np.where(z < U64(s.intron_ppm + s.not_annotated_ppm), 1, 2)).astype(np.uint32)
+            out = np.zeros(count, dtype=RECORD_DTYPE)
+            out["key"] = (cb << U64(24)) | umi
+            out["gene"] = np.where(intergenic, np.uint32(NO_GENE), g.astype(np.uint32)) | (mark << np.uint32(24))
+            out["read_idx"] = i.astype(np.uint32)
+        return out
+
+    # ---- device generator -------------------------------------------------------------------------------------
+    def params(self) -> _SynthParams:
+        s = self.spec
+        p = _SynthParams()
+        p.seed = s.seed
+        p.n_reads_total = s.n_reads
+        p.n_cells, p.n_genes, p.cb_len, p.umi_len = s.n_cells, s.n_genes, s.cb_len, s.umi_len
+        p.cell_cdf = self.cell_cdf.ctypes.data
+        p.cell_barcode = self.cell_barcode.ctypes.data
+        p.cell_reads = self.cell_reads.ctypes.data
+        p.gene_cdf = self.gene_cdf.ctypes.data
+        p.gene_weight = self.gene_weight.ctypes.data
+        p.cb_error_ppm, p.intergenic_ppm = s.cb_error_ppm, s.intergenic_ppm
+        p.intron_ppm, p.not_annotated_ppm = s.intron_ppm, s.not_annotated_ppm
+        p.reads_per_umi = s.reads_per_umi
+        return p
+
+    def generate_device(self, device: int, first: int, count: int, out_ptr: int, stream: int = 0):
+        lib = load_library()
+        p = self.params()
+        rc = lib.dge_synth_generate_device(device, C.byref(p), first, count, C.c_void_p(out_ptr), C.c_void_p(stream))
+        if rc != 0:
+            raise RuntimeError(f"dge_synth_generate_device failed with {rc}")
+
+
+def write_packed(path: str, recs: np.ndarray, cb_len: int, umi_len: int, n_genes: int, gene_names: Optional[Sequence[str]] = None):
+    """DGER0001 stream for the oracle drivers (oracle/common/dge_io.h)."""
+    blob = ("\n".join(gene_names)).encode() if gene_names else b""
+    with open(path, "wb") as f:
+        f.write(b"DGER0001")
+        f.write(np.array([recs.shape[0]], dtype="<u8").tobytes())
+        f.write(np.array([cb_len, umi_len, n_genes, 0], dtype="<u4").tobytes())
+        f.write(np.array([len(blob)], dtype="<u8").tobytes())
+        f.write(blob)
+        f.write(np.ascontiguousarray(recs, dtype=RECORD_DTYPE).tobytes())
+
+
+def records_from_strings(reads, gene_ids: dict, first_idx: int = 0) -> np.ndarray:
+    """reads: iterable of (cb, umi, gene_name_or_None, mark_bits).  Gene ids are assigned by `gene_ids` (name -> id)."""
+    reads = list(reads)
+    out = np.zeros(len(reads), dtype=RECORD_DTYPE)
+    for i, (cb, umi, gene, mark) in enumerate(reads):
+        gid = NO_GENE if not gene else gene_ids.setdefault(gene, len(gene_ids))
+        out["key"][i] = (pack_seq(cb) << 24) | pack_seq(umi)
+        out["gene"][i] = gid | (mark << 24)
+        out["read_idx"][i] = first_idx + i
+    return out

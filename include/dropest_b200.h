@@ -1,0 +1,255 @@
+/* dropest_b200.h -- C ABI of the B200-native dropEst count-matrix hot path.
+ *
+ * dropEst has no plugin/FFI ABI of its own: the seam is the C++ class Estimation::CellsDataContainer
+ * (reference Estimation/CellsDataContainer.h:82-122).  This header is the flat C boundary the host-side C++ facade
+ * (dropest_b200/host/CellsDataContainer.h, same class/method names as the reference) binds to; each entry point cites the
+ * reference interface it replaces.  Plain pointers and sizes only; no exceptions cross the ABI (status codes +
+ * dge_last_error()); one handle = one caller thread at a time, exactly like the reference container.
+ *
+ * All computation happens in hand-written sm_100a CUDA kernels (dropest_b200/csrc).  There is NO CPU fallback: every call
+ * fails with DGE_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef DROPEST_B200_H
+#define DROPEST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGE_ABI_VERSION 1
+
+/* ---- the per-read record --------------------------------------------------------------------------------------------
+ * Replaces Estimation::ReadInfo (reference Estimation/ReadInfo.h:9-24) + Tools::ReadParameters (Tools/ReadParameters.h:9-50)
+ * on the fill path.  16 bytes, little endian:
+ *   key      bits[63:24] cell barcode, 2 bits/base (A=0 C=1 G=2 T=3), first base most significant, right aligned (<= 20 bp)
+ *            bits[23:0]  UMI, same coding (<= 12 bp)
+ *   gene     bits[23:0]  gene id in [0, n_genes) or DGE_NO_GENE (read has no gene: "intergenic", CellsDataContainer.cpp:73-78)
+ *            bits[26:24] UMI::Mark bits of the read (reference Estimation/UMI.h:16-22): 1 not-annotated, 2 exon, 4 intron
+ *            bits[31:27] reserved, must be 0
+ *   read_idx global 0-based position of the read in the input stream.  First-seen order of barcodes and genes
+ *            (cell ids, StringIndexer ids) is derived from it, so records may be passed in ANY order / any batching.
+ */
+typedef struct dge_record16 {
+    uint64_t key;
+    uint32_t gene;
+    uint32_t read_idx;
+} dge_record16;
+
+#define DGE_NO_GENE 0xFFFFFFu
+#define DGE_MARK_NOT_ANNOTATED 1u
+#define DGE_MARK_EXON 2u
+#define DGE_MARK_INTRON 4u
+
+/* status codes */
+enum {
+    DGE_OK = 0,
+    DGE_ERR_INVALID = 1,   /* bad argument / bad config                                              */
+    DGE_ERR_STATE = 2,     /* call order violated (mirrors the reference's runtime_error throws)      */
+    DGE_ERR_CUDA = 3,      /* CUDA runtime failure or no device                                       */
+    DGE_ERR_CAPACITY = 4,  /* a device table overflowed (too many distinct barcodes for the key width) */
+    DGE_ERR_IO = 5,        /* whitelist file unreadable / malformed                                   */
+    DGE_ERR_INTERNAL = 6
+};
+
+/* CB merge strategy, selected like MergeStrategyFactory::get_cb_strat (reference Merge/MergeStrategyFactory.cpp:61-103) */
+enum {
+    DGE_MERGE_NONE = 0,           /* DummyMergeStrategy            (no -m)                         */
+    DGE_MERGE_REAL = 1,           /* RealBarcodesMergeStrategy     (-m, barcodes_file set)         */
+    DGE_MERGE_SIMPLE = 2,         /* SimpleMergeStrategy           (-m, no barcodes_file)          */
+    DGE_MERGE_POISSON_REAL = 3,   /* PoissonRealBarcodesMergeStrategy (-M, barcodes_file set)      */
+    DGE_MERGE_POISSON_SIMPLE = 4, /* PoissonSimpleMergeStrategy    (-M, no barcodes_file)          */
+    DGE_MERGE_ALL = 5             /* MergeAllMergeStrategy         (merge_type=all)                */
+};
+
+enum { DGE_BARCODES_CONST = 0, DGE_BARCODES_INDROP = 1 }; /* MergeStrategyFactory.cpp:113-126 */
+enum { DGE_UMI_MERGE_SIMPLE = 0, DGE_UMI_MERGE_DIRECTIONAL = 1 }; /* MergeStrategyFactory.cpp:105-111 */
+
+/* Configuration = constructor arguments of CellsDataContainer (CellsDataContainer.h:82-85) + the keys
+ * MergeStrategyFactory reads (MergeStrategyFactory.cpp:23-59), same defaults (dge_config_default). */
+typedef struct dge_config {
+    uint32_t abi_version;       /* DGE_ABI_VERSION */
+    int32_t  device;            /* CUDA device ordinal */
+    uint32_t cb_len;            /* barcode length in bases (<= 20) */
+    uint32_t umi_len;           /* UMI length in bases (<= 12) */
+    uint32_t n_genes;           /* gene ids are in [0, n_genes) (<= 2^24 - 1) */
+    uint32_t merge_type;        /* DGE_MERGE_* */
+    uint32_t barcodes_type;     /* DGE_BARCODES_* */
+    uint32_t umi_merge_type;    /* DGE_UMI_MERGE_* */
+    uint32_t min_genes_before_merge; /* default 10 */
+    uint32_t min_genes_after_merge;  /* default 10; effective value is max(after, before) (MergeStrategyAbstract.cpp:8-11) */
+    uint32_t max_cb_merge_edit_distance;
+    uint32_t max_umi_merge_edit_distance; /* default 1 */
+    double   min_merge_fraction;     /* default 0.2 */
+    double   max_merge_prob;         /* default 1e-4 */
+    double   max_real_merge_prob;    /* default 1e-7 */
+    double   umi_merge_mult;         /* default 2 */
+    uint32_t query_mark_mask;   /* bit m (m in 1..7) set <=> an accumulated UMI mark equal to m matches (UMI.cpp:76-85).
+                                   Default "eEBA" = marks {2,3,6,7} = 0xCC (CellsDataContainer.cpp:17, UMI.cpp:123-154) */
+    int32_t  max_cells;         /* -C: keep the top N filtered cells; <= 0 keeps all (CellsDataContainer.cpp:268-272) */
+    uint32_t reads_output;      /* -R: matrix values are read counts instead of UMI counts (ResultsPrinter.cpp:345) */
+    uint32_t reserved0;
+    const char *barcodes_file;  /* whitelist in the reference's own file format (BarcodesParser.cpp:117-144); NULL/"" = none */
+    uint64_t max_barcodes_hint; /* upper bound on distinct barcodes, 0 = automatic */
+} dge_config;
+
+typedef struct dge_handle dge_handle;
+
+/* Global / per-stage numbers.  Counter names follow the reference getters (CellsDataContainer.h:113-118). */
+typedef struct dge_summary {
+    uint64_t n_reads;               /* records passed to dge_add_batch* */
+    uint64_t total_cells_number;    /* distinct barcodes seen                 (total_cells_number)        */
+    uint64_t real_cells_number;     /*                                         (real_cells_number)         */
+    uint64_t filtered_cells_number; /* filtered_cells().size()                                            */
+    uint64_t n_genes_seen;          /* gene_indexer().values().size()                                     */
+    uint64_t n_umigs;               /* distinct (cell, gene, UMI) currently held                          */
+    uint64_t intergenic_reads;      /* intergenic_reads_num()        */
+    uint64_t has_exon_reads;        /* has_exon_reads_num()          */
+    uint64_t has_intron_reads;      /* has_intron_reads_num()        */
+    uint64_t has_not_annotated_reads; /* has_not_annotated_reads_num() */
+    uint64_t cm_nnz;                /* non-zeros of the filtered matrix `cm`   */
+    uint64_t cm_raw_nnz;            /* non-zeros of `cm_raw`                    */
+    uint64_t n_merged;              /* cells merged into another cell (MergeStrategyBase.cpp:53) */
+    uint64_t n_excluded;            /* cells excluded by the merge      (MergeStrategyBase.cpp:54) */
+} dge_summary;
+
+/* Per-cell row returned by dge_get_cells; one per requested cell, in the requested order. */
+typedef struct dge_cell_info {
+    uint64_t barcode;        /* 2-bit packed, same coding as dge_record16.key >> 24                */
+    uint32_t first_read_idx; /* smallest read_idx of the barcode (defines the reference's cell id) */
+    uint32_t flags;          /* bit0 is_real, bit1 is_merged, bit2 is_excluded (Cell.cpp:110-128)  */
+    int32_t  n_genes;        /* Cell::size()                                                       */
+    int32_t  umis_stat;      /* Cell::umis_number()  = Stats TOTAL_UMIS_PER_CB (a counter) */
+    int32_t  reads_stat;     /* Stats TOTAL_READS_PER_CB                                           */
+    int32_t  requested_genes_num;
+    int32_t  requested_umis_num;
+    int32_t  merge_target;   /* index INTO THE SAME RETURNED LIST of the cell this one was merged into, or own index */
+} dge_cell_info;
+
+#define DGE_CELL_REAL 1u
+#define DGE_CELL_MERGED 2u
+#define DGE_CELL_EXCLUDED 4u
+
+enum { DGE_CELLS_ALL = 0, DGE_CELLS_REAL = 1, DGE_CELLS_FILTERED = 2 };
+enum { DGE_MATRIX_CM = 0, DGE_MATRIX_CM_RAW = 1 };
+
+/* Per-stage device time of the last dge_set_initialized + dge_merge_and_filter, CUDA-event timed on the handle's stream. */
+typedef struct dge_timings {
+    float ms_fill;        /* records -> sorted distinct (cell,gene,UMI) + per-cell tables (add_record work)  */
+    float ms_init;        /* set_initialized: requested sizes, real/filtered cells                            */
+    float ms_merge;       /* CB merge phase 1 + 2 + applying merges                                           */
+    float ms_finish;      /* UMI merge, final sizes/filter, matrices                                          */
+    float ms_total;
+    float ms_dedup_kernel; /* the dominant kernel (umig_dedup_sort), summed over its launches                 */
+    uint32_t n_kernel_launches;
+    uint32_t n_dedup_launches;
+} dge_timings;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------------ */
+
+/* Fill `cfg` with the reference defaults (MergeStrategyFactory.cpp:23-59; query marks "eEBA"). */
+void dge_config_default(dge_config *cfg);
+
+/* = CellsDataContainer::CellsDataContainer (CellsDataContainer.cpp:20-37) + MergeStrategyFactory strategy selection. */
+int dge_create(const dge_config *cfg, dge_handle **out);
+void dge_destroy(dge_handle *h);
+
+/* Last error message of this handle (or of a failed dge_create when h == NULL). Never NULL. */
+const char *dge_last_error(const dge_handle *h);
+
+/* ---- fill: replaces CellsDataContainer::add_record (CellsDataContainer.cpp:59-88), n reads per call ------------------
+ * dge_add_batch        : `recs` is HOST memory; copied to the device asynchronously (pinned staging); no ownership taken.
+ * dge_add_batch_device : `recs` is DEVICE memory on cfg.device; referenced, NOT copied -- it must stay valid and unmodified
+ *                        until dge_set_initialized returns.
+ * Both fail with DGE_ERR_STATE after dge_set_initialized ("Container is already initialized", CellsDataContainer.cpp:61-62). */
+int dge_add_batch(dge_handle *h, const dge_record16 *recs, size_t n);
+int dge_add_batch_device(dge_handle *h, const dge_record16 *recs, size_t n);
+
+/* = CellsDataContainer::set_initialized (CellsDataContainer.cpp:163-175): runs the whole per-read grouping on the device.
+ * DGE_ERR_STATE when called twice (":165-166"). */
+int dge_set_initialized(dge_handle *h);
+
+/* = CellsDataContainer::merge_and_filter (CellsDataContainer.cpp:39-57). DGE_ERR_STATE before dge_set_initialized
+ * ("You must initialize container", ":41-42"). */
+int dge_merge_and_filter(dge_handle *h);
+
+/* Optional: run on this CUDA stream (a cudaStream_t passed as void*); default is a stream owned by the handle. */
+int dge_set_stream(dge_handle *h, void *cuda_stream);
+
+/* ---- query surface (CellsDataContainer.h:99-121, ResultsPrinter.cpp:334-396) ----------------------------------------- */
+int dge_get_summary(dge_handle *h, dge_summary *out);
+int dge_get_timings(dge_handle *h, dge_timings *out);
+
+/* Cells of one class, in the reference's order: ALL and REAL by cell id (= first-seen order), FILTERED in
+ * filtered_cells() order (ascending compare_cells, CellsDataContainer.cpp:329-344).  `out` has room for `capacity` rows;
+ * *n_out receives the number available (call with capacity 0 to size). */
+int dge_get_cells(dge_handle *h, int which, dge_cell_info *out, size_t capacity, size_t *n_out);
+
+/* Count matrix in compressed-column form, columns = cells (ResultsPrinter.cpp:334-396, 433-442):
+ *   DGE_MATRIX_CM     columns = filtered_cells() in order, values = UMIs (or reads with reads_output) whose mark matches the query
+ *   DGE_MATRIX_CM_RAW columns = real cells by cell id, values = all UMIs (or reads)
+ * indptr has n_cols+1 entries; `gene_ids`/`values` have nnz entries, gene ids ascending within a column and expressed as the
+ * caller's gene ids.  Any output pointer may be NULL; *n_cols / *nnz are always written. */
+int dge_get_matrix(dge_handle *h, int which, int64_t *indptr, int32_t *gene_ids, int32_t *values,
+                   size_t *n_cols, size_t *nnz);
+
+/* Gene ids in first-seen order (= gene_indexer().values(), StringIndexer.cpp:10-18). */
+int dge_get_gene_order(dge_handle *h, int32_t *gene_ids, size_t capacity, size_t *n_out);
+
+/* (barcode_from, barcode_to) for every cell whose merge target is not itself, ordered by source cell id
+ * (= ResultsPrinter::get_merge_targets, ResultsPrinter.cpp:316-332). */
+int dge_get_merge_pairs(dge_handle *h, uint64_t *from, uint64_t *to, size_t capacity, size_t *n_out);
+
+/* Every distinct (cell, gene, UMI) currently held, for the cells of class `which` (order: cell order of dge_get_cells,
+ * then gene id, then UMI value): = walking Cell::genes() / Gene::umis() (Cell.h:22, Gene.h:19).  cell_index indexes the
+ * list dge_get_cells(which) returns. Any output pointer may be NULL. */
+int dge_get_umigs(dge_handle *h, int which, uint32_t *cell_index, int32_t *gene_ids, uint32_t *umis,
+                  uint32_t *read_counts, uint8_t *marks, size_t capacity, size_t *n_out);
+
+/* ---- helpers that mirror reference utilities on the path (host-side, exact restatements used by the facade and tests) -- */
+
+/* Tools::edit_distance (Tools/UtilFunctions.cpp:32-65), literal behaviour including the banded quirks. */
+unsigned dge_edit_distance(const char *s1, const char *s2, int skip_n, unsigned max_ed);
+/* Tools::hamming_distance (Tools/UtilFunctions.cpp:67-82); returns UINT32_MAX when lengths differ. */
+unsigned dge_hamming_distance(const char *s1, const char *s2, int skip_n);
+
+/* Whitelist loaded by the handle (BarcodesParser::init, BarcodesParser.cpp:88-100): number of parts, then per part the
+ * token count and token length; tokens are returned reverse-complemented exactly as the reference stores them. */
+int dge_whitelist_shape(dge_handle *h, uint32_t *n_parts, uint32_t *part_sizes, uint32_t *part_lengths, size_t capacity);
+int dge_whitelist_token(dge_handle *h, uint32_t part, uint32_t index, char *out, size_t capacity);
+
+/* ---- synthetic read streams (bench + tests) -------------------------------------------------------------
+ * Counter-based generator: record i depends only on (seed, i) and the tables, so any slice can be produced anywhere
+ * (host mirror: dropest_b200/synth.py).  `out_device` is DEVICE memory for `count` records, filled with reads
+ * [first, first+count). */
+typedef struct dge_synth_params {
+    uint64_t seed;
+    uint64_t n_reads_total;       /* sizes the per-(cell,gene) UMI pools */
+    uint32_t n_cells, n_genes, cb_len, umi_len;
+    const uint64_t *cell_cdf;     /* [n_cells] HOST: inclusive cumulative weights scaled to 2^64 (last = UINT64_MAX) */
+    const uint64_t *cell_barcode; /* [n_cells] HOST: 2-bit packed true barcodes                                     */
+    const uint64_t *cell_reads;   /* [n_cells] HOST: expected reads per cell                                        */
+    const uint64_t *gene_cdf;     /* [n_genes] HOST: inclusive cumulative weights scaled to 2^64                    */
+    const uint32_t *gene_weight;  /* [n_genes] HOST: weight scaled to 2^32                                          */
+    uint32_t cb_error_ppm;        /* reads per million with one substituted barcode base */
+    uint32_t intergenic_ppm;
+    uint32_t intron_ppm, not_annotated_ppm; /* remaining reads are exonic */
+    uint32_t reads_per_umi;       /* pool divisor (>= 1) */
+    uint32_t reserved;
+} dge_synth_params;
+
+int dge_synth_generate_device(int device, const dge_synth_params *p, uint64_t first, uint64_t count,
+                              dge_record16 *out_device, void *cuda_stream);
+
+/* Route records to `n_ranks` owners by barcode hash (the multi-GPU partition step before the all-to-all).
+ * in/out are DEVICE memory, out has room for n records; counts[n_ranks] (HOST) receives the per-rank segment sizes;
+ * segment r starts at sum(counts[0..r)). */
+int dge_route_by_barcode_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, dge_record16 *out,
+                                uint64_t *counts, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DROPEST_B200_H */

@@ -1,0 +1,180 @@
+"""Shared machinery of the parity tests: run one workload through the CUDA path (C ABI) and through the CPU oracle, compare.
+
+The oracle (oracle/_ref = compiled reference, or oracle/_build = our restatement) is only ever the CHECKER here.
+"""
+from __future__ import annotations
+
+import os
+import tempfile
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+import dropest_b200 as dg
+from dropest_b200.synth import SynthSpec, SynthTables, read_whitelist, write_packed
+
+import oracle_io
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+WL_SYNTH_7_9 = os.path.join(GOLDEN, "wl_synth_7x9.txt")      # 96 x 128 tokens of 7 and 9 bp (10x-like split)
+WL_SYNTH_8_8 = os.path.join(GOLDEN, "wl_synth_8x8.txt")      # 64 x 64 tokens of 8 bp (inDrop v3-like)
+WL_CLOSE_4_4 = os.path.join(GOLDEN, "wl_close_4x4.txt")      # tiny, tokens at distance 1 of each other: exercises ties
+WL_TEST_EST = os.path.join(GOLDEN, "wl_test_est.txt")        # the reference's own 3 x 3 inDrop fixture
+
+MERGE_NAMES = {"none": dg.MERGE_NONE, "real": dg.MERGE_REAL, "simple": dg.MERGE_SIMPLE,
+               "poisson_real": dg.MERGE_POISSON_REAL, "poisson_simple": dg.MERGE_POISSON_SIMPLE, "all": dg.MERGE_ALL}
+
+
+@dataclass
+class Case:
+    name: str
+    spec: Optional[SynthSpec] = None
+    recs: Optional[np.ndarray] = None            # explicit records instead of a synthetic spec
+    cb_len: int = 16
+    umi_len: int = 12
+    n_genes: int = 1
+    gene_names: Optional[list] = None
+    merge: str = "none"
+    barcodes: Optional[str] = None
+    barcodes_type: str = "const"
+    min_genes_before: int = 10
+    min_genes_after: int = 10
+    max_cb_ed: int = 2
+    min_frac: float = 0.2
+    marks: str = "eEBA"
+    max_cells: int = -1
+    reads_output: bool = False
+    dump_umis: bool = True
+    n_batches: int = 3
+    shuffle: bool = True
+    extra: dict = field(default_factory=dict)
+
+
+def small_case(n_reads=20000, n_cells=40, n_genes=60, merge="real", **kw) -> Case:
+    wl = read_whitelist(WL_SYNTH_7_9)
+    spec = SynthSpec(n_reads=n_reads, n_cells=n_cells, n_genes=n_genes, cb_len=16, umi_len=10, whitelist_parts=wl,
+                     cb_error_ppm=kw.pop("cb_error_ppm", 60000), reads_per_umi=kw.pop("reads_per_umi", 3), seed=kw.pop("seed", 7))
+    return Case(name=f"small_{n_reads}", spec=spec, cb_len=16, umi_len=10, n_genes=n_genes, merge=merge,
+                barcodes=WL_SYNTH_7_9 if merge in ("real", "poisson_real") else None, barcodes_type="const",
+                min_genes_before=kw.pop("min_genes_before", 5), min_genes_after=kw.pop("min_genes_after", 10), **kw)
+
+
+def gpu_run(case: Case, recs: Optional[np.ndarray], device_generate: bool = False, tables: Optional[SynthTables] = None):
+    cfg = dg.Config(cb_len=case.cb_len, umi_len=case.umi_len, n_genes=case.n_genes, merge_type=MERGE_NAMES[case.merge],
+                    barcodes_type=dg.BARCODES_INDROP if case.barcodes_type == "indrop" else dg.BARCODES_CONST,
+                    barcodes_file=case.barcodes, min_genes_before_merge=case.min_genes_before,
+                    min_genes_after_merge=case.min_genes_after, max_cb_merge_edit_distance=case.max_cb_ed,
+                    min_merge_fraction=case.min_frac, marks=case.marks, max_cells=case.max_cells,
+                    reads_output=case.reads_output, max_barcodes_hint=case.extra.get("max_barcodes_hint", 1 << 16))
+    c = dg.Container(cfg)
+    if device_generate:
+        import torch
+
+        n = case.spec.n_reads
+        buf = torch.empty(n * 16, dtype=torch.uint8, device="cuda:0")
+        tables.generate_device(0, 0, n, buf.data_ptr())
+        torch.cuda.synchronize()
+        c.add_batch_device(buf.data_ptr(), n, keepalive=buf)
+    else:
+        order = np.arange(recs.shape[0])
+        if case.shuffle:
+            np.random.default_rng(123).shuffle(order)
+        for part in np.array_split(order, max(1, case.n_batches)):
+            c.add_batch(recs[part])
+    c.set_initialized()
+    pre = c.cells(dg.CELLS_FILTERED)
+    c.merge_and_filter()
+    out = {
+        "summary": c.summary(),
+        "timings": c.timings(),
+        "filtered_pre": pre,
+        "all": c.cells(dg.CELLS_ALL),
+        "real": c.cells(dg.CELLS_REAL),
+        "filtered": c.cells(dg.CELLS_FILTERED),
+        "cm": c.matrix(dg.MATRIX_CM),
+        "cm_raw": c.matrix(dg.MATRIX_CM_RAW),
+        "gene_order": c.gene_order(),
+        "merge_pairs": c.merge_pairs(),
+    }
+    if case.dump_umis:
+        out["umigs"] = c.umigs(dg.CELLS_ALL)
+    c.close()
+    return out
+
+
+def run_case(case: Case, device_generate: bool = False, kind: str = "any"):
+    tables = None
+    if case.spec is not None:
+        tables = SynthTables(case.spec)
+        recs = tables.generate_host(0, case.spec.n_reads)
+    else:
+        recs = case.recs
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "reads.bin")
+        write_packed(path, recs, case.cb_len, case.umi_len, case.n_genes, case.gene_names)
+        ora = oracle_io.run_oracle(path, kind=kind, merge=case.merge, barcodes=case.barcodes, barcodes_type=case.barcodes_type,
+                                   min_genes_before=case.min_genes_before, min_genes_after=case.min_genes_after,
+                                   max_cb_ed=case.max_cb_ed, min_frac=case.min_frac, marks=case.marks, max_cells=case.max_cells,
+                                   reads_output=case.reads_output, dump_umis=case.dump_umis)
+    gpu = gpu_run(case, recs, device_generate=device_generate, tables=tables)
+    return {"case": case, "oracle": ora, "gpu": gpu, "recs": recs}
+
+
+def _gene_id_of_name(case: Case, names):
+    if case.gene_names:
+        lut = {n: i for i, n in enumerate(case.gene_names)}
+        return np.array([lut[n] for n in names], dtype=np.int64)
+    return np.array([int(n[1:]) for n in names], dtype=np.int64)
+
+
+def assert_parity(res, check_umigs: bool = True):
+    case, ora, gpu = res["case"], res["oracle"], res["gpu"]
+    # ---- cells, in first-seen order
+    o_bc = np.array([dg.pack_seq(s) for s in oracle_io.strings(ora["cell_barcodes"])], dtype=np.uint64)
+    g_all = gpu["all"]
+    assert g_all.shape[0] == o_bc.shape[0] == int(ora["n_cells"][0]) == gpu["summary"]["total_cells_number"], "total cells"
+    np.testing.assert_array_equal(g_all["barcode"], o_bc, err_msg="cell id order (first seen)")
+    np.testing.assert_array_equal(g_all["flags"], ora["cell_flags"].astype(np.uint32), err_msg="real/merged/excluded flags")
+    np.testing.assert_array_equal(g_all["umis_stat"], ora["cell_umis_stat"], err_msg="TOTAL_UMIS_PER_CB")
+    np.testing.assert_array_equal(g_all["reads_stat"], ora["cell_reads_stat"], err_msg="TOTAL_READS_PER_CB")
+    np.testing.assert_array_equal(g_all["n_genes"], ora["cell_n_genes"], err_msg="genes per cell")
+    np.testing.assert_array_equal(g_all["requested_genes_num"], ora["cell_req_genes"].astype(np.int32), err_msg="requested genes")
+    np.testing.assert_array_equal(g_all["requested_umis_num"], ora["cell_req_umis"].astype(np.int32), err_msg="requested umis")
+    np.testing.assert_array_equal(g_all["merge_target"].astype(np.int64), ora["merge_targets"], err_msg="merge_targets")
+    # ---- filtered cells (order matters), before and after the merge
+    np.testing.assert_array_equal(gpu["filtered_pre"]["barcode"], o_bc[ora["filtered_pre_merge"]], err_msg="filtered cells at set_initialized")
+    np.testing.assert_array_equal(gpu["filtered"]["barcode"], o_bc[ora["filtered_cells"]], err_msg="filtered cells")
+    assert gpu["summary"]["real_cells_number"] == int(ora["real_cells_number"][0])
+    for k in ("intergenic_reads", "has_exon_reads", "has_intron_reads", "has_not_annotated_reads"):
+        assert gpu["summary"][k] == int(ora[k][0]), k
+    # ---- gene first-seen order
+    o_gene_ids = _gene_id_of_name(case, oracle_io.strings(ora["gene_names"]))
+    np.testing.assert_array_equal(gpu["gene_order"].astype(np.int64), o_gene_ids, err_msg="gene indexer order")
+    # ---- matrices: (column, gene, value) with genes ascending inside a column
+    for name, pref in (("cm", "cm"), ("cm_raw", "cm_raw")):
+        indptr, genes, vals = gpu[name]
+        col = np.repeat(np.arange(indptr.shape[0] - 1), np.diff(indptr))
+        o_col, o_gene, o_val = ora[pref + "_col"], o_gene_ids[ora[pref + "_gene"]] if ora[pref + "_gene"].size else ora[pref + "_gene"], ora[pref + "_val"]
+        # oracle triplets are ordered by gene_indexer id inside a column; ours by caller gene id
+        o_order = np.lexsort((o_gene, o_col))
+        assert col.shape[0] == o_col.shape[0], f"{name} nnz {col.shape[0]} vs {o_col.shape[0]}"
+        np.testing.assert_array_equal(col, o_col[o_order], err_msg=f"{name} columns")
+        np.testing.assert_array_equal(genes.astype(np.int64), o_gene[o_order], err_msg=f"{name} genes")
+        np.testing.assert_array_equal(vals.astype(np.int64), o_val[o_order], err_msg=f"{name} values")
+    n_cols_raw = gpu["cm_raw"][0].shape[0] - 1
+    assert n_cols_raw == ora["cm_raw_cells"].shape[0]
+    np.testing.assert_array_equal(gpu["real"]["barcode"], o_bc[ora["cm_raw_cells"]], err_msg="cm_raw column order")
+    # ---- every (cell, gene, UMI, reads, mark)
+    if check_umigs and case.dump_umis and "umi_cell" in ora:
+        o_umi = np.array([dg.pack_seq(s) for s in oracle_io.strings(ora["umi_seq"])], dtype=np.uint64)
+        o = np.stack([ora["umi_cell"].astype(np.uint64), o_gene_ids[ora["umi_gene"]].astype(np.uint64), o_umi,
+                      ora["umi_count"].astype(np.uint64), ora["umi_mark"].astype(np.uint64)], axis=1)
+        u = gpu["umigs"]
+        g = np.stack([u["cell"].astype(np.uint64), u["gene"].astype(np.uint64), u["umi"].astype(np.uint64),
+                      u["count"].astype(np.uint64), u["mark"].astype(np.uint64)], axis=1)
+        o = o[np.lexsort((o[:, 2], o[:, 1], o[:, 0]))]
+        g = g[np.lexsort((g[:, 2], g[:, 1], g[:, 0]))]
+        assert o.shape == g.shape, f"distinct (cell,gene,umi): {g.shape[0]} vs oracle {o.shape[0]}"
+        np.testing.assert_array_equal(g, o, err_msg="(cell, gene, umi, reads, mark)")

@@ -1,0 +1,214 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.  Bit-exact bar."""
+import numpy as np
+import pytest
+
+import dropest_b200 as dg
+from dropest_b200.synth import SynthSpec, SynthTables, read_whitelist, records_from_strings
+
+import parity_utils as pu
+
+pytestmark = pytest.mark.gpu
+
+# Fixture of the reference's Tests/TestEstimation.cpp:33-80 (17 reads, 7 barcodes)
+FIXTURE_READS = [
+    ("AAATTAGGTCCA", "AAACCT", "Gene1"), ("AAATTAGGTCCA", "CCCCCT", "Gene2"), ("AAATTAGGTCCA", "ACCCCT", "Gene3"),
+    ("AAATTAGGTCCA", "ACCCCT", "Gene4"), ("AAATTAGGTCCC", "CAACCT", "Gene1"), ("AAATTAGGTCCC", "CAACCT", "Gene10"),
+    ("AAATTAGGTCCC", "CAACCT", "Gene20"), ("AAATTAGGTCCG", "CAACCT", "Gene1"), ("AAATTAGGTCGG", "AAACCT", "Gene1"),
+    ("AAATTAGGTCGG", "CCCCCT", "Gene2"), ("CCCTTAGGTCCA", "CCATTC", "Gene3"), ("CCCTTAGGTCCA", "CCCCCT", "Gene2"),
+    ("CCCTTAGGTCCA", "ACCCCT", "Gene3"), ("CAATTAGGTCCG", "CAACCT", "Gene1"), ("CAATTAGGTCCG", "AAACCT", "Gene1"),
+    ("CAATTAGGTCCG", "CCCCCT", "Gene2"), ("AAAAAAAAAAAA", "CCCCCT", "Gene2"),
+]
+
+
+def fixture_case(**kw):
+    gene_ids = {}
+    recs = records_from_strings([(cb, umi, g, 2) for cb, umi, g in FIXTURE_READS], gene_ids)
+    names = [n for n, _ in sorted(gene_ids.items(), key=lambda kv: kv[1])]
+    return pu.Case(name="test_est_fixture", recs=recs, cb_len=12, umi_len=6, n_genes=len(names), gene_names=names, merge="real",
+                   barcodes=pu.WL_TEST_EST, barcodes_type="indrop", min_genes_before=0, min_genes_after=0, max_cb_ed=7,
+                   min_frac=0.0, shuffle=False, n_batches=1, **kw)
+
+
+def test_synth_device_matches_host():
+    import torch
+
+    spec = SynthSpec(n_reads=200_000, n_cells=300, n_genes=500, cb_len=16, umi_len=12, whitelist_parts=read_whitelist(pu.WL_SYNTH_7_9))
+    t = SynthTables(spec)
+    host = t.generate_host(1000, 100_000)
+    buf = torch.empty(100_000 * 16, dtype=torch.uint8, device="cuda:0")
+    t.generate_device(0, 1000, 100_000, buf.data_ptr())
+    dev = np.frombuffer(buf.cpu().numpy().tobytes(), dtype=dg.RECORD_DTYPE)
+    np.testing.assert_array_equal(dev, host)
+
+
+def test_reference_fixture_merge_by_real_barcodes():
+    """Tests/TestEstimation.cpp:237-280 (testMergeByRealBarcodes) through the CUDA path, checked against the oracle AND the
+    literal expectations written in the reference test."""
+    res = pu.run_case(fixture_case())
+    pu.assert_parity(res)
+    g = res["gpu"]
+    assert g["summary"]["total_cells_number"] == 7
+    assert g["filtered"].shape[0] == 2
+    assert list(g["filtered"]["n_genes"]) == [3, 4]
+    assert list(g["all"]["merge_target"]) == [0, 1, 1, 0, 0, 0, 6]
+    assert [bool(f & 2) for f in g["all"]["flags"]] == [False, False, True, True, True, True, False]
+    assert sum(bool(f & 4) for f in g["all"]["flags"]) == 1
+    u = g["umigs"]
+    names = res["case"].gene_names
+
+    def reads(cell, gene, umi):
+        m = (u["cell"] == cell) & (u["gene"] == names.index(gene)) & (u["umi"] == dg.pack_seq(umi))
+        assert m.sum() == 1
+        return int(u["count"][m][0])
+
+    c0, c1 = 1, 0  # filtered order is [cell 1, cell 0]
+    assert reads(c0, "Gene1", "CAACCT") == 2
+    assert reads(c1, "Gene1", "AAACCT") == 3
+    assert reads(c1, "Gene2", "CCCCCT") == 4
+    assert reads(c1, "Gene3", "ACCCCT") == 2
+    assert reads(c1, "Gene3", "CCATTC") == 1
+
+
+def test_fill_only_small():
+    res = pu.run_case(pu.small_case(n_reads=30000, n_cells=50, n_genes=80, merge="none"))
+    pu.assert_parity(res)
+
+
+def test_fill_device_resident_input():
+    res = pu.run_case(pu.small_case(n_reads=50000, n_cells=60, n_genes=100, merge="none"), device_generate=True)
+    pu.assert_parity(res)
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+def test_merge_real_small(seed):
+    res = pu.run_case(pu.small_case(n_reads=60000, n_cells=30, n_genes=120, merge="real", seed=seed))
+    pu.assert_parity(res)
+    assert res["gpu"]["summary"]["n_merged"] > 0
+
+
+def test_merge_real_medium():
+    res = pu.run_case(pu.small_case(n_reads=600_000, n_cells=400, n_genes=2000, merge="real", min_genes_before=20, min_genes_after=50,
+                                    cb_error_ppm=20000, reads_per_umi=4))
+    pu.assert_parity(res)
+
+
+def test_merge_real_indrop_like_8x8():
+    wl = read_whitelist(pu.WL_SYNTH_8_8)
+    spec = SynthSpec(n_reads=80000, n_cells=40, n_genes=150, cb_len=16, umi_len=6, whitelist_parts=wl, cb_error_ppm=80000, seed=3)
+    case = pu.Case(name="indrop_like", spec=spec, cb_len=16, umi_len=6, n_genes=150, merge="real", barcodes=pu.WL_SYNTH_8_8,
+                   barcodes_type="indrop", min_genes_before=5, min_genes_after=10)
+    res = pu.run_case(case)
+    pu.assert_parity(res)
+
+
+@pytest.mark.parametrize("min_frac", [0.0, 0.2])
+def test_close_whitelist_ties_and_far_classes(min_frac):
+    """Whitelist tokens one substitution apart: several neighbours per class, exact ties, distance classes >= 2."""
+    rng = np.random.default_rng(5)
+    wl = read_whitelist(pu.WL_CLOSE_4_4)
+    true_cbs = [a + b for a in wl[0] for b in wl[1]][:20]
+    reads = []
+    genes = [f"G{i}" for i in range(12)]
+    for cb in true_cbs:
+        for _ in range(int(rng.integers(5, 40))):
+            c = list(cb)
+            r = rng.random()
+            if r < 0.25:
+                p = int(rng.integers(0, 8)); c[p] = "ACGT"[(("ACGT".index(c[p])) + int(rng.integers(1, 4))) % 4]
+            if r < 0.08:
+                p = int(rng.integers(0, 8)); c[p] = "ACGT"[(("ACGT".index(c[p])) + int(rng.integers(1, 4))) % 4]
+            umi = "".join("ACGT"[int(x)] for x in rng.integers(0, 2, size=4))
+            reads.append(("".join(c), umi, genes[int(rng.integers(0, 12))], int(rng.choice([1, 2, 4, 6]))))
+    gene_ids = {}
+    recs = records_from_strings(reads, gene_ids)
+    names = [n for n, _ in sorted(gene_ids.items(), key=lambda kv: kv[1])]
+    case = pu.Case(name="close_wl", recs=recs, cb_len=8, umi_len=4, n_genes=len(names), gene_names=names, merge="real",
+                   barcodes=pu.WL_CLOSE_4_4, barcodes_type="const", min_genes_before=1, min_genes_after=2, min_frac=min_frac)
+    res = pu.run_case(case)
+    pu.assert_parity(res)
+
+
+def test_reads_output_max_cells_and_marks():
+    res = pu.run_case(pu.small_case(n_reads=40000, n_cells=30, n_genes=90, merge="real", reads_output=True, max_cells=12, marks="eB"))
+    pu.assert_parity(res)
+    assert res["gpu"]["filtered"].shape[0] == 12
+
+
+def test_intergenic_only_and_empty_inputs():
+    # barcodes that only ever appear without a gene still become cells (CellsDataContainer.cpp:64-78)
+    gene_ids = {}
+    recs = records_from_strings([("ACGTACGT", "ACGT", None, 2), ("ACGTACGT", "ACGA", None, 2), ("TTTTACGT", "ACGT", "G1", 2),
+                                 ("TTTTACGT", "ACGT", "G1", 4), ("TTTTACGT", "ACGT", "G2", 1)], gene_ids)
+    case = pu.Case(name="intergenic", recs=recs, cb_len=8, umi_len=4, n_genes=2, gene_names=["G1", "G2"], merge="none",
+                   min_genes_before=0, min_genes_after=0, shuffle=False, n_batches=2)
+    res = pu.run_case(case)
+    pu.assert_parity(res)
+    assert res["gpu"]["summary"]["intergenic_reads"] == 2
+    empty = pu.Case(name="empty", recs=np.zeros(0, dtype=dg.RECORD_DTYPE), cb_len=8, umi_len=4, n_genes=2, merge="none")
+    out = pu.gpu_run(empty, empty.recs)
+    assert out["summary"]["total_cells_number"] == 0 and out["cm"][0].shape[0] == 1
+
+
+def test_call_order_errors_mirror_reference_throws():
+    c = dg.Container(dg.Config(cb_len=8, umi_len=4, n_genes=2))
+    with pytest.raises(dg.DgeError) as e:
+        c.merge_and_filter()  # "You must initialize container" (CellsDataContainer.cpp:41-42)
+    assert e.value.code == 2 and "initialize" in str(e.value)
+    c.set_initialized()
+    with pytest.raises(dg.DgeError) as e:
+        c.add_batch(np.zeros(1, dtype=dg.RECORD_DTYPE))  # "Container is already initialized" (CellsDataContainer.cpp:61-62)
+    assert e.value.code == 2
+    with pytest.raises(dg.DgeError):
+        c.set_initialized()
+    c.close()
+
+
+def test_full_size_invariants_20m():
+    """Size-independent properties on a stream the oracle cannot chew in seconds: totals are conserved and the result does not
+    depend on batching / order."""
+    import torch
+
+    wl = read_whitelist(pu.WL_SYNTH_7_9)
+    spec = SynthSpec(n_reads=20_000_000, n_cells=2000, n_genes=5000, cb_len=16, umi_len=12, whitelist_parts=wl)
+    t = SynthTables(spec)
+    n = spec.n_reads
+    buf = torch.empty(n * 16, dtype=torch.uint8, device="cuda:0")
+    t.generate_device(0, 0, n, buf.data_ptr())
+    torch.cuda.synchronize()
+
+    def run(split):
+        cfg = dg.Config(cb_len=16, umi_len=12, n_genes=5000, merge_type=dg.MERGE_REAL, barcodes_type=dg.BARCODES_CONST,
+                        barcodes_file=pu.WL_SYNTH_7_9, min_genes_before_merge=20, min_genes_after_merge=50)
+        c = dg.Container(cfg)
+        if split == 1:
+            c.add_batch_device(buf.data_ptr(), n)
+        else:
+            step = n // split
+            for k in range(split):
+                lo, hi = k * step, (n if k == split - 1 else (k + 1) * step)
+                c.add_batch_device(buf.data_ptr() + lo * 16, hi - lo)
+        c.set_initialized()
+        c.merge_and_filter()
+        s = c.summary()
+        allc = c.cells(dg.CELLS_ALL)
+        cm = c.matrix(dg.MATRIX_CM)
+        raw = c.matrix(dg.MATRIX_CM_RAW)
+        filt = c.cells(dg.CELLS_FILTERED)
+        c.close()
+        return s, allc, cm, raw, filt
+
+    s1, all1, cm1, raw1, f1 = run(1)
+    s2, all2, cm2, raw2, f2 = run(7)
+    assert s1 == s2
+    np.testing.assert_array_equal(all1, all2)
+    for a, b in zip(cm1 + raw1, cm2 + raw2):
+        np.testing.assert_array_equal(a, b)
+    # conservation: every read is either intergenic or counted once in TOTAL_READS of an unmerged cell
+    unmerged = (all1["flags"] & 2) == 0
+    assert int(all1["reads_stat"][unmerged].sum()) + s1["intergenic_reads"] == n
+    assert s1["has_exon_reads"] + s1["has_intron_reads"] + s1["has_not_annotated_reads"] == n - s1["intergenic_reads"]
+    # filtered cells ascend in (requested genes, requested umis)
+    k = f1["requested_genes_num"].astype(np.int64) * (1 << 32) + f1["requested_umis_num"]
+    assert np.all(np.diff(k) >= 0)
+    # cm_raw column sums == distinct UMIs of real cells that were never merge targets
+    assert raw1[0][-1] == raw1[1].shape[0]
