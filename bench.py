@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s of the dropEst count-matrix hot path on B200 (BASELINE.json metric), one JSON line on stdout.
+
+A "step" = one full pass of the hot path over one synthetic read stream:
+    dge_reset -> dge_add_batch_device (barcode table + key packing) -> dge_set_initialized (grouping, per-cell tables,
+    real/filtered cells) -> dge_merge_and_filter (whitelist CB merge, final filter, cm / cm_raw in HBM)
+`value`  : device-timed (CUDA events on the launching stream), 16-byte records already resident in HBM.
+`e2e`    : the same pass through the C ABI with HOST (pinned) records: H2D inside the timed region + D2H of the count matrix.
+`--impl reference` : the reference's own CPU implementation of the path (oracle/_ref = its unmodified sources, else our
+                      CPU restatement) on a bounded sample of the same workload.
+Workload (config.workload): BASELINE.json configs[1] "10x v3: 400M reads / 10k cells / 30k genes, 16bp CB + 12bp UMI, 1 GPU",
+per GPU (weak scaling for N > 1: every rank owns its own 10k-cell population, reads routed by barcode hash with one
+NCCL all-to-all inside the timed step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = {
+    "name": "10x v3: 400M reads / 10k cells / 30k genes, 16bp CB + 12bp UMI, 1 GPU",
+    "n_reads": 400_000_000, "n_cells": 10_000, "n_genes": 30_000, "cb_len": 16, "umi_len": 12,
+    "min_genes_before": 20, "min_genes_after": 100, "min_frac": 0.2, "max_cb_ed": 2,
+}
+ALGO_BYTES_PER_READ = 48  # 3 x 16-byte record (read once, scatter once, re-read once)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(p.get("sm_max_mhz", 1965.0))
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def product_whitelist(path: str, n1: int = 2048, n2: int = 3328, seed: int = 11):
+    """Synthetic product-form 7+9 whitelist (the real 10x v3 list is not a product of parts).  Tokens of one
+    part all have base-sum == 0 mod 4, so any two differ in >= 2 positions, like a real error-tolerant whitelist."""
+    rng = np.random.default_rng(seed)
+
+    def part(length, n):
+        free = rng.choice(4 ** (length - 1), size=n, replace=False)
+        toks = []
+        for v in free:
+            b = [(int(v) >> (2 * i)) & 3 for i in range(length - 1)]
+            b.append((-sum(b)) % 4)
+            toks.append("".join("ACGT"[x] for x in b))
+        return toks
+
+    with open(path, "w") as f:
+        f.write(" ".join(part(7, n1)) + "\n")
+        f.write(" ".join(part(9, n2)) + "\n")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, smax, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax = max(smax, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        # "under load" = samples in the upper half of what was seen
+        load = [x for x in sm if x >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_spec(n_reads, n_cells, wl_parts, seed=42):
+    from dropest_b200.synth import SynthSpec
+
+    return SynthSpec(n_reads=n_reads, n_cells=n_cells, n_genes=WORKLOAD["n_genes"], cb_len=WORKLOAD["cb_len"], umi_len=WORKLOAD["umi_len"],
+                     seed=seed, whitelist_parts=wl_parts)
+
+
+def cpu_reference_run(wl_path, wl_parts, sample_reads, timeout=1200):
+    """One timed run of the CPU implementation on a scaled replica of the workload (same reads per cell, same genes)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_io
+    from dropest_b200.synth import SynthTables, write_packed
+
+    n_cells = max(10, int(round(sample_reads * WORKLOAD["n_cells"] / WORKLOAD["n_reads"])))
+    spec = make_spec(sample_reads, n_cells, wl_parts, seed=43)
+    recs = SynthTables(spec).generate_host(0, sample_reads)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "sample.bin")
+        write_packed(path, recs, spec.cb_len, spec.umi_len, spec.n_genes)
+        res = oracle_io.run_oracle(path, merge="real", barcodes=wl_path, barcodes_type="const", min_genes_before=WORKLOAD["min_genes_before"],
+                                   min_genes_after=WORKLOAD["min_genes_after"], max_cb_ed=WORKLOAD["max_cb_ed"], min_frac=WORKLOAD["min_frac"],
+                                   dump_umis=False, timeout=timeout)
+    secs = float(res["t_fill_s"][0] + res["t_init_s"][0] + res["t_merge_s"][0])
+    return {"value": sample_reads / secs, "seconds": secs, "kind": res["_kind"], "cores": 1,
+            "sample": f"{sample_reads} reads / {n_cells} cells / {spec.n_genes} genes scaled replica of the workload "
+                      f"(add_record loop {float(res['t_fill_s'][0]):.2f} s + set_initialized {float(res['t_init_s'][0]):.2f} s + "
+                      f"merge_and_filter {float(res['t_merge_s'][0]):.2f} s; single thread: the reference dropest is single-threaded)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=WORKLOAD["n_reads"], help="reads per GPU (default: the BASELINE config)")
+    ap.add_argument("--cells", type=int, default=WORKLOAD["n_cells"])
+    ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    hbm_peak, peak_src, _ = measured_peaks()
+
+    cache = os.path.join(tempfile.gettempdir(), f"dge_bench_{os.getuid()}")
+    os.makedirs(cache, exist_ok=True)
+    wl_path = os.path.join(cache, f"wl_7x9_2048x3328_r{rank}.txt")
+    product_whitelist(wl_path)
+    from dropest_b200.synth import SynthTables, read_whitelist
+
+    wl_parts = read_whitelist(wl_path)
+    config = {"workload": WORKLOAD["name"], "reads_per_gpu": args.reads, "cells_per_gpu": args.cells, "genes": WORKLOAD["n_genes"],
+              "cb_len": 16, "umi_len": 12, "merge": "RealBarcodesMergeStrategy, synthetic product whitelist 2048x3328 (7+9 bp)",
+              "min_genes_before_merge": 20, "min_genes_after_merge": 100, "l2_policy": "inputs (6.4 GB) larger than L2",
+              "partition": "barcode-hash, one NCCL all-to-all per step" if world > 1 else "single GPU"}
+
+    # ------------------------------------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        last = None
+        for it in range(args.warmup + args.steps):
+            if it < args.warmup and it > 0:
+                continue  # one warm-up run of a CPU program is enough to page the binary in
+            last = cpu_reference_run(wl_path, wl_parts, args.cpu_sample_reads)
+            if it >= args.warmup:
+                vals.append(last["value"])
+        v = float(np.mean(vals))
+        line = {"impl": "reference", "metric": "reads/sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1000.0 * args.cpu_sample_reads / v, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+                "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------------------------------ our arm
+    import torch
+    import dropest_b200 as dg
+
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    n = args.reads
+    # every rank draws its slice of one global stream over world*cells cells (different seed per world size keeps N=1 == configs[1])
+    spec = make_spec(n * world, args.cells * world, wl_parts)
+    tables = SynthTables(spec)
+    raw = torch.empty(n * 16, dtype=torch.uint8, device=f"cuda:{dev}")
+    tables.generate_device(dev, rank * n, n, raw.data_ptr())
+    torch.cuda.synchronize()
+
+    cfg = dg.Config(cb_len=16, umi_len=12, n_genes=WORKLOAD["n_genes"], device=dev, merge_type=dg.MERGE_REAL, barcodes_type=dg.BARCODES_CONST,
+                    barcodes_file=wl_path, min_genes_before_merge=WORKLOAD["min_genes_before"], min_genes_after_merge=WORKLOAD["min_genes_after"],
+                    max_cb_merge_edit_distance=WORKLOAD["max_cb_ed"], min_merge_fraction=WORKLOAD["min_frac"])
+    cont = dg.Container(cfg)
+    stream = torch.cuda.current_stream()
+    cont.set_stream(stream.cuda_stream)
+    lib = dg.load_library()
+
+    routed = recv = None
+    if world > 1:
+        import ctypes as C
+
+        routed = torch.empty_like(raw)
+        recv = torch.empty(int(n * 1.25) * 16 + 4096, dtype=torch.uint8, device=f"cuda:{dev}")
+
+    def exchange():
+        """route by barcode hash (our kernel) + ONE all-to-all-v over NCCL; returns (ptr, count) of the records this rank owns"""
+        import ctypes as C
+        import torch.distributed as dist
+
+        counts = np.zeros(world, dtype=np.uint64)
+        rc = lib.dge_route_by_barcode_device(dev, C.c_void_p(raw.data_ptr()), n, world, C.c_void_p(routed.data_ptr()), counts.ctypes.data,
+                                             C.c_void_p(stream.cuda_stream))
+        assert rc == 0
+        send = torch.tensor(counts.astype(np.int64), device=f"cuda:{dev}")
+        got = torch.empty_like(send)
+        dist.all_to_all_single(got, send)
+        in_split = [int(x) * 16 for x in counts]
+        out_split = [int(x) * 16 for x in got.cpu().tolist()]
+        total = sum(out_split)
+        assert total <= recv.numel(), "receive buffer too small"
+        dist.all_to_all_single(recv[:total], routed, output_split_sizes=out_split, input_split_sizes=in_split)
+        return recv.data_ptr(), total // 16
+
+    def step():
+        cont.reset()
+        if world > 1:
+            ptr, cnt = exchange()
+        else:
+            ptr, cnt = raw.data_ptr(), n
+        cont.add_batch_device(ptr, cnt)
+        cont.set_initialized()
+        cont.merge_and_filter()
+        return cnt
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dedup_ms, dedup_launches, launches, stage = 0.0, 0, 0, {"ms_fill": 0.0, "ms_init": 0.0, "ms_merge": 0.0, "ms_finish": 0.0}
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+        t = cont.timings()
+        dedup_ms += t["ms_dedup_kernel"]; dedup_launches += t["n_dedup_launches"]; launches += t["n_kernel_launches"]
+        for k in stage:
+            stage[k] += t[k]
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    summary = cont.summary()
+    if world > 1:
+        import torch.distributed as dist
+
+        tmax = torch.tensor([ms], device=f"cuda:{dev}")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    total_reads = n * world * args.steps
+    value = total_reads / (ms / 1000.0)
+
+    # ---- e2e: host (pinned) records -> C ABI -> count matrix back on the host
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(n * 16, dtype=torch.uint8, pin_memory=True)
+        host.copy_(raw)
+        torch.cuda.synchronize()
+        d2h = 0
+
+        def e2e_step():
+            nonlocal d2h
+            cont.reset()
+            cont.add_batch_ptr(host.data_ptr(), n)
+            cont.set_initialized()
+            cont.merge_and_filter()
+            indptr, genes, vals = cont.matrix(dg.MATRIX_CM)
+            d2h = indptr.nbytes // 2 + genes.nbytes + vals.nbytes
+            return int(vals.sum())
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, min(args.steps, 3))):
+            checksum = e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / max(1, min(args.steps, 3))
+        if world > 1:
+            import torch.distributed as dist
+
+            tt = torch.tensor([dt], device=f"cuda:{dev}")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": n * world / dt, "unit": "reads/s", "h2d_bytes_per_step": n * 16 * world, "d2h_bytes_per_step": int(d2h) * world,
+               "note": "per-rank host records, no cross-rank routing" if world > 1 else "cm checksum %d" % checksum}
+        del host
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (umig dedup+sort), timed live with CUDA events inside the library
+    n_keys = n - summary["intergenic_reads"] if world == 1 else None
+    roof = None
+    if dedup_launches and n_keys:
+        # algorithmic bytes of one launch: every grouped key read once (8 B) + every distinct (cell,gene,UMI) written once (8 B key + 4 B value)
+        algo = n_keys * 8 + summary["n_umigs"] * 12
+        ach = algo / (dedup_ms / dedup_launches / 1000.0) / 1e9
+        roof = {"kernel": "k_dedup_sort", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "ms_per_launch": dedup_ms / dedup_launches,
+                "algorithmic_bytes_per_launch": algo}
+    path_gbs = value / world * ALGO_BYTES_PER_READ / 1e9
+    line = {"metric": "reads/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roof,
+            "roofline_path": {"bound": "hbm", "achieved": path_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": path_gbs / hbm_peak,
+                              "bytes_per_read": ALGO_BYTES_PER_READ, "note": "whole hot path per GPU, BASELINE.md definition"},
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+            "result": {k: summary[k] for k in ("total_cells_number", "real_cells_number", "filtered_cells_number", "n_umigs", "cm_nnz", "n_merged", "n_excluded")}}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cb = cpu_reference_run(wl_path, wl_parts, args.cpu_sample_reads)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": "reads/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+        except Exception as e:  # the checker is missing: say so, do not hide it
+            line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 1, "kind": "unavailable", "sample": str(e)[:200]}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

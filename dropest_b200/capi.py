@@ -38,7 +38,7 @@ assert CELL_INFO_DTYPE.itemsize == 40
 # exported symbols of include/dropest_b200.h (checked by tests/test_abi.py)
 EXPORTS = [
     "dge_config_default", "dge_create", "dge_destroy", "dge_last_error", "dge_add_batch", "dge_add_batch_device",
-    "dge_set_initialized", "dge_merge_and_filter", "dge_set_stream", "dge_get_summary", "dge_get_timings", "dge_get_cells",
+    "dge_set_initialized", "dge_merge_and_filter", "dge_reset", "dge_set_stream", "dge_get_summary", "dge_get_timings", "dge_get_cells",
     "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
     "dge_route_by_barcode_device",
@@ -114,6 +114,7 @@ def load_library():
     lib.dge_add_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.dge_set_initialized.argtypes = [C.c_void_p]
     lib.dge_merge_and_filter.argtypes = [C.c_void_p]
+    lib.dge_reset.argtypes = [C.c_void_p]
     lib.dge_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.dge_get_summary.argtypes = [C.c_void_p, C.POINTER(_Summary)]
     lib.dge_get_timings.argtypes = [C.c_void_p, C.POINTER(_Timings)]
@@ -254,6 +255,10 @@ class Container:
 
     def set_initialized(self):
         self._check(self._lib.dge_set_initialized(self._h))
+        self._keepalive.clear()
+
+    def reset(self):
+        self._check(self._lib.dge_reset(self._h))
         self._keepalive.clear()
 
     def merge_and_filter(self):

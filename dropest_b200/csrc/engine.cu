@@ -16,6 +16,7 @@
 #include "whitelist.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <map>
@@ -72,7 +73,7 @@ struct dge_handle
 
     // fill-stage device state
     DevBuf tab, gene_first, ctr, staging[2], ctr_counts;
-    std::vector<std::unique_ptr<KeyChunk>> chunks;
+    std::vector<std::unique_ptr<KeyChunk>> chunks, chunk_pool;
     std::vector<DevBuf *> chunk_counts;
     DevBuf chunk_count_pool;
     size_t n_chunk_counters = 0;
@@ -90,8 +91,17 @@ struct dge_handle
     FillCounters counters{};
     uint64_t total_cells = 0;
 
-    SortCombine sc;
+    SortCombine sc, sc2; // sc2: the (much smaller) cell-merge pass, so neither resizes the other's workspaces
     SortCombineStats sc_stats;
+    // merge-stage workspaces (grow only, reused across runs)
+    DevBuf d_jobs, d_isect, d_cb, d_umis, d_count, d_nb, d_moves, mkeys, mvals, ekey, eval, keep, keep_off, xkey, xval, mat_nnz;
+    std::vector<uint32_t> h_isect, h_pc_to_real, h_nb_pc, h_umis, h_nb_off, h_nbs;
+    std::vector<int> h_nb_count;
+    std::vector<uint64_t> h_cbs;
+    std::vector<PairJob> h_jobs;
+    std::vector<MoveJob> h_moves;
+    std::vector<long> h_target;
+    bool wl_uploaded = false;
 
     // host state
     std::vector<HostCell> real;            // cell-id (first-seen) order
@@ -119,6 +129,21 @@ struct dge_handle
 
 namespace
 {
+
+// DGE_TRACE=1 prints host-side wall-clock stage marks to stderr (replaces the reference's Tools::trace_time, Logs.cpp:63-71)
+struct Tracer
+{
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Tracer() : on(std::getenv("DGE_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what)
+    {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[dge] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 int fail(dge_handle *h, int code, const std::string &msg)
 {
@@ -156,6 +181,8 @@ template <class T> T d2h_scalar(const void *src, cudaStream_t st)
     return v;
 }
 
+void reset_fill_state(dge_handle *h);
+
 void ensure_device(dge_handle *h)
 {
     DGE_CUDA(cudaSetDevice(h->cfg.device));
@@ -180,6 +207,12 @@ void ensure_device(dge_handle *h)
     h->table_cap = size_t(1) << kl.tb;
 
     h->tab.reserve(h->table_cap * sizeof(CellSlot));
+    h->device_ready = true;
+    reset_fill_state(h);
+}
+
+void reset_fill_state(dge_handle *h)
+{
     k_table_init<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->tab.as<CellSlot>(), h->table_cap);
     h->gene_first.reserve(size_t(h->cfg.n_genes) * 4);
     k_fill_u32<<<grid_for(h->cfg.n_genes, 256), 256, 0, h->stream>>>(h->gene_first.as<uint32_t>(), h->cfg.n_genes, NONE32);
@@ -192,7 +225,6 @@ void ensure_device(dge_handle *h)
     DGE_CUDA(cudaMemsetAsync(h->chunk_count_pool.p, 0, 4096 * sizeof(unsigned long long), h->stream));
     DGE_LAUNCH_CHECK();
     h->launches += 2;
-    h->device_ready = true;
 }
 
 // One batch already resident on the device: barcode-table insert + key packing into a fresh chunk.
@@ -200,7 +232,9 @@ void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n)
 {
     if (n == 0) return;
     if (h->n_chunk_counters >= 4096) throw std::runtime_error("too many batches (max 4096); use larger batches");
-    auto chunk = std::unique_ptr<KeyChunk>(new KeyChunk());
+    std::unique_ptr<KeyChunk> chunk;
+    if (!h->chunk_pool.empty()) { chunk = std::move(h->chunk_pool.back()); h->chunk_pool.pop_back(); }
+    else chunk.reset(new KeyChunk());
     chunk->capacity = n;
     chunk->keys.reserve(n * 8);
     chunk->d_count = h->chunk_count_pool.as<unsigned long long>() + h->n_chunk_counters++;
@@ -228,19 +262,38 @@ bool compare_cells(const HostCell &a, const HostCell &b)
     return a.cb < b.cb;
 }
 
-// update_filtered_gene_counts (CellsDataContainer.cpp:250-276)
+// Stable LSD radix sort of `idx` by 16-bit digits of key(idx) (host; n ~ 1e5, replaces std::sort with a comparator).
+template <class KeyFn> void radix_pass16(std::vector<uint32_t> &idx, std::vector<uint32_t> &tmp, KeyFn key)
+{
+    std::vector<uint32_t> cnt(65537, 0);
+    for (uint32_t i : idx) ++cnt[size_t(key(i)) + 1];
+    bool single = false;
+    for (size_t d = 0; d < 65536; ++d) if (cnt[d + 1] == idx.size()) single = true;
+    if (single) return; // all keys share this digit
+    for (size_t d = 0; d < 65536; ++d) cnt[d + 1] += cnt[d];
+    tmp.resize(idx.size());
+    for (uint32_t i : idx) tmp[cnt[key(i)]++] = i;
+    idx.swap(tmp);
+}
+
+// update_filtered_gene_counts (CellsDataContainer.cpp:250-276): real cells with enough requested genes, ascending by
+// compare_cells = (requested genes, requested umis, TOTAL_UMIS stat, barcode) -- a total order, so any sort gives the same list.
 void update_filtered(dge_handle *h, uint32_t threshold, int cell_threshold)
 {
-    h->filtered.clear();
+    std::vector<uint32_t> &f = h->filtered;
+    f.clear();
     for (uint32_t i = 0; i < h->real.size(); ++i)
     {
         const HostCell &c = h->real[i];
-        if (!c.real) continue;
-        if (uint32_t(c.req_genes) >= threshold) h->filtered.push_back(i);
+        if (c.real && uint32_t(c.req_genes) >= threshold) f.push_back(i);
     }
-    std::sort(h->filtered.begin(), h->filtered.end(), [&](uint32_t x, uint32_t y) { return compare_cells(h->real[x], h->real[y]); });
-    if (cell_threshold > 0 && size_t(cell_threshold) < h->filtered.size())
-        h->filtered.erase(h->filtered.begin(), h->filtered.end() - cell_threshold);
+    std::vector<uint32_t> tmp;
+    const std::vector<HostCell> &R = h->real;
+    for (int sh = 0; sh < 48; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return uint32_t(R[i].cb >> sh) & 0xFFFFu; });
+    for (int sh = 0; sh < 32; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return (uint32_t(R[i].umis_stat) >> sh) & 0xFFFFu; });
+    for (int sh = 0; sh < 32; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return (uint32_t(R[i].req_umis) >> sh) & 0xFFFFu; });
+    for (int sh = 0; sh < 32; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return (uint32_t(R[i].req_genes) >> sh) & 0xFFFFu; });
+    if (cell_threshold > 0 && size_t(cell_threshold) < f.size()) f.erase(f.begin(), f.end() - cell_threshold);
 }
 
 // (Re)build CG / PC tables from the current sorted U list.
@@ -320,6 +373,7 @@ void do_set_initialized(dge_handle *h)
 {
     ensure_device(h);
     cudaStream_t st = h->stream;
+    Tracer tr;
     DGE_CUDA(cudaEventRecord(h->ev[0], st));
 
     // ---- collect compact keys of all batches into one array (chunks were produced at add time)
@@ -366,11 +420,10 @@ void do_set_initialized(dge_handle *h)
         int ovf = d2h_scalar<int>(h->overflow_flag.p, st);
         if (ovf) throw std::runtime_error("sub-bucket hash table overflow in umig_dedup_sort");
     }
-    for (auto &c : h->chunks) if (h->chunks.size() > 1) c->keys.release();
 
+    tr.mark("init: group (sortcombine)");
     build_segments(h);
-    unsigned long long *d_total = reinterpret_cast<unsigned long long *>(h->ctr.as<FillCounters>());
-    (void)d_total;
+    tr.mark("init: segments");
     h->misc.reserve(64);
     DGE_CUDA(cudaMemsetAsync(h->misc.p, 0, 8, st));
     k_count_occupied<<<grid_for(h->table_cap, 256), 256, 0, st>>>(h->tab.as<CellSlot>(), h->table_cap, h->misc.as<unsigned long long>());
@@ -420,11 +473,14 @@ void do_set_initialized(dge_handle *h)
                 rows.push_back(r);
             }
     }
-    std::sort(rows.begin(), rows.end(), [](const CellRow &a, const CellRow &b) { return a.first_idx < b.first_idx; });
+    std::vector<uint32_t> order(rows.size()), order_tmp;
+    std::iota(order.begin(), order.end(), 0u);
+    for (int sh = 0; sh < 32; sh += 16) radix_pass16(order, order_tmp, [&](uint32_t i) { return (rows[i].first_idx >> sh) & 0xFFFFu; });
     h->real.clear();
     h->real.reserve(rows.size());
-    for (auto const &r : rows)
+    for (uint32_t ri : order)
     {
+        const CellRow &r = rows[ri];
         HostCell c;
         c.cb = r.cb; c.slot = r.slot; c.pc = r.pc; c.first_idx = r.first_idx; c.n_intergenic = r.n_intergenic;
         c.n_genes = int32_t(r.n_genes); c.umis_stat = int32_t(r.n_umis); c.n_umis_distinct = int32_t(r.n_umis);
@@ -432,6 +488,7 @@ void do_set_initialized(dge_handle *h)
         c.target = int32_t(h->real.size());
         h->real.push_back(c);
     }
+    tr.mark("init: real cells -> host");
     // gene first-seen order (StringIndexer::add, StringIndexer.cpp:10-18)
     {
         std::vector<uint32_t> gf;
@@ -445,6 +502,7 @@ void do_set_initialized(dge_handle *h)
         for (auto const &p : seen) h->gene_order.push_back(p.second);
     }
     update_filtered(h, 0, -1); // set_initialized: update_cell_sizes(query, 0, -1)  (CellsDataContainer.cpp:168)
+    tr.mark("init: gene order + filtered");
     DGE_CUDA(cudaEventRecord(h->ev[2], st));
     DGE_CUDA(cudaStreamSynchronize(st));
     h->state = 1;
@@ -478,30 +536,29 @@ void upload_whitelist(dge_handle *h)
     }
 }
 
-std::vector<uint32_t> run_intersections(dge_handle *h, const std::vector<PairJob> &jobs)
+// Device intersections for a flat job list; results land in h->h_isect (same order).
+void run_intersections(dge_handle *h, const std::vector<PairJob> &jobs)
 {
-    std::vector<uint32_t> out;
-    if (jobs.empty()) return out;
-    DevBuf djobs, dout;
-    djobs.reserve(jobs.size() * sizeof(PairJob)); dout.reserve(jobs.size() * 4);
-    DGE_CUDA(cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(PairJob), cudaMemcpyHostToDevice, h->stream));
-    k_intersect<<<unsigned(jobs.size()), 128, 0, h->stream>>>(djobs.as<PairJob>(), uint32_t(jobs.size()), h->ukey.as<uint64_t>(),
+    h->h_isect.assign(jobs.size(), 0);
+    if (jobs.empty()) return;
+    h->d_jobs.reserve(jobs.size() * sizeof(PairJob)); h->d_isect.reserve(jobs.size() * 4);
+    DGE_CUDA(cudaMemcpyAsync(h->d_jobs.p, jobs.data(), jobs.size() * sizeof(PairJob), cudaMemcpyHostToDevice, h->stream));
+    k_intersect<<<unsigned(jobs.size()), 128, 0, h->stream>>>(h->d_jobs.as<PairJob>(), uint32_t(jobs.size()), h->ukey.as<uint64_t>(),
                                                               h->pc_u_start.as<uint32_t>(), h->pc_slot.as<uint32_t>(), h->kl.gb + h->kl.ub,
-                                                              dout.as<uint32_t>());
+                                                              h->d_isect.as<uint32_t>());
     DGE_LAUNCH_CHECK();
     ++h->launches;
-    d2h(out, dout.p, jobs.size(), h->stream);
+    DGE_CUDA(cudaMemcpyAsync(h->h_isect.data(), h->d_isect.p, jobs.size() * 4, cudaMemcpyDeviceToHost, h->stream));
     DGE_CUDA(cudaStreamSynchronize(h->stream));
-    return out;
 }
 
 // RealBarcodesMergeStrategy::get_best_merge_target (RealBarcodesMergeStrategy.cpp:31-61) over an ORDERED neighbour list.
-long best_target_real(const dge_handle *h, uint32_t base, const std::vector<uint32_t> &nbs, const std::vector<uint32_t> &isect)
+long best_target_real(const dge_handle *h, uint32_t base, const uint32_t *nbs, const uint32_t *isect, size_t n_nb)
 {
     if (nbs[0] == base) return long(base);
     double max_frac = 0;
     uint32_t best = nbs[0];
-    for (size_t k = 0; k < nbs.size(); ++k)
+    for (size_t k = 0; k < n_nb; ++k)
     {
         double frac = 0.5 * isect[k] * (1. / h->real[base].umis_stat + 1. / h->real[nbs[k]].umis_stat);
         if (max_frac < frac) { max_frac = frac; best = nbs[k]; }
@@ -510,46 +567,48 @@ long best_target_real(const dge_handle *h, uint32_t base, const std::vector<uint
     return long(best);
 }
 
-// Phase 1 for RealBarcodesMergeStrategy: target (index into real, or -1) for every filtered cell.
-std::vector<long> phase1_real(dge_handle *h)
+// Phase 1 for RealBarcodesMergeStrategy: target (index into real, or -1) for every real cell.
+void phase1_real(dge_handle *h, std::vector<long> &target)
 {
     cudaStream_t st = h->stream;
     const size_t n = h->real.size();
-    std::vector<long> target(n, -2);
-    if (n == 0) return target;
-    std::unordered_map<uint64_t, uint32_t> by_cb;
-    by_cb.reserve(n * 2);
-    for (uint32_t i = 0; i < n; ++i) by_cb.emplace(h->real[i].cb, i);
-    std::vector<uint32_t> pc_to_real_keys;
-    std::unordered_map<uint32_t, uint32_t> by_pc;
-    by_pc.reserve(n * 2);
-    for (uint32_t i = 0; i < n; ++i) if (h->real[i].pc != NONE32) by_pc.emplace(h->real[i].pc, i);
+    target.assign(n, -2);
+    if (n == 0) return;
+    std::vector<uint32_t> &pc_to_real = h->h_pc_to_real;
+    pc_to_real.assign(size_t(h->n_pc) + 1, NONE32);
+    for (uint32_t i = 0; i < n; ++i) if (h->real[i].pc != NONE32) pc_to_real[h->real[i].pc] = i;
 
-    std::vector<int> nb_count(n, NB_SLOW);
-    std::vector<uint32_t> nb_pc(n * WL_K, NONE32);
+    std::vector<int> &nb_count = h->h_nb_count;
+    std::vector<uint32_t> &nb_pc = h->h_nb_pc;
+    nb_count.assign(n, NB_SLOW);
+    nb_pc.resize(n * WL_K);
     if (h->wl_fast)
     {
-        upload_whitelist(h);
-        std::vector<uint64_t> cbs(n);
-        std::vector<uint32_t> umis(n);
-        for (size_t i = 0; i < n; ++i) { cbs[i] = h->real[i].cb; umis[i] = uint32_t(h->real[i].umis_stat); }
-        DevBuf dcb, dumis, dcount, dnb;
-        dcb.reserve(n * 8); dumis.reserve(n * 4); dcount.reserve(n * 4); dnb.reserve(n * WL_K * 4);
-        DGE_CUDA(cudaMemcpyAsync(dcb.p, cbs.data(), n * 8, cudaMemcpyHostToDevice, st));
-        DGE_CUDA(cudaMemcpyAsync(dumis.p, umis.data(), n * 4, cudaMemcpyHostToDevice, st));
-        k_wl_class01<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(dcb.as<uint64_t>(), dumis.as<uint32_t>(), uint32_t(n), h->wl_dev, h->tab.as<CellSlot>(),
-                                                                            h->kl.tb, h->slot_pc.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(),
-                                                                            h->pc_u_start.as<uint32_t>(), h->cfg.min_genes_before_merge,
-                                                                            dcount.as<int>(), dnb.as<uint32_t>());
+        if (!h->wl_uploaded) { upload_whitelist(h); h->wl_uploaded = true; }
+        h->h_cbs.resize(n); h->h_umis.resize(n);
+        for (size_t i = 0; i < n; ++i) { h->h_cbs[i] = h->real[i].cb; h->h_umis[i] = uint32_t(h->real[i].umis_stat); }
+        h->d_cb.reserve(n * 8); h->d_umis.reserve(n * 4); h->d_count.reserve(n * 4); h->d_nb.reserve(n * WL_K * 4);
+        DGE_CUDA(cudaMemcpyAsync(h->d_cb.p, h->h_cbs.data(), n * 8, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(cudaMemcpyAsync(h->d_umis.p, h->h_umis.data(), n * 4, cudaMemcpyHostToDevice, st));
+        k_wl_class01<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>(), uint32_t(n), h->wl_dev,
+                                                                            h->tab.as<CellSlot>(), h->kl.tb, h->slot_pc.as<uint32_t>(),
+                                                                            h->pc_cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(),
+                                                                            h->cfg.min_genes_before_merge, h->d_count.as<int>(), h->d_nb.as<uint32_t>());
         DGE_LAUNCH_CHECK();
         ++h->launches;
-        d2h(nb_count, dcount.p, n, st);
-        d2h(nb_pc, dnb.p, n * WL_K, st);
+        DGE_CUDA(cudaMemcpyAsync(nb_count.data(), h->d_count.p, n * 4, cudaMemcpyDeviceToHost, st));
+        DGE_CUDA(cudaMemcpyAsync(nb_pc.data(), h->d_nb.p, n * WL_K * 4, cudaMemcpyDeviceToHost, st));
         DGE_CUDA(cudaStreamSynchronize(st));
     }
 
-    // exact host path for the cells the fast path could not settle
+    // exact host path (built lazily: most runs never need it)
+    std::unordered_map<uint64_t, uint32_t> by_cb;
     auto exact_neighbours = [&](uint32_t i) {
+        if (by_cb.empty())
+        {
+            by_cb.reserve(n * 2);
+            for (uint32_t r = 0; r < n; ++r) by_cb.emplace(h->real[r].cb, r);
+        }
         const std::string cb = unpack_seq(h->real[i].cb, h->cfg.cb_len);
         auto lookup = [&](const std::string &s) -> long {
             uint64_t v;
@@ -557,7 +616,7 @@ std::vector<long> phase1_real(dge_handle *h)
             auto it = by_cb.find(v);
             return it == by_cb.end() ? -1 : long(it->second);
         };
-        // Any barcode known to the container but not real fails the size test below exactly like in the reference.
+        // a barcode known to the container but not real fails the size test exactly like in the reference
         auto eligible = [&](long id) {
             return uint32_t(h->real[size_t(id)].n_genes) >= h->cfg.min_genes_before_merge &&
                    h->real[size_t(id)].umis_stat >= h->real[i].umis_stat;
@@ -566,41 +625,58 @@ std::vector<long> phase1_real(dge_handle *h)
         return std::vector<uint32_t>(ids.begin(), ids.end());
     };
 
-    std::vector<std::vector<uint32_t>> nbs(n);
-    std::vector<PairJob> jobs;
-    std::vector<std::pair<uint32_t, uint32_t>> job_owner; // (cell, k)
+    // neighbour lists in CSR form
+    std::vector<uint32_t> &off = h->h_nb_off, &nbs = h->h_nbs;
+    off.assign(n + 1, 0);
+    std::unordered_map<uint32_t, std::vector<uint32_t>> slow_lists;
     for (uint32_t i = 0; i < n; ++i)
     {
-        if (nb_count[i] == NB_SELF) { target[i] = long(i); continue; }
-        if (nb_count[i] == NB_SLOW) nbs[i] = exact_neighbours(i);
-        else
-            for (int k = 0; k < nb_count[i]; ++k) nbs[i].push_back(by_pc.at(nb_pc[size_t(i) * WL_K + size_t(k)]));
-        if (nbs[i].empty()) { target[i] = -1; continue; }
-        if (nbs[i][0] == i) { target[i] = long(i); continue; }
-        for (uint32_t k = 0; k < nbs[i].size(); ++k)
+        uint32_t c = 0;
+        if (nb_count[i] == NB_SELF) target[i] = long(i);
+        else if (nb_count[i] == NB_SLOW)
         {
-            // a cell without UMIs (pc == NONE32) intersects nothing
-            if (h->real[i].pc == NONE32 || h->real[nbs[i][k]].pc == NONE32) continue;
-            jobs.push_back(PairJob{h->real[i].pc, h->real[nbs[i][k]].pc});
-            job_owner.emplace_back(i, k);
+            auto &lst = slow_lists[i];
+            lst = exact_neighbours(i);
+            c = uint32_t(lst.size());
+            if (lst.empty()) target[i] = -1;
+            else if (lst[0] == i) { target[i] = long(i); c = 0; }
+        }
+        else c = uint32_t(nb_count[i]);
+        off[i + 1] = off[i] + c;
+    }
+    nbs.resize(off[n]);
+    std::vector<PairJob> &jobs = h->h_jobs;
+    jobs.resize(off[n]);
+    const uint32_t empty_pc = h->n_pc; // the empty sentinel cell: intersects nothing
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const uint32_t c = off[i + 1] - off[i];
+        if (!c) continue;
+        if (nb_count[i] == NB_SLOW) { auto const &lst = slow_lists[i]; std::copy(lst.begin(), lst.end(), nbs.begin() + off[i]); }
+        else for (uint32_t k = 0; k < c; ++k) nbs[off[i] + k] = pc_to_real[nb_pc[size_t(i) * WL_K + k]];
+        for (uint32_t k = 0; k < c; ++k)
+        {
+            const uint32_t a = h->real[i].pc, b = h->real[nbs[off[i] + k]].pc;
+            jobs[off[i] + k] = PairJob{a == NONE32 ? empty_pc : a, b == NONE32 ? empty_pc : b};
         }
     }
-    std::vector<uint32_t> isect_flat = run_intersections(h, jobs);
-    std::vector<std::vector<uint32_t>> isect(n);
-    for (uint32_t i = 0; i < n; ++i) isect[i].assign(nbs[i].size(), 0);
-    for (size_t j = 0; j < jobs.size(); ++j) isect[job_owner[j].first][job_owner[j].second] = isect_flat[j];
+    run_intersections(h, jobs);
+    const std::vector<uint32_t> &isect = h->h_isect;
 
     for (uint32_t i = 0; i < n; ++i)
     {
         if (target[i] != -2) continue;
-        // The fast path reports the neighbour SET of the nearest class; the reference walks them in the order left by
-        // two unstable sorts.  That order only matters on exact ties of the best fraction: replay it then.
+        const uint32_t c = off[i + 1] - off[i];
+        const uint32_t *my_nbs = nbs.data() + off[i];
+        const uint32_t *my_is = isect.data() + off[i];
+        // The fast path reports the neighbour SET of the nearest class; the reference walks them in the order left by two
+        // unstable sorts.  That order only matters on exact ties of the best fraction: replay it then.
         if (nb_count[i] > 1)
         {
             double best = -1; int n_best = 0;
-            for (size_t k = 0; k < nbs[i].size(); ++k)
+            for (uint32_t k = 0; k < c; ++k)
             {
-                double frac = 0.5 * isect[i][k] * (1. / h->real[i].umis_stat + 1. / h->real[nbs[i][k]].umis_stat);
+                double frac = 0.5 * my_is[k] * (1. / h->real[i].umis_stat + 1. / h->real[my_nbs[k]].umis_stat);
                 if (frac > best) { best = frac; n_best = 1; } else if (frac == best) ++n_best;
             }
             if (n_best > 1 && !(best < h->cfg.min_merge_fraction))
@@ -608,25 +684,30 @@ std::vector<long> phase1_real(dge_handle *h)
                 std::vector<uint32_t> ordered = exact_neighbours(i);
                 std::vector<uint32_t> isect_ord(ordered.size(), 0);
                 for (size_t a = 0; a < ordered.size(); ++a)
-                    for (size_t b = 0; b < nbs[i].size(); ++b)
-                        if (nbs[i][b] == ordered[a]) isect_ord[a] = isect[i][b];
-                nbs[i] = ordered; isect[i] = isect_ord;
+                    for (uint32_t b = 0; b < c; ++b)
+                        if (my_nbs[b] == ordered[a]) isect_ord[a] = my_is[b];
+                target[i] = best_target_real(h, i, ordered.data(), isect_ord.data(), ordered.size());
+                continue;
             }
         }
-        target[i] = best_target_real(h, i, nbs[i], isect[i]);
+        target[i] = best_target_real(h, i, my_nbs, my_is, c);
     }
-    return target;
 }
 
 // Phase 2: MergeStrategyBase::merge_inited second loop + reassign (MergeStrategyBase.cpp:29-82), on real-cell indices.
+// `reassigned_to` sets are intrusive singly linked lists (child_head/child_next): a cell sits in at most one list.
 void phase2(dge_handle *h, const std::vector<long> &target)
 {
     const size_t n = h->real.size();
-    std::vector<uint32_t> reassign(n);
+    std::vector<uint32_t> reassign(n), child_head(n, NONE32), child_tail(n, NONE32), child_next(n, NONE32);
     std::iota(reassign.begin(), reassign.end(), 0u);
-    std::unordered_map<uint32_t, std::vector<uint32_t>> reassigned_to;
     h->merge_events.clear();
     h->n_merged = h->n_excluded = 0;
+    auto append = [&](uint32_t t, uint32_t c) {
+        child_next[c] = NONE32;
+        if (child_head[t] == NONE32) child_head[t] = c; else child_next[child_tail[t]] = c;
+        child_tail[t] = c;
+    };
     for (uint32_t base : h->filtered)
     {
         long t = target[base];
@@ -640,16 +721,17 @@ void phase2(dge_handle *h, const std::vector<long> &target)
         src.merged = true;
         h->merge_events.emplace_back(base, uint32_t(t));
         ++h->n_merged;
-        // reassign
+        // reassign: base and everything previously re-pointed at base now point at t
         reassign[base] = uint32_t(t);
-        auto &to_t = reassigned_to[uint32_t(t)];
-        to_t.push_back(base);
-        auto it = reassigned_to.find(base);
-        if (it != reassigned_to.end())
+        uint32_t c = child_head[base];
+        child_head[base] = child_tail[base] = NONE32;
+        append(uint32_t(t), base);
+        while (c != NONE32)
         {
-            std::vector<uint32_t> moved = it->second;
-            for (uint32_t r : moved) { reassign[r] = uint32_t(t); reassigned_to[uint32_t(t)].push_back(r); }
-            reassigned_to[base].clear();
+            uint32_t nx = child_next[c];
+            reassign[c] = uint32_t(t);
+            append(uint32_t(t), c);
+            c = nx;
         }
     }
     for (uint32_t i = 0; i < n; ++i) h->real[i].target = int32_t(reassign[i]);
@@ -660,68 +742,70 @@ void apply_merges(dge_handle *h)
 {
     if (h->merge_events.empty()) return;
     cudaStream_t st = h->stream;
-    // absorbed sets: content of X after all events = own ∪ originals absorbed (sequential semantics of merge_cells)
-    std::unordered_map<uint32_t, std::vector<uint32_t>> absorbed;
+    // merge_cells copies the source's CURRENT content, i.e. the source's own UMIs plus everything merged into it earlier
+    // (sequential semantics): keep, per cell, the list of originals absorbed so far (spliced on merge).
+    const size_t n = h->real.size();
+    std::vector<uint32_t> head(n, NONE32), tail(n, NONE32), next(n, NONE32);
+    std::vector<MoveJob> &jobs = h->h_moves;
+    jobs.clear();
+    uint64_t total = 0;
+    auto emit = [&](uint32_t o, uint32_t dst) {
+        const HostCell &src = h->real[o];
+        if (src.pc == NONE32 || src.n_umis_distinct == 0) return;
+        jobs.push_back(MoveJob{src.pc, h->real[dst].slot, uint32_t(total)});
+        total += uint64_t(src.n_umis_distinct);
+    };
     for (auto const &e : h->merge_events)
     {
-        std::vector<uint32_t> add{e.first};
-        auto it = absorbed.find(e.first);
-        if (it != absorbed.end()) add.insert(add.end(), it->second.begin(), it->second.end());
-        auto &dst = absorbed[e.second];
-        dst.insert(dst.end(), add.begin(), add.end());
+        const uint32_t src = e.first, dst = e.second;
+        emit(src, dst);
+        for (uint32_t o = head[src]; o != NONE32; o = next[o]) emit(o, dst);
+        // absorbed(dst) += [src] + absorbed(src)   (src is frozen from now on: splice its list)
+        next[src] = head[src];
+        const uint32_t last = tail[src] == NONE32 ? src : tail[src];
+        if (head[dst] == NONE32) head[dst] = src; else next[tail[dst]] = src;
+        tail[dst] = last;
+        head[src] = tail[src] = NONE32;
+        if (total >= 0xFFFFFFF0ull) throw std::runtime_error("merge volume exceeds 2^32 entries");
     }
-    std::vector<MoveJob> jobs;
-    uint64_t total = 0;
-    for (auto const &kv : absorbed)
-        for (uint32_t o : kv.second)
-        {
-            const HostCell &src = h->real[o];
-            if (src.pc == NONE32 || src.n_umis_distinct == 0) continue;
-            if (total + uint64_t(src.n_umis_distinct) >= 0xFFFFFFF0ull) throw std::runtime_error("merge volume exceeds 2^32 entries");
-            jobs.push_back(MoveJob{src.pc, h->real[kv.first].slot, uint32_t(total)});
-            total += uint64_t(src.n_umis_distinct);
-        }
     if (jobs.empty()) return;
-    DevBuf djobs, mkeys, mvals, ekey, eval, keep, keep_off, xkey, xval;
-    djobs.reserve(jobs.size() * sizeof(MoveJob));
-    mkeys.reserve(total * 8); mvals.reserve(total * 4); ekey.reserve(total * 8); eval.reserve(total * 4);
-    DGE_CUDA(cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(MoveJob), cudaMemcpyHostToDevice, st));
+    h->d_moves.reserve(jobs.size() * sizeof(MoveJob));
+    h->mkeys.reserve(total * 8); h->mvals.reserve(total * 4); h->ekey.reserve(total * 8); h->eval.reserve(total * 4);
+    DGE_CUDA(cudaMemcpyAsync(h->d_moves.p, jobs.data(), jobs.size() * sizeof(MoveJob), cudaMemcpyHostToDevice, st));
     const int gub = h->kl.gb + h->kl.ub;
-    k_gather_relabel<<<grid_for(jobs.size(), 1, 148 * 16), 256, 0, st>>>(djobs.as<MoveJob>(), uint32_t(jobs.size()), h->ukey.as<uint64_t>(),
+    k_gather_relabel<<<grid_for(jobs.size(), 1, 148 * 16), 256, 0, st>>>(h->d_moves.as<MoveJob>(), uint32_t(jobs.size()), h->ukey.as<uint64_t>(),
                                                                         h->uval.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), gub,
-                                                                        mkeys.as<uint64_t>(), mvals.as<uint32_t>());
+                                                                        h->mkeys.as<uint64_t>(), h->mvals.as<uint32_t>());
     DGE_LAUNCH_CHECK();
     ++h->launches;
     const int l1_bits = std::min(choose_l1_bits(total), h->kl.kb - 3);
-    const uint32_t *n_e_ptr = h->sc.run(mkeys.as<uint64_t>(), mvals.as<uint32_t>(), total, h->kl.kb, l1_bits, nullptr, mkeys.as<uint64_t>(),
-                                        ekey.as<uint64_t>(), eval.as<uint32_t>(), h->overflow_flag.as<int>(), st, &h->sc_stats);
+    const uint32_t *n_e_ptr = h->sc2.run(h->mkeys.as<uint64_t>(), h->mvals.as<uint32_t>(), total, h->kl.kb, l1_bits, nullptr, h->mkeys.as<uint64_t>(),
+                                         h->ekey.as<uint64_t>(), h->eval.as<uint32_t>(), h->overflow_flag.as<int>(), st, &h->sc_stats);
     const uint32_t n_e = d2h_scalar<uint32_t>(n_e_ptr, st);
-    h->sc.collect_timing();
+    h->sc2.collect_timing();
     if (d2h_scalar<int>(h->overflow_flag.p, st)) throw std::runtime_error("sub-bucket hash table overflow while merging cells");
-    keep.reserve(size_t(n_e + 1) * 4); keep_off.reserve(size_t(n_e + 1) * 4);
-    k_probe_merge<<<grid_for(n_e, 256), 256, 0, st>>>(ekey.as<uint64_t>(), eval.as<uint32_t>(), n_e, h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(),
-                                                       h->slot_pc.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), gub, keep.as<uint32_t>());
+    h->keep.reserve(size_t(n_e + 1) * 4); h->keep_off.reserve(size_t(n_e + 1) * 4);
+    k_probe_merge<<<grid_for(n_e, 256), 256, 0, st>>>(h->ekey.as<uint64_t>(), h->eval.as<uint32_t>(), n_e, h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(),
+                                                       h->slot_pc.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), gub, h->keep.as<uint32_t>());
     ++h->launches;
-    const uint32_t *n_x_ptr = device_exclusive_scan(keep.as<uint32_t>(), keep_off.as<uint32_t>(), n_e, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+    const uint32_t *n_x_ptr = device_exclusive_scan(h->keep.as<uint32_t>(), h->keep_off.as<uint32_t>(), n_e, h->scan_scratch.as<uint32_t>(), st, &h->launches);
     const uint32_t n_x = d2h_scalar<uint32_t>(n_x_ptr, st);
     if (n_x)
     {
         if (uint64_t(h->n_u) + n_x >= 0xFFFFFFF0ull) throw std::runtime_error("too many distinct UMIs after merging");
-        xkey.reserve(size_t(n_x) * 8); xval.reserve(size_t(n_x) * 4);
-        k_compact_keep<<<grid_for(n_e, 256), 256, 0, st>>>(ekey.as<uint64_t>(), eval.as<uint32_t>(), n_e, keep.as<uint32_t>(), keep_off.as<uint32_t>(),
-                                                            xkey.as<uint64_t>(), xval.as<uint32_t>());
+        h->xkey.reserve(size_t(n_x) * 8); h->xval.reserve(size_t(n_x) * 4);
+        k_compact_keep<<<grid_for(n_e, 256), 256, 0, st>>>(h->ekey.as<uint64_t>(), h->eval.as<uint32_t>(), n_e, h->keep.as<uint32_t>(), h->keep_off.as<uint32_t>(),
+                                                            h->xkey.as<uint64_t>(), h->xval.as<uint32_t>());
         const size_t n_new = size_t(h->n_u) + n_x;
         h->ukey2.reserve(n_new * 8); h->uval2.reserve(n_new * 4);
-        k_merge_rank<<<grid_for(n_new, 256), 256, 0, st>>>(h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), h->n_u, xkey.as<uint64_t>(), xval.as<uint32_t>(), n_x,
+        k_merge_rank<<<grid_for(n_new, 256), 256, 0, st>>>(h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), h->n_u, h->xkey.as<uint64_t>(), h->xval.as<uint32_t>(), n_x,
                                                             h->ukey2.as<uint64_t>(), h->uval2.as<uint32_t>());
         DGE_LAUNCH_CHECK();
         h->launches += 2;
-        DGE_CUDA(cudaStreamSynchronize(st));
         std::swap(h->ukey.p, h->ukey2.p); std::swap(h->ukey.bytes, h->ukey2.bytes);
         std::swap(h->uval.p, h->uval2.p); std::swap(h->uval.bytes, h->uval2.bytes);
         h->n_u = uint32_t(n_new);
     }
-    DGE_CUDA(cudaStreamSynchronize(st));
     build_segments(h);
 }
 
@@ -735,13 +819,12 @@ void build_matrix(dge_handle *h, MatrixDev &m, const std::vector<uint32_t> &col_
     if (m.n_cols == 0) { DGE_CUDA(cudaMemsetAsync(m.indptr.p, 0, 8, st)); return; }
     m.cols.reserve(m.n_cols * 4);
     DGE_CUDA(cudaMemcpyAsync(m.cols.p, col_pcs.data(), m.n_cols * 4, cudaMemcpyHostToDevice, st));
-    DevBuf nnz;
-    nnz.reserve((m.n_cols + 2) * 4);
+    h->mat_nnz.reserve((m.n_cols + 2) * 4);
     k_matrix_col_nnz<<<grid_for(m.n_cols * 32, 256), 256, 0, st>>>(m.cols.as<uint32_t>(), uint32_t(m.n_cols), h->pc_cg_start.as<uint32_t>(),
-                                                                   h->cg_req.as<uint32_t>(), filtered ? 1 : 0, nnz.as<uint32_t>());
+                                                                   h->cg_req.as<uint32_t>(), filtered ? 1 : 0, h->mat_nnz.as<uint32_t>());
     ++h->launches;
-    DGE_CUDA(cudaMemsetAsync(nnz.as<uint32_t>() + m.n_cols, 0, 4, st));
-    device_exclusive_scan(nnz.as<uint32_t>(), m.indptr.as<uint32_t>(), m.n_cols + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+    DGE_CUDA(cudaMemsetAsync(h->mat_nnz.as<uint32_t>() + m.n_cols, 0, 4, st));
+    device_exclusive_scan(h->mat_nnz.as<uint32_t>(), m.indptr.as<uint32_t>(), m.n_cols + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
     m.nnz = d2h_scalar<uint32_t>(m.indptr.as<uint32_t>() + m.n_cols, st);
     m.gene.reserve(std::max<size_t>(m.nnz, 1) * 4); m.val.reserve(std::max<size_t>(m.nnz, 1) * 4);
     const uint32_t *values;
@@ -749,26 +832,32 @@ void build_matrix(dge_handle *h, MatrixDev &m, const std::vector<uint32_t> &col_
     if (filtered) { values = h->cfg.reads_output ? h->cg_req_reads.as<uint32_t>() : h->cg_req.as<uint32_t>(); mode = 0; }
     else if (h->cfg.reads_output) { values = h->cg_reads.as<uint32_t>(); mode = 2; }
     else { values = nullptr; mode = 1; }
-    k_matrix_fill<<<grid_for(m.n_cols * 32, 256), 256, 0, st>>>(m.cols.as<uint32_t>(), uint32_t(m.n_cols), m.indptr.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(),
-                                                                h->cg_key.as<uint64_t>(), values, h->cg_start.as<uint32_t>(), mode,
-                                                                (1u << h->kl.gb) - 1, m.gene.as<int32_t>(), m.val.as<int32_t>());
+    k_matrix_fill<<<unsigned(m.n_cols), 256, 0, st>>>(m.cols.as<uint32_t>(), uint32_t(m.n_cols), m.indptr.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(),
+                                                      h->cg_key.as<uint64_t>(), values, h->cg_start.as<uint32_t>(), mode,
+                                                      (1u << h->kl.gb) - 1, m.gene.as<int32_t>(), m.val.as<int32_t>());
     DGE_LAUNCH_CHECK();
     ++h->launches;
 }
+
 
 void do_merge_and_filter(dge_handle *h)
 {
     DGE_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t st = h->stream;
+    Tracer tr;
     DGE_CUDA(cudaEventRecord(h->ev[3], st));
     build_slot_pc(h);
 
     // ---- CB merge (MergeStrategyAbstract::merge, MergeStrategyAbstract.cpp:13-23)
     if (h->cfg.merge_type == DGE_MERGE_REAL)
     {
-        std::vector<long> target = phase1_real(h);
-        phase2(h, target);
+        phase1_real(h, h->h_target);
+        tr.mark("merge: phase 1");
+        phase2(h, h->h_target);
+        tr.mark("merge: phase 2");
         apply_merges(h);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        tr.mark("merge: apply");
     }
     else if (h->cfg.merge_type != DGE_MERGE_NONE)
         throw std::runtime_error("merge_type not implemented on the device path yet");
@@ -795,6 +884,7 @@ void do_merge_and_filter(dge_handle *h)
     }
     for (auto &c : h->real) c.real = !c.merged && !c.excluded && uint32_t(c.n_genes) >= h->cfg.min_genes_before_merge;
     update_filtered(h, h->min_after_eff, h->cfg.max_cells);
+    tr.mark("finish: sizes + filter");
 
     // ---- matrices
     std::vector<uint32_t> cols;
@@ -808,6 +898,7 @@ void do_merge_and_filter(dge_handle *h)
     build_matrix(h, h->cm_raw, raw_cols, false);
     DGE_CUDA(cudaEventRecord(h->ev[5], st));
     DGE_CUDA(cudaStreamSynchronize(st));
+    tr.mark("finish: matrices");
     h->state = 2;
 
     auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]); return ms; };
@@ -1000,6 +1091,25 @@ int dge_add_batch(dge_handle *h, const dge_record16 *recs, size_t n)
             fill_from_device(h, stg.as<dge_record16>(), m);
             DGE_CUDA(cudaEventRecord(evt, h->stream));
         }
+        return int(DGE_OK);
+    });
+}
+
+int dge_reset(dge_handle *h)
+{
+    if (!h) return DGE_ERR_INVALID;
+    return guarded(h, [&] {
+        DGE_CUDA(cudaSetDevice(h->cfg.device));
+        if (h->stream) DGE_CUDA(cudaStreamSynchronize(h->stream));
+        for (auto &c : h->chunks) h->chunk_pool.push_back(std::move(c));
+        h->chunks.clear();
+        h->n_chunk_counters = 0; h->n_reads = 0; h->n_keys = 0; h->n_u = h->n_cg = h->n_pc = 0;
+        h->real.clear(); h->filtered.clear(); h->gene_order.clear(); h->merge_events.clear();
+        h->n_merged = h->n_excluded = 0; h->total_cells = 0;
+        h->cm.built = h->cm_raw.built = false;
+        h->timings = dge_timings{}; h->sc_stats = SortCombineStats{}; h->launches = 0;
+        h->state = 0;
+        if (h->device_ready) reset_fill_state(h);
         return int(DGE_OK);
     });
 }

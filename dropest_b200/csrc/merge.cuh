@@ -8,6 +8,7 @@
 #pragma once
 #include "common.cuh"
 #include "fill.cuh"
+#include "scan.cuh"
 
 namespace dge
 {
@@ -321,35 +322,33 @@ __global__ void k_matrix_col_nnz(const uint32_t *__restrict__ col_pc, uint32_t n
     }
 }
 
-// fill: one warp per column, ordered compaction by ballot
-__global__ void k_matrix_fill(const uint32_t *__restrict__ col_pc, uint32_t n_cols, const uint32_t *__restrict__ col_off,
-                              const uint32_t *__restrict__ pc_cg_start, const uint64_t *__restrict__ cg_key,
-                              const uint32_t *__restrict__ values, const uint32_t *__restrict__ cg_start, int mode, uint32_t gene_mask,
-                              int32_t *__restrict__ out_gene, int32_t *__restrict__ out_val)
+// fill: one block per column, ordered compaction by block scan (genes stay ascending inside a column)
+__global__ void __launch_bounds__(256) k_matrix_fill(const uint32_t *__restrict__ col_pc, uint32_t n_cols, const uint32_t *__restrict__ col_off,
+                                                     const uint32_t *__restrict__ pc_cg_start, const uint64_t *__restrict__ cg_key,
+                                                     const uint32_t *__restrict__ values, const uint32_t *__restrict__ cg_start, int mode,
+                                                     uint32_t gene_mask, int32_t *__restrict__ out_gene, int32_t *__restrict__ out_val)
 {
     // mode 0: value = values[i] (skip zeros); mode 1: value = cg_start[i+1]-cg_start[i] (all UMIs); mode 2: value = values[i], keep all
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t c = warp_global; c < n_cols; c += n_warps)
+    __shared__ uint32_t ws[33];
+    for (uint32_t c = blockIdx.x; c < n_cols; c += gridDim.x)
     {
         const uint32_t pc = col_pc[c];
         const uint32_t s = pc_cg_start[pc], e = pc_cg_start[pc + 1];
         uint32_t pos = col_off[c];
-        for (uint32_t i0 = s; i0 < e; i0 += 32)
+        for (uint32_t i0 = s; i0 < e; i0 += blockDim.x)
         {
-            const uint32_t i = i0 + lane;
+            const uint32_t i = i0 + threadIdx.x;
             uint32_t v = 0;
             if (i < e) v = mode == 1 ? cg_start[i + 1] - cg_start[i] : values[i];
-            const bool keepit = i < e && (mode != 0 || v > 0);
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, keepit);
+            const uint32_t keepit = (i < e && (mode != 0 || v > 0)) ? 1u : 0u;
+            uint32_t total;
+            const uint32_t ex = block_exclusive_scan(keepit, ws, &total);
             if (keepit)
             {
-                const uint32_t p = pos + __popc(m & ((1u << lane) - 1));
-                out_gene[p] = int32_t(uint32_t(cg_key[i]) & gene_mask);
-                out_val[p] = int32_t(v);
+                out_gene[pos + ex] = int32_t(uint32_t(cg_key[i]) & gene_mask);
+                out_val[pos + ex] = int32_t(v);
             }
-            pos += __popc(m);
+            pos += total;
         }
     }
 }

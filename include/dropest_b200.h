@@ -175,6 +175,10 @@ int dge_set_initialized(dge_handle *h);
  * ("You must initialize container", ":41-42"). */
 int dge_merge_and_filter(dge_handle *h);
 
+/* Forget all reads and results but keep the configuration and every device workspace, so that the next run of the
+ * same size allocates nothing (the reference equivalent is constructing a fresh CellsDataContainer). */
+int dge_reset(dge_handle *h);
+
 /* Optional: run on this CUDA stream (a cudaStream_t passed as void*); default is a stream owned by the handle. */
 int dge_set_stream(dge_handle *h, void *cuda_stream);
 
