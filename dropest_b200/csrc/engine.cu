@@ -907,9 +907,8 @@ void do_merge_and_filter(dge_handle *h)
     h->timings.ms_merge = el(3, 4);
     h->timings.ms_finish = el(4, 5);
     h->timings.ms_total = h->timings.ms_fill + h->timings.ms_init + h->timings.ms_merge + h->timings.ms_finish;
-    h->timings.ms_dedup_kernel = h->sc_stats.dedup_ms;
+    // ms_dedup_kernel / n_dedup_launches stay those of the main grouping pass (set in set_initialized): the dominant launch
     h->timings.n_kernel_launches = h->launches + h->sc_stats.launches;
-    h->timings.n_dedup_launches = h->sc_stats.dedup_launches;
 }
 
 // host copies for the query surface -----------------------------------------------------------------------------------

@@ -86,27 +86,56 @@ __global__ void __launch_bounds__(FILL_THREADS) k_fill_compact(const Rec16 *__re
 
     uint32_t c_inter = 0, c_exon = 0, c_intron = 0, c_na = 0;
     const size_t n_tiles = (n + FILL_TILE - 1) / FILL_TILE;
+    const uint32_t tmask = (1u << kl.tb) - 1;
     for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
     {
         const size_t base = tile * FILL_TILE;
         uint64_t keys[FILL_ITEMS];
+        uint4 raw[FILL_ITEMS];
+        uint4 probe[FILL_ITEMS];
+        uint32_t slot0[FILL_ITEMS], gfirst[FILL_ITEMS];
         uint32_t n_valid = 0;
+        // phase 1: all record loads in flight
+#pragma unroll
+        for (int j = 0; j < FILL_ITEMS; ++j)
+        {
+            const size_t i = base + size_t(j) * FILL_THREADS + threadIdx.x;
+            raw[j] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            if (i < n) raw[j] = __ldg(reinterpret_cast<const uint4 *>(recs) + i);
+        }
+        // phase 2: first probe of the barcode table + gene first-seen word, all in flight (random L2 accesses)
+#pragma unroll
+        for (int j = 0; j < FILL_ITEMS; ++j)
+        {
+            const uint64_t k = (uint64_t(raw[j].y) << 32) | raw[j].x;
+            slot0[j] = uint32_t(barcode_hash(k >> 24) >> (64 - kl.tb));
+            probe[j] = __ldcg(reinterpret_cast<const uint4 *>(&tab[slot0[j]]));
+            const uint32_t gene = raw[j].z & 0xFFFFFFu;
+            gfirst[j] = gene < n_genes ? gene_first[gene] : 0u;
+        }
+        // phase 3: resolve
 #pragma unroll
         for (int j = 0; j < FILL_ITEMS; ++j)
         {
             const size_t i = base + size_t(j) * FILL_THREADS + threadIdx.x;
             keys[j] = EMPTY64;
             if (i >= n) continue;
-            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(recs) + i);
-            const uint64_t k = (uint64_t(raw.y) << 32) | raw.x;
+            const uint64_t k = (uint64_t(raw[j].y) << 32) | raw[j].x;
             const uint64_t cb = k >> 24;
             const uint32_t umi = uint32_t(k) & 0xFFFFFFu;
-            const uint32_t gene = raw.z & 0xFFFFFFu;
-            const uint32_t mark = (raw.z >> 24) & 7u;
-            const uint32_t idx = raw.w;
-            const uint32_t slot = table_insert(tab, kl.tb, cb);
-            if (slot == NONE32) { ctr->table_overflow = 1; continue; }
-            if (idx < tab[slot].first_idx) atomicMin(&tab[slot].first_idx, idx);
+            const uint32_t gene = raw[j].z & 0xFFFFFFu;
+            const uint32_t mark = (raw[j].z >> 24) & 7u;
+            const uint32_t idx = raw[j].w;
+            uint32_t slot = slot0[j];
+            uint32_t seen_first = probe[j].z;
+            if (((uint64_t(probe[j].y) << 32) | probe[j].x) != cb)
+            {
+                slot = table_insert(tab, kl.tb, cb);
+                if (slot == NONE32) { ctr->table_overflow = 1; continue; }
+                seen_first = tab[slot].first_idx;
+            }
+            (void)tmask;
+            if (idx < seen_first) atomicMin(&tab[slot].first_idx, idx);
             if (gene == NO_GENE)
             {
                 atomicAdd(&tab[slot].n_intergenic, 1u);
@@ -114,7 +143,7 @@ __global__ void __launch_bounds__(FILL_THREADS) k_fill_compact(const Rec16 *__re
                 continue;
             }
             if (gene >= n_genes) { ctr->bad_gene = 1; continue; }
-            if (idx < gene_first[gene]) atomicMin(&gene_first[gene], idx);
+            if (idx < gfirst[j]) atomicMin(&gene_first[gene], idx);
             c_exon += (mark >> 1) & 1u; c_intron += (mark >> 2) & 1u; c_na += mark & 1u;
             keys[j] = kl.compose(slot, gene, umi, mark);
             if (nb1) atomicAdd(&hist[keys[j] >> l1_shift], 1u);

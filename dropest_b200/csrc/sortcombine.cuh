@@ -14,6 +14,8 @@
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
+#include <chrono>
+#include <cstdlib>
 
 namespace dge
 {
@@ -22,11 +24,28 @@ constexpr int SC_THREADS = 512;
 constexpr int SC_ITEMS = 16;
 constexpr int SC_TILE = SC_THREADS * SC_ITEMS; // 8192 keys per block tile
 constexpr int SC_MAX_NB1 = 4096;               // max L1 buckets
-constexpr int SC_MAX_P2 = 1024;                // max sub-buckets per L1 bucket
-constexpr int SC_TARGET = 1536;                // target records per sub-bucket
+constexpr int SC_MAX_P2 = 2048;                // max sub-buckets per L1 bucket
 constexpr int SC_SAMPLE = 8192;                // max sample size per L1 bucket
-constexpr int SC_HT = 4096;                    // shared-memory hash table slots per sub-bucket
+constexpr int SC_HT_MAX = 4096;                // largest shared-memory hash table (slots) per sub-bucket
 constexpr int SC_DEDUP_THREADS = 256;
+
+// Tunables (environment overrides are for experiments; defaults are what the benchmarks use).
+struct SortCombineTuning
+{
+    int l1_target = 200000; // records per L1 bucket
+    int target = 1024;      // records per sub-bucket
+    int ht = 2048;          // hash-table slots per sub-bucket (power of two, >= 2 * expected distinct keys)
+    SortCombineTuning()
+    {
+        if (const char *e = std::getenv("DGE_L1_TARGET")) l1_target = std::max(1000, atoi(e));
+        if (const char *e = std::getenv("DGE_SC_TARGET")) target = std::max(64, atoi(e));
+        if (const char *e = std::getenv("DGE_SC_HT")) ht = atoi(e);
+        int p = 256;
+        while (p < ht && p < SC_HT_MAX) p <<= 1;
+        ht = p;
+    }
+};
+inline const SortCombineTuning &sc_tuning() { static SortCombineTuning t; return t; }
 
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool HAS_VAL> __device__ __forceinline__ void bitonic_sort_smem(uint64_t *k, uint32_t *v, int P)
@@ -111,7 +130,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_l1_scatter(const uint64_t *__res
 
 // Single block.  From the L1 offsets derive, per bucket, the number of sub-buckets p2 and of block tiles, and their
 // exclusive scans (sb_base, tile_base; entry [nb1] = totals).
-__global__ void __launch_bounds__(1024) k_l1_plan(const uint32_t *__restrict__ l1_off, int nb1, uint32_t *__restrict__ p2,
+__global__ void __launch_bounds__(1024) k_l1_plan(const uint32_t *__restrict__ l1_off, int nb1, uint32_t SC_TARGET, uint32_t *__restrict__ p2,
                                                   uint32_t *__restrict__ sb_base, uint32_t *__restrict__ tile_base)
 {
     __shared__ uint32_t ws[33];
@@ -253,20 +272,137 @@ __global__ void __launch_bounds__(SC_THREADS) k_l2_pass(const uint64_t *__restri
     }
 }
 
+// ---- "direct" variants: rank with one L2 atomic per key on the bucket cursor itself (cursors of the L1 level are padded to
+// 256 B so they spread over all L2 slices).  No shared-memory ranking, no block-wide phases: every thread keeps several
+// independent load -> atomic -> store chains in flight, which is what a latency-bound scatter needs.
+constexpr int SC_CURSOR_PAD = 64; // uint32 stride of the padded L1 cursors
+
+__global__ void k_pad_cursor(const uint32_t *__restrict__ l1_off, int nb1, uint32_t *__restrict__ padded)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb1) padded[size_t(b) * SC_CURSOR_PAD] = l1_off[b];
+}
+
+constexpr int SCD_THREADS = 256;
+constexpr int SCD_ITEMS = 8;
+
+template <bool HAS_VAL>
+__global__ void __launch_bounds__(SCD_THREADS) k_l1_scatter_direct(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, size_t n,
+                                                                    int shift, uint32_t *__restrict__ cursor_pad,
+                                                                    uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
+{
+    const size_t base = size_t(blockIdx.x) * (SCD_THREADS * SCD_ITEMS);
+    uint64_t k[SCD_ITEMS];
+    uint32_t pos[SCD_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SCD_ITEMS; ++j)
+    {
+        size_t i = base + size_t(j) * SCD_THREADS + threadIdx.x;
+        if (i < n) k[j] = keys[i];
+    }
+#pragma unroll
+    for (int j = 0; j < SCD_ITEMS; ++j)
+    {
+        size_t i = base + size_t(j) * SCD_THREADS + threadIdx.x;
+        if (i < n) pos[j] = atomicAdd(&cursor_pad[size_t(k[j] >> shift) * SC_CURSOR_PAD], 1u);
+    }
+#pragma unroll
+    for (int j = 0; j < SCD_ITEMS; ++j)
+    {
+        size_t i = base + size_t(j) * SCD_THREADS + threadIdx.x;
+        if (i < n)
+        {
+            out_keys[pos[j]] = k[j];
+            if (HAS_VAL) out_vals[pos[j]] = vals[i];
+        }
+    }
+}
+
+template <bool SCATTER, bool HAS_VAL>
+__global__ void __launch_bounds__(SCD_THREADS) k_l2_pass_direct(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                                 const uint32_t *__restrict__ l1_off, int nb1, const uint32_t *__restrict__ p2,
+                                                                 const uint32_t *__restrict__ sb_base, const uint32_t *__restrict__ tile_base,
+                                                                 const uint64_t *__restrict__ splitters, uint32_t *__restrict__ sub_cnt_or_cursor,
+                                                                 uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
+{
+    __shared__ uint64_t spl[SC_MAX_P2];
+    const uint32_t blk = blockIdx.x;
+    if (blk >= tile_base[nb1]) return;
+    int b; uint32_t tile;
+    block_to_bucket_tile(tile_base, nb1, blk, &b, &tile);
+    const uint32_t np = p2[b];
+    const uint32_t off = l1_off[b], end = l1_off[b + 1];
+    const uint32_t t0 = off + tile * SC_TILE;
+    const uint32_t t1 = min(end, t0 + uint32_t(SC_TILE));
+    uint32_t *__restrict__ cur = sub_cnt_or_cursor + sb_base[b];
+    for (uint32_t i = threadIdx.x; i + 1 < np; i += blockDim.x) spl[i] = splitters[size_t(b) * SC_MAX_P2 + i];
+    __syncthreads();
+    for (uint32_t c0 = t0; c0 < t1; c0 += SCD_THREADS * SCD_ITEMS)
+    {
+        uint64_t k[SCD_ITEMS];
+        uint32_t pos[SCD_ITEMS];
+#pragma unroll
+        for (int j = 0; j < SCD_ITEMS; ++j)
+        {
+            uint32_t i = c0 + uint32_t(j) * SCD_THREADS + threadIdx.x;
+            if (i < t1) k[j] = keys[i];
+        }
+#pragma unroll
+        for (int j = 0; j < SCD_ITEMS; ++j)
+        {
+            uint32_t i = c0 + uint32_t(j) * SCD_THREADS + threadIdx.x;
+            if (i < t1)
+            {
+                const uint32_t s = np > 1 ? sub_bucket_of(spl, np - 1, k[j] >> 3) : 0u;
+                if (SCATTER) pos[j] = atomicAdd(&cur[s], 1u);
+                else atomicAdd(&cur[s], 1u);
+            }
+        }
+        if (SCATTER)
+        {
+#pragma unroll
+            for (int j = 0; j < SCD_ITEMS; ++j)
+            {
+                uint32_t i = c0 + uint32_t(j) * SCD_THREADS + threadIdx.x;
+                if (i < t1)
+                {
+                    out_keys[pos[j]] = k[j];
+                    if (HAS_VAL) out_vals[pos[j]] = vals[i];
+                }
+            }
+        }
+    }
+}
+
 // One block per sub-bucket.  keys[s..e) -> distinct ukeys, ascending, written back IN PLACE at keys[s..s+m), values at
 // uvals[s..s+m); ucount[sb] = m.
+//   1. stream the records through a shared-memory hash table (atomicCAS claims a slot, atomicAdd/atomicOr combine values)
+//   2. compact the occupied slots
+//   3. stable LSD radix sort (8-bit digits) of the m distinct keys on the bits that actually vary inside the sub-bucket;
+//      ranking is atomic-free: every warp owns a contiguous slice and a private digit histogram, equal digits inside a
+//      32-key group are resolved with __match_any_sync
+constexpr int SC_RADIX_BITS = 8;
+constexpr int SC_RADIX = 1 << SC_RADIX_BITS;
+constexpr int SC_DEDUP_WARPS = SC_DEDUP_THREADS / 32;
+
+inline size_t dedup_smem_bytes(int ht) { return size_t(ht) * 26 + SC_DEDUP_WARPS * SC_RADIX * 2 + 64; }
+
 template <bool HAS_VAL>
 __global__ void __launch_bounds__(SC_DEDUP_THREADS) k_dedup_sort(uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals_in,
                                                                  uint32_t *__restrict__ uvals, const uint32_t *__restrict__ sub_off,
                                                                  const uint32_t *__restrict__ n_sub_ptr, uint32_t *__restrict__ ucount,
-                                                                 int *__restrict__ overflow)
+                                                                 int *__restrict__ overflow, const int SC_HT)
 {
     extern __shared__ unsigned char smem_raw[];
-    unsigned long long *ht_key = reinterpret_cast<unsigned long long *>(smem_raw);
-    uint64_t *list_key = reinterpret_cast<uint64_t *>(ht_key + SC_HT);
-    uint32_t *ht_val = reinterpret_cast<uint32_t *>(list_key + SC_HT);
-    uint32_t *list_val = ht_val + SC_HT;
+    unsigned long long *bufA_key = reinterpret_cast<unsigned long long *>(smem_raw);            // hash table keys, later ping-pong buffer
+    unsigned long long *bufB_key = bufA_key + SC_HT;                                             // compacted list
+    uint32_t *bufA_val = reinterpret_cast<uint32_t *>(bufB_key + SC_HT);
+    uint32_t *bufB_val = bufA_val + SC_HT;
+    uint16_t *rank_s = reinterpret_cast<uint16_t *>(bufB_val + SC_HT);                           // per element rank inside (warp, digit)
+    uint16_t *hist = rank_s + SC_HT;                                                             // [warp][digit]
     __shared__ uint32_t m_s;
+    __shared__ unsigned long long red_or, red_and;
+    __shared__ uint32_t ws[33];
 
     const uint32_t sb = blockIdx.x;
     if (sb >= *n_sub_ptr) return;
@@ -276,10 +412,11 @@ __global__ void __launch_bounds__(SC_DEDUP_THREADS) k_dedup_sort(uint64_t *__res
         if (threadIdx.x == 0) ucount[sb] = 0;
         return;
     }
-    for (int i = threadIdx.x; i < SC_HT; i += blockDim.x) { ht_key[i] = EMPTY64; ht_val[i] = 0; }
-    if (threadIdx.x == 0) m_s = 0;
+    for (int i = threadIdx.x; i < SC_HT; i += blockDim.x) { bufA_key[i] = EMPTY64; bufA_val[i] = 0; }
+    if (threadIdx.x == 0) { m_s = 0; red_or = 0; red_and = EMPTY64; }
     __syncthreads();
 
+    // ---- 1. hash-combine
     for (uint32_t i = s + threadIdx.x; i < e; i += blockDim.x)
     {
         const uint64_t key = keys[i];
@@ -289,10 +426,10 @@ __global__ void __launch_bounds__(SC_DEDUP_THREADS) k_dedup_sort(uint64_t *__res
         int probes = 0;
         while (true)
         {
-            unsigned long long cur = ht_key[slot];
+            unsigned long long cur = bufA_key[slot];
             if (cur == EMPTY64)
             {
-                cur = atomicCAS(&ht_key[slot], EMPTY64, (unsigned long long)uk);
+                cur = atomicCAS(&bufA_key[slot], EMPTY64, (unsigned long long)uk);
                 if (cur == EMPTY64) cur = uk;
             }
             if (cur == uk) break;
@@ -301,39 +438,105 @@ __global__ void __launch_bounds__(SC_DEDUP_THREADS) k_dedup_sort(uint64_t *__res
         }
         if (slot != NONE32)
         {
-            uint32_t old = atomicAdd(&ht_val[slot], v & VAL_COUNT_MASK);
-            uint32_t mk = v & ~VAL_COUNT_MASK;
-            if ((old & mk) != mk) atomicOr(&ht_val[slot], mk);
+            const uint32_t old = atomicAdd(&bufA_val[slot], v & VAL_COUNT_MASK);
+            const uint32_t mk = v & ~VAL_COUNT_MASK;
+            if ((old & mk) != mk) atomicOr(&bufA_val[slot], mk);
         }
     }
     __syncthreads();
 
-    // compact occupied slots (order irrelevant: sorted next)
+    // ---- 2. compact occupied slots into B (order irrelevant), and find which key bits vary
+    unsigned long long t_or = 0, t_and = EMPTY64;
     for (int i = threadIdx.x; i < SC_HT; i += blockDim.x)
     {
-        unsigned long long kk = ht_key[i];
-        bool occ = kk != EMPTY64;
-        unsigned mask = __ballot_sync(0xFFFFFFFFu, occ);
+        const unsigned long long kk = bufA_key[i];
+        const bool occ = kk != EMPTY64;
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, occ);
         uint32_t basepos = 0;
         if ((threadIdx.x & 31) == 0 && mask) basepos = atomicAdd(&m_s, uint32_t(__popc(mask)));
         basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
         if (occ)
         {
-            uint32_t pos = basepos + __popc(mask & ((1u << (threadIdx.x & 31)) - 1));
-            list_key[pos] = kk;
-            list_val[pos] = ht_val[i];
+            const uint32_t pos = basepos + __popc(mask & ((1u << (threadIdx.x & 31)) - 1));
+            bufB_key[pos] = kk;
+            bufB_val[pos] = bufA_val[i];
+            t_or |= kk; t_and &= kk;
         }
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        t_or |= __shfl_xor_sync(0xFFFFFFFFu, t_or, d);
+        t_and &= __shfl_xor_sync(0xFFFFFFFFu, t_and, d);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicOr(&red_or, t_or); atomicAnd(&red_and, t_and); }
     __syncthreads();
     const uint32_t m = m_s;
-    int P = 2;
-    while (uint32_t(P) < m) P <<= 1;
-    for (int i = m + threadIdx.x; i < P; i += blockDim.x) { list_key[i] = EMPTY64; list_val[i] = 0; }
-    bitonic_sort_smem<true>(list_key, list_val, P);
+    const unsigned long long varying = red_or & ~red_and; // bits that differ between at least two keys
+    const int top_bit = varying ? 63 - __clzll((long long)varying) : -1;
+
+    // ---- 3. LSD radix sort of B[0..m) ; ping-pong B <-> A
+    unsigned long long *src_k = bufB_key, *dst_k = bufA_key;
+    uint32_t *src_v = bufB_val, *dst_v = bufA_val;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t chunk = ((m + SC_DEDUP_WARPS * 32 - 1) / (SC_DEDUP_WARPS * 32)) * 32; // per-warp slice, multiple of 32
+    const uint32_t w_begin = min(m, warp * chunk), w_end = min(m, w_begin + chunk);
+    uint16_t *my_hist = hist + warp * SC_RADIX;
+    for (int shift = 0; shift <= top_bit; shift += SC_RADIX_BITS)
+    {
+        if (((varying >> shift) & (SC_RADIX - 1)) == 0) continue; // this digit is constant: nothing to do (uniform branch)
+        for (int i = threadIdx.x; i < SC_DEDUP_WARPS * SC_RADIX / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(hist)[i] = 0;
+        __syncthreads();
+        for (uint32_t g = w_begin; g < w_end; g += 32)
+        {
+            const uint32_t i = g + lane;
+            const bool valid = i < w_end;
+            const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid);
+            if (valid)
+            {
+                const uint32_t d = uint32_t(src_k[i] >> shift) & (SC_RADIX - 1);
+                const unsigned peers = __match_any_sync(vmask, d);
+                const int leader = __ffs(peers) - 1;
+                uint32_t old = 0;
+                if (int(lane) == leader) { old = my_hist[d]; my_hist[d] = uint16_t(old + __popc(peers)); }
+                old = __shfl_sync(peers, old, leader);
+                rank_s[i] = uint16_t(old + __popc(peers & ((1u << lane) - 1)));
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // exclusive scan over (digit major, warp minor): thread d owns digit d
+            const uint32_t d = threadIdx.x;
+            uint32_t run = 0;
+            uint16_t c[SC_DEDUP_WARPS];
+#pragma unroll
+            for (int w = 0; w < SC_DEDUP_WARPS; ++w) { c[w] = hist[w * SC_RADIX + d]; run += c[w]; }
+            uint32_t total;
+            uint32_t basev = block_exclusive_scan(run, ws, &total);
+#pragma unroll
+            for (int w = 0; w < SC_DEDUP_WARPS; ++w) { hist[w * SC_RADIX + d] = uint16_t(basev); basev += c[w]; }
+        }
+        __syncthreads();
+        for (uint32_t g = w_begin; g < w_end; g += 32)
+        {
+            const uint32_t i = g + lane;
+            if (i < w_end)
+            {
+                const unsigned long long kk = src_k[i];
+                const uint32_t d = uint32_t(kk >> shift) & (SC_RADIX - 1);
+                const uint32_t pos = uint32_t(my_hist[d]) + rank_s[i];
+                dst_k[pos] = kk;
+                dst_v[pos] = src_v[i];
+            }
+        }
+        __syncthreads();
+        unsigned long long *tk = src_k; src_k = dst_k; dst_k = tk;
+        uint32_t *tv = src_v; src_v = dst_v; dst_v = tv;
+    }
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
     {
-        keys[s + i] = list_key[i];
-        uvals[s + i] = list_val[i];
+        keys[s + i] = src_k[i];
+        uvals[s + i] = src_v[i];
     }
     if (threadIdx.x == 0) ucount[sb] = m;
 }
@@ -358,7 +561,7 @@ __global__ void __launch_bounds__(256) k_compact_uniques(const uint64_t *__restr
 // ---------------------------------------------------------------------------------------------------------------------
 struct SortCombineWorkspace
 {
-    DevBuf keysA, valsA, valsB, uvals_sparse, small, splitters, sub_cnt, sub_off, ucount, u_off, scan_scratch;
+    DevBuf keysA, valsA, valsB, uvals_sparse, small, splitters, sub_cnt, sub_off, ucount, u_off, scan_scratch, cursor_pad;
 };
 
 struct SortCombineStats
@@ -370,7 +573,7 @@ struct SortCombineStats
 
 inline int choose_l1_bits(size_t n)
 {
-    int b = ceil_log2_u64(div_up<uint64_t>(n ? n : 1, 200000));
+    int b = ceil_log2_u64(div_up<uint64_t>(n ? n : 1, uint64_t(sc_tuning().l1_target)));
     if (b < 6) b = 6;
     if (b > 12) b = 12;
     return b;
@@ -398,8 +601,8 @@ public:
         static bool done = false;
         if (done) return;
         DGE_CUDA(cudaFuncSetAttribute(k_splitters, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SAMPLE * 8));
-        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_HT * 24));
-        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_HT * 24));
+        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dedup_smem_bytes(SC_HT_MAX))));
+        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dedup_smem_bytes(SC_HT_MAX))));
         done = true;
     }
 
@@ -417,6 +620,7 @@ public:
         ws.small.reserve(stride * 6 * sizeof(uint32_t));
         uint32_t *hist = ws.small.as<uint32_t>(), *l1_off = hist + stride, *cursor = l1_off + stride, *p2 = cursor + stride,
                  *sb_base = p2 + stride, *tile_base = sb_base + stride;
+        const int SC_TARGET = sc_tuning().target, SC_HT = sc_tuning().ht;
         const size_t nsb_bound = n / SC_TARGET + size_t(nb1) + 1;
         const size_t tiles_bound = n / SC_TILE + size_t(nb1) + 1;
         ws.keysA.reserve(n * 8);
@@ -429,6 +633,16 @@ public:
         ws.u_off.reserve((nsb_bound + 1) * 4);
         ws.scan_scratch.reserve(scan_scratch_elems(nsb_bound + 1) * 4);
         unsigned &L = stats->launches;
+        const bool trace = std::getenv("DGE_TRACE") != nullptr;
+        auto t_prev = std::chrono::steady_clock::now();
+        auto mark = [&](const char *what) {
+            if (!trace) return;
+            cudaStreamSynchronize(st);
+            auto t1 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[dge]   sc(n=%zu) %-18s %8.3f ms\n", n, what, std::chrono::duration<double, std::milli>(t1 - t_prev).count());
+            t_prev = t1;
+        };
+        mark("alloc");
 
         // ---- L1
         if (l1_hist_pre)
@@ -441,37 +655,65 @@ public:
         }
         DGE_CUDA(cudaMemsetAsync(hist + nb1, 0, sizeof(uint32_t), st));
         device_exclusive_scan(hist, l1_off, stride, ws.scan_scratch.as<uint32_t>(), st, &L);
-        DGE_CUDA(cudaMemcpyAsync(cursor, l1_off, stride * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         uint64_t *keysA = ws.keysA.as<uint64_t>();
-        const unsigned g_tiles = unsigned(div_up(n, size_t(SC_TILE)));
-        if (has_val)
-            k_l1_scatter<true><<<g_tiles, SC_THREADS, 0, st>>>(keys_in, vals_in, n, shift, nb1, cursor, keysA, ws.valsA.as<uint32_t>());
+        static const int direct = std::getenv("DGE_DIRECT") ? atoi(std::getenv("DGE_DIRECT")) : 0;
+        if (direct & 1)
+        {
+            ws.cursor_pad.reserve(size_t(nb1) * SC_CURSOR_PAD * 4);
+            k_pad_cursor<<<div_up(nb1, 256), 256, 0, st>>>(l1_off, nb1, ws.cursor_pad.as<uint32_t>());
+            const unsigned g = unsigned(div_up(n, size_t(SCD_THREADS * SCD_ITEMS)));
+            if (has_val)
+                k_l1_scatter_direct<true><<<g, SCD_THREADS, 0, st>>>(keys_in, vals_in, n, shift, ws.cursor_pad.as<uint32_t>(), keysA, ws.valsA.as<uint32_t>());
+            else
+                k_l1_scatter_direct<false><<<g, SCD_THREADS, 0, st>>>(keys_in, nullptr, n, shift, ws.cursor_pad.as<uint32_t>(), keysA, nullptr);
+            L += 2;
+        }
         else
-            k_l1_scatter<false><<<g_tiles, SC_THREADS, 0, st>>>(keys_in, nullptr, n, shift, nb1, cursor, keysA, nullptr);
-        ++L;
+        {
+            DGE_CUDA(cudaMemcpyAsync(cursor, l1_off, stride * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+            const unsigned g_tiles = unsigned(div_up(n, size_t(SC_TILE)));
+            if (has_val)
+                k_l1_scatter<true><<<g_tiles, SC_THREADS, 0, st>>>(keys_in, vals_in, n, shift, nb1, cursor, keysA, ws.valsA.as<uint32_t>());
+            else
+                k_l1_scatter<false><<<g_tiles, SC_THREADS, 0, st>>>(keys_in, nullptr, n, shift, nb1, cursor, keysA, nullptr);
+            ++L;
+        }
+        mark("l1 hist+scatter");
 
         // ---- L2
-        k_l1_plan<<<1, 1024, 0, st>>>(l1_off, nb1, p2, sb_base, tile_base); ++L;
+        k_l1_plan<<<1, 1024, 0, st>>>(l1_off, nb1, uint32_t(SC_TARGET), p2, sb_base, tile_base); ++L;
         k_splitters<<<nb1, SC_THREADS, SC_SAMPLE * 8, st>>>(keysA, l1_off, p2, ws.splitters.as<uint64_t>()); ++L;
+        mark("plan+splitters");
         uint32_t *sub_cnt = ws.sub_cnt.as<uint32_t>(), *sub_off = ws.sub_off.as<uint32_t>();
         DGE_CUDA(cudaMemsetAsync(sub_cnt, 0, (nsb_bound + 1) * 4, st));
-        if (has_val)
-            k_l2_pass<false, true><<<unsigned(tiles_bound), SC_THREADS, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base,
-                                                                                  ws.splitters.as<uint64_t>(), sub_cnt, nullptr, nullptr);
+        if (direct & 4)
+            k_l2_pass_direct<false, false><<<unsigned(tiles_bound), SCD_THREADS, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base,
+                                                                                          ws.splitters.as<uint64_t>(), sub_cnt, nullptr, nullptr);
         else
             k_l2_pass<false, false><<<unsigned(tiles_bound), SC_THREADS, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base,
                                                                                    ws.splitters.as<uint64_t>(), sub_cnt, nullptr, nullptr);
         ++L;
+        mark("l2 hist");
         device_exclusive_scan(sub_cnt, sub_off, nsb_bound + 1, ws.scan_scratch.as<uint32_t>(), st, &L);
         // cursors = copy of offsets (sub_cnt reused)
         DGE_CUDA(cudaMemcpyAsync(sub_cnt, sub_off, (nsb_bound + 1) * 4, cudaMemcpyDeviceToDevice, st));
-        if (has_val)
+        if (direct & 2)
+        {
+            if (has_val)
+                k_l2_pass_direct<true, true><<<unsigned(tiles_bound), SCD_THREADS, 0, st>>>(keysA, ws.valsA.as<uint32_t>(), l1_off, nb1, p2, sb_base, tile_base,
+                                                                                            ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp, ws.valsB.as<uint32_t>());
+            else
+                k_l2_pass_direct<true, false><<<unsigned(tiles_bound), SCD_THREADS, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base,
+                                                                                             ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp, nullptr);
+        }
+        else if (has_val)
             k_l2_pass<true, true><<<unsigned(tiles_bound), SC_THREADS, 0, st>>>(keysA, ws.valsA.as<uint32_t>(), l1_off, nb1, p2, sb_base, tile_base,
                                                                                  ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp, ws.valsB.as<uint32_t>());
         else
             k_l2_pass<true, false><<<unsigned(tiles_bound), SC_THREADS, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base,
                                                                                   ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp, nullptr);
         ++L;
+        mark("l2 scan+scatter");
 
         // ---- L3: dedup + sort per sub-bucket
         const uint32_t *n_sub_ptr = sb_base + nb1;
@@ -479,18 +721,20 @@ public:
         DGE_CUDA(cudaMemsetAsync(ucount, 0, (nsb_bound + 1) * 4, st));
         DGE_CUDA(cudaEventRecord(ev0, st));
         if (has_val)
-            k_dedup_sort<true><<<unsigned(nsb_bound), SC_DEDUP_THREADS, SC_HT * 24, st>>>(keys_tmp, ws.valsB.as<uint32_t>(), ws.uvals_sparse.as<uint32_t>(),
-                                                                                           sub_off, n_sub_ptr, ucount, overflow_flag);
+            k_dedup_sort<true><<<unsigned(nsb_bound), SC_DEDUP_THREADS, dedup_smem_bytes(SC_HT), st>>>(keys_tmp, ws.valsB.as<uint32_t>(), ws.uvals_sparse.as<uint32_t>(),
+                                                                                           sub_off, n_sub_ptr, ucount, overflow_flag, SC_HT);
         else
-            k_dedup_sort<false><<<unsigned(nsb_bound), SC_DEDUP_THREADS, SC_HT * 24, st>>>(keys_tmp, nullptr, ws.uvals_sparse.as<uint32_t>(),
-                                                                                            sub_off, n_sub_ptr, ucount, overflow_flag);
+            k_dedup_sort<false><<<unsigned(nsb_bound), SC_DEDUP_THREADS, dedup_smem_bytes(SC_HT), st>>>(keys_tmp, nullptr, ws.uvals_sparse.as<uint32_t>(),
+                                                                                            sub_off, n_sub_ptr, ucount, overflow_flag, SC_HT);
         DGE_CUDA(cudaEventRecord(ev1, st));
         ++L; ++stats->dedup_launches;
         pending_dedup_event = true;
+        mark("dedup_sort");
         const uint32_t *n_u_ptr = device_exclusive_scan(ucount, u_off, nsb_bound + 1, ws.scan_scratch.as<uint32_t>(), st, &L);
         k_compact_uniques<<<148 * 8, 256, 0, st>>>(keys_tmp, ws.uvals_sparse.as<uint32_t>(), sub_off, u_off, ucount, n_sub_ptr, out_keys, out_vals);
         ++L;
         DGE_LAUNCH_CHECK();
+        mark("scan+compact");
         last_stats = stats;
         return n_u_ptr;
     }
