@@ -9,24 +9,16 @@ import parity_utils as pu
 
 pytestmark = pytest.mark.gpu
 
-# Fixture of the reference's Tests/TestEstimation.cpp:33-80 (17 reads, 7 barcodes)
-FIXTURE_READS = [
-    ("AAATTAGGTCCA", "AAACCT", "Gene1"), ("AAATTAGGTCCA", "CCCCCT", "Gene2"), ("AAATTAGGTCCA", "ACCCCT", "Gene3"),
-    ("AAATTAGGTCCA", "ACCCCT", "Gene4"), ("AAATTAGGTCCC", "CAACCT", "Gene1"), ("AAATTAGGTCCC", "CAACCT", "Gene10"),
-    ("AAATTAGGTCCC", "CAACCT", "Gene20"), ("AAATTAGGTCCG", "CAACCT", "Gene1"), ("AAATTAGGTCGG", "AAACCT", "Gene1"),
-    ("AAATTAGGTCGG", "CCCCCT", "Gene2"), ("CCCTTAGGTCCA", "CCATTC", "Gene3"), ("CCCTTAGGTCCA", "CCCCCT", "Gene2"),
-    ("CCCTTAGGTCCA", "ACCCCT", "Gene3"), ("CAATTAGGTCCG", "CAACCT", "Gene1"), ("CAATTAGGTCCG", "AAACCT", "Gene1"),
-    ("CAATTAGGTCCG", "CCCCCT", "Gene2"), ("AAAAAAAAAAAA", "CCCCCT", "Gene2"),
-]
+import golden_cases
+from golden_cases import fixture_case
 
 
-def fixture_case(**kw):
-    gene_ids = {}
-    recs = records_from_strings([(cb, umi, g, 2) for cb, umi, g in FIXTURE_READS], gene_ids)
-    names = [n for n, _ in sorted(gene_ids.items(), key=lambda kv: kv[1])]
-    return pu.Case(name="test_est_fixture", recs=recs, cb_len=12, umi_len=6, n_genes=len(names), gene_names=names, merge="real",
-                   barcodes=pu.WL_TEST_EST, barcodes_type="indrop", min_genes_before=0, min_genes_after=0, max_cb_ed=7,
-                   min_frac=0.0, shuffle=False, n_batches=1, **kw)
+@pytest.mark.parametrize("name", ["fixture", "real_7x9", "none_7x9", "real_8x8_reads"])
+def test_gpu_reproduces_golden_reference_outputs(name):
+    """CUDA path vs the committed outputs of the compiled, unmodified reference (no oracle binary needed on the GPU box)."""
+    case = golden_cases.cases()[name]
+    gpu = pu.gpu_run(case, golden_cases.case_records(case))
+    pu.assert_parity({"case": case, "oracle": golden_cases.load_golden(name), "gpu": gpu})
 
 
 def test_synth_device_matches_host():
