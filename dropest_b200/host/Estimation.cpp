@@ -1,0 +1,488 @@
+// Estimation.cpp -- implementation of the host-side mirror declared in Estimation.h (see there for the reference citations).
+#include "Estimation.h"
+
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include <zlib.h>
+
+namespace Tools
+{
+	ReadParameters ReadParameters::parse_encoded_id(const std::string &encoded_id)
+	{
+		size_t umi_start_pos = encoded_id.rfind('#');
+		if (umi_start_pos == std::string::npos) throw std::runtime_error("ERROR: unable to parse out UMI in: " + encoded_id);
+		size_t cb_start_pos = encoded_id.rfind('!', umi_start_pos);
+		if (cb_start_pos == std::string::npos) throw std::runtime_error("ERROR: unable to parse out cell barcode in: " + encoded_id);
+		return ReadParameters(encoded_id.substr(cb_start_pos + 1, umi_start_pos - cb_start_pos - 1), encoded_id.substr(umi_start_pos + 1), "", "");
+	}
+
+	unsigned edit_distance(const char *s1, const char *s2, bool skip_n, unsigned max_ed) { return dge_edit_distance(s1, s2, skip_n ? 1 : 0, max_ed); }
+
+	unsigned hamming_distance(const std::string &s1, const std::string &s2, bool skip_n)
+	{
+		if (s1.size() != s2.size()) throw std::runtime_error("Strings should have equal length");
+		return dge_hamming_distance(s1.c_str(), s2.c_str(), skip_n ? 1 : 0);
+	}
+}
+
+namespace Estimation
+{
+	const std::string UMI::Mark::DEFAULT_CODE = "eEBA";
+
+	UMI::Mark UMI::Mark::get_by_code(char code)
+	{
+		Mark mark;
+		switch (code)
+		{
+			case 'e': mark.add(HAS_EXONS); return mark;
+			case 'i': mark.add(HAS_INTRONS); return mark;
+			case 'E': mark.add(HAS_EXONS); mark.add(HAS_NOT_ANNOTATED); return mark;
+			case 'I': mark.add(HAS_INTRONS); mark.add(HAS_NOT_ANNOTATED); return mark;
+			case 'B': mark.add(HAS_EXONS); mark.add(HAS_INTRONS); return mark;
+			case 'A': mark.add(HAS_EXONS); mark.add(HAS_INTRONS); mark.add(HAS_NOT_ANNOTATED); return mark;
+			default: throw std::runtime_error(std::string("Unexpected gene match levels: ") + code);
+		}
+	}
+
+	std::vector<UMI::Mark> UMI::Mark::get_by_code(const std::string &code)
+	{
+		std::vector<Mark> levels;
+		for (char c : code) levels.push_back(get_by_code(c));
+		return levels;
+	}
+
+	bool Gene::has(const std::string &umi) const
+	{
+		try { return _umis.find(_umi_indexer->get_index(umi)) != _umis.end(); }
+		catch (std::out_of_range &) { return false; }
+	}
+
+	size_t Gene::number_of_requested_umis(const UMI::Mark::query_t &query, bool return_reads) const
+	{
+		size_t n = 0;
+		for (auto const &u : _umis)
+			if (u.second.mark().match(query)) n += return_reads ? u.second.read_count() : 1;
+		return n;
+	}
+
+	size_t Gene::number_of_umis(bool return_reads) const
+	{
+		if (!return_reads) return _umis.size();
+		size_t n = 0;
+		for (auto const &u : _umis) n += u.second.read_count();
+		return n;
+	}
+
+	Cell::s_ul_hash_t Cell::requested_umis_per_gene(const UMI::Mark::query_t &query_marks, bool return_reads) const
+	{
+		s_ul_hash_t res;
+		for (auto const &g : _genes)
+		{
+			size_t n = g.second.number_of_requested_umis(query_marks, return_reads);
+			if (n) res.emplace(_gene_indexer->get_value(g.first), n);
+		}
+		return res;
+	}
+
+	namespace Merge
+	{
+		void RealBarcodesMergeStrategy::configure(dge_config &cfg) const
+		{
+			cfg.merge_type = DGE_MERGE_REAL;
+			cfg.barcodes_type = _parser->indrop ? DGE_BARCODES_INDROP : DGE_BARCODES_CONST;
+			cfg.barcodes_file = _parser->filename.c_str();
+			cfg.max_cb_merge_edit_distance = _max_merge_edit_distance;
+			cfg.min_merge_fraction = _min_merge_fraction;
+		}
+
+		std::shared_ptr<MergeStrategyAbstract> MergeStrategyFactory::get_cb_strat(bool merge_tags, bool use_poisson) const
+		{
+			if (!merge_tags) return std::make_shared<DummyMergeStrategy>(min_genes_before_merge, min_genes_after_merge);
+			if (use_poisson || merge_type == "all" || barcodes_filename.empty())
+				throw std::runtime_error("this merge strategy is not available on the device path yet");
+			std::shared_ptr<BarcodesParsing::BarcodesParser> parser;
+			if (barcodes_type == "indrop") parser = std::make_shared<BarcodesParsing::InDropBarcodesParser>(barcodes_filename);
+			else if (barcodes_type == "const") parser = std::make_shared<BarcodesParsing::ConstLengthBarcodesParser>(barcodes_filename);
+			else throw std::runtime_error("Unexpected barcodes type: " + barcodes_type);
+			return std::make_shared<RealBarcodesMergeStrategy>(parser, min_genes_before_merge, min_genes_after_merge, max_merge_edit_distance, min_merge_fraction);
+		}
+
+		std::shared_ptr<UMIs::MergeUMIsStrategyAbstract> MergeStrategyFactory::get_umi(bool advanced) const
+		{
+			if (advanced) throw std::runtime_error("directional UMI merge is not available on the device path yet");
+			return std::make_shared<UMIs::MergeUMIsStrategySimple>(max_umi_merge_edit_distance);
+		}
+	}
+
+	// ---- CellsDataContainer ---------------------------------------------------------------------------------------------
+	static bool pack2bit(const std::string &s, uint64_t &out)
+	{
+		out = 0;
+		for (char c : s)
+		{
+			unsigned b;
+			switch (c) { case 'A': b = 0; break; case 'C': b = 1; break; case 'G': b = 2; break; case 'T': b = 3; break; default: return false; }
+			out = (out << 2) | b;
+		}
+		return true;
+	}
+
+	static std::string unpack2bit(uint64_t v, unsigned len)
+	{
+		std::string s(len, 'A');
+		for (unsigned i = 0; i < len; ++i) s[len - 1 - i] = "ACGT"[(v >> (2 * i)) & 3];
+		return s;
+	}
+
+	CellsDataContainer::CellsDataContainer(const std::shared_ptr<Merge::MergeStrategyAbstract> &merge_strategy,
+	                                       const std::shared_ptr<Merge::UMIs::MergeUMIsStrategyAbstract> &umi_merge_strategy,
+	                                       const std::vector<UMI::Mark> &gene_match_levels, bool, int max_cells_num, int device,
+	                                       size_t n_genes_hint, bool reads_output)
+		: _merge_strategy(merge_strategy), _umi_merge_strategy(umi_merge_strategy), _max_cells_num(max_cells_num)
+		, _query_marks(gene_match_levels), _device(device), _reads_output(reads_output), _batch_capacity(n_genes_hint)
+	{
+		// _batch_capacity temporarily carries the gene-space hint until the handle exists
+		std::memset(&_summary, 0, sizeof(_summary));
+	}
+
+	CellsDataContainer::~CellsDataContainer() { if (_h) dge_destroy(_h); }
+
+	void CellsDataContainer::check(int rc) const
+	{
+		if (rc == DGE_OK) return;
+		std::string msg = dge_last_error(_h);
+		if (rc == DGE_ERR_STATE) throw std::runtime_error(msg); // same messages as the reference's throws
+		throw std::runtime_error("dropest_b200: " + msg);
+	}
+
+	void CellsDataContainer::ensure_handle()
+	{
+		if (_h) return;
+		dge_config cfg;
+		dge_config_default(&cfg);
+		cfg.device = _device;
+		cfg.cb_len = _cb_len ? _cb_len : 16;
+		cfg.umi_len = _umi_len ? _umi_len : 10;
+		cfg.n_genes = uint32_t(_batch_capacity);
+		cfg.min_genes_before_merge = uint32_t(_merge_strategy->min_genes_before_merge());
+		cfg.min_genes_after_merge = uint32_t(_merge_strategy->min_genes_after_merge());
+		cfg.max_cells = _max_cells_num;
+		cfg.reads_output = _reads_output ? 1 : 0;
+		cfg.query_mark_mask = 0;
+		for (auto const &m : _query_marks) cfg.query_mark_mask |= 1u << m.bits();
+		_merge_strategy->configure(cfg);
+		_umi_merge_strategy->configure(cfg);
+		int rc = dge_create(&cfg, &_h);
+		if (rc != DGE_OK) throw std::runtime_error(std::string("dropest_b200: ") + dge_last_error(nullptr));
+		_batch_capacity = size_t(1) << 20;
+		_batch.reserve(_batch_capacity);
+	}
+
+	void CellsDataContainer::flush()
+	{
+		if (_batch.empty()) return;
+		check(dge_add_batch(_h, _batch.data(), _batch.size()));
+		_batch.clear();
+	}
+
+	void CellsDataContainer::add_record(const ReadInfo &read_info)
+	{
+		if (_is_initialized) throw std::runtime_error("Container is already initialized");
+		const std::string &cb = read_info.params.cell_barcode(), &umi = read_info.params.umi();
+		if (!_h)
+		{
+			_cb_len = unsigned(cb.size()); _umi_len = unsigned(umi.size());
+			if (_cb_len > 20 || _umi_len > 12) throw std::runtime_error("barcode/UMI too long for the packed record (20/12 bp)");
+			ensure_handle();
+		}
+		if (cb.size() != _cb_len || umi.size() != _umi_len)
+			throw std::runtime_error("the device path needs constant barcode and UMI lengths");
+		uint64_t cbv, umiv;
+		if (!pack2bit(cb, cbv) || !pack2bit(umi, umiv))
+			throw std::runtime_error("barcodes / UMIs containing N are not supported on the device path yet: " + cb + " " + umi);
+		dge_record16 r;
+		r.key = (cbv << 24) | umiv;
+		uint32_t gene = DGE_NO_GENE;
+		if (!read_info.gene.empty()) gene = uint32_t(_gene_indexer.add(read_info.gene));
+		r.gene = gene | (uint32_t(read_info.umi_mark.bits()) << 24);
+		r.read_idx = uint32_t(_n_records++);
+		_batch.push_back(r);
+		if (_batch.size() >= _batch_capacity) flush();
+	}
+
+	void CellsDataContainer::set_initialized()
+	{
+		if (_is_initialized) throw std::runtime_error("Container is already initialized");
+		ensure_handle();
+		flush();
+		check(dge_set_initialized(_h));
+		_is_initialized = true;
+		_cells_loaded = _genes_loaded = false;
+	}
+
+	void CellsDataContainer::merge_and_filter()
+	{
+		if (!_is_initialized) throw std::runtime_error("You must initialize container");
+		check(dge_merge_and_filter(_h));
+		_is_merged = true;
+		_cells_loaded = _genes_loaded = false;
+	}
+
+	void CellsDataContainer::load_cells() const
+	{
+		if (_cells_loaded) return;
+		if (!_is_initialized) throw std::runtime_error("You must initialize container");
+		size_t n = 0;
+		check(dge_get_cells(_h, DGE_CELLS_ALL, nullptr, 0, &n));
+		std::vector<dge_cell_info> info(n);
+		if (n) check(dge_get_cells(_h, DGE_CELLS_ALL, info.data(), n, &n));
+		_cells.assign(n, Cell());
+		_cell_ids_by_cb.clear();
+		_merge_targets.resize(n);
+		for (size_t i = 0; i < n; ++i)
+		{
+			Cell &c = _cells[i];
+			c._barcode = unpack2bit(info[i].barcode, _cb_len);
+			c._is_real = info[i].flags & DGE_CELL_REAL; c._is_merged = info[i].flags & DGE_CELL_MERGED; c._is_excluded = info[i].flags & DGE_CELL_EXCLUDED;
+			c._n_genes = size_t(info[i].n_genes);
+			c._requested_genes_num = size_t(info[i].requested_genes_num); c._requested_umis_num = size_t(info[i].requested_umis_num);
+			c._stats = Stats(info[i].reads_stat, info[i].umis_stat);
+			c._gene_indexer = &_gene_indexer;
+			_cell_ids_by_cb.emplace(c._barcode, i);
+			_merge_targets[i] = size_t(info[i].merge_target);
+		}
+		size_t nf = 0;
+		check(dge_get_cells(_h, DGE_CELLS_FILTERED, nullptr, 0, &nf));
+		std::vector<dge_cell_info> finfo(nf);
+		if (nf) check(dge_get_cells(_h, DGE_CELLS_FILTERED, finfo.data(), nf, &nf));
+		_filtered_cells.resize(nf);
+		for (size_t k = 0; k < nf; ++k) _filtered_cells[k] = _cell_ids_by_cb.at(unpack2bit(finfo[k].barcode, _cb_len));
+		check(dge_get_summary(_h, &_summary));
+		_cells_loaded = true;
+		_genes_loaded = false;
+	}
+
+	void CellsDataContainer::load_genes() const
+	{
+		load_cells();
+		if (_genes_loaded) return;
+		size_t n = 0;
+		check(dge_get_umigs(_h, DGE_CELLS_ALL, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &n));
+		std::vector<uint32_t> cell(n), umi(n), reads(n);
+		std::vector<int32_t> gene(n);
+		std::vector<uint8_t> mark(n);
+		if (n) check(dge_get_umigs(_h, DGE_CELLS_ALL, cell.data(), gene.data(), umi.data(), reads.data(), mark.data(), n, &n));
+		for (auto &c : _cells) c._genes.clear();
+		for (size_t k = 0; k < n; ++k)
+		{
+			Cell &c = _cells.at(cell[k]);
+			auto git = c._genes.emplace(size_t(gene[k]), Gene(&_umi_indexer)).first;
+			UMI::Mark m;
+			if (mark[k] & 1) m.add(UMI::Mark::HAS_NOT_ANNOTATED);
+			if (mark[k] & 2) m.add(UMI::Mark::HAS_EXONS);
+			if (mark[k] & 4) m.add(UMI::Mark::HAS_INTRONS);
+			git->second._umis.emplace(_umi_indexer.add(unpack2bit(umi[k], _umi_len)), UMI(reads[k], m));
+		}
+		_genes_loaded = true;
+	}
+
+	size_t CellsDataContainer::total_cells_number() const { load_cells(); return _cells.size(); }
+	size_t CellsDataContainer::cell_id_by_cb(const std::string &barcode) const { load_cells(); return _cell_ids_by_cb.at(barcode); }
+	const CellsDataContainer::ids_t &CellsDataContainer::filtered_cells() const { load_cells(); return _filtered_cells; }
+	const CellsDataContainer::ids_t &CellsDataContainer::merge_targets() const { load_cells(); return _merge_targets; }
+	const Cell &CellsDataContainer::cell(size_t index) const { load_genes(); return _cells.at(index); }
+	size_t CellsDataContainer::intergenic_reads_num() const { load_cells(); return size_t(_summary.intergenic_reads); }
+	size_t CellsDataContainer::has_exon_reads_num() const { load_cells(); return size_t(_summary.has_exon_reads); }
+	size_t CellsDataContainer::has_intron_reads_num() const { load_cells(); return size_t(_summary.has_intron_reads); }
+	size_t CellsDataContainer::has_not_annotated_reads_num() const { load_cells(); return size_t(_summary.has_not_annotated_reads); }
+	size_t CellsDataContainer::real_cells_number() const { load_cells(); return size_t(_summary.real_cells_number); }
+	const StringIndexer &CellsDataContainer::umi_indexer() const { load_genes(); return _umi_indexer; }
+
+	CellsDataContainer::s_i_hash_t CellsDataContainer::get_stat_by_real_cells(Stats::CellStatType type) const
+	{
+		load_cells();
+		s_i_hash_t res;
+		for (auto const &c : _cells)
+			if (c.is_real()) res[c.barcode()] = c.stats().get(type);
+		return res;
+	}
+
+	// ---- ResultsPrinter ---------------------------------------------------------------------------------------------------
+	ResultsPrinter::SparseMatrix ResultsPrinter::get_count_matrix(const CellsDataContainer &container, bool filtered) const
+	{
+		SparseMatrix m;
+		dge_handle *h = container.handle();
+		size_t n_cols = 0, nnz = 0;
+		const int which = filtered ? DGE_MATRIX_CM : DGE_MATRIX_CM_RAW;
+		if (dge_get_matrix(h, which, nullptr, nullptr, nullptr, &n_cols, &nnz) != DGE_OK) throw std::runtime_error(dge_last_error(h));
+		std::vector<int64_t> indptr(n_cols + 1);
+		std::vector<int32_t> genes(nnz), vals(nnz);
+		if (dge_get_matrix(h, which, indptr.data(), genes.data(), vals.data(), &n_cols, &nnz) != DGE_OK) throw std::runtime_error(dge_last_error(h));
+		size_t n_cells = 0;
+		const int cls = filtered ? DGE_CELLS_FILTERED : DGE_CELLS_REAL;
+		dge_get_cells(h, cls, nullptr, 0, &n_cells);
+		std::vector<dge_cell_info> info(n_cells);
+		if (n_cells) dge_get_cells(h, cls, info.data(), n_cells, &n_cells);
+		for (auto const &ci : info) m.col_names.push_back(unpack2bit(ci.barcode, container.cb_length()));
+
+		// Row numbering = first time a gene name is met while walking columns (ResultsPrinter.cpp:345-356 / :379-388).  For the
+		// filtered matrix the reference walks, per column, a std::unordered_map<std::string,size_t> built in gene-index order
+		// (Cell.cpp:54-68): reproduce that walk with the same container so row order matches under the same libstdc++.
+		const StringIndexer &gi = container.gene_indexer();
+		std::unordered_map<int32_t, int32_t> row_of_gene;
+		std::vector<int32_t> row(nnz);
+		for (size_t c = 0; c < n_cols; ++c)
+		{
+			if (filtered)
+			{
+				std::unordered_map<std::string, size_t> per_gene;
+				for (int64_t k = indptr[c]; k < indptr[c + 1]; ++k) per_gene.emplace(gi.get_value(size_t(genes[size_t(k)])), size_t(genes[size_t(k)]));
+				for (auto const &pg : per_gene)
+					if (row_of_gene.emplace(int32_t(pg.second), int32_t(row_of_gene.size())).second) m.row_names.push_back(pg.first);
+			}
+			else
+				for (int64_t k = indptr[c]; k < indptr[c + 1]; ++k)
+					if (row_of_gene.emplace(genes[size_t(k)], int32_t(row_of_gene.size())).second) m.row_names.push_back(gi.get_value(size_t(genes[size_t(k)])));
+			for (int64_t k = indptr[c]; k < indptr[c + 1]; ++k) row[size_t(k)] = row_of_gene.at(genes[size_t(k)]);
+		}
+		// Eigen::SparseMatrix::setFromTriplets (ResultsPrinter.cpp:436-437): column-major, row indices ascending inside a column
+		m.p.resize(n_cols + 1);
+		m.i.resize(nnz); m.x.resize(nnz);
+		std::vector<std::pair<int32_t, int32_t>> colbuf;
+		for (size_t c = 0; c < n_cols; ++c)
+		{
+			m.p[c] = int32_t(indptr[c]);
+			colbuf.clear();
+			for (int64_t k = indptr[c]; k < indptr[c + 1]; ++k) colbuf.emplace_back(row[size_t(k)], vals[size_t(k)]);
+			std::sort(colbuf.begin(), colbuf.end());
+			for (size_t k = 0; k < colbuf.size(); ++k) { m.i[size_t(indptr[c]) + k] = colbuf[k].first; m.x[size_t(indptr[c]) + k] = double(colbuf[k].second); }
+		}
+		m.p[n_cols] = int32_t(nnz);
+		return m;
+	}
+
+	void ResultsPrinter::save_mtx(const SparseMatrix &m, const std::string &filename_base)
+	{
+		// Matrix::writeMM(d$cm, base.mtx) + write.table(colnames / rownames)  (ResultsPrinter.cpp:81-91)
+		std::ofstream f(filename_base + ".mtx");
+		f << "%%MatrixMarket matrix coordinate real general\n";
+		f << m.row_names.size() << " " << m.col_names.size() << " " << m.i.size() << "\n";
+		for (size_t c = 0; c + 1 < m.p.size(); ++c)
+			for (int32_t k = m.p[c]; k < m.p[c + 1]; ++k) f << (m.i[size_t(k)] + 1) << " " << (c + 1) << " " << int64_t(m.x[size_t(k)]) << "\n";
+		std::ofstream fc(filename_base + ".cells.tsv");
+		for (auto const &n : m.col_names) fc << n << "\n";
+		std::ofstream fg(filename_base + ".genes.tsv");
+		for (auto const &n : m.row_names) fg << n << "\n";
+	}
+
+	// ---- minimal writer of R's serialization format (XDR, version 2), gzip-compressed like saveRDS(compress=TRUE) --------------
+	namespace
+	{
+		class RdsWriter
+		{
+			gzFile _f;
+			std::unordered_map<std::string, int> _sym; // symbol reference table (REFSXP indices start at 1)
+
+			void raw(const void *p, size_t n) { if (gzwrite(_f, p, unsigned(n)) != int(n)) throw std::runtime_error("rds: write failed"); }
+
+		public:
+			explicit RdsWriter(const std::string &fname) : _f(gzopen(fname.c_str(), "wb"))
+			{
+				if (!_f) throw std::runtime_error("can't write " + fname);
+				raw("X\n", 2);
+				i32(2); i32(0x00030600); i32(0x00020300); // format 2, written by R 3.6.0, readable from 2.3.0
+			}
+			~RdsWriter() { if (_f) gzclose(_f); }
+			void i32(int32_t v) { unsigned char b[4] = {(unsigned char)(v >> 24), (unsigned char)(v >> 16), (unsigned char)(v >> 8), (unsigned char)v}; raw(b, 4); }
+			void f64(double d) { uint64_t u; std::memcpy(&u, &d, 8); unsigned char b[8]; for (int k = 0; k < 8; ++k) b[k] = (unsigned char)(u >> (56 - 8 * k)); raw(b, 8); }
+			void flags(int type, bool obj = false, bool attr = false, bool tag = false, int levels = 0)
+			{
+				i32(type | (obj ? 1 << 8 : 0) | (attr ? 1 << 9 : 0) | (tag ? 1 << 10 : 0) | (levels << 12));
+			}
+			void charsxp(const std::string &s) { flags(9, false, false, false, 64 /* ASCII */); i32(int32_t(s.size())); raw(s.data(), s.size()); }
+			void symbol(const std::string &s)
+			{
+				auto it = _sym.find(s);
+				if (it != _sym.end()) { i32((it->second << 8) | 255); return; } // REFSXP
+				_sym.emplace(s, int(_sym.size()) + 1);
+				flags(1);
+				charsxp(s);
+			}
+			void nil() { i32(254); }
+			void tagged(const std::string &name) { flags(2, false, false, true); symbol(name); } // pairlist cell header; value follows
+			void strvec_body(const std::vector<std::string> &v) { i32(int32_t(v.size())); for (auto const &s : v) charsxp(s); }
+			void strvec(const std::vector<std::string> &v) { flags(16); strvec_body(v); }
+			void intvec(const std::vector<int32_t> &v, const std::vector<std::string> *names = nullptr)
+			{
+				flags(13, false, names != nullptr);
+				i32(int32_t(v.size()));
+				for (int32_t x : v) i32(x);
+				if (names) { tagged("names"); strvec(*names); nil(); }
+			}
+			void realvec(const std::vector<double> &v) { flags(14); i32(int32_t(v.size())); for (double x : v) f64(x); }
+			void named_strvec(const std::vector<std::string> &v, const std::vector<std::string> &names)
+			{
+				flags(16, false, true); strvec_body(v);
+				tagged("names"); strvec(names); nil();
+			}
+			void list_header(size_t n) { flags(19, false, true); i32(int32_t(n)); }
+			void list_names(const std::vector<std::string> &names) { tagged("names"); strvec(names); nil(); }
+			void dgcmatrix(const ResultsPrinter::SparseMatrix &m)
+			{
+				// S4 object of class "dgCMatrix" (package Matrix): slots i, p, Dim, Dimnames, x, factors
+				flags(25, true, true);
+				tagged("i"); intvec(m.i);
+				tagged("p"); intvec(m.p);
+				tagged("Dim"); intvec({int32_t(m.row_names.size()), int32_t(m.col_names.size())});
+				tagged("Dimnames"); flags(19); i32(2); strvec(m.row_names); strvec(m.col_names);
+				tagged("x"); realvec(m.x);
+				tagged("factors"); flags(19); i32(0);
+				tagged("class"); flags(16, false, true); strvec_body({"dgCMatrix"}); tagged("package"); strvec({"Matrix"}); nil();
+				nil();
+			}
+		};
+	}
+
+	void ResultsPrinter::save_rds(const CellsDataContainer &container, const SparseMatrix &cm, const SparseMatrix &cm_raw,
+	                              const std::string &filename_base) const
+	{
+		// d <- list(cm, cm_raw, merge_targets, aligned_reads_per_cell, aligned_umis_per_cell, requested_umis_per_cb); saveRDS(d, base.rds)
+		// (field names and meaning: ResultsPrinter.cpp:47-57; docs/dropest.rst:178-194).  The diagnostic tables that need per-chromosome
+		// statistics or per-UMI quality (reads_per_chr_per_cells, saturation_info, mean_reads_per_umi, reads_per_umi_per_cell) are not produced.
+		std::vector<std::string> mt_from, mt_to, real_names;
+		std::vector<int32_t> reads, umis, req_umis;
+		const auto &targets = container.merge_targets();
+		for (size_t i = 0; i < container.total_cells_number(); ++i)
+		{
+			const Cell &c = container.cell(i);
+			if (targets[i] != i) { mt_from.push_back(c.barcode()); mt_to.push_back(container.cell(targets[i]).barcode()); }
+			if (!c.is_real()) continue;
+			real_names.push_back(c.barcode());
+			reads.push_back(c.stats().get(Stats::TOTAL_READS_PER_CB));
+			umis.push_back(c.stats().get(Stats::TOTAL_UMIS_PER_CB));
+			req_umis.push_back(int32_t(c.requested_umis_num()));
+		}
+		RdsWriter w(filename_base + ".rds");
+		w.list_header(6);
+		w.dgcmatrix(cm);
+		w.dgcmatrix(cm_raw);
+		w.named_strvec(mt_to, mt_from);
+		w.intvec(reads, &real_names);
+		w.intvec(umis, &real_names);
+		w.intvec(req_umis, &real_names);
+		w.list_names({"cm", "cm_raw", "merge_targets", "aligned_reads_per_cell", "aligned_umis_per_cell", "requested_umis_per_cb"});
+	}
+
+	void ResultsPrinter::save_results(const CellsDataContainer &container, const std::string &filename) const
+	{
+		std::string base = filename;
+		auto pos = filename.find_last_of('.');
+		if (pos != std::string::npos && filename.substr(pos + 1) == "rds") base = filename.substr(0, pos); // extract_filename_base, :93-100
+		SparseMatrix cm = get_count_matrix(container, true), cm_raw = get_count_matrix(container, false);
+		save_rds(container, cm, cm_raw, base);
+		if (write_matrix) save_mtx(cm, base);
+	}
+}

@@ -1,0 +1,389 @@
+// Estimation.h -- host-side C++ mirror of the reference's container surface for the count-matrix hot path.
+//
+// Same namespaces, class names, method names, argument meaning and exception behaviour as the reference
+// (Estimation/CellsDataContainer.h:82-122, Cell.h, Gene.h, UMI.h, Stats.h, StringIndexer.h, ReadInfo.h,
+// Merge/MergeStrategyFactory.h:55-58), so that dropest.cpp:239-254 and ResultsPrinter-style consumers compile against it
+// unchanged.  All grouping / merging work is done by the CUDA library behind include/dropest_b200.h; this layer only packs
+// reads into 16-byte records, batches them, and materialises query results lazily.  No CPU implementation of the path lives here.
+#pragma once
+
+#include "../../include/dropest_b200.h"
+
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace Tools
+{
+	// Tools::ReadParameters (Tools/ReadParameters.h:9-50): only what the container reads.
+	class ReadParameters
+	{
+		std::string _cell_barcode, _umi, _cell_barcode_quality, _umi_quality;
+
+	public:
+		ReadParameters(const std::string &cell_barcode, const std::string &umi, const std::string &cell_barcode_quality,
+		               const std::string &umi_quality)
+			: _cell_barcode(cell_barcode), _umi(umi), _cell_barcode_quality(cell_barcode_quality), _umi_quality(umi_quality)
+		{
+			if (cell_barcode.empty() || umi.empty())
+				throw std::runtime_error("Wrong read parameters: '" + cell_barcode + "' '" + umi + "'");
+		}
+		// "prefix!CB#UMI" read-name codec (Tools/ReadParameters.cpp:42-56)
+		static ReadParameters parse_encoded_id(const std::string &encoded_id);
+		std::string encoded_id(const std::string &id_prefix) const { return id_prefix + '!' + _cell_barcode + '#' + _umi; }
+		const std::string &cell_barcode() const { return _cell_barcode; }
+		const std::string &umi() const { return _umi; }
+		const std::string &cell_barcode_quality() const { return _cell_barcode_quality; }
+		const std::string &umi_quality() const { return _umi_quality; }
+	};
+
+	unsigned edit_distance(const char *s1, const char *s2, bool skip_n = true, unsigned max_ed = 10000); // UtilFunctions.cpp:32-65
+	unsigned hamming_distance(const std::string &s1, const std::string &s2, bool skip_n = true);         // UtilFunctions.cpp:67-82
+}
+
+namespace Estimation
+{
+	class StringIndexer // StringIndexer.h
+	{
+	public:
+		using index_t = size_t;
+		using values_t = std::vector<std::string>;
+
+	private:
+		values_t _values;
+		std::unordered_map<std::string, index_t> _indexes;
+
+	public:
+		const values_t &values() const { return _values; }
+		const std::string &get_value(index_t index) const { return _values.at(index); }
+		index_t get_index(const std::string &value) const { return _indexes.at(value); }
+		index_t add(const std::string &value)
+		{
+			auto it = _indexes.emplace(value, _indexes.size());
+			if (it.second) _values.push_back(value);
+			return it.first->second;
+		}
+	};
+
+	class UMI // UMI.h
+	{
+	public:
+		class Mark
+		{
+		public:
+			enum MarkType { NONE = 0, HAS_NOT_ANNOTATED = 1, HAS_EXONS = 2, HAS_INTRONS = 4 };
+			using query_t = std::vector<Mark>;
+
+		private:
+			char _mark;
+
+		public:
+			static const std::string DEFAULT_CODE; // "eEBA" (CellsDataContainer.cpp:17)
+			explicit Mark(MarkType type = NONE) : _mark(char(type)) {}
+			void add(const Mark &mark) { _mark |= mark._mark; }
+			void add(MarkType type) { _mark |= char(type); }
+			bool check(MarkType type) const { return _mark & type; }
+			bool match(const std::vector<Mark> &match_levels) const // exact equality, UMI.cpp:76-85
+			{
+				for (auto const &m : match_levels)
+					if (_mark == m._mark) return true;
+				return false;
+			}
+			bool operator==(const MarkType &other) const { return _mark == other; }
+			bool operator==(const Mark &other) const { return _mark == other._mark; }
+			int bits() const { return _mark; }
+			static Mark get_by_code(char code);                       // UMI.cpp:123-154
+			static std::vector<Mark> get_by_code(const std::string &code);
+		};
+
+	private:
+		size_t _read_count;
+		Mark _mark;
+
+	public:
+		explicit UMI(size_t read_count = 0, Mark mark = Mark()) : _read_count(read_count), _mark(mark) {}
+		size_t read_count() const { return _read_count; }
+		const Mark &mark() const { return _mark; }
+	};
+
+	class ReadInfo // ReadInfo.h:9-24
+	{
+	public:
+		const Tools::ReadParameters params;
+		const std::string gene;
+		const std::string chromosome_name;
+		const UMI::Mark umi_mark;
+		ReadInfo(const Tools::ReadParameters &params, const std::string &gene, const std::string &chromosome_name, const UMI::Mark &umi_mark)
+			: params(params), gene(gene), chromosome_name(chromosome_name), umi_mark(umi_mark) {}
+	};
+
+	class Stats // Stats.h (per-cell counters; per-chromosome tables are not on this path yet)
+	{
+	public:
+		enum CellStatType { TOTAL_READS_PER_CB, TOTAL_UMIS_PER_CB, CELL_STAT_SIZE };
+		using stat_t = int;
+
+	private:
+		int _stat_data[CELL_STAT_SIZE];
+
+	public:
+		Stats() { _stat_data[0] = _stat_data[1] = 0; }
+		Stats(int reads, int umis) { _stat_data[TOTAL_READS_PER_CB] = reads; _stat_data[TOTAL_UMIS_PER_CB] = umis; }
+		stat_t get(CellStatType type) const { return _stat_data[type]; }
+	};
+
+	class Gene // Gene.h
+	{
+	public:
+		using umis_t = std::map<StringIndexer::index_t, UMI>;
+
+	private:
+		umis_t _umis;
+		const StringIndexer *_umi_indexer;
+		friend class CellsDataContainer;
+
+	public:
+		explicit Gene(const StringIndexer *umi_indexer = nullptr) : _umi_indexer(umi_indexer) {}
+		const UMI &at(const std::string &umi) const { return _umis.at(_umi_indexer->get_index(umi)); }
+		const umis_t &umis() const { return _umis; }
+		size_t size() const { return _umis.size(); }
+		bool has(const std::string &umi) const;
+		size_t number_of_requested_umis(const UMI::Mark::query_t &query, bool return_reads) const; // Gene.cpp:60-79
+		size_t number_of_umis(bool return_reads) const;                                             // Gene.cpp:81-93
+	};
+
+	class Cell // Cell.h
+	{
+	public:
+		using genes_t = std::map<StringIndexer::index_t, Gene>;
+		using s_ul_hash_t = std::unordered_map<std::string, size_t>;
+
+	private:
+		std::string _barcode;
+		bool _is_real = false, _is_merged = false, _is_excluded = false;
+		size_t _requested_genes_num = 0, _requested_umis_num = 0, _n_genes = 0;
+		genes_t _genes;
+		Stats _stats;
+		const StringIndexer *_gene_indexer = nullptr;
+		friend class CellsDataContainer;
+
+	public:
+		bool is_merged() const { return _is_merged; }
+		bool is_excluded() const { return _is_excluded; }
+		bool is_real() const { return _is_real; }                       // Cell.cpp:125-128
+		std::string barcode() const { return _barcode; }
+		const char *barcode_c() const { return _barcode.c_str(); }
+		size_t umis_number() const { return size_t(_stats.get(Stats::TOTAL_UMIS_PER_CB)); } // Cell.cpp:105-108
+		size_t requested_genes_num() const { return _requested_genes_num; }
+		size_t requested_umis_num() const { return _requested_umis_num; }
+		const Stats &stats() const { return _stats; }
+		const genes_t &genes() const { return _genes; }
+		size_t size() const { return _n_genes; }
+		const Gene &at(const std::string &gene) const { return _genes.at(_gene_indexer->get_index(gene)); }
+		s_ul_hash_t requested_umis_per_gene(const UMI::Mark::query_t &query_marks, bool return_reads) const; // Cell.cpp:54-68
+	};
+
+	namespace Merge
+	{
+		// Strategy objects are descriptors here: they carry exactly the constructor arguments of the reference classes and are
+		// translated into dge_config; the strategy code itself runs on the device (dropest_b200/csrc/merge.cuh + engine.cu).
+		class MergeStrategyAbstract
+		{
+			size_t _min_genes_before_merge, _min_genes_after_merge;
+
+		public:
+			MergeStrategyAbstract(size_t min_genes_before_merge, size_t min_genes_after_merge)
+				: _min_genes_before_merge(min_genes_before_merge)
+				, _min_genes_after_merge(std::max(min_genes_after_merge, min_genes_before_merge)) {} // MergeStrategyAbstract.cpp:8-11
+			virtual ~MergeStrategyAbstract() {}
+			virtual std::string merge_type() const = 0;
+			virtual void configure(dge_config &cfg) const = 0;
+			size_t min_genes_before_merge() const { return _min_genes_before_merge; }
+			size_t min_genes_after_merge() const { return _min_genes_after_merge; }
+		};
+
+		class DummyMergeStrategy : public MergeStrategyAbstract
+		{
+		public:
+			DummyMergeStrategy(size_t before, size_t after) : MergeStrategyAbstract(before, after) {}
+			std::string merge_type() const override { return "No"; }
+			void configure(dge_config &cfg) const override { cfg.merge_type = DGE_MERGE_NONE; }
+		};
+
+		namespace BarcodesParsing
+		{
+			// file name + flavour; loading/reverse-complementing happens in the library (whitelist.hpp)
+			class BarcodesParser
+			{
+			public:
+				std::string filename;
+				bool indrop;
+				BarcodesParser(const std::string &barcodes_filename, bool indrop) : filename(barcodes_filename), indrop(indrop) {}
+				virtual ~BarcodesParser() {}
+			};
+			class InDropBarcodesParser : public BarcodesParser
+			{
+			public:
+				explicit InDropBarcodesParser(const std::string &f) : BarcodesParser(f, true) {}
+			};
+			class ConstLengthBarcodesParser : public BarcodesParser
+			{
+			public:
+				explicit ConstLengthBarcodesParser(const std::string &f) : BarcodesParser(f, false) {}
+			};
+		}
+
+		class RealBarcodesMergeStrategy : public MergeStrategyAbstract
+		{
+		public:
+			using barcodes_parser_ptr = std::shared_ptr<BarcodesParsing::BarcodesParser>;
+
+		private:
+			barcodes_parser_ptr _parser;
+			unsigned _max_merge_edit_distance;
+			double _min_merge_fraction;
+
+		public:
+			RealBarcodesMergeStrategy(const barcodes_parser_ptr &barcodes_parser, size_t min_genes_before_merge, size_t min_genes_after_merge,
+			                          unsigned max_merge_edit_distance, double min_merge_fraction)
+				: MergeStrategyAbstract(min_genes_before_merge, min_genes_after_merge), _parser(barcodes_parser)
+				, _max_merge_edit_distance(max_merge_edit_distance), _min_merge_fraction(min_merge_fraction) {}
+			std::string merge_type() const override { return "Real CBs"; }
+			void configure(dge_config &cfg) const override;
+		};
+
+		namespace UMIs
+		{
+			class MergeUMIsStrategyAbstract
+			{
+			public:
+				virtual ~MergeUMIsStrategyAbstract() {}
+				virtual void configure(dge_config &cfg) const = 0;
+			};
+			class MergeUMIsStrategySimple : public MergeUMIsStrategyAbstract
+			{
+				unsigned _max_merge_distance;
+
+			public:
+				explicit MergeUMIsStrategySimple(unsigned max_merge_distance) : _max_merge_distance(max_merge_distance) {}
+				void configure(dge_config &cfg) const override
+				{
+					cfg.umi_merge_type = DGE_UMI_MERGE_SIMPLE;
+					cfg.max_umi_merge_edit_distance = _max_merge_distance;
+				}
+			};
+		}
+
+		// MergeStrategyFactory (MergeStrategyFactory.cpp:23-126) with the XML values passed in directly (no boost::property_tree here)
+		class MergeStrategyFactory
+		{
+		public:
+			std::string merge_type = "none", barcodes_type = "indrop", barcodes_filename;
+			size_t min_genes_before_merge = 10, min_genes_after_merge = 10;
+			unsigned max_merge_edit_distance = 2, max_umi_merge_edit_distance = 1;
+			double min_merge_fraction = 0.2, max_merge_prob = 1e-4, max_real_cb_merge_prob = 1e-7, umi_merge_mult = 2;
+
+			std::shared_ptr<MergeStrategyAbstract> get_cb_strat(bool merge_tags, bool use_poisson) const;
+			std::shared_ptr<UMIs::MergeUMIsStrategyAbstract> get_umi(bool advanced) const;
+		};
+	}
+
+	class CellsDataContainer // CellsDataContainer.h:33-122
+	{
+	public:
+		using s_ul_hash_t = std::unordered_map<std::string, size_t>;
+		using s_i_hash_t = std::unordered_map<std::string, int>;
+		using ids_t = std::vector<size_t>;
+		using names_t = std::vector<std::string>;
+
+	private:
+		std::shared_ptr<Merge::MergeStrategyAbstract> _merge_strategy;
+		std::shared_ptr<Merge::UMIs::MergeUMIsStrategyAbstract> _umi_merge_strategy;
+		const int _max_cells_num;
+		const UMI::Mark::query_t _query_marks;
+		bool _is_initialized = false, _is_merged = false;
+		int _device;
+		bool _reads_output;
+
+		dge_handle *_h = nullptr;
+		unsigned _cb_len = 0, _umi_len = 0;
+		std::vector<dge_record16> _batch; // pending records (flushed in blocks of _batch_capacity)
+		size_t _batch_capacity;
+		uint64_t _n_records = 0;
+		std::vector<ReadInfo> _deferred; // reads buffered until the first flush fixes cb/umi lengths and the gene-id space
+
+		StringIndexer _gene_indexer; // built on the host at ingest: ids are first-seen ranks like the reference's
+		mutable StringIndexer _umi_indexer;
+
+		// lazily materialised query state
+		mutable bool _cells_loaded = false, _genes_loaded = false;
+		mutable std::vector<Cell> _cells;
+		mutable std::unordered_map<std::string, size_t> _cell_ids_by_cb;
+		mutable ids_t _filtered_cells, _merge_targets;
+		mutable dge_summary _summary;
+
+		void ensure_handle();
+		void flush();
+		void check(int rc) const;
+		void load_cells() const;
+		void load_genes() const;
+
+	public:
+		// `n_genes_hint`: capacity of the gene-id space given to the device (genes are still indexed first-seen on the host)
+		CellsDataContainer(const std::shared_ptr<Merge::MergeStrategyAbstract> &merge_strategy,
+		                   const std::shared_ptr<Merge::UMIs::MergeUMIsStrategyAbstract> &umi_merge_strategy,
+		                   const std::vector<UMI::Mark> &gene_match_levels, bool save_umi_merge_targets = false, int max_cells_num = -1,
+		                   int device = 0, size_t n_genes_hint = 1u << 17, bool reads_output = false);
+		~CellsDataContainer();
+		CellsDataContainer(const CellsDataContainer &) = delete;
+		CellsDataContainer &operator=(const CellsDataContainer &) = delete;
+
+		void add_record(const ReadInfo &read_info);   // throws std::runtime_error("Container is already initialized") after set_initialized
+		void set_initialized();                        // throws if called twice
+		void merge_and_filter();                       // throws std::runtime_error("You must initialize container")
+
+		size_t total_cells_number() const;
+		size_t cell_id_by_cb(const std::string &barcode) const; // throws std::out_of_range
+		const ids_t &filtered_cells() const;
+		const ids_t &merge_targets() const;
+		const UMI::Mark::query_t &gene_match_level() const { return _query_marks; }
+		s_i_hash_t get_stat_by_real_cells(Stats::CellStatType type) const;
+		const Cell &cell(size_t index) const;
+		size_t intergenic_reads_num() const;
+		size_t has_exon_reads_num() const;
+		size_t has_intron_reads_num() const;
+		size_t has_not_annotated_reads_num() const;
+		size_t real_cells_number() const;
+		std::string merge_type() const { return _merge_strategy->merge_type(); }
+		const StringIndexer &gene_indexer() const { return _gene_indexer; }
+		const StringIndexer &umi_indexer() const; // UMI strings of the held UMIs (ids in (cell, gene, umi) order, not first-seen)
+
+		// direct access for high-volume consumers (ResultsPrinter): matrices straight from the device, no per-cell maps
+		dge_handle *handle() const { return _h; }
+		bool reads_output() const { return _reads_output; }
+		unsigned cb_length() const { return _cb_len; }
+	};
+
+	// ResultsPrinter (ResultsPrinter.cpp:23-91,334-453): count matrices -> MatrixMarket + cells/genes tsv and an R-readable .rds
+	class ResultsPrinter
+	{
+		bool write_matrix, reads_output;
+
+	public:
+		ResultsPrinter(bool write_matrix, bool reads_output) : write_matrix(write_matrix), reads_output(reads_output) {}
+		void save_results(const CellsDataContainer &container, const std::string &filename) const;
+
+		struct SparseMatrix // dgCMatrix layout: column-compressed, rows ascending inside a column
+		{
+			std::vector<int32_t> i, p;
+			std::vector<double> x;
+			std::vector<std::string> row_names, col_names;
+		};
+		SparseMatrix get_count_matrix(const CellsDataContainer &container, bool filtered) const; // :334-396 incl. the first-met row order
+		static void save_mtx(const SparseMatrix &m, const std::string &filename_base);            // :81-91
+		void save_rds(const CellsDataContainer &container, const SparseMatrix &cm, const SparseMatrix &cm_raw, const std::string &filename_base) const;
+	};
+}

@@ -1,0 +1,128 @@
+// tests/cpp/test_facade.cpp -- the reference's own container tests (Tests/TestEstimation.cpp), re-typed against the host-side
+// mirror dropest_b200/host/Estimation.h.  Same calls, same expectations; Boost.Test is absent so checks are plain macros.
+// Needs a CUDA device (run by tests/test_facade.py under -m gpu).  usage: test_facade <whitelist test_est> <out dir>
+#include "../../dropest_b200/host/Estimation.h"
+
+#include <iostream>
+
+using namespace Estimation;
+using Mark = UMI::Mark;
+
+static int failures = 0;
+#define CHECK(cond) do { if (!(cond)) { std::cerr << "CHECK failed: " #cond " (line " << __LINE__ << ")\n"; ++failures; } } while (0)
+#define CHECK_EQUAL(a, b) do { auto _a = (a); auto _b = (b); if (!(_a == _b)) { std::cerr << "CHECK_EQUAL failed: " #a " == " #b " (" << _a << " vs " << _b << ", line " << __LINE__ << ")\n"; ++failures; } } while (0)
+#define CHECK_THROW(expr, ex) do { bool _t = false; try { expr; } catch (ex &) { _t = true; } if (!_t) { std::cerr << "CHECK_THROW failed: " #expr " (line " << __LINE__ << ")\n"; ++failures; } } while (0)
+
+static ReadInfo read_info(const std::string &cell_barcode, const std::string &umi, const std::string &gene,
+                          const std::string &chr_name = "", const Mark &mark = Mark(Mark::HAS_EXONS))
+{
+	return ReadInfo(Tools::ReadParameters(cell_barcode, umi, "", umi), gene, chr_name, mark);
+}
+
+int main(int argc, char **argv)
+{
+	if (argc < 3) { std::cerr << "usage: test_facade <whitelist> <out dir>\n"; return 2; }
+	const std::string whitelist = argv[1], out_dir = argv[2];
+	try
+	{
+		// Fixture, Tests/TestEstimation.cpp:33-80
+		auto barcodes_parser = std::shared_ptr<Merge::BarcodesParsing::BarcodesParser>(new Merge::BarcodesParsing::InDropBarcodesParser(whitelist));
+		auto real_cb_strat = std::make_shared<Merge::RealBarcodesMergeStrategy>(barcodes_parser, 0, 0, 7, 0);
+		auto umi_merge_strat = std::make_shared<Merge::UMIs::MergeUMIsStrategySimple>(1);
+		auto any_mark = Mark::get_by_code(Mark::DEFAULT_CODE);
+		CellsDataContainer container_full(real_cb_strat, umi_merge_strat, any_mark, false, -1, 0, 64);
+		static const char *reads[][3] = {
+			{"AAATTAGGTCCA", "AAACCT", "Gene1"}, {"AAATTAGGTCCA", "CCCCCT", "Gene2"}, {"AAATTAGGTCCA", "ACCCCT", "Gene3"},
+			{"AAATTAGGTCCA", "ACCCCT", "Gene4"}, {"AAATTAGGTCCC", "CAACCT", "Gene1"}, {"AAATTAGGTCCC", "CAACCT", "Gene10"},
+			{"AAATTAGGTCCC", "CAACCT", "Gene20"}, {"AAATTAGGTCCG", "CAACCT", "Gene1"}, {"AAATTAGGTCGG", "AAACCT", "Gene1"},
+			{"AAATTAGGTCGG", "CCCCCT", "Gene2"}, {"CCCTTAGGTCCA", "CCATTC", "Gene3"}, {"CCCTTAGGTCCA", "CCCCCT", "Gene2"},
+			{"CCCTTAGGTCCA", "ACCCCT", "Gene3"}, {"CAATTAGGTCCG", "CAACCT", "Gene1"}, {"CAATTAGGTCCG", "AAACCT", "Gene1"},
+			{"CAATTAGGTCCG", "CCCCCT", "Gene2"}, {"AAAAAAAAAAAA", "CCCCCT", "Gene2"}};
+		for (auto const &r : reads) container_full.add_record(read_info(r[0], r[1], r[2]));
+		CHECK_THROW(container_full.merge_and_filter(), std::runtime_error); // "You must initialize container"
+		container_full.set_initialized();
+		CHECK_THROW(container_full.add_record(read_info("AAATTAGGTCCA", "AAACCT", "Gene1")), std::runtime_error);
+		CHECK_THROW(container_full.set_initialized(), std::runtime_error);
+
+		// testMergeByRealBarcodes, Tests/TestEstimation.cpp:237-280
+		container_full.merge_and_filter();
+		CHECK_EQUAL(container_full.total_cells_number(), size_t(7));
+		CHECK_EQUAL(container_full.filtered_cells().size(), size_t(2));
+		auto &cell0 = container_full.cell(container_full.filtered_cells()[0]);
+		auto &cell1 = container_full.cell(container_full.filtered_cells()[1]);
+		CHECK_EQUAL(cell0.size(), size_t(3));
+		CHECK_EQUAL(cell1.size(), size_t(4));
+		CHECK_EQUAL(cell0.at("Gene1").size(), size_t(1));
+		CHECK_EQUAL(cell0.at("Gene1").at("CAACCT").read_count(), size_t(2));
+		CHECK_EQUAL(cell1.at("Gene1").size(), size_t(2));
+		CHECK_EQUAL(cell1.at("Gene1").at("AAACCT").read_count(), size_t(3));
+		CHECK_EQUAL(cell1.at("Gene2").size(), size_t(1));
+		CHECK_EQUAL(cell1.at("Gene2").at("CCCCCT").read_count(), size_t(4));
+		CHECK_EQUAL(cell1.at("Gene3").size(), size_t(2));
+		CHECK_EQUAL(cell1.at("Gene3").at("ACCCCT").read_count(), size_t(2));
+		CHECK_EQUAL(cell1.at("Gene3").at("CCATTC").read_count(), size_t(1));
+		CHECK(!container_full.cell(0).is_merged());
+		CHECK(!container_full.cell(1).is_merged());
+		CHECK(container_full.cell(2).is_merged());
+		CHECK(container_full.cell(3).is_merged());
+		CHECK(container_full.cell(4).is_merged());
+		CHECK(container_full.cell(5).is_merged());
+		CHECK(!container_full.cell(6).is_merged());
+		size_t excluded_num = 0;
+		for (size_t i = 0; i < container_full.total_cells_number(); ++i) excluded_num += container_full.cell(i).is_excluded();
+		CHECK_EQUAL(excluded_num, size_t(1));
+		CHECK_EQUAL(container_full.cell_id_by_cb("CCCTTAGGTCCA"), size_t(4));
+		CHECK_THROW(container_full.cell_id_by_cb("GGGGGGGGGGGG"), std::out_of_range);
+		CHECK_EQUAL(container_full.merge_targets()[5], size_t(0));
+		CHECK_EQUAL(container_full.gene_indexer().get_value(0), std::string("Gene1"));
+		CHECK_EQUAL(container_full.merge_type(), std::string("Real CBs"));
+
+		// testUmiExclusion, Tests/TestEstimation.cpp:369-397 (Mark accumulation + exact-match query semantics)
+		{
+			CellsDataContainer container(real_cb_strat, umi_merge_strat, Mark::get_by_code("e"), false, -1, 0, 64);
+			container.add_record(read_info("AAATTAGGTCCA", "AAACCT", "Gene1"));
+			container.add_record(read_info("AAATTAGGTCCA", "CCCCCT", "Gene2"));
+			container.add_record(read_info("AAATTAGGTCCA", "ACCCCT", "Gene3"));
+			container.add_record(read_info("AAATTAGGTCCA", "ACCCCT", "Gene4"));
+			container.add_record(read_info("AAATTAGGTCCA", "TTTTTT", "Gene3", "chr1", Mark(Mark::HAS_NOT_ANNOTATED)));
+			container.add_record(read_info("AAATTAGGTCCA", "ACCCCT", "Gene4", "chr1", Mark(Mark::HAS_NOT_ANNOTATED)));
+			container.set_initialized();
+			container.merge_and_filter();
+			CHECK(container.cell(0).at("Gene3").at("TTTTTT").mark().check(Mark::HAS_NOT_ANNOTATED));
+			CHECK(container.cell(0).at("Gene4").at("ACCCCT").mark().check(Mark::HAS_NOT_ANNOTATED));
+			auto requested = container.cell(0).requested_umis_per_gene(container.gene_match_level(), true);
+			CHECK_EQUAL(requested.at("Gene3"), size_t(1));
+			CHECK_THROW(requested.at("Gene4"), std::out_of_range);
+			CHECK_EQUAL(container.cell(0).at("Gene4").at("ACCCCT").read_count(), size_t(2));
+		}
+
+		// testEditDistance, Tests/TestTools.cpp:47-54 ; testReadParams :56-87 (codec part)
+		CHECK_EQUAL(Tools::edit_distance("ATTTTC", "ATTTGC"), 1u);
+		CHECK_EQUAL(Tools::edit_distance("ATTTTCC", "ATTTGNC"), 1u);
+		CHECK_EQUAL(Tools::edit_distance("ATTTTCC", "ATTTGNC", false), 2u);
+		CHECK_EQUAL(Tools::edit_distance("ATTTTCC", "ATTTGTC"), 2u);
+		CHECK_EQUAL(Tools::edit_distance("ATTTTCC", "ATTTTCC"), 0u);
+		auto rp = Tools::ReadParameters::parse_encoded_id("@111!ATTTGC#ATATC");
+		CHECK_EQUAL(rp.cell_barcode(), std::string("ATTTGC"));
+		CHECK_EQUAL(rp.umi(), std::string("ATATC"));
+		CHECK_THROW(Tools::ReadParameters::parse_encoded_id("ATTTG#ATAT"), std::runtime_error);
+
+		// ResultsPrinter::save_results (ResultsPrinter.cpp:23-91): files consumed by dropReport / dropestr
+		ResultsPrinter printer(true, false);
+		printer.save_results(container_full, out_dir + "/cell.counts.rds");
+		auto cm = printer.get_count_matrix(container_full, true);
+		CHECK_EQUAL(cm.col_names.size(), size_t(2));
+		CHECK_EQUAL(cm.col_names[0], std::string("AAATTAGGTCCC"));
+		CHECK_EQUAL(cm.col_names[1], std::string("AAATTAGGTCCA"));
+		double total = 0;
+		for (double v : cm.x) total += v;
+		CHECK_EQUAL(total, 3.0 + 6.0); // cell 1: 3 genes x 1 UMI ; merged cell 0: Gene1 2, Gene2 1, Gene3 2, Gene4 1
+	}
+	catch (std::exception &e)
+	{
+		std::cerr << "unexpected exception: " << e.what() << "\n";
+		return 1;
+	}
+	std::cout << (failures ? "FAILED" : "OK") << " (" << failures << " failures)\n";
+	return failures ? 1 : 0;
+}

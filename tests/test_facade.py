@@ -1,0 +1,109 @@
+"""The host-side C++ mirror of CellsDataContainer / ResultsPrinter (dropest_b200/host) running the reference's own test
+sequence on the GPU, and a structural check of the files it writes (.rds parsed back by a minimal reader, .mtx, tsv)."""
+import gzip
+import os
+import struct
+import subprocess
+
+import pytest
+
+import parity_utils as pu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "dropest_b200", "lib", "test_facade")
+
+
+class Rds:
+    """Just enough of R's XDR serialization (version 2) to read back what ResultsPrinter::save_rds writes."""
+
+    def __init__(self, data):
+        self.d, self.o, self.syms = data, 0, []
+
+    def i32(self):
+        v = struct.unpack(">i", self.d[self.o:self.o + 4])[0]
+        self.o += 4
+        return v
+
+    def item(self):
+        fl = self.i32()
+        t = fl & 255
+        has_attr, has_tag = bool(fl & (1 << 9)), bool(fl & (1 << 10))
+        if t == 254:
+            return None
+        if t == 255:
+            return self.syms[(fl >> 8) - 1]
+        if t == 1:
+            s = self.item()
+            self.syms.append(s)
+            return s
+        if t == 9:
+            n = self.i32()
+            s = self.d[self.o:self.o + n].decode()
+            self.o += n
+            return s
+        if t == 2:  # pairlist -> dict
+            out = {}
+            while True:
+                tag = self.item() if has_tag else None
+                out[tag] = self.item()
+                fl = self.i32()
+                if (fl & 255) == 254:
+                    return out
+                assert (fl & 255) == 2
+                has_tag = bool(fl & (1 << 10))
+        if t in (13, 14, 16, 19):
+            n = self.i32()
+            if t == 13:
+                v = list(struct.unpack(f">{n}i", self.d[self.o:self.o + 4 * n])); self.o += 4 * n
+            elif t == 14:
+                v = list(struct.unpack(f">{n}d", self.d[self.o:self.o + 8 * n])); self.o += 8 * n
+            else:
+                v = [self.item() for _ in range(n)]
+            attr = self.item() if has_attr else None
+            return {"v": v, "attr": attr} if attr else v
+        if t == 25:
+            return {"S4": self.item()}
+        raise ValueError(f"unexpected SEXP type {t}")
+
+
+@pytest.mark.gpu
+def test_reference_container_tests_through_the_cpp_facade(tmp_path):
+    assert os.path.exists(BIN), "build the facade test first: python -c 'import __graft_entry__ as g; g.build()'"
+    r = subprocess.run([BIN, pu.WL_TEST_EST, str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "OK (0 failures)" in r.stdout
+    # ---- MatrixMarket + names (ResultsPrinter.cpp:81-91)
+    lines = open(tmp_path / "cell.counts.mtx").read().split("\n")
+    assert lines[0].startswith("%%MatrixMarket matrix coordinate")
+    nrow, ncol, nnz = map(int, lines[1].split())
+    assert (ncol, nnz) == (2, 7) and nrow == 6
+    cells = open(tmp_path / "cell.counts.cells.tsv").read().split()
+    genes = open(tmp_path / "cell.counts.genes.tsv").read().split()
+    assert cells == ["AAATTAGGTCCC", "AAATTAGGTCCA"] and sorted(genes) == sorted(["Gene1", "Gene10", "Gene20", "Gene2", "Gene3", "Gene4"])
+    trip = [tuple(map(int, l.split())) for l in lines[2:2 + nnz]]
+    assert all(1 <= i <= nrow and 1 <= j <= ncol for i, j, _ in trip)
+    assert [t[1] for t in trip] == sorted(t[1] for t in trip)  # column-major
+    by = {(genes[i - 1], cells[j - 1]): v for i, j, v in trip}
+    assert by[("Gene1", "AAATTAGGTCCA")] == 2 and by[("Gene3", "AAATTAGGTCCA")] == 2 and by[("Gene10", "AAATTAGGTCCC")] == 1
+    # ---- .rds: list(cm = dgCMatrix, cm_raw, merge_targets, ...), the contract of docs/dropest.rst:178-194
+    raw = gzip.open(tmp_path / "cell.counts.rds").read()
+    assert raw[:2] == b"X\n"
+    rd = Rds(raw)
+    rd.o = 2
+    assert rd.i32() == 2
+    rd.i32(); rd.i32()
+    d = rd.item()
+    names = d["attr"]["names"]
+    assert names == ["cm", "cm_raw", "merge_targets", "aligned_reads_per_cell", "aligned_umis_per_cell", "requested_umis_per_cb"]
+    cm = d["v"][0]["S4"]
+    assert cm["class"]["v"] == ["dgCMatrix"] and cm["class"]["attr"]["package"] == ["Matrix"]
+    assert cm["Dim"] == [6, 2] and cm["p"] == [0, 3, 7] and len(cm["i"]) == 7 and sum(cm["x"]) == 9.0
+    assert cm["Dimnames"][1] == cells and cm["Dimnames"][0] == genes
+    for c in range(2):
+        col = cm["i"][cm["p"][c]:cm["p"][c + 1]]
+        assert col == sorted(col)  # row indices ascending inside a column (dgCMatrix invariant)
+    mt = d["v"][2]
+    assert dict(zip(mt["attr"]["names"], mt["v"])) == {"AAATTAGGTCCG": "AAATTAGGTCCC", "AAATTAGGTCGG": "AAATTAGGTCCA",
+                                                      "CCCTTAGGTCCA": "AAATTAGGTCCA", "CAATTAGGTCCG": "AAATTAGGTCCA"}
+    umis = d["v"][4]
+    assert dict(zip(umis["attr"]["names"], umis["v"])) == {"AAATTAGGTCCA": 12, "AAATTAGGTCCC": 4}
