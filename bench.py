@@ -201,7 +201,7 @@ def main():
 
     cfg = dg.Config(cb_len=16, umi_len=12, n_genes=WORKLOAD["n_genes"], device=dev, merge_type=dg.MERGE_REAL, barcodes_type=dg.BARCODES_CONST,
                     barcodes_file=wl_path, min_genes_before_merge=WORKLOAD["min_genes_before"], min_genes_after_merge=WORKLOAD["min_genes_after"],
-                    max_cb_merge_edit_distance=WORKLOAD["max_cb_ed"], min_merge_fraction=WORKLOAD["min_frac"])
+                    max_cb_merge_edit_distance=WORKLOAD["max_cb_ed"], min_merge_fraction=WORKLOAD["min_frac"], sharded=world > 1)
     cont = dg.Container(cfg)
     stream = torch.cuda.current_stream()
     cont.set_stream(stream.cuda_stream)
@@ -209,29 +209,16 @@ def main():
 
     routed = recv = None
     if world > 1:
-        import ctypes as C
+        from dropest_b200 import dist as dgdist
 
         routed = torch.empty_like(raw)
         recv = torch.empty(int(n * 1.25) * 16 + 4096, dtype=torch.uint8, device=f"cuda:{dev}")
 
     def exchange():
         """route by barcode hash (our kernel) + ONE all-to-all-v over NCCL; returns (ptr, count) of the records this rank owns"""
-        import ctypes as C
-        import torch.distributed as dist
-
-        counts = np.zeros(world, dtype=np.uint64)
-        rc = lib.dge_route_by_barcode_device(dev, C.c_void_p(raw.data_ptr()), n, world, C.c_void_p(routed.data_ptr()), counts.ctypes.data,
-                                             C.c_void_p(stream.cuda_stream))
-        assert rc == 0
-        send = torch.tensor(counts.astype(np.int64), device=f"cuda:{dev}")
-        got = torch.empty_like(send)
-        dist.all_to_all_single(got, send)
-        in_split = [int(x) * 16 for x in counts]
-        out_split = [int(x) * 16 for x in got.cpu().tolist()]
-        total = sum(out_split)
-        assert total <= recv.numel(), "receive buffer too small"
-        dist.all_to_all_single(recv[:total], routed, output_split_sizes=out_split, input_split_sizes=in_split)
-        return recv.data_ptr(), total // 16
+        counts = dgdist.route_device(dev, raw.data_ptr(), n, world, routed.data_ptr(), stream.cuda_stream)
+        got, cnt = dgdist.exchange(routed, counts, recv=recv)
+        return got.data_ptr(), cnt
 
     def step():
         cont.reset()
@@ -335,7 +322,9 @@ def main():
             "roofline_path": {"bound": "hbm", "achieved": path_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": path_gbs / hbm_peak,
                               "bytes_per_read": ALGO_BYTES_PER_READ, "note": "whole hot path per GPU, BASELINE.md definition"},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
-            "result": {k: summary[k] for k in ("total_cells_number", "real_cells_number", "filtered_cells_number", "n_umigs", "cm_nnz", "n_merged", "n_excluded")}}
+            "result": {k: summary[k] for k in ("total_cells_number", "real_cells_number", "filtered_cells_number", "n_umigs", "cm_nnz", "n_merged", "n_excluded", "n_unresolved")}}
+    if world > 1:
+        line["config"]["merge"] += "; RANK-LOCAL candidates only (cross-rank CB merge not implemented: see result.n_unresolved on rank 0)"
     if world == 1 and not args.no_cpu_baseline:
         try:
             cb = cpu_reference_run(wl_path, wl_parts, args.cpu_sample_reads)

@@ -59,7 +59,7 @@ class _Config(C.Structure):
         ("max_cb_merge_edit_distance", C.c_uint32), ("max_umi_merge_edit_distance", C.c_uint32),
         ("min_merge_fraction", C.c_double), ("max_merge_prob", C.c_double), ("max_real_merge_prob", C.c_double),
         ("umi_merge_mult", C.c_double), ("query_mark_mask", C.c_uint32), ("max_cells", C.c_int32),
-        ("reads_output", C.c_uint32), ("reserved0", C.c_uint32), ("barcodes_file", C.c_char_p),
+        ("reads_output", C.c_uint32), ("sharded", C.c_uint32), ("barcodes_file", C.c_char_p),
         ("max_barcodes_hint", C.c_uint64),
     ]
 
@@ -68,7 +68,7 @@ class _Summary(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_reads", "total_cells_number", "real_cells_number", "filtered_cells_number", "n_genes_seen", "n_umigs",
         "intergenic_reads", "has_exon_reads", "has_intron_reads", "has_not_annotated_reads", "cm_nnz", "cm_raw_nnz",
-        "n_merged", "n_excluded")]
+        "n_merged", "n_excluded", "n_unresolved")]
 
 
 class _Timings(C.Structure):
@@ -182,6 +182,7 @@ class Config:
     max_cells: int = -1
     reads_output: bool = False
     max_barcodes_hint: int = 0
+    sharded: bool = False
     _keep: list = field(default_factory=list, repr=False)
 
     def to_c(self) -> _Config:
@@ -195,6 +196,7 @@ class Config:
             setattr(c, name, getattr(self, name))
         c.query_mark_mask = marks_to_mask(self.marks)
         c.reads_output = 1 if self.reads_output else 0
+        c.sharded = 1 if self.sharded else 0
         if self.barcodes_file:
             b = self.barcodes_file.encode()
             self._keep.append(b)

@@ -108,7 +108,7 @@ struct dge_handle
     std::vector<uint32_t> filtered;        // indices into real, ascending compare_cells
     std::vector<int32_t> gene_order;       // gene ids in first-seen order
     std::vector<std::pair<uint32_t, uint32_t>> merge_events; // (src real idx, dst real idx) in application order
-    uint64_t n_merged = 0, n_excluded = 0;
+    uint64_t n_merged = 0, n_excluded = 0, n_unresolved = 0;
     Whitelist wl;
     bool wl_fast = false;
     DevBuf wl_tokens[WL_MAX_PARTS];
@@ -573,6 +573,7 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
     cudaStream_t st = h->stream;
     const size_t n = h->real.size();
     target.assign(n, -2);
+    h->n_unresolved = 0;
     if (n == 0) return;
     std::vector<uint32_t> &pc_to_real = h->h_pc_to_real;
     pc_to_real.assign(size_t(h->n_pc) + 1, NONE32);
@@ -633,6 +634,11 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
     {
         uint32_t c = 0;
         if (nb_count[i] == NB_SELF) target[i] = long(i);
+        else if (nb_count[i] == NB_SLOW && h->cfg.sharded)
+        {   // candidates may live on another shard: never guess, leave the cell as it is and report it
+            target[i] = long(i);
+            ++h->n_unresolved;
+        }
         else if (nb_count[i] == NB_SLOW)
         {
             auto &lst = slow_lists[i];
@@ -1104,7 +1110,7 @@ int dge_reset(dge_handle *h)
         h->chunks.clear();
         h->n_chunk_counters = 0; h->n_reads = 0; h->n_keys = 0; h->n_u = h->n_cg = h->n_pc = 0;
         h->real.clear(); h->filtered.clear(); h->gene_order.clear(); h->merge_events.clear();
-        h->n_merged = h->n_excluded = 0; h->total_cells = 0;
+        h->n_merged = h->n_excluded = h->n_unresolved = 0; h->total_cells = 0;
         h->cm.built = h->cm_raw.built = false;
         h->timings = dge_timings{}; h->sc_stats = SortCombineStats{}; h->launches = 0;
         h->state = 0;
@@ -1147,6 +1153,7 @@ int dge_get_summary(dge_handle *h, dge_summary *out)
     out->cm_raw_nnz = h->cm_raw.built ? h->cm_raw.nnz : 0;
     out->n_merged = h->n_merged;
     out->n_excluded = h->n_excluded;
+    out->n_unresolved = h->n_unresolved;
     return DGE_OK;
 }
 

@@ -90,7 +90,9 @@ typedef struct dge_config {
                                    Default "eEBA" = marks {2,3,6,7} = 0xCC (CellsDataContainer.cpp:17, UMI.cpp:123-154) */
     int32_t  max_cells;         /* -C: keep the top N filtered cells; <= 0 keeps all (CellsDataContainer.cpp:268-272) */
     uint32_t reads_output;      /* -R: matrix values are read counts instead of UMI counts (ResultsPrinter.cpp:345) */
-    uint32_t reserved0;
+    uint32_t sharded;           /* 1 = this handle holds one barcode-hash shard of a multi-GPU run: a cell whose whitelist merge
+                                   candidates are not on this shard is left unmerged and counted in dge_summary.n_unresolved
+                                   (cross-rank CB merge is not implemented yet); 0 = the handle sees every barcode */
     const char *barcodes_file;  /* whitelist in the reference's own file format (BarcodesParser.cpp:117-144); NULL/"" = none */
     uint64_t max_barcodes_hint; /* upper bound on distinct barcodes, 0 = automatic */
 } dge_config;
@@ -113,6 +115,7 @@ typedef struct dge_summary {
     uint64_t cm_raw_nnz;            /* non-zeros of `cm_raw`                    */
     uint64_t n_merged;              /* cells merged into another cell (MergeStrategyBase.cpp:53) */
     uint64_t n_excluded;            /* cells excluded by the merge      (MergeStrategyBase.cpp:54) */
+    uint64_t n_unresolved;          /* sharded runs only: cells whose merge candidates live on another shard (left unmerged) */
 } dge_summary;
 
 /* Per-cell row returned by dge_get_cells; one per requested cell, in the requested order. */

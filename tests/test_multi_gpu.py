@@ -1,0 +1,91 @@
+"""2-GPU run (NCCL): barcode-hash shard + all-to-all + per-rank grouping must reproduce the single-GPU count matrix
+(merge = none: every barcode lives wholly on one rank, so per-rank results are exact).  Skipped with fewer than 2 GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import parity_utils as pu
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _spec(n_total):
+    from dropest_b200.synth import SynthSpec, read_whitelist
+
+    return SynthSpec(n_reads=n_total, n_cells=80, n_genes=150, cb_len=16, umi_len=10, whitelist_parts=read_whitelist(pu.WL_SYNTH_7_9), seed=9)
+
+
+def _triplets(c, dg):
+    cells = c.cells(dg.CELLS_REAL)
+    indptr, genes, vals = c.matrix(dg.MATRIX_CM_RAW)
+    col = np.repeat(np.arange(indptr.shape[0] - 1), np.diff(indptr))
+    return np.stack([cells["barcode"][col].astype(np.uint64), genes.astype(np.uint64), vals.astype(np.uint64)], axis=1)
+
+
+def _worker(rank, world, port, n_total, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    import dropest_b200 as dg
+    from dropest_b200 import dist as dgdist
+    from dropest_b200.synth import SynthTables
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    per = n_total // world
+    raw = torch.empty(per * 16, dtype=torch.uint8, device=f"cuda:{rank}")
+    SynthTables(_spec(n_total)).generate_device(rank, rank * per, per, raw.data_ptr())
+    routed = torch.empty_like(raw)
+    counts = dgdist.route_device(rank, raw.data_ptr(), per, world, routed.data_ptr())
+    got, cnt = dgdist.exchange(routed, counts)
+    torch.cuda.synchronize()
+    c = dg.Container(dg.Config(cb_len=16, umi_len=10, n_genes=150, device=rank, merge_type=dg.MERGE_NONE, min_genes_before_merge=5,
+                               min_genes_after_merge=5, sharded=True, max_barcodes_hint=1 << 16))
+    c.add_batch_device(got.data_ptr(), cnt, keepalive=got)
+    c.set_initialized()
+    c.merge_and_filter()
+    np.save(os.path.join(out_dir, f"trip{rank}.npy"), _triplets(c, dg))
+    np.save(os.path.join(out_dir, f"sum{rank}.npy"), np.array([c.summary()[k] for k in ("total_cells_number", "real_cells_number", "intergenic_reads", "n_umigs")]))
+    c.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_shards_reproduce_single_gpu_matrix(tmp_path):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    import dropest_b200 as dg
+    from dropest_b200.synth import SynthTables
+
+    world, n_total = 2, 200_000
+    mp.spawn(_worker, args=(world, _free_port(), n_total, str(tmp_path)), nprocs=world, join=True)
+    recs = SynthTables(_spec(n_total)).generate_host(0, n_total)
+    c = dg.Container(dg.Config(cb_len=16, umi_len=10, n_genes=150, merge_type=dg.MERGE_NONE, min_genes_before_merge=5, min_genes_after_merge=5,
+                               max_barcodes_hint=1 << 16))
+    c.add_batch(recs)
+    c.set_initialized()
+    c.merge_and_filter()
+    single = _triplets(c, dg)
+    s = c.summary()
+    c.close()
+    multi = np.concatenate([np.load(tmp_path / f"trip{r}.npy") for r in range(world)])
+    order = lambda t: t[np.lexsort((t[:, 1], t[:, 0]))]
+    np.testing.assert_array_equal(order(multi), order(single))
+    sums = sum(np.load(tmp_path / f"sum{r}.npy") for r in range(world))
+    assert list(sums) == [s["total_cells_number"], s["real_cells_number"], s["intergenic_reads"], s["n_umigs"]]
