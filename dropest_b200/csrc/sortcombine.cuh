@@ -391,8 +391,11 @@ template <bool HAS_VAL>
 __global__ void __launch_bounds__(SC_DEDUP_THREADS) k_dedup_sort(uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals_in,
                                                                  uint32_t *__restrict__ uvals, const uint32_t *__restrict__ sub_off,
                                                                  const uint32_t *__restrict__ n_sub_ptr, uint32_t *__restrict__ ucount,
-                                                                 int *__restrict__ overflow, const int SC_HT)
+                                                                 int *__restrict__ overflow, const int SC_HT,
+                                                                 const uint32_t n_min, const uint32_t n_max)
 {
+    // size classes: this launch only handles sub-buckets with n_min < records <= n_max (records <= 0.85 * SC_HT can never
+    // overflow the table whatever the duplication rate; the last class takes everything larger and reports overflow)
     extern __shared__ unsigned char smem_raw[];
     unsigned long long *bufA_key = reinterpret_cast<unsigned long long *>(smem_raw);            // hash table keys, later ping-pong buffer
     unsigned long long *bufB_key = bufA_key + SC_HT;                                             // compacted list
@@ -407,11 +410,7 @@ __global__ void __launch_bounds__(SC_DEDUP_THREADS) k_dedup_sort(uint64_t *__res
     const uint32_t sb = blockIdx.x;
     if (sb >= *n_sub_ptr) return;
     const uint32_t s = sub_off[sb], e = sub_off[sb + 1];
-    if (e == s)
-    {
-        if (threadIdx.x == 0) ucount[sb] = 0;
-        return;
-    }
+    if (e - s <= n_min || e - s > n_max) return; // another size class (ucount was zeroed by the host; empty buckets stay 0)
     for (int i = threadIdx.x; i < SC_HT; i += blockDim.x) { bufA_key[i] = EMPTY64; bufA_val[i] = 0; }
     if (threadIdx.x == 0) { m_s = 0; red_or = 0; red_and = EMPTY64; }
     __syncthreads();
@@ -598,12 +597,15 @@ public:
 
     static void configure()
     {
-        static bool done = false;
-        if (done) return;
+        // the attribute is per device: keep one flag per device ordinal (a process may drive several GPUs)
+        static bool done[64] = {false};
+        int dev = 0;
+        DGE_CUDA(cudaGetDevice(&dev));
+        if (dev < 64 && done[dev]) return;
         DGE_CUDA(cudaFuncSetAttribute(k_splitters, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SAMPLE * 8));
         DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dedup_smem_bytes(SC_HT_MAX))));
         DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dedup_smem_bytes(SC_HT_MAX))));
-        done = true;
+        if (dev < 64) done[dev] = true;
     }
 
     // Layout of ws.small (uint32): [hist nb1+1][l1_off nb1+1][cursor nb1+1][p2 nb1+1][sb_base nb1+1][tile_base nb1+1]
@@ -720,14 +722,26 @@ public:
         uint32_t *ucount = ws.ucount.as<uint32_t>(), *u_off = ws.u_off.as<uint32_t>();
         DGE_CUDA(cudaMemsetAsync(ucount, 0, (nsb_bound + 1) * 4, st));
         DGE_CUDA(cudaEventRecord(ev0, st));
-        if (has_val)
-            k_dedup_sort<true><<<unsigned(nsb_bound), SC_DEDUP_THREADS, dedup_smem_bytes(SC_HT), st>>>(keys_tmp, ws.valsB.as<uint32_t>(), ws.uvals_sparse.as<uint32_t>(),
-                                                                                           sub_off, n_sub_ptr, ucount, overflow_flag, SC_HT);
-        else
-            k_dedup_sort<false><<<unsigned(nsb_bound), SC_DEDUP_THREADS, dedup_smem_bytes(SC_HT), st>>>(keys_tmp, nullptr, ws.uvals_sparse.as<uint32_t>(),
-                                                                                            sub_off, n_sub_ptr, ucount, overflow_flag, SC_HT);
+        {
+            const uint32_t cut = uint32_t(SC_HT * 0.85);
+            auto launch = [&](int ht, uint32_t lo, uint32_t hi) {
+                if (has_val)
+                    k_dedup_sort<true><<<unsigned(nsb_bound), SC_DEDUP_THREADS, dedup_smem_bytes(ht), st>>>(keys_tmp, ws.valsB.as<uint32_t>(), ws.uvals_sparse.as<uint32_t>(),
+                                                                                                          sub_off, n_sub_ptr, ucount, overflow_flag, ht, lo, hi);
+                else
+                    k_dedup_sort<false><<<unsigned(nsb_bound), SC_DEDUP_THREADS, dedup_smem_bytes(ht), st>>>(keys_tmp, nullptr, ws.uvals_sparse.as<uint32_t>(),
+                                                                                                           sub_off, n_sub_ptr, ucount, overflow_flag, ht, lo, hi);
+                ++L;
+            };
+            if (SC_HT < SC_HT_MAX)
+            {
+                launch(SC_HT, 0u, cut);                    // the common class
+                launch(SC_HT_MAX, cut, 0xFFFFFFFFu);       // oversized sub-buckets (sampling tail, heavy duplicates)
+            }
+            else launch(SC_HT, 0u, 0xFFFFFFFFu);
+        }
         DGE_CUDA(cudaEventRecord(ev1, st));
-        ++L; ++stats->dedup_launches;
+        ++stats->dedup_launches;
         pending_dedup_event = true;
         mark("dedup_sort");
         const uint32_t *n_u_ptr = device_exclusive_scan(ucount, u_off, nsb_bound + 1, ws.scan_scratch.as<uint32_t>(), st, &L);

@@ -77,7 +77,15 @@ __global__ void __launch_bounds__(256) k_synth(SynthDev p, uint64_t first, uint6
 
 __host__ __device__ inline uint32_t rank_of(uint64_t cb, uint32_t n_ranks)
 {
-    return uint32_t(((barcode_hash(cb) >> 32) * uint64_t(n_ranks)) >> 32);
+    // owner = floor(hash32 * n_ranks / 2^32).  Written with an explicit 32x32 multiply-high: ptxas 12.9 mis-folds the
+    // 64-bit form ((h >> 32) * n) >> 32 into the shared-memory address computation (observed: every key -> rank 0).
+    // low hash word: the barcode table takes its slot from the TOP bits of the same hash, and the two must stay independent
+    const uint32_t hi = uint32_t(barcode_hash(cb));
+#ifdef __CUDA_ARCH__
+    return __umulhi(hi, n_ranks);
+#else
+    return uint32_t((uint64_t(hi) * n_ranks) >> 32);
+#endif
 }
 
 __global__ void __launch_bounds__(256) k_route_count(const dge_record16 *__restrict__ in, size_t n, uint32_t n_ranks, unsigned long long *__restrict__ counts)

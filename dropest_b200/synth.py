@@ -42,7 +42,7 @@ def barcode_hash(cb: np.ndarray) -> np.ndarray:
 
 def rank_of(cb: np.ndarray, n_ranks: int) -> np.ndarray:
     """Owner rank of a barcode: host mirror of rank_of in csrc/synth.cu (multi-GPU routing)."""
-    return (((barcode_hash(cb) >> U64(32)) * U64(n_ranks)) >> U64(32)).astype(np.uint32)
+    return (((barcode_hash(cb) & U64(0xFFFFFFFF)) * U64(n_ranks)) >> U64(32)).astype(np.uint32)
 
 
 def read_whitelist(path: str, indrop: bool = False) -> List[List[str]]:

@@ -204,3 +204,24 @@ def test_full_size_invariants_20m():
     assert np.all(np.diff(k) >= 0)
     # cm_raw column sums == distinct UMIs of real cells that were never merge targets
     assert raw1[0][-1] == raw1[1].shape[0]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_route_kernel_matches_host_mirror(world):
+    """dge_route_by_barcode_device (the partition step before the all-to-all) against its numpy mirror."""
+    import torch
+    from dropest_b200 import dist as dgdist
+
+    spec = SynthSpec(n_reads=50_000, n_cells=300, n_genes=100, cb_len=16, umi_len=10, whitelist_parts=read_whitelist(pu.WL_SYNTH_7_9))
+    recs = SynthTables(spec).generate_host(0, spec.n_reads)
+    raw = torch.from_numpy(np.frombuffer(recs.tobytes(), dtype=np.uint8).copy()).cuda()
+    out = torch.empty_like(raw)
+    counts = dgdist.route_device(0, raw.data_ptr(), recs.shape[0], world, out.data_ptr())
+    exp_sorted, exp_counts = dgdist.route_host(recs, world)
+    np.testing.assert_array_equal(counts, exp_counts)
+    got = dgdist.records_from_tensor(out)
+    off = 0
+    for r in range(world):
+        seg, exp = got[off:off + int(counts[r])], exp_sorted[off:off + int(counts[r])]
+        np.testing.assert_array_equal(np.sort(seg, order=["read_idx"]), np.sort(exp, order=["read_idx"]))
+        off += int(counts[r])

@@ -86,6 +86,7 @@ def test_two_gpu_shards_reproduce_single_gpu_matrix(tmp_path):
     c.close()
     multi = np.concatenate([np.load(tmp_path / f"trip{r}.npy") for r in range(world)])
     order = lambda t: t[np.lexsort((t[:, 1], t[:, 0]))]
-    np.testing.assert_array_equal(order(multi), order(single))
     sums = sum(np.load(tmp_path / f"sum{r}.npy") for r in range(world))
+    print("per-rank sums", [np.load(tmp_path / f"sum{r}.npy").tolist() for r in range(world)], "single", s)
+    np.testing.assert_array_equal(order(multi), order(single))
     assert list(sums) == [s["total_cells_number"], s["real_cells_number"], s["intergenic_reads"], s["n_umigs"]]
