@@ -101,4 +101,25 @@ struct DevBuf
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// A grow-only page-locked host buffer (D2H / H2D staging at full PCIe speed, truly asynchronous copies).
+struct PinnedBuf
+{
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    void reserve(size_t n)
+    {
+        if (n <= bytes) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        size_t want = n + (n >> 3) + 4096;
+        DGE_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        bytes = want;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
 } // namespace dge

@@ -83,7 +83,7 @@ struct dge_handle
 
     // grouped state
     DevBuf keys_all, ukey, uval, ukey2, uval2, overflow_flag;
-    DevBuf cg_key, cg_start, cg_req, cg_reads, cg_req_reads;
+    DevBuf cg_key, cg_start, cg_pc, cg_req, cg_reads, cg_req_reads;
     DevBuf pc_slot, pc_u_start, pc_cg_start, pc_reads, pc_req_genes, pc_req_umis, slot_pc;
     DevBuf tile_a, tile_b, scan_scratch, flags, flags_off, rows_dev, misc;
     uint32_t n_u = 0, n_cg = 0, n_pc = 0;
@@ -95,13 +95,16 @@ struct dge_handle
     SortCombineStats sc_stats;
     // merge-stage workspaces (grow only, reused across runs)
     DevBuf d_jobs, d_isect, d_cb, d_umis, d_count, d_nb, d_moves, mkeys, mvals, ekey, eval, keep, keep_off, xkey, xval, mat_nnz;
-    std::vector<uint32_t> h_isect, h_pc_to_real, h_nb_pc, h_umis, h_nb_off, h_nbs;
+    uint32_t *isect_p = nullptr;
+    std::vector<uint32_t> h_pc_to_real, h_nb_pc, h_umis, h_nb_off, h_nbs;
     std::vector<int> h_nb_count;
     std::vector<uint64_t> h_cbs;
     std::vector<PairJob> h_jobs;
     std::vector<MoveJob> h_moves;
     std::vector<long> h_target;
+    std::vector<uint64_t> h_sortkey;
     bool wl_uploaded = false;
+    PinnedBuf pin_rows, pin_nbc, pin_nbp, pin_isect, pin_misc;
 
     // host state
     std::vector<HostCell> real;            // cell-id (first-seen) order
@@ -136,9 +139,11 @@ struct Tracer
     bool on;
     std::chrono::steady_clock::time_point t0;
     Tracer() : on(std::getenv("DGE_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    cudaStream_t st = nullptr;
     void mark(const char *what)
     {
         if (!on) return;
+        cudaStreamSynchronize(st); // tracing only (st may be the default stream): make the marks mean device time
         auto t1 = std::chrono::steady_clock::now();
         fprintf(stderr, "[dge] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
@@ -171,6 +176,14 @@ template <class T> void d2h(std::vector<T> &dst, const void *src, size_t n, cuda
 {
     dst.resize(n);
     if (n) DGE_CUDA(cudaMemcpyAsync(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+}
+
+// device -> pinned host; valid after the stream is synchronised
+template <class T> T *d2h_pinned(PinnedBuf &dst, const void *src, size_t n, cudaStream_t st)
+{
+    dst.reserve(std::max<size_t>(n, 1) * sizeof(T));
+    if (n) DGE_CUDA(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    return dst.as<T>();
 }
 
 template <class T> T d2h_scalar(const void *src, cudaStream_t st)
@@ -282,17 +295,37 @@ void update_filtered(dge_handle *h, uint32_t threshold, int cell_threshold)
 {
     std::vector<uint32_t> &f = h->filtered;
     f.clear();
-    for (uint32_t i = 0; i < h->real.size(); ++i)
+    const std::vector<HostCell> &R = h->real;
+    bool fits = true;
+    for (uint32_t i = 0; i < R.size(); ++i)
     {
-        const HostCell &c = h->real[i];
-        if (c.real && uint32_t(c.req_genes) >= threshold) f.push_back(i);
+        const HostCell &c = R[i];
+        if (!(c.real && uint32_t(c.req_genes) >= threshold)) continue;
+        f.push_back(i);
+        fits &= uint32_t(c.req_genes) < (1u << 16) && uint32_t(c.req_umis) < (1u << 24) && uint32_t(c.umis_stat) < (1u << 24);
     }
     std::vector<uint32_t> tmp;
-    const std::vector<HostCell> &R = h->real;
-    for (int sh = 0; sh < 48; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return uint32_t(R[i].cb >> sh) & 0xFFFFu; });
-    for (int sh = 0; sh < 32; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return (uint32_t(R[i].umis_stat) >> sh) & 0xFFFFu; });
-    for (int sh = 0; sh < 32; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return (uint32_t(R[i].req_umis) >> sh) & 0xFFFFu; });
-    for (int sh = 0; sh < 32; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return (uint32_t(R[i].req_genes) >> sh) & 0xFFFFu; });
+    if (fits)
+    {   // one 64-bit composite key (genes:16 | umis:24 | stat:24), 4 radix passes; barcode only breaks exact ties
+        std::vector<uint64_t> &key = h->h_sortkey;
+        key.resize(R.size());
+        for (uint32_t i : f) key[i] = (uint64_t(uint32_t(R[i].req_genes)) << 48) | (uint64_t(uint32_t(R[i].req_umis)) << 24) | uint64_t(uint32_t(R[i].umis_stat));
+        for (int sh = 0; sh < 64; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return uint32_t(key[i] >> sh) & 0xFFFFu; });
+        for (size_t a = 0; a < f.size();)
+        {
+            size_t b = a + 1;
+            while (b < f.size() && key[f[b]] == key[f[a]]) ++b;
+            if (b - a > 1) std::sort(f.begin() + long(a), f.begin() + long(b), [&](uint32_t x, uint32_t y) { return R[x].cb < R[y].cb; });
+            a = b;
+        }
+    }
+    else
+    {
+        for (int sh = 0; sh < 48; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return uint32_t(R[i].cb >> sh) & 0xFFFFu; });
+        for (int sh = 0; sh < 32; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return (uint32_t(R[i].umis_stat) >> sh) & 0xFFFFu; });
+        for (int sh = 0; sh < 32; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return (uint32_t(R[i].req_umis) >> sh) & 0xFFFFu; });
+        for (int sh = 0; sh < 32; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return (uint32_t(R[i].req_genes) >> sh) & 0xFFFFu; });
+    }
     if (cell_threshold > 0 && size_t(cell_threshold) < f.size()) f.erase(f.begin(), f.end() - cell_threshold);
 }
 
@@ -323,22 +356,28 @@ void build_segments(dge_handle *h)
     h->n_pc = d2h_scalar<uint32_t>(tot_pc, st);
 
     const size_t ncg = h->n_cg, npc = h->n_pc;
-    h->cg_key.reserve((ncg + 1) * 8); h->cg_start.reserve((ncg + 1) * 4);
+    h->cg_key.reserve((ncg + 1) * 8); h->cg_start.reserve((ncg + 1) * 4); h->cg_pc.reserve((ncg + 1) * 4);
     h->cg_req.reserve((ncg + 1) * 4); h->cg_reads.reserve((ncg + 1) * 4);
     if (h->cfg.reads_output) h->cg_req_reads.reserve((ncg + 1) * 4);
     h->pc_slot.reserve((npc + 2) * 4); h->pc_u_start.reserve((npc + 2) * 4); h->pc_cg_start.reserve((npc + 2) * 4);
-    h->pc_reads.reserve((npc + 1) * 4); h->pc_req_genes.reserve((npc + 1) * 4); h->pc_req_umis.reserve((npc + 1) * 4);
-    k_seg_write<<<unsigned(nt), SEG_THREADS, 0, st>>>(h->ukey.as<uint64_t>(), n_u, ub, gub, ta, tb, h->cg_key.as<uint64_t>(),
-                                                       h->cg_start.as<uint32_t>(), h->pc_slot.as<uint32_t>(), h->pc_u_start.as<uint32_t>(),
-                                                       h->pc_cg_start.as<uint32_t>());
+    h->pc_reads.reserve((npc + 2) * 4); h->pc_req_genes.reserve((npc + 2) * 4); h->pc_req_umis.reserve((npc + 2) * 4);
+    DGE_CUDA(cudaMemsetAsync(h->cg_req.p, 0, (ncg + 1) * 4, st));
+    DGE_CUDA(cudaMemsetAsync(h->cg_reads.p, 0, (ncg + 1) * 4, st));
+    if (h->cfg.reads_output) DGE_CUDA(cudaMemsetAsync(h->cg_req_reads.p, 0, (ncg + 1) * 4, st));
+    DGE_CUDA(cudaMemsetAsync(h->pc_reads.p, 0, (npc + 2) * 4, st));
+    DGE_CUDA(cudaMemsetAsync(h->pc_req_genes.p, 0, (npc + 2) * 4, st));
+    DGE_CUDA(cudaMemsetAsync(h->pc_req_umis.p, 0, (npc + 2) * 4, st));
+    k_seg_write<<<unsigned(nt), SEG_THREADS, 0, st>>>(h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), n_u, ub, gub, h->cfg.query_mark_mask, ta, tb,
+                                                       h->cg_key.as<uint64_t>(), h->cg_start.as<uint32_t>(), h->cg_pc.as<uint32_t>(),
+                                                       h->cg_req.as<uint32_t>(), h->cg_reads.as<uint32_t>(),
+                                                       h->cfg.reads_output ? h->cg_req_reads.as<uint32_t>() : nullptr,
+                                                       h->pc_slot.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(),
+                                                       h->pc_reads.as<uint32_t>(), h->pc_req_umis.as<uint32_t>());
     k_seg_sentinels<<<1, 1, 0, st>>>(n_u, h->n_cg, h->n_pc, h->cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), h->pc_cg_start.as<uint32_t>());
-    k_cg_reduce<<<grid_for(ncg, 256), 256, 0, st>>>(h->uval.as<uint32_t>(), h->cg_start.as<uint32_t>(), h->n_cg, h->cfg.query_mark_mask,
-                                                     h->cg_req.as<uint32_t>(), h->cg_reads.as<uint32_t>(),
-                                                     h->cfg.reads_output ? h->cg_req_reads.as<uint32_t>() : nullptr);
-    k_pc_reduce<<<grid_for(npc, 256), 256, 0, st>>>(h->cg_req.as<uint32_t>(), h->cg_reads.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(), h->n_pc,
-                                                     h->pc_reads.as<uint32_t>(), h->pc_req_genes.as<uint32_t>(), h->pc_req_umis.as<uint32_t>());
+    k_pc_req_genes<<<grid_for(div_up(ncg, size_t(8)), 256), 256, 0, st>>>(h->cg_req.as<uint32_t>(), h->cg_pc.as<uint32_t>(), h->n_cg,
+                                                                           h->pc_req_genes.as<uint32_t>());
     DGE_LAUNCH_CHECK();
-    h->launches += 4;
+    h->launches += 3;
 }
 
 void build_slot_pc(dge_handle *h)
@@ -365,8 +404,9 @@ void gather_rows(dge_handle *h, const std::vector<uint32_t> &pcs, std::vector<Ce
                                                                         h->rows_dev.as<CellRow>());
     DGE_LAUNCH_CHECK();
     ++h->launches;
-    d2h(rows, h->rows_dev.p, pcs.size(), h->stream);
+    const CellRow *p = d2h_pinned<CellRow>(h->pin_rows, h->rows_dev.p, pcs.size(), h->stream);
     DGE_CUDA(cudaStreamSynchronize(h->stream));
+    rows.assign(p, p + pcs.size());
 }
 
 void do_set_initialized(dge_handle *h)
@@ -374,6 +414,7 @@ void do_set_initialized(dge_handle *h)
     ensure_device(h);
     cudaStream_t st = h->stream;
     Tracer tr;
+    tr.st = st;
     DGE_CUDA(cudaEventRecord(h->ev[0], st));
 
     // ---- collect compact keys of all batches into one array (chunks were produced at add time)
@@ -433,6 +474,8 @@ void do_set_initialized(dge_handle *h)
 
     // ---- real cells -> host (Cell::is_real, Cell.cpp:125-128: n_genes >= min_genes_before_merge)
     std::vector<CellRow> rows;
+    const CellRow *rows_p = nullptr;
+    size_t n_rows = 0;
     if (h->n_pc)
     {
         h->flags.reserve((size_t(h->n_pc) + 1) * 4); h->flags_off.reserve((size_t(h->n_pc) + 1) * 4);
@@ -449,15 +492,16 @@ void do_set_initialized(dge_handle *h)
                                                                           h->pc_req_umis.as<uint32_t>(), h->rows_dev.as<CellRow>());
             DGE_LAUNCH_CHECK();
             ++h->launches;
-            d2h(rows, h->rows_dev.p, n_real, st);
+            rows_p = d2h_pinned<CellRow>(h->pin_rows, h->rows_dev.p, n_real, st);
+            n_rows = n_real;
             DGE_CUDA(cudaStreamSynchronize(st));
         }
     }
     // min_genes_before_merge == 0 makes every barcode real, including barcodes that only have intergenic reads
     // (they own no UMI and are not in the PC table): pick them up from the barcode table.
-    std::vector<CellSlot> extra_slots;
     if (h->cfg.min_genes_before_merge == 0 && h->total_cells > h->n_pc)
     {
+        rows.assign(rows_p, rows_p + n_rows);
         std::vector<CellSlot> tab_host;
         d2h(tab_host, h->tab.p, h->table_cap, st);
         std::vector<uint32_t> pc_slots;
@@ -472,15 +516,17 @@ void do_set_initialized(dge_handle *h)
                 r.cb = tab_host[s].cb; r.slot = uint32_t(s); r.pc = NONE32; r.first_idx = tab_host[s].first_idx; r.n_intergenic = tab_host[s].n_intergenic;
                 rows.push_back(r);
             }
+        rows_p = rows.data();
+        n_rows = rows.size();
     }
-    std::vector<uint32_t> order(rows.size()), order_tmp;
+    std::vector<uint32_t> order(n_rows), order_tmp;
     std::iota(order.begin(), order.end(), 0u);
-    for (int sh = 0; sh < 32; sh += 16) radix_pass16(order, order_tmp, [&](uint32_t i) { return (rows[i].first_idx >> sh) & 0xFFFFu; });
+    for (int sh = 0; sh < 32; sh += 16) radix_pass16(order, order_tmp, [&](uint32_t i) { return (rows_p[i].first_idx >> sh) & 0xFFFFu; });
     h->real.clear();
-    h->real.reserve(rows.size());
+    h->real.reserve(n_rows);
     for (uint32_t ri : order)
     {
-        const CellRow &r = rows[ri];
+        const CellRow &r = rows_p[ri];
         HostCell c;
         c.cb = r.cb; c.slot = r.slot; c.pc = r.pc; c.first_idx = r.first_idx; c.n_intergenic = r.n_intergenic;
         c.n_genes = int32_t(r.n_genes); c.umis_stat = int32_t(r.n_umis); c.n_umis_distinct = int32_t(r.n_umis);
@@ -491,15 +537,13 @@ void do_set_initialized(dge_handle *h)
     tr.mark("init: real cells -> host");
     // gene first-seen order (StringIndexer::add, StringIndexer.cpp:10-18)
     {
-        std::vector<uint32_t> gf;
-        d2h(gf, h->gene_first.p, h->cfg.n_genes, st);
+        const uint32_t *gf = d2h_pinned<uint32_t>(h->pin_misc, h->gene_first.p, h->cfg.n_genes, st);
         DGE_CUDA(cudaStreamSynchronize(st));
-        std::vector<std::pair<uint32_t, int32_t>> seen;
+        std::vector<uint32_t> seen, seen_tmp;
         for (uint32_t g = 0; g < h->cfg.n_genes; ++g)
-            if (gf[g] != NONE32) seen.emplace_back(gf[g], int32_t(g));
-        std::sort(seen.begin(), seen.end());
-        h->gene_order.clear();
-        for (auto const &p : seen) h->gene_order.push_back(p.second);
+            if (gf[g] != NONE32) seen.push_back(g);
+        for (int sh = 0; sh < 32; sh += 16) radix_pass16(seen, seen_tmp, [&](uint32_t g) { return (gf[g] >> sh) & 0xFFFFu; });
+        h->gene_order.assign(seen.begin(), seen.end());
     }
     update_filtered(h, 0, -1); // set_initialized: update_cell_sizes(query, 0, -1)  (CellsDataContainer.cpp:168)
     tr.mark("init: gene order + filtered");
@@ -539,7 +583,8 @@ void upload_whitelist(dge_handle *h)
 // Device intersections for a flat job list; results land in h->h_isect (same order).
 void run_intersections(dge_handle *h, const std::vector<PairJob> &jobs)
 {
-    h->h_isect.assign(jobs.size(), 0);
+    h->pin_isect.reserve(std::max<size_t>(jobs.size(), 1) * 4);
+    h->isect_p = h->pin_isect.as<uint32_t>();
     if (jobs.empty()) return;
     h->d_jobs.reserve(jobs.size() * sizeof(PairJob)); h->d_isect.reserve(jobs.size() * 4);
     DGE_CUDA(cudaMemcpyAsync(h->d_jobs.p, jobs.data(), jobs.size() * sizeof(PairJob), cudaMemcpyHostToDevice, h->stream));
@@ -548,7 +593,7 @@ void run_intersections(dge_handle *h, const std::vector<PairJob> &jobs)
                                                               h->d_isect.as<uint32_t>());
     DGE_LAUNCH_CHECK();
     ++h->launches;
-    DGE_CUDA(cudaMemcpyAsync(h->h_isect.data(), h->d_isect.p, jobs.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    DGE_CUDA(cudaMemcpyAsync(h->isect_p, h->d_isect.p, jobs.size() * 4, cudaMemcpyDeviceToHost, h->stream));
     DGE_CUDA(cudaStreamSynchronize(h->stream));
 }
 
@@ -579,10 +624,10 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
     pc_to_real.assign(size_t(h->n_pc) + 1, NONE32);
     for (uint32_t i = 0; i < n; ++i) if (h->real[i].pc != NONE32) pc_to_real[h->real[i].pc] = i;
 
-    std::vector<int> &nb_count = h->h_nb_count;
-    std::vector<uint32_t> &nb_pc = h->h_nb_pc;
-    nb_count.assign(n, NB_SLOW);
-    nb_pc.resize(n * WL_K);
+    h->pin_nbc.reserve(n * 4); h->pin_nbp.reserve(n * WL_K * 4);
+    int *nb_count = h->pin_nbc.as<int>();
+    uint32_t *nb_pc = h->pin_nbp.as<uint32_t>();
+    std::fill(nb_count, nb_count + n, int(NB_SLOW));
     if (h->wl_fast)
     {
         if (!h->wl_uploaded) { upload_whitelist(h); h->wl_uploaded = true; }
@@ -597,8 +642,8 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
                                                                             h->cfg.min_genes_before_merge, h->d_count.as<int>(), h->d_nb.as<uint32_t>());
         DGE_LAUNCH_CHECK();
         ++h->launches;
-        DGE_CUDA(cudaMemcpyAsync(nb_count.data(), h->d_count.p, n * 4, cudaMemcpyDeviceToHost, st));
-        DGE_CUDA(cudaMemcpyAsync(nb_pc.data(), h->d_nb.p, n * WL_K * 4, cudaMemcpyDeviceToHost, st));
+        DGE_CUDA(cudaMemcpyAsync(nb_count, h->d_count.p, n * 4, cudaMemcpyDeviceToHost, st));
+        DGE_CUDA(cudaMemcpyAsync(nb_pc, h->d_nb.p, n * WL_K * 4, cudaMemcpyDeviceToHost, st));
         DGE_CUDA(cudaStreamSynchronize(st));
     }
 
@@ -667,14 +712,14 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
         }
     }
     run_intersections(h, jobs);
-    const std::vector<uint32_t> &isect = h->h_isect;
+    const uint32_t *isect = h->isect_p;
 
     for (uint32_t i = 0; i < n; ++i)
     {
         if (target[i] != -2) continue;
         const uint32_t c = off[i + 1] - off[i];
         const uint32_t *my_nbs = nbs.data() + off[i];
-        const uint32_t *my_is = isect.data() + off[i];
+        const uint32_t *my_is = isect + off[i];
         // The fast path reports the neighbour SET of the nearest class; the reference walks them in the order left by two
         // unstable sorts.  That order only matters on exact ties of the best fraction: replay it then.
         if (nb_count[i] > 1)
@@ -708,6 +753,7 @@ void phase2(dge_handle *h, const std::vector<long> &target)
     std::vector<uint32_t> reassign(n), child_head(n, NONE32), child_tail(n, NONE32), child_next(n, NONE32);
     std::iota(reassign.begin(), reassign.end(), 0u);
     h->merge_events.clear();
+    h->merge_events.reserve(h->filtered.size());
     h->n_merged = h->n_excluded = 0;
     auto append = [&](uint32_t t, uint32_t c) {
         child_next[c] = NONE32;
@@ -748,6 +794,8 @@ void apply_merges(dge_handle *h)
 {
     if (h->merge_events.empty()) return;
     cudaStream_t st = h->stream;
+    Tracer tr;
+    tr.st = st;
     // merge_cells copies the source's CURRENT content, i.e. the source's own UMIs plus everything merged into it earlier
     // (sequential semantics): keep, per cell, the list of originals absorbed so far (spliced on merge).
     const size_t n = h->real.size();
@@ -775,6 +823,7 @@ void apply_merges(dge_handle *h)
         if (total >= 0xFFFFFFF0ull) throw std::runtime_error("merge volume exceeds 2^32 entries");
     }
     if (jobs.empty()) return;
+    tr.mark("  apply: host job list");
     h->d_moves.reserve(jobs.size() * sizeof(MoveJob));
     h->mkeys.reserve(total * 8); h->mvals.reserve(total * 4); h->ekey.reserve(total * 8); h->eval.reserve(total * 4);
     DGE_CUDA(cudaMemcpyAsync(h->d_moves.p, jobs.data(), jobs.size() * sizeof(MoveJob), cudaMemcpyHostToDevice, st));
@@ -789,6 +838,7 @@ void apply_merges(dge_handle *h)
                                          h->ekey.as<uint64_t>(), h->eval.as<uint32_t>(), h->overflow_flag.as<int>(), st, &h->sc_stats);
     const uint32_t n_e = d2h_scalar<uint32_t>(n_e_ptr, st);
     h->sc2.collect_timing();
+    tr.mark("  apply: gather + combine");
     if (d2h_scalar<int>(h->overflow_flag.p, st)) throw std::runtime_error("sub-bucket hash table overflow while merging cells");
     h->keep.reserve(size_t(n_e + 1) * 4); h->keep_off.reserve(size_t(n_e + 1) * 4);
     k_probe_merge<<<grid_for(n_e, 256), 256, 0, st>>>(h->ekey.as<uint64_t>(), h->eval.as<uint32_t>(), n_e, h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(),
@@ -812,7 +862,9 @@ void apply_merges(dge_handle *h)
         std::swap(h->uval.p, h->uval2.p); std::swap(h->uval.bytes, h->uval2.bytes);
         h->n_u = uint32_t(n_new);
     }
+    tr.mark("  apply: probe + merge_rank");
     build_segments(h);
+    tr.mark("  apply: segments");
 }
 
 void build_matrix(dge_handle *h, MatrixDev &m, const std::vector<uint32_t> &col_pcs, bool filtered)
@@ -851,6 +903,7 @@ void do_merge_and_filter(dge_handle *h)
     DGE_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t st = h->stream;
     Tracer tr;
+    tr.st = st;
     DGE_CUDA(cudaEventRecord(h->ev[3], st));
     build_slot_pc(h);
 
@@ -876,9 +929,12 @@ void do_merge_and_filter(dge_handle *h)
     // ---- update_cell_sizes (CellsDataContainer.cpp:111-125): requested sizes of every cell, real = !merged && !excluded && size >= min
     if (!h->merge_events.empty())
     {
+        // only merge TARGETS changed content: every other cell keeps the sizes read at set_initialized
         std::vector<uint32_t> pcs, owners;
+        std::vector<char> is_target(h->real.size(), 0);
+        for (auto const &e : h->merge_events) is_target[e.second] = 1;
         for (uint32_t i = 0; i < h->real.size(); ++i)
-            if (h->real[i].pc != NONE32) { pcs.push_back(h->real[i].pc); owners.push_back(i); }
+            if (is_target[i] && h->real[i].pc != NONE32) { pcs.push_back(h->real[i].pc); owners.push_back(i); }
         std::vector<CellRow> rows;
         gather_rows(h, pcs, rows);
         for (size_t k = 0; k < rows.size(); ++k)

@@ -45,15 +45,21 @@ __global__ void __launch_bounds__(SEG_THREADS) k_seg_count(const uint64_t *__res
     if (threadIdx.x == 0) tile_cell[blockIdx.x] = tot;
 }
 
-// pass 2: write segment starts
-__global__ void __launch_bounds__(SEG_THREADS) k_seg_write(const uint64_t *__restrict__ ukey, uint32_t n_u, int ub, int gub,
+// pass 2: write segment starts AND reduce values into the (cell,gene) / cell rows.  Every thread owns SEG_ITEMS consecutive
+// distinct UMIs, accumulates per run in registers and flushes a run with a few no-return atomics (rows are zeroed by the host):
+// work per thread is uniform however long a gene's or a cell's UMI list is.
+__global__ void __launch_bounds__(SEG_THREADS) k_seg_write(const uint64_t *__restrict__ ukey, const uint32_t *__restrict__ uval, uint32_t n_u,
+                                                           int ub, int gub, uint32_t query_mask,
                                                            const uint32_t *__restrict__ tile_cg_off, const uint32_t *__restrict__ tile_cell_off,
-                                                           uint64_t *__restrict__ cg_key, uint32_t *__restrict__ cg_start,
-                                                           uint32_t *__restrict__ pc_slot, uint32_t *__restrict__ pc_u_start, uint32_t *__restrict__ pc_cg_start)
+                                                           uint64_t *__restrict__ cg_key, uint32_t *__restrict__ cg_start, uint32_t *__restrict__ cg_pc,
+                                                           uint32_t *__restrict__ cg_req, uint32_t *__restrict__ cg_reads, uint32_t *__restrict__ cg_req_reads,
+                                                           uint32_t *__restrict__ pc_slot, uint32_t *__restrict__ pc_u_start, uint32_t *__restrict__ pc_cg_start,
+                                                           uint32_t *__restrict__ pc_reads, uint32_t *__restrict__ pc_req_umis)
 {
     __shared__ uint32_t ws[33];
     const uint32_t base = blockIdx.x * SEG_TILE + threadIdx.x * SEG_ITEMS;
     uint64_t cur[SEG_ITEMS];
+    uint32_t val[SEG_ITEMS];
     uint8_t hcg[SEG_ITEMS], hcell[SEG_ITEMS];
     uint32_t ncg = 0, ncell = 0;
     uint64_t prev = (base > 0 && base <= n_u) ? ukey[base - 1] : 0;
@@ -65,6 +71,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_seg_write(const uint64_t *__res
         if (i < n_u)
         {
             cur[k] = ukey[i];
+            val[k] = uval[i];
             bool first = i == 0;
             hcg[k] = first || (cur[k] >> ub) != (prev >> ub);
             hcell[k] = first || (cur[k] >> gub) != (prev >> gub);
@@ -75,6 +82,40 @@ __global__ void __launch_bounds__(SEG_THREADS) k_seg_write(const uint64_t *__res
     uint32_t tot;
     uint32_t rcg = block_exclusive_scan(ncg, ws, &tot) + tile_cg_off[blockIdx.x];
     uint32_t rcell = block_exclusive_scan(ncell, ws, &tot) + tile_cell_off[blockIdx.x];
+    // rows being accumulated: the run that continues from the previous thread has rank (exclusive rank - 1)
+    // A run that both starts and ends inside this thread's chunk is owned exclusively: plain stores.  Only the run continuing
+    // from the previous thread and the run still open at the end of the chunk can be shared: atomics.
+    uint32_t a_req = 0, a_reads = 0, a_rreads = 0, c_reads = 0, c_req = 0;
+    bool cg_owned = false, cell_owned = false; // current run started in this chunk
+    auto flush_cg = [&](uint32_t row, bool exclusive) {
+        if (a_reads)
+        {
+            if (exclusive)
+            {
+                cg_req[row] = a_req; cg_reads[row] = a_reads;
+                if (cg_req_reads) cg_req_reads[row] = a_rreads;
+            }
+            else
+            {
+                if (a_req) atomicAdd(&cg_req[row], a_req);
+                atomicAdd(&cg_reads[row], a_reads);
+                if (cg_req_reads && a_rreads) atomicAdd(&cg_req_reads[row], a_rreads);
+            }
+        }
+        a_req = a_reads = a_rreads = 0;
+    };
+    auto flush_cell = [&](uint32_t row, bool exclusive) {
+        if (c_reads)
+        {
+            if (exclusive) { pc_reads[row] = c_reads; pc_req_umis[row] = c_req; }
+            else
+            {
+                atomicAdd(&pc_reads[row], c_reads);
+                if (c_req) atomicAdd(&pc_req_umis[row], c_req);
+            }
+        }
+        c_reads = c_req = 0;
+    };
 #pragma unroll
     for (int k = 0; k < SEG_ITEMS; ++k)
     {
@@ -83,6 +124,8 @@ __global__ void __launch_bounds__(SEG_THREADS) k_seg_write(const uint64_t *__res
         {
             if (hcell[k])
             {
+                flush_cell(rcell - 1, cell_owned);
+                cell_owned = true;
                 pc_slot[rcell] = uint32_t(cur[k] >> gub);
                 pc_u_start[rcell] = i;
                 pc_cg_start[rcell] = rcg; // a cell head is also a cg head: rcg is that cg's rank
@@ -90,11 +133,40 @@ __global__ void __launch_bounds__(SEG_THREADS) k_seg_write(const uint64_t *__res
             }
             if (hcg[k])
             {
+                flush_cg(rcg - 1, cg_owned);
+                cg_owned = true;
                 cg_key[rcg] = cur[k] >> ub;
                 cg_start[rcg] = i;
+                cg_pc[rcg] = rcell - 1;
                 ++rcg;
             }
+            const uint32_t c = val[k] & VAL_COUNT_MASK, m = val[k] >> VAL_MARK_SHIFT;
+            const bool match = (query_mask >> m) & 1u;
+            a_req += match; a_reads += c; a_rreads += match ? c : 0u;
+            c_reads += c; c_req += match;
         }
+    }
+    if (base < n_u) { flush_cg(rcg - 1, false); flush_cell(rcell - 1, false); }
+}
+
+// requested genes per cell = number of its (cell,gene) rows with at least one matching UMI (Cell.cpp:130-143)
+__global__ void __launch_bounds__(256) k_pc_req_genes(const uint32_t *__restrict__ cg_req, const uint32_t *__restrict__ cg_pc, uint32_t n_cg,
+                                                      uint32_t *__restrict__ pc_req_genes)
+{
+    constexpr int ITEMS = 8;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) * ITEMS; base < n_cg; base += gridDim.x * blockDim.x * ITEMS)
+    {
+        uint32_t row = NONE32, acc = 0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k)
+        {
+            const uint32_t i = base + k;
+            if (i >= n_cg) break;
+            const uint32_t pc = cg_pc[i];
+            if (pc != row) { if (acc) atomicAdd(&pc_req_genes[row], acc); row = pc; acc = 0; }
+            acc += cg_req[i] > 0;
+        }
+        if (acc) atomicAdd(&pc_req_genes[row], acc);
     }
 }
 

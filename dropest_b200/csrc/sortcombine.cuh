@@ -35,11 +35,14 @@ struct SortCombineTuning
     int l1_target = 200000; // records per L1 bucket
     int target = 1024;      // records per sub-bucket
     int ht = 2048;          // hash-table slots per sub-bucket (power of two, >= 2 * expected distinct keys)
+    int dedup_threads = 256; // threads per dedup block (32..256, power of two)
     SortCombineTuning()
     {
         if (const char *e = std::getenv("DGE_L1_TARGET")) l1_target = std::max(1000, atoi(e));
         if (const char *e = std::getenv("DGE_SC_TARGET")) target = std::max(64, atoi(e));
         if (const char *e = std::getenv("DGE_SC_HT")) ht = atoi(e);
+        if (const char *e = std::getenv("DGE_DEDUP_THREADS")) dedup_threads = atoi(e);
+        if (dedup_threads != 512 && dedup_threads != 1024) dedup_threads = 256;
         int p = 256;
         while (p < ht && p < SC_HT_MAX) p <<= 1;
         ht = p;
@@ -87,11 +90,12 @@ __global__ void __launch_bounds__(SC_THREADS) k_l1_hist(const uint64_t *__restri
 
 // One tile of SC_TILE keys per block: rank inside the block with shared-memory atomics, reserve one run per (block, bucket)
 // with a single global atomicAdd, then write.
-template <bool HAS_VAL>
-__global__ void __launch_bounds__(SC_THREADS) k_l1_scatter(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, size_t n,
-                                                           int shift, int nb1, uint32_t *__restrict__ cursor,
-                                                           uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
+template <bool HAS_VAL, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_l1_scatter(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, size_t n,
+                                                        int shift, int nb1, uint32_t *__restrict__ cursor,
+                                                        uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
 {
+    constexpr int SC_ITEMS = ITEMS, SC_THREADS = THREADS, SC_TILE = THREADS * ITEMS;
     __shared__ uint32_t cnt[SC_MAX_NB1];
     for (int i = threadIdx.x; i < nb1; i += blockDim.x) cnt[i] = 0;
     __syncthreads();
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_l1_scatter(const uint64_t *__res
 
 // Single block.  From the L1 offsets derive, per bucket, the number of sub-buckets p2 and of block tiles, and their
 // exclusive scans (sb_base, tile_base; entry [nb1] = totals).
-__global__ void __launch_bounds__(1024) k_l1_plan(const uint32_t *__restrict__ l1_off, int nb1, uint32_t SC_TARGET, uint32_t *__restrict__ p2,
+__global__ void __launch_bounds__(1024) k_l1_plan(const uint32_t *__restrict__ l1_off, int nb1, uint32_t SC_TARGET, uint32_t SC_TILE, uint32_t *__restrict__ p2,
                                                   uint32_t *__restrict__ sb_base, uint32_t *__restrict__ tile_base)
 {
     __shared__ uint32_t ws[33];
@@ -208,13 +212,14 @@ __device__ __forceinline__ void block_to_bucket_tile(const uint32_t *__restrict_
     *tile = blk - tile_base[lo];
 }
 
-template <bool SCATTER, bool HAS_VAL>
-__global__ void __launch_bounds__(SC_THREADS) k_l2_pass(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                                        const uint32_t *__restrict__ l1_off, int nb1, const uint32_t *__restrict__ p2,
-                                                        const uint32_t *__restrict__ sb_base, const uint32_t *__restrict__ tile_base,
-                                                        const uint64_t *__restrict__ splitters, uint32_t *__restrict__ sub_cnt_or_cursor,
-                                                        uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
+template <bool SCATTER, bool HAS_VAL, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_l2_pass(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                     const uint32_t *__restrict__ l1_off, int nb1, const uint32_t *__restrict__ p2,
+                                                     const uint32_t *__restrict__ sb_base, const uint32_t *__restrict__ tile_base,
+                                                     const uint64_t *__restrict__ splitters, uint32_t *__restrict__ sub_cnt_or_cursor,
+                                                     uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
 {
+    constexpr int SC_ITEMS = ITEMS, SC_THREADS = THREADS, SC_TILE = THREADS * ITEMS;
     __shared__ uint64_t spl[SC_MAX_P2];
     __shared__ uint32_t cnt[SC_MAX_P2];
     const uint32_t blk = blockIdx.x;
@@ -272,108 +277,6 @@ __global__ void __launch_bounds__(SC_THREADS) k_l2_pass(const uint64_t *__restri
     }
 }
 
-// ---- "direct" variants: rank with one L2 atomic per key on the bucket cursor itself (cursors of the L1 level are padded to
-// 256 B so they spread over all L2 slices).  No shared-memory ranking, no block-wide phases: every thread keeps several
-// independent load -> atomic -> store chains in flight, which is what a latency-bound scatter needs.
-constexpr int SC_CURSOR_PAD = 64; // uint32 stride of the padded L1 cursors
-
-__global__ void k_pad_cursor(const uint32_t *__restrict__ l1_off, int nb1, uint32_t *__restrict__ padded)
-{
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nb1) padded[size_t(b) * SC_CURSOR_PAD] = l1_off[b];
-}
-
-constexpr int SCD_THREADS = 256;
-constexpr int SCD_ITEMS = 8;
-
-template <bool HAS_VAL>
-__global__ void __launch_bounds__(SCD_THREADS) k_l1_scatter_direct(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, size_t n,
-                                                                    int shift, uint32_t *__restrict__ cursor_pad,
-                                                                    uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
-{
-    const size_t base = size_t(blockIdx.x) * (SCD_THREADS * SCD_ITEMS);
-    uint64_t k[SCD_ITEMS];
-    uint32_t pos[SCD_ITEMS];
-#pragma unroll
-    for (int j = 0; j < SCD_ITEMS; ++j)
-    {
-        size_t i = base + size_t(j) * SCD_THREADS + threadIdx.x;
-        if (i < n) k[j] = keys[i];
-    }
-#pragma unroll
-    for (int j = 0; j < SCD_ITEMS; ++j)
-    {
-        size_t i = base + size_t(j) * SCD_THREADS + threadIdx.x;
-        if (i < n) pos[j] = atomicAdd(&cursor_pad[size_t(k[j] >> shift) * SC_CURSOR_PAD], 1u);
-    }
-#pragma unroll
-    for (int j = 0; j < SCD_ITEMS; ++j)
-    {
-        size_t i = base + size_t(j) * SCD_THREADS + threadIdx.x;
-        if (i < n)
-        {
-            out_keys[pos[j]] = k[j];
-            if (HAS_VAL) out_vals[pos[j]] = vals[i];
-        }
-    }
-}
-
-template <bool SCATTER, bool HAS_VAL>
-__global__ void __launch_bounds__(SCD_THREADS) k_l2_pass_direct(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                                                 const uint32_t *__restrict__ l1_off, int nb1, const uint32_t *__restrict__ p2,
-                                                                 const uint32_t *__restrict__ sb_base, const uint32_t *__restrict__ tile_base,
-                                                                 const uint64_t *__restrict__ splitters, uint32_t *__restrict__ sub_cnt_or_cursor,
-                                                                 uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
-{
-    __shared__ uint64_t spl[SC_MAX_P2];
-    const uint32_t blk = blockIdx.x;
-    if (blk >= tile_base[nb1]) return;
-    int b; uint32_t tile;
-    block_to_bucket_tile(tile_base, nb1, blk, &b, &tile);
-    const uint32_t np = p2[b];
-    const uint32_t off = l1_off[b], end = l1_off[b + 1];
-    const uint32_t t0 = off + tile * SC_TILE;
-    const uint32_t t1 = min(end, t0 + uint32_t(SC_TILE));
-    uint32_t *__restrict__ cur = sub_cnt_or_cursor + sb_base[b];
-    for (uint32_t i = threadIdx.x; i + 1 < np; i += blockDim.x) spl[i] = splitters[size_t(b) * SC_MAX_P2 + i];
-    __syncthreads();
-    for (uint32_t c0 = t0; c0 < t1; c0 += SCD_THREADS * SCD_ITEMS)
-    {
-        uint64_t k[SCD_ITEMS];
-        uint32_t pos[SCD_ITEMS];
-#pragma unroll
-        for (int j = 0; j < SCD_ITEMS; ++j)
-        {
-            uint32_t i = c0 + uint32_t(j) * SCD_THREADS + threadIdx.x;
-            if (i < t1) k[j] = keys[i];
-        }
-#pragma unroll
-        for (int j = 0; j < SCD_ITEMS; ++j)
-        {
-            uint32_t i = c0 + uint32_t(j) * SCD_THREADS + threadIdx.x;
-            if (i < t1)
-            {
-                const uint32_t s = np > 1 ? sub_bucket_of(spl, np - 1, k[j] >> 3) : 0u;
-                if (SCATTER) pos[j] = atomicAdd(&cur[s], 1u);
-                else atomicAdd(&cur[s], 1u);
-            }
-        }
-        if (SCATTER)
-        {
-#pragma unroll
-            for (int j = 0; j < SCD_ITEMS; ++j)
-            {
-                uint32_t i = c0 + uint32_t(j) * SCD_THREADS + threadIdx.x;
-                if (i < t1)
-                {
-                    out_keys[pos[j]] = k[j];
-                    if (HAS_VAL) out_vals[pos[j]] = vals[i];
-                }
-            }
-        }
-    }
-}
-
 // One block per sub-bucket.  keys[s..e) -> distinct ukeys, ascending, written back IN PLACE at keys[s..s+m), values at
 // uvals[s..s+m); ucount[sb] = m.
 //   1. stream the records through a shared-memory hash table (atomicCAS claims a slot, atomicAdd/atomicOr combine values)
@@ -385,10 +288,10 @@ constexpr int SC_RADIX_BITS = 8;
 constexpr int SC_RADIX = 1 << SC_RADIX_BITS;
 constexpr int SC_DEDUP_WARPS = SC_DEDUP_THREADS / 32;
 
-inline size_t dedup_smem_bytes(int ht) { return size_t(ht) * 26 + SC_DEDUP_WARPS * SC_RADIX * 2 + 64; }
+inline size_t dedup_smem_bytes(int ht, int threads = SC_DEDUP_THREADS) { return size_t(ht) * 28 + size_t(threads / 32) * SC_RADIX * 2 + 64; }
 
 template <bool HAS_VAL>
-__global__ void __launch_bounds__(SC_DEDUP_THREADS) k_dedup_sort(uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals_in,
+__global__ void __launch_bounds__(1024) k_dedup_sort(uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals_in,
                                                                  uint32_t *__restrict__ uvals, const uint32_t *__restrict__ sub_off,
                                                                  const uint32_t *__restrict__ n_sub_ptr, uint32_t *__restrict__ ucount,
                                                                  int *__restrict__ overflow, const int SC_HT,
@@ -402,7 +305,8 @@ __global__ void __launch_bounds__(SC_DEDUP_THREADS) k_dedup_sort(uint64_t *__res
     uint32_t *bufA_val = reinterpret_cast<uint32_t *>(bufB_key + SC_HT);
     uint32_t *bufB_val = bufA_val + SC_HT;
     uint16_t *rank_s = reinterpret_cast<uint16_t *>(bufB_val + SC_HT);                           // per element rank inside (warp, digit)
-    uint16_t *hist = rank_s + SC_HT;                                                             // [warp][digit]
+    uint16_t *list_slot = rank_s + SC_HT;                                                        // table slot of the i-th distinct key
+    uint16_t *hist = list_slot + SC_HT;                                                          // [warp][digit]
     __shared__ uint32_t m_s;
     __shared__ unsigned long long red_or, red_and;
     __shared__ uint32_t ws[33];
@@ -415,52 +319,63 @@ __global__ void __launch_bounds__(SC_DEDUP_THREADS) k_dedup_sort(uint64_t *__res
     if (threadIdx.x == 0) { m_s = 0; red_or = 0; red_and = EMPTY64; }
     __syncthreads();
 
-    // ---- 1. hash-combine
-    for (uint32_t i = s + threadIdx.x; i < e; i += blockDim.x)
+    // ---- 1. hash-combine; the thread that claims a slot also appends the key to the compact list (warp-aggregated cursor)
+    for (uint32_t i0 = s; i0 < e; i0 += blockDim.x)
     {
-        const uint64_t key = keys[i];
-        const uint64_t uk = key >> 3;
-        const uint32_t v = HAS_VAL ? vals_in[i] : (1u | (uint32_t(key & 7) << VAL_MARK_SHIFT));
-        uint32_t slot = uint32_t((uk * 0x9E3779B97F4A7C15ull) >> 40) & (SC_HT - 1);
-        int probes = 0;
-        while (true)
+        const uint32_t i = i0 + threadIdx.x;
+        bool is_new = false;
+        uint32_t slot = NONE32;
+        uint64_t uk = 0;
+        if (i < e)
         {
-            unsigned long long cur = bufA_key[slot];
-            if (cur == EMPTY64)
+            const uint64_t key = keys[i];
+            uk = key >> 3;
+            const uint32_t v = HAS_VAL ? vals_in[i] : (1u | (uint32_t(key & 7) << VAL_MARK_SHIFT));
+            slot = uint32_t((uk * 0x9E3779B97F4A7C15ull) >> 40) & (SC_HT - 1);
+            int probes = 0;
+            while (true)
             {
-                cur = atomicCAS(&bufA_key[slot], EMPTY64, (unsigned long long)uk);
-                if (cur == EMPTY64) cur = uk;
+                unsigned long long cur = bufA_key[slot];
+                if (cur == EMPTY64)
+                {
+                    cur = atomicCAS(&bufA_key[slot], EMPTY64, (unsigned long long)uk);
+                    if (cur == EMPTY64) { cur = uk; is_new = true; }
+                }
+                if (cur == uk) break;
+                slot = (slot + 1) & (SC_HT - 1);
+                if (++probes >= SC_HT) { atomicExch(overflow, 1); slot = NONE32; break; }
             }
-            if (cur == uk) break;
-            slot = (slot + 1) & (SC_HT - 1);
-            if (++probes >= SC_HT) { atomicExch(overflow, 1); slot = NONE32; break; }
+            if (slot != NONE32)
+            {
+                const uint32_t old = atomicAdd(&bufA_val[slot], v & VAL_COUNT_MASK);
+                const uint32_t mk = v & ~VAL_COUNT_MASK;
+                if ((old & mk) != mk) atomicOr(&bufA_val[slot], mk);
+            }
         }
-        if (slot != NONE32)
+        const unsigned newmask = __ballot_sync(0xFFFFFFFFu, is_new);
+        if (newmask)
         {
-            const uint32_t old = atomicAdd(&bufA_val[slot], v & VAL_COUNT_MASK);
-            const uint32_t mk = v & ~VAL_COUNT_MASK;
-            if ((old & mk) != mk) atomicOr(&bufA_val[slot], mk);
+            uint32_t basepos = 0;
+            if ((threadIdx.x & 31) == 0) basepos = atomicAdd(&m_s, uint32_t(__popc(newmask)));
+            basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
+            if (is_new)
+            {
+                const uint32_t pos = basepos + __popc(newmask & ((1u << (threadIdx.x & 31)) - 1));
+                bufB_key[pos] = uk;
+                list_slot[pos] = uint16_t(slot);
+            }
         }
     }
     __syncthreads();
 
-    // ---- 2. compact occupied slots into B (order irrelevant), and find which key bits vary
+    // ---- 2. fetch the combined values of the listed keys, and find which key bits vary
+    const uint32_t m = m_s;
     unsigned long long t_or = 0, t_and = EMPTY64;
-    for (int i = threadIdx.x; i < SC_HT; i += blockDim.x)
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
     {
-        const unsigned long long kk = bufA_key[i];
-        const bool occ = kk != EMPTY64;
-        const unsigned mask = __ballot_sync(0xFFFFFFFFu, occ);
-        uint32_t basepos = 0;
-        if ((threadIdx.x & 31) == 0 && mask) basepos = atomicAdd(&m_s, uint32_t(__popc(mask)));
-        basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
-        if (occ)
-        {
-            const uint32_t pos = basepos + __popc(mask & ((1u << (threadIdx.x & 31)) - 1));
-            bufB_key[pos] = kk;
-            bufB_val[pos] = bufA_val[i];
-            t_or |= kk; t_and &= kk;
-        }
+        const unsigned long long kk = bufB_key[i];
+        bufB_val[i] = bufA_val[list_slot[i]];
+        t_or |= kk; t_and &= kk;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1)
@@ -470,7 +385,6 @@ __global__ void __launch_bounds__(SC_DEDUP_THREADS) k_dedup_sort(uint64_t *__res
     }
     if ((threadIdx.x & 31) == 0) { atomicOr(&red_or, t_or); atomicAnd(&red_and, t_and); }
     __syncthreads();
-    const uint32_t m = m_s;
     const unsigned long long varying = red_or & ~red_and; // bits that differ between at least two keys
     const int top_bit = varying ? 63 - __clzll((long long)varying) : -1;
 
@@ -478,13 +392,14 @@ __global__ void __launch_bounds__(SC_DEDUP_THREADS) k_dedup_sort(uint64_t *__res
     unsigned long long *src_k = bufB_key, *dst_k = bufA_key;
     uint32_t *src_v = bufB_val, *dst_v = bufA_val;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t chunk = ((m + SC_DEDUP_WARPS * 32 - 1) / (SC_DEDUP_WARPS * 32)) * 32; // per-warp slice, multiple of 32
+    const uint32_t n_warps = blockDim.x >> 5;
+    const uint32_t chunk = ((m + n_warps * 32 - 1) / (n_warps * 32)) * 32; // per-warp slice, multiple of 32
     const uint32_t w_begin = min(m, warp * chunk), w_end = min(m, w_begin + chunk);
     uint16_t *my_hist = hist + warp * SC_RADIX;
     for (int shift = 0; shift <= top_bit; shift += SC_RADIX_BITS)
     {
         if (((varying >> shift) & (SC_RADIX - 1)) == 0) continue; // this digit is constant: nothing to do (uniform branch)
-        for (int i = threadIdx.x; i < SC_DEDUP_WARPS * SC_RADIX / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(hist)[i] = 0;
+        for (int i = threadIdx.x; i < int(n_warps) * SC_RADIX / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(hist)[i] = 0;
         __syncthreads();
         for (uint32_t g = w_begin; g < w_end; g += 32)
         {
@@ -504,16 +419,20 @@ __global__ void __launch_bounds__(SC_DEDUP_THREADS) k_dedup_sort(uint64_t *__res
             __syncwarp();
         }
         __syncthreads();
-        {   // exclusive scan over (digit major, warp minor): thread d owns digit d
+        {   // exclusive scan over (digit major, warp minor): thread d < SC_RADIX owns digit d (blockDim >= SC_RADIX)
             const uint32_t d = threadIdx.x;
             uint32_t run = 0;
-            uint16_t c[SC_DEDUP_WARPS];
-#pragma unroll
-            for (int w = 0; w < SC_DEDUP_WARPS; ++w) { c[w] = hist[w * SC_RADIX + d]; run += c[w]; }
+            if (d < SC_RADIX)
+                for (uint32_t w = 0; w < n_warps; ++w) run += hist[w * SC_RADIX + d];
             uint32_t total;
             uint32_t basev = block_exclusive_scan(run, ws, &total);
-#pragma unroll
-            for (int w = 0; w < SC_DEDUP_WARPS; ++w) { hist[w * SC_RADIX + d] = uint16_t(basev); basev += c[w]; }
+            if (d < SC_RADIX)
+                for (uint32_t w = 0; w < n_warps; ++w)
+                {
+                    const uint32_t c = hist[w * SC_RADIX + d];
+                    hist[w * SC_RADIX + d] = uint16_t(basev);
+                    basev += c;
+                }
         }
         __syncthreads();
         for (uint32_t g = w_begin; g < w_end; g += 32)
@@ -560,7 +479,7 @@ __global__ void __launch_bounds__(256) k_compact_uniques(const uint64_t *__restr
 // ---------------------------------------------------------------------------------------------------------------------
 struct SortCombineWorkspace
 {
-    DevBuf keysA, valsA, valsB, uvals_sparse, small, splitters, sub_cnt, sub_off, ucount, u_off, scan_scratch, cursor_pad;
+    DevBuf keysA, valsA, valsB, uvals_sparse, small, splitters, sub_cnt, sub_off, ucount, u_off, scan_scratch;
 };
 
 struct SortCombineStats
@@ -603,8 +522,8 @@ public:
         DGE_CUDA(cudaGetDevice(&dev));
         if (dev < 64 && done[dev]) return;
         DGE_CUDA(cudaFuncSetAttribute(k_splitters, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SAMPLE * 8));
-        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dedup_smem_bytes(SC_HT_MAX))));
-        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dedup_smem_bytes(SC_HT_MAX))));
+        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dedup_smem_bytes(SC_HT_MAX, 1024))));
+        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dedup_smem_bytes(SC_HT_MAX, 1024))));
         if (dev < 64) done[dev] = true;
     }
 
@@ -624,7 +543,6 @@ public:
                  *sb_base = p2 + stride, *tile_base = sb_base + stride;
         const int SC_TARGET = sc_tuning().target, SC_HT = sc_tuning().ht;
         const size_t nsb_bound = n / SC_TARGET + size_t(nb1) + 1;
-        const size_t tiles_bound = n / SC_TILE + size_t(nb1) + 1;
         ws.keysA.reserve(n * 8);
         if (has_val) { ws.valsA.reserve(n * 4); ws.valsB.reserve(n * 4); }
         ws.uvals_sparse.reserve(n * 4);
@@ -658,62 +576,50 @@ public:
         DGE_CUDA(cudaMemsetAsync(hist + nb1, 0, sizeof(uint32_t), st));
         device_exclusive_scan(hist, l1_off, stride, ws.scan_scratch.as<uint32_t>(), st, &L);
         uint64_t *keysA = ws.keysA.as<uint64_t>();
-        static const int direct = std::getenv("DGE_DIRECT") ? atoi(std::getenv("DGE_DIRECT")) : 0;
-        if (direct & 1)
-        {
-            ws.cursor_pad.reserve(size_t(nb1) * SC_CURSOR_PAD * 4);
-            k_pad_cursor<<<div_up(nb1, 256), 256, 0, st>>>(l1_off, nb1, ws.cursor_pad.as<uint32_t>());
-            const unsigned g = unsigned(div_up(n, size_t(SCD_THREADS * SCD_ITEMS)));
-            if (has_val)
-                k_l1_scatter_direct<true><<<g, SCD_THREADS, 0, st>>>(keys_in, vals_in, n, shift, ws.cursor_pad.as<uint32_t>(), keysA, ws.valsA.as<uint32_t>());
-            else
-                k_l1_scatter_direct<false><<<g, SCD_THREADS, 0, st>>>(keys_in, nullptr, n, shift, ws.cursor_pad.as<uint32_t>(), keysA, nullptr);
-            L += 2;
+        DGE_CUDA(cudaMemcpyAsync(cursor, l1_off, stride * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        static const int shape = std::getenv("DGE_TILE") ? atoi(std::getenv("DGE_TILE")) : 2;
+        size_t tile = 0;
+#define DGE_L1(IDX, T, I)                                                                                                          \
+        if (shape == IDX)                                                                                                          \
+        {                                                                                                                          \
+            tile = size_t(T) * I;                                                                                                  \
+            const unsigned g_tiles = unsigned(div_up(n, tile));                                                                    \
+            if (has_val) k_l1_scatter<true, T, I><<<g_tiles, T, 0, st>>>(keys_in, vals_in, n, shift, nb1, cursor, keysA, ws.valsA.as<uint32_t>()); \
+            else k_l1_scatter<false, T, I><<<g_tiles, T, 0, st>>>(keys_in, nullptr, n, shift, nb1, cursor, keysA, nullptr);        \
         }
-        else
-        {
-            DGE_CUDA(cudaMemcpyAsync(cursor, l1_off, stride * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-            const unsigned g_tiles = unsigned(div_up(n, size_t(SC_TILE)));
-            if (has_val)
-                k_l1_scatter<true><<<g_tiles, SC_THREADS, 0, st>>>(keys_in, vals_in, n, shift, nb1, cursor, keysA, ws.valsA.as<uint32_t>());
-            else
-                k_l1_scatter<false><<<g_tiles, SC_THREADS, 0, st>>>(keys_in, nullptr, n, shift, nb1, cursor, keysA, nullptr);
-            ++L;
-        }
+        DGE_L1(0, 512, 16) DGE_L1(1, 256, 16) DGE_L1(2, 256, 8) DGE_L1(3, 128, 16) DGE_L1(4, 512, 8) DGE_L1(5, 1024, 8)
+#undef DGE_L1
+        if (!tile) throw std::runtime_error("DGE_TILE out of range");
+        ++L;
         mark("l1 hist+scatter");
 
         // ---- L2
-        k_l1_plan<<<1, 1024, 0, st>>>(l1_off, nb1, uint32_t(SC_TARGET), p2, sb_base, tile_base); ++L;
+        const size_t tiles_bound = n / tile + size_t(nb1) + 1;
+        k_l1_plan<<<1, 1024, 0, st>>>(l1_off, nb1, uint32_t(SC_TARGET), uint32_t(tile), p2, sb_base, tile_base); ++L;
         k_splitters<<<nb1, SC_THREADS, SC_SAMPLE * 8, st>>>(keysA, l1_off, p2, ws.splitters.as<uint64_t>()); ++L;
         mark("plan+splitters");
         uint32_t *sub_cnt = ws.sub_cnt.as<uint32_t>(), *sub_off = ws.sub_off.as<uint32_t>();
         DGE_CUDA(cudaMemsetAsync(sub_cnt, 0, (nsb_bound + 1) * 4, st));
-        if (direct & 4)
-            k_l2_pass_direct<false, false><<<unsigned(tiles_bound), SCD_THREADS, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base,
-                                                                                          ws.splitters.as<uint64_t>(), sub_cnt, nullptr, nullptr);
-        else
-            k_l2_pass<false, false><<<unsigned(tiles_bound), SC_THREADS, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base,
-                                                                                   ws.splitters.as<uint64_t>(), sub_cnt, nullptr, nullptr);
+#define DGE_L2H(IDX, T, I)                                                                                                         \
+        if (shape == IDX) k_l2_pass<false, false, T, I><<<unsigned(tiles_bound), T, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base, \
+                                                                                              ws.splitters.as<uint64_t>(), sub_cnt, nullptr, nullptr);
+        DGE_L2H(0, 512, 16) DGE_L2H(1, 256, 16) DGE_L2H(2, 256, 8) DGE_L2H(3, 128, 16) DGE_L2H(4, 512, 8) DGE_L2H(5, 1024, 8)
+#undef DGE_L2H
         ++L;
         mark("l2 hist");
         device_exclusive_scan(sub_cnt, sub_off, nsb_bound + 1, ws.scan_scratch.as<uint32_t>(), st, &L);
         // cursors = copy of offsets (sub_cnt reused)
         DGE_CUDA(cudaMemcpyAsync(sub_cnt, sub_off, (nsb_bound + 1) * 4, cudaMemcpyDeviceToDevice, st));
-        if (direct & 2)
-        {
-            if (has_val)
-                k_l2_pass_direct<true, true><<<unsigned(tiles_bound), SCD_THREADS, 0, st>>>(keysA, ws.valsA.as<uint32_t>(), l1_off, nb1, p2, sb_base, tile_base,
-                                                                                            ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp, ws.valsB.as<uint32_t>());
-            else
-                k_l2_pass_direct<true, false><<<unsigned(tiles_bound), SCD_THREADS, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base,
-                                                                                             ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp, nullptr);
+#define DGE_L2S(IDX, T, I)                                                                                                         \
+        if (shape == IDX)                                                                                                          \
+        {                                                                                                                          \
+            if (has_val) k_l2_pass<true, true, T, I><<<unsigned(tiles_bound), T, 0, st>>>(keysA, ws.valsA.as<uint32_t>(), l1_off, nb1, p2, sb_base, tile_base, \
+                                                                                           ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp, ws.valsB.as<uint32_t>()); \
+            else k_l2_pass<true, false, T, I><<<unsigned(tiles_bound), T, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base, \
+                                                                                    ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp, nullptr); \
         }
-        else if (has_val)
-            k_l2_pass<true, true><<<unsigned(tiles_bound), SC_THREADS, 0, st>>>(keysA, ws.valsA.as<uint32_t>(), l1_off, nb1, p2, sb_base, tile_base,
-                                                                                 ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp, ws.valsB.as<uint32_t>());
-        else
-            k_l2_pass<true, false><<<unsigned(tiles_bound), SC_THREADS, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base,
-                                                                                  ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp, nullptr);
+        DGE_L2S(0, 512, 16) DGE_L2S(1, 256, 16) DGE_L2S(2, 256, 8) DGE_L2S(3, 128, 16) DGE_L2S(4, 512, 8) DGE_L2S(5, 1024, 8)
+#undef DGE_L2S
         ++L;
         mark("l2 scan+scatter");
 
@@ -725,11 +631,12 @@ public:
         {
             const uint32_t cut = uint32_t(SC_HT * 0.85);
             auto launch = [&](int ht, uint32_t lo, uint32_t hi) {
+                const int thr = sc_tuning().dedup_threads;
                 if (has_val)
-                    k_dedup_sort<true><<<unsigned(nsb_bound), SC_DEDUP_THREADS, dedup_smem_bytes(ht), st>>>(keys_tmp, ws.valsB.as<uint32_t>(), ws.uvals_sparse.as<uint32_t>(),
+                    k_dedup_sort<true><<<unsigned(nsb_bound), thr, dedup_smem_bytes(ht, thr), st>>>(keys_tmp, ws.valsB.as<uint32_t>(), ws.uvals_sparse.as<uint32_t>(),
                                                                                                           sub_off, n_sub_ptr, ucount, overflow_flag, ht, lo, hi);
                 else
-                    k_dedup_sort<false><<<unsigned(nsb_bound), SC_DEDUP_THREADS, dedup_smem_bytes(ht), st>>>(keys_tmp, nullptr, ws.uvals_sparse.as<uint32_t>(),
+                    k_dedup_sort<false><<<unsigned(nsb_bound), thr, dedup_smem_bytes(ht, thr), st>>>(keys_tmp, nullptr, ws.uvals_sparse.as<uint32_t>(),
                                                                                                            sub_off, n_sub_ptr, ucount, overflow_flag, ht, lo, hi);
                 ++L;
             };
