@@ -228,6 +228,8 @@ def main():
             ptr, cnt = raw.data_ptr(), n
         cont.add_batch_device(ptr, cnt)
         cont.set_initialized()
+        if world > 1:
+            dgdist.merge_across_ranks(cont, f"cuda:{dev}")  # exact cross-rank whitelist merge: two all-gathers
         cont.merge_and_filter()
         return cnt
 
@@ -324,7 +326,7 @@ def main():
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "result": {k: summary[k] for k in ("total_cells_number", "real_cells_number", "filtered_cells_number", "n_umigs", "cm_nnz", "n_merged", "n_excluded", "n_unresolved")}}
     if world > 1:
-        line["config"]["merge"] += "; RANK-LOCAL candidates only (cross-rank CB merge not implemented: see result.n_unresolved on rank 0)"
+        line["config"]["merge"] += "; cross-rank merge via all-gather of candidate cells (dge_dist_*), result.* are rank 0's shard"
     if world == 1 and not args.no_cpu_baseline:
         try:
             cb = cpu_reference_run(wl_path, wl_parts, args.cpu_sample_reads)

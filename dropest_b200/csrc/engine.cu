@@ -39,6 +39,7 @@ struct HostCell
     int32_t n_umis_distinct = 0;
     bool merged = false, excluded = false, real = true;
     int32_t target = -1; // index into `real`
+    uint64_t merged_to_cb = EMPTY64; // sharded runs: barcode of a merge target living on another rank
 };
 
 struct KeyChunk
@@ -105,6 +106,15 @@ struct dge_handle
     std::vector<uint64_t> h_sortkey;
     bool wl_uploaded = false;
     PinnedBuf pin_rows, pin_nbc, pin_nbp, pin_isect, pin_misc;
+    // cross-rank merge state (sharded runs)
+    DevBuf dist_infos, dist_keys, dist_vals, dist_jobs;
+    std::vector<dge_dist_child> g_infos;
+    std::vector<uint32_t> g_off;
+    const uint64_t *g_keys = nullptr;
+    const uint32_t *g_vals = nullptr;
+    std::vector<uint32_t> dist_targets;
+    bool dist_done = false, slot_pc_built = false;
+    uint64_t n_order_ties = 0;
 
     // host state
     std::vector<HostCell> real;            // cell-id (first-seen) order
@@ -388,6 +398,7 @@ void build_slot_pc(dge_handle *h)
         k_build_slot_pc<<<grid_for(h->n_pc, 256), 256, 0, h->stream>>>(h->pc_slot.as<uint32_t>(), h->n_pc, h->slot_pc.as<uint32_t>());
     DGE_LAUNCH_CHECK();
     h->launches += 2;
+    h->slot_pc_built = true;
 }
 
 void gather_rows(dge_handle *h, const std::vector<uint32_t> &pcs, std::vector<CellRow> &rows)
@@ -790,6 +801,8 @@ void phase2(dge_handle *h, const std::vector<long> &target)
 }
 
 // Apply the recorded merges to the device lists.
+void apply_moved(dge_handle *h, uint64_t total);
+
 void apply_merges(dge_handle *h)
 {
     if (h->merge_events.empty()) return;
@@ -825,14 +838,25 @@ void apply_merges(dge_handle *h)
     if (jobs.empty()) return;
     tr.mark("  apply: host job list");
     h->d_moves.reserve(jobs.size() * sizeof(MoveJob));
-    h->mkeys.reserve(total * 8); h->mvals.reserve(total * 4); h->ekey.reserve(total * 8); h->eval.reserve(total * 4);
+    h->mkeys.reserve(total * 8); h->mvals.reserve(total * 4);
     DGE_CUDA(cudaMemcpyAsync(h->d_moves.p, jobs.data(), jobs.size() * sizeof(MoveJob), cudaMemcpyHostToDevice, st));
-    const int gub = h->kl.gb + h->kl.ub;
     k_gather_relabel<<<grid_for(jobs.size(), 1, 148 * 16), 256, 0, st>>>(h->d_moves.as<MoveJob>(), uint32_t(jobs.size()), h->ukey.as<uint64_t>(),
-                                                                        h->uval.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), gub,
+                                                                        h->uval.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), h->kl.gb + h->kl.ub,
                                                                         h->mkeys.as<uint64_t>(), h->mvals.as<uint32_t>());
     DGE_LAUNCH_CHECK();
     ++h->launches;
+    apply_moved(h, total);
+}
+
+// h->mkeys / h->mvals hold `total` re-labelled (target cell, gene, umi) entries: combine them and fold them into U
+// (Gene::merge, Gene.cpp:26-36: existing UMIs get counts added and marks ORed, new UMIs are inserted), then rebuild the tables.
+void apply_moved(dge_handle *h, uint64_t total)
+{
+    cudaStream_t st = h->stream;
+    Tracer tr;
+    tr.st = st;
+    const int gub = h->kl.gb + h->kl.ub;
+    h->ekey.reserve(total * 8); h->eval.reserve(total * 4);
     const int l1_bits = std::min(choose_l1_bits(total), h->kl.kb - 3);
     const uint32_t *n_e_ptr = h->sc2.run(h->mkeys.as<uint64_t>(), h->mvals.as<uint32_t>(), total, h->kl.kb, l1_bits, nullptr, h->mkeys.as<uint64_t>(),
                                          h->ekey.as<uint64_t>(), h->eval.as<uint32_t>(), h->overflow_flag.as<int>(), st, &h->sc_stats);
@@ -905,10 +929,13 @@ void do_merge_and_filter(dge_handle *h)
     Tracer tr;
     tr.st = st;
     DGE_CUDA(cudaEventRecord(h->ev[3], st));
-    build_slot_pc(h);
+    if (!h->slot_pc_built) build_slot_pc(h);
 
     // ---- CB merge (MergeStrategyAbstract::merge, MergeStrategyAbstract.cpp:13-23)
-    if (h->cfg.merge_type == DGE_MERGE_REAL)
+    if (h->dist_done)
+    {   // sharded run: phase 1/2 were done across ranks by dge_dist_eval_children / dge_dist_apply
+    }
+    else if (h->cfg.merge_type == DGE_MERGE_REAL)
     {
         phase1_real(h, h->h_target);
         tr.mark("merge: phase 1");
@@ -927,12 +954,13 @@ void do_merge_and_filter(dge_handle *h)
     if (h->cfg.umi_merge_type != DGE_UMI_MERGE_SIMPLE) throw std::runtime_error("directional UMI merge not implemented on the device path yet");
 
     // ---- update_cell_sizes (CellsDataContainer.cpp:111-125): requested sizes of every cell, real = !merged && !excluded && size >= min
-    if (!h->merge_events.empty())
+    if (!h->merge_events.empty() || !h->dist_targets.empty())
     {
         // only merge TARGETS changed content: every other cell keeps the sizes read at set_initialized
         std::vector<uint32_t> pcs, owners;
         std::vector<char> is_target(h->real.size(), 0);
         for (auto const &e : h->merge_events) is_target[e.second] = 1;
+        for (uint32_t t : h->dist_targets) is_target[t] = 1;
         for (uint32_t i = 0; i < h->real.size(); ++i)
             if (is_target[i] && h->real[i].pc != NONE32) { pcs.push_back(h->real[i].pc); owners.push_back(i); }
         std::vector<CellRow> rows;
@@ -1168,6 +1196,7 @@ int dge_reset(dge_handle *h)
         h->real.clear(); h->filtered.clear(); h->gene_order.clear(); h->merge_events.clear();
         h->n_merged = h->n_excluded = h->n_unresolved = 0; h->total_cells = 0;
         h->cm.built = h->cm_raw.built = false;
+        h->dist_done = false; h->slot_pc_built = false; h->dist_targets.clear(); h->g_infos.clear(); h->n_order_ties = 0;
         h->timings = dge_timings{}; h->sc_stats = SortCombineStats{}; h->launches = 0;
         h->state = 0;
         if (h->device_ready) reset_fill_state(h);
@@ -1188,6 +1217,249 @@ int dge_merge_and_filter(dge_handle *h)
     if (h->state == 0) return fail(h, DGE_ERR_STATE, "You must initialize container");
     if (h->state == 2) return fail(h, DGE_ERR_STATE, "merge_and_filter was already run");
     return guarded(h, [&] { do_merge_and_filter(h); return int(DGE_OK); });
+}
+
+// ---- cross-rank whitelist merge (see include/dropest_b200.h) ---------------------------------------------------------------
+static void dist_check(dge_handle *h)
+{
+    if (h->state != 1) throw std::runtime_error("cross-rank merge runs between dge_set_initialized and dge_merge_and_filter");
+    if (!h->cfg.sharded || h->cfg.merge_type != DGE_MERGE_REAL) throw std::runtime_error("cross-rank merge needs sharded = 1 and merge_type = DGE_MERGE_REAL");
+}
+
+int dge_dist_export_children(dge_handle *h, const dge_dist_child **infos_device, const uint64_t **keys_device,
+                             const uint32_t **vals_device, uint64_t *n_children, uint64_t *n_entries)
+{
+    if (!h || !infos_device || !keys_device || !vals_device || !n_children || !n_entries) return fail(h, DGE_ERR_INVALID, "null argument");
+    return guarded(h, [&] {
+        dist_check(h);
+        DGE_CUDA(cudaSetDevice(h->cfg.device));
+        cudaStream_t st = h->stream;
+        if (!h->slot_pc_built) build_slot_pc(h);
+        const size_t n = h->real.size();
+        // which local real cells are whitelist barcodes themselves (target = self)?
+        std::vector<char> is_self(n, 0);
+        if (h->wl_fast && n)
+        {
+            if (!h->wl_uploaded) { upload_whitelist(h); h->wl_uploaded = true; }
+            h->h_cbs.resize(n); h->h_umis.resize(n);
+            for (size_t i = 0; i < n; ++i) { h->h_cbs[i] = h->real[i].cb; h->h_umis[i] = uint32_t(h->real[i].umis_stat); }
+            h->d_cb.reserve(n * 8); h->d_umis.reserve(n * 4); h->d_count.reserve(n * 4); h->d_nb.reserve(n * WL_K * 4);
+            DGE_CUDA(cudaMemcpyAsync(h->d_cb.p, h->h_cbs.data(), n * 8, cudaMemcpyHostToDevice, st));
+            DGE_CUDA(cudaMemcpyAsync(h->d_umis.p, h->h_umis.data(), n * 4, cudaMemcpyHostToDevice, st));
+            k_wl_class01<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>(), uint32_t(n), h->wl_dev,
+                                                                                h->tab.as<CellSlot>(), h->kl.tb, h->slot_pc.as<uint32_t>(),
+                                                                                h->pc_cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(),
+                                                                                h->cfg.min_genes_before_merge, h->d_count.as<int>(), h->d_nb.as<uint32_t>());
+            DGE_LAUNCH_CHECK();
+            ++h->launches;
+            const int *cnt = d2h_pinned<int>(h->pin_nbc, h->d_count.p, n, st);
+            DGE_CUDA(cudaStreamSynchronize(st));
+            for (size_t i = 0; i < n; ++i) is_self[i] = cnt[i] == NB_SELF;
+        }
+        else
+            for (size_t i = 0; i < n; ++i) is_self[i] = h->wl.contains(unpack_seq(h->real[i].cb, h->cfg.cb_len));
+        std::vector<dge_dist_child> infos;
+        std::vector<MoveJobLite> jobs;
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            const HostCell &c = h->real[i];
+            if (is_self[i]) { h->real[i].target = int32_t(i); continue; }
+            dge_dist_child ci;
+            ci.barcode = c.cb; ci.umis_stat = c.umis_stat; ci.reads_stat = c.reads_stat; ci.n_genes = c.n_genes;
+            ci.n_intergenic = c.n_intergenic; ci.n_entries = c.pc == NONE32 ? 0u : uint32_t(c.n_umis_distinct); ci.local_index = i;
+            if (ci.n_entries) jobs.push_back(MoveJobLite{c.pc, uint32_t(total)});
+            total += ci.n_entries;
+            infos.push_back(ci);
+        }
+        if (total >= 0xFFFFFFF0ull) throw std::runtime_error("children volume exceeds 2^32 entries");
+        h->dist_infos.reserve(std::max<size_t>(infos.size(), 1) * sizeof(dge_dist_child));
+        h->dist_keys.reserve(std::max<uint64_t>(total, 1) * 8); h->dist_vals.reserve(std::max<uint64_t>(total, 1) * 4);
+        if (!infos.empty()) DGE_CUDA(cudaMemcpyAsync(h->dist_infos.p, infos.data(), infos.size() * sizeof(dge_dist_child), cudaMemcpyHostToDevice, st));
+        if (!jobs.empty())
+        {
+            h->dist_jobs.reserve(jobs.size() * sizeof(MoveJobLite));
+            DGE_CUDA(cudaMemcpyAsync(h->dist_jobs.p, jobs.data(), jobs.size() * sizeof(MoveJobLite), cudaMemcpyHostToDevice, st));
+            k_export_cells<<<grid_for(jobs.size(), 1, 148 * 16), 256, 0, st>>>(h->dist_jobs.as<MoveJobLite>(), uint32_t(jobs.size()), h->ukey.as<uint64_t>(),
+                                                                              h->uval.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), h->kl.gb + h->kl.ub,
+                                                                              h->dist_keys.as<uint64_t>(), h->dist_vals.as<uint32_t>());
+            DGE_LAUNCH_CHECK();
+            ++h->launches;
+        }
+        DGE_CUDA(cudaStreamSynchronize(st));
+        *infos_device = h->dist_infos.as<dge_dist_child>(); *keys_device = h->dist_keys.as<uint64_t>(); *vals_device = h->dist_vals.as<uint32_t>();
+        *n_children = infos.size(); *n_entries = total;
+        return int(DGE_OK);
+    });
+}
+
+int dge_dist_copy_children(dge_handle *h, dge_dist_child *infos_dst_device, uint64_t *keys_dst_device, uint32_t *vals_dst_device,
+                           uint64_t n_children, uint64_t n_entries)
+{
+    if (!h) return DGE_ERR_INVALID;
+    return guarded(h, [&] {
+        dist_check(h);
+        DGE_CUDA(cudaSetDevice(h->cfg.device));
+        if (n_children) DGE_CUDA(cudaMemcpyAsync(infos_dst_device, h->dist_infos.p, n_children * sizeof(dge_dist_child), cudaMemcpyDeviceToDevice, h->stream));
+        if (n_entries)
+        {
+            DGE_CUDA(cudaMemcpyAsync(keys_dst_device, h->dist_keys.p, n_entries * 8, cudaMemcpyDeviceToDevice, h->stream));
+            DGE_CUDA(cudaMemcpyAsync(vals_dst_device, h->dist_vals.p, n_entries * 4, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        DGE_CUDA(cudaStreamSynchronize(h->stream));
+        return int(DGE_OK);
+    });
+}
+
+int dge_dist_eval_children(dge_handle *h, const dge_dist_child *infos_device, uint64_t n_children, const uint64_t *keys_device,
+                           const uint32_t *vals_device, uint64_t n_entries, dge_dist_result *results_host)
+{
+    if (!h || (n_children && (!infos_device || !results_host))) return fail(h, DGE_ERR_INVALID, "null argument");
+    return guarded(h, [&] {
+        dist_check(h);
+        DGE_CUDA(cudaSetDevice(h->cfg.device));
+        cudaStream_t st = h->stream;
+        if (!h->wl_fast) throw std::runtime_error("cross-rank merge needs a whitelist with equal-length, N-free parts");
+        if (!h->slot_pc_built) build_slot_pc(h);
+        if (!h->wl_uploaded) { upload_whitelist(h); h->wl_uploaded = true; }
+        const size_t n = size_t(n_children);
+        h->g_infos.resize(n);
+        h->g_keys = keys_device; h->g_vals = vals_device;
+        if (n) DGE_CUDA(cudaMemcpyAsync(h->g_infos.data(), infos_device, n * sizeof(dge_dist_child), cudaMemcpyDeviceToHost, st));
+        DGE_CUDA(cudaStreamSynchronize(st));
+        h->g_off.assign(n + 1, 0);
+        for (size_t i = 0; i < n; ++i) h->g_off[i + 1] = h->g_off[i] + h->g_infos[i].n_entries;
+        if (h->g_off[n] != n_entries) throw std::runtime_error("children lists do not add up to n_entries");
+        if (!n) return int(DGE_OK);
+        // local candidates of every child: distance classes 0/1 against THIS rank's cells
+        h->h_cbs.resize(n); h->h_umis.resize(n);
+        for (size_t i = 0; i < n; ++i) { h->h_cbs[i] = h->g_infos[i].barcode; h->h_umis[i] = uint32_t(h->g_infos[i].umis_stat); }
+        h->d_cb.reserve(n * 8); h->d_umis.reserve(n * 4); h->d_count.reserve(n * 4); h->d_nb.reserve(n * WL_K * 4);
+        DGE_CUDA(cudaMemcpyAsync(h->d_cb.p, h->h_cbs.data(), n * 8, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(cudaMemcpyAsync(h->d_umis.p, h->h_umis.data(), n * 4, cudaMemcpyHostToDevice, st));
+        k_wl_class01<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>(), uint32_t(n), h->wl_dev,
+                                                                            h->tab.as<CellSlot>(), h->kl.tb, h->slot_pc.as<uint32_t>(),
+                                                                            h->pc_cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(),
+                                                                            h->cfg.min_genes_before_merge, h->d_count.as<int>(), h->d_nb.as<uint32_t>());
+        DGE_LAUNCH_CHECK();
+        ++h->launches;
+        const int *nb_count = d2h_pinned<int>(h->pin_nbc, h->d_count.p, n, st);
+        const uint32_t *nb_pc = d2h_pinned<uint32_t>(h->pin_nbp, h->d_nb.p, n * WL_K, st);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        std::vector<ForeignJob> jobs;
+        std::vector<uint32_t> job_off(n + 1, 0);
+        for (size_t i = 0; i < n; ++i)
+        {
+            const int c = nb_count[i] > 0 ? nb_count[i] : 0; // NB_SLOW / overflow: no class-0/1 candidate here
+            for (int k = 0; k < c; ++k) jobs.push_back(ForeignJob{h->g_off[i], h->g_infos[i].n_entries, nb_pc[i * WL_K + size_t(k)]});
+            job_off[i + 1] = uint32_t(jobs.size());
+        }
+        const uint32_t *isect = nullptr;
+        if (!jobs.empty())
+        {
+            h->d_jobs.reserve(jobs.size() * sizeof(ForeignJob)); h->d_isect.reserve(jobs.size() * 4);
+            DGE_CUDA(cudaMemcpyAsync(h->d_jobs.p, jobs.data(), jobs.size() * sizeof(ForeignJob), cudaMemcpyHostToDevice, st));
+            k_intersect_foreign<<<unsigned(jobs.size()), 128, 0, st>>>(h->d_jobs.as<ForeignJob>(), uint32_t(jobs.size()), keys_device, h->ukey.as<uint64_t>(),
+                                                                       h->pc_u_start.as<uint32_t>(), h->pc_slot.as<uint32_t>(), h->kl.gb + h->kl.ub,
+                                                                       h->d_isect.as<uint32_t>());
+            DGE_LAUNCH_CHECK();
+            ++h->launches;
+            isect = d2h_pinned<uint32_t>(h->pin_isect, h->d_isect.p, jobs.size(), st);
+            DGE_CUDA(cudaStreamSynchronize(st));
+        }
+        std::vector<uint32_t> &pc_to_real = h->h_pc_to_real;
+        pc_to_real.assign(size_t(h->n_pc) + 1, NONE32);
+        for (uint32_t i = 0; i < h->real.size(); ++i) if (h->real[i].pc != NONE32) pc_to_real[h->real[i].pc] = i;
+        for (size_t i = 0; i < n; ++i)
+        {
+            dge_dist_result r;
+            r.best_fraction = 0; r.best_barcode = EMPTY64; r.n_neighbours = job_off[i + 1] - job_off[i]; r.n_best = 0;
+            for (uint32_t j = job_off[i]; j < job_off[i + 1]; ++j)
+            {
+                const HostCell &nb = h->real[pc_to_real[jobs[j].nb_pc]];
+                // same expression as RealBarcodesMergeStrategy.cpp:46-47
+                const double frac = 0.5 * isect[j] * (1. / size_t(h->g_infos[i].umis_stat) + 1. / size_t(nb.umis_stat));
+                if (r.n_best == 0 || r.best_fraction < frac) { r.best_fraction = frac; r.best_barcode = nb.cb; r.n_best = 1; }
+                else if (frac == r.best_fraction) { ++r.n_best; r.best_barcode = std::min<uint64_t>(r.best_barcode, nb.cb); }
+            }
+            results_host[i] = r;
+        }
+        return int(DGE_OK);
+    });
+}
+
+int dge_dist_apply(dge_handle *h, const dge_dist_result *all, uint32_t world, uint32_t my_rank, const uint32_t *child_rank)
+{
+    if (!h || world == 0 || (!h->g_infos.empty() && (!all || !child_rank))) return fail(h, DGE_ERR_INVALID, "null argument");
+    return guarded(h, [&] {
+        dist_check(h);
+        DGE_CUDA(cudaSetDevice(h->cfg.device));
+        cudaStream_t st = h->stream;
+        const size_t n = h->g_infos.size();
+        std::unordered_map<uint64_t, uint32_t> by_cb;
+        by_cb.reserve(h->real.size() * 2);
+        for (uint32_t i = 0; i < h->real.size(); ++i) by_cb.emplace(h->real[i].cb, i);
+        std::vector<ForeignMove> moves;
+        uint64_t total = 0;
+        h->n_merged = h->n_excluded = h->n_unresolved = h->n_order_ties = 0;
+        h->dist_targets.clear();
+        for (size_t c = 0; c < n; ++c)
+        {
+            const dge_dist_child &ci = h->g_infos[c];
+            const bool mine = child_rank[c] == my_rank;
+            uint32_t n_nb = 0, n_best = 0;
+            double best = 0;
+            uint64_t best_cb = EMPTY64;
+            for (uint32_t r = 0; r < world; ++r)
+            {
+                const dge_dist_result &res = all[size_t(r) * n + c];
+                if (!res.n_neighbours) continue;
+                n_nb += res.n_neighbours;
+                if (n_best == 0 || best < res.best_fraction) { best = res.best_fraction; best_cb = res.best_barcode; n_best = res.n_best; }
+                else if (res.best_fraction == best) { n_best += res.n_best; best_cb = std::min(best_cb, res.best_barcode); }
+            }
+            if (n_nb == 0)
+            {   // no class-0/1 candidate anywhere: the fall-through to farther classes is not distributed yet
+                if (mine) ++h->n_unresolved;
+                continue;
+            }
+            const bool excluded = best < h->cfg.min_merge_fraction; // RealBarcodesMergeStrategy.cpp:57-58
+            if (!excluded && n_best > 1 && mine) ++h->n_order_ties;    // order-dependent in the reference; we take the smallest barcode
+            if (mine)
+            {
+                HostCell &cell = h->real[ci.local_index];
+                if (excluded) { cell.excluded = true; ++h->n_excluded; }
+                else { cell.merged = true; cell.merged_to_cb = best_cb; ++h->n_merged; }
+            }
+            if (excluded) continue;
+            auto it = by_cb.find(best_cb);
+            if (it == by_cb.end()) continue; // the target lives on another rank
+            HostCell &dst = h->real[it->second];
+            dst.umis_stat += ci.umis_stat; dst.reads_stat += ci.reads_stat; dst.n_intergenic += ci.n_intergenic; // Stats::merge, Stats.cpp:29-43
+            h->dist_targets.push_back(it->second);
+            if (ci.n_entries)
+            {
+                moves.push_back(ForeignMove{h->g_off[c], ci.n_entries, dst.slot, uint32_t(total)});
+                total += ci.n_entries;
+            }
+        }
+        if (total >= 0xFFFFFFF0ull) throw std::runtime_error("merge volume exceeds 2^32 entries");
+        if (!moves.empty())
+        {
+            h->d_moves.reserve(moves.size() * sizeof(ForeignMove));
+            h->mkeys.reserve(total * 8); h->mvals.reserve(total * 4);
+            DGE_CUDA(cudaMemcpyAsync(h->d_moves.p, moves.data(), moves.size() * sizeof(ForeignMove), cudaMemcpyHostToDevice, st));
+            k_gather_relabel_foreign<<<grid_for(moves.size(), 1, 148 * 16), 256, 0, st>>>(h->d_moves.as<ForeignMove>(), uint32_t(moves.size()), h->g_keys, h->g_vals,
+                                                                                         h->kl.gb + h->kl.ub, h->mkeys.as<uint64_t>(), h->mvals.as<uint32_t>());
+            DGE_LAUNCH_CHECK();
+            ++h->launches;
+            apply_moved(h, total);
+        }
+        DGE_CUDA(cudaStreamSynchronize(st));
+        for (uint32_t i = 0; i < h->real.size(); ++i) if (h->real[i].merged_to_cb == EMPTY64) h->real[i].target = int32_t(i);
+        h->dist_done = true;
+        return int(DGE_OK);
+    });
 }
 
 int dge_get_summary(dge_handle *h, dge_summary *out)
@@ -1290,13 +1562,17 @@ int dge_get_merge_pairs(dge_handle *h, uint64_t *from, uint64_t *to, size_t capa
     if (!h || !n_out) return fail(h, DGE_ERR_INVALID, "null argument");
     if (h->state != 2) return fail(h, DGE_ERR_STATE, "merge targets exist after merge_and_filter");
     size_t n = 0;
-    for (auto const &c : h->real) n += uint32_t(c.target) != uint32_t(&c - h->real.data());
+    for (auto const &c : h->real) n += (uint32_t(c.target) != uint32_t(&c - h->real.data())) || c.merged_to_cb != EMPTY64;
     *n_out = n;
     if (from && to && capacity >= n)
     {
         size_t k = 0;
         for (uint32_t i = 0; i < h->real.size(); ++i)
-            if (uint32_t(h->real[i].target) != i) { from[k] = h->real[i].cb; to[k] = h->real[size_t(h->real[i].target)].cb; ++k; }
+        {
+            const HostCell &c = h->real[i];
+            if (c.merged_to_cb != EMPTY64) { from[k] = c.cb; to[k] = c.merged_to_cb; ++k; }
+            else if (uint32_t(c.target) != i) { from[k] = c.cb; to[k] = h->real[size_t(c.target)].cb; ++k; }
+        }
     }
     return DGE_OK;
 }

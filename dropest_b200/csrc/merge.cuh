@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(256) k_wl_class01(const uint64_t *__restrict__
 }
 
 struct PairJob { uint32_t a_pc, b_pc; };
+struct MoveJobLite { uint32_t src_pc, out_off; };
 
 // One block per pair: every (gene, umi) of A is searched in B's sorted range.
 __global__ void __launch_bounds__(128) k_intersect(const PairJob *__restrict__ jobs, uint32_t n_jobs, const uint64_t *__restrict__ ukey,
@@ -147,6 +148,75 @@ __global__ void __launch_bounds__(128) k_intersect(const PairJob *__restrict__ j
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
     __syncthreads();
     if (threadIdx.x == 0) out[job] = red[0] + red[1] + red[2] + red[3];
+}
+
+// ---- cross-rank merge: candidate cells ("children") travel as (gene|umi, value) lists --------------------------------
+struct ForeignJob { uint32_t off, n, nb_pc; };          // child entries [off, off+n) of the gathered list vs local cell nb_pc
+struct ForeignMove { uint32_t off, n, dst_slot, out_off; };
+
+// |child ∩ local cell|: every (gene,umi) of the child is searched in the local cell's sorted range
+__global__ void __launch_bounds__(128) k_intersect_foreign(const ForeignJob *__restrict__ jobs, uint32_t n_jobs, const uint64_t *__restrict__ ckeys,
+                                                           const uint64_t *__restrict__ ukey, const uint32_t *__restrict__ pc_u_start,
+                                                           const uint32_t *__restrict__ pc_slot, int gub, uint32_t *__restrict__ out)
+{
+    __shared__ uint32_t red[4];
+    const uint32_t job = blockIdx.x;
+    if (job >= n_jobs) return;
+    const ForeignJob j = jobs[job];
+    const uint32_t bs = pc_u_start[j.nb_pc], be = pc_u_start[j.nb_pc + 1];
+    const uint64_t b_prefix = uint64_t(pc_slot[j.nb_pc]) << gub;
+    uint32_t cnt = 0;
+    for (uint32_t i = threadIdx.x; i < j.n; i += blockDim.x)
+    {
+        const uint64_t want = b_prefix | ckeys[j.off + i];
+        uint32_t lo = bs, hi = be;
+        while (lo < hi)
+        {
+            uint32_t mid = (lo + hi) >> 1;
+            if (ukey[mid] < want) lo = mid + 1; else hi = mid;
+        }
+        cnt += lo < be && ukey[lo] == want;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xFFFFFFFFu, cnt, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) out[job] = red[0] + red[1] + red[2] + red[3];
+}
+
+// export: (gene|umi) part + value of the listed local cells, concatenated
+__global__ void __launch_bounds__(256) k_export_cells(const MoveJobLite *__restrict__ jobs, uint32_t n_jobs, const uint64_t *__restrict__ ukey,
+                                                      const uint32_t *__restrict__ uval, const uint32_t *__restrict__ pc_u_start, int gub,
+                                                      uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
+{
+    const uint64_t gu_mask = (1ull << gub) - 1;
+    for (uint32_t j = blockIdx.x; j < n_jobs; j += gridDim.x)
+    {
+        const MoveJobLite job = jobs[j];
+        const uint32_t s = pc_u_start[job.src_pc], e = pc_u_start[job.src_pc + 1];
+        for (uint32_t i = s + threadIdx.x; i < e; i += blockDim.x)
+        {
+            out_keys[job.out_off + (i - s)] = ukey[i] & gu_mask;
+            out_vals[job.out_off + (i - s)] = uval[i];
+        }
+    }
+}
+
+// foreign child lists re-labelled to a local destination slot, as sortcombine input
+__global__ void __launch_bounds__(256) k_gather_relabel_foreign(const ForeignMove *__restrict__ jobs, uint32_t n_jobs, const uint64_t *__restrict__ ckeys,
+                                                                const uint32_t *__restrict__ cvals, int gub, uint64_t *__restrict__ out_keys,
+                                                                uint32_t *__restrict__ out_vals)
+{
+    for (uint32_t j = blockIdx.x; j < n_jobs; j += gridDim.x)
+    {
+        const ForeignMove job = jobs[j];
+        const uint64_t prefix = uint64_t(job.dst_slot) << gub;
+        for (uint32_t i = threadIdx.x; i < job.n; i += blockDim.x)
+        {
+            out_keys[job.out_off + i] = (prefix | ckeys[job.off + i]) << 3;
+            out_vals[job.out_off + i] = cvals[job.off + i];
+        }
+    }
 }
 
 // ---- applying merges -------------------------------------------------------------------------------------------------

@@ -155,6 +155,16 @@ public:
         return res;
     }
 
+    // Is `cb` itself a whitelist barcode (every part equals a token)?  Such a cell is its own merge target.
+    bool contains(const std::string &cb) const
+    {
+        std::vector<std::string> p;
+        try { p = split(cb); } catch (std::exception &) { return false; }
+        for (size_t k = 0; k < parts.size(); ++k)
+            if (std::find(parts[k].begin(), parts[k].end(), p[k]) == parts[k].end()) return false;
+        return true;
+    }
+
     // True when every part has one token length, tokens are N-free, and the lengths add up to cb_len:
     // then distance classes 0/1 are Hamming classes and the device fast path is exact.
     bool fast_path_ok(size_t cb_len) const

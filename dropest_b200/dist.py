@@ -53,3 +53,46 @@ def exchange(routed, counts: np.ndarray, recv=None, group=None):
 
 def records_from_tensor(t) -> np.ndarray:
     return np.frombuffer(t.cpu().numpy().tobytes(), dtype=RECORD_DTYPE)
+
+
+def merge_across_ranks(cont, device: str, group=None):
+    """Exact whitelist merge for sharded runs: two all-gathers around three local library steps.
+    Call between cont.set_initialized() and cont.merge_and_filter()."""
+    import torch
+    import torch.distributed as dist
+
+    from .capi import DIST_RESULT_DTYPE
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nc, ne = cont.dist_export_children()
+    mine = torch.tensor([nc, ne], dtype=torch.int64, device=device)
+    counts = torch.empty(world * 2, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, mine, group=group)
+    counts = counts.cpu().numpy().reshape(world, 2)
+    max_nc, max_ne = int(counts[:, 0].max()), int(counts[:, 1].max())
+    ncs, nes = counts[:, 0], counts[:, 1]
+    tot_nc, tot_ne = int(ncs.sum()), int(nes.sum())
+    if tot_nc == 0:
+        cont.dist_apply(np.zeros(0, dtype=DIST_RESULT_DTYPE), world, rank, np.zeros(0, dtype=np.uint32))
+        return {"children": 0, "entries": 0}
+    send_i = torch.zeros(max(max_nc, 1) * 32, dtype=torch.uint8, device=device)
+    send_k = torch.zeros(max(max_ne, 1) * 8, dtype=torch.uint8, device=device)
+    send_v = torch.zeros(max(max_ne, 1) * 4, dtype=torch.uint8, device=device)
+    cont.dist_copy_children(send_i.data_ptr(), send_k.data_ptr(), send_v.data_ptr(), nc, ne)
+    all_i = torch.empty(world * send_i.numel(), dtype=torch.uint8, device=device)
+    all_k = torch.empty(world * send_k.numel(), dtype=torch.uint8, device=device)
+    all_v = torch.empty(world * send_v.numel(), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(all_i, send_i, group=group)   # children summaries
+    dist.all_gather_into_tensor(all_k, send_k, group=group)   # their (gene|umi) lists ...
+    dist.all_gather_into_tensor(all_v, send_v, group=group)   # ... and values
+    g_i = torch.cat([all_i[r * send_i.numel(): r * send_i.numel() + int(ncs[r]) * 32] for r in range(world)])
+    g_k = torch.cat([all_k[r * send_k.numel(): r * send_k.numel() + int(nes[r]) * 8] for r in range(world)])
+    g_v = torch.cat([all_v[r * send_v.numel(): r * send_v.numel() + int(nes[r]) * 4] for r in range(world)])
+    local = cont.dist_eval_children(g_i.data_ptr(), tot_nc, g_k.data_ptr(), g_v.data_ptr(), tot_ne)
+    res_t = torch.from_numpy(np.frombuffer(local.tobytes(), dtype=np.uint8).copy()).to(device)
+    all_r = torch.empty(world * res_t.numel(), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(all_r, res_t, group=group)    # per-rank best candidate of every child
+    all_results = np.frombuffer(all_r.cpu().numpy().tobytes(), dtype=DIST_RESULT_DTYPE)
+    child_rank = np.repeat(np.arange(world, dtype=np.uint32), ncs.astype(np.int64))
+    cont.dist_apply(all_results, world, rank, child_rank)     # g_k / g_v stay alive until here
+    return {"children": tot_nc, "entries": tot_ne}

@@ -256,6 +256,45 @@ int dge_synth_generate_device(int device, const dge_synth_params *p, uint64_t fi
 int dge_route_by_barcode_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, dge_record16 *out,
                                 uint64_t *counts, void *cuda_stream);
 
+/* ---- cross-rank whitelist merge for sharded runs ---------------------------------------------------
+ * With reads sharded by barcode hash a cell and its merge candidates usually live on different ranks.  The exchange itself
+ * (two all-gathers) is done by the caller with whatever transport it has (NCCL in bench.py / dropest_b200/dist.py); the
+ * library provides the three local steps.  Sequence on every rank, after dge_set_initialized:
+ *   1. dge_dist_export_children : real cells that are not whitelist barcodes ("children"), as one info row per cell and the
+ *                                 concatenated (gene|umi, value) lists -- DEVICE pointers, valid until dge_dist_apply
+ *   2. [all-gather infos, keys, vals over ranks, concatenated in rank order]
+ *   3. dge_dist_eval_children   : every child of every rank against THIS rank's cells (distance classes 0/1, eligibility,
+ *                                 (gene,umi) overlap): one dge_dist_result per child (HOST array)
+ *   4. [all-gather the results]
+ *   5. dge_dist_apply           : combines the per-rank results exactly like RealBarcodesMergeStrategy::get_best_merge_target,
+ *                                 merges children whose target lives here, flags local children as merged / excluded
+ *   6. dge_merge_and_filter     : continues with the UMI merge, final sizes, filter and matrices
+ * Children without any class-0/1 candidate on any rank are left unmerged and counted in dge_summary.n_unresolved. */
+typedef struct dge_dist_child {
+    uint64_t barcode;
+    int32_t  umis_stat, reads_stat, n_genes;
+    uint32_t n_intergenic;
+    uint32_t n_entries;   /* length of the child's (gene|umi, value) list */
+    uint32_t local_index; /* opaque to other ranks */
+} dge_dist_child;
+
+typedef struct dge_dist_result {
+    double   best_fraction;   /* max over this rank's eligible neighbours of 0.5*I*(1/U_child + 1/U_nb) */
+    uint64_t best_barcode;    /* the neighbour reaching it */
+    uint32_t n_neighbours;    /* eligible neighbours found on this rank (0 = none) */
+    uint32_t n_best;          /* how many of them reach best_fraction exactly (ties) */
+} dge_dist_result;
+
+int dge_dist_export_children(dge_handle *h, const dge_dist_child **infos_device, const uint64_t **keys_device,
+                             const uint32_t **vals_device, uint64_t *n_children, uint64_t *n_entries);
+/* copies the export of step 1 into caller-owned DEVICE buffers (e.g. the send buffers of the all-gather) */
+int dge_dist_copy_children(dge_handle *h, dge_dist_child *infos_dst_device, uint64_t *keys_dst_device, uint32_t *vals_dst_device,
+                           uint64_t n_children, uint64_t n_entries);
+int dge_dist_eval_children(dge_handle *h, const dge_dist_child *infos_device, uint64_t n_children, const uint64_t *keys_device,
+                           const uint32_t *vals_device, uint64_t n_entries, dge_dist_result *results_host);
+int dge_dist_apply(dge_handle *h, const dge_dist_result *all_results_host, uint32_t world, uint32_t my_rank,
+                   const uint32_t *child_rank_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,90 @@ def _triplets(c, dg):
     return np.stack([cells["barcode"][col].astype(np.uint64), genes.astype(np.uint64), vals.astype(np.uint64)], axis=1)
 
 
+def _cm_triplets(c, dg, which_cells, which_matrix):
+    cells = c.cells(which_cells)
+    indptr, genes, vals = c.matrix(which_matrix)
+    col = np.repeat(np.arange(indptr.shape[0] - 1), np.diff(indptr))
+    return np.stack([cells["barcode"][col].astype(np.uint64), genes.astype(np.uint64), vals.astype(np.uint64)], axis=1)
+
+
+def _worker_real(rank, world, port, n_total, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    import dropest_b200 as dg
+    from dropest_b200 import dist as dgdist
+    from dropest_b200.synth import SynthTables
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    per = n_total // world
+    raw = torch.empty(per * 16, dtype=torch.uint8, device=f"cuda:{rank}")
+    SynthTables(_spec(n_total)).generate_device(rank, rank * per, per, raw.data_ptr())
+    routed = torch.empty_like(raw)
+    counts = dgdist.route_device(rank, raw.data_ptr(), per, world, routed.data_ptr())
+    got, cnt = dgdist.exchange(routed, counts)
+    torch.cuda.synchronize()
+    c = dg.Container(dg.Config(cb_len=16, umi_len=10, n_genes=150, device=rank, merge_type=dg.MERGE_REAL, barcodes_type=dg.BARCODES_CONST,
+                               barcodes_file=pu.WL_SYNTH_7_9, min_genes_before_merge=5, min_genes_after_merge=10, sharded=True,
+                               max_barcodes_hint=1 << 16))
+    c.add_batch_device(got.data_ptr(), cnt, keepalive=got)
+    c.set_initialized()
+    stats = dgdist.merge_across_ranks(c, f"cuda:{rank}")
+    c.merge_and_filter()
+    np.save(os.path.join(out_dir, f"cm{rank}.npy"), _cm_triplets(c, dg, dg.CELLS_FILTERED, dg.MATRIX_CM))
+    np.save(os.path.join(out_dir, f"raw{rank}.npy"), _cm_triplets(c, dg, dg.CELLS_REAL, dg.MATRIX_CM_RAW))
+    a, b = c.merge_pairs()
+    np.save(os.path.join(out_dir, f"pairs{rank}.npy"), np.stack([a, b], axis=1))
+    filt = c.cells(dg.CELLS_FILTERED)
+    np.save(os.path.join(out_dir, f"filt{rank}.npy"), np.stack([filt["barcode"], filt["umis_stat"].astype(np.uint64), filt["reads_stat"].astype(np.uint64),
+                                                             filt["requested_genes_num"].astype(np.uint64)], axis=1))
+    s = c.summary()
+    np.save(os.path.join(out_dir, f"sum{rank}.npy"), np.array([s[k] for k in ("n_merged", "n_excluded", "n_unresolved", "real_cells_number", "filtered_cells_number")]))
+    c.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_cross_rank_whitelist_merge_is_exact(tmp_path):
+    """Sharded run + cross-rank merge (dge_dist_*): the union of the per-rank results equals the single-GPU result."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    import dropest_b200 as dg
+    from dropest_b200.synth import SynthTables
+
+    world, n_total = 2, 300_000
+    mp.spawn(_worker_real, args=(world, _free_port(), n_total, str(tmp_path)), nprocs=world, join=True)
+    recs = SynthTables(_spec(n_total)).generate_host(0, n_total)
+    c = dg.Container(dg.Config(cb_len=16, umi_len=10, n_genes=150, merge_type=dg.MERGE_REAL, barcodes_type=dg.BARCODES_CONST,
+                               barcodes_file=pu.WL_SYNTH_7_9, min_genes_before_merge=5, min_genes_after_merge=10, max_barcodes_hint=1 << 16))
+    c.add_batch(recs)
+    c.set_initialized()
+    c.merge_and_filter()
+    order = lambda t: t[np.lexsort(tuple(t[:, k] for k in reversed(range(t.shape[1]))))]
+    cat = lambda name: np.concatenate([np.load(tmp_path / f"{name}{r}.npy") for r in range(world)])
+    s = c.summary()
+    sums = sum(np.load(tmp_path / f"sum{r}.npy") for r in range(world))
+    print("sums", sums, "single", s)
+    assert s["n_merged"] > 0
+    assert list(sums) == [s["n_merged"], s["n_excluded"], 0, s["real_cells_number"], s["filtered_cells_number"]]
+    a, b = c.merge_pairs()
+    np.testing.assert_array_equal(order(cat("pairs")), order(np.stack([a, b], axis=1)))
+    np.testing.assert_array_equal(order(cat("cm")), order(_cm_triplets(c, dg, dg.CELLS_FILTERED, dg.MATRIX_CM)))
+    np.testing.assert_array_equal(order(cat("raw")), order(_cm_triplets(c, dg, dg.CELLS_REAL, dg.MATRIX_CM_RAW)))
+    filt = c.cells(dg.CELLS_FILTERED)
+    single_f = np.stack([filt["barcode"], filt["umis_stat"].astype(np.uint64), filt["reads_stat"].astype(np.uint64),
+                         filt["requested_genes_num"].astype(np.uint64)], axis=1)
+    np.testing.assert_array_equal(order(cat("filt")), order(single_f))
+    c.close()
+
+
 def _worker(rank, world, port, n_total, out_dir):
     import torch
     import torch.distributed as dist
