@@ -112,7 +112,7 @@ struct dge_handle
     std::vector<uint32_t> g_off;
     const uint64_t *g_keys = nullptr;
     const uint32_t *g_vals = nullptr;
-    std::vector<uint32_t> dist_targets;
+    std::vector<uint32_t> dist_targets, g_best_local;
     bool dist_done = false, slot_pc_built = false;
     uint64_t n_order_ties = 0;
 
@@ -1323,10 +1323,10 @@ int dge_dist_eval_children(dge_handle *h, const dge_dist_child *infos_device, ui
         if (!h->slot_pc_built) build_slot_pc(h);
         if (!h->wl_uploaded) { upload_whitelist(h); h->wl_uploaded = true; }
         const size_t n = size_t(n_children);
-        h->g_infos.resize(n);
         h->g_keys = keys_device; h->g_vals = vals_device;
-        if (n) DGE_CUDA(cudaMemcpyAsync(h->g_infos.data(), infos_device, n * sizeof(dge_dist_child), cudaMemcpyDeviceToHost, st));
+        const dge_dist_child *pinned_infos = d2h_pinned<dge_dist_child>(h->pin_rows, infos_device, n, st);
         DGE_CUDA(cudaStreamSynchronize(st));
+        h->g_infos.assign(pinned_infos, pinned_infos + n);
         h->g_off.assign(n + 1, 0);
         for (size_t i = 0; i < n; ++i) h->g_off[i + 1] = h->g_off[i] + h->g_infos[i].n_entries;
         if (h->g_off[n] != n_entries) throw std::runtime_error("children lists do not add up to n_entries");
@@ -1370,17 +1370,23 @@ int dge_dist_eval_children(dge_handle *h, const dge_dist_child *infos_device, ui
         std::vector<uint32_t> &pc_to_real = h->h_pc_to_real;
         pc_to_real.assign(size_t(h->n_pc) + 1, NONE32);
         for (uint32_t i = 0; i < h->real.size(); ++i) if (h->real[i].pc != NONE32) pc_to_real[h->real[i].pc] = i;
+        h->g_best_local.assign(n, NONE32);
         for (size_t i = 0; i < n; ++i)
         {
             dge_dist_result r;
             r.best_fraction = 0; r.best_barcode = EMPTY64; r.n_neighbours = job_off[i + 1] - job_off[i]; r.n_best = 0;
             for (uint32_t j = job_off[i]; j < job_off[i + 1]; ++j)
             {
-                const HostCell &nb = h->real[pc_to_real[jobs[j].nb_pc]];
+                const uint32_t nb_idx = pc_to_real[jobs[j].nb_pc];
+                const HostCell &nb = h->real[nb_idx];
                 // same expression as RealBarcodesMergeStrategy.cpp:46-47
                 const double frac = 0.5 * isect[j] * (1. / size_t(h->g_infos[i].umis_stat) + 1. / size_t(nb.umis_stat));
-                if (r.n_best == 0 || r.best_fraction < frac) { r.best_fraction = frac; r.best_barcode = nb.cb; r.n_best = 1; }
-                else if (frac == r.best_fraction) { ++r.n_best; r.best_barcode = std::min<uint64_t>(r.best_barcode, nb.cb); }
+                if (r.n_best == 0 || r.best_fraction < frac) { r.best_fraction = frac; r.best_barcode = nb.cb; r.n_best = 1; h->g_best_local[i] = nb_idx; }
+                else if (frac == r.best_fraction)
+                {
+                    ++r.n_best;
+                    if (nb.cb < r.best_barcode) { r.best_barcode = nb.cb; h->g_best_local[i] = nb_idx; }
+                }
             }
             results_host[i] = r;
         }
@@ -1396,9 +1402,6 @@ int dge_dist_apply(dge_handle *h, const dge_dist_result *all, uint32_t world, ui
         DGE_CUDA(cudaSetDevice(h->cfg.device));
         cudaStream_t st = h->stream;
         const size_t n = h->g_infos.size();
-        std::unordered_map<uint64_t, uint32_t> by_cb;
-        by_cb.reserve(h->real.size() * 2);
-        for (uint32_t i = 0; i < h->real.size(); ++i) by_cb.emplace(h->real[i].cb, i);
         std::vector<ForeignMove> moves;
         uint64_t total = 0;
         h->n_merged = h->n_excluded = h->n_unresolved = h->n_order_ties = 0;
@@ -1432,11 +1435,12 @@ int dge_dist_apply(dge_handle *h, const dge_dist_result *all, uint32_t world, ui
                 else { cell.merged = true; cell.merged_to_cb = best_cb; ++h->n_merged; }
             }
             if (excluded) continue;
-            auto it = by_cb.find(best_cb);
-            if (it == by_cb.end()) continue; // the target lives on another rank
-            HostCell &dst = h->real[it->second];
+            // the global winner is ours iff it is the local best recorded by dge_dist_eval_children
+            const uint32_t dst_idx = h->g_best_local[c];
+            if (dst_idx == NONE32 || h->real[dst_idx].cb != best_cb) continue; // the target lives on another rank
+            HostCell &dst = h->real[dst_idx];
             dst.umis_stat += ci.umis_stat; dst.reads_stat += ci.reads_stat; dst.n_intergenic += ci.n_intergenic; // Stats::merge, Stats.cpp:29-43
-            h->dist_targets.push_back(it->second);
+            h->dist_targets.push_back(dst_idx);
             if (ci.n_entries)
             {
                 moves.push_back(ForeignMove{h->g_off[c], ci.n_entries, dst.slot, uint32_t(total)});

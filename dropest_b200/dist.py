@@ -63,8 +63,22 @@ def merge_across_ranks(cont, device: str, group=None):
 
     from .capi import DIST_RESULT_DTYPE
 
+    import os
+    import time
+
+    trace = os.environ.get("DGE_TRACE") and dist.get_rank(group) == 0
+    t_prev = [time.perf_counter()]
+
+    def mark(what):
+        if trace:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            print(f"[dge] dist: {what:<28s} {1000 * (now - t_prev[0]):8.3f} ms", flush=True)
+            t_prev[0] = now
+
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     nc, ne = cont.dist_export_children()
+    mark("export children")
     mine = torch.tensor([nc, ne], dtype=torch.int64, device=device)
     counts = torch.empty(world * 2, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(counts, mine, group=group)
@@ -85,14 +99,19 @@ def merge_across_ranks(cont, device: str, group=None):
     dist.all_gather_into_tensor(all_i, send_i, group=group)   # children summaries
     dist.all_gather_into_tensor(all_k, send_k, group=group)   # their (gene|umi) lists ...
     dist.all_gather_into_tensor(all_v, send_v, group=group)   # ... and values
+    mark("all-gather children")
     g_i = torch.cat([all_i[r * send_i.numel(): r * send_i.numel() + int(ncs[r]) * 32] for r in range(world)])
     g_k = torch.cat([all_k[r * send_k.numel(): r * send_k.numel() + int(nes[r]) * 8] for r in range(world)])
     g_v = torch.cat([all_v[r * send_v.numel(): r * send_v.numel() + int(nes[r]) * 4] for r in range(world)])
+    mark("concatenate")
     local = cont.dist_eval_children(g_i.data_ptr(), tot_nc, g_k.data_ptr(), g_v.data_ptr(), tot_ne)
-    res_t = torch.from_numpy(np.frombuffer(local.tobytes(), dtype=np.uint8).copy()).to(device)
+    mark("eval children")
+    res_t = torch.from_numpy(local.view(np.uint8)).to(device)
     all_r = torch.empty(world * res_t.numel(), dtype=torch.uint8, device=device)
     dist.all_gather_into_tensor(all_r, res_t, group=group)    # per-rank best candidate of every child
-    all_results = np.frombuffer(all_r.cpu().numpy().tobytes(), dtype=DIST_RESULT_DTYPE)
+    all_results = all_r.cpu().numpy().view(DIST_RESULT_DTYPE)
     child_rank = np.repeat(np.arange(world, dtype=np.uint32), ncs.astype(np.int64))
+    mark("all-gather results")
     cont.dist_apply(all_results, world, rank, child_rank)     # g_k / g_v stay alive until here
+    mark("apply")
     return {"children": tot_nc, "entries": tot_ne}
