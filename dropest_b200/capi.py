@@ -327,6 +327,19 @@ class Container:
                                              C.byref(nc), C.byref(nnz)))
         return indptr, genes, vals
 
+    def matrix_shape(self, which: int):
+        nc, nnz = C.c_size_t(0), C.c_size_t(0)
+        self._check(self._lib.dge_get_matrix(self._h, which, None, None, None, C.byref(nc), C.byref(nnz)))
+        return int(nc.value), int(nnz.value)
+
+    def matrix_into(self, which: int, indptr_ptr: int, genes_ptr: int, vals_ptr: int):
+        """Copy the matrix into caller-owned host buffers (int64[n_cols+1], int32[nnz], int32[nnz]); page-locked buffers get
+        full PCIe speed."""
+        nc, nnz = C.c_size_t(0), C.c_size_t(0)
+        self._check(self._lib.dge_get_matrix(self._h, which, C.c_void_p(indptr_ptr), C.c_void_p(genes_ptr), C.c_void_p(vals_ptr),
+                                             C.byref(nc), C.byref(nnz)))
+        return int(nc.value), int(nnz.value)
+
     def gene_order(self) -> np.ndarray:
         n = C.c_size_t(0)
         self._check(self._lib.dge_get_gene_order(self._h, None, 0, C.byref(n)))

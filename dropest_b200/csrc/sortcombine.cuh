@@ -288,25 +288,30 @@ constexpr int SC_RADIX_BITS = 8;
 constexpr int SC_RADIX = 1 << SC_RADIX_BITS;
 constexpr int SC_DEDUP_WARPS = SC_DEDUP_THREADS / 32;
 
-inline size_t dedup_smem_bytes(int ht, int threads = SC_DEDUP_THREADS) { return size_t(ht) * 28 + size_t(threads / 32) * SC_RADIX * 2 + 64; }
+// shared memory: table ht x (8 B key + 4 B value) + three u16 arrays of `cap` entries (index list ping-pong + ranks) + histograms
+inline size_t dedup_smem_bytes(int ht, int cap, int threads = SC_DEDUP_THREADS)
+{
+    return size_t(ht) * 12 + size_t(cap) * 6 + size_t(threads / 32) * SC_RADIX * 2 + 64;
+}
 
 template <bool HAS_VAL>
 __global__ void __launch_bounds__(1024) k_dedup_sort(uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals_in,
                                                                  uint32_t *__restrict__ uvals, const uint32_t *__restrict__ sub_off,
                                                                  const uint32_t *__restrict__ n_sub_ptr, uint32_t *__restrict__ ucount,
-                                                                 int *__restrict__ overflow, const int SC_HT,
+                                                                 int *__restrict__ overflow, const int SC_HT, const int SC_CAP,
                                                                  const uint32_t n_min, const uint32_t n_max)
 {
     // size classes: this launch only handles sub-buckets with n_min < records <= n_max (records <= 0.85 * SC_HT can never
-    // overflow the table whatever the duplication rate; the last class takes everything larger and reports overflow)
+    // overflow the table whatever the duplication rate; the last class takes everything larger and reports overflow).
+    // Keys and values never leave the hash table: what gets compacted and radix-sorted is the list of occupied SLOT INDICES
+    // (2 bytes each), so a pass moves 2 B per key instead of 12 B and five blocks fit per SM.
     extern __shared__ unsigned char smem_raw[];
-    unsigned long long *bufA_key = reinterpret_cast<unsigned long long *>(smem_raw);            // hash table keys, later ping-pong buffer
-    unsigned long long *bufB_key = bufA_key + SC_HT;                                             // compacted list
-    uint32_t *bufA_val = reinterpret_cast<uint32_t *>(bufB_key + SC_HT);
-    uint32_t *bufB_val = bufA_val + SC_HT;
-    uint16_t *rank_s = reinterpret_cast<uint16_t *>(bufB_val + SC_HT);                           // per element rank inside (warp, digit)
-    uint16_t *list_slot = rank_s + SC_HT;                                                        // table slot of the i-th distinct key
-    uint16_t *hist = list_slot + SC_HT;                                                          // [warp][digit]
+    unsigned long long *ht_key = reinterpret_cast<unsigned long long *>(smem_raw);
+    uint32_t *ht_val = reinterpret_cast<uint32_t *>(ht_key + SC_HT);
+    uint16_t *idxA = reinterpret_cast<uint16_t *>(ht_val + SC_HT);   // slot index list (SC_CAP entries)
+    uint16_t *idxB = idxA + SC_CAP;                                  // ping-pong partner
+    uint16_t *rank_s = idxB + SC_CAP;                                // per element rank inside (warp, digit)
+    uint16_t *hist = rank_s + SC_CAP;                                // [warp][digit]
     __shared__ uint32_t m_s;
     __shared__ unsigned long long red_or, red_and;
     __shared__ uint32_t ws[33];
@@ -315,31 +320,31 @@ __global__ void __launch_bounds__(1024) k_dedup_sort(uint64_t *__restrict__ keys
     if (sb >= *n_sub_ptr) return;
     const uint32_t s = sub_off[sb], e = sub_off[sb + 1];
     if (e - s <= n_min || e - s > n_max) return; // another size class (ucount was zeroed by the host; empty buckets stay 0)
-    for (int i = threadIdx.x; i < SC_HT; i += blockDim.x) { bufA_key[i] = EMPTY64; bufA_val[i] = 0; }
+    for (int i = threadIdx.x; i < SC_HT; i += blockDim.x) { ht_key[i] = EMPTY64; ht_val[i] = 0; }
     if (threadIdx.x == 0) { m_s = 0; red_or = 0; red_and = EMPTY64; }
     __syncthreads();
 
-    // ---- 1. hash-combine; the thread that claims a slot also appends the key to the compact list (warp-aggregated cursor)
+    // ---- 1. hash-combine; the thread that claims a slot appends the slot index to the list (warp-aggregated cursor)
+    unsigned long long t_or = 0, t_and = EMPTY64;
     for (uint32_t i0 = s; i0 < e; i0 += blockDim.x)
     {
         const uint32_t i = i0 + threadIdx.x;
         bool is_new = false;
         uint32_t slot = NONE32;
-        uint64_t uk = 0;
         if (i < e)
         {
             const uint64_t key = keys[i];
-            uk = key >> 3;
+            const uint64_t uk = key >> 3;
             const uint32_t v = HAS_VAL ? vals_in[i] : (1u | (uint32_t(key & 7) << VAL_MARK_SHIFT));
             slot = uint32_t((uk * 0x9E3779B97F4A7C15ull) >> 40) & (SC_HT - 1);
             int probes = 0;
             while (true)
             {
-                unsigned long long cur = bufA_key[slot];
+                unsigned long long cur = ht_key[slot];
                 if (cur == EMPTY64)
                 {
-                    cur = atomicCAS(&bufA_key[slot], EMPTY64, (unsigned long long)uk);
-                    if (cur == EMPTY64) { cur = uk; is_new = true; }
+                    cur = atomicCAS(&ht_key[slot], EMPTY64, (unsigned long long)uk);
+                    if (cur == EMPTY64) { cur = uk; is_new = true; t_or |= uk; t_and &= uk; }
                 }
                 if (cur == uk) break;
                 slot = (slot + 1) & (SC_HT - 1);
@@ -347,9 +352,9 @@ __global__ void __launch_bounds__(1024) k_dedup_sort(uint64_t *__restrict__ keys
             }
             if (slot != NONE32)
             {
-                const uint32_t old = atomicAdd(&bufA_val[slot], v & VAL_COUNT_MASK);
+                const uint32_t old = atomicAdd(&ht_val[slot], v & VAL_COUNT_MASK);
                 const uint32_t mk = v & ~VAL_COUNT_MASK;
-                if ((old & mk) != mk) atomicOr(&bufA_val[slot], mk);
+                if ((old & mk) != mk) atomicOr(&ht_val[slot], mk);
             }
         }
         const unsigned newmask = __ballot_sync(0xFFFFFFFFu, is_new);
@@ -361,22 +366,11 @@ __global__ void __launch_bounds__(1024) k_dedup_sort(uint64_t *__restrict__ keys
             if (is_new)
             {
                 const uint32_t pos = basepos + __popc(newmask & ((1u << (threadIdx.x & 31)) - 1));
-                bufB_key[pos] = uk;
-                list_slot[pos] = uint16_t(slot);
+                if (pos < uint32_t(SC_CAP)) idxA[pos] = uint16_t(slot); else atomicExch(overflow, 1);
             }
         }
     }
-    __syncthreads();
-
-    // ---- 2. fetch the combined values of the listed keys, and find which key bits vary
-    const uint32_t m = m_s;
-    unsigned long long t_or = 0, t_and = EMPTY64;
-    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
-    {
-        const unsigned long long kk = bufB_key[i];
-        bufB_val[i] = bufA_val[list_slot[i]];
-        t_or |= kk; t_and &= kk;
-    }
+    // which key bits vary inside the sub-bucket (only those digits need a pass)
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1)
     {
@@ -385,12 +379,12 @@ __global__ void __launch_bounds__(1024) k_dedup_sort(uint64_t *__restrict__ keys
     }
     if ((threadIdx.x & 31) == 0) { atomicOr(&red_or, t_or); atomicAnd(&red_and, t_and); }
     __syncthreads();
+    const uint32_t m = min(m_s, uint32_t(SC_CAP));
     const unsigned long long varying = red_or & ~red_and; // bits that differ between at least two keys
     const int top_bit = varying ? 63 - __clzll((long long)varying) : -1;
 
-    // ---- 3. LSD radix sort of B[0..m) ; ping-pong B <-> A
-    unsigned long long *src_k = bufB_key, *dst_k = bufA_key;
-    uint32_t *src_v = bufB_val, *dst_v = bufA_val;
+    // ---- 2. stable LSD radix sort of the index list by the keys they point to; ping-pong idxA <-> idxB
+    uint16_t *src = idxA, *dst = idxB;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_warps = blockDim.x >> 5;
     const uint32_t chunk = ((m + n_warps * 32 - 1) / (n_warps * 32)) * 32; // per-warp slice, multiple of 32
@@ -408,7 +402,7 @@ __global__ void __launch_bounds__(1024) k_dedup_sort(uint64_t *__restrict__ keys
             const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid);
             if (valid)
             {
-                const uint32_t d = uint32_t(src_k[i] >> shift) & (SC_RADIX - 1);
+                const uint32_t d = uint32_t(ht_key[src[i]] >> shift) & (SC_RADIX - 1);
                 const unsigned peers = __match_any_sync(vmask, d);
                 const int leader = __ffs(peers) - 1;
                 uint32_t old = 0;
@@ -440,21 +434,19 @@ __global__ void __launch_bounds__(1024) k_dedup_sort(uint64_t *__restrict__ keys
             const uint32_t i = g + lane;
             if (i < w_end)
             {
-                const unsigned long long kk = src_k[i];
-                const uint32_t d = uint32_t(kk >> shift) & (SC_RADIX - 1);
-                const uint32_t pos = uint32_t(my_hist[d]) + rank_s[i];
-                dst_k[pos] = kk;
-                dst_v[pos] = src_v[i];
+                const uint16_t sl = src[i];
+                const uint32_t d = uint32_t(ht_key[sl] >> shift) & (SC_RADIX - 1);
+                dst[uint32_t(my_hist[d]) + rank_s[i]] = sl;
             }
         }
         __syncthreads();
-        unsigned long long *tk = src_k; src_k = dst_k; dst_k = tk;
-        uint32_t *tv = src_v; src_v = dst_v; dst_v = tv;
+        uint16_t *t = src; src = dst; dst = t;
     }
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
     {
-        keys[s + i] = src_k[i];
-        uvals[s + i] = src_v[i];
+        const uint16_t sl = src[i];
+        keys[s + i] = ht_key[sl];
+        uvals[s + i] = ht_val[sl];
     }
     if (threadIdx.x == 0) ucount[sb] = m;
 }
@@ -522,8 +514,8 @@ public:
         DGE_CUDA(cudaGetDevice(&dev));
         if (dev < 64 && done[dev]) return;
         DGE_CUDA(cudaFuncSetAttribute(k_splitters, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SAMPLE * 8));
-        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dedup_smem_bytes(SC_HT_MAX, 1024))));
-        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dedup_smem_bytes(SC_HT_MAX, 1024))));
+        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dedup_smem_bytes(SC_HT_MAX, SC_HT_MAX, 1024))));
+        DGE_CUDA(cudaFuncSetAttribute(k_dedup_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dedup_smem_bytes(SC_HT_MAX, SC_HT_MAX, 1024))));
         if (dev < 64) done[dev] = true;
     }
 
@@ -632,12 +624,13 @@ public:
             const uint32_t cut = uint32_t(SC_HT * 0.85);
             auto launch = [&](int ht, uint32_t lo, uint32_t hi) {
                 const int thr = sc_tuning().dedup_threads;
+                const int cap = hi == 0xFFFFFFFFu ? ht : int(((hi + 31) / 32) * 32); // distinct keys <= records <= hi in a bounded class
                 if (has_val)
-                    k_dedup_sort<true><<<unsigned(nsb_bound), thr, dedup_smem_bytes(ht, thr), st>>>(keys_tmp, ws.valsB.as<uint32_t>(), ws.uvals_sparse.as<uint32_t>(),
-                                                                                                          sub_off, n_sub_ptr, ucount, overflow_flag, ht, lo, hi);
+                    k_dedup_sort<true><<<unsigned(nsb_bound), thr, dedup_smem_bytes(ht, cap, thr), st>>>(keys_tmp, ws.valsB.as<uint32_t>(), ws.uvals_sparse.as<uint32_t>(),
+                                                                                                               sub_off, n_sub_ptr, ucount, overflow_flag, ht, cap, lo, hi);
                 else
-                    k_dedup_sort<false><<<unsigned(nsb_bound), thr, dedup_smem_bytes(ht, thr), st>>>(keys_tmp, nullptr, ws.uvals_sparse.as<uint32_t>(),
-                                                                                                           sub_off, n_sub_ptr, ucount, overflow_flag, ht, lo, hi);
+                    k_dedup_sort<false><<<unsigned(nsb_bound), thr, dedup_smem_bytes(ht, cap, thr), st>>>(keys_tmp, nullptr, ws.uvals_sparse.as<uint32_t>(),
+                                                                                                                sub_off, n_sub_ptr, ucount, overflow_flag, ht, cap, lo, hi);
                 ++L;
             };
             if (SC_HT < SC_HT_MAX)
