@@ -16,6 +16,8 @@ from .capi import (  # noqa: F401
     MERGE_POISSON_REAL,
     MERGE_POISSON_SIMPLE,
     MERGE_ALL,
+    UMI_MERGE_SIMPLE,
+    UMI_MERGE_DIRECTIONAL,
     BARCODES_CONST,
     BARCODES_INDROP,
     CELLS_ALL,

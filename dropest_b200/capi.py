@@ -47,6 +47,7 @@ EXPORTS = [
     "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
     "dge_route_by_barcode_device", "dge_dist_export_children", "dge_dist_copy_children", "dge_dist_eval_children", "dge_dist_apply",
+    "dge_umi_first_size", "dge_umi_first_export", "dge_umi_first_import",
 ]
 
 
@@ -73,7 +74,7 @@ class _Summary(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_reads", "total_cells_number", "real_cells_number", "filtered_cells_number", "n_genes_seen", "n_umigs",
         "intergenic_reads", "has_exon_reads", "has_intron_reads", "has_not_annotated_reads", "cm_nnz", "cm_raw_nnz",
-        "n_merged", "n_excluded", "n_unresolved")]
+        "n_merged", "n_excluded", "n_unresolved", "n_umis_merged", "n_umi_segments_replayed")]
 
 
 class _Timings(C.Structure):
@@ -141,6 +142,9 @@ def load_library():
     lib.dge_dist_copy_children.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
     lib.dge_dist_eval_children.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.dge_dist_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.dge_umi_first_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+    lib.dge_umi_first_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.dge_umi_first_import.argtypes = [C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -296,6 +300,17 @@ class Container:
         all_results = np.ascontiguousarray(all_results, dtype=DIST_RESULT_DTYPE)
         child_rank = np.ascontiguousarray(child_rank, dtype=np.uint32)
         self._check(self._lib.dge_dist_apply(self._h, all_results.ctypes.data, world, rank, child_rank.ctypes.data))
+
+    def umi_first_size(self) -> int:
+        n = C.c_size_t(0)
+        self._check(self._lib.dge_umi_first_size(self._h, C.byref(n)))
+        return int(n.value)
+
+    def umi_first_export(self, dst_device_ptr: int):
+        self._check(self._lib.dge_umi_first_export(self._h, dst_device_ptr))
+
+    def umi_first_import(self, src_device_ptr: int):
+        self._check(self._lib.dge_umi_first_import(self._h, src_device_ptr))
 
     # ---- query
     def summary(self) -> dict:

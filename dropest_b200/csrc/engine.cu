@@ -13,12 +13,14 @@
 #include "scan.cuh"
 #include "segments.cuh"
 #include "sortcombine.cuh"
+#include "umimerge.cuh"
 #include "whitelist.hpp"
 
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <limits>
 #include <map>
 #include <memory>
 #include <numeric>
@@ -73,7 +75,8 @@ struct dge_handle
     uint32_t min_after_eff = 0;
 
     // fill-stage device state
-    DevBuf tab, gene_first, ctr, staging[2], ctr_counts;
+    DevBuf tab, gene_first, umi_first, ctr, staging[2], ctr_counts;
+    bool track_umi_first = false; // strategies that depend on the UMI indexer's first-seen order
     std::vector<std::unique_ptr<KeyChunk>> chunks, chunk_pool;
     std::vector<DevBuf *> chunk_counts;
     DevBuf chunk_count_pool;
@@ -107,6 +110,9 @@ struct dge_handle
     bool wl_uploaded = false;
     PinnedBuf pin_rows, pin_nbc, pin_nbp, pin_isect, pin_misc;
     // cross-rank merge state (sharded runs)
+    DevBuf umi_lists, umi_ctr, umi_pc_dec, umi_seg, umi_flat, umi_pairs;
+    PinnedBuf pin_umi;
+    uint64_t n_umis_merged = 0, n_umi_segments_replayed = 0;
     DevBuf dist_infos, dist_keys, dist_vals, dist_jobs;
     std::vector<dge_dist_child> g_infos;
     std::vector<uint32_t> g_off;
@@ -228,6 +234,8 @@ void ensure_device(dge_handle *h)
     if (kl.tb < 10) throw std::runtime_error("key layout does not fit 64 bits: reduce n_genes or umi_len");
     kl.kb = kl.tb + kl.gb + kl.ub + 3;
     h->table_cap = size_t(1) << kl.tb;
+    h->track_umi_first = h->cfg.umi_merge_type == DGE_UMI_MERGE_DIRECTIONAL;
+    if (h->track_umi_first && kl.ub > 26) throw std::runtime_error("directional UMI merge supports UMIs of up to 13 bases");
 
     h->tab.reserve(h->table_cap * sizeof(CellSlot));
     h->device_ready = true;
@@ -239,6 +247,13 @@ void reset_fill_state(dge_handle *h)
     k_table_init<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->tab.as<CellSlot>(), h->table_cap);
     h->gene_first.reserve(size_t(h->cfg.n_genes) * 4);
     k_fill_u32<<<grid_for(h->cfg.n_genes, 256), 256, 0, h->stream>>>(h->gene_first.as<uint32_t>(), h->cfg.n_genes, NONE32);
+    if (h->track_umi_first)
+    {
+        const size_t n_umi = size_t(1) << h->kl.ub;
+        h->umi_first.reserve(n_umi * 4);
+        k_fill_u32<<<grid_for(n_umi, 256), 256, 0, h->stream>>>(h->umi_first.as<uint32_t>(), n_umi, NONE32);
+        ++h->launches;
+    }
     h->ctr.reserve(sizeof(FillCounters));
     DGE_CUDA(cudaMemsetAsync(h->ctr.p, 0, sizeof(FillCounters), h->stream));
     h->overflow_flag.reserve(sizeof(int));
@@ -267,7 +282,8 @@ void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n)
     unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(FILL_TILE)), 148 * 8));
     k_fill_compact<<<grid, FILL_THREADS, 0, h->stream>>>(reinterpret_cast<const Rec16 *>(recs), n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes,
                                                           h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(), h->ctr.as<FillCounters>(),
-                                                          /*l1_shift*/ 63, /*nb1*/ 0, nullptr);
+                                                          /*l1_shift*/ 63, /*nb1*/ 0, nullptr,
+                                                          h->track_umi_first ? h->umi_first.as<uint32_t>() : nullptr);
     DGE_LAUNCH_CHECK();
     DGE_CUDA(cudaMemcpyAsync(chunk->d_count, &h->ctr.as<FillCounters>()->n_keys, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
     ++h->launches;
@@ -922,6 +938,176 @@ void build_matrix(dge_handle *h, MatrixDev &m, const std::vector<uint32_t> &col_
 }
 
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Exact host replay of MergeUMIsStrategyDirectional::find_targets (MergeUMIsStrategyDirectional.cpp:57-116) for one segment:
+// items arrive in U order (ascending UMI value); the reference lists them in UMI-id (first-seen) order and std::sort-s by reads.
+// Returns, per item, the index of its root or NONE32.
+struct UmiItem { uint32_t umi, reads, first, idx; };
+
+void umi_directional_replay(const dge_handle *h, std::vector<UmiItem> &items, std::vector<uint32_t> &root)
+{
+    const unsigned max_ed = h->cfg.max_umi_merge_edit_distance;
+    const double mult = h->cfg.umi_merge_mult;
+    std::sort(items.begin(), items.end(), [](const UmiItem &a, const UmiItem &b) { return a.first < b.first; }); // distinct keys: a total order
+    std::sort(items.begin(), items.end(), [](const UmiItem &a, const UmiItem &b) { return a.reads < b.reads; }); // same call as the reference
+    const size_t n = items.size();
+    std::vector<std::string> seq(n);
+    for (size_t i = 0; i < n; ++i) seq[i] = unpack_seq(items[i].umi, h->cfg.umi_len);
+    std::vector<long> tgt(n, -1);
+    for (size_t s = 0; s < n; ++s)
+    {
+        unsigned min_ed = std::numeric_limits<unsigned>::max();
+        for (long d = long(n) - 1; d > long(s); --d)
+        {
+            if (double(items[s].reads) * mult > double(items[size_t(d)].reads)) break;
+            const unsigned ed = edit_distance_ref(seq[s].c_str(), seq[size_t(d)].c_str(), true, max_ed);
+            if (ed > max_ed) continue;
+            if (ed < min_ed)
+            {
+                tgt[s] = d;
+                if (ed <= 1) break;
+                min_ed = ed;
+            }
+        }
+    }
+    root.assign(n, NONE32);
+    for (long i = long(n) - 1; i >= 0; --i)
+    {
+        if (tgt[size_t(i)] < 0) continue;
+        long r = tgt[size_t(i)];
+        while (tgt[size_t(r)] >= 0) r = tgt[size_t(r)];
+        root[size_t(i)] = uint32_t(r);
+    }
+}
+
+// MergeUMIsStrategyDirectional::merge over every (real cell, gene) segment.  Returns true when U changed.
+bool umi_merge_directional(dge_handle *h)
+{
+    cudaStream_t st = h->stream;
+    h->n_umis_merged = 0; h->n_umi_segments_replayed = 0;
+    if (h->n_cg == 0 || h->n_u == 0) return false;
+    const uint32_t n_cg = h->n_cg, n_pc = h->n_pc;
+    // real flags per present cell
+    std::vector<uint32_t> real_pcs;
+    for (auto const &c : h->real) if (c.real && c.pc != NONE32) real_pcs.push_back(c.pc);
+    if (real_pcs.empty()) return false;
+    h->flags.reserve((size_t(n_pc) + 2) * 4);
+    DGE_CUDA(cudaMemsetAsync(h->flags.p, 0, (size_t(n_pc) + 2) * 4, st));
+    h->misc.reserve(real_pcs.size() * 4);
+    DGE_CUDA(cudaMemcpyAsync(h->misc.p, real_pcs.data(), real_pcs.size() * 4, cudaMemcpyHostToDevice, st));
+    k_flag_list<<<grid_for(real_pcs.size(), 256, 1u << 30), 256, 0, st>>>(h->misc.as<uint32_t>(), uint32_t(real_pcs.size()), h->flags.as<uint32_t>());
+    ++h->launches;
+
+    const uint32_t list_cap = n_cg; // worst case: every segment deferred
+    h->umi_lists.reserve(size_t(list_cap) * 2 * 4);
+    h->umi_ctr.reserve(32);
+    h->umi_pc_dec.reserve((size_t(n_pc) + 2) * 4);
+    DGE_CUDA(cudaMemsetAsync(h->umi_ctr.p, 0, 32, st));
+    DGE_CUDA(cudaMemsetAsync(h->umi_pc_dec.p, 0, (size_t(n_pc) + 2) * 4, st));
+    UmiDirParams p{h->kl.ub, int(h->cfg.umi_len), h->cfg.max_umi_merge_edit_distance, h->cfg.umi_merge_mult};
+    UmiDirOut o{};
+    o.big_list = h->umi_lists.as<uint32_t>(); o.big_cap = list_cap;
+    o.host_list = h->umi_lists.as<uint32_t>() + list_cap; o.host_cap = list_cap;
+    o.big_count = h->umi_ctr.as<uint32_t>(); o.host_count = h->umi_ctr.as<uint32_t>() + 1;
+    o.n_merged = reinterpret_cast<unsigned long long *>(h->umi_ctr.as<uint32_t>() + 2);
+    o.pc_dec = h->umi_pc_dec.as<uint32_t>();
+    k_umi_dir_warp<<<grid_for(div_up(size_t(n_cg), size_t(32)), 8, 148 * 8), 256, 0, st>>>(h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), h->cg_start.as<uint32_t>(),
+                                                                                          h->cg_pc.as<uint32_t>(), n_cg, h->flags.as<uint32_t>(),
+                                                                                          h->umi_first.as<uint32_t>(), p, o);
+    DGE_LAUNCH_CHECK();
+    ++h->launches;
+    uint32_t n_big = d2h_scalar<uint32_t>(o.big_count, st);
+    if (n_big)
+    {
+        static bool attr_set[64] = {};
+        int dev = 0; cudaGetDevice(&dev);
+        const size_t smem = size_t(UMI_BLOCK_CAP) * 16;
+        if (!attr_set[dev & 63]) { DGE_CUDA(cudaFuncSetAttribute(k_umi_dir_block, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr_set[dev & 63] = true; }
+        k_umi_dir_block<<<std::min<uint32_t>(n_big, 148 * 4), 256, smem, st>>>(h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), h->cg_start.as<uint32_t>(),
+                                                                                h->cg_pc.as<uint32_t>(), o.big_list, n_big, h->umi_first.as<uint32_t>(), p, o);
+        DGE_LAUNCH_CHECK();
+        ++h->launches;
+    }
+    const uint32_t n_host = d2h_scalar<uint32_t>(o.host_count, st);
+    std::vector<uint32_t> host_dec_pc, host_dec_n;
+    if (n_host)
+    {   // exact replay of the segments whose outcome depends on how std::sort ordered equal read counts
+        h->n_umi_segments_replayed = n_host;
+        h->umi_seg.reserve(size_t(n_host + 1) * 4 * 4);
+        uint32_t *seg_start = h->umi_seg.as<uint32_t>(), *seg_n = seg_start + (n_host + 1), *seg_pc = seg_n + (n_host + 1), *seg_off = seg_pc + (n_host + 1);
+        k_umi_seg_meta<<<grid_for(n_host, 256, 1u << 30), 256, 0, st>>>(o.host_list, n_host, h->cg_start.as<uint32_t>(), h->cg_pc.as<uint32_t>(), seg_start, seg_n, seg_pc);
+        DGE_CUDA(cudaMemsetAsync(seg_n + n_host, 0, 4, st));
+        const uint32_t *tot = device_exclusive_scan(seg_n, seg_off, size_t(n_host) + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+        (void)tot;
+        std::vector<uint32_t> hs_start, hs_off, hs_pc;
+        d2h(hs_start, seg_start, n_host, st); d2h(hs_off, seg_off, size_t(n_host) + 1, st); d2h(hs_pc, seg_pc, n_host, st);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        const size_t flat = hs_off[n_host];
+        h->umi_flat.reserve(std::max<size_t>(flat, 1) * 3 * 4);
+        uint32_t *f_umi = h->umi_flat.as<uint32_t>(), *f_val = f_umi + flat, *f_first = f_val + flat;
+        k_umi_seg_gather<<<std::min<uint32_t>(n_host, 148 * 8), 128, 0, st>>>(seg_start, seg_off, n_host, h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(),
+                                                                               h->umi_first.as<uint32_t>(), h->kl.ub, f_umi, f_val, f_first);
+        DGE_LAUNCH_CHECK();
+        h->launches += 2;
+        const uint32_t *hf = d2h_pinned<uint32_t>(h->pin_umi, f_umi, flat * 3, st);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        std::vector<uint2> pairs;
+        std::vector<UmiItem> items;
+        std::vector<uint32_t> root;
+        uint64_t merged_host = 0;
+        for (uint32_t k = 0; k < n_host; ++k)
+        {
+            const uint32_t off = hs_off[k], n = hs_off[k + 1] - off;
+            items.resize(n);
+            for (uint32_t i = 0; i < n; ++i) items[i] = UmiItem{hf[off + i], hf[flat + off + i] & VAL_COUNT_MASK, hf[2 * flat + off + i], i};
+            umi_directional_replay(h, items, root);
+            uint32_t m = 0;
+            for (uint32_t i = 0; i < n; ++i)
+                if (root[i] != NONE32) { pairs.push_back(make_uint2(hs_start[k] + items[i].idx, hs_start[k] + items[root[i]].idx)); ++m; }
+            if (m) { host_dec_pc.push_back(hs_pc[k]); host_dec_n.push_back(m); merged_host += m; }
+        }
+        if (!pairs.empty())
+        {
+            h->umi_pairs.reserve(pairs.size() * sizeof(uint2));
+            DGE_CUDA(cudaMemcpyAsync(h->umi_pairs.p, pairs.data(), pairs.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+            for (int phase = 0; phase < 2; ++phase)
+                k_umi_apply_pairs<<<grid_for(pairs.size(), 256, 1u << 30), 256, 0, st>>>(h->umi_pairs.as<uint2>(), uint32_t(pairs.size()), h->uval.as<uint32_t>(), phase);
+            DGE_LAUNCH_CHECK();
+            h->launches += 2;
+            DGE_CUDA(cudaStreamSynchronize(st));
+        }
+        h->n_umis_merged += merged_host;
+    }
+    const unsigned long long merged_dev = d2h_scalar<unsigned long long>(o.n_merged, st);
+    h->n_umis_merged += merged_dev;
+    if (h->n_umis_merged == 0) return false;
+
+    // TOTAL_UMIS_PER_CB decrements (Cell.cpp:39)
+    {
+        const uint32_t *dec = d2h_pinned<uint32_t>(h->pin_umi, h->umi_pc_dec.p, n_pc, st);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        std::vector<uint32_t> dec_all(dec, dec + n_pc);
+        for (size_t k = 0; k < host_dec_pc.size(); ++k) dec_all[host_dec_pc[k]] += host_dec_n[k];
+        for (auto &c : h->real) if (c.real && c.pc != NONE32) c.umis_stat -= int32_t(dec_all[c.pc]);
+    }
+    // drop the merged entries and rebuild the segment tables (cells and genes stay, so PC / CG indices keep their meaning)
+    h->keep.reserve(size_t(h->n_u + 1) * 4); h->keep_off.reserve(size_t(h->n_u + 1) * 4);
+    k_flag_live<<<grid_for(h->n_u, 256), 256, 0, st>>>(h->uval.as<uint32_t>(), h->n_u, h->keep.as<uint32_t>());
+    const uint32_t *n_live_ptr = device_exclusive_scan(h->keep.as<uint32_t>(), h->keep_off.as<uint32_t>(), h->n_u, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+    const uint32_t n_live = d2h_scalar<uint32_t>(n_live_ptr, st);
+    h->ukey2.reserve(size_t(n_live + 1) * 8); h->uval2.reserve(size_t(n_live + 1) * 4);
+    k_compact_keep<<<grid_for(h->n_u, 256), 256, 0, st>>>(h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), h->n_u, h->keep.as<uint32_t>(), h->keep_off.as<uint32_t>(),
+                                                           h->ukey2.as<uint64_t>(), h->uval2.as<uint32_t>());
+    DGE_LAUNCH_CHECK();
+    h->launches += 2;
+    std::swap(h->ukey.p, h->ukey2.p); std::swap(h->ukey.bytes, h->ukey2.bytes);
+    std::swap(h->uval.p, h->uval2.p); std::swap(h->uval.bytes, h->uval2.bytes);
+    h->n_u = n_live;
+    build_segments(h);
+    return true;
+}
+
 void do_merge_and_filter(dge_handle *h)
 {
     DGE_CUDA(cudaSetDevice(h->cfg.device));
@@ -949,20 +1135,10 @@ void do_merge_and_filter(dge_handle *h)
         throw std::runtime_error("merge_type not implemented on the device path yet");
     DGE_CUDA(cudaEventRecord(h->ev[4], st));
 
-    // ---- UMI merge: MergeUMIsStrategySimple only touches UMIs containing 'N' (MergeUMIsStrategySimple.cpp:21-59);
-    // 2-bit records cannot carry N, so there is nothing to repair here.
-    if (h->cfg.umi_merge_type != DGE_UMI_MERGE_SIMPLE) throw std::runtime_error("directional UMI merge not implemented on the device path yet");
-
-    // ---- update_cell_sizes (CellsDataContainer.cpp:111-125): requested sizes of every cell, real = !merged && !excluded && size >= min
-    if (!h->merge_events.empty() || !h->dist_targets.empty())
-    {
-        // only merge TARGETS changed content: every other cell keeps the sizes read at set_initialized
-        std::vector<uint32_t> pcs, owners;
-        std::vector<char> is_target(h->real.size(), 0);
-        for (auto const &e : h->merge_events) is_target[e.second] = 1;
-        for (uint32_t t : h->dist_targets) is_target[t] = 1;
-        for (uint32_t i = 0; i < h->real.size(); ++i)
-            if (is_target[i] && h->real[i].pc != NONE32) { pcs.push_back(h->real[i].pc); owners.push_back(i); }
+    // ---- sizes of merge targets changed; Cell::is_real (Cell.cpp:125-128) is evaluated on the merged content from here on
+    auto refresh_rows = [&](const std::vector<uint32_t> &owners) {
+        std::vector<uint32_t> pcs;
+        for (uint32_t i : owners) pcs.push_back(h->real[i].pc);
         std::vector<CellRow> rows;
         gather_rows(h, pcs, rows);
         for (size_t k = 0; k < rows.size(); ++k)
@@ -971,8 +1147,35 @@ void do_merge_and_filter(dge_handle *h)
             c.n_genes = int32_t(rows[k].n_genes); c.req_genes = int32_t(rows[k].req_genes); c.req_umis = int32_t(rows[k].req_umis);
             c.n_umis_distinct = int32_t(rows[k].n_umis);
         }
+    };
+    if (!h->merge_events.empty() || !h->dist_targets.empty())
+    {
+        // only merge TARGETS changed content: every other cell keeps the sizes read at set_initialized
+        std::vector<uint32_t> owners;
+        std::vector<char> is_target(h->real.size(), 0);
+        for (auto const &e : h->merge_events) is_target[e.second] = 1;
+        for (uint32_t t : h->dist_targets) is_target[t] = 1;
+        for (uint32_t i = 0; i < h->real.size(); ++i)
+            if (is_target[i] && h->real[i].pc != NONE32) owners.push_back(i);
+        refresh_rows(owners);
     }
     for (auto &c : h->real) c.real = !c.merged && !c.excluded && uint32_t(c.n_genes) >= h->cfg.min_genes_before_merge;
+
+    // ---- UMI merge (CellsDataContainer.cpp:47).  MergeUMIsStrategySimple only touches UMIs containing 'N'
+    // (MergeUMIsStrategySimple.cpp:21-59) and 2-bit records cannot carry N, so it has nothing to repair here.
+    if (h->cfg.umi_merge_type == DGE_UMI_MERGE_DIRECTIONAL)
+    {
+        if (umi_merge_directional(h))
+        {   // requested sizes of every real cell may have changed (update_cell_sizes, CellsDataContainer.cpp:111-125)
+            std::vector<uint32_t> owners;
+            for (uint32_t i = 0; i < h->real.size(); ++i)
+                if (h->real[i].real && h->real[i].pc != NONE32) owners.push_back(i);
+            refresh_rows(owners);
+        }
+        tr.mark("umi merge: directional");
+    }
+    else if (h->cfg.umi_merge_type != DGE_UMI_MERGE_SIMPLE) throw std::runtime_error("unknown umi_merge_type");
+
     update_filtered(h, h->min_after_eff, h->cfg.max_cells);
     tr.mark("finish: sizes + filter");
 
@@ -1466,6 +1669,41 @@ int dge_dist_apply(dge_handle *h, const dge_dist_result *all, uint32_t world, ui
     });
 }
 
+int dge_umi_first_size(dge_handle *h, size_t *n_entries)
+{
+    if (!h || !n_entries) return fail(h, DGE_ERR_INVALID, "null argument");
+    return guarded(h, [&] {
+        ensure_device(h);
+        *n_entries = h->track_umi_first ? size_t(1) << h->kl.ub : 0;
+        return DGE_OK;
+    });
+}
+
+int dge_umi_first_export(dge_handle *h, uint32_t *dst_device)
+{
+    if (!h || !dst_device) return fail(h, DGE_ERR_INVALID, "null argument");
+    return guarded(h, [&]() -> int {
+        ensure_device(h);
+        if (!h->track_umi_first) return fail(h, DGE_ERR_STATE, "the configured strategies do not track UMI first-seen order");
+        DGE_CUDA(cudaMemcpyAsync(dst_device, h->umi_first.p, (size_t(1) << h->kl.ub) * 4, cudaMemcpyDeviceToDevice, h->stream));
+        DGE_CUDA(cudaStreamSynchronize(h->stream));
+        return DGE_OK;
+    });
+}
+
+int dge_umi_first_import(dge_handle *h, const uint32_t *src_device)
+{
+    if (!h || !src_device) return fail(h, DGE_ERR_INVALID, "null argument");
+    return guarded(h, [&]() -> int {
+        ensure_device(h);
+        if (!h->track_umi_first) return fail(h, DGE_ERR_STATE, "the configured strategies do not track UMI first-seen order");
+        if (h->state == 2) return fail(h, DGE_ERR_STATE, "import the UMI first-seen table before merge_and_filter");
+        DGE_CUDA(cudaMemcpyAsync(h->umi_first.p, src_device, (size_t(1) << h->kl.ub) * 4, cudaMemcpyDeviceToDevice, h->stream));
+        DGE_CUDA(cudaStreamSynchronize(h->stream));
+        return DGE_OK;
+    });
+}
+
 int dge_get_summary(dge_handle *h, dge_summary *out)
 {
     if (!h || !out) return fail(h, DGE_ERR_INVALID, "null argument");
@@ -1486,6 +1724,8 @@ int dge_get_summary(dge_handle *h, dge_summary *out)
     out->n_merged = h->n_merged;
     out->n_excluded = h->n_excluded;
     out->n_unresolved = h->n_unresolved;
+    out->n_umis_merged = h->n_umis_merged;
+    out->n_umi_segments_replayed = h->n_umi_segments_replayed;
     return DGE_OK;
 }
 

@@ -76,7 +76,8 @@ __device__ __forceinline__ uint32_t table_find(const CellSlot *tab, int tb, uint
 // records -> compact keys (dense, order irrelevant) + L1 histogram of the keys + global read counters.
 __global__ void __launch_bounds__(FILL_THREADS) k_fill_compact(const Rec16 *__restrict__ recs, size_t n, CellSlot *__restrict__ tab, KeyLayout kl,
                                                                uint32_t n_genes, uint32_t *__restrict__ gene_first, uint64_t *__restrict__ out_keys,
-                                                               FillCounters *__restrict__ ctr, int l1_shift, int nb1, uint32_t *__restrict__ l1_hist)
+                                                               FillCounters *__restrict__ ctr, int l1_shift, int nb1, uint32_t *__restrict__ l1_hist,
+                                                               uint32_t *__restrict__ umi_first)
 {
     __shared__ uint32_t hist[SC_MAX_NB1];
     __shared__ uint32_t ws[33];
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(FILL_THREADS) k_fill_compact(const Rec16 *__re
             }
             if (gene >= n_genes) { ctr->bad_gene = 1; continue; }
             if (idx < gfirst[j]) atomicMin(&gene_first[gene], idx);
+            if (umi_first) atomicMin(&umi_first[umi], idx); // UMI ids are first-seen ranks too (StringIndexer via Gene::add_umi, Gene.cpp:17-24)
             c_exon += (mark >> 1) & 1u; c_intron += (mark >> 2) & 1u; c_na += mark & 1u;
             keys[j] = kl.compose(slot, gene, umi, mark);
             if (nb1) atomicAdd(&hist[keys[j] >> l1_shift], 1u);

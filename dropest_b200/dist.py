@@ -55,6 +55,25 @@ def records_from_tensor(t) -> np.ndarray:
     return np.frombuffer(t.cpu().numpy().tobytes(), dtype=RECORD_DTYPE)
 
 
+def sync_umi_first_seen(cont, device: str, group=None):
+    """Min-reduce the per-UMI first-seen read index across ranks (the reference's UMI StringIndexer is global).  No-op unless the
+    configured strategies depend on UMI id order (directional UMI merge).  Call after the last add_batch on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    n = cont.umi_first_size()
+    if n == 0 or dist.get_world_size(group) == 1:
+        return 0
+    t = torch.empty(n, dtype=torch.int32, device=device)
+    cont.umi_first_export(t.data_ptr())
+    t.bitwise_xor_(-2 ** 31)            # u32 order -> signed order, so that MIN works on the int32 view
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    t.bitwise_xor_(-2 ** 31)
+    torch.cuda.synchronize()
+    cont.umi_first_import(t.data_ptr())
+    return n
+
+
 def merge_across_ranks(cont, device: str, group=None):
     """Exact whitelist merge for sharded runs: two all-gathers around three local library steps.
     Call between cont.set_initialized() and cont.merge_and_filter()."""

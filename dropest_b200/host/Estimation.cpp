@@ -1,6 +1,8 @@
 // Estimation.cpp -- implementation of the host-side mirror declared in Estimation.h (see there for the reference citations).
 #include "Estimation.h"
 
+#include <limits>
+
 #include <algorithm>
 #include <cstring>
 #include <fstream>
@@ -112,8 +114,41 @@ namespace Estimation
 
 		std::shared_ptr<UMIs::MergeUMIsStrategyAbstract> MergeStrategyFactory::get_umi(bool advanced) const
 		{
-			if (advanced) throw std::runtime_error("directional UMI merge is not available on the device path yet");
+			if (advanced) return std::make_shared<UMIs::MergeUMIsStrategyDirectional>(umi_merge_mult, max_umi_merge_edit_distance);
 			return std::make_shared<UMIs::MergeUMIsStrategySimple>(max_umi_merge_edit_distance);
+		}
+
+		// MergeUMIsStrategyDirectional::find_targets / find_target (MergeUMIsStrategyDirectional.cpp:57-116) for N-free UMIs:
+		// sort by reads, scan candidates from the largest, keep the first one at the smallest distance, follow chains to the root.
+		UMIs::MergeUMIsStrategyDirectional::merge_targets_t UMIs::MergeUMIsStrategyDirectional::find_targets(umi_vec_t &umis) const
+		{
+			std::sort(umis.begin(), umis.end(), [](const UmiWrap &a, const UmiWrap &b) { return a.n_reads < b.n_reads; });
+			const size_t n = umis.size();
+			std::vector<long> tgt(n, -1);
+			for (size_t s = 0; s < n; ++s)
+			{
+				if (umis[s].sequence.find('N') != std::string::npos)
+					throw std::runtime_error("UMIs containing N are not supported by the packed record yet");
+				unsigned best_ed = std::numeric_limits<unsigned>::max();
+				for (long d = long(n) - 1; d > long(s); --d)
+				{
+					if (umis[s].n_reads * _mult > umis[size_t(d)].n_reads) break;
+					const unsigned ed = Tools::edit_distance(umis[s].sequence.c_str(), umis[size_t(d)].sequence.c_str(), true, _max_edit_distance);
+					if (ed > _max_edit_distance || ed >= best_ed) continue;
+					tgt[s] = d;
+					if (ed <= 1) break;
+					best_ed = ed;
+				}
+			}
+			merge_targets_t res;
+			for (size_t s = 0; s < n; ++s)
+			{
+				if (tgt[s] < 0) continue;
+				long r = tgt[s];
+				while (tgt[size_t(r)] >= 0) r = tgt[size_t(r)];
+				res[umis[s].sequence] = umis[size_t(r)].sequence;
+			}
+			return res;
 		}
 	}
 

@@ -275,6 +275,33 @@ namespace Estimation
 					cfg.max_umi_merge_edit_distance = _max_merge_distance;
 				}
 			};
+			// MergeUMIsStrategyDirectional (MergeUMIsStrategyDirectional.h:13-44): the container-wide merge runs on the device;
+			// find_targets is the reference's public per-segment entry point, kept as a host function for callers and tests.
+			class MergeUMIsStrategyDirectional : public MergeUMIsStrategyAbstract
+			{
+			public:
+				struct UmiWrap
+				{
+					std::string sequence;
+					size_t n_reads;
+					UmiWrap(const std::string &sequence, size_t n_reads) : sequence(sequence), n_reads(n_reads) {}
+				};
+				using umi_vec_t = std::vector<UmiWrap>;
+				using merge_targets_t = std::unordered_map<std::string, std::string>;
+
+				explicit MergeUMIsStrategyDirectional(double mult = 2, unsigned max_edit_distance = 1) : _mult(mult), _max_edit_distance(max_edit_distance) {}
+				merge_targets_t find_targets(umi_vec_t &umis) const;
+				void configure(dge_config &cfg) const override
+				{
+					cfg.umi_merge_type = DGE_UMI_MERGE_DIRECTIONAL;
+					cfg.max_umi_merge_edit_distance = _max_edit_distance;
+					cfg.umi_merge_mult = _mult;
+				}
+
+			private:
+				double _mult;
+				unsigned _max_edit_distance;
+			};
 		}
 
 		// MergeStrategyFactory (MergeStrategyFactory.cpp:23-126) with the XML values passed in directly (no boost::property_tree here)

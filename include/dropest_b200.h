@@ -116,6 +116,8 @@ typedef struct dge_summary {
     uint64_t n_merged;              /* cells merged into another cell (MergeStrategyBase.cpp:53) */
     uint64_t n_excluded;            /* cells excluded by the merge      (MergeStrategyBase.cpp:54) */
     uint64_t n_unresolved;          /* sharded runs only: cells whose merge candidates live on another shard (left unmerged) */
+    uint64_t n_umis_merged;         /* UMIs merged into another UMI by the UMI merge strategy (MergeUMIsStrategyDirectional.cpp:43) */
+    uint64_t n_umi_segments_replayed; /* (cell, gene) segments whose UMI merge was replayed on the host for exact tie order */
 } dge_summary;
 
 /* Per-cell row returned by dge_get_cells; one per requested cell, in the requested order. */
@@ -294,6 +296,15 @@ int dge_dist_eval_children(dge_handle *h, const dge_dist_child *infos_device, ui
                            const uint32_t *vals_device, uint64_t n_entries, dge_dist_result *results_host);
 int dge_dist_apply(dge_handle *h, const dge_dist_result *all_results_host, uint32_t world, uint32_t my_rank,
                    const uint32_t *child_rank_host);
+
+/* Sharded runs with a strategy that depends on the UMI indexer's first-seen order (directional UMI merge): every rank tracks
+ * min(read_idx) per packed UMI over ITS reads; the reference's StringIndexer is global, so the tables have to be min-reduced
+ * across ranks before dge_merge_and_filter.  dge_umi_first_size gives the table length (4^umi_len entries, 0 when the
+ * configured strategies do not need it); export/import copy it to / from caller-owned DEVICE memory (u32 per entry,
+ * 0xFFFFFFFF = UMI not seen) around the caller's all-reduce(min).  Reference: StringIndexer.cpp:10-18 via Gene.cpp:17-24. */
+int dge_umi_first_size(dge_handle *h, size_t *n_entries);
+int dge_umi_first_export(dge_handle *h, uint32_t *dst_device);
+int dge_umi_first_import(dge_handle *h, const uint32_t *src_device);
 
 #ifdef __cplusplus
 }

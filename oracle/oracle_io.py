@@ -62,7 +62,7 @@ def oracle_binary(kind: str = "any") -> str:
 def run_oracle(in_path: str, kind: str = "any", merge: str = "none", barcodes: Optional[str] = None,
                barcodes_type: str = "const", min_genes_before: int = 10, min_genes_after: int = 10, max_cb_ed: int = 2,
                min_frac: float = 0.2, marks: str = "eEBA", max_cells: int = -1, reads_output: bool = False,
-               dump_umis: bool = False, umi_merge: str = "simple", max_umi_ed: int = 1, limit: int = 0,
+               dump_umis: bool = False, umi_merge: str = "simple", max_umi_ed: int = 1, umi_mult: float = 2.0, limit: int = 0,
                max_merge_prob: float = 1e-4, max_real_merge_prob: float = 1e-7, init_only: bool = False,
                timeout: Optional[float] = None) -> Dict[str, np.ndarray]:
     exe = oracle_binary(kind)
@@ -70,7 +70,7 @@ def run_oracle(in_path: str, kind: str = "any", merge: str = "none", barcodes: O
         out = os.path.join(td, "out.dgeo")
         cmd = [exe, "--in", in_path, "--out", out, "--merge", merge, "--min-genes-before", str(min_genes_before),
                "--min-genes-after", str(min_genes_after), "--max-cb-ed", str(max_cb_ed), "--min-frac", repr(min_frac),
-               "--marks", marks, "--max-cells", str(max_cells), "--umi-merge", umi_merge, "--max-umi-ed", str(max_umi_ed),
+               "--marks", marks, "--max-cells", str(max_cells), "--umi-merge", umi_merge, "--max-umi-ed", str(max_umi_ed), "--umi-mult", repr(float(umi_mult)),
                "--max-merge-prob", repr(max_merge_prob), "--max-real-merge-prob", repr(max_real_merge_prob)]
         if barcodes:
             cmd += ["--barcodes", barcodes, "--barcodes-type", barcodes_type]

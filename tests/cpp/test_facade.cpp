@@ -96,6 +96,33 @@ int main(int argc, char **argv)
 			CHECK_EQUAL(container.cell(0).at("Gene4").at("ACCCCT").read_count(), size_t(2));
 		}
 
+		// testUMIMergeStrategyDirectional, Tests/TestEstimation.cpp:588-608: the per-segment entry point ...
+		{
+			using Strat = Merge::UMIs::MergeUMIsStrategyDirectional;
+			auto directional = std::make_shared<Strat>();
+			Strat::umi_vec_t umis;
+			umis.emplace_back("AAA", 2); umis.emplace_back("AAC", 5); umis.emplace_back("AAT", 6);
+			umis.emplace_back("AGT", 20); umis.emplace_back("CCC", 10); umis.emplace_back("TCC", 20);
+			auto targets = directional->find_targets(umis);
+			CHECK_EQUAL(targets.size(), size_t(3));
+			CHECK_EQUAL(targets.at("AAA"), std::string("AGT"));
+			CHECK_EQUAL(targets.at("AAT"), std::string("AGT"));
+			CHECK_EQUAL(targets.at("CCC"), std::string("TCC"));
+			// ... and the same six UMIs through the container (device path): AAA+AAT -> AGT (28 reads), CCC -> TCC (30), AAC stays
+			CellsDataContainer container(std::make_shared<Merge::DummyMergeStrategy>(0, 0), directional, any_mark, false, -1, 0, 64);
+			static const struct { const char *umi; int reads; } seg[] = {{"AAA", 2}, {"AAC", 5}, {"AAT", 6}, {"AGT", 20}, {"CCC", 10}, {"TCC", 20}};
+			for (auto const &u : seg)
+				for (int k = 0; k < u.reads; ++k) container.add_record(read_info("AAATTAGGTCCA", u.umi, "Gene1"));
+			container.set_initialized();
+			container.merge_and_filter();
+			auto const &gene = container.cell(0).at("Gene1");
+			CHECK_EQUAL(gene.size(), size_t(3));
+			CHECK_EQUAL(gene.at("AGT").read_count(), size_t(28));
+			CHECK_EQUAL(gene.at("TCC").read_count(), size_t(30));
+			CHECK_EQUAL(gene.at("AAC").read_count(), size_t(5));
+			CHECK_EQUAL(container.cell(0).umis_number(), size_t(3));
+		}
+
 		// testEditDistance, Tests/TestTools.cpp:47-54 ; testReadParams :56-87 (codec part)
 		CHECK_EQUAL(Tools::edit_distance("ATTTTC", "ATTTGC"), 1u);
 		CHECK_EQUAL(Tools::edit_distance("ATTTTCC", "ATTTGNC"), 1u);

@@ -46,6 +46,9 @@ class Case:
     marks: str = "eEBA"
     max_cells: int = -1
     reads_output: bool = False
+    umi_merge: str = "simple"
+    max_umi_ed: int = 1
+    umi_mult: float = 2.0
     dump_umis: bool = True
     n_batches: int = 3
     shuffle: bool = True
@@ -67,6 +70,8 @@ def gpu_run(case: Case, recs: Optional[np.ndarray], device_generate: bool = Fals
                     barcodes_file=case.barcodes, min_genes_before_merge=case.min_genes_before,
                     min_genes_after_merge=case.min_genes_after, max_cb_merge_edit_distance=case.max_cb_ed,
                     min_merge_fraction=case.min_frac, marks=case.marks, max_cells=case.max_cells,
+                    umi_merge_type=dg.UMI_MERGE_DIRECTIONAL if case.umi_merge == "directional" else dg.UMI_MERGE_SIMPLE,
+                    max_umi_merge_edit_distance=case.max_umi_ed, umi_merge_mult=case.umi_mult,
                     reads_output=case.reads_output, max_barcodes_hint=case.extra.get("max_barcodes_hint", 1 << 16))
     c = dg.Container(cfg)
     if device_generate:
@@ -117,7 +122,8 @@ def run_case(case: Case, device_generate: bool = False, kind: str = "any"):
         ora = oracle_io.run_oracle(path, kind=kind, merge=case.merge, barcodes=case.barcodes, barcodes_type=case.barcodes_type,
                                    min_genes_before=case.min_genes_before, min_genes_after=case.min_genes_after,
                                    max_cb_ed=case.max_cb_ed, min_frac=case.min_frac, marks=case.marks, max_cells=case.max_cells,
-                                   reads_output=case.reads_output, dump_umis=case.dump_umis)
+                                   reads_output=case.reads_output, dump_umis=case.dump_umis, umi_merge=case.umi_merge,
+                                   max_umi_ed=case.max_umi_ed, umi_mult=case.umi_mult)
     gpu = gpu_run(case, recs, device_generate=device_generate, tables=tables)
     return {"case": case, "oracle": ora, "gpu": gpu, "recs": recs}
 

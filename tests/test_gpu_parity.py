@@ -225,3 +225,30 @@ def test_route_kernel_matches_host_mirror(world):
         seg, exp = got[off:off + int(counts[r])], exp_sorted[off:off + int(counts[r])]
         np.testing.assert_array_equal(np.sort(seg, order=["read_idx"]), np.sort(exp, order=["read_idx"]))
         off += int(counts[r])
+
+
+def _directional_case(umi_len, n_genes, n_reads, seed, **kw):
+    wl = read_whitelist(pu.WL_SYNTH_7_9)
+    spec = SynthSpec(n_reads=n_reads, n_cells=25, n_genes=n_genes, cb_len=16, umi_len=umi_len, whitelist_parts=wl, cb_error_ppm=50000,
+                     reads_per_umi=kw.pop("reads_per_umi", 3), seed=seed)
+    return pu.Case(name=f"directional_{umi_len}_{n_genes}", spec=spec, cb_len=16, umi_len=umi_len, n_genes=n_genes, merge=kw.pop("merge", "real"),
+                   barcodes=pu.WL_SYNTH_7_9, min_genes_before=3, min_genes_after=5, umi_merge="directional", **kw)
+
+
+@pytest.mark.parametrize("umi_len,n_genes,max_ed,mult", [(5, 40, 1, 2.0), (4, 12, 1, 2.0), (6, 8, 2, 2.0), (5, 20, 1, 1.0), (5, 6, 3, 0.5),
+                                                         (8, 3, 1, 2.0)])
+def test_directional_umi_merge(umi_len, n_genes, max_ed, mult):
+    """`-u`: dense UMI neighbourhoods (short UMIs) so that segments of every size class merge, with ties between equal read
+    counts (<= 16 UMIs: stable order on the device; larger: exact host replay of std::sort)."""
+    case = _directional_case(umi_len, n_genes, 60000, seed=11 + umi_len, max_umi_ed=max_ed, umi_mult=mult)
+    res = pu.run_case(case)
+    pu.assert_parity(res)
+    s = res["gpu"]["summary"]
+    assert s["n_umis_merged"] > 0
+
+
+def test_directional_umi_merge_large_segments():
+    """Two genes and 5-base UMIs: segments of several hundred UMIs (block-per-segment kernel and the host replay)."""
+    case = _directional_case(5, 2, 150000, seed=5, reads_per_umi=6, merge="none")
+    res = pu.run_case(case)
+    pu.assert_parity(res)

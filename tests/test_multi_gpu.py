@@ -19,10 +19,16 @@ def _free_port():
     return p
 
 
-def _spec(n_total):
+def _spec(n_total, umi_len=10, n_genes=150):
     from dropest_b200.synth import SynthSpec, read_whitelist
 
-    return SynthSpec(n_reads=n_total, n_cells=80, n_genes=150, cb_len=16, umi_len=10, whitelist_parts=read_whitelist(pu.WL_SYNTH_7_9), seed=9)
+    return SynthSpec(n_reads=n_total, n_cells=80, n_genes=n_genes, cb_len=16, umi_len=umi_len, whitelist_parts=read_whitelist(pu.WL_SYNTH_7_9), seed=9)
+
+
+def _real_config(dg, umi_len, n_genes, directional, **kw):
+    return dg.Config(cb_len=16, umi_len=umi_len, n_genes=n_genes, merge_type=dg.MERGE_REAL, barcodes_type=dg.BARCODES_CONST,
+                     barcodes_file=pu.WL_SYNTH_7_9, min_genes_before_merge=5, min_genes_after_merge=10, max_barcodes_hint=1 << 16,
+                     umi_merge_type=dg.UMI_MERGE_DIRECTIONAL if directional else dg.UMI_MERGE_SIMPLE, **kw)
 
 
 def _triplets(c, dg):
@@ -39,7 +45,7 @@ def _cm_triplets(c, dg, which_cells, which_matrix):
     return np.stack([cells["barcode"][col].astype(np.uint64), genes.astype(np.uint64), vals.astype(np.uint64)], axis=1)
 
 
-def _worker_real(rank, world, port, n_total, out_dir):
+def _worker_real(rank, world, port, n_total, out_dir, umi_len, n_genes, directional):
     import torch
     import torch.distributed as dist
 
@@ -53,15 +59,14 @@ def _worker_real(rank, world, port, n_total, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     per = n_total // world
     raw = torch.empty(per * 16, dtype=torch.uint8, device=f"cuda:{rank}")
-    SynthTables(_spec(n_total)).generate_device(rank, rank * per, per, raw.data_ptr())
+    SynthTables(_spec(n_total, umi_len, n_genes)).generate_device(rank, rank * per, per, raw.data_ptr())
     routed = torch.empty_like(raw)
     counts = dgdist.route_device(rank, raw.data_ptr(), per, world, routed.data_ptr())
     got, cnt = dgdist.exchange(routed, counts)
     torch.cuda.synchronize()
-    c = dg.Container(dg.Config(cb_len=16, umi_len=10, n_genes=150, device=rank, merge_type=dg.MERGE_REAL, barcodes_type=dg.BARCODES_CONST,
-                               barcodes_file=pu.WL_SYNTH_7_9, min_genes_before_merge=5, min_genes_after_merge=10, sharded=True,
-                               max_barcodes_hint=1 << 16))
+    c = dg.Container(_real_config(dg, umi_len, n_genes, directional, device=rank, sharded=True))
     c.add_batch_device(got.data_ptr(), cnt, keepalive=got)
+    dgdist.sync_umi_first_seen(c, f"cuda:{rank}")
     c.set_initialized()
     stats = dgdist.merge_across_ranks(c, f"cuda:{rank}")
     c.merge_and_filter()
@@ -73,14 +78,17 @@ def _worker_real(rank, world, port, n_total, out_dir):
     np.save(os.path.join(out_dir, f"filt{rank}.npy"), np.stack([filt["barcode"], filt["umis_stat"].astype(np.uint64), filt["reads_stat"].astype(np.uint64),
                                                              filt["requested_genes_num"].astype(np.uint64)], axis=1))
     s = c.summary()
-    np.save(os.path.join(out_dir, f"sum{rank}.npy"), np.array([s[k] for k in ("n_merged", "n_excluded", "n_unresolved", "real_cells_number", "filtered_cells_number")]))
+    np.save(os.path.join(out_dir, f"sum{rank}.npy"), np.array([s[k] for k in ("n_merged", "n_excluded", "n_unresolved", "real_cells_number", "filtered_cells_number",
+                                                                                "n_umis_merged")]))
     c.close()
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_gpu_cross_rank_whitelist_merge_is_exact(tmp_path):
-    """Sharded run + cross-rank merge (dge_dist_*): the union of the per-rank results equals the single-GPU result."""
+@pytest.mark.parametrize("umi_len,n_genes,directional", [(10, 150, False), (5, 20, True)])
+def test_two_gpu_cross_rank_whitelist_merge_is_exact(tmp_path, umi_len, n_genes, directional):
+    """Sharded run + cross-rank merge (dge_dist_*): the union of the per-rank results equals the single-GPU result.
+    With the directional UMI merge the per-UMI first-seen table is min-reduced across ranks first."""
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -91,10 +99,9 @@ def test_two_gpu_cross_rank_whitelist_merge_is_exact(tmp_path):
     from dropest_b200.synth import SynthTables
 
     world, n_total = 2, 300_000
-    mp.spawn(_worker_real, args=(world, _free_port(), n_total, str(tmp_path)), nprocs=world, join=True)
-    recs = SynthTables(_spec(n_total)).generate_host(0, n_total)
-    c = dg.Container(dg.Config(cb_len=16, umi_len=10, n_genes=150, merge_type=dg.MERGE_REAL, barcodes_type=dg.BARCODES_CONST,
-                               barcodes_file=pu.WL_SYNTH_7_9, min_genes_before_merge=5, min_genes_after_merge=10, max_barcodes_hint=1 << 16))
+    mp.spawn(_worker_real, args=(world, _free_port(), n_total, str(tmp_path), umi_len, n_genes, directional), nprocs=world, join=True)
+    recs = SynthTables(_spec(n_total, umi_len, n_genes)).generate_host(0, n_total)
+    c = dg.Container(_real_config(dg, umi_len, n_genes, directional))
     c.add_batch(recs)
     c.set_initialized()
     c.merge_and_filter()
@@ -104,7 +111,8 @@ def test_two_gpu_cross_rank_whitelist_merge_is_exact(tmp_path):
     sums = sum(np.load(tmp_path / f"sum{r}.npy") for r in range(world))
     print("sums", sums, "single", s)
     assert s["n_merged"] > 0
-    assert list(sums) == [s["n_merged"], s["n_excluded"], 0, s["real_cells_number"], s["filtered_cells_number"]]
+    assert list(sums) == [s["n_merged"], s["n_excluded"], 0, s["real_cells_number"], s["filtered_cells_number"], s["n_umis_merged"]]
+    assert (s["n_umis_merged"] > 0) == directional
     a, b = c.merge_pairs()
     np.testing.assert_array_equal(order(cat("pairs")), order(np.stack([a, b], axis=1)))
     np.testing.assert_array_equal(order(cat("cm")), order(_cm_triplets(c, dg, dg.CELLS_FILTERED, dg.MATRIX_CM)))
