@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
+#include "sortdedup.cuh"
 #include <chrono>
 #include <cstdlib>
 
@@ -621,7 +622,6 @@ public:
         DGE_CUDA(cudaMemsetAsync(ucount, 0, (nsb_bound + 1) * 4, st));
         DGE_CUDA(cudaEventRecord(ev0, st));
         {
-            const uint32_t cut = uint32_t(SC_HT * 0.85);
             auto launch = [&](int ht, uint32_t lo, uint32_t hi) {
                 const int thr = sc_tuning().dedup_threads;
                 const int cap = hi == 0xFFFFFFFFu ? ht : int(((hi + 31) / 32) * 32); // distinct keys <= records <= hi in a bounded class
@@ -633,12 +633,27 @@ public:
                                                                                                                 sub_off, n_sub_ptr, ucount, overflow_flag, ht, cap, lo, hi);
                 ++L;
             };
-            if (SC_HT < SC_HT_MAX)
-            {
-                launch(SC_HT, 0u, cut);                    // the common class
-                launch(SC_HT_MAX, cut, 0xFFFFFFFFu);       // oversized sub-buckets (sampling tail, heavy duplicates)
+            static const bool use_hash = std::getenv("DGE_HASH_DEDUP") != nullptr;
+            if (!has_val && !use_hash)
+            {   // comparison sort + run detection, size-classed by the threads a sub-bucket needs (16 keys per thread);
+                // anything larger than 4096 records (sampling tail, one heavily duplicated key) streams through the hash kernel
+                uint32_t *uv = ws.uvals_sparse.as<uint32_t>();
+                k_sort_dedup<64><<<unsigned(nsb_bound), 64, 0, st>>>(keys_tmp, uv, sub_off, n_sub_ptr, ucount, 0u, 1024u);
+                k_sort_dedup<128><<<unsigned(nsb_bound), 128, 0, st>>>(keys_tmp, uv, sub_off, n_sub_ptr, ucount, 1024u, 2048u);
+                k_sort_dedup<256><<<unsigned(nsb_bound), 256, 0, st>>>(keys_tmp, uv, sub_off, n_sub_ptr, ucount, 2048u, 4096u);
+                L += 3;
+                launch(SC_HT_MAX, 4096u, 0xFFFFFFFFu);
             }
-            else launch(SC_HT, 0u, 0xFFFFFFFFu);
+            else
+            {
+                const uint32_t cut = uint32_t(SC_HT * 0.85);
+                if (SC_HT < SC_HT_MAX)
+                {
+                    launch(SC_HT, 0u, cut);                    // the common class
+                    launch(SC_HT_MAX, cut, 0xFFFFFFFFu);       // oversized sub-buckets (sampling tail, heavy duplicates)
+                }
+                else launch(SC_HT, 0u, 0xFFFFFFFFu);
+            }
         }
         DGE_CUDA(cudaEventRecord(ev1, st));
         ++stats->dedup_launches;
