@@ -94,7 +94,8 @@ class _SynthParams(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "lib", "libdropest_b200.so")
+    # DGE_LIB: development override to A/B two builds of the same library (compile-time kernel variants)
+    return os.environ.get("DGE_LIB") or os.path.join(_HERE, "lib", "libdropest_b200.so")
 
 
 _lib = None

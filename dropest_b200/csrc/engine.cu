@@ -16,6 +16,8 @@
 #include "umimerge.cuh"
 #include "whitelist.hpp"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -89,7 +91,8 @@ struct dge_handle
     DevBuf keys_all, ukey, uval, ukey2, uval2, overflow_flag;
     DevBuf cg_key, cg_start, cg_pc, cg_req, cg_reads, cg_req_reads;
     DevBuf pc_slot, pc_u_start, pc_cg_start, pc_reads, pc_req_genes, pc_req_umis, slot_pc;
-    DevBuf tile_a, tile_b, scan_scratch, flags, flags_off, rows_dev, misc;
+    DevBuf tile_a, tile_b, scan_scratch, flags, flags_off, rows_dev, rows_dev2, misc, cub_tmp, sort_k[2], sort_v[2];
+    PinnedBuf pin_filtered, pin_fkeys;
     uint32_t n_u = 0, n_cg = 0, n_pc = 0;
     size_t n_keys = 0;
     FillCounters counters{};
@@ -212,6 +215,17 @@ template <class T> T d2h_scalar(const void *src, cudaStream_t st)
 
 void reset_fill_state(dge_handle *h);
 
+// Radix sort of (key, value) pairs on the low `end_bit` key bits.  Used ONLY for per-cell / per-gene tables (~1e5 rows: cell-id
+// order, compare_cells order, gene first-seen order) -- library code (CUB), not part of the per-read path.
+void device_sort_pairs(dge_handle *h, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, size_t n, int end_bit)
+{
+    size_t bytes = 0;
+    DGE_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, int(n), 0, end_bit, h->stream));
+    h->cub_tmp.reserve(bytes + 16);
+    DGE_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, kin, kout, vin, vout, int(n), 0, end_bit, h->stream));
+    h->launches += 4;
+}
+
 void ensure_device(dge_handle *h)
 {
     DGE_CUDA(cudaSetDevice(h->cfg.device));
@@ -291,29 +305,37 @@ void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n)
     h->n_reads += n;
 }
 
-bool compare_cells(const HostCell &a, const HostCell &b)
-{
-    // CellsDataContainer::compare_cells (CellsDataContainer.cpp:329-344); barcode strings of equal length over ACGT compare
-    // like their 2-bit packings.
-    if (a.req_genes != b.req_genes) return a.req_genes < b.req_genes;
-    if (a.req_umis != b.req_umis) return a.req_umis < b.req_umis;
-    if (a.umis_stat != b.umis_stat) return a.umis_stat < b.umis_stat;
-    return a.cb < b.cb;
-}
+// CellsDataContainer::compare_cells (CellsDataContainer.cpp:329-344) orders by (requested genes, requested umis, TOTAL_UMIS stat,
+// barcode); barcode strings of equal length over ACGT compare like their 2-bit packings.  update_filtered sorts by exactly that.
 
-// Stable LSD radix sort of `idx` by 16-bit digits of key(idx) (host; n ~ 1e5, replaces std::sort with a comparator).
-template <class KeyFn> void radix_pass16(std::vector<uint32_t> &idx, std::vector<uint32_t> &tmp, KeyFn key)
+// Stable LSD radix sort of (key, idx) pairs by 8-bit digits (host; n ~ 1e5 cells, replaces std::sort with a comparator).
+// Digits on which all keys agree are skipped; 256 write streams keep the scatter cache friendly.
+struct HostPairSorter
 {
-    std::vector<uint32_t> cnt(65537, 0);
-    for (uint32_t i : idx) ++cnt[size_t(key(i)) + 1];
-    bool single = false;
-    for (size_t d = 0; d < 65536; ++d) if (cnt[d + 1] == idx.size()) single = true;
-    if (single) return; // all keys share this digit
-    for (size_t d = 0; d < 65536; ++d) cnt[d + 1] += cnt[d];
-    tmp.resize(idx.size());
-    for (uint32_t i : idx) tmp[cnt[key(i)]++] = i;
-    idx.swap(tmp);
-}
+    std::vector<uint64_t> key, key2;
+    std::vector<uint32_t> idx, idx2;
+    void sort(size_t n, int key_bits)
+    {
+        key2.resize(n); idx2.resize(n);
+        if (n < 2) return;
+        uint64_t all_or = 0, all_and = ~0ull;
+        for (size_t i = 0; i < n; ++i) { all_or |= key[i]; all_and &= key[i]; }
+        const uint64_t varying = all_or & ~all_and;
+        for (int sh = 0; sh < key_bits; sh += 8)
+        {
+            if (((varying >> sh) & 0xFFu) == 0) continue;
+            size_t cnt[257] = {0};
+            for (size_t i = 0; i < n; ++i) ++cnt[((key[i] >> sh) & 0xFFu) + 1];
+            for (int d = 0; d < 256; ++d) cnt[d + 1] += cnt[d];
+            for (size_t i = 0; i < n; ++i)
+            {
+                const size_t o = cnt[(key[i] >> sh) & 0xFFu]++;
+                key2[o] = key[i]; idx2[o] = idx[i];
+            }
+            key.swap(key2); idx.swap(idx2);
+        }
+    }
+};
 
 // update_filtered_gene_counts (CellsDataContainer.cpp:250-276): real cells with enough requested genes, ascending by
 // compare_cells = (requested genes, requested umis, TOTAL_UMIS stat, barcode) -- a total order, so any sort gives the same list.
@@ -322,35 +344,44 @@ void update_filtered(dge_handle *h, uint32_t threshold, int cell_threshold)
     std::vector<uint32_t> &f = h->filtered;
     f.clear();
     const std::vector<HostCell> &R = h->real;
+    static thread_local HostPairSorter ps;
+    ps.key.clear(); ps.idx.clear();
     bool fits = true;
     for (uint32_t i = 0; i < R.size(); ++i)
     {
         const HostCell &c = R[i];
         if (!(c.real && uint32_t(c.req_genes) >= threshold)) continue;
-        f.push_back(i);
+        // one 64-bit composite key (genes:16 | umis:24 | stat:24); the barcode only breaks exact ties
+        ps.key.push_back((uint64_t(uint32_t(c.req_genes)) << 48) | (uint64_t(uint32_t(c.req_umis)) << 24) | uint64_t(uint32_t(c.umis_stat)));
+        ps.idx.push_back(i);
         fits &= uint32_t(c.req_genes) < (1u << 16) && uint32_t(c.req_umis) < (1u << 24) && uint32_t(c.umis_stat) < (1u << 24);
     }
-    std::vector<uint32_t> tmp;
     if (fits)
-    {   // one 64-bit composite key (genes:16 | umis:24 | stat:24), 4 radix passes; barcode only breaks exact ties
-        std::vector<uint64_t> &key = h->h_sortkey;
-        key.resize(R.size());
-        for (uint32_t i : f) key[i] = (uint64_t(uint32_t(R[i].req_genes)) << 48) | (uint64_t(uint32_t(R[i].req_umis)) << 24) | uint64_t(uint32_t(R[i].umis_stat));
-        for (int sh = 0; sh < 64; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return uint32_t(key[i] >> sh) & 0xFFFFu; });
+    {
+        ps.sort(ps.key.size(), 64);
+        f.assign(ps.idx.begin(), ps.idx.end());
+        const std::vector<uint64_t> &key = ps.key;
         for (size_t a = 0; a < f.size();)
         {
             size_t b = a + 1;
-            while (b < f.size() && key[f[b]] == key[f[a]]) ++b;
+            while (b < f.size() && key[b] == key[a]) ++b;
             if (b - a > 1) std::sort(f.begin() + long(a), f.begin() + long(b), [&](uint32_t x, uint32_t y) { return R[x].cb < R[y].cb; });
             a = b;
         }
     }
     else
-    {
-        for (int sh = 0; sh < 48; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return uint32_t(R[i].cb >> sh) & 0xFFFFu; });
-        for (int sh = 0; sh < 32; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return (uint32_t(R[i].umis_stat) >> sh) & 0xFFFFu; });
-        for (int sh = 0; sh < 32; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return (uint32_t(R[i].req_umis) >> sh) & 0xFFFFu; });
-        for (int sh = 0; sh < 32; sh += 16) radix_pass16(f, tmp, [&](uint32_t i) { return (uint32_t(R[i].req_genes) >> sh) & 0xFFFFu; });
+    {   // counters beyond the packed widths: successive stable passes, least significant criterion first
+        f.assign(ps.idx.begin(), ps.idx.end());
+        auto pass = [&](int bits, auto keyfn) {
+            ps.key.resize(f.size()); ps.idx = f;
+            for (size_t i = 0; i < f.size(); ++i) ps.key[i] = keyfn(R[f[i]]);
+            ps.sort(f.size(), bits);
+            f.assign(ps.idx.begin(), ps.idx.end());
+        };
+        pass(48, [](const HostCell &c) { return uint64_t(c.cb); });
+        pass(32, [](const HostCell &c) { return uint64_t(uint32_t(c.umis_stat)); });
+        pass(32, [](const HostCell &c) { return uint64_t(uint32_t(c.req_umis)); });
+        pass(32, [](const HostCell &c) { return uint64_t(uint32_t(c.req_genes)); });
     }
     if (cell_threshold > 0 && size_t(cell_threshold) < f.size()) f.erase(f.begin(), f.end() - cell_threshold);
 }
@@ -498,11 +529,16 @@ void do_set_initialized(dge_handle *h)
     ++h->launches;
     h->total_cells = d2h_scalar<unsigned long long>(h->misc.p, st);
     DGE_CUDA(cudaEventRecord(h->ev[1], st));
+    tr.mark("init:  count occupied");
 
     // ---- real cells -> host (Cell::is_real, Cell.cpp:125-128: n_genes >= min_genes_before_merge)
     std::vector<CellRow> rows;
     const CellRow *rows_p = nullptr;
     size_t n_rows = 0;
+    bool rows_sorted = false;            // rows_p already in cell-id order, dev_filtered = compare_cells order of all of them
+    const uint32_t *dev_filtered = nullptr;
+    const uint64_t *dev_fkeys = nullptr;
+    int dev_filter_overflow = 0;
     if (h->n_pc)
     {
         h->flags.reserve((size_t(h->n_pc) + 1) * 4); h->flags_off.reserve((size_t(h->n_pc) + 1) * 4);
@@ -519,11 +555,29 @@ void do_set_initialized(dge_handle *h)
                                                                           h->pc_req_umis.as<uint32_t>(), h->rows_dev.as<CellRow>());
             DGE_LAUNCH_CHECK();
             ++h->launches;
-            rows_p = d2h_pinned<CellRow>(h->pin_rows, h->rows_dev.p, n_real, st);
+            // cell-id order (first-seen barcode order, CellsDataContainer.cpp:64-69) and the set_initialized filtered order
+            // (all real cells, ascending compare_cells) are computed on the device: the host only receives sorted tables
+            for (int b = 0; b < 2; ++b) { h->sort_k[b].reserve(size_t(n_real) * 8); h->sort_v[b].reserve(size_t(n_real) * 4); }
+            h->rows_dev2.reserve(size_t(n_real) * sizeof(CellRow));
+            const unsigned g = grid_for(n_real, 256);
+            k_rows_first_keys<<<g, 256, 0, st>>>(h->rows_dev.as<CellRow>(), n_real, h->sort_k[0].as<uint64_t>(), h->sort_v[0].as<uint32_t>());
+            device_sort_pairs(h, h->sort_k[0].as<uint64_t>(), h->sort_k[1].as<uint64_t>(), h->sort_v[0].as<uint32_t>(), h->sort_v[1].as<uint32_t>(), n_real, 32);
+            k_rows_permute<<<g, 256, 0, st>>>(h->rows_dev.as<CellRow>(), h->sort_v[1].as<uint32_t>(), n_real, h->rows_dev2.as<CellRow>());
+            DGE_CUDA(cudaMemsetAsync(h->overflow_flag.p, 0, sizeof(int), st));
+            k_rows_filter_keys<<<g, 256, 0, st>>>(h->rows_dev2.as<CellRow>(), n_real, h->sort_k[0].as<uint64_t>(), h->sort_v[0].as<uint32_t>(), h->overflow_flag.as<int>());
+            device_sort_pairs(h, h->sort_k[0].as<uint64_t>(), h->sort_k[1].as<uint64_t>(), h->sort_v[0].as<uint32_t>(), h->sort_v[1].as<uint32_t>(), n_real, 64);
+            DGE_LAUNCH_CHECK();
+            h->launches += 3;
+            rows_p = d2h_pinned<CellRow>(h->pin_rows, h->rows_dev2.p, n_real, st);
+            dev_filtered = d2h_pinned<uint32_t>(h->pin_filtered, h->sort_v[1].p, n_real, st);
+            dev_fkeys = d2h_pinned<uint64_t>(h->pin_fkeys, h->sort_k[1].p, n_real, st);
+            DGE_CUDA(cudaMemcpyAsync(&dev_filter_overflow, h->overflow_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             n_rows = n_real;
             DGE_CUDA(cudaStreamSynchronize(st));
+            rows_sorted = true;
         }
     }
+    tr.mark("init:  rows d2h");
     // min_genes_before_merge == 0 makes every barcode real, including barcodes that only have intergenic reads
     // (they own no UMI and are not in the PC table): pick them up from the barcode table.
     if (h->cfg.min_genes_before_merge == 0 && h->total_cells > h->n_pc)
@@ -545,15 +599,22 @@ void do_set_initialized(dge_handle *h)
             }
         rows_p = rows.data();
         n_rows = rows.size();
+        rows_sorted = false;
     }
-    std::vector<uint32_t> order(n_rows), order_tmp;
-    std::iota(order.begin(), order.end(), 0u);
-    for (int sh = 0; sh < 32; sh += 16) radix_pass16(order, order_tmp, [&](uint32_t i) { return (rows_p[i].first_idx >> sh) & 0xFFFFu; });
+    static thread_local HostPairSorter order_sorter;
+    if (!rows_sorted)
+    {
+        order_sorter.key.resize(n_rows); order_sorter.idx.resize(n_rows);
+        for (size_t i = 0; i < n_rows; ++i) { order_sorter.key[i] = rows_p[i].first_idx; order_sorter.idx[i] = uint32_t(i); }
+        order_sorter.sort(n_rows, 32);
+    }
+    const std::vector<uint32_t> &order = order_sorter.idx;
+    tr.mark("init:  order sort");
     h->real.clear();
     h->real.reserve(n_rows);
-    for (uint32_t ri : order)
+    for (size_t k = 0; k < n_rows; ++k)
     {
-        const CellRow &r = rows_p[ri];
+        const CellRow &r = rows_p[rows_sorted ? k : size_t(order[k])];
         HostCell c;
         c.cb = r.cb; c.slot = r.slot; c.pc = r.pc; c.first_idx = r.first_idx; c.n_intergenic = r.n_intergenic;
         c.n_genes = int32_t(r.n_genes); c.umis_stat = int32_t(r.n_umis); c.n_umis_distinct = int32_t(r.n_umis);
@@ -566,13 +627,28 @@ void do_set_initialized(dge_handle *h)
     {
         const uint32_t *gf = d2h_pinned<uint32_t>(h->pin_misc, h->gene_first.p, h->cfg.n_genes, st);
         DGE_CUDA(cudaStreamSynchronize(st));
-        std::vector<uint32_t> seen, seen_tmp;
+        static thread_local HostPairSorter gs;
+        gs.key.clear(); gs.idx.clear();
         for (uint32_t g = 0; g < h->cfg.n_genes; ++g)
-            if (gf[g] != NONE32) seen.push_back(g);
-        for (int sh = 0; sh < 32; sh += 16) radix_pass16(seen, seen_tmp, [&](uint32_t g) { return (gf[g] >> sh) & 0xFFFFu; });
-        h->gene_order.assign(seen.begin(), seen.end());
+            if (gf[g] != NONE32) { gs.key.push_back(gf[g]); gs.idx.push_back(g); }
+        gs.sort(gs.key.size(), 32);
+        h->gene_order.assign(gs.idx.begin(), gs.idx.end());
     }
-    update_filtered(h, 0, -1); // set_initialized: update_cell_sizes(query, 0, -1)  (CellsDataContainer.cpp:168)
+    tr.mark("init:  gene order");
+    // set_initialized: update_cell_sizes(query, 0, -1)  (CellsDataContainer.cpp:168) -- every real cell, ascending compare_cells
+    if (rows_sorted && !dev_filter_overflow)
+    {
+        std::vector<uint32_t> &f = h->filtered;
+        f.assign(dev_filtered, dev_filtered + n_rows);
+        for (size_t a = 0; a + 1 < f.size();)
+        {   // exact ties of (genes, umis, stat) are ordered by barcode
+            size_t b = a + 1;
+            while (b < f.size() && dev_fkeys[b] == dev_fkeys[a]) ++b;
+            if (b - a > 1) std::sort(f.begin() + long(a), f.begin() + long(b), [&](uint32_t x, uint32_t y) { return h->real[x].cb < h->real[y].cb; });
+            a = b;
+        }
+    }
+    else update_filtered(h, 0, -1);
     tr.mark("init: gene order + filtered");
     DGE_CUDA(cudaEventRecord(h->ev[2], st));
     DGE_CUDA(cudaStreamSynchronize(st));
@@ -643,6 +719,7 @@ long best_target_real(const dge_handle *h, uint32_t base, const uint32_t *nbs, c
 void phase1_real(dge_handle *h, std::vector<long> &target)
 {
     cudaStream_t st = h->stream;
+    Tracer tr; tr.st = st;
     const size_t n = h->real.size();
     target.assign(n, -2);
     h->n_unresolved = 0;
@@ -673,6 +750,7 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
         DGE_CUDA(cudaMemcpyAsync(nb_pc, h->d_nb.p, n * WL_K * 4, cudaMemcpyDeviceToHost, st));
         DGE_CUDA(cudaStreamSynchronize(st));
     }
+    tr.mark("merge:  p1 wl kernel + d2h");
 
     // exact host path (built lazily: most runs never need it)
     std::unordered_map<uint64_t, uint32_t> by_cb;
@@ -740,6 +818,7 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
     }
     run_intersections(h, jobs);
     const uint32_t *isect = h->isect_p;
+    tr.mark("merge:  p1 jobs + intersections");
 
     for (uint32_t i = 0; i < n; ++i)
     {
@@ -777,8 +856,11 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
 void phase2(dge_handle *h, const std::vector<long> &target)
 {
     const size_t n = h->real.size();
-    std::vector<uint32_t> reassign(n), child_head(n, NONE32), child_tail(n, NONE32), child_next(n, NONE32);
-    std::iota(reassign.begin(), reassign.end(), 0u);
+    // the loop walks cells in size order, i.e. randomly in cell-id order: keep what it touches in a compact 16-byte row
+    struct Row { int32_t umis, reads; uint32_t intergenic, reassign; };
+    std::vector<Row> row(n);
+    std::vector<uint32_t> child_head(n, NONE32), child_tail(n, NONE32), child_next(n, NONE32);
+    for (uint32_t i = 0; i < n; ++i) row[i] = Row{h->real[i].umis_stat, h->real[i].reads_stat, h->real[i].n_intergenic, i};
     h->merge_events.clear();
     h->merge_events.reserve(h->filtered.size());
     h->n_merged = h->n_excluded = 0;
@@ -791,29 +873,35 @@ void phase2(dge_handle *h, const std::vector<long> &target)
     {
         long t = target[base];
         if (t < 0) { h->real[base].excluded = true; ++h->n_excluded; continue; }
-        if (uint32_t(t) != reassign[size_t(t)]) t = long(reassign[size_t(t)]);
+        if (uint32_t(t) == base) continue;              // keeps itself (reassign[base] == base: nothing was merged into a merged cell yet)
+        t = long(row[size_t(t)].reassign);
         if (uint32_t(t) == base) continue;
         // merge_cells (CellsDataContainer.cpp:90-104): Stats::merge adds every counter (Stats.cpp:29-43)
-        HostCell &src = h->real[base];
-        HostCell &dst = h->real[size_t(t)];
-        dst.umis_stat += src.umis_stat; dst.reads_stat += src.reads_stat; dst.n_intergenic += src.n_intergenic;
-        src.merged = true;
+        Row &src = row[base];
+        Row &dst = row[size_t(t)];
+        dst.umis += src.umis; dst.reads += src.reads; dst.intergenic += src.intergenic;
         h->merge_events.emplace_back(base, uint32_t(t));
         ++h->n_merged;
         // reassign: base and everything previously re-pointed at base now point at t
-        reassign[base] = uint32_t(t);
+        src.reassign = uint32_t(t);
         uint32_t c = child_head[base];
         child_head[base] = child_tail[base] = NONE32;
         append(uint32_t(t), base);
         while (c != NONE32)
         {
             uint32_t nx = child_next[c];
-            reassign[c] = uint32_t(t);
+            row[c].reassign = uint32_t(t);
             append(uint32_t(t), c);
             c = nx;
         }
     }
-    for (uint32_t i = 0; i < n; ++i) h->real[i].target = int32_t(reassign[i]);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        HostCell &c = h->real[i];
+        c.umis_stat = row[i].umis; c.reads_stat = row[i].reads; c.n_intergenic = row[i].intergenic;
+        c.target = int32_t(row[i].reassign);
+        if (row[i].reassign != i) c.merged = true;
+    }
 }
 
 // Apply the recorded merges to the device lists.
@@ -832,11 +920,15 @@ void apply_merges(dge_handle *h)
     std::vector<MoveJob> &jobs = h->h_moves;
     jobs.clear();
     uint64_t total = 0;
+    struct Row { uint32_t pc, slot, n_umis; };
+    std::vector<Row> row(n); // compact copy of what the loop touches (merge events come in size order = random cell-id order)
+    for (uint32_t i = 0; i < n; ++i) row[i] = Row{h->real[i].pc, h->real[i].slot, uint32_t(h->real[i].n_umis_distinct)};
+    jobs.reserve(h->merge_events.size());
     auto emit = [&](uint32_t o, uint32_t dst) {
-        const HostCell &src = h->real[o];
-        if (src.pc == NONE32 || src.n_umis_distinct == 0) return;
-        jobs.push_back(MoveJob{src.pc, h->real[dst].slot, uint32_t(total)});
-        total += uint64_t(src.n_umis_distinct);
+        const Row &src = row[o];
+        if (src.pc == NONE32 || src.n_umis == 0) return;
+        jobs.push_back(MoveJob{src.pc, row[dst].slot, uint32_t(total)});
+        total += uint64_t(src.n_umis);
     };
     for (auto const &e : h->merge_events)
     {

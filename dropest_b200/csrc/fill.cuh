@@ -12,7 +12,13 @@ namespace dge
 struct Rec16 { unsigned long long key; uint32_t gene; uint32_t read_idx; };
 
 constexpr int FILL_THREADS = 256;
-constexpr int FILL_ITEMS = 8;
+#ifndef DGE_FILL_ITEMS
+#define DGE_FILL_ITEMS 8
+#endif
+#ifndef DGE_FILL_MINB
+#define DGE_FILL_MINB 1
+#endif
+constexpr int FILL_ITEMS = DGE_FILL_ITEMS;
 constexpr int FILL_TILE = FILL_THREADS * FILL_ITEMS;
 
 struct FillCounters
@@ -74,7 +80,7 @@ __device__ __forceinline__ uint32_t table_find(const CellSlot *tab, int tb, uint
 }
 
 // records -> compact keys (dense, order irrelevant) + L1 histogram of the keys + global read counters.
-__global__ void __launch_bounds__(FILL_THREADS) k_fill_compact(const Rec16 *__restrict__ recs, size_t n, CellSlot *__restrict__ tab, KeyLayout kl,
+__global__ void __launch_bounds__(FILL_THREADS, DGE_FILL_MINB) k_fill_compact(const Rec16 *__restrict__ recs, size_t n, CellSlot *__restrict__ tab, KeyLayout kl,
                                                                uint32_t n_genes, uint32_t *__restrict__ gene_first, uint64_t *__restrict__ out_keys,
                                                                FillCounters *__restrict__ ctr, int l1_shift, int nb1, uint32_t *__restrict__ l1_hist,
                                                                uint32_t *__restrict__ umi_first)

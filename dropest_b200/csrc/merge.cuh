@@ -349,6 +349,31 @@ __global__ void k_gather_rows_flagged(const uint32_t *__restrict__ flags, const 
     }
 }
 
+// ---- ordering of the real-cell rows on the device (cell-id order = first-seen order; compare_cells order) -------------
+__global__ void k_rows_first_keys(const CellRow *__restrict__ rows, uint32_t n, uint64_t *__restrict__ key, uint32_t *__restrict__ idx)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { key[i] = rows[i].first_idx; idx[i] = i; }
+}
+
+__global__ void k_rows_permute(const CellRow *__restrict__ rows, const uint32_t *__restrict__ perm, uint32_t n, CellRow *__restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = rows[perm[i]];
+}
+
+// compare_cells key (CellsDataContainer.cpp:329-344): requested genes : 16 | requested umis : 24 | TOTAL_UMIS stat : 24; the barcode
+// breaks exact ties (host).  *overflow is set when a counter does not fit its field (the host then sorts with full widths).
+__global__ void k_rows_filter_keys(const CellRow *__restrict__ rows, uint32_t n, uint64_t *__restrict__ key, uint32_t *__restrict__ idx,
+                                   int *__restrict__ overflow)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const CellRow r = rows[i];
+        if (r.req_genes >= (1u << 16) || r.req_umis >= (1u << 24) || r.n_umis >= (1u << 24)) *overflow = 1;
+        key[i] = (uint64_t(r.req_genes) << 48) | (uint64_t(r.req_umis & 0xFFFFFFu) << 24) | uint64_t(r.n_umis & 0xFFFFFFu);
+        idx[i] = i;
+    }
+}
+
 // rows for an explicit list of present cells (after merges)
 __global__ void k_gather_rows_list(const uint32_t *__restrict__ pcs, uint32_t n, const CellSlot *__restrict__ tab,
                                    const uint32_t *__restrict__ pc_slot, const uint32_t *__restrict__ pc_cg_start,

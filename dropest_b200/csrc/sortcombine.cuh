@@ -34,7 +34,7 @@ constexpr int SC_DEDUP_THREADS = 256;
 struct SortCombineTuning
 {
     int l1_target = 200000; // records per L1 bucket
-    int target = 1024;      // records per sub-bucket
+    int target = 832;       // records per sub-bucket (most then fit the 1024-key class of the merge sort)
     int ht = 2048;          // hash-table slots per sub-bucket (power of two, >= 2 * expected distinct keys)
     int dedup_threads = 256; // threads per dedup block (32..256, power of two)
     SortCombineTuning()
@@ -103,21 +103,35 @@ __global__ void __launch_bounds__(THREADS) k_l1_scatter(const uint64_t *__restri
     const size_t base = size_t(blockIdx.x) * SC_TILE;
     uint64_t k[SC_ITEMS];
     uint32_t r[SC_ITEMS];
+    // all loads of the tile first (the shared-memory atomics below would otherwise serialise them: one DRAM round trip per item)
 #pragma unroll
     for (int j = 0; j < SC_ITEMS; ++j)
     {
         size_t i = base + size_t(j) * SC_THREADS + threadIdx.x;
-        if (i < n)
-        {
-            k[j] = keys[i];
-            r[j] = atomicAdd(&cnt[k[j] >> shift], 1u);
-        }
+        k[j] = i < n ? __ldg(keys + i) : EMPTY64;
+    }
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j)
+    {
+        size_t i = base + size_t(j) * SC_THREADS + threadIdx.x;
+        if (i < n) r[j] = atomicAdd(&cnt[k[j] >> shift], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nb1; i += blockDim.x)
-    {
-        uint32_t c = cnt[i];
-        if (c) cnt[i] = atomicAdd(&cursor[i], c);
+    {   // one global atomicAdd per non-empty (tile, bucket); all of a thread's atomics are issued before any result is consumed
+        constexpr int PER = SC_MAX_NB1 / THREADS;
+        uint32_t c[PER], o[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q)
+        {
+            const int i = q * THREADS + int(threadIdx.x);
+            c[q] = i < nb1 ? cnt[i] : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < PER; ++q)
+            if (c[q]) o[q] = atomicAdd(&cursor[q * THREADS + int(threadIdx.x)], c[q]);
+#pragma unroll
+        for (int q = 0; q < PER; ++q)
+            if (c[q]) cnt[q * THREADS + int(threadIdx.x)] = o[q];
     }
     __syncthreads();
 #pragma unroll
@@ -241,26 +255,40 @@ __global__ void __launch_bounds__(THREADS) k_l2_pass(const uint64_t *__restrict_
     uint64_t k[SC_ITEMS];
     uint32_t r[SC_ITEMS];
     uint16_t sbk[SC_ITEMS];
+    // all loads of the tile first, then the splitter searches, then the shared-memory atomics
 #pragma unroll
     for (int j = 0; j < SC_ITEMS; ++j)
     {
         uint32_t i = t0 + uint32_t(j) * SC_THREADS + threadIdx.x;
-        if (i < t1)
-        {
-            k[j] = keys[i];
-            uint32_t s = np > 1 ? sub_bucket_of(spl, np - 1, k[j] >> 3) : 0u;
-            sbk[j] = uint16_t(s);
-            r[j] = atomicAdd(&cnt[s], 1u);
-        }
+        k[j] = i < t1 ? __ldg(keys + i) : EMPTY64;
+    }
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j)
+        sbk[j] = uint16_t(np > 1 ? sub_bucket_of(spl, np - 1, k[j] >> 3) : 0u);
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j)
+    {
+        uint32_t i = t0 + uint32_t(j) * SC_THREADS + threadIdx.x;
+        if (i < t1) r[j] = atomicAdd(&cnt[sbk[j]], 1u);
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < np; i += blockDim.x)
-    {
-        uint32_t c = cnt[i];
-        if (c)
+    {   // all of a thread's global atomics in flight together
+        constexpr int PER = SC_MAX_P2 / THREADS;
+        uint32_t c[PER], o[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q)
         {
-            uint32_t old = atomicAdd(&sub_cnt_or_cursor[sb0 + i], c);
-            if (SCATTER) cnt[i] = old;
+            const uint32_t i = uint32_t(q * THREADS) + threadIdx.x;
+            c[q] = i < np ? cnt[i] : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < PER; ++q)
+            if (c[q]) o[q] = atomicAdd(&sub_cnt_or_cursor[sb0 + uint32_t(q * THREADS) + threadIdx.x], c[q]);
+        if (SCATTER)
+        {
+#pragma unroll
+            for (int q = 0; q < PER; ++q)
+                if (c[q]) cnt[uint32_t(q * THREADS) + threadIdx.x] = o[q];
         }
     }
     if (!SCATTER) return;
@@ -300,7 +328,8 @@ __global__ void __launch_bounds__(1024) k_dedup_sort(uint64_t *__restrict__ keys
                                                                  uint32_t *__restrict__ uvals, const uint32_t *__restrict__ sub_off,
                                                                  const uint32_t *__restrict__ n_sub_ptr, uint32_t *__restrict__ ucount,
                                                                  int *__restrict__ overflow, const int SC_HT, const int SC_CAP,
-                                                                 const uint32_t n_min, const uint32_t n_max)
+                                                                 const uint32_t n_min, const uint32_t n_max,
+                                                                 const uint32_t *__restrict__ list = nullptr, const uint32_t *__restrict__ list_count = nullptr)
 {
     // size classes: this launch only handles sub-buckets with n_min < records <= n_max (records <= 0.85 * SC_HT can never
     // overflow the table whatever the duplication rate; the last class takes everything larger and reports overflow).
@@ -317,10 +346,14 @@ __global__ void __launch_bounds__(1024) k_dedup_sort(uint64_t *__restrict__ keys
     __shared__ unsigned long long red_or, red_and;
     __shared__ uint32_t ws[33];
 
-    const uint32_t sb = blockIdx.x;
-    if (sb >= *n_sub_ptr) return;
+    // work items: either every sub-bucket (filtered by size class) or the entries of a work list (persistent blocks)
+    const uint32_t n_items = list ? *list_count : *n_sub_ptr;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x)
+    {
+    const uint32_t sb = list ? list[item] : item;
     const uint32_t s = sub_off[sb], e = sub_off[sb + 1];
-    if (e - s <= n_min || e - s > n_max) return; // another size class (ucount was zeroed by the host; empty buckets stay 0)
+    if (e - s <= n_min || e - s > n_max) continue; // another size class (ucount was zeroed by the host; empty buckets stay 0)
+    __syncthreads(); // previous item fully written out before the table is cleared
     for (int i = threadIdx.x; i < SC_HT; i += blockDim.x) { ht_key[i] = EMPTY64; ht_val[i] = 0; }
     if (threadIdx.x == 0) { m_s = 0; red_or = 0; red_and = EMPTY64; }
     __syncthreads();
@@ -450,6 +483,7 @@ __global__ void __launch_bounds__(1024) k_dedup_sort(uint64_t *__restrict__ keys
         uvals[s + i] = ht_val[sl];
     }
     if (threadIdx.x == 0) ucount[sb] = m;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_compact_uniques(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ uvals,
@@ -472,7 +506,7 @@ __global__ void __launch_bounds__(256) k_compact_uniques(const uint64_t *__restr
 // ---------------------------------------------------------------------------------------------------------------------
 struct SortCombineWorkspace
 {
-    DevBuf keysA, valsA, valsB, uvals_sparse, small, splitters, sub_cnt, sub_off, ucount, u_off, scan_scratch;
+    DevBuf keysA, valsA, valsB, uvals_sparse, small, splitters, sub_cnt, sub_off, ucount, u_off, scan_scratch, cls_list, cls_count;
 };
 
 struct SortCombineStats
@@ -545,6 +579,8 @@ public:
         ws.ucount.reserve((nsb_bound + 1) * 4);
         ws.u_off.reserve((nsb_bound + 1) * 4);
         ws.scan_scratch.reserve(scan_scratch_elems(nsb_bound + 1) * 4);
+        ws.cls_list.reserve((nsb_bound + 1) * 4 * MS_CLASSES);
+        ws.cls_count.reserve(MS_CLASSES * 4);
         unsigned &L = stats->launches;
         const bool trace = std::getenv("DGE_TRACE") != nullptr;
         auto t_prev = std::chrono::steady_clock::now();
@@ -634,15 +670,30 @@ public:
                 ++L;
             };
             static const bool use_hash = std::getenv("DGE_HASH_DEDUP") != nullptr;
+            static const int ms_items = std::getenv("DGE_MS_ITEMS") ? atoi(std::getenv("DGE_MS_ITEMS")) : 16;
+            static const int ms_bps = std::getenv("DGE_MS_BPS") ? atoi(std::getenv("DGE_MS_BPS")) : 128; // grid >> resident blocks: late blocks balance the tail
             if (!has_val && !use_hash)
-            {   // comparison sort + run detection, size-classed by the threads a sub-bucket needs (16 keys per thread);
-                // anything larger than 4096 records (sampling tail, one heavily duplicated key) streams through the hash kernel
+            {   // comparison sort + run detection on per-size-class work lists (persistent blocks); anything larger than the
+                // biggest class (sampling tail, one heavily duplicated key) streams through the hash-table kernel
                 uint32_t *uv = ws.uvals_sparse.as<uint32_t>();
-                k_sort_dedup<64><<<unsigned(nsb_bound), 64, 0, st>>>(keys_tmp, uv, sub_off, n_sub_ptr, ucount, 0u, 1024u);
-                k_sort_dedup<128><<<unsigned(nsb_bound), 128, 0, st>>>(keys_tmp, uv, sub_off, n_sub_ptr, ucount, 1024u, 2048u);
-                k_sort_dedup<256><<<unsigned(nsb_bound), 256, 0, st>>>(keys_tmp, uv, sub_off, n_sub_ptr, ucount, 2048u, 4096u);
-                L += 3;
-                launch(SC_HT_MAX, 4096u, 0xFFFFFFFFu);
+                uint32_t *cc = ws.cls_count.as<uint32_t>(), *cl = ws.cls_list.as<uint32_t>();
+                const size_t ls = nsb_bound + 1;
+                DGE_CUDA(cudaMemsetAsync(cc, 0, MS_CLASSES * 4, st));
+                const uint32_t c0 = 64u * ms_items, c1 = 2 * c0, c2 = 4 * c0;
+                k_classify_sub<<<148 * 4, 256, 0, st>>>(sub_off, n_sub_ptr, c0, c1, c2, cc, cl, ls);
+                auto grid = [&](int threads, int dflt) { return unsigned(148 * (ms_bps > 0 ? std::max(1, ms_bps * 64 / threads) : dflt)); };
+                static const bool la = std::getenv("DGE_MS_NO_LOOKAHEAD") == nullptr;
+#define DGE_MS(T, I, LA, C, DFLT) k_sort_dedup<T, I, LA><<<grid(T, DFLT), T, 0, st>>>(keys_tmp, uv, sub_off, cl + C * ls, cc + C, ucount)
+                if (ms_items == 16 && la) { DGE_MS(64, 16, true, 0, 12); DGE_MS(128, 16, true, 1, 6); DGE_MS(256, 16, true, 2, 3); }
+                else if (ms_items == 16) { DGE_MS(64, 16, false, 0, 12); DGE_MS(128, 16, false, 1, 6); DGE_MS(256, 16, false, 2, 3); }
+                else if (la) { DGE_MS(64, 8, true, 0, 24); DGE_MS(128, 8, true, 1, 12); DGE_MS(256, 8, true, 2, 6); }
+                else { DGE_MS(64, 8, false, 0, 24); DGE_MS(128, 8, false, 1, 12); DGE_MS(256, 8, false, 2, 6); }
+#undef DGE_MS
+                L += 4;
+                const int thr = sc_tuning().dedup_threads;
+                k_dedup_sort<false><<<148 * 2, thr, dedup_smem_bytes(SC_HT_MAX, SC_HT_MAX, thr), st>>>(keys_tmp, nullptr, uv, sub_off, n_sub_ptr, ucount, overflow_flag,
+                                                                                                        SC_HT_MAX, SC_HT_MAX, 0u, 0xFFFFFFFFu, cl + 3 * ls, cc + 3);
+                ++L;
             }
             else
             {

@@ -14,10 +14,32 @@
 namespace dge
 {
 
-constexpr int MS_ITEMS = 16;
+// shared-memory index of logical element i: one pad word per ITEMS keys makes "thread t touches element ITEMS*t + j" conflict-free
+template <int ITEMS> __device__ __forceinline__ int ms_phys(int i)
+{
+    static_assert(ITEMS == 8 || ITEMS == 16, "ITEMS");
+    return i + (i >> (ITEMS == 16 ? 4 : 3));
+}
 
-// shared-memory index of logical element i: one pad word per 16 keys makes "thread t touches element 16*t + j" conflict-free
-__device__ __forceinline__ int ms_phys(int i) { return i + (i >> 4); }
+constexpr int MS_CLASSES = 4; // 3 comparison-sort size classes + the hash-table tail
+#ifndef DGE_MS_WARPS
+#define DGE_MS_WARPS 24
+#endif
+constexpr int MS_WARPS_PER_SM = DGE_MS_WARPS; // occupancy target of the sort kernels (caps registers per thread)
+
+// Bins the sub-buckets by size into per-class work lists (order inside a list is irrelevant).
+__global__ void __launch_bounds__(256) k_classify_sub(const uint32_t *__restrict__ sub_off, const uint32_t *__restrict__ n_sub_ptr, uint32_t c0, uint32_t c1,
+                                                      uint32_t c2, uint32_t *__restrict__ cls_count, uint32_t *__restrict__ cls_list, size_t list_stride)
+{
+    const uint32_t nsb = *n_sub_ptr;
+    for (uint32_t sb = blockIdx.x * blockDim.x + threadIdx.x; sb < nsb; sb += gridDim.x * blockDim.x)
+    {
+        const uint32_t n = sub_off[sb + 1] - sub_off[sb];
+        if (n == 0) continue;
+        const int c = n <= c0 ? 0 : n <= c1 ? 1 : n <= c2 ? 2 : 3;
+        cls_list[size_t(c) * list_stride + atomicAdd(&cls_count[c], 1u)] = sb;
+    }
+}
 
 __device__ __forceinline__ void ms_ce(uint64_t &a, uint64_t &b)
 {
@@ -43,126 +65,148 @@ template <int N> __device__ __forceinline__ void ms_thread_sort(uint64_t (&k)[N]
             }
 }
 
-// keys[s..e) of sub-bucket blockIdx.x -> distinct ukeys ascending, IN PLACE at keys[s..s+m), values (count | mark<<29) at
-// uvals[s..s+m), ucount[sb] = m.  Only sub-buckets with n_min < size <= n_max (<= THREADS*16) are handled by this launch.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_sort_dedup(uint64_t *__restrict__ keys, uint32_t *__restrict__ uvals,
-                                                        const uint32_t *__restrict__ sub_off, const uint32_t *__restrict__ n_sub_ptr,
-                                                        uint32_t *__restrict__ ucount, const uint32_t n_min, const uint32_t n_max)
+// Work item = one sub-bucket from `list`: keys[s..e) -> distinct ukeys ascending, IN PLACE at keys[s..s+m), values
+// (count | mark<<29) at uvals[s..s+m), ucount[sb] = m.  Persistent blocks stride over the list; sizes must be <= THREADS*ITEMS.
+template <int THREADS, int ITEMS, bool LOOKAHEAD>
+__global__ void __launch_bounds__(THREADS, MS_WARPS_PER_SM * 32 / THREADS) k_sort_dedup(uint64_t *__restrict__ keys, uint32_t *__restrict__ uvals,
+                                                        const uint32_t *__restrict__ sub_off, const uint32_t *__restrict__ list,
+                                                        const uint32_t *__restrict__ list_count, uint32_t *__restrict__ ucount)
 {
-    constexpr int CAP = THREADS * MS_ITEMS;
-    __shared__ uint64_t sk[CAP + CAP / 16 + 1];
+    constexpr int CAP = THREADS * ITEMS;
+    __shared__ uint64_t sk[CAP + CAP / ITEMS + 1];
     __shared__ uint32_t ws[33];
-    const uint32_t sb = blockIdx.x;
-    if (sb >= *n_sub_ptr) return;
-    const uint32_t s = sub_off[sb];
-    const int n = int(sub_off[sb + 1] - s);
-    if (uint32_t(n) <= n_min || uint32_t(n) > n_max) return;
     const int t = threadIdx.x;
-
-#pragma unroll
-    for (int j = 0; j < MS_ITEMS; ++j)
+    const int p0 = t * ITEMS;
+    const int row = ms_phys<ITEMS>(p0); // the ITEMS elements of a thread are contiguous in shared memory
+    const uint32_t n_items = *list_count;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x)
     {
-        const int i = j * THREADS + t;
-        sk[ms_phys(i)] = i < n ? keys[s + i] : EMPTY64;
-    }
-    __syncthreads();
-    uint64_t k[MS_ITEMS];
-    const int p0 = t * MS_ITEMS;
-    const int row = ms_phys(p0); // 17 * t: the 16 elements of a thread are contiguous in shared memory
+        const uint32_t sb = list[item];
+        const uint32_t s = sub_off[sb];
+        const int n = int(sub_off[sb + 1] - s);
 #pragma unroll
-    for (int j = 0; j < MS_ITEMS; ++j) k[j] = sk[row + j];
-    if (p0 < n) ms_thread_sort(k);
-
-    // threads needed to cover n keys, rounded up to a power of two: levels above it have nothing to merge
-    int need = 1;
-    while (need * MS_ITEMS < n) need <<= 1;
-    for (int w = 1; w < need; w <<= 1)
-    {
+        for (int j = 0; j < ITEMS; ++j)
+        {
+            const int i = j * THREADS + t;
+            sk[ms_phys<ITEMS>(i)] = i < n ? keys[s + i] : EMPTY64;
+        }
         __syncthreads();
+        uint64_t k[ITEMS];
 #pragma unroll
-        for (int j = 0; j < MS_ITEMS; ++j) sk[row + j] = k[j];
-        __syncthreads();
-        const int first = t & ~(2 * w - 1);
-        const int a_beg = first * MS_ITEMS, cnt = w * MS_ITEMS, b_beg = a_beg + cnt;
-        const int a_cnt = min(max(n - a_beg, 0), cnt), b_cnt = min(max(n - b_beg, 0), cnt);
-        const int diag = (t - first) * MS_ITEMS;
-        if (diag >= a_cnt + b_cnt) continue;           // this thread's output range holds padding only (k[] is not read again)
-        if (b_cnt == 0) continue;                      // nothing to merge with: the A run stays where it is
-        int lo = max(0, diag - b_cnt), hi = min(diag, a_cnt);
-        while (lo < hi)
-        {
-            const int mid = (lo + hi) >> 1;
-            const uint64_t a = sk[ms_phys(a_beg + mid)], b = sk[ms_phys(b_beg + diag - 1 - mid)];
-            if (a <= b) lo = mid + 1; else hi = mid;
-        }
-        int ai = lo, bi = diag - lo;
-        uint64_t ka = ai < a_cnt ? sk[ms_phys(a_beg + ai)] : EMPTY64;
-        uint64_t kb = bi < b_cnt ? sk[ms_phys(b_beg + bi)] : EMPTY64;
-#pragma unroll
-        for (int j = 0; j < MS_ITEMS; ++j)
-        {
-            const bool ta = bi >= b_cnt || (ai < a_cnt && ka <= kb);
-            k[j] = ta ? ka : kb;
-            if (ta) { ++ai; ka = ai < a_cnt ? sk[ms_phys(a_beg + ai)] : EMPTY64; }
-            else { ++bi; kb = bi < b_cnt ? sk[ms_phys(b_beg + bi)] : EMPTY64; }
-        }
-    }
+        for (int j = 0; j < ITEMS; ++j) k[j] = sk[row + j];
+        if (p0 < n) ms_thread_sort(k);
 
-    // ---- runs of equal ukey
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < MS_ITEMS; ++j) sk[row + j] = k[j];
-    __syncthreads();
-    const int nv = min(max(n - p0, 0), MS_ITEMS);
-    uint32_t head_mask = 0;
-    {
-        uint64_t prev = p0 > 0 && nv > 0 ? (sk[ms_phys(p0 - 1)] >> 3) : EMPTY64; // a ukey has 61 bits: never equal to EMPTY64
-#pragma unroll
-        for (int j = 0; j < MS_ITEMS; ++j)
+        // threads needed to cover n keys, rounded up to a power of two: levels above it have nothing to merge
+        int need = 1;
+        while (need * ITEMS < n) need <<= 1;
+        for (int w = 1; w < need; w <<= 1)
         {
-            const uint64_t uk = k[j] >> 3;
-            if (j < nv && uk != prev) head_mask |= 1u << j;
-            prev = uk;
-        }
-    }
-    uint32_t total;
-    const uint32_t base = block_exclusive_scan(uint32_t(__popc(head_mask)), ws, &total);
-    if (nv > 0)
-    {
-        // the run of the last key may continue in the following threads' elements
-        uint32_t run_cnt = 0, run_mark = 0;
-        uint64_t cur = EMPTY64;
-        if (nv == MS_ITEMS)
-        {
-            cur = k[MS_ITEMS - 1] >> 3;
-            for (int q = p0 + MS_ITEMS; q < n; ++q)
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) sk[row + j] = k[j];
+            __syncthreads();
+            const int first = t & ~(2 * w - 1);
+            const int a_beg = first * ITEMS, cnt = w * ITEMS, b_beg = a_beg + cnt;
+            const int a_cnt = min(max(n - a_beg, 0), cnt), b_cnt = min(max(n - b_beg, 0), cnt);
+            const int diag = (t - first) * ITEMS;
+            if (diag >= a_cnt + b_cnt) continue;           // this thread's output range holds padding only (k[] is not read again)
+            if (b_cnt == 0) continue;                      // nothing to merge with: the A run stays where it is
+            int lo = max(0, diag - b_cnt), hi = min(diag, a_cnt);
+            while (lo < hi)
             {
-                const uint64_t x = sk[ms_phys(q)];
-                if ((x >> 3) != cur) break;
-                ++run_cnt; run_mark |= uint32_t(x) & 7u;
+                const int mid = (lo + hi) >> 1;
+                const uint64_t a = sk[ms_phys<ITEMS>(a_beg + mid)], b = sk[ms_phys<ITEMS>(b_beg + diag - 1 - mid)];
+                if (a <= b) lo = mid + 1; else hi = mid;
             }
-        }
-        uint64_t *ok = keys + s + base;
-        uint32_t *ov = uvals + s + base;
+            // serial merge; an exhausted side reads as EMPTY64 = the largest word, so plain <= picks the live side
+            int ai = lo, bi = diag - lo;
+            auto ld_a = [&](int i) { return i < a_cnt ? sk[ms_phys<ITEMS>(a_beg + i)] : EMPTY64; };
+            auto ld_b = [&](int i) { return i < b_cnt ? sk[ms_phys<ITEMS>(b_beg + i)] : EMPTY64; };
+            if (LOOKAHEAD)
+            {   // one element of look-ahead per side: the load issued in a step is consumed a step later
+                uint64_t a0 = ld_a(ai), a1 = ld_a(ai + 1), b0 = ld_b(bi), b1 = ld_b(bi + 1);
 #pragma unroll
-        for (int j = MS_ITEMS - 1; j >= 0; --j)
-        {
-            if (j < nv)
-            {
-                const uint64_t uk = k[j] >> 3;
-                if (uk != cur) { cur = uk; run_cnt = 0; run_mark = 0; }
-                ++run_cnt; run_mark |= uint32_t(k[j]) & 7u;
-                if (head_mask & (1u << j))
+                for (int j = 0; j < ITEMS; ++j)
                 {
-                    const int o = __popc(head_mask & ((1u << j) - 1u));
-                    ok[o] = uk;
-                    ov[o] = run_cnt | (run_mark << VAL_MARK_SHIFT);
+                    const bool ta = a0 <= b0;
+                    k[j] = ta ? a0 : b0;
+                    ai += ta ? 1 : 0; bi += ta ? 0 : 1;
+                    const int nx = ta ? ai + 1 : bi + 1;
+                    const bool ok = nx < (ta ? a_cnt : b_cnt);
+                    const uint64_t v = ok ? sk[ms_phys<ITEMS>((ta ? a_beg : b_beg) + nx)] : EMPTY64;
+                    a0 = ta ? a1 : a0; a1 = ta ? v : a1;
+                    b0 = ta ? b0 : b1; b1 = ta ? b1 : v;
+                }
+            }
+            else
+            {
+                uint64_t ka = ld_a(ai), kb = ld_b(bi);
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j)
+                {
+                    const bool ta = ka <= kb;
+                    k[j] = ta ? ka : kb;
+                    if (ta) { ++ai; ka = ld_a(ai); } else { ++bi; kb = ld_b(bi); }
                 }
             }
         }
+
+        // ---- runs of equal ukey
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) sk[row + j] = k[j];
+        __syncthreads();
+        const int nv = min(max(n - p0, 0), ITEMS);
+        uint32_t head_mask = 0;
+        {
+            uint64_t prev = p0 > 0 && nv > 0 ? (sk[ms_phys<ITEMS>(p0 - 1)] >> 3) : EMPTY64; // a ukey has 61 bits: never equal to EMPTY64
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+            {
+                const uint64_t uk = k[j] >> 3;
+                if (j < nv && uk != prev) head_mask |= 1u << j;
+                prev = uk;
+            }
+        }
+        uint32_t total;
+        const uint32_t base = block_exclusive_scan(uint32_t(__popc(head_mask)), ws, &total);
+        if (nv > 0)
+        {
+            // the run of the last key may continue in the following threads' elements
+            uint32_t run_cnt = 0, run_mark = 0;
+            uint64_t cur = EMPTY64;
+            if (nv == ITEMS)
+            {
+                cur = k[ITEMS - 1] >> 3;
+                for (int q = p0 + ITEMS; q < n; ++q)
+                {
+                    const uint64_t x = sk[ms_phys<ITEMS>(q)];
+                    if ((x >> 3) != cur) break;
+                    ++run_cnt; run_mark |= uint32_t(x) & 7u;
+                }
+            }
+            uint64_t *ok = keys + s + base;
+            uint32_t *ov = uvals + s + base;
+#pragma unroll
+            for (int j = ITEMS - 1; j >= 0; --j)
+            {
+                if (j < nv)
+                {
+                    const uint64_t uk = k[j] >> 3;
+                    if (uk != cur) { cur = uk; run_cnt = 0; run_mark = 0; }
+                    ++run_cnt; run_mark |= uint32_t(k[j]) & 7u;
+                    if (head_mask & (1u << j))
+                    {
+                        const int o = __popc(head_mask & ((1u << j) - 1u));
+                        ok[o] = uk;
+                        ov[o] = run_cnt | (run_mark << VAL_MARK_SHIFT);
+                    }
+                }
+            }
+        }
+        if (t == 0) ucount[sb] = total;
+        __syncthreads(); // sk is reloaded by the next item
     }
-    if (t == 0) ucount[sb] = total;
 }
 
 } // namespace dge

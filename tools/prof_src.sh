@@ -1,0 +1,8 @@
+# usage: prof_src.sh <out> <kernel-regex> <skip>  -- ncu full capture + raw csv + source-page csv (SASS with stall samples)
+O=$1; K=$2; S=${3:-0}
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s $S -c 1 -f -o gpurun_out/$O \
+   python bench.py --reads 100000000 --cells 2500 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/$O.log 2>&1
+ncu -i gpurun_out/$O.ncu-rep --page raw --csv > gpurun_out/$O.csv 2>/dev/null
+ncu -i gpurun_out/$O.ncu-rep --page source --csv > gpurun_out/$O.src.csv 2>/dev/null
+rm -f gpurun_out/$O.ncu-rep
+ls -la gpurun_out/$O.*
