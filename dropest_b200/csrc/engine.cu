@@ -89,7 +89,7 @@ struct dge_handle
 
     // grouped state
     DevBuf keys_all, ukey, uval, ukey2, uval2, overflow_flag;
-    DevBuf cg_key, cg_start, cg_pc, cg_req, cg_reads, cg_req_reads;
+    DevBuf cg_gene, cg_start, cg_pc, cg_req, cg_reads, cg_req_reads;
     DevBuf pc_slot, pc_u_start, pc_cg_start, pc_reads, pc_req_genes, pc_req_umis, slot_pc;
     DevBuf tile_a, tile_b, scan_scratch, flags, flags_off, rows_dev, rows_dev2, misc, cub_tmp, sort_k[2], sort_v[2];
     PinnedBuf pin_filtered, pin_fkeys;
@@ -413,7 +413,7 @@ void build_segments(dge_handle *h)
     h->n_pc = d2h_scalar<uint32_t>(tot_pc, st);
 
     const size_t ncg = h->n_cg, npc = h->n_pc;
-    h->cg_key.reserve((ncg + 1) * 8); h->cg_start.reserve((ncg + 1) * 4); h->cg_pc.reserve((ncg + 1) * 4);
+    h->cg_gene.reserve((ncg + 1) * 4); h->cg_start.reserve((ncg + 1) * 4); h->cg_pc.reserve((ncg + 1) * 4);
     h->cg_req.reserve((ncg + 1) * 4); h->cg_reads.reserve((ncg + 1) * 4);
     if (h->cfg.reads_output) h->cg_req_reads.reserve((ncg + 1) * 4);
     h->pc_slot.reserve((npc + 2) * 4); h->pc_u_start.reserve((npc + 2) * 4); h->pc_cg_start.reserve((npc + 2) * 4);
@@ -424,8 +424,8 @@ void build_segments(dge_handle *h)
     DGE_CUDA(cudaMemsetAsync(h->pc_reads.p, 0, (npc + 2) * 4, st));
     DGE_CUDA(cudaMemsetAsync(h->pc_req_genes.p, 0, (npc + 2) * 4, st));
     DGE_CUDA(cudaMemsetAsync(h->pc_req_umis.p, 0, (npc + 2) * 4, st));
-    k_seg_write<<<unsigned(nt), SEG_THREADS, 0, st>>>(h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), n_u, ub, gub, h->cfg.query_mark_mask, ta, tb,
-                                                       h->cg_key.as<uint64_t>(), h->cg_start.as<uint32_t>(), h->cg_pc.as<uint32_t>(),
+    k_seg_write<<<unsigned(nt), SEG_THREADS, 0, st>>>(h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), n_u, ub, gub, h->cfg.query_mark_mask, (1u << h->kl.gb) - 1, ta, tb,
+                                                       h->cg_gene.as<uint32_t>(), h->cg_start.as<uint32_t>(), h->cg_pc.as<uint32_t>(),
                                                        h->cg_req.as<uint32_t>(), h->cg_reads.as<uint32_t>(),
                                                        h->cfg.reads_output ? h->cg_req_reads.as<uint32_t>() : nullptr,
                                                        h->pc_slot.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(),
@@ -986,7 +986,7 @@ void apply_moved(dge_handle *h, uint64_t total)
                                                             h->xkey.as<uint64_t>(), h->xval.as<uint32_t>());
         const size_t n_new = size_t(h->n_u) + n_x;
         h->ukey2.reserve(n_new * 8); h->uval2.reserve(n_new * 4);
-        k_merge_rank<<<grid_for(n_new, 256), 256, 0, st>>>(h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), h->n_u, h->xkey.as<uint64_t>(), h->xval.as<uint32_t>(), n_x,
+        k_merge_rank<<<148 * 8, 256, 0, st>>>(h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), h->n_u, h->xkey.as<uint64_t>(), h->xval.as<uint32_t>(), n_x,
                                                             h->ukey2.as<uint64_t>(), h->uval2.as<uint32_t>());
         DGE_LAUNCH_CHECK();
         h->launches += 2;
@@ -1023,8 +1023,7 @@ void build_matrix(dge_handle *h, MatrixDev &m, const std::vector<uint32_t> &col_
     else if (h->cfg.reads_output) { values = h->cg_reads.as<uint32_t>(); mode = 2; }
     else { values = nullptr; mode = 1; }
     k_matrix_fill<<<unsigned(m.n_cols), 256, 0, st>>>(m.cols.as<uint32_t>(), uint32_t(m.n_cols), m.indptr.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(),
-                                                      h->cg_key.as<uint64_t>(), values, h->cg_start.as<uint32_t>(), mode,
-                                                      (1u << h->kl.gb) - 1, m.gene.as<int32_t>(), m.val.as<int32_t>());
+                                                      h->cg_gene.as<uint32_t>(), values, h->cg_start.as<uint32_t>(), mode, m.gene.as<int32_t>(), m.val.as<int32_t>());
     DGE_LAUNCH_CHECK();
     ++h->launches;
 }

@@ -16,7 +16,7 @@ constexpr int FILL_THREADS = 256;
 #define DGE_FILL_ITEMS 8
 #endif
 #ifndef DGE_FILL_MINB
-#define DGE_FILL_MINB 1
+#define DGE_FILL_MINB 2
 #endif
 constexpr int FILL_ITEMS = DGE_FILL_ITEMS;
 constexpr int FILL_TILE = FILL_THREADS * FILL_ITEMS;

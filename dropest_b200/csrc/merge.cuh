@@ -285,25 +285,45 @@ __global__ void __launch_bounds__(256) k_compact_keep(const uint64_t *__restrict
 
 // Merge of two sorted key/value arrays with disjoint keys (A = current list, B = extras) by ranking:
 //   position of A[i] = i + lower_bound(B, A[i]);  position of B[j] = j + lower_bound(A, B[j]).
+// A is the long list (all of U), B the short one: A is walked in tiles of consecutive elements whose ranks in B are confined to
+// the range spanned by the tile's first and last key (two full searches per tile, a handful of steps per element); every B
+// element does one full search over A.
 __global__ void __launch_bounds__(256) k_merge_rank(const uint64_t *__restrict__ akey, const uint32_t *__restrict__ aval, uint32_t na,
                                                     const uint64_t *__restrict__ bkey, const uint32_t *__restrict__ bval, uint32_t nb,
                                                     uint64_t *__restrict__ okey, uint32_t *__restrict__ oval)
 {
-    const uint32_t total = na + nb;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
-    {
-        const bool from_a = t < na;
-        const uint32_t i = from_a ? t : t - na;
-        const uint64_t key = from_a ? akey[i] : bkey[i];
-        const uint64_t *other = from_a ? bkey : akey;
-        uint32_t lo = 0, hi = from_a ? nb : na;
+    constexpr uint32_t TILE = 2048;
+    __shared__ uint32_t rng[2];
+    auto lower_bound = [](const uint64_t *__restrict__ v, uint32_t lo, uint32_t hi, uint64_t key) {
         while (lo < hi)
         {
-            uint32_t mid = (lo + hi) >> 1;
-            if (other[mid] < key) lo = mid + 1; else hi = mid;
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(v + mid) < key) lo = mid + 1; else hi = mid;
         }
-        okey[i + lo] = key;
-        oval[i + lo] = from_a ? aval[i] : bval[i];
+        return lo;
+    };
+    const uint32_t n_tiles = (na + TILE - 1) / TILE;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    {
+        const uint32_t i0 = tile * TILE, i1 = min(na, i0 + TILE);
+        if (threadIdx.x < 2) rng[threadIdx.x] = lower_bound(bkey, 0, nb, akey[threadIdx.x == 0 ? i0 : i1 - 1]);
+        __syncthreads();
+        const uint32_t lo0 = rng[0], hi0 = rng[1];
+        for (uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x)
+        {
+            const uint64_t key = akey[i];
+            const uint32_t lo = lower_bound(bkey, lo0, hi0, key);
+            okey[i + lo] = key;
+            oval[i + lo] = aval[i];
+        }
+        __syncthreads();
+    }
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nb; j += gridDim.x * blockDim.x)
+    {
+        const uint64_t key = bkey[j];
+        const uint32_t lo = lower_bound(akey, 0, na, key);
+        okey[j + lo] = key;
+        oval[j + lo] = bval[j];
     }
 }
 
@@ -419,9 +439,9 @@ __global__ void k_matrix_col_nnz(const uint32_t *__restrict__ col_pc, uint32_t n
 
 // fill: one block per column, ordered compaction by block scan (genes stay ascending inside a column)
 __global__ void __launch_bounds__(256) k_matrix_fill(const uint32_t *__restrict__ col_pc, uint32_t n_cols, const uint32_t *__restrict__ col_off,
-                                                     const uint32_t *__restrict__ pc_cg_start, const uint64_t *__restrict__ cg_key,
+                                                     const uint32_t *__restrict__ pc_cg_start, const uint32_t *__restrict__ cg_gene,
                                                      const uint32_t *__restrict__ values, const uint32_t *__restrict__ cg_start, int mode,
-                                                     uint32_t gene_mask, int32_t *__restrict__ out_gene, int32_t *__restrict__ out_val)
+                                                     int32_t *__restrict__ out_gene, int32_t *__restrict__ out_val)
 {
     // mode 0: value = values[i] (skip zeros); mode 1: value = cg_start[i+1]-cg_start[i] (all UMIs); mode 2: value = values[i], keep all
     __shared__ uint32_t ws[33];
@@ -440,7 +460,7 @@ __global__ void __launch_bounds__(256) k_matrix_fill(const uint32_t *__restrict_
             const uint32_t ex = block_exclusive_scan(keepit, ws, &total);
             if (keepit)
             {
-                out_gene[pos + ex] = int32_t(uint32_t(cg_key[i]) & gene_mask);
+                out_gene[pos + ex] = int32_t(cg_gene[i]);
                 out_val[pos + ex] = int32_t(v);
             }
             pos += total;

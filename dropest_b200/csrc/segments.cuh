@@ -1,6 +1,6 @@
 // segments.cuh -- segmented reductions over the sorted distinct (cell, gene, UMI) list.
 //   U   : ukey[n_u] ascending, uval[n_u] = reads | mark<<29
-//   CG  : one row per (cell, gene): cg_key = ukey >> ub, cg_start (into U), cg_req (#UMIs whose mark matches the query),
+//   CG  : one row per (cell, gene): cg_gene = gene id, cg_start (into U), cg_req (#UMIs whose mark matches the query),
 //         cg_reads (all reads), cg_req_reads (reads of matching UMIs)           -> values of cm / cm_raw
 //   PC  : one row per cell that owns at least one UMI ("present cell"), in slot order: pc_slot, pc_u_start, pc_cg_start,
 //         pc_reads, pc_req_genes, pc_req_umis
@@ -14,7 +14,7 @@ namespace dge
 {
 
 constexpr int SEG_THREADS = 256;
-constexpr int SEG_ITEMS = 8;
+constexpr int SEG_ITEMS = 4;
 constexpr int SEG_TILE = SEG_THREADS * SEG_ITEMS;
 
 // pass 1: heads per tile
@@ -46,17 +46,20 @@ __global__ void __launch_bounds__(SEG_THREADS) k_seg_count(const uint64_t *__res
 }
 
 // pass 2: write segment starts AND reduce values into the (cell,gene) / cell rows.  Every thread owns SEG_ITEMS consecutive
-// distinct UMIs, accumulates per run in registers and flushes a run with a few no-return atomics (rows are zeroed by the host):
-// work per thread is uniform however long a gene's or a cell's UMI list is.
+// distinct UMIs and accumulates per run in registers.  The (cell,gene) rows of a tile are assembled in shared memory (runs shared
+// by several threads are combined with shared-memory atomics) and copied out fully coalesced; only the run continuing from
+// the previous tile and the last row of the tile (which may continue in the next one) touch global memory with atomics
+// (the rows are zeroed by the host).  Cell rows are few: warp-reduced, then one global atomic per warp and cell.
 __global__ void __launch_bounds__(SEG_THREADS) k_seg_write(const uint64_t *__restrict__ ukey, const uint32_t *__restrict__ uval, uint32_t n_u,
-                                                           int ub, int gub, uint32_t query_mask,
+                                                           int ub, int gub, uint32_t query_mask, uint32_t gene_mask,
                                                            const uint32_t *__restrict__ tile_cg_off, const uint32_t *__restrict__ tile_cell_off,
-                                                           uint64_t *__restrict__ cg_key, uint32_t *__restrict__ cg_start, uint32_t *__restrict__ cg_pc,
+                                                           uint32_t *__restrict__ cg_gene, uint32_t *__restrict__ cg_start, uint32_t *__restrict__ cg_pc,
                                                            uint32_t *__restrict__ cg_req, uint32_t *__restrict__ cg_reads, uint32_t *__restrict__ cg_req_reads,
                                                            uint32_t *__restrict__ pc_slot, uint32_t *__restrict__ pc_u_start, uint32_t *__restrict__ pc_cg_start,
                                                            uint32_t *__restrict__ pc_reads, uint32_t *__restrict__ pc_req_umis)
 {
     __shared__ uint32_t ws[33];
+    __shared__ uint32_t s_gene[SEG_TILE], s_start[SEG_TILE], s_pc[SEG_TILE], s_req[SEG_TILE], s_reads[SEG_TILE], s_rreads[SEG_TILE];
     const uint32_t base = blockIdx.x * SEG_TILE + threadIdx.x * SEG_ITEMS;
     uint64_t cur[SEG_ITEMS];
     uint32_t val[SEG_ITEMS];
@@ -79,40 +82,41 @@ __global__ void __launch_bounds__(SEG_THREADS) k_seg_write(const uint64_t *__res
             prev = cur[k];
         }
     }
-    uint32_t tot;
-    uint32_t rcg = block_exclusive_scan(ncg, ws, &tot) + tile_cg_off[blockIdx.x];
-    uint32_t rcell = block_exclusive_scan(ncell, ws, &tot) + tile_cell_off[blockIdx.x];
-    // rows being accumulated: the run that continues from the previous thread has rank (exclusive rank - 1)
-    // A run that both starts and ends inside this thread's chunk is owned exclusively: plain stores.  Only the run continuing
-    // from the previous thread and the run still open at the end of the chunk can be shared: atomics.
+    uint32_t tot_cg, tot_cell;
+    int lcg = int(block_exclusive_scan(ncg, ws, &tot_cg));          // local rank of this thread's first head inside the tile
+    const uint32_t cg_off = tile_cg_off[blockIdx.x];
+    uint32_t rcell = block_exclusive_scan(ncell, ws, &tot_cell) + tile_cell_off[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < tot_cg; i += SEG_THREADS) { s_req[i] = 0; s_reads[i] = 0; s_rreads[i] = 0; }
+    __syncthreads();
+
     uint32_t a_req = 0, a_reads = 0, a_rreads = 0, c_reads = 0, c_req = 0;
-    bool cg_owned = false, cell_owned = false; // current run started in this chunk
-    auto flush_cg = [&](uint32_t row, bool exclusive) {
+    bool cg_owned = false; // current run started in this chunk
+    // local row -1 = the run continuing from the previous tile: straight to global memory
+    auto flush_cg = [&](int lrow, bool exclusive) {
         if (a_reads)
         {
-            if (exclusive)
+            if (lrow < 0)
             {
-                cg_req[row] = a_req; cg_reads[row] = a_reads;
-                if (cg_req_reads) cg_req_reads[row] = a_rreads;
-            }
-            else
-            {
+                const uint32_t row = cg_off - 1;
                 if (a_req) atomicAdd(&cg_req[row], a_req);
                 atomicAdd(&cg_reads[row], a_reads);
                 if (cg_req_reads && a_rreads) atomicAdd(&cg_req_reads[row], a_rreads);
             }
+            else if (exclusive) { s_req[lrow] = a_req; s_reads[lrow] = a_reads; s_rreads[lrow] = a_rreads; }
+            else
+            {
+                if (a_req) atomicAdd(&s_req[lrow], a_req);
+                atomicAdd(&s_reads[lrow], a_reads);
+                if (a_rreads) atomicAdd(&s_rreads[lrow], a_rreads);
+            }
         }
         a_req = a_reads = a_rreads = 0;
     };
-    auto flush_cell = [&](uint32_t row, bool exclusive) {
+    auto flush_cell = [&](uint32_t row) {
         if (c_reads)
         {
-            if (exclusive) { pc_reads[row] = c_reads; pc_req_umis[row] = c_req; }
-            else
-            {
-                atomicAdd(&pc_reads[row], c_reads);
-                if (c_req) atomicAdd(&pc_req_umis[row], c_req);
-            }
+            atomicAdd(&pc_reads[row], c_reads);
+            if (c_req) atomicAdd(&pc_req_umis[row], c_req);
         }
         c_reads = c_req = 0;
     };
@@ -124,21 +128,20 @@ __global__ void __launch_bounds__(SEG_THREADS) k_seg_write(const uint64_t *__res
         {
             if (hcell[k])
             {
-                flush_cell(rcell - 1, cell_owned);
-                cell_owned = true;
+                flush_cell(rcell - 1);
                 pc_slot[rcell] = uint32_t(cur[k] >> gub);
                 pc_u_start[rcell] = i;
-                pc_cg_start[rcell] = rcg; // a cell head is also a cg head: rcg is that cg's rank
+                pc_cg_start[rcell] = cg_off + uint32_t(lcg); // a cell head is also a cg head: lcg is that cg's local rank
                 ++rcell;
             }
             if (hcg[k])
             {
-                flush_cg(rcg - 1, cg_owned);
+                flush_cg(lcg - 1, cg_owned);
                 cg_owned = true;
-                cg_key[rcg] = cur[k] >> ub;
-                cg_start[rcg] = i;
-                cg_pc[rcg] = rcell - 1;
-                ++rcg;
+                s_gene[lcg] = uint32_t(cur[k] >> ub) & gene_mask;
+                s_start[lcg] = i;
+                s_pc[lcg] = rcell - 1;
+                ++lcg;
             }
             const uint32_t c = val[k] & VAL_COUNT_MASK, m = val[k] >> VAL_MARK_SHIFT;
             const bool match = (query_mask >> m) & 1u;
@@ -146,7 +149,39 @@ __global__ void __launch_bounds__(SEG_THREADS) k_seg_write(const uint64_t *__res
             c_reads += c; c_req += match;
         }
     }
-    if (base < n_u) { flush_cg(rcg - 1, false); flush_cell(rcell - 1, false); }
+    if (base < n_u) flush_cg(lcg - 1, false);
+    // open cell run at the end of the chunk: when no thread of the warp saw a cell head, the whole warp sits inside ONE cell
+    {
+        const bool warp_one_cell = __all_sync(0xFFFFFFFFu, ncell == 0);
+        if (warp_one_cell)
+        {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1)
+            {
+                c_reads += __shfl_down_sync(0xFFFFFFFFu, c_reads, d);
+                c_req += __shfl_down_sync(0xFFFFFFFFu, c_req, d);
+            }
+            if ((threadIdx.x & 31) == 0 && rcell > 0) flush_cell(rcell - 1);
+        }
+        else if (base < n_u) flush_cell(rcell - 1);
+    }
+    __syncthreads();
+    for (uint32_t l = threadIdx.x; l < tot_cg; l += SEG_THREADS)
+    {
+        const uint32_t g = cg_off + l;
+        cg_gene[g] = s_gene[l]; cg_start[g] = s_start[l]; cg_pc[g] = s_pc[l];
+        if (l + 1 < tot_cg)
+        {
+            cg_req[g] = s_req[l]; cg_reads[g] = s_reads[l];
+            if (cg_req_reads) cg_req_reads[g] = s_rreads[l];
+        }
+        else
+        {   // the last row of the tile may continue in the next tile
+            if (s_req[l]) atomicAdd(&cg_req[g], s_req[l]);
+            if (s_reads[l]) atomicAdd(&cg_reads[g], s_reads[l]);
+            if (cg_req_reads && s_rreads[l]) atomicAdd(&cg_req_reads[g], s_rreads[l]);
+        }
+    }
 }
 
 // requested genes per cell = number of its (cell,gene) rows with at least one matching UMI (Cell.cpp:130-143)
