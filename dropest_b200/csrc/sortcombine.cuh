@@ -306,6 +306,154 @@ __global__ void __launch_bounds__(THREADS) k_l2_pass(const uint64_t *__restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Staged scatter: the tile is reordered by bucket in shared memory before it leaves the SM, so a bucket's keys of one tile go
+// out as ONE contiguous run (consecutive threads -> consecutive addresses) instead of one 8-byte partial-sector write per key.
+// What bounds a partition pass on B200 is the number of L2 write transactions, not bytes: runs cut them by the run length.
+
+// cnt[0..nb) = per-bucket counts of the tile  ->  cnt[b] = tile-local start of bucket b, gd[b] = global run start - cnt[b]
+// (one global atomicAdd per non-empty bucket, all of a thread's atomics in flight together).  PER * blockDim.x >= nb.
+template <int PER>
+__device__ __forceinline__ void tile_bucket_offsets(uint32_t *cnt, uint32_t *gd, uint32_t nb, uint32_t *__restrict__ cursor, uint32_t *ws)
+{
+    uint32_t c[PER], o[PER], sum = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q)
+    {
+        const uint32_t i = threadIdx.x * PER + q;
+        c[q] = i < nb ? cnt[i] : 0u;
+        sum += c[q];
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q)
+    {
+        o[q] = 0;
+        if (c[q]) o[q] = atomicAdd(&cursor[threadIdx.x * PER + q], c[q]);
+    }
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan(sum, ws, &tot);
+#pragma unroll
+    for (int q = 0; q < PER; ++q)
+    {
+        const uint32_t i = threadIdx.x * PER + q;
+        if (i < nb) { cnt[i] = ex; gd[i] = o[q] - ex; }
+        ex += c[q];
+    }
+    __syncthreads();
+}
+
+// L1: bucket = key >> shift.  Dynamic shared memory: cnt[nb1] | gd[nb1] | keys[THREADS*ITEMS].
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_l1_scatter_staged(const uint64_t *__restrict__ keys, size_t n, int shift, int nb1,
+                                                               uint32_t *__restrict__ cursor, uint64_t *__restrict__ out_keys)
+{
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int PER = SC_MAX_NB1 / THREADS;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint32_t ws[33];
+    uint64_t *sk = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(sk + TILE);
+    uint32_t *gd = cnt + nb1;
+    for (int i = threadIdx.x; i < nb1; i += THREADS) cnt[i] = 0;
+    __syncthreads();
+    const size_t base = size_t(blockIdx.x) * TILE;
+    const uint32_t n_tile = uint32_t(min(size_t(TILE), n - base));
+    uint64_t k[ITEMS];
+    uint32_t r[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+    {
+        const uint32_t i = uint32_t(j) * THREADS + threadIdx.x;
+        k[j] = i < n_tile ? __ldg(keys + base + i) : EMPTY64;
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+    {
+        const uint32_t i = uint32_t(j) * THREADS + threadIdx.x;
+        if (i < n_tile) r[j] = atomicAdd(&cnt[k[j] >> shift], 1u);
+    }
+    __syncthreads();
+    tile_bucket_offsets<PER>(cnt, gd, uint32_t(nb1), cursor, ws);
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+    {
+        const uint32_t i = uint32_t(j) * THREADS + threadIdx.x;
+        if (i < n_tile) sk[cnt[k[j] >> shift] + r[j]] = k[j];
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_tile; i += THREADS)
+    {
+        const uint64_t key = sk[i];
+        out_keys[gd[key >> shift] + i] = key;
+    }
+}
+
+// L2: bucket = position among the L1 bucket's sampled splitters.  Dynamic shared memory:
+// spl[SC_MAX_P2] (u64) | keys[TILE] (u64) | cnt[SC_MAX_P2] | gd[SC_MAX_P2] | ids[TILE] (u16).
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_l2_scatter_staged(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ l1_off, int nb1,
+                                                               const uint32_t *__restrict__ p2, const uint32_t *__restrict__ sb_base,
+                                                               const uint32_t *__restrict__ tile_base, const uint64_t *__restrict__ splitters,
+                                                               uint32_t *__restrict__ cursor, uint64_t *__restrict__ out_keys)
+{
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int PER = SC_MAX_P2 / THREADS;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint32_t ws[33];
+    uint64_t *spl = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *sk = spl + SC_MAX_P2;
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(sk + TILE);
+    uint32_t *gd = cnt + SC_MAX_P2;
+    uint16_t *ids = reinterpret_cast<uint16_t *>(gd + SC_MAX_P2);
+    const uint32_t blk = blockIdx.x;
+    if (blk >= tile_base[nb1]) return;
+    int b; uint32_t tile;
+    block_to_bucket_tile(tile_base, nb1, blk, &b, &tile);
+    const uint32_t np = p2[b];
+    const uint32_t off = l1_off[b], end = l1_off[b + 1];
+    const uint32_t t0 = off + tile * TILE;
+    const uint32_t n_tile = min(end - t0, uint32_t(TILE));
+    for (uint32_t i = threadIdx.x; i < np; i += THREADS)
+    {
+        cnt[i] = 0;
+        if (i + 1 < np) spl[i] = splitters[size_t(b) * SC_MAX_P2 + i];
+    }
+    __syncthreads();
+    uint64_t k[ITEMS];
+    uint32_t r[ITEMS];
+    uint16_t sbk[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+    {
+        const uint32_t i = uint32_t(j) * THREADS + threadIdx.x;
+        k[j] = i < n_tile ? __ldg(keys + t0 + i) : EMPTY64;
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+        sbk[j] = uint16_t(np > 1 ? sub_bucket_of(spl, np - 1, k[j] >> 3) : 0u);
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+    {
+        const uint32_t i = uint32_t(j) * THREADS + threadIdx.x;
+        if (i < n_tile) r[j] = atomicAdd(&cnt[sbk[j]], 1u);
+    }
+    __syncthreads();
+    tile_bucket_offsets<PER>(cnt, gd, np, cursor + sb_base[b], ws);
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+    {
+        const uint32_t i = uint32_t(j) * THREADS + threadIdx.x;
+        if (i < n_tile)
+        {
+            const uint32_t p = cnt[sbk[j]] + r[j];
+            sk[p] = k[j];
+            ids[p] = sbk[j];
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_tile; i += THREADS) out_keys[gd[ids[i]] + i] = sk[i];
+}
+
 // One block per sub-bucket.  keys[s..e) -> distinct ukeys, ascending, written back IN PLACE at keys[s..s+m), values at
 // uvals[s..s+m); ucount[sb] = m.
 //   1. stream the records through a shared-memory hash table (atomicCAS claims a slot, atomicAdd/atomicOr combine values)
@@ -607,18 +755,44 @@ public:
         uint64_t *keysA = ws.keysA.as<uint64_t>();
         DGE_CUDA(cudaMemcpyAsync(cursor, l1_off, stride * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         static const int shape = std::getenv("DGE_TILE") ? atoi(std::getenv("DGE_TILE")) : 2;
+        static const int staged = std::getenv("DGE_STAGED") ? atoi(std::getenv("DGE_STAGED")) : 1; // bit0: L1, bit1: L2 (measured: staging pays at L1 only)
+        static const int stile = std::getenv("DGE_STILE") ? atoi(std::getenv("DGE_STILE")) : 2;    // staged tile shape (1024 x 8 measured best)
         size_t tile = 0;
+        if (!has_val && (staged & 1))
+        {
+#define DGE_L1S(IDX, T, I)                                                                                                         \
+            if (stile == IDX)                                                                                                      \
+            {                                                                                                                      \
+                const size_t smem = size_t(T) * I * 8 + size_t(nb1) * 8;                                                           \
+                static bool attr_done = false;                                                                                     \
+                if (!attr_done) { DGE_CUDA(cudaFuncSetAttribute(k_l1_scatter_staged<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done = true; } \
+                k_l1_scatter_staged<T, I><<<unsigned(div_up(n, size_t(T) * I)), T, smem, st>>>(keys_in, n, shift, nb1, cursor, keysA); \
+            }
+            DGE_L1S(0, 512, 16) DGE_L1S(1, 256, 16) DGE_L1S(2, 1024, 8) DGE_L1S(3, 256, 8)
+#undef DGE_L1S
+        }
+        else
+        {
 #define DGE_L1(IDX, T, I)                                                                                                          \
         if (shape == IDX)                                                                                                          \
         {                                                                                                                          \
-            tile = size_t(T) * I;                                                                                                  \
-            const unsigned g_tiles = unsigned(div_up(n, tile));                                                                    \
+            const unsigned g_tiles = unsigned(div_up(n, size_t(T) * I));                                                           \
             if (has_val) k_l1_scatter<true, T, I><<<g_tiles, T, 0, st>>>(keys_in, vals_in, n, shift, nb1, cursor, keysA, ws.valsA.as<uint32_t>()); \
             else k_l1_scatter<false, T, I><<<g_tiles, T, 0, st>>>(keys_in, nullptr, n, shift, nb1, cursor, keysA, nullptr);        \
         }
         DGE_L1(0, 512, 16) DGE_L1(1, 256, 16) DGE_L1(2, 256, 8) DGE_L1(3, 128, 16) DGE_L1(4, 512, 8) DGE_L1(5, 1024, 8)
 #undef DGE_L1
-        if (!tile) throw std::runtime_error("DGE_TILE out of range");
+        }
+        // the L2 passes walk the L1 buckets in tiles of this many keys
+        const bool l2_staged = !has_val && (staged & 2);
+        static const int s2tile = std::getenv("DGE_S2TILE") ? atoi(std::getenv("DGE_S2TILE")) : 0;
+        if (l2_staged) tile = s2tile == 0 ? 256 * 16 : s2tile == 1 ? 256 * 8 : 512 * 16;
+        else
+        {
+            const int T[6] = {512, 256, 256, 128, 512, 1024}, I[6] = {16, 16, 8, 16, 8, 8};
+            if (shape < 0 || shape > 5) throw std::runtime_error("DGE_TILE out of range");
+            tile = size_t(T[shape]) * I[shape];
+        }
         ++L;
         mark("l1 hist+scatter");
 
@@ -629,16 +803,32 @@ public:
         mark("plan+splitters");
         uint32_t *sub_cnt = ws.sub_cnt.as<uint32_t>(), *sub_off = ws.sub_off.as<uint32_t>();
         DGE_CUDA(cudaMemsetAsync(sub_cnt, 0, (nsb_bound + 1) * 4, st));
-#define DGE_L2H(IDX, T, I)                                                                                                         \
-        if (shape == IDX) k_l2_pass<false, false, T, I><<<unsigned(tiles_bound), T, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base, \
-                                                                                              ws.splitters.as<uint64_t>(), sub_cnt, nullptr, nullptr);
-        DGE_L2H(0, 512, 16) DGE_L2H(1, 256, 16) DGE_L2H(2, 256, 8) DGE_L2H(3, 128, 16) DGE_L2H(4, 512, 8) DGE_L2H(5, 1024, 8)
+#define DGE_L2H(COND, T, I)                                                                                                        \
+        if (COND) k_l2_pass<false, false, T, I><<<unsigned(tiles_bound), T, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base, \
+                                                                                      ws.splitters.as<uint64_t>(), sub_cnt, nullptr, nullptr);
+        if (l2_staged) { DGE_L2H(s2tile == 0, 256, 16) DGE_L2H(s2tile == 1, 256, 8) DGE_L2H(s2tile == 2, 512, 16) }
+        else { DGE_L2H(shape == 0, 512, 16) DGE_L2H(shape == 1, 256, 16) DGE_L2H(shape == 2, 256, 8) DGE_L2H(shape == 3, 128, 16) DGE_L2H(shape == 4, 512, 8) DGE_L2H(shape == 5, 1024, 8) }
 #undef DGE_L2H
         ++L;
         mark("l2 hist");
         device_exclusive_scan(sub_cnt, sub_off, nsb_bound + 1, ws.scan_scratch.as<uint32_t>(), st, &L);
         // cursors = copy of offsets (sub_cnt reused)
         DGE_CUDA(cudaMemcpyAsync(sub_cnt, sub_off, (nsb_bound + 1) * 4, cudaMemcpyDeviceToDevice, st));
+        if (l2_staged)
+        {
+#define DGE_L2SS(IDX, T, I)                                                                                                        \
+            if (s2tile == IDX)                                                                                                     \
+            {                                                                                                                      \
+                const size_t smem = size_t(SC_MAX_P2) * 16 + size_t(T) * I * 10;                                                   \
+                static bool attr_done = false;                                                                                     \
+                if (!attr_done) { DGE_CUDA(cudaFuncSetAttribute(k_l2_scatter_staged<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done = true; } \
+                k_l2_scatter_staged<T, I><<<unsigned(tiles_bound), T, smem, st>>>(keysA, l1_off, nb1, p2, sb_base, tile_base, ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp); \
+            }
+            DGE_L2SS(0, 256, 16) DGE_L2SS(1, 256, 8) DGE_L2SS(2, 512, 16)
+#undef DGE_L2SS
+        }
+        else
+        {
 #define DGE_L2S(IDX, T, I)                                                                                                         \
         if (shape == IDX)                                                                                                          \
         {                                                                                                                          \
@@ -649,6 +839,7 @@ public:
         }
         DGE_L2S(0, 512, 16) DGE_L2S(1, 256, 16) DGE_L2S(2, 256, 8) DGE_L2S(3, 128, 16) DGE_L2S(4, 512, 8) DGE_L2S(5, 1024, 8)
 #undef DGE_L2S
+        }
         ++L;
         mark("l2 scan+scatter");
 
