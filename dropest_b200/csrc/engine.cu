@@ -12,6 +12,7 @@
 #include "merge.cuh"
 #include "scan.cuh"
 #include "segments.cuh"
+#include "simplemerge.cuh"
 #include "sortcombine.cuh"
 #include "umimerge.cuh"
 #include "whitelist.hpp"
@@ -27,6 +28,7 @@
 #include <memory>
 #include <numeric>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 using namespace dge;
@@ -111,6 +113,10 @@ struct dge_handle
     std::vector<long> h_target;
     std::vector<uint64_t> h_sortkey;
     bool wl_uploaded = false;
+    // SimpleMergeStrategy workspaces
+    DevBuf sm_jobs, sm_ikeys, sm_ekey, sm_eval, sm_ngenes, sm_umis, sm_cb, sm_pcnt, sm_poff, sm_pairs, sm_pkey, sm_pval, sm_frac, sm_best;
+    PinnedBuf pin_best;
+    uint64_t n_simple_replayed = 0;
     PinnedBuf pin_rows, pin_nbc, pin_nbp, pin_isect, pin_misc;
     // cross-rank merge state (sharded runs)
     DevBuf umi_lists, umi_ctr, umi_pc_dec, umi_seg, umi_flat, umi_pairs;
@@ -248,8 +254,9 @@ void ensure_device(dge_handle *h)
     if (kl.tb < 10) throw std::runtime_error("key layout does not fit 64 bits: reduce n_genes or umi_len");
     kl.kb = kl.tb + kl.gb + kl.ub + 3;
     h->table_cap = size_t(1) << kl.tb;
-    h->track_umi_first = h->cfg.umi_merge_type == DGE_UMI_MERGE_DIRECTIONAL;
-    if (h->track_umi_first && kl.ub > 26) throw std::runtime_error("directional UMI merge supports UMIs of up to 13 bases");
+    // strategies whose tie rules depend on the UMI indexer's first-seen order (UMI ids): directional UMI merge, simple CB merge
+    h->track_umi_first = h->cfg.umi_merge_type == DGE_UMI_MERGE_DIRECTIONAL || h->cfg.merge_type == DGE_MERGE_SIMPLE;
+    if (h->track_umi_first && kl.ub > 26) throw std::runtime_error("directional UMI merge / simple CB merge support UMIs of up to 13 bases");
 
     h->tab.reserve(h->table_cap * sizeof(CellSlot));
     h->device_ready = true;
@@ -851,6 +858,208 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// SimpleMergeStrategy (Merge/SimpleMergeStrategy.cpp).  Device: inverted index, common UMI-gene counts, best candidate per base
+// (simplemerge.cuh).  Host: the final threshold compare in the reference's own expression, and an exact replay with the
+// reference's containers for the bases whose outcome depends on hash-iteration order (near-ties of the top fraction).
+struct SimpleReplay
+{
+    bool ready = false;
+    std::vector<uint64_t> E;                 // sorted inverted index [gu : gub | real idx : rb]
+    std::vector<uint32_t> gene_rank;         // gene id -> StringIndexer id
+    std::vector<uint32_t> umi_first;         // UMI value -> first read index (orders UMI ids)
+    std::vector<size_t> gid;                 // real idx -> reference cell id (first-seen rank among ALL barcodes)
+    std::unordered_map<size_t, uint32_t> ridx_of_gid;
+    std::vector<uint32_t> pos_in_filtered;   // real idx -> position in filtered_cells()
+};
+
+void simple_replay_prepare(dge_handle *h, SimpleReplay &R, uint32_t n_e)
+{
+    cudaStream_t st = h->stream;
+    const size_t n = h->real.size();
+    d2h(R.E, h->sm_ekey.p, n_e, st);
+    d2h(R.umi_first, h->umi_first.p, size_t(1) << h->kl.ub, st);
+    std::vector<CellSlot> tab;
+    d2h(tab, h->tab.p, h->table_cap, st);
+    DGE_CUDA(cudaStreamSynchronize(st));
+    R.gene_rank.assign(h->cfg.n_genes, NONE32);
+    for (size_t r = 0; r < h->gene_order.size(); ++r) R.gene_rank[size_t(h->gene_order[r])] = uint32_t(r);
+    std::vector<uint32_t> firsts;
+    firsts.reserve(size_t(h->total_cells));
+    for (auto const &s : tab) if (s.cb != EMPTY64) firsts.push_back(s.first_idx);
+    std::sort(firsts.begin(), firsts.end());
+    R.gid.resize(n);
+    R.ridx_of_gid.reserve(n * 2);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        R.gid[i] = size_t(std::lower_bound(firsts.begin(), firsts.end(), h->real[i].first_idx) - firsts.begin());
+        R.ridx_of_gid.emplace(R.gid[i], i);
+    }
+    R.pos_in_filtered.assign(n, NONE32);
+    for (uint32_t p = 0; p < h->filtered.size(); ++p) R.pos_in_filtered[h->filtered[p]] = p;
+    R.ready = true;
+}
+
+// SimpleMergeStrategy::get_merge_target for one base cell, with the reference's containers and insertion sequences.
+long simple_replay(dge_handle *h, SimpleReplay &R, uint32_t base, int rb)
+{
+    cudaStream_t st = h->stream;
+    const HostCell &bc = h->real[base];
+    const int ub = h->kl.ub, gub = h->kl.gb + h->kl.ub;
+    uint32_t range[2];
+    DGE_CUDA(cudaMemcpyAsync(range, h->pc_u_start.as<uint32_t>() + bc.pc, 8, cudaMemcpyDeviceToHost, st));
+    DGE_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint64_t> mine;
+    d2h(mine, h->ukey.as<uint64_t>() + range[0], range[1] - range[0], st);
+    DGE_CUDA(cudaStreamSynchronize(st));
+    struct Item { uint32_t gene_rank, umi_first; uint64_t gu; };
+    std::vector<Item> items;
+    items.reserve(mine.size());
+    const uint64_t gu_mask = (1ull << gub) - 1, rmask = (1ull << rb) - 1;
+    for (uint64_t uk : mine)
+    {
+        const uint64_t gu = uk & gu_mask;
+        items.push_back(Item{R.gene_rank[size_t(gu >> ub)], R.umi_first[size_t(gu & ((1ull << ub) - 1))], gu});
+    }
+    // Cell::genes() is a std::map over gene ids, Gene::umis() a std::map over UMI ids: ascending StringIndexer ids
+    std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.gene_rank != b.gene_rank ? a.gene_rank < b.gene_rank : a.umi_first < b.umi_first; });
+    std::unordered_map<size_t, size_t> common; // u_u_hash_t
+    std::vector<uint32_t> members;
+    for (auto const &it : items)
+    {
+        auto lo = std::lower_bound(R.E.begin(), R.E.end(), it.gu << rb);
+        auto hi = std::lower_bound(lo, R.E.end(), (it.gu + 1) << rb);
+        members.clear();
+        for (auto e = lo; e != hi; ++e) members.push_back(uint32_t(*e & rmask));
+        // init() walks filtered_cells() in order and emplaces every cell into the set of each of its UMI-genes
+        std::sort(members.begin(), members.end(), [&](uint32_t a, uint32_t b) { return R.pos_in_filtered[a] < R.pos_in_filtered[b]; });
+        std::unordered_set<size_t> cells; // sul_set_t
+        for (uint32_t m : members) cells.emplace(R.gid[m]);
+        for (size_t other : cells)
+        {
+            if (other == R.gid[base]) continue;
+            if (h->real[R.ridx_of_gid.at(other)].n_genes >= bc.n_genes) common[other]++;
+        }
+    }
+    long top = -1, top_genes = -1;
+    double top_frac = -1;
+    const std::string base_cb = unpack_seq(bc.cb, h->cfg.cb_len);
+    for (auto const &kv : common)
+    {
+        const uint32_t o = R.ridx_of_gid.at(kv.first);
+        const HostCell &oc = h->real[o];
+        const double frac = 0.5 * kv.second * (1. / size_t(bc.umis_stat) + 1. / size_t(oc.umis_stat));
+        if (frac - top_frac > 0.00001 || (std::abs(frac - top_frac) < 0.00001 && long(oc.n_genes) > top_genes))
+        {
+            const int ed = int(edit_distance_ref(base_cb.c_str(), unpack_seq(oc.cb, h->cfg.cb_len).c_str()));
+            if (ed >= int(h->cfg.max_cb_merge_edit_distance)) continue;
+            top = long(o); top_frac = frac; top_genes = long(oc.n_genes);
+        }
+    }
+    if (top_frac < h->cfg.min_merge_fraction) return long(base);
+    return top;
+}
+
+void phase1_simple(dge_handle *h, std::vector<long> &target)
+{
+    cudaStream_t st = h->stream;
+    Tracer tr; tr.st = st;
+    const size_t n = h->real.size();
+    target.resize(n);
+    for (size_t i = 0; i < n; ++i) target[i] = long(i);
+    h->n_simple_replayed = 0;
+    if (n < 2) return;
+    const int gub = h->kl.gb + h->kl.ub;
+    const int rb = std::max(1, ceil_log2_u64(n));
+    if (gub + rb + 3 > 64) throw std::runtime_error("simple merge: key layout does not fit 64 bits");
+
+    // ---- inverted index over the UMIs of every real (= filtered at this point) cell
+    std::vector<UmigJob> jobs;
+    jobs.reserve(n);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const HostCell &c = h->real[i];
+        if (c.pc == NONE32 || c.n_umis_distinct == 0) continue;
+        jobs.push_back(UmigJob{c.pc, i, uint32_t(total)});
+        total += uint64_t(c.n_umis_distinct);
+    }
+    if (total == 0) return;
+    if (total >= 0xFFFFFFF0ull) throw std::runtime_error("simple merge: more than 2^32 UMIs in real cells");
+    h->sm_jobs.reserve(jobs.size() * sizeof(UmigJob));
+    h->sm_ikeys.reserve(total * 8); h->sm_ekey.reserve(total * 8); h->sm_eval.reserve(total * 4);
+    DGE_CUDA(cudaMemcpyAsync(h->sm_jobs.p, jobs.data(), jobs.size() * sizeof(UmigJob), cudaMemcpyHostToDevice, st));
+    k_umig_keys<<<grid_for(jobs.size(), 1, 148 * 16), 256, 0, st>>>(h->sm_jobs.as<UmigJob>(), uint32_t(jobs.size()), h->ukey.as<uint64_t>(),
+                                                                   h->pc_u_start.as<uint32_t>(), gub, rb, h->sm_ikeys.as<uint64_t>());
+    DGE_LAUNCH_CHECK();
+    ++h->launches;
+    const int kb1 = gub + rb + 3;
+    const uint32_t *n_e_ptr = h->sc2.run(h->sm_ikeys.as<uint64_t>(), nullptr, total, kb1, std::min(choose_l1_bits(total), kb1 - 3), nullptr, h->sm_ikeys.as<uint64_t>(),
+                                         h->sm_ekey.as<uint64_t>(), h->sm_eval.as<uint32_t>(), h->overflow_flag.as<int>(), st, &h->sc_stats);
+    const uint32_t n_e = d2h_scalar<uint32_t>(n_e_ptr, st);
+    h->sc2.collect_timing();
+    if (d2h_scalar<int>(h->overflow_flag.p, st)) throw std::runtime_error("sub-bucket hash table overflow while indexing UMI-genes");
+    tr.mark("merge:  simple: inverted index");
+
+    // ---- per-cell columns the kernels need
+    std::vector<uint32_t> ng(n), um(n);
+    std::vector<uint64_t> cbs(n);
+    for (size_t i = 0; i < n; ++i) { ng[i] = uint32_t(h->real[i].n_genes); um[i] = uint32_t(h->real[i].umis_stat); cbs[i] = h->real[i].cb; }
+    h->sm_ngenes.reserve(n * 4); h->sm_umis.reserve(n * 4); h->sm_cb.reserve(n * 8);
+    DGE_CUDA(cudaMemcpyAsync(h->sm_ngenes.p, ng.data(), n * 4, cudaMemcpyHostToDevice, st));
+    DGE_CUDA(cudaMemcpyAsync(h->sm_umis.p, um.data(), n * 4, cudaMemcpyHostToDevice, st));
+    DGE_CUDA(cudaMemcpyAsync(h->sm_cb.p, cbs.data(), n * 8, cudaMemcpyHostToDevice, st));
+
+    // ---- (base, other) pairs inside every run, then their multiplicities
+    h->sm_pcnt.reserve((size_t(n_e) + 1) * 4); h->sm_poff.reserve((size_t(n_e) + 1) * 4);
+    k_pairs<false><<<grid_for(n_e, 256), 256, 0, st>>>(h->sm_ekey.as<uint64_t>(), n_e, rb, h->sm_ngenes.as<uint32_t>(), h->sm_pcnt.as<uint32_t>(), nullptr, nullptr);
+    ++h->launches;
+    DGE_CUDA(cudaMemsetAsync(h->sm_pcnt.as<uint32_t>() + n_e, 0, 4, st));
+    device_exclusive_scan(h->sm_pcnt.as<uint32_t>(), h->sm_poff.as<uint32_t>(), size_t(n_e) + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+    const uint32_t n_pairs = d2h_scalar<uint32_t>(h->sm_poff.as<uint32_t>() + n_e, st);
+    tr.mark("merge:  simple: pair count");
+    if (n_pairs == 0) return;
+    h->sm_pairs.reserve(size_t(n_pairs) * 8); h->sm_pkey.reserve(size_t(n_pairs) * 8); h->sm_pval.reserve(size_t(n_pairs) * 4);
+    k_pairs<true><<<grid_for(n_e, 256), 256, 0, st>>>(h->sm_ekey.as<uint64_t>(), n_e, rb, h->sm_ngenes.as<uint32_t>(), nullptr, h->sm_poff.as<uint32_t>(),
+                                                      h->sm_pairs.as<uint64_t>());
+    DGE_LAUNCH_CHECK();
+    ++h->launches;
+    const int kb2 = 2 * rb + 3;
+    const uint32_t *n_p_ptr = h->sc2.run(h->sm_pairs.as<uint64_t>(), nullptr, n_pairs, kb2, std::min(choose_l1_bits(n_pairs), kb2 - 3), nullptr, h->sm_pairs.as<uint64_t>(),
+                                         h->sm_pkey.as<uint64_t>(), h->sm_pval.as<uint32_t>(), h->overflow_flag.as<int>(), st, &h->sc_stats);
+    const uint32_t n_p = d2h_scalar<uint32_t>(n_p_ptr, st);
+    h->sc2.collect_timing();
+    if (d2h_scalar<int>(h->overflow_flag.p, st)) throw std::runtime_error("sub-bucket hash table overflow while counting common UMI-genes");
+    tr.mark("merge:  simple: common counts");
+
+    // ---- best candidate per base
+    h->sm_frac.reserve(size_t(n_p) * 8); h->sm_best.reserve(n * sizeof(BaseBest));
+    DGE_CUDA(cudaMemsetAsync(h->sm_best.p, 0xFF, n * sizeof(BaseBest), st)); // best = NONE32: no candidate
+    k_pair_eval<<<grid_for(n_p, 256), 256, 0, st>>>(h->sm_pkey.as<uint64_t>(), h->sm_pval.as<uint32_t>(), n_p, rb, h->sm_cb.as<uint64_t>(), h->sm_umis.as<uint32_t>(),
+                                                    int(h->cfg.cb_len), int(h->cfg.max_cb_merge_edit_distance), h->sm_frac.as<double>());
+    k_base_best<<<grid_for(n_p, 256), 256, 0, st>>>(h->sm_pkey.as<uint64_t>(), h->sm_pval.as<uint32_t>(), h->sm_frac.as<double>(), n_p, rb, 2e-5, h->sm_best.as<BaseBest>());
+    DGE_LAUNCH_CHECK();
+    h->launches += 2;
+    const BaseBest *bb = d2h_pinned<BaseBest>(h->pin_best, h->sm_best.p, n, st);
+    DGE_CUDA(cudaStreamSynchronize(st));
+    SimpleReplay R;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const BaseBest r = bb[i];
+        if (r.best == NONE32) continue; // no admissible candidate: top fraction stays -1 < min_merge_fraction -> the cell keeps itself
+        if (!r.ambiguous)
+        {
+            const double frac = 0.5 * size_t(r.count) * (1. / size_t(h->real[i].umis_stat) + 1. / size_t(h->real[r.best].umis_stat));
+            if (!(frac < h->cfg.min_merge_fraction)) target[i] = long(r.best);
+            continue;
+        }
+        if (!R.ready) simple_replay_prepare(h, R, n_e);
+        target[i] = simple_replay(h, R, i, rb);
+        ++h->n_simple_replayed;
+    }
+    tr.mark("merge:  simple: targets");
+}
+
 // Phase 2: MergeStrategyBase::merge_inited second loop + reassign (MergeStrategyBase.cpp:29-82), on real-cell indices.
 // `reassigned_to` sets are intrusive singly linked lists (child_head/child_next): a cell sits in at most one list.
 void phase2(dge_handle *h, const std::vector<long> &target)
@@ -1222,8 +1431,19 @@ void do_merge_and_filter(dge_handle *h)
         DGE_CUDA(cudaStreamSynchronize(st));
         tr.mark("merge: apply");
     }
+    else if (h->cfg.merge_type == DGE_MERGE_SIMPLE)
+    {
+        if (h->cfg.sharded) throw std::runtime_error("SimpleMergeStrategy is not available on sharded (multi-GPU) handles yet");
+        phase1_simple(h, h->h_target);
+        tr.mark("merge: phase 1 (simple)");
+        phase2(h, h->h_target);
+        tr.mark("merge: phase 2");
+        apply_merges(h);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        tr.mark("merge: apply");
+    }
     else if (h->cfg.merge_type != DGE_MERGE_NONE)
-        throw std::runtime_error("merge_type not implemented on the device path yet");
+        throw std::runtime_error("merge_type not implemented on the device path yet (Poisson strategies, merge_type=all)");
     DGE_CUDA(cudaEventRecord(h->ev[4], st));
 
     // ---- sizes of merge targets changed; Cell::is_real (Cell.cpp:125-128) is evaluated on the merged content from here on
@@ -1817,6 +2037,7 @@ int dge_get_summary(dge_handle *h, dge_summary *out)
     out->n_unresolved = h->n_unresolved;
     out->n_umis_merged = h->n_umis_merged;
     out->n_umi_segments_replayed = h->n_umi_segments_replayed;
+    out->n_cb_merge_replayed = h->n_simple_replayed;
     return DGE_OK;
 }
 

@@ -118,6 +118,7 @@ typedef struct dge_summary {
     uint64_t n_unresolved;          /* sharded runs only: cells whose merge candidates live on another shard (left unmerged) */
     uint64_t n_umis_merged;         /* UMIs merged into another UMI by the UMI merge strategy (MergeUMIsStrategyDirectional.cpp:43) */
     uint64_t n_umi_segments_replayed; /* (cell, gene) segments whose UMI merge was replayed on the host for exact tie order */
+    uint64_t n_cb_merge_replayed;   /* SimpleMergeStrategy: base cells whose target was replayed on the host (near-ties of the top fraction) */
 } dge_summary;
 
 /* Per-cell row returned by dge_get_cells; one per requested cell, in the requested order. */

@@ -252,3 +252,61 @@ def test_directional_umi_merge_large_segments():
     case = _directional_case(5, 2, 150000, seed=5, reads_per_umi=6, merge="none")
     res = pu.run_case(case)
     pu.assert_parity(res)
+
+
+# ---- SimpleMergeStrategy (no whitelist: Drop-seq style protocols), reference Merge/SimpleMergeStrategy.cpp -----------------------
+@pytest.mark.parametrize("seed", [7, 9])
+def test_merge_simple_small(seed):
+    res = pu.run_case(pu.small_case(n_reads=60000, n_cells=30, n_genes=120, merge="simple", seed=seed))
+    pu.assert_parity(res)
+    assert res["gpu"]["summary"]["n_merged"] > 0
+
+
+def test_merge_simple_medium_strict_edit_distance():
+    """max_cb_merge_edit_distance is a STRICT bound in this strategy (SimpleMergeStrategy.cpp:70): 1 forbids every merge."""
+    for max_ed in (1, 2, 3):
+        res = pu.run_case(pu.small_case(n_reads=300_000, n_cells=200, n_genes=800, merge="simple", min_genes_before=10, min_genes_after=20,
+                                        cb_error_ppm=30000, reads_per_umi=3, max_cb_ed=max_ed))
+        pu.assert_parity(res)
+        if max_ed == 1:
+            assert res["gpu"]["summary"]["n_merged"] == 0
+
+
+@pytest.mark.parametrize("min_frac", [0.0, 0.1, 0.2])
+def test_merge_simple_ties_replayed_in_reference_order(min_frac):
+    """Bases with two or three admissible candidates (edit distance 1) that share the SAME number of UMI-genes and have the SAME
+    size: exactly equal fractions, so the target depends on the iteration order of the reference's unordered containers --
+    the host replay has to reproduce it."""
+    rng = np.random.default_rng(11)
+    genes = [f"G{i}" for i in range(6)]
+    umis = ["".join("ACGT"[(v >> (2 * k)) & 3] for k in range(4)) for v in range(256)]
+    reads = []
+
+    def mutate(cb, pos, step):
+        return cb[:pos] + "ACGT"[("ACGT".index(cb[pos]) + step) % 4] + cb[pos + 1:]
+
+    for grp in range(16):
+        base = "".join("ACGT"[int(x)] for x in rng.integers(0, 4, 10))
+        n_parents = 2 + grp % 2
+        parents = [mutate(base, 1 + 3 * k, 1 + (grp + k) % 3) for k in range(n_parents)]
+        pool = [(g, u) for g in genes[:4] for u in rng.choice(umis, 3, replace=False)]      # the base's UMI-genes: 4 genes
+        for g, u in pool:
+            for _ in range(int(rng.integers(1, 3))):
+                reads.append((base, u, g, 2))
+        share = len(pool) // n_parents
+        for k, p in enumerate(parents):
+            mine = pool[k * share:(k + 1) * share]                                          # same number shared with every parent
+            extra = [(g, u) for g in genes for u in rng.choice(umis, 2, replace=False)]
+            extra = [x for x in extra if x not in pool][:10]                                # same total size for every parent
+            for g, u in mine + extra:
+                reads.append((p, u, g, 2))
+    order = rng.permutation(len(reads))
+    reads = [reads[i] for i in order]
+    gene_ids = {}
+    recs = records_from_strings(reads, gene_ids)
+    names = [n for n, _ in sorted(gene_ids.items(), key=lambda kv: kv[1])]
+    case = pu.Case(name="simple_ties", recs=recs, cb_len=10, umi_len=4, n_genes=len(names), gene_names=names, merge="simple",
+                   min_genes_before=2, min_genes_after=2, min_frac=min_frac, max_cb_ed=2, shuffle=False, n_batches=2)
+    res = pu.run_case(case)
+    pu.assert_parity(res)
+    assert res["gpu"]["summary"]["n_cb_merge_replayed"] > 0
