@@ -13,7 +13,7 @@ import golden_cases
 from golden_cases import fixture_case
 
 
-@pytest.mark.parametrize("name", ["fixture", "real_7x9", "none_7x9", "real_8x8_reads"])
+@pytest.mark.parametrize("name", ["fixture", "real_7x9", "none_7x9", "simple_7x9", "real_8x8_reads"])
 def test_gpu_reproduces_golden_reference_outputs(name):
     """CUDA path vs the committed outputs of the compiled, unmodified reference (no oracle binary needed on the GPU box)."""
     case = golden_cases.cases()[name]
