@@ -1060,6 +1060,33 @@ void phase1_simple(dge_handle *h, std::vector<long> &target)
     tr.mark("merge:  simple: targets");
 }
 
+// MergeAllMergeStrategy::get_merge_target for every filtered cell (MergeAllMergeStrategy.h:16-50): all-pairs on the device.
+void phase1_all(dge_handle *h, std::vector<long> &target)
+{
+    cudaStream_t st = h->stream;
+    const size_t n = h->real.size();
+    target.resize(n);
+    for (size_t i = 0; i < n; ++i) target[i] = long(i);
+    const std::vector<uint32_t> &f = h->filtered;
+    const size_t m = f.size();
+    if (m < 2) return;
+    if (m >= (size_t(1) << 27)) throw std::runtime_error("merge_type=all: too many filtered cells");
+    if (h->cfg.max_cb_merge_edit_distance > 63) throw std::runtime_error("merge_type=all: max_cb_merge_edit_distance must be < 64");
+    std::vector<uint64_t> cbs(m);
+    std::vector<uint32_t> um(m), tg(m);
+    for (size_t k = 0; k < m; ++k) { cbs[k] = h->real[f[k]].cb; um[k] = uint32_t(h->real[f[k]].umis_stat); }
+    h->sm_cb.reserve(m * 8); h->sm_umis.reserve(m * 4); h->sm_ngenes.reserve(m * 4);
+    DGE_CUDA(cudaMemcpyAsync(h->sm_cb.p, cbs.data(), m * 8, cudaMemcpyHostToDevice, st));
+    DGE_CUDA(cudaMemcpyAsync(h->sm_umis.p, um.data(), m * 4, cudaMemcpyHostToDevice, st));
+    k_merge_all_targets<<<unsigned(std::min<size_t>(m, 148 * 16)), 256, 0, st>>>(h->sm_cb.as<uint64_t>(), h->sm_umis.as<uint32_t>(), uint32_t(m), int(h->cfg.cb_len),
+                                                                                 h->cfg.max_cb_merge_edit_distance, h->sm_ngenes.as<uint32_t>());
+    DGE_LAUNCH_CHECK();
+    ++h->launches;
+    DGE_CUDA(cudaMemcpyAsync(tg.data(), h->sm_ngenes.p, m * 4, cudaMemcpyDeviceToHost, st));
+    DGE_CUDA(cudaStreamSynchronize(st));
+    for (size_t k = 0; k < m; ++k) target[f[k]] = long(f[tg[k]]);
+}
+
 // Phase 2: MergeStrategyBase::merge_inited second loop + reassign (MergeStrategyBase.cpp:29-82), on real-cell indices.
 // `reassigned_to` sets are intrusive singly linked lists (child_head/child_next): a cell sits in at most one list.
 void phase2(dge_handle *h, const std::vector<long> &target)
@@ -1442,8 +1469,18 @@ void do_merge_and_filter(dge_handle *h)
         DGE_CUDA(cudaStreamSynchronize(st));
         tr.mark("merge: apply");
     }
+    else if (h->cfg.merge_type == DGE_MERGE_ALL)
+    {
+        if (h->cfg.sharded) throw std::runtime_error("merge_type=all is not available on sharded (multi-GPU) handles yet");
+        phase1_all(h, h->h_target);
+        tr.mark("merge: phase 1 (all)");
+        phase2(h, h->h_target);
+        apply_merges(h);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        tr.mark("merge: apply");
+    }
     else if (h->cfg.merge_type != DGE_MERGE_NONE)
-        throw std::runtime_error("merge_type not implemented on the device path yet (Poisson strategies, merge_type=all)");
+        throw std::runtime_error("merge_type not implemented on the device path yet (Poisson strategies)");
     DGE_CUDA(cudaEventRecord(h->ev[4], st));
 
     // ---- sizes of merge targets changed; Cell::is_real (Cell.cpp:125-128) is evaluated on the merged content from here on

@@ -135,4 +135,62 @@ __global__ void __launch_bounds__(256) k_base_best(const uint64_t *__restrict__ 
     }
 }
 
+// ---- MergeAllMergeStrategy (reference Estimation/Merge/MergeAllMergeStrategy.h:16-50) -------------------------------------
+// Tools::edit_distance(a, b, skip_n = false, max_ed) on 2-bit packed barcodes: the banded single-column recurrence of
+// UtilFunctions.cpp:32-65 kept literally (cells outside the band keep stale values, early return of the running row minimum).
+__device__ inline unsigned packed_edit_distance_banded(uint64_t a, uint64_t b, int len, unsigned max_ed)
+{
+    int col[24];
+    for (int i = 0; i <= len; ++i) col[i] = i;
+    const int band = int(min(max_ed, 64u));
+    for (int j = 1; j <= len; ++j)
+    {
+        const int first = max(0, j - band), last = min(len, j + band);
+        int diag = col[first];
+        col[first] = j;
+        int row_best = j;
+        const uint32_t cb = uint32_t(b >> (2 * (len - j))) & 3u;
+        for (int i = first + 1; i <= last; ++i)
+        {
+            const int above = col[i];
+            const uint32_t ca = uint32_t(a >> (2 * (len - i))) & 3u;
+            const int v = min(min(above + 1, col[i - 1] + 1), diag + (ca == cb ? 0 : 1));
+            row_best = min(row_best, v + abs(i - j));
+            col[i] = v;
+            diag = above;
+        }
+        if (unsigned(row_best) > max_ed) return unsigned(row_best);
+    }
+    return unsigned(col[len]);
+}
+
+// One block per base cell (cells in filtered_cells() order).  Candidates: cells with MORE UMIs within the edit distance; the winner has
+// the smallest distance, then the most UMIs, then the earliest position (the reference's strict comparisons keep the first one).
+__global__ void __launch_bounds__(256) k_merge_all_targets(const uint64_t *__restrict__ cb, const uint32_t *__restrict__ umis, uint32_t n, int cb_len,
+                                                           unsigned max_ed, uint32_t *__restrict__ target)
+{
+    __shared__ unsigned long long best_s;
+    for (uint32_t base = blockIdx.x; base < n; base += gridDim.x)
+    {
+        if (threadIdx.x == 0) best_s = ~0ull;
+        __syncthreads();
+        const uint64_t my_cb = cb[base];
+        const uint32_t my_umis = umis[base];
+        unsigned long long best = ~0ull;
+        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x)
+        {
+            const uint32_t u = umis[j];
+            if (u <= my_umis) continue;
+            const unsigned ed = packed_edit_distance_banded(my_cb, cb[j], cb_len, max_ed);
+            if (ed > max_ed) continue;
+            const unsigned long long key = ((unsigned long long)(ed & 63u) << 58) | ((unsigned long long)(0x7FFFFFFFu - u) << 27) | j;
+            best = min(best, key);
+        }
+        atomicMin(&best_s, best);
+        __syncthreads();
+        if (threadIdx.x == 0) target[base] = best_s == ~0ull ? base : uint32_t(best_s & ((1ull << 27) - 1));
+        __syncthreads();
+    }
+}
+
 } // namespace dge

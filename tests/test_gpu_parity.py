@@ -310,3 +310,32 @@ def test_merge_simple_ties_replayed_in_reference_order(min_frac):
     res = pu.run_case(case)
     pu.assert_parity(res)
     assert res["gpu"]["summary"]["n_cb_merge_replayed"] > 0
+
+
+# ---- MergeAllMergeStrategy (merge_type=all), reference Merge/MergeAllMergeStrategy.h:16-50 ----------------------------------------
+@pytest.mark.parametrize("max_ed", [1, 2, 3])
+def test_merge_all_small(max_ed):
+    res = pu.run_case(pu.small_case(n_reads=60000, n_cells=30, n_genes=120, merge="all", seed=21, max_cb_ed=max_ed))
+    pu.assert_parity(res)
+    assert res["gpu"]["summary"]["n_merged"] > 0
+
+
+def test_merge_all_short_barcodes_many_neighbours():
+    """8-base barcodes drawn at random: plenty of cells within the edit distance of each other, chains of merges and equal
+    (distance, size) candidates where the earliest filtered cell has to win."""
+    rng = np.random.default_rng(3)
+    cbs = ["".join("ACGT"[int(x)] for x in rng.integers(0, 3, 8)) for _ in range(120)]
+    genes = [f"G{i}" for i in range(8)]
+    reads = []
+    for cb in cbs:
+        for _ in range(int(rng.integers(3, 12))):
+            reads.append((cb, "".join("ACGT"[int(x)] for x in rng.integers(0, 4, 5)), genes[int(rng.integers(0, 8))], 2))
+    reads = [reads[i] for i in rng.permutation(len(reads))]
+    gene_ids = {}
+    recs = records_from_strings(reads, gene_ids)
+    names = [n for n, _ in sorted(gene_ids.items(), key=lambda kv: kv[1])]
+    case = pu.Case(name="all_short", recs=recs, cb_len=8, umi_len=5, n_genes=len(names), gene_names=names, merge="all",
+                   min_genes_before=2, min_genes_after=2, max_cb_ed=2, shuffle=False, n_batches=2)
+    res = pu.run_case(case)
+    pu.assert_parity(res)
+    assert res["gpu"]["summary"]["n_merged"] > 10
