@@ -103,8 +103,10 @@ namespace Estimation
 		std::shared_ptr<MergeStrategyAbstract> MergeStrategyFactory::get_cb_strat(bool merge_tags, bool use_poisson) const
 		{
 			if (!merge_tags) return std::make_shared<DummyMergeStrategy>(min_genes_before_merge, min_genes_after_merge);
-			if (use_poisson || merge_type == "all" || barcodes_filename.empty())
-				throw std::runtime_error("this merge strategy is not available on the device path yet");
+			if (use_poisson) throw std::runtime_error("the Poisson merge strategies (-M) are not available on the device path yet");
+			if (merge_type == "all") return std::make_shared<MergeAllMergeStrategy>(min_genes_before_merge, min_genes_after_merge, max_merge_edit_distance);
+			if (barcodes_filename.empty())
+				return std::make_shared<SimpleMergeStrategy>(min_genes_before_merge, min_genes_after_merge, max_merge_edit_distance, min_merge_fraction);
 			std::shared_ptr<BarcodesParsing::BarcodesParser> parser;
 			if (barcodes_type == "indrop") parser = std::make_shared<BarcodesParsing::InDropBarcodesParser>(barcodes_filename);
 			else if (barcodes_type == "const") parser = std::make_shared<BarcodesParsing::ConstLengthBarcodesParser>(barcodes_filename);

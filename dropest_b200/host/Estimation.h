@@ -255,6 +255,42 @@ namespace Estimation
 			void configure(dge_config &cfg) const override;
 		};
 
+		// SimpleMergeStrategy (SimpleMergeStrategy.h:12-38): no whitelist, candidates = cells sharing UMI-genes
+		class SimpleMergeStrategy : public MergeStrategyAbstract
+		{
+			unsigned _max_merge_edit_distance;
+			double _min_merge_fraction;
+
+		public:
+			SimpleMergeStrategy(size_t min_genes_before_merge, size_t min_genes_after_merge, unsigned max_merge_edit_distance, double min_merge_fraction)
+				: MergeStrategyAbstract(min_genes_before_merge, min_genes_after_merge)
+				, _max_merge_edit_distance(max_merge_edit_distance), _min_merge_fraction(min_merge_fraction) {}
+			std::string merge_type() const override { return "Simple"; }
+			void configure(dge_config &cfg) const override
+			{
+				cfg.merge_type = DGE_MERGE_SIMPLE;
+				cfg.max_cb_merge_edit_distance = _max_merge_edit_distance;
+				cfg.min_merge_fraction = _min_merge_fraction;
+			}
+		};
+
+		// MergeAllMergeStrategy (MergeAllMergeStrategy.h:13-61): nearest larger cell within the edit distance
+		class MergeAllMergeStrategy : public MergeStrategyAbstract
+		{
+			unsigned _max_merge_edit_distance;
+
+		public:
+			MergeAllMergeStrategy(size_t min_genes_before_merge, size_t min_genes_after_merge, unsigned max_merge_edit_distance)
+				: MergeStrategyAbstract(min_genes_before_merge, min_genes_after_merge), _max_merge_edit_distance(max_merge_edit_distance) {}
+			std::string merge_type() const override { return "Merge all"; }
+			void configure(dge_config &cfg) const override
+			{
+				cfg.merge_type = DGE_MERGE_ALL;
+				cfg.max_cb_merge_edit_distance = _max_merge_edit_distance;
+				cfg.min_merge_fraction = 0;
+			}
+		};
+
 		namespace UMIs
 		{
 			class MergeUMIsStrategyAbstract

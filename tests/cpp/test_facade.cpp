@@ -123,6 +123,31 @@ int main(int argc, char **argv)
 			CHECK_EQUAL(container.cell(0).umis_number(), size_t(3));
 		}
 
+		// MergeStrategyFactory::get_cb_strat (MergeStrategyFactory.cpp:61-89) + SimpleMergeStrategy through the container
+		{
+			Merge::MergeStrategyFactory factory;
+			factory.min_genes_before_merge = 0; factory.min_genes_after_merge = 0;
+			CHECK_EQUAL(factory.get_cb_strat(false, false)->merge_type(), std::string("No"));
+			CHECK_EQUAL(factory.get_cb_strat(true, false)->merge_type(), std::string("Simple"));   // no barcodes file
+			factory.merge_type = "all";
+			CHECK_EQUAL(factory.get_cb_strat(true, false)->merge_type(), std::string("Merge all"));
+			factory.merge_type = "";
+			CellsDataContainer container(factory.get_cb_strat(true, false), umi_merge_strat, any_mark, false, -1, 0, 64);
+			static const char *big[][2] = {{"AAAAAA", "Gene1"}, {"AAAAAC", "Gene1"}, {"AAAAAG", "Gene2"}, {"AAAAAT", "Gene3"}, {"AAAACA", "Gene4"}, {"AAAACC", "Gene5"}};
+			static const char *small_[][2] = {{"AAAAAA", "Gene1"}, {"AAAAAG", "Gene2"}, {"AAAAAT", "Gene3"}, {"TTTTTT", "Gene5"}};
+			for (auto const &r : big) container.add_record(read_info("AAATTAGGTCCA", r[0], r[1]));
+			for (auto const &r : small_) container.add_record(read_info("AAATTAGGTCCC", r[0], r[1]));   // edit distance 1, shares 3 of its 4 UMI-genes
+			for (auto const &r : small_) container.add_record(read_info("CCCTTAGGTCCC", r[0], r[1]));   // same content, edit distance 4: must stay
+			container.set_initialized();
+			container.merge_and_filter();
+			CHECK_EQUAL(container.merge_type(), std::string("Simple"));
+			CHECK_EQUAL(container.merge_targets().at(1), size_t(0));
+			CHECK_EQUAL(container.merge_targets().at(2), size_t(2));
+			CHECK(container.cell(1).is_merged());
+			CHECK_EQUAL(container.cell(0).at("Gene1").at("AAAAAA").read_count(), size_t(2));
+			CHECK_EQUAL(container.cell(0).size(), size_t(5));
+		}
+
 		// testEditDistance, Tests/TestTools.cpp:47-54 ; testReadParams :56-87 (codec part)
 		CHECK_EQUAL(Tools::edit_distance("ATTTTC", "ATTTGC"), 1u);
 		CHECK_EQUAL(Tools::edit_distance("ATTTTCC", "ATTTGNC"), 1u);
