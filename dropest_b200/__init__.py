@@ -30,4 +30,5 @@ from .capi import (  # noqa: F401
     pack_seq,
     unpack_seq,
     marks_to_mask,
+    collisions_adjusted_sizes,
 )

@@ -47,7 +47,7 @@ EXPORTS = [
     "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
     "dge_route_by_barcode_device", "dge_dist_export_children", "dge_dist_copy_children", "dge_dist_eval_children", "dge_dist_apply",
-    "dge_umi_first_size", "dge_umi_first_export", "dge_umi_first_import",
+    "dge_umi_first_size", "dge_umi_first_export", "dge_umi_first_import", "dge_collisions_adjusted_sizes",
 ]
 
 
@@ -133,6 +133,7 @@ def load_library():
     lib.dge_edit_distance.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint]
     lib.dge_edit_distance.restype = C.c_uint
     lib.dge_hamming_distance.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    lib.dge_collisions_adjusted_sizes.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint32)]
     lib.dge_hamming_distance.restype = C.c_uint
     lib.dge_whitelist_shape.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_size_t]
     lib.dge_whitelist_token.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]
@@ -403,6 +404,19 @@ class Container:
 
 def edit_distance(a: str, b: str, skip_n: bool = True, max_ed: int = 10000) -> int:
     return int(load_library().dge_edit_distance(a.encode(), b.encode(), 1 if skip_n else 0, max_ed))
+
+
+def collisions_adjusted_sizes(umi_probabilities, max_gene_expression: int, device: int = 0):
+    """Tools::CollisionsAdjuster (CollisionsAdjuster.cpp:12-49) on the device: adjusted sizes for s = 1..max_gene_expression.
+    Returns (uint64 array, first step that forced the exact-order rerun or 0)."""
+    p = np.ascontiguousarray(umi_probabilities, dtype=np.float64)
+    out = np.zeros(int(max_gene_expression), dtype=np.uint64)
+    rerun = C.c_uint32(0)
+    lib = load_library()
+    rc = lib.dge_collisions_adjusted_sizes(device, p.ctypes.data, p.shape[0], int(max_gene_expression), out.ctypes.data, C.byref(rerun))
+    if rc != 0:
+        raise DgeError(rc, lib.dge_last_error(None).decode())
+    return out, int(rerun.value)
 
 
 def hamming_distance(a: str, b: str, skip_n: bool = True) -> int:

@@ -7,6 +7,7 @@
 //                         UMI merge, update_cell_sizes, matrices         -> segments.cuh + k_matrix_*
 // There is no CPU implementation of the grouping here: without a CUDA device every entry point fails.
 #include "../../include/dropest_b200.h"
+#include "collisions.cuh"
 #include "common.cuh"
 #include "fill.cuh"
 #include "merge.cuh"
@@ -2207,6 +2208,54 @@ int dge_get_umigs(dge_handle *h, int which, uint32_t *cell_index, int32_t *gene_
                 if (marks) marks[k] = uint8_t(uv[i] >> VAL_MARK_SHIFT);
             }
         }
+        return int(DGE_OK);
+    });
+}
+
+int dge_collisions_adjusted_sizes(int device, const double *umi_probabilities, size_t n_umis, size_t max_gene_expression,
+                                  uint64_t *adjusted_sizes, uint32_t *exact_rerun)
+{
+    if (exact_rerun) *exact_rerun = 0;
+    if ((!umi_probabilities && n_umis) || (!adjusted_sizes && max_gene_expression)) return fail(nullptr, DGE_ERR_INVALID, "null argument");
+    if (max_gene_expression == 0) return DGE_OK;
+    return guarded(nullptr, [&] {
+        DGE_CUDA(cudaSetDevice(device));
+        cudaStream_t st = nullptr;
+        DGE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
+        DevBuf p, neg, terms, partial, state, adj;
+        const size_t n = n_umis;
+        p.reserve(std::max<size_t>(n, 1) * 8); neg.reserve(std::max<size_t>(n, 1) * 8);
+        const unsigned blocks = unsigned(std::max<size_t>(1, std::min<size_t>(div_up(n, size_t(CA_THREADS)), 148 * 8)));
+        partial.reserve(size_t(blocks) * 8); state.reserve(sizeof(CollisionsState)); adj.reserve(max_gene_expression * 8);
+        DGE_CUDA(cudaMemcpyAsync(p.p, umi_probabilities, n * 8, cudaMemcpyHostToDevice, st));
+        std::vector<double> ones(n, 1.0);
+        // worst-case difference between two association orders of the sum, propagated through 1/(1-q): see collisions.cuh
+        const double drift = std::max(1e-13, double(n) * 4e-15);
+        const bool force_exact = std::getenv("DGE_CA_FORCE_EXACT") != nullptr; // tests: exercise the sequential-order path
+        for (int exact = force_exact ? 1 : 0; exact < 2; ++exact)
+        {
+            DGE_CUDA(cudaMemcpyAsync(neg.p, ones.data(), n * 8, cudaMemcpyHostToDevice, st));
+            DGE_CUDA(cudaMemsetAsync(state.p, 0, sizeof(CollisionsState), st));
+            if (exact) terms.reserve(std::max<size_t>(n, 1) * 8);
+            for (size_t s = 1; s <= max_gene_expression; ++s)
+            {
+                if (exact)
+                    k_collisions_step<true><<<blocks, CA_THREADS, 0, st>>>(p.as<double>(), neg.as<double>(), terms.as<double>(), n, s, state.as<CollisionsState>(),
+                                                                          partial.as<double>(), adj.as<unsigned long long>(), drift);
+                else
+                    k_collisions_step<false><<<blocks, CA_THREADS, 0, st>>>(p.as<double>(), neg.as<double>(), nullptr, n, s, state.as<CollisionsState>(),
+                                                                           partial.as<double>(), adj.as<unsigned long long>(), drift);
+            }
+            DGE_LAUNCH_CHECK();
+            CollisionsState hs;
+            DGE_CUDA(cudaMemcpyAsync(&hs, state.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+            DGE_CUDA(cudaStreamSynchronize(st));
+            if (!exact && hs.risky == 0) break;
+            if (!exact && exact_rerun) *exact_rerun = hs.risky;
+        }
+        DGE_CUDA(cudaMemcpyAsync(adjusted_sizes, adj.p, max_gene_expression * 8, cudaMemcpyDeviceToHost, st));
+        DGE_CUDA(cudaStreamSynchronize(st));
         return int(DGE_OK);
     });
 }

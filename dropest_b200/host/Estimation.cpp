@@ -28,6 +28,29 @@ namespace Tools
 		if (s1.size() != s2.size()) throw std::runtime_error("Strings should have equal length");
 		return dge_hamming_distance(s1.c_str(), s2.c_str(), skip_n ? 1 : 0);
 	}
+
+	void CollisionsAdjuster::init(const probs_vec_t &umi_probabilities, size_t max_gene_expression)
+	{
+		_umi_probabilities = umi_probabilities;
+		_adjusted_sizes.clear();
+		update_adjusted_sizes(max_gene_expression);
+	}
+
+	void CollisionsAdjuster::update_adjusted_sizes(size_t max_gene_expression)
+	{
+		if (max_gene_expression <= _adjusted_sizes.size()) return;
+		// the recurrence has no closed form to resume from on the host side: recompute the table up to the new size on the device
+		std::vector<uint64_t> table(max_gene_expression);
+		if (dge_collisions_adjusted_sizes(_device, _umi_probabilities.data(), _umi_probabilities.size(), max_gene_expression, table.data(), nullptr) != DGE_OK)
+			throw std::runtime_error(std::string("dropest_b200: ") + dge_last_error(nullptr));
+		_adjusted_sizes.assign(table.begin(), table.end());
+	}
+
+	size_t CollisionsAdjuster::estimate_adjusted_gene_expression(size_t expression)
+	{
+		if (expression > _adjusted_sizes.size()) update_adjusted_sizes(expression);
+		return _adjusted_sizes.at(expression - 1);
+	}
 }
 
 namespace Estimation

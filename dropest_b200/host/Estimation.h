@@ -42,6 +42,26 @@ namespace Tools
 
 	unsigned edit_distance(const char *s1, const char *s2, bool skip_n = true, unsigned max_ed = 10000); // UtilFunctions.cpp:32-65
 	unsigned hamming_distance(const std::string &s1, const std::string &s2, bool skip_n = true);         // UtilFunctions.cpp:67-82
+
+	// Tools::CollisionsAdjuster (Tools/CollisionsAdjuster.h:8-33): same interface; the table of adjusted sizes is computed on the
+	// device (dge_collisions_adjusted_sizes) and extended on demand like update_adjusted_sizes does.
+	class CollisionsAdjuster
+	{
+	public:
+		using size_vec_t = std::vector<size_t>;
+		using probs_vec_t = std::vector<double>;
+
+	private:
+		size_vec_t _adjusted_sizes;
+		probs_vec_t _umi_probabilities;
+		int _device;
+		void update_adjusted_sizes(size_t max_gene_expression);
+
+	public:
+		explicit CollisionsAdjuster(int device = 0) : _device(device) {}
+		void init(const probs_vec_t &umi_probabilities, size_t max_gene_expression = 0);
+		size_t estimate_adjusted_gene_expression(size_t expression);
+	};
 }
 
 namespace Estimation

@@ -220,6 +220,14 @@ int dge_get_umigs(dge_handle *h, int which, uint32_t *cell_index, int32_t *gene_
 
 /* ---- helpers that mirror reference utilities on the path (host-side, exact restatements used by the facade and tests) -- */
 
+/* Tools::CollisionsAdjuster (reference Tools/CollisionsAdjuster.cpp:12-49; used by PoissonTargetEstimator.cpp:99-100):
+ * adjusted_sizes[s-1] = CollisionsAdjuster::estimate_adjusted_gene_expression(s) for s = 1..max_gene_expression after
+ * init(umi_probabilities).  Host pointers; the recurrence runs on `device` (FP64, parallel over the UMI space).  *exact_rerun
+ * (optional) receives the first step at which the parallel sum came too close to a rounding boundary, in which case the whole
+ * table was recomputed with the reference's sequential summation order (0 = the fast pass was provably sufficient). */
+int dge_collisions_adjusted_sizes(int device, const double *umi_probabilities, size_t n_umis, size_t max_gene_expression,
+                                  uint64_t *adjusted_sizes, uint32_t *exact_rerun);
+
 /* Tools::edit_distance (Tools/UtilFunctions.cpp:32-65), literal behaviour including the banded quirks. */
 unsigned dge_edit_distance(const char *s1, const char *s2, int skip_n, unsigned max_ed);
 /* Tools::hamming_distance (Tools/UtilFunctions.cpp:67-82); returns UINT32_MAX when lengths differ. */

@@ -159,6 +159,16 @@ int main(int argc, char **argv)
 		CHECK_EQUAL(rp.umi(), std::string("ATATC"));
 		CHECK_THROW(Tools::ReadParameters::parse_encoded_id("ATTTG#ATAT"), std::runtime_error);
 
+		// Tools::CollisionsAdjuster (CollisionsAdjuster.cpp:12-49): values observed on the compiled reference (ref_pins.json)
+		{
+			Tools::CollisionsAdjuster adjuster;
+			adjuster.init(std::vector<double>(4096, 1.0 / 4096));
+			CHECK_EQUAL(adjuster.estimate_adjusted_gene_expression(100), size_t(101));
+			CHECK_EQUAL(adjuster.estimate_adjusted_gene_expression(1000), size_t(1146));
+			CHECK_EQUAL(adjuster.estimate_adjusted_gene_expression(3000), size_t(5400));
+			CHECK_EQUAL(adjuster.estimate_adjusted_gene_expression(10), size_t(10));
+		}
+
 		// ResultsPrinter::save_results (ResultsPrinter.cpp:23-91): files consumed by dropReport / dropestr
 		ResultsPrinter printer(true, false);
 		printer.save_results(container_full, out_dir + "/cell.counts.rds");
