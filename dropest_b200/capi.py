@@ -80,7 +80,7 @@ class _Summary(C.Structure):
 class _Timings(C.Structure):
     _fields_ = [("ms_fill", C.c_float), ("ms_init", C.c_float), ("ms_merge", C.c_float), ("ms_finish", C.c_float),
                 ("ms_total", C.c_float), ("ms_dedup_kernel", C.c_float), ("n_kernel_launches", C.c_uint32),
-                ("n_dedup_launches", C.c_uint32)]
+                ("n_dedup_launches", C.c_uint32), ("ms_fill_kernel", C.c_float), ("n_fill_launches", C.c_uint32)]
 
 
 class _SynthParams(C.Structure):

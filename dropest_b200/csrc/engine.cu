@@ -89,6 +89,8 @@ struct dge_handle
     uint64_t n_reads = 0;
     int staging_turn = 0;
     cudaEvent_t staging_ev[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> fill_ev; // start/stop pairs around the fill kernel of every batch of the current run
+    size_t n_fill_ev = 0;
 
     // grouped state
     DevBuf keys_all, ukey, uval, ukey2, uval2, overflow_flag;
@@ -152,6 +154,7 @@ struct dge_handle
     {
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         for (auto &e : staging_ev) if (e) cudaEventDestroy(e);
+        for (auto &e : fill_ev) if (e) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -301,12 +304,45 @@ void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n)
     // the kernel appends through FillCounters::n_keys; give every chunk its own cursor by pointing a private counter struct at it
     // (we keep one FillCounters per handle and move the cursor: n_keys is reset per chunk and accumulated on the host later)
     DGE_CUDA(cudaMemsetAsync(&h->ctr.as<FillCounters>()->n_keys, 0, sizeof(unsigned long long), h->stream));
-    unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(FILL_TILE)), 148 * 8));
-    k_fill_compact<<<grid, FILL_THREADS, 0, h->stream>>>(reinterpret_cast<const Rec16 *>(recs), n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes,
-                                                          h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(), h->ctr.as<FillCounters>(),
-                                                          /*l1_shift*/ 63, /*nb1*/ 0, nullptr,
-                                                          h->track_umi_first ? h->umi_first.as<uint32_t>() : nullptr);
+    if (h->n_fill_ev + 2 > h->fill_ev.size())
+    {
+        h->fill_ev.resize(h->n_fill_ev + 2, nullptr);
+        DGE_CUDA(cudaEventCreate(&h->fill_ev[h->n_fill_ev]));
+        DGE_CUDA(cudaEventCreate(&h->fill_ev[h->n_fill_ev + 1]));
+    }
+    DGE_CUDA(cudaEventRecord(h->fill_ev[h->n_fill_ev], h->stream));
+    // variant 0: 256 threads x 8 records, gene first-seen words gathered from global memory
+    // variant 1: 1024 threads x 4 records, one block per SM, gene first-seen words served from a shared-memory copy (needs n_genes * 4 B of it)
+    static const int fill_variant = std::getenv("DGE_FILL_VARIANT") ? atoi(std::getenv("DGE_FILL_VARIANT")) : 1;
+    const size_t gene_smem = size_t(h->cfg.n_genes) * 4;
+    uint32_t *umi_first = h->track_umi_first ? h->umi_first.as<uint32_t>() : nullptr;
+    if (fill_variant == 1 && gene_smem <= 160 * 1024)
+    {
+        auto kern = k_fill_compact<1024, 4, 1, true>;
+        static bool attr_done[64] = {};
+        if (!attr_done[h->cfg.device & 63]) { DGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_done[h->cfg.device & 63] = true; }
+        unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(1024 * 4)), 148));
+        kern<<<grid, 1024, gene_smem, h->stream>>>(reinterpret_cast<const Rec16 *>(recs), n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes,
+                                                    h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(), h->ctr.as<FillCounters>(), umi_first);
+    }
+    else if (fill_variant == 2 && gene_smem <= 100 * 1024)
+    {
+        auto kern = k_fill_compact<512, 4, 2, true>;
+        static bool attr_done[64] = {};
+        if (!attr_done[h->cfg.device & 63]) { DGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_done[h->cfg.device & 63] = true; }
+        unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(512 * 4)), 148 * 2));
+        kern<<<grid, 512, gene_smem, h->stream>>>(reinterpret_cast<const Rec16 *>(recs), n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes,
+                                                   h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(), h->ctr.as<FillCounters>(), umi_first);
+    }
+    else
+    {
+        unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(256 * 8)), 148 * 8));
+        k_fill_compact<256, 8, 2, false><<<grid, 256, 0, h->stream>>>(reinterpret_cast<const Rec16 *>(recs), n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes,
+                                                                      h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(), h->ctr.as<FillCounters>(), umi_first);
+    }
     DGE_LAUNCH_CHECK();
+    DGE_CUDA(cudaEventRecord(h->fill_ev[h->n_fill_ev + 1], h->stream));
+    h->n_fill_ev += 2;
     DGE_CUDA(cudaMemcpyAsync(chunk->d_count, &h->ctr.as<FillCounters>()->n_keys, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
     ++h->launches;
     h->chunks.push_back(std::move(chunk));
@@ -667,6 +703,13 @@ void do_set_initialized(dge_handle *h)
     h->timings.ms_dedup_kernel = h->sc_stats.dedup_ms;
     h->timings.n_kernel_launches = h->launches + h->sc_stats.launches;
     h->timings.n_dedup_launches = h->sc_stats.dedup_launches;
+    h->timings.ms_fill_kernel = 0;
+    for (size_t e = 0; e + 1 < h->n_fill_ev; e += 2)
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->fill_ev[e], h->fill_ev[e + 1]) == cudaSuccess) h->timings.ms_fill_kernel += ms;
+    }
+    h->timings.n_fill_launches = uint32_t(h->n_fill_ev / 2);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1744,7 +1787,7 @@ int dge_reset(dge_handle *h)
         if (h->stream) DGE_CUDA(cudaStreamSynchronize(h->stream));
         for (auto &c : h->chunks) h->chunk_pool.push_back(std::move(c));
         h->chunks.clear();
-        h->n_chunk_counters = 0; h->n_reads = 0; h->n_keys = 0; h->n_u = h->n_cg = h->n_pc = 0;
+        h->n_chunk_counters = 0; h->n_fill_ev = 0; h->n_reads = 0; h->n_keys = 0; h->n_u = h->n_cg = h->n_pc = 0;
         h->real.clear(); h->filtered.clear(); h->gene_order.clear(); h->merge_events.clear();
         h->n_merged = h->n_excluded = h->n_unresolved = 0; h->total_cells = 0;
         h->cm.built = h->cm_raw.built = false;

@@ -11,15 +11,6 @@ namespace dge
 
 struct Rec16 { unsigned long long key; uint32_t gene; uint32_t read_idx; };
 
-constexpr int FILL_THREADS = 256;
-#ifndef DGE_FILL_ITEMS
-#define DGE_FILL_ITEMS 8
-#endif
-#ifndef DGE_FILL_MINB
-#define DGE_FILL_MINB 2
-#endif
-constexpr int FILL_ITEMS = DGE_FILL_ITEMS;
-constexpr int FILL_TILE = FILL_THREADS * FILL_ITEMS;
 
 struct FillCounters
 {
@@ -80,16 +71,23 @@ __device__ __forceinline__ uint32_t table_find(const CellSlot *tab, int tb, uint
 }
 
 // records -> compact keys (dense, order irrelevant) + L1 histogram of the keys + global read counters.
-__global__ void __launch_bounds__(FILL_THREADS, DGE_FILL_MINB) k_fill_compact(const Rec16 *__restrict__ recs, size_t n, CellSlot *__restrict__ tab, KeyLayout kl,
+// SMEM_GENES: the gene first-seen words are served from a per-block shared-memory copy (a stale UPPER bound of the global value: the
+// global word only ever decreases, so `idx < copy` is necessary for `idx < global` and no update can be missed).  A random 4-byte
+// gather costs one L1 wavefront per lane in global memory and a few bank cycles in shared memory.
+template <int FILL_THREADS, int FILL_ITEMS, int MINB, bool SMEM_GENES>
+__global__ void __launch_bounds__(FILL_THREADS, MINB) k_fill_compact(const Rec16 *__restrict__ recs, size_t n, CellSlot *__restrict__ tab, KeyLayout kl,
                                                                uint32_t n_genes, uint32_t *__restrict__ gene_first, uint64_t *__restrict__ out_keys,
-                                                               FillCounters *__restrict__ ctr, int l1_shift, int nb1, uint32_t *__restrict__ l1_hist,
-                                                               uint32_t *__restrict__ umi_first)
+                                                               FillCounters *__restrict__ ctr, uint32_t *__restrict__ umi_first)
 {
-    __shared__ uint32_t hist[SC_MAX_NB1];
+    constexpr int FILL_TILE = FILL_THREADS * FILL_ITEMS;
+    extern __shared__ uint32_t gfirst_s[];
     __shared__ uint32_t ws[33];
     __shared__ unsigned long long out_base_s;
-    for (int i = threadIdx.x; i < nb1; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
+    if (SMEM_GENES)
+    {
+        for (uint32_t i = threadIdx.x; i < n_genes; i += FILL_THREADS) gfirst_s[i] = gene_first[i];
+        __syncthreads();
+    }
 
     uint32_t c_inter = 0, c_exon = 0, c_intron = 0, c_na = 0;
     const size_t n_tiles = (n + FILL_TILE - 1) / FILL_TILE;
@@ -118,7 +116,7 @@ __global__ void __launch_bounds__(FILL_THREADS, DGE_FILL_MINB) k_fill_compact(co
             slot0[j] = uint32_t(barcode_hash(k >> 24) >> (64 - kl.tb));
             probe[j] = __ldcg(reinterpret_cast<const uint4 *>(&tab[slot0[j]]));
             const uint32_t gene = raw[j].z & 0xFFFFFFu;
-            gfirst[j] = gene < n_genes ? gene_first[gene] : 0u;
+            gfirst[j] = gene < n_genes ? (SMEM_GENES ? gfirst_s[gene] : gene_first[gene]) : 0u;
         }
         // phase 3: resolve
 #pragma unroll
@@ -150,11 +148,14 @@ __global__ void __launch_bounds__(FILL_THREADS, DGE_FILL_MINB) k_fill_compact(co
                 continue;
             }
             if (gene >= n_genes) { ctr->bad_gene = 1; continue; }
-            if (idx < gfirst[j]) atomicMin(&gene_first[gene], idx);
+            if (idx < gfirst[j])
+            {
+                atomicMin(&gene_first[gene], idx);
+                if (SMEM_GENES) atomicMin(&gfirst_s[gene], idx);
+            }
             if (umi_first) atomicMin(&umi_first[umi], idx); // UMI ids are first-seen ranks too (StringIndexer via Gene::add_umi, Gene.cpp:17-24)
             c_exon += (mark >> 1) & 1u; c_intron += (mark >> 2) & 1u; c_na += mark & 1u;
             keys[j] = kl.compose(slot, gene, umi, mark);
-            if (nb1) atomicAdd(&hist[keys[j] >> l1_shift], 1u);
             ++n_valid;
         }
         uint32_t total;
@@ -178,9 +179,6 @@ __global__ void __launch_bounds__(FILL_THREADS, DGE_FILL_MINB) k_fill_compact(co
     reduce_add(c_exon, &ctr->has_exon);
     reduce_add(c_intron, &ctr->has_intron);
     reduce_add(c_na, &ctr->has_not_annotated);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nb1; i += blockDim.x)
-        if (hist[i]) atomicAdd(&l1_hist[i], hist[i]);
 }
 
 __global__ void k_count_occupied(const CellSlot *__restrict__ tab, size_t cap, unsigned long long *out)

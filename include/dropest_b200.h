@@ -148,9 +148,11 @@ typedef struct dge_timings {
     float ms_merge;       /* CB merge phase 1 + 2 + applying merges                                           */
     float ms_finish;      /* UMI merge, final sizes/filter, matrices                                          */
     float ms_total;
-    float ms_dedup_kernel; /* the dominant kernel (umig_dedup_sort), summed over its launches                 */
+    float ms_dedup_kernel; /* sub-bucket sort + dedup (k_sort_dedup size classes + hash tail), summed over its launches */
     uint32_t n_kernel_launches;
     uint32_t n_dedup_launches;
+    float ms_fill_kernel; /* k_fill_compact, summed over the batches of this run (CUDA events on the launching stream) */
+    uint32_t n_fill_launches;
 } dge_timings;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------------ */
