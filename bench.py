@@ -289,10 +289,15 @@ def main():
         torch.cuda.synchronize()
         d2h = 0
         # result buffers of the caller: page-locked, sized once from the warm-up result (a user would size them from dge_get_matrix)
-        nc0, nnz0 = cont.matrix_shape(dg.MATRIX_CM)
-        out_indptr = torch.empty(int(nc0 * 1.2) + 1024, dtype=torch.int64, pin_memory=True)
-        out_genes = torch.empty(int(nnz0 * 1.2) + 1024, dtype=torch.int32, pin_memory=True)
-        out_vals = torch.empty(int(nnz0 * 1.2) + 1024, dtype=torch.int32, pin_memory=True)
+        # result buffers of the caller: page-locked, (re)sized by the untimed warm-up call below (a user sizes them from dge_get_matrix)
+        bufs = {"indptr": None, "genes": None, "vals": None}
+
+        def ensure_bufs(nc, nnz):
+            if bufs["indptr"] is None or bufs["indptr"].numel() < nc + 1:
+                bufs["indptr"] = torch.empty(int(nc * 1.2) + 1024, dtype=torch.int64, pin_memory=True)
+            if bufs["genes"] is None or bufs["genes"].numel() < nnz:
+                bufs["genes"] = torch.empty(int(nnz * 1.2) + 1024, dtype=torch.int32, pin_memory=True)
+                bufs["vals"] = torch.empty(int(nnz * 1.2) + 1024, dtype=torch.int32, pin_memory=True)
 
         def e2e_step():
             nonlocal d2h
@@ -303,8 +308,8 @@ def main():
                 dgdist.merge_across_ranks(cont, f"cuda:{dev}")
             cont.merge_and_filter()
             nc, nnz = cont.matrix_shape(dg.MATRIX_CM)
-            assert nc + 1 <= out_indptr.numel() and nnz <= out_genes.numel()
-            cont.matrix_into(dg.MATRIX_CM, out_indptr.data_ptr(), out_genes.data_ptr(), out_vals.data_ptr())
+            ensure_bufs(nc, nnz)  # allocates in the warm-up call only
+            cont.matrix_into(dg.MATRIX_CM, bufs["indptr"].data_ptr(), bufs["genes"].data_ptr(), bufs["vals"].data_ptr())
             d2h = (nc + 1) * 4 + nnz * 8
             return nnz
 
@@ -315,7 +320,7 @@ def main():
             nnz_last = e2e_step()
         barrier()
         dt = (time.perf_counter() - t0) / max(1, min(args.steps, 3))
-        checksum = int(out_vals[:nnz_last].sum())  # the matrix is on the host when the timed region ends; summing it is the reader's work
+        checksum = int(bufs["vals"][:nnz_last].sum())  # the matrix is on the host when the timed region ends; summing it is the reader's work
         if world > 1:
             import torch.distributed as dist
 
