@@ -284,8 +284,14 @@ def main():
     # ---- e2e: host (pinned) records -> C ABI -> count matrix back on the host
     e2e = None
     if not args.no_e2e:
-        host = torch.empty(n * 16, dtype=torch.uint8, pin_memory=True)
-        host.copy_(raw)
+        # the caller's page-locked read arrays: key words and gene|mark words (dge_add_batch_soa; read_idx = stream position)
+        rec_dev = raw.view(torch.int64).view(-1, 2)
+        host_keys = torch.empty(n, dtype=torch.int64, pin_memory=True)
+        host_genes = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        host_keys.copy_(rec_dev[:, 0])
+        host_genes.copy_((rec_dev[:, 1] & 0xFFFFFFFF).to(torch.int32))
+        idx0 = int((rec_dev[0, 1] >> 32) & 0xFFFFFFFF)  # the synthetic stream numbers its reads consecutively from this rank's offset
+        del rec_dev
         torch.cuda.synchronize()
         d2h = 0
         # result buffers of the caller: page-locked, sized once from the warm-up result (a user would size them from dge_get_matrix)
@@ -302,7 +308,7 @@ def main():
         def e2e_step():
             nonlocal d2h
             cont.reset()
-            cont.add_batch_ptr(host.data_ptr(), n)
+            cont.add_batch_soa_ptr(host_keys.data_ptr(), host_genes.data_ptr(), n, idx0)
             cont.set_initialized()
             if world > 1:
                 dgdist.merge_across_ranks(cont, f"cuda:{dev}")
@@ -327,10 +333,10 @@ def main():
             tt = torch.tensor([dt], device=f"cuda:{dev}")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-        e2e = {"value": n * world / dt, "unit": "reads/s", "h2d_bytes_per_step": n * 16 * world, "d2h_bytes_per_step": int(d2h) * world,
+        e2e = {"value": n * world / dt, "unit": "reads/s", "h2d_bytes_per_step": n * 12 * world, "d2h_bytes_per_step": int(d2h) * world,
                "note": ("per-rank host records already owned by the rank (no routing), cross-rank merge included; " if world > 1 else "")
                        + "cm checksum %d" % checksum}
-        del host
+        del host_keys, host_genes
 
     if rank != 0:
         return

@@ -42,7 +42,7 @@ assert DIST_CHILD_DTYPE.itemsize == 32 and DIST_RESULT_DTYPE.itemsize == 24
 
 # exported symbols of include/dropest_b200.h (checked by tests/test_abi.py)
 EXPORTS = [
-    "dge_config_default", "dge_create", "dge_destroy", "dge_last_error", "dge_add_batch", "dge_add_batch_device",
+    "dge_config_default", "dge_create", "dge_destroy", "dge_last_error", "dge_add_batch", "dge_add_batch_device", "dge_add_batch_soa",
     "dge_set_initialized", "dge_merge_and_filter", "dge_reset", "dge_set_stream", "dge_get_summary", "dge_get_timings", "dge_get_cells",
     "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
@@ -119,6 +119,7 @@ def load_library():
     lib.dge_last_error.restype = C.c_char_p
     lib.dge_add_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.dge_add_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.dge_add_batch_soa.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64]
     lib.dge_set_initialized.argtypes = [C.c_void_p]
     lib.dge_merge_and_filter.argtypes = [C.c_void_p]
     lib.dge_reset.argtypes = [C.c_void_p]
@@ -262,6 +263,15 @@ class Container:
 
     def add_batch_ptr(self, host_ptr: int, n: int):
         self._check(self._lib.dge_add_batch(self._h, C.c_void_p(host_ptr), n))
+
+    def add_batch_soa_ptr(self, keys_ptr: int, genes_ptr: int, n: int, first_read_idx: int = 0):
+        self._check(self._lib.dge_add_batch_soa(self._h, C.c_void_p(keys_ptr), C.c_void_p(genes_ptr), n, first_read_idx))
+
+    def add_batch_soa(self, keys: np.ndarray, genes: np.ndarray, first_read_idx: int = 0):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        genes = np.ascontiguousarray(genes, dtype=np.uint32)
+        assert keys.shape == genes.shape
+        self._check(self._lib.dge_add_batch_soa(self._h, keys.ctypes.data, genes.ctypes.data, keys.shape[0], first_read_idx))
 
     def add_batch_device(self, dev_ptr: int, n: int, keepalive=None):
         if keepalive is not None:

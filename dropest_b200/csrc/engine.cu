@@ -89,6 +89,8 @@ struct dge_handle
     uint64_t n_reads = 0;
     int staging_turn = 0;
     cudaEvent_t staging_ev[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copied_ev[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> fill_ev; // start/stop pairs around the fill kernel of every batch of the current run
     size_t n_fill_ev = 0;
 
@@ -154,6 +156,8 @@ struct dge_handle
     {
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         for (auto &e : staging_ev) if (e) cudaEventDestroy(e);
+        for (auto &e : copied_ev) if (e) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         for (auto &e : fill_ev) if (e) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -291,8 +295,10 @@ void reset_fill_state(dge_handle *h)
 }
 
 // One batch already resident on the device: barcode-table insert + key packing into a fresh chunk.
-void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n)
+void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n, const unsigned long long *soa_keys = nullptr,
+                      const uint32_t *soa_genes = nullptr, uint32_t soa_first = 0)
 {
+    const bool soa = soa_keys != nullptr;
     if (n == 0) return;
     if (h->n_chunk_counters >= 4096) throw std::runtime_error("too many batches (max 4096); use larger batches");
     std::unique_ptr<KeyChunk> chunk;
@@ -316,30 +322,37 @@ void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n)
     static const int fill_variant = std::getenv("DGE_FILL_VARIANT") ? atoi(std::getenv("DGE_FILL_VARIANT")) : 1;
     const size_t gene_smem = size_t(h->cfg.n_genes) * 4;
     uint32_t *umi_first = h->track_umi_first ? h->umi_first.as<uint32_t>() : nullptr;
+    const Rec16 *r16 = reinterpret_cast<const Rec16 *>(recs);
+#define DGE_FILL_ARGS r16, n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes, h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(), \
+                      h->ctr.as<FillCounters>(), umi_first, soa_keys, soa_genes, soa_first
+    auto set_smem = [&](const void *kern) {
+        DGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    };
     if (fill_variant == 1 && gene_smem <= 160 * 1024)
     {
-        auto kern = k_fill_compact<1024, 4, 1, true>;
-        static bool attr_done[64] = {};
-        if (!attr_done[h->cfg.device & 63]) { DGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_done[h->cfg.device & 63] = true; }
         unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(1024 * 4)), 148));
-        kern<<<grid, 1024, gene_smem, h->stream>>>(reinterpret_cast<const Rec16 *>(recs), n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes,
-                                                    h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(), h->ctr.as<FillCounters>(), umi_first);
-    }
-    else if (fill_variant == 2 && gene_smem <= 100 * 1024)
-    {
-        auto kern = k_fill_compact<512, 4, 2, true>;
-        static bool attr_done[64] = {};
-        if (!attr_done[h->cfg.device & 63]) { DGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_done[h->cfg.device & 63] = true; }
-        unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(512 * 4)), 148 * 2));
-        kern<<<grid, 512, gene_smem, h->stream>>>(reinterpret_cast<const Rec16 *>(recs), n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes,
-                                                   h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(), h->ctr.as<FillCounters>(), umi_first);
+        if (soa)
+        {
+            auto kern = k_fill_compact<1024, 4, 1, true, true>;
+            static bool done[64] = {};
+            if (!done[h->cfg.device & 63]) { set_smem(reinterpret_cast<const void *>(kern)); done[h->cfg.device & 63] = true; }
+            kern<<<grid, 1024, gene_smem, h->stream>>>(DGE_FILL_ARGS);
+        }
+        else
+        {
+            auto kern = k_fill_compact<1024, 4, 1, true, false>;
+            static bool done[64] = {};
+            if (!done[h->cfg.device & 63]) { set_smem(reinterpret_cast<const void *>(kern)); done[h->cfg.device & 63] = true; }
+            kern<<<grid, 1024, gene_smem, h->stream>>>(DGE_FILL_ARGS);
+        }
     }
     else
     {
         unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(256 * 8)), 148 * 8));
-        k_fill_compact<256, 8, 2, false><<<grid, 256, 0, h->stream>>>(reinterpret_cast<const Rec16 *>(recs), n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes,
-                                                                      h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(), h->ctr.as<FillCounters>(), umi_first);
+        if (soa) k_fill_compact<256, 8, 2, false, true><<<grid, 256, 0, h->stream>>>(DGE_FILL_ARGS);
+        else k_fill_compact<256, 8, 2, false, false><<<grid, 256, 0, h->stream>>>(DGE_FILL_ARGS);
     }
+#undef DGE_FILL_ARGS
     DGE_LAUNCH_CHECK();
     DGE_CUDA(cudaEventRecord(h->fill_ev[h->n_fill_ev + 1], h->stream));
     h->n_fill_ev += 2;
@@ -1754,29 +1767,62 @@ int dge_add_batch_device(dge_handle *h, const dge_record16 *recs, size_t n)
     return guarded(h, [&] { ensure_device(h); fill_from_device(h, recs, n); return int(DGE_OK); });
 }
 
+// Host batches: double-buffered device staging filled on a COPY stream, consumed by the fill kernel on the main stream, so the H2D
+// copy of slice k+1 overlaps the fill kernel of slice k (the copies are truly asynchronous when the host memory is page-locked).
+static void add_host_slices(dge_handle *h, const dge_record16 *recs, const unsigned long long *keys, const uint32_t *genes, size_t n, uint64_t first_idx)
+{
+    ensure_device(h);
+    if (!h->copy_stream)
+    {
+        DGE_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : h->copied_ev) DGE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const bool soa = keys != nullptr;
+    const size_t slice = size_t(32) << 20; // records per staging slice
+    // the copy stream must not run ahead of work already queued on the main stream that still reads the staging buffers
+    for (size_t off = 0; off < n; off += slice)
+    {
+        const size_t m = std::min(slice, n - off);
+        const int turn = h->staging_turn;
+        DevBuf &stg = h->staging[turn];
+        h->staging_turn ^= 1;
+        // the fill kernel that last read this staging buffer must have finished before it is overwritten
+        DGE_CUDA(cudaStreamWaitEvent(h->copy_stream, h->staging_ev[turn], 0));
+        if (stg.bytes < m * 16) { DGE_CUDA(cudaEventSynchronize(h->staging_ev[turn])); stg.reserve(m * 16); }
+        if (soa)
+        {
+            unsigned long long *dk = stg.as<unsigned long long>();
+            uint32_t *dg = reinterpret_cast<uint32_t *>(dk + m);
+            DGE_CUDA(cudaMemcpyAsync(dk, keys + off, m * 8, cudaMemcpyHostToDevice, h->copy_stream));
+            DGE_CUDA(cudaMemcpyAsync(dg, genes + off, m * 4, cudaMemcpyHostToDevice, h->copy_stream));
+            DGE_CUDA(cudaEventRecord(h->copied_ev[turn], h->copy_stream));
+            DGE_CUDA(cudaStreamWaitEvent(h->stream, h->copied_ev[turn], 0));
+            fill_from_device(h, nullptr, m, dk, dg, uint32_t(first_idx + off));
+        }
+        else
+        {
+            DGE_CUDA(cudaMemcpyAsync(stg.p, recs + off, m * sizeof(dge_record16), cudaMemcpyHostToDevice, h->copy_stream));
+            DGE_CUDA(cudaEventRecord(h->copied_ev[turn], h->copy_stream));
+            DGE_CUDA(cudaStreamWaitEvent(h->stream, h->copied_ev[turn], 0));
+            fill_from_device(h, stg.as<dge_record16>(), m);
+        }
+        DGE_CUDA(cudaEventRecord(h->staging_ev[turn], h->stream));
+    }
+}
+
 int dge_add_batch(dge_handle *h, const dge_record16 *recs, size_t n)
 {
     if (!h || (!recs && n)) return fail(h, DGE_ERR_INVALID, "null argument");
     if (h->state != 0) return fail(h, DGE_ERR_STATE, "Container is already initialized");
-    return guarded(h, [&] {
-        ensure_device(h);
-        // double-buffered staging: copy slice k+1 while the fill kernel of slice k runs (single stream keeps order; the
-        // copy engine overlaps with the previous kernel when the host memory is pinned)
-        const size_t slice = size_t(32) << 20; // records per staging slice
-        for (size_t off = 0; off < n; off += slice)
-        {
-            const size_t m = std::min(slice, n - off);
-            DevBuf &stg = h->staging[h->staging_turn];
-            cudaEvent_t evt = h->staging_ev[h->staging_turn];
-            h->staging_turn ^= 1;
-            DGE_CUDA(cudaEventSynchronize(evt)); // the kernel that last read this staging buffer has finished
-            stg.reserve(m * sizeof(dge_record16));
-            DGE_CUDA(cudaMemcpyAsync(stg.p, recs + off, m * sizeof(dge_record16), cudaMemcpyHostToDevice, h->stream));
-            fill_from_device(h, stg.as<dge_record16>(), m);
-            DGE_CUDA(cudaEventRecord(evt, h->stream));
-        }
-        return int(DGE_OK);
-    });
+    return guarded(h, [&] { add_host_slices(h, recs, nullptr, nullptr, n, 0); return int(DGE_OK); });
+}
+
+int dge_add_batch_soa(dge_handle *h, const uint64_t *keys, const uint32_t *genes, size_t n, uint64_t first_read_idx)
+{
+    if (!h || ((!keys || !genes) && n)) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state != 0) return fail(h, DGE_ERR_STATE, "Container is already initialized");
+    if (first_read_idx + n > 0xFFFFFFFFull) return fail(h, DGE_ERR_INVALID, "read_idx beyond 2^32");
+    return guarded(h, [&] { add_host_slices(h, nullptr, reinterpret_cast<const unsigned long long *>(keys), genes, n, first_read_idx); return int(DGE_OK); });
 }
 
 int dge_reset(dge_handle *h)

@@ -74,10 +74,14 @@ __device__ __forceinline__ uint32_t table_find(const CellSlot *tab, int tb, uint
 // SMEM_GENES: the gene first-seen words are served from a per-block shared-memory copy (a stale UPPER bound of the global value: the
 // global word only ever decreases, so `idx < copy` is necessary for `idx < global` and no update can be missed).  A random 4-byte
 // gather costs one L1 wavefront per lane in global memory and a few bank cycles in shared memory.
-template <int FILL_THREADS, int FILL_ITEMS, int MINB, bool SMEM_GENES>
+// SOA: the batch arrives as two arrays (64-bit key words, 32-bit gene|mark words) and read_idx = soa_first_idx + position: 12 bytes per
+// read cross PCIe instead of 16 (dge_add_batch_soa).
+template <int FILL_THREADS, int FILL_ITEMS, int MINB, bool SMEM_GENES, bool SOA>
 __global__ void __launch_bounds__(FILL_THREADS, MINB) k_fill_compact(const Rec16 *__restrict__ recs, size_t n, CellSlot *__restrict__ tab, KeyLayout kl,
                                                                uint32_t n_genes, uint32_t *__restrict__ gene_first, uint64_t *__restrict__ out_keys,
-                                                               FillCounters *__restrict__ ctr, uint32_t *__restrict__ umi_first)
+                                                               FillCounters *__restrict__ ctr, uint32_t *__restrict__ umi_first,
+                                                               const unsigned long long *__restrict__ soa_keys = nullptr,
+                                                               const uint32_t *__restrict__ soa_genes = nullptr, uint32_t soa_first_idx = 0)
 {
     constexpr int FILL_TILE = FILL_THREADS * FILL_ITEMS;
     extern __shared__ uint32_t gfirst_s[];
@@ -106,7 +110,15 @@ __global__ void __launch_bounds__(FILL_THREADS, MINB) k_fill_compact(const Rec16
         {
             const size_t i = base + size_t(j) * FILL_THREADS + threadIdx.x;
             raw[j] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            if (i < n) raw[j] = __ldg(reinterpret_cast<const uint4 *>(recs) + i);
+            if (i < n)
+            {
+                if (SOA)
+                {
+                    const unsigned long long kw = __ldg(soa_keys + i);
+                    raw[j] = make_uint4(uint32_t(kw), uint32_t(kw >> 32), __ldg(soa_genes + i), soa_first_idx + uint32_t(i));
+                }
+                else raw[j] = __ldg(reinterpret_cast<const uint4 *>(recs) + i);
+            }
         }
         // phase 2: first probe of the barcode table + gene first-seen word, all in flight (random L2 accesses)
 #pragma unroll

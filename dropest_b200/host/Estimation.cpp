@@ -238,14 +238,16 @@ namespace Estimation
 		int rc = dge_create(&cfg, &_h);
 		if (rc != DGE_OK) throw std::runtime_error(std::string("dropest_b200: ") + dge_last_error(nullptr));
 		_batch_capacity = size_t(1) << 20;
-		_batch.reserve(_batch_capacity);
+		_batch_keys.reserve(_batch_capacity); _batch_genes.reserve(_batch_capacity);
 	}
 
 	void CellsDataContainer::flush()
 	{
-		if (_batch.empty()) return;
-		check(dge_add_batch(_h, _batch.data(), _batch.size()));
-		_batch.clear();
+		if (_batch_keys.empty()) return;
+		// add_record is called in stream order, so the read index is implicit: 12 bytes per read go to the device
+		check(dge_add_batch_soa(_h, _batch_keys.data(), _batch_genes.data(), _batch_keys.size(), _batch_first));
+		_batch_first += _batch_keys.size();
+		_batch_keys.clear(); _batch_genes.clear();
 	}
 
 	void CellsDataContainer::add_record(const ReadInfo &read_info)
@@ -263,14 +265,12 @@ namespace Estimation
 		uint64_t cbv, umiv;
 		if (!pack2bit(cb, cbv) || !pack2bit(umi, umiv))
 			throw std::runtime_error("barcodes / UMIs containing N are not supported on the device path yet: " + cb + " " + umi);
-		dge_record16 r;
-		r.key = (cbv << 24) | umiv;
 		uint32_t gene = DGE_NO_GENE;
 		if (!read_info.gene.empty()) gene = uint32_t(_gene_indexer.add(read_info.gene));
-		r.gene = gene | (uint32_t(read_info.umi_mark.bits()) << 24);
-		r.read_idx = uint32_t(_n_records++);
-		_batch.push_back(r);
-		if (_batch.size() >= _batch_capacity) flush();
+		_batch_keys.push_back((cbv << 24) | umiv);
+		_batch_genes.push_back(gene | (uint32_t(read_info.umi_mark.bits()) << 24));
+		++_n_records;
+		if (_batch_keys.size() >= _batch_capacity) flush();
 	}
 
 	void CellsDataContainer::set_initialized()

@@ -393,7 +393,9 @@ namespace Estimation
 
 		dge_handle *_h = nullptr;
 		unsigned _cb_len = 0, _umi_len = 0;
-		std::vector<dge_record16> _batch; // pending records (flushed in blocks of _batch_capacity)
+		std::vector<uint64_t> _batch_keys;  // pending records as two arrays (dge_add_batch_soa), flushed in blocks of _batch_capacity
+		std::vector<uint32_t> _batch_genes;
+		uint64_t _batch_first = 0;          // stream position of the first pending record
 		size_t _batch_capacity;
 		uint64_t _n_records = 0;
 		std::vector<ReadInfo> _deferred; // reads buffered until the first flush fixes cb/umi lengths and the gene-id space

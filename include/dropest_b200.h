@@ -171,9 +171,14 @@ const char *dge_last_error(const dge_handle *h);
  * dge_add_batch        : `recs` is HOST memory; copied to the device asynchronously (pinned staging); no ownership taken.
  * dge_add_batch_device : `recs` is DEVICE memory on cfg.device; referenced, NOT copied -- it must stay valid and unmodified
  *                        until dge_set_initialized returns.
- * Both fail with DGE_ERR_STATE after dge_set_initialized ("Container is already initialized", CellsDataContainer.cpp:61-62). */
+ * dge_add_batch_soa    : HOST memory, structure of arrays: keys[i] = dge_record16.key, genes[i] = dge_record16.gene, and
+ *                        read_idx = first_read_idx + i (the stream position is implicit when reads arrive in stream order, which is
+ *                        how BamProcessor::save_read calls add_record): 12 bytes per read cross PCIe instead of 16.
+ * Host batches are staged in slices on a copy stream, so the copy of one slice overlaps the fill kernel of the previous one.
+ * All fail with DGE_ERR_STATE after dge_set_initialized ("Container is already initialized", CellsDataContainer.cpp:61-62). */
 int dge_add_batch(dge_handle *h, const dge_record16 *recs, size_t n);
 int dge_add_batch_device(dge_handle *h, const dge_record16 *recs, size_t n);
+int dge_add_batch_soa(dge_handle *h, const uint64_t *keys, const uint32_t *genes, size_t n, uint64_t first_read_idx);
 
 /* = CellsDataContainer::set_initialized (CellsDataContainer.cpp:163-175): runs the whole per-read grouping on the device.
  * DGE_ERR_STATE when called twice (":165-166"). */

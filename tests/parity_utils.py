@@ -82,6 +82,13 @@ def gpu_run(case: Case, recs: Optional[np.ndarray], device_generate: bool = Fals
         tables.generate_device(0, 0, n, buf.data_ptr())
         torch.cuda.synchronize()
         c.add_batch_device(buf.data_ptr(), n, keepalive=buf)
+    elif case.extra.get("soa"):
+        # structure-of-arrays batches in stream order: read_idx is implicit (dge_add_batch_soa)
+        assert np.array_equal(recs["read_idx"], recs["read_idx"][0] + np.arange(recs.shape[0], dtype=np.uint32))
+        bounds = np.linspace(0, recs.shape[0], max(1, case.n_batches) + 1).astype(np.int64)
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            if b > a:
+                c.add_batch_soa(recs["key"][a:b], recs["gene"][a:b], first_read_idx=int(recs["read_idx"][a]))
     else:
         order = np.arange(recs.shape[0])
         if case.shuffle:

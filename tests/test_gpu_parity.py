@@ -339,3 +339,12 @@ def test_merge_all_short_barcodes_many_neighbours():
     res = pu.run_case(case)
     pu.assert_parity(res)
     assert res["gpu"]["summary"]["n_merged"] > 10
+
+
+def test_soa_batches_with_implicit_read_index():
+    """dge_add_batch_soa: key / gene arrays, read_idx = stream position; same results as the 16-byte records."""
+    case = pu.small_case(n_reads=80000, n_cells=40, n_genes=150, merge="real", seed=31)
+    case.extra["soa"] = True
+    case.n_batches = 4
+    res = pu.run_case(case)
+    pu.assert_parity(res)
