@@ -871,19 +871,22 @@ public:
                 const size_t ls = nsb_bound + 1;
                 DGE_CUDA(cudaMemsetAsync(cc, 0, MS_CLASSES * 4, st));
                 const uint32_t c0 = 64u * ms_items, c1 = 2 * c0, c2 = 4 * c0;
-                k_classify_sub<<<148 * 4, 256, 0, st>>>(sub_off, n_sub_ptr, c0, c1, c2, cc, cl, ls);
+                static const bool warp_class = std::getenv("DGE_MS_WARP") != nullptr; // measured neutral at C2 (the sort is ALU-bound, not barrier-bound): off
+                const uint32_t cw = warp_class && ms_items == 16 ? 32u * 16u : 0u; // sub-buckets of <= 512 keys: one warp each
+                k_classify_sub<<<148 * 4, 256, 0, st>>>(sub_off, n_sub_ptr, cw, c0, c1, c2, cc, cl, ls);
                 auto grid = [&](int threads, int dflt) { return unsigned(148 * (ms_bps > 0 ? std::max(1, ms_bps * 64 / threads) : dflt)); };
                 static const bool la = std::getenv("DGE_MS_NO_LOOKAHEAD") == nullptr;
-#define DGE_MS(T, I, LA, C, DFLT) k_sort_dedup<T, I, LA><<<grid(T, DFLT), T, 0, st>>>(keys_tmp, uv, sub_off, cl + C * ls, cc + C, ucount)
+                if (cw) k_sort_dedup_warp<4, 16><<<grid(128, 6), 128, 0, st>>>(keys_tmp, uv, sub_off, cl, cc, ucount);
+#define DGE_MS(T, I, LA, C, DFLT) k_sort_dedup<T, I, LA><<<grid(T, DFLT), T, 0, st>>>(keys_tmp, uv, sub_off, cl + (C + 1) * ls, cc + (C + 1), ucount)
                 if (ms_items == 16 && la) { DGE_MS(64, 16, true, 0, 12); DGE_MS(128, 16, true, 1, 6); DGE_MS(256, 16, true, 2, 3); }
                 else if (ms_items == 16) { DGE_MS(64, 16, false, 0, 12); DGE_MS(128, 16, false, 1, 6); DGE_MS(256, 16, false, 2, 3); }
                 else if (la) { DGE_MS(64, 8, true, 0, 24); DGE_MS(128, 8, true, 1, 12); DGE_MS(256, 8, true, 2, 6); }
                 else { DGE_MS(64, 8, false, 0, 24); DGE_MS(128, 8, false, 1, 12); DGE_MS(256, 8, false, 2, 6); }
 #undef DGE_MS
-                L += 4;
+                L += 5;
                 const int thr = sc_tuning().dedup_threads;
                 k_dedup_sort<false><<<148 * 2, thr, dedup_smem_bytes(SC_HT_MAX, SC_HT_MAX, thr), st>>>(keys_tmp, nullptr, uv, sub_off, n_sub_ptr, ucount, overflow_flag,
-                                                                                                        SC_HT_MAX, SC_HT_MAX, 0u, 0xFFFFFFFFu, cl + 3 * ls, cc + 3);
+                                                                                                        SC_HT_MAX, SC_HT_MAX, 0u, 0xFFFFFFFFu, cl + 4 * ls, cc + 4);
                 ++L;
             }
             else

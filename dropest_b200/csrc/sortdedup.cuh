@@ -21,22 +21,23 @@ template <int ITEMS> __device__ __forceinline__ int ms_phys(int i)
     return i + (i >> (ITEMS == 16 ? 4 : 3));
 }
 
-constexpr int MS_CLASSES = 4; // 3 comparison-sort size classes + the hash-table tail
+constexpr int MS_CLASSES = 5; // warp class + 3 block size classes + the hash-table tail
 #ifndef DGE_MS_WARPS
 #define DGE_MS_WARPS 24
 #endif
 constexpr int MS_WARPS_PER_SM = DGE_MS_WARPS; // occupancy target of the sort kernels (caps registers per thread)
 
 // Bins the sub-buckets by size into per-class work lists (order inside a list is irrelevant).
-__global__ void __launch_bounds__(256) k_classify_sub(const uint32_t *__restrict__ sub_off, const uint32_t *__restrict__ n_sub_ptr, uint32_t c0, uint32_t c1,
-                                                      uint32_t c2, uint32_t *__restrict__ cls_count, uint32_t *__restrict__ cls_list, size_t list_stride)
+__global__ void __launch_bounds__(256) k_classify_sub(const uint32_t *__restrict__ sub_off, const uint32_t *__restrict__ n_sub_ptr, uint32_t cw, uint32_t c0,
+                                                      uint32_t c1, uint32_t c2, uint32_t *__restrict__ cls_count, uint32_t *__restrict__ cls_list,
+                                                      size_t list_stride)
 {
     const uint32_t nsb = *n_sub_ptr;
     for (uint32_t sb = blockIdx.x * blockDim.x + threadIdx.x; sb < nsb; sb += gridDim.x * blockDim.x)
     {
         const uint32_t n = sub_off[sb + 1] - sub_off[sb];
         if (n == 0) continue;
-        const int c = n <= c0 ? 0 : n <= c1 ? 1 : n <= c2 ? 2 : 3;
+        const int c = n <= cw ? 0 : n <= c0 ? 1 : n <= c1 ? 2 : n <= c2 ? 3 : 4;
         cls_list[size_t(c) * list_stride + atomicAdd(&cls_count[c], 1u)] = sb;
     }
 }
@@ -206,6 +207,135 @@ __global__ void __launch_bounds__(THREADS, MS_WARPS_PER_SM * 32 / THREADS) k_sor
         }
         if (t == 0) ucount[sb] = total;
         __syncthreads(); // sk is reloaded by the next item
+    }
+}
+
+// Warp-synchronous variant for sub-buckets of <= 32*ITEMS keys: every warp of the block owns a private shared-memory region and walks
+// the work list on its own -- no block barriers at all (the merge levels of the block version spend a third of their stall cycles
+// in __syncthreads skew), one merge level less than the 64-thread class.
+template <int WARPS, int ITEMS>
+__global__ void __launch_bounds__(WARPS * 32, MS_WARPS_PER_SM / WARPS) k_sort_dedup_warp(uint64_t *__restrict__ keys, uint32_t *__restrict__ uvals,
+                                                                                     const uint32_t *__restrict__ sub_off, const uint32_t *__restrict__ list,
+                                                                                     const uint32_t *__restrict__ list_count, uint32_t *__restrict__ ucount)
+{
+    constexpr int CAP = 32 * ITEMS;
+    constexpr int REGION = CAP + CAP / ITEMS + 1;
+    __shared__ uint64_t sk_all[WARPS * REGION];
+    const int t = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint64_t *sk = sk_all + warp * REGION;
+    const int p0 = t * ITEMS;
+    const int row = ms_phys<ITEMS>(p0);
+    const uint32_t n_items = *list_count;
+    for (uint32_t item = blockIdx.x * WARPS + warp; item < n_items; item += gridDim.x * WARPS)
+    {
+        const uint32_t sb = list[item];
+        const uint32_t s = sub_off[sb];
+        const int n = int(sub_off[sb + 1] - s);
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
+        {
+            const int i = j * 32 + t;
+            sk[ms_phys<ITEMS>(i)] = i < n ? keys[s + i] : EMPTY64;
+        }
+        __syncwarp();
+        uint64_t k[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) k[j] = sk[row + j];
+        if (p0 < n) ms_thread_sort(k);
+        int need = 1;
+        while (need * ITEMS < n) need <<= 1;
+        for (int w = 1; w < need; w <<= 1)
+        {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) sk[row + j] = k[j];
+            __syncwarp();
+            const int first = t & ~(2 * w - 1);
+            const int a_beg = first * ITEMS, cnt = w * ITEMS, b_beg = a_beg + cnt;
+            const int a_cnt = min(max(n - a_beg, 0), cnt), b_cnt = min(max(n - b_beg, 0), cnt);
+            const int diag = (t - first) * ITEMS;
+            if (diag >= a_cnt + b_cnt) continue;
+            if (b_cnt == 0) continue;
+            int lo = max(0, diag - b_cnt), hi = min(diag, a_cnt);
+            while (lo < hi)
+            {
+                const int mid = (lo + hi) >> 1;
+                const uint64_t a = sk[ms_phys<ITEMS>(a_beg + mid)], b = sk[ms_phys<ITEMS>(b_beg + diag - 1 - mid)];
+                if (a <= b) lo = mid + 1; else hi = mid;
+            }
+            int ai = lo, bi = diag - lo;
+            auto ld_a = [&](int i) { return i < a_cnt ? sk[ms_phys<ITEMS>(a_beg + i)] : EMPTY64; };
+            auto ld_b = [&](int i) { return i < b_cnt ? sk[ms_phys<ITEMS>(b_beg + i)] : EMPTY64; };
+            uint64_t a0 = ld_a(ai), a1 = ld_a(ai + 1), b0 = ld_b(bi), b1 = ld_b(bi + 1);
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+            {
+                const bool ta = a0 <= b0;
+                k[j] = ta ? a0 : b0;
+                ai += ta ? 1 : 0; bi += ta ? 0 : 1;
+                const int nx = ta ? ai + 1 : bi + 1;
+                const bool ok = nx < (ta ? a_cnt : b_cnt);
+                const uint64_t v = ok ? sk[ms_phys<ITEMS>((ta ? a_beg : b_beg) + nx)] : EMPTY64;
+                a0 = ta ? a1 : a0; a1 = ta ? v : a1;
+                b0 = ta ? b0 : b1; b1 = ta ? b1 : v;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) sk[row + j] = k[j];
+        __syncwarp();
+        const int nv = min(max(n - p0, 0), ITEMS);
+        uint32_t head_mask = 0;
+        {
+            uint64_t prev = p0 > 0 && nv > 0 ? (sk[ms_phys<ITEMS>(p0 - 1)] >> 3) : EMPTY64;
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+            {
+                const uint64_t uk = k[j] >> 3;
+                if (j < nv && uk != prev) head_mask |= 1u << j;
+                prev = uk;
+            }
+        }
+        const uint32_t heads = uint32_t(__popc(head_mask));
+        const uint32_t inc = warp_inclusive_scan(heads);
+        const uint32_t base = inc - heads;
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        if (nv > 0)
+        {
+            uint32_t run_cnt = 0, run_mark = 0;
+            uint64_t cur = EMPTY64;
+            if (nv == ITEMS)
+            {
+                cur = k[ITEMS - 1] >> 3;
+                for (int q = p0 + ITEMS; q < n; ++q)
+                {
+                    const uint64_t x = sk[ms_phys<ITEMS>(q)];
+                    if ((x >> 3) != cur) break;
+                    ++run_cnt; run_mark |= uint32_t(x) & 7u;
+                }
+            }
+            uint64_t *ok = keys + s + base;
+            uint32_t *ov = uvals + s + base;
+#pragma unroll
+            for (int j = ITEMS - 1; j >= 0; --j)
+            {
+                if (j < nv)
+                {
+                    const uint64_t uk = k[j] >> 3;
+                    if (uk != cur) { cur = uk; run_cnt = 0; run_mark = 0; }
+                    ++run_cnt; run_mark |= uint32_t(k[j]) & 7u;
+                    if (head_mask & (1u << j))
+                    {
+                        const int o = __popc(head_mask & ((1u << j) - 1u));
+                        ok[o] = uk;
+                        ov[o] = run_cnt | (run_mark << VAL_MARK_SHIFT);
+                    }
+                }
+            }
+        }
+        if (t == 0) ucount[sb] = total;
+        __syncwarp();
     }
 }
 

@@ -1,5 +1,9 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -1
-run2() { echo "=== $*"; env "$@" timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel'], round(d['roofline']['ms_per_launch'],3), round(d['roofline']['frac'],3), d['roofline_second']['kernel'], round(d['roofline_second']['ms_per_launch'],3))"; }
-run2 DGE_FILL_VARIANT=0
-run2 DGE_FILL_VARIANT=1
-run2 DGE_FILL_VARIANT=2
+run() { echo "=== $*"; env "$@" DGE_TRACE=1 timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e 2>&1 | grep -E "sc\(n=3" | tail -7 | grep -E "${PAT:-plan|l2 hist|l2 scan|dedup|compact}" | sed -E 's/\[dge\]   sc\(n=[0-9]+\) //' | tr '\n' ' '; echo; }
+run DGE_MS_NO_WARP=1
+run DGE_SC_TARGET=832
+run DGE_SC_TARGET=448
+run DGE_SC_TARGET=416
+run DGE_SC_TARGET=384
+run DGE_SC_TARGET=352
+run DGE_SC_TARGET=416 DGE_MS_BPS=256
