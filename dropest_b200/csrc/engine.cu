@@ -984,8 +984,9 @@ long simple_replay(dge_handle *h, SimpleReplay &R, uint32_t base, int rb)
     std::vector<uint32_t> members;
     for (auto const &it : items)
     {
-        auto lo = std::lower_bound(R.E.begin(), R.E.end(), it.gu << rb);
-        auto hi = std::lower_bound(lo, R.E.end(), (it.gu + 1) << rb);
+        const uint64_t sg = umig_scramble(it.gu, gub); // the index is sorted by the scrambled (gene, umi) word
+        auto lo = std::lower_bound(R.E.begin(), R.E.end(), sg << rb);
+        auto hi = std::lower_bound(lo, R.E.end(), (sg + 1) << rb);
         members.clear();
         for (auto e = lo; e != hi; ++e) members.push_back(uint32_t(*e & rmask));
         // init() walks filtered_cells() in order and emplaces every cell into the set of each of its UMI-genes
@@ -1162,8 +1163,17 @@ void phase2(dge_handle *h, const std::vector<long> &target)
         if (child_head[t] == NONE32) child_head[t] = c; else child_next[child_tail[t]] = c;
         child_tail[t] = c;
     };
-    for (uint32_t base : h->filtered)
+    const std::vector<uint32_t> &F = h->filtered;
+    for (size_t fi = 0; fi < F.size(); ++fi)
     {
+        const uint32_t base = F[fi];
+        if (fi + 8 < F.size())
+        {   // the walk is random in cell-id order: pull the rows of a later iteration into cache
+            const uint32_t nb = F[fi + 8];
+            __builtin_prefetch(&row[nb]);
+            const long nt = target[nb];
+            if (nt >= 0) __builtin_prefetch(&row[size_t(nt)]);
+        }
         long t = target[base];
         if (t < 0) { h->real[base].excluded = true; ++h->n_excluded; continue; }
         if (uint32_t(t) == base) continue;              // keeps itself (reassign[base] == base: nothing was merged into a merged cell yet)
@@ -1223,8 +1233,15 @@ void apply_merges(dge_handle *h)
         jobs.push_back(MoveJob{src.pc, row[dst].slot, uint32_t(total)});
         total += uint64_t(src.n_umis);
     };
-    for (auto const &e : h->merge_events)
+    for (size_t ei = 0; ei < h->merge_events.size(); ++ei)
     {
+        const auto &e = h->merge_events[ei];
+        if (ei + 8 < h->merge_events.size())
+        {
+            const auto &ne = h->merge_events[ei + 8];
+            __builtin_prefetch(&row[ne.first]); __builtin_prefetch(&row[ne.second]);
+            __builtin_prefetch(&head[ne.first]); __builtin_prefetch(&head[ne.second]); __builtin_prefetch(&tail[ne.second]);
+        }
         const uint32_t src = e.first, dst = e.second;
         emit(src, dst);
         for (uint32_t o = head[src]; o != NONE32; o = next[o]) emit(o, dst);

@@ -16,7 +16,21 @@ namespace dge
 
 struct UmigJob { uint32_t pc, real_idx, out_off; };
 
-// (gene, umi) of every UMI of the listed cells, tagged with the cell's index in the real-cell list: [gu : gub | real_idx : rb] << 3
+// Bijective scrambling of a (gene, umi) word inside its `bits` bits.  The inverted index only needs equal (gene, umi) to be adjacent, not
+// any particular order of the groups; scrambling spreads the Zipf-distributed gene ids evenly over the radix buckets of the sort
+// (without it a handful of L1 buckets would hold half of the keys and overflow the sub-bucket capacity).
+__host__ __device__ inline uint64_t umig_scramble(uint64_t gu, int bits)
+{
+    const uint64_t mask = bits >= 64 ? ~0ull : ((1ull << bits) - 1);
+    const int h = bits / 2 > 0 ? bits / 2 : 1;
+    gu = (gu * 0x9E3779B97F4A7C15ull) & mask;
+    gu ^= gu >> h;
+    gu = (gu * 0xD6E8FEB86659FD93ull) & mask;
+    gu ^= gu >> h;
+    return gu;
+}
+
+// (gene, umi) of every UMI of the listed cells, tagged with the cell's index in the real-cell list: [scramble(gu) : gub | real_idx : rb] << 3
 __global__ void __launch_bounds__(256) k_umig_keys(const UmigJob *__restrict__ jobs, uint32_t n_jobs, const uint64_t *__restrict__ ukey,
                                                    const uint32_t *__restrict__ pc_u_start, int gub, int rb, uint64_t *__restrict__ out_keys)
 {
@@ -26,7 +40,7 @@ __global__ void __launch_bounds__(256) k_umig_keys(const UmigJob *__restrict__ j
         const UmigJob job = jobs[j];
         const uint32_t s = pc_u_start[job.pc], n = pc_u_start[job.pc + 1] - s;
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
-            out_keys[job.out_off + i] = (((ukey[s + i] & gu_mask) << rb) | job.real_idx) << 3;
+            out_keys[job.out_off + i] = ((umig_scramble(ukey[s + i] & gu_mask, gub) << rb) | job.real_idx) << 3;
     }
 }
 

@@ -348,3 +348,54 @@ def test_soa_batches_with_implicit_read_index():
     case.n_batches = 4
     res = pu.run_case(case)
     pu.assert_parity(res)
+
+
+def test_merge_simple_dropseq_like_2m():
+    """Drop-seq shaped stream (12 bp barcodes, 8 bp UMIs, no whitelist -> SimpleMergeStrategy) at a size where the inverted index and
+    the pair lists are non-trivial; checked against the oracle."""
+    wl = read_whitelist(pu.WL_SYNTH_8_8)
+    parts = [[t[:6] for t in wl[0]], [t[:6] for t in wl[1]]]
+    parts = [sorted(set(p)) for p in parts]
+    spec = SynthSpec(n_reads=2_000_000, n_cells=1500, n_genes=3000, cb_len=12, umi_len=8, whitelist_parts=parts, cb_error_ppm=40000,
+                     reads_per_umi=3, seed=17)
+    case = pu.Case(name="dropseq_simple", spec=spec, cb_len=12, umi_len=8, n_genes=3000, merge="simple", min_genes_before=10,
+                   min_genes_after=30, max_cb_ed=2, dump_umis=False, n_batches=5)
+    res = pu.run_case(case)
+    pu.assert_parity(res)
+    assert res["gpu"]["summary"]["n_merged"] > 300
+
+
+def test_full_size_invariants_simple_merge_20m():
+    """SimpleMergeStrategy at 20 M reads: the result does not depend on batching, totals are conserved."""
+    import torch
+
+    wl = read_whitelist(pu.WL_SYNTH_7_9)
+    spec = SynthSpec(n_reads=20_000_000, n_cells=2000, n_genes=5000, cb_len=16, umi_len=10, whitelist_parts=wl, seed=23)
+    t = SynthTables(spec)
+    n = spec.n_reads
+    buf = torch.empty(n * 16, dtype=torch.uint8, device="cuda:0")
+    t.generate_device(0, 0, n, buf.data_ptr())
+    torch.cuda.synchronize()
+
+    def run(split):
+        cfg = dg.Config(cb_len=16, umi_len=10, n_genes=5000, merge_type=dg.MERGE_SIMPLE, min_genes_before_merge=20, min_genes_after_merge=50,
+                        max_cb_merge_edit_distance=2)
+        c = dg.Container(cfg)
+        step = n // split
+        for k in range(split):
+            lo, hi = k * step, (n if k == split - 1 else (k + 1) * step)
+            c.add_batch_device(buf.data_ptr() + lo * 16, hi - lo)
+        c.set_initialized()
+        c.merge_and_filter()
+        out = (c.summary(), c.cells(dg.CELLS_ALL), c.matrix(dg.MATRIX_CM))
+        c.close()
+        return out
+
+    s1, all1, cm1 = run(1)
+    s2, all2, cm2 = run(5)
+    assert s1 == s2 and s1["n_merged"] > 1000
+    np.testing.assert_array_equal(all1, all2)
+    for a, b in zip(cm1, cm2):
+        np.testing.assert_array_equal(a, b)
+    unmerged = (all1["flags"] & 2) == 0
+    assert int(all1["reads_stat"][unmerged].sum()) + s1["intergenic_reads"] == n
