@@ -118,6 +118,9 @@ struct dge_handle
     std::vector<long> h_target;
     std::vector<uint64_t> h_sortkey;
     bool wl_uploaded = false;
+    bool rows_on_device = false; // rows_dev2 holds the real cells in cell-id order (same order as `real`)
+    DevBuf p1_pc, p1_map, p1_cnt, p1_off, p1_target, p1_flag;
+    PinnedBuf pin_p1t, pin_p1f;
     // SimpleMergeStrategy workspaces
     DevBuf sm_jobs, sm_ikeys, sm_ekey, sm_eval, sm_ngenes, sm_umis, sm_cb, sm_pcnt, sm_poff, sm_pairs, sm_pkey, sm_pval, sm_frac, sm_best;
     PinnedBuf pin_best;
@@ -634,6 +637,7 @@ void do_set_initialized(dge_handle *h)
             rows_sorted = true;
         }
     }
+    h->rows_on_device = rows_sorted;
     tr.mark("init:  rows d2h");
     // min_genes_before_merge == 0 makes every barcode real, including barcodes that only have intergenic reads
     // (they own no UMI and are not in the PC table): pick them up from the barcode table.
@@ -657,6 +661,7 @@ void do_set_initialized(dge_handle *h)
         rows_p = rows.data();
         n_rows = rows.size();
         rows_sorted = false;
+        h->rows_on_device = false;
     }
     static thread_local HostPairSorter order_sorter;
     if (!rows_sorted)
@@ -788,22 +793,31 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
     target.assign(n, -2);
     h->n_unresolved = 0;
     if (n == 0) return;
-    std::vector<uint32_t> &pc_to_real = h->h_pc_to_real;
-    pc_to_real.assign(size_t(h->n_pc) + 1, NONE32);
-    for (uint32_t i = 0; i < n; ++i) if (h->real[i].pc != NONE32) pc_to_real[h->real[i].pc] = i;
-
     h->pin_nbc.reserve(n * 4); h->pin_nbp.reserve(n * WL_K * 4);
     int *nb_count = h->pin_nbc.as<int>();
     uint32_t *nb_pc = h->pin_nbp.as<uint32_t>();
-    std::fill(nb_count, nb_count + n, int(NB_SLOW));
+    std::vector<char> todo(n, 1);        // cells whose target the host still has to work out
+    bool have_nb_pc = false;
+    const bool device_rows = h->rows_on_device && !h->cfg.sharded && h->wl_fast;
     if (h->wl_fast)
     {
         if (!h->wl_uploaded) { upload_whitelist(h); h->wl_uploaded = true; }
-        h->h_cbs.resize(n); h->h_umis.resize(n);
-        for (size_t i = 0; i < n; ++i) { h->h_cbs[i] = h->real[i].cb; h->h_umis[i] = uint32_t(h->real[i].umis_stat); }
         h->d_cb.reserve(n * 8); h->d_umis.reserve(n * 4); h->d_count.reserve(n * 4); h->d_nb.reserve(n * WL_K * 4);
-        DGE_CUDA(cudaMemcpyAsync(h->d_cb.p, h->h_cbs.data(), n * 8, cudaMemcpyHostToDevice, st));
-        DGE_CUDA(cudaMemcpyAsync(h->d_umis.p, h->h_umis.data(), n * 4, cudaMemcpyHostToDevice, st));
+        if (device_rows)
+        {   // the per-cell columns come straight from the rows gathered at set_initialized (nothing changed since)
+            h->p1_pc.reserve(n * 4); h->p1_map.reserve((size_t(h->n_pc) + 2) * 4);
+            k_fill_u32<<<grid_for(size_t(h->n_pc) + 1, 256), 256, 0, st>>>(h->p1_map.as<uint32_t>(), size_t(h->n_pc) + 1, NONE32);
+            k_p1_columns<<<grid_for(n, 256), 256, 0, st>>>(h->rows_dev2.as<CellRow>(), uint32_t(n), h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>(),
+                                                           h->p1_pc.as<uint32_t>(), h->p1_map.as<uint32_t>());
+            h->launches += 2;
+        }
+        else
+        {
+            h->h_cbs.resize(n); h->h_umis.resize(n);
+            for (size_t i = 0; i < n; ++i) { h->h_cbs[i] = h->real[i].cb; h->h_umis[i] = uint32_t(h->real[i].umis_stat); }
+            DGE_CUDA(cudaMemcpyAsync(h->d_cb.p, h->h_cbs.data(), n * 8, cudaMemcpyHostToDevice, st));
+            DGE_CUDA(cudaMemcpyAsync(h->d_umis.p, h->h_umis.data(), n * 4, cudaMemcpyHostToDevice, st));
+        }
         k_wl_class01<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>(), uint32_t(n), h->wl_dev,
                                                                             h->tab.as<CellSlot>(), h->kl.tb, h->slot_pc.as<uint32_t>(),
                                                                             h->pc_cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(),
@@ -811,9 +825,46 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
         DGE_LAUNCH_CHECK();
         ++h->launches;
         DGE_CUDA(cudaMemcpyAsync(nb_count, h->d_count.p, n * 4, cudaMemcpyDeviceToHost, st));
+        if (device_rows)
+        {   // intersections and the best neighbour per cell on the device; only ties / far classes come back to the host logic
+            h->p1_cnt.reserve((n + 1) * 4); h->p1_off.reserve((n + 1) * 4); h->p1_target.reserve(n * 4); h->p1_flag.reserve(n * 4);
+            k_p1_counts<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), uint32_t(n), h->p1_cnt.as<uint32_t>());
+            DGE_CUDA(cudaMemsetAsync(h->p1_cnt.as<uint32_t>() + n, 0, 4, st));
+            device_exclusive_scan(h->p1_cnt.as<uint32_t>(), h->p1_off.as<uint32_t>(), n + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+            const uint32_t n_jobs = d2h_scalar<uint32_t>(h->p1_off.as<uint32_t>() + n, st);
+            h->d_jobs.reserve(std::max<size_t>(n_jobs, 1) * sizeof(PairJob)); h->d_isect.reserve(std::max<size_t>(n_jobs, 1) * 4);
+            k_p1_jobs<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), h->d_nb.as<uint32_t>(), h->p1_pc.as<uint32_t>(), h->p1_off.as<uint32_t>(), uint32_t(n),
+                                                        h->d_jobs.as<PairJob>());
+            if (n_jobs)
+                k_intersect<<<n_jobs, 128, 0, st>>>(h->d_jobs.as<PairJob>(), n_jobs, h->ukey.as<uint64_t>(), h->pc_u_start.as<uint32_t>(),
+                                                    h->pc_slot.as<uint32_t>(), h->kl.gb + h->kl.ub, h->d_isect.as<uint32_t>());
+            k_p1_best<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), h->d_nb.as<uint32_t>(), h->p1_off.as<uint32_t>(), h->d_isect.as<uint32_t>(),
+                                                        h->d_umis.as<uint32_t>(), h->p1_map.as<uint32_t>(), uint32_t(n), h->cfg.min_merge_fraction,
+                                                        h->p1_target.as<int>(), h->p1_flag.as<uint32_t>());
+            DGE_LAUNCH_CHECK();
+            h->launches += 4;
+            const int *dt = d2h_pinned<int>(h->pin_p1t, h->p1_target.p, n, st);
+            const uint32_t *df = d2h_pinned<uint32_t>(h->pin_p1f, h->p1_flag.p, n, st);
+            DGE_CUDA(cudaStreamSynchronize(st));
+            size_t n_todo = 0;
+            for (size_t i = 0; i < n; ++i)
+            {
+                const int c = nb_count[i];
+                if (c == NB_SELF) { target[i] = long(i); todo[i] = 0; }
+                else if (c > 0 && !df[i]) { target[i] = long(dt[i]); todo[i] = 0; }
+                else ++n_todo;
+            }
+            if (n_todo == 0) { tr.mark("merge:  p1 device pass"); return; }
+        }
         DGE_CUDA(cudaMemcpyAsync(nb_pc, h->d_nb.p, n * WL_K * 4, cudaMemcpyDeviceToHost, st));
         DGE_CUDA(cudaStreamSynchronize(st));
+        have_nb_pc = true;
     }
+    else std::fill(nb_count, nb_count + n, int(NB_SLOW));
+    (void)have_nb_pc;
+    std::vector<uint32_t> &pc_to_real = h->h_pc_to_real;
+    pc_to_real.assign(size_t(h->n_pc) + 1, NONE32);
+    for (uint32_t i = 0; i < n; ++i) if (h->real[i].pc != NONE32) pc_to_real[h->real[i].pc] = i;
     tr.mark("merge:  p1 wl kernel + d2h");
 
     // exact host path (built lazily: most runs never need it)
@@ -847,6 +898,7 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
     for (uint32_t i = 0; i < n; ++i)
     {
         uint32_t c = 0;
+        if (!todo[i]) { off[i + 1] = off[i]; continue; } // settled by the device pass
         if (nb_count[i] == NB_SELF) target[i] = long(i);
         else if (nb_count[i] == NB_SLOW && h->cfg.sharded)
         {   // candidates may live on another shard: never guess, leave the cell as it is and report it

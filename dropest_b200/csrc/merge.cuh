@@ -219,6 +219,56 @@ __global__ void __launch_bounds__(256) k_gather_relabel_foreign(const ForeignMov
     }
 }
 
+// ---- phase 1 of the whitelist merge on the device (RealBarcodesMergeStrategy::get_best_merge_target, .cpp:31-61) ----------------
+// columns of the real-cell rows (cell-id order) + present-cell -> real-cell map
+struct CellRow;
+__global__ void k_p1_columns(const CellRow *__restrict__ rows, uint32_t n, uint64_t *__restrict__ cb, uint32_t *__restrict__ umis,
+                             uint32_t *__restrict__ pc, uint32_t *__restrict__ pc_to_real);
+
+__global__ void k_p1_counts(const int *__restrict__ nb_count, uint32_t n, uint32_t *__restrict__ cnt)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cnt[i] = nb_count[i] > 0 ? uint32_t(nb_count[i]) : 0u;
+}
+
+__global__ void k_p1_jobs(const int *__restrict__ nb_count, const uint32_t *__restrict__ nb_pc, const uint32_t *__restrict__ pc, const uint32_t *__restrict__ off,
+                          uint32_t n, PairJob *__restrict__ jobs)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int c = nb_count[i];
+        for (int k = 0; k < c; ++k) jobs[off[i] + k] = PairJob{pc[i], nb_pc[size_t(i) * WL_K + k]};
+    }
+}
+
+// target[i] = real index of the neighbour with the largest fraction 0.5 * I * (1/U_base + 1/U_nb) (first one on ties of the running
+// maximum, like the reference's strict <), -1 when that maximum is below min_merge_fraction.  needs_host[i] is set when the best
+// fraction is reached by more than one neighbour and is admissible: the reference's neighbour order then decides (host replay).
+__global__ void k_p1_best(const int *__restrict__ nb_count, const uint32_t *__restrict__ nb_pc, const uint32_t *__restrict__ off,
+                          const uint32_t *__restrict__ isect, const uint32_t *__restrict__ umis, const uint32_t *__restrict__ pc_to_real, uint32_t n,
+                          double min_frac, int *__restrict__ target, uint32_t *__restrict__ needs_host)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int c = nb_count[i];
+        target[i] = -2; needs_host[i] = 0;
+        if (c <= 0) continue;
+        const double inv_base = __ddiv_rn(1., double(umis[i]));
+        double max_frac = 0;
+        uint32_t best = pc_to_real[nb_pc[size_t(i) * WL_K]];
+        double top = -1; int n_top = 0;
+        for (int k = 0; k < c; ++k)
+        {
+            const uint32_t nb = pc_to_real[nb_pc[size_t(i) * WL_K + k]];
+            const double frac = __dmul_rn(__dmul_rn(0.5, double(isect[off[i] + k])), __dadd_rn(inv_base, __ddiv_rn(1., double(umis[nb]))));
+            if (max_frac < frac) { max_frac = frac; best = nb; }
+            if (frac > top) { top = frac; n_top = 1; } else if (frac == top) ++n_top;
+        }
+        if (c > 1 && n_top > 1 && !(top < min_frac)) needs_host[i] = 1;
+        if (pc_to_real[nb_pc[size_t(i) * WL_K]] == i) target[i] = int(i); // first neighbour is the base itself (.cpp:33-34)
+        else target[i] = max_frac < min_frac ? -1 : int(best);
+    }
+}
+
 // ---- applying merges -------------------------------------------------------------------------------------------------
 struct MoveJob { uint32_t src_pc, dst_slot, out_off; };   // out_off = exclusive prefix of the source sizes
 
@@ -341,6 +391,17 @@ struct CellRow
     uint32_t n_genes, n_umis, n_reads, req_genes, req_umis;
     uint32_t pad;
 };
+
+__global__ void k_p1_columns(const CellRow *__restrict__ rows, uint32_t n, uint64_t *__restrict__ cb, uint32_t *__restrict__ umis,
+                             uint32_t *__restrict__ pc, uint32_t *__restrict__ pc_to_real)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const CellRow r = rows[i];
+        cb[i] = r.cb; umis[i] = r.n_umis; pc[i] = r.pc;
+        if (r.pc != NONE32) pc_to_real[r.pc] = i;
+    }
+}
 
 __global__ void k_real_flags(const uint32_t *__restrict__ pc_cg_start, uint32_t n_pc, uint32_t min_genes, uint32_t *__restrict__ flags)
 {
