@@ -454,6 +454,114 @@ __global__ void __launch_bounds__(THREADS) k_l2_scatter_staged(const uint64_t *_
     for (uint32_t i = threadIdx.x; i < n_tile; i += THREADS) out_keys[gd[ids[i]] + i] = sk[i];
 }
 
+// L2 in ONE launch: a block owns a whole L1 bucket.  Phase A walks the bucket once (splitter search, shared-memory histogram, the
+// sub-bucket id of every key parked in a 2-byte side array), an in-block scan turns the histogram into the bucket's sub-bucket
+// offsets (written straight into the global offset table: sub-buckets of a bucket are contiguous inside the bucket's range), phase B
+// walks the bucket again and scatters with shared-memory cursors.  No per-tile global atomics, no exact-histogram launch, no
+// device-wide scan, one splitter search per key.
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_l2_bucket(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ l1_off,
+                                                       const uint32_t *__restrict__ p2, const uint32_t *__restrict__ sb_base,
+                                                       const uint64_t *__restrict__ splitters, uint16_t *__restrict__ ids,
+                                                       uint32_t *__restrict__ sub_off, uint64_t *__restrict__ out_keys,
+                                                       const uint32_t *__restrict__ order)
+{
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int PER = SC_MAX_P2 / THREADS;
+    __shared__ uint64_t spl[SC_MAX_P2];
+    __shared__ uint32_t cnt[SC_MAX_P2];
+    __shared__ uint32_t ws[33];
+    const int b = order ? int(order[blockIdx.x]) : int(blockIdx.x);
+    const uint32_t np = p2[b];
+    const uint32_t off = l1_off[b], nbk = l1_off[b + 1] - off;
+    if (nbk == 0 || np == 0) return;
+    const uint32_t sb0 = sb_base[b];
+    for (uint32_t i = threadIdx.x; i < np; i += THREADS)
+    {
+        cnt[i] = 0;
+        if (i + 1 < np) spl[i] = splitters[size_t(b) * SC_MAX_P2 + i];
+    }
+    __syncthreads();
+    for (uint32_t base = 0; base < nbk; base += TILE)
+    {
+        uint64_t k[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
+        {
+            const uint32_t i = base + uint32_t(j) * THREADS + threadIdx.x;
+            k[j] = i < nbk ? __ldg(keys + off + i) : EMPTY64;
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
+        {
+            const uint32_t i = base + uint32_t(j) * THREADS + threadIdx.x;
+            if (i < nbk)
+            {
+                const uint32_t sid = np > 1 ? sub_bucket_of(spl, np - 1, k[j] >> 3) : 0u;
+                ids[off + i] = uint16_t(sid);
+                atomicAdd(&cnt[sid], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    {   // exclusive scan of the histogram -> shared-memory cursors + global sub-bucket offsets
+        uint32_t c[PER], sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q)
+        {
+            const uint32_t i = threadIdx.x * PER + q;
+            c[q] = i < np ? cnt[i] : 0u;
+            sum += c[q];
+        }
+        uint32_t tot;
+        uint32_t ex = block_exclusive_scan(sum, ws, &tot);
+#pragma unroll
+        for (int q = 0; q < PER; ++q)
+        {
+            const uint32_t i = threadIdx.x * PER + q;
+            if (i < np) { cnt[i] = ex; sub_off[sb0 + i] = off + ex; }
+            ex += c[q];
+        }
+    }
+    __syncthreads();
+    for (uint32_t base = 0; base < nbk; base += TILE)
+    {
+        uint64_t k[ITEMS];
+        uint16_t sid[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
+        {
+            const uint32_t i = base + uint32_t(j) * THREADS + threadIdx.x;
+            k[j] = i < nbk ? __ldg(keys + off + i) : EMPTY64;
+            sid[j] = i < nbk ? ids[off + i] : uint16_t(0);
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
+        {
+            const uint32_t i = base + uint32_t(j) * THREADS + threadIdx.x;
+            if (i < nbk) out_keys[off + atomicAdd(&cnt[sid[j]], 1u)] = k[j];
+        }
+    }
+}
+
+__global__ void k_set_u32_at(uint32_t *p, const uint32_t *idx, uint32_t v) { p[*idx] = v; }
+
+// L1 buckets by decreasing size (longest first: the one-block-per-bucket pass then ends with the small ones). nb1 <= 4096.
+__global__ void __launch_bounds__(1024) k_bucket_order(const uint32_t *__restrict__ l1_off, int nb1, uint32_t *__restrict__ order)
+{
+    __shared__ uint64_t kk[SC_MAX_NB1];
+    __shared__ uint32_t vv[SC_MAX_NB1];
+    int P = 2;
+    while (P < nb1) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+    {
+        kk[i] = i < nb1 ? uint64_t(0xFFFFFFFFu - (l1_off[i + 1] - l1_off[i])) : EMPTY64;
+        vv[i] = uint32_t(i);
+    }
+    bitonic_sort_smem<true>(kk, vv, P);
+    for (int i = threadIdx.x; i < nb1; i += blockDim.x) order[i] = vv[i];
+}
+
 // One block per sub-bucket.  keys[s..e) -> distinct ukeys, ascending, written back IN PLACE at keys[s..s+m), values at
 // uvals[s..s+m); ucount[sb] = m.
 //   1. stream the records through a shared-memory hash table (atomicCAS claims a slot, atomicAdd/atomicOr combine values)
@@ -654,7 +762,7 @@ __global__ void __launch_bounds__(256) k_compact_uniques(const uint64_t *__restr
 // ---------------------------------------------------------------------------------------------------------------------
 struct SortCombineWorkspace
 {
-    DevBuf keysA, valsA, valsB, uvals_sparse, small, splitters, sub_cnt, sub_off, ucount, u_off, scan_scratch, cls_list, cls_count;
+    DevBuf keysA, valsA, valsB, uvals_sparse, small, splitters, sub_cnt, sub_off, ucount, u_off, scan_scratch, cls_list, cls_count, ids, order;
 };
 
 struct SortCombineStats
@@ -802,6 +910,24 @@ public:
         k_splitters<<<nb1, SC_THREADS, SC_SAMPLE * 8, st>>>(keysA, l1_off, p2, ws.splitters.as<uint64_t>()); ++L;
         mark("plan+splitters");
         uint32_t *sub_cnt = ws.sub_cnt.as<uint32_t>(), *sub_off = ws.sub_off.as<uint32_t>();
+        static const int l2_bucket = std::getenv("DGE_L2_BUCKET") ? atoi(std::getenv("DGE_L2_BUCKET")) : 3; // 0 = the two-launch tile path
+        if (!has_val && l2_bucket)
+        {
+            ws.ids.reserve(n * 2 + 64);
+            ws.order.reserve(size_t(nb1) * 4);
+            uint32_t *order = ws.order.as<uint32_t>();
+            k_bucket_order<<<1, 1024, 0, st>>>(l1_off, nb1, order);
+            ++L;
+            if (l2_bucket == 1) k_l2_bucket<512, 8><<<nb1, 512, 0, st>>>(keysA, l1_off, p2, sb_base, ws.splitters.as<uint64_t>(), ws.ids.as<uint16_t>(), sub_off, keys_tmp, order);
+            else if (l2_bucket == 2) k_l2_bucket<1024, 4><<<nb1, 1024, 0, st>>>(keysA, l1_off, p2, sb_base, ws.splitters.as<uint64_t>(), ws.ids.as<uint16_t>(), sub_off, keys_tmp, order);
+            else if (l2_bucket == 3) k_l2_bucket<1024, 8><<<nb1, 1024, 0, st>>>(keysA, l1_off, p2, sb_base, ws.splitters.as<uint64_t>(), ws.ids.as<uint16_t>(), sub_off, keys_tmp, order);
+            else k_l2_bucket<1024, 4><<<nb1, 1024, 0, st>>>(keysA, l1_off, p2, sb_base, ws.splitters.as<uint64_t>(), ws.ids.as<uint16_t>(), sub_off, keys_tmp, nullptr);
+            k_set_u32_at<<<1, 1, 0, st>>>(sub_off, sb_base + nb1, uint32_t(n));
+            L += 2;
+            mark("l2 bucket pass");
+        }
+        else
+        {
         DGE_CUDA(cudaMemsetAsync(sub_cnt, 0, (nsb_bound + 1) * 4, st));
 #define DGE_L2H(COND, T, I)                                                                                                        \
         if (COND) k_l2_pass<false, false, T, I><<<unsigned(tiles_bound), T, 0, st>>>(keysA, nullptr, l1_off, nb1, p2, sb_base, tile_base, \
@@ -843,6 +969,7 @@ public:
         ++L;
         mark("l2 scan+scatter");
 
+        }
         // ---- L3: dedup + sort per sub-bucket
         const uint32_t *n_sub_ptr = sb_base + nb1;
         uint32_t *ucount = ws.ucount.as<uint32_t>(), *u_off = ws.u_off.as<uint32_t>();
