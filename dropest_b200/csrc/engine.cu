@@ -98,8 +98,8 @@ struct dge_handle
     DevBuf keys_all, ukey, uval, ukey2, uval2, overflow_flag;
     DevBuf cg_gene, cg_start, cg_pc, cg_req, cg_reads, cg_req_reads;
     DevBuf pc_slot, pc_u_start, pc_cg_start, pc_reads, pc_req_genes, pc_req_umis, slot_pc;
-    DevBuf tile_a, tile_b, scan_scratch, flags, flags_off, rows_dev, rows_dev2, misc, cub_tmp, sort_k[2], sort_v[2];
-    PinnedBuf pin_filtered, pin_fkeys;
+    DevBuf tile_a, tile_b, scan_scratch, flags, flags_off, rows_dev, rows_dev2, misc, cub_tmp, sort_k[2], sort_v[2], gsort_k[2], gsort_v[2];
+    PinnedBuf pin_filtered, pin_fkeys, pin_gene_ids;
     uint32_t n_u = 0, n_cg = 0, n_pc = 0;
     size_t n_keys = 0;
     FillCounters counters{};
@@ -115,6 +115,8 @@ struct dge_handle
     std::vector<uint64_t> h_cbs;
     std::vector<PairJob> h_jobs;
     std::vector<MoveJob> h_moves;
+    uint64_t moves_total = 0;
+    bool moves_ready = false;
     std::vector<long> h_target;
     std::vector<uint64_t> h_sortkey;
     bool wl_uploaded = false;
@@ -597,7 +599,8 @@ void do_set_initialized(dge_handle *h)
     size_t n_rows = 0;
     bool rows_sorted = false;            // rows_p already in cell-id order, dev_filtered = compare_cells order of all of them
     const uint32_t *dev_filtered = nullptr;
-    const uint64_t *dev_fkeys = nullptr;
+    const uint64_t *dev_gene_keys = nullptr;
+    const uint32_t *dev_gene_ids = nullptr;
     int dev_filter_overflow = 0;
     if (h->n_pc)
     {
@@ -624,14 +627,28 @@ void do_set_initialized(dge_handle *h)
             device_sort_pairs(h, h->sort_k[0].as<uint64_t>(), h->sort_k[1].as<uint64_t>(), h->sort_v[0].as<uint32_t>(), h->sort_v[1].as<uint32_t>(), n_real, 32);
             k_rows_permute<<<g, 256, 0, st>>>(h->rows_dev.as<CellRow>(), h->sort_v[1].as<uint32_t>(), n_real, h->rows_dev2.as<CellRow>());
             DGE_CUDA(cudaMemsetAsync(h->overflow_flag.p, 0, sizeof(int), st));
-            k_rows_filter_keys<<<g, 256, 0, st>>>(h->rows_dev2.as<CellRow>(), n_real, h->sort_k[0].as<uint64_t>(), h->sort_v[0].as<uint32_t>(), h->overflow_flag.as<int>());
-            device_sort_pairs(h, h->sort_k[0].as<uint64_t>(), h->sort_k[1].as<uint64_t>(), h->sort_v[0].as<uint32_t>(), h->sort_v[1].as<uint32_t>(), n_real, 64);
+            // compare_cells order: stable sort by barcode, then stable sort by the packed (genes, umis, stat) counters
+            k_rows_cb_keys<<<g, 256, 0, st>>>(h->rows_dev2.as<CellRow>(), n_real, h->sort_k[0].as<uint64_t>(), h->sort_v[0].as<uint32_t>());
+            device_sort_pairs(h, h->sort_k[0].as<uint64_t>(), h->sort_k[1].as<uint64_t>(), h->sort_v[0].as<uint32_t>(), h->sort_v[1].as<uint32_t>(), n_real,
+                              int(2 * h->cfg.cb_len));
+            k_rows_filter_keys<<<g, 256, 0, st>>>(h->rows_dev2.as<CellRow>(), h->sort_v[1].as<uint32_t>(), n_real, h->sort_k[0].as<uint64_t>(), h->overflow_flag.as<int>());
+            device_sort_pairs(h, h->sort_k[0].as<uint64_t>(), h->sort_k[1].as<uint64_t>(), h->sort_v[1].as<uint32_t>(), h->sort_v[0].as<uint32_t>(), n_real, 64);
             DGE_LAUNCH_CHECK();
-            h->launches += 3;
+            h->launches += 4;
             rows_p = d2h_pinned<CellRow>(h->pin_rows, h->rows_dev2.p, n_real, st);
-            dev_filtered = d2h_pinned<uint32_t>(h->pin_filtered, h->sort_v[1].p, n_real, st);
-            dev_fkeys = d2h_pinned<uint64_t>(h->pin_fkeys, h->sort_k[1].p, n_real, st);
+            dev_filtered = d2h_pinned<uint32_t>(h->pin_filtered, h->sort_v[0].p, n_real, st);
             DGE_CUDA(cudaMemcpyAsync(&dev_filter_overflow, h->overflow_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            // gene first-seen order on the device as well
+            if (h->cfg.n_genes > 0)
+            {
+                const uint32_t ng = h->cfg.n_genes;
+                for (int b = 0; b < 2; ++b) { h->gsort_k[b].reserve(size_t(ng) * 8); h->gsort_v[b].reserve(size_t(ng) * 4); }
+                k_gene_first_keys<<<grid_for(ng, 256), 256, 0, st>>>(h->gene_first.as<uint32_t>(), ng, h->gsort_k[0].as<uint64_t>(), h->gsort_v[0].as<uint32_t>());
+                device_sort_pairs(h, h->gsort_k[0].as<uint64_t>(), h->gsort_k[1].as<uint64_t>(), h->gsort_v[0].as<uint32_t>(), h->gsort_v[1].as<uint32_t>(), ng, 32);
+                ++h->launches;
+                dev_gene_keys = d2h_pinned<uint64_t>(h->pin_fkeys, h->gsort_k[1].p, ng, st);
+                dev_gene_ids = d2h_pinned<uint32_t>(h->pin_gene_ids, h->gsort_v[1].p, ng, st);
+            }
             n_rows = n_real;
             DGE_CUDA(cudaStreamSynchronize(st));
             rows_sorted = true;
@@ -686,6 +703,13 @@ void do_set_initialized(dge_handle *h)
     }
     tr.mark("init: real cells -> host");
     // gene first-seen order (StringIndexer::add, StringIndexer.cpp:10-18)
+    if (dev_gene_ids)
+    {   // sorted on the device: genes never seen carry NONE32 and sort to the end
+        size_t seen = 0;
+        while (seen < h->cfg.n_genes && dev_gene_keys[seen] != uint64_t(NONE32)) ++seen;
+        h->gene_order.assign(dev_gene_ids, dev_gene_ids + seen);
+    }
+    else
     {
         const uint32_t *gf = d2h_pinned<uint32_t>(h->pin_misc, h->gene_first.p, h->cfg.n_genes, st);
         DGE_CUDA(cudaStreamSynchronize(st));
@@ -698,18 +722,7 @@ void do_set_initialized(dge_handle *h)
     }
     tr.mark("init:  gene order");
     // set_initialized: update_cell_sizes(query, 0, -1)  (CellsDataContainer.cpp:168) -- every real cell, ascending compare_cells
-    if (rows_sorted && !dev_filter_overflow)
-    {
-        std::vector<uint32_t> &f = h->filtered;
-        f.assign(dev_filtered, dev_filtered + n_rows);
-        for (size_t a = 0; a + 1 < f.size();)
-        {   // exact ties of (genes, umis, stat) are ordered by barcode
-            size_t b = a + 1;
-            while (b < f.size() && dev_fkeys[b] == dev_fkeys[a]) ++b;
-            if (b - a > 1) std::sort(f.begin() + long(a), f.begin() + long(b), [&](uint32_t x, uint32_t y) { return h->real[x].cb < h->real[y].cb; });
-            a = b;
-        }
-    }
+    if (rows_sorted && !dev_filter_overflow) h->filtered.assign(dev_filtered, dev_filtered + n_rows); // exact total order, ties included
     else update_filtered(h, 0, -1);
     tr.mark("init: gene order + filtered");
     DGE_CUDA(cudaEventRecord(h->ev[2], st));
@@ -1203,13 +1216,29 @@ void phase2(dge_handle *h, const std::vector<long> &target)
 {
     const size_t n = h->real.size();
     // the loop walks cells in size order, i.e. randomly in cell-id order: keep what it touches in a compact 16-byte row
-    struct Row { int32_t umis, reads; uint32_t intergenic, reassign; };
+    // ... and, in the same walk, the move jobs of apply_merges: merge_cells copies the source's CURRENT content, i.e. its own UMIs plus
+    // everything merged into it earlier -- exactly the cells re-pointed at it so far (the child lists of `reassign`).
+    struct Row { int32_t umis, reads; uint32_t intergenic, reassign, pc, slot, n_umis, pad; };
     std::vector<Row> row(n);
     std::vector<uint32_t> child_head(n, NONE32), child_tail(n, NONE32), child_next(n, NONE32);
-    for (uint32_t i = 0; i < n; ++i) row[i] = Row{h->real[i].umis_stat, h->real[i].reads_stat, h->real[i].n_intergenic, i};
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const HostCell &c = h->real[i];
+        row[i] = Row{c.umis_stat, c.reads_stat, c.n_intergenic, i, c.pc, c.slot, uint32_t(c.n_umis_distinct), 0};
+    }
     h->merge_events.clear();
     h->merge_events.reserve(h->filtered.size());
     h->n_merged = h->n_excluded = 0;
+    std::vector<MoveJob> &jobs = h->h_moves;
+    jobs.clear();
+    jobs.reserve(h->filtered.size());
+    uint64_t total = 0;
+    auto emit = [&](uint32_t o, uint32_t dst) {
+        const Row &src = row[o];
+        if (src.pc == NONE32 || src.n_umis == 0) return;
+        jobs.push_back(MoveJob{src.pc, row[dst].slot, uint32_t(total)});
+        total += uint64_t(src.n_umis);
+    };
     auto append = [&](uint32_t t, uint32_t c) {
         child_next[c] = NONE32;
         if (child_head[t] == NONE32) child_head[t] = c; else child_next[child_tail[t]] = c;
@@ -1219,13 +1248,6 @@ void phase2(dge_handle *h, const std::vector<long> &target)
     for (size_t fi = 0; fi < F.size(); ++fi)
     {
         const uint32_t base = F[fi];
-        if (fi + 8 < F.size())
-        {   // the walk is random in cell-id order: pull the rows of a later iteration into cache
-            const uint32_t nb = F[fi + 8];
-            __builtin_prefetch(&row[nb]);
-            const long nt = target[nb];
-            if (nt >= 0) __builtin_prefetch(&row[size_t(nt)]);
-        }
         long t = target[base];
         if (t < 0) { h->real[base].excluded = true; ++h->n_excluded; continue; }
         if (uint32_t(t) == base) continue;              // keeps itself (reassign[base] == base: nothing was merged into a merged cell yet)
@@ -1237,6 +1259,7 @@ void phase2(dge_handle *h, const std::vector<long> &target)
         dst.umis += src.umis; dst.reads += src.reads; dst.intergenic += src.intergenic;
         h->merge_events.emplace_back(base, uint32_t(t));
         ++h->n_merged;
+        emit(base, uint32_t(t));
         // reassign: base and everything previously re-pointed at base now point at t
         src.reassign = uint32_t(t);
         uint32_t c = child_head[base];
@@ -1246,10 +1269,14 @@ void phase2(dge_handle *h, const std::vector<long> &target)
         {
             uint32_t nx = child_next[c];
             row[c].reassign = uint32_t(t);
+            emit(c, uint32_t(t));
             append(uint32_t(t), c);
             c = nx;
         }
+        if (total >= 0xFFFFFFF0ull) throw std::runtime_error("merge volume exceeds 2^32 entries");
     }
+    h->moves_total = total;
+    h->moves_ready = true;
     for (uint32_t i = 0; i < n; ++i)
     {
         HostCell &c = h->real[i];
@@ -1268,43 +1295,11 @@ void apply_merges(dge_handle *h)
     cudaStream_t st = h->stream;
     Tracer tr;
     tr.st = st;
-    // merge_cells copies the source's CURRENT content, i.e. the source's own UMIs plus everything merged into it earlier
-    // (sequential semantics): keep, per cell, the list of originals absorbed so far (spliced on merge).
-    const size_t n = h->real.size();
-    std::vector<uint32_t> head(n, NONE32), tail(n, NONE32), next(n, NONE32);
+    // the move jobs (source cell -> destination slot, with the sequential merge_cells semantics) were produced by phase2
+    if (!h->moves_ready) throw std::runtime_error("apply_merges without phase 2");
     std::vector<MoveJob> &jobs = h->h_moves;
-    jobs.clear();
-    uint64_t total = 0;
-    struct Row { uint32_t pc, slot, n_umis; };
-    std::vector<Row> row(n); // compact copy of what the loop touches (merge events come in size order = random cell-id order)
-    for (uint32_t i = 0; i < n; ++i) row[i] = Row{h->real[i].pc, h->real[i].slot, uint32_t(h->real[i].n_umis_distinct)};
-    jobs.reserve(h->merge_events.size());
-    auto emit = [&](uint32_t o, uint32_t dst) {
-        const Row &src = row[o];
-        if (src.pc == NONE32 || src.n_umis == 0) return;
-        jobs.push_back(MoveJob{src.pc, row[dst].slot, uint32_t(total)});
-        total += uint64_t(src.n_umis);
-    };
-    for (size_t ei = 0; ei < h->merge_events.size(); ++ei)
-    {
-        const auto &e = h->merge_events[ei];
-        if (ei + 8 < h->merge_events.size())
-        {
-            const auto &ne = h->merge_events[ei + 8];
-            __builtin_prefetch(&row[ne.first]); __builtin_prefetch(&row[ne.second]);
-            __builtin_prefetch(&head[ne.first]); __builtin_prefetch(&head[ne.second]); __builtin_prefetch(&tail[ne.second]);
-        }
-        const uint32_t src = e.first, dst = e.second;
-        emit(src, dst);
-        for (uint32_t o = head[src]; o != NONE32; o = next[o]) emit(o, dst);
-        // absorbed(dst) += [src] + absorbed(src)   (src is frozen from now on: splice its list)
-        next[src] = head[src];
-        const uint32_t last = tail[src] == NONE32 ? src : tail[src];
-        if (head[dst] == NONE32) head[dst] = src; else next[tail[dst]] = src;
-        tail[dst] = last;
-        head[src] = tail[src] = NONE32;
-        if (total >= 0xFFFFFFF0ull) throw std::runtime_error("merge volume exceeds 2^32 entries");
-    }
+    const uint64_t total = h->moves_total;
+    h->moves_ready = false;
     if (jobs.empty()) return;
     tr.mark("  apply: host job list");
     h->d_moves.reserve(jobs.size() * sizeof(MoveJob));

@@ -441,18 +441,30 @@ __global__ void k_rows_permute(const CellRow *__restrict__ rows, const uint32_t 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = rows[perm[i]];
 }
 
-// compare_cells key (CellsDataContainer.cpp:329-344): requested genes : 16 | requested umis : 24 | TOTAL_UMIS stat : 24; the barcode
-// breaks exact ties (host).  *overflow is set when a counter does not fit its field (the host then sorts with full widths).
-__global__ void k_rows_filter_keys(const CellRow *__restrict__ rows, uint32_t n, uint64_t *__restrict__ key, uint32_t *__restrict__ idx,
+// compare_cells (CellsDataContainer.cpp:329-344): ascending (requested genes, requested umis, TOTAL_UMIS stat, barcode).  Two stable
+// radix sorts: first by barcode (k_rows_cb_keys), then by the packed counters genes : 16 | umis : 24 | stat : 24 (k_rows_filter_keys,
+// values = the permutation left by the first sort).  *overflow is set when a counter does not fit its field (the host then sorts
+// with full widths).
+__global__ void k_rows_cb_keys(const CellRow *__restrict__ rows, uint32_t n, uint64_t *__restrict__ key, uint32_t *__restrict__ idx)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { key[i] = rows[i].cb; idx[i] = i; }
+}
+
+__global__ void k_rows_filter_keys(const CellRow *__restrict__ rows, const uint32_t *__restrict__ perm, uint32_t n, uint64_t *__restrict__ key,
                                    int *__restrict__ overflow)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
-        const CellRow r = rows[i];
+        const CellRow r = rows[perm[i]];
         if (r.req_genes >= (1u << 16) || r.req_umis >= (1u << 24) || r.n_umis >= (1u << 24)) *overflow = 1;
         key[i] = (uint64_t(r.req_genes) << 48) | (uint64_t(r.req_umis & 0xFFFFFFu) << 24) | uint64_t(r.n_umis & 0xFFFFFFu);
-        idx[i] = i;
     }
+}
+
+// gene ids that occur, with their first read index as sort key (StringIndexer order, StringIndexer.cpp:10-18)
+__global__ void k_gene_first_keys(const uint32_t *__restrict__ gene_first, uint32_t n_genes, uint64_t *__restrict__ key, uint32_t *__restrict__ idx)
+{
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_genes; g += gridDim.x * blockDim.x) { key[g] = gene_first[g]; idx[g] = g; }
 }
 
 // rows for an explicit list of present cells (after merges)
