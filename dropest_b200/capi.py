@@ -47,6 +47,7 @@ EXPORTS = [
     "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
     "dge_route_by_barcode_device", "dge_dist_export_children", "dge_dist_copy_children", "dge_dist_eval_children", "dge_dist_apply",
+    "dge_dist_apply_device",
     "dge_umi_first_size", "dge_umi_first_export", "dge_umi_first_import", "dge_collisions_adjusted_sizes",
 ]
 
@@ -145,6 +146,7 @@ def load_library():
     lib.dge_dist_copy_children.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
     lib.dge_dist_eval_children.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.dge_dist_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.dge_dist_apply_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.dge_umi_first_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
     lib.dge_umi_first_export.argtypes = [C.c_void_p, C.c_void_p]
     lib.dge_umi_first_import.argtypes = [C.c_void_p, C.c_void_p]
@@ -312,6 +314,10 @@ class Container:
         all_results = np.ascontiguousarray(all_results, dtype=DIST_RESULT_DTYPE)
         child_rank = np.ascontiguousarray(child_rank, dtype=np.uint32)
         self._check(self._lib.dge_dist_apply(self._h, all_results.ctypes.data, world, rank, child_rank.ctypes.data))
+
+    def dist_apply_device(self, all_results_dev_ptr: int, world: int, rank: int, child_rank: np.ndarray):
+        child_rank = np.ascontiguousarray(child_rank, dtype=np.uint32)
+        self._check(self._lib.dge_dist_apply_device(self._h, C.c_void_p(all_results_dev_ptr), world, rank, child_rank.ctypes.data))
 
     def umi_first_size(self) -> int:
         n = C.c_size_t(0)

@@ -2037,11 +2037,10 @@ int dge_dist_eval_children(dge_handle *h, const dge_dist_child *infos_device, ui
         if (h->g_off[n] != n_entries) throw std::runtime_error("children lists do not add up to n_entries");
         if (!n) return int(DGE_OK);
         // local candidates of every child: distance classes 0/1 against THIS rank's cells
-        h->h_cbs.resize(n); h->h_umis.resize(n);
-        for (size_t i = 0; i < n; ++i) { h->h_cbs[i] = h->g_infos[i].barcode; h->h_umis[i] = uint32_t(h->g_infos[i].umis_stat); }
+        static_assert(sizeof(DistChildDev) == sizeof(dge_dist_child) && sizeof(DistResult) == sizeof(dge_dist_result), "ABI structs");
         h->d_cb.reserve(n * 8); h->d_umis.reserve(n * 4); h->d_count.reserve(n * 4); h->d_nb.reserve(n * WL_K * 4);
-        DGE_CUDA(cudaMemcpyAsync(h->d_cb.p, h->h_cbs.data(), n * 8, cudaMemcpyHostToDevice, st));
-        DGE_CUDA(cudaMemcpyAsync(h->d_umis.p, h->h_umis.data(), n * 4, cudaMemcpyHostToDevice, st));
+        k_dist_child_columns<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const DistChildDev *>(infos_device), n, h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>());
+        ++h->launches;
         k_wl_class01<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>(), uint32_t(n), h->wl_dev,
                                                                             h->tab.as<CellSlot>(), h->kl.tb, h->slot_pc.as<uint32_t>(),
                                                                             h->pc_cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(),
@@ -2099,10 +2098,58 @@ int dge_dist_eval_children(dge_handle *h, const dge_dist_child *infos_device, ui
     });
 }
 
+// `red[c]` = the candidates of child c combined over all ranks (k_dist_reduce, or the host loop of dge_dist_apply)
+static int dist_apply_reduced(dge_handle *h, const dge_dist_result *red, uint32_t my_rank, const uint32_t *child_rank);
+
 int dge_dist_apply(dge_handle *h, const dge_dist_result *all, uint32_t world, uint32_t my_rank, const uint32_t *child_rank)
 {
     if (!h || world == 0 || (!h->g_infos.empty() && (!all || !child_rank))) return fail(h, DGE_ERR_INVALID, "null argument");
     return guarded(h, [&] {
+        const size_t n = h->g_infos.size();
+        std::vector<dge_dist_result> red(n);
+        for (size_t c = 0; c < n; ++c)
+        {
+            uint32_t n_nb = 0, n_best = 0;
+            double best = 0;
+            uint64_t best_cb = EMPTY64;
+            for (uint32_t r = 0; r < world; ++r)
+            {
+                const dge_dist_result &res = all[size_t(r) * n + c];
+                if (!res.n_neighbours) continue;
+                n_nb += res.n_neighbours;
+                if (n_best == 0 || best < res.best_fraction) { best = res.best_fraction; best_cb = res.best_barcode; n_best = res.n_best; }
+                else if (res.best_fraction == best) { n_best += res.n_best; best_cb = std::min(best_cb, res.best_barcode); }
+            }
+            red[c].best_fraction = best; red[c].best_barcode = best_cb; red[c].n_neighbours = n_nb; red[c].n_best = n_best;
+        }
+        return dist_apply_reduced(h, red.data(), my_rank, child_rank);
+    });
+}
+
+int dge_dist_apply_device(dge_handle *h, const dge_dist_result *all_device, uint32_t world, uint32_t my_rank, const uint32_t *child_rank)
+{
+    if (!h || world == 0 || (!h->g_infos.empty() && (!all_device || !child_rank))) return fail(h, DGE_ERR_INVALID, "null argument");
+    return guarded(h, [&] {
+        DGE_CUDA(cudaSetDevice(h->cfg.device));
+        cudaStream_t st = h->stream;
+        const size_t n = h->g_infos.size();
+        const dge_dist_result *red = nullptr;
+        if (n)
+        {   // the combination over ranks runs on the device: O(children) comes back instead of O(children x ranks)
+            h->dist_jobs.reserve(n * sizeof(dge_dist_result));
+            k_dist_reduce<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const DistResult *>(all_device), world, n, h->dist_jobs.as<DistResult>());
+            DGE_LAUNCH_CHECK();
+            ++h->launches;
+            red = d2h_pinned<dge_dist_result>(h->pin_isect, h->dist_jobs.p, n, st);
+            DGE_CUDA(cudaStreamSynchronize(st));
+        }
+        return dist_apply_reduced(h, red, my_rank, child_rank);
+    });
+}
+
+static int dist_apply_reduced(dge_handle *h, const dge_dist_result *red, uint32_t my_rank, const uint32_t *child_rank)
+{
+    {
         dist_check(h);
         DGE_CUDA(cudaSetDevice(h->cfg.device));
         cudaStream_t st = h->stream;
@@ -2115,17 +2162,9 @@ int dge_dist_apply(dge_handle *h, const dge_dist_result *all, uint32_t world, ui
         {
             const dge_dist_child &ci = h->g_infos[c];
             const bool mine = child_rank[c] == my_rank;
-            uint32_t n_nb = 0, n_best = 0;
-            double best = 0;
-            uint64_t best_cb = EMPTY64;
-            for (uint32_t r = 0; r < world; ++r)
-            {
-                const dge_dist_result &res = all[size_t(r) * n + c];
-                if (!res.n_neighbours) continue;
-                n_nb += res.n_neighbours;
-                if (n_best == 0 || best < res.best_fraction) { best = res.best_fraction; best_cb = res.best_barcode; n_best = res.n_best; }
-                else if (res.best_fraction == best) { n_best += res.n_best; best_cb = std::min(best_cb, res.best_barcode); }
-            }
+            const uint32_t n_nb = red[c].n_neighbours, n_best = red[c].n_best;
+            const double best = red[c].best_fraction;
+            const uint64_t best_cb = red[c].best_barcode;
             if (n_nb == 0)
             {   // no class-0/1 candidate anywhere: the fall-through to farther classes is not distributed yet
                 if (mine) ++h->n_unresolved;
@@ -2168,7 +2207,7 @@ int dge_dist_apply(dge_handle *h, const dge_dist_result *all, uint32_t world, ui
         for (uint32_t i = 0; i < h->real.size(); ++i) if (h->real[i].merged_to_cb == EMPTY64) h->real[i].target = int32_t(i);
         h->dist_done = true;
         return int(DGE_OK);
-    });
+    }
 }
 
 int dge_umi_first_size(dge_handle *h, size_t *n_entries)

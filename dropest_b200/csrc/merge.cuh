@@ -269,6 +269,42 @@ __global__ void k_p1_best(const int *__restrict__ nb_count, const uint32_t *__re
     }
 }
 
+// ---- sharded runs: combine the per-rank candidates of every child (dge_dist_apply) --------------------------------------------
+struct DistResult { double best_fraction; unsigned long long best_barcode; uint32_t n_neighbours, n_best; }; // = dge_dist_result
+
+// all[r * n + c] = rank r's best local candidate of child c  ->  red[c] = the combination over ranks in rank order, with the rule of
+// RealBarcodesMergeStrategy::get_best_merge_target (strict < keeps the first maximum; exact ties add up and keep the smallest barcode)
+__global__ void k_dist_reduce(const DistResult *__restrict__ all, uint32_t world, size_t n, DistResult *__restrict__ red)
+{
+    for (size_t c = size_t(blockIdx.x) * blockDim.x + threadIdx.x; c < n; c += size_t(gridDim.x) * blockDim.x)
+    {
+        uint32_t n_nb = 0, n_best = 0;
+        double best = 0;
+        unsigned long long best_cb = EMPTY64;
+        for (uint32_t r = 0; r < world; ++r)
+        {
+            const DistResult res = all[size_t(r) * n + c];
+            if (!res.n_neighbours) continue;
+            n_nb += res.n_neighbours;
+            if (n_best == 0 || best < res.best_fraction) { best = res.best_fraction; best_cb = res.best_barcode; n_best = res.n_best; }
+            else if (res.best_fraction == best) { n_best += res.n_best; best_cb = min(best_cb, res.best_barcode); }
+        }
+        DistResult o;
+        o.best_fraction = best; o.best_barcode = best_cb; o.n_neighbours = n_nb; o.n_best = n_best;
+        red[c] = o;
+    }
+}
+
+// candidate columns of the gathered children straight from their device-resident summaries
+struct DistChildDev { unsigned long long barcode; int32_t umis_stat, reads_stat, n_genes; uint32_t n_intergenic, n_entries, local_index; }; // = dge_dist_child
+__global__ void k_dist_child_columns(const DistChildDev *__restrict__ infos, size_t n, uint64_t *__restrict__ cb, uint32_t *__restrict__ umis)
+{
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    {
+        cb[i] = infos[i].barcode; umis[i] = uint32_t(infos[i].umis_stat);
+    }
+}
+
 // ---- applying merges -------------------------------------------------------------------------------------------------
 struct MoveJob { uint32_t src_pc, dst_slot, out_off; };   // out_off = exclusive prefix of the source sizes
 

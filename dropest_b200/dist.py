@@ -128,9 +128,9 @@ def merge_across_ranks(cont, device: str, group=None):
     res_t = torch.from_numpy(local.view(np.uint8)).to(device)
     all_r = torch.empty(world * res_t.numel(), dtype=torch.uint8, device=device)
     dist.all_gather_into_tensor(all_r, res_t, group=group)    # per-rank best candidate of every child
-    all_results = all_r.cpu().numpy().view(DIST_RESULT_DTYPE)
     child_rank = np.repeat(np.arange(world, dtype=np.uint32), ncs.astype(np.int64))
     mark("all-gather results")
-    cont.dist_apply(all_results, world, rank, child_rank)     # g_k / g_v stay alive until here
+    torch.cuda.current_stream().synchronize()
+    cont.dist_apply_device(all_r.data_ptr(), world, rank, child_rank)   # combination over ranks on the device; g_k / g_v stay alive until here
     mark("apply")
     return {"children": tot_nc, "entries": tot_ne}

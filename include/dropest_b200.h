@@ -312,6 +312,10 @@ int dge_dist_eval_children(dge_handle *h, const dge_dist_child *infos_device, ui
                            const uint32_t *vals_device, uint64_t n_entries, dge_dist_result *results_host);
 int dge_dist_apply(dge_handle *h, const dge_dist_result *all_results_host, uint32_t world, uint32_t my_rank,
                    const uint32_t *child_rank_host);
+/* Same, with the all-gathered results still in DEVICE memory: the combination over ranks runs in a kernel and only one
+ * combined row per child is read back (O(children) instead of O(children x ranks) on the host). */
+int dge_dist_apply_device(dge_handle *h, const dge_dist_result *all_results_device, uint32_t world, uint32_t my_rank,
+                          const uint32_t *child_rank);
 
 /* Sharded runs with a strategy that depends on the UMI indexer's first-seen order (directional UMI merge): every rank tracks
  * min(read_idx) per packed UMI over ITS reads; the reference's StringIndexer is global, so the tables have to be min-reduced
