@@ -24,6 +24,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 #include <map>
 #include <memory>
@@ -132,7 +133,7 @@ struct dge_handle
     DevBuf umi_lists, umi_ctr, umi_pc_dec, umi_seg, umi_flat, umi_pairs;
     PinnedBuf pin_umi;
     uint64_t n_umis_merged = 0, n_umi_segments_replayed = 0;
-    DevBuf dist_infos, dist_keys, dist_vals, dist_jobs;
+    DevBuf dist_infos, dist_keys, dist_vals, dist_jobs, dist_cb, dist_umis, dist_eoff;
     std::vector<dge_dist_child> g_infos;
     std::vector<uint32_t> g_off;
     const uint64_t *g_keys = nullptr;
@@ -2047,6 +2048,43 @@ int dge_dist_eval_children(dge_handle *h, const dge_dist_child *infos_device, ui
                                                                             h->cfg.min_genes_before_merge, h->d_count.as<int>(), h->d_nb.as<uint32_t>());
         DGE_LAUNCH_CHECK();
         ++h->launches;
+        if (h->rows_on_device)
+        {   // jobs, intersections and the best local candidate per child in kernels; one result row per child comes back
+            const size_t nl = h->real.size();
+            const DistChildDev *infos = reinterpret_cast<const DistChildDev *>(infos_device);
+            h->dist_cb.reserve(std::max<size_t>(nl, 1) * 8); h->dist_umis.reserve(std::max<size_t>(nl, 1) * 4);
+            h->p1_pc.reserve(std::max<size_t>(nl, 1) * 4); h->p1_map.reserve((size_t(h->n_pc) + 2) * 4);
+            k_fill_u32<<<grid_for(size_t(h->n_pc) + 1, 256), 256, 0, st>>>(h->p1_map.as<uint32_t>(), size_t(h->n_pc) + 1, NONE32);
+            if (nl)
+                k_p1_columns<<<grid_for(nl, 256), 256, 0, st>>>(h->rows_dev2.as<CellRow>(), uint32_t(nl), h->dist_cb.as<uint64_t>(), h->dist_umis.as<uint32_t>(),
+                                                               h->p1_pc.as<uint32_t>(), h->p1_map.as<uint32_t>());
+            h->p1_cnt.reserve((n + 1) * 4); h->p1_off.reserve((n + 1) * 4); h->dist_eoff.reserve((n + 1) * 4);
+            k_dist_entry_counts<<<grid_for(n, 256), 256, 0, st>>>(infos, n, h->p1_cnt.as<uint32_t>());
+            DGE_CUDA(cudaMemsetAsync(h->p1_cnt.as<uint32_t>() + n, 0, 4, st));
+            device_exclusive_scan(h->p1_cnt.as<uint32_t>(), h->dist_eoff.as<uint32_t>(), n + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+            k_p1_counts<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), uint32_t(n), h->p1_cnt.as<uint32_t>());
+            DGE_CUDA(cudaMemsetAsync(h->p1_cnt.as<uint32_t>() + n, 0, 4, st));
+            device_exclusive_scan(h->p1_cnt.as<uint32_t>(), h->p1_off.as<uint32_t>(), n + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+            const uint32_t n_jobs = d2h_scalar<uint32_t>(h->p1_off.as<uint32_t>() + n, st);
+            h->d_jobs.reserve(std::max<size_t>(n_jobs, 1) * sizeof(ForeignJob)); h->d_isect.reserve(std::max<size_t>(n_jobs, 1) * 4);
+            k_dist_jobs<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), h->d_nb.as<uint32_t>(), infos, h->dist_eoff.as<uint32_t>(), h->p1_off.as<uint32_t>(), n,
+                                                          h->d_jobs.as<ForeignJob>());
+            if (n_jobs)
+                k_intersect_foreign<<<n_jobs, 128, 0, st>>>(h->d_jobs.as<ForeignJob>(), n_jobs, keys_device, h->ukey.as<uint64_t>(), h->pc_u_start.as<uint32_t>(),
+                                                            h->pc_slot.as<uint32_t>(), h->kl.gb + h->kl.ub, h->d_isect.as<uint32_t>());
+            h->dist_jobs.reserve(n * sizeof(DistResult)); h->p1_target.reserve(n * 4);
+            k_dist_best<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), h->d_nb.as<uint32_t>(), h->p1_off.as<uint32_t>(), h->d_isect.as<uint32_t>(), infos,
+                                                          h->p1_map.as<uint32_t>(), h->dist_cb.as<uint64_t>(), h->dist_umis.as<uint32_t>(), n,
+                                                          h->dist_jobs.as<DistResult>(), h->p1_target.as<uint32_t>());
+            DGE_LAUNCH_CHECK();
+            h->launches += 7;
+            const dge_dist_result *pr = d2h_pinned<dge_dist_result>(h->pin_isect, h->dist_jobs.p, n, st);
+            const uint32_t *pb = d2h_pinned<uint32_t>(h->pin_nbc, h->p1_target.p, n, st);
+            DGE_CUDA(cudaStreamSynchronize(st));
+            std::memcpy(results_host, pr, n * sizeof(dge_dist_result));
+            h->g_best_local.assign(pb, pb + n);
+            return int(DGE_OK);
+        }
         const int *nb_count = d2h_pinned<int>(h->pin_nbc, h->d_count.p, n, st);
         const uint32_t *nb_pc = d2h_pinned<uint32_t>(h->pin_nbp, h->d_nb.p, n * WL_K, st);
         DGE_CUDA(cudaStreamSynchronize(st));

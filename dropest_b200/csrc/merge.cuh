@@ -305,6 +305,53 @@ __global__ void k_dist_child_columns(const DistChildDev *__restrict__ infos, siz
     }
 }
 
+// ---- sharded runs: candidates of the gathered children against THIS rank's cells, without the host (dge_dist_eval_children) ---------
+__global__ void k_dist_entry_counts(const DistChildDev *__restrict__ infos, size_t n, uint32_t *__restrict__ cnt)
+{
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) cnt[i] = infos[i].n_entries;
+}
+
+__global__ void k_dist_jobs(const int *__restrict__ nb_count, const uint32_t *__restrict__ nb_pc, const DistChildDev *__restrict__ infos,
+                            const uint32_t *__restrict__ entry_off, const uint32_t *__restrict__ job_off, size_t n, ForeignJob *__restrict__ jobs)
+{
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    {
+        const int c = nb_count[i];
+        for (int k = 0; k < c; ++k) jobs[job_off[i] + k] = ForeignJob{entry_off[i], infos[i].n_entries, nb_pc[i * WL_K + size_t(k)]};
+    }
+}
+
+// best local candidate of every child: largest 0.5 * I * (1/U_child + 1/U_nb) (RealBarcodesMergeStrategy.cpp:46-47, same operation order),
+// exact ties counted and resolved towards the smallest barcode (the combination over ranks applies the same rule)
+__global__ void k_dist_best(const int *__restrict__ nb_count, const uint32_t *__restrict__ nb_pc, const uint32_t *__restrict__ job_off,
+                            const uint32_t *__restrict__ isect, const DistChildDev *__restrict__ infos, const uint32_t *__restrict__ pc_to_real,
+                            const uint64_t *__restrict__ local_cb, const uint32_t *__restrict__ local_umis, size_t n,
+                            DistResult *__restrict__ res, uint32_t *__restrict__ best_local)
+{
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    {
+        const int c = nb_count[i] > 0 ? nb_count[i] : 0;
+        DistResult r;
+        r.best_fraction = 0; r.best_barcode = EMPTY64; r.n_neighbours = uint32_t(c); r.n_best = 0;
+        uint32_t bl = NONE32;
+        const double inv_child = __ddiv_rn(1., double(size_t(infos[i].umis_stat)));
+        for (int k = 0; k < c; ++k)
+        {
+            const uint32_t nb = pc_to_real[nb_pc[i * WL_K + size_t(k)]];
+            const double frac = __dmul_rn(__dmul_rn(0.5, double(isect[job_off[i] + k])), __dadd_rn(inv_child, __ddiv_rn(1., double(local_umis[nb]))));
+            const unsigned long long cb = local_cb[nb];
+            if (r.n_best == 0 || r.best_fraction < frac) { r.best_fraction = frac; r.best_barcode = cb; r.n_best = 1; bl = nb; }
+            else if (frac == r.best_fraction)
+            {
+                ++r.n_best;
+                if (cb < r.best_barcode) { r.best_barcode = cb; bl = nb; }
+            }
+        }
+        res[i] = r;
+        best_local[i] = bl;
+    }
+}
+
 // ---- applying merges -------------------------------------------------------------------------------------------------
 struct MoveJob { uint32_t src_pc, dst_slot, out_off; };   // out_off = exclusive prefix of the source sizes
 
