@@ -50,7 +50,7 @@ def measured_traffic():
     `ncu --set full` captures summarised in profiles/ (file written by tools/traffic_from_ncu.py); {} when absent."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return {k: v["dram_bytes_per_launch"] for k, v in json.load(f).items()}
+            return {k: v["dram_bytes_per_launch"] for k, v in json.load(f).items() if isinstance(v, dict)}
     except Exception:
         return {}
 
