@@ -1002,13 +1002,15 @@ public:
                 const uint32_t cw = warp_class && ms_items == 16 ? 32u * 16u : 0u; // sub-buckets of <= 512 keys: one warp each
                 k_classify_sub<<<148 * 4, 256, 0, st>>>(sub_off, n_sub_ptr, cw, c0, c1, c2, cc, cl, ls);
                 auto grid = [&](int threads, int dflt) { return unsigned(148 * (ms_bps > 0 ? std::max(1, ms_bps * 64 / threads) : dflt)); };
-                static const bool la = std::getenv("DGE_MS_NO_LOOKAHEAD") == nullptr;
+                // merge-step formulation: 0 = one element of look-ahead per side, 1 = predicated without look-ahead (default: fewest
+                // ALU instructions among the proven ones; the sort is ALU-pipe bound), 2 = 1 + sentinel slot instead of a predicated load
+                static const int mv = std::getenv("DGE_MS_VARIANT") ? atoi(std::getenv("DGE_MS_VARIANT")) : 1;
                 if (cw) k_sort_dedup_warp<4, 16><<<grid(128, 6), 128, 0, st>>>(keys_tmp, uv, sub_off, cl, cc, ucount);
-#define DGE_MS(T, I, LA, C, DFLT) k_sort_dedup<T, I, LA><<<grid(T, DFLT), T, 0, st>>>(keys_tmp, uv, sub_off, cl + (C + 1) * ls, cc + (C + 1), ucount)
-                if (ms_items == 16 && la) { DGE_MS(64, 16, true, 0, 12); DGE_MS(128, 16, true, 1, 6); DGE_MS(256, 16, true, 2, 3); }
-                else if (ms_items == 16) { DGE_MS(64, 16, false, 0, 12); DGE_MS(128, 16, false, 1, 6); DGE_MS(256, 16, false, 2, 3); }
-                else if (la) { DGE_MS(64, 8, true, 0, 24); DGE_MS(128, 8, true, 1, 12); DGE_MS(256, 8, true, 2, 6); }
-                else { DGE_MS(64, 8, false, 0, 24); DGE_MS(128, 8, false, 1, 12); DGE_MS(256, 8, false, 2, 6); }
+#define DGE_MS(T, I, V, C, DFLT) k_sort_dedup<T, I, V><<<grid(T, DFLT), T, 0, st>>>(keys_tmp, uv, sub_off, cl + (C + 1) * ls, cc + (C + 1), ucount)
+                if (ms_items == 16 && mv == 0) { DGE_MS(64, 16, 0, 0, 12); DGE_MS(128, 16, 0, 1, 6); DGE_MS(256, 16, 0, 2, 3); }
+                else if (ms_items == 16 && mv == 2) { DGE_MS(64, 16, 2, 0, 12); DGE_MS(128, 16, 2, 1, 6); DGE_MS(256, 16, 2, 2, 3); }
+                else if (ms_items == 16) { DGE_MS(64, 16, 1, 0, 12); DGE_MS(128, 16, 1, 1, 6); DGE_MS(256, 16, 1, 2, 3); }
+                else { DGE_MS(64, 8, 1, 0, 24); DGE_MS(128, 8, 1, 1, 12); DGE_MS(256, 8, 1, 2, 6); }
 #undef DGE_MS
                 L += 5;
                 const int thr = sc_tuning().dedup_threads;

@@ -68,7 +68,7 @@ template <int N> __device__ __forceinline__ void ms_thread_sort(uint64_t (&k)[N]
 
 // Work item = one sub-bucket from `list`: keys[s..e) -> distinct ukeys ascending, IN PLACE at keys[s..s+m), values
 // (count | mark<<29) at uvals[s..s+m), ucount[sb] = m.  Persistent blocks stride over the list; sizes must be <= THREADS*ITEMS.
-template <int THREADS, int ITEMS, bool LOOKAHEAD>
+template <int THREADS, int ITEMS, int MERGE>
 __global__ void __launch_bounds__(THREADS, MS_WARPS_PER_SM * 32 / THREADS) k_sort_dedup(uint64_t *__restrict__ keys, uint32_t *__restrict__ uvals,
                                                         const uint32_t *__restrict__ sub_off, const uint32_t *__restrict__ list,
                                                         const uint32_t *__restrict__ list_count, uint32_t *__restrict__ ucount)
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(THREADS, MS_WARPS_PER_SM * 32 / THREADS) k_sor
     const int p0 = t * ITEMS;
     const int row = ms_phys<ITEMS>(p0); // the ITEMS elements of a thread are contiguous in shared memory
     const uint32_t n_items = *list_count;
+    if (t == 0) sk[CAP + CAP / ITEMS] = EMPTY64; // sentinel slot (never overwritten: element indices stop one word short of it)
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x)
     {
         const uint32_t sb = list[item];
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(THREADS, MS_WARPS_PER_SM * 32 / THREADS) k_sor
             int ai = lo, bi = diag - lo;
             auto ld_a = [&](int i) { return i < a_cnt ? sk[ms_phys<ITEMS>(a_beg + i)] : EMPTY64; };
             auto ld_b = [&](int i) { return i < b_cnt ? sk[ms_phys<ITEMS>(b_beg + i)] : EMPTY64; };
-            if (LOOKAHEAD)
+            if (MERGE == 0)
             {   // one element of look-ahead per side: the load issued in a step is consumed a step later
                 uint64_t a0 = ld_a(ai), a1 = ld_a(ai + 1), b0 = ld_b(bi), b1 = ld_b(bi + 1);
 #pragma unroll
@@ -139,15 +140,38 @@ __global__ void __launch_bounds__(THREADS, MS_WARPS_PER_SM * 32 / THREADS) k_sor
                     b0 = ta ? b0 : b1; b1 = ta ? b1 : v;
                 }
             }
-            else
-            {
-                uint64_t ka = ld_a(ai), kb = ld_b(bi);
+            else if (MERGE == 1)
+            {   // no look-ahead, fully predicated: fewer ALU instructions per merged key, one dependent shared-memory load per step
+                int ia = a_beg + ai, ib = b_beg + bi;
+                const int ea = a_beg + a_cnt, eb = b_beg + b_cnt;
+                uint64_t ka = ia < ea ? sk[ms_phys<ITEMS>(ia)] : EMPTY64, kb = ib < eb ? sk[ms_phys<ITEMS>(ib)] : EMPTY64;
 #pragma unroll
                 for (int j = 0; j < ITEMS; ++j)
                 {
                     const bool ta = ka <= kb;
                     k[j] = ta ? ka : kb;
-                    if (ta) { ++ai; ka = ld_a(ai); } else { ++bi; kb = ld_b(bi); }
+                    ia += ta ? 1 : 0; ib += ta ? 0 : 1;
+                    const int idx = ta ? ia : ib;
+                    const uint64_t v = idx < (ta ? ea : eb) ? sk[ms_phys<ITEMS>(idx)] : EMPTY64;
+                    if (ta) ka = v; else kb = v;
+                }
+            }
+            else
+            {   // as MERGE == 1, but an exhausted side reads a sentinel slot (the spare last word of the buffer, kept at EMPTY64)
+                // instead of predicating the load: address select, no default moves
+                constexpr int SENT = CAP + CAP / ITEMS;
+                int ia = a_beg + ai, ib = b_beg + bi;
+                const int ea = a_beg + a_cnt, eb = b_beg + b_cnt;
+                uint64_t ka = sk[ia < ea ? ms_phys<ITEMS>(ia) : SENT], kb = sk[ib < eb ? ms_phys<ITEMS>(ib) : SENT];
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j)
+                {
+                    const bool ta = ka <= kb;
+                    k[j] = ta ? ka : kb;
+                    ia += ta ? 1 : 0; ib += ta ? 0 : 1;
+                    const int idx = ta ? ia : ib;
+                    const uint64_t v = sk[idx < (ta ? ea : eb) ? ms_phys<ITEMS>(idx) : SENT];
+                    if (ta) ka = v; else kb = v;
                 }
             }
         }
