@@ -419,6 +419,171 @@ static long target_all(const Container &c, size_t base)
 	return target != std::numeric_limits<size_t>::max() ? long(target) : long(base);
 }
 
+// ---- the -M strategies: PoissonTargetEstimator.cpp:14-119, PoissonRealBarcodesMergeStrategy.cpp:20-51, PoissonSimpleMergeStrategy.cpp:15-42,
+// CellsDataContainer::umi_distribution (CellsDataContainer.cpp:182-197), Tools::CollisionsAdjuster (CollisionsAdjuster.cpp:12-49),
+// Tools::fpow (UtilFunctions.cpp:13-30).  ppois is R's (absent here): the same restatement as oracle/shim/RInside.h, so that port and
+// compiled reference agree bit for bit; it feeds a threshold compare only (third-party arithmetic, unpinned by the reference).
+static double fpow(double base, long exp)
+{
+	if (exp == 1) return base;
+	double result = 1;
+	while (exp)
+	{
+		if (exp & 1) result *= base;
+		exp >>= 1;
+		base *= base;
+	}
+	return result;
+}
+
+namespace ppois_restated
+{
+	static double log_pmf(long k, double lambda) { return -lambda + k * std::log(lambda) - std::lgamma(double(k) + 1.0); }
+	static double lower(long x, double lambda)
+	{
+		if (x < 0) return 0;
+		if (lambda <= 0) return 1;
+		double s = 0;
+		for (long k = x; k >= 0; --k)
+		{
+			double t = std::exp(log_pmf(k, lambda));
+			s += t;
+			if (double(k) < lambda && t < s * 1e-17) break;
+		}
+		return s > 1 ? 1 : s;
+	}
+	static double upper(long x, double lambda) // P[X > x]
+	{
+		if (x < 0) return 1;
+		if (lambda <= 0) return 0;
+		if (double(x + 1) < lambda) return 1 - lower(x, lambda);
+		double s = 0;
+		for (long k = x + 1;; ++k)
+		{
+			double t = std::exp(log_pmf(k, lambda));
+			s += t;
+			if (t <= s * 1e-17 || k > x + 100000) break;
+		}
+		return s > 1 ? 1 : s;
+	}
+}
+
+struct PoissonEstimator
+{
+	double max_merge_prob, max_real_cb_merge_prob;
+	std::vector<double> umi_dist, neg_prod;       // _umi_distribution; CollisionsAdjuster::_umi_probabilities_neg_prod
+	std::vector<size_t> adjusted;                 // CollisionsAdjuster::_adjusted_sizes
+	double sum_collisions = 0;
+	size_t last_total = 0;
+	std::map<std::pair<size_t, size_t>, double> memo; // _estimated_gene_intersections (a cache: its container type cannot change a value)
+
+	void init(const Container &c) // PoissonTargetEstimator::init over CellsDataContainer::umi_distribution()
+	{
+		std::unordered_map<std::string, size_t> dist; // s_ul_hash_t: its iteration order fixes the order of the probability vector
+		for (size_t cell_id : c.filtered)
+			for (auto const &g : c.cells[cell_id].genes)
+				for (auto const &u : g.second) dist[c.umi_idx.values[u.first]]++;
+		double sum = 0;
+		for (auto const &it : dist) sum += it.second;
+		for (auto const &it : dist) umi_dist.push_back(it.second / sum);
+		neg_prod.assign(umi_dist.size(), 1);
+	}
+
+	size_t adjust(size_t expression) // CollisionsAdjuster::estimate_adjusted_gene_expression + update_adjusted_sizes
+	{
+		for (size_t s = adjusted.size() + 1; s <= expression; ++s)
+		{
+			const size_t total = s + size_t(sum_collisions);
+			double new_umi_prob = 0;
+			for (size_t i = 0; i < umi_dist.size(); ++i)
+			{
+				neg_prod[i] *= fpow(1 - umi_dist[i], long(total - last_total));
+				new_umi_prob += umi_dist[i] * (1 - neg_prod[i]);
+			}
+			last_total = total;
+			const double collision_num = 1.0 / (1.0 - new_umi_prob) - 1.0;
+			sum_collisions += collision_num;
+			adjusted.push_back(size_t(std::lround(s + sum_collisions)));
+		}
+		return adjusted.at(expression - 1);
+	}
+
+	double genes_intersection(size_t g1, size_t g2) // estimate_genes_intersection_size, PoissonTargetEstimator.cpp:92-119
+	{
+		if (g1 > g2) std::swap(g1, g2);
+		g1 = adjust(g1);
+		g2 = adjust(g2);
+		auto key = std::make_pair(g1, g2);
+		auto it = memo.find(key);
+		if (it != memo.end()) return it->second;
+		const size_t d = g2 - g1;
+		double est = 0;
+		for (size_t i = 0; i < umi_dist.size(); ++i)
+		{
+			const double min_prob = fpow(1 - umi_dist[i], long(g1));
+			const double max_prob = min_prob * fpow(1 - umi_dist[i], long(d));
+			est += (1 - min_prob) * (1 - max_prob);
+		}
+		memo.emplace(key, est);
+		return est;
+	}
+
+	double merge_probability(const Container &c, size_t a, size_t b) // estimate_intersection_prob, :66-90
+	{
+		const Cell &c1 = c.cells[a], &c2 = c.cells[b];
+		const size_t isz = Container::intersect(c1, c2);
+		if (isz == 0) return 1;
+		double expected = 0;
+		for (auto const &g1 : c1.genes)
+		{
+			auto g2 = c2.genes.find(g1.first);
+			if (g2 == c2.genes.end()) continue;
+			expected += genes_intersection(g1.second.size(), g2->second.size());
+		}
+		return ppois_restated::upper(long(isz) - 1, expected);
+	}
+
+	long best_target(const Container &c, size_t base, const std::vector<size_t> &nb) // get_best_merge_target, :14-44
+	{
+		const bool base_is_real = base == nb.at(0);
+		double thr = base_is_real ? max_merge_prob : max_real_cb_merge_prob;
+		thr /= nb.size();
+		long best = -1;
+		double min_prob = 2;
+		for (size_t n : nb)
+		{
+			if (n == base) continue;
+			const double prob = merge_probability(c, base, n);
+			if (prob < min_prob) { min_prob = prob; best = long(n); }
+		}
+		if (min_prob > thr) return base_is_real ? long(base) : -1;
+		return best;
+	}
+};
+
+// PoissonRealBarcodesMergeStrategy: RealBarcodesMergeStrategy::get_merge_target (:22-29) with the Poisson best-target rule
+static long target_poisson_real(const Container &c, const Whitelist &wl, PoissonEstimator &est, size_t base)
+{
+	std::vector<size_t> nb = real_neighbours(c, wl, base, true);
+	if (nb.empty()) return -1;
+	return est.best_target(c, base, nb);
+}
+
+// PoissonSimpleMergeStrategy::get_merge_target, PoissonSimpleMergeStrategy.cpp:15-42
+static long target_poisson_simple(const Container &c, const umig_index_t &idx, PoissonEstimator &est, size_t base)
+{
+	auto cand = common_umigs(c, idx, base);
+	std::vector<size_t> nb;
+	for (auto const &kv : cand)
+	{
+		if (edit_distance(c.cells[base].barcode, c.cells[kv.first].barcode) > c.p.max_cb_ed) continue;
+		nb.push_back(kv.first);
+	}
+	if (nb.empty()) return long(base);
+	const long t = est.best_target(c, base, nb);
+	return t != -1 ? t : long(base);
+}
+
 // MergeStrategyBase::merge_inited + reassign, MergeStrategyBase.cpp:11-82
 static void merge_cells_stage(Container &c, const Whitelist &wl)
 {
@@ -427,13 +592,17 @@ static void merge_cells_stage(Container &c, const Whitelist &wl)
 	std::iota(c.merge_targets.begin(), c.merge_targets.end(), 0);
 	if (c.p.merge == "none") return; // DummyMergeStrategy.h:12-17
 	umig_index_t idx;
-	if (c.p.merge == "simple") idx = build_umig_index(c);
+	if (c.p.merge == "simple" || c.p.merge == "poisson_simple") idx = build_umig_index(c);
+	PoissonEstimator est{c.p.max_merge_prob, c.p.max_real_merge_prob};
+	if (c.p.merge == "poisson_simple" || c.p.merge == "poisson_real") est.init(c);
 	std::vector<long> targets(c.filtered.size());
 	for (size_t k = 0; k < c.filtered.size(); ++k)
 	{
 		if (c.p.merge == "real") targets[k] = target_real(c, wl, c.filtered[k]);
 		else if (c.p.merge == "simple") targets[k] = target_simple(c, idx, c.filtered[k]);
 		else if (c.p.merge == "all") targets[k] = target_all(c, c.filtered[k]);
+		else if (c.p.merge == "poisson_real") targets[k] = target_poisson_real(c, wl, est, c.filtered[k]);
+		else if (c.p.merge == "poisson_simple") targets[k] = target_poisson_simple(c, idx, est, c.filtered[k]);
 		else throw std::runtime_error("merge type not restated in oracle/port: " + c.p.merge);
 	}
 	std::unordered_map<size_t, std::unordered_set<size_t>> moved_to;

@@ -35,6 +35,9 @@ def cases():
         "real_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="real", seed=11),
         "none_7x9": pu.small_case(n_reads=20000, n_cells=25, n_genes=60, merge="none", seed=12),
         "simple_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="simple", seed=14),
+        # -M strategies: the oracle port is pinned against these; the CUDA path does not implement them yet
+        "poisson_simple_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="poisson_simple", seed=15),
+        "poisson_real_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="poisson_real", seed=16),
         "real_8x8_reads": pu.Case(name="real_8x8_reads",
                                   spec=SynthSpec(n_reads=25000, n_cells=20, n_genes=70, cb_len=16, umi_len=6, whitelist_parts=wl8,
                                                  cb_error_ppm=80000, seed=13),
