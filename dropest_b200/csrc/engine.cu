@@ -1873,6 +1873,8 @@ static void add_host_slices(dge_handle *h, const dge_record16 *recs, const unsig
         }
         DGE_CUDA(cudaEventRecord(h->staging_ev[turn], h->stream));
     }
+    // the caller owns the host arrays again when the call returns: wait for the last H2D copy (not for the fill kernels)
+    DGE_CUDA(cudaStreamSynchronize(h->copy_stream));
 }
 
 int dge_add_batch(dge_handle *h, const dge_record16 *recs, size_t n)
@@ -1898,7 +1900,7 @@ int dge_reset(dge_handle *h)
         if (h->stream) DGE_CUDA(cudaStreamSynchronize(h->stream));
         for (auto &c : h->chunks) h->chunk_pool.push_back(std::move(c));
         h->chunks.clear();
-        h->n_chunk_counters = 0; h->n_fill_ev = 0; h->n_reads = 0; h->n_keys = 0; h->n_u = h->n_cg = h->n_pc = 0;
+        h->n_chunk_counters = 0; h->n_fill_ev = 0; h->moves_ready = false; h->n_reads = 0; h->n_keys = 0; h->n_u = h->n_cg = h->n_pc = 0;
         h->real.clear(); h->filtered.clear(); h->gene_order.clear(); h->merge_events.clear();
         h->n_merged = h->n_excluded = h->n_unresolved = 0; h->total_cells = 0;
         h->cm.built = h->cm_raw.built = false;

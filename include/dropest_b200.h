@@ -174,7 +174,8 @@ const char *dge_last_error(const dge_handle *h);
  * dge_add_batch_soa    : HOST memory, structure of arrays: keys[i] = dge_record16.key, genes[i] = dge_record16.gene, and
  *                        read_idx = first_read_idx + i (the stream position is implicit when reads arrive in stream order, which is
  *                        how BamProcessor::save_read calls add_record): 12 bytes per read cross PCIe instead of 16.
- * Host batches are staged in slices on a copy stream, so the copy of one slice overlaps the fill kernel of the previous one.
+ * Host batches are staged in slices on a copy stream, so the copy of one slice overlaps the fill kernel of the previous one; the
+ * host arrays may be reused as soon as the call returns (it waits for the last copy, not for the kernels).
  * All fail with DGE_ERR_STATE after dge_set_initialized ("Container is already initialized", CellsDataContainer.cpp:61-62). */
 int dge_add_batch(dge_handle *h, const dge_record16 *recs, size_t n);
 int dge_add_batch_device(dge_handle *h, const dge_record16 *recs, size_t n);
