@@ -38,6 +38,8 @@ def cases():
         # -M strategies: the oracle port is pinned against these; the CUDA path does not implement them yet
         "poisson_simple_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="poisson_simple", seed=15),
         "poisson_real_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="poisson_real", seed=16),
+        "all_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="all", seed=17),
+        "directional_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=40, merge="real", seed=18, umi_merge="directional", reads_per_umi=6),
         "real_8x8_reads": pu.Case(name="real_8x8_reads",
                                   spec=SynthSpec(n_reads=25000, n_cells=20, n_genes=70, cb_len=16, umi_len=6, whitelist_parts=wl8,
                                                  cb_error_ppm=80000, seed=13),
@@ -62,7 +64,8 @@ def run_oracle_on(case: pu.Case, kind: str = "any"):
         return oracle_io.run_oracle(path, kind=kind, merge=case.merge, barcodes=case.barcodes, barcodes_type=case.barcodes_type,
                                     min_genes_before=case.min_genes_before, min_genes_after=case.min_genes_after,
                                     max_cb_ed=case.max_cb_ed, min_frac=case.min_frac, marks=case.marks, max_cells=case.max_cells,
-                                    reads_output=case.reads_output, dump_umis=True)
+                                    reads_output=case.reads_output, dump_umis=True, umi_merge=case.umi_merge, max_umi_ed=case.max_umi_ed,
+                                    umi_mult=case.umi_mult)
 
 
 def load_golden(name: str):

@@ -69,7 +69,7 @@ def test_golden_pins_equal_literal_expectations_of_reference_tests():
 
 
 @needs_port
-@pytest.mark.parametrize("name", ["fixture", "real_7x9", "none_7x9", "simple_7x9", "poisson_simple_7x9", "poisson_real_7x9", "real_8x8_reads"])
+@pytest.mark.parametrize("name", ["fixture", "real_7x9", "none_7x9", "simple_7x9", "poisson_simple_7x9", "poisson_real_7x9", "all_7x9", "directional_7x9", "real_8x8_reads"])
 def test_port_reproduces_golden_reference_outputs(name):
     res = golden_cases.run_oracle_on(golden_cases.cases()[name], kind="port")
     assert res["_kind"] == "port"
