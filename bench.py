@@ -55,23 +55,7 @@ def measured_traffic():
         return {}
 
 
-def product_whitelist(path: str, n1: int = 2048, n2: int = 3328, seed: int = 11):
-    """Synthetic product-form 7+9 whitelist (the real 10x v3 list is not a product of parts).  Tokens of one
-    part all have base-sum == 0 mod 4, so any two differ in >= 2 positions, like a real error-tolerant whitelist."""
-    rng = np.random.default_rng(seed)
-
-    def part(length, n):
-        free = rng.choice(4 ** (length - 1), size=n, replace=False)
-        toks = []
-        for v in free:
-            b = [(int(v) >> (2 * i)) & 3 for i in range(length - 1)]
-            b.append((-sum(b)) % 4)
-            toks.append("".join("ACGT"[x] for x in b))
-        return toks
-
-    with open(path, "w") as f:
-        f.write(" ".join(part(7, n1)) + "\n")
-        f.write(" ".join(part(9, n2)) + "\n")
+from dropest_b200.synth import product_whitelist  # noqa: E402  (the bench whitelist; shared with tests/test_bench_shape.py)
 
 
 class ClockSampler(threading.Thread):
@@ -118,14 +102,27 @@ def make_spec(n_reads, n_cells, wl_parts, seed=42):
                      seed=seed, whitelist_parts=wl_parts)
 
 
-def cpu_reference_run(wl_path, wl_parts, sample_reads, timeout=1200):
-    """One timed run of the CPU implementation on a scaled replica of the workload (same reads per cell, same genes)."""
+def sample_case(wl_path, wl_parts, sample_reads):
+    """The bounded sample both the CPU reference and (for `parity_on_sample`) the CUDA path run on: a scaled replica of the
+    workload -- same reads per cell, same genes, same whitelist, same thresholds."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_io
-    from dropest_b200.synth import SynthTables, write_packed
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity_utils as pu
 
     n_cells = max(10, int(round(sample_reads * WORKLOAD["n_cells"] / WORKLOAD["n_reads"])))
     spec = make_spec(sample_reads, n_cells, wl_parts, seed=43)
+    return pu.Case(name="bench_sample", spec=spec, cb_len=spec.cb_len, umi_len=spec.umi_len, n_genes=spec.n_genes, merge="real", barcodes=wl_path,
+                   barcodes_type="const", min_genes_before=WORKLOAD["min_genes_before"], min_genes_after=WORKLOAD["min_genes_after"],
+                   max_cb_ed=WORKLOAD["max_cb_ed"], min_frac=WORKLOAD["min_frac"], dump_umis=False, n_batches=3, extra={"max_barcodes_hint": 0})
+
+
+def cpu_reference_run(wl_path, wl_parts, sample_reads, timeout=1800, keep=False):
+    """One timed run of the CPU implementation on the sample (oracle/_ref = the compiled unmodified reference when present)."""
+    case = sample_case(wl_path, wl_parts, sample_reads)
+    import oracle_io
+    from dropest_b200.synth import SynthTables, write_packed
+
+    spec = case.spec
     recs = SynthTables(spec).generate_host(0, sample_reads)
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "sample.bin")
@@ -134,10 +131,28 @@ def cpu_reference_run(wl_path, wl_parts, sample_reads, timeout=1200):
                                    min_genes_after=WORKLOAD["min_genes_after"], max_cb_ed=WORKLOAD["max_cb_ed"], min_frac=WORKLOAD["min_frac"],
                                    dump_umis=False, timeout=timeout)
     secs = float(res["t_fill_s"][0] + res["t_init_s"][0] + res["t_merge_s"][0])
-    return {"value": sample_reads / secs, "seconds": secs, "kind": res["_kind"], "cores": 1,
-            "sample": f"{sample_reads} reads / {n_cells} cells / {spec.n_genes} genes scaled replica of the workload "
-                      f"(add_record loop {float(res['t_fill_s'][0]):.2f} s + set_initialized {float(res['t_init_s'][0]):.2f} s + "
-                      f"merge_and_filter {float(res['t_merge_s'][0]):.2f} s; single thread: the reference dropest is single-threaded)"}
+    out = {"value": sample_reads / secs, "seconds": secs, "kind": res["_kind"], "cores": 1, "n_cells": spec.n_cells,
+           "sample": f"{sample_reads} reads / {spec.n_cells} cells / {spec.n_genes} genes scaled replica of the workload "
+                     f"(add_record loop {float(res['t_fill_s'][0]):.2f} s + set_initialized {float(res['t_init_s'][0]):.2f} s + "
+                     f"merge_and_filter {float(res['t_merge_s'][0]):.2f} s; single thread: the reference dropest is single-threaded)"}
+    if keep:
+        out["_case"], out["_recs"], out["_oracle"] = case, recs, res
+    return out
+
+
+def parity_on_sample(cb):
+    """The CUDA path on the very sample the CPU reference just ran on, compared field by field (cells in first-seen order, flags,
+    merge_targets, per-cell stats, filtered order, cm and cm_raw triplets): tests/parity_utils.assert_parity.  The oracle is only the
+    checker here."""
+    import parity_utils as pu
+
+    try:
+        gpu = pu.gpu_run(cb["_case"], cb["_recs"])
+        pu.assert_parity({"case": cb["_case"], "oracle": cb["_oracle"], "gpu": gpu}, check_umigs=False)
+        s = gpu["summary"]
+        return True, {"n_merged": s["n_merged"], "n_excluded": s["n_excluded"], "cm_nnz": s["cm_nnz"], "filtered_cells_number": s["filtered_cells_number"]}
+    except AssertionError as e:
+        return False, {"mismatch": str(e)[:300]}
 
 
 def main():
@@ -148,7 +163,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=WORKLOAD["n_reads"], help="reads per GPU (default: the BASELINE config)")
     ap.add_argument("--cells", type=int, default=WORKLOAD["n_cells"])
-    ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
+    ap.add_argument("--cpu-sample-reads", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -174,18 +189,28 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        vals = []
-        last = None
-        for it in range(args.warmup + args.steps):
-            if it < args.warmup and it > 0:
-                continue  # one warm-up run of a CPU program is enough to page the binary in
+        # Every step = one full run of the reference's CPU path on the sample.  The sample is sized so that the per-cell merge cost
+        # is represented (>= 250 cells); the number of runs is bounded by a wall-clock budget so the arm ends within a few minutes
+        # (a single-threaded CPU run has no warm-up effect beyond paging the binary in: one untimed run, then up to `steps` timed).
+        budget_s = float(os.environ.get("DGE_REF_BUDGET_S", "300"))
+        t_begin = time.perf_counter()
+        vals, last = [], None
+        if args.warmup > 0:
+            cpu_reference_run(wl_path, wl_parts, min(args.cpu_sample_reads, 1_000_000))
+        for it in range(args.steps):
             last = cpu_reference_run(wl_path, wl_parts, args.cpu_sample_reads)
-            if it >= args.warmup:
-                vals.append(last["value"])
+            vals.append(last["value"])
+            if time.perf_counter() - t_begin + last["seconds"] * 1.3 > budget_s and len(vals) >= 2:
+                break
         v = float(np.mean(vals))
+        ref_config = dict(config)
+        ref_config["sample_reads"] = args.cpu_sample_reads
+        ref_config["sample_cells"] = last["n_cells"]
+        ref_config["note"] = ("reference arm: every step runs the CPU path on a %d-read / %d-cell scaled replica of the workload named above "
+                              "(same reads per cell, genes, whitelist, thresholds); reads/s is per sample read" % (args.cpu_sample_reads, last["n_cells"]))
         line = {"impl": "reference", "metric": "reads/sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1000.0 * args.cpu_sample_reads / v, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
+                "steps_run": len(vals), "warmup": args.warmup, "ms_per_step": 1000.0 * args.cpu_sample_reads / v, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": ref_config,
                 "cpu_baseline": {"value": v, "unit": "reads/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
                 "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -380,10 +405,14 @@ def main():
         line["config"]["merge"] += "; cross-rank merge via all-gather of candidate cells (dge_dist_*), result.* are rank 0's shard"
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cb = cpu_reference_run(wl_path, wl_parts, args.cpu_sample_reads)
+            cb = cpu_reference_run(wl_path, wl_parts, args.cpu_sample_reads, keep=True)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "reads/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+            ok, info = parity_on_sample(cb)
+            line["parity_on_sample"] = ok
+            line["parity_detail"] = info
         except Exception as e:  # the checker is missing: say so, do not hide it
             line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 1, "kind": "unavailable", "sample": str(e)[:200]}
+            line["parity_on_sample"] = None
     print(json.dumps(line))
 
 

@@ -14,6 +14,16 @@ struct CudaError : std::runtime_error
     explicit CudaError(const std::string &m) : std::runtime_error(m) {}
 };
 
+// malformed caller input (-> DGE_ERR_INVALID) and exhausted device tables (-> DGE_ERR_CAPACITY)
+struct InvalidInput : std::runtime_error
+{
+    explicit InvalidInput(const std::string &m) : std::runtime_error(m) {}
+};
+struct CapacityError : std::runtime_error
+{
+    explicit CapacityError(const std::string &m) : std::runtime_error(m) {}
+};
+
 #define DGE_CUDA(expr)                                                                                         \
     do {                                                                                                       \
         cudaError_t _e = (expr);                                                                               \
@@ -45,6 +55,7 @@ struct __align__(16) CellSlot
 struct KeyLayout
 {
     int tb, gb, ub, kb;
+    int cbb; // 2 * cb_len: barcode bits of dge_record16.key >> 24 (record validation)
     __host__ __device__ uint64_t compose(uint32_t slot, uint32_t gene, uint32_t umi, uint32_t mark) const
     {
         return (((uint64_t(slot) << gb | gene) << ub | umi) << 3) | mark;

@@ -199,6 +199,8 @@ template <class F> int guarded(dge_handle *h, F &&f)
 {
     try { return f(); }
     catch (CudaError &e) { return fail(h, DGE_ERR_CUDA, e.what()); }
+    catch (InvalidInput &e) { return fail(h, DGE_ERR_INVALID, e.what()); }
+    catch (CapacityError &e) { return fail(h, DGE_ERR_CAPACITY, e.what()); }
     catch (std::bad_alloc &) { return fail(h, DGE_ERR_INTERNAL, "out of host memory"); }
     catch (std::exception &e) { return fail(h, DGE_ERR_INTERNAL, e.what()); }
 }
@@ -267,6 +269,7 @@ void ensure_device(dge_handle *h)
     kl.tb = std::min(std::min(tb_max, 28), std::max(10, want));
     if (kl.tb < 10) throw std::runtime_error("key layout does not fit 64 bits: reduce n_genes or umi_len");
     kl.kb = kl.tb + kl.gb + kl.ub + 3;
+    kl.cbb = int(2 * h->cfg.cb_len);
     h->table_cap = size_t(1) << kl.tb;
     // strategies whose tie rules depend on the UMI indexer's first-seen order (UMI ids): directional UMI merge, simple CB merge
     h->track_umi_first = h->cfg.umi_merge_type == DGE_UMI_MERGE_DIRECTIONAL || h->cfg.merge_type == DGE_MERGE_SIMPLE;
@@ -545,11 +548,13 @@ void do_set_initialized(dge_handle *h)
     DGE_CUDA(cudaMemcpyAsync(&h->counters, h->ctr.p, sizeof(FillCounters), cudaMemcpyDeviceToHost, st));
     DGE_CUDA(cudaStreamSynchronize(st));
     if (h->counters.table_overflow)
-        throw std::runtime_error("barcode table overflow: more distinct barcodes than the table holds; set max_barcodes_hint");
-    if (h->counters.bad_gene) throw std::runtime_error("record with gene id >= n_genes");
+        throw CapacityError("barcode table overflow: more distinct barcodes than the table holds; set max_barcodes_hint (or shard across GPUs)");
+    if (h->counters.bad_gene) throw InvalidInput("record with gene id >= n_genes");
+    if (h->counters.bad_record)
+        throw InvalidInput("malformed record: barcode / UMI bits beyond cb_len / umi_len, reserved bits of the gene word set, or read_idx == 0xFFFFFFFF");
     size_t n_keys = 0;
     for (size_t c = 0; c < h->chunks.size(); ++c) { h->chunks[c]->count = size_t(counts[c]); n_keys += h->chunks[c]->count; }
-    if (n_keys >= 0xFFFFFFF0ull) throw std::runtime_error("more than 2^32 reads with genes on one device: shard across GPUs");
+    if (n_keys >= 0xFFFFFFF0ull) throw CapacityError("more than 2^32 reads with genes on one device (32-bit positions): shard across GPUs");
     h->n_keys = n_keys;
 
     const uint64_t *keys_in = nullptr;

@@ -21,6 +21,7 @@ struct FillCounters
     unsigned long long has_not_annotated;
     int table_overflow;
     int bad_gene;
+    int bad_record; // key bits beyond the configured barcode / UMI lengths, reserved gene-word bits, or read_idx == 0xFFFFFFFF
 };
 
 __global__ void k_table_init(CellSlot *tab, size_t cap)
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(FILL_THREADS, MINB) k_fill_compact(const Rec16
             const uint32_t gene = raw[j].z & 0xFFFFFFu;
             const uint32_t mark = (raw[j].z >> 24) & 7u;
             const uint32_t idx = raw[j].w;
+            if ((cb >> kl.cbb) != 0 || (umi >> kl.ub) != 0 || (raw[j].z >> 27) != 0 || idx == NONE32) { ctr->bad_record = 1; continue; }
             uint32_t slot = slot0[j];
             uint32_t seen_first = probe[j].z;
             if (((uint64_t(probe[j].y) << 32) | probe[j].x) != cb)

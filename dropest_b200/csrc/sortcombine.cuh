@@ -816,6 +816,9 @@ public:
                         int *overflow_flag, cudaStream_t st, SortCombineStats *stats)
     {
         configure();
+        int cur_dev = 0; // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: one flag per ordinal
+        DGE_CUDA(cudaGetDevice(&cur_dev));
+        cur_dev &= 63;
         if (!ev0) { DGE_CUDA(cudaEventCreate(&ev0)); DGE_CUDA(cudaEventCreate(&ev1)); }
         const bool has_val = vals_in != nullptr;
         const int nb1 = 1 << l1_bits;
@@ -872,8 +875,8 @@ public:
             if (stile == IDX)                                                                                                      \
             {                                                                                                                      \
                 const size_t smem = size_t(T) * I * 8 + size_t(nb1) * 8;                                                           \
-                static bool attr_done = false;                                                                                     \
-                if (!attr_done) { DGE_CUDA(cudaFuncSetAttribute(k_l1_scatter_staged<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done = true; } \
+                static bool attr_done[64] = {};                                                                                    \
+                if (!attr_done[cur_dev]) { DGE_CUDA(cudaFuncSetAttribute(k_l1_scatter_staged<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[cur_dev] = true; } \
                 k_l1_scatter_staged<T, I><<<unsigned(div_up(n, size_t(T) * I)), T, smem, st>>>(keys_in, n, shift, nb1, cursor, keysA); \
             }
             DGE_L1S(0, 512, 16) DGE_L1S(1, 256, 16) DGE_L1S(2, 1024, 8) DGE_L1S(3, 256, 8)
@@ -946,8 +949,8 @@ public:
             if (s2tile == IDX)                                                                                                     \
             {                                                                                                                      \
                 const size_t smem = size_t(SC_MAX_P2) * 16 + size_t(T) * I * 10;                                                   \
-                static bool attr_done = false;                                                                                     \
-                if (!attr_done) { DGE_CUDA(cudaFuncSetAttribute(k_l2_scatter_staged<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done = true; } \
+                static bool attr_done[64] = {};                                                                                    \
+                if (!attr_done[cur_dev]) { DGE_CUDA(cudaFuncSetAttribute(k_l2_scatter_staged<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[cur_dev] = true; } \
                 k_l2_scatter_staged<T, I><<<unsigned(tiles_bound), T, smem, st>>>(keysA, l1_off, nb1, p2, sb_base, tile_base, ws.splitters.as<uint64_t>(), sub_cnt, keys_tmp); \
             }
             DGE_L2SS(0, 256, 16) DGE_L2SS(1, 256, 8) DGE_L2SS(2, 512, 16)

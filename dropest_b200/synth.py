@@ -188,6 +188,26 @@ class SynthTables:
             raise RuntimeError(f"dge_synth_generate_device failed with {rc}")
 
 
+def product_whitelist(path: str, n1: int = 2048, n2: int = 3328, seed: int = 11, len1: int = 7, len2: int = 9):
+    """Synthetic product-form whitelist file (default 7+9 bp, 2048 x 3328 tokens: the 10x v3-like list of BASELINE configs[1];
+    the real 10x v3 list is not a product of parts).  Tokens of one part all have base-sum == 0 mod 4, so any
+    two differ in >= 2 positions, like a real error-tolerant whitelist."""
+    rng = np.random.default_rng(seed)
+
+    def part(length, n):
+        free = rng.choice(4 ** (length - 1), size=n, replace=False)
+        toks = []
+        for v in free:
+            b = [(int(v) >> (2 * i)) & 3 for i in range(length - 1)]
+            b.append((-sum(b)) % 4)
+            toks.append("".join("ACGT"[x] for x in b))
+        return toks
+
+    with open(path, "w") as f:
+        f.write(" ".join(part(len1, n1)) + "\n")
+        f.write(" ".join(part(len2, n2)) + "\n")
+
+
 def write_packed(path: str, recs: np.ndarray, cb_len: int, umi_len: int, n_genes: int, gene_names: Optional[Sequence[str]] = None):
     """DGER0001 stream for the oracle drivers (oracle/common/dge_io.h)."""
     blob = ("\n".join(gene_names)).encode() if gene_names else b""

@@ -155,6 +155,25 @@ def test_call_order_errors_mirror_reference_throws():
     c.close()
 
 
+@pytest.mark.parametrize("key,gene,idx", [((0x1234 << 24) | (1 << 8), 1, 0),            # UMI bits beyond umi_len
+                                          ((1 << 16) << 24, 1, 0),                      # barcode bits beyond cb_len
+                                          (0x1234 << 24, 1 | (1 << 27), 0),             # reserved bits of the gene word
+                                          (0x1234 << 24, 1, 0xFFFFFFFF),                # read_idx collides with the "none" sentinel
+                                          (0x1234 << 24, 5, 0)])                        # gene id >= n_genes
+def test_malformed_records_are_rejected(key, gene, idx):
+    """A record whose fields do not fit the configured lengths would silently corrupt the grouping key: DGE_ERR_INVALID instead."""
+    c = dg.Container(dg.Config(cb_len=8, umi_len=4, n_genes=2))
+    recs = np.zeros(3, dtype=dg.RECORD_DTYPE)
+    recs["key"] = [0x1111 << 24, key, 0x2222 << 24]
+    recs["gene"] = [0 | (2 << 24), gene | (2 << 24) if gene < (1 << 24) else gene, 1 | (2 << 24)]
+    recs["read_idx"] = [1, idx, 2]
+    c.add_batch(recs)
+    with pytest.raises(dg.DgeError) as e:
+        c.set_initialized()
+    assert e.value.code == 1
+    c.close()
+
+
 def test_full_size_invariants_20m():
     """Size-independent properties on a stream the oracle cannot chew in seconds: totals are conserved and the result does not
     depend on batching / order."""
