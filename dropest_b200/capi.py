@@ -75,7 +75,7 @@ class _Summary(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_reads", "total_cells_number", "real_cells_number", "filtered_cells_number", "n_genes_seen", "n_umigs",
         "intergenic_reads", "has_exon_reads", "has_intron_reads", "has_not_annotated_reads", "cm_nnz", "cm_raw_nnz",
-        "n_merged", "n_excluded", "n_unresolved", "n_umis_merged", "n_umi_segments_replayed", "n_cb_merge_replayed")]
+        "n_merged", "n_excluded", "n_unresolved", "n_umis_merged", "n_umi_segments_replayed", "n_cb_merge_replayed", "n_host_flow")]
 
 
 class _Timings(C.Structure):

@@ -67,6 +67,14 @@ struct KeyLayout
     __host__ __device__ uint64_t gu_of_ukey(uint64_t ukey) const { return ukey & ((1ull << (gb + ub)) - 1); }
 };
 
+// A run of packed keys produced by one block of the fill kernel (k_fill_pipe): the L1 partition pass consumes a list of them.
+struct KeyRegion
+{
+    const uint64_t *keys;
+    uint32_t count;
+    uint32_t tile0; // index of the region's first tile in the partition pass (k_region_tiles)
+};
+
 __host__ __device__ inline uint64_t mix64(uint64_t x)
 {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdull;

@@ -153,6 +153,19 @@ struct dge_handle
     DevBuf wl_tokens[WL_MAX_PARTS];
     WhitelistDev wl_dev{};
 
+    // device-resident cell state: the host mirror (`real`, `filtered`, `gene_order`) is built lazily, only when the query surface
+    // or a host-side strategy asks for it (materialize_host); the whitelist merge itself runs without it (merge_device_flow)
+    DevBuf cell_state, df_ctr, move_size, move_off, real_flag, real_off, cols_f, cols_r, fsort_k[2], fsort_v[2];
+    PinnedBuf pin_state, pin_ctr;
+    uint32_t n_real_rows = 0;        // rows of rows_dev2 (real cells at set_initialized, cell-id order)
+    uint32_t n_filtered_dev = 0;     // device flow: length of the final filtered list (fsort_v[..], see dev_filtered_buf)
+    int dev_filtered_buf = 0;
+    int init_filter_overflow = 0;    // packed compare_cells keys did not fit at set_initialized: the host re-sorts with full widths
+    int host_stage = 0;              // 0 no host mirror yet, 1 mirror of set_initialized, 2 merge results applied
+    bool lazy_rows = false;          // rows_dev2 / sort_v[0] / gsort_* hold everything the mirror needs
+    bool dev_merged = false;         // the merge ran in the device flow
+    uint64_t sum_real = 0, sum_filtered = 0, sum_genes_seen = 0, n_host_fallback = 0;
+
     MatrixDev cm, cm_raw;
     dge_timings timings{};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -533,6 +546,108 @@ void gather_rows(dge_handle *h, const std::vector<uint32_t> &pcs, std::vector<Ce
     rows.assign(p, p + pcs.size());
 }
 
+// Host mirror of the real cells (cell-id order), the gene indexer order and the set_initialized filtered list, from tables that
+// were sorted on the device (rows_sorted) or gathered unsorted.
+void build_host_mirror(dge_handle *h, const CellRow *rows_p, size_t n_rows, bool rows_sorted, const uint32_t *dev_filtered,
+                       const uint64_t *dev_gene_keys, const uint32_t *dev_gene_ids, int dev_filter_overflow, Tracer &tr)
+{
+    cudaStream_t st = h->stream;
+    static thread_local HostPairSorter order_sorter;
+    if (!rows_sorted)
+    {
+        order_sorter.key.resize(n_rows); order_sorter.idx.resize(n_rows);
+        for (size_t i = 0; i < n_rows; ++i) { order_sorter.key[i] = rows_p[i].first_idx; order_sorter.idx[i] = uint32_t(i); }
+        order_sorter.sort(n_rows, 32);
+    }
+    const std::vector<uint32_t> &order = order_sorter.idx;
+    tr.mark("init:  order sort");
+    h->real.clear();
+    h->real.reserve(n_rows);
+    for (size_t k = 0; k < n_rows; ++k)
+    {
+        const CellRow &r = rows_p[rows_sorted ? k : size_t(order[k])];
+        HostCell c;
+        c.cb = r.cb; c.slot = r.slot; c.pc = r.pc; c.first_idx = r.first_idx; c.n_intergenic = r.n_intergenic;
+        c.n_genes = int32_t(r.n_genes); c.umis_stat = int32_t(r.n_umis); c.n_umis_distinct = int32_t(r.n_umis);
+        c.reads_stat = int32_t(r.n_reads); c.req_genes = int32_t(r.req_genes); c.req_umis = int32_t(r.req_umis);
+        c.target = int32_t(h->real.size());
+        h->real.push_back(c);
+    }
+    tr.mark("init: real cells -> host");
+    // gene first-seen order (StringIndexer::add, StringIndexer.cpp:10-18)
+    if (dev_gene_ids)
+    {   // sorted on the device: genes never seen carry NONE32 and sort to the end
+        size_t seen = 0;
+        while (seen < h->cfg.n_genes && dev_gene_keys[seen] != uint64_t(NONE32)) ++seen;
+        h->gene_order.assign(dev_gene_ids, dev_gene_ids + seen);
+    }
+    else
+    {
+        const uint32_t *gf = d2h_pinned<uint32_t>(h->pin_misc, h->gene_first.p, h->cfg.n_genes, st);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        static thread_local HostPairSorter gs;
+        gs.key.clear(); gs.idx.clear();
+        for (uint32_t g = 0; g < h->cfg.n_genes; ++g)
+            if (gf[g] != NONE32) { gs.key.push_back(gf[g]); gs.idx.push_back(g); }
+        gs.sort(gs.key.size(), 32);
+        h->gene_order.assign(gs.idx.begin(), gs.idx.end());
+    }
+    tr.mark("init:  gene order");
+    // set_initialized: update_cell_sizes(query, 0, -1)  (CellsDataContainer.cpp:168) -- every real cell, ascending compare_cells
+    if (rows_sorted && !dev_filter_overflow) h->filtered.assign(dev_filtered, dev_filtered + n_rows); // exact total order, ties included
+    else update_filtered(h, 0, -1);
+    tr.mark("init: gene order + filtered");
+    h->host_stage = 1;
+}
+
+// Lazy part of set_initialized: copies the device-sorted tables to the host and builds the mirror.  After a device-flow merge the
+// merge outcome (CellState, refreshed rows, final filtered list) is applied on top (stage 2).
+void materialize_host(dge_handle *h)
+{
+    const int want = h->state >= 2 ? 2 : 1;
+    if (h->host_stage >= want || h->state == 0) return;
+    DGE_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    Tracer tr; tr.st = st;
+    const size_t n = h->n_real_rows;
+    if (h->host_stage == 0)
+    {
+        if (!h->lazy_rows) throw std::runtime_error("host mirror missing");
+        const CellRow *rows_p = d2h_pinned<CellRow>(h->pin_rows, h->rows_dev2.p, n, st);
+        const uint32_t *dev_filtered = d2h_pinned<uint32_t>(h->pin_filtered, h->sort_v[0].p, n, st);
+        const uint64_t *gk = nullptr; const uint32_t *gi = nullptr;
+        if (h->cfg.n_genes > 0)
+        {
+            gk = d2h_pinned<uint64_t>(h->pin_fkeys, h->gsort_k[1].p, h->cfg.n_genes, st);
+            gi = d2h_pinned<uint32_t>(h->pin_gene_ids, h->gsort_v[1].p, h->cfg.n_genes, st);
+        }
+        DGE_CUDA(cudaStreamSynchronize(st));
+        build_host_mirror(h, rows_p, n, true, dev_filtered, gk, gi, h->init_filter_overflow, tr);
+    }
+    if (want == 2 && h->host_stage < 2)
+    {
+        if (!h->dev_merged) throw std::runtime_error("merge results missing on the host");
+        // refreshed sizes of the merge targets + counters, flags and targets of every cell + the final filtered list
+        const CellRow *rows_p = d2h_pinned<CellRow>(h->pin_rows, h->rows_dev2.p, n, st);
+        const CellState *cs = d2h_pinned<CellState>(h->pin_state, h->cell_state.p, n, st);
+        const uint32_t *fl = d2h_pinned<uint32_t>(h->pin_filtered, h->fsort_v[h->dev_filtered_buf].p, h->n_filtered_dev, st);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < n; ++i)
+        {
+            HostCell &c = h->real[i];
+            const CellRow &r = rows_p[i];
+            c.n_genes = int32_t(r.n_genes); c.req_genes = int32_t(r.req_genes); c.req_umis = int32_t(r.req_umis); c.n_umis_distinct = int32_t(r.n_umis);
+            c.umis_stat = cs[i].umis_stat; c.reads_stat = cs[i].reads_stat; c.n_intergenic = cs[i].n_intergenic;
+            c.real = (cs[i].flags & 1u) != 0; c.merged = (cs[i].flags & 2u) != 0; c.excluded = (cs[i].flags & 4u) != 0;
+            c.target = cs[i].target < 0 ? int32_t(i) : cs[i].target;
+        }
+        const uint32_t nf = h->n_filtered_dev;
+        const uint32_t skip = (h->cfg.max_cells > 0 && uint32_t(h->cfg.max_cells) < nf) ? nf - uint32_t(h->cfg.max_cells) : 0u;
+        h->filtered.assign(fl + skip, fl + nf);
+        h->host_stage = 2;
+    }
+}
+
 void do_set_initialized(dge_handle *h)
 {
     ensure_device(h);
@@ -592,10 +707,15 @@ void do_set_initialized(dge_handle *h)
     build_segments(h);
     tr.mark("init: segments");
     h->misc.reserve(64);
-    DGE_CUDA(cudaMemsetAsync(h->misc.p, 0, 8, st));
+    DGE_CUDA(cudaMemsetAsync(h->misc.p, 0, 16, st));
     k_count_occupied<<<grid_for(h->table_cap, 256), 256, 0, st>>>(h->tab.as<CellSlot>(), h->table_cap, h->misc.as<unsigned long long>());
-    ++h->launches;
-    h->total_cells = d2h_scalar<unsigned long long>(h->misc.p, st);
+    k_count_seen<<<grid_for(h->cfg.n_genes, 256), 256, 0, st>>>(h->gene_first.as<uint32_t>(), h->cfg.n_genes, h->misc.as<unsigned long long>() + 1);
+    h->launches += 2;
+    unsigned long long occ_seen[2] = {0, 0};
+    DGE_CUDA(cudaMemcpyAsync(occ_seen, h->misc.p, 16, cudaMemcpyDeviceToHost, st));
+    DGE_CUDA(cudaStreamSynchronize(st));
+    h->total_cells = occ_seen[0];
+    const uint64_t n_genes_seen = occ_seen[1];
     DGE_CUDA(cudaEventRecord(h->ev[1], st));
     tr.mark("init:  count occupied");
 
@@ -608,6 +728,9 @@ void do_set_initialized(dge_handle *h)
     const uint64_t *dev_gene_keys = nullptr;
     const uint32_t *dev_gene_ids = nullptr;
     int dev_filter_overflow = 0;
+    bool lazy_ok = false;
+    static const bool eager_host = std::getenv("DGE_EAGER_HOST") != nullptr; // experiments: build the host mirror at set_initialized
+    h->n_real_rows = 0;
     if (h->n_pc)
     {
         h->flags.reserve((size_t(h->n_pc) + 1) * 4); h->flags_off.reserve((size_t(h->n_pc) + 1) * 4);
@@ -641,8 +764,6 @@ void do_set_initialized(dge_handle *h)
             device_sort_pairs(h, h->sort_k[0].as<uint64_t>(), h->sort_k[1].as<uint64_t>(), h->sort_v[1].as<uint32_t>(), h->sort_v[0].as<uint32_t>(), n_real, 64);
             DGE_LAUNCH_CHECK();
             h->launches += 4;
-            rows_p = d2h_pinned<CellRow>(h->pin_rows, h->rows_dev2.p, n_real, st);
-            dev_filtered = d2h_pinned<uint32_t>(h->pin_filtered, h->sort_v[0].p, n_real, st);
             DGE_CUDA(cudaMemcpyAsync(&dev_filter_overflow, h->overflow_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             // gene first-seen order on the device as well
             if (h->cfg.n_genes > 0)
@@ -652,9 +773,20 @@ void do_set_initialized(dge_handle *h)
                 k_gene_first_keys<<<grid_for(ng, 256), 256, 0, st>>>(h->gene_first.as<uint32_t>(), ng, h->gsort_k[0].as<uint64_t>(), h->gsort_v[0].as<uint32_t>());
                 device_sort_pairs(h, h->gsort_k[0].as<uint64_t>(), h->gsort_k[1].as<uint64_t>(), h->gsort_v[0].as<uint32_t>(), h->gsort_v[1].as<uint32_t>(), ng, 32);
                 ++h->launches;
-                dev_gene_keys = d2h_pinned<uint64_t>(h->pin_fkeys, h->gsort_k[1].p, ng, st);
-                dev_gene_ids = d2h_pinned<uint32_t>(h->pin_gene_ids, h->gsort_v[1].p, ng, st);
             }
+            // the host copies are made lazily (materialize_host) unless something below needs them now
+            lazy_ok = !(h->cfg.min_genes_before_merge == 0 && h->total_cells > h->n_pc) && !eager_host;
+            if (!lazy_ok)
+            {
+                rows_p = d2h_pinned<CellRow>(h->pin_rows, h->rows_dev2.p, n_real, st);
+                dev_filtered = d2h_pinned<uint32_t>(h->pin_filtered, h->sort_v[0].p, n_real, st);
+                if (h->cfg.n_genes > 0)
+                {
+                    dev_gene_keys = d2h_pinned<uint64_t>(h->pin_fkeys, h->gsort_k[1].p, h->cfg.n_genes, st);
+                    dev_gene_ids = d2h_pinned<uint32_t>(h->pin_gene_ids, h->gsort_v[1].p, h->cfg.n_genes, st);
+                }
+            }
+            h->n_real_rows = n_real;
             n_rows = n_real;
             DGE_CUDA(cudaStreamSynchronize(st));
             rows_sorted = true;
@@ -686,51 +818,21 @@ void do_set_initialized(dge_handle *h)
         rows_sorted = false;
         h->rows_on_device = false;
     }
-    static thread_local HostPairSorter order_sorter;
-    if (!rows_sorted)
-    {
-        order_sorter.key.resize(n_rows); order_sorter.idx.resize(n_rows);
-        for (size_t i = 0; i < n_rows; ++i) { order_sorter.key[i] = rows_p[i].first_idx; order_sorter.idx[i] = uint32_t(i); }
-        order_sorter.sort(n_rows, 32);
-    }
-    const std::vector<uint32_t> &order = order_sorter.idx;
-    tr.mark("init:  order sort");
-    h->real.clear();
-    h->real.reserve(n_rows);
-    for (size_t k = 0; k < n_rows; ++k)
-    {
-        const CellRow &r = rows_p[rows_sorted ? k : size_t(order[k])];
-        HostCell c;
-        c.cb = r.cb; c.slot = r.slot; c.pc = r.pc; c.first_idx = r.first_idx; c.n_intergenic = r.n_intergenic;
-        c.n_genes = int32_t(r.n_genes); c.umis_stat = int32_t(r.n_umis); c.n_umis_distinct = int32_t(r.n_umis);
-        c.reads_stat = int32_t(r.n_reads); c.req_genes = int32_t(r.req_genes); c.req_umis = int32_t(r.req_umis);
-        c.target = int32_t(h->real.size());
-        h->real.push_back(c);
-    }
-    tr.mark("init: real cells -> host");
-    // gene first-seen order (StringIndexer::add, StringIndexer.cpp:10-18)
-    if (dev_gene_ids)
-    {   // sorted on the device: genes never seen carry NONE32 and sort to the end
-        size_t seen = 0;
-        while (seen < h->cfg.n_genes && dev_gene_keys[seen] != uint64_t(NONE32)) ++seen;
-        h->gene_order.assign(dev_gene_ids, dev_gene_ids + seen);
+    h->lazy_rows = rows_sorted && lazy_ok;
+    h->init_filter_overflow = dev_filter_overflow;
+    h->dev_merged = false;
+    if (h->lazy_rows)
+    {   // no host mirror yet: materialize_host builds it on demand
+        h->real.clear(); h->filtered.clear(); h->gene_order.clear();
+        h->host_stage = 0;
+        h->sum_real = h->sum_filtered = n_rows;
+        h->sum_genes_seen = n_genes_seen;
     }
     else
     {
-        const uint32_t *gf = d2h_pinned<uint32_t>(h->pin_misc, h->gene_first.p, h->cfg.n_genes, st);
-        DGE_CUDA(cudaStreamSynchronize(st));
-        static thread_local HostPairSorter gs;
-        gs.key.clear(); gs.idx.clear();
-        for (uint32_t g = 0; g < h->cfg.n_genes; ++g)
-            if (gf[g] != NONE32) { gs.key.push_back(gf[g]); gs.idx.push_back(g); }
-        gs.sort(gs.key.size(), 32);
-        h->gene_order.assign(gs.idx.begin(), gs.idx.end());
+        build_host_mirror(h, rows_p, n_rows, rows_sorted, dev_filtered, dev_gene_keys, dev_gene_ids, dev_filter_overflow, tr);
+        h->sum_real = h->real.size(); h->sum_filtered = h->filtered.size(); h->sum_genes_seen = h->gene_order.size();
     }
-    tr.mark("init:  gene order");
-    // set_initialized: update_cell_sizes(query, 0, -1)  (CellsDataContainer.cpp:168) -- every real cell, ascending compare_cells
-    if (rows_sorted && !dev_filter_overflow) h->filtered.assign(dev_filtered, dev_filtered + n_rows); // exact total order, ties included
-    else update_filtered(h, 0, -1);
-    tr.mark("init: gene order + filtered");
     DGE_CUDA(cudaEventRecord(h->ev[2], st));
     DGE_CUDA(cudaStreamSynchronize(st));
     h->state = 1;
@@ -803,6 +905,42 @@ long best_target_real(const dge_handle *h, uint32_t base, const uint32_t *nbs, c
     return long(best);
 }
 
+// Phase 1 of the whitelist merge for the n real cells of rows_dev2, entirely on the device: neighbour classes 0/1, pair jobs,
+// (gene,UMI) intersections, best target per cell.  Leaves d_count (neighbour count / NB_SELF / NB_SLOW), p1_target and p1_flag
+// (1 = order-dependent tie: the reference's neighbour order decides) in device memory.
+void p1_device_pass(dge_handle *h, size_t n)
+{
+    cudaStream_t st = h->stream;
+    if (!h->wl_uploaded) { upload_whitelist(h); h->wl_uploaded = true; }
+    h->d_cb.reserve(n * 8); h->d_umis.reserve(n * 4); h->d_count.reserve(n * 4); h->d_nb.reserve(n * WL_K * 4);
+    h->p1_pc.reserve(n * 4); h->p1_map.reserve((size_t(h->n_pc) + 2) * 4);
+    k_fill_u32<<<grid_for(size_t(h->n_pc) + 1, 256), 256, 0, st>>>(h->p1_map.as<uint32_t>(), size_t(h->n_pc) + 1, NONE32);
+    k_p1_columns<<<grid_for(n, 256), 256, 0, st>>>(h->rows_dev2.as<CellRow>(), uint32_t(n), h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>(),
+                                                   h->p1_pc.as<uint32_t>(), h->p1_map.as<uint32_t>());
+    k_wl_class01<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>(), uint32_t(n), h->wl_dev,
+                                                                        h->tab.as<CellSlot>(), h->kl.tb, h->slot_pc.as<uint32_t>(),
+                                                                        h->pc_cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(),
+                                                                        h->cfg.min_genes_before_merge, h->d_count.as<int>(), h->d_nb.as<uint32_t>());
+    DGE_LAUNCH_CHECK();
+    h->launches += 3;
+    h->p1_cnt.reserve((n + 1) * 4); h->p1_off.reserve((n + 1) * 4); h->p1_target.reserve(n * 4); h->p1_flag.reserve(n * 4);
+    k_p1_counts<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), uint32_t(n), h->p1_cnt.as<uint32_t>());
+    DGE_CUDA(cudaMemsetAsync(h->p1_cnt.as<uint32_t>() + n, 0, 4, st));
+    device_exclusive_scan(h->p1_cnt.as<uint32_t>(), h->p1_off.as<uint32_t>(), n + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+    const uint32_t n_jobs = d2h_scalar<uint32_t>(h->p1_off.as<uint32_t>() + n, st);
+    h->d_jobs.reserve(std::max<size_t>(n_jobs, 1) * sizeof(PairJob)); h->d_isect.reserve(std::max<size_t>(n_jobs, 1) * 4);
+    k_p1_jobs<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), h->d_nb.as<uint32_t>(), h->p1_pc.as<uint32_t>(), h->p1_off.as<uint32_t>(), uint32_t(n),
+                                                h->d_jobs.as<PairJob>());
+    if (n_jobs)
+        k_intersect<<<n_jobs, 128, 0, st>>>(h->d_jobs.as<PairJob>(), n_jobs, h->ukey.as<uint64_t>(), h->pc_u_start.as<uint32_t>(),
+                                            h->pc_slot.as<uint32_t>(), h->kl.gb + h->kl.ub, h->d_isect.as<uint32_t>());
+    k_p1_best<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), h->d_nb.as<uint32_t>(), h->p1_off.as<uint32_t>(), h->d_isect.as<uint32_t>(),
+                                                h->d_umis.as<uint32_t>(), h->p1_map.as<uint32_t>(), uint32_t(n), h->cfg.min_merge_fraction,
+                                                h->p1_target.as<int>(), h->p1_flag.as<uint32_t>());
+    DGE_LAUNCH_CHECK();
+    h->launches += 4;
+}
+
 // Phase 1 for RealBarcodesMergeStrategy: target (index into real, or -1) for every real cell.
 void phase1_real(dge_handle *h, std::vector<long> &target)
 {
@@ -823,45 +961,10 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
         if (!h->wl_uploaded) { upload_whitelist(h); h->wl_uploaded = true; }
         h->d_cb.reserve(n * 8); h->d_umis.reserve(n * 4); h->d_count.reserve(n * 4); h->d_nb.reserve(n * WL_K * 4);
         if (device_rows)
-        {   // the per-cell columns come straight from the rows gathered at set_initialized (nothing changed since)
-            h->p1_pc.reserve(n * 4); h->p1_map.reserve((size_t(h->n_pc) + 2) * 4);
-            k_fill_u32<<<grid_for(size_t(h->n_pc) + 1, 256), 256, 0, st>>>(h->p1_map.as<uint32_t>(), size_t(h->n_pc) + 1, NONE32);
-            k_p1_columns<<<grid_for(n, 256), 256, 0, st>>>(h->rows_dev2.as<CellRow>(), uint32_t(n), h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>(),
-                                                           h->p1_pc.as<uint32_t>(), h->p1_map.as<uint32_t>());
-            h->launches += 2;
-        }
-        else
-        {
-            h->h_cbs.resize(n); h->h_umis.resize(n);
-            for (size_t i = 0; i < n; ++i) { h->h_cbs[i] = h->real[i].cb; h->h_umis[i] = uint32_t(h->real[i].umis_stat); }
-            DGE_CUDA(cudaMemcpyAsync(h->d_cb.p, h->h_cbs.data(), n * 8, cudaMemcpyHostToDevice, st));
-            DGE_CUDA(cudaMemcpyAsync(h->d_umis.p, h->h_umis.data(), n * 4, cudaMemcpyHostToDevice, st));
-        }
-        k_wl_class01<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>(), uint32_t(n), h->wl_dev,
-                                                                            h->tab.as<CellSlot>(), h->kl.tb, h->slot_pc.as<uint32_t>(),
-                                                                            h->pc_cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(),
-                                                                            h->cfg.min_genes_before_merge, h->d_count.as<int>(), h->d_nb.as<uint32_t>());
-        DGE_LAUNCH_CHECK();
-        ++h->launches;
-        DGE_CUDA(cudaMemcpyAsync(nb_count, h->d_count.p, n * 4, cudaMemcpyDeviceToHost, st));
-        if (device_rows)
-        {   // intersections and the best neighbour per cell on the device; only ties / far classes come back to the host logic
-            h->p1_cnt.reserve((n + 1) * 4); h->p1_off.reserve((n + 1) * 4); h->p1_target.reserve(n * 4); h->p1_flag.reserve(n * 4);
-            k_p1_counts<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), uint32_t(n), h->p1_cnt.as<uint32_t>());
-            DGE_CUDA(cudaMemsetAsync(h->p1_cnt.as<uint32_t>() + n, 0, 4, st));
-            device_exclusive_scan(h->p1_cnt.as<uint32_t>(), h->p1_off.as<uint32_t>(), n + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
-            const uint32_t n_jobs = d2h_scalar<uint32_t>(h->p1_off.as<uint32_t>() + n, st);
-            h->d_jobs.reserve(std::max<size_t>(n_jobs, 1) * sizeof(PairJob)); h->d_isect.reserve(std::max<size_t>(n_jobs, 1) * 4);
-            k_p1_jobs<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), h->d_nb.as<uint32_t>(), h->p1_pc.as<uint32_t>(), h->p1_off.as<uint32_t>(), uint32_t(n),
-                                                        h->d_jobs.as<PairJob>());
-            if (n_jobs)
-                k_intersect<<<n_jobs, 128, 0, st>>>(h->d_jobs.as<PairJob>(), n_jobs, h->ukey.as<uint64_t>(), h->pc_u_start.as<uint32_t>(),
-                                                    h->pc_slot.as<uint32_t>(), h->kl.gb + h->kl.ub, h->d_isect.as<uint32_t>());
-            k_p1_best<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), h->d_nb.as<uint32_t>(), h->p1_off.as<uint32_t>(), h->d_isect.as<uint32_t>(),
-                                                        h->d_umis.as<uint32_t>(), h->p1_map.as<uint32_t>(), uint32_t(n), h->cfg.min_merge_fraction,
-                                                        h->p1_target.as<int>(), h->p1_flag.as<uint32_t>());
-            DGE_LAUNCH_CHECK();
-            h->launches += 4;
+        {   // the per-cell columns come straight from the rows gathered at set_initialized (nothing changed since); intersections and
+            // the best neighbour per cell on the device; only ties / far classes come back to the host logic
+            p1_device_pass(h, n);
+            DGE_CUDA(cudaMemcpyAsync(nb_count, h->d_count.p, n * 4, cudaMemcpyDeviceToHost, st));
             const int *dt = d2h_pinned<int>(h->pin_p1t, h->p1_target.p, n, st);
             const uint32_t *df = d2h_pinned<uint32_t>(h->pin_p1f, h->p1_flag.p, n, st);
             DGE_CUDA(cudaStreamSynchronize(st));
@@ -874,6 +977,20 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
                 else ++n_todo;
             }
             if (n_todo == 0) { tr.mark("merge:  p1 device pass"); return; }
+        }
+        else
+        {
+            h->h_cbs.resize(n); h->h_umis.resize(n);
+            for (size_t i = 0; i < n; ++i) { h->h_cbs[i] = h->real[i].cb; h->h_umis[i] = uint32_t(h->real[i].umis_stat); }
+            DGE_CUDA(cudaMemcpyAsync(h->d_cb.p, h->h_cbs.data(), n * 8, cudaMemcpyHostToDevice, st));
+            DGE_CUDA(cudaMemcpyAsync(h->d_umis.p, h->h_umis.data(), n * 4, cudaMemcpyHostToDevice, st));
+            k_wl_class01<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>(), uint32_t(n), h->wl_dev,
+                                                                                h->tab.as<CellSlot>(), h->kl.tb, h->slot_pc.as<uint32_t>(),
+                                                                                h->pc_cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(),
+                                                                                h->cfg.min_genes_before_merge, h->d_count.as<int>(), h->d_nb.as<uint32_t>());
+            DGE_LAUNCH_CHECK();
+            ++h->launches;
+            DGE_CUDA(cudaMemcpyAsync(nb_count, h->d_count.p, n * 4, cudaMemcpyDeviceToHost, st));
         }
         DGE_CUDA(cudaMemcpyAsync(nb_pc, h->d_nb.p, n * WL_K * 4, cudaMemcpyDeviceToHost, st));
         DGE_CUDA(cudaStreamSynchronize(st));
@@ -1362,18 +1479,26 @@ void apply_moved(dge_handle *h, uint64_t total)
     tr.mark("  apply: segments");
 }
 
+// columns = present-cell indices in DEVICE memory
+void build_matrix_cols(dge_handle *h, MatrixDev &m, const uint32_t *d_cols, size_t n_cols, bool filtered);
+
 void build_matrix(dge_handle *h, MatrixDev &m, const std::vector<uint32_t> &col_pcs, bool filtered)
 {
+    m.cols.reserve(std::max<size_t>(col_pcs.size(), 1) * 4);
+    if (!col_pcs.empty()) DGE_CUDA(cudaMemcpyAsync(m.cols.p, col_pcs.data(), col_pcs.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    build_matrix_cols(h, m, m.cols.as<uint32_t>(), col_pcs.size(), filtered);
+}
+
+void build_matrix_cols(dge_handle *h, MatrixDev &m, const uint32_t *d_cols, size_t n_cols, bool filtered)
+{
     cudaStream_t st = h->stream;
-    m.n_cols = col_pcs.size();
+    m.n_cols = n_cols;
     m.nnz = 0;
     m.built = true;
     m.indptr.reserve((m.n_cols + 2) * 4);
     if (m.n_cols == 0) { DGE_CUDA(cudaMemsetAsync(m.indptr.p, 0, 8, st)); return; }
-    m.cols.reserve(m.n_cols * 4);
-    DGE_CUDA(cudaMemcpyAsync(m.cols.p, col_pcs.data(), m.n_cols * 4, cudaMemcpyHostToDevice, st));
     h->mat_nnz.reserve((m.n_cols + 2) * 4);
-    k_matrix_col_nnz<<<grid_for(m.n_cols * 32, 256), 256, 0, st>>>(m.cols.as<uint32_t>(), uint32_t(m.n_cols), h->pc_cg_start.as<uint32_t>(),
+    k_matrix_col_nnz<<<grid_for(m.n_cols * 32, 256), 256, 0, st>>>(d_cols, uint32_t(m.n_cols), h->pc_cg_start.as<uint32_t>(),
                                                                    h->cg_req.as<uint32_t>(), filtered ? 1 : 0, h->mat_nnz.as<uint32_t>());
     ++h->launches;
     DGE_CUDA(cudaMemsetAsync(h->mat_nnz.as<uint32_t>() + m.n_cols, 0, 4, st));
@@ -1385,7 +1510,7 @@ void build_matrix(dge_handle *h, MatrixDev &m, const std::vector<uint32_t> &col_
     if (filtered) { values = h->cfg.reads_output ? h->cg_req_reads.as<uint32_t>() : h->cg_req.as<uint32_t>(); mode = 0; }
     else if (h->cfg.reads_output) { values = h->cg_reads.as<uint32_t>(); mode = 2; }
     else { values = nullptr; mode = 1; }
-    k_matrix_fill<<<unsigned(m.n_cols), 256, 0, st>>>(m.cols.as<uint32_t>(), uint32_t(m.n_cols), m.indptr.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(),
+    k_matrix_fill<<<unsigned(m.n_cols), 256, 0, st>>>(d_cols, uint32_t(m.n_cols), m.indptr.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(),
                                                       h->cg_gene.as<uint32_t>(), values, h->cg_start.as<uint32_t>(), mode, m.gene.as<int32_t>(), m.val.as<int32_t>());
     DGE_LAUNCH_CHECK();
     ++h->launches;
@@ -1562,6 +1687,100 @@ bool umi_merge_directional(dge_handle *h)
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// merge_and_filter without host cell rows (DummyMergeStrategy / RealBarcodesMergeStrategy, default UMI strategy, single shard):
+// phase 1 (p1_device_pass), phase 2 + merge_cells (k_phase2_*: every target is a whitelist barcode that keeps itself, so the
+// sequential loop of MergeStrategyBase.cpp:29-51 is order-free), refreshed sizes, final filter in compare_cells order and the two
+// matrices -- all from the device-resident CellRow / CellState tables.  Returns false (nothing modified) when a cell needs the
+// exact host logic: a far distance class, an order-dependent tie, a merge chain, counters beyond the packed sort key.
+bool merge_device_flow(dge_handle *h)
+{
+    cudaStream_t st = h->stream;
+    Tracer tr; tr.st = st;
+    const size_t n = h->n_real_rows;
+    const uint32_t n32 = uint32_t(n);
+    CellRow *rows = h->rows_dev2.as<CellRow>();
+    h->cell_state.reserve(std::max<size_t>(n, 1) * sizeof(CellState));
+    h->df_ctr.reserve(sizeof(DevFlowCounters));
+    CellState *cs = h->cell_state.as<CellState>();
+    DevFlowCounters *ctr = h->df_ctr.as<DevFlowCounters>();
+    DGE_CUDA(cudaMemsetAsync(ctr, 0, sizeof(DevFlowCounters), st));
+    const unsigned g = grid_for(n, 256);
+    k_state_init<<<g, 256, 0, st>>>(rows, n32, cs);
+    ++h->launches;
+    DevFlowCounters hc{};
+    const bool real_merge = h->cfg.merge_type == DGE_MERGE_REAL;
+    if (real_merge)
+    {
+        p1_device_pass(h, n);
+        h->move_size.reserve((n + 1) * 4); h->move_off.reserve((n + 1) * 4);
+        k_p1_finalize<<<g, 256, 0, st>>>(h->d_count.as<int>(), h->p1_target.as<int>(), h->p1_flag.as<uint32_t>(), n32, cs, ctr);
+        k_phase2_sizes<<<g, 256, 0, st>>>(rows, cs, n32, h->move_size.as<uint32_t>(), ctr);
+        DGE_CUDA(cudaMemsetAsync(h->move_size.as<uint32_t>() + n, 0, 4, st));
+        device_exclusive_scan(h->move_size.as<uint32_t>(), h->move_off.as<uint32_t>(), n + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+        h->launches += 2;
+        uint32_t total = 0;
+        DGE_CUDA(cudaMemcpyAsync(&hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));
+        DGE_CUDA(cudaMemcpyAsync(&total, h->move_off.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+        DGE_CUDA(cudaStreamSynchronize(st));
+        tr.mark("merge: phase 1 (device)");
+        if (hc.n_todo || hc.n_chain) return false;
+        h->d_moves.reserve(std::max<size_t>(n, 1) * sizeof(MoveJob));
+        k_phase2_apply<<<g, 256, 0, st>>>(rows, cs, n32, h->move_off.as<uint32_t>(), h->n_pc, h->d_moves.as<MoveJob>(), ctr);
+        ++h->launches;
+        if (total)
+        {
+            h->mkeys.reserve(size_t(total) * 8); h->mvals.reserve(size_t(total) * 4);
+            k_gather_relabel<<<grid_for(n, 1, 148 * 16), 256, 0, st>>>(h->d_moves.as<MoveJob>(), n32, h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(),
+                                                                      h->pc_u_start.as<uint32_t>(), h->kl.gb + h->kl.ub, h->mkeys.as<uint64_t>(), h->mvals.as<uint32_t>());
+            DGE_LAUNCH_CHECK();
+            ++h->launches;
+            apply_moved(h, total);
+        }
+        tr.mark("merge: phase 2 + apply (device)");
+    }
+    DGE_CUDA(cudaEventRecord(h->ev[4], st));
+
+    // ---- refreshed sizes, is_real, final filter (update_filtered_gene_counts, CellsDataContainer.cpp:250-276)
+    h->real_flag.reserve((n + 1) * 4); h->real_off.reserve((n + 1) * 4);
+    k_refresh_rows<<<g, 256, 0, st>>>(rows, cs, n32, h->pc_cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), h->pc_req_genes.as<uint32_t>(),
+                                      h->pc_req_umis.as<uint32_t>(), h->cfg.min_genes_before_merge, h->real_flag.as<uint32_t>());
+    DGE_CUDA(cudaMemsetAsync(h->real_flag.as<uint32_t>() + n, 0, 4, st));
+    device_exclusive_scan(h->real_flag.as<uint32_t>(), h->real_off.as<uint32_t>(), n + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+    for (int b = 0; b < 2; ++b) { h->fsort_k[b].reserve(std::max<size_t>(n, 1) * 8); h->fsort_v[b].reserve(std::max<size_t>(n, 1) * 4); }
+    // stable sort by barcode, then stable sort by the packed (genes, umis, stat) counters; cells outside the filter sort to the end
+    k_rows_cb_keys<<<g, 256, 0, st>>>(rows, n32, h->fsort_k[0].as<uint64_t>(), h->fsort_v[0].as<uint32_t>());
+    device_sort_pairs(h, h->fsort_k[0].as<uint64_t>(), h->fsort_k[1].as<uint64_t>(), h->fsort_v[0].as<uint32_t>(), h->fsort_v[1].as<uint32_t>(), n,
+                      int(2 * h->cfg.cb_len));
+    k_final_filter_keys<<<g, 256, 0, st>>>(rows, cs, h->fsort_v[1].as<uint32_t>(), n32, h->min_after_eff, h->fsort_k[0].as<uint64_t>(), ctr);
+    device_sort_pairs(h, h->fsort_k[0].as<uint64_t>(), h->fsort_k[1].as<uint64_t>(), h->fsort_v[1].as<uint32_t>(), h->fsort_v[0].as<uint32_t>(), n, 64);
+    h->dev_filtered_buf = 0;
+    h->launches += 3;
+    uint32_t n_real_final = 0;
+    DGE_CUDA(cudaMemcpyAsync(&hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    DGE_CUDA(cudaMemcpyAsync(&n_real_final, h->real_off.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+    DGE_CUDA(cudaStreamSynchronize(st));
+    if (hc.key_overflow) throw std::runtime_error("per-cell counters beyond the packed compare_cells key of the device flow; rerun with DGE_HOST_FLOW=1");
+    h->n_merged = hc.n_merged; h->n_excluded = hc.n_excluded; h->n_unresolved = 0;
+    h->n_filtered_dev = hc.n_filtered;
+    tr.mark("finish: sizes + filter (device)");
+
+    // ---- matrices: cm over the filtered list (last max_cells of it with -C), cm_raw over the real cells in cell-id order
+    const uint32_t nf = hc.n_filtered;
+    const uint32_t skip = (h->cfg.max_cells > 0 && uint32_t(h->cfg.max_cells) < nf) ? nf - uint32_t(h->cfg.max_cells) : 0u;
+    h->cols_f.reserve(std::max<size_t>(nf, 1) * 4); h->cols_r.reserve(std::max<size_t>(n_real_final, 1) * 4);
+    if (nf - skip)
+        k_cols_from_list<<<grid_for(nf - skip, 256), 256, 0, st>>>(rows, h->fsort_v[0].as<uint32_t>() + skip, nf - skip, h->n_pc, h->cols_f.as<uint32_t>());
+    k_cols_from_flags<<<g, 256, 0, st>>>(rows, h->real_flag.as<uint32_t>(), h->real_off.as<uint32_t>(), n32, h->n_pc, h->cols_r.as<uint32_t>());
+    h->launches += 2;
+    build_matrix_cols(h, h->cm, h->cols_f.as<uint32_t>(), nf - skip, true);
+    build_matrix_cols(h, h->cm_raw, h->cols_r.as<uint32_t>(), n_real_final, false);
+    h->sum_real = n_real_final;
+    h->sum_filtered = nf - skip;
+    h->dev_merged = true;
+    return true;
+}
+
 void do_merge_and_filter(dge_handle *h)
 {
     DGE_CUDA(cudaSetDevice(h->cfg.device));
@@ -1570,6 +1789,29 @@ void do_merge_and_filter(dge_handle *h)
     tr.st = st;
     DGE_CUDA(cudaEventRecord(h->ev[3], st));
     if (!h->slot_pc_built) build_slot_pc(h);
+
+    // ---- device flow: no host cell rows at all (the common configurations); anything it cannot decide exactly -> host flow
+    static const bool no_dev_flow = std::getenv("DGE_HOST_FLOW") != nullptr;
+    const bool dev_flow = !no_dev_flow && h->lazy_rows && !h->cfg.sharded && !h->dist_done && h->n_real_rows > 0 &&
+                          (h->cfg.merge_type == DGE_MERGE_NONE || (h->cfg.merge_type == DGE_MERGE_REAL && h->wl_fast)) &&
+                          h->cfg.umi_merge_type == DGE_UMI_MERGE_SIMPLE && h->cfg.min_genes_before_merge > 0;
+    if (dev_flow && merge_device_flow(h))
+    {
+        DGE_CUDA(cudaEventRecord(h->ev[5], st));
+        DGE_CUDA(cudaStreamSynchronize(st));
+        tr.mark("finish: matrices");
+        h->state = 2;
+        auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]); return ms; };
+        h->timings.ms_fill = el(0, 1);
+        h->timings.ms_init = el(1, 2);
+        h->timings.ms_merge = el(3, 4);
+        h->timings.ms_finish = el(4, 5);
+        h->timings.ms_total = h->timings.ms_fill + h->timings.ms_init + h->timings.ms_merge + h->timings.ms_finish;
+        h->timings.n_kernel_launches = h->launches + h->sc_stats.launches;
+        return;
+    }
+    if (dev_flow) ++h->n_host_fallback;
+    materialize_host(h);
 
     // ---- CB merge (MergeStrategyAbstract::merge, MergeStrategyAbstract.cpp:13-23)
     if (h->dist_done)
@@ -1668,6 +1910,9 @@ void do_merge_and_filter(dge_handle *h)
     DGE_CUDA(cudaStreamSynchronize(st));
     tr.mark("finish: matrices");
     h->state = 2;
+    h->host_stage = 2;
+    h->sum_real = raw_cols.size();
+    h->sum_filtered = h->filtered.size();
 
     auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]); return ms; };
     h->timings.ms_fill = el(0, 1);
@@ -1909,6 +2154,8 @@ int dge_reset(dge_handle *h)
         h->real.clear(); h->filtered.clear(); h->gene_order.clear(); h->merge_events.clear();
         h->n_merged = h->n_excluded = h->n_unresolved = 0; h->total_cells = 0;
         h->cm.built = h->cm_raw.built = false;
+        h->host_stage = 0; h->lazy_rows = false; h->dev_merged = false; h->n_real_rows = 0; h->n_filtered_dev = 0;
+        h->sum_real = h->sum_filtered = h->sum_genes_seen = 0; h->n_host_fallback = 0;
         h->dist_done = false; h->slot_pc_built = false; h->dist_targets.clear(); h->g_infos.clear(); h->n_order_ties = 0;
         h->timings = dge_timings{}; h->sc_stats = SortCombineStats{}; h->launches = 0;
         h->state = 0;
@@ -1947,6 +2194,7 @@ int dge_dist_export_children(dge_handle *h, const dge_dist_child **infos_device,
         dist_check(h);
         DGE_CUDA(cudaSetDevice(h->cfg.device));
         cudaStream_t st = h->stream;
+        materialize_host(h);
         if (!h->slot_pc_built) build_slot_pc(h);
         const size_t n = h->real.size();
         // which local real cells are whitelist barcodes themselves (target = self)?
@@ -2297,9 +2545,9 @@ int dge_get_summary(dge_handle *h, dge_summary *out)
     std::memset(out, 0, sizeof(*out));
     out->n_reads = h->n_reads;
     out->total_cells_number = h->total_cells;
-    for (auto const &c : h->real) out->real_cells_number += c.real;
-    out->filtered_cells_number = h->filtered.size();
-    out->n_genes_seen = h->gene_order.size();
+    out->real_cells_number = h->sum_real;
+    out->filtered_cells_number = h->sum_filtered;
+    out->n_genes_seen = h->sum_genes_seen;
     out->n_umigs = h->n_u;
     out->intergenic_reads = h->counters.intergenic;
     out->has_exon_reads = h->counters.has_exon;
@@ -2313,6 +2561,7 @@ int dge_get_summary(dge_handle *h, dge_summary *out)
     out->n_umis_merged = h->n_umis_merged;
     out->n_umi_segments_replayed = h->n_umi_segments_replayed;
     out->n_cb_merge_replayed = h->n_simple_replayed;
+    out->n_host_flow = h->n_host_fallback;
     return DGE_OK;
 }
 
@@ -2329,6 +2578,7 @@ int dge_get_cells(dge_handle *h, int which, dge_cell_info *out, size_t capacity,
     if (h->state == 0) return fail(h, DGE_ERR_STATE, "You must initialize container");
     return guarded(h, [&] {
         DGE_CUDA(cudaSetDevice(h->cfg.device));
+        materialize_host(h);
         if (which == DGE_CELLS_ALL)
         {
             AllCells all = collect_all_cells(h);
@@ -2383,15 +2633,19 @@ int dge_get_gene_order(dge_handle *h, int32_t *gene_ids, size_t capacity, size_t
 {
     if (!h || !n_out) return fail(h, DGE_ERR_INVALID, "null argument");
     if (h->state == 0) return fail(h, DGE_ERR_STATE, "You must initialize container");
-    *n_out = h->gene_order.size();
-    if (gene_ids && capacity >= h->gene_order.size()) std::copy(h->gene_order.begin(), h->gene_order.end(), gene_ids);
-    return DGE_OK;
+    return guarded(h, [&] {
+        materialize_host(h);
+        *n_out = h->gene_order.size();
+        if (gene_ids && capacity >= h->gene_order.size()) std::copy(h->gene_order.begin(), h->gene_order.end(), gene_ids);
+        return int(DGE_OK);
+    });
 }
 
 int dge_get_merge_pairs(dge_handle *h, uint64_t *from, uint64_t *to, size_t capacity, size_t *n_out)
 {
     if (!h || !n_out) return fail(h, DGE_ERR_INVALID, "null argument");
     if (h->state != 2) return fail(h, DGE_ERR_STATE, "merge targets exist after merge_and_filter");
+    { const int rc = guarded(h, [&] { materialize_host(h); return int(DGE_OK); }); if (rc != DGE_OK) return rc; }
     size_t n = 0;
     for (auto const &c : h->real) n += (uint32_t(c.target) != uint32_t(&c - h->real.data())) || c.merged_to_cb != EMPTY64;
     *n_out = n;
@@ -2415,6 +2669,7 @@ int dge_get_umigs(dge_handle *h, int which, uint32_t *cell_index, int32_t *gene_
     if (h->state == 0) return fail(h, DGE_ERR_STATE, "You must initialize container");
     return guarded(h, [&] {
         DGE_CUDA(cudaSetDevice(h->cfg.device));
+        materialize_host(h);
         std::vector<uint32_t> pcs;
         if (which == DGE_CELLS_ALL) { AllCells all = collect_all_cells(h); pcs = all.pc; }
         else if (which == DGE_CELLS_REAL) { for (auto const &c : h->real) if (c.real) pcs.push_back(c.pc); }

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "scan.cuh"
 #include "sortcombine.cuh"
+#include "tma.cuh"
 
 namespace dge
 {
@@ -203,6 +204,239 @@ __global__ void k_count_occupied(const CellSlot *__restrict__ tab, size_t cap, u
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, d);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+// genes that occur in the stream (= gene_indexer().values().size())
+__global__ void k_count_seen(const uint32_t *__restrict__ first, size_t n, unsigned long long *out)
+{
+    uint32_t c = 0;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) c += first[i] != NONE32;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_fill_pipe -- the same per-read work as k_fill_compact, restructured for Blackwell's asynchronous data movement:
+//   * one persistent block per SM; a PRODUCER warp streams record tiles from HBM into a ring of shared-memory stages with bulk
+//     asynchronous copies (cp.async.bulk -> UBLKCP, completion on an mbarrier); CONS_WARPS consumer warps take the records out of
+//     shared memory.  The record loads therefore cost the consumers no issue slots and no scoreboard stalls, and because the only
+//     synchronisation is the per-stage full/empty mbarrier pair (no __syncthreads in the loop) the warps drift apart: while some wait for
+//     their barcode-table probes (random 16-byte L2 accesses), others pack keys or write results.
+//   * output: every block appends to its OWN region of the key buffer through a shared-memory cursor (one warp-aggregated shared atomic
+//     per warp and tile, no global atomics, no block scan); the regions are consumed as a list by the L1 partition pass
+//     (k_l1_scatter_regions), so the keys are never made dense.
+//   * the L1 histogram (top 12 key bits) is accumulated in shared memory on the way and flushed once per block: the partition pass
+//     needs no histogram pass of its own.
+//   * gene first-seen: a 16-bit upper bound of (first read index >> 16) per gene in shared memory filters out all but the reads of the
+//     64 Ki-read granule in which a gene first occurs; those go to the global atomicMin.  (A stale / racy bound is only ever too
+//     large, which costs an extra trip, never a missed update.)
+template <int CONS_WARPS, int ITEMS, int STAGES, bool SOA>
+__global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
+    k_fill_pipe(const Rec16 *__restrict__ recs, size_t n, CellSlot *__restrict__ tab, KeyLayout kl, uint32_t n_genes, uint32_t *__restrict__ gene_first,
+                uint64_t *__restrict__ out_keys, size_t region_cap, KeyRegion *__restrict__ regions, FillCounters *__restrict__ ctr,
+                uint32_t *__restrict__ umi_first, uint32_t *__restrict__ hist12, const unsigned long long *__restrict__ soa_keys,
+                const uint32_t *__restrict__ soa_genes, uint32_t soa_first_idx)
+{
+    constexpr int CONS = CONS_WARPS * 32;
+    constexpr int TILE = CONS * ITEMS;
+    constexpr int STAGE_BYTES = TILE * 16;
+    extern __shared__ __align__(128) unsigned char fp_smem[];
+    uint16_t *g16 = reinterpret_cast<uint16_t *>(fp_smem + size_t(STAGES) * STAGE_BYTES);
+    uint32_t *hist_s = reinterpret_cast<uint32_t *>(g16 + ((n_genes + 7u) & ~7u));
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
+    __shared__ uint32_t cursor_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (uint32_t i = threadIdx.x; i < n_genes; i += blockDim.x)
+    {
+        const uint32_t f = gene_first[i];
+        g16[i] = f == NONE32 ? uint16_t(0xFFFF) : uint16_t(f >> 16);
+    }
+    for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) hist_s[i] = 0;
+    if (threadIdx.x == 0)
+    {
+        cursor_s = 0;
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONS_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const size_t n_tiles = (n + TILE - 1) / TILE;
+    uint32_t c_inter = 0, c_exon = 0, c_intron = 0, c_na = 0;
+    if (warp == CONS_WARPS)
+    {   // ---- producer
+        if (lane == 0)
+        {
+            uint32_t k = 0;
+            for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k)
+            {
+                const int s = int(k % STAGES);
+                const uint32_t round = k / STAGES;
+                mbar_wait(&empty_bar[s], (round & 1u) ^ 1u);
+                const size_t base = tile * TILE;
+                const uint32_t cnt = uint32_t(min(size_t(TILE), n - base));
+                unsigned char *stage = fp_smem + size_t(s) * STAGE_BYTES;
+                if (SOA)
+                {
+                    const uint32_t kbytes = (cnt * 8u + 15u) & ~15u, gbytes = (cnt * 4u + 15u) & ~15u;
+                    mbar_arrive_expect_tx(&full_bar[s], kbytes + gbytes);
+                    bulk_g2s(stage, soa_keys + base, kbytes, &full_bar[s]);
+                    bulk_g2s(stage + TILE * 8, soa_genes + base, gbytes, &full_bar[s]);
+                }
+                else
+                {
+                    mbar_arrive_expect_tx(&full_bar[s], cnt * 16u);
+                    bulk_g2s(stage, recs + base, cnt * 16u, &full_bar[s]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    else
+    {   // ---- consumers
+        const int ctid = threadIdx.x; // consumer warps are warps 0 .. CONS_WARPS-1
+        uint64_t *my_out = out_keys + size_t(blockIdx.x) * region_cap;
+        const int hshift = kl.kb - 12;
+        uint32_t k = 0;
+        for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k)
+        {
+            const int s = int(k % STAGES);
+            const uint32_t round = k / STAGES;
+            const size_t base = tile * TILE;
+            const uint32_t cnt = uint32_t(min(size_t(TILE), n - base));
+            const unsigned char *stage = fp_smem + size_t(s) * STAGE_BYTES;
+            uint4 raw[ITEMS];
+            mbar_wait(&full_bar[s], round & 1u);
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+            {
+                const uint32_t i = uint32_t(j) * CONS + ctid;
+                raw[j] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                if (i < cnt)
+                {
+                    if (SOA)
+                    {
+                        const uint2 kw = reinterpret_cast<const uint2 *>(stage)[i];
+                        raw[j] = make_uint4(kw.x, kw.y, reinterpret_cast<const uint32_t *>(stage + TILE * 8)[i], soa_first_idx + uint32_t(base) + i);
+                    }
+                    else raw[j] = reinterpret_cast<const uint4 *>(stage)[i];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]); // the stage may be refilled: this warp holds its records in registers
+            // first probe of the barcode table for all records of the thread (random L2 accesses, all in flight together)
+            uint4 probe[ITEMS];
+            uint32_t slot0[ITEMS];
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+            {
+                const uint64_t kk = (uint64_t(raw[j].y) << 32) | raw[j].x;
+                slot0[j] = uint32_t(barcode_hash(kk >> 24) >> (64 - kl.tb));
+                probe[j] = __ldcg(reinterpret_cast<const uint4 *>(&tab[slot0[j]]));
+            }
+            uint64_t keys[ITEMS];
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+            {
+                const uint32_t i = uint32_t(j) * CONS + ctid;
+                keys[j] = EMPTY64;
+                if (i >= cnt) continue;
+                const uint64_t kk = (uint64_t(raw[j].y) << 32) | raw[j].x;
+                const uint64_t cb = kk >> 24;
+                const uint32_t umi = uint32_t(kk) & 0xFFFFFFu;
+                const uint32_t gene = raw[j].z & 0xFFFFFFu;
+                const uint32_t mark = (raw[j].z >> 24) & 7u;
+                const uint32_t idx = raw[j].w;
+                if ((cb >> kl.cbb) != 0 || (umi >> kl.ub) != 0 || (raw[j].z >> 27) != 0 || idx == NONE32) { ctr->bad_record = 1; continue; }
+                uint32_t slot = slot0[j];
+                uint32_t seen_first = probe[j].z;
+                if (((uint64_t(probe[j].y) << 32) | probe[j].x) != cb)
+                {
+                    slot = table_insert(tab, kl.tb, cb);
+                    if (slot == NONE32) { ctr->table_overflow = 1; continue; }
+                    seen_first = tab[slot].first_idx;
+                }
+                if (idx < seen_first) atomicMin(&tab[slot].first_idx, idx);
+                if (gene == NO_GENE)
+                {
+                    atomicAdd(&tab[slot].n_intergenic, 1u);
+                    ++c_inter;
+                    continue;
+                }
+                if (gene >= n_genes) { ctr->bad_gene = 1; continue; }
+                const uint32_t hi = idx >> 16;
+                const uint32_t bound = g16[gene];
+                if (hi <= bound)
+                {
+                    if (idx < __ldcg(&gene_first[gene])) atomicMin(&gene_first[gene], idx);
+                    if (hi < bound) g16[gene] = uint16_t(hi);
+                }
+                if (umi_first) atomicMin(&umi_first[umi], idx);
+                c_exon += (mark >> 1) & 1u; c_intron += (mark >> 2) & 1u; c_na += mark & 1u;
+                keys[j] = kl.compose(slot, gene, umi, mark);
+            }
+            // append to the block's region: one shared-memory atomic per warp and tile
+            unsigned vm[ITEMS];
+            uint32_t nv = 0;
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) { vm[j] = __ballot_sync(0xFFFFFFFFu, keys[j] != EMPTY64); nv += __popc(vm[j]); }
+            uint32_t pos = 0;
+            if (lane == 0 && nv) pos = atomicAdd(&cursor_s, nv);
+            pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+            const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+            {
+                if (keys[j] != EMPTY64)
+                {
+                    my_out[pos + __popc(vm[j] & lt)] = keys[j];
+                    atomicAdd(&hist_s[uint32_t(keys[j] >> hshift)], 1u);
+                }
+                pos += __popc(vm[j]);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x)
+        if (hist_s[i]) atomicAdd(&hist12[i], hist_s[i]);
+    if (threadIdx.x == 0)
+    {
+        KeyRegion r;
+        r.keys = out_keys + size_t(blockIdx.x) * region_cap; r.count = cursor_s; r.tile0 = 0;
+        regions[blockIdx.x] = r;
+        if (cursor_s) atomicAdd(&ctr->n_keys, (unsigned long long)cursor_s);
+    }
+    auto reduce_add = [&](uint32_t v, unsigned long long *dst) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, (unsigned long long)v);
+    };
+    reduce_add(c_inter, &ctr->intergenic);
+    reduce_add(c_exon, &ctr->has_exon);
+    reduce_add(c_intron, &ctr->has_intron);
+    reduce_add(c_na, &ctr->has_not_annotated);
+}
+
+// tile0 of every region = exclusive prefix of ceil(count / tile) (single block; a few thousand regions at most); total in *n_tiles
+__global__ void __launch_bounds__(1024) k_region_tiles(KeyRegion *__restrict__ regions, uint32_t n_regions, uint32_t tile, uint32_t *__restrict__ n_tiles)
+{
+    __shared__ uint32_t ws[33];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_regions; base += blockDim.x)
+    {
+        const uint32_t r = base + threadIdx.x;
+        const uint32_t t = r < n_regions ? (regions[r].count + tile - 1) / tile : 0u;
+        uint32_t tot;
+        const uint32_t ex = block_exclusive_scan(t, ws, &tot);
+        if (r < n_regions) regions[r].tile0 = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_tiles = carry;
 }
 
 } // namespace dge

@@ -624,4 +624,166 @@ __global__ void __launch_bounds__(256) k_matrix_fill(const uint32_t *__restrict_
     }
 }
 
+// ---- device-resident merge flow (RealBarcodesMergeStrategy without host cell rows) ------------------------------------------------
+// Per real cell (cell-id order, parallel to the CellRow table): the Stats counters that are counters and not set sizes
+// (TOTAL_UMIS_PER_CB / TOTAL_READS_PER_CB are ADDED on merges, Stats.cpp:29-43), the merge target and the Cell flags.
+struct CellState
+{
+    int32_t umis_stat, reads_stat;
+    uint32_t n_intergenic;
+    int32_t target;      // real-cell index, -1 = excluded by the merge, DF_TODO = the device pass could not decide
+    uint32_t flags;      // DGE_CELL_REAL 1 | DGE_CELL_MERGED 2 | DGE_CELL_EXCLUDED 4
+    uint32_t is_target;  // received at least one merged cell
+};
+constexpr int32_t DF_TODO = -3;
+
+struct DevFlowCounters
+{
+    uint32_t n_todo, n_chain, n_merged, n_excluded, n_real, n_filtered, key_overflow, pad;
+};
+
+__global__ void k_state_init(const CellRow *__restrict__ rows, uint32_t n, CellState *__restrict__ st)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const CellRow r = rows[i];
+        CellState s;
+        s.umis_stat = int32_t(r.n_umis); s.reads_stat = int32_t(r.n_reads); s.n_intergenic = r.n_intergenic;
+        s.target = int32_t(i); s.flags = 1u; s.is_target = 0;
+        st[i] = s;
+    }
+}
+
+// Phase 1 outcome per cell: whitelist barcodes keep themselves, cells settled by k_p1_best take its target, everything else
+// (far distance classes, order-dependent ties, neighbour overflow) is counted in n_todo: the exact host path then takes the run.
+__global__ void k_p1_finalize(const int *__restrict__ nb_count, const int *__restrict__ p1_target, const uint32_t *__restrict__ p1_flag, uint32_t n,
+                              CellState *__restrict__ st, DevFlowCounters *__restrict__ ctr)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int c = nb_count[i];
+        int32_t t;
+        if (c == NB_SELF) t = int32_t(i);
+        else if (c > 0 && !p1_flag[i]) t = p1_target[i];
+        else { t = DF_TODO; atomicAdd(&ctr->n_todo, 1u); }
+        st[i].target = t;
+    }
+}
+
+// Sizes of the lists that move (phase 2, MergeStrategyBase.cpp:29-51).  With RealBarcodesMergeStrategy every target is a whitelist
+// barcode that keeps itself, so no chain of merges exists and phase 2 is order-free; n_chain counts violations (-> host path).
+__global__ void k_phase2_sizes(const CellRow *__restrict__ rows, const CellState *__restrict__ st, uint32_t n, uint32_t *__restrict__ move_size,
+                               DevFlowCounters *__restrict__ ctr)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int32_t t = st[i].target;
+        uint32_t sz = 0;
+        if (t >= 0 && uint32_t(t) != i)
+        {
+            if (st[t].target != t) atomicAdd(&ctr->n_chain, 1u);
+            if (rows[i].pc != NONE32) sz = rows[i].n_umis;
+        }
+        move_size[i] = sz;
+    }
+}
+
+// merge_cells (CellsDataContainer.cpp:90-104) for every cell with a foreign target: Stats::merge adds the source's counters, the
+// source is flagged merged; target -1 excludes the cell (MergeStrategyBase.cpp:33-37).  One move job per cell (an empty one --
+// the sentinel cell n_pc -- for cells that move nothing).
+__global__ void k_phase2_apply(const CellRow *__restrict__ rows, CellState *__restrict__ st, uint32_t n, const uint32_t *__restrict__ move_off,
+                               uint32_t empty_pc, MoveJob *__restrict__ moves, DevFlowCounters *__restrict__ ctr)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int32_t t = st[i].target;
+        MoveJob job{empty_pc, 0u, move_off[i]};
+        if (t < 0)
+        {
+            st[i].flags = (st[i].flags & ~1u) | 4u;
+            atomicAdd(&ctr->n_excluded, 1u);
+        }
+        else if (uint32_t(t) != i)
+        {
+            const CellRow r = rows[i];
+            st[i].flags |= 2u;
+            atomicAdd(&ctr->n_merged, 1u);
+            atomicAdd(&st[t].umis_stat, int32_t(r.n_umis));
+            atomicAdd(&st[t].reads_stat, int32_t(r.n_reads));
+            atomicAdd(&st[t].n_intergenic, r.n_intergenic);
+            st[t].is_target = 1u;
+            if (r.pc != NONE32 && r.n_umis) job = MoveJob{r.pc, rows[t].slot, move_off[i]};
+        }
+        moves[i] = job;
+    }
+}
+
+// After the lists were merged and the segment tables rebuilt: sizes of the merge targets (the only cells whose content changed),
+// Cell::is_real (Cell.cpp:125-128) on the merged content, and the flag column for the cm_raw columns.
+__global__ void k_refresh_rows(CellRow *__restrict__ rows, CellState *__restrict__ st, uint32_t n, const uint32_t *__restrict__ pc_cg_start,
+                               const uint32_t *__restrict__ pc_u_start, const uint32_t *__restrict__ pc_req_genes, const uint32_t *__restrict__ pc_req_umis,
+                               uint32_t min_genes, uint32_t *__restrict__ real_flag)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        CellState s = st[i];
+        uint32_t n_genes = rows[i].n_genes;
+        if (s.is_target)
+        {
+            const uint32_t pc = rows[i].pc;
+            if (pc != NONE32)
+            {
+                n_genes = pc_cg_start[pc + 1] - pc_cg_start[pc];
+                rows[i].n_genes = n_genes;
+                rows[i].n_umis = pc_u_start[pc + 1] - pc_u_start[pc];
+                rows[i].req_genes = pc_req_genes[pc];
+                rows[i].req_umis = pc_req_umis[pc];
+            }
+        }
+        const bool real = !(s.flags & 6u) && n_genes >= min_genes;
+        s.flags = (s.flags & ~1u) | (real ? 1u : 0u);
+        st[i].flags = s.flags;
+        real_flag[i] = real ? 1u : 0u;
+    }
+}
+
+// compare_cells keys (CellsDataContainer.cpp:329-344) of the final filter: `perm` is the barcode order (stable first sort); cells
+// that are not real or have too few requested genes get the largest key and sort to the end; n_filtered counts the others.
+__global__ void k_final_filter_keys(const CellRow *__restrict__ rows, const CellState *__restrict__ st, const uint32_t *__restrict__ perm, uint32_t n,
+                                    uint32_t min_req_genes, uint64_t *__restrict__ key, DevFlowCounters *__restrict__ ctr)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t c = perm[i];
+        const CellRow r = rows[c];
+        const CellState s = st[c];
+        if (!(s.flags & 1u) || r.req_genes < min_req_genes) { key[i] = EMPTY64; continue; }
+        const uint32_t stat = uint32_t(s.umis_stat);
+        if (r.req_genes >= (1u << 16) - 1 || r.req_umis >= (1u << 24) || stat >= (1u << 24)) ctr->key_overflow = 1;
+        key[i] = (uint64_t(r.req_genes) << 48) | (uint64_t(r.req_umis & 0xFFFFFFu) << 24) | uint64_t(stat & 0xFFFFFFu);
+        atomicAdd(&ctr->n_filtered, 1u);
+    }
+}
+
+// matrix columns: present-cell index of the listed real cells (cells without UMIs -> the empty sentinel cell)
+__global__ void k_cols_from_list(const CellRow *__restrict__ rows, const uint32_t *__restrict__ list, uint32_t n, uint32_t empty_pc, uint32_t *__restrict__ cols)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t pc = rows[list[i]].pc;
+        cols[i] = pc == NONE32 ? empty_pc : pc;
+    }
+}
+
+__global__ void k_cols_from_flags(const CellRow *__restrict__ rows, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ off, uint32_t n,
+                                  uint32_t empty_pc, uint32_t *__restrict__ cols)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (flag[i])
+        {
+            const uint32_t pc = rows[i].pc;
+            cols[off[i]] = pc == NONE32 ? empty_pc : pc;
+        }
+}
+
 } // namespace dge

@@ -388,6 +388,79 @@ __global__ void __launch_bounds__(THREADS) k_l1_scatter_staged(const uint64_t *_
     }
 }
 
+// L1 scatter straight from the fill kernel's per-block key regions (no dense key array, no histogram pass): block = one tile of one
+// region.  Dynamic shared memory as k_l1_scatter_staged.
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_l1_scatter_regions(const KeyRegion *__restrict__ regions, uint32_t n_regions, const uint32_t *__restrict__ n_tiles_ptr,
+                                                                int shift, int nb1, uint32_t *__restrict__ cursor, uint64_t *__restrict__ out_keys)
+{
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int PER = SC_MAX_NB1 / THREADS;
+    if (blockIdx.x >= *n_tiles_ptr) return;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint32_t ws[33];
+    __shared__ uint32_t reg_s;
+    uint64_t *sk = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(sk + TILE);
+    uint32_t *gd = cnt + nb1;
+    for (int i = threadIdx.x; i < nb1; i += THREADS) cnt[i] = 0;
+    if (threadIdx.x == 0)
+    {   // largest r with regions[r].tile0 <= blockIdx.x (regions without tiles repeat the next region's tile0)
+        uint32_t lo = 0, hi = n_regions - 1;
+        while (lo < hi)
+        {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (regions[mid].tile0 <= blockIdx.x) lo = mid; else hi = mid - 1;
+        }
+        reg_s = lo;
+    }
+    __syncthreads();
+    const KeyRegion reg = regions[reg_s];
+    const uint32_t t_in = blockIdx.x - reg.tile0;
+    const uint64_t *__restrict__ keys = reg.keys + size_t(t_in) * TILE;
+    const uint32_t n_tile = min(uint32_t(TILE), reg.count - t_in * uint32_t(TILE));
+    uint64_t k[ITEMS];
+    uint32_t r[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+    {
+        const uint32_t i = uint32_t(j) * THREADS + threadIdx.x;
+        k[j] = i < n_tile ? __ldg(keys + i) : EMPTY64;
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+    {
+        const uint32_t i = uint32_t(j) * THREADS + threadIdx.x;
+        if (i < n_tile) r[j] = atomicAdd(&cnt[k[j] >> shift], 1u);
+    }
+    __syncthreads();
+    tile_bucket_offsets<PER>(cnt, gd, uint32_t(nb1), cursor, ws);
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+    {
+        const uint32_t i = uint32_t(j) * THREADS + threadIdx.x;
+        if (i < n_tile) sk[cnt[k[j] >> shift] + r[j]] = k[j];
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_tile; i += THREADS)
+    {
+        const uint64_t key = sk[i];
+        out_keys[gd[key >> shift] + i] = key;
+    }
+}
+
+// fold the fill kernel's 12-bit histogram to the chosen L1 width
+__global__ void k_hist_fold(const uint32_t *__restrict__ hist12, int l1_bits, uint32_t *__restrict__ out)
+{
+    const int nb1 = 1 << l1_bits, per = 1 << (12 - l1_bits);
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb1; b += gridDim.x * blockDim.x)
+    {
+        uint32_t sum = 0;
+        for (int q = 0; q < per; ++q) sum += hist12[b * per + q];
+        out[b] = sum;
+    }
+}
+
 // L2: bucket = position among the L1 bucket's sampled splitters.  Dynamic shared memory:
 // spl[SC_MAX_P2] (u64) | keys[TILE] (u64) | cnt[SC_MAX_P2] | gd[SC_MAX_P2] | ids[TILE] (u16).
 template <int THREADS, int ITEMS>
@@ -791,6 +864,16 @@ public:
     SortCombineWorkspace ws;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
+    // Optional input of the NEXT run(): the keys live in per-block regions of the fill kernel instead of one dense array
+    // (keys_in is ignored, l1_hist_pre must be given).  region_tiles: device scratch word.
+    const KeyRegion *src_regions = nullptr;
+    uint32_t n_src_regions = 0;
+    uint32_t *src_region_tiles = nullptr;
+    void set_regions(const KeyRegion *regions, uint32_t n_regions, uint32_t *region_tiles)
+    {
+        src_regions = regions; n_src_regions = n_regions; src_region_tiles = region_tiles;
+    }
+
     ~SortCombine()
     {
         if (ev0) cudaEventDestroy(ev0);
@@ -869,7 +952,18 @@ public:
         static const int staged = std::getenv("DGE_STAGED") ? atoi(std::getenv("DGE_STAGED")) : 1; // bit0: L1, bit1: L2 (measured: staging pays at L1 only)
         static const int stile = std::getenv("DGE_STILE") ? atoi(std::getenv("DGE_STILE")) : 2;    // staged tile shape (1024 x 8 measured best)
         size_t tile = 0;
-        if (!has_val && (staged & 1))
+        if (src_regions)
+        {   // keys straight from the fill kernel's regions (1024 x 8 staged tiles)
+            if (has_val || !l1_hist_pre) throw std::runtime_error("region input needs a precomputed histogram and no values");
+            constexpr int T = 1024, I = 8;
+            const size_t smem = size_t(T) * I * 8 + size_t(nb1) * 8;
+            static bool attr_done[64] = {};
+            if (!attr_done[cur_dev]) { DGE_CUDA(cudaFuncSetAttribute(k_l1_scatter_regions<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[cur_dev] = true; }
+            const unsigned g_tiles = unsigned(n / (size_t(T) * I) + n_src_regions + 1); // upper bound; blocks beyond the real count exit
+            k_l1_scatter_regions<T, I><<<g_tiles, T, smem, st>>>(src_regions, n_src_regions, src_region_tiles, shift, nb1, cursor, keysA);
+            src_regions = nullptr;
+        }
+        else if (!has_val && (staged & 1))
         {
 #define DGE_L1S(IDX, T, I)                                                                                                         \
             if (stile == IDX)                                                                                                      \

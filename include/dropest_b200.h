@@ -119,6 +119,8 @@ typedef struct dge_summary {
     uint64_t n_umis_merged;         /* UMIs merged into another UMI by the UMI merge strategy (MergeUMIsStrategyDirectional.cpp:43) */
     uint64_t n_umi_segments_replayed; /* (cell, gene) segments whose UMI merge was replayed on the host for exact tie order */
     uint64_t n_cb_merge_replayed;   /* SimpleMergeStrategy: base cells whose target was replayed on the host (near-ties of the top fraction) */
+    uint64_t n_host_flow;           /* 1 when merge_and_filter left the device-resident flow for the host logic (far distance classes,
+                                       order-dependent ties of the best fraction: exactness first), 0 when everything ran on the device */
 } dge_summary;
 
 /* Per-cell row returned by dge_get_cells; one per requested cell, in the requested order. */

@@ -28,7 +28,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi._Config) == 112
     assert capi.CELL_INFO_DTYPE.itemsize == 40
     assert capi.RECORD_DTYPE.itemsize == 16
-    assert ctypes.sizeof(capi._Summary) == 18 * 8
+    assert ctypes.sizeof(capi._Summary) == 19 * 8
     assert ctypes.sizeof(capi._SynthParams) == 96
 
 
