@@ -155,6 +155,101 @@ def parity_on_sample(cb):
         return False, {"mismatch": str(e)[:300]}
 
 
+def exchange_diagnostics(pipe, cont, raw, stream, torch, dist, n, world):
+    """One-off measurements outside the timed region that name the limiter of the N > 1 step: the routing kernels alone, one
+    unsliced all-to-all of the routed records alone (NVLink bound: 16 B x (N-1)/N of the reads leave every GPU), and the fill alone."""
+    import numpy as np
+    from dropest_b200 import dist as dgdist
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    torch.cuda.synchronize(); dist.barrier()
+    ev[0].record(stream)
+    counts = dgdist.route_slices_device(pipe.device, raw.data_ptr(), n, world, pipe.routed.data_ptr(), pipe.slice_len, pipe.n_slices, stream.cuda_stream)
+    ev[1].record(stream)
+    torch.cuda.synchronize(); dist.barrier()
+    # unsliced all-to-all of the same volume (segments of the first slice layout are not contiguous per destination across slices, so
+    # send equal splits of the routed buffer: same bytes on the wire)
+    per = (n // world) * 16
+    recv = pipe.recv[: per * world]
+    ev[2].record(stream)
+    dist.all_to_all_single(recv, pipe.routed[: per * world])
+    ev[3].record(stream)
+    torch.cuda.synchronize()
+    ms_route = ev[0].elapsed_time(ev[1])
+    ms_a2a = ev[2].elapsed_time(ev[3])
+    wire = per * (world - 1)
+    return {"diag_ms_route_kernels": ms_route, "diag_ms_all_to_all_unsliced": ms_a2a, "diag_a2a_gbytes_out_per_gpu": wire / 1e9,
+            "diag_a2a_gbs_per_gpu": wire / 1e9 / (ms_a2a / 1e3)}
+
+
+def verify_sharded(args, dg, dgdist, torch, wl_path, wl_parts, dev, rank, world, stream):
+    """The N-GPU pipeline (routing, all-to-all, per-rank grouping, cross-rank merge) on one global stream of --verify-reads reads must
+    give exactly the single-GPU result: union of the shards' cm / cm_raw triplets (barcode, gene, value), merge pairs and filtered-cell
+    rows == those of one handle that sees every read (computed on rank 0)."""
+    import pickle
+
+    import numpy as np
+    import torch.distributed as dist
+    from dropest_b200.synth import SynthTables
+
+    V = (args.verify_reads // world) * world
+    cells = max(50, int(round(V * WORKLOAD["n_cells"] / WORKLOAD["n_reads"])))
+    tables = SynthTables(make_spec(V, cells, wl_parts, seed=47))
+    per = V // world
+    buf = torch.empty(per * 16, dtype=torch.uint8, device=f"cuda:{dev}")
+    tables.generate_device(dev, rank * per, per, buf.data_ptr())
+
+    def config(sharded):
+        return dg.Config(cb_len=16, umi_len=12, n_genes=WORKLOAD["n_genes"], device=dev, merge_type=dg.MERGE_REAL, barcodes_type=dg.BARCODES_CONST,
+                         barcodes_file=wl_path, min_genes_before_merge=WORKLOAD["min_genes_before"], min_genes_after_merge=WORKLOAD["min_genes_after"],
+                         max_cb_merge_edit_distance=WORKLOAD["max_cb_ed"], min_merge_fraction=WORKLOAD["min_frac"], sharded=sharded)
+
+    def collect(c):
+        def trip(cells_kind, mat):
+            cl = c.cells(cells_kind)
+            indptr, genes, vals = c.matrix(mat)
+            col = np.repeat(np.arange(indptr.shape[0] - 1), np.diff(indptr))
+            return np.stack([cl["barcode"][col].astype(np.uint64), genes.astype(np.uint64), vals.astype(np.uint64)], axis=1)
+
+        filt = c.cells(dg.CELLS_FILTERED)
+        a, b = c.merge_pairs()
+        return {"cm": trip(dg.CELLS_FILTERED, dg.MATRIX_CM), "raw": trip(dg.CELLS_REAL, dg.MATRIX_CM_RAW), "pairs": np.stack([a, b], axis=1),
+                "filt": np.stack([filt["barcode"], filt["umis_stat"].astype(np.uint64), filt["reads_stat"].astype(np.uint64),
+                                  filt["requested_genes_num"].astype(np.uint64)], axis=1)}
+
+    c = dg.Container(config(True))
+    c.set_stream(stream.cuda_stream)
+    pipe = dgdist.PipelinedExchange(dev, per, world, n_slices=4)
+    pipe.run(c, buf.data_ptr(), stream)
+    c.set_initialized()
+    dgdist.merge_across_ranks(c, f"cuda:{dev}")
+    c.merge_and_filter()
+    mine = collect(c)
+    s = c.summary()
+    c.close()
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(pickle.dumps(mine), gathered, dst=0)
+    nm = torch.tensor([s["n_merged"], s["n_excluded"]], device=f"cuda:{dev}")
+    dist.all_reduce(nm)
+    if rank != 0:
+        return None
+    full = torch.empty(V * 16, dtype=torch.uint8, device=f"cuda:{dev}")
+    tables.generate_device(dev, 0, V, full.data_ptr())
+    c1 = dg.Container(config(False))
+    c1.add_batch_device(full.data_ptr(), V)
+    c1.set_initialized()
+    c1.merge_and_filter()
+    ref = collect(c1)
+    s1 = c1.summary()
+    c1.close()
+    order = lambda t: t[np.lexsort(tuple(t[:, k] for k in reversed(range(t.shape[1]))))] if t.shape[0] else t
+    shards = [pickle.loads(g) for g in gathered]
+    match = all(np.array_equal(order(np.concatenate([sh[k] for sh in shards])), order(ref[k])) for k in ("cm", "raw", "pairs", "filt"))
+    match = match and int(nm[0]) == s1["n_merged"] and int(nm[1]) == s1["n_excluded"]
+    return {"reads": V, "cells": cells, "match": bool(match), "n_merged": s1["n_merged"], "n_excluded": s1["n_excluded"], "cm_nnz": s1["cm_nnz"],
+            "what": "union of the %d shards' cm / cm_raw triplets, merge pairs and filtered-cell rows == single-GPU run on the same stream" % world}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -166,6 +261,9 @@ def main():
     ap.add_argument("--cpu-sample-reads", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--slices", type=int, default=8, help="N > 1: slices of the pipelined route / all-to-all / fill")
+    ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the sharded == single-GPU check")
+    ap.add_argument("--verify-reads", type=int, default=16_000_000)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -242,30 +340,33 @@ def main():
     cont.set_stream(stream.cuda_stream)
     lib = dg.load_library()
 
-    routed = recv = None
+    pipe = None
     if world > 1:
         from dropest_b200 import dist as dgdist
 
-        routed = torch.empty_like(raw)
-        recv = torch.empty(int(n * 1.25) * 16 + 4096, dtype=torch.uint8, device=f"cuda:{dev}")
+        pipe = dgdist.PipelinedExchange(dev, n, world, n_slices=args.slices)
+    phase_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(max(1, args.steps))]
+    phase_ms = {"ms_route_a2a_fill": 0.0, "ms_group_init": 0.0, "ms_dist_merge": 0.0, "ms_filter_matrices": 0.0}
 
-    def exchange():
-        """route by barcode hash (our kernel) + ONE all-to-all-v over NCCL; returns (ptr, count) of the records this rank owns"""
-        counts = dgdist.route_device(dev, raw.data_ptr(), n, world, routed.data_ptr(), stream.cuda_stream)
-        got, cnt = dgdist.exchange(routed, counts, recv=recv)
-        return got.data_ptr(), cnt
-
-    def step():
+    def step(k=None):
+        """k = index of the timed step (records the phase events), None = warm-up"""
+        ev = phase_ev[k] if k is not None else None
         cont.reset()
+        if ev: ev[0].record(stream)
         if world > 1:
-            ptr, cnt = exchange()
+            # barcode-hash routing (our kernel) + all-to-all-v over NCCL in slices, overlapped with the fill of the received slices
+            cnt = pipe.run(cont, raw.data_ptr(), stream)
         else:
-            ptr, cnt = raw.data_ptr(), n
-        cont.add_batch_device(ptr, cnt)
+            cnt = n
+            cont.add_batch_device(raw.data_ptr(), n)
+        if ev: ev[1].record(stream)
         cont.set_initialized()
+        if ev: ev[2].record(stream)
         if world > 1:
-            dgdist.merge_across_ranks(cont, f"cuda:{dev}")  # exact cross-rank whitelist merge: two all-gathers
+            dgdist.merge_across_ranks(cont, f"cuda:{dev}")  # exact cross-rank whitelist merge: every rank works on its own cells
+        if ev: ev[3].record(stream)
         cont.merge_and_filter()
+        if ev: ev[4].record(stream)
         return cnt
 
     def barrier():
@@ -285,8 +386,8 @@ def main():
     dedup_ms, dedup_launches, launches, stage = 0.0, 0, 0, {"ms_fill": 0.0, "ms_init": 0.0, "ms_merge": 0.0, "ms_finish": 0.0}
     fill_ms, fill_launches = 0.0, 0
     ev0.record(stream)
-    for _ in range(args.steps):
-        step()
+    for k in range(args.steps):
+        step(k)
         t = cont.timings()
         dedup_ms += t["ms_dedup_kernel"]; dedup_launches += t["n_dedup_launches"]; launches += t["n_kernel_launches"]
         fill_ms += t["ms_fill_kernel"]; fill_launches += t["n_fill_launches"]
@@ -295,6 +396,9 @@ def main():
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
+    for evs in phase_ev[: args.steps]:
+        for name, a, b in zip(phase_ms, evs[:-1], evs[1:]):
+            phase_ms[name] += a.elapsed_time(b) / args.steps
     clocks = sampler.stop()
     summary = cont.summary()
     if world > 1:
@@ -330,10 +434,22 @@ def main():
                 bufs["genes"] = torch.empty(int(nnz * 1.2) + 1024, dtype=torch.int32, pin_memory=True)
                 bufs["vals"] = torch.empty(int(nnz * 1.2) + 1024, dtype=torch.int32, pin_memory=True)
 
+        host_aos = None
+        if world > 1:
+            # multi-GPU: the rank's own slice of the stream as 16-byte records on the host; they are copied to the device, routed by
+            # barcode hash, exchanged (pipelined all-to-all) and filled -- the same path as `value` plus the H2D copy
+            host_aos = torch.empty(n * 16, dtype=torch.uint8, pin_memory=True)
+            host_aos.copy_(raw)
+            torch.cuda.synchronize()
+
         def e2e_step():
             nonlocal d2h
             cont.reset()
-            cont.add_batch_soa_ptr(host_keys.data_ptr(), host_genes.data_ptr(), n, idx0)
+            if world > 1:
+                raw.copy_(host_aos, non_blocking=True)
+                pipe.run(cont, raw.data_ptr(), stream)
+            else:
+                cont.add_batch_soa_ptr(host_keys.data_ptr(), host_genes.data_ptr(), n, idx0)
             cont.set_initialized()
             if world > 1:
                 dgdist.merge_across_ranks(cont, f"cuda:{dev}")
@@ -358,11 +474,25 @@ def main():
             tt = torch.tensor([dt], device=f"cuda:{dev}")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-        e2e = {"value": n * world / dt, "unit": "reads/s", "h2d_bytes_per_step": n * 12 * world, "d2h_bytes_per_step": int(d2h) * world,
-               "note": ("per-rank host records already owned by the rank (no routing), cross-rank merge included; " if world > 1 else "")
+        e2e = {"value": n * world / dt, "unit": "reads/s", "h2d_bytes_per_step": n * (16 if world > 1 else 12) * world, "d2h_bytes_per_step": int(d2h) * world,
+               "note": ("per-rank host records (16 B) -> H2D -> barcode-hash routing + pipelined all-to-all + fill, cross-rank merge included; " if world > 1 else "")
                        + "cm checksum %d" % checksum}
         del host_keys, host_genes
 
+    # ---- N > 1: the sharded pipeline against a single-GPU run on one global stream (outside the timed region)
+    verify = None
+    if world > 1 and not args.no_verify:
+        verify = verify_sharded(args, dg, dgdist, torch, wl_path, wl_parts, dev, rank, world, stream)
+    # ---- N > 1: what the step is made of (CUDA events on the launching stream, mean over the timed steps, max over ranks)
+    breakdown = None
+    if world > 1:
+        import torch.distributed as dist
+
+        diag = exchange_diagnostics(pipe, cont, raw, stream, torch, dist, n, world)
+        names = list(phase_ms) + list(diag)
+        t = torch.tensor([phase_ms[k] for k in phase_ms] + [diag[k] for k in diag], device=f"cuda:{dev}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        breakdown = {k: float(v) for k, v in zip(names, t.tolist())}
     if rank != 0:
         return
     # ---- roofline of the dominant kernel, timed live with CUDA events inside the library (on the launching stream).
@@ -402,7 +532,13 @@ def main():
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "result": {k: summary[k] for k in ("total_cells_number", "real_cells_number", "filtered_cells_number", "n_umigs", "cm_nnz", "n_merged", "n_excluded", "n_unresolved")}}
     if world > 1:
-        line["config"]["merge"] += "; cross-rank merge via all-gather of candidate cells (dge_dist_*), result.* are rank 0's shard"
+        line["config"]["workload"] = ("10x v3 sharded by barcode hash: %d x (%dM reads / %d cells) = %dM reads / %d cells / 30k genes, 16bp CB + 12bp UMI, %d GPUs "
+                                      "(BASELINE configs[3] '4B reads / 100k cells on 8 GPUs' at the per-GPU size of configs[1])"
+                                      % (world, n // 1_000_000, args.cells, n * world // 1_000_000, args.cells * world, world))
+        line["config"]["merge"] += "; exact cross-rank merge (dge_dist_step: all-gather of target summaries + 3 small all-to-alls), result.* are rank 0's shard"
+        line["config"]["exchange"] = "%d slices: route kernel -> NCCL all_to_all_single (async) -> fill, overlapped" % pipe.n_slices
+        line["step_breakdown_ms"] = breakdown
+        line["verify"] = verify
     if world == 1 and not args.no_cpu_baseline:
         try:
             cb = cpu_reference_run(wl_path, wl_parts, args.cpu_sample_reads, keep=True)

@@ -35,10 +35,8 @@ CELL_INFO_DTYPE = np.dtype(
 )
 assert CELL_INFO_DTYPE.itemsize == 40
 
-DIST_CHILD_DTYPE = np.dtype([("barcode", "<u8"), ("umis_stat", "<i4"), ("reads_stat", "<i4"), ("n_genes", "<i4"),
-                             ("n_intergenic", "<u4"), ("n_entries", "<u4"), ("local_index", "<u4")])
-DIST_RESULT_DTYPE = np.dtype([("best_fraction", "<f8"), ("best_barcode", "<u8"), ("n_neighbours", "<u4"), ("n_best", "<u4")])
-assert DIST_CHILD_DTYPE.itemsize == 32 and DIST_RESULT_DTYPE.itemsize == 24
+DIST_MAX_WORLD = 64
+DIST_DONE, DIST_ALLGATHER, DIST_ALLTOALL = 0, 1, 2
 
 # exported symbols of include/dropest_b200.h (checked by tests/test_abi.py)
 EXPORTS = [
@@ -46,8 +44,7 @@ EXPORTS = [
     "dge_set_initialized", "dge_merge_and_filter", "dge_reset", "dge_set_stream", "dge_get_summary", "dge_get_timings", "dge_get_cells",
     "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
-    "dge_route_by_barcode_device", "dge_dist_export_children", "dge_dist_copy_children", "dge_dist_eval_children", "dge_dist_apply",
-    "dge_dist_apply_device",
+    "dge_route_by_barcode_device", "dge_route_slices_device", "dge_dist_step",
     "dge_umi_first_size", "dge_umi_first_export", "dge_umi_first_import", "dge_collisions_adjusted_sizes",
 ]
 
@@ -76,6 +73,12 @@ class _Summary(C.Structure):
         "n_reads", "total_cells_number", "real_cells_number", "filtered_cells_number", "n_genes_seen", "n_umigs",
         "intergenic_reads", "has_exon_reads", "has_intron_reads", "has_not_annotated_reads", "cm_nnz", "cm_raw_nnz",
         "n_merged", "n_excluded", "n_unresolved", "n_umis_merged", "n_umi_segments_replayed", "n_cb_merge_replayed", "n_host_flow")]
+
+
+class _DistIO(C.Structure):
+    """dge_dist_io (include/dropest_b200.h): one step of the cross-rank merge state machine."""
+    _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("collective", C.c_uint32), ("stage", C.c_uint32), ("send", C.c_void_p),
+                ("send_bytes", C.c_uint64 * DIST_MAX_WORLD), ("recv", C.c_void_p), ("recv_bytes", C.c_uint64 * DIST_MAX_WORLD)]
 
 
 class _Timings(C.Structure):
@@ -141,12 +144,7 @@ def load_library():
     lib.dge_whitelist_token.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]
     lib.dge_synth_generate_device.argtypes = [C.c_int, C.POINTER(_SynthParams), C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.dge_route_by_barcode_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.dge_dist_export_children.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
-                                             C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-    lib.dge_dist_copy_children.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
-    lib.dge_dist_eval_children.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
-    lib.dge_dist_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
-    lib.dge_dist_apply_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.dge_dist_step.argtypes = [C.c_void_p, C.POINTER(_DistIO)]
     lib.dge_umi_first_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
     lib.dge_umi_first_export.argtypes = [C.c_void_p, C.c_void_p]
     lib.dge_umi_first_import.argtypes = [C.c_void_p, C.c_void_p]
@@ -295,29 +293,15 @@ class Container:
         self._check(self._lib.dge_merge_and_filter(self._h))
 
     # ---- cross-rank merge steps (sharded runs); the collectives live in dropest_b200/dist.py
-    def dist_export_children(self):
-        p = [C.c_void_p(), C.c_void_p(), C.c_void_p()]
-        nc, ne = C.c_uint64(0), C.c_uint64(0)
-        self._check(self._lib.dge_dist_export_children(self._h, C.byref(p[0]), C.byref(p[1]), C.byref(p[2]), C.byref(nc), C.byref(ne)))
-        return int(nc.value), int(ne.value)
+    def dist_io(self, world: int, rank: int) -> "_DistIO":
+        io = _DistIO()
+        io.world, io.rank = world, rank
+        return io
 
-    def dist_copy_children(self, infos_ptr: int, keys_ptr: int, vals_ptr: int, n_children: int, n_entries: int):
-        self._check(self._lib.dge_dist_copy_children(self._h, C.c_void_p(infos_ptr), C.c_void_p(keys_ptr), C.c_void_p(vals_ptr), n_children, n_entries))
-
-    def dist_eval_children(self, infos_ptr: int, n_children: int, keys_ptr: int, vals_ptr: int, n_entries: int) -> np.ndarray:
-        res = np.zeros(n_children, dtype=DIST_RESULT_DTYPE)
-        self._check(self._lib.dge_dist_eval_children(self._h, C.c_void_p(infos_ptr), n_children, C.c_void_p(keys_ptr), C.c_void_p(vals_ptr),
-                                                     n_entries, res.ctypes.data))
-        return res
-
-    def dist_apply(self, all_results: np.ndarray, world: int, rank: int, child_rank: np.ndarray):
-        all_results = np.ascontiguousarray(all_results, dtype=DIST_RESULT_DTYPE)
-        child_rank = np.ascontiguousarray(child_rank, dtype=np.uint32)
-        self._check(self._lib.dge_dist_apply(self._h, all_results.ctypes.data, world, rank, child_rank.ctypes.data))
-
-    def dist_apply_device(self, all_results_dev_ptr: int, world: int, rank: int, child_rank: np.ndarray):
-        child_rank = np.ascontiguousarray(child_rank, dtype=np.uint32)
-        self._check(self._lib.dge_dist_apply_device(self._h, C.c_void_p(all_results_dev_ptr), world, rank, child_rank.ctypes.data))
+    def dist_step(self, io: "_DistIO") -> int:
+        """One step of the cross-rank whitelist merge (dge_dist_step); returns io.collective."""
+        self._check(self._lib.dge_dist_step(self._h, C.byref(io)))
+        return int(io.collective)
 
     def umi_first_size(self) -> int:
         n = C.c_size_t(0)

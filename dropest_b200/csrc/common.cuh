@@ -75,6 +75,14 @@ struct KeyRegion
     uint32_t tile0; // index of the region's first tile in the partition pass (k_region_tiles)
 };
 
+// One tile of the L1 partition pass over the key regions (k_region_tiles -> k_l1_scatter_regions)
+struct KeyTile
+{
+    const uint64_t *keys;
+    uint32_t count;
+    uint32_t pad;
+};
+
 __host__ __device__ inline uint64_t mix64(uint64_t x)
 {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdull;

@@ -8,6 +8,7 @@
 // There is no CPU implementation of the grouping here: without a CUDA device every entry point fails.
 #include "../../include/dropest_b200.h"
 #include "collisions.cuh"
+#include "distmerge.cuh"
 #include "common.cuh"
 #include "fill.cuh"
 #include "merge.cuh"
@@ -82,6 +83,9 @@ struct dge_handle
 
     // fill-stage device state
     DevBuf tab, gene_first, umi_first, ctr, staging[2], ctr_counts;
+    DevBuf regions, hist12, hist_fold, region_tiles, key_tiles; // k_fill_pipe output: per-block key regions of every batch + the 12-bit L1 histogram
+    uint32_t n_regions = 0;
+    bool pipe_fill = false;       // the batches of this run were filled by k_fill_pipe (regions instead of dense chunks)
     bool track_umi_first = false; // strategies that depend on the UMI indexer's first-seen order
     std::vector<std::unique_ptr<KeyChunk>> chunks, chunk_pool;
     std::vector<DevBuf *> chunk_counts;
@@ -134,11 +138,10 @@ struct dge_handle
     PinnedBuf pin_umi;
     uint64_t n_umis_merged = 0, n_umi_segments_replayed = 0;
     DevBuf dist_infos, dist_keys, dist_vals, dist_jobs, dist_cb, dist_umis, dist_eoff;
-    std::vector<dge_dist_child> g_infos;
     std::vector<uint32_t> g_off;
     const uint64_t *g_keys = nullptr;
     const uint32_t *g_vals = nullptr;
-    std::vector<uint32_t> dist_targets, g_best_local;
+    std::vector<uint32_t> dist_targets;
     bool dist_done = false, slot_pc_built = false;
     uint64_t n_order_ties = 0;
 
@@ -165,6 +168,19 @@ struct dge_handle
     bool lazy_rows = false;          // rows_dev2 / sort_v[0] / gsort_* hold everything the mirror needs
     bool dev_merged = false;         // the merge ran in the device flow
     uint64_t sum_real = 0, sum_filtered = 0, sum_genes_seen = 0, n_host_fallback = 0;
+
+    // cross-rank merge state machine (dge_dist_step)
+    int dist_stage = 0;
+    uint32_t dist_world = 0, dist_rank = 0, n_self = 0, n_all = 0, n_pairs = 0, g_mask = 0;
+    uint64_t n_dist_slow = 0, n_dist_ties = 0;
+    DevBuf x_self_flag, x_self_one, x_self_off, x_self_idx, x_self_send, x_all, x_gcb, x_ggi, x_rank_off, x_nb_count, x_nb_gi, x_pair_cnt, x_pair_off,
+        x_pair_child, x_pair_gi, x_pair_pos, x_pair_eoff, x_pair_isect, x_dest, x_lay, x_send, x_local_jobs, x_local_isect, x_kept, x_rl, x_job_base,
+        x_reply_base, x_fjobs, x_fisect, x_reply, x_best, x_tie, x_merged_cb, x_clay, x_ccur, x_commit, x_commit_send, x_cl, x_cbase, x_fmoves,
+        x_fsize, x_foff, x_bad;
+    std::vector<uint32_t> hx_rank_off, hx_reply_base_recv;
+    std::vector<DistBlobLayout> hx_lay, hx_rl;
+    std::vector<SelfRec> hx_all;
+    std::vector<CellRow> hx_rows;
 
     MatrixDev cm, cm_raw;
     dge_timings timings{};
@@ -307,6 +323,10 @@ void reset_fill_state(dge_handle *h)
     }
     h->ctr.reserve(sizeof(FillCounters));
     DGE_CUDA(cudaMemsetAsync(h->ctr.p, 0, sizeof(FillCounters), h->stream));
+    h->hist12.reserve(4096 * 4); h->hist_fold.reserve(4096 * 4); h->region_tiles.reserve(64);
+    h->regions.reserve(size_t(4096) * 148 * sizeof(KeyRegion)); // every batch adds one region per block (<= 4096 batches)
+    DGE_CUDA(cudaMemsetAsync(h->hist12.p, 0, 4096 * 4, h->stream));
+    h->n_regions = 0; h->pipe_fill = false;
     h->overflow_flag.reserve(sizeof(int));
     DGE_CUDA(cudaMemsetAsync(h->overflow_flag.p, 0, sizeof(int), h->stream));
     h->scan_scratch.reserve(((size_t(1) << 20) + 64) * 4); // enough for any scan of < 2^32 elements
@@ -314,6 +334,36 @@ void reset_fill_state(dge_handle *h)
     DGE_CUDA(cudaMemsetAsync(h->chunk_count_pool.p, 0, 4096 * sizeof(unsigned long long), h->stream));
     DGE_LAUNCH_CHECK();
     h->launches += 2;
+}
+
+// Experiment kept behind DGE_L2_WINDOW=1 (default off): pin the barcode table's lines with a persisting access-policy window on the
+// launching stream for the duration of the fill kernel.  Measured on B200 at C2: the L2 set-aside it needs slows every later kernel
+// of the step (L2 partition pass 4.2 -> 8.1 ms) and the fill kernel itself does not gain (4.1 -> 5.0 ms): rejected.
+void set_table_l2_window(dge_handle *h, bool on)
+{
+    static const bool enabled = std::getenv("DGE_L2_WINDOW") && atoi(std::getenv("DGE_L2_WINDOW")) == 1;
+    if (!enabled) return;
+    static size_t persist_max[64] = {}, window_max[64] = {};
+    static bool queried[64] = {};
+    const int dev = h->cfg.device & 63;
+    if (!queried[dev])
+    {
+        cudaDeviceProp prop;
+        DGE_CUDA(cudaGetDeviceProperties(&prop, h->cfg.device));
+        persist_max[dev] = size_t(prop.persistingL2CacheMaxSize);
+        window_max[dev] = size_t(prop.accessPolicyMaxWindowSize);
+        if (persist_max[dev]) DGE_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist_max[dev]));
+        queried[dev] = true;
+    }
+    if (!persist_max[dev] || !window_max[dev]) return;
+    cudaStreamAttrValue attr{};
+    const size_t bytes = h->table_cap * sizeof(CellSlot);
+    attr.accessPolicyWindow.base_ptr = on ? h->tab.p : nullptr;
+    attr.accessPolicyWindow.num_bytes = on ? std::min(bytes, window_max[dev]) : 0;
+    attr.accessPolicyWindow.hitRatio = on ? float(std::min(1.0, double(persist_max[dev]) / double(std::max<size_t>(bytes, 1)))) : 0.f;
+    attr.accessPolicyWindow.hitProp = on ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    DGE_CUDA(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
 }
 
 // One batch already resident on the device: barcode-table insert + key packing into a fresh chunk.
@@ -327,7 +377,6 @@ void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n, const u
     if (!h->chunk_pool.empty()) { chunk = std::move(h->chunk_pool.back()); h->chunk_pool.pop_back(); }
     else chunk.reset(new KeyChunk());
     chunk->capacity = n;
-    chunk->keys.reserve(n * 8);
     chunk->d_count = h->chunk_count_pool.as<unsigned long long>() + h->n_chunk_counters++;
     // the kernel appends through FillCounters::n_keys; give every chunk its own cursor by pointing a private counter struct at it
     // (we keep one FillCounters per handle and move the cursor: n_keys is reset per chunk and accumulated on the host later)
@@ -341,7 +390,66 @@ void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n, const u
     DGE_CUDA(cudaEventRecord(h->fill_ev[h->n_fill_ev], h->stream));
     // variant 0: 256 threads x 8 records, gene first-seen words gathered from global memory
     // variant 1: 1024 threads x 4 records, one block per SM, gene first-seen words served from a shared-memory copy (needs n_genes * 4 B of it)
-    static const int fill_variant = std::getenv("DGE_FILL_VARIANT") ? atoi(std::getenv("DGE_FILL_VARIANT")) : 1;
+    // variant 2 (default): k_fill_pipe -- bulk-async record tiles through a shared-memory ring, per-block output regions, fused L1 histogram
+    static const int fill_variant = std::getenv("DGE_FILL_VARIANT") ? atoi(std::getenv("DGE_FILL_VARIANT")) : 2;
+    // shape of the pipelined kernel: consumer warps x records per thread x ring stages (DGE_FILL_SHAPE picks among the instantiations)
+    static const int fill_shape = std::getenv("DGE_FILL_SHAPE") ? atoi(std::getenv("DGE_FILL_SHAPE")) : 0;
+    auto pipe_launch = [&](auto cw_c, auto it_c, auto stg_c) -> bool {
+        constexpr int CW = decltype(cw_c)::value, IT = decltype(it_c)::value, STG = decltype(stg_c)::value, TILE = CW * 32 * IT;
+        const size_t smem = size_t(STG) * TILE * 16 + size_t((h->cfg.n_genes + 7u) & ~7u) * 2 + 4096 * 4;
+        const bool first_batch = h->chunks.empty();
+        if (smem > 224 * 1024 || !(first_batch || h->pipe_fill)) return false;
+        const void *src0 = soa ? static_cast<const void *>(soa_keys) : static_cast<const void *>(recs);
+        if ((reinterpret_cast<uintptr_t>(src0) & 15u) || (soa && (reinterpret_cast<uintptr_t>(soa_genes) & 15u)))
+            throw InvalidInput("device record arrays must be 16-byte aligned");
+        const size_t n_tiles = div_up(n, size_t(TILE));
+        const unsigned grid = unsigned(std::min<size_t>(n_tiles, 148));
+        const size_t region_cap = div_up(n_tiles, size_t(grid)) * TILE;
+        chunk->keys.reserve(size_t(grid) * region_cap * 8);
+        KeyRegion *regs = h->regions.as<KeyRegion>() + h->n_regions;
+        const Rec16 *r16p = reinterpret_cast<const Rec16 *>(recs);
+        uint32_t *umi_first_p = h->track_umi_first ? h->umi_first.as<uint32_t>() : nullptr;
+        set_table_l2_window(h, true);
+        static bool done[64][2] = {};
+        if (soa)
+        {
+            auto kern = k_fill_pipe<CW, IT, STG, true>;
+            if (!done[h->cfg.device & 63][1]) { DGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); done[h->cfg.device & 63][1] = true; }
+            kern<<<grid, (CW + 1) * 32, smem, h->stream>>>(r16p, n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes, h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(),
+                                                          region_cap, regs, h->ctr.as<FillCounters>(), umi_first_p, h->hist12.as<uint32_t>(), soa_keys, soa_genes, soa_first);
+        }
+        else
+        {
+            auto kern = k_fill_pipe<CW, IT, STG, false>;
+            if (!done[h->cfg.device & 63][0]) { DGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); done[h->cfg.device & 63][0] = true; }
+            kern<<<grid, (CW + 1) * 32, smem, h->stream>>>(r16p, n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes, h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(),
+                                                          region_cap, regs, h->ctr.as<FillCounters>(), umi_first_p, h->hist12.as<uint32_t>(), nullptr, nullptr, 0u);
+        }
+        DGE_LAUNCH_CHECK();
+        set_table_l2_window(h, false);
+        h->n_regions += grid;
+        h->pipe_fill = true;
+        DGE_CUDA(cudaEventRecord(h->fill_ev[h->n_fill_ev + 1], h->stream));
+        h->n_fill_ev += 2;
+        DGE_CUDA(cudaMemcpyAsync(chunk->d_count, &h->ctr.as<FillCounters>()->n_keys, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
+        ++h->launches;
+        h->chunks.push_back(std::move(chunk));
+        h->n_reads += n;
+        return true;
+    };
+    if (fill_variant == 2)
+    {
+        using std::integral_constant;
+        bool ok;
+        if (fill_shape == 1) ok = pipe_launch(integral_constant<int, 31>{}, integral_constant<int, 4>{}, integral_constant<int, 2>{});
+        else if (fill_shape == 2) ok = pipe_launch(integral_constant<int, 16>{}, integral_constant<int, 8>{}, integral_constant<int, 2>{});
+        else if (fill_shape == 3) ok = pipe_launch(integral_constant<int, 24>{}, integral_constant<int, 4>{}, integral_constant<int, 3>{});
+        else if (fill_shape == 4) ok = pipe_launch(integral_constant<int, 12>{}, integral_constant<int, 8>{}, integral_constant<int, 3>{});
+        else if (fill_shape == 5) ok = pipe_launch(integral_constant<int, 24>{}, integral_constant<int, 4>{}, integral_constant<int, 2>{});
+        else ok = pipe_launch(integral_constant<int, 30>{}, integral_constant<int, 4>{}, integral_constant<int, 2>{}); // measured best at C2
+        if (ok) return;
+    }
+    chunk->keys.reserve(n * 8);
     const size_t gene_smem = size_t(h->cfg.n_genes) * 4;
     uint32_t *umi_first = h->track_umi_first ? h->umi_first.as<uint32_t>() : nullptr;
     const Rec16 *r16 = reinterpret_cast<const Rec16 *>(recs);
@@ -641,6 +749,13 @@ void materialize_host(dge_handle *h)
             c.real = (cs[i].flags & 1u) != 0; c.merged = (cs[i].flags & 2u) != 0; c.excluded = (cs[i].flags & 4u) != 0;
             c.target = cs[i].target < 0 ? int32_t(i) : cs[i].target;
         }
+        if (h->dist_done && n)
+        {   // children merged into a cell of another rank: the target's barcode (dge_get_merge_pairs)
+            std::vector<unsigned long long> mcb;
+            d2h(mcb, h->x_merged_cb.p, n, st);
+            DGE_CUDA(cudaStreamSynchronize(st));
+            for (size_t i = 0; i < n; ++i) h->real[i].merged_to_cb = mcb[i];
+        }
         const uint32_t nf = h->n_filtered_dev;
         const uint32_t skip = (h->cfg.max_cells > 0 && uint32_t(h->cfg.max_cells) < nf) ? nf - uint32_t(h->cfg.max_cells) : 0u;
         h->filtered.assign(fl + skip, fl + nf);
@@ -673,7 +788,8 @@ void do_set_initialized(dge_handle *h)
     h->n_keys = n_keys;
 
     const uint64_t *keys_in = nullptr;
-    if (h->chunks.size() == 1) keys_in = h->chunks[0]->keys.as<uint64_t>();
+    if (h->pipe_fill) { /* the keys stay in the fill kernel's per-block regions: consumed as a list by the L1 partition pass */ }
+    else if (h->chunks.size() == 1) keys_in = h->chunks[0]->keys.as<uint64_t>();
     else if (h->chunks.size() > 1)
     {
         h->keys_all.reserve(n_keys * 8);
@@ -694,8 +810,20 @@ void do_set_initialized(dge_handle *h)
     if (n_keys)
     {
         const int l1_bits = std::min(choose_l1_bits(n_keys), h->kl.kb - 3);
-        // the compact-key array doubles as the L2 scatter target / in-place dedup buffer
-        const uint32_t *n_u_ptr = h->sc.run(keys_in, nullptr, n_keys, h->kl.kb, l1_bits, nullptr, const_cast<uint64_t *>(keys_in),
+        const uint32_t *l1_hist = nullptr;
+        uint64_t *keys_tmp = const_cast<uint64_t *>(keys_in); // the compact-key array doubles as the L2 scatter target / in-place dedup buffer
+        if (h->pipe_fill)
+        {
+            h->key_tiles.reserve((n_keys / (1024 * 8) + h->n_regions + 2) * sizeof(KeyTile));
+            k_region_tiles<<<1, 1024, 0, st>>>(h->regions.as<KeyRegion>(), h->n_regions, 1024 * 8, h->region_tiles.as<uint32_t>(), h->key_tiles.as<KeyTile>());
+            k_hist_fold<<<4, 256, 0, st>>>(h->hist12.as<uint32_t>(), l1_bits, h->hist_fold.as<uint32_t>());
+            h->launches += 2;
+            l1_hist = h->hist_fold.as<uint32_t>();
+            h->keys_all.reserve(n_keys * 8);
+            keys_tmp = h->keys_all.as<uint64_t>();
+            h->sc.set_regions(h->key_tiles.as<KeyTile>(), h->n_regions, h->region_tiles.as<uint32_t>());
+        }
+        const uint32_t *n_u_ptr = h->sc.run(keys_in, nullptr, n_keys, h->kl.kb, l1_bits, l1_hist, keys_tmp,
                                             h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), h->overflow_flag.as<int>(), st, &h->sc_stats);
         h->n_u = d2h_scalar<uint32_t>(n_u_ptr, st);
         h->sc.collect_timing();
@@ -1693,6 +1821,8 @@ bool umi_merge_directional(dge_handle *h)
 // sequential loop of MergeStrategyBase.cpp:29-51 is order-free), refreshed sizes, final filter in compare_cells order and the two
 // matrices -- all from the device-resident CellRow / CellState tables.  Returns false (nothing modified) when a cell needs the
 // exact host logic: a far distance class, an order-dependent tie, a merge chain, counters beyond the packed sort key.
+void merge_device_finish(dge_handle *h);
+
 bool merge_device_flow(dge_handle *h)
 {
     cudaStream_t st = h->stream;
@@ -1740,7 +1870,23 @@ bool merge_device_flow(dge_handle *h)
         tr.mark("merge: phase 2 + apply (device)");
     }
     DGE_CUDA(cudaEventRecord(h->ev[4], st));
+    merge_device_finish(h);
+    return true;
+}
 
+// Second half of the device flow (also the tail of the cross-rank merge, dge_dist_step): refreshed sizes of the merge targets,
+// is_real, final filter in compare_cells order, cm / cm_raw.
+void merge_device_finish(dge_handle *h)
+{
+    cudaStream_t st = h->stream;
+    Tracer tr; tr.st = st;
+    const size_t n = h->n_real_rows;
+    const uint32_t n32 = uint32_t(n);
+    CellRow *rows = h->rows_dev2.as<CellRow>();
+    CellState *cs = h->cell_state.as<CellState>();
+    DevFlowCounters *ctr = h->df_ctr.as<DevFlowCounters>();
+    DevFlowCounters hc{};
+    const unsigned g = grid_for(n, 256);
     // ---- refreshed sizes, is_real, final filter (update_filtered_gene_counts, CellsDataContainer.cpp:250-276)
     h->real_flag.reserve((n + 1) * 4); h->real_off.reserve((n + 1) * 4);
     k_refresh_rows<<<g, 256, 0, st>>>(rows, cs, n32, h->pc_cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), h->pc_req_genes.as<uint32_t>(),
@@ -1778,7 +1924,6 @@ bool merge_device_flow(dge_handle *h)
     h->sum_real = n_real_final;
     h->sum_filtered = nf - skip;
     h->dev_merged = true;
-    return true;
 }
 
 void do_merge_and_filter(dge_handle *h)
@@ -1787,7 +1932,7 @@ void do_merge_and_filter(dge_handle *h)
     cudaStream_t st = h->stream;
     Tracer tr;
     tr.st = st;
-    DGE_CUDA(cudaEventRecord(h->ev[3], st));
+    if (!h->dist_done) DGE_CUDA(cudaEventRecord(h->ev[3], st));
     if (!h->slot_pc_built) build_slot_pc(h);
 
     // ---- device flow: no host cell rows at all (the common configurations); anything it cannot decide exactly -> host flow
@@ -1795,7 +1940,18 @@ void do_merge_and_filter(dge_handle *h)
     const bool dev_flow = !no_dev_flow && h->lazy_rows && !h->cfg.sharded && !h->dist_done && h->n_real_rows > 0 &&
                           (h->cfg.merge_type == DGE_MERGE_NONE || (h->cfg.merge_type == DGE_MERGE_REAL && h->wl_fast)) &&
                           h->cfg.umi_merge_type == DGE_UMI_MERGE_SIMPLE && h->cfg.min_genes_before_merge > 0;
-    if (dev_flow && merge_device_flow(h))
+    // sharded run: phase 1/2 ran across ranks in dge_dist_step; with a UMI merge strategy that changes U (-u) the host tail below
+    // continues from the merged state, otherwise the device tail finishes the run
+    const bool after_dist = h->dist_done && h->cfg.umi_merge_type != DGE_UMI_MERGE_SIMPLE;
+    if (h->dist_done) merge_device_finish(h);
+    if (after_dist)
+    {
+        DGE_CUDA(cudaStreamSynchronize(st));
+        h->state = 2;           // materialize_host applies the merge outcome (flags, counters, refreshed target sizes)
+        materialize_host(h);
+        h->state = 1;
+    }
+    else if (h->dist_done || (dev_flow && merge_device_flow(h)))
     {
         DGE_CUDA(cudaEventRecord(h->ev[5], st));
         DGE_CUDA(cudaStreamSynchronize(st));
@@ -1814,9 +1970,7 @@ void do_merge_and_filter(dge_handle *h)
     materialize_host(h);
 
     // ---- CB merge (MergeStrategyAbstract::merge, MergeStrategyAbstract.cpp:13-23)
-    if (h->dist_done)
-    {   // sharded run: phase 1/2 were done across ranks by dge_dist_eval_children / dge_dist_apply
-    }
+    if (after_dist) {}
     else if (h->cfg.merge_type == DGE_MERGE_REAL)
     {
         phase1_real(h, h->h_target);
@@ -1996,6 +2150,50 @@ void fill_info(const dge_handle *h, const HostCell &c, dge_cell_info &ci)
 
 } // namespace
 
+namespace
+{
+template <class T> void h2d_vec(DevBuf &dst, const std::vector<T> &src, cudaStream_t st)
+{
+    dst.reserve(std::max<size_t>(src.size(), 1) * sizeof(T));
+    if (!src.empty()) DGE_CUDA(cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+
+// Exact host enumeration for the few children the device walk cannot settle (no eligible class-1 neighbour anywhere -> farther
+// distance classes; duplicated whitelist tokens): RealBarcodesMergeStrategy::get_real_neighbour_cbs against the gathered self cells.
+struct DistHostView
+{
+    std::unordered_map<uint64_t, uint32_t> by_cb;
+    void build(const std::vector<SelfRec> &all)
+    {
+        by_cb.reserve(all.size() * 2);
+        for (uint32_t i = 0; i < all.size(); ++i) by_cb.emplace(all[i].cb, i);
+    }
+};
+
+std::vector<long> dist_exact_neighbours(const dge_handle *h, const DistHostView &v, const CellRow &child)
+{
+    auto lookup = [&](const std::string &sq) -> long {
+        uint64_t packed;
+        if (!pack_seq(sq, packed)) return -1;
+        auto it = v.by_cb.find(packed);
+        return it == v.by_cb.end() ? -1 : long(it->second);
+    };
+    auto eligible = [&](long gi) { return h->hx_all[size_t(gi)].umis >= child.n_umis; };
+    return h->wl.neighbours(unpack_seq(child.cb, h->cfg.cb_len), false, lookup, eligible);
+}
+
+void dist_fetch_host_tables(dge_handle *h)
+{
+    cudaStream_t st = h->stream;
+    if (h->hx_all.size() != h->n_all || h->hx_rows.size() != h->n_real_rows)
+    {
+        d2h(h->hx_all, h->x_all.p, h->n_all, st);
+        d2h(h->hx_rows, h->rows_dev2.p, h->n_real_rows, st);
+        DGE_CUDA(cudaStreamSynchronize(st));
+    }
+}
+} // namespace
+
 // =====================================================================================================================
 extern "C" {
 
@@ -2103,11 +2301,11 @@ static void add_host_slices(dge_handle *h, const dge_record16 *recs, const unsig
         h->staging_turn ^= 1;
         // the fill kernel that last read this staging buffer must have finished before it is overwritten
         DGE_CUDA(cudaStreamWaitEvent(h->copy_stream, h->staging_ev[turn], 0));
-        if (stg.bytes < m * 16) { DGE_CUDA(cudaEventSynchronize(h->staging_ev[turn])); stg.reserve(m * 16); }
+        if (stg.bytes < m * 16 + 64) { DGE_CUDA(cudaEventSynchronize(h->staging_ev[turn])); stg.reserve(m * 16 + 64); }
         if (soa)
         {
             unsigned long long *dk = stg.as<unsigned long long>();
-            uint32_t *dg = reinterpret_cast<uint32_t *>(dk + m);
+            uint32_t *dg = reinterpret_cast<uint32_t *>(dk + ((m + 1) & ~size_t(1))); // 16-byte aligned (bulk copies)
             DGE_CUDA(cudaMemcpyAsync(dk, keys + off, m * 8, cudaMemcpyHostToDevice, h->copy_stream));
             DGE_CUDA(cudaMemcpyAsync(dg, genes + off, m * 4, cudaMemcpyHostToDevice, h->copy_stream));
             DGE_CUDA(cudaEventRecord(h->copied_ev[turn], h->copy_stream));
@@ -2156,7 +2354,7 @@ int dge_reset(dge_handle *h)
         h->cm.built = h->cm_raw.built = false;
         h->host_stage = 0; h->lazy_rows = false; h->dev_merged = false; h->n_real_rows = 0; h->n_filtered_dev = 0;
         h->sum_real = h->sum_filtered = h->sum_genes_seen = 0; h->n_host_fallback = 0;
-        h->dist_done = false; h->slot_pc_built = false; h->dist_targets.clear(); h->g_infos.clear(); h->n_order_ties = 0;
+        h->dist_done = false; h->slot_pc_built = false; h->dist_targets.clear(); h->n_order_ties = 0; h->dist_stage = 0;
         h->timings = dge_timings{}; h->sc_stats = SortCombineStats{}; h->launches = 0;
         h->state = 0;
         if (h->device_ready) reset_fill_state(h);
@@ -2179,328 +2377,413 @@ int dge_merge_and_filter(dge_handle *h)
     return guarded(h, [&] { do_merge_and_filter(h); return int(DGE_OK); });
 }
 
-// ---- cross-rank whitelist merge (see include/dropest_b200.h) ---------------------------------------------------------------
-static void dist_check(dge_handle *h)
+// ---- cross-rank whitelist merge (see include/dropest_b200.h and csrc/distmerge.cuh) ----------------------------------------------
+extern "C" int dge_dist_step(dge_handle *h, dge_dist_io *io)
 {
-    if (h->state != 1) throw std::runtime_error("cross-rank merge runs between dge_set_initialized and dge_merge_and_filter");
-    if (!h->cfg.sharded || h->cfg.merge_type != DGE_MERGE_REAL) throw std::runtime_error("cross-rank merge needs sharded = 1 and merge_type = DGE_MERGE_REAL");
-}
-
-int dge_dist_export_children(dge_handle *h, const dge_dist_child **infos_device, const uint64_t **keys_device,
-                             const uint32_t **vals_device, uint64_t *n_children, uint64_t *n_entries)
-{
-    if (!h || !infos_device || !keys_device || !vals_device || !n_children || !n_entries) return fail(h, DGE_ERR_INVALID, "null argument");
-    return guarded(h, [&] {
-        dist_check(h);
-        DGE_CUDA(cudaSetDevice(h->cfg.device));
-        cudaStream_t st = h->stream;
-        materialize_host(h);
-        if (!h->slot_pc_built) build_slot_pc(h);
-        const size_t n = h->real.size();
-        // which local real cells are whitelist barcodes themselves (target = self)?
-        std::vector<char> is_self(n, 0);
-        if (h->wl_fast && n)
-        {
-            if (!h->wl_uploaded) { upload_whitelist(h); h->wl_uploaded = true; }
-            h->h_cbs.resize(n); h->h_umis.resize(n);
-            for (size_t i = 0; i < n; ++i) { h->h_cbs[i] = h->real[i].cb; h->h_umis[i] = uint32_t(h->real[i].umis_stat); }
-            h->d_cb.reserve(n * 8); h->d_umis.reserve(n * 4); h->d_count.reserve(n * 4); h->d_nb.reserve(n * WL_K * 4);
-            DGE_CUDA(cudaMemcpyAsync(h->d_cb.p, h->h_cbs.data(), n * 8, cudaMemcpyHostToDevice, st));
-            DGE_CUDA(cudaMemcpyAsync(h->d_umis.p, h->h_umis.data(), n * 4, cudaMemcpyHostToDevice, st));
-            k_wl_class01<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>(), uint32_t(n), h->wl_dev,
-                                                                                h->tab.as<CellSlot>(), h->kl.tb, h->slot_pc.as<uint32_t>(),
-                                                                                h->pc_cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(),
-                                                                                h->cfg.min_genes_before_merge, h->d_count.as<int>(), h->d_nb.as<uint32_t>());
-            DGE_LAUNCH_CHECK();
-            ++h->launches;
-            const int *cnt = d2h_pinned<int>(h->pin_nbc, h->d_count.p, n, st);
-            DGE_CUDA(cudaStreamSynchronize(st));
-            for (size_t i = 0; i < n; ++i) is_self[i] = cnt[i] == NB_SELF;
-        }
-        else
-            for (size_t i = 0; i < n; ++i) is_self[i] = h->wl.contains(unpack_seq(h->real[i].cb, h->cfg.cb_len));
-        std::vector<dge_dist_child> infos;
-        std::vector<MoveJobLite> jobs;
-        uint64_t total = 0;
-        for (uint32_t i = 0; i < n; ++i)
-        {
-            const HostCell &c = h->real[i];
-            if (is_self[i]) { h->real[i].target = int32_t(i); continue; }
-            dge_dist_child ci;
-            ci.barcode = c.cb; ci.umis_stat = c.umis_stat; ci.reads_stat = c.reads_stat; ci.n_genes = c.n_genes;
-            ci.n_intergenic = c.n_intergenic; ci.n_entries = c.pc == NONE32 ? 0u : uint32_t(c.n_umis_distinct); ci.local_index = i;
-            if (ci.n_entries) jobs.push_back(MoveJobLite{c.pc, uint32_t(total)});
-            total += ci.n_entries;
-            infos.push_back(ci);
-        }
-        if (total >= 0xFFFFFFF0ull) throw std::runtime_error("children volume exceeds 2^32 entries");
-        h->dist_infos.reserve(std::max<size_t>(infos.size(), 1) * sizeof(dge_dist_child));
-        h->dist_keys.reserve(std::max<uint64_t>(total, 1) * 8); h->dist_vals.reserve(std::max<uint64_t>(total, 1) * 4);
-        if (!infos.empty()) DGE_CUDA(cudaMemcpyAsync(h->dist_infos.p, infos.data(), infos.size() * sizeof(dge_dist_child), cudaMemcpyHostToDevice, st));
-        if (!jobs.empty())
-        {
-            h->dist_jobs.reserve(jobs.size() * sizeof(MoveJobLite));
-            DGE_CUDA(cudaMemcpyAsync(h->dist_jobs.p, jobs.data(), jobs.size() * sizeof(MoveJobLite), cudaMemcpyHostToDevice, st));
-            k_export_cells<<<grid_for(jobs.size(), 1, 148 * 16), 256, 0, st>>>(h->dist_jobs.as<MoveJobLite>(), uint32_t(jobs.size()), h->ukey.as<uint64_t>(),
-                                                                              h->uval.as<uint32_t>(), h->pc_u_start.as<uint32_t>(), h->kl.gb + h->kl.ub,
-                                                                              h->dist_keys.as<uint64_t>(), h->dist_vals.as<uint32_t>());
-            DGE_LAUNCH_CHECK();
-            ++h->launches;
-        }
-        DGE_CUDA(cudaStreamSynchronize(st));
-        *infos_device = h->dist_infos.as<dge_dist_child>(); *keys_device = h->dist_keys.as<uint64_t>(); *vals_device = h->dist_vals.as<uint32_t>();
-        *n_children = infos.size(); *n_entries = total;
-        return int(DGE_OK);
-    });
-}
-
-int dge_dist_copy_children(dge_handle *h, dge_dist_child *infos_dst_device, uint64_t *keys_dst_device, uint32_t *vals_dst_device,
-                           uint64_t n_children, uint64_t n_entries)
-{
-    if (!h) return DGE_ERR_INVALID;
-    return guarded(h, [&] {
-        dist_check(h);
-        DGE_CUDA(cudaSetDevice(h->cfg.device));
-        if (n_children) DGE_CUDA(cudaMemcpyAsync(infos_dst_device, h->dist_infos.p, n_children * sizeof(dge_dist_child), cudaMemcpyDeviceToDevice, h->stream));
-        if (n_entries)
-        {
-            DGE_CUDA(cudaMemcpyAsync(keys_dst_device, h->dist_keys.p, n_entries * 8, cudaMemcpyDeviceToDevice, h->stream));
-            DGE_CUDA(cudaMemcpyAsync(vals_dst_device, h->dist_vals.p, n_entries * 4, cudaMemcpyDeviceToDevice, h->stream));
-        }
-        DGE_CUDA(cudaStreamSynchronize(h->stream));
-        return int(DGE_OK);
-    });
-}
-
-int dge_dist_eval_children(dge_handle *h, const dge_dist_child *infos_device, uint64_t n_children, const uint64_t *keys_device,
-                           const uint32_t *vals_device, uint64_t n_entries, dge_dist_result *results_host)
-{
-    if (!h || (n_children && (!infos_device || !results_host))) return fail(h, DGE_ERR_INVALID, "null argument");
-    return guarded(h, [&] {
-        dist_check(h);
-        DGE_CUDA(cudaSetDevice(h->cfg.device));
-        cudaStream_t st = h->stream;
+    if (!h || !io) return fail(h, DGE_ERR_INVALID, "null argument");
+    return guarded(h, [&]() -> int {
+        if (h->state != 1) throw std::runtime_error("dge_dist_step runs between dge_set_initialized and dge_merge_and_filter");
+        if (!h->cfg.sharded || h->cfg.merge_type != DGE_MERGE_REAL) throw std::runtime_error("dge_dist_step needs sharded = 1 and merge_type = DGE_MERGE_REAL");
         if (!h->wl_fast) throw std::runtime_error("cross-rank merge needs a whitelist with equal-length, N-free parts");
-        if (!h->slot_pc_built) build_slot_pc(h);
-        if (!h->wl_uploaded) { upload_whitelist(h); h->wl_uploaded = true; }
-        const size_t n = size_t(n_children);
-        h->g_keys = keys_device; h->g_vals = vals_device;
-        const dge_dist_child *pinned_infos = d2h_pinned<dge_dist_child>(h->pin_rows, infos_device, n, st);
-        DGE_CUDA(cudaStreamSynchronize(st));
-        h->g_infos.assign(pinned_infos, pinned_infos + n);
-        h->g_off.assign(n + 1, 0);
-        for (size_t i = 0; i < n; ++i) h->g_off[i + 1] = h->g_off[i] + h->g_infos[i].n_entries;
-        if (h->g_off[n] != n_entries) throw std::runtime_error("children lists do not add up to n_entries");
-        if (!n) return int(DGE_OK);
-        // local candidates of every child: distance classes 0/1 against THIS rank's cells
-        static_assert(sizeof(DistChildDev) == sizeof(dge_dist_child) && sizeof(DistResult) == sizeof(dge_dist_result), "ABI structs");
-        h->d_cb.reserve(n * 8); h->d_umis.reserve(n * 4); h->d_count.reserve(n * 4); h->d_nb.reserve(n * WL_K * 4);
-        k_dist_child_columns<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const DistChildDev *>(infos_device), n, h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>());
-        ++h->launches;
-        k_wl_class01<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(h->d_cb.as<uint64_t>(), h->d_umis.as<uint32_t>(), uint32_t(n), h->wl_dev,
-                                                                            h->tab.as<CellSlot>(), h->kl.tb, h->slot_pc.as<uint32_t>(),
-                                                                            h->pc_cg_start.as<uint32_t>(), h->pc_u_start.as<uint32_t>(),
-                                                                            h->cfg.min_genes_before_merge, h->d_count.as<int>(), h->d_nb.as<uint32_t>());
-        DGE_LAUNCH_CHECK();
-        ++h->launches;
-        if (h->rows_on_device)
-        {   // jobs, intersections and the best local candidate per child in kernels; one result row per child comes back
-            const size_t nl = h->real.size();
-            const DistChildDev *infos = reinterpret_cast<const DistChildDev *>(infos_device);
-            h->dist_cb.reserve(std::max<size_t>(nl, 1) * 8); h->dist_umis.reserve(std::max<size_t>(nl, 1) * 4);
-            h->p1_pc.reserve(std::max<size_t>(nl, 1) * 4); h->p1_map.reserve((size_t(h->n_pc) + 2) * 4);
-            k_fill_u32<<<grid_for(size_t(h->n_pc) + 1, 256), 256, 0, st>>>(h->p1_map.as<uint32_t>(), size_t(h->n_pc) + 1, NONE32);
-            if (nl)
-                k_p1_columns<<<grid_for(nl, 256), 256, 0, st>>>(h->rows_dev2.as<CellRow>(), uint32_t(nl), h->dist_cb.as<uint64_t>(), h->dist_umis.as<uint32_t>(),
-                                                               h->p1_pc.as<uint32_t>(), h->p1_map.as<uint32_t>());
-            h->p1_cnt.reserve((n + 1) * 4); h->p1_off.reserve((n + 1) * 4); h->dist_eoff.reserve((n + 1) * 4);
-            k_dist_entry_counts<<<grid_for(n, 256), 256, 0, st>>>(infos, n, h->p1_cnt.as<uint32_t>());
-            DGE_CUDA(cudaMemsetAsync(h->p1_cnt.as<uint32_t>() + n, 0, 4, st));
-            device_exclusive_scan(h->p1_cnt.as<uint32_t>(), h->dist_eoff.as<uint32_t>(), n + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
-            k_p1_counts<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), uint32_t(n), h->p1_cnt.as<uint32_t>());
-            DGE_CUDA(cudaMemsetAsync(h->p1_cnt.as<uint32_t>() + n, 0, 4, st));
-            device_exclusive_scan(h->p1_cnt.as<uint32_t>(), h->p1_off.as<uint32_t>(), n + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
-            const uint32_t n_jobs = d2h_scalar<uint32_t>(h->p1_off.as<uint32_t>() + n, st);
-            h->d_jobs.reserve(std::max<size_t>(n_jobs, 1) * sizeof(ForeignJob)); h->d_isect.reserve(std::max<size_t>(n_jobs, 1) * 4);
-            k_dist_jobs<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), h->d_nb.as<uint32_t>(), infos, h->dist_eoff.as<uint32_t>(), h->p1_off.as<uint32_t>(), n,
-                                                          h->d_jobs.as<ForeignJob>());
-            if (n_jobs)
-                k_intersect_foreign<<<n_jobs, 128, 0, st>>>(h->d_jobs.as<ForeignJob>(), n_jobs, keys_device, h->ukey.as<uint64_t>(), h->pc_u_start.as<uint32_t>(),
-                                                            h->pc_slot.as<uint32_t>(), h->kl.gb + h->kl.ub, h->d_isect.as<uint32_t>());
-            h->dist_jobs.reserve(n * sizeof(DistResult)); h->p1_target.reserve(n * 4);
-            k_dist_best<<<grid_for(n, 256), 256, 0, st>>>(h->d_count.as<int>(), h->d_nb.as<uint32_t>(), h->p1_off.as<uint32_t>(), h->d_isect.as<uint32_t>(), infos,
-                                                          h->p1_map.as<uint32_t>(), h->dist_cb.as<uint64_t>(), h->dist_umis.as<uint32_t>(), n,
-                                                          h->dist_jobs.as<DistResult>(), h->p1_target.as<uint32_t>());
-            DGE_LAUNCH_CHECK();
-            h->launches += 7;
-            const dge_dist_result *pr = d2h_pinned<dge_dist_result>(h->pin_isect, h->dist_jobs.p, n, st);
-            const uint32_t *pb = d2h_pinned<uint32_t>(h->pin_nbc, h->p1_target.p, n, st);
-            DGE_CUDA(cudaStreamSynchronize(st));
-            std::memcpy(results_host, pr, n * sizeof(dge_dist_result));
-            h->g_best_local.assign(pb, pb + n);
-            return int(DGE_OK);
-        }
-        const int *nb_count = d2h_pinned<int>(h->pin_nbc, h->d_count.p, n, st);
-        const uint32_t *nb_pc = d2h_pinned<uint32_t>(h->pin_nbp, h->d_nb.p, n * WL_K, st);
-        DGE_CUDA(cudaStreamSynchronize(st));
-        std::vector<ForeignJob> jobs;
-        std::vector<uint32_t> job_off(n + 1, 0);
-        for (size_t i = 0; i < n; ++i)
-        {
-            const int c = nb_count[i] > 0 ? nb_count[i] : 0; // NB_SLOW / overflow: no class-0/1 candidate here
-            for (int k = 0; k < c; ++k) jobs.push_back(ForeignJob{h->g_off[i], h->g_infos[i].n_entries, nb_pc[i * WL_K + size_t(k)]});
-            job_off[i + 1] = uint32_t(jobs.size());
-        }
-        const uint32_t *isect = nullptr;
-        if (!jobs.empty())
-        {
-            h->d_jobs.reserve(jobs.size() * sizeof(ForeignJob)); h->d_isect.reserve(jobs.size() * 4);
-            DGE_CUDA(cudaMemcpyAsync(h->d_jobs.p, jobs.data(), jobs.size() * sizeof(ForeignJob), cudaMemcpyHostToDevice, st));
-            k_intersect_foreign<<<unsigned(jobs.size()), 128, 0, st>>>(h->d_jobs.as<ForeignJob>(), uint32_t(jobs.size()), keys_device, h->ukey.as<uint64_t>(),
-                                                                       h->pc_u_start.as<uint32_t>(), h->pc_slot.as<uint32_t>(), h->kl.gb + h->kl.ub,
-                                                                       h->d_isect.as<uint32_t>());
-            DGE_LAUNCH_CHECK();
-            ++h->launches;
-            isect = d2h_pinned<uint32_t>(h->pin_isect, h->d_isect.p, jobs.size(), st);
-            DGE_CUDA(cudaStreamSynchronize(st));
-        }
-        std::vector<uint32_t> &pc_to_real = h->h_pc_to_real;
-        pc_to_real.assign(size_t(h->n_pc) + 1, NONE32);
-        for (uint32_t i = 0; i < h->real.size(); ++i) if (h->real[i].pc != NONE32) pc_to_real[h->real[i].pc] = i;
-        h->g_best_local.assign(n, NONE32);
-        for (size_t i = 0; i < n; ++i)
-        {
-            dge_dist_result r;
-            r.best_fraction = 0; r.best_barcode = EMPTY64; r.n_neighbours = job_off[i + 1] - job_off[i]; r.n_best = 0;
-            for (uint32_t j = job_off[i]; j < job_off[i + 1]; ++j)
+        if (io->world == 0 || io->world > DGE_DIST_MAX_WORLD || io->rank >= io->world) throw InvalidInput("bad world / rank");
+        DGE_CUDA(cudaSetDevice(h->cfg.device));
+        cudaStream_t st = h->stream;
+        const uint32_t world = io->world, me = io->rank;
+        const size_t n = h->n_real_rows;
+        const uint32_t n32 = uint32_t(n);
+        const unsigned g = grid_for(std::max<size_t>(n, 1), 256);
+        CellRow *rows = h->rows_dev2.as<CellRow>();
+        const int gub = h->kl.gb + h->kl.ub;
+        std::memset(io->send_bytes, 0, sizeof(io->send_bytes));
+        io->send = nullptr;
+        io->stage = uint32_t(h->dist_stage);
+
+        if (h->dist_stage == 0)
+        {   // ---- self cells -> all-gather
+            if (n && !h->lazy_rows) throw std::runtime_error("cross-rank merge needs the device-resident cell rows (min_genes_before_merge > 0)");
+            DGE_CUDA(cudaEventRecord(h->ev[3], st));
+            h->dist_world = world; h->dist_rank = me;
+            if (!h->wl_uploaded) { upload_whitelist(h); h->wl_uploaded = true; }
+            h->cell_state.reserve(std::max<size_t>(n, 1) * sizeof(CellState));
+            h->df_ctr.reserve(sizeof(DevFlowCounters));
+            DGE_CUDA(cudaMemsetAsync(h->df_ctr.p, 0, sizeof(DevFlowCounters), st));
+            h->x_bad.reserve(16);
+            DGE_CUDA(cudaMemsetAsync(h->x_bad.p, 0, 16, st));
+            h->x_self_flag.reserve((n + 1) * 4); h->x_self_one.reserve((n + 1) * 4); h->x_self_off.reserve((n + 1) * 4);
+            h->n_self = 0;
+            if (n)
             {
-                const uint32_t nb_idx = pc_to_real[jobs[j].nb_pc];
-                const HostCell &nb = h->real[nb_idx];
-                // same expression as RealBarcodesMergeStrategy.cpp:46-47
-                const double frac = 0.5 * isect[j] * (1. / size_t(h->g_infos[i].umis_stat) + 1. / size_t(nb.umis_stat));
-                if (r.n_best == 0 || r.best_fraction < frac) { r.best_fraction = frac; r.best_barcode = nb.cb; r.n_best = 1; h->g_best_local[i] = nb_idx; }
-                else if (frac == r.best_fraction)
-                {
-                    ++r.n_best;
-                    if (nb.cb < r.best_barcode) { r.best_barcode = nb.cb; h->g_best_local[i] = nb_idx; }
-                }
+                k_state_init<<<g, 256, 0, st>>>(rows, n32, h->cell_state.as<CellState>());
+                k_wl_self<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(rows, n32, h->wl_dev, h->x_self_flag.as<uint32_t>());
+                k_self_is_one<<<g, 256, 0, st>>>(h->x_self_flag.as<uint32_t>(), n32, h->x_self_one.as<uint32_t>());
+                DGE_CUDA(cudaMemsetAsync(h->x_self_one.as<uint32_t>() + n, 0, 4, st));
+                device_exclusive_scan(h->x_self_one.as<uint32_t>(), h->x_self_off.as<uint32_t>(), n + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+                h->n_self = d2h_scalar<uint32_t>(h->x_self_off.as<uint32_t>() + n, st);
+                h->launches += 3;
             }
-            results_host[i] = r;
+            h->x_self_send.reserve(std::max<size_t>(h->n_self, 1) * sizeof(SelfRec)); h->x_self_idx.reserve(std::max<size_t>(h->n_self, 1) * 4);
+            if (h->n_self)
+                k_self_export<<<g, 256, 0, st>>>(rows, h->x_self_flag.as<uint32_t>(), h->x_self_off.as<uint32_t>(), n32, h->x_self_send.as<SelfRec>(),
+                                                 h->x_self_idx.as<uint32_t>());
+            DGE_LAUNCH_CHECK();
+            DGE_CUDA(cudaStreamSynchronize(st));
+            io->collective = DGE_DIST_ALLGATHER;
+            io->send = h->x_self_send.p;
+            io->send_bytes[0] = uint64_t(h->n_self) * sizeof(SelfRec);
+            h->dist_stage = 1;
+            return DGE_OK;
         }
-        return int(DGE_OK);
-    });
-}
 
-// `red[c]` = the candidates of child c combined over all ranks (k_dist_reduce, or the host loop of dge_dist_apply)
-static int dist_apply_reduced(dge_handle *h, const dge_dist_result *red, uint32_t my_rank, const uint32_t *child_rank);
-
-int dge_dist_apply(dge_handle *h, const dge_dist_result *all, uint32_t world, uint32_t my_rank, const uint32_t *child_rank)
-{
-    if (!h || world == 0 || (!h->g_infos.empty() && (!all || !child_rank))) return fail(h, DGE_ERR_INVALID, "null argument");
-    return guarded(h, [&] {
-        const size_t n = h->g_infos.size();
-        std::vector<dge_dist_result> red(n);
-        for (size_t c = 0; c < n; ++c)
-        {
-            uint32_t n_nb = 0, n_best = 0;
-            double best = 0;
-            uint64_t best_cb = EMPTY64;
+        if (h->dist_stage == 1)
+        {   // ---- gathered self cells -> table; candidates of the local children; pairs packed per owner of the candidate
+            h->hx_rank_off.assign(world + 1, 0);
             for (uint32_t r = 0; r < world; ++r)
             {
-                const dge_dist_result &res = all[size_t(r) * n + c];
-                if (!res.n_neighbours) continue;
-                n_nb += res.n_neighbours;
-                if (n_best == 0 || best < res.best_fraction) { best = res.best_fraction; best_cb = res.best_barcode; n_best = res.n_best; }
-                else if (res.best_fraction == best) { n_best += res.n_best; best_cb = std::min(best_cb, res.best_barcode); }
+                if (io->recv_bytes[r] % sizeof(SelfRec)) throw InvalidInput("all-gather piece is not a whole number of summaries");
+                h->hx_rank_off[r + 1] = h->hx_rank_off[r] + uint32_t(io->recv_bytes[r] / sizeof(SelfRec));
             }
-            red[c].best_fraction = best; red[c].best_barcode = best_cb; red[c].n_neighbours = n_nb; red[c].n_best = n_best;
-        }
-        return dist_apply_reduced(h, red.data(), my_rank, child_rank);
-    });
-}
-
-int dge_dist_apply_device(dge_handle *h, const dge_dist_result *all_device, uint32_t world, uint32_t my_rank, const uint32_t *child_rank)
-{
-    if (!h || world == 0 || (!h->g_infos.empty() && (!all_device || !child_rank))) return fail(h, DGE_ERR_INVALID, "null argument");
-    return guarded(h, [&] {
-        DGE_CUDA(cudaSetDevice(h->cfg.device));
-        cudaStream_t st = h->stream;
-        const size_t n = h->g_infos.size();
-        const dge_dist_result *red = nullptr;
-        if (n)
-        {   // the combination over ranks runs on the device: O(children) comes back instead of O(children x ranks)
-            h->dist_jobs.reserve(n * sizeof(dge_dist_result));
-            k_dist_reduce<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const DistResult *>(all_device), world, n, h->dist_jobs.as<DistResult>());
-            DGE_LAUNCH_CHECK();
-            ++h->launches;
-            red = d2h_pinned<dge_dist_result>(h->pin_isect, h->dist_jobs.p, n, st);
+            h->n_all = h->hx_rank_off[world];
+            if (h->hx_rank_off[me + 1] - h->hx_rank_off[me] != h->n_self) throw InvalidInput("all-gather does not contain this rank's own piece");
+            h->hx_all.clear(); h->hx_rows.clear();
+            h->x_all.reserve(std::max<size_t>(h->n_all, 1) * sizeof(SelfRec));
+            if (h->n_all) DGE_CUDA(cudaMemcpyAsync(h->x_all.p, io->recv, size_t(h->n_all) * sizeof(SelfRec), cudaMemcpyDeviceToDevice, st));
+            h2d_vec(h->x_rank_off, h->hx_rank_off, st);
+            uint32_t cap = 64;
+            while (cap < 2 * h->n_all) cap <<= 1;
+            h->g_mask = cap - 1;
+            h->x_gcb.reserve(size_t(cap) * 8); h->x_ggi.reserve(size_t(cap) * 4);
+            DGE_CUDA(cudaMemsetAsync(h->x_gcb.p, 0xFF, size_t(cap) * 8, st));
+            if (h->n_all)
+                k_g_build<<<grid_for(h->n_all, 256), 256, 0, st>>>(h->x_all.as<SelfRec>(), h->n_all, h->x_gcb.as<unsigned long long>(), h->x_ggi.as<uint32_t>(), h->g_mask);
+            h->x_nb_count.reserve((n + 1) * 4); h->x_nb_gi.reserve(std::max<size_t>(n, 1) * WL_K * 4);
+            h->x_pair_cnt.reserve((n + 1) * 4); h->x_pair_off.reserve((n + 1) * 4);
+            uint32_t n_pairs = 0;
+            std::vector<int> nbc;
+            if (n)
+            {
+                k_wl_class01_g<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(rows, h->x_self_flag.as<uint32_t>(), n32, h->wl_dev,
+                                                                                      h->x_gcb.as<unsigned long long>(), h->x_ggi.as<uint32_t>(), h->g_mask,
+                                                                                      h->x_all.as<SelfRec>(), h->x_nb_count.as<int>(), h->x_nb_gi.as<uint32_t>());
+                k_p1_counts<<<g, 256, 0, st>>>(h->x_nb_count.as<int>(), n32, h->x_pair_cnt.as<uint32_t>());
+                DGE_CUDA(cudaMemsetAsync(h->x_pair_cnt.as<uint32_t>() + n, 0, 4, st));
+                device_exclusive_scan(h->x_pair_cnt.as<uint32_t>(), h->x_pair_off.as<uint32_t>(), n + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+                DGE_LAUNCH_CHECK();
+                h->launches += 3;
+                d2h(nbc, h->x_nb_count.p, n, st);
+                n_pairs = d2h_scalar<uint32_t>(h->x_pair_off.as<uint32_t>() + n, st);
+            }
+            // children the device walk could not settle: exact enumeration on the host (rare)
+            std::vector<uint32_t> slow;
+            for (uint32_t i = 0; i < n; ++i) if (nbc[i] == NB_SLOW) slow.push_back(i);
+            std::vector<uint32_t> extra_child, extra_gi;
+            h->n_dist_slow = slow.size();
+            if (!slow.empty())
+            {
+                dist_fetch_host_tables(h);
+                DistHostView view; view.build(h->hx_all);
+                std::vector<uint32_t> pcnt, poff;
+                d2h(pcnt, h->x_pair_cnt.p, n + 1, st); d2h(poff, h->x_pair_off.p, n + 1, st);
+                DGE_CUDA(cudaStreamSynchronize(st));
+                for (uint32_t i : slow)
+                {
+                    std::vector<long> ids = dist_exact_neighbours(h, view, h->hx_rows[i]);
+                    if (!ids.empty() && h->hx_all[size_t(ids[0])].cb == h->hx_rows[i].cb) { nbc[i] = NB_SELF; continue; } // the cell is a whitelist barcode itself
+                    poff[i] = n_pairs + uint32_t(extra_child.size());
+                    pcnt[i] = uint32_t(ids.size());
+                    nbc[i] = 0; // no neighbour within the distance bound: excluded below
+                    for (long id : ids) { extra_child.push_back(i); extra_gi.push_back(uint32_t(id)); }
+                }
+                DGE_CUDA(cudaMemcpyAsync(h->x_pair_cnt.p, pcnt.data(), (n + 1) * 4, cudaMemcpyHostToDevice, st));
+                DGE_CUDA(cudaMemcpyAsync(h->x_pair_off.p, poff.data(), (n + 1) * 4, cudaMemcpyHostToDevice, st));
+                DGE_CUDA(cudaMemcpyAsync(h->x_nb_count.p, nbc.data(), n * 4, cudaMemcpyHostToDevice, st));
+                DGE_CUDA(cudaStreamSynchronize(st));
+            }
+            const uint32_t n_dev_pairs = n_pairs;
+            n_pairs += uint32_t(extra_child.size());
+            h->n_pairs = n_pairs;
+            const size_t np1 = std::max<size_t>(n_pairs, 1);
+            h->x_pair_child.reserve(np1 * 4); h->x_pair_gi.reserve(np1 * 4); h->x_pair_pos.reserve(np1 * 4); h->x_pair_eoff.reserve(np1 * 4);
+            h->x_pair_isect.reserve(np1 * 4); h->x_local_jobs.reserve(np1 * sizeof(PairJob)); h->x_local_isect.reserve(np1 * 4);
+            if (n_dev_pairs)
+                k_dist_pairs<<<g, 256, 0, st>>>(nbc.empty() ? nullptr : h->x_nb_count.as<int>(), h->x_nb_gi.as<uint32_t>(), h->x_pair_off.as<uint32_t>(), n32,
+                                                h->x_pair_child.as<uint32_t>(), h->x_pair_gi.as<uint32_t>());
+            if (!extra_child.empty())
+            {
+                DGE_CUDA(cudaMemcpyAsync(h->x_pair_child.as<uint32_t>() + n_dev_pairs, extra_child.data(), extra_child.size() * 4, cudaMemcpyHostToDevice, st));
+                DGE_CUDA(cudaMemcpyAsync(h->x_pair_gi.as<uint32_t>() + n_dev_pairs, extra_gi.data(), extra_gi.size() * 4, cudaMemcpyHostToDevice, st));
+            }
+            // per destination: pairs and entries
+            h->x_dest.reserve(size_t(4) * DIST_MAX_WORLD * 4);
+            DGE_CUDA(cudaMemsetAsync(h->x_dest.p, 0, size_t(4) * DIST_MAX_WORLD * 4, st));
+            uint32_t *dest_pairs = h->x_dest.as<uint32_t>(), *dest_entries = dest_pairs + DIST_MAX_WORLD, *cur_pairs = dest_entries + DIST_MAX_WORLD,
+                     *cur_entries = cur_pairs + DIST_MAX_WORLD;
+            std::vector<uint32_t> hd(2 * DIST_MAX_WORLD, 0);
+            if (n_pairs)
+            {
+                k_dist_count<<<grid_for(n_pairs, 256), 256, 0, st>>>(h->x_pair_child.as<uint32_t>(), h->x_pair_gi.as<uint32_t>(), n_pairs, rows, h->x_rank_off.as<uint32_t>(),
+                                                                    world, me, dest_pairs, dest_entries);
+                DGE_CUDA(cudaMemcpyAsync(hd.data(), h->x_dest.p, 2 * DIST_MAX_WORLD * 4, cudaMemcpyDeviceToHost, st));
+                DGE_CUDA(cudaStreamSynchronize(st));
+            }
+            h->hx_lay.assign(world, DistBlobLayout{~0ull, 0, 0});
+            uint64_t total_bytes = 0;
+            for (uint32_t d = 0; d < world; ++d)
+            {
+                const uint32_t np = hd[d], ne = hd[DIST_MAX_WORLD + d];
+                if (!np) continue;
+                h->hx_lay[d] = DistBlobLayout{total_bytes, np, ne};
+                io->send_bytes[d] = dist_blob_bytes(np, ne);
+                total_bytes += io->send_bytes[d];
+            }
+            h2d_vec(h->x_lay, h->hx_lay, st);
+            h->x_send.reserve(std::max<uint64_t>(total_bytes, 16));
+            if (total_bytes) DGE_CUDA(cudaMemsetAsync(h->x_send.p, 0, total_bytes, st));
+            if (n_pairs)
+            {
+                k_dist_pack_heads<<<grid_for(n_pairs, 256), 256, 0, st>>>(h->x_pair_child.as<uint32_t>(), h->x_pair_gi.as<uint32_t>(), n_pairs, rows, h->x_all.as<SelfRec>(),
+                                                                         h->x_rank_off.as<uint32_t>(), world, me, h->x_self_idx.as<uint32_t>(), h->n_pc,
+                                                                         h->x_lay.as<DistBlobLayout>(), cur_pairs, cur_entries, h->x_send.as<unsigned char>(),
+                                                                         h->x_pair_pos.as<uint32_t>(), h->x_pair_eoff.as<uint32_t>(), h->x_local_jobs.as<PairJob>());
+                k_dist_blob_headers<<<1, DIST_MAX_WORLD, 0, st>>>(h->x_lay.as<DistBlobLayout>(), world, h->x_send.as<unsigned char>());
+                k_dist_pack_lists<<<unsigned(std::min<uint32_t>(n_pairs, 148 * 16)), 128, 0, st>>>(h->x_pair_child.as<uint32_t>(), h->x_pair_gi.as<uint32_t>(), n_pairs, rows,
+                                                                                                  h->x_rank_off.as<uint32_t>(), world, me, h->x_lay.as<DistBlobLayout>(),
+                                                                                                  h->x_pair_eoff.as<uint32_t>(), h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(),
+                                                                                                  h->pc_u_start.as<uint32_t>(), gub, h->x_send.as<unsigned char>());
+                k_intersect<<<n_pairs, 128, 0, st>>>(h->x_local_jobs.as<PairJob>(), n_pairs, h->ukey.as<uint64_t>(), h->pc_u_start.as<uint32_t>(), h->pc_slot.as<uint32_t>(),
+                                                     gub, h->x_local_isect.as<uint32_t>());
+                DGE_LAUNCH_CHECK();
+                h->launches += 5;
+            }
             DGE_CUDA(cudaStreamSynchronize(st));
+            io->collective = DGE_DIST_ALLTOALL;
+            io->send = h->x_send.p;
+            h->dist_stage = 2;
+            return DGE_OK;
         }
-        return dist_apply_reduced(h, red, my_rank, child_rank);
-    });
-}
 
-static int dist_apply_reduced(dge_handle *h, const dge_dist_result *red, uint32_t my_rank, const uint32_t *child_rank)
-{
-    {
-        dist_check(h);
-        DGE_CUDA(cudaSetDevice(h->cfg.device));
-        cudaStream_t st = h->stream;
-        const size_t n = h->g_infos.size();
-        std::vector<ForeignMove> moves;
-        uint64_t total = 0;
-        h->n_merged = h->n_excluded = h->n_unresolved = h->n_order_ties = 0;
-        h->dist_targets.clear();
-        for (size_t c = 0; c < n; ++c)
-        {
-            const dge_dist_child &ci = h->g_infos[c];
-            const bool mine = child_rank[c] == my_rank;
-            const uint32_t n_nb = red[c].n_neighbours, n_best = red[c].n_best;
-            const double best = red[c].best_fraction;
-            const uint64_t best_cb = red[c].best_barcode;
-            if (n_nb == 0)
-            {   // no class-0/1 candidate anywhere: the fall-through to farther classes is not distributed yet
-                if (mine) ++h->n_unresolved;
-                continue;
-            }
-            const bool excluded = best < h->cfg.min_merge_fraction; // RealBarcodesMergeStrategy.cpp:57-58
-            if (!excluded && n_best > 1 && mine) ++h->n_order_ties;    // order-dependent in the reference; we take the smallest barcode
-            if (mine)
+        if (h->dist_stage == 2)
+        {   // ---- received pairs: |child ∩ candidate| for every one of them -> replies
+            h->hx_rl.assign(world, DistBlobLayout{~0ull, 0, 0});
+            uint64_t total = 0;
+            for (uint32_t sr = 0; sr < world; ++sr) total += io->recv_bytes[sr];
+            h->x_kept.reserve(std::max<uint64_t>(total, 16));
+            if (total) DGE_CUDA(cudaMemcpyAsync(h->x_kept.p, io->recv, total, cudaMemcpyDeviceToDevice, st));
+            std::vector<unsigned long long> hdr(size_t(2) * world, 0);
+            uint64_t base = 0;
+            for (uint32_t sr = 0; sr < world; ++sr)
             {
-                HostCell &cell = h->real[ci.local_index];
-                if (excluded) { cell.excluded = true; ++h->n_excluded; }
-                else { cell.merged = true; cell.merged_to_cb = best_cb; ++h->n_merged; }
+                if (io->recv_bytes[sr])
+                {
+                    if (io->recv_bytes[sr] < 16 || (io->recv_bytes[sr] & 15)) throw InvalidInput("malformed pair blob");
+                    DGE_CUDA(cudaMemcpyAsync(&hdr[size_t(2) * sr], h->x_kept.as<unsigned char>() + base, 16, cudaMemcpyDeviceToHost, st));
+                }
+                base += io->recv_bytes[sr];
             }
-            if (excluded) continue;
-            // the global winner is ours iff it is the local best recorded by dge_dist_eval_children
-            const uint32_t dst_idx = h->g_best_local[c];
-            if (dst_idx == NONE32 || h->real[dst_idx].cb != best_cb) continue; // the target lives on another rank
-            HostCell &dst = h->real[dst_idx];
-            dst.umis_stat += ci.umis_stat; dst.reads_stat += ci.reads_stat; dst.n_intergenic += ci.n_intergenic; // Stats::merge, Stats.cpp:29-43
-            h->dist_targets.push_back(dst_idx);
-            if (ci.n_entries)
+            DGE_CUDA(cudaStreamSynchronize(st));
+            std::vector<uint32_t> job_base(world + 1, 0), reply_base(world + 1, 0);
+            base = 0;
+            for (uint32_t sr = 0; sr < world; ++sr)
             {
-                moves.push_back(ForeignMove{h->g_off[c], ci.n_entries, dst.slot, uint32_t(total)});
-                total += ci.n_entries;
+                const uint32_t np = uint32_t(hdr[size_t(2) * sr]), ne = uint32_t(hdr[size_t(2) * sr + 1]);
+                if (io->recv_bytes[sr])
+                {
+                    if (dist_blob_bytes(np, ne) != io->recv_bytes[sr]) throw InvalidInput("pair blob size does not match its header");
+                    h->hx_rl[sr] = DistBlobLayout{base, np, ne};
+                }
+                job_base[sr + 1] = job_base[sr] + np;
+                reply_base[sr + 1] = reply_base[sr] + ((np + 3u) & ~3u);
+                io->send_bytes[sr] = uint64_t((np + 3u) & ~3u) * 4;
+                base += io->recv_bytes[sr];
             }
+            h2d_vec(h->x_rl, h->hx_rl, st); h2d_vec(h->x_job_base, job_base, st); h2d_vec(h->x_reply_base, reply_base, st);
+            const uint32_t n_jobs = job_base[world];
+            h->x_fjobs.reserve(std::max<size_t>(n_jobs, 1) * sizeof(ForeignJob)); h->x_fisect.reserve(std::max<size_t>(n_jobs, 1) * 4);
+            h->x_reply.reserve(std::max<size_t>(reply_base[world], 4) * 4);
+            DGE_CUDA(cudaMemsetAsync(h->x_reply.p, 0, std::max<size_t>(reply_base[world], 4) * 4, st));
+            if (n_jobs)
+            {
+                k_dist_recv_jobs<<<grid_for(n_jobs, 256), 256, 0, st>>>(h->x_kept.as<unsigned char>(), h->x_rl.as<DistBlobLayout>(), h->x_job_base.as<uint32_t>(), world, rows,
+                                                                       h->x_self_idx.as<uint32_t>(), h->n_self, h->n_pc, h->x_fjobs.as<ForeignJob>(), h->x_bad.as<int>());
+                k_intersect_foreign<<<n_jobs, 128, 0, st>>>(h->x_fjobs.as<ForeignJob>(), n_jobs, h->x_kept.as<uint64_t>(), h->ukey.as<uint64_t>(), h->pc_u_start.as<uint32_t>(),
+                                                            h->pc_slot.as<uint32_t>(), gub, h->x_fisect.as<uint32_t>());
+                k_dist_reply<<<grid_for(n_jobs, 256), 256, 0, st>>>(h->x_fisect.as<uint32_t>(), h->x_job_base.as<uint32_t>(), h->x_reply_base.as<uint32_t>(), world,
+                                                                   h->x_reply.as<uint32_t>());
+                DGE_LAUNCH_CHECK();
+                h->launches += 3;
+            }
+            DGE_CUDA(cudaStreamSynchronize(st));
+            io->collective = DGE_DIST_ALLTOALL;
+            io->send = h->x_reply.p;
+            h->dist_stage = 3;
+            return DGE_OK;
         }
-        if (total >= 0xFFFFFFF0ull) throw std::runtime_error("merge volume exceeds 2^32 entries");
-        if (!moves.empty())
-        {
-            h->d_moves.reserve(moves.size() * sizeof(ForeignMove));
-            h->mkeys.reserve(total * 8); h->mvals.reserve(total * 4);
-            DGE_CUDA(cudaMemcpyAsync(h->d_moves.p, moves.data(), moves.size() * sizeof(ForeignMove), cudaMemcpyHostToDevice, st));
-            k_gather_relabel_foreign<<<grid_for(moves.size(), 1, 148 * 16), 256, 0, st>>>(h->d_moves.as<ForeignMove>(), uint32_t(moves.size()), h->g_keys, h->g_vals,
-                                                                                         h->kl.gb + h->kl.ub, h->mkeys.as<uint64_t>(), h->mvals.as<uint32_t>());
-            DGE_LAUNCH_CHECK();
-            ++h->launches;
-            apply_moved(h, total);
+
+        if (h->dist_stage == 3)
+        {   // ---- replies -> best target per child -> commits to the owners of remote targets
+            h->hx_reply_base_recv.assign(world + 1, 0);
+            for (uint32_t d = 0; d < world; ++d)
+            {
+                const uint32_t np = h->hx_lay[d].base == ~0ull ? 0u : h->hx_lay[d].n_pairs;
+                if (io->recv_bytes[d] != uint64_t((np + 3u) & ~3u) * 4) throw InvalidInput("reply size does not match the pairs sent");
+                h->hx_reply_base_recv[d + 1] = h->hx_reply_base_recv[d] + ((np + 3u) & ~3u);
+            }
+            h2d_vec(h->x_reply_base, h->hx_reply_base_recv, st);
+            const uint32_t n_pairs = h->n_pairs;
+            h->x_best.reserve((n + 1) * 4); h->x_tie.reserve((n + 1) * 4); h->x_merged_cb.reserve(std::max<size_t>(n, 1) * 8);
+            if (n_pairs)
+                k_dist_collect<<<grid_for(n_pairs, 256), 256, 0, st>>>(h->x_pair_gi.as<uint32_t>(), h->x_pair_pos.as<uint32_t>(), n_pairs, h->x_rank_off.as<uint32_t>(), world,
+                                                                      h->x_local_isect.as<uint32_t>(), static_cast<const uint32_t *>(io->recv), h->x_reply_base.as<uint32_t>(),
+                                                                      h->x_pair_isect.as<uint32_t>());
+            std::vector<uint32_t> tie;
+            if (n)
+            {
+                k_dist_best2<<<g, 256, 0, st>>>(h->x_pair_off.as<uint32_t>(), h->x_pair_cnt.as<uint32_t>(), h->x_pair_gi.as<uint32_t>(), h->x_pair_isect.as<uint32_t>(), rows,
+                                                h->x_all.as<SelfRec>(), n32, h->cfg.min_merge_fraction, h->x_best.as<int>(), h->x_tie.as<uint32_t>());
+                DGE_LAUNCH_CHECK();
+                d2h(tie, h->x_tie.p, n, st);
+                DGE_CUDA(cudaStreamSynchronize(st));
+            }
+            // order-dependent ties of the best fraction: replay the reference's neighbour order on the host (rare)
+            std::vector<uint32_t> tied;
+            for (uint32_t i = 0; i < n; ++i) if (tie[i]) tied.push_back(i);
+            h->n_dist_ties = tied.size();
+            if (!tied.empty())
+            {
+                dist_fetch_host_tables(h);
+                DistHostView view; view.build(h->hx_all);
+                std::vector<uint32_t> pcnt, poff, pgi, pis;
+                std::vector<int> best;
+                d2h(pcnt, h->x_pair_cnt.p, n + 1, st); d2h(poff, h->x_pair_off.p, n + 1, st);
+                d2h(pgi, h->x_pair_gi.p, n_pairs, st); d2h(pis, h->x_pair_isect.p, n_pairs, st); d2h(best, h->x_best.p, n, st);
+                DGE_CUDA(cudaStreamSynchronize(st));
+                for (uint32_t i : tied)
+                {
+                    const CellRow &c = h->hx_rows[i];
+                    std::vector<long> ids = dist_exact_neighbours(h, view, c);
+                    double max_frac = 0;
+                    long best_gi = ids.empty() ? -1 : ids[0];
+                    for (long id : ids)
+                    {
+                        uint32_t isect = 0;
+                        for (uint32_t k = 0; k < pcnt[i]; ++k) if (pgi[poff[i] + k] == uint32_t(id)) isect = pis[poff[i] + k];
+                        const double frac = 0.5 * isect * (1. / c.n_umis + 1. / h->hx_all[size_t(id)].umis); // RealBarcodesMergeStrategy.cpp:46-47
+                        if (max_frac < frac) { max_frac = frac; best_gi = id; }
+                    }
+                    int bp = -1;
+                    if (best_gi >= 0 && !(max_frac < h->cfg.min_merge_fraction))
+                        for (uint32_t k = 0; k < pcnt[i]; ++k) if (pgi[poff[i] + k] == uint32_t(best_gi)) bp = int(poff[i] + k);
+                    best[i] = bp;
+                }
+                DGE_CUDA(cudaMemcpyAsync(h->x_best.p, best.data(), n * 4, cudaMemcpyHostToDevice, st));
+                DGE_CUDA(cudaStreamSynchronize(st));
+            }
+            // commits: capacity per destination = pairs sent to it
+            std::vector<DistBlobLayout> clay(world, DistBlobLayout{0, 0, 0});
+            uint64_t cbytes = 0;
+            for (uint32_t d = 0; d < world; ++d)
+            {
+                const uint32_t np = h->hx_lay[d].base == ~0ull ? 0u : h->hx_lay[d].n_pairs;
+                clay[d] = DistBlobLayout{cbytes, np, 0};
+                cbytes += uint64_t(np) * sizeof(DistCommitRec);
+            }
+            h2d_vec(h->x_clay, clay, st);
+            h->x_commit.reserve(std::max<uint64_t>(cbytes, 16)); h->x_commit_send.reserve(std::max<uint64_t>(cbytes, 16));
+            h->x_ccur.reserve(DIST_MAX_WORLD * 4);
+            DGE_CUDA(cudaMemsetAsync(h->x_ccur.p, 0, DIST_MAX_WORLD * 4, st));
+            std::vector<uint32_t> ccur(DIST_MAX_WORLD, 0);
+            if (n)
+            {
+                k_dist_decide<<<g, 256, 0, st>>>(h->x_nb_count.as<int>(), h->x_best.as<int>(), h->x_pair_gi.as<uint32_t>(), h->x_pair_pos.as<uint32_t>(), rows,
+                                                 h->x_all.as<SelfRec>(), h->x_rank_off.as<uint32_t>(), world, me, h->x_self_idx.as<uint32_t>(), n32,
+                                                 h->cell_state.as<CellState>(), h->x_merged_cb.as<unsigned long long>(), h->x_clay.as<DistBlobLayout>(),
+                                                 h->x_ccur.as<uint32_t>(), h->x_commit.as<unsigned char>());
+                k_dist_flag_remote<<<g, 256, 0, st>>>(h->cell_state.as<CellState>(), n32, h->df_ctr.as<DevFlowCounters>());
+                DGE_LAUNCH_CHECK();
+                h->launches += 4;
+                DGE_CUDA(cudaMemcpyAsync(ccur.data(), h->x_ccur.p, DIST_MAX_WORLD * 4, cudaMemcpyDeviceToHost, st));
+                DGE_CUDA(cudaStreamSynchronize(st));
+            }
+            uint64_t off = 0;
+            for (uint32_t d = 0; d < world; ++d)
+            {
+                const uint64_t b = uint64_t(ccur[d]) * sizeof(DistCommitRec);
+                if (b) DGE_CUDA(cudaMemcpyAsync(h->x_commit_send.as<unsigned char>() + off, h->x_commit.as<unsigned char>() + clay[d].base, b, cudaMemcpyDeviceToDevice, st));
+                io->send_bytes[d] = b;
+                off += b;
+            }
+            DGE_CUDA(cudaStreamSynchronize(st));
+            io->collective = DGE_DIST_ALLTOALL;
+            io->send = h->x_commit_send.p;
+            h->dist_stage = 4;
+            return DGE_OK;
         }
-        DGE_CUDA(cudaStreamSynchronize(st));
-        for (uint32_t i = 0; i < h->real.size(); ++i) if (h->real[i].merged_to_cb == EMPTY64) h->real[i].target = int32_t(i);
-        h->dist_done = true;
-        return int(DGE_OK);
-    }
+
+        if (h->dist_stage == 4)
+        {   // ---- received commits: Stats::merge into the targets, foreign lists + local moves folded into U
+            std::vector<DistBlobLayout> cl(world, DistBlobLayout{0, 0, 0});
+            std::vector<uint32_t> c_base(world + 1, 0);
+            uint64_t base = 0;
+            for (uint32_t sr = 0; sr < world; ++sr)
+            {
+                if (io->recv_bytes[sr] % sizeof(DistCommitRec)) throw InvalidInput("malformed commit piece");
+                cl[sr] = DistBlobLayout{base, uint32_t(io->recv_bytes[sr] / sizeof(DistCommitRec)), 0};
+                c_base[sr + 1] = c_base[sr] + cl[sr].n_pairs;
+                base += io->recv_bytes[sr];
+            }
+            const uint32_t n_commits = c_base[world];
+            h2d_vec(h->x_cl, cl, st); h2d_vec(h->x_cbase, c_base, st);
+            h->x_fmoves.reserve(std::max<size_t>(n_commits, 1) * sizeof(ForeignMove)); h->x_fsize.reserve((size_t(n_commits) + 1) * 4); h->x_foff.reserve((size_t(n_commits) + 1) * 4);
+            CellState *cs = h->cell_state.as<CellState>();
+            DevFlowCounters *ctr = h->df_ctr.as<DevFlowCounters>();
+            if (n_commits)
+                k_dist_apply_commits<<<grid_for(n_commits, 256), 256, 0, st>>>(static_cast<const unsigned char *>(io->recv), h->x_cl.as<DistBlobLayout>(), h->x_cbase.as<uint32_t>(),
+                                                                              world, h->x_kept.as<unsigned char>(), h->x_rl.as<DistBlobLayout>(), rows, h->x_self_idx.as<uint32_t>(),
+                                                                              cs, h->x_fsize.as<uint32_t>(), h->x_fmoves.as<ForeignMove>(), h->x_bad.as<int>());
+            DGE_CUDA(cudaMemsetAsync(h->x_fsize.as<uint32_t>() + n_commits, 0, 4, st));
+            device_exclusive_scan(h->x_fsize.as<uint32_t>(), h->x_foff.as<uint32_t>(), size_t(n_commits) + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+            h->move_size.reserve((n + 1) * 4); h->move_off.reserve((n + 1) * 4);
+            if (n) k_phase2_sizes<<<g, 256, 0, st>>>(rows, cs, n32, h->move_size.as<uint32_t>(), ctr);
+            DGE_CUDA(cudaMemsetAsync(h->move_size.as<uint32_t>() + n, 0, 4, st));
+            device_exclusive_scan(h->move_size.as<uint32_t>(), h->move_off.as<uint32_t>(), n + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+            uint32_t f_total = 0, l_total = 0;
+            int bad[4] = {0, 0, 0, 0};
+            DevFlowCounters hc{};
+            DGE_CUDA(cudaMemcpyAsync(&f_total, h->x_foff.as<uint32_t>() + n_commits, 4, cudaMemcpyDeviceToHost, st));
+            DGE_CUDA(cudaMemcpyAsync(&l_total, h->move_off.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+            DGE_CUDA(cudaMemcpyAsync(bad, h->x_bad.p, 16, cudaMemcpyDeviceToHost, st));
+            DGE_CUDA(cudaMemcpyAsync(&hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));
+            DGE_CUDA(cudaStreamSynchronize(st));
+            if (bad[0]) throw InvalidInput("inconsistent cross-rank merge messages");
+            if (hc.n_chain) throw std::runtime_error("merge chain in the cross-rank whitelist merge");
+            const uint64_t total = uint64_t(f_total) + l_total;
+            if (total >= 0xFFFFFFF0ull) throw CapacityError("merge volume exceeds 2^32 entries");
+            h->d_moves.reserve(std::max<size_t>(n, 1) * sizeof(MoveJob));
+            if (n) k_phase2_apply<<<g, 256, 0, st>>>(rows, cs, n32, h->move_off.as<uint32_t>(), h->n_pc, h->d_moves.as<MoveJob>(), ctr);
+            if (total)
+            {
+                h->mkeys.reserve(total * 8); h->mvals.reserve(total * 4);
+                if (l_total)
+                    k_gather_relabel<<<grid_for(n, 1, 148 * 16), 256, 0, st>>>(h->d_moves.as<MoveJob>(), n32, h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(),
+                                                                              h->pc_u_start.as<uint32_t>(), gub, h->mkeys.as<uint64_t>(), h->mvals.as<uint32_t>());
+                if (f_total)
+                    k_dist_gather_foreign<<<unsigned(std::min<uint32_t>(n_commits, 148 * 16)), 256, 0, st>>>(h->x_fmoves.as<ForeignMove>(), h->x_foff.as<uint32_t>(), n_commits, l_total,
+                                                                                                            h->x_kept.as<unsigned char>(), gub, h->mkeys.as<uint64_t>(),
+                                                                                                            h->mvals.as<uint32_t>());
+                DGE_LAUNCH_CHECK();
+                h->launches += 3;
+                if (!h->slot_pc_built) build_slot_pc(h);
+                apply_moved(h, total);
+            }
+            DGE_CUDA(cudaEventRecord(h->ev[4], st));
+            DGE_CUDA(cudaStreamSynchronize(st));
+            h->dist_done = true;
+            h->n_unresolved = 0;
+            io->collective = DGE_DIST_DONE;
+            h->dist_stage = 5;
+            return DGE_OK;
+        }
+        throw std::runtime_error("dge_dist_step called after it reported DGE_DIST_DONE");
+    });
 }
 
 int dge_umi_first_size(dge_handle *h, size_t *n_entries)

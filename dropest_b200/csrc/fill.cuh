@@ -268,6 +268,7 @@ __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
     {   // ---- producer
         if (lane == 0)
         {
+            const uint64_t pol = l2_policy_evict_first();
             uint32_t k = 0;
             for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k)
             {
@@ -281,13 +282,13 @@ __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
                 {
                     const uint32_t kbytes = (cnt * 8u + 15u) & ~15u, gbytes = (cnt * 4u + 15u) & ~15u;
                     mbar_arrive_expect_tx(&full_bar[s], kbytes + gbytes);
-                    bulk_g2s(stage, soa_keys + base, kbytes, &full_bar[s]);
-                    bulk_g2s(stage + TILE * 8, soa_genes + base, gbytes, &full_bar[s]);
+                    bulk_g2s_hint(stage, soa_keys + base, kbytes, &full_bar[s], pol);
+                    bulk_g2s_hint(stage + TILE * 8, soa_genes + base, gbytes, &full_bar[s], pol);
                 }
                 else
                 {
                     mbar_arrive_expect_tx(&full_bar[s], cnt * 16u);
-                    bulk_g2s(stage, recs + base, cnt * 16u, &full_bar[s]);
+                    bulk_g2s_hint(stage, recs + base, cnt * 16u, &full_bar[s], pol);
                 }
             }
         }
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
             {
                 if (keys[j] != EMPTY64)
                 {
-                    my_out[pos + __popc(vm[j] & lt)] = keys[j];
+                    __stcs(reinterpret_cast<unsigned long long *>(my_out + pos + __popc(vm[j] & lt)), (unsigned long long)keys[j]); // written once, read once much later
                     atomicAdd(&hist_s[uint32_t(keys[j] >> hshift)], 1u);
                 }
                 pos += __popc(vm[j]);
@@ -418,8 +419,10 @@ __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
     reduce_add(c_na, &ctr->has_not_annotated);
 }
 
-// tile0 of every region = exclusive prefix of ceil(count / tile) (single block; a few thousand regions at most); total in *n_tiles
-__global__ void __launch_bounds__(1024) k_region_tiles(KeyRegion *__restrict__ regions, uint32_t n_regions, uint32_t tile, uint32_t *__restrict__ n_tiles)
+// tile0 of every region = exclusive prefix of ceil(count / tile) (single block; a few thousand regions at most), one descriptor per
+// tile for the partition pass (its blocks then start with ONE load instead of a search through the region table); total in *n_tiles
+__global__ void __launch_bounds__(1024) k_region_tiles(KeyRegion *__restrict__ regions, uint32_t n_regions, uint32_t tile, uint32_t *__restrict__ n_tiles,
+                                                       KeyTile *__restrict__ tiles)
 {
     __shared__ uint32_t ws[33];
     __shared__ uint32_t carry;
@@ -428,10 +431,21 @@ __global__ void __launch_bounds__(1024) k_region_tiles(KeyRegion *__restrict__ r
     for (uint32_t base = 0; base < n_regions; base += blockDim.x)
     {
         const uint32_t r = base + threadIdx.x;
-        const uint32_t t = r < n_regions ? (regions[r].count + tile - 1) / tile : 0u;
+        const uint32_t cnt = r < n_regions ? regions[r].count : 0u;
+        const uint32_t t = (cnt + tile - 1) / tile;
         uint32_t tot;
         const uint32_t ex = block_exclusive_scan(t, ws, &tot);
-        if (r < n_regions) regions[r].tile0 = carry + ex;
+        if (r < n_regions)
+        {
+            regions[r].tile0 = carry + ex;
+            const uint64_t *k = regions[r].keys;
+            for (uint32_t q = 0; q < t; ++q)
+            {
+                KeyTile d;
+                d.keys = k + size_t(q) * tile; d.count = min(tile, cnt - q * tile); d.pad = 0;
+                tiles[carry + ex + q] = d;
+            }
+        }
         __syncthreads();
         if (threadIdx.x == 0) carry += tot;
         __syncthreads();

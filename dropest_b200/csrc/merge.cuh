@@ -698,7 +698,8 @@ __global__ void k_phase2_apply(const CellRow *__restrict__ rows, CellState *__re
     {
         const int32_t t = st[i].target;
         MoveJob job{empty_pc, 0u, move_off[i]};
-        if (t < 0)
+        if (t < -1) {} // merged into a cell of another rank (sharded runs): flagged by k_dist_flag_remote, nothing moves locally
+        else if (t < 0)
         {
             st[i].flags = (st[i].flags & ~1u) | 4u;
             atomicAdd(&ctr->n_excluded, 1u);

@@ -37,11 +37,13 @@ struct SortCombineTuning
     int target = 832;       // records per sub-bucket (most then fit the 1024-key class of the merge sort)
     int ht = 2048;          // hash-table slots per sub-bucket (power of two, >= 2 * expected distinct keys)
     int dedup_threads = 256; // threads per dedup block (32..256, power of two)
+    int sample = 8192;       // keys sampled per L1 bucket for its sub-bucket splitters (<= SC_SAMPLE)
     SortCombineTuning()
     {
         if (const char *e = std::getenv("DGE_L1_TARGET")) l1_target = std::max(1000, atoi(e));
         if (const char *e = std::getenv("DGE_SC_TARGET")) target = std::max(64, atoi(e));
         if (const char *e = std::getenv("DGE_SC_HT")) ht = atoi(e);
+        if (const char *e = std::getenv("DGE_SC_SAMPLE")) sample = std::min(SC_SAMPLE, std::max(256, atoi(e)));
         if (const char *e = std::getenv("DGE_DEDUP_THREADS")) dedup_threads = atoi(e);
         if (dedup_threads != 512 && dedup_threads != 1024) dedup_threads = 256;
         int p = 256;
@@ -184,14 +186,14 @@ __global__ void __launch_bounds__(1024) k_l1_plan(const uint32_t *__restrict__ l
 
 // One block per L1 bucket: strided sample of ukeys, bitonic sort in shared memory, pick p2-1 splitters.
 __global__ void __launch_bounds__(SC_THREADS) k_splitters(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ l1_off,
-                                                          const uint32_t *__restrict__ p2, uint64_t *__restrict__ splitters)
+                                                          const uint32_t *__restrict__ p2, uint64_t *__restrict__ splitters, uint32_t max_sample)
 {
     extern __shared__ uint64_t samp[];
     const int b = blockIdx.x;
     const uint32_t np = p2[b];
     if (np <= 1) return;
     const uint32_t off = l1_off[b], nb = l1_off[b + 1] - off;
-    const uint32_t S = min(nb, uint32_t(SC_SAMPLE));
+    const uint32_t S = min(nb, max_sample);
     int P = 2;
     while (uint32_t(P) < S) P <<= 1;
     for (int i = threadIdx.x; i < P; i += blockDim.x)
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(THREADS) k_l1_scatter_staged(const uint64_t *_
 // L1 scatter straight from the fill kernel's per-block key regions (no dense key array, no histogram pass): block = one tile of one
 // region.  Dynamic shared memory as k_l1_scatter_staged.
 template <int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS) k_l1_scatter_regions(const KeyRegion *__restrict__ regions, uint32_t n_regions, const uint32_t *__restrict__ n_tiles_ptr,
+__global__ void __launch_bounds__(THREADS) k_l1_scatter_regions(const KeyTile *__restrict__ tiles, const uint32_t *__restrict__ n_tiles_ptr,
                                                                 int shift, int nb1, uint32_t *__restrict__ cursor, uint64_t *__restrict__ out_keys)
 {
     constexpr int TILE = THREADS * ITEMS;
@@ -399,26 +401,14 @@ __global__ void __launch_bounds__(THREADS) k_l1_scatter_regions(const KeyRegion 
     if (blockIdx.x >= *n_tiles_ptr) return;
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint32_t ws[33];
-    __shared__ uint32_t reg_s;
     uint64_t *sk = reinterpret_cast<uint64_t *>(smem_raw);
     uint32_t *cnt = reinterpret_cast<uint32_t *>(sk + TILE);
     uint32_t *gd = cnt + nb1;
+    const KeyTile td = tiles[blockIdx.x];
     for (int i = threadIdx.x; i < nb1; i += THREADS) cnt[i] = 0;
-    if (threadIdx.x == 0)
-    {   // largest r with regions[r].tile0 <= blockIdx.x (regions without tiles repeat the next region's tile0)
-        uint32_t lo = 0, hi = n_regions - 1;
-        while (lo < hi)
-        {
-            const uint32_t mid = (lo + hi + 1) >> 1;
-            if (regions[mid].tile0 <= blockIdx.x) lo = mid; else hi = mid - 1;
-        }
-        reg_s = lo;
-    }
     __syncthreads();
-    const KeyRegion reg = regions[reg_s];
-    const uint32_t t_in = blockIdx.x - reg.tile0;
-    const uint64_t *__restrict__ keys = reg.keys + size_t(t_in) * TILE;
-    const uint32_t n_tile = min(uint32_t(TILE), reg.count - t_in * uint32_t(TILE));
+    const uint64_t *__restrict__ keys = td.keys;
+    const uint32_t n_tile = td.count;
     uint64_t k[ITEMS];
     uint32_t r[ITEMS];
 #pragma unroll
@@ -866,12 +856,12 @@ public:
 
     // Optional input of the NEXT run(): the keys live in per-block regions of the fill kernel instead of one dense array
     // (keys_in is ignored, l1_hist_pre must be given).  region_tiles: device scratch word.
-    const KeyRegion *src_regions = nullptr;
+    const KeyTile *src_tiles = nullptr;
     uint32_t n_src_regions = 0;
     uint32_t *src_region_tiles = nullptr;
-    void set_regions(const KeyRegion *regions, uint32_t n_regions, uint32_t *region_tiles)
+    void set_regions(const KeyTile *tiles, uint32_t n_regions, uint32_t *region_tiles)
     {
-        src_regions = regions; n_src_regions = n_regions; src_region_tiles = region_tiles;
+        src_tiles = tiles; n_src_regions = n_regions; src_region_tiles = region_tiles;
     }
 
     ~SortCombine()
@@ -952,7 +942,7 @@ public:
         static const int staged = std::getenv("DGE_STAGED") ? atoi(std::getenv("DGE_STAGED")) : 1; // bit0: L1, bit1: L2 (measured: staging pays at L1 only)
         static const int stile = std::getenv("DGE_STILE") ? atoi(std::getenv("DGE_STILE")) : 2;    // staged tile shape (1024 x 8 measured best)
         size_t tile = 0;
-        if (src_regions)
+        if (src_tiles)
         {   // keys straight from the fill kernel's regions (1024 x 8 staged tiles)
             if (has_val || !l1_hist_pre) throw std::runtime_error("region input needs a precomputed histogram and no values");
             constexpr int T = 1024, I = 8;
@@ -960,8 +950,8 @@ public:
             static bool attr_done[64] = {};
             if (!attr_done[cur_dev]) { DGE_CUDA(cudaFuncSetAttribute(k_l1_scatter_regions<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[cur_dev] = true; }
             const unsigned g_tiles = unsigned(n / (size_t(T) * I) + n_src_regions + 1); // upper bound; blocks beyond the real count exit
-            k_l1_scatter_regions<T, I><<<g_tiles, T, smem, st>>>(src_regions, n_src_regions, src_region_tiles, shift, nb1, cursor, keysA);
-            src_regions = nullptr;
+            k_l1_scatter_regions<T, I><<<g_tiles, T, smem, st>>>(src_tiles, src_region_tiles, shift, nb1, cursor, keysA);
+            src_tiles = nullptr;
         }
         else if (!has_val && (staged & 1))
         {
@@ -1004,7 +994,7 @@ public:
         // ---- L2
         const size_t tiles_bound = n / tile + size_t(nb1) + 1;
         k_l1_plan<<<1, 1024, 0, st>>>(l1_off, nb1, uint32_t(SC_TARGET), uint32_t(tile), p2, sb_base, tile_base); ++L;
-        k_splitters<<<nb1, SC_THREADS, SC_SAMPLE * 8, st>>>(keysA, l1_off, p2, ws.splitters.as<uint64_t>()); ++L;
+        k_splitters<<<nb1, SC_THREADS, SC_SAMPLE * 8, st>>>(keysA, l1_off, p2, ws.splitters.as<uint64_t>(), uint32_t(sc_tuning().sample)); ++L;
         mark("plan+splitters");
         uint32_t *sub_cnt = ws.sub_cnt.as<uint32_t>(), *sub_off = ws.sub_off.as<uint32_t>();
         static const int l2_bucket = std::getenv("DGE_L2_BUCKET") ? atoi(std::getenv("DGE_L2_BUCKET")) : 3; // 0 = the two-launch tile path

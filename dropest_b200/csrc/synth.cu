@@ -133,6 +133,30 @@ __global__ void __launch_bounds__(256) k_route_scatter(const dge_record16 *__res
     }
 }
 
+// per-slice destination histogram: counts[s * 64 + r] for slices of `slice_len` records (a multiple of the 2048-record tile)
+__global__ void __launch_bounds__(256) k_route_count_slices(const dge_record16 *__restrict__ in, size_t n, uint32_t n_ranks, size_t slice_len,
+                                                            unsigned long long *__restrict__ counts)
+{
+    __shared__ uint32_t h[64];
+    const size_t n_tiles = (n + 2047) / 2048;
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    {
+        if (threadIdx.x < 64) h[threadIdx.x] = 0;
+        __syncthreads();
+        const size_t base = tile * 2048;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+            const size_t i = base + size_t(j) * 256 + threadIdx.x;
+            if (i < n) atomicAdd(&h[rank_of(in[i].key >> 24, n_ranks)], 1u);
+        }
+        __syncthreads();
+        const size_t sl = base / slice_len;
+        if (threadIdx.x < n_ranks && h[threadIdx.x]) atomicAdd(&counts[sl * 64 + threadIdx.x], (unsigned long long)h[threadIdx.x]);
+        __syncthreads();
+    }
+}
+
 thread_local std::string g_err;
 
 } // namespace
@@ -204,6 +228,52 @@ int dge_route_by_barcode_device(int device, const dge_record16 *in, size_t n, ui
         return DGE_OK;
     }
     catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_route_by_barcode_device: %s\n", e.what()); return DGE_ERR_CUDA; }
+}
+
+/* Routing for a PIPELINED exchange: the input is cut into n_slices slices of slice_len records (a multiple of 2048; the last one may be
+ * shorter); slice s is written to out[s * slice_len ...) grouped by destination rank, counts[s * n_ranks + r] (HOST) = its segment sizes.
+ * One pass counts all slices (single host synchronisation), then one scatter launch per slice is queued on the stream: the caller can
+ * start the all-to-all of slice s as soon as the stream reaches it while later slices are still being routed. */
+int dge_route_slices_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, size_t slice_len, uint32_t n_slices, dge_record16 *out,
+                            uint64_t *counts, void *cuda_stream)
+{
+    if (!counts || n_ranks == 0 || n_ranks > 64 || n_slices == 0 || n_slices > 256 || slice_len == 0 || (slice_len % 2048) || (n && (!in || !out)) ||
+        size_t(n_slices) * slice_len < n)
+        return DGE_ERR_INVALID;
+    try
+    {
+        DGE_CUDA(cudaSetDevice(device));
+        cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+        static thread_local DevBuf d_counts; // reused across steps: [n_slices][64] counts, then [n_slices][64] cursors
+        const size_t words = size_t(n_slices) * 64;
+        d_counts.reserve(words * 2 * 8);
+        DGE_CUDA(cudaMemsetAsync(d_counts.p, 0, words * 8, st));
+        unsigned long long *cnt = d_counts.as<unsigned long long>(), *cursor = cnt + words;
+        std::vector<unsigned long long> hc(words, 0), off(words, 0);
+        if (n)
+        {
+            unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(2048)), 148 * 16));
+            k_route_count_slices<<<grid, 256, 0, st>>>(in, n, n_ranks, slice_len, cnt);
+            DGE_LAUNCH_CHECK();
+            DGE_CUDA(cudaMemcpyAsync(hc.data(), cnt, words * 8, cudaMemcpyDeviceToHost, st));
+            DGE_CUDA(cudaStreamSynchronize(st));
+            for (uint32_t sl = 0; sl < n_slices; ++sl)
+                for (uint32_t r = 1; r < n_ranks; ++r) off[size_t(sl) * 64 + r] = off[size_t(sl) * 64 + r - 1] + hc[size_t(sl) * 64 + r - 1];
+            DGE_CUDA(cudaMemcpyAsync(cursor, off.data(), words * 8, cudaMemcpyHostToDevice, st));
+            for (uint32_t sl = 0; sl < n_slices; ++sl)
+            {
+                const size_t s0 = size_t(sl) * slice_len;
+                if (s0 >= n) break;
+                const size_t m = std::min(slice_len, n - s0);
+                k_route_scatter<<<unsigned(div_up(m, size_t(256 * ROUTE_ITEMS))), 256, 0, st>>>(in + s0, m, n_ranks, cursor + size_t(sl) * 64, out + s0);
+            }
+            DGE_LAUNCH_CHECK();
+        }
+        for (uint32_t sl = 0; sl < n_slices; ++sl)
+            for (uint32_t r = 0; r < n_ranks; ++r) counts[size_t(sl) * n_ranks + r] = hc[size_t(sl) * 64 + r];
+        return DGE_OK;
+    }
+    catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_route_slices_device: %s\n", e.what()); return DGE_ERR_CUDA; }
 }
 
 } // extern "C"

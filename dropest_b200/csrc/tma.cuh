@@ -63,4 +63,19 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                  : "memory");
 }
 
+// L2 eviction policy for data that is read exactly once (keeps the streamed records from evicting the barcode table)
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
+
+__device__ __forceinline__ void bulk_g2s_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_addr(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+                 : "memory");
+}
+
 } // namespace dge

@@ -30,6 +30,65 @@ def route_device(device: int, in_ptr: int, n: int, world: int, out_ptr: int, str
     return counts
 
 
+def route_slices_device(device: int, in_ptr: int, n: int, world: int, out_ptr: int, slice_len: int, n_slices: int, stream: int = 0) -> np.ndarray:
+    """dge_route_slices_device: counts[n_slices, world]; the scatter launches of the slices are queued on `stream` when this returns."""
+    counts = np.zeros((n_slices, world), dtype=np.uint64)
+    rc = load_library().dge_route_slices_device(device, C.c_void_p(in_ptr), n, world, slice_len, n_slices, C.c_void_p(out_ptr), counts.ctypes.data,
+                                                C.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError(f"dge_route_slices_device failed with {rc}")
+    return counts
+
+
+class PipelinedExchange:
+    """Barcode-hash routing + all-to-all in slices, overlapped with the fill of the slices already received:
+        slice s: route kernel (our stream) -> all_to_all_single (NCCL's stream, async) -> dge_add_batch_device (our stream)
+    The per-slice split sizes of ALL slices come from one counting pass + one all-gather, so the loop itself never waits for the host."""
+
+    def __init__(self, device: int, n: int, world: int, n_slices: int = 8, slack: float = 1.25, group=None):
+        import torch
+
+        self.device, self.n, self.world, self.group = device, n, world, group
+        self.slice_len = ((n + n_slices - 1) // n_slices + 2047) // 2048 * 2048
+        self.n_slices = (n + self.slice_len - 1) // self.slice_len
+        dev = f"cuda:{device}"
+        self.routed = torch.empty(n * 16, dtype=torch.uint8, device=dev)
+        self.recv_cap = int(self.slice_len * slack) + 4096
+        self.recv = torch.empty(self.n_slices * self.recv_cap * 16, dtype=torch.uint8, device=dev)
+
+    def run(self, cont, raw_ptr: int, stream) -> int:
+        """Routes, exchanges and fills; returns the number of records this rank owns.  The receive buffers are referenced by the
+        container until its set_initialized returns."""
+        import torch
+        import torch.distributed as dist
+
+        world, S = self.world, self.n_slices
+        counts = route_slices_device(self.device, raw_ptr, self.n, world, self.routed.data_ptr(), self.slice_len, S, stream.cuda_stream)
+        mine = torch.from_numpy(counts.astype(np.int64).reshape(-1)).to(self.routed.device)
+        allc = torch.empty(world * mine.numel(), dtype=torch.int64, device=self.routed.device)
+        dist.all_gather_into_tensor(allc, mine, group=self.group)
+        allc = allc.cpu().numpy().reshape(world, S, world)          # [source, slice, destination]
+        rank = dist.get_rank(self.group)
+        total, pending = 0, None
+        for s in range(S):
+            in_split = [int(x) * 16 for x in counts[s]]
+            out_split = [int(x) * 16 for x in allc[:, s, rank]]
+            got = sum(out_split) // 16
+            if got > self.recv_cap:
+                raise RuntimeError("receive slice buffer too small: raise `slack`")
+            src = self.routed[s * self.slice_len * 16: s * self.slice_len * 16 + sum(in_split)]
+            dst = self.recv[s * self.recv_cap * 16: s * self.recv_cap * 16 + got * 16]
+            work = dist.all_to_all_single(dst, src, output_split_sizes=out_split, input_split_sizes=in_split, group=self.group, async_op=True)
+            if pending is not None:
+                pending[0].wait()                                    # our stream waits for that slice's all-to-all only
+                cont.add_batch_device(pending[1], pending[2])
+            pending = (work, dst.data_ptr(), got)
+            total += got
+        pending[0].wait()
+        cont.add_batch_device(pending[1], pending[2])
+        return total
+
+
 def exchange(routed, counts: np.ndarray, recv=None, group=None):
     """ONE all-to-all-v of 16-byte records.  `routed`: uint8 tensor (n*16) already grouped by destination rank, `counts`:
     records per destination.  Returns (uint8 tensor view of the received records, number of records)."""
@@ -74,63 +133,132 @@ def sync_umi_first_seen(cont, device: str, group=None):
     return n
 
 
-def merge_across_ranks(cont, device: str, group=None):
-    """Exact whitelist merge for sharded runs: two all-gathers around three local library steps.
-    Call between cont.set_initialized() and cont.merge_and_filter()."""
+def _empty_u8(n: int, device):
     import torch
-    import torch.distributed as dist
 
-    from .capi import DIST_RESULT_DTYPE
+    return torch.empty(max(int(n), 16), dtype=torch.uint8, device=device)
 
+
+def merge_across_ranks(cont, device: str, group=None):
+    """Exact whitelist merge for sharded runs: drives the library's state machine (dge_dist_step) and performs
+    the collectives it asks for over torch.distributed (NCCL on GPUs).  Every rank works on its own cells only: one all-gather of
+    16-byte target summaries, then three small all-to-alls (candidate pairs with the child lists, intersection sizes, commits).
+    Call between cont.set_initialized() and cont.merge_and_filter().  Returns the bytes this rank sent per step."""
     import os
     import time
 
-    trace = os.environ.get("DGE_TRACE") and dist.get_rank(group) == 0
-    t_prev = [time.perf_counter()]
+    import torch
+    import torch.distributed as dist
 
-    def mark(what):
-        if trace:
-            torch.cuda.synchronize()
-            now = time.perf_counter()
-            print(f"[dge] dist: {what:<28s} {1000 * (now - t_prev[0]):8.3f} ms", flush=True)
-            t_prev[0] = now
+    from .capi import DIST_ALLGATHER, DIST_DONE
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    nc, ne = cont.dist_export_children()
-    mark("export children")
-    mine = torch.tensor([nc, ne], dtype=torch.int64, device=device)
-    counts = torch.empty(world * 2, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(counts, mine, group=group)
-    counts = counts.cpu().numpy().reshape(world, 2)
-    max_nc, max_ne = int(counts[:, 0].max()), int(counts[:, 1].max())
-    ncs, nes = counts[:, 0], counts[:, 1]
-    tot_nc, tot_ne = int(ncs.sum()), int(nes.sum())
-    if tot_nc == 0:
-        cont.dist_apply(np.zeros(0, dtype=DIST_RESULT_DTYPE), world, rank, np.zeros(0, dtype=np.uint32))
-        return {"children": 0, "entries": 0}
-    send_i = torch.zeros(max(max_nc, 1) * 32, dtype=torch.uint8, device=device)
-    send_k = torch.zeros(max(max_ne, 1) * 8, dtype=torch.uint8, device=device)
-    send_v = torch.zeros(max(max_ne, 1) * 4, dtype=torch.uint8, device=device)
-    cont.dist_copy_children(send_i.data_ptr(), send_k.data_ptr(), send_v.data_ptr(), nc, ne)
-    all_i = torch.empty(world * send_i.numel(), dtype=torch.uint8, device=device)
-    all_k = torch.empty(world * send_k.numel(), dtype=torch.uint8, device=device)
-    all_v = torch.empty(world * send_v.numel(), dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(all_i, send_i, group=group)   # children summaries
-    dist.all_gather_into_tensor(all_k, send_k, group=group)   # their (gene|umi) lists ...
-    dist.all_gather_into_tensor(all_v, send_v, group=group)   # ... and values
-    mark("all-gather children")
-    g_i = torch.cat([all_i[r * send_i.numel(): r * send_i.numel() + int(ncs[r]) * 32] for r in range(world)])
-    g_k = torch.cat([all_k[r * send_k.numel(): r * send_k.numel() + int(nes[r]) * 8] for r in range(world)])
-    g_v = torch.cat([all_v[r * send_v.numel(): r * send_v.numel() + int(nes[r]) * 4] for r in range(world)])
-    mark("concatenate")
-    local = cont.dist_eval_children(g_i.data_ptr(), tot_nc, g_k.data_ptr(), g_v.data_ptr(), tot_ne)
-    mark("eval children")
-    res_t = torch.from_numpy(local.view(np.uint8)).to(device)
-    all_r = torch.empty(world * res_t.numel(), dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(all_r, res_t, group=group)    # per-rank best candidate of every child
-    child_rank = np.repeat(np.arange(world, dtype=np.uint32), ncs.astype(np.int64))
-    mark("all-gather results")
-    torch.cuda.current_stream().synchronize()
-    cont.dist_apply_device(all_r.data_ptr(), world, rank, child_rank)   # combination over ranks on the device; g_k / g_v stay alive until here
-    mark("apply")
-    return {"children": tot_nc, "entries": tot_ne}
+    trace = os.environ.get("DGE_TRACE") and rank == 0
+    io = cont.dist_io(world, rank)
+    keep = []        # receive buffers stay alive until the step that consumes them has returned
+    sent = []
+    t_prev = time.perf_counter()
+    while True:
+        # the library runs on its own stream (or the caller's, set_stream) and returns with that stream synchronised; torch's
+        # collectives below are ordered after it by the host, and we synchronise torch's stream before handing buffers back
+        kind = cont.dist_step(io)
+        if trace:
+            now = time.perf_counter()
+            print(f"[dge] dist: step {io.stage} (library)          {1000 * (now - t_prev):8.3f} ms", flush=True)
+            t_prev = now
+        if kind == DIST_DONE:
+            break
+        if kind == DIST_ALLGATHER:
+            mine = int(io.send_bytes[0])
+            sizes_t = torch.empty(world, dtype=torch.int64, device=device)
+            dist.all_gather_into_tensor(sizes_t, torch.tensor([mine], dtype=torch.int64, device=device), group=group)
+            sizes = [int(x) for x in sizes_t.cpu().tolist()]
+            mx = max(max(sizes), 16)
+            send = _empty_u8(mx, device)
+            if mine:
+                send[:mine].copy_(_as_tensor(io.send, mine, device))
+            gathered = _empty_u8(mx * world, device)
+            dist.all_gather_into_tensor(gathered[: mx * world], send[:mx], group=group)
+            recv = torch.cat([gathered[r * mx: r * mx + sizes[r]] for r in range(world)]) if sum(sizes) else _empty_u8(16, device)
+            out_sizes = sizes
+            sent.append(mine)
+        else:
+            in_split = [int(io.send_bytes[d]) for d in range(world)]
+            send_sizes = torch.tensor(in_split, dtype=torch.int64, device=device)
+            recv_sizes = torch.empty_like(send_sizes)
+            dist.all_to_all_single(recv_sizes, send_sizes, group=group)
+            out_split = [int(x) for x in recv_sizes.cpu().tolist()]
+            total_in, total_out = sum(in_split), sum(out_split)
+            send = _as_tensor(io.send, total_in, device) if total_in else _empty_u8(16, device)[:0]
+            recv = _empty_u8(total_out, device)
+            dist.all_to_all_single(recv[:total_out], send[:total_in], output_split_sizes=out_split, input_split_sizes=in_split, group=group)
+            out_sizes = out_split
+            sent.append(total_in)
+        torch.cuda.current_stream().synchronize()
+        keep = [recv]
+        io.recv = recv.data_ptr()
+        for r in range(world):
+            io.recv_bytes[r] = out_sizes[r]
+        if trace:
+            now = time.perf_counter()
+            print(f"[dge] dist: collective after step {io.stage}     {1000 * (now - t_prev):8.3f} ms ({sent[-1]} bytes sent)", flush=True)
+            t_prev = now
+    del keep
+    return {"bytes_sent": sent}
+
+
+def _as_tensor(ptr: int, nbytes: int, device):
+    """A uint8 torch view of `nbytes` of library-owned device memory (valid until the next dge_dist_step)."""
+    import torch
+
+    class _Mem:
+        pass
+
+    m = _Mem()
+    m.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(m, device=device)
+
+
+def merge_across_handles(conts):
+    """The same protocol with every 'rank' a handle in THIS process (all on one GPU or on several): the collectives are plain copies.
+    Used by the single-GPU tests of the cross-rank merge and as a reference implementation of the transport."""
+    import torch
+
+    from .capi import DIST_ALLGATHER, DIST_DONE
+
+    world = len(conts)
+    ios = [c.dist_io(world, r) for r, c in enumerate(conts)]
+    devs = [torch.device("cuda", c.cfg.device) for c in conts]
+    keep = []
+    while True:
+        kinds = [c.dist_step(io) for c, io in zip(conts, ios)]
+        assert len(set(kinds)) == 1, f"handles disagree on the collective: {kinds}"
+        if kinds[0] == DIST_DONE:
+            break
+        new_keep = []
+        if kinds[0] == DIST_ALLGATHER:
+            pieces = [(_as_tensor(io.send, int(io.send_bytes[0]), devs[r]).clone() if io.send_bytes[0] else _empty_u8(16, devs[r])[:0]) for r, io in enumerate(ios)]
+            for r, io in enumerate(ios):
+                recv = torch.cat([p.to(devs[r]) for p in pieces]) if sum(p.numel() for p in pieces) else _empty_u8(16, devs[r])[:0]
+                recv = torch.cat([recv, _empty_u8(16, devs[r])])  # never a null pointer
+                new_keep.append(recv)
+                io.recv = recv.data_ptr()
+                for s in range(world):
+                    io.recv_bytes[s] = pieces[s].numel()
+        else:
+            blobs = []
+            for r, io in enumerate(ios):
+                total = sum(int(io.send_bytes[d]) for d in range(world))
+                whole = _as_tensor(io.send, total, devs[r]).clone() if total else _empty_u8(16, devs[r])[:0]
+                offs = np.concatenate([[0], np.cumsum([int(io.send_bytes[d]) for d in range(world)])]).astype(np.int64)
+                blobs.append([whole[int(offs[d]): int(offs[d + 1])] for d in range(world)])
+            for r, io in enumerate(ios):
+                parts = [blobs[s][r].to(devs[r]) for s in range(world)]
+                recv = torch.cat(parts + [_empty_u8(16, devs[r])])
+                new_keep.append(recv)
+                io.recv = recv.data_ptr()
+                for s in range(world):
+                    io.recv_bytes[s] = parts[s].numel()
+        torch.cuda.synchronize()
+        keep = new_keep
+    del keep

@@ -90,9 +90,8 @@ typedef struct dge_config {
                                    Default "eEBA" = marks {2,3,6,7} = 0xCC (CellsDataContainer.cpp:17, UMI.cpp:123-154) */
     int32_t  max_cells;         /* -C: keep the top N filtered cells; <= 0 keeps all (CellsDataContainer.cpp:268-272) */
     uint32_t reads_output;      /* -R: matrix values are read counts instead of UMI counts (ResultsPrinter.cpp:345) */
-    uint32_t sharded;           /* 1 = this handle holds one barcode-hash shard of a multi-GPU run: a cell whose whitelist merge
-                                   candidates are not on this shard is left unmerged and counted in dge_summary.n_unresolved
-                                   (cross-rank CB merge is not implemented yet); 0 = the handle sees every barcode */
+    uint32_t sharded;           /* 1 = this handle holds one barcode-hash shard of a multi-GPU run: the whitelist merge runs across
+                                   ranks with dge_dist_step (exact) before dge_merge_and_filter; 0 = the handle sees every barcode */
     const char *barcodes_file;  /* whitelist in the reference's own file format (BarcodesParser.cpp:117-144); NULL/"" = none */
     uint64_t max_barcodes_hint; /* upper bound on distinct barcodes, 0 = automatic */
 } dge_config;
@@ -115,7 +114,8 @@ typedef struct dge_summary {
     uint64_t cm_raw_nnz;            /* non-zeros of `cm_raw`                    */
     uint64_t n_merged;              /* cells merged into another cell (MergeStrategyBase.cpp:53) */
     uint64_t n_excluded;            /* cells excluded by the merge      (MergeStrategyBase.cpp:54) */
-    uint64_t n_unresolved;          /* sharded runs only: cells whose merge candidates live on another shard (left unmerged) */
+    uint64_t n_unresolved;          /* sharded handles whose merge_and_filter ran WITHOUT dge_dist_step: cells left unmerged because their
+                                       candidates may live on another shard (0 after dge_dist_step) */
     uint64_t n_umis_merged;         /* UMIs merged into another UMI by the UMI merge strategy (MergeUMIsStrategyDirectional.cpp:43) */
     uint64_t n_umi_segments_replayed; /* (cell, gene) segments whose UMI merge was replayed on the host for exact tie order */
     uint64_t n_cb_merge_replayed;   /* SimpleMergeStrategy: base cells whose target was replayed on the host (near-ties of the top fraction) */
@@ -277,48 +277,41 @@ int dge_synth_generate_device(int device, const dge_synth_params *p, uint64_t fi
 int dge_route_by_barcode_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, dge_record16 *out,
                                 uint64_t *counts, void *cuda_stream);
 
+/* Routing for a PIPELINED exchange: `in` is cut into n_slices slices of slice_len records (a multiple of 2048; the last may be shorter);
+ * slice s is written to out[s * slice_len ...) grouped by destination rank, counts[s * n_ranks + r] (HOST) = its segment sizes.  One
+ * pass counts all slices (the only host synchronisation), then one scatter launch per slice is queued on the stream and the call
+ * returns: the all-to-all of slice s can start as soon as the stream reaches it, while later slices are still being routed and
+ * earlier ones are already being filled (dge_add_batch_device per received slice). */
+int dge_route_slices_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, size_t slice_len, uint32_t n_slices,
+                            dge_record16 *out, uint64_t *counts, void *cuda_stream);
+
 /* ---- cross-rank whitelist merge for sharded runs ---------------------------------------------------
- * With reads sharded by barcode hash a cell and its merge candidates usually live on different ranks.  The exchange itself
- * (two all-gathers) is done by the caller with whatever transport it has (NCCL in bench.py / dropest_b200/dist.py); the
- * library provides the three local steps.  Sequence on every rank, after dge_set_initialized:
- *   1. dge_dist_export_children : real cells that are not whitelist barcodes ("children"), as one info row per cell and the
- *                                 concatenated (gene|umi, value) lists -- DEVICE pointers, valid until dge_dist_apply
- *   2. [all-gather infos, keys, vals over ranks, concatenated in rank order]
- *   3. dge_dist_eval_children   : every child of every rank against THIS rank's cells (distance classes 0/1, eligibility,
- *                                 (gene,umi) overlap): one dge_dist_result per child (HOST array)
- *   4. [all-gather the results]
- *   5. dge_dist_apply           : combines the per-rank results exactly like RealBarcodesMergeStrategy::get_best_merge_target,
- *                                 merges children whose target lives here, flags local children as merged / excluded
- *   6. dge_merge_and_filter     : continues with the UMI merge, final sizes, filter and matrices
- * Children without any class-0/1 candidate on any rank are left unmerged and counted in dge_summary.n_unresolved. */
-typedef struct dge_dist_child {
-    uint64_t barcode;
-    int32_t  umis_stat, reads_stat, n_genes;
-    uint32_t n_intergenic;
-    uint32_t n_entries;   /* length of the child's (gene|umi, value) list */
-    uint32_t local_index; /* opaque to other ranks */
-} dge_dist_child;
+ * With reads sharded by barcode hash a cell and its merge candidates usually live on different ranks.  The merge is exact
+ * (RealBarcodesMergeStrategy.cpp:22-114 incl. the fall-through to farther distance classes and the neighbour order on ties) and every
+ * rank only works on ITS OWN cells.  The library is a state machine, the caller owns the transport (NCCL in bench.py /
+ * dropest_b200/dist.py, plain copies in the single-GPU multi-handle tests): call dge_dist_step after dge_set_initialized; while it
+ * asks for a collective (io->collective != DGE_DIST_DONE) perform it on the bytes it points to and call again with the received bytes:
+ *   step 1  -> ALLGATHER  16-byte summaries of the real cells that are whitelist barcodes (the only possible merge targets)
+ *   step 2  -> ALLTOALL   per owner of a candidate: the (child, candidate) pairs with the child's (gene|umi, value) list
+ *   step 3  -> ALLTOALL   one u32 per received pair: |child ∩ candidate| (MergeStrategyBase.cpp:100-147)
+ *   step 4  -> ALLTOALL   one 16-byte commit per child merged into a cell of another rank (its Stats counters, Stats.cpp:29-43)
+ *   step 5  -> DONE       commits applied; continue with dge_merge_and_filter (UMI merge, final sizes, filter, matrices)
+ * ALLGATHER: every rank contributes send_bytes[0] bytes; recv = the pieces of rank 0..world-1 concatenated, recv_bytes[r] their sizes.
+ * ALLTOALL : piece d (send_bytes[d] bytes, pieces concatenated in rank order starting at `send`) goes to rank d; recv likewise by source.
+ * All pointers are DEVICE memory on cfg.device; `send` stays valid until the next call, `recv` must stay valid during the call only. */
+#define DGE_DIST_MAX_WORLD 64
+enum { DGE_DIST_DONE = 0, DGE_DIST_ALLGATHER = 1, DGE_DIST_ALLTOALL = 2 };
+typedef struct dge_dist_io {
+    uint32_t world, rank;                          /* set by the caller before the first step */
+    uint32_t collective;                           /* out: DGE_DIST_* */
+    uint32_t stage;                                /* out: number of the step just executed (diagnostics) */
+    const void *send;                              /* out */
+    uint64_t send_bytes[DGE_DIST_MAX_WORLD];       /* out */
+    const void *recv;                              /* in: result of the collective requested by the previous step */
+    uint64_t recv_bytes[DGE_DIST_MAX_WORLD];       /* in */
+} dge_dist_io;
 
-typedef struct dge_dist_result {
-    double   best_fraction;   /* max over this rank's eligible neighbours of 0.5*I*(1/U_child + 1/U_nb) */
-    uint64_t best_barcode;    /* the neighbour reaching it */
-    uint32_t n_neighbours;    /* eligible neighbours found on this rank (0 = none) */
-    uint32_t n_best;          /* how many of them reach best_fraction exactly (ties) */
-} dge_dist_result;
-
-int dge_dist_export_children(dge_handle *h, const dge_dist_child **infos_device, const uint64_t **keys_device,
-                             const uint32_t **vals_device, uint64_t *n_children, uint64_t *n_entries);
-/* copies the export of step 1 into caller-owned DEVICE buffers (e.g. the send buffers of the all-gather) */
-int dge_dist_copy_children(dge_handle *h, dge_dist_child *infos_dst_device, uint64_t *keys_dst_device, uint32_t *vals_dst_device,
-                           uint64_t n_children, uint64_t n_entries);
-int dge_dist_eval_children(dge_handle *h, const dge_dist_child *infos_device, uint64_t n_children, const uint64_t *keys_device,
-                           const uint32_t *vals_device, uint64_t n_entries, dge_dist_result *results_host);
-int dge_dist_apply(dge_handle *h, const dge_dist_result *all_results_host, uint32_t world, uint32_t my_rank,
-                   const uint32_t *child_rank_host);
-/* Same, with the all-gathered results still in DEVICE memory: the combination over ranks runs in a kernel and only one
- * combined row per child is read back (O(children) instead of O(children x ranks) on the host). */
-int dge_dist_apply_device(dge_handle *h, const dge_dist_result *all_results_device, uint32_t world, uint32_t my_rank,
-                          const uint32_t *child_rank);
+int dge_dist_step(dge_handle *h, dge_dist_io *io);
 
 /* Sharded runs with a strategy that depends on the UMI indexer's first-seen order (directional UMI merge): every rank tracks
  * min(read_idx) per packed UMI over ITS reads; the reference's StringIndexer is global, so the tables have to be min-reduced

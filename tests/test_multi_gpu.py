@@ -60,12 +60,12 @@ def _worker_real(rank, world, port, n_total, out_dir, umi_len, n_genes, directio
     per = n_total // world
     raw = torch.empty(per * 16, dtype=torch.uint8, device=f"cuda:{rank}")
     SynthTables(_spec(n_total, umi_len, n_genes)).generate_device(rank, rank * per, per, raw.data_ptr())
-    routed = torch.empty_like(raw)
-    counts = dgdist.route_device(rank, raw.data_ptr(), per, world, routed.data_ptr())
-    got, cnt = dgdist.exchange(routed, counts)
-    torch.cuda.synchronize()
     c = dg.Container(_real_config(dg, umi_len, n_genes, directional, device=rank, sharded=True))
-    c.add_batch_device(got.data_ptr(), cnt, keepalive=got)
+    stream = torch.cuda.current_stream()
+    c.set_stream(stream.cuda_stream)
+    pipe = dgdist.PipelinedExchange(rank, per, world, n_slices=5)   # routing + sliced all-to-all overlapped with the fill
+    cnt = pipe.run(c, raw.data_ptr(), stream)
+    torch.cuda.synchronize()
     dgdist.sync_umi_first_seen(c, f"cuda:{rank}")
     c.set_initialized()
     stats = dgdist.merge_across_ranks(c, f"cuda:{rank}")
