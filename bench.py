@@ -164,7 +164,11 @@ def exchange_diagnostics(pipe, cont, raw, stream, torch, dist, n, world):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     torch.cuda.synchronize(); dist.barrier()
     ev[0].record(stream)
-    counts = dgdist.route_slices_device(pipe.device, raw.data_ptr(), n, world, pipe.routed.data_ptr(), pipe.slice_len, pipe.n_slices, stream.cuda_stream)
+    dgdist.route_count_slices(pipe.device, raw.data_ptr(), n, world, pipe.slice_len, pipe.n_slices, pipe.cursors.data_ptr(), stream.cuda_stream)
+    for s in range(pipe.n_slices):
+        n_slice = min(pipe.slice_len, n - s * pipe.slice_len)
+        dgdist.route_scatter_slice(pipe.device, raw.data_ptr() + s * pipe.slice_len * 16, n_slice, world, pipe.cursors.data_ptr() + s * 64 * 8,
+                                   pipe.routed.data_ptr() + s * pipe.slice_len * 16, stream.cuda_stream)
     ev[1].record(stream)
     torch.cuda.synchronize(); dist.barrier()
     # unsliced all-to-all of the same volume (segments of the first slice layout are not contiguous per destination across slices, so

@@ -44,7 +44,7 @@ EXPORTS = [
     "dge_set_initialized", "dge_merge_and_filter", "dge_reset", "dge_set_stream", "dge_get_summary", "dge_get_timings", "dge_get_cells",
     "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
-    "dge_route_by_barcode_device", "dge_route_slices_device", "dge_dist_step",
+    "dge_route_by_barcode_device", "dge_route_count_slices_device", "dge_route_scatter_slice_device", "dge_dist_step",
     "dge_umi_first_size", "dge_umi_first_export", "dge_umi_first_import", "dge_collisions_adjusted_sizes",
 ]
 
@@ -144,6 +144,8 @@ def load_library():
     lib.dge_whitelist_token.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]
     lib.dge_synth_generate_device.argtypes = [C.c_int, C.POINTER(_SynthParams), C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.dge_route_by_barcode_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dge_route_count_slices_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dge_route_scatter_slice_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dge_dist_step.argtypes = [C.c_void_p, C.POINTER(_DistIO)]
     lib.dge_umi_first_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
     lib.dge_umi_first_export.argtypes = [C.c_void_p, C.c_void_p]

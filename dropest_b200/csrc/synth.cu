@@ -230,25 +230,22 @@ int dge_route_by_barcode_device(int device, const dge_record16 *in, size_t n, ui
     catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_route_by_barcode_device: %s\n", e.what()); return DGE_ERR_CUDA; }
 }
 
-/* Routing for a PIPELINED exchange: the input is cut into n_slices slices of slice_len records (a multiple of 2048; the last one may be
- * shorter); slice s is written to out[s * slice_len ...) grouped by destination rank, counts[s * n_ranks + r] (HOST) = its segment sizes.
- * One pass counts all slices (single host synchronisation), then one scatter launch per slice is queued on the stream: the caller can
- * start the all-to-all of slice s as soon as the stream reaches it while later slices are still being routed. */
-int dge_route_slices_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, size_t slice_len, uint32_t n_slices, dge_record16 *out,
-                            uint64_t *counts, void *cuda_stream)
+/* Routing for a PIPELINED exchange, step 1: the input is cut into n_slices slices of slice_len records (a multiple of 2048; the last one
+ * may be shorter).  One pass counts the destinations of every slice: counts[s * n_ranks + r] (HOST) and, in `cursors_device`
+ * (n_slices * 64 uint64, DEVICE, caller-owned), the exclusive prefix of every slice's segments.  Synchronises the stream once. */
+int dge_route_count_slices_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, size_t slice_len, uint32_t n_slices,
+                                  uint64_t *counts, uint64_t *cursors_device, void *cuda_stream)
 {
-    if (!counts || n_ranks == 0 || n_ranks > 64 || n_slices == 0 || n_slices > 256 || slice_len == 0 || (slice_len % 2048) || (n && (!in || !out)) ||
-        size_t(n_slices) * slice_len < n)
+    if (!counts || !cursors_device || n_ranks == 0 || n_ranks > 64 || n_slices == 0 || n_slices > 256 || slice_len == 0 || (slice_len % 2048) ||
+        (n && !in) || size_t(n_slices) * slice_len < n)
         return DGE_ERR_INVALID;
     try
     {
         DGE_CUDA(cudaSetDevice(device));
         cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-        static thread_local DevBuf d_counts; // reused across steps: [n_slices][64] counts, then [n_slices][64] cursors
         const size_t words = size_t(n_slices) * 64;
-        d_counts.reserve(words * 2 * 8);
-        DGE_CUDA(cudaMemsetAsync(d_counts.p, 0, words * 8, st));
-        unsigned long long *cnt = d_counts.as<unsigned long long>(), *cursor = cnt + words;
+        unsigned long long *cnt = reinterpret_cast<unsigned long long *>(cursors_device);
+        DGE_CUDA(cudaMemsetAsync(cnt, 0, words * 8, st));
         std::vector<unsigned long long> hc(words, 0), off(words, 0);
         if (n)
         {
@@ -259,21 +256,36 @@ int dge_route_slices_device(int device, const dge_record16 *in, size_t n, uint32
             DGE_CUDA(cudaStreamSynchronize(st));
             for (uint32_t sl = 0; sl < n_slices; ++sl)
                 for (uint32_t r = 1; r < n_ranks; ++r) off[size_t(sl) * 64 + r] = off[size_t(sl) * 64 + r - 1] + hc[size_t(sl) * 64 + r - 1];
-            DGE_CUDA(cudaMemcpyAsync(cursor, off.data(), words * 8, cudaMemcpyHostToDevice, st));
-            for (uint32_t sl = 0; sl < n_slices; ++sl)
-            {
-                const size_t s0 = size_t(sl) * slice_len;
-                if (s0 >= n) break;
-                const size_t m = std::min(slice_len, n - s0);
-                k_route_scatter<<<unsigned(div_up(m, size_t(256 * ROUTE_ITEMS))), 256, 0, st>>>(in + s0, m, n_ranks, cursor + size_t(sl) * 64, out + s0);
-            }
-            DGE_LAUNCH_CHECK();
+            DGE_CUDA(cudaMemcpyAsync(cnt, off.data(), words * 8, cudaMemcpyHostToDevice, st));
+            DGE_CUDA(cudaStreamSynchronize(st)); // `off` is a local
         }
         for (uint32_t sl = 0; sl < n_slices; ++sl)
             for (uint32_t r = 0; r < n_ranks; ++r) counts[size_t(sl) * n_ranks + r] = hc[size_t(sl) * 64 + r];
         return DGE_OK;
     }
-    catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_route_slices_device: %s\n", e.what()); return DGE_ERR_CUDA; }
+    catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_route_count_slices_device: %s\n", e.what()); return DGE_ERR_CUDA; }
+}
+
+/* Step 2, once per slice and fully asynchronous: the slice's records grouped by destination rank into out[0 .. n_slice), segment r at the
+ * prefix prepared by step 1 (`slice_cursors_device` = cursors_device + 64 * slice; consumed by the launch).  The caller queues the
+ * all-to-all of the slice right behind it and goes on with the next slice. */
+int dge_route_scatter_slice_device(int device, const dge_record16 *in_slice, size_t n_slice, uint32_t n_ranks, uint64_t *slice_cursors_device,
+                                   dge_record16 *out_slice, void *cuda_stream)
+{
+    if (n_ranks == 0 || n_ranks > 64 || !slice_cursors_device || (n_slice && (!in_slice || !out_slice))) return DGE_ERR_INVALID;
+    try
+    {
+        DGE_CUDA(cudaSetDevice(device));
+        cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+        if (n_slice)
+        {
+            k_route_scatter<<<unsigned(div_up(n_slice, size_t(256 * ROUTE_ITEMS))), 256, 0, st>>>(in_slice, n_slice, n_ranks,
+                                                                                                 reinterpret_cast<unsigned long long *>(slice_cursors_device), out_slice);
+            DGE_LAUNCH_CHECK();
+        }
+        return DGE_OK;
+    }
+    catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_route_scatter_slice_device: %s\n", e.what()); return DGE_ERR_CUDA; }
 }
 
 } // extern "C"

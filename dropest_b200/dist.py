@@ -30,14 +30,21 @@ def route_device(device: int, in_ptr: int, n: int, world: int, out_ptr: int, str
     return counts
 
 
-def route_slices_device(device: int, in_ptr: int, n: int, world: int, out_ptr: int, slice_len: int, n_slices: int, stream: int = 0) -> np.ndarray:
-    """dge_route_slices_device: counts[n_slices, world]; the scatter launches of the slices are queued on `stream` when this returns."""
+def route_count_slices(device: int, in_ptr: int, n: int, world: int, slice_len: int, n_slices: int, cursors_ptr: int, stream: int = 0) -> np.ndarray:
+    """dge_route_count_slices_device: counts[n_slices, world] on the host, per-slice segment prefixes in the caller's device scratch."""
     counts = np.zeros((n_slices, world), dtype=np.uint64)
-    rc = load_library().dge_route_slices_device(device, C.c_void_p(in_ptr), n, world, slice_len, n_slices, C.c_void_p(out_ptr), counts.ctypes.data,
-                                                C.c_void_p(stream))
+    rc = load_library().dge_route_count_slices_device(device, C.c_void_p(in_ptr), n, world, slice_len, n_slices, counts.ctypes.data,
+                                                      C.c_void_p(cursors_ptr), C.c_void_p(stream))
     if rc != 0:
-        raise RuntimeError(f"dge_route_slices_device failed with {rc}")
+        raise RuntimeError(f"dge_route_count_slices_device failed with {rc}")
     return counts
+
+
+def route_scatter_slice(device: int, in_ptr: int, n_slice: int, world: int, cursors_ptr: int, out_ptr: int, stream: int = 0):
+    rc = load_library().dge_route_scatter_slice_device(device, C.c_void_p(in_ptr), n_slice, world, C.c_void_p(cursors_ptr), C.c_void_p(out_ptr),
+                                                       C.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError(f"dge_route_scatter_slice_device failed with {rc}")
 
 
 class PipelinedExchange:
@@ -55,6 +62,7 @@ class PipelinedExchange:
         self.routed = torch.empty(n * 16, dtype=torch.uint8, device=dev)
         self.recv_cap = int(self.slice_len * slack) + 4096
         self.recv = torch.empty(self.n_slices * self.recv_cap * 16, dtype=torch.uint8, device=dev)
+        self.cursors = torch.empty(self.n_slices * 64, dtype=torch.int64, device=dev)
 
     def run(self, cont, raw_ptr: int, stream) -> int:
         """Routes, exchanges and fills; returns the number of records this rank owns.  The receive buffers are referenced by the
@@ -63,21 +71,26 @@ class PipelinedExchange:
         import torch.distributed as dist
 
         world, S = self.world, self.n_slices
-        counts = route_slices_device(self.device, raw_ptr, self.n, world, self.routed.data_ptr(), self.slice_len, S, stream.cuda_stream)
+        sp = stream.cuda_stream
+        counts = route_count_slices(self.device, raw_ptr, self.n, world, self.slice_len, S, self.cursors.data_ptr(), sp)
         mine = torch.from_numpy(counts.astype(np.int64).reshape(-1)).to(self.routed.device)
         allc = torch.empty(world * mine.numel(), dtype=torch.int64, device=self.routed.device)
         dist.all_gather_into_tensor(allc, mine, group=self.group)
-        allc = allc.cpu().numpy().reshape(world, S, world)          # [source, slice, destination]
+        allc = allc.cpu().numpy().reshape(world, S, world)          # [source, slice, destination]; nothing else is queued yet: a short wait
         rank = dist.get_rank(self.group)
         total, pending = 0, None
         for s in range(S):
+            n_slice = min(self.slice_len, self.n - s * self.slice_len)
+            off = s * self.slice_len * 16
+            route_scatter_slice(self.device, raw_ptr + off, n_slice, world, self.cursors.data_ptr() + s * 64 * 8, self.routed.data_ptr() + off, sp)
             in_split = [int(x) * 16 for x in counts[s]]
             out_split = [int(x) * 16 for x in allc[:, s, rank]]
             got = sum(out_split) // 16
             if got > self.recv_cap:
                 raise RuntimeError("receive slice buffer too small: raise `slack`")
-            src = self.routed[s * self.slice_len * 16: s * self.slice_len * 16 + sum(in_split)]
+            src = self.routed[off: off + sum(in_split)]
             dst = self.recv[s * self.recv_cap * 16: s * self.recv_cap * 16 + got * 16]
+            # NCCL's stream waits for what is queued on ours so far (= this slice's scatter), not for the later slices
             work = dist.all_to_all_single(dst, src, output_split_sizes=out_split, input_split_sizes=in_split, group=self.group, async_op=True)
             if pending is not None:
                 pending[0].wait()                                    # our stream waits for that slice's all-to-all only

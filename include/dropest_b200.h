@@ -277,13 +277,17 @@ int dge_synth_generate_device(int device, const dge_synth_params *p, uint64_t fi
 int dge_route_by_barcode_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, dge_record16 *out,
                                 uint64_t *counts, void *cuda_stream);
 
-/* Routing for a PIPELINED exchange: `in` is cut into n_slices slices of slice_len records (a multiple of 2048; the last may be shorter);
- * slice s is written to out[s * slice_len ...) grouped by destination rank, counts[s * n_ranks + r] (HOST) = its segment sizes.  One
- * pass counts all slices (the only host synchronisation), then one scatter launch per slice is queued on the stream and the call
- * returns: the all-to-all of slice s can start as soon as the stream reaches it, while later slices are still being routed and
- * earlier ones are already being filled (dge_add_batch_device per received slice). */
-int dge_route_slices_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, size_t slice_len, uint32_t n_slices,
-                            dge_record16 *out, uint64_t *counts, void *cuda_stream);
+/* Routing for a PIPELINED exchange (route kernel -> all-to-all -> fill, slice by slice).
+ * Step 1, dge_route_count_slices_device: `in` is cut into n_slices slices of slice_len records (a multiple of 2048; the last may be
+ * shorter); one pass counts the destinations of every slice: counts[s * n_ranks + r] (HOST) and, in `cursors_device` (n_slices * 64
+ * uint64, DEVICE, caller-owned), the exclusive prefix of every slice's segments.  The only host synchronisation of the exchange.
+ * Step 2, dge_route_scatter_slice_device, once per slice and asynchronous: the slice grouped by destination rank into out_slice,
+ * segment r at the prefix of step 1 (slice_cursors_device = cursors_device + 64 * slice, consumed by the launch).  The caller queues the
+ * slice's all-to-all behind it and goes on; received slices are filled with dge_add_batch_device while later ones still travel. */
+int dge_route_count_slices_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, size_t slice_len, uint32_t n_slices,
+                                  uint64_t *counts, uint64_t *cursors_device, void *cuda_stream);
+int dge_route_scatter_slice_device(int device, const dge_record16 *in_slice, size_t n_slice, uint32_t n_ranks, uint64_t *slice_cursors_device,
+                                   dge_record16 *out_slice, void *cuda_stream);
 
 /* ---- cross-rank whitelist merge for sharded runs ---------------------------------------------------
  * With reads sharded by barcode hash a cell and its merge candidates usually live on different ranks.  The merge is exact

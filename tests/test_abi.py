@@ -24,6 +24,13 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert set(capi.EXPORTS) <= set(syms)
 
 
+def test_every_export_has_a_ctypes_prototype():
+    """A missing argtypes list makes ctypes pass 64-bit sizes / pointers as 32-bit ints."""
+    lib = dg.load_library()
+    missing = [s for s in capi.EXPORTS if getattr(lib, s).argtypes is None]
+    assert not missing, missing
+
+
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi._Config) == 112
     assert capi.CELL_INFO_DTYPE.itemsize == 40
