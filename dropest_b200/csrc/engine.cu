@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "fill.cuh"
 #include "merge.cuh"
+#include "poisson.cuh"
 #include "scan.cuh"
 #include "segments.cuh"
 #include "simplemerge.cuh"
@@ -168,6 +169,13 @@ struct dge_handle
     bool lazy_rows = false;          // rows_dev2 / sort_v[0] / gsort_* hold everything the mirror needs
     bool dev_merged = false;         // the merge ran in the device flow
     uint64_t sum_real = 0, sum_filtered = 0, sum_genes_seen = 0, n_host_fallback = 0;
+
+    // PoissonTargetEstimator state (-M): UMI distribution, CollisionsAdjuster table, per-pair work
+    DevBuf pp_pc_real, pp_real_pc, pp_hist, pp_p, pp_adj, pp_cnt, pp_off, pp_spairs, pp_skey, pp_sval, pp_est, pp_prob, pp_flag, pp_best, pp_misc;
+    PinnedBuf pin_pp;
+    bool pp_ready = false;
+    uint32_t pp_max_gene_size = 0;
+    uint64_t n_poisson_replayed = 0;
 
     // cross-rank merge state machine (dge_dist_step)
     int dist_stage = 0;
@@ -979,6 +987,42 @@ void do_set_initialized(dge_handle *h)
     h->timings.n_fill_launches = uint32_t(h->n_fill_ev / 2);
 }
 
+// Tools::CollisionsAdjuster table on the device: adj[s-1] = estimate_adjusted_gene_expression(s), s = 1..max_expr, for the UMI
+// probabilities d_p (device).  Fast pass with a parallel sum; when a step comes too close to a rounding boundary the table is
+// recomputed with the terms summed in index order (collisions.cuh).
+void collisions_adjusted_device(cudaStream_t st, const double *d_p, size_t n, size_t max_expr, unsigned long long *d_adj, uint32_t *exact_rerun)
+{
+    DevBuf neg, terms, partial, state;
+    neg.reserve(std::max<size_t>(n, 1) * 8);
+    const unsigned blocks = unsigned(std::max<size_t>(1, std::min<size_t>(div_up(n, size_t(CA_THREADS)), 148 * 8)));
+    partial.reserve(size_t(blocks) * 8); state.reserve(sizeof(CollisionsState));
+    std::vector<double> ones(n, 1.0);
+    // worst-case difference between two association orders of the sum, propagated through 1/(1-q): see collisions.cuh
+    const double drift = std::max(1e-13, double(n) * 4e-15);
+    const bool force_exact = std::getenv("DGE_CA_FORCE_EXACT") != nullptr; // tests: exercise the sequential-order path
+    for (int exact = force_exact ? 1 : 0; exact < 2; ++exact)
+    {
+        DGE_CUDA(cudaMemcpyAsync(neg.p, ones.data(), n * 8, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(cudaMemsetAsync(state.p, 0, sizeof(CollisionsState), st));
+        if (exact) terms.reserve(std::max<size_t>(n, 1) * 8);
+        for (size_t s = 1; s <= max_expr; ++s)
+        {
+            if (exact)
+                k_collisions_step<true><<<blocks, CA_THREADS, 0, st>>>(d_p, neg.as<double>(), terms.as<double>(), n, s, state.as<CollisionsState>(),
+                                                                      partial.as<double>(), d_adj, drift);
+            else
+                k_collisions_step<false><<<blocks, CA_THREADS, 0, st>>>(d_p, neg.as<double>(), nullptr, n, s, state.as<CollisionsState>(),
+                                                                       partial.as<double>(), d_adj, drift);
+        }
+        DGE_LAUNCH_CHECK();
+        CollisionsState hs;
+        DGE_CUDA(cudaMemcpyAsync(&hs, state.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        DGE_CUDA(cudaStreamSynchronize(st));
+        if (!exact && hs.risky == 0) break;
+        if (!exact && exact_rerun) *exact_rerun = hs.risky;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 void upload_whitelist(dge_handle *h)
 {
@@ -1232,6 +1276,93 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// PoissonTargetEstimator (reference Merge/PoissonTargetEstimator.cpp).  init(): UMI distribution over the filtered cells + the
+// CollisionsAdjuster table; then estimate_intersection_prob for a batch of (base, other) pairs of real-cell indices.
+void poisson_init(dge_handle *h)
+{
+    if (h->pp_ready) return;
+    cudaStream_t st = h->stream;
+    const size_t n = h->real.size();
+    if (!h->slot_pc_built) build_slot_pc(h);
+    // real flag per present cell + real index -> present cell
+    std::vector<uint32_t> pc_real(size_t(h->n_pc) + 2, 0), real_pc(std::max<size_t>(n, 1), h->n_pc);
+    for (size_t i = 0; i < n; ++i)
+    {
+        const HostCell &c = h->real[i];
+        if (c.pc == NONE32) continue;
+        real_pc[i] = c.pc;
+        if (c.real) pc_real[c.pc] = 1; // filtered_cells() at merge time = every real cell
+    }
+    h->pp_pc_real.reserve(pc_real.size() * 4); h->pp_real_pc.reserve(real_pc.size() * 4);
+    DGE_CUDA(cudaMemcpyAsync(h->pp_pc_real.p, pc_real.data(), pc_real.size() * 4, cudaMemcpyHostToDevice, st));
+    DGE_CUDA(cudaMemcpyAsync(h->pp_real_pc.p, real_pc.data(), real_pc.size() * 4, cudaMemcpyHostToDevice, st));
+    DGE_CUDA(cudaStreamSynchronize(st));
+    const size_t n_umi = size_t(1) << h->kl.ub;
+    h->pp_hist.reserve(n_umi * 8); h->pp_p.reserve(n_umi * 8); h->pp_misc.reserve(64);
+    DGE_CUDA(cudaMemsetAsync(h->pp_hist.p, 0, n_umi * 8, st));
+    DGE_CUDA(cudaMemsetAsync(h->pp_misc.p, 0, 64, st));
+    unsigned long long *total = h->pp_misc.as<unsigned long long>();
+    uint32_t *max_size = reinterpret_cast<uint32_t *>(total + 1);
+    if (h->n_u)
+        k_umi_hist<<<grid_for(h->n_u, 256), 256, 0, st>>>(h->ukey.as<uint64_t>(), h->n_u, h->kl.ub, h->kl.gb + h->kl.ub, h->slot_pc.as<uint32_t>(),
+                                                          h->pp_pc_real.as<uint32_t>(), h->pp_hist.as<unsigned long long>());
+    k_hist_total<<<grid_for(n_umi, 256), 256, 0, st>>>(h->pp_hist.as<unsigned long long>(), n_umi, total);
+    k_hist_to_prob<<<grid_for(n_umi, 256), 256, 0, st>>>(h->pp_hist.as<unsigned long long>(), n_umi, total, h->pp_p.as<double>());
+    if (h->n_cg)
+        k_max_gene_size<<<grid_for(h->n_cg, 256), 256, 0, st>>>(h->cg_start.as<uint32_t>(), h->cg_pc.as<uint32_t>(), h->n_cg, h->pp_pc_real.as<uint32_t>(), max_size);
+    DGE_LAUNCH_CHECK();
+    h->launches += 4;
+    h->pp_max_gene_size = d2h_scalar<uint32_t>(max_size, st);
+    const size_t m = std::max<uint32_t>(h->pp_max_gene_size, 1);
+    h->pp_adj.reserve(m * 8);
+    uint32_t rerun = 0;
+    collisions_adjusted_device(st, h->pp_p.as<double>(), n_umi, m, h->pp_adj.as<unsigned long long>(), &rerun);
+    h->pp_ready = true;
+}
+
+// prob[p] = PoissonTargetEstimator::estimate_intersection_prob(base, other).merge_probability for the flagged pairs (2.0 for the others).
+// d_pkey[p] = (base << rb) | other (real-cell indices), d_pval[p] = intersection size, all DEVICE arrays of n_p entries.
+void poisson_eval_pairs(dge_handle *h, const uint64_t *d_pkey, const uint32_t *d_pval, const uint32_t *d_flag, uint32_t n_p, int rb, double *d_prob)
+{
+    poisson_init(h);
+    if (!n_p) return;
+    cudaStream_t st = h->stream;
+    h->pp_cnt.reserve((size_t(n_p) + 1) * 4); h->pp_off.reserve((size_t(n_p) + 1) * 4);
+    const unsigned g = grid_for(n_p, 256);
+    k_pp_shared<false><<<g, 256, 0, st>>>(d_pkey, d_flag, n_p, rb, h->pp_real_pc.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(), h->cg_gene.as<uint32_t>(),
+                                          h->cg_start.as<uint32_t>(), h->pp_adj.as<unsigned long long>(), h->pp_cnt.as<uint32_t>(), nullptr, nullptr);
+    DGE_CUDA(cudaMemsetAsync(h->pp_cnt.as<uint32_t>() + n_p, 0, 4, st));
+    device_exclusive_scan(h->pp_cnt.as<uint32_t>(), h->pp_off.as<uint32_t>(), size_t(n_p) + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+    const uint32_t n_shared = d2h_scalar<uint32_t>(h->pp_off.as<uint32_t>() + n_p, st);
+    uint32_t n_sp = 0;
+    h->pp_skey.reserve(std::max<size_t>(n_shared, 1) * 8); h->pp_sval.reserve(std::max<size_t>(n_shared, 1) * 4);
+    if (n_shared)
+    {
+        if (h->pp_max_gene_size && d2h_scalar<unsigned long long>(h->pp_adj.as<unsigned long long>() + (h->pp_max_gene_size - 1), st) >= (1ull << 29))
+            throw CapacityError("adjusted gene sizes beyond 2^29");
+        h->pp_spairs.reserve(size_t(n_shared) * 8);
+        k_pp_shared<true><<<g, 256, 0, st>>>(d_pkey, d_flag, n_p, rb, h->pp_real_pc.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(), h->cg_gene.as<uint32_t>(),
+                                             h->cg_start.as<uint32_t>(), h->pp_adj.as<unsigned long long>(), nullptr, h->pp_off.as<uint32_t>(),
+                                             h->pp_spairs.as<uint64_t>());
+        DGE_LAUNCH_CHECK();
+        const int kb = 58 + 3;
+        const uint32_t *n_sp_ptr = h->sc2.run(h->pp_spairs.as<uint64_t>(), nullptr, n_shared, kb, std::min(choose_l1_bits(n_shared), kb - 3), nullptr,
+                                              h->pp_spairs.as<uint64_t>(), h->pp_skey.as<uint64_t>(), h->pp_sval.as<uint32_t>(), h->overflow_flag.as<int>(), st,
+                                              &h->sc_stats);
+        n_sp = d2h_scalar<uint32_t>(n_sp_ptr, st);
+        h->sc2.collect_timing();
+        if (d2h_scalar<int>(h->overflow_flag.p, st)) throw std::runtime_error("sub-bucket hash table overflow while collecting gene size pairs");
+    }
+    h->pp_est.reserve(std::max<size_t>(n_sp, 1) * 8);
+    if (n_sp)
+        k_pp_est<<<std::min<uint32_t>(n_sp, 148 * 16), 256, 0, st>>>(h->pp_skey.as<uint64_t>(), n_sp, h->pp_p.as<double>(), size_t(1) << h->kl.ub, h->pp_est.as<double>());
+    k_pp_lambda<<<g, 256, 0, st>>>(d_pkey, d_pval, d_flag, n_p, rb, h->pp_real_pc.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(), h->cg_gene.as<uint32_t>(),
+                                   h->cg_start.as<uint32_t>(), h->pp_adj.as<unsigned long long>(), h->pp_skey.as<uint64_t>(), n_sp, h->pp_est.as<double>(), d_prob);
+    DGE_LAUNCH_CHECK();
+    h->launches += 4;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // SimpleMergeStrategy (Merge/SimpleMergeStrategy.cpp).  Device: inverted index, common UMI-gene counts, best candidate per base
 // (simplemerge.cuh).  Host: the final threshold compare in the reference's own expression, and an exact replay with the
 // reference's containers for the bases whose outcome depends on hash-iteration order (near-ties of the top fraction).
@@ -1273,8 +1404,9 @@ void simple_replay_prepare(dge_handle *h, SimpleReplay &R, uint32_t n_e)
     R.ready = true;
 }
 
-// SimpleMergeStrategy::get_merge_target for one base cell, with the reference's containers and insertion sequences.
-long simple_replay(dge_handle *h, SimpleReplay &R, uint32_t base, int rb)
+// SimpleMergeStrategy::get_cells_with_common_umigs for one base cell with the reference's containers and insertion sequences:
+// (other real idx, common UMI-genes) in the iteration order of the reference's unordered_map.
+std::vector<std::pair<uint32_t, size_t>> simple_replay_candidates(dge_handle *h, SimpleReplay &R, uint32_t base, int rb)
 {
     cudaStream_t st = h->stream;
     const HostCell &bc = h->real[base];
@@ -1315,12 +1447,22 @@ long simple_replay(dge_handle *h, SimpleReplay &R, uint32_t base, int rb)
             if (h->real[R.ridx_of_gid.at(other)].n_genes >= bc.n_genes) common[other]++;
         }
     }
+    std::vector<std::pair<uint32_t, size_t>> res;
+    res.reserve(common.size());
+    for (auto const &kv : common) res.emplace_back(R.ridx_of_gid.at(kv.first), kv.second);
+    return res;
+}
+
+// SimpleMergeStrategy::get_merge_target for one base cell (SimpleMergeStrategy.cpp:48-88) over the replayed candidate order.
+long simple_replay(dge_handle *h, SimpleReplay &R, uint32_t base, int rb)
+{
+    const HostCell &bc = h->real[base];
     long top = -1, top_genes = -1;
     double top_frac = -1;
     const std::string base_cb = unpack_seq(bc.cb, h->cfg.cb_len);
-    for (auto const &kv : common)
+    for (auto const &kv : simple_replay_candidates(h, R, base, rb))
     {
-        const uint32_t o = R.ridx_of_gid.at(kv.first);
+        const uint32_t o = kv.first;
         const HostCell &oc = h->real[o];
         const double frac = 0.5 * kv.second * (1. / size_t(bc.umis_stat) + 1. / size_t(oc.umis_stat));
         if (frac - top_frac > 0.00001 || (std::abs(frac - top_frac) < 0.00001 && long(oc.n_genes) > top_genes))
@@ -1334,7 +1476,7 @@ long simple_replay(dge_handle *h, SimpleReplay &R, uint32_t base, int rb)
     return top;
 }
 
-void phase1_simple(dge_handle *h, std::vector<long> &target)
+void phase1_simple(dge_handle *h, std::vector<long> &target, bool poisson = false)
 {
     cudaStream_t st = h->stream;
     Tracer tr; tr.st = st;
@@ -1406,6 +1548,64 @@ void phase1_simple(dge_handle *h, std::vector<long> &target)
     if (d2h_scalar<int>(h->overflow_flag.p, st)) throw std::runtime_error("sub-bucket hash table overflow while counting common UMI-genes");
     tr.mark("merge:  simple: common counts");
 
+    if (poisson)
+    {   // ---- PoissonSimpleMergeStrategy::get_merge_target (PoissonSimpleMergeStrategy.cpp:15-42)
+        h->pp_flag.reserve(size_t(n_p) * 4); h->pp_prob.reserve(size_t(n_p) * 8); h->pp_best.reserve(n * sizeof(PoissonBest));
+        k_pp_admissible<<<grid_for(n_p, 256), 256, 0, st>>>(h->sm_pkey.as<uint64_t>(), n_p, rb, h->sm_cb.as<uint64_t>(), int(h->cfg.cb_len),
+                                                            int(h->cfg.max_cb_merge_edit_distance), h->pp_flag.as<uint32_t>());
+        ++h->launches;
+        poisson_eval_pairs(h, h->sm_pkey.as<uint64_t>(), h->sm_pval.as<uint32_t>(), h->pp_flag.as<uint32_t>(), n_p, rb, h->pp_prob.as<double>());
+        tr.mark("merge:  poisson: pair probabilities");
+        std::vector<PoissonBest> init(n, PoissonBest{NONE32, 0u, 2.0, 0u, 0u});
+        DGE_CUDA(cudaMemcpyAsync(h->pp_best.p, init.data(), n * sizeof(PoissonBest), cudaMemcpyHostToDevice, st));
+        // base (!= first neighbour) is never "real" here: the threshold is max_real_cb_merge_prob / #neighbours (PoissonTargetEstimator.cpp:17-22)
+        k_pp_best<<<grid_for(n_p, 256), 256, 0, st>>>(h->sm_pkey.as<uint64_t>(), h->pp_flag.as<uint32_t>(), h->pp_prob.as<double>(), n_p, rb,
+                                                      h->cfg.max_real_merge_prob, h->pp_best.as<PoissonBest>());
+        DGE_LAUNCH_CHECK();
+        ++h->launches;
+        std::vector<PoissonBest> pb;
+        d2h(pb, h->pp_best.p, n, st);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        SimpleReplay R;
+        std::vector<uint64_t> hk;
+        std::vector<double> hp;
+        std::vector<uint32_t> hf;
+        h->n_poisson_replayed = 0;
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            const PoissonBest r = pb[i];
+            if (r.n_nb == 0) continue; // no neighbour within the edit distance: the cell keeps itself (:33-34)
+            const double thr = h->cfg.max_real_merge_prob / double(r.n_nb);
+            if (!r.ambiguous)
+            {
+                if (!(r.min_prob > thr)) target[i] = long(r.best);
+                continue;
+            }
+            // near-tie: walk the neighbours in the reference's iteration order with the device's probabilities
+            if (!R.ready)
+            {
+                simple_replay_prepare(h, R, n_e);
+                d2h(hk, h->sm_pkey.p, n_p, st); d2h(hp, h->pp_prob.p, n_p, st); d2h(hf, h->pp_flag.p, n_p, st);
+                DGE_CUDA(cudaStreamSynchronize(st));
+            }
+            ++h->n_poisson_replayed;
+            const uint64_t lo_key = uint64_t(i) << rb;
+            const size_t lo = size_t(std::lower_bound(hk.begin(), hk.end(), lo_key) - hk.begin());
+            long best = -1;
+            double min_prob = 2;
+            for (auto const &kv : simple_replay_candidates(h, R, i, rb))
+            {
+                size_t q = lo;
+                while (q < hk.size() && (hk[q] >> rb) == i && uint32_t(hk[q] & ((1ull << rb) - 1)) != kv.first) ++q;
+                if (q >= hk.size() || (hk[q] >> rb) != i || !hf[q]) continue; // beyond the edit distance
+                if (hp[q] < min_prob) { min_prob = hp[q]; best = long(kv.first); }
+            }
+            if (best >= 0 && !(min_prob > thr)) target[i] = best;
+        }
+        tr.mark("merge:  poisson: targets");
+        return;
+    }
+
     // ---- best candidate per base
     h->sm_frac.reserve(size_t(n_p) * 8); h->sm_best.reserve(n * sizeof(BaseBest));
     DGE_CUDA(cudaMemsetAsync(h->sm_best.p, 0xFF, n * sizeof(BaseBest), st)); // best = NONE32: no candidate
@@ -1432,6 +1632,78 @@ void phase1_simple(dge_handle *h, std::vector<long> &target)
         ++h->n_simple_replayed;
     }
     tr.mark("merge:  simple: targets");
+}
+
+// PoissonRealBarcodesMergeStrategy (Merge/PoissonRealBarcodesMergeStrategy.cpp:20-51): neighbours from the whitelist walk with
+// get_max_merge_dist = (min == 0 ? 2 : min + 1), i.e. always beyond the nearest class -- the exact enumerator of whitelist.hpp on the
+// host (this strategy is used on small inputs; the reference spends ~2 ms per cell in the same enumeration), intersections and
+// probabilities on the device, PoissonTargetEstimator::get_best_merge_target (.cpp:14-44) over the ordered neighbour lists.
+void phase1_poisson_real(dge_handle *h, std::vector<long> &target)
+{
+    cudaStream_t st = h->stream;
+    const size_t n = h->real.size();
+    target.assign(n, -1);
+    h->n_unresolved = 0;
+    if (n == 0) return;
+    const int rb = std::max(1, ceil_log2_u64(n));
+    std::unordered_map<uint64_t, uint32_t> by_cb;
+    by_cb.reserve(n * 2);
+    for (uint32_t r = 0; r < n; ++r) by_cb.emplace(h->real[r].cb, r);
+    std::vector<std::vector<long>> nbs(n);
+    std::vector<uint64_t> pkey;
+    std::vector<PairJob> jobs;
+    const uint32_t empty_pc = h->n_pc;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        auto lookup = [&](const std::string &sq) -> long {
+            uint64_t v;
+            if (!pack_seq(sq, v)) return -1;
+            auto it = by_cb.find(v);
+            return it == by_cb.end() ? -1 : long(it->second);
+        };
+        auto eligible = [&](long id) {
+            return uint32_t(h->real[size_t(id)].n_genes) >= h->cfg.min_genes_before_merge && h->real[size_t(id)].umis_stat >= h->real[i].umis_stat;
+        };
+        nbs[i] = h->wl.neighbours(unpack_seq(h->real[i].cb, h->cfg.cb_len), true, lookup, eligible);
+        for (long id : nbs[i])
+        {
+            if (uint32_t(id) == i) continue;
+            pkey.push_back((uint64_t(i) << rb) | uint64_t(id));
+            const uint32_t a = h->real[i].pc, b = h->real[size_t(id)].pc;
+            jobs.push_back(PairJob{a == NONE32 ? empty_pc : a, b == NONE32 ? empty_pc : b});
+        }
+    }
+    std::vector<double> prob(pkey.size(), 2.0);
+    if (!pkey.empty())
+    {
+        run_intersections(h, jobs);
+        const uint32_t n_p = uint32_t(pkey.size());
+        h->sm_pkey.reserve(size_t(n_p) * 8); h->sm_pval.reserve(size_t(n_p) * 4); h->pp_flag.reserve(size_t(n_p) * 4); h->pp_prob.reserve(size_t(n_p) * 8);
+        DGE_CUDA(cudaMemcpyAsync(h->sm_pkey.p, pkey.data(), size_t(n_p) * 8, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(cudaMemcpyAsync(h->sm_pval.p, h->d_isect.p, size_t(n_p) * 4, cudaMemcpyDeviceToDevice, st));
+        k_fill_u32<<<grid_for(n_p, 256), 256, 0, st>>>(h->pp_flag.as<uint32_t>(), n_p, 1u);
+        poisson_eval_pairs(h, h->sm_pkey.as<uint64_t>(), h->sm_pval.as<uint32_t>(), h->pp_flag.as<uint32_t>(), n_p, rb, h->pp_prob.as<double>());
+        DGE_CUDA(cudaMemcpyAsync(prob.data(), h->pp_prob.p, size_t(n_p) * 8, cudaMemcpyDeviceToHost, st));
+        DGE_CUDA(cudaStreamSynchronize(st));
+    }
+    size_t q = 0;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const std::vector<long> &lst = nbs[i];
+        if (lst.empty()) { target[i] = -1; continue; } // RealBarcodesMergeStrategy.cpp:26-27
+        const bool base_is_real_cb = uint32_t(lst[0]) == i;
+        double max_prob = (base_is_real_cb ? h->cfg.max_merge_prob : h->cfg.max_real_merge_prob) / double(lst.size());
+        long best = -1;
+        double min_prob = 2;
+        for (long id : lst)
+        {
+            if (uint32_t(id) == i) continue;
+            const double pr = prob[q++];
+            if (pr < min_prob) { min_prob = pr; best = id; }
+        }
+        if (min_prob > max_prob) target[i] = base_is_real_cb ? long(i) : -1;
+        else target[i] = best;
+    }
 }
 
 // MergeAllMergeStrategy::get_merge_target for every filtered cell (MergeAllMergeStrategy.h:16-50): all-pairs on the device.
@@ -2002,8 +2274,29 @@ void do_merge_and_filter(dge_handle *h)
         DGE_CUDA(cudaStreamSynchronize(st));
         tr.mark("merge: apply");
     }
-    else if (h->cfg.merge_type != DGE_MERGE_NONE)
-        throw std::runtime_error("merge_type not implemented on the device path yet (Poisson strategies)");
+    else if (h->cfg.merge_type == DGE_MERGE_POISSON_SIMPLE)
+    {
+        if (h->cfg.sharded) throw std::runtime_error("PoissonSimpleMergeStrategy is not available on sharded (multi-GPU) handles yet");
+        phase1_simple(h, h->h_target, true);
+        tr.mark("merge: phase 1 (poisson simple)");
+        phase2(h, h->h_target);
+        tr.mark("merge: phase 2");
+        apply_merges(h);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        tr.mark("merge: apply");
+    }
+    else if (h->cfg.merge_type == DGE_MERGE_POISSON_REAL)
+    {
+        if (h->cfg.sharded) throw std::runtime_error("PoissonRealBarcodesMergeStrategy is not available on sharded (multi-GPU) handles yet");
+        phase1_poisson_real(h, h->h_target);
+        tr.mark("merge: phase 1 (poisson real)");
+        phase2(h, h->h_target);
+        tr.mark("merge: phase 2");
+        apply_merges(h);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        tr.mark("merge: apply");
+    }
+    else if (h->cfg.merge_type != DGE_MERGE_NONE) throw std::runtime_error("unknown merge_type");
     DGE_CUDA(cudaEventRecord(h->ev[4], st));
 
     // ---- sizes of merge targets changed; Cell::is_real (Cell.cpp:125-128) is evaluated on the merged content from here on
@@ -2353,7 +2646,7 @@ int dge_reset(dge_handle *h)
         h->n_merged = h->n_excluded = h->n_unresolved = 0; h->total_cells = 0;
         h->cm.built = h->cm_raw.built = false;
         h->host_stage = 0; h->lazy_rows = false; h->dev_merged = false; h->n_real_rows = 0; h->n_filtered_dev = 0;
-        h->sum_real = h->sum_filtered = h->sum_genes_seen = 0; h->n_host_fallback = 0;
+        h->sum_real = h->sum_filtered = h->sum_genes_seen = 0; h->n_host_fallback = 0; h->pp_ready = false; h->n_poisson_replayed = 0;
         h->dist_done = false; h->slot_pc_built = false; h->dist_targets.clear(); h->n_order_ties = 0; h->dist_stage = 0;
         h->timings = dge_timings{}; h->sc_stats = SortCombineStats{}; h->launches = 0;
         h->state = 0;
@@ -2998,37 +3291,10 @@ int dge_collisions_adjusted_sizes(int device, const double *umi_probabilities, s
         cudaStream_t st = nullptr;
         DGE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
-        DevBuf p, neg, terms, partial, state, adj;
-        const size_t n = n_umis;
-        p.reserve(std::max<size_t>(n, 1) * 8); neg.reserve(std::max<size_t>(n, 1) * 8);
-        const unsigned blocks = unsigned(std::max<size_t>(1, std::min<size_t>(div_up(n, size_t(CA_THREADS)), 148 * 8)));
-        partial.reserve(size_t(blocks) * 8); state.reserve(sizeof(CollisionsState)); adj.reserve(max_gene_expression * 8);
-        DGE_CUDA(cudaMemcpyAsync(p.p, umi_probabilities, n * 8, cudaMemcpyHostToDevice, st));
-        std::vector<double> ones(n, 1.0);
-        // worst-case difference between two association orders of the sum, propagated through 1/(1-q): see collisions.cuh
-        const double drift = std::max(1e-13, double(n) * 4e-15);
-        const bool force_exact = std::getenv("DGE_CA_FORCE_EXACT") != nullptr; // tests: exercise the sequential-order path
-        for (int exact = force_exact ? 1 : 0; exact < 2; ++exact)
-        {
-            DGE_CUDA(cudaMemcpyAsync(neg.p, ones.data(), n * 8, cudaMemcpyHostToDevice, st));
-            DGE_CUDA(cudaMemsetAsync(state.p, 0, sizeof(CollisionsState), st));
-            if (exact) terms.reserve(std::max<size_t>(n, 1) * 8);
-            for (size_t s = 1; s <= max_gene_expression; ++s)
-            {
-                if (exact)
-                    k_collisions_step<true><<<blocks, CA_THREADS, 0, st>>>(p.as<double>(), neg.as<double>(), terms.as<double>(), n, s, state.as<CollisionsState>(),
-                                                                          partial.as<double>(), adj.as<unsigned long long>(), drift);
-                else
-                    k_collisions_step<false><<<blocks, CA_THREADS, 0, st>>>(p.as<double>(), neg.as<double>(), nullptr, n, s, state.as<CollisionsState>(),
-                                                                           partial.as<double>(), adj.as<unsigned long long>(), drift);
-            }
-            DGE_LAUNCH_CHECK();
-            CollisionsState hs;
-            DGE_CUDA(cudaMemcpyAsync(&hs, state.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
-            DGE_CUDA(cudaStreamSynchronize(st));
-            if (!exact && hs.risky == 0) break;
-            if (!exact && exact_rerun) *exact_rerun = hs.risky;
-        }
+        DevBuf p, adj;
+        p.reserve(std::max<size_t>(n_umis, 1) * 8); adj.reserve(max_gene_expression * 8);
+        DGE_CUDA(cudaMemcpyAsync(p.p, umi_probabilities, n_umis * 8, cudaMemcpyHostToDevice, st));
+        collisions_adjusted_device(st, p.as<double>(), n_umis, max_gene_expression, adj.as<unsigned long long>(), exact_rerun);
         DGE_CUDA(cudaMemcpyAsync(adjusted_sizes, adj.p, max_gene_expression * 8, cudaMemcpyDeviceToHost, st));
         DGE_CUDA(cudaStreamSynchronize(st));
         return int(DGE_OK);

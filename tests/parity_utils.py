@@ -49,6 +49,8 @@ class Case:
     umi_merge: str = "simple"
     max_umi_ed: int = 1
     umi_mult: float = 2.0
+    max_merge_prob: float = 1e-4
+    max_real_merge_prob: float = 1e-7
     dump_umis: bool = True
     n_batches: int = 3
     shuffle: bool = True
@@ -72,6 +74,7 @@ def gpu_run(case: Case, recs: Optional[np.ndarray], device_generate: bool = Fals
                     min_merge_fraction=case.min_frac, marks=case.marks, max_cells=case.max_cells,
                     umi_merge_type=dg.UMI_MERGE_DIRECTIONAL if case.umi_merge == "directional" else dg.UMI_MERGE_SIMPLE,
                     max_umi_merge_edit_distance=case.max_umi_ed, umi_merge_mult=case.umi_mult,
+                    max_merge_prob=case.max_merge_prob, max_real_merge_prob=case.max_real_merge_prob,
                     reads_output=case.reads_output, max_barcodes_hint=case.extra.get("max_barcodes_hint", 1 << 16))
     c = dg.Container(cfg)
     if device_generate:
@@ -130,7 +133,8 @@ def run_case(case: Case, device_generate: bool = False, kind: str = "any"):
                                    min_genes_before=case.min_genes_before, min_genes_after=case.min_genes_after,
                                    max_cb_ed=case.max_cb_ed, min_frac=case.min_frac, marks=case.marks, max_cells=case.max_cells,
                                    reads_output=case.reads_output, dump_umis=case.dump_umis, umi_merge=case.umi_merge,
-                                   max_umi_ed=case.max_umi_ed, umi_mult=case.umi_mult)
+                                   max_umi_ed=case.max_umi_ed, umi_mult=case.umi_mult, max_merge_prob=case.max_merge_prob,
+                                   max_real_merge_prob=case.max_real_merge_prob)
     gpu = gpu_run(case, recs, device_generate=device_generate, tables=tables)
     return {"case": case, "oracle": ora, "gpu": gpu, "recs": recs}
 

@@ -13,7 +13,8 @@ import golden_cases
 from golden_cases import fixture_case
 
 
-@pytest.mark.parametrize("name", ["fixture", "real_7x9", "none_7x9", "simple_7x9", "real_8x8_reads"])
+@pytest.mark.parametrize("name", ["fixture", "real_7x9", "none_7x9", "simple_7x9", "real_8x8_reads", "poisson_simple_7x9", "poisson_real_7x9", "all_7x9",
+                                  "directional_7x9"])
 def test_gpu_reproduces_golden_reference_outputs(name):
     """CUDA path vs the committed outputs of the compiled, unmodified reference (no oracle binary needed on the GPU box)."""
     case = golden_cases.cases()[name]
@@ -418,3 +419,37 @@ def test_full_size_invariants_simple_merge_20m():
         np.testing.assert_array_equal(a, b)
     unmerged = (all1["flags"] & 2) == 0
     assert int(all1["reads_stat"][unmerged].sum()) + s1["intergenic_reads"] == n
+
+
+# ---- precise merge (-M): PoissonSimpleMergeStrategy / PoissonRealBarcodesMergeStrategy on top of PoissonTargetEstimator ----------------------
+@pytest.mark.parametrize("seed,probs", [(21, (1e-4, 1e-7)), (22, (1e-2, 1e-3)), (23, (0.5, 0.2))])
+def test_merge_poisson_simple_small(seed, probs):
+    """-M without a whitelist; the thresholds range from the defaults to values that accept most candidates (so that argmin over
+    several neighbours and chains of merges occur)."""
+    res = pu.run_case(pu.small_case(n_reads=60000, n_cells=30, n_genes=120, merge="poisson_simple", seed=seed, max_merge_prob=probs[0],
+                                    max_real_merge_prob=probs[1]), kind="reference")
+    pu.assert_parity(res)
+    if probs[1] >= 1e-3:
+        assert res["gpu"]["summary"]["n_merged"] > 0
+
+
+def test_merge_poisson_simple_dropseq_like():
+    """BASELINE configs[4] shape (12 bp barcodes, 8 bp UMIs -> 65 536-UMI space where collisions are material, no whitelist, -M with the
+    drop_seq.xml probabilities 1e-5 / 1e-7), scaled down."""
+    wl = read_whitelist(pu.WL_SYNTH_8_8)
+    parts = [sorted(set(t[:6] for t in wl[0])), sorted(set(t[:6] for t in wl[1]))]
+    spec = SynthSpec(n_reads=400_000, n_cells=300, n_genes=2000, cb_len=12, umi_len=8, whitelist_parts=parts, cb_error_ppm=40000, reads_per_umi=3, seed=27)
+    case = pu.Case(name="dropseq_poisson", spec=spec, cb_len=12, umi_len=8, n_genes=2000, merge="poisson_simple", min_genes_before=10, min_genes_after=30,
+                   max_cb_ed=2, max_merge_prob=1e-5, max_real_merge_prob=1e-7, dump_umis=False, n_batches=3)
+    res = pu.run_case(case, kind="reference")
+    pu.assert_parity(res)
+    assert res["gpu"]["summary"]["n_merged"] > 50
+
+
+@pytest.mark.parametrize("seed,probs", [(31, (1e-4, 1e-7)), (32, (0.3, 0.05))])
+def test_merge_poisson_real_small(seed, probs):
+    """-M with a whitelist: neighbours beyond the nearest distance class (get_max_merge_dist = min + 1), whitelist barcodes that merge
+    into other whitelist barcodes, chains in phase 2."""
+    res = pu.run_case(pu.small_case(n_reads=40000, n_cells=25, n_genes=100, merge="poisson_real", seed=seed, max_merge_prob=probs[0],
+                                    max_real_merge_prob=probs[1]), kind="reference")
+    pu.assert_parity(res)
