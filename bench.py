@@ -28,11 +28,28 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = {
-    "name": "10x v3: 400M reads / 10k cells / 30k genes, 16bp CB + 12bp UMI, 1 GPU",
-    "n_reads": 400_000_000, "n_cells": 10_000, "n_genes": 30_000, "cb_len": 16, "umi_len": 12,
-    "min_genes_before": 20, "min_genes_after": 100, "min_frac": 0.2, "max_cb_ed": 2,
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (default)
+    "c2": {"name": "10x v3: 400M reads / 10k cells / 30k genes, 16bp CB + 12bp UMI, 1 GPU",
+           "n_reads": 400_000_000, "n_cells": 10_000, "n_genes": 30_000, "cb_len": 16, "umi_len": 12,
+           "min_genes_before": 20, "min_genes_after": 100, "min_frac": 0.2, "max_cb_ed": 2, "merge": "real", "whitelist": "product_7x9",
+           "barcodes_type": "const", "max_merge_prob": 1e-4, "max_real_merge_prob": 1e-7,
+           "merge_desc": "RealBarcodesMergeStrategy, synthetic product whitelist 2048x3328 (7+9 bp)"},
+    # configs[2]: inDrop v3 on the reference's own whitelist (configs/indrop_v3.xml)
+    "c3": {"name": "inDrop v3: 200M reads / 5k cells, two-part barcode + whitelist merge, 1 GPU",
+           "n_reads": 200_000_000, "n_cells": 5_000, "n_genes": 30_000, "cb_len": 16, "umi_len": 6,
+           "min_genes_before": 20, "min_genes_after": 100, "min_frac": 0.2, "max_cb_ed": 2, "merge": "real", "whitelist": "indrop_v3",
+           "barcodes_type": "indrop", "max_merge_prob": 1e-5, "max_real_merge_prob": 1e-7,
+           "merge_desc": "RealBarcodesMergeStrategy, data/barcodes/indrop_v3 (384 x 384, 8+8 bp), barcodes_type=indrop"},
+    # configs[4]: Drop-seq, the per-GPU share of "1B reads / 50k cells on 4 GPUs" (configs/drop_seq.xml: no whitelist; -M = PoissonSimpleMergeStrategy
+    # with Tools::CollisionsAdjuster, probabilities 1e-5 / 1e-7)
+    "c5": {"name": "Drop-seq: 1B reads / 50k cells, 12bp CB + 8bp UMI with CollisionsAdjuster, 4 GPUs -- per-GPU share 250M reads / 12.5k cells, 1 GPU",
+           "n_reads": 250_000_000, "n_cells": 12_500, "n_genes": 30_000, "cb_len": 12, "umi_len": 8,
+           "min_genes_before": 20, "min_genes_after": 100, "min_frac": 0.2, "max_cb_ed": 2, "merge": "poisson_simple", "whitelist": None,
+           "barcodes_type": "const", "max_merge_prob": 1e-5, "max_real_merge_prob": 1e-7,
+           "merge_desc": "PoissonSimpleMergeStrategy (-M) + Tools::CollisionsAdjuster, no whitelist"},
 }
+WORKLOAD = dict(WORKLOADS["c2"])
 ALGO_BYTES_PER_READ = 48  # 3 x 16-byte record (read once, scatter once, re-read once)
 
 
@@ -111,9 +128,10 @@ def sample_case(wl_path, wl_parts, sample_reads):
 
     n_cells = max(10, int(round(sample_reads * WORKLOAD["n_cells"] / WORKLOAD["n_reads"])))
     spec = make_spec(sample_reads, n_cells, wl_parts, seed=43)
-    return pu.Case(name="bench_sample", spec=spec, cb_len=spec.cb_len, umi_len=spec.umi_len, n_genes=spec.n_genes, merge="real", barcodes=wl_path,
-                   barcodes_type="const", min_genes_before=WORKLOAD["min_genes_before"], min_genes_after=WORKLOAD["min_genes_after"],
-                   max_cb_ed=WORKLOAD["max_cb_ed"], min_frac=WORKLOAD["min_frac"], dump_umis=False, n_batches=3, extra={"max_barcodes_hint": 0})
+    return pu.Case(name="bench_sample", spec=spec, cb_len=spec.cb_len, umi_len=spec.umi_len, n_genes=spec.n_genes, merge=WORKLOAD["merge"], barcodes=wl_path,
+                   barcodes_type=WORKLOAD["barcodes_type"], min_genes_before=WORKLOAD["min_genes_before"], min_genes_after=WORKLOAD["min_genes_after"],
+                   max_cb_ed=WORKLOAD["max_cb_ed"], min_frac=WORKLOAD["min_frac"], max_merge_prob=WORKLOAD["max_merge_prob"],
+                   max_real_merge_prob=WORKLOAD["max_real_merge_prob"], dump_umis=False, n_batches=3, extra={"max_barcodes_hint": 0})
 
 
 def cpu_reference_run(wl_path, wl_parts, sample_reads, timeout=1800, keep=False):
@@ -127,8 +145,9 @@ def cpu_reference_run(wl_path, wl_parts, sample_reads, timeout=1800, keep=False)
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "sample.bin")
         write_packed(path, recs, spec.cb_len, spec.umi_len, spec.n_genes)
-        res = oracle_io.run_oracle(path, merge="real", barcodes=wl_path, barcodes_type="const", min_genes_before=WORKLOAD["min_genes_before"],
-                                   min_genes_after=WORKLOAD["min_genes_after"], max_cb_ed=WORKLOAD["max_cb_ed"], min_frac=WORKLOAD["min_frac"],
+        res = oracle_io.run_oracle(path, merge=WORKLOAD["merge"], barcodes=wl_path, barcodes_type=WORKLOAD["barcodes_type"],
+                                   min_genes_before=WORKLOAD["min_genes_before"], min_genes_after=WORKLOAD["min_genes_after"], max_cb_ed=WORKLOAD["max_cb_ed"],
+                                   min_frac=WORKLOAD["min_frac"], max_merge_prob=WORKLOAD["max_merge_prob"], max_real_merge_prob=WORKLOAD["max_real_merge_prob"],
                                    dump_umis=False, timeout=timeout)
     secs = float(res["t_fill_s"][0] + res["t_init_s"][0] + res["t_merge_s"][0])
     out = {"value": sample_reads / secs, "seconds": secs, "kind": res["_kind"], "cores": 1, "n_cells": spec.n_cells,
@@ -204,8 +223,8 @@ def verify_sharded(args, dg, dgdist, torch, wl_path, wl_parts, dev, rank, world,
     tables.generate_device(dev, rank * per, per, buf.data_ptr())
 
     def config(sharded):
-        return dg.Config(cb_len=16, umi_len=12, n_genes=WORKLOAD["n_genes"], device=dev, merge_type=dg.MERGE_REAL, barcodes_type=dg.BARCODES_CONST,
-                         barcodes_file=wl_path, min_genes_before_merge=WORKLOAD["min_genes_before"], min_genes_after_merge=WORKLOAD["min_genes_after"],
+        return dg.Config(cb_len=WORKLOAD["cb_len"], umi_len=WORKLOAD["umi_len"], n_genes=WORKLOAD["n_genes"], device=dev, merge_type=dg.MERGE_REAL,
+                         barcodes_type=dg.BARCODES_INDROP if WORKLOAD["barcodes_type"] == "indrop" else dg.BARCODES_CONST, barcodes_file=wl_path, min_genes_before_merge=WORKLOAD["min_genes_before"], min_genes_after_merge=WORKLOAD["min_genes_after"],
                          max_cb_merge_edit_distance=WORKLOAD["max_cb_ed"], min_merge_fraction=WORKLOAD["min_frac"], sharded=sharded)
 
     def collect(c):
@@ -260,8 +279,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=WORKLOAD["n_reads"], help="reads per GPU (default: the BASELINE config)")
-    ap.add_argument("--cells", type=int, default=WORKLOAD["n_cells"])
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS), help="c2 = BASELINE configs[1] (default, the headline); c3 / c5 = configs[2] / [4]")
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the chosen BASELINE config)")
+    ap.add_argument("--cells", type=int, default=0)
     ap.add_argument("--cpu-sample-reads", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -269,6 +289,9 @@ def main():
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the sharded == single-GPU check")
     ap.add_argument("--verify-reads", type=int, default=16_000_000)
     args = ap.parse_args()
+    WORKLOAD.clear(); WORKLOAD.update(WORKLOADS[args.config])
+    args.reads = args.reads or WORKLOAD["n_reads"]
+    args.cells = args.cells or WORKLOAD["n_cells"]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -277,14 +300,20 @@ def main():
 
     cache = os.path.join(tempfile.gettempdir(), f"dge_bench_{os.getuid()}")
     os.makedirs(cache, exist_ok=True)
-    wl_path = os.path.join(cache, f"wl_7x9_2048x3328_r{rank}.txt")
-    product_whitelist(wl_path)
     from dropest_b200.synth import SynthTables, read_whitelist
 
-    wl_parts = read_whitelist(wl_path)
+    wl_path, wl_parts = None, None
+    if WORKLOAD["whitelist"] == "product_7x9":
+        wl_path = os.path.join(cache, f"wl_7x9_2048x3328_r{rank}.txt")
+        product_whitelist(wl_path)
+        wl_parts = read_whitelist(wl_path)
+    elif WORKLOAD["whitelist"] == "indrop_v3":
+        wl_path = os.path.join(ROOT, "tests", "golden", "ref_barcodes", "indrop_v3")  # copy of the reference's data/barcodes/indrop_v3
+        wl_parts = read_whitelist(wl_path, indrop=True)
     config = {"workload": WORKLOAD["name"], "reads_per_gpu": args.reads, "cells_per_gpu": args.cells, "genes": WORKLOAD["n_genes"],
-              "cb_len": 16, "umi_len": 12, "merge": "RealBarcodesMergeStrategy, synthetic product whitelist 2048x3328 (7+9 bp)",
-              "min_genes_before_merge": 20, "min_genes_after_merge": 100, "l2_policy": "inputs (6.4 GB) larger than L2",
+              "cb_len": WORKLOAD["cb_len"], "umi_len": WORKLOAD["umi_len"], "merge": WORKLOAD["merge_desc"],
+              "min_genes_before_merge": WORKLOAD["min_genes_before"], "min_genes_after_merge": WORKLOAD["min_genes_after"],
+              "l2_policy": "inputs (%.1f GB) larger than L2" % (args.reads * 16 / 1e9),
               "partition": "barcode-hash, one NCCL all-to-all per step" if world > 1 else "single GPU"}
 
     # ------------------------------------------------------------------------------------------------ reference arm
@@ -336,9 +365,14 @@ def main():
     tables.generate_device(dev, rank * n, n, raw.data_ptr())
     torch.cuda.synchronize()
 
-    cfg = dg.Config(cb_len=16, umi_len=12, n_genes=WORKLOAD["n_genes"], device=dev, merge_type=dg.MERGE_REAL, barcodes_type=dg.BARCODES_CONST,
+    merge_types = {"real": dg.MERGE_REAL, "simple": dg.MERGE_SIMPLE, "poisson_simple": dg.MERGE_POISSON_SIMPLE, "poisson_real": dg.MERGE_POISSON_REAL}
+    if world > 1 and WORKLOAD["merge"] != "real":
+        raise SystemExit("only the whitelist merge (config c2 / c3) runs sharded; use --gpus 1 for --config " + args.config)
+    cfg = dg.Config(cb_len=WORKLOAD["cb_len"], umi_len=WORKLOAD["umi_len"], n_genes=WORKLOAD["n_genes"], device=dev, merge_type=merge_types[WORKLOAD["merge"]],
+                    barcodes_type=dg.BARCODES_INDROP if WORKLOAD["barcodes_type"] == "indrop" else dg.BARCODES_CONST,
                     barcodes_file=wl_path, min_genes_before_merge=WORKLOAD["min_genes_before"], min_genes_after_merge=WORKLOAD["min_genes_after"],
-                    max_cb_merge_edit_distance=WORKLOAD["max_cb_ed"], min_merge_fraction=WORKLOAD["min_frac"], sharded=world > 1)
+                    max_cb_merge_edit_distance=WORKLOAD["max_cb_ed"], min_merge_fraction=WORKLOAD["min_frac"], max_merge_prob=WORKLOAD["max_merge_prob"],
+                    max_real_merge_prob=WORKLOAD["max_real_merge_prob"], sharded=world > 1)
     cont = dg.Container(cfg)
     stream = torch.cuda.current_stream()
     cont.set_stream(stream.cuda_stream)

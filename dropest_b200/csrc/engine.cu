@@ -1327,37 +1327,39 @@ void poisson_eval_pairs(dge_handle *h, const uint64_t *d_pkey, const uint32_t *d
     poisson_init(h);
     if (!n_p) return;
     cudaStream_t st = h->stream;
-    h->pp_cnt.reserve((size_t(n_p) + 1) * 4); h->pp_off.reserve((size_t(n_p) + 1) * 4);
     const unsigned g = grid_for(n_p, 256);
-    k_pp_shared<false><<<g, 256, 0, st>>>(d_pkey, d_flag, n_p, rb, h->pp_real_pc.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(), h->cg_gene.as<uint32_t>(),
-                                          h->cg_start.as<uint32_t>(), h->pp_adj.as<unsigned long long>(), h->pp_cnt.as<uint32_t>(), nullptr, nullptr);
-    DGE_CUDA(cudaMemsetAsync(h->pp_cnt.as<uint32_t>() + n_p, 0, 4, st));
-    device_exclusive_scan(h->pp_cnt.as<uint32_t>(), h->pp_off.as<uint32_t>(), size_t(n_p) + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
-    const uint32_t n_shared = d2h_scalar<uint32_t>(h->pp_off.as<uint32_t>() + n_p, st);
-    uint32_t n_sp = 0;
-    h->pp_skey.reserve(std::max<size_t>(n_shared, 1) * 8); h->pp_sval.reserve(std::max<size_t>(n_shared, 1) * 4);
-    if (n_shared)
+    if (h->pp_max_gene_size && d2h_scalar<unsigned long long>(h->pp_adj.as<unsigned long long>() + (h->pp_max_gene_size - 1), st) >= (1ull << 29))
+        throw CapacityError("adjusted gene sizes beyond 2^29");
+    // distinct adjusted size pairs -> hash set (grown until the load factor stays below 1/2)
+    uint32_t cap = 1u << 16, n_sp = 0;
+    h->pp_misc.reserve(64);
+    int *full = reinterpret_cast<int *>(h->pp_misc.as<unsigned long long>() + 4);
+    while (true)
     {
-        if (h->pp_max_gene_size && d2h_scalar<unsigned long long>(h->pp_adj.as<unsigned long long>() + (h->pp_max_gene_size - 1), st) >= (1ull << 29))
-            throw CapacityError("adjusted gene sizes beyond 2^29");
-        h->pp_spairs.reserve(size_t(n_shared) * 8);
-        k_pp_shared<true><<<g, 256, 0, st>>>(d_pkey, d_flag, n_p, rb, h->pp_real_pc.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(), h->cg_gene.as<uint32_t>(),
-                                             h->cg_start.as<uint32_t>(), h->pp_adj.as<unsigned long long>(), nullptr, h->pp_off.as<uint32_t>(),
-                                             h->pp_spairs.as<uint64_t>());
+        h->pp_skey.reserve(size_t(cap) * 8); h->pp_cnt.reserve((size_t(cap) + 1) * 4); h->pp_off.reserve((size_t(cap) + 1) * 4);
+        DGE_CUDA(cudaMemsetAsync(h->pp_skey.p, 0xFF, size_t(cap) * 8, st));
+        DGE_CUDA(cudaMemsetAsync(full, 0, 4, st));
+        k_pp_shared<<<g, 256, 0, st>>>(d_pkey, d_flag, n_p, rb, h->pp_real_pc.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(), h->cg_gene.as<uint32_t>(),
+                                       h->cg_start.as<uint32_t>(), h->pp_adj.as<unsigned long long>(), h->pp_skey.as<unsigned long long>(), cap - 1, full);
+        k_sp_occupied<<<grid_for(cap, 256), 256, 0, st>>>(h->pp_skey.as<unsigned long long>(), cap, h->pp_cnt.as<uint32_t>());
+        DGE_CUDA(cudaMemsetAsync(h->pp_cnt.as<uint32_t>() + cap, 0, 4, st));
+        device_exclusive_scan(h->pp_cnt.as<uint32_t>(), h->pp_off.as<uint32_t>(), size_t(cap) + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
         DGE_LAUNCH_CHECK();
-        const int kb = 58 + 3;
-        const uint32_t *n_sp_ptr = h->sc2.run(h->pp_spairs.as<uint64_t>(), nullptr, n_shared, kb, std::min(choose_l1_bits(n_shared), kb - 3), nullptr,
-                                              h->pp_spairs.as<uint64_t>(), h->pp_skey.as<uint64_t>(), h->pp_sval.as<uint32_t>(), h->overflow_flag.as<int>(), st,
-                                              &h->sc_stats);
-        n_sp = d2h_scalar<uint32_t>(n_sp_ptr, st);
-        h->sc2.collect_timing();
-        if (d2h_scalar<int>(h->overflow_flag.p, st)) throw std::runtime_error("sub-bucket hash table overflow while collecting gene size pairs");
+        n_sp = d2h_scalar<uint32_t>(h->pp_off.as<uint32_t>() + cap, st);
+        const int is_full = d2h_scalar<int>(full, st);
+        if (!is_full && n_sp <= cap / 2) break;
+        if (cap >= (1u << 30)) throw CapacityError("too many distinct gene size pairs");
+        cap <<= 2;
     }
-    h->pp_est.reserve(std::max<size_t>(n_sp, 1) * 8);
+    h->pp_sval.reserve(std::max<size_t>(n_sp, 1) * 4); h->pp_est.reserve(size_t(cap) * 8);
     if (n_sp)
-        k_pp_est<<<std::min<uint32_t>(n_sp, 148 * 16), 256, 0, st>>>(h->pp_skey.as<uint64_t>(), n_sp, h->pp_p.as<double>(), size_t(1) << h->kl.ub, h->pp_est.as<double>());
+    {
+        k_sp_list<<<grid_for(cap, 256), 256, 0, st>>>(h->pp_skey.as<unsigned long long>(), h->pp_cnt.as<uint32_t>(), h->pp_off.as<uint32_t>(), cap, h->pp_sval.as<uint32_t>());
+        k_pp_est<<<std::min<uint32_t>(n_sp, 148 * 16), 256, 0, st>>>(h->pp_skey.as<unsigned long long>(), h->pp_sval.as<uint32_t>(), n_sp, h->pp_p.as<double>(),
+                                                                    size_t(1) << h->kl.ub, h->pp_est.as<double>());
+    }
     k_pp_lambda<<<g, 256, 0, st>>>(d_pkey, d_pval, d_flag, n_p, rb, h->pp_real_pc.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(), h->cg_gene.as<uint32_t>(),
-                                   h->cg_start.as<uint32_t>(), h->pp_adj.as<unsigned long long>(), h->pp_skey.as<uint64_t>(), n_sp, h->pp_est.as<double>(), d_prob);
+                                   h->cg_start.as<uint32_t>(), h->pp_adj.as<unsigned long long>(), h->pp_skey.as<unsigned long long>(), cap - 1, h->pp_est.as<double>(), d_prob);
     DGE_LAUNCH_CHECK();
     h->launches += 4;
 }

@@ -229,8 +229,24 @@ __global__ void k_count_seen(const uint32_t *__restrict__ first, size_t n, unsig
 //   * the L1 histogram (top 12 key bits) is accumulated in shared memory on the way and flushed once per block: the partition pass
 //     needs no histogram pass of its own.
 //   * gene first-seen: a 16-bit upper bound of (first read index >> 16) per gene in shared memory filters out all but the reads of the
-//     64 Ki-read granule in which a gene first occurs; those go to the global atomicMin.  (A stale / racy bound is only ever too
-//     large, which costs an extra trip, never a missed update.)
+//     64 Ki-read granule in which a gene first occurs; those go to the global atomicMin.  The bound is lowered with a shared-memory
+//     atomic and READ without synchronisation: a stale value is only ever too large, which costs an extra trip to the global word,
+//     never a missed update (compute-sanitizer racecheck reports exactly this read, see profiles/).
+// 16-bit atomic minimum in shared memory (CAS on the containing word); updates are rare: a few per gene and block
+__device__ __forceinline__ void smem_min_u16(uint16_t *arr, uint32_t i, uint32_t v)
+{
+    uint32_t *w = reinterpret_cast<uint32_t *>(arr) + (i >> 1);
+    const int sh = int(i & 1u) * 16;
+    uint32_t old = *reinterpret_cast<volatile uint32_t *>(w);
+    while (true)
+    {
+        if (v >= ((old >> sh) & 0xFFFFu)) return;
+        const uint32_t prev = atomicCAS(w, old, (old & ~(0xFFFFu << sh)) | (v << sh));
+        if (prev == old) return;
+        old = prev;
+    }
+}
+
 template <int CONS_WARPS, int ITEMS, int STAGES, bool SOA>
 __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
     k_fill_pipe(const Rec16 *__restrict__ recs, size_t n, CellSlot *__restrict__ tab, KeyLayout kl, uint32_t n_genes, uint32_t *__restrict__ gene_first,
@@ -371,7 +387,7 @@ __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
                 if (hi <= bound)
                 {
                     if (idx < __ldcg(&gene_first[gene])) atomicMin(&gene_first[gene], idx);
-                    if (hi < bound) g16[gene] = uint16_t(hi);
+                    if (hi < bound) smem_min_u16(g16, gene, hi);
                 }
                 if (umi_first) atomicMin(&umi_first[umi], idx);
                 c_exon += (mark >> 1) & 1u; c_intron += (mark >> 2) & 1u; c_na += mark & 1u;

@@ -5,7 +5,7 @@
 //   CellsDataContainer::umi_distribution (:182-197)                  k_umi_hist: per packed UMI, the number of (cell, gene) pairs of filtered
 //                                                                    cells that hold it; p_i = count / sum (k_hist_to_prob)
 //   estimate_genes_intersection_size (:92-119), memoised per        the distinct adjusted size pairs of ALL candidate pairs are collected
-//     (adjusted size a <= b): sum_i (1-(1-p_i)^a)(1-(1-p_i)^a(1-p_i)^(b-a))   (k_pp_count / k_pp_emit + SortCombine) and evaluated once each, one block
+//     (adjusted size a <= b): sum_i (1-(1-p_i)^a)(1-(1-p_i)^a(1-p_i)^(b-a))   in a hash set (k_pp_shared) and evaluated once each, one block
 //                                                                    per pair over the UMI space (k_pp_est; Tools::fpow's multiplication order)
 //   estimate_intersection_prob (:68-90): lambda = sum over shared    k_pp_lambda: merge join of the two cells' (cell, gene) rows, lambda summed in
 //     genes, p = ppois(I - 1, lambda, lower = FALSE) = P[X >= I]     gene-id order, upper Poisson tail from its definition
@@ -74,50 +74,82 @@ __global__ void k_pp_admissible(const uint64_t *__restrict__ pkey, uint32_t n_p,
     }
 }
 
-// merge join of the (cell, gene) rows of both cells of a pair: WRITE = false counts the shared genes, WRITE = true emits their adjusted
-// size pairs [(min << 29) | max] << 3 (SortCombine input)
-template <bool WRITE>
+// The distinct adjusted size pairs (a <= b) live in an open-addressing hash set in global memory: key = (a << 29) | b, EMPTY64 = free.
+// A few pairs -- (1,1), (1,2), ... -- occur millions of times, so the set is filled by insert-if-absent (no sorting of duplicates).
+__device__ __forceinline__ bool sp_insert(unsigned long long *__restrict__ set, uint32_t mask, unsigned long long key)
+{
+    uint32_t s = uint32_t(mix64(key)) & mask;
+    for (uint32_t probes = 0; probes <= mask; ++probes)
+    {
+        unsigned long long cur = set[s];
+        if (cur == key) return true;
+        if (cur == EMPTY64)
+        {
+            cur = atomicCAS(&set[s], EMPTY64, key);
+            if (cur == EMPTY64 || cur == key) return true;
+        }
+        s = (s + 1) & mask;
+    }
+    return false;
+}
+
+__device__ __forceinline__ uint32_t sp_find(const unsigned long long *__restrict__ set, uint32_t mask, unsigned long long key)
+{
+    uint32_t s = uint32_t(mix64(key)) & mask;
+    while (set[s] != key) s = (s + 1) & mask; // every looked-up key was inserted before
+    return s;
+}
+
+// merge join of the (cell, gene) rows of both cells of every admissible pair: the adjusted size pair of each shared gene goes into the set;
+// n_inserted counts NEW keys (load factor check), *full is raised when the table is exhausted
 __global__ void k_pp_shared(const uint64_t *__restrict__ pkey, const uint32_t *__restrict__ flag, uint32_t n_p, int rb, const uint32_t *__restrict__ real_pc,
                             const uint32_t *__restrict__ pc_cg_start, const uint32_t *__restrict__ cg_gene, const uint32_t *__restrict__ cg_start,
-                            const unsigned long long *__restrict__ adj, uint32_t *__restrict__ cnt, const uint32_t *__restrict__ off,
-                            uint64_t *__restrict__ out)
+                            const unsigned long long *__restrict__ adj, unsigned long long *__restrict__ set, uint32_t mask, int *__restrict__ full)
 {
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_p; p += gridDim.x * blockDim.x)
     {
-        uint32_t c = 0;
-        if (flag[p])
+        if (!flag[p]) continue;
+        const uint64_t k = pkey[p];
+        const uint32_t pa = real_pc[uint32_t(k >> rb)], pb = real_pc[uint32_t(k & ((1ull << rb) - 1))];
+        uint32_t i = pc_cg_start[pa], ie = pc_cg_start[pa + 1], j = pc_cg_start[pb], je = pc_cg_start[pb + 1];
+        unsigned long long last = EMPTY64;
+        while (i < ie && j < je)
         {
-            const uint64_t k = pkey[p];
-            const uint32_t pa = real_pc[uint32_t(k >> rb)], pb = real_pc[uint32_t(k & ((1ull << rb) - 1))];
-            uint32_t i = pc_cg_start[pa], ie = pc_cg_start[pa + 1], j = pc_cg_start[pb], je = pc_cg_start[pb + 1];
-            while (i < ie && j < je)
+            const uint32_t gi = cg_gene[i], gj = cg_gene[j];
+            if (gi == gj)
             {
-                const uint32_t gi = cg_gene[i], gj = cg_gene[j];
-                if (gi == gj)
-                {
-                    if (WRITE)
-                    {
-                        unsigned long long s1 = adj[cg_start[i + 1] - cg_start[i] - 1], s2 = adj[cg_start[j + 1] - cg_start[j] - 1];
-                        if (s1 > s2) { const unsigned long long t = s1; s1 = s2; s2 = t; }
-                        out[off[p] + c] = ((s1 << 29) | s2) << 3;
-                    }
-                    ++c; ++i; ++j;
-                }
-                else if (gi < gj) ++i; else ++j;
+                unsigned long long s1 = adj[cg_start[i + 1] - cg_start[i] - 1], s2 = adj[cg_start[j + 1] - cg_start[j] - 1];
+                if (s1 > s2) { const unsigned long long t = s1; s1 = s2; s2 = t; }
+                const unsigned long long key = (s1 << 29) | s2;
+                if (key != last) { if (!sp_insert(set, mask, key)) *full = 1; last = key; }
+                ++i; ++j;
             }
+            else if (gi < gj) ++i; else ++j;
         }
-        if (!WRITE) cnt[p] = c;
     }
 }
 
+__global__ void k_sp_occupied(const unsigned long long *__restrict__ set, uint32_t cap, uint32_t *__restrict__ occ)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) occ[i] = set[i] != EMPTY64;
+}
+
+__global__ void k_sp_list(const unsigned long long *__restrict__ set, const uint32_t *__restrict__ occ, const uint32_t *__restrict__ off, uint32_t cap,
+                          uint32_t *__restrict__ slots)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x)
+        if (occ[i]) slots[off[i]] = i;
+}
+
 // est(a, b) = sum_i (1 - q_i^a) (1 - q_i^a q_i^(b-a)), q_i = 1 - p_i (PoissonTargetEstimator.cpp:109-115), one block per distinct pair
-__global__ void __launch_bounds__(256) k_pp_est(const uint64_t *__restrict__ size_pairs, uint32_t n_pairs, const double *__restrict__ p, size_t n_umi,
-                                                double *__restrict__ est)
+__global__ void __launch_bounds__(256) k_pp_est(const unsigned long long *__restrict__ set, const uint32_t *__restrict__ slots, uint32_t n_pairs,
+                                                const double *__restrict__ p, size_t n_umi, double *__restrict__ est)
 {
     __shared__ double red[256];
     for (uint32_t u = blockIdx.x; u < n_pairs; u += gridDim.x)
     {
-        const uint64_t k = size_pairs[u];
+        const uint32_t slot = slots[u];
+        const uint64_t k = set[slot];
         const long long a = (long long)(k >> 29), b = (long long)(k & ((1ull << 29) - 1));
         double acc = 0;
         for (size_t i = threadIdx.x; i < n_umi; i += 256)
@@ -136,7 +168,7 @@ __global__ void __launch_bounds__(256) k_pp_est(const uint64_t *__restrict__ siz
             if (int(threadIdx.x) < w) red[threadIdx.x] = __dadd_rn(red[threadIdx.x], red[threadIdx.x + w]);
             __syncthreads();
         }
-        if (threadIdx.x == 0) est[u] = red[0];
+        if (threadIdx.x == 0) est[slot] = red[0];
         __syncthreads();
     }
 }
@@ -171,8 +203,8 @@ __device__ inline double poisson_upper(long long x, double lambda)
 // lambda and merge probability of every admissible pair (estimate_intersection_prob, PoissonTargetEstimator.cpp:68-90)
 __global__ void k_pp_lambda(const uint64_t *__restrict__ pkey, const uint32_t *__restrict__ pval, const uint32_t *__restrict__ flag, uint32_t n_p, int rb,
                             const uint32_t *__restrict__ real_pc, const uint32_t *__restrict__ pc_cg_start, const uint32_t *__restrict__ cg_gene,
-                            const uint32_t *__restrict__ cg_start, const unsigned long long *__restrict__ adj, const uint64_t *__restrict__ size_pairs,
-                            uint32_t n_size_pairs, const double *__restrict__ est, double *__restrict__ prob)
+                            const uint32_t *__restrict__ cg_start, const unsigned long long *__restrict__ adj, const unsigned long long *__restrict__ set,
+                            uint32_t mask, const double *__restrict__ est, double *__restrict__ prob)
 {
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_p; p += gridDim.x * blockDim.x)
     {
@@ -188,14 +220,7 @@ __global__ void k_pp_lambda(const uint64_t *__restrict__ pkey, const uint32_t *_
             {
                 unsigned long long s1 = adj[cg_start[i + 1] - cg_start[i] - 1], s2 = adj[cg_start[j + 1] - cg_start[j] - 1];
                 if (s1 > s2) { const unsigned long long t = s1; s1 = s2; s2 = t; }
-                const uint64_t want = (s1 << 29) | s2;
-                uint32_t lo = 0, hi = n_size_pairs;
-                while (lo < hi)
-                {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (size_pairs[mid] < want) lo = mid + 1; else hi = mid;
-                }
-                lambda = __dadd_rn(lambda, est[lo]);
+                lambda = __dadd_rn(lambda, est[sp_find(set, mask, (s1 << 29) | s2)]);
                 ++i; ++j;
             }
             else if (gi < gj) ++i; else ++j;

@@ -1093,12 +1093,18 @@ public:
                 // ALU instructions among the proven ones; the sort is ALU-pipe bound), 2 = 1 + sentinel slot instead of a predicated load
                 static const int mv = std::getenv("DGE_MS_VARIANT") ? atoi(std::getenv("DGE_MS_VARIANT")) : 1;
                 if (cw) k_sort_dedup_warp<4, 16><<<grid(128, 6), 128, 0, st>>>(keys_tmp, uv, sub_off, cl, cc, ucount);
-#define DGE_MS(T, I, V, C, DFLT) k_sort_dedup<T, I, V><<<grid(T, DFLT), T, 0, st>>>(keys_tmp, uv, sub_off, cl + (C + 1) * ls, cc + (C + 1), ucount)
-                if (ms_items == 16 && mv == 0) { DGE_MS(64, 16, 0, 0, 12); DGE_MS(128, 16, 0, 1, 6); DGE_MS(256, 16, 0, 2, 3); }
-                else if (ms_items == 16 && mv == 2) { DGE_MS(64, 16, 2, 0, 12); DGE_MS(128, 16, 2, 1, 6); DGE_MS(256, 16, 2, 2, 3); }
-                else if (ms_items == 16) { DGE_MS(64, 16, 1, 0, 12); DGE_MS(128, 16, 1, 1, 6); DGE_MS(256, 16, 1, 2, 3); }
-                else { DGE_MS(64, 8, 1, 0, 24); DGE_MS(128, 8, 1, 1, 12); DGE_MS(256, 8, 1, 2, 6); }
+                static const bool ms_bulk = !(std::getenv("DGE_MS_BULK") && atoi(std::getenv("DGE_MS_BULK")) == 0); // bulk-async staging + prefetch of the next item
+#define DGE_MS_NB(T, I, V, C, DFLT) k_sort_dedup<T, I, V, false><<<grid(T, DFLT), T, 0, st>>>(keys_tmp, uv, sub_off, cl + (C + 1) * ls, cc + (C + 1), ucount)
+#define DGE_MS(T, I, V, C, DFLT)                                                                                                        \
+                if (ms_bulk) k_sort_dedup<T, I, V, true><<<grid(T, DFLT), T, 0, st>>>(keys_tmp, uv, sub_off, cl + (C + 1) * ls, cc + (C + 1), ucount); \
+                else DGE_MS_NB(T, I, V, C, DFLT)
+                // (the 4096-key class is a handful of sub-buckets and would need 66 KB of staging: plain loads)
+                if (ms_items == 16 && mv == 0) { DGE_MS(64, 16, 0, 0, 12); DGE_MS(128, 16, 0, 1, 6); DGE_MS_NB(256, 16, 0, 2, 3); }
+                else if (ms_items == 16 && mv == 2) { DGE_MS(64, 16, 2, 0, 12); DGE_MS(128, 16, 2, 1, 6); DGE_MS_NB(256, 16, 2, 2, 3); }
+                else if (ms_items == 16) { DGE_MS(64, 16, 1, 0, 12); DGE_MS(128, 16, 1, 1, 6); DGE_MS_NB(256, 16, 1, 2, 3); }
+                else { DGE_MS(64, 8, 1, 0, 24); DGE_MS(128, 8, 1, 1, 12); DGE_MS_NB(256, 8, 1, 2, 6); }
 #undef DGE_MS
+#undef DGE_MS_NB
                 L += 5;
                 const int thr = sc_tuning().dedup_threads;
                 k_dedup_sort<false><<<148 * 2, thr, dedup_smem_bytes(SC_HT_MAX, SC_HT_MAX, thr), st>>>(keys_tmp, nullptr, uv, sub_off, n_sub_ptr, ucount, overflow_flag,

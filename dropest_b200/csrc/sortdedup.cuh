@@ -10,6 +10,7 @@
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
+#include "tma.cuh"
 
 namespace dge
 {
@@ -68,34 +69,74 @@ template <int N> __device__ __forceinline__ void ms_thread_sort(uint64_t (&k)[N]
 
 // Work item = one sub-bucket from `list`: keys[s..e) -> distinct ukeys ascending, IN PLACE at keys[s..s+m), values
 // (count | mark<<29) at uvals[s..s+m), ucount[sb] = m.  Persistent blocks stride over the list; sizes must be <= THREADS*ITEMS.
-template <int THREADS, int ITEMS, int MERGE>
+// BULK = true: the sub-bucket arrives in shared memory by ONE bulk asynchronous copy (cp.async.bulk -> UBLKCP, completion on an mbarrier)
+// issued by thread 0, and the copy of the NEXT work item is issued as soon as every thread holds its keys of the current one in
+// registers: the global-memory latency of a work item hides behind the sort of the previous one, and the load costs the threads no
+// LDG / STS issue slots (the kernel is issue-bound).  The staging buffer is linear; a thread takes its ITEMS consecutive keys in a rotated
+// order (element (j + t) mod ITEMS at step j), which spreads a warp's 8-byte loads over all banks.
+template <int THREADS, int ITEMS, int MERGE, bool BULK>
 __global__ void __launch_bounds__(THREADS, MS_WARPS_PER_SM * 32 / THREADS) k_sort_dedup(uint64_t *__restrict__ keys, uint32_t *__restrict__ uvals,
                                                         const uint32_t *__restrict__ sub_off, const uint32_t *__restrict__ list,
                                                         const uint32_t *__restrict__ list_count, uint32_t *__restrict__ ucount)
 {
     constexpr int CAP = THREADS * ITEMS;
     __shared__ uint64_t sk[CAP + CAP / ITEMS + 1];
+    __shared__ __align__(16) uint64_t raw[BULK ? CAP + 2 : 2];
+    __shared__ uint64_t bar;
     __shared__ uint32_t ws[33];
     const int t = threadIdx.x;
     const int p0 = t * ITEMS;
     const int row = ms_phys<ITEMS>(p0); // the ITEMS elements of a thread are contiguous in shared memory
     const uint32_t n_items = *list_count;
     if (t == 0) sk[CAP + CAP / ITEMS] = EMPTY64; // sentinel slot (never overwritten: element indices stop one word short of it)
+    uint32_t parity = 0;
+    // bulk copies need 16-byte aligned addresses and sizes: start at the even key index at or below the sub-bucket's first key
+    auto issue_load = [&](uint32_t it) {
+        const uint32_t sb_n = list[it];
+        const uint32_t s_n = sub_off[sb_n], e_n = sub_off[sb_n + 1];
+        const uint32_t s_al = s_n & ~1u;
+        const uint32_t bytes = (((e_n - s_al) + 1u) & ~1u) * 8u;
+        mbar_arrive_expect_tx(&bar, bytes);
+        bulk_g2s(raw, keys + s_al, bytes, &bar);
+    };
+    if (BULK)
+    {
+        if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+        __syncthreads();
+        if (t == 0 && blockIdx.x < n_items) issue_load(blockIdx.x);
+    }
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x)
     {
         const uint32_t sb = list[item];
         const uint32_t s = sub_off[sb];
         const int n = int(sub_off[sb + 1] - s);
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j)
-        {
-            const int i = j * THREADS + t;
-            sk[ms_phys<ITEMS>(i)] = i < n ? keys[s + i] : EMPTY64;
-        }
-        __syncthreads();
         uint64_t k[ITEMS];
+        if (BULK)
+        {
+            mbar_wait(&bar, parity);
+            parity ^= 1u;
+            const int shift = int(s & 1u);
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) k[j] = sk[row + j];
+            for (int j = 0; j < ITEMS; ++j)
+            {
+                const int i = p0 + ((j + t) & (ITEMS - 1));
+                k[j] = i < n ? raw[shift + i] : EMPTY64;
+            }
+            __syncthreads(); // every thread holds its keys: the staging buffer may take the next work item
+            if (t == 0 && item + gridDim.x < n_items) issue_load(item + gridDim.x);
+        }
+        else
+        {
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+            {
+                const int i = j * THREADS + t;
+                sk[ms_phys<ITEMS>(i)] = i < n ? keys[s + i] : EMPTY64;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) k[j] = sk[row + j];
+        }
         if (p0 < n) ms_thread_sort(k);
 
         // threads needed to cover n keys, rounded up to a power of two: levels above it have nothing to merge

@@ -12,13 +12,17 @@
 
 namespace Tools
 {
+	// Read names written by droptag end in "!<cell barcode>#<UMI>" (Tools/ReadParameters.cpp:42-56): the last '#' starts the UMI, the last
+	// '!' before it starts the barcode.  Same two failure messages as the reference, since callers print them.
 	ReadParameters ReadParameters::parse_encoded_id(const std::string &encoded_id)
 	{
-		size_t umi_start_pos = encoded_id.rfind('#');
-		if (umi_start_pos == std::string::npos) throw std::runtime_error("ERROR: unable to parse out UMI in: " + encoded_id);
-		size_t cb_start_pos = encoded_id.rfind('!', umi_start_pos);
-		if (cb_start_pos == std::string::npos) throw std::runtime_error("ERROR: unable to parse out cell barcode in: " + encoded_id);
-		return ReadParameters(encoded_id.substr(cb_start_pos + 1, umi_start_pos - cb_start_pos - 1), encoded_id.substr(umi_start_pos + 1), "", "");
+		const char *const begin = encoded_id.data();
+		const char *hash = nullptr, *bang = nullptr;
+		for (const char *c = begin + encoded_id.size(); c != begin && !hash;) if (*--c == '#') hash = c;
+		if (!hash) throw std::runtime_error("ERROR: unable to parse out UMI in: " + encoded_id);
+		for (const char *c = hash + 1; c != begin && !bang;) if (*--c == '!') bang = c;
+		if (!bang) throw std::runtime_error("ERROR: unable to parse out cell barcode in: " + encoded_id);
+		return ReadParameters(std::string(bang + 1, hash), std::string(hash + 1, begin + encoded_id.size()), "", "");
 	}
 
 	unsigned edit_distance(const char *s1, const char *s2, bool skip_n, unsigned max_ed) { return dge_edit_distance(s1, s2, skip_n ? 1 : 0, max_ed); }
@@ -123,18 +127,31 @@ namespace Estimation
 			cfg.min_merge_fraction = _min_merge_fraction;
 		}
 
+		std::shared_ptr<BarcodesParsing::BarcodesParser> MergeStrategyFactory::get_barcodes_parser() const
+		{
+			if (barcodes_type == "indrop") return std::make_shared<BarcodesParsing::InDropBarcodesParser>(barcodes_filename);
+			if (barcodes_type == "const") return std::make_shared<BarcodesParsing::ConstLengthBarcodesParser>(barcodes_filename);
+			throw std::runtime_error("Unexpected barcodes type: " + barcodes_type);
+		}
+
+		// MergeStrategyFactory::get_cb_strat / get_cb_poisson_strat (MergeStrategyFactory.cpp:61-103)
 		std::shared_ptr<MergeStrategyAbstract> MergeStrategyFactory::get_cb_strat(bool merge_tags, bool use_poisson) const
 		{
 			if (!merge_tags) return std::make_shared<DummyMergeStrategy>(min_genes_before_merge, min_genes_after_merge);
-			if (use_poisson) throw std::runtime_error("the Poisson merge strategies (-M) are not available on the device path yet");
+			if (use_poisson)
+			{
+				PoissonTargetEstimator target_estimator(max_merge_prob, max_real_cb_merge_prob);
+				if (barcodes_filename.empty())
+					return std::make_shared<PoissonSimpleMergeStrategy>(target_estimator, unsigned(min_genes_before_merge), unsigned(min_genes_after_merge),
+					                                                    max_merge_edit_distance);
+				return std::make_shared<PoissonRealBarcodesMergeStrategy>(target_estimator, get_barcodes_parser(), min_genes_before_merge,
+				                                                          min_genes_after_merge, max_merge_edit_distance);
+			}
 			if (merge_type == "all") return std::make_shared<MergeAllMergeStrategy>(min_genes_before_merge, min_genes_after_merge, max_merge_edit_distance);
 			if (barcodes_filename.empty())
 				return std::make_shared<SimpleMergeStrategy>(min_genes_before_merge, min_genes_after_merge, max_merge_edit_distance, min_merge_fraction);
-			std::shared_ptr<BarcodesParsing::BarcodesParser> parser;
-			if (barcodes_type == "indrop") parser = std::make_shared<BarcodesParsing::InDropBarcodesParser>(barcodes_filename);
-			else if (barcodes_type == "const") parser = std::make_shared<BarcodesParsing::ConstLengthBarcodesParser>(barcodes_filename);
-			else throw std::runtime_error("Unexpected barcodes type: " + barcodes_type);
-			return std::make_shared<RealBarcodesMergeStrategy>(parser, min_genes_before_merge, min_genes_after_merge, max_merge_edit_distance, min_merge_fraction);
+			return std::make_shared<RealBarcodesMergeStrategy>(get_barcodes_parser(), min_genes_before_merge, min_genes_after_merge, max_merge_edit_distance,
+			                                                   min_merge_fraction);
 		}
 
 		std::shared_ptr<UMIs::MergeUMIsStrategyAbstract> MergeStrategyFactory::get_umi(bool advanced) const
@@ -426,9 +443,12 @@ namespace Estimation
 
 	void ResultsPrinter::save_mtx(const SparseMatrix &m, const std::string &filename_base)
 	{
-		// Matrix::writeMM(d$cm, base.mtx) + write.table(colnames / rownames)  (ResultsPrinter.cpp:81-91)
+		// Matrix::writeMM(d$cm, base.mtx) + write.table(colnames / rownames)  (ResultsPrinter.cpp:81-91).  writeMM hands a dgCMatrix to
+		// CHOLMOD's MatrixMarket writer (third party, not in the reference tree: Matrix >= 1.2 / SuiteSparse cholmod_write_sparse), which
+		// declares a real matrix whose entries are all integer-valued -- as every count matrix is -- as "integer" and prints the
+		// entries without a fraction, 1-based, column by column.  Parity of this file is unpinned (no reference test reads it back).
 		std::ofstream f(filename_base + ".mtx");
-		f << "%%MatrixMarket matrix coordinate real general\n";
+		f << "%%MatrixMarket matrix coordinate integer general\n";
 		f << m.row_names.size() << " " << m.col_names.size() << " " << m.i.size() << "\n";
 		for (size_t c = 0; c + 1 < m.p.size(); ++c)
 			for (int32_t k = m.p[c]; k < m.p[c + 1]; ++k) f << (m.i[size_t(k)] + 1) << " " << (c + 1) << " " << int64_t(m.x[size_t(k)]) << "\n";

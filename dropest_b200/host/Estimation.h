@@ -311,6 +311,63 @@ namespace Estimation
 			}
 		};
 
+		// PoissonTargetEstimator (PoissonTargetEstimator.h:20-66): here the two thresholds; the estimator itself (UMI distribution,
+		// CollisionsAdjuster, per-pair lambda and Poisson tail) runs on the device (dropest_b200/csrc/poisson.cuh)
+		class PoissonTargetEstimator
+		{
+		public:
+			const double max_merge_prob, max_real_cb_merge_prob;
+			PoissonTargetEstimator(double max_merge_prob, double max_real_cb_merge_prob)
+				: max_merge_prob(max_merge_prob), max_real_cb_merge_prob(max_real_cb_merge_prob) {}
+		};
+
+		// PoissonSimpleMergeStrategy (PoissonSimpleMergeStrategy.h): -M without a whitelist
+		class PoissonSimpleMergeStrategy : public MergeStrategyAbstract
+		{
+			PoissonTargetEstimator _target_estimator;
+			unsigned _max_merge_edit_distance;
+
+		public:
+			PoissonSimpleMergeStrategy(const PoissonTargetEstimator &target_estimator, unsigned min_genes_before_merge, unsigned min_genes_after_merge,
+			                           unsigned max_merge_edit_distance)
+				: MergeStrategyAbstract(min_genes_before_merge, min_genes_after_merge), _target_estimator(target_estimator)
+				, _max_merge_edit_distance(max_merge_edit_distance) {}
+			std::string merge_type() const override { return "Poisson Simple"; }
+			void configure(dge_config &cfg) const override
+			{
+				cfg.merge_type = DGE_MERGE_POISSON_SIMPLE;
+				cfg.max_cb_merge_edit_distance = _max_merge_edit_distance;
+				cfg.min_merge_fraction = 0;
+				cfg.max_merge_prob = _target_estimator.max_merge_prob;
+				cfg.max_real_merge_prob = _target_estimator.max_real_cb_merge_prob;
+			}
+		};
+
+		// PoissonRealBarcodesMergeStrategy (PoissonRealBarcodesMergeStrategy.h): -M with a whitelist
+		class PoissonRealBarcodesMergeStrategy : public MergeStrategyAbstract
+		{
+			PoissonTargetEstimator _target_estimator;
+			RealBarcodesMergeStrategy::barcodes_parser_ptr _parser;
+			unsigned _max_merge_edit_distance;
+
+		public:
+			PoissonRealBarcodesMergeStrategy(const PoissonTargetEstimator &target_estimator, const RealBarcodesMergeStrategy::barcodes_parser_ptr &barcodes_parser,
+			                                 size_t min_genes_before_merge, size_t min_genes_after_merge, unsigned max_merge_edit_distance)
+				: MergeStrategyAbstract(min_genes_before_merge, min_genes_after_merge), _target_estimator(target_estimator), _parser(barcodes_parser)
+				, _max_merge_edit_distance(max_merge_edit_distance) {}
+			std::string merge_type() const override { return "Poisson Real CBs"; }
+			void configure(dge_config &cfg) const override
+			{
+				cfg.merge_type = DGE_MERGE_POISSON_REAL;
+				cfg.barcodes_type = _parser->indrop ? DGE_BARCODES_INDROP : DGE_BARCODES_CONST;
+				cfg.barcodes_file = _parser->filename.c_str();
+				cfg.max_cb_merge_edit_distance = _max_merge_edit_distance;
+				cfg.min_merge_fraction = 0;
+				cfg.max_merge_prob = _target_estimator.max_merge_prob;
+				cfg.max_real_merge_prob = _target_estimator.max_real_cb_merge_prob;
+			}
+		};
+
 		namespace UMIs
 		{
 			class MergeUMIsStrategyAbstract
@@ -370,6 +427,7 @@ namespace Estimation
 			double min_merge_fraction = 0.2, max_merge_prob = 1e-4, max_real_cb_merge_prob = 1e-7, umi_merge_mult = 2;
 
 			std::shared_ptr<MergeStrategyAbstract> get_cb_strat(bool merge_tags, bool use_poisson) const;
+			std::shared_ptr<BarcodesParsing::BarcodesParser> get_barcodes_parser() const; // MergeStrategyFactory.cpp:113-126
 			std::shared_ptr<UMIs::MergeUMIsStrategyAbstract> get_umi(bool advanced) const;
 		};
 	}

@@ -148,6 +148,29 @@ int main(int argc, char **argv)
 			CHECK_EQUAL(container.cell(0).size(), size_t(5));
 		}
 
+		// -M: MergeStrategyFactory::get_cb_poisson_strat (MergeStrategyFactory.cpp:91-103) + PoissonSimpleMergeStrategy through the container.
+		// Same reads as above: the small cell shares 3 UMI-genes with the big one 1 substitution away; with only 7 distinct UMIs in the whole
+		// container the expected random overlap is large (lambda ~ 0.6, P[X >= 3] ~ 0.02), so the thresholds are raised for this toy input;
+		// the copy 3 substitutions away is outside max_merge_edit_distance and stays.
+		{
+			Merge::MergeStrategyFactory factory;
+			factory.min_genes_before_merge = 0; factory.min_genes_after_merge = 0;
+			factory.max_merge_prob = 0.5; factory.max_real_cb_merge_prob = 0.5;
+			CHECK_EQUAL(factory.get_cb_strat(true, true)->merge_type(), std::string("Poisson Simple"));
+			CellsDataContainer container(factory.get_cb_strat(true, true), umi_merge_strat, any_mark, false, -1, 0, 64);
+			static const char *big[][2] = {{"AAAAAA", "Gene1"}, {"AAAAAC", "Gene1"}, {"AAAAAG", "Gene2"}, {"AAAAAT", "Gene3"}, {"AAAACA", "Gene4"}, {"AAAACC", "Gene5"}};
+			static const char *small_[][2] = {{"AAAAAA", "Gene1"}, {"AAAAAG", "Gene2"}, {"AAAAAT", "Gene3"}, {"TTTTTT", "Gene5"}};
+			for (auto const &r : big) container.add_record(read_info("AAATTAGGTCCA", r[0], r[1]));
+			for (auto const &r : small_) container.add_record(read_info("AAATTAGGTCCC", r[0], r[1]));
+			for (auto const &r : small_) container.add_record(read_info("CCCTTAGGTCCC", r[0], r[1]));
+			container.set_initialized();
+			container.merge_and_filter();
+			CHECK_EQUAL(container.merge_type(), std::string("Poisson Simple"));
+			CHECK_EQUAL(container.merge_targets().at(1), size_t(0));
+			CHECK_EQUAL(container.merge_targets().at(2), size_t(2));
+			CHECK(container.cell(1).is_merged());
+		}
+
 		// testEditDistance, Tests/TestTools.cpp:47-54 ; testReadParams :56-87 (codec part)
 		CHECK_EQUAL(Tools::edit_distance("ATTTTC", "ATTTGC"), 1u);
 		CHECK_EQUAL(Tools::edit_distance("ATTTTCC", "ATTTGNC"), 1u);
