@@ -27,6 +27,10 @@ from .capi import (  # noqa: F401
     MATRIX_CM_RAW,
     RECORD_DTYPE,
     NO_GENE,
+    FLAG_UMI_N,
+    FLAG_CB_N,
+    CB_N_BIT,
+    UMI_N_BIT,
     pack_seq,
     unpack_seq,
     marks_to_mask,

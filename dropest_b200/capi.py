@@ -16,7 +16,9 @@ UMI_MERGE_SIMPLE, UMI_MERGE_DIRECTIONAL = 0, 1
 CELLS_ALL, CELLS_REAL, CELLS_FILTERED = 0, 1, 2
 MATRIX_CM, MATRIX_CM_RAW = 0, 1
 NO_GENE = 0xFFFFFF
-ABI_VERSION = 1
+FLAG_UMI_N, FLAG_CB_N = 1 << 27, 1 << 28     # dge_record16.gene flags: key field = index into the N-UMI / N-barcode list
+CB_N_BIT, UMI_N_BIT = 1 << 40, 1 << 31       # how the query surface reports such entries
+ABI_VERSION = 2
 
 RECORD_DTYPE = np.dtype([("key", "<u8"), ("gene", "<u4"), ("read_idx", "<u4")])
 
@@ -41,7 +43,7 @@ DIST_DONE, DIST_ALLGATHER, DIST_ALLTOALL = 0, 1, 2
 # exported symbols of include/dropest_b200.h (checked by tests/test_abi.py)
 EXPORTS = [
     "dge_config_default", "dge_create", "dge_destroy", "dge_last_error", "dge_add_batch", "dge_add_batch_device", "dge_add_batch_soa",
-    "dge_set_initialized", "dge_merge_and_filter", "dge_reset", "dge_set_stream", "dge_get_summary", "dge_get_timings", "dge_get_cells",
+    "dge_set_initialized", "dge_merge_and_filter", "dge_reset", "dge_set_stream", "dge_set_n_strings", "dge_get_summary", "dge_get_timings", "dge_get_cells",
     "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
     "dge_route_by_barcode_device", "dge_route_count_slices_device", "dge_route_scatter_slice_device", "dge_dist_step",
@@ -64,7 +66,7 @@ class _Config(C.Structure):
         ("min_merge_fraction", C.c_double), ("max_merge_prob", C.c_double), ("max_real_merge_prob", C.c_double),
         ("umi_merge_mult", C.c_double), ("query_mark_mask", C.c_uint32), ("max_cells", C.c_int32),
         ("reads_output", C.c_uint32), ("sharded", C.c_uint32), ("barcodes_file", C.c_char_p),
-        ("max_barcodes_hint", C.c_uint64),
+        ("max_barcodes_hint", C.c_uint64), ("allow_n", C.c_uint32), ("reserved0", C.c_uint32),
     ]
 
 
@@ -147,6 +149,7 @@ def load_library():
     lib.dge_route_count_slices_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dge_route_scatter_slice_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dge_dist_step.argtypes = [C.c_void_p, C.POINTER(_DistIO)]
+    lib.dge_set_n_strings.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
     lib.dge_umi_first_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
     lib.dge_umi_first_export.argtypes = [C.c_void_p, C.c_void_p]
     lib.dge_umi_first_import.argtypes = [C.c_void_p, C.c_void_p]
@@ -202,6 +205,7 @@ class Config:
     reads_output: bool = False
     max_barcodes_hint: int = 0
     sharded: bool = False
+    allow_n: bool = False
     _keep: list = field(default_factory=list, repr=False)
 
     def to_c(self) -> _Config:
@@ -216,6 +220,7 @@ class Config:
         c.query_mark_mask = marks_to_mask(self.marks)
         c.reads_output = 1 if self.reads_output else 0
         c.sharded = 1 if self.sharded else 0
+        c.allow_n = 1 if self.allow_n else 0
         if self.barcodes_file:
             b = self.barcodes_file.encode()
             self._keep.append(b)
@@ -295,6 +300,11 @@ class Container:
         self._check(self._lib.dge_merge_and_filter(self._h))
 
     # ---- cross-rank merge steps (sharded runs); the collectives live in dropest_b200/dist.py
+    def set_n_strings(self, which: int, strings):
+        """The strings behind DGE_FLAG_UMI_N (which = 0) / DGE_FLAG_CB_N (which = 1) record indices (dge_set_n_strings)."""
+        blob = "".join(strings).encode()
+        self._check(self._lib.dge_set_n_strings(self._h, which, blob, len(strings)))
+
     def dist_io(self, world: int, rank: int) -> "_DistIO":
         io = _DistIO()
         io.world, io.rank = world, rank

@@ -37,6 +37,8 @@ struct CapacityError : std::runtime_error
 constexpr uint64_t EMPTY64 = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 constexpr uint32_t NO_GENE = 0xFFFFFFu;
+constexpr uint32_t FLAG_UMI_N = 1u << 27, FLAG_CB_N = 1u << 28; // dge_record16.gene flags (include/dropest_b200.h)
+constexpr uint64_t CB_N_BIT = 1ull << 40;                         // marks a barcode-table entry that is an index into the N-barcode list
 
 // count | mark << 29  (count < 2^29 reads per UMI)
 constexpr int VAL_MARK_SHIFT = 29;
@@ -56,6 +58,9 @@ struct KeyLayout
 {
     int tb, gb, ub, kb;
     int cbb; // 2 * cb_len: barcode bits of dge_record16.key >> 24 (record validation)
+    int ul;  // 2 * umi_len: bits of a plain (N-free) UMI; with allow_n the UMI field is ub = max(ul, 20) + 1 bits wide and an N-UMI is stored as
+             // [1 : index into the caller's N-UMI list], a barcode with N as [1 << 40 | index] in the barcode table
+    int ne;  // allow_n
     __host__ __device__ uint64_t compose(uint32_t slot, uint32_t gene, uint32_t umi, uint32_t mark) const
     {
         return (((uint64_t(slot) << gb | gene) << ub | umi) << 3) | mark;

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) k_wl_self(const CellRow *__restrict__ row
     const uint32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (cell >= n) return;
     const uint64_t cb = rows[cell].cb;
+    if (cb & CB_N_BIT) { if (lane == 0) self_flag[cell] = 0u; return; } // barcode with N: never a whitelist barcode itself
     bool all_exact = true, multi = false;
     for (int k = 0; k < wl.n_parts; ++k)
     {
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(256) k_wl_class01_g(const CellRow *__restrict_
     if (sf) { if (lane == 0) nb_count[cell] = NB_SELF; return; } // a whitelist barcode (also with duplicated tokens: its first neighbour is itself)
     const uint64_t cb = rows[cell].cb;
     const uint32_t base_umis = rows[cell].n_umis;
+    if (cb & CB_N_BIT) { if (lane == 0) nb_count[cell] = NB_SLOW; return; } // exact enumeration with N wildcards on the host
     int n_exact_parts = 0, missing_part = -1;
     uint32_t part_vals[WL_MAX_PARTS];
     for (int k = 0; k < wl.n_parts; ++k)

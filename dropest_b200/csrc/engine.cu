@@ -73,6 +73,7 @@ struct dge_handle
     dge_config cfg{};
     std::string barcodes_file;
     std::string err;
+    std::string n_umi_strings, n_cb_strings; // dge_set_n_strings: the strings behind DGE_FLAG_UMI_N / DGE_FLAG_CB_N indices
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int state = 0; // 0 filling, 1 initialized, 2 merged
@@ -274,6 +275,26 @@ template <class T> T d2h_scalar(const void *src, cudaStream_t st)
 
 void reset_fill_state(dge_handle *h);
 
+// Barcode / UMI as the strings the reference sees: 2-bit unpacked, or -- entries made from DGE_FLAG_CB_N / DGE_FLAG_UMI_N records -- the
+// caller's string with its N's (dge_set_n_strings).
+std::string cb_string(const dge_handle *h, uint64_t cb)
+{
+    if (!(cb & CB_N_BIT)) return unpack_seq(cb, h->cfg.cb_len);
+    const size_t idx = size_t(cb & (CB_N_BIT - 1)), len = h->cfg.cb_len;
+    if ((idx + 1) * len > h->n_cb_strings.size()) throw InvalidInput("barcode index beyond the N-barcode list (dge_set_n_strings)");
+    return h->n_cb_strings.substr(idx * len, len);
+}
+
+bool umi_is_n(const dge_handle *h, uint32_t umi) { return h->kl.ne && ((umi >> (h->kl.ub - 1)) & 1u); }
+
+std::string umi_string(const dge_handle *h, uint32_t umi)
+{
+    if (!umi_is_n(h, umi)) return unpack_seq(umi, h->cfg.umi_len);
+    const size_t idx = size_t(umi & ((1u << (h->kl.ub - 1)) - 1)), len = h->cfg.umi_len;
+    if ((idx + 1) * len > h->n_umi_strings.size()) throw InvalidInput("UMI index beyond the N-UMI list (dge_set_n_strings)");
+    return h->n_umi_strings.substr(idx * len, len);
+}
+
 // Radix sort of (key, value) pairs on the low `end_bit` key bits.  Used ONLY for per-cell / per-gene tables (~1e5 rows: cell-id
 // order, compare_cells order, gene first-seen order) -- library code (CUB), not part of the per-read path.
 void device_sort_pairs(dge_handle *h, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, size_t n, int end_bit)
@@ -299,7 +320,9 @@ void ensure_device(dge_handle *h)
 
     // key layout: [slot:tb | gene:gb | umi:ub | mark:3]
     KeyLayout &kl = h->kl;
-    kl.ub = int(2 * h->cfg.umi_len);
+    kl.ul = int(2 * h->cfg.umi_len);
+    kl.ne = h->cfg.allow_n ? 1 : 0;
+    kl.ub = kl.ne ? std::max(kl.ul, 20) + 1 : kl.ul; // allow_n: [1 : index of an N-UMI string] needs a flag bit and room for the index
     kl.gb = std::max(1, ceil_log2_u64(h->cfg.n_genes));
     const int tb_max = 61 - kl.gb - kl.ub;
     int want = h->cfg.max_barcodes_hint ? ceil_log2_u64(2 * h->cfg.max_barcodes_hint) : 22;
@@ -309,7 +332,8 @@ void ensure_device(dge_handle *h)
     kl.cbb = int(2 * h->cfg.cb_len);
     h->table_cap = size_t(1) << kl.tb;
     // strategies whose tie rules depend on the UMI indexer's first-seen order (UMI ids): directional UMI merge, simple CB merge
-    h->track_umi_first = h->cfg.umi_merge_type == DGE_UMI_MERGE_DIRECTIONAL || h->cfg.merge_type == DGE_MERGE_SIMPLE;
+    h->track_umi_first = h->cfg.umi_merge_type == DGE_UMI_MERGE_DIRECTIONAL || h->cfg.merge_type == DGE_MERGE_SIMPLE ||
+                         h->cfg.merge_type == DGE_MERGE_POISSON_SIMPLE || h->cfg.allow_n; // N repair walks UMIs in StringIndexer order
     if (h->track_umi_first && kl.ub > 26) throw std::runtime_error("directional UMI merge / simple CB merge support UMIs of up to 13 bases");
 
     h->tab.reserve(h->table_cap * sizeof(CellSlot));
@@ -560,7 +584,12 @@ void update_filtered(dge_handle *h, uint32_t threshold, int cell_threshold)
         {
             size_t b = a + 1;
             while (b < f.size() && key[b] == key[a]) ++b;
-            if (b - a > 1) std::sort(f.begin() + long(a), f.begin() + long(b), [&](uint32_t x, uint32_t y) { return R[x].cb < R[y].cb; });
+            if (b - a > 1)
+                std::sort(f.begin() + long(a), f.begin() + long(b), [&](uint32_t x, uint32_t y) {
+                    // barcode strings; N-free strings of one length compare like their 2-bit packings
+                    if (!((R[x].cb | R[y].cb) & CB_N_BIT)) return R[x].cb < R[y].cb;
+                    return cb_string(h, R[x].cb) < cb_string(h, R[y].cb);
+                });
             a = b;
         }
     }
@@ -710,7 +739,10 @@ void build_host_mirror(dge_handle *h, const CellRow *rows_p, size_t n_rows, bool
     }
     tr.mark("init:  gene order");
     // set_initialized: update_cell_sizes(query, 0, -1)  (CellsDataContainer.cpp:168) -- every real cell, ascending compare_cells
-    if (rows_sorted && !dev_filter_overflow) h->filtered.assign(dev_filtered, dev_filtered + n_rows); // exact total order, ties included
+    bool any_n_cb = false;
+    if (h->kl.ne) for (auto const &c : h->real) any_n_cb |= (c.cb & CB_N_BIT) != 0;
+    // (the device sort orders barcodes by their packing: not the string order once a barcode contains N)
+    if (rows_sorted && !dev_filter_overflow && !any_n_cb) h->filtered.assign(dev_filtered, dev_filtered + n_rows); // exact total order, ties included
     else update_filtered(h, 0, -1);
     tr.mark("init: gene order + filtered");
     h->host_stage = 1;
@@ -1183,7 +1215,7 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
             by_cb.reserve(n * 2);
             for (uint32_t r = 0; r < n; ++r) by_cb.emplace(h->real[r].cb, r);
         }
-        const std::string cb = unpack_seq(h->real[i].cb, h->cfg.cb_len);
+        const std::string cb = cb_string(h, h->real[i].cb);
         auto lookup = [&](const std::string &s) -> long {
             uint64_t v;
             if (!pack_seq(s, v)) return -1;
@@ -1461,7 +1493,7 @@ long simple_replay(dge_handle *h, SimpleReplay &R, uint32_t base, int rb)
     const HostCell &bc = h->real[base];
     long top = -1, top_genes = -1;
     double top_frac = -1;
-    const std::string base_cb = unpack_seq(bc.cb, h->cfg.cb_len);
+    const std::string base_cb = cb_string(h, bc.cb);
     for (auto const &kv : simple_replay_candidates(h, R, base, rb))
     {
         const uint32_t o = kv.first;
@@ -1469,7 +1501,7 @@ long simple_replay(dge_handle *h, SimpleReplay &R, uint32_t base, int rb)
         const double frac = 0.5 * kv.second * (1. / size_t(bc.umis_stat) + 1. / size_t(oc.umis_stat));
         if (frac - top_frac > 0.00001 || (std::abs(frac - top_frac) < 0.00001 && long(oc.n_genes) > top_genes))
         {
-            const int ed = int(edit_distance_ref(base_cb.c_str(), unpack_seq(oc.cb, h->cfg.cb_len).c_str()));
+            const int ed = int(edit_distance_ref(base_cb.c_str(), cb_string(h, oc.cb).c_str()));
             if (ed >= int(h->cfg.max_cb_merge_edit_distance)) continue;
             top = long(o); top_frac = frac; top_genes = long(oc.n_genes);
         }
@@ -1666,7 +1698,7 @@ void phase1_poisson_real(dge_handle *h, std::vector<long> &target)
         auto eligible = [&](long id) {
             return uint32_t(h->real[size_t(id)].n_genes) >= h->cfg.min_genes_before_merge && h->real[size_t(id)].umis_stat >= h->real[i].umis_stat;
         };
-        nbs[i] = h->wl.neighbours(unpack_seq(h->real[i].cb, h->cfg.cb_len), true, lookup, eligible);
+        nbs[i] = h->wl.neighbours(cb_string(h, h->real[i].cb), true, lookup, eligible);
         for (long id : nbs[i])
         {
             if (uint32_t(id) == i) continue;
@@ -1934,7 +1966,7 @@ void umi_directional_replay(const dge_handle *h, std::vector<UmiItem> &items, st
     std::sort(items.begin(), items.end(), [](const UmiItem &a, const UmiItem &b) { return a.reads < b.reads; }); // same call as the reference
     const size_t n = items.size();
     std::vector<std::string> seq(n);
-    for (size_t i = 0; i < n; ++i) seq[i] = unpack_seq(items[i].umi, h->cfg.umi_len);
+    for (size_t i = 0; i < n; ++i) seq[i] = umi_string(h, items[i].umi);
     std::vector<long> tgt(n, -1);
     for (size_t s = 0; s < n; ++s)
     {
@@ -2095,6 +2127,162 @@ bool umi_merge_directional(dge_handle *h)
 // sequential loop of MergeStrategyBase.cpp:29-51 is order-free), refreshed sizes, final filter in compare_cells order and the two
 // matrices -- all from the device-resident CellRow / CellState tables.  Returns false (nothing modified) when a cell needs the
 // exact host logic: a far distance class, an order-dependent tie, a merge chain, counters beyond the packed sort key.
+// MergeUMIsStrategySimple::merge (Merge/UMIs/MergeUMIsStrategySimple.cpp:21-112): every UMI with N of a real cell goes to the N-free UMI of
+// its (cell, gene) at the smallest Hamming distance (N matches anything; ties: more reads, then the smaller UMI id) when that is within
+// max_umi_merge_edit_distance, else its N's are replaced by random bases (MergeUMIsStrategyAbstract.cpp:11-23: the process-wide rand(),
+// seeded with 42 by the strategy's constructor).  The segments that hold an N-UMI are found on the device; the decisions replay the
+// reference's own traversal on the host -- cells by id, genes by StringIndexer id, bad UMIs in the iteration order of an
+// unordered_set<string> filled in UMI-id order -- because that order decides which random numbers a UMI gets.  Returns true when U changed.
+bool umi_repair_n(dge_handle *h)
+{
+    if (!h->kl.ne || h->n_cg == 0 || h->n_u == 0) return false;
+    cudaStream_t st = h->stream;
+    const uint32_t n_cg = h->n_cg, n_pc = h->n_pc;
+    std::vector<uint32_t> pc_real(size_t(n_pc) + 2, 0), pc_to_real(size_t(n_pc) + 2, NONE32);
+    for (uint32_t i = 0; i < h->real.size(); ++i)
+    {
+        const HostCell &c = h->real[i];
+        if (c.pc == NONE32) continue;
+        pc_to_real[c.pc] = i;
+        if (c.real) pc_real[c.pc] = 1;
+    }
+    h->flags.reserve(pc_real.size() * 4);
+    DGE_CUDA(cudaMemcpyAsync(h->flags.p, pc_real.data(), pc_real.size() * 4, cudaMemcpyHostToDevice, st));
+    h->umi_lists.reserve(size_t(n_cg) * 4 + 64); h->umi_ctr.reserve(32);
+    DGE_CUDA(cudaMemsetAsync(h->umi_ctr.p, 0, 32, st));
+    uint32_t *list = h->umi_lists.as<uint32_t>();
+    k_seg_has_n<<<grid_for(n_cg, 256), 256, 0, st>>>(h->ukey.as<uint64_t>(), h->cg_start.as<uint32_t>(), h->cg_pc.as<uint32_t>(), n_cg, h->flags.as<uint32_t>(),
+                                                     h->kl.ub, list, h->umi_ctr.as<uint32_t>());
+    DGE_LAUNCH_CHECK();
+    ++h->launches;
+    const uint32_t n_seg = d2h_scalar<uint32_t>(h->umi_ctr.p, st);
+    if (!n_seg) return false;
+    // segment tables -> host
+    h->umi_seg.reserve(size_t(n_seg + 1) * 5 * 4);
+    uint32_t *seg_start = h->umi_seg.as<uint32_t>(), *seg_n = seg_start + (n_seg + 1), *seg_pc = seg_n + (n_seg + 1), *seg_off = seg_pc + (n_seg + 1),
+             *seg_gene = seg_off + (n_seg + 1);
+    k_umi_seg_meta<<<grid_for(n_seg, 256, 1u << 30), 256, 0, st>>>(list, n_seg, h->cg_start.as<uint32_t>(), h->cg_pc.as<uint32_t>(), seg_start, seg_n, seg_pc);
+    k_gather_u32<<<grid_for(n_seg, 256), 256, 0, st>>>(h->cg_gene.as<uint32_t>(), list, n_seg, seg_gene);
+    DGE_CUDA(cudaMemsetAsync(seg_n + n_seg, 0, 4, st));
+    device_exclusive_scan(seg_n, seg_off, size_t(n_seg) + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+    std::vector<uint32_t> hs_start, hs_off, hs_pc, hs_gene;
+    d2h(hs_start, seg_start, n_seg, st); d2h(hs_off, seg_off, size_t(n_seg) + 1, st); d2h(hs_pc, seg_pc, n_seg, st); d2h(hs_gene, seg_gene, n_seg, st);
+    DGE_CUDA(cudaStreamSynchronize(st));
+    const size_t flat = hs_off[n_seg];
+    h->umi_flat.reserve(std::max<size_t>(flat, 1) * 3 * 4);
+    uint32_t *f_umi = h->umi_flat.as<uint32_t>(), *f_val = f_umi + flat, *f_first = f_val + flat;
+    k_umi_seg_gather<<<std::min<uint32_t>(n_seg, 148 * 8), 128, 0, st>>>(seg_start, seg_off, n_seg, h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(),
+                                                                          h->umi_first.as<uint32_t>(), h->kl.ub, f_umi, f_val, f_first);
+    DGE_LAUNCH_CHECK();
+    h->launches += 3;
+    const uint32_t *hf = d2h_pinned<uint32_t>(h->pin_umi, f_umi, flat * 3, st);
+    DGE_CUDA(cudaStreamSynchronize(st));
+    // the reference's traversal order: cells by id (= index in `real`), genes by StringIndexer id (first-seen rank)
+    std::vector<uint32_t> gene_rank(h->cfg.n_genes, NONE32);
+    for (size_t r = 0; r < h->gene_order.size(); ++r) gene_rank[size_t(h->gene_order[r])] = uint32_t(r);
+    std::vector<uint32_t> order(n_seg);
+    std::iota(order.begin(), order.end(), 0u);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        const uint32_t ca = pc_to_real[hs_pc[a]], cb = pc_to_real[hs_pc[b]];
+        return ca != cb ? ca < cb : gene_rank[hs_gene[a]] < gene_rank[hs_gene[b]];
+    });
+    const unsigned max_ed = h->cfg.max_umi_merge_edit_distance;
+    const int gub = h->kl.gb + h->kl.ub;
+    std::vector<uint2> pairs;                // (source U index, existing target U index)
+    std::vector<uint32_t> kill;              // sources whose target is a new UMI
+    std::vector<uint64_t> new_keys;          // [slot | gene | new umi] << 3
+    std::vector<uint32_t> new_vals;
+    std::vector<uint32_t> dec_real;          // TOTAL_UMIS_PER_CB decrements (Cell.cpp:39), one per repaired UMI
+    struct Item { uint32_t umi, val, first, idx; std::string seq; };
+    std::vector<Item> items;
+    srand(42); // MergeUMIsStrategySimple::MergeUMIsStrategySimple (MergeUMIsStrategySimple.cpp:15-19)
+    for (uint32_t k : order)
+    {
+        const uint32_t off = hs_off[k], n = hs_off[k + 1] - off;
+        items.resize(n);
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            items[i] = Item{hf[off + i], hf[flat + off + i], hf[2 * flat + off + i], i, std::string()};
+            items[i].seq = umi_string(h, items[i].umi);
+        }
+        std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.first < b.first; }); // Gene::umis(): std::map over UMI ids
+        std::unordered_set<std::string> bad_umis; // s_hash_t
+        for (auto const &it : items) if (it.seq.find('N') != std::string::npos) bad_umis.insert(it.seq);
+        const uint32_t ridx = pc_to_real[hs_pc[k]];
+        const HostCell &cell = h->real[ridx];
+        for (auto const &bad : bad_umis)
+        {
+            unsigned min_ed = std::numeric_limits<unsigned>::max();
+            long best = -1, best_size = 0;
+            for (size_t t = 0; t < items.size(); ++t)
+            {
+                if (bad_umis.find(items[t].seq) != bad_umis.end()) continue;
+                const unsigned ed = hamming_distance_ref(items[t].seq, bad);
+                const long reads = long(items[t].val & VAL_COUNT_MASK);
+                if (ed < min_ed || (ed == min_ed && reads > best_size)) { min_ed = ed; best = long(t); best_size = reads; }
+            }
+            size_t src = 0;
+            while (items[src].seq != bad) ++src;
+            const uint32_t src_u = hs_start[k] + items[src].idx;
+            if (best < 0 || min_ed > max_ed)
+            {   // fix_n_umi_with_random
+                std::string fixed(bad);
+                for (char &c : fixed) if (c == 'N') c = "ACGT"[size_t(rand()) % 4];
+                uint64_t packed = 0;
+                pack_seq(fixed, packed);
+                kill.push_back(src_u);
+                new_keys.push_back(((((uint64_t(cell.slot) << h->kl.gb) | hs_gene[k]) << h->kl.ub) | packed) << 3);
+                new_vals.push_back(items[src].val);
+            }
+            else pairs.push_back(make_uint2(src_u, hs_start[k] + items[size_t(best)].idx));
+            dec_real.push_back(ridx);
+        }
+    }
+    (void)gub;
+    // apply: counts / marks into existing targets, sources removed, repaired UMIs that are new (or equal an existing one by chance) folded in
+    if (!pairs.empty())
+    {
+        h->umi_pairs.reserve(pairs.size() * sizeof(uint2));
+        DGE_CUDA(cudaMemcpyAsync(h->umi_pairs.p, pairs.data(), pairs.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+        for (int phase = 0; phase < 2; ++phase)
+            k_umi_apply_pairs<<<grid_for(pairs.size(), 256, 1u << 30), 256, 0, st>>>(h->umi_pairs.as<uint2>(), uint32_t(pairs.size()), h->uval.as<uint32_t>(), phase);
+    }
+    if (!kill.empty())
+    {
+        h->misc.reserve(kill.size() * 4);
+        DGE_CUDA(cudaMemcpyAsync(h->misc.p, kill.data(), kill.size() * 4, cudaMemcpyHostToDevice, st));
+        k_zero_list<<<grid_for(kill.size(), 256), 256, 0, st>>>(h->misc.as<uint32_t>(), uint32_t(kill.size()), h->uval.as<uint32_t>());
+    }
+    DGE_LAUNCH_CHECK();
+    DGE_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t r : dec_real) h->real[r].umis_stat -= 1;
+    h->n_umis_merged += dec_real.size();
+    h->keep.reserve(size_t(h->n_u + 1) * 4); h->keep_off.reserve(size_t(h->n_u + 1) * 4);
+    k_flag_live<<<grid_for(h->n_u, 256), 256, 0, st>>>(h->uval.as<uint32_t>(), h->n_u, h->keep.as<uint32_t>());
+    const uint32_t *n_live_ptr = device_exclusive_scan(h->keep.as<uint32_t>(), h->keep_off.as<uint32_t>(), h->n_u, h->scan_scratch.as<uint32_t>(), st, &h->launches);
+    const uint32_t n_live = d2h_scalar<uint32_t>(n_live_ptr, st);
+    h->ukey2.reserve(size_t(n_live + 1) * 8); h->uval2.reserve(size_t(n_live + 1) * 4);
+    k_compact_keep<<<grid_for(h->n_u, 256), 256, 0, st>>>(h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), h->n_u, h->keep.as<uint32_t>(), h->keep_off.as<uint32_t>(),
+                                                           h->ukey2.as<uint64_t>(), h->uval2.as<uint32_t>());
+    DGE_LAUNCH_CHECK();
+    h->launches += 2;
+    std::swap(h->ukey.p, h->ukey2.p); std::swap(h->ukey.bytes, h->ukey2.bytes);
+    std::swap(h->uval.p, h->uval2.p); std::swap(h->uval.bytes, h->uval2.bytes);
+    h->n_u = n_live;
+    build_segments(h);
+    if (!new_keys.empty())
+    {
+        build_slot_pc(h);
+        const uint64_t total = new_keys.size();
+        h->mkeys.reserve(total * 8); h->mvals.reserve(total * 4);
+        DGE_CUDA(cudaMemcpyAsync(h->mkeys.p, new_keys.data(), total * 8, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(cudaMemcpyAsync(h->mvals.p, new_vals.data(), total * 4, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(cudaStreamSynchronize(st));
+        apply_moved(h, total);
+    }
+    return true;
+}
+
 void merge_device_finish(dge_handle *h);
 
 bool merge_device_flow(dge_handle *h)
@@ -2110,10 +2298,16 @@ bool merge_device_flow(dge_handle *h)
     DevFlowCounters *ctr = h->df_ctr.as<DevFlowCounters>();
     DGE_CUDA(cudaMemsetAsync(ctr, 0, sizeof(DevFlowCounters), st));
     const unsigned g = grid_for(n, 256);
-    k_state_init<<<g, 256, 0, st>>>(rows, n32, cs);
+    k_state_init<<<g, 256, 0, st>>>(rows, n32, cs, h->kl.ne ? ctr : nullptr);
     ++h->launches;
     DevFlowCounters hc{};
     const bool real_merge = h->cfg.merge_type == DGE_MERGE_REAL;
+    if (h->kl.ne && !real_merge)
+    {   // barcodes containing N among the real cells: their place in compare_cells ties is a string order -> host flow
+        DGE_CUDA(cudaMemcpyAsync(&hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));
+        DGE_CUDA(cudaStreamSynchronize(st));
+        if (hc.n_todo) return false;
+    }
     if (real_merge)
     {
         p1_device_pass(h, n);
@@ -2211,7 +2405,12 @@ void do_merge_and_filter(dge_handle *h)
 
     // ---- device flow: no host cell rows at all (the common configurations); anything it cannot decide exactly -> host flow
     static const bool no_dev_flow = std::getenv("DGE_HOST_FLOW") != nullptr;
-    const bool dev_flow = !no_dev_flow && h->lazy_rows && !h->cfg.sharded && !h->dist_done && h->n_real_rows > 0 &&
+    if (h->counters.n_flagged)
+    {
+        if (h->cfg.sharded) throw std::runtime_error("barcodes / UMIs with N are not supported on sharded (multi-GPU) handles yet");
+        if (h->cfg.umi_merge_type == DGE_UMI_MERGE_DIRECTIONAL) throw std::runtime_error("UMIs / barcodes with N are not supported with the directional UMI merge (-u) yet");
+    }
+    const bool dev_flow = !no_dev_flow && h->lazy_rows && !h->cfg.sharded && !h->dist_done && h->n_real_rows > 0 && !h->counters.n_flagged &&
                           (h->cfg.merge_type == DGE_MERGE_NONE || (h->cfg.merge_type == DGE_MERGE_REAL && h->wl_fast)) &&
                           h->cfg.umi_merge_type == DGE_UMI_MERGE_SIMPLE && h->cfg.min_genes_before_merge > 0;
     // sharded run: phase 1/2 ran across ranks in dge_dist_step; with a UMI merge strategy that changes U (-u) the host tail below
@@ -2242,6 +2441,13 @@ void do_merge_and_filter(dge_handle *h)
     }
     if (dev_flow) ++h->n_host_fallback;
     materialize_host(h);
+
+    if (h->kl.ne && (h->cfg.merge_type == DGE_MERGE_SIMPLE || h->cfg.merge_type == DGE_MERGE_ALL || h->cfg.merge_type == DGE_MERGE_POISSON_SIMPLE))
+    {   // these strategies compare barcodes on the device (2-bit Levenshtein): a REAL cell whose barcode contains N has no packed form
+        for (auto const &c : h->real)
+            if (c.cb & CB_N_BIT)
+                throw std::runtime_error("a real cell's barcode contains N: not supported by the no-whitelist merge strategies yet (" + cb_string(h, c.cb) + ")");
+    }
 
     // ---- CB merge (MergeStrategyAbstract::merge, MergeStrategyAbstract.cpp:13-23)
     if (after_dist) {}
@@ -2341,6 +2547,18 @@ void do_merge_and_filter(dge_handle *h)
         tr.mark("umi merge: directional");
     }
     else if (h->cfg.umi_merge_type != DGE_UMI_MERGE_SIMPLE) throw std::runtime_error("unknown umi_merge_type");
+    else if (h->kl.ne && h->counters.n_flagged)
+    {   // MergeUMIsStrategySimple: UMIs with N of the real cells
+        h->n_umis_merged = 0;
+        if (umi_repair_n(h))
+        {
+            std::vector<uint32_t> owners;
+            for (uint32_t i = 0; i < h->real.size(); ++i)
+                if (h->real[i].real && h->real[i].pc != NONE32) owners.push_back(i);
+            refresh_rows(owners);
+        }
+        tr.mark("umi merge: N repair");
+    }
 
     update_filtered(h, h->min_after_eff, h->cfg.max_cells);
     tr.mark("finish: sizes + filter");
@@ -2474,7 +2692,7 @@ std::vector<long> dist_exact_neighbours(const dge_handle *h, const DistHostView 
         return it == v.by_cb.end() ? -1 : long(it->second);
     };
     auto eligible = [&](long gi) { return h->hx_all[size_t(gi)].umis >= child.n_umis; };
-    return h->wl.neighbours(unpack_seq(child.cb, h->cfg.cb_len), false, lookup, eligible);
+    return h->wl.neighbours(cb_string(h, child.cb), false, lookup, eligible);
 }
 
 void dist_fetch_host_tables(dge_handle *h)
@@ -2564,6 +2782,20 @@ int dge_set_stream(dge_handle *h, void *cuda_stream)
         if (h->own_stream) cudaStreamDestroy(h->stream);
         h->stream = static_cast<cudaStream_t>(cuda_stream);
         h->own_stream = false;
+        return int(DGE_OK);
+    });
+}
+
+int dge_set_n_strings(dge_handle *h, int which, const char *strings, size_t n)
+{
+    if (!h || (n && !strings) || (which != 0 && which != 1)) return fail(h, DGE_ERR_INVALID, "bad argument");
+    if (!h->cfg.allow_n) return fail(h, DGE_ERR_STATE, "dge_set_n_strings needs dge_config.allow_n = 1");
+    return guarded(h, [&] {
+        const size_t len = which == 0 ? h->cfg.umi_len : h->cfg.cb_len;
+        std::string &dst = which == 0 ? h->n_umi_strings : h->n_cb_strings;
+        dst.assign(strings ? strings : "", n * len);
+        for (char c : dst)
+            if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') throw InvalidInput("N-string lists hold A, C, G, T, N only");
         return int(DGE_OK);
     });
 }
@@ -2696,6 +2928,7 @@ extern "C" int dge_dist_step(dge_handle *h, dge_dist_io *io)
         if (h->dist_stage == 0)
         {   // ---- self cells -> all-gather
             if (n && !h->lazy_rows) throw std::runtime_error("cross-rank merge needs the device-resident cell rows (min_genes_before_merge > 0)");
+            if (h->counters.n_flagged) throw std::runtime_error("barcodes / UMIs with N are not supported on sharded (multi-GPU) handles yet");
             DGE_CUDA(cudaEventRecord(h->ev[3], st));
             h->dist_world = world; h->dist_rank = me;
             if (!h->wl_uploaded) { upload_whitelist(h); h->wl_uploaded = true; }
@@ -2708,7 +2941,7 @@ extern "C" int dge_dist_step(dge_handle *h, dge_dist_io *io)
             h->n_self = 0;
             if (n)
             {
-                k_state_init<<<g, 256, 0, st>>>(rows, n32, h->cell_state.as<CellState>());
+                k_state_init<<<g, 256, 0, st>>>(rows, n32, h->cell_state.as<CellState>(), nullptr);
                 k_wl_self<<<unsigned(div_up(n * 32, size_t(256))), 256, 0, st>>>(rows, n32, h->wl_dev, h->x_self_flag.as<uint32_t>());
                 k_self_is_one<<<g, 256, 0, st>>>(h->x_self_flag.as<uint32_t>(), n32, h->x_self_one.as<uint32_t>());
                 DGE_CUDA(cudaMemsetAsync(h->x_self_one.as<uint32_t>() + n, 0, 4, st));
@@ -3273,7 +3506,11 @@ int dge_get_umigs(dge_handle *h, int which, uint32_t *cell_index, int32_t *gene_
             {
                 if (cell_index) cell_index[k] = uint32_t(ci);
                 if (gene_ids) gene_ids[k] = int32_t(h->kl.gene_of_ukey(uk[i]));
-                if (umis) umis[k] = h->kl.umi_of_ukey(uk[i]);
+                if (umis)
+                {
+                    const uint32_t u = h->kl.umi_of_ukey(uk[i]);
+                    umis[k] = umi_is_n(h, u) ? (0x80000000u | (u & ((1u << (h->kl.ub - 1)) - 1))) : u; // DGE_UMI_N_BIT | index into the N-UMI list
+                }
                 if (read_counts) read_counts[k] = uv[i] & VAL_COUNT_MASK;
                 if (marks) marks[k] = uint8_t(uv[i] >> VAL_MARK_SHIFT);
             }

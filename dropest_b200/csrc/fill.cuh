@@ -22,6 +22,7 @@ struct FillCounters
     unsigned long long has_not_annotated;
     int table_overflow;
     int bad_gene;
+    unsigned long long n_flagged; // reads carrying DGE_FLAG_UMI_N / DGE_FLAG_CB_N
     int bad_record; // key bits beyond the configured barcode / UMI lengths, reserved gene-word bits, or read_idx == 0xFFFFFFFF
 };
 
@@ -37,6 +38,27 @@ __global__ void k_table_init(CellSlot *tab, size_t cap)
 __global__ void k_fill_u32(uint32_t *p, size_t n, uint32_t v)
 {
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = v;
+}
+
+// Validates the barcode / UMI fields of a record against the configured lengths and turns N-list indices (DGE_FLAG_UMI_N / DGE_FLAG_CB_N)
+// into their internal form: UMI -> [1 : index] inside the ub-bit field, barcode -> CB_N_BIT | index.  false = malformed record.
+__device__ __forceinline__ bool decode_n_flags(const KeyLayout &kl, uint32_t gene_word, uint64_t &cb, uint32_t &umi)
+{
+    if (gene_word >> 29) return false;
+    if (gene_word & (FLAG_UMI_N | FLAG_CB_N))
+    {
+        if (!kl.ne) return false;
+        if (gene_word & FLAG_UMI_N)
+        {
+            if (umi >> (kl.ub - 1)) return false;
+            umi |= 1u << (kl.ub - 1);
+        }
+        else if (umi >> kl.ul) return false;
+        if (gene_word & FLAG_CB_N) cb |= CB_N_BIT; // 40 index bits: any value fits
+        else if (cb >> kl.cbb) return false;
+        return true;
+    }
+    return (cb >> kl.cbb) == 0 && (umi >> kl.ul) == 0;
 }
 
 // Insert-or-find; returns the slot index (= internal cell id) or NONE32 when the table is full.
@@ -140,12 +162,13 @@ __global__ void __launch_bounds__(FILL_THREADS, MINB) k_fill_compact(const Rec16
             keys[j] = EMPTY64;
             if (i >= n) continue;
             const uint64_t k = (uint64_t(raw[j].y) << 32) | raw[j].x;
-            const uint64_t cb = k >> 24;
-            const uint32_t umi = uint32_t(k) & 0xFFFFFFu;
+            uint64_t cb = k >> 24;
+            uint32_t umi = uint32_t(k) & 0xFFFFFFu;
             const uint32_t gene = raw[j].z & 0xFFFFFFu;
             const uint32_t mark = (raw[j].z >> 24) & 7u;
             const uint32_t idx = raw[j].w;
-            if ((cb >> kl.cbb) != 0 || (umi >> kl.ub) != 0 || (raw[j].z >> 27) != 0 || idx == NONE32) { ctr->bad_record = 1; continue; }
+            if (!decode_n_flags(kl, raw[j].z, cb, umi) || idx == NONE32) { ctr->bad_record = 1; continue; }
+                if (raw[j].z & (FLAG_UMI_N | FLAG_CB_N)) atomicAdd(&ctr->n_flagged, 1ull);
             uint32_t slot = slot0[j];
             uint32_t seen_first = probe[j].z;
             if (((uint64_t(probe[j].y) << 32) | probe[j].x) != cb)
@@ -360,12 +383,13 @@ __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
                 keys[j] = EMPTY64;
                 if (i >= cnt) continue;
                 const uint64_t kk = (uint64_t(raw[j].y) << 32) | raw[j].x;
-                const uint64_t cb = kk >> 24;
-                const uint32_t umi = uint32_t(kk) & 0xFFFFFFu;
+                uint64_t cb = kk >> 24;
+                uint32_t umi = uint32_t(kk) & 0xFFFFFFu;
                 const uint32_t gene = raw[j].z & 0xFFFFFFu;
                 const uint32_t mark = (raw[j].z >> 24) & 7u;
                 const uint32_t idx = raw[j].w;
-                if ((cb >> kl.cbb) != 0 || (umi >> kl.ub) != 0 || (raw[j].z >> 27) != 0 || idx == NONE32) { ctr->bad_record = 1; continue; }
+                if (!decode_n_flags(kl, raw[j].z, cb, umi) || idx == NONE32) { ctr->bad_record = 1; continue; }
+                if (raw[j].z & (FLAG_UMI_N | FLAG_CB_N)) atomicAdd(&ctr->n_flagged, 1ull);
                 uint32_t slot = slot0[j];
                 uint32_t seen_first = probe[j].z;
                 if (((uint64_t(probe[j].y) << 32) | probe[j].x) != cb)

@@ -45,6 +45,11 @@ __global__ void __launch_bounds__(256) k_wl_class01(const uint64_t *__restrict__
     if (cell >= n_cells) return;
     const uint64_t cb = cell_cb[cell];
     const uint32_t base_umis = cell_umis[cell];
+    if (cb & CB_N_BIT)
+    {   // a barcode containing N (an index into the caller's list): the exact enumeration with N wildcards runs on the host
+        if (lane == 0) nb_count[cell] = NB_SLOW;
+        return;
+    }
 
     // per part: count of exact tokens, and up to 32 distance-1 tokens kept as a per-lane register (one per lane) + overflow flag
     int n_exact_parts = 0;
@@ -642,11 +647,12 @@ struct DevFlowCounters
     uint32_t n_todo, n_chain, n_merged, n_excluded, n_real, n_filtered, key_overflow, pad;
 };
 
-__global__ void k_state_init(const CellRow *__restrict__ rows, uint32_t n, CellState *__restrict__ st)
+__global__ void k_state_init(const CellRow *__restrict__ rows, uint32_t n, CellState *__restrict__ st, DevFlowCounters *__restrict__ count_n_barcodes)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         const CellRow r = rows[i];
+        if (count_n_barcodes && (r.cb & CB_N_BIT)) atomicAdd(&count_n_barcodes->n_todo, 1u);
         CellState s;
         s.umis_stat = int32_t(r.n_umis); s.reads_stat = int32_t(r.n_reads); s.n_intergenic = r.n_intergenic;
         s.target = int32_t(i); s.flags = 1u; s.is_target = 0;

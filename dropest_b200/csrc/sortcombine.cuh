@@ -1093,7 +1093,11 @@ public:
                 // ALU instructions among the proven ones; the sort is ALU-pipe bound), 2 = 1 + sentinel slot instead of a predicated load
                 static const int mv = std::getenv("DGE_MS_VARIANT") ? atoi(std::getenv("DGE_MS_VARIANT")) : 1;
                 if (cw) k_sort_dedup_warp<4, 16><<<grid(128, 6), 128, 0, st>>>(keys_tmp, uv, sub_off, cl, cc, ucount);
-                static const bool ms_bulk = !(std::getenv("DGE_MS_BULK") && atoi(std::getenv("DGE_MS_BULK")) == 0); // bulk-async staging + prefetch of the next item
+                // bulk-async staging of the sub-bucket + prefetch of the next work item (k_sort_dedup<.., BULK = true>): measured on B200 at C2
+                // 6.74 ms against 6.53 ms for the plain coalesced loads (profiles/r2_sort_dedup_bulk_ab.txt) -- with 12 resident blocks per SM the
+                // load latency is already hidden and the kernel is ALU-bound, so the extra barrier and shared memory cost more than the
+                // saved LDG/STS issue slots.  Kept selectable (DGE_MS_BULK=1), off by default.
+                static const bool ms_bulk = std::getenv("DGE_MS_BULK") && atoi(std::getenv("DGE_MS_BULK")) == 1;
 #define DGE_MS_NB(T, I, V, C, DFLT) k_sort_dedup<T, I, V, false><<<grid(T, DFLT), T, 0, st>>>(keys_tmp, uv, sub_off, cl + (C + 1) * ls, cc + (C + 1), ucount)
 #define DGE_MS(T, I, V, C, DFLT)                                                                                                        \
                 if (ms_bulk) k_sort_dedup<T, I, V, true><<<grid(T, DFLT), T, 0, st>>>(keys_tmp, uv, sub_off, cl + (C + 1) * ls, cc + (C + 1), ucount); \

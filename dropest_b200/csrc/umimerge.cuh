@@ -265,6 +265,29 @@ __global__ void k_umi_apply_pairs(const uint2 *__restrict__ pairs, uint32_t n, u
     else uval[pr.x] = 0;
 }
 
+// (cell, gene) segments of real cells that hold a UMI with N: inside a segment U is sorted by the UMI field and N-UMIs carry its top
+// bit, so the segment's last entry tells
+__global__ void k_seg_has_n(const uint64_t *__restrict__ ukey, const uint32_t *__restrict__ cg_start, const uint32_t *__restrict__ cg_pc, uint32_t n_cg,
+                            const uint32_t *__restrict__ pc_real, int ub, uint32_t *__restrict__ list, uint32_t *__restrict__ count)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cg; i += gridDim.x * blockDim.x)
+    {
+        if (!pc_real[cg_pc[i]]) continue;
+        const uint32_t e = cg_start[i + 1];
+        if (e > cg_start[i] && ((ukey[e - 1] >> (ub - 1)) & 1ull)) list[atomicAdd(count, 1u)] = i;
+    }
+}
+
+__global__ void k_gather_u32(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t n, uint32_t *__restrict__ dst)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+
+__global__ void k_zero_list(const uint32_t *__restrict__ idx, uint32_t n, uint32_t *__restrict__ uval)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) uval[idx[i]] = 0;
+}
+
 __global__ void k_flag_live(const uint32_t *__restrict__ uval, uint32_t n, uint32_t *__restrict__ keep)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) keep[i] = uval[i] != 0;

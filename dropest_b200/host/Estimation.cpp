@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstring>
 #include <fstream>
+#include <iostream>
 #include <sstream>
 
 #include <zlib.h>
@@ -252,19 +253,60 @@ namespace Estimation
 		for (auto const &m : _query_marks) cfg.query_mark_mask |= 1u << m.bits();
 		_merge_strategy->configure(cfg);
 		_umi_merge_strategy->configure(cfg);
+		// Barcodes / UMIs containing N travel as indices into _n_cbs / _n_umis (DGE_FLAG_CB_N / DGE_FLAG_UMI_N).  That costs the grouping key
+		// one more UMI bit; when it would leave fewer than 2^22 barcode slots (12-base UMIs with a gene space > 2^14) N reads are skipped
+		// and counted instead (skipped_n_reads()) -- pass a tighter n_genes_hint to keep them.
+		{
+			unsigned gb = 1;
+			while ((size_t(1) << gb) < size_t(cfg.n_genes)) ++gb;
+			const unsigned ub_n = std::max(2 * cfg.umi_len, 20u) + 1;
+			_allow_n = 61 >= gb + ub_n + 22;
+		}
+		cfg.allow_n = _allow_n ? 1 : 0;
 		int rc = dge_create(&cfg, &_h);
 		if (rc != DGE_OK) throw std::runtime_error(std::string("dropest_b200: ") + dge_last_error(nullptr));
 		_batch_capacity = size_t(1) << 20;
 		_batch_keys.reserve(_batch_capacity); _batch_genes.reserve(_batch_capacity);
 	}
 
+	void CellsDataContainer::upload_n_strings()
+	{
+		if (!_n_dirty || !_h) return;
+		std::string blob;
+		for (auto const &v : _n_umis.values()) blob += v;
+		check(dge_set_n_strings(_h, 0, blob.c_str(), _n_umis.values().size()));
+		blob.clear();
+		for (auto const &v : _n_cbs.values()) blob += v;
+		check(dge_set_n_strings(_h, 1, blob.c_str(), _n_cbs.values().size()));
+		_n_dirty = false;
+	}
+
+	std::string CellsDataContainer::barcode_string(uint64_t packed) const
+	{
+		return (packed & DGE_CB_N_BIT) ? _n_cbs.get_value(size_t(packed & (DGE_CB_N_BIT - 1))) : unpack2bit(packed, _cb_len);
+	}
+
+	std::string CellsDataContainer::umi_string(uint32_t packed) const
+	{
+		return (packed & DGE_UMI_N_BIT) ? _n_umis.get_value(size_t(packed & ~DGE_UMI_N_BIT)) : unpack2bit(packed, _umi_len);
+	}
+
 	void CellsDataContainer::flush()
 	{
 		if (_batch_keys.empty()) return;
-		// add_record is called in stream order, so the read index is implicit: 12 bytes per read go to the device
-		check(dge_add_batch_soa(_h, _batch_keys.data(), _batch_genes.data(), _batch_keys.size(), _batch_first));
-		_batch_first += _batch_keys.size();
-		_batch_keys.clear(); _batch_genes.clear();
+		if (!_batch_gaps)
+		{   // add_record is called in stream order, so the read index is implicit: 12 bytes per read go to the device
+			check(dge_add_batch_soa(_h, _batch_keys.data(), _batch_genes.data(), _batch_keys.size(), _batch_first));
+		}
+		else
+		{   // skipped reads left gaps in the numbering: 16-byte records with explicit stream positions
+			std::vector<dge_record16> recs(_batch_keys.size());
+			for (size_t i = 0; i < recs.size(); ++i) recs[i] = dge_record16{_batch_keys[i], _batch_genes[i], _batch_idx[i]};
+			check(dge_add_batch(_h, recs.data(), recs.size()));
+		}
+		_batch_first = _n_records;
+		_batch_gaps = false;
+		_batch_keys.clear(); _batch_genes.clear(); _batch_idx.clear();
 	}
 
 	void CellsDataContainer::add_record(const ReadInfo &read_info)
@@ -279,13 +321,34 @@ namespace Estimation
 		}
 		if (cb.size() != _cb_len || umi.size() != _umi_len)
 			throw std::runtime_error("the device path needs constant barcode and UMI lengths");
+		// N-free sequences are 2-bit packed; a sequence with N is passed as its index in the container's N-string list (the reference keeps
+		// such reads: the barcode is a cell of its own, the UMI is repaired by MergeUMIsStrategySimple after the barcode merge)
 		uint64_t cbv, umiv;
-		if (!pack2bit(cb, cbv) || !pack2bit(umi, umiv))
-			throw std::runtime_error("barcodes / UMIs containing N are not supported on the device path yet: " + cb + " " + umi);
+		uint32_t flags = 0;
+		if (!_allow_n && (cb.find('N') != std::string::npos || umi.find('N') != std::string::npos))
+		{
+			if (_skipped_n_reads++ == 0)
+				std::cerr << "dropest_b200: reads whose barcode / UMI contains N are skipped (no room for the N flag in the grouping key: lower n_genes_hint)\n";
+			++_n_records;   // the skipped read keeps its position in the stream: the pending batch now has a gap (flush sends explicit read indices)
+			_batch_gaps = true;
+			return;
+		}
+		if (!pack2bit(cb, cbv))
+		{
+			if (cb.find_first_not_of("ACGTN") != std::string::npos) throw std::runtime_error("unexpected character in the cell barcode: " + cb);
+			cbv = _n_cbs.add(cb); flags |= DGE_FLAG_CB_N; _n_dirty = true;
+		}
+		if (!pack2bit(umi, umiv))
+		{
+			if (umi.find_first_not_of("ACGTN") != std::string::npos) throw std::runtime_error("unexpected character in the UMI: " + umi);
+			umiv = _n_umis.add(umi); flags |= DGE_FLAG_UMI_N; _n_dirty = true;
+			if (umiv >> (std::max(2 * _umi_len, 20u))) throw std::runtime_error("too many distinct UMIs containing N");
+		}
 		uint32_t gene = DGE_NO_GENE;
 		if (!read_info.gene.empty()) gene = uint32_t(_gene_indexer.add(read_info.gene));
 		_batch_keys.push_back((cbv << 24) | umiv);
-		_batch_genes.push_back(gene | (uint32_t(read_info.umi_mark.bits()) << 24));
+		_batch_genes.push_back(gene | (uint32_t(read_info.umi_mark.bits()) << 24) | flags);
+		_batch_idx.push_back(uint32_t(_n_records));
 		++_n_records;
 		if (_batch_keys.size() >= _batch_capacity) flush();
 	}
@@ -295,6 +358,7 @@ namespace Estimation
 		if (_is_initialized) throw std::runtime_error("Container is already initialized");
 		ensure_handle();
 		flush();
+		upload_n_strings();
 		check(dge_set_initialized(_h));
 		_is_initialized = true;
 		_cells_loaded = _genes_loaded = false;
@@ -322,7 +386,7 @@ namespace Estimation
 		for (size_t i = 0; i < n; ++i)
 		{
 			Cell &c = _cells[i];
-			c._barcode = unpack2bit(info[i].barcode, _cb_len);
+			c._barcode = barcode_string(info[i].barcode);
 			c._is_real = info[i].flags & DGE_CELL_REAL; c._is_merged = info[i].flags & DGE_CELL_MERGED; c._is_excluded = info[i].flags & DGE_CELL_EXCLUDED;
 			c._n_genes = size_t(info[i].n_genes);
 			c._requested_genes_num = size_t(info[i].requested_genes_num); c._requested_umis_num = size_t(info[i].requested_umis_num);
@@ -336,7 +400,7 @@ namespace Estimation
 		std::vector<dge_cell_info> finfo(nf);
 		if (nf) check(dge_get_cells(_h, DGE_CELLS_FILTERED, finfo.data(), nf, &nf));
 		_filtered_cells.resize(nf);
-		for (size_t k = 0; k < nf; ++k) _filtered_cells[k] = _cell_ids_by_cb.at(unpack2bit(finfo[k].barcode, _cb_len));
+		for (size_t k = 0; k < nf; ++k) _filtered_cells[k] = _cell_ids_by_cb.at(barcode_string(finfo[k].barcode));
 		check(dge_get_summary(_h, &_summary));
 		_cells_loaded = true;
 		_genes_loaded = false;
@@ -361,7 +425,7 @@ namespace Estimation
 			if (mark[k] & 1) m.add(UMI::Mark::HAS_NOT_ANNOTATED);
 			if (mark[k] & 2) m.add(UMI::Mark::HAS_EXONS);
 			if (mark[k] & 4) m.add(UMI::Mark::HAS_INTRONS);
-			git->second._umis.emplace(_umi_indexer.add(unpack2bit(umi[k], _umi_len)), UMI(reads[k], m));
+			git->second._umis.emplace(_umi_indexer.add(umi_string(umi[k])), UMI(reads[k], m));
 		}
 		_genes_loaded = true;
 	}
@@ -403,7 +467,7 @@ namespace Estimation
 		dge_get_cells(h, cls, nullptr, 0, &n_cells);
 		std::vector<dge_cell_info> info(n_cells);
 		if (n_cells) dge_get_cells(h, cls, info.data(), n_cells, &n_cells);
-		for (auto const &ci : info) m.col_names.push_back(unpack2bit(ci.barcode, container.cb_length()));
+		for (auto const &ci : info) m.col_names.push_back(container.barcode_string(ci.barcode));
 
 		// Row numbering = first time a gene name is met while walking columns (ResultsPrinter.cpp:345-356 / :379-388).  For the
 		// filtered matrix the reference walks, per column, a std::unordered_map<std::string,size_t> built in gene-index order

@@ -453,6 +453,12 @@ namespace Estimation
 		unsigned _cb_len = 0, _umi_len = 0;
 		std::vector<uint64_t> _batch_keys;  // pending records as two arrays (dge_add_batch_soa), flushed in blocks of _batch_capacity
 		std::vector<uint32_t> _batch_genes;
+		std::vector<uint32_t> _batch_idx;   // stream positions of the pending records (used when skipped reads left gaps)
+		bool _batch_gaps = false;
+		StringIndexer _n_umis, _n_cbs;      // UMIs / barcodes containing N, passed to the device as indices (DGE_FLAG_UMI_N / DGE_FLAG_CB_N)
+		bool _n_dirty = false, _allow_n = false;
+		uint64_t _skipped_n_reads = 0;
+		void upload_n_strings();
 		uint64_t _batch_first = 0;          // stream position of the first pending record
 		size_t _batch_capacity;
 		uint64_t _n_records = 0;
@@ -508,6 +514,9 @@ namespace Estimation
 		dge_handle *handle() const { return _h; }
 		bool reads_output() const { return _reads_output; }
 		unsigned cb_length() const { return _cb_len; }
+		uint64_t skipped_n_reads() const { return _skipped_n_reads; } // reads dropped because the key had no room for the N flag (see ensure_handle)
+		std::string barcode_string(uint64_t packed) const; // 2-bit unpacked, or the N-string behind DGE_CB_N_BIT | index
+		std::string umi_string(uint32_t packed) const;
 	};
 
 	// ResultsPrinter (ResultsPrinter.cpp:23-91,334-453): count matrices -> MatrixMarket + cells/genes tsv and an R-readable .rds

@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from .capi import NO_GENE, RECORD_DTYPE, _SynthParams, load_library, pack_seq
+from .capi import CB_N_BIT, FLAG_CB_N, FLAG_UMI_N, NO_GENE, RECORD_DTYPE, UMI_N_BIT, _SynthParams, load_library, pack_seq, unpack_seq
 
 U64 = np.uint64
 _M64 = (1 << 64) - 1
@@ -208,16 +208,75 @@ def product_whitelist(path: str, n1: int = 2048, n2: int = 3328, seed: int = 11,
         f.write(" ".join(part(len2, n2)) + "\n")
 
 
-def write_packed(path: str, recs: np.ndarray, cb_len: int, umi_len: int, n_genes: int, gene_names: Optional[Sequence[str]] = None):
-    """DGER0001 stream for the oracle drivers (oracle/common/dge_io.h)."""
+def write_packed(path: str, recs: np.ndarray, cb_len: int, umi_len: int, n_genes: int, gene_names: Optional[Sequence[str]] = None,
+                 n_lists: Optional["NLists"] = None):
+    """DGER0001 stream for the oracle drivers (oracle/common/dge_io.h); DGER0002 (+ the two N-string lists) when `n_lists` is given."""
     blob = ("\n".join(gene_names)).encode() if gene_names else b""
     with open(path, "wb") as f:
-        f.write(b"DGER0001")
+        f.write(b"DGER0002" if n_lists is not None else b"DGER0001")
         f.write(np.array([recs.shape[0]], dtype="<u8").tobytes())
         f.write(np.array([cb_len, umi_len, n_genes, 0], dtype="<u4").tobytes())
         f.write(np.array([len(blob)], dtype="<u8").tobytes())
         f.write(blob)
+        if n_lists is not None:
+            for lst in (n_lists.umis, n_lists.cbs):
+                b = ("\n".join(lst)).encode()
+                f.write(np.array([len(b)], dtype="<u8").tobytes())
+                f.write(b)
         f.write(np.ascontiguousarray(recs, dtype=RECORD_DTYPE).tobytes())
+
+
+class NLists:
+    """The caller-side lists behind DGE_FLAG_UMI_N / DGE_FLAG_CB_N record indices: equal strings get equal indices."""
+
+    def __init__(self):
+        self.umis, self.cbs = [], []
+        self._u, self._c = {}, {}
+
+    def umi_index(self, s: str) -> int:
+        if s not in self._u:
+            self._u[s] = len(self.umis)
+            self.umis.append(s)
+        return self._u[s]
+
+    def cb_index(self, s: str) -> int:
+        if s not in self._c:
+            self._c[s] = len(self.cbs)
+            self.cbs.append(s)
+        return self._c[s]
+
+    def pack_cb(self, s: str) -> int:
+        """barcode string -> what dge_cell_info.barcode reports"""
+        return (CB_N_BIT | self._c[s]) if "N" in s else pack_seq(s)
+
+    def pack_umi(self, s: str) -> int:
+        """UMI string -> what dge_get_umigs reports"""
+        return (UMI_N_BIT | self._u[s]) if "N" in s else pack_seq(s)
+
+
+def inject_n(recs: np.ndarray, cb_len: int, umi_len: int, umi_ppm: int, cb_ppm: int, seed: int = 1) -> "tuple[np.ndarray, NLists]":
+    """Replaces, in a random subset of reads, one or two UMI bases (umi_ppm) / one barcode base (cb_ppm) by N and re-encodes those reads as
+    indices into the returned N-string lists (DGE_FLAG_UMI_N / DGE_FLAG_CB_N)."""
+    rng = np.random.default_rng(seed)
+    out = recs.copy()
+    lists = NLists()
+    n = recs.shape[0]
+    pick_u = np.flatnonzero(rng.integers(0, 1_000_000, n) < umi_ppm)
+    pick_c = np.flatnonzero(rng.integers(0, 1_000_000, n) < cb_ppm)
+    for i in pick_u:
+        u = list(unpack_seq(int(recs["key"][i]) & 0xFFFFFF, umi_len))
+        for p in rng.choice(umi_len, size=int(rng.integers(1, 3)), replace=False):
+            u[int(p)] = "N"
+        idx = lists.umi_index("".join(u))
+        out["key"][i] = (int(out["key"][i]) & ~0xFFFFFF) | idx
+        out["gene"][i] = int(out["gene"][i]) | FLAG_UMI_N
+    for i in pick_c:
+        c = list(unpack_seq(int(recs["key"][i]) >> 24, cb_len))
+        c[int(rng.integers(0, cb_len))] = "N"
+        idx = lists.cb_index("".join(c))
+        out["key"][i] = (idx << 24) | (int(out["key"][i]) & 0xFFFFFF)
+        out["gene"][i] = int(out["gene"][i]) | FLAG_CB_N
+    return out, lists
 
 
 def records_from_strings(reads, gene_ids: dict, first_idx: int = 0) -> np.ndarray:

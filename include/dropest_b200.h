@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define DGE_ABI_VERSION 1
+#define DGE_ABI_VERSION 2
 
 /* ---- the per-read record --------------------------------------------------------------------------------------------
  * Replaces Estimation::ReadInfo (reference Estimation/ReadInfo.h:9-24) + Tools::ReadParameters (Tools/ReadParameters.h:9-50)
@@ -28,7 +28,12 @@ extern "C" {
  *            bits[23:0]  UMI, same coding (<= 12 bp)
  *   gene     bits[23:0]  gene id in [0, n_genes) or DGE_NO_GENE (read has no gene: "intergenic", CellsDataContainer.cpp:73-78)
  *            bits[26:24] UMI::Mark bits of the read (reference Estimation/UMI.h:16-22): 1 not-annotated, 2 exon, 4 intron
- *            bits[31:27] reserved, must be 0
+ *            bit 27      DGE_FLAG_UMI_N: the UMI contains 'N'; key bits[23:0] hold the index of the UMI string in the caller's N-UMI list
+ *            bit 28      DGE_FLAG_CB_N : the barcode contains 'N'; key bits[63:24] hold the index of the barcode string in the N-barcode list
+ *                        (both need dge_config.allow_n = 1 and the lists passed with dge_set_n_strings; equal strings = equal indices.
+ *                        The reference keeps such reads as barcodes / UMIs of their own and repairs N-UMIs of real cells in
+ *                        MergeUMIsStrategySimple, Merge/UMIs/MergeUMIsStrategySimple.cpp:21-112)
+ *            bits[31:29] reserved, must be 0
  *   read_idx global 0-based position of the read in the input stream.  First-seen order of barcodes and genes
  *            (cell ids, StringIndexer ids) is derived from it, so records may be passed in ANY order / any batching.
  */
@@ -42,6 +47,11 @@ typedef struct dge_record16 {
 #define DGE_MARK_NOT_ANNOTATED 1u
 #define DGE_MARK_EXON 2u
 #define DGE_MARK_INTRON 4u
+#define DGE_FLAG_UMI_N (1u << 27)
+#define DGE_FLAG_CB_N (1u << 28)
+/* how the query surface reports them: dge_cell_info.barcode = DGE_CB_N_BIT | index, dge_get_umigs umis[] = DGE_UMI_N_BIT | index */
+#define DGE_CB_N_BIT (1ull << 40)
+#define DGE_UMI_N_BIT (1u << 31)
 
 /* status codes */
 enum {
@@ -94,6 +104,9 @@ typedef struct dge_config {
                                    ranks with dge_dist_step (exact) before dge_merge_and_filter; 0 = the handle sees every barcode */
     const char *barcodes_file;  /* whitelist in the reference's own file format (BarcodesParser.cpp:117-144); NULL/"" = none */
     uint64_t max_barcodes_hint; /* upper bound on distinct barcodes, 0 = automatic */
+    uint32_t allow_n;           /* 1 = records may carry DGE_FLAG_UMI_N / DGE_FLAG_CB_N.  The grouping key then spends one more bit on the UMI field
+                                   (and at least 21): with 12-base UMIs and > 16 k genes the barcode table halves (2^21 slots) */
+    uint32_t reserved0;
 } dge_config;
 
 typedef struct dge_handle dge_handle;
@@ -194,6 +207,11 @@ int dge_merge_and_filter(dge_handle *h);
 /* Forget all reads and results but keep the configuration and every device workspace, so that the next run of the
  * same size allocates nothing (the reference equivalent is constructing a fresh CellsDataContainer). */
 int dge_reset(dge_handle *h);
+
+/* The strings behind DGE_FLAG_UMI_N (which = 0: umi_len characters each) or DGE_FLAG_CB_N (which = 1: cb_len characters each) indices, concatenated
+ * without separators; replaces the previous list.  Needed by the host-side exact paths only (N repair of MergeUMIsStrategySimple, whitelist
+ * walk of barcodes containing N): call any time before dge_merge_and_filter. */
+int dge_set_n_strings(dge_handle *h, int which, const char *strings, size_t n);
 
 /* Optional: run on this CUDA stream (a cudaStream_t passed as void*); default is a stream owned by the handle. */
 int dge_set_stream(dge_handle *h, void *cuda_stream);

@@ -3,6 +3,8 @@
 // (dropest_b200/oracle_io.py).  Nothing in the product path includes this header.
 //
 //   DGER0001  packed read stream  : header + optional gene-name blob + dge_record16[n]
+//   DGER0002  the same + two string lists (UMIs / barcodes containing N) between the gene names and the records; a record whose
+//             gene word has bit 27 (bit 28) set carries an index into the N-UMI (N-barcode) list instead of a packed sequence
 //   DGEO0001  oracle output       : directory of named typed arrays
 //
 // The 16-byte record is the same layout as include/dropest_b200.h:dge_record16 (restated here so the
@@ -50,7 +52,17 @@ namespace dge_io
 	{
 		uint32_t cb_len = 0, umi_len = 0, n_genes = 0, n_chr = 0;
 		std::vector<std::string> gene_names; // empty => "g<id>"
+		std::vector<std::string> n_umis, n_cbs; // DGER0002: sequences containing N, referenced by index
 		std::vector<Record16> recs;
+
+		std::string cb_of(const Record16 &r) const
+		{
+			return (r.gene & (1u << 28)) ? n_cbs.at(size_t(r.key >> 24)) : unpack_seq(r.key >> 24, cb_len);
+		}
+		std::string umi_of(const Record16 &r) const
+		{
+			return (r.gene & (1u << 27)) ? n_umis.at(size_t(r.key & 0xFFFFFFu)) : unpack_seq(r.key & 0xFFFFFFu, umi_len);
+		}
 
 		std::string gene_name(uint32_t id) const
 		{
@@ -66,7 +78,8 @@ namespace dge_io
 		if (!f) throw std::runtime_error("can't open " + fname);
 		char magic[8];
 		f.read(magic, 8);
-		if (std::memcmp(magic, "DGER0001", 8) != 0) throw std::runtime_error("bad magic in " + fname);
+		const bool v2 = std::memcmp(magic, "DGER0002", 8) == 0;
+		if (!v2 && std::memcmp(magic, "DGER0001", 8) != 0) throw std::runtime_error("bad magic in " + fname);
 		uint64_t n = 0, names_bytes = 0;
 		ReadStream s;
 		f.read((char *)&n, 8);
@@ -84,6 +97,24 @@ namespace dge_io
 				if (end == std::string::npos) end = blob.size();
 				s.gene_names.push_back(blob.substr(start, end - start));
 				start = end + 1;
+			}
+		}
+		if (v2)
+		{
+			for (std::vector<std::string> *lst : {&s.n_umis, &s.n_cbs})
+			{
+				uint64_t bytes = 0;
+				f.read((char *)&bytes, 8);
+				std::string blob(bytes, '\0');
+				if (bytes) f.read(&blob[0], bytes);
+				size_t start = 0;
+				while (start < blob.size())
+				{
+					size_t end = blob.find('\n', start);
+					if (end == std::string::npos) end = blob.size();
+					lst->push_back(blob.substr(start, end - start));
+					start = end + 1;
+				}
 			}
 		}
 		s.recs.resize(n);

@@ -839,7 +839,7 @@ int main(int argc, char **argv)
 			{
 				const dge_io::Record16 &r = s.recs[i];
 				const uint32_t gid = r.gene & 0xFFFFFFu;
-				c.add_record(dge_io::unpack_seq(r.key >> 24, s.cb_len), dge_io::unpack_seq(r.key & 0xFFFFFFu, s.umi_len),
+				c.add_record(s.cb_of(r), s.umi_of(r),
 				             gid == dge_io::NO_GENE ? std::string() : gnames.at(gid), int((r.gene >> 24) & 7));
 			}
 			t_fill = now_s() - t0;

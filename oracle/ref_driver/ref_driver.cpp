@@ -184,8 +184,7 @@ int main(int argc, char **argv)
 			for (uint32_t g = 0; g < s.n_genes; ++g) gnames[g] = s.gene_name(g);
 			auto decode = [&](const dge_io::Record16 &r) {
 				uint32_t gid = r.gene & 0xFFFFFFu;
-				return ReadInfo(Tools::ReadParameters(dge_io::unpack_seq(r.key >> 24, s.cb_len),
-				                                      dge_io::unpack_seq(r.key & 0xFFFFFFu, s.umi_len), "", ""),
+				return ReadInfo(Tools::ReadParameters(s.cb_of(r), s.umi_of(r), "", ""),
 				                gid == dge_io::NO_GENE ? std::string() : gnames.at(gid), "", mark_of((r.gene >> 24) & 7));
 			};
 			if (a.stream)

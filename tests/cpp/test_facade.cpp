@@ -148,6 +148,33 @@ int main(int argc, char **argv)
 			CHECK_EQUAL(container.cell(0).size(), size_t(5));
 		}
 
+		// testUMIMergeStrategySimple, Tests/TestEstimation.cpp:505-540: UMIs containing N travel as indices into the container's N-string list
+		// and are repaired after the barcode merge (nearest N-free UMI within max_umi_merge_edit_distance, else random bases)
+		{
+			CellsDataContainer container(real_cb_strat, umi_merge_strat, any_mark);
+			static const char *r1[] = {"AAACCT", "AAACCT", "AAACCG", "AAACCN", "CCCCCT", "ACCCCT"};
+			static const char *r2[] = {"TTTTTT", "TTTNNG", "TTGNNG", "ACCCCT", "NNNNNN"};
+			for (auto u : r1) container.add_record(read_info("AAATTAGGTCCA", u, "Gene1"));
+			for (auto u : r2) container.add_record(read_info("AAATTAGGTCCA", u, "Gene2"));
+			container.add_record(read_info("AAATTAGGNCCA", "ACGTAC", "Gene3")); // a barcode with N is a cell of its own (N matches any base in the whitelist walk)
+			container.set_initialized();
+			CHECK_EQUAL(container.total_cells_number(), size_t(2));
+			CHECK_EQUAL(container.cell(1).barcode(), std::string("AAATTAGGNCCA"));
+			CHECK_EQUAL(container.cell(0).at("Gene1").size(), size_t(5));          // before the repair the N-UMI is a UMI of its own
+			CHECK_EQUAL(container.cell(0).at("Gene1").at("AAACCN").read_count(), size_t(1));
+			container.merge_and_filter();
+			CHECK_EQUAL(container.cell(0).at("Gene1").size(), size_t(4));
+			CHECK_EQUAL(container.cell(0).at("Gene2").size(), size_t(3));
+			CHECK_EQUAL(container.cell(0).at("Gene1").at("AAACCT").read_count(), size_t(3)); // AAACCN -> AAACCT (distance 0 to both AAACCT and AAACCG, more reads wins)
+			CHECK_EQUAL(container.cell(0).at("Gene1").at("AAACCG").read_count(), size_t(1));
+			CHECK_EQUAL(container.cell(0).at("Gene1").at("CCCCCT").read_count(), size_t(1));
+			CHECK_EQUAL(container.cell(0).at("Gene1").at("ACCCCT").read_count(), size_t(1));
+			CHECK(container.cell(0).at("Gene2").has("TTTTTT"));
+			CHECK(container.cell(0).at("Gene2").has("ACCCCT"));
+			for (auto const &umi : container.cell(0).at("Gene2").umis())
+				CHECK_EQUAL(container.umi_indexer().get_value(umi.first).find('N'), std::string::npos);
+		}
+
 		// -M: MergeStrategyFactory::get_cb_poisson_strat (MergeStrategyFactory.cpp:91-103) + PoissonSimpleMergeStrategy through the container.
 		// Same reads as above: the small cell shares 3 UMI-genes with the big one 1 substitution away; with only 7 distinct UMIs in the whole
 		// container the expected random overlap is large (lambda ~ 0.6, P[X >= 3] ~ 0.02), so the thresholds are raised for this toy input;

@@ -52,6 +52,7 @@ class Case:
     max_merge_prob: float = 1e-4
     max_real_merge_prob: float = 1e-7
     dump_umis: bool = True
+    n_lists: Optional[object] = None             # dropest_b200.synth.NLists: the records carry barcodes / UMIs with N as indices into it
     n_batches: int = 3
     shuffle: bool = True
     extra: dict = field(default_factory=dict)
@@ -75,8 +76,12 @@ def gpu_run(case: Case, recs: Optional[np.ndarray], device_generate: bool = Fals
                     umi_merge_type=dg.UMI_MERGE_DIRECTIONAL if case.umi_merge == "directional" else dg.UMI_MERGE_SIMPLE,
                     max_umi_merge_edit_distance=case.max_umi_ed, umi_merge_mult=case.umi_mult,
                     max_merge_prob=case.max_merge_prob, max_real_merge_prob=case.max_real_merge_prob,
-                    reads_output=case.reads_output, max_barcodes_hint=case.extra.get("max_barcodes_hint", 1 << 16))
+                    reads_output=case.reads_output, max_barcodes_hint=case.extra.get("max_barcodes_hint", 1 << 16),
+                    allow_n=case.n_lists is not None)
     c = dg.Container(cfg)
+    if case.n_lists is not None:
+        c.set_n_strings(0, case.n_lists.umis)
+        c.set_n_strings(1, case.n_lists.cbs)
     if device_generate:
         import torch
 
@@ -128,7 +133,7 @@ def run_case(case: Case, device_generate: bool = False, kind: str = "any"):
         recs = case.recs
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "reads.bin")
-        write_packed(path, recs, case.cb_len, case.umi_len, case.n_genes, case.gene_names)
+        write_packed(path, recs, case.cb_len, case.umi_len, case.n_genes, case.gene_names, n_lists=case.n_lists)
         ora = oracle_io.run_oracle(path, kind=kind, merge=case.merge, barcodes=case.barcodes, barcodes_type=case.barcodes_type,
                                    min_genes_before=case.min_genes_before, min_genes_after=case.min_genes_after,
                                    max_cb_ed=case.max_cb_ed, min_frac=case.min_frac, marks=case.marks, max_cells=case.max_cells,
@@ -149,7 +154,9 @@ def _gene_id_of_name(case: Case, names):
 def assert_parity(res, check_umigs: bool = True):
     case, ora, gpu = res["case"], res["oracle"], res["gpu"]
     # ---- cells, in first-seen order
-    o_bc = np.array([dg.pack_seq(s) for s in oracle_io.strings(ora["cell_barcodes"])], dtype=np.uint64)
+    pack_cb = case.n_lists.pack_cb if case.n_lists is not None else dg.pack_seq
+    pack_umi = case.n_lists.pack_umi if case.n_lists is not None else dg.pack_seq
+    o_bc = np.array([pack_cb(s) for s in oracle_io.strings(ora["cell_barcodes"])], dtype=np.uint64)
     g_all = gpu["all"]
     assert g_all.shape[0] == o_bc.shape[0] == int(ora["n_cells"][0]) == gpu["summary"]["total_cells_number"], "total cells"
     np.testing.assert_array_equal(g_all["barcode"], o_bc, err_msg="cell id order (first seen)")
@@ -185,7 +192,7 @@ def assert_parity(res, check_umigs: bool = True):
     np.testing.assert_array_equal(gpu["real"]["barcode"], o_bc[ora["cm_raw_cells"]], err_msg="cm_raw column order")
     # ---- every (cell, gene, UMI, reads, mark)
     if check_umigs and case.dump_umis and "umi_cell" in ora:
-        o_umi = np.array([dg.pack_seq(s) for s in oracle_io.strings(ora["umi_seq"])], dtype=np.uint64)
+        o_umi = np.array([pack_umi(s) for s in oracle_io.strings(ora["umi_seq"])], dtype=np.uint64)
         o = np.stack([ora["umi_cell"].astype(np.uint64), o_gene_ids[ora["umi_gene"]].astype(np.uint64), o_umi,
                       ora["umi_count"].astype(np.uint64), ora["umi_mark"].astype(np.uint64)], axis=1)
         u = gpu["umigs"]

@@ -32,7 +32,7 @@ def test_every_export_has_a_ctypes_prototype():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(capi._Config) == 112
+    assert ctypes.sizeof(capi._Config) == 120
     assert capi.CELL_INFO_DTYPE.itemsize == 40
     assert capi.RECORD_DTYPE.itemsize == 16
     assert ctypes.sizeof(capi._Summary) == 19 * 8

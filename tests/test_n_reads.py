@@ -1,0 +1,67 @@
+"""Reads whose barcode / UMI contains N: the CUDA path keeps them like the reference does -- the barcode is a cell of its own,
+the UMI a UMI of its own until MergeUMIsStrategySimple repairs the N-UMIs of the real cells (nearest N-free UMI of the same (cell, gene)
+within max_umi_merge_edit_distance, ties: more reads, then UMI id; else the N's are replaced with the process-wide rand() seeded 42,
+consumed in the iteration order of the reference's unordered_set) -- checked field by field against the compiled reference."""
+import numpy as np
+import pytest
+
+import dropest_b200 as dg
+from dropest_b200.synth import SynthSpec, SynthTables, inject_n, read_whitelist
+
+import oracle_io
+import parity_utils as pu
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(merge, umi_len, n_genes, n_reads, n_cells, seed, umi_ppm, cb_ppm, **kw):
+    wl = read_whitelist(pu.WL_SYNTH_7_9)
+    spec = SynthSpec(n_reads=n_reads, n_cells=n_cells, n_genes=n_genes, cb_len=16, umi_len=umi_len, whitelist_parts=wl, cb_error_ppm=50000,
+                     reads_per_umi=kw.pop("reads_per_umi", 3), seed=seed)
+    recs = SynthTables(spec).generate_host(0, n_reads)
+    recs, lists = inject_n(recs, 16, umi_len, umi_ppm, cb_ppm, seed=seed)
+    return pu.Case(name=f"n_reads_{merge}_{umi_len}", recs=recs, cb_len=16, umi_len=umi_len, n_genes=n_genes, merge=merge,
+                   barcodes=pu.WL_SYNTH_7_9 if merge == "real" else None, barcodes_type="const", min_genes_before=kw.pop("min_genes_before", 5),
+                   min_genes_after=kw.pop("min_genes_after", 10), n_lists=lists, **kw), lists
+
+
+@pytest.mark.parametrize("merge", ["none", "real"])
+@pytest.mark.parametrize("umi_len,n_genes,max_umi_ed", [(10, 120, 1), (5, 15, 1), (6, 30, 2), (12, 60, 0)])
+def test_n_umis_are_repaired_like_the_reference(merge, umi_len, n_genes, max_umi_ed):
+    """3 % of the reads get one or two N's in the UMI.  Short UMIs / few genes make dense segments where a nearest N-free UMI exists
+    (ties on distance and read count included), long ones mostly take the random fill; both orders come from the reference's containers."""
+    if not oracle_io.available("reference"):
+        pytest.skip("oracle/_ref (compiled reference) is not built")
+    case, lists = _case(merge, umi_len, n_genes, 60000, 30, seed=40 + umi_len, umi_ppm=30000, cb_ppm=0, max_umi_ed=max_umi_ed)
+    res = pu.run_case(case, kind="reference")
+    pu.assert_parity(res)
+    assert res["gpu"]["summary"]["n_umis_merged"] > 0
+    u = res["gpu"]["umigs"]
+    real_cells = np.flatnonzero(res["gpu"]["all"]["flags"] & 1)
+    assert not np.any((u["umi"][np.isin(u["cell"], real_cells)] & dg.UMI_N_BIT) != 0), "an N-UMI survived in a real cell"
+
+
+def test_n_barcodes_are_cells_of_their_own_and_merge_through_the_whitelist_walk():
+    """1 % of the reads get an N in the barcode: those barcodes are cells of their own; the ones that become real take the exact host
+    enumeration (N matches any base, BarcodesParser.cpp:21-74) and merge into their whitelist neighbour."""
+    if not oracle_io.available("reference"):
+        pytest.skip("oracle/_ref (compiled reference) is not built")
+    case, lists = _case("real", 10, 80, 80000, 12, seed=51, umi_ppm=5000, cb_ppm=10000, min_genes_before=2, min_genes_after=5)
+    res = pu.run_case(case, kind="reference")
+    pu.assert_parity(res)
+    allc = res["gpu"]["all"]
+    is_n = (allc["barcode"] & np.uint64(dg.CB_N_BIT)) != 0
+    assert is_n.sum() > 50
+    assert np.any(is_n & ((allc["flags"] & 2) != 0)), "no barcode with N was merged: the test does not exercise the host walk"
+
+
+def test_flagged_records_need_allow_n():
+    recs = np.zeros(1, dtype=dg.RECORD_DTYPE)
+    recs["key"] = [(0x1234 << 24) | 3]
+    recs["gene"] = [1 | (2 << 24) | dg.FLAG_UMI_N]
+    c = dg.Container(dg.Config(cb_len=8, umi_len=4, n_genes=2))
+    c.add_batch(recs)
+    with pytest.raises(dg.DgeError) as e:
+        c.set_initialized()
+    assert e.value.code == 1
+    c.close()
