@@ -534,7 +534,7 @@ def main():
     if rank != 0:
         return
     # ---- roofline of the dominant kernel, timed live with CUDA events inside the library (on the launching stream).
-    # Two launches compete for "dominant": k_fill_compact (records -> barcode table + packed keys) and the sub-bucket sort+dedup
+    # Two launches compete for "dominant": k_fill_pipe (records -> barcode table + packed keys) and the sub-bucket sort+dedup
     # (k_sort_dedup, its size classes are timed as one unit).  Both are reported; "roofline" is the one with the longer launch.
     n_keys = n - summary["intergenic_reads"] if world == 1 else None
     roof, roof_other = None, None
@@ -545,8 +545,8 @@ def main():
             # algorithmic bytes of one launch: every 16-byte record read once + one packed 8-byte key written per read with a gene
             algo = n * 16 + n_keys * 8
             per = fill_ms / fill_launches
-            cands.append((per, {"kernel": "k_fill_compact", "bound": "hbm", "achieved": algo / (per / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                "frac": algo / (per / 1e3) / 1e9 / hbm_peak, "traffic": traffic.get("k_fill_compact"), "peak_source": peak_src,
+            cands.append((per, {"kernel": "k_fill_pipe", "bound": "hbm", "achieved": algo / (per / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": algo / (per / 1e3) / 1e9 / hbm_peak, "traffic": traffic.get("k_fill_pipe"), "peak_source": peak_src,
                                 "ms_per_launch": per, "algorithmic_bytes_per_launch": algo}))
         if dedup_launches:
             # every grouped key read once (8 B) + every distinct (cell,gene,UMI) written once (8 B key + 4 B value)
