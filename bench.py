@@ -182,6 +182,21 @@ def exchange_diagnostics(pipe, cont, raw, stream, torch, dist, n, world):
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     torch.cuda.synchronize(); dist.barrier()
+    if isinstance(pipe, dgdist.PeerExchange):
+        # the routing kernels alone (count pass + scatter into the peer-mapped buffer), then the fill alone pulling from the peers
+        ev[0].record(stream)
+        dgdist.route_count_slices(pipe.device, raw.data_ptr(), n, world, ((n + 2047) // 2048) * 2048, 1, pipe.cursors.data_ptr(), stream.cuda_stream)
+        dgdist.route_scatter_slice(pipe.device, raw.data_ptr(), n, world, pipe.cursors.data_ptr(), pipe.routed_ptr, stream.cuda_stream)
+        ev[1].record(stream)
+        torch.cuda.synchronize(); dist.barrier()
+        cont.reset()
+        pipe.run(cont, raw.data_ptr(), stream)
+        cont.set_initialized()                      # the library reads its fill-kernel events here
+        torch.cuda.synchronize(); dist.barrier()
+        ms_pull = cont.timings()["ms_fill_kernel"]
+        cont.reset()
+        return {"diag_ms_route_kernels": ev[0].elapsed_time(ev[1]), "diag_ms_fill_kernels_pulling": ms_pull,
+                "diag_pulled_gbytes_per_gpu": pipe.bytes_pulled / 1e9, "diag_pull_gbs_per_gpu": pipe.bytes_pulled / 1e9 / max(ms_pull / 1e3, 1e-9)}
     ev[0].record(stream)
     dgdist.route_count_slices(pipe.device, raw.data_ptr(), n, world, pipe.slice_len, pipe.n_slices, pipe.cursors.data_ptr(), stream.cuda_stream)
     for s in range(pipe.n_slices):
@@ -242,7 +257,7 @@ def verify_sharded(args, dg, dgdist, torch, wl_path, wl_parts, dev, rank, world,
 
     c = dg.Container(config(True))
     c.set_stream(stream.cuda_stream)
-    pipe = dgdist.PipelinedExchange(dev, per, world, n_slices=4)
+    pipe = dgdist.PeerExchange(dev, per, world) if args.exchange == "peer" else dgdist.PipelinedExchange(dev, per, world, n_slices=4)
     pipe.run(c, buf.data_ptr(), stream)
     c.set_initialized()
     dgdist.merge_across_ranks(c, f"cuda:{dev}")
@@ -250,6 +265,9 @@ def verify_sharded(args, dg, dgdist, torch, wl_path, wl_parts, dev, rank, world,
     mine = collect(c)
     s = c.summary()
     c.close()
+    if args.exchange == "peer":
+        torch.cuda.synchronize(); dist.barrier()   # nobody reads this rank's routed buffer any more
+        pipe.close()
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(pickle.dumps(mine), gathered, dst=0)
     nm = torch.tensor([s["n_merged"], s["n_excluded"]], device=f"cuda:{dev}")
@@ -285,7 +303,10 @@ def main():
     ap.add_argument("--cpu-sample-reads", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--slices", type=int, default=8, help="N > 1: slices of the pipelined route / all-to-all / fill")
+    ap.add_argument("--slices", type=int, default=8, help="N > 1, --exchange nccl: slices of the pipelined route / all-to-all / fill")
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
+                    help="N > 1: 'peer' = the owners' fill kernels pull the routed records out of the sources' HBM over NVLink (no all-to-all pass); "
+                         "'nccl' = scatter -> NCCL all-to-all -> fill in slices")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the sharded == single-GPU check")
     ap.add_argument("--verify-reads", type=int, default=16_000_000)
     args = ap.parse_args()
@@ -314,7 +335,8 @@ def main():
               "cb_len": WORKLOAD["cb_len"], "umi_len": WORKLOAD["umi_len"], "merge": WORKLOAD["merge_desc"],
               "min_genes_before_merge": WORKLOAD["min_genes_before"], "min_genes_after_merge": WORKLOAD["min_genes_after"],
               "l2_policy": "inputs (%.1f GB) larger than L2" % (args.reads * 16 / 1e9),
-              "partition": "barcode-hash, one NCCL all-to-all per step" if world > 1 else "single GPU"}
+              "partition": ("barcode-hash; " + ("owners' fill kernels pull the routed records from the sources' HBM over NVLink (CUDA IPC peer memory)" if args.exchange == "peer"
+                                              else "sliced NCCL all-to-all overlapped with the fill")) if world > 1 else "single GPU"}
 
     # ------------------------------------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -382,7 +404,7 @@ def main():
     if world > 1:
         from dropest_b200 import dist as dgdist
 
-        pipe = dgdist.PipelinedExchange(dev, n, world, n_slices=args.slices)
+        pipe = dgdist.PeerExchange(dev, n, world) if args.exchange == "peer" else dgdist.PipelinedExchange(dev, n, world, n_slices=args.slices)
     phase_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(max(1, args.steps))]
     phase_ms = {"ms_route_a2a_fill": 0.0, "ms_group_init": 0.0, "ms_dist_merge": 0.0, "ms_filter_matrices": 0.0}
 
@@ -392,7 +414,8 @@ def main():
         cont.reset()
         if ev: ev[0].record(stream)
         if world > 1:
-            # barcode-hash routing (our kernel) + all-to-all-v over NCCL in slices, overlapped with the fill of the received slices
+            # barcode-hash routing (our kernels); --exchange peer: the fill pulls the routed records out of the sources' HBM over NVLink,
+            # --exchange nccl: all-to-all-v over NCCL in slices, overlapped with the fill of the received slices
             cnt = pipe.run(cont, raw.data_ptr(), stream)
         else:
             cnt = n
@@ -513,7 +536,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         e2e = {"value": n * world / dt, "unit": "reads/s", "h2d_bytes_per_step": n * (16 if world > 1 else 12) * world, "d2h_bytes_per_step": int(d2h) * world,
-               "note": ("per-rank host records (16 B) -> H2D -> barcode-hash routing + pipelined all-to-all + fill, cross-rank merge included; " if world > 1 else "")
+               "note": ("per-rank host records (16 B) -> H2D -> barcode-hash routing + exchange (%s) + fill, cross-rank merge included; " % args.exchange if world > 1 else "")
                        + "cm checksum %d" % checksum}
         del host_keys, host_genes
 
@@ -574,7 +597,9 @@ def main():
                                       "(BASELINE configs[3] '4B reads / 100k cells on 8 GPUs' at the per-GPU size of configs[1])"
                                       % (world, n // 1_000_000, args.cells, n * world // 1_000_000, args.cells * world, world))
         line["config"]["merge"] += "; exact cross-rank merge (dge_dist_step: all-gather of target summaries + 3 small all-to-alls), result.* are rank 0's shard"
-        line["config"]["exchange"] = "%d slices: route kernel -> NCCL all_to_all_single (async) -> fill, overlapped" % pipe.n_slices
+        line["config"]["exchange"] = ("peer: count pass -> scatter by owner into a CUDA-IPC buffer of the source's HBM -> all-gather of segment sizes -> "
+                                      "every owner's k_fill_pipe bulk-copies its segments over NVLink (no all-to-all pass)" if args.exchange == "peer"
+                                      else "%d slices: route kernel -> NCCL all_to_all_single (async) -> fill, overlapped" % pipe.n_slices)
         line["step_breakdown_ms"] = breakdown
         line["verify"] = verify
     if world == 1 and not args.no_cpu_baseline:

@@ -42,11 +42,12 @@ DIST_DONE, DIST_ALLGATHER, DIST_ALLTOALL = 0, 1, 2
 
 # exported symbols of include/dropest_b200.h (checked by tests/test_abi.py)
 EXPORTS = [
-    "dge_config_default", "dge_create", "dge_destroy", "dge_last_error", "dge_add_batch", "dge_add_batch_device", "dge_add_batch_soa",
+    "dge_config_default", "dge_create", "dge_destroy", "dge_last_error", "dge_add_batch", "dge_add_batch_device", "dge_add_batch_segments_device", "dge_add_batch_soa",
     "dge_set_initialized", "dge_merge_and_filter", "dge_reset", "dge_set_stream", "dge_set_n_strings", "dge_get_summary", "dge_get_timings", "dge_get_cells",
     "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
     "dge_route_by_barcode_device", "dge_route_count_slices_device", "dge_route_scatter_slice_device", "dge_dist_step",
+    "dge_peer_alloc", "dge_peer_free", "dge_peer_open", "dge_peer_close",
     "dge_umi_first_size", "dge_umi_first_export", "dge_umi_first_import", "dge_collisions_adjusted_sizes",
 ]
 
@@ -149,6 +150,11 @@ def load_library():
     lib.dge_route_count_slices_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dge_route_scatter_slice_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dge_dist_step.argtypes = [C.c_void_p, C.POINTER(_DistIO)]
+    lib.dge_add_batch_segments_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint32]
+    lib.dge_peer_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.dge_peer_free.argtypes = [C.c_int, C.c_void_p]
+    lib.dge_peer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.dge_peer_close.argtypes = [C.c_int, C.c_void_p]
     lib.dge_set_n_strings.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
     lib.dge_umi_first_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
     lib.dge_umi_first_export.argtypes = [C.c_void_p, C.c_void_p]
@@ -284,6 +290,15 @@ class Container:
         if keepalive is not None:
             self._keepalive.append(keepalive)
         self._check(self._lib.dge_add_batch_device(self._h, C.c_void_p(dev_ptr), n))
+
+    def add_batch_segments_device(self, dev_ptrs, counts, keepalive=None):
+        """ONE fill launch over several device record arrays (local or peer-mapped); see dge_add_batch_segments_device."""
+        if keepalive is not None:
+            self._keepalive.append(keepalive)
+        k = len(dev_ptrs)
+        ptrs = (C.c_void_p * max(k, 1))(*[C.c_void_p(int(p)) for p in dev_ptrs])
+        cnts = (C.c_uint64 * max(k, 1))(*[int(x) for x in counts])
+        self._check(self._lib.dge_add_batch_segments_device(self._h, ptrs, cnts, k))
 
     def set_stream(self, cuda_stream: int):
         self._check(self._lib.dge_set_stream(self._h, C.c_void_p(cuda_stream)))

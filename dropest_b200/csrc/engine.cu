@@ -400,9 +400,17 @@ void set_table_l2_window(dge_handle *h, bool on)
 
 // One batch already resident on the device: barcode-table insert + key packing into a fresh chunk.
 void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n, const unsigned long long *soa_keys = nullptr,
-                      const uint32_t *soa_genes = nullptr, uint32_t soa_first = 0)
+                      const uint32_t *soa_genes = nullptr, uint32_t soa_first = 0, const dge_record16 *const *segs = nullptr,
+                      const uint64_t *seg_counts = nullptr, uint32_t n_segs = 0)
 {
+    // segs != nullptr: ONE launch over several record arrays (the exchange of a sharded run: this rank's own segment plus the segments
+    // it pulls out of the peers' HBM); recs / n are then ignored
     const bool soa = soa_keys != nullptr;
+    if (segs)
+    {
+        n = 0;
+        for (uint32_t k = 0; k < n_segs; ++k) n += seg_counts[k];
+    }
     if (n == 0) return;
     if (h->n_chunk_counters >= 4096) throw std::runtime_error("too many batches (max 4096); use larger batches");
     std::unique_ptr<KeyChunk> chunk;
@@ -431,15 +439,41 @@ void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n, const u
         const size_t smem = size_t(STG) * TILE * 16 + size_t((h->cfg.n_genes + 7u) & ~7u) * 2 + 4096 * 4;
         const bool first_batch = h->chunks.empty();
         if (smem > 224 * 1024 || !(first_batch || h->pipe_fill)) return false;
-        const void *src0 = soa ? static_cast<const void *>(soa_keys) : static_cast<const void *>(recs);
+        const void *src0 = soa ? static_cast<const void *>(soa_keys) : segs ? nullptr : static_cast<const void *>(recs);
         if ((reinterpret_cast<uintptr_t>(src0) & 15u) || (soa && (reinterpret_cast<uintptr_t>(soa_genes) & 15u)))
             throw InvalidInput("device record arrays must be 16-byte aligned");
-        const size_t n_tiles = div_up(n, size_t(TILE));
+        FillSegs fs;
+        memset(&fs, 0, sizeof(fs));
+        if (segs)
+        {
+            for (uint32_t k = 0; k < n_segs; ++k)
+            {
+                if (seg_counts[k] == 0) continue;
+                if (fs.n_segs == FILL_MAX_SEGS) throw InvalidInput("too many segments in one batch (max 64)");
+                if (reinterpret_cast<uintptr_t>(segs[k]) & 15u) throw InvalidInput("device record arrays must be 16-byte aligned");
+                fs.base[fs.n_segs] = reinterpret_cast<const Rec16 *>(segs[k]);
+                fs.count[fs.n_segs++] = seg_counts[k];
+            }
+        }
+        else { fs.base[0] = reinterpret_cast<const Rec16 *>(recs); fs.count[0] = n; fs.n_segs = 1; }
+        size_t n_tiles = 0;
+        uint32_t min_tiles = ~0u;
+        for (uint32_t k = 0; k < fs.n_segs; ++k)
+        {
+            const size_t t = div_up(size_t(fs.count[k]), size_t(TILE));
+            n_tiles += t;
+            min_tiles = std::min<uint32_t>(min_tiles, uint32_t(t));
+        }
+        if (n_tiles >= (size_t(1) << 31)) throw CapacityError("batch too large for one fill launch");
+        fs.rr_rounds = min_tiles;
+        fs.n_tiles = uint32_t(n_tiles);
+        for (uint32_t k = 0; k < fs.n_segs; ++k)
+            fs.rem_start[k + 1] = fs.rem_start[k] + uint32_t(div_up(size_t(fs.count[k]), size_t(TILE))) - min_tiles;
+        for (uint32_t k = fs.n_segs; k < FILL_MAX_SEGS; ++k) fs.rem_start[k + 1] = ~0u; // the search of fill_seg_tile stops here at the latest
         const unsigned grid = unsigned(std::min<size_t>(n_tiles, 148));
         const size_t region_cap = div_up(n_tiles, size_t(grid)) * TILE;
         chunk->keys.reserve(size_t(grid) * region_cap * 8);
         KeyRegion *regs = h->regions.as<KeyRegion>() + h->n_regions;
-        const Rec16 *r16p = reinterpret_cast<const Rec16 *>(recs);
         uint32_t *umi_first_p = h->track_umi_first ? h->umi_first.as<uint32_t>() : nullptr;
         set_table_l2_window(h, true);
         static bool done[64][2] = {};
@@ -447,14 +481,14 @@ void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n, const u
         {
             auto kern = k_fill_pipe<CW, IT, STG, true>;
             if (!done[h->cfg.device & 63][1]) { DGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); done[h->cfg.device & 63][1] = true; }
-            kern<<<grid, (CW + 1) * 32, smem, h->stream>>>(r16p, n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes, h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(),
+            kern<<<grid, (CW + 1) * 32, smem, h->stream>>>(fs, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes, h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(),
                                                           region_cap, regs, h->ctr.as<FillCounters>(), umi_first_p, h->hist12.as<uint32_t>(), soa_keys, soa_genes, soa_first);
         }
         else
         {
             auto kern = k_fill_pipe<CW, IT, STG, false>;
             if (!done[h->cfg.device & 63][0]) { DGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); done[h->cfg.device & 63][0] = true; }
-            kern<<<grid, (CW + 1) * 32, smem, h->stream>>>(r16p, n, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes, h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(),
+            kern<<<grid, (CW + 1) * 32, smem, h->stream>>>(fs, h->tab.as<CellSlot>(), h->kl, h->cfg.n_genes, h->gene_first.as<uint32_t>(), chunk->keys.as<uint64_t>(),
                                                           region_cap, regs, h->ctr.as<FillCounters>(), umi_first_p, h->hist12.as<uint32_t>(), nullptr, nullptr, 0u);
         }
         DGE_LAUNCH_CHECK();
@@ -480,6 +514,13 @@ void fill_from_device(dge_handle *h, const dge_record16 *recs, size_t n, const u
         else if (fill_shape == 5) ok = pipe_launch(integral_constant<int, 24>{}, integral_constant<int, 4>{}, integral_constant<int, 2>{});
         else ok = pipe_launch(integral_constant<int, 30>{}, integral_constant<int, 4>{}, integral_constant<int, 2>{}); // measured best at C2
         if (ok) return;
+    }
+    if (segs)
+    {   // the older kernels take one array: one batch per segment (give the pooled objects back first)
+        h->chunk_pool.push_back(std::move(chunk));
+        --h->n_chunk_counters;
+        for (uint32_t k = 0; k < n_segs; ++k) fill_from_device(h, segs[k], size_t(seg_counts[k]));
+        return;
     }
     chunk->keys.reserve(n * 8);
     const size_t gene_smem = size_t(h->cfg.n_genes) * 4;
@@ -2798,6 +2839,15 @@ int dge_set_n_strings(dge_handle *h, int which, const char *strings, size_t n)
             if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') throw InvalidInput("N-string lists hold A, C, G, T, N only");
         return int(DGE_OK);
     });
+}
+
+int dge_add_batch_segments_device(dge_handle *h, const dge_record16 *const *segs, const uint64_t *counts, uint32_t n_segs)
+{
+    if (!h || (n_segs && (!segs || !counts))) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state != 0) return fail(h, DGE_ERR_STATE, "Container is already initialized");
+    for (uint32_t k = 0; k < n_segs; ++k)
+        if (!segs[k] && counts[k]) return fail(h, DGE_ERR_INVALID, "null segment");
+    return guarded(h, [&] { ensure_device(h); fill_from_device(h, nullptr, 0, nullptr, nullptr, 0, segs, counts, n_segs); return int(DGE_OK); });
 }
 
 int dge_add_batch_device(dge_handle *h, const dge_record16 *recs, size_t n)

@@ -270,9 +270,40 @@ __device__ __forceinline__ void smem_min_u16(uint16_t *arr, uint32_t i, uint32_t
     }
 }
 
+// The input of one k_fill_pipe launch: up to FILL_MAX_SEGS record arrays (local HBM or a peer's, mapped with dge_peer_open).  Tiles never
+// straddle segments.  Tile order: `rr_rounds` rounds that take one tile of every segment in turn (so that tiles pulled over NVLink and
+// local tiles alternate in every block and the link is busy for the whole launch), then what is left of the longer segments, one after
+// the other.  v -> (segment, tile in segment) is a bijection; blocks walk v = j * grid + (block + j) % grid, a rotation per round, because
+// with a plain block-stride walk v % n_segs would be the same in every round whenever n_segs divides the grid size.
+constexpr int FILL_MAX_SEGS = 64;
+struct FillSegs
+{
+    const Rec16 *base[FILL_MAX_SEGS];
+    unsigned long long count[FILL_MAX_SEGS];
+    uint32_t rem_start[FILL_MAX_SEGS + 1]; // exclusive prefix of (tiles of the segment - rr_rounds)
+    uint32_t n_segs, rr_rounds, n_tiles, pad;
+};
+
+template <int TILE>
+__device__ __forceinline__ void fill_seg_tile(const FillSegs &fs, uint32_t v, uint32_t &seg, size_t &base, uint32_t &cnt)
+{
+    uint32_t i;
+    const uint32_t rr = fs.rr_rounds * fs.n_segs;
+    if (v < rr) { seg = v % fs.n_segs; i = v / fs.n_segs; }
+    else
+    {
+        const uint32_t w = v - rr;
+        seg = 0;
+        while (w >= fs.rem_start[seg + 1]) ++seg;
+        i = fs.rr_rounds + (w - fs.rem_start[seg]);
+    }
+    base = size_t(i) * TILE;
+    cnt = uint32_t(min(size_t(TILE), size_t(fs.count[seg]) - base));
+}
+
 template <int CONS_WARPS, int ITEMS, int STAGES, bool SOA>
 __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
-    k_fill_pipe(const Rec16 *__restrict__ recs, size_t n, CellSlot *__restrict__ tab, KeyLayout kl, uint32_t n_genes, uint32_t *__restrict__ gene_first,
+    k_fill_pipe(const __grid_constant__ FillSegs fs, CellSlot *__restrict__ tab, KeyLayout kl, uint32_t n_genes, uint32_t *__restrict__ gene_first,
                 uint64_t *__restrict__ out_keys, size_t region_cap, KeyRegion *__restrict__ regions, FillCounters *__restrict__ ctr,
                 uint32_t *__restrict__ umi_first, uint32_t *__restrict__ hist12, const unsigned long long *__restrict__ soa_keys,
                 const uint32_t *__restrict__ soa_genes, uint32_t soa_first_idx)
@@ -301,21 +332,24 @@ __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
     }
     __syncthreads();
 
-    const size_t n_tiles = (n + TILE - 1) / TILE;
+    const uint32_t n_tiles = fs.n_tiles;
     uint32_t c_inter = 0, c_exon = 0, c_intron = 0, c_na = 0;
     if (warp == CONS_WARPS)
     {   // ---- producer
         if (lane == 0)
         {
             const uint64_t pol = l2_policy_evict_first();
-            uint32_t k = 0;
-            for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k)
+            for (uint32_t k = 0; k * gridDim.x < n_tiles; ++k)
             {
+                const uint32_t v = k * gridDim.x + (blockIdx.x + k) % gridDim.x;
+                if (v >= n_tiles) break; // only in the last round
                 const int s = int(k % STAGES);
                 const uint32_t round = k / STAGES;
                 mbar_wait(&empty_bar[s], (round & 1u) ^ 1u);
-                const size_t base = tile * TILE;
-                const uint32_t cnt = uint32_t(min(size_t(TILE), n - base));
+                uint32_t seg, cnt;
+                size_t base;
+                fill_seg_tile<TILE>(fs, v, seg, base, cnt);
+                const Rec16 *recs = fs.base[seg];
                 unsigned char *stage = fp_smem + size_t(s) * STAGE_BYTES;
                 if (SOA)
                 {
@@ -338,13 +372,15 @@ __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
         const int ctid = threadIdx.x; // consumer warps are warps 0 .. CONS_WARPS-1
         uint64_t *my_out = out_keys + size_t(blockIdx.x) * region_cap;
         const int hshift = kl.kb - 12;
-        uint32_t k = 0;
-        for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k)
+        for (uint32_t k = 0; k * gridDim.x < n_tiles; ++k)
         {
+            const uint32_t v = k * gridDim.x + (blockIdx.x + k) % gridDim.x;
+            if (v >= n_tiles) break;
             const int s = int(k % STAGES);
             const uint32_t round = k / STAGES;
-            const size_t base = tile * TILE;
-            const uint32_t cnt = uint32_t(min(size_t(TILE), n - base));
+            uint32_t seg, cnt;
+            size_t base;
+            fill_seg_tile<TILE>(fs, v, seg, base, cnt);
             const unsigned char *stage = fp_smem + size_t(s) * STAGE_BYTES;
             uint4 raw[ITEMS];
             mbar_wait(&full_bar[s], round & 1u);

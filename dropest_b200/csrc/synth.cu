@@ -288,4 +288,57 @@ int dge_route_scatter_slice_device(int device, const dge_record16 *in_slice, siz
     catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_route_scatter_slice_device: %s\n", e.what()); return DGE_ERR_CUDA; }
 }
 
+/* ---- peer memory for the exchange: the routed records stay in the SOURCE rank's HBM and the owner's fill kernel pulls its segment
+ * straight out of it over NVLink (bulk-async copies of k_fill_pipe's producer warp), so the all-to-all pass and its receive buffer do not exist.
+ * One process per GPU: the buffer is a plain cudaMalloc allocation exported as a CUDA IPC handle (64 bytes, sent to the peers by any transport). */
+int dge_peer_alloc(int device, size_t bytes, void **ptr, unsigned char handle[64])
+{
+    if (!ptr || !handle || bytes == 0) return DGE_ERR_INVALID;
+    try
+    {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+        DGE_CUDA(cudaSetDevice(device));
+        void *p = nullptr;
+        DGE_CUDA(cudaMalloc(&p, bytes));
+        cudaIpcMemHandle_t hd;
+        cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+        if (e != cudaSuccess) { cudaFree(p); throw std::runtime_error(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+        memcpy(handle, &hd, 64);
+        *ptr = p;
+        return DGE_OK;
+    }
+    catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_peer_alloc: %s\n", e.what()); return DGE_ERR_CUDA; }
+}
+
+int dge_peer_free(int device, void *ptr)
+{
+    if (!ptr) return DGE_OK;
+    try { DGE_CUDA(cudaSetDevice(device)); DGE_CUDA(cudaFree(ptr)); return DGE_OK; }
+    catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_peer_free: %s\n", e.what()); return DGE_ERR_CUDA; }
+}
+
+/* Maps a peer's buffer (handle from ITS dge_peer_alloc) into this process, for loads by kernels running on `device`. */
+int dge_peer_open(int device, const unsigned char handle[64], void **ptr)
+{
+    if (!ptr || !handle) return DGE_ERR_INVALID;
+    try
+    {
+        DGE_CUDA(cudaSetDevice(device));
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, handle, 64);
+        void *p = nullptr;
+        DGE_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        *ptr = p;
+        return DGE_OK;
+    }
+    catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_peer_open: %s\n", e.what()); return DGE_ERR_CUDA; }
+}
+
+int dge_peer_close(int device, void *ptr)
+{
+    if (!ptr) return DGE_OK;
+    try { DGE_CUDA(cudaSetDevice(device)); DGE_CUDA(cudaIpcCloseMemHandle(ptr)); return DGE_OK; }
+    catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_peer_close: %s\n", e.what()); return DGE_ERR_CUDA; }
+}
+
 } // extern "C"

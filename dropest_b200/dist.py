@@ -102,6 +102,82 @@ class PipelinedExchange:
         return total
 
 
+class PeerExchange:
+    """Barcode-hash routing with the exchange fused into the fill (one process per GPU of one NVLink / NVSwitch node):
+        count pass -> scatter by owner into a buffer of THIS rank's HBM that every peer has mapped (CUDA IPC)
+        -> all-gather of the segment sizes (doubles as the "scatter done" barrier)
+        -> the fill kernel of every owner pulls its segment out of each source's buffer over NVLink (bulk-async copies of the producer warp)
+    No all-to-all pass, no receive buffer: the records cross NVLink exactly once, inside the kernel that consumes them."""
+
+    def __init__(self, device: int, n: int, world: int, group=None, fused: bool = True):
+        import torch
+        import torch.distributed as dist
+
+        self.device, self.n, self.world, self.group, self.fused = device, n, world, group, fused
+        self.rank = dist.get_rank(group)
+        lib = load_library()
+        handle = C.create_string_buffer(64)
+        p = C.c_void_p()
+        if lib.dge_peer_alloc(device, max(n, 1) * 16, C.byref(p), handle) != 0:
+            raise RuntimeError("dge_peer_alloc failed: " + lib.dge_last_error(None).decode())
+        self.routed_ptr = p.value
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.peer_ptr = []
+        for r in range(world):
+            if r == self.rank:
+                self.peer_ptr.append(self.routed_ptr)
+                continue
+            q = C.c_void_p()
+            if lib.dge_peer_open(device, handles[r], C.byref(q)) != 0:
+                raise RuntimeError("dge_peer_open failed: " + lib.dge_last_error(None).decode())
+            self.peer_ptr.append(q.value)
+        dev = f"cuda:{device}"
+        self.cursors = torch.empty(64, dtype=torch.int64, device=dev)
+        self.token = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.bytes_pulled = 0
+
+    def close(self):
+        lib = load_library()
+        for r, q in enumerate(self.peer_ptr):
+            if r != self.rank and q:
+                lib.dge_peer_close(self.device, C.c_void_p(q))
+        self.peer_ptr = []
+        if self.routed_ptr:
+            lib.dge_peer_free(self.device, C.c_void_p(self.routed_ptr))
+            self.routed_ptr = None
+
+    def run(self, cont, raw_ptr: int, stream) -> int:
+        """Routes and fills; returns the number of records this rank owns.  The peers' buffers are read until this rank's
+        set_initialized has run; the next run() starts with a barrier, so a source never overwrites records a peer still needs."""
+        import torch
+        import torch.distributed as dist
+
+        world, rank = self.world, self.rank
+        sp = stream.cuda_stream
+        dist.all_reduce(self.token, group=self.group)                # every peer is done with the previous step's buffers
+        counts = route_count_slices(self.device, raw_ptr, self.n, world, ((self.n + 2047) // 2048) * 2048 or 2048, 1, self.cursors.data_ptr(), sp)
+        route_scatter_slice(self.device, raw_ptr, self.n, world, self.cursors.data_ptr(), self.routed_ptr, sp)
+        mine = torch.from_numpy(counts.astype(np.int64).reshape(-1)).to(self.token.device)
+        allc = torch.empty(world * world, dtype=torch.int64, device=self.token.device)
+        dist.all_gather_into_tensor(allc, mine, group=self.group)    # completes after every rank's scatter (stream order on each rank)
+        allc = allc.cpu().numpy().reshape(world, world)               # [source, destination]
+        ptrs, cnts = [], []
+        for k in range(world):
+            src = (rank + k) % world                                  # own segment first, then the peers in rotation
+            ptrs.append(self.peer_ptr[src] + int(allc[src, :rank].sum()) * 16)
+            cnts.append(int(allc[src, rank]))
+        total = sum(cnts)
+        self.bytes_pulled = (total - cnts[0]) * 16
+        if self.fused:
+            cont.add_batch_segments_device(ptrs, cnts)                # ONE launch: local and remote tiles alternate inside every block
+        else:
+            for p, c in zip(ptrs, cnts):
+                if c:
+                    cont.add_batch_device(p, c)
+        return total
+
+
 def exchange(routed, counts: np.ndarray, recv=None, group=None):
     """ONE all-to-all-v of 16-byte records.  `routed`: uint8 tensor (n*16) already grouped by destination rank, `counts`:
     records per destination.  Returns (uint8 tensor view of the received records, number of records)."""

@@ -194,6 +194,12 @@ const char *dge_last_error(const dge_handle *h);
  * All fail with DGE_ERR_STATE after dge_set_initialized ("Container is already initialized", CellsDataContainer.cpp:61-62). */
 int dge_add_batch(dge_handle *h, const dge_record16 *recs, size_t n);
 int dge_add_batch_device(dge_handle *h, const dge_record16 *recs, size_t n);
+
+/* Several device-resident record arrays in ONE fill launch (same result as one dge_add_batch_device per array, in any order).  Arrays may
+ * live in a peer GPU's HBM (dge_peer_open): the kernel's bulk-async copies then pull them over NVLink, and local and remote tiles
+ * alternate inside every block, so the transfer is hidden behind the per-read work -- the exchange of a sharded run
+ * without an all-to-all pass.  Empty segments are allowed; at most 64 non-empty ones; 16-byte aligned. */
+int dge_add_batch_segments_device(dge_handle *h, const dge_record16 *const *segs, const uint64_t *counts, uint32_t n_segs);
 int dge_add_batch_soa(dge_handle *h, const uint64_t *keys, const uint32_t *genes, size_t n, uint64_t first_read_idx);
 
 /* = CellsDataContainer::set_initialized (CellsDataContainer.cpp:163-175): runs the whole per-read grouping on the device.
@@ -306,6 +312,15 @@ int dge_route_count_slices_device(int device, const dge_record16 *in, size_t n, 
                                   uint64_t *counts, uint64_t *cursors_device, void *cuda_stream);
 int dge_route_scatter_slice_device(int device, const dge_record16 *in_slice, size_t n_slice, uint32_t n_ranks, uint64_t *slice_cursors_device,
                                    dge_record16 *out_slice, void *cuda_stream);
+
+/* Peer memory for the exchange (one process per GPU of one NVLink/NVSwitch node).  Instead of scatter -> all-to-all -> fill, the routed
+ * records stay in the SOURCE rank's HBM (a dge_peer_alloc buffer, exported as a 64-byte CUDA IPC handle that the caller sends to the
+ * peers by any transport) and every owner's fill kernel pulls its segment out of it over NVLink: dge_add_batch_device accepts pointers
+ * returned by dge_peer_open.  The caller orders the steps (a barrier before a source overwrites the buffer, one after its scatter). */
+int dge_peer_alloc(int device, size_t bytes, void **ptr, unsigned char handle[64]);
+int dge_peer_free(int device, void *ptr);
+int dge_peer_open(int device, const unsigned char handle[64], void **ptr);
+int dge_peer_close(int device, void *ptr);
 
 /* ---- cross-rank whitelist merge for sharded runs ---------------------------------------------------
  * With reads sharded by barcode hash a cell and its merge candidates usually live on different ranks.  The merge is exact

@@ -90,6 +90,16 @@ def gpu_run(case: Case, recs: Optional[np.ndarray], device_generate: bool = Fals
         tables.generate_device(0, 0, n, buf.data_ptr())
         torch.cuda.synchronize()
         c.add_batch_device(buf.data_ptr(), n, keepalive=buf)
+    elif case.extra.get("segments"):
+        # ONE fill launch over several device arrays of very different lengths (dge_add_batch_segments_device), empty ones included
+        import torch
+
+        cuts = [int(recs.shape[0] * f) for f in case.extra["segments"]]
+        bounds = [0] + sorted(cuts) + [recs.shape[0]]
+        perm = np.random.default_rng(7).permutation(recs.shape[0]) if case.shuffle else np.arange(recs.shape[0])
+        bufs = [torch.from_numpy(np.ascontiguousarray(recs[perm[a:b]]).view(np.uint8).reshape(-1).copy()).cuda() for a, b in zip(bounds[:-1], bounds[1:])]
+        bufs = [b if b.numel() else torch.empty(16, dtype=torch.uint8, device="cuda:0") for b in bufs]
+        c.add_batch_segments_device([b.data_ptr() for b in bufs], [b1 - a1 for a1, b1 in zip(bounds[:-1], bounds[1:])], keepalive=bufs)
     elif case.extra.get("soa"):
         # structure-of-arrays batches in stream order: read_idx is implicit (dge_add_batch_soa)
         assert np.array_equal(recs["read_idx"], recs["read_idx"][0] + np.arange(recs.shape[0], dtype=np.uint32))

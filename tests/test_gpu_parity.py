@@ -370,6 +370,17 @@ def test_soa_batches_with_implicit_read_index():
     pu.assert_parity(res)
 
 
+@pytest.mark.parametrize("cuts", [(0.5,), (0.001, 0.001, 0.4, 0.95), (0.3, 0.31, 0.9)])
+def test_segment_batches_in_one_launch(cuts):
+    """dge_add_batch_segments_device: several device arrays (here: shuffled reads cut into very uneven pieces, an empty one included)
+    consumed by ONE fill launch with interleaved tiles -- the shape of the peer-memory exchange -- give the reference's result."""
+    case = pu.small_case(n_reads=120000, n_cells=40, n_genes=150, merge="real", seed=33)
+    case.extra["segments"] = cuts
+    case.shuffle = True
+    res = pu.run_case(case)
+    pu.assert_parity(res)
+
+
 def test_merge_simple_dropseq_like_2m():
     """Drop-seq shaped stream (12 bp barcodes, 8 bp UMIs, no whitelist -> SimpleMergeStrategy) at a size where the inverted index and
     the pair lists are non-trivial; checked against the oracle."""

@@ -45,7 +45,7 @@ def _cm_triplets(c, dg, which_cells, which_matrix):
     return np.stack([cells["barcode"][col].astype(np.uint64), genes.astype(np.uint64), vals.astype(np.uint64)], axis=1)
 
 
-def _worker_real(rank, world, port, n_total, out_dir, umi_len, n_genes, directional):
+def _worker_real(rank, world, port, n_total, out_dir, umi_len, n_genes, directional, exchange):
     import torch
     import torch.distributed as dist
 
@@ -63,7 +63,10 @@ def _worker_real(rank, world, port, n_total, out_dir, umi_len, n_genes, directio
     c = dg.Container(_real_config(dg, umi_len, n_genes, directional, device=rank, sharded=True))
     stream = torch.cuda.current_stream()
     c.set_stream(stream.cuda_stream)
-    pipe = dgdist.PipelinedExchange(rank, per, world, n_slices=5)   # routing + sliced all-to-all overlapped with the fill
+    if exchange == "peer":   # the fill kernel pulls the routed records out of the other rank's HBM (CUDA IPC peer memory over NVLink)
+        pipe = dgdist.PeerExchange(rank, per, world)
+    else:                    # routing + sliced NCCL all-to-all overlapped with the fill
+        pipe = dgdist.PipelinedExchange(rank, per, world, n_slices=5)
     cnt = pipe.run(c, raw.data_ptr(), stream)
     torch.cuda.synchronize()
     dgdist.sync_umi_first_seen(c, f"cuda:{rank}")
@@ -81,12 +84,15 @@ def _worker_real(rank, world, port, n_total, out_dir, umi_len, n_genes, directio
     np.save(os.path.join(out_dir, f"sum{rank}.npy"), np.array([s[k] for k in ("n_merged", "n_excluded", "n_unresolved", "real_cells_number", "filtered_cells_number",
                                                                                 "n_umis_merged")]))
     c.close()
+    torch.cuda.synchronize()
     dist.barrier()
+    if exchange == "peer":
+        pipe.close()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("umi_len,n_genes,directional", [(10, 150, False), (5, 20, True)])
-def test_two_gpu_cross_rank_whitelist_merge_is_exact(tmp_path, umi_len, n_genes, directional):
+@pytest.mark.parametrize("umi_len,n_genes,directional,exchange", [(10, 150, False, "peer"), (10, 150, False, "nccl"), (5, 20, True, "peer")])
+def test_two_gpu_cross_rank_whitelist_merge_is_exact(tmp_path, umi_len, n_genes, directional, exchange):
     """Sharded run + cross-rank merge (dge_dist_*): the union of the per-rank results equals the single-GPU result.
     With the directional UMI merge the per-UMI first-seen table is min-reduced across ranks first."""
     import torch
@@ -99,7 +105,7 @@ def test_two_gpu_cross_rank_whitelist_merge_is_exact(tmp_path, umi_len, n_genes,
     from dropest_b200.synth import SynthTables
 
     world, n_total = 2, 300_000
-    mp.spawn(_worker_real, args=(world, _free_port(), n_total, str(tmp_path), umi_len, n_genes, directional), nprocs=world, join=True)
+    mp.spawn(_worker_real, args=(world, _free_port(), n_total, str(tmp_path), umi_len, n_genes, directional, exchange), nprocs=world, join=True)
     recs = SynthTables(_spec(n_total, umi_len, n_genes)).generate_host(0, n_total)
     c = dg.Container(_real_config(dg, umi_len, n_genes, directional))
     c.add_batch(recs)
