@@ -100,8 +100,22 @@ __global__ void __launch_bounds__(256) k_route_count(const dge_record16 *__restr
 }
 
 constexpr int ROUTE_ITEMS = 8;
-__global__ void __launch_bounds__(256) k_route_scatter(const dge_record16 *__restrict__ in, size_t n, uint32_t n_ranks,
-                                                       unsigned long long *__restrict__ cursor, dge_record16 *__restrict__ out)
+// Position of every lane among the lanes of its warp that hold the same destination + ONE shared-memory atomic per (warp, destination):
+// with 2-8 destinations a per-lane atomicAdd on the destination counter serialises 4-16 ways.
+__device__ __forceinline__ uint32_t route_rank_in_tile(uint32_t rk, uint32_t *cnt, bool valid)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned m = __match_any_sync(0xFFFFFFFFu, valid ? rk : 0xFFFFFFFFu);
+    const int leader = __ffs(m) - 1;
+    uint32_t p = 0;
+    if (valid && int(lane) == leader) p = atomicAdd(&cnt[rk], uint32_t(__popc(m)));
+    p = __shfl_sync(0xFFFFFFFFu, p, leader);
+    return p + uint32_t(__popc(m & ((1u << lane) - 1u)));
+}
+
+// direct variant (default): every record stored straight to its slot of the destination run
+__global__ void __launch_bounds__(256) k_route_scatter_direct(const dge_record16 *__restrict__ in, size_t n, uint32_t n_ranks,
+                                                              unsigned long long *__restrict__ cursor, dge_record16 *__restrict__ out)
 {
     __shared__ uint32_t cnt[64];
     __shared__ unsigned long long basep[64];
@@ -114,13 +128,15 @@ __global__ void __launch_bounds__(256) k_route_scatter(const dge_record16 *__res
     for (int j = 0; j < ROUTE_ITEMS; ++j)
     {
         size_t i = base + size_t(j) * 256 + threadIdx.x;
-        if (i < n)
-        {
-            rec[j] = reinterpret_cast<const uint4 *>(in)[i];
-            uint64_t key = (uint64_t(rec[j].y) << 32) | rec[j].x;
-            rk[j] = rank_of(key >> 24, n_ranks);
-            pos[j] = atomicAdd(&cnt[rk[j]], 1u);
-        }
+        if (i < n) rec[j] = reinterpret_cast<const uint4 *>(in)[i];
+    }
+#pragma unroll
+    for (int j = 0; j < ROUTE_ITEMS; ++j)
+    {
+        size_t i = base + size_t(j) * 256 + threadIdx.x;
+        const bool valid = i < n;
+        rk[j] = valid ? rank_of(((uint64_t(rec[j].y) << 32) | rec[j].x) >> 24, n_ranks) : 0u;
+        pos[j] = route_rank_in_tile(rk[j], cnt, valid);
     }
     __syncthreads();
     if (threadIdx.x < n_ranks && cnt[threadIdx.x]) basep[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
@@ -130,6 +146,65 @@ __global__ void __launch_bounds__(256) k_route_scatter(const dge_record16 *__res
     {
         size_t i = base + size_t(j) * 256 + threadIdx.x;
         if (i < n) reinterpret_cast<uint4 *>(out)[basep[rk[j]] + pos[j]] = rec[j];
+    }
+}
+
+// Staged variant (A/B only, DGE_ROUTE_STAGED=1): the 2048-record tile is REORDERED BY DESTINATION IN SHARED MEMORY and written as one contiguous run
+// per destination (coalesced full-sector stores; a scattered 16-byte store costs an L2 write transaction of its own), one global
+// atomicAdd per (tile, destination).  Order inside a destination segment is arbitrary: first-seen order travels in read_idx.
+__global__ void __launch_bounds__(256) k_route_scatter(const dge_record16 *__restrict__ in, size_t n, uint32_t n_ranks,
+                                                       unsigned long long *__restrict__ cursor, dge_record16 *__restrict__ out)
+{
+    __shared__ uint32_t cnt[64], start[65];
+    __shared__ unsigned long long basep[64];
+    __shared__ uint4 staged[256 * ROUTE_ITEMS];
+    if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t base = size_t(blockIdx.x) * 256 * ROUTE_ITEMS;
+    const uint32_t in_tile = uint32_t(min(size_t(256 * ROUTE_ITEMS), n - base));
+    uint4 rec[ROUTE_ITEMS];
+    uint32_t rk[ROUTE_ITEMS], pos[ROUTE_ITEMS];
+#pragma unroll
+    for (int j = 0; j < ROUTE_ITEMS; ++j)
+    {
+        const uint32_t i = uint32_t(j) * 256 + threadIdx.x;
+        if (i < in_tile) rec[j] = __ldcs(reinterpret_cast<const uint4 *>(in) + base + i); // read once
+    }
+#pragma unroll
+    for (int j = 0; j < ROUTE_ITEMS; ++j)
+    {
+        const uint32_t i = uint32_t(j) * 256 + threadIdx.x;
+        const bool valid = i < in_tile;
+        rk[j] = 0;
+        if (valid) rk[j] = rank_of(((uint64_t(rec[j].y) << 32) | rec[j].x) >> 24, n_ranks);
+        pos[j] = route_rank_in_tile(rk[j], cnt, valid);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        uint32_t acc = 0;
+        for (uint32_t r = 0; r < n_ranks; ++r) { start[r] = acc; acc += cnt[r]; }
+        start[n_ranks] = acc;
+    }
+    if (threadIdx.x < n_ranks && cnt[threadIdx.x]) basep[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ROUTE_ITEMS; ++j)
+    {
+        const uint32_t i = uint32_t(j) * 256 + threadIdx.x;
+        if (i < in_tile) staged[start[rk[j]] + pos[j]] = rec[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ROUTE_ITEMS; ++j)
+    {
+        const uint32_t i = uint32_t(j) * 256 + threadIdx.x;
+        if (i < in_tile)
+        {
+            uint32_t d = 0;
+            while (i >= start[d + 1]) ++d;
+            reinterpret_cast<uint4 *>(out)[basep[d] + (i - start[d])] = staged[i];
+        }
     }
 }
 
@@ -144,11 +219,18 @@ __global__ void __launch_bounds__(256) k_route_count_slices(const dge_record16 *
         if (threadIdx.x < 64) h[threadIdx.x] = 0;
         __syncthreads();
         const size_t base = tile * 2048;
+        unsigned long long key[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {   // all loads of the tile in flight before the first shared-memory atomic
+            const size_t i = base + size_t(j) * 256 + threadIdx.x;
+            key[j] = i < n ? __ldcs(reinterpret_cast<const unsigned long long *>(in + i)) : 0ull;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
         {
-            const size_t i = base + size_t(j) * 256 + threadIdx.x;
-            if (i < n) atomicAdd(&h[rank_of(in[i].key >> 24, n_ranks)], 1u);
+            const bool valid = base + size_t(j) * 256 + threadIdx.x < n;
+            (void)route_rank_in_tile(valid ? rank_of(key[j] >> 24, n_ranks) : 0u, h, valid);
         }
         __syncthreads();
         const size_t sl = base / slice_len;
@@ -279,8 +361,15 @@ int dge_route_scatter_slice_device(int device, const dge_record16 *in_slice, siz
         cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
         if (n_slice)
         {
-            k_route_scatter<<<unsigned(div_up(n_slice, size_t(256 * ROUTE_ITEMS))), 256, 0, st>>>(in_slice, n_slice, n_ranks,
-                                                                                                 reinterpret_cast<unsigned long long *>(slice_cursors_device), out_slice);
+            // staging the tile by destination in shared memory LOSES here (3.46 vs 2.79 ms at 400 M reads, 2 destinations; profiles/r2_route_kernels_ab.txt):
+            // with the warp-aggregated ranking a warp already writes at most n_ranks contiguous runs
+            static const bool staged = std::getenv("DGE_ROUTE_STAGED") && atoi(std::getenv("DGE_ROUTE_STAGED")) == 1;
+            if (staged)
+                k_route_scatter<<<unsigned(div_up(n_slice, size_t(256 * ROUTE_ITEMS))), 256, 0, st>>>(in_slice, n_slice, n_ranks,
+                                                                                                     reinterpret_cast<unsigned long long *>(slice_cursors_device), out_slice);
+            else
+                k_route_scatter_direct<<<unsigned(div_up(n_slice, size_t(256 * ROUTE_ITEMS))), 256, 0, st>>>(in_slice, n_slice, n_ranks,
+                                                                                                            reinterpret_cast<unsigned long long *>(slice_cursors_device), out_slice);
             DGE_LAUNCH_CHECK();
         }
         return DGE_OK;
