@@ -408,6 +408,8 @@ def main():
     phase_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(max(1, args.steps))]
     phase_ms = {"ms_route_a2a_fill": 0.0, "ms_group_init": 0.0, "ms_dist_merge": 0.0, "ms_filter_matrices": 0.0}
 
+    owned_reads = n
+
     def step(k=None):
         """k = index of the timed step (records the phase events), None = warm-up"""
         ev = phase_ev[k] if k is not None else None
@@ -420,6 +422,8 @@ def main():
         else:
             cnt = n
             cont.add_batch_device(raw.data_ptr(), n)
+        nonlocal owned_reads
+        owned_reads = cnt
         if ev: ev[1].record(stream)
         cont.set_initialized()
         if ev: ev[2].record(stream)
@@ -552,8 +556,15 @@ def main():
         diag = exchange_diagnostics(pipe, cont, raw, stream, torch, dist, n, world)
         names = list(phase_ms) + list(diag)
         t = torch.tensor([phase_ms[k] for k in phase_ms] + [diag[k] for k in diag], device=f"cuda:{dev}", dtype=torch.float64)
+        every = torch.empty(world * t.numel(), device=f"cuda:{dev}", dtype=torch.float64)
+        owned = torch.empty(world, device=f"cuda:{dev}", dtype=torch.float64)
+        dist.all_gather_into_tensor(every, t)
+        dist.all_gather_into_tensor(owned, torch.tensor([float(owned_reads)], device=f"cuda:{dev}", dtype=torch.float64))
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         breakdown = {k: float(v) for k, v in zip(names, t.tolist())}
+        # per rank (the step is as slow as its slowest shard: barcode-hash sharding leaves a few per cent of imbalance)
+        breakdown["per_rank"] = {"reads_owned": [int(x) for x in owned.tolist()],
+                                 **{k: [round(float(every[r * t.numel() + i]), 3) for r in range(world)] for i, k in enumerate(list(phase_ms))}}
     if rank != 0:
         return
     # ---- roofline of the dominant kernel, timed live with CUDA events inside the library (on the launching stream).

@@ -16,6 +16,7 @@
 #include "scan.cuh"
 #include "sortdedup.cuh"
 #include <chrono>
+#include <cooperative_groups.h>
 #include <cstdlib>
 
 namespace dge
@@ -527,7 +528,7 @@ __global__ void __launch_bounds__(THREADS) k_l2_bucket(const uint64_t *__restric
                                                        const uint32_t *__restrict__ p2, const uint32_t *__restrict__ sb_base,
                                                        const uint64_t *__restrict__ splitters, uint16_t *__restrict__ ids,
                                                        uint32_t *__restrict__ sub_off, uint64_t *__restrict__ out_keys,
-                                                       const uint32_t *__restrict__ order)
+                                                       const uint32_t *__restrict__ order, uint32_t giant = 0xFFFFFFFFu)
 {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int PER = SC_MAX_P2 / THREADS;
@@ -537,7 +538,7 @@ __global__ void __launch_bounds__(THREADS) k_l2_bucket(const uint64_t *__restric
     const int b = order ? int(order[blockIdx.x]) : int(blockIdx.x);
     const uint32_t np = p2[b];
     const uint32_t off = l1_off[b], nbk = l1_off[b + 1] - off;
-    if (nbk == 0 || np == 0) return;
+    if (nbk == 0 || np == 0 || nbk > giant) return; // buckets above `giant` keys belong to k_l2_bucket_cluster
     const uint32_t sb0 = sb_base[b];
     for (uint32_t i = threadIdx.x; i < np; i += THREADS)
     {
@@ -604,6 +605,120 @@ __global__ void __launch_bounds__(THREADS) k_l2_bucket(const uint64_t *__restric
             const uint32_t i = base + uint32_t(j) * THREADS + threadIdx.x;
             if (i < nbk) out_keys[off + atomicAdd(&cnt[sid[j]], 1u)] = k[j];
         }
+    }
+}
+
+// The same pass for the LONG L1 buckets (one barcode with a few per cent of all reads lands in a single bucket, whatever the radix width:
+// the top key bits are its table slot).  A block per bucket would make that block the critical path of the whole grouping
+// (0.3 M keys per ms and block: a 3.6 M-key bucket = 12 ms against 4 ms for everything else), so a bucket longer than `giant` keys is
+// shared by a thread-block CLUSTER of 8 CTAs: every CTA takes an eighth of the keys, the per-CTA sub-bucket histograms stay in shared
+// memory and are combined through DISTRIBUTED SHARED MEMORY (each CTA reads the 8 histograms: totals -> the bucket's offsets, the
+// counts of the lower-ranked CTAs -> its own cursors), then every CTA scatters its slice.  Clusters walk the size-ordered bucket list
+// and stop at the first bucket that is not long.
+template <int THREADS, int ITEMS>
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(THREADS)
+    k_l2_bucket_cluster(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ l1_off, const uint32_t *__restrict__ p2,
+                        const uint32_t *__restrict__ sb_base, const uint64_t *__restrict__ splitters, uint16_t *__restrict__ ids,
+                        uint32_t *__restrict__ sub_off, uint64_t *__restrict__ out_keys, const uint32_t *__restrict__ order, int nb1, uint32_t giant)
+{
+    namespace cg = cooperative_groups;
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int PER = SC_MAX_P2 / THREADS;
+    constexpr uint32_t CL = 8;
+    __shared__ uint64_t spl[SC_MAX_P2];
+    __shared__ uint32_t cnt[SC_MAX_P2], cur[SC_MAX_P2];
+    __shared__ uint32_t ws[33];
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t crank = cluster.block_rank();
+    const uint32_t n_clusters = gridDim.x / CL;
+    for (uint32_t g = blockIdx.x / CL; g < uint32_t(nb1); g += n_clusters)
+    {
+        const int b = int(order[g]);
+        const uint32_t off = l1_off[b], nbk = l1_off[b + 1] - off;
+        if (nbk <= giant) break; // the list is sorted by decreasing size; uniform over the cluster
+        const uint32_t np = p2[b];
+        const uint32_t sb0 = sb_base[b];
+        for (uint32_t i = threadIdx.x; i < np; i += THREADS)
+        {
+            cnt[i] = 0;
+            if (i + 1 < np) spl[i] = splitters[size_t(b) * SC_MAX_P2 + i];
+        }
+        __syncthreads();
+        // this CTA's slice of the bucket, in whole tiles
+        const uint32_t tiles = (nbk + TILE - 1) / TILE;
+        const uint32_t lo = uint32_t((uint64_t(tiles) * crank) / CL) * TILE, hi = min(nbk, uint32_t((uint64_t(tiles) * (crank + 1)) / CL) * TILE);
+        for (uint32_t base = lo; base < hi; base += TILE)
+        {
+            uint64_t k[ITEMS];
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+            {
+                const uint32_t i = base + uint32_t(j) * THREADS + threadIdx.x;
+                k[j] = i < hi ? __ldg(keys + off + i) : EMPTY64;
+            }
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+            {
+                const uint32_t i = base + uint32_t(j) * THREADS + threadIdx.x;
+                if (i < hi)
+                {
+                    const uint32_t sid = np > 1 ? sub_bucket_of(spl, np - 1, k[j] >> 3) : 0u;
+                    ids[off + i] = uint16_t(sid);
+                    atomicAdd(&cnt[sid], 1u);
+                }
+            }
+        }
+        cluster.sync(); // every CTA's histogram is complete and visible
+        {
+            uint32_t c[PER], pre[PER], sum = 0;
+#pragma unroll
+            for (int q = 0; q < PER; ++q)
+            {
+                const uint32_t i = threadIdx.x * PER + q;
+                c[q] = 0; pre[q] = 0;
+                if (i < np)
+                    for (uint32_t r = 0; r < CL; ++r)
+                    {
+                        const uint32_t v = cluster.map_shared_rank(cnt, r)[i];
+                        c[q] += v;
+                        if (r < crank) pre[q] += v;
+                    }
+                sum += c[q];
+            }
+            uint32_t tot;
+            uint32_t ex = block_exclusive_scan(sum, ws, &tot);
+#pragma unroll
+            for (int q = 0; q < PER; ++q)
+            {
+                const uint32_t i = threadIdx.x * PER + q;
+                if (i < np)
+                {
+                    cur[i] = ex + pre[q];
+                    if (crank == 0) sub_off[sb0 + i] = off + ex;
+                }
+                ex += c[q];
+            }
+        }
+        cluster.sync(); // nobody reads the histograms any more (they are zeroed for the next bucket); cursors are in place
+        for (uint32_t base = lo; base < hi; base += TILE)
+        {
+            uint64_t k[ITEMS];
+            uint16_t sid[ITEMS];
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+            {
+                const uint32_t i = base + uint32_t(j) * THREADS + threadIdx.x;
+                k[j] = i < hi ? __ldg(keys + off + i) : EMPTY64;
+                sid[j] = i < hi ? ids[off + i] : uint16_t(0);
+            }
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+            {
+                const uint32_t i = base + uint32_t(j) * THREADS + threadIdx.x;
+                if (i < hi) out_keys[off + atomicAdd(&cur[sid[j]], 1u)] = k[j];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -826,6 +941,10 @@ __global__ void __launch_bounds__(256) k_compact_uniques(const uint64_t *__restr
 struct SortCombineWorkspace
 {
     DevBuf keysA, valsA, valsB, uvals_sparse, small, splitters, sub_cnt, sub_off, ucount, u_off, scan_scratch, cls_list, cls_count, ids, order;
+    // side stream of the long-bucket cluster kernel (runs beside the block-per-bucket kernel: disjoint buckets)
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    int side_dev = -1, max_clusters = 0;
 };
 
 struct SortCombineStats
@@ -1007,7 +1126,40 @@ public:
             ++L;
             if (l2_bucket == 1) k_l2_bucket<512, 8><<<nb1, 512, 0, st>>>(keysA, l1_off, p2, sb_base, ws.splitters.as<uint64_t>(), ws.ids.as<uint16_t>(), sub_off, keys_tmp, order);
             else if (l2_bucket == 2) k_l2_bucket<1024, 4><<<nb1, 1024, 0, st>>>(keysA, l1_off, p2, sb_base, ws.splitters.as<uint64_t>(), ws.ids.as<uint16_t>(), sub_off, keys_tmp, order);
-            else if (l2_bucket == 3) k_l2_bucket<1024, 8><<<nb1, 1024, 0, st>>>(keysA, l1_off, p2, sb_base, ws.splitters.as<uint64_t>(), ws.ids.as<uint16_t>(), sub_off, keys_tmp, order);
+            else if (l2_bucket == 3)
+            {
+                // long buckets: shared by 8-CTA clusters on a side stream, beside the block-per-bucket kernel (disjoint buckets, disjoint outputs)
+                const uint32_t giant = std::getenv("DGE_L2_GIANT") ? uint32_t(atoll(std::getenv("DGE_L2_GIANT"))) : 786432u; // read per run: the tests lower it
+                const bool clusters = giant != 0xFFFFFFFFu && giant != 0;
+                if (clusters)
+                {
+                    int dev = 0;
+                    DGE_CUDA(cudaGetDevice(&dev));
+                    if (ws.side_dev != dev)
+                    {
+                        DGE_CUDA(cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking));
+                        DGE_CUDA(cudaEventCreateWithFlags(&ws.fork_ev, cudaEventDisableTiming));
+                        DGE_CUDA(cudaEventCreateWithFlags(&ws.join_ev, cudaEventDisableTiming));
+                        // clusters that can be resident together (8 CTAs must share a GPC): more would only queue behind them
+                        cudaLaunchConfig_t lc = {};
+                        lc.gridDim = dim3(8 * 64); lc.blockDim = dim3(1024); lc.dynamicSmemBytes = 0;
+                        cudaLaunchAttribute at[1];
+                        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                        lc.attrs = at; lc.numAttrs = 1;
+                        int mc = 0;
+                        if (cudaOccupancyMaxActiveClusters(&mc, k_l2_bucket_cluster<1024, 8>, &lc) != cudaSuccess || mc < 1) { (void)cudaGetLastError(); mc = 16; }
+                        ws.max_clusters = std::min(mc, 64);
+                        ws.side_dev = dev;
+                    }
+                    DGE_CUDA(cudaEventRecord(ws.fork_ev, st));
+                    DGE_CUDA(cudaStreamWaitEvent(ws.side, ws.fork_ev, 0));
+                    k_l2_bucket_cluster<1024, 8><<<ws.max_clusters * 8, 1024, 0, ws.side>>>(keysA, l1_off, p2, sb_base, ws.splitters.as<uint64_t>(), ws.ids.as<uint16_t>(), sub_off, keys_tmp, order, nb1, giant);
+                    DGE_CUDA(cudaEventRecord(ws.join_ev, ws.side));
+                    ++L;
+                }
+                k_l2_bucket<1024, 8><<<nb1, 1024, 0, st>>>(keysA, l1_off, p2, sb_base, ws.splitters.as<uint64_t>(), ws.ids.as<uint16_t>(), sub_off, keys_tmp, order, clusters ? giant : 0xFFFFFFFFu);
+                if (clusters) DGE_CUDA(cudaStreamWaitEvent(st, ws.join_ev, 0));
+            }
             else k_l2_bucket<1024, 4><<<nb1, 1024, 0, st>>>(keysA, l1_off, p2, sb_base, ws.splitters.as<uint64_t>(), ws.ids.as<uint16_t>(), sub_off, keys_tmp, nullptr);
             k_set_u32_at<<<1, 1, 0, st>>>(sub_off, sb_base + nb1, uint32_t(n));
             L += 2;

@@ -381,6 +381,19 @@ def test_segment_batches_in_one_launch(cuts):
     pu.assert_parity(res)
 
 
+@pytest.mark.parametrize("giant", [1000, 50000])
+def test_long_l1_buckets_shared_by_clusters(monkeypatch, giant):
+    """k_l2_bucket_cluster (8-CTA clusters, histograms combined through distributed shared memory) takes the L1 buckets longer than
+    DGE_L2_GIANT keys; with the threshold lowered every bucket (1000) or only the longest ones (50000) go through it."""
+    monkeypatch.setenv("DGE_L2_GIANT", str(giant))
+    wl = read_whitelist(pu.WL_SYNTH_7_9)
+    spec = SynthSpec(n_reads=3_000_000, n_cells=300, n_genes=2000, cb_len=16, umi_len=10, whitelist_parts=wl, cb_error_ppm=20000, seed=29)
+    case = pu.Case(name="giant_buckets", spec=spec, cb_len=16, umi_len=10, n_genes=2000, merge="real", barcodes=pu.WL_SYNTH_7_9,
+                   min_genes_before=10, min_genes_after=30, dump_umis=False, n_batches=2)
+    res = pu.run_case(case)
+    pu.assert_parity(res)
+
+
 def test_merge_simple_dropseq_like_2m():
     """Drop-seq shaped stream (12 bp barcodes, 8 bp UMIs, no whitelist -> SimpleMergeStrategy) at a size where the inverted index and
     the pair lists are non-trivial; checked against the oracle."""
