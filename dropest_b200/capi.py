@@ -43,6 +43,7 @@ DIST_DONE, DIST_ALLGATHER, DIST_ALLTOALL = 0, 1, 2
 # exported symbols of include/dropest_b200.h (checked by tests/test_abi.py)
 EXPORTS = [
     "dge_config_default", "dge_create", "dge_destroy", "dge_last_error", "dge_add_batch", "dge_add_batch_device", "dge_add_batch_segments_device", "dge_add_batch_soa",
+    "dge_add_batch_chr", "dge_add_batch_soa_chr", "dge_add_batch_chr_device", "dge_get_chr_stats",
     "dge_set_initialized", "dge_merge_and_filter", "dge_reset", "dge_set_stream", "dge_set_n_strings", "dge_get_summary", "dge_get_timings", "dge_get_cells",
     "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
@@ -151,6 +152,10 @@ def load_library():
     lib.dge_route_scatter_slice_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dge_dist_step.argtypes = [C.c_void_p, C.POINTER(_DistIO)]
     lib.dge_add_batch_segments_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint32]
+    lib.dge_add_batch_chr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.dge_add_batch_soa_chr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64]
+    lib.dge_add_batch_chr_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.dge_get_chr_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.c_void_p]
     lib.dge_peer_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
     lib.dge_peer_free.argtypes = [C.c_int, C.c_void_p]
     lib.dge_peer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
@@ -285,6 +290,35 @@ class Container:
         genes = np.ascontiguousarray(genes, dtype=np.uint32)
         assert keys.shape == genes.shape
         self._check(self._lib.dge_add_batch_soa(self._h, keys.ctypes.data, genes.ctypes.data, keys.shape[0], first_read_idx))
+
+    def add_batch_chr(self, recs: np.ndarray, chr_ids: np.ndarray):
+        """Host records + the chromosome id of every read (uint8): also feeds the per-chromosome Stats counters."""
+        recs = np.ascontiguousarray(recs, dtype=RECORD_DTYPE)
+        chr_ids = np.ascontiguousarray(chr_ids, dtype=np.uint8)
+        assert chr_ids.shape[0] == recs.shape[0]
+        self._check(self._lib.dge_add_batch_chr(self._h, recs.ctypes.data, chr_ids.ctypes.data, recs.shape[0]))
+
+    def add_batch_soa_chr(self, keys: np.ndarray, genes: np.ndarray, chr_ids: np.ndarray, first_read_idx: int = 0):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        genes = np.ascontiguousarray(genes, dtype=np.uint32)
+        chr_ids = np.ascontiguousarray(chr_ids, dtype=np.uint8)
+        assert keys.shape == genes.shape == chr_ids.shape
+        self._check(self._lib.dge_add_batch_soa_chr(self._h, keys.ctypes.data, genes.ctypes.data, chr_ids.ctypes.data, keys.shape[0], first_read_idx))
+
+    def add_batch_chr_device(self, dev_ptr: int, chr_dev_ptr: int, n: int, keepalive=None):
+        if keepalive is not None:
+            self._keepalive.append(keepalive)
+        self._check(self._lib.dge_add_batch_chr_device(self._h, C.c_void_p(dev_ptr), C.c_void_p(chr_dev_ptr), n))
+
+    def chr_stats(self):
+        """(counts[n_real_cells, n_chr, 3] int32 -- exon / intron / intergenic reads, cells in CELLS_REAL order --, presented[3, n_chr] bool)"""
+        n_cells, n_chr = C.c_size_t(0), C.c_uint32(0)
+        self._check(self._lib.dge_get_chr_stats(self._h, None, 0, C.byref(n_cells), C.byref(n_chr), None))
+        counts = np.zeros((n_cells.value, n_chr.value, 3), dtype=np.int32)
+        presented = np.zeros((3, n_chr.value), dtype=np.uint8)
+        if n_chr.value:
+            self._check(self._lib.dge_get_chr_stats(self._h, counts.ctypes.data, n_cells.value, C.byref(n_cells), C.byref(n_chr), presented.ctypes.data))
+        return counts, presented.astype(bool)
 
     def add_batch_device(self, dev_ptr: int, n: int, keepalive=None):
         if keepalive is not None:

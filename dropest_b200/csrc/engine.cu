@@ -8,6 +8,7 @@
 // There is no CPU implementation of the grouping here: without a CUDA device every entry point fails.
 #include "../../include/dropest_b200.h"
 #include "collisions.cuh"
+#include "chrstats.cuh"
 #include "distmerge.cuh"
 #include "common.cuh"
 #include "fill.cuh"
@@ -95,6 +96,10 @@ struct dge_handle
     size_t n_chunk_counters = 0;
     uint64_t n_reads = 0;
     int staging_turn = 0;
+    // per-(cell, chromosome) read counters (chrstats.cuh); allocated by the first batch that brings a chromosome array
+    DevBuf chr_tab, chr_ctr, chr_export, chr_staging[2];
+    size_t chr_cap = 0;
+    bool chr_used = false;
     cudaEvent_t staging_ev[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copied_ev[2] = {nullptr, nullptr};
@@ -359,6 +364,12 @@ void reset_fill_state(dge_handle *h)
     h->regions.reserve(size_t(4096) * 148 * sizeof(KeyRegion)); // every batch adds one region per block (<= 4096 batches)
     DGE_CUDA(cudaMemsetAsync(h->hist12.p, 0, 4096 * 4, h->stream));
     h->n_regions = 0; h->pipe_fill = false;
+    if (h->chr_cap)
+    {
+        DGE_CUDA(cudaMemsetAsync(h->chr_tab.p, 0, h->chr_cap * sizeof(ChrEntry), h->stream));
+        DGE_CUDA(cudaMemsetAsync(h->chr_ctr.p, 0, sizeof(ChrCounters), h->stream));
+    }
+    h->chr_used = false;
     h->overflow_flag.reserve(sizeof(int));
     DGE_CUDA(cudaMemsetAsync(h->overflow_flag.p, 0, sizeof(int), h->stream));
     h->scan_scratch.reserve(((size_t(1) << 20) + 64) * 4); // enough for any scan of < 2^32 elements
@@ -2857,9 +2868,37 @@ int dge_add_batch_device(dge_handle *h, const dge_record16 *recs, size_t n)
     return guarded(h, [&] { ensure_device(h); fill_from_device(h, recs, n); return int(DGE_OK); });
 }
 
+// Per-chromosome counters of one batch (device arrays); runs behind the batch's fill kernel, which has inserted every barcode.
+static void chr_stats_from_device(dge_handle *h, const dge_record16 *recs, const unsigned long long *soa_keys, const uint32_t *soa_genes,
+                                  const uint8_t *chr, size_t n)
+{
+    if (n == 0) return;
+    if (h->kl.tb > 24) throw CapacityError("per-chromosome statistics need at most 2^24 barcode slots (lower max_barcodes_hint)");
+    if (!h->chr_cap)
+    {
+        int bits = std::min(26, std::max(12, h->kl.tb + 3));
+        h->chr_cap = size_t(1) << bits;
+        h->chr_tab.reserve(h->chr_cap * sizeof(ChrEntry));
+        h->chr_ctr.reserve(sizeof(ChrCounters) + 16);
+        DGE_CUDA(cudaMemsetAsync(h->chr_tab.p, 0, h->chr_cap * sizeof(ChrEntry), h->stream));
+        DGE_CUDA(cudaMemsetAsync(h->chr_ctr.p, 0, sizeof(ChrCounters), h->stream));
+    }
+    h->chr_used = true;
+    const unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(256)), size_t(148) * 16));
+    if (soa_keys)
+        k_chr_stats<true><<<grid, 256, 0, h->stream>>>(nullptr, soa_keys, soa_genes, chr, n, h->tab.as<CellSlot>(), h->kl, h->chr_tab.as<ChrEntry>(),
+                                                      uint32_t(h->chr_cap - 1), h->chr_ctr.as<ChrCounters>());
+    else
+        k_chr_stats<false><<<grid, 256, 0, h->stream>>>(reinterpret_cast<const Rec16 *>(recs), nullptr, nullptr, chr, n, h->tab.as<CellSlot>(), h->kl,
+                                                       h->chr_tab.as<ChrEntry>(), uint32_t(h->chr_cap - 1), h->chr_ctr.as<ChrCounters>());
+    DGE_LAUNCH_CHECK();
+    ++h->launches;
+}
+
 // Host batches: double-buffered device staging filled on a COPY stream, consumed by the fill kernel on the main stream, so the H2D
 // copy of slice k+1 overlaps the fill kernel of slice k (the copies are truly asynchronous when the host memory is page-locked).
-static void add_host_slices(dge_handle *h, const dge_record16 *recs, const unsigned long long *keys, const uint32_t *genes, size_t n, uint64_t first_idx)
+static void add_host_slices(dge_handle *h, const dge_record16 *recs, const unsigned long long *keys, const uint32_t *genes, size_t n, uint64_t first_idx,
+                            const uint8_t *chr = nullptr)
 {
     ensure_device(h);
     if (!h->copy_stream)
@@ -2879,6 +2918,14 @@ static void add_host_slices(dge_handle *h, const dge_record16 *recs, const unsig
         // the fill kernel that last read this staging buffer must have finished before it is overwritten
         DGE_CUDA(cudaStreamWaitEvent(h->copy_stream, h->staging_ev[turn], 0));
         if (stg.bytes < m * 16 + 64) { DGE_CUDA(cudaEventSynchronize(h->staging_ev[turn])); stg.reserve(m * 16 + 64); }
+        uint8_t *dchr = nullptr;
+        if (chr)
+        {
+            DevBuf &cs = h->chr_staging[turn];
+            if (cs.bytes < m + 64) { DGE_CUDA(cudaEventSynchronize(h->staging_ev[turn])); cs.reserve(m + 64); }
+            dchr = cs.as<uint8_t>();
+            DGE_CUDA(cudaMemcpyAsync(dchr, chr + off, m, cudaMemcpyHostToDevice, h->copy_stream));
+        }
         if (soa)
         {
             unsigned long long *dk = stg.as<unsigned long long>();
@@ -2888,6 +2935,7 @@ static void add_host_slices(dge_handle *h, const dge_record16 *recs, const unsig
             DGE_CUDA(cudaEventRecord(h->copied_ev[turn], h->copy_stream));
             DGE_CUDA(cudaStreamWaitEvent(h->stream, h->copied_ev[turn], 0));
             fill_from_device(h, nullptr, m, dk, dg, uint32_t(first_idx + off));
+            if (chr) chr_stats_from_device(h, nullptr, dk, dg, dchr, m);
         }
         else
         {
@@ -2895,6 +2943,7 @@ static void add_host_slices(dge_handle *h, const dge_record16 *recs, const unsig
             DGE_CUDA(cudaEventRecord(h->copied_ev[turn], h->copy_stream));
             DGE_CUDA(cudaStreamWaitEvent(h->stream, h->copied_ev[turn], 0));
             fill_from_device(h, stg.as<dge_record16>(), m);
+            if (chr) chr_stats_from_device(h, stg.as<dge_record16>(), nullptr, nullptr, dchr, m);
         }
         DGE_CUDA(cudaEventRecord(h->staging_ev[turn], h->stream));
     }
@@ -2915,6 +2964,96 @@ int dge_add_batch_soa(dge_handle *h, const uint64_t *keys, const uint32_t *genes
     if (h->state != 0) return fail(h, DGE_ERR_STATE, "Container is already initialized");
     if (first_read_idx + n > 0xFFFFFFFFull) return fail(h, DGE_ERR_INVALID, "read_idx beyond 2^32");
     return guarded(h, [&] { add_host_slices(h, nullptr, reinterpret_cast<const unsigned long long *>(keys), genes, n, first_read_idx); return int(DGE_OK); });
+}
+
+int dge_add_batch_chr(dge_handle *h, const dge_record16 *recs, const uint8_t *chr, size_t n)
+{
+    if (!h || ((!recs || !chr) && n)) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state != 0) return fail(h, DGE_ERR_STATE, "Container is already initialized");
+    return guarded(h, [&] { add_host_slices(h, recs, nullptr, nullptr, n, 0, chr); return int(DGE_OK); });
+}
+
+int dge_add_batch_soa_chr(dge_handle *h, const uint64_t *keys, const uint32_t *genes, const uint8_t *chr, size_t n, uint64_t first_read_idx)
+{
+    if (!h || ((!keys || !genes || !chr) && n)) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state != 0) return fail(h, DGE_ERR_STATE, "Container is already initialized");
+    if (first_read_idx + n > 0xFFFFFFFFull) return fail(h, DGE_ERR_INVALID, "read_idx beyond 2^32");
+    return guarded(h, [&] { add_host_slices(h, nullptr, reinterpret_cast<const unsigned long long *>(keys), genes, n, first_read_idx, chr); return int(DGE_OK); });
+}
+
+int dge_add_batch_chr_device(dge_handle *h, const dge_record16 *recs, const uint8_t *chr, size_t n)
+{
+    if (!h || ((!recs || !chr) && n)) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state != 0) return fail(h, DGE_ERR_STATE, "Container is already initialized");
+    return guarded(h, [&] { ensure_device(h); fill_from_device(h, recs, n); chr_stats_from_device(h, recs, nullptr, nullptr, chr, n); return int(DGE_OK); });
+}
+
+// Stats::get(CellChrStatType) for the real cells, Stats::merge applied (Stats.cpp:29-63): counts[cell][chr][0 exon | 1 intron | 2 intergenic]
+int dge_get_chr_stats(dge_handle *h, int32_t *counts, size_t capacity_cells, size_t *n_cells, uint32_t *n_chr, uint8_t *presented)
+{
+    if (!h || !n_cells || !n_chr) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state != 2) return fail(h, DGE_ERR_STATE, "per-chromosome statistics are read after merge_and_filter");
+    return guarded(h, [&] {
+        DGE_CUDA(cudaSetDevice(h->cfg.device));
+        if (h->cfg.sharded) throw std::runtime_error("per-chromosome statistics are not available on sharded (multi-GPU) handles yet");
+        materialize_host(h);
+        std::vector<uint32_t> pos(h->real.size(), NONE32);
+        size_t nr = 0;
+        for (size_t i = 0; i < h->real.size(); ++i) if (h->real[i].real) pos[i] = uint32_t(nr++);
+        *n_cells = nr;
+        *n_chr = 0;
+        if (!h->chr_used) return int(DGE_OK);
+        ChrCounters cc;
+        DGE_CUDA(cudaMemcpyAsync(&cc, h->chr_ctr.p, sizeof(cc), cudaMemcpyDeviceToHost, h->stream));
+        DGE_CUDA(cudaStreamSynchronize(h->stream));
+        if (cc.overflow) throw CapacityError("per-chromosome counter table overflow (raise max_barcodes_hint)");
+        if (cc.missing_cell) throw std::runtime_error("internal: a chromosome batch named a barcode the fill had not seen");
+        *n_chr = cc.max_chr + 1;
+        if (!counts && !presented) return int(DGE_OK);
+        if (counts && capacity_cells < nr) throw InvalidInput("dge_get_chr_stats: capacity_cells is smaller than the number of real cells");
+        // occupied entries -> host (a query outside the per-read path: a few MB)
+        h->chr_export.reserve(h->chr_cap * sizeof(ChrEntry));
+        unsigned long long *d_n = reinterpret_cast<unsigned long long *>(h->chr_ctr.as<unsigned char>() + sizeof(ChrCounters));
+        DGE_CUDA(cudaMemsetAsync(d_n, 0, 8, h->stream));
+        k_chr_export<<<unsigned(div_up(h->chr_cap, size_t(256))), 256, 0, h->stream>>>(h->chr_tab.as<ChrEntry>(), h->chr_cap, h->chr_export.as<ChrEntry>(), d_n);
+        DGE_LAUNCH_CHECK();
+        unsigned long long n_ent = 0;
+        DGE_CUDA(cudaMemcpyAsync(&n_ent, d_n, 8, cudaMemcpyDeviceToHost, h->stream));
+        DGE_CUDA(cudaStreamSynchronize(h->stream));
+        std::vector<ChrEntry> ent;
+        ent.resize(size_t(n_ent));
+        if (n_ent) DGE_CUDA(cudaMemcpy(ent.data(), h->chr_export.p, size_t(n_ent) * sizeof(ChrEntry), cudaMemcpyDeviceToHost));
+        const uint32_t nc = *n_chr;
+        if (counts) std::fill(counts, counts + nr * nc * 3, 0);
+        if (presented) std::fill(presented, presented + size_t(3) * nc, uint8_t(0));
+        std::unordered_map<uint32_t, uint32_t> by_slot;
+        by_slot.reserve(h->real.size() * 2);
+        for (size_t i = 0; i < h->real.size(); ++i) by_slot.emplace(h->real[i].slot, uint32_t(i));
+        for (auto const &e : ent)
+        {
+            const uint32_t key = e.key - 1u, slot = key >> 8, c = key & 255u;
+            if (presented)
+            {
+                if (e.exon) presented[0 * nc + c] = 1;
+                if (e.intron) presented[1 * nc + c] = 1;
+                if (e.intergenic) presented[2 * nc + c] = 1;
+            }
+            if (!counts) continue;
+            auto it = by_slot.find(slot);
+            if (it == by_slot.end()) continue; // never a real cell: neither reported nor a merge source
+            uint32_t f = it->second;
+            for (int hop = 0; hop < 64; ++hop)
+            {   // merge targets are final (MergeStrategyBase::reassign); follow defensively
+                const int32_t t = h->real[f].target;
+                if (t < 0 || uint32_t(t) == f || !h->real[f].merged) break;
+                f = uint32_t(t);
+            }
+            if (pos[f] == NONE32) continue; // excluded, or merged into a cell of another kind
+            int32_t *row = counts + (size_t(pos[f]) * nc + c) * 3;
+            row[0] += int32_t(e.exon); row[1] += int32_t(e.intron); row[2] += int32_t(e.intergenic);
+        }
+        return int(DGE_OK);
+    });
 }
 
 int dge_reset(dge_handle *h)

@@ -106,6 +106,25 @@ namespace Estimation
 		return n;
 	}
 
+	Gene::s_ul_hash_t Gene::requested_reads_per_umi(const UMI::Mark::query_t &query) const
+	{
+		s_ul_hash_t res;
+		for (auto const &u : _umis)
+			if (u.second.mark().match(query)) res.emplace(_umi_indexer->get_value(u.first), u.second.read_count());
+		return res;
+	}
+
+	Cell::ss_ul_hash_t Cell::requested_reads_per_umi_per_gene(const UMI::Mark::query_t &query_marks) const
+	{
+		ss_ul_hash_t res;
+		for (auto const &g : _genes)
+		{
+			Gene::s_ul_hash_t r(g.second.requested_reads_per_umi(query_marks));
+			if (!r.empty()) res.emplace(_gene_indexer->get_value(g.first), r);
+		}
+		return res;
+	}
+
 	Cell::s_ul_hash_t Cell::requested_umis_per_gene(const UMI::Mark::query_t &query_marks, bool return_reads) const
 	{
 		s_ul_hash_t res;
@@ -296,17 +315,19 @@ namespace Estimation
 		if (_batch_keys.empty()) return;
 		if (!_batch_gaps)
 		{   // add_record is called in stream order, so the read index is implicit: 12 bytes per read go to the device
-			check(dge_add_batch_soa(_h, _batch_keys.data(), _batch_genes.data(), _batch_keys.size(), _batch_first));
+			if (_chr_overflow) check(dge_add_batch_soa(_h, _batch_keys.data(), _batch_genes.data(), _batch_keys.size(), _batch_first));
+			else check(dge_add_batch_soa_chr(_h, _batch_keys.data(), _batch_genes.data(), _batch_chr.data(), _batch_keys.size(), _batch_first));
 		}
 		else
 		{   // skipped reads left gaps in the numbering: 16-byte records with explicit stream positions
 			std::vector<dge_record16> recs(_batch_keys.size());
 			for (size_t i = 0; i < recs.size(); ++i) recs[i] = dge_record16{_batch_keys[i], _batch_genes[i], _batch_idx[i]};
-			check(dge_add_batch(_h, recs.data(), recs.size()));
+			if (_chr_overflow) check(dge_add_batch(_h, recs.data(), recs.size()));
+			else check(dge_add_batch_chr(_h, recs.data(), _batch_chr.data(), recs.size()));
 		}
 		_batch_first = _n_records;
 		_batch_gaps = false;
-		_batch_keys.clear(); _batch_genes.clear(); _batch_idx.clear();
+		_batch_keys.clear(); _batch_genes.clear(); _batch_idx.clear(); _batch_chr.clear();
 	}
 
 	void CellsDataContainer::add_record(const ReadInfo &read_info)
@@ -346,6 +367,34 @@ namespace Estimation
 		}
 		uint32_t gene = DGE_NO_GENE;
 		if (!read_info.gene.empty()) gene = uint32_t(_gene_indexer.add(read_info.gene));
+		// Stats::inc(CellChrStatType, chromosome) of add_record / update_cell_stats (CellsDataContainer.cpp:73-78, 313-322): the id is
+		// assigned and the statistic's chromosome set grows only when this read is counted
+		uint8_t chr_id = 0;
+		if (!_chr_overflow)
+		{
+			const unsigned m = read_info.umi_mark.bits();
+			const bool inter = read_info.gene.empty();
+			if (inter || (m & 6u))
+			{
+				const size_t id = _chromosome_indexer.add(read_info.chromosome_name);
+				if (id > 255)
+				{
+					_chr_overflow = true;
+					std::cerr << "dropest_b200: more than 256 chromosome names; reads_per_chr_per_cells is not produced\n";
+				}
+				else
+				{
+					chr_id = uint8_t(id);
+					if (inter) _presented_chromosomes[Stats::INTERGENIC_READS_PER_CHR_PER_CELL].insert(id);
+					else
+					{
+						if (m & 2u) _presented_chromosomes[Stats::EXON_READS_PER_CHR_PER_CELL].insert(id);
+						if (m & 4u) _presented_chromosomes[Stats::INTRON_READS_PER_CHR_PER_CELL].insert(id);
+					}
+				}
+			}
+		}
+		_batch_chr.push_back(chr_id);
 		_batch_keys.push_back((cbv << 24) | umiv);
 		_batch_genes.push_back(gene | (uint32_t(read_info.umi_mark.bits()) << 24) | flags);
 		_batch_idx.push_back(uint32_t(_n_records));
@@ -449,6 +498,31 @@ namespace Estimation
 		for (auto const &c : _cells)
 			if (c.is_real()) res[c.barcode()] = c.stats().get(type);
 		return res;
+	}
+
+	void CellsDataContainer::get_stat_by_real_cells(Stats::CellChrStatType stat, names_t &cell_barcodes, names_t &chromosome_names, counts_t &counts) const
+	{
+		if (_chr_overflow) throw std::runtime_error("per-chromosome statistics were dropped: more than 256 chromosome names");
+		load_cells();
+		size_t n_cells = 0;
+		uint32_t n_chr = 0;
+		check(dge_get_chr_stats(_h, nullptr, 0, &n_cells, &n_chr, nullptr));
+		std::vector<int32_t> dense(n_cells * n_chr * 3 + 1);
+		if (n_chr) check(dge_get_chr_stats(_h, dense.data(), n_cells, &n_cells, &n_chr, nullptr));
+		const auto &presented = _presented_chromosomes[stat];
+		size_t k = 0; // index among the real cells (DGE_CELLS_REAL order = cell-id order)
+		for (auto const &c : _cells)
+		{
+			if (!c.is_real()) continue;
+			const int32_t *row = dense.data() + k * n_chr * 3;
+			++k;
+			bool any = false;
+			for (uint32_t ch = 0; ch < n_chr && !any; ++ch) any = row[ch * 3 + stat] != 0;
+			if (!any) continue; // Stats::get returns false for a cell without an entry for this statistic (Stats.cpp:50-54)
+			for (size_t id : presented) counts.push_back(id < n_chr ? row[id * 3 + stat] : 0);
+			cell_barcodes.push_back(c.barcode());
+		}
+		for (size_t id : presented) chromosome_names.push_back(_chromosome_indexer.get_value(id)); // Stats::presented_chromosomes, :65-73
 	}
 
 	// ---- ResultsPrinter ---------------------------------------------------------------------------------------------------
@@ -566,7 +640,23 @@ namespace Estimation
 				for (int32_t x : v) i32(x);
 				if (names) { tagged("names"); strvec(*names); nil(); }
 			}
-			void realvec(const std::vector<double> &v) { flags(14); i32(int32_t(v.size())); for (double x : v) f64(x); }
+			void realvec(const std::vector<double> &v, const std::vector<std::string> *names = nullptr)
+			{
+				flags(14, false, names != nullptr);
+				i32(int32_t(v.size()));
+				for (double x : v) f64(x);
+				if (names) { tagged("names"); strvec(*names); nil(); }
+			}
+			// integer matrix, column-major, with dimnames (what Rcpp's IntegerMatrix + rownames/colnames wraps to)
+			void intmatrix(const std::vector<int32_t> &col_major, const std::vector<std::string> &row_names, const std::vector<std::string> &col_names)
+			{
+				flags(13, false, true);
+				i32(int32_t(col_major.size()));
+				for (int32_t x : col_major) i32(x);
+				tagged("dim"); intvec({int32_t(row_names.size()), int32_t(col_names.size())});
+				tagged("dimnames"); flags(19); i32(2); strvec(row_names); strvec(col_names);
+				nil();
+			}
 			void named_strvec(const std::vector<std::string> &v, const std::vector<std::string> &names)
 			{
 				flags(16, false, true); strvec_body(v);
@@ -593,12 +683,14 @@ namespace Estimation
 	void ResultsPrinter::save_rds(const CellsDataContainer &container, const SparseMatrix &cm, const SparseMatrix &cm_raw,
 	                              const std::string &filename_base) const
 	{
-		// d <- list(cm, cm_raw, merge_targets, aligned_reads_per_cell, aligned_umis_per_cell, requested_umis_per_cb); saveRDS(d, base.rds)
-		// (field names and meaning: ResultsPrinter.cpp:47-57; docs/dropest.rst:178-194).  The diagnostic tables that need per-chromosome
-		// statistics or per-UMI quality (reads_per_chr_per_cells, saturation_info, mean_reads_per_umi, reads_per_umi_per_cell) are not produced.
-		std::vector<std::string> mt_from, mt_to, real_names;
-		std::vector<int32_t> reads, umis, req_umis;
+		// d <- list(cm, cm_raw, reads_per_chr_per_cells, mean_reads_per_umi, saturation_info, merge_targets, aligned_reads_per_cell,
+		// aligned_umis_per_cell, requested_umis_per_cb, requested_reads_per_cb); saveRDS(d, base.rds) -- field names, order and meaning:
+		// ResultsPrinter.cpp:36-57, docs/dropest.rst:178-194.  reads_per_umi_per_cell (only with -u info, needs per-UMI base qualities) is not produced.
+		std::vector<std::string> mt_from, mt_to, real_names, sat_cbs, sat_umis;
+		std::vector<int32_t> reads, umis, req_umis, req_reads, sat_reads;
+		std::vector<double> mean_rpu;
 		const auto &targets = container.merge_targets();
+		const auto &query = container.gene_match_level();
 		for (size_t i = 0; i < container.total_cells_number(); ++i)
 		{
 			const Cell &c = container.cell(i);
@@ -608,16 +700,55 @@ namespace Estimation
 			reads.push_back(c.stats().get(Stats::TOTAL_READS_PER_CB));
 			umis.push_back(c.stats().get(Stats::TOTAL_UMIS_PER_CB));
 			req_umis.push_back(int32_t(c.requested_umis_num()));
+			size_t rr = 0;                                            // get_requested_umis_per_cb(container, true), :398-431
+			for (auto const &g : c.requested_umis_per_gene(query, true)) rr += g.second;
+			req_reads.push_back(int32_t(rr));
+			size_t n_umis = 0;                                        // get_mean_reads_per_umi, :227-258 (0 / 0 = NaN for a cell without UMIs, as in R)
+			double n_reads = 0.0;
+			for (auto const &g : c.genes())
+			{
+				for (auto const &u : g.second.umis()) n_reads += double(u.second.read_count());
+				n_umis += g.second.size();
+			}
+			mean_rpu.push_back(n_reads / double(n_umis));
+			for (auto const &g : c.requested_reads_per_umi_per_gene(query)) // get_saturation_analysis_info, :113-138
+				for (auto const &u : g.second)
+				{
+					sat_cbs.push_back(c.barcode()); sat_umis.push_back(u.first); sat_reads.push_back(int32_t(u.second));
+				}
 		}
+		const bool chr_tables = container.chromosome_stats_available();
 		RdsWriter w(filename_base + ".rds");
-		w.list_header(6);
+		w.list_header(chr_tables ? 10 : 9);
 		w.dgcmatrix(cm);
 		w.dgcmatrix(cm_raw);
+		if (chr_tables)
+		{   // get_reads_per_chr_per_cell_info, :140-166: list(Exon, Intron, Intergenic) of cells x chromosomes integer matrices
+			w.list_header(3);
+			for (auto stat : {Stats::EXON_READS_PER_CHR_PER_CELL, Stats::INTRON_READS_PER_CHR_PER_CELL, Stats::INTERGENIC_READS_PER_CHR_PER_CELL})
+			{
+				CellsDataContainer::names_t cells, chrs;
+				CellsDataContainer::counts_t counts;
+				container.get_stat_by_real_cells(stat, cells, chrs, counts);
+				std::vector<int32_t> col_major(counts.size());
+				for (size_t r = 0; r < cells.size(); ++r)
+					for (size_t ch = 0; ch < chrs.size(); ++ch) col_major[ch * cells.size() + r] = counts[r * chrs.size() + ch]; // create_matrix transposes, :102-111
+				w.intmatrix(col_major, cells, chrs);
+			}
+			w.list_names({"Exon", "Intron", "Intergenic"});
+		}
+		w.realvec(mean_rpu, &real_names);
+		w.list_header(3); w.intvec(sat_reads); w.strvec(sat_cbs); w.strvec(sat_umis); w.list_names({"reads", "cbs", "umis"});
 		w.named_strvec(mt_to, mt_from);
 		w.intvec(reads, &real_names);
 		w.intvec(umis, &real_names);
 		w.intvec(req_umis, &real_names);
-		w.list_names({"cm", "cm_raw", "merge_targets", "aligned_reads_per_cell", "aligned_umis_per_cell", "requested_umis_per_cb"});
+		w.intvec(req_reads, &real_names);
+		std::vector<std::string> fields = {"cm", "cm_raw"};
+		if (chr_tables) fields.push_back("reads_per_chr_per_cells");
+		for (const char *f : {"mean_reads_per_umi", "saturation_info", "merge_targets", "aligned_reads_per_cell", "aligned_umis_per_cell",
+		                      "requested_umis_per_cb", "requested_reads_per_cb"}) fields.push_back(f);
+		w.list_names(fields);
 	}
 
 	void ResultsPrinter::save_results(const CellsDataContainer &container, const std::string &filename) const

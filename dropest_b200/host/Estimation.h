@@ -14,6 +14,7 @@
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 namespace Tools
@@ -140,10 +141,11 @@ namespace Estimation
 			: params(params), gene(gene), chromosome_name(chromosome_name), umi_mark(umi_mark) {}
 	};
 
-	class Stats // Stats.h (per-cell counters; per-chromosome tables are not on this path yet)
+	class Stats // Stats.h (per-cell counters; the per-chromosome tables are read from the device by CellsDataContainer::get_stat_by_real_cells)
 	{
 	public:
 		enum CellStatType { TOTAL_READS_PER_CB, TOTAL_UMIS_PER_CB, CELL_STAT_SIZE };
+		enum CellChrStatType { EXON_READS_PER_CHR_PER_CELL = 0, INTRON_READS_PER_CHR_PER_CELL, INTERGENIC_READS_PER_CHR_PER_CELL, CHROMOSOME_STAT_SIZE };
 		using stat_t = int;
 
 	private:
@@ -173,6 +175,8 @@ namespace Estimation
 		bool has(const std::string &umi) const;
 		size_t number_of_requested_umis(const UMI::Mark::query_t &query, bool return_reads) const; // Gene.cpp:60-79
 		size_t number_of_umis(bool return_reads) const;                                             // Gene.cpp:81-93
+		using s_ul_hash_t = std::unordered_map<std::string, size_t>;
+		s_ul_hash_t requested_reads_per_umi(const UMI::Mark::query_t &query) const;                 // Gene.cpp:95-107
 	};
 
 	class Cell // Cell.h
@@ -204,6 +208,8 @@ namespace Estimation
 		size_t size() const { return _n_genes; }
 		const Gene &at(const std::string &gene) const { return _genes.at(_gene_indexer->get_index(gene)); }
 		s_ul_hash_t requested_umis_per_gene(const UMI::Mark::query_t &query_marks, bool return_reads) const; // Cell.cpp:54-68
+		using ss_ul_hash_t = std::unordered_map<std::string, s_ul_hash_t>;
+		ss_ul_hash_t requested_reads_per_umi_per_gene(const UMI::Mark::query_t &query_marks) const;          // Cell.cpp:70-83
 	};
 
 	namespace Merge
@@ -454,6 +460,12 @@ namespace Estimation
 		std::vector<uint64_t> _batch_keys;  // pending records as two arrays (dge_add_batch_soa), flushed in blocks of _batch_capacity
 		std::vector<uint32_t> _batch_genes;
 		std::vector<uint32_t> _batch_idx;   // stream positions of the pending records (used when skipped reads left gaps)
+		std::vector<uint8_t> _batch_chr;    // chromosome id of the pending records (Stats' per-chromosome tables)
+		// Stats' process-wide statics (Stats.cpp:5-7, 23-28, 79-88): chromosome ids in first-seen order -- assigned when a read is COUNTED for a
+		// chromosome, not when it is merely seen -- and, per statistic, the ids it has counted (iterated in this container's order, :65-73)
+		StringIndexer _chromosome_indexer;
+		std::unordered_set<size_t> _presented_chromosomes[Stats::CHROMOSOME_STAT_SIZE];
+		bool _chr_overflow = false;         // more than 256 chromosome names: the per-chromosome tables are dropped (1-byte side array)
 		bool _batch_gaps = false;
 		StringIndexer _n_umis, _n_cbs;      // UMIs / barcodes containing N, passed to the device as indices (DGE_FLAG_UMI_N / DGE_FLAG_CB_N)
 		bool _n_dirty = false, _allow_n = false;
@@ -500,6 +512,11 @@ namespace Estimation
 		const ids_t &merge_targets() const;
 		const UMI::Mark::query_t &gene_match_level() const { return _query_marks; }
 		s_i_hash_t get_stat_by_real_cells(Stats::CellStatType type) const;
+		// CellsDataContainer.cpp:292-307: real cells that counted anything for `stat` (cell-id order), the chromosomes `stat` has seen, and one
+		// count per (listed cell, listed chromosome), cell-major
+		using counts_t = std::vector<int>;
+		void get_stat_by_real_cells(Stats::CellChrStatType stat, names_t &cell_barcodes, names_t &chromosome_names, counts_t &counts) const;
+		bool chromosome_stats_available() const { return !_chr_overflow; }
 		const Cell &cell(size_t index) const;
 		size_t intergenic_reads_num() const;
 		size_t has_exon_reads_num() const;

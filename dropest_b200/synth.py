@@ -209,13 +209,14 @@ def product_whitelist(path: str, n1: int = 2048, n2: int = 3328, seed: int = 11,
 
 
 def write_packed(path: str, recs: np.ndarray, cb_len: int, umi_len: int, n_genes: int, gene_names: Optional[Sequence[str]] = None,
-                 n_lists: Optional["NLists"] = None):
-    """DGER0001 stream for the oracle drivers (oracle/common/dge_io.h); DGER0002 (+ the two N-string lists) when `n_lists` is given."""
+                 n_lists: Optional["NLists"] = None, chr_ids: Optional[np.ndarray] = None):
+    """DGER0001 stream for the oracle drivers (oracle/common/dge_io.h); DGER0002 (+ the two N-string lists) when `n_lists` is given;
+    `chr_ids` (uint8 per record) is appended after the records and announced by the header's n_chr field."""
     blob = ("\n".join(gene_names)).encode() if gene_names else b""
     with open(path, "wb") as f:
         f.write(b"DGER0002" if n_lists is not None else b"DGER0001")
         f.write(np.array([recs.shape[0]], dtype="<u8").tobytes())
-        f.write(np.array([cb_len, umi_len, n_genes, 0], dtype="<u4").tobytes())
+        f.write(np.array([cb_len, umi_len, n_genes, 0 if chr_ids is None else int(chr_ids.max()) + 1 if chr_ids.size else 1], dtype="<u4").tobytes())
         f.write(np.array([len(blob)], dtype="<u8").tobytes())
         f.write(blob)
         if n_lists is not None:
@@ -224,6 +225,9 @@ def write_packed(path: str, recs: np.ndarray, cb_len: int, umi_len: int, n_genes
                 f.write(np.array([len(b)], dtype="<u8").tobytes())
                 f.write(b)
         f.write(np.ascontiguousarray(recs, dtype=RECORD_DTYPE).tobytes())
+        if chr_ids is not None:
+            assert chr_ids.shape[0] == recs.shape[0]
+            f.write(np.ascontiguousarray(chr_ids, dtype=np.uint8).tobytes())
 
 
 class NLists:

@@ -202,6 +202,14 @@ int dge_add_batch_device(dge_handle *h, const dge_record16 *recs, size_t n);
 int dge_add_batch_segments_device(dge_handle *h, const dge_record16 *const *segs, const uint64_t *counts, uint32_t n_segs);
 int dge_add_batch_soa(dge_handle *h, const uint64_t *keys, const uint32_t *genes, size_t n, uint64_t first_read_idx);
 
+/* The same batches with the chromosome of every read as a 1-byte side array (ids < 256, assigned by the caller in first-seen order like
+ * Stats::get_index, reference Estimation/Stats.cpp:79-88).  Feeds the per-(cell, chromosome) counters of Stats
+ * (EXON / INTRON / INTERGENIC_READS_PER_CHR_PER_CELL: CellsDataContainer.cpp:73-78, 309-327, Stats.cpp:23-28); batches added without a
+ * chromosome array simply do not count there.  chr is HOST memory for the first two, DEVICE memory for the third. */
+int dge_add_batch_chr(dge_handle *h, const dge_record16 *recs, const uint8_t *chr, size_t n);
+int dge_add_batch_soa_chr(dge_handle *h, const uint64_t *keys, const uint32_t *genes, const uint8_t *chr, size_t n, uint64_t first_read_idx);
+int dge_add_batch_chr_device(dge_handle *h, const dge_record16 *recs, const uint8_t *chr, size_t n);
+
 /* = CellsDataContainer::set_initialized (CellsDataContainer.cpp:163-175): runs the whole per-read grouping on the device.
  * DGE_ERR_STATE when called twice (":165-166"). */
 int dge_set_initialized(dge_handle *h);
@@ -238,6 +246,14 @@ int dge_get_cells(dge_handle *h, int which, dge_cell_info *out, size_t capacity,
  * caller's gene ids.  Any output pointer may be NULL; *n_cols / *nnz are always written. */
 int dge_get_matrix(dge_handle *h, int which, int64_t *indptr, int32_t *gene_ids, int32_t *values,
                    size_t *n_cols, size_t *nnz);
+
+/* Per-chromosome read counters of the real cells (CellsDataContainer::get_stat_by_real_cells(CellChrStatType, ...), reference
+ * CellsDataContainer.cpp:292-307 + Stats::get, Stats.cpp:50-63), after merge_and_filter, with Stats::merge applied (the counters of a merged
+ * cell belong to its merge target, Stats.cpp:36-42).  counts[(cell * n_chr + chr) * 3 + t], t = 0 exon, 1 intron, 2 intergenic; cells in
+ * DGE_CELLS_REAL order; n_chr = largest chromosome id seen + 1.  presented[t * n_chr + chr] = 1 when ANY cell counted chromosome chr for
+ * statistic t (Stats::presented_chromosomes; the reference lists a cell in a statistic's table only if one of its counters is non-zero).
+ * Size query: counts = presented = NULL.  Not available on sharded handles yet. */
+int dge_get_chr_stats(dge_handle *h, int32_t *counts, size_t capacity_cells, size_t *n_cells, uint32_t *n_chr, uint8_t *presented);
 
 /* Gene ids in first-seen order (= gene_indexer().values(), StringIndexer.cpp:10-18). */
 int dge_get_gene_order(dge_handle *h, int32_t *gene_ids, size_t capacity, size_t *n_out);

@@ -5,13 +5,14 @@
 //   DGER0001  packed read stream  : header + optional gene-name blob + dge_record16[n]
 //   DGER0002  the same + two string lists (UMIs / barcodes containing N) between the gene names and the records; a record whose
 //             gene word has bit 27 (bit 28) set carries an index into the N-UMI (N-barcode) list instead of a packed sequence
+//             either format: header n_chr > 0 => one chromosome id (uint8) per record follows the records (chromosome name "chr<id>")
 //   DGEO0001  oracle output       : directory of named typed arrays
 //
 // The 16-byte record is the same layout as include/dropest_b200.h:dge_record16 (restated here so the
 // oracle does not depend on product headers):
 //   key      bits[63:24] cell barcode, 2 bit/base A=0 C=1 G=2 T=3, first base most significant, right-aligned
 //            bits[23:0]  UMI, same coding
-//   gene     bits[23:0] gene id (0xFFFFFF = no gene / intergenic), bits[26:24] UMI::Mark bits, bits[31:27] chromosome id
+//   gene     bits[23:0] gene id (0xFFFFFF = no gene / intergenic), bits[26:24] UMI::Mark bits, bit 27 / 28 N escapes (DGER0002)
 //   read_idx global 0-based position of the read in the stream
 #pragma once
 #include <cstdint>
@@ -54,6 +55,9 @@ namespace dge_io
 		std::vector<std::string> gene_names; // empty => "g<id>"
 		std::vector<std::string> n_umis, n_cbs; // DGER0002: sequences containing N, referenced by index
 		std::vector<Record16> recs;
+		std::vector<uint8_t> chr; // empty, or one chromosome id per record
+
+		std::string chr_name(size_t i) const { return chr.empty() ? std::string() : "chr" + std::to_string(unsigned(chr[i])); }
 
 		std::string cb_of(const Record16 &r) const
 		{
@@ -119,6 +123,11 @@ namespace dge_io
 		}
 		s.recs.resize(n);
 		f.read((char *)s.recs.data(), n * sizeof(Record16));
+		if (s.n_chr)
+		{
+			s.chr.resize(n);
+			f.read((char *)s.chr.data(), n);
+		}
 		if (!f) throw std::runtime_error("short read in " + fname);
 		return s;
 	}

@@ -85,6 +85,7 @@ struct Cell
 	int total_reads = 0, total_umis = 0; // Stats TOTAL_READS_PER_CB / TOTAL_UMIS_PER_CB: counters, not set sizes
 	bool merged = false, excluded = false;
 	size_t requested_genes = 0, requested_umis = 0;
+	std::unordered_map<size_t, int> chr_stat[3]; // Stats::_chromosome_stat_data: exon, intron, intergenic reads per chromosome id
 };
 
 struct Params
@@ -107,6 +108,18 @@ struct Container
 	std::vector<size_t> filtered, merge_targets;
 	size_t intergenic = 0, has_exon = 0, has_intron = 0, has_na = 0, n_real = 0;
 	bool initialized = false;
+	// Stats' process-wide statics (Stats.cpp:5-7): chromosome ids in first-seen order, the ids each statistic has seen
+	std::unordered_map<std::string, size_t> chr_ids;
+	strs_t chr_names;
+	std::unordered_set<size_t> presented[3];
+
+	void chr_inc(Cell &cell, int stat, const std::string &chr) // Stats::inc(CellChrStatType, subtype), Stats.cpp:23-28 + get_index :79-88
+	{
+		auto it = chr_ids.emplace(chr, chr_ids.size());
+		if (it.second) chr_names.push_back(chr);
+		presented[stat].insert(it.first->second);
+		cell.chr_stat[stat][it.first->second]++;
+	}
 
 	size_t min_after() const { return std::max(p.min_genes_after, p.min_genes_before); } // MergeStrategyAbstract.cpp:8-11
 
@@ -118,13 +131,13 @@ struct Container
 	}
 
 	// CellsDataContainer::add_record, CellsDataContainer.cpp:59-88 (+ :356-364, :309-327)
-	void add_record(const std::string &cb, const std::string &umi, const std::string &gene, int mark)
+	void add_record(const std::string &cb, const std::string &umi, const std::string &gene, int mark, const std::string &chr = std::string())
 	{
 		if (initialized) throw std::runtime_error("Container is already initialized");
 		auto res = cell_by_cb.emplace(cb, cell_by_cb.size());
 		if (res.second) { cells.emplace_back(); cells.back().barcode = cb; }
 		Cell &cell = cells[res.first->second];
-		if (gene.empty()) { ++intergenic; return; }
+		if (gene.empty()) { chr_inc(cell, 2, chr); ++intergenic; return; }
 		const size_t g = gene_idx.add(gene);
 		const size_t u = umi_idx.add(umi);
 		umis_t &umis = cell.genes[g];
@@ -133,8 +146,8 @@ struct Container
 		ins.first->second.mark |= mark;
 		if (ins.second) cell.total_umis++;
 		cell.total_reads++;
-		if (mark & 2) ++has_exon;
-		if (mark & 4) ++has_intron;
+		if (mark & 2) { chr_inc(cell, 0, chr); ++has_exon; }
+		if (mark & 4) { chr_inc(cell, 1, chr); ++has_intron; }
 		if (mark & 1) ++has_na;
 	}
 
@@ -217,6 +230,8 @@ struct Container
 		}
 		dst.total_reads += src.total_reads;
 		dst.total_umis += src.total_umis;
+		for (int t = 0; t < 3; ++t)
+			for (auto const &kv : src.chr_stat[t]) dst.chr_stat[t][kv.first] += kv.second;
 		src.merged = true;
 	}
 };
@@ -840,7 +855,7 @@ int main(int argc, char **argv)
 				const dge_io::Record16 &r = s.recs[i];
 				const uint32_t gid = r.gene & 0xFFFFFFu;
 				c.add_record(s.cb_of(r), s.umi_of(r),
-				             gid == dge_io::NO_GENE ? std::string() : gnames.at(gid), int((r.gene >> 24) & 7));
+				             gid == dge_io::NO_GENE ? std::string() : gnames.at(gid), int((r.gene >> 24) & 7), s.chr_name(i));
 			}
 			t_fill = now_s() - t0;
 		}
@@ -878,6 +893,28 @@ int main(int argc, char **argv)
 		w.add("filtered_cells", dge_io::I64, std::vector<int64_t>(c.filtered.begin(), c.filtered.end()));
 		w.add("merge_targets", dge_io::I64, std::vector<int64_t>(c.merge_targets.begin(), c.merge_targets.end()));
 		w.add_strings("gene_names", c.gene_idx.values);
+		{   // get_stat_by_real_cells(CellChrStatType, ...), CellsDataContainer.cpp:292-307 + Stats::get / presented_chromosomes, Stats.cpp:50-73
+			const char *names[3] = {"chr_exon", "chr_intron", "chr_intergenic"};
+			for (int t = 0; t < 3; ++t)
+			{
+				strs_t cells_out, chrs;
+				std::vector<int32_t> counts;
+				for (auto const &cell : c.cells)
+				{
+					if (!c.is_real(cell) || cell.chr_stat[t].empty()) continue;
+					for (size_t id : c.presented[t])
+					{
+						auto it = cell.chr_stat[t].find(id);
+						counts.push_back(it == cell.chr_stat[t].end() ? 0 : it->second);
+					}
+					cells_out.push_back(cell.barcode);
+				}
+				for (size_t id : c.presented[t]) chrs.push_back(c.chr_names[id]);
+				w.add_strings(std::string(names[t]) + "_cells", cells_out);
+				w.add_strings(std::string(names[t]) + "_chrs", chrs);
+				w.add(std::string(names[t]) + "_counts", dge_io::I32, counts);
+			}
+		}
 		{   // cm: ResultsPrinter.cpp:334-361 (row order: first met while walking the per-cell unordered_map of Cell.cpp:54-68)
 			std::vector<int64_t> col, gene, val;
 			strs_t row_names;

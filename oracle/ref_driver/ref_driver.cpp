@@ -182,15 +182,16 @@ int main(int argc, char **argv)
 			n_reads = a.limit ? std::min(a.limit, s.recs.size()) : s.recs.size();
 			std::vector<std::string> gnames(s.n_genes);
 			for (uint32_t g = 0; g < s.n_genes; ++g) gnames[g] = s.gene_name(g);
-			auto decode = [&](const dge_io::Record16 &r) {
+			auto decode = [&](size_t i) {
+				const dge_io::Record16 &r = s.recs[i];
 				uint32_t gid = r.gene & 0xFFFFFFu;
 				return ReadInfo(Tools::ReadParameters(s.cb_of(r), s.umi_of(r), "", ""),
-				                gid == dge_io::NO_GENE ? std::string() : gnames.at(gid), "", mark_of((r.gene >> 24) & 7));
+				                gid == dge_io::NO_GENE ? std::string() : gnames.at(gid), s.chr_name(i), mark_of((r.gene >> 24) & 7));
 			};
 			if (a.stream)
 			{
 				double t0 = now_s();
-				for (size_t i = 0; i < n_reads; ++i) container.add_record(decode(s.recs[i]));
+				for (size_t i = 0; i < n_reads; ++i) container.add_record(decode(i));
 				t_fill = now_s() - t0;
 			}
 			else
@@ -204,7 +205,7 @@ int main(int argc, char **argv)
 					double t0 = now_s();
 					std::vector<ReadInfo> infos;
 					infos.reserve(end - start);
-					for (size_t i = start; i < end; ++i) infos.push_back(decode(s.recs[i]));
+					for (size_t i = start; i < end; ++i) infos.push_back(decode(i));
 					double t1 = now_s();
 					for (auto const &ri : infos) container.add_record(ri);
 					double t2 = now_s();
@@ -300,6 +301,22 @@ int main(int argc, char **argv)
 			w.add("cm_raw_cells", dge_io::I64, cells);
 			w.add("cm_raw_col", dge_io::I64, col); w.add("cm_raw_gene", dge_io::I64, gene); w.add("cm_raw_val", dge_io::I64, val);
 			w.add_strings("cm_raw_row_names", row_names);
+		}
+
+		// per-chromosome statistics of the real cells: CellsDataContainer::get_stat_by_real_cells(CellChrStatType, ...) exactly as
+		// ResultsPrinter::get_reads_per_chr_per_cell_info calls it (ResultsPrinter.cpp:140-166); counts are cell-major
+		{
+			const char *names[3] = {"chr_exon", "chr_intron", "chr_intergenic"};
+			const Stats::CellChrStatType types[3] = {Stats::EXON_READS_PER_CHR_PER_CELL, Stats::INTRON_READS_PER_CHR_PER_CELL, Stats::INTERGENIC_READS_PER_CHR_PER_CELL};
+			for (int t = 0; t < 3; ++t)
+			{
+				std::vector<std::string> cells, chrs;
+				std::vector<int> counts;
+				container.get_stat_by_real_cells(types[t], cells, chrs, counts);
+				w.add_strings(std::string(names[t]) + "_cells", cells);
+				w.add_strings(std::string(names[t]) + "_chrs", chrs);
+				w.add(std::string(names[t]) + "_counts", dge_io::I32, std::vector<int32_t>(counts.begin(), counts.end()));
+			}
 		}
 
 		if (a.dump_umis)

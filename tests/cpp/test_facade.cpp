@@ -38,7 +38,9 @@ int main(int argc, char **argv)
 			{"AAATTAGGTCGG", "CCCCCT", "Gene2"}, {"CCCTTAGGTCCA", "CCATTC", "Gene3"}, {"CCCTTAGGTCCA", "CCCCCT", "Gene2"},
 			{"CCCTTAGGTCCA", "ACCCCT", "Gene3"}, {"CAATTAGGTCCG", "CAACCT", "Gene1"}, {"CAATTAGGTCCG", "AAACCT", "Gene1"},
 			{"CAATTAGGTCCG", "CCCCCT", "Gene2"}, {"AAAAAAAAAAAA", "CCCCCT", "Gene2"}};
-		for (auto const &r : reads) container_full.add_record(read_info(r[0], r[1], r[2]));
+		// chromosome names (not part of the reference fixture, which leaves them empty): one per gene family, for the per-chromosome Stats tables
+		auto chr_of = [](const std::string &gene) { return gene == "Gene1" ? std::string("chr1") : gene == "Gene2" ? std::string("chr2") : std::string("chr3"); };
+		for (auto const &r : reads) container_full.add_record(read_info(r[0], r[1], r[2], chr_of(r[2])));
 		CHECK_THROW(container_full.merge_and_filter(), std::runtime_error); // "You must initialize container"
 		container_full.set_initialized();
 		CHECK_THROW(container_full.add_record(read_info("AAATTAGGTCCA", "AAACCT", "Gene1")), std::runtime_error);
@@ -217,6 +219,29 @@ int main(int argc, char **argv)
 			CHECK_EQUAL(adjuster.estimate_adjusted_gene_expression(1000), size_t(1146));
 			CHECK_EQUAL(adjuster.estimate_adjusted_gene_expression(3000), size_t(5400));
 			CHECK_EQUAL(adjuster.estimate_adjusted_gene_expression(10), size_t(10));
+		}
+
+		// get_stat_by_real_cells(CellChrStatType, ...), CellsDataContainer.cpp:292-307: Stats::merge has added the merged cells' counters
+		{
+			CellsDataContainer::names_t cells, chrs;
+			CellsDataContainer::counts_t counts;
+			container_full.get_stat_by_real_cells(Stats::EXON_READS_PER_CHR_PER_CELL, cells, chrs, counts);
+			CHECK_EQUAL(cells.size(), size_t(2));
+			CHECK_EQUAL(chrs.size(), size_t(3));
+			CHECK_EQUAL(counts.size(), size_t(6));
+			if (cells.size() == 2 && chrs.size() == 3 && counts.size() == 6)
+			{
+				CHECK_EQUAL(cells[0], std::string("AAATTAGGTCCA"));
+				CHECK_EQUAL(cells[1], std::string("AAATTAGGTCCC"));
+				for (size_t k = 0; k < 3; ++k)
+				{
+					CHECK_EQUAL(counts[k], 4);                                   // AAATTAGGTCCA + its three merged barcodes: 4 reads on each chromosome
+					CHECK_EQUAL(counts[3 + k], chrs[k] == "chr2" ? 0 : 2);       // AAATTAGGTCCC + AAATTAGGTCCG
+				}
+			}
+			cells.clear(); chrs.clear(); counts.clear();
+			container_full.get_stat_by_real_cells(Stats::INTERGENIC_READS_PER_CHR_PER_CELL, cells, chrs, counts);
+			CHECK_EQUAL(cells.size() + chrs.size() + counts.size(), size_t(0));
 		}
 
 		// ResultsPrinter::save_results (ResultsPrinter.cpp:23-91): files consumed by dropReport / dropestr

@@ -40,6 +40,8 @@ def cases():
         "poisson_real_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="poisson_real", seed=16),
         "all_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="all", seed=17),
         "directional_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=40, merge="real", seed=18, umi_merge="directional", reads_per_umi=6),
+        # per-chromosome Stats tables (row a4): a chromosome id per read, whitelist merge so that Stats::merge matters
+        "real_7x9_chr": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="real", seed=19, extra={"n_chr": 7}),
         "real_8x8_reads": pu.Case(name="real_8x8_reads",
                                   spec=SynthSpec(n_reads=25000, n_cells=20, n_genes=70, cb_len=16, umi_len=6, whitelist_parts=wl8,
                                                  cb_error_ppm=80000, seed=13),
@@ -56,11 +58,17 @@ def case_records(case: pu.Case) -> np.ndarray:
     return case.recs
 
 
+def case_chr_ids(case: pu.Case, recs: np.ndarray):
+    if case.chr_ids is None and case.extra.get("n_chr"):
+        case.chr_ids = pu.synth_chr_ids(recs, int(case.extra["n_chr"]))
+    return case.chr_ids
+
+
 def run_oracle_on(case: pu.Case, kind: str = "any"):
     recs = case_records(case)
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "reads.bin")
-        write_packed(path, recs, case.cb_len, case.umi_len, case.n_genes, case.gene_names)
+        write_packed(path, recs, case.cb_len, case.umi_len, case.n_genes, case.gene_names, chr_ids=case_chr_ids(case, recs))
         return oracle_io.run_oracle(path, kind=kind, merge=case.merge, barcodes=case.barcodes, barcodes_type=case.barcodes_type,
                                     min_genes_before=case.min_genes_before, min_genes_after=case.min_genes_after,
                                     max_cb_ed=case.max_cb_ed, min_frac=case.min_frac, marks=case.marks, max_cells=case.max_cells,

@@ -52,6 +52,7 @@ class Case:
     max_merge_prob: float = 1e-4
     max_real_merge_prob: float = 1e-7
     dump_umis: bool = True
+    chr_ids: Optional[np.ndarray] = None         # uint8 chromosome id per read -> per-chromosome Stats tables are fed and compared
     n_lists: Optional[object] = None             # dropest_b200.synth.NLists: the records carry barcodes / UMIs with N as indices into it
     n_batches: int = 3
     shuffle: bool = True
@@ -111,8 +112,13 @@ def gpu_run(case: Case, recs: Optional[np.ndarray], device_generate: bool = Fals
         order = np.arange(recs.shape[0])
         if case.shuffle:
             np.random.default_rng(123).shuffle(order)
-        for part in np.array_split(order, max(1, case.n_batches)):
-            c.add_batch(recs[part])
+        for k, part in enumerate(np.array_split(order, max(1, case.n_batches))):
+            if case.chr_ids is None:
+                c.add_batch(recs[part])
+            elif k % 2 == 0 or not np.array_equal(recs["read_idx"][part], recs["read_idx"][part[0]] + np.arange(part.shape[0], dtype=np.uint32)):
+                c.add_batch_chr(recs[part], case.chr_ids[part])
+            else:   # consecutive reads: the structure-of-arrays form
+                c.add_batch_soa_chr(recs["key"][part], recs["gene"][part], case.chr_ids[part], first_read_idx=int(recs["read_idx"][part[0]]))
     c.set_initialized()
     pre = c.cells(dg.CELLS_FILTERED)
     c.merge_and_filter()
@@ -128,6 +134,8 @@ def gpu_run(case: Case, recs: Optional[np.ndarray], device_generate: bool = Fals
         "gene_order": c.gene_order(),
         "merge_pairs": c.merge_pairs(),
     }
+    if case.chr_ids is not None:
+        out["chr_stats"] = c.chr_stats()
     if case.dump_umis:
         out["umigs"] = c.umigs(dg.CELLS_ALL)
     c.close()
@@ -143,7 +151,9 @@ def run_case(case: Case, device_generate: bool = False, kind: str = "any"):
         recs = case.recs
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "reads.bin")
-        write_packed(path, recs, case.cb_len, case.umi_len, case.n_genes, case.gene_names, n_lists=case.n_lists)
+        if case.extra.get("n_chr") and case.chr_ids is None:
+            case.chr_ids = synth_chr_ids(recs, int(case.extra["n_chr"]))
+        write_packed(path, recs, case.cb_len, case.umi_len, case.n_genes, case.gene_names, n_lists=case.n_lists, chr_ids=case.chr_ids)
         ora = oracle_io.run_oracle(path, kind=kind, merge=case.merge, barcodes=case.barcodes, barcodes_type=case.barcodes_type,
                                    min_genes_before=case.min_genes_before, min_genes_after=case.min_genes_after,
                                    max_cb_ed=case.max_cb_ed, min_frac=case.min_frac, marks=case.marks, max_cells=case.max_cells,
@@ -152,6 +162,15 @@ def run_case(case: Case, device_generate: bool = False, kind: str = "any"):
                                    max_real_merge_prob=case.max_real_merge_prob)
     gpu = gpu_run(case, recs, device_generate=device_generate, tables=tables)
     return {"case": case, "oracle": ora, "gpu": gpu, "recs": recs}
+
+
+def synth_chr_ids(recs: np.ndarray, n_chr: int) -> np.ndarray:
+    """A chromosome per read: genes live on one chromosome each, reads without a gene fall anywhere; the last chromosome only ever
+    sees intergenic reads (the per-statistic column sets differ, Stats::presented_chromosomes)."""
+    gene = (recs["gene"] & np.uint32(0xFFFFFF)).astype(np.uint64)
+    by_gene = ((gene * np.uint64(2654435761)) >> np.uint64(13)) % np.uint64(max(1, n_chr - 1))
+    anywhere = ((recs["read_idx"].astype(np.uint64) * np.uint64(40503)) >> np.uint64(3)) % np.uint64(n_chr)
+    return np.where(gene == 0xFFFFFF, anywhere, by_gene).astype(np.uint8)
 
 
 def _gene_id_of_name(case: Case, names):
@@ -197,6 +216,21 @@ def assert_parity(res, check_umigs: bool = True):
         np.testing.assert_array_equal(col, o_col[o_order], err_msg=f"{name} columns")
         np.testing.assert_array_equal(genes.astype(np.int64), o_gene[o_order], err_msg=f"{name} genes")
         np.testing.assert_array_equal(vals.astype(np.int64), o_val[o_order], err_msg=f"{name} values")
+    # ---- per-chromosome Stats tables: rows = real cells that counted anything for the statistic (cell-id order), columns = the
+    # chromosomes the statistic has seen in ANY cell; compared as {(barcode, chromosome id): count} + the row list + the column set
+    if "chr_stats" in gpu:
+        counts, presented = gpu["chr_stats"]
+        real_bc = gpu["real"]["barcode"]
+        assert counts.shape[0] == real_bc.shape[0]
+        for t, name in enumerate(("chr_exon", "chr_intron", "chr_intergenic")):
+            o_cells = np.array([pack_cb(x) for x in oracle_io.strings(ora[name + "_cells"])], dtype=np.uint64)
+            o_chrs = np.array([int(x[3:]) for x in oracle_io.strings(ora[name + "_chrs"])], dtype=np.int64)
+            o_counts = ora[name + "_counts"].reshape(o_cells.shape[0], o_chrs.shape[0]) if o_cells.size else np.zeros((0, o_chrs.shape[0]), dtype=np.int32)
+            mine = counts[:, :, t]
+            rows = np.flatnonzero(mine.sum(axis=1) > 0)
+            np.testing.assert_array_equal(real_bc[rows], o_cells, err_msg=f"{name}: cells listed")
+            assert sorted(np.flatnonzero(presented[t]).tolist()) == sorted(o_chrs.tolist()), f"{name}: presented chromosomes"
+            np.testing.assert_array_equal(mine[rows][:, o_chrs], o_counts, err_msg=f"{name}: counts")
     n_cols_raw = gpu["cm_raw"][0].shape[0] - 1
     assert n_cols_raw == ora["cm_raw_cells"].shape[0]
     np.testing.assert_array_equal(gpu["real"]["barcode"], o_bc[ora["cm_raw_cells"]], err_msg="cm_raw column order")

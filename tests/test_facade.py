@@ -94,7 +94,8 @@ def test_reference_container_tests_through_the_cpp_facade(tmp_path):
     rd.i32(); rd.i32()
     d = rd.item()
     names = d["attr"]["names"]
-    assert names == ["cm", "cm_raw", "merge_targets", "aligned_reads_per_cell", "aligned_umis_per_cell", "requested_umis_per_cb"]
+    assert names == ["cm", "cm_raw", "reads_per_chr_per_cells", "mean_reads_per_umi", "saturation_info", "merge_targets", "aligned_reads_per_cell",
+                     "aligned_umis_per_cell", "requested_umis_per_cb", "requested_reads_per_cb"]   # ResultsPrinter.cpp:47-57
     cm = d["v"][0]["S4"]
     assert cm["class"]["v"] == ["dgCMatrix"] and cm["class"]["attr"]["package"] == ["Matrix"]
     assert cm["Dim"] == [6, 2] and cm["p"] == [0, 3, 7] and len(cm["i"]) == 7 and sum(cm["x"]) == 9.0
@@ -102,8 +103,26 @@ def test_reference_container_tests_through_the_cpp_facade(tmp_path):
     for c in range(2):
         col = cm["i"][cm["p"][c]:cm["p"][c + 1]]
         assert col == sorted(col)  # row indices ascending inside a column (dgCMatrix invariant)
-    mt = d["v"][2]
+    # reads_per_chr_per_cells = list(Exon, Intron, Intergenic) of cells x chromosomes integer matrices (ResultsPrinter.cpp:140-166)
+    rpc = d["v"][2]
+    assert rpc["attr"]["names"] == ["Exon", "Intron", "Intergenic"]
+    exon = rpc["v"][0]
+    assert exon["attr"]["dim"] == [2, 3] and exon["attr"]["dimnames"][0] == ["AAATTAGGTCCA", "AAATTAGGTCCC"]
+    chrs = exon["attr"]["dimnames"][1]
+    assert sorted(chrs) == ["chr1", "chr2", "chr3"]
+    got = {(r, chrs[c]): exon["v"][c * 2 + r] for r in range(2) for c in range(3)}   # column-major
+    assert got == {(0, "chr1"): 4, (0, "chr2"): 4, (0, "chr3"): 4, (1, "chr1"): 2, (1, "chr2"): 0, (1, "chr3"): 2}
+    assert rpc["v"][1]["attr"]["dim"] == [0, 0] and rpc["v"][2]["attr"]["dim"] == [0, 0]
+    mrpu = d["v"][3]
+    assert mrpu["attr"]["names"] == ["AAATTAGGTCCA", "AAATTAGGTCCC"] and mrpu["v"] == [12 / 6, 4 / 3]   # reads / distinct UMIs held after the merge
+    sat = d["v"][4]
+    assert sat["attr"]["names"] == ["reads", "cbs", "umis"]
+    sat_rows = sorted(zip(sat["v"][1], sat["v"][2], sat["v"][0]))
+    assert len(sat_rows) == 9 and sum(r for _, _, r in sat_rows) == 16 and ("AAATTAGGTCCA", "CCCCCT", 4) in sat_rows
+    mt = d["v"][5]
     assert dict(zip(mt["attr"]["names"], mt["v"])) == {"AAATTAGGTCCG": "AAATTAGGTCCC", "AAATTAGGTCGG": "AAATTAGGTCCA",
                                                       "CCCTTAGGTCCA": "AAATTAGGTCCA", "CAATTAGGTCCG": "AAATTAGGTCCA"}
-    umis = d["v"][4]
+    umis = d["v"][7]
     assert dict(zip(umis["attr"]["names"], umis["v"])) == {"AAATTAGGTCCA": 12, "AAATTAGGTCCC": 4}
+    rreads = d["v"][9]
+    assert dict(zip(rreads["attr"]["names"], rreads["v"])) == {"AAATTAGGTCCA": 12, "AAATTAGGTCCC": 4}

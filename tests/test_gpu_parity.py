@@ -14,11 +14,13 @@ from golden_cases import fixture_case
 
 
 @pytest.mark.parametrize("name", ["fixture", "real_7x9", "none_7x9", "simple_7x9", "real_8x8_reads", "poisson_simple_7x9", "poisson_real_7x9", "all_7x9",
-                                  "directional_7x9"])
+                                  "directional_7x9", "real_7x9_chr"])
 def test_gpu_reproduces_golden_reference_outputs(name):
     """CUDA path vs the committed outputs of the compiled, unmodified reference (no oracle binary needed on the GPU box)."""
     case = golden_cases.cases()[name]
-    gpu = pu.gpu_run(case, golden_cases.case_records(case))
+    recs = golden_cases.case_records(case)
+    golden_cases.case_chr_ids(case, recs)
+    gpu = pu.gpu_run(case, recs)
     pu.assert_parity({"case": case, "oracle": golden_cases.load_golden(name), "gpu": gpu})
 
 
@@ -379,6 +381,22 @@ def test_segment_batches_in_one_launch(cuts):
     case.shuffle = True
     res = pu.run_case(case)
     pu.assert_parity(res)
+
+
+@pytest.mark.parametrize("merge", ["none", "real"])
+def test_per_chromosome_stats(merge):
+    """Stats' EXON / INTRON / INTERGENIC_READS_PER_CHR_PER_CELL (row a4): the chromosome side array feeds the (cell, chromosome) counter
+    table; with a CB merge the counters of merged cells are added to their targets (Stats::merge); equal to the reference's
+    get_stat_by_real_cells output, including which cells and which chromosomes each table lists."""
+    case = pu.small_case(n_reads=150000, n_cells=50, n_genes=200, merge=merge, seed=41)
+    case.extra["n_chr"] = 7
+    case.n_batches = 4
+    case.shuffle = False
+    res = pu.run_case(case)
+    pu.assert_parity(res)
+    counts, presented = res["gpu"]["chr_stats"]
+    assert counts[:, :, 0].sum() > 0 and counts[:, :, 1].sum() > 0 and counts[:, :, 2].sum() > 0
+    assert presented[2, 6] and not presented[0, 6] and not presented[1, 6]   # the last chromosome only ever holds intergenic reads
 
 
 @pytest.mark.parametrize("giant", [1000, 50000])
