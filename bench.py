@@ -304,6 +304,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--slices", type=int, default=8, help="N > 1, --exchange nccl: slices of the pipelined route / all-to-all / fill")
+    ap.add_argument("--chr", type=int, default=0, metavar="N_CHR",
+                    help="N = 1: also feed Stats' per-chromosome counters (a 1-byte chromosome id per read, N_CHR chromosomes; dge_add_batch_chr_device)")
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
                     help="N > 1: 'peer' = the owners' fill kernels pull the routed records out of the sources' HBM over NVLink (no all-to-all pass); "
                          "'nccl' = scatter -> NCCL all-to-all -> fill in slices")
@@ -409,6 +411,18 @@ def main():
     phase_ms = {"ms_route_a2a_fill": 0.0, "ms_group_init": 0.0, "ms_dist_merge": 0.0, "ms_filter_matrices": 0.0}
 
     owned_reads = n
+    chr_ids = None
+    if args.chr and world == 1:
+        # a chromosome per read (genes live on one chromosome each, reads without a gene fall anywhere), made on the device outside the timed region
+        chr_ids = torch.empty(n, dtype=torch.uint8, device=f"cuda:{dev}")
+        rec64 = raw.view(torch.int64).view(-1, 2)
+        for a in range(0, n, 1 << 26):
+            w = rec64[a:a + (1 << 26), 1]
+            gene = w & 0xFFFFFF
+            idx = (w >> 32) & 0xFFFFFFFF
+            chr_ids[a:a + (1 << 26)] = torch.where(gene == 0xFFFFFF, (idx * 40503 >> 3) % args.chr, (gene * 2654435761 >> 13) % max(1, args.chr - 1)).to(torch.uint8)
+        del rec64
+        config["chromosomes"] = args.chr
 
     def step(k=None):
         """k = index of the timed step (records the phase events), None = warm-up"""
@@ -421,7 +435,10 @@ def main():
             cnt = pipe.run(cont, raw.data_ptr(), stream)
         else:
             cnt = n
-            cont.add_batch_device(raw.data_ptr(), n)
+            if chr_ids is not None:
+                cont.add_batch_chr_device(raw.data_ptr(), chr_ids.data_ptr(), n)
+            else:
+                cont.add_batch_device(raw.data_ptr(), n)
         nonlocal owned_reads
         owned_reads = cnt
         if ev: ev[1].record(stream)

@@ -24,53 +24,93 @@ __device__ __forceinline__ uint32_t chr_hash(uint32_t k)
     return k;
 }
 
-template <bool SOA>
+// ITEMS reads per thread, every stage issued for all of them before the next one (record loads -> barcode-table probes -> counter-table
+// probes -> atomics): the kernel is a chain of three dependent memory round trips per read, so its speed is the number of chains in flight
+// (one read per thread: 17 ms at 400 M reads, long_scoreboard 150 cycles per issue; profiles/r2_chr_stats_notes.txt).
+template <bool SOA, int ITEMS>
 __global__ void __launch_bounds__(256) k_chr_stats(const Rec16 *__restrict__ recs, const unsigned long long *__restrict__ soa_keys,
                                                    const uint32_t *__restrict__ soa_genes, const uint8_t *__restrict__ chr, size_t n,
                                                    const CellSlot *__restrict__ tab, KeyLayout kl, ChrEntry *__restrict__ ct, uint32_t mask,
                                                    ChrCounters *__restrict__ cc)
 {
     uint32_t max_chr = 0;
-    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    const uint32_t tmask = (1u << kl.tb) - 1;
+    const size_t n_tiles = (n + size_t(256) * ITEMS - 1) / (size_t(256) * ITEMS);
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
     {
-        uint64_t kk;
-        uint32_t gw;
-        if (SOA) { kk = soa_keys[i]; gw = soa_genes[i]; }
-        else
+        const size_t base = tile * 256 * ITEMS;
+        uint64_t cb[ITEMS];
+        uint32_t what[ITEMS], c[ITEMS], slot[ITEMS]; // what: bit0 exon, bit1 intron, bit2 intergenic; 0 = nothing to count
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
         {
-            const uint4 r = __ldcs(reinterpret_cast<const uint4 *>(recs) + i);
-            kk = (uint64_t(r.y) << 32) | r.x; gw = r.z;
-        }
-        const uint32_t gene = gw & 0xFFFFFFu, mark = (gw >> 24) & 7u;
-        const bool inter = gene == NO_GENE;
-        if (!inter && !(mark & 6u)) continue; // nothing is counted per chromosome for this read
-        uint64_t cb = kk >> 24;
-        uint32_t umi = uint32_t(kk) & 0xFFFFFFu;
-        if (!decode_n_flags(kl, gw, cb, umi)) continue; // malformed: the fill kernel has reported it
-        const uint32_t slot = table_find(tab, kl.tb, cb);
-        if (slot == NONE32) { cc->missing_cell = 1; continue; }
-        const uint32_t c = chr[i];
-        max_chr = max(max_chr, c);
-        const uint32_t key = ((slot << 8) | c) + 1u;
-        uint32_t s = chr_hash(key) & mask;
-        bool found = false;
-        for (int probes = 0; probes < 4096; ++probes)
-        {
-            uint32_t cur = __ldcg(&ct[s].key);
-            if (cur == 0u)
+            const size_t i = base + size_t(j) * 256 + threadIdx.x;
+            what[j] = 0; cb[j] = 0; c[j] = 0;
+            if (i >= n) continue;
+            uint64_t kk;
+            uint32_t gw;
+            if (SOA) { kk = soa_keys[i]; gw = soa_genes[i]; }
+            else
             {
-                cur = atomicCAS(&ct[s].key, 0u, key);
-                if (cur == 0u) cur = key; // claimed
+                const uint4 r = __ldcs(reinterpret_cast<const uint4 *>(recs) + i);
+                kk = (uint64_t(r.y) << 32) | r.x; gw = r.z;
             }
-            if (cur == key) { found = true; break; }
-            s = (s + 1) & mask;
+            c[j] = chr[i];
+            const uint32_t gene = gw & 0xFFFFFFu, mark = (gw >> 24) & 7u;
+            uint32_t w = gene == NO_GENE ? 4u : ((mark >> 1) & 3u);
+            uint64_t b = kk >> 24;
+            uint32_t umi = uint32_t(kk) & 0xFFFFFFu;
+            if (w && !decode_n_flags(kl, gw, b, umi)) w = 0; // malformed: the fill kernel has reported it
+            what[j] = w; cb[j] = b;
         }
-        if (!found) { cc->overflow = 1; continue; }
-        if (inter) atomicAdd(&ct[s].intergenic, 1u);
-        else
+        // barcode table: first probe of all reads in flight together, the rare displaced barcode walks on
+        unsigned long long first[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
         {
-            if (mark & 2u) atomicAdd(&ct[s].exon, 1u);
-            if (mark & 4u) atomicAdd(&ct[s].intron, 1u);
+            slot[j] = uint32_t(barcode_hash(cb[j]) >> (64 - kl.tb));
+            first[j] = what[j] ? __ldcg(&tab[slot[j]].cb) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
+        {
+            if (!what[j]) continue;
+            unsigned long long cur = first[j];
+            int probes = 0;
+            while (cur != cb[j] && cur != EMPTY64 && ++probes < 8192) { slot[j] = (slot[j] + 1) & tmask; cur = __ldcg(&tab[slot[j]].cb); }
+            if (cur != cb[j]) { cc->missing_cell = 1; what[j] = 0; }
+        }
+        // counter table: same scheme
+        uint32_t key[ITEMS], s[ITEMS], k0[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
+        {
+            key[j] = ((slot[j] << 8) | c[j]) + 1u;
+            s[j] = chr_hash(key[j]) & mask;
+            k0[j] = what[j] ? __ldcg(&ct[s[j]].key) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
+        {
+            if (!what[j]) continue;
+            max_chr = max(max_chr, c[j]);
+            uint32_t cur = k0[j];
+            bool found = false;
+            for (int probes = 0; probes < 4096; ++probes)
+            {
+                if (cur == 0u)
+                {
+                    cur = atomicCAS(&ct[s[j]].key, 0u, key[j]);
+                    if (cur == 0u) cur = key[j]; // claimed
+                }
+                if (cur == key[j]) { found = true; break; }
+                s[j] = (s[j] + 1) & mask;
+                cur = __ldcg(&ct[s[j]].key);
+            }
+            if (!found) { cc->overflow = 1; continue; }
+            if (what[j] & 4u) atomicAdd(&ct[s[j]].intergenic, 1u);
+            if (what[j] & 1u) atomicAdd(&ct[s[j]].exon, 1u);
+            if (what[j] & 2u) atomicAdd(&ct[s[j]].intron, 1u);
         }
     }
 #pragma unroll

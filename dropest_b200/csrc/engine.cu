@@ -2884,12 +2884,12 @@ static void chr_stats_from_device(dge_handle *h, const dge_record16 *recs, const
         DGE_CUDA(cudaMemsetAsync(h->chr_ctr.p, 0, sizeof(ChrCounters), h->stream));
     }
     h->chr_used = true;
-    const unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(256)), size_t(148) * 16));
+    const unsigned grid = unsigned(std::min<size_t>(div_up(n, size_t(256) * 4), size_t(148) * 8));
     if (soa_keys)
-        k_chr_stats<true><<<grid, 256, 0, h->stream>>>(nullptr, soa_keys, soa_genes, chr, n, h->tab.as<CellSlot>(), h->kl, h->chr_tab.as<ChrEntry>(),
+        k_chr_stats<true, 4><<<grid, 256, 0, h->stream>>>(nullptr, soa_keys, soa_genes, chr, n, h->tab.as<CellSlot>(), h->kl, h->chr_tab.as<ChrEntry>(),
                                                       uint32_t(h->chr_cap - 1), h->chr_ctr.as<ChrCounters>());
     else
-        k_chr_stats<false><<<grid, 256, 0, h->stream>>>(reinterpret_cast<const Rec16 *>(recs), nullptr, nullptr, chr, n, h->tab.as<CellSlot>(), h->kl,
+        k_chr_stats<false, 4><<<grid, 256, 0, h->stream>>>(reinterpret_cast<const Rec16 *>(recs), nullptr, nullptr, chr, n, h->tab.as<CellSlot>(), h->kl,
                                                        h->chr_tab.as<ChrEntry>(), uint32_t(h->chr_cap - 1), h->chr_ctr.as<ChrCounters>());
     DGE_LAUNCH_CHECK();
     ++h->launches;
