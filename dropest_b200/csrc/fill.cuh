@@ -316,6 +316,8 @@ __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
     uint32_t *hist_s = reinterpret_cast<uint32_t *>(g16 + ((n_genes + 7u) & ~7u));
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
     __shared__ uint32_t cursor_s;
+    __shared__ uint32_t stage_cnt[STAGES], stage_base[STAGES]; // records in the stage / its first record's position in the segment: written by the
+                                                               // producer before it arms the stage's barrier, read by the consumers after their wait
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (uint32_t i = threadIdx.x; i < n_genes; i += blockDim.x)
@@ -351,6 +353,7 @@ __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
                 fill_seg_tile<TILE>(fs, v, seg, base, cnt);
                 const Rec16 *recs = fs.base[seg];
                 unsigned char *stage = fp_smem + size_t(s) * STAGE_BYTES;
+                stage_cnt[s] = cnt; stage_base[s] = uint32_t(base);
                 if (SOA)
                 {
                     const uint32_t kbytes = (cnt * 8u + 15u) & ~15u, gbytes = (cnt * 4u + 15u) & ~15u;
@@ -378,12 +381,10 @@ __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
             if (v >= n_tiles) break;
             const int s = int(k % STAGES);
             const uint32_t round = k / STAGES;
-            uint32_t seg, cnt;
-            size_t base;
-            fill_seg_tile<TILE>(fs, v, seg, base, cnt);
             const unsigned char *stage = fp_smem + size_t(s) * STAGE_BYTES;
             uint4 raw[ITEMS];
             mbar_wait(&full_bar[s], round & 1u);
+            const uint32_t cnt = stage_cnt[s], base = stage_base[s];
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j)
             {
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 1)
             {
                 const uint64_t kk = (uint64_t(raw[j].y) << 32) | raw[j].x;
                 slot0[j] = uint32_t(barcode_hash(kk >> 24) >> (64 - kl.tb));
-                probe[j] = __ldcg(reinterpret_cast<const uint4 *>(&tab[slot0[j]]));
+                probe[j] = __ldcg(reinterpret_cast<const uint4 *>(&tab[slot0[j]])); // (through L1 instead: measured neutral -- ~200 KB of the SM's 256 KB are shared memory here)
             }
             uint64_t keys[ITEMS];
 #pragma unroll
