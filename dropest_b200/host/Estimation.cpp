@@ -341,7 +341,15 @@ namespace Estimation
 			ensure_handle();
 		}
 		if (cb.size() != _cb_len || umi.size() != _umi_len)
-			throw std::runtime_error("the device path needs constant barcode and UMI lengths");
+		{   // the packed record has one barcode / UMI length per run (the first read's); reads of another length (variable-length inDrop v1/2
+			// barcodes) are counted and skipped, not fatal -- the skipped read keeps its stream position like a skipped N read
+			if (_skipped_length_reads++ == 0)
+				std::cerr << "dropest_b200: reads whose barcode / UMI length differs from the first read's (" << _cb_len << " / " << _umi_len
+				          << ") are skipped; skipped_length_reads() reports how many\n";
+			++_n_records;
+			_batch_gaps = true;
+			return;
+		}
 		// N-free sequences are 2-bit packed; a sequence with N is passed as its index in the container's N-string list (the reference keeps
 		// such reads: the barcode is a cell of its own, the UMI is repaired by MergeUMIsStrategySimple after the barcode merge)
 		uint64_t cbv, umiv;

@@ -469,7 +469,7 @@ namespace Estimation
 		bool _batch_gaps = false;
 		StringIndexer _n_umis, _n_cbs;      // UMIs / barcodes containing N, passed to the device as indices (DGE_FLAG_UMI_N / DGE_FLAG_CB_N)
 		bool _n_dirty = false, _allow_n = false;
-		uint64_t _skipped_n_reads = 0;
+		uint64_t _skipped_n_reads = 0, _skipped_length_reads = 0;
 		void upload_n_strings();
 		uint64_t _batch_first = 0;          // stream position of the first pending record
 		size_t _batch_capacity;
@@ -531,6 +531,7 @@ namespace Estimation
 		dge_handle *handle() const { return _h; }
 		bool reads_output() const { return _reads_output; }
 		unsigned cb_length() const { return _cb_len; }
+		uint64_t skipped_length_reads() const { return _skipped_length_reads; } // reads of another barcode / UMI length than the first read's
 		uint64_t skipped_n_reads() const { return _skipped_n_reads; } // reads dropped because the key had no room for the N flag (see ensure_handle)
 		std::string barcode_string(uint64_t packed) const; // 2-bit unpacked, or the N-string behind DGE_CB_N_BIT | index
 		std::string umi_string(uint32_t packed) const;

@@ -177,6 +177,20 @@ int main(int argc, char **argv)
 				CHECK_EQUAL(container.umi_indexer().get_value(umi.first).find('N'), std::string::npos);
 		}
 
+		// reads whose barcode / UMI length differs from the run's are counted and skipped (never fatal), and keep their stream position
+		{
+			CellsDataContainer container(real_cb_strat, umi_merge_strat, any_mark);
+			container.add_record(read_info("AAATTAGGTCCA", "AAACCT", "Gene1"));
+			container.add_record(read_info("AAATTAGGTCC", "AAACCT", "Gene1"));    // 11-base barcode
+			container.add_record(read_info("CCCTTAGGTCCA", "AAACC", "Gene2"));    // 5-base UMI
+			container.add_record(read_info("CCCTTAGGTCCA", "AAACCT", "Gene2"));
+			container.set_initialized();
+			CHECK_EQUAL(container.skipped_length_reads(), uint64_t(2));
+			CHECK_EQUAL(container.total_cells_number(), size_t(2));
+			CHECK_EQUAL(container.cell(1).barcode(), std::string("CCCTTAGGTCCA"));
+			CHECK_EQUAL(container.cell(1).at("Gene2").at("AAACCT").read_count(), size_t(1));
+		}
+
 		// -M: MergeStrategyFactory::get_cb_poisson_strat (MergeStrategyFactory.cpp:91-103) + PoissonSimpleMergeStrategy through the container.
 		// Same reads as above: the small cell shares 3 UMI-genes with the big one 1 substitution away; with only 7 distinct UMIs in the whole
 		// container the expected random overlap is large (lambda ~ 0.6, P[X >= 3] ~ 0.02), so the thresholds are raised for this toy input;
