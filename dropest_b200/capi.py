@@ -48,7 +48,7 @@ EXPORTS = [
     "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
     "dge_route_by_barcode_device", "dge_route_count_slices_device", "dge_route_scatter_slice_device", "dge_dist_step",
-    "dge_peer_alloc", "dge_peer_free", "dge_peer_open", "dge_peer_close",
+    "dge_route_scatter_bounded_device", "dge_peer_alloc", "dge_peer_free", "dge_peer_open", "dge_peer_close",
     "dge_umi_first_size", "dge_umi_first_export", "dge_umi_first_import", "dge_collisions_adjusted_sizes",
 ]
 
@@ -156,6 +156,7 @@ def load_library():
     lib.dge_add_batch_soa_chr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64]
     lib.dge_add_batch_chr_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.dge_get_chr_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.c_void_p]
+    lib.dge_route_scatter_bounded_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dge_peer_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
     lib.dge_peer_free.argtypes = [C.c_int, C.c_void_p]
     lib.dge_peer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]

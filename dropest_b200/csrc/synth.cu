@@ -149,6 +149,55 @@ __global__ void __launch_bounds__(256) k_route_scatter_direct(const dge_record16
     }
 }
 
+// Single-pass variant: no counting pass.  Destination d owns the fixed window out[d * cap, (d + 1) * cap); tiles append to it through the global
+// cursor (which ends up holding the segment's size).  A tile that would run past the window writes nothing and raises *overflow: the caller
+// then repeats the routing with the exact two-pass scheme (counts first), so the result never depends on the window size.
+__global__ void __launch_bounds__(256) k_route_scatter_bounded(const dge_record16 *__restrict__ in, size_t n, uint32_t n_ranks, unsigned long long cap,
+                                                               unsigned long long *__restrict__ cursor, unsigned int *__restrict__ overflow,
+                                                               dge_record16 *__restrict__ out)
+{
+    __shared__ uint32_t cnt[64];
+    __shared__ unsigned long long basep[64];
+    if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t base = size_t(blockIdx.x) * 256 * ROUTE_ITEMS;
+    uint4 rec[ROUTE_ITEMS];
+    uint32_t rk[ROUTE_ITEMS], pos[ROUTE_ITEMS];
+#pragma unroll
+    for (int j = 0; j < ROUTE_ITEMS; ++j)
+    {
+        size_t i = base + size_t(j) * 256 + threadIdx.x;
+        if (i < n) rec[j] = __ldcs(reinterpret_cast<const uint4 *>(in) + i);
+    }
+#pragma unroll
+    for (int j = 0; j < ROUTE_ITEMS; ++j)
+    {
+        size_t i = base + size_t(j) * 256 + threadIdx.x;
+        const bool valid = i < n;
+        rk[j] = valid ? rank_of(((uint64_t(rec[j].y) << 32) | rec[j].x) >> 24, n_ranks) : 0u;
+        pos[j] = route_rank_in_tile(rk[j], cnt, valid);
+    }
+    __syncthreads();
+    if (threadIdx.x < n_ranks)
+    {
+        unsigned long long b = 0;
+        if (cnt[threadIdx.x])
+        {
+            b = atomicAdd(&cursor[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
+            if (b + cnt[threadIdx.x] > cap) { atomicExch(overflow, 1u); b = ~0ull; }
+            else b += (unsigned long long)threadIdx.x * cap;
+        }
+        basep[threadIdx.x] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ROUTE_ITEMS; ++j)
+    {
+        size_t i = base + size_t(j) * 256 + threadIdx.x;
+        if (i < n && basep[rk[j]] != ~0ull) reinterpret_cast<uint4 *>(out)[basep[rk[j]] + pos[j]] = rec[j];
+    }
+}
+
 // Staged variant (A/B only, DGE_ROUTE_STAGED=1): the 2048-record tile is REORDERED BY DESTINATION IN SHARED MEMORY and written as one contiguous run
 // per destination (coalesced full-sector stores; a scattered 16-byte store costs an L2 write transaction of its own), one global
 // atomicAdd per (tile, destination).  Order inside a destination segment is arbitrary: first-seen order travels in read_idx.
@@ -375,6 +424,30 @@ int dge_route_scatter_slice_device(int device, const dge_record16 *in_slice, siz
         return DGE_OK;
     }
     catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_route_scatter_slice_device: %s\n", e.what()); return DGE_ERR_CUDA; }
+}
+
+/* Single-pass routing (no counting pass): destination d gets the window out[d * seg_capacity, (d + 1) * seg_capacity).  `state_device` = n_ranks + 1
+ * uint64 words, zeroed by the call: [0, n_ranks) end up as the segment sizes, word n_ranks != 0 means a window overflowed -- the contents of
+ * `out` are then unusable and the caller falls back to dge_route_count_slices_device + dge_route_scatter_slice_device.  Asynchronous. */
+int dge_route_scatter_bounded_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, size_t seg_capacity, uint64_t *state_device,
+                                     dge_record16 *out, void *cuda_stream)
+{
+    if (n_ranks == 0 || n_ranks > 64 || !state_device || seg_capacity == 0 || (n && (!in || !out))) return DGE_ERR_INVALID;
+    try
+    {
+        DGE_CUDA(cudaSetDevice(device));
+        cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+        DGE_CUDA(cudaMemsetAsync(state_device, 0, (size_t(n_ranks) + 1) * 8, st));
+        if (n)
+        {
+            k_route_scatter_bounded<<<unsigned(div_up(n, size_t(256 * ROUTE_ITEMS))), 256, 0, st>>>(
+                in, n, n_ranks, (unsigned long long)seg_capacity, reinterpret_cast<unsigned long long *>(state_device),
+                reinterpret_cast<unsigned int *>(state_device + n_ranks), out);
+            DGE_LAUNCH_CHECK();
+        }
+        return DGE_OK;
+    }
+    catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_route_scatter_bounded_device: %s\n", e.what()); return DGE_ERR_CUDA; }
 }
 
 /* ---- peer memory for the exchange: the routed records stay in the SOURCE rank's HBM and the owner's fill kernel pulls its segment

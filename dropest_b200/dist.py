@@ -109,16 +109,19 @@ class PeerExchange:
         -> the fill kernel of every owner pulls its segment out of each source's buffer over NVLink (bulk-async copies of the producer warp)
     No all-to-all pass, no receive buffer: the records cross NVLink exactly once, inside the kernel that consumes them."""
 
-    def __init__(self, device: int, n: int, world: int, group=None, fused: bool = True):
+    def __init__(self, device: int, n: int, world: int, group=None, fused: bool = True, slack: float = 1.25):
         import torch
         import torch.distributed as dist
 
         self.device, self.n, self.world, self.group, self.fused = device, n, world, group, fused
         self.rank = dist.get_rank(group)
+        # every destination owns a window of `cap` records in the routed buffer (single-pass routing); a skewed batch that overflows a
+        # window is routed again with exact counts into the same buffer (dense layout: n records always fit)
+        self.cap = (int(max(n, 1) / world * slack) + 4096 + 15) // 16 * 16
         lib = load_library()
         handle = C.create_string_buffer(64)
         p = C.c_void_p()
-        if lib.dge_peer_alloc(device, max(n, 1) * 16, C.byref(p), handle) != 0:
+        if lib.dge_peer_alloc(device, max(self.cap * world, max(n, 1)) * 16, C.byref(p), handle) != 0:
             raise RuntimeError("dge_peer_alloc failed: " + lib.dge_last_error(None).decode())
         self.routed_ptr = p.value
         handles = [None] * world
@@ -134,8 +137,10 @@ class PeerExchange:
             self.peer_ptr.append(q.value)
         dev = f"cuda:{device}"
         self.cursors = torch.empty(64, dtype=torch.int64, device=dev)
+        self.state = torch.empty(world + 1, dtype=torch.int64, device=dev)
         self.token = torch.zeros(1, dtype=torch.int32, device=dev)
         self.bytes_pulled = 0
+        self.n_fallbacks = 0
 
     def close(self):
         lib = load_library()
@@ -155,17 +160,34 @@ class PeerExchange:
 
         world, rank = self.world, self.rank
         sp = stream.cuda_stream
+        lib = load_library()
         dist.all_reduce(self.token, group=self.group)                # every peer is done with the previous step's buffers
-        counts = route_count_slices(self.device, raw_ptr, self.n, world, ((self.n + 2047) // 2048) * 2048 or 2048, 1, self.cursors.data_ptr(), sp)
-        route_scatter_slice(self.device, raw_ptr, self.n, world, self.cursors.data_ptr(), self.routed_ptr, sp)
-        mine = torch.from_numpy(counts.astype(np.int64).reshape(-1)).to(self.token.device)
-        allc = torch.empty(world * world, dtype=torch.int64, device=self.token.device)
-        dist.all_gather_into_tensor(allc, mine, group=self.group)    # completes after every rank's scatter (stream order on each rank)
-        allc = allc.cpu().numpy().reshape(world, world)               # [source, destination]
+        # single-pass routing into per-destination windows; sizes + overflow flag of every rank in one all-gather, which completes after
+        # every rank's scatter (stream order on each rank): the "scatter done" barrier
+        if lib.dge_route_scatter_bounded_device(self.device, C.c_void_p(raw_ptr), self.n, world, self.cap, C.c_void_p(self.state.data_ptr()),
+                                                C.c_void_p(self.routed_ptr), C.c_void_p(sp)) != 0:
+            raise RuntimeError("dge_route_scatter_bounded_device failed")
+        alls = torch.empty(world * (world + 1), dtype=torch.int64, device=self.token.device)
+        dist.all_gather_into_tensor(alls, self.state, group=self.group)
+        alls = alls.cpu().numpy().reshape(world, world + 1)
+        if not alls[:, world].any():
+            allc = alls[:, :world]                                    # [source, destination]
+            seg_off = lambda src: rank * self.cap
+        else:
+            # a window overflowed somewhere (one barcode with a large share of the reads): every rank routes again with exact counts
+            self.n_fallbacks += 1
+            dist.all_reduce(self.token, group=self.group)            # nobody still reads a window of the failed attempt (nobody started)
+            counts = route_count_slices(self.device, raw_ptr, self.n, world, ((self.n + 2047) // 2048) * 2048 or 2048, 1, self.cursors.data_ptr(), sp)
+            route_scatter_slice(self.device, raw_ptr, self.n, world, self.cursors.data_ptr(), self.routed_ptr, sp)
+            mine = torch.from_numpy(counts.astype(np.int64).reshape(-1)).to(self.token.device)
+            allc_t = torch.empty(world * world, dtype=torch.int64, device=self.token.device)
+            dist.all_gather_into_tensor(allc_t, mine, group=self.group)
+            allc = allc_t.cpu().numpy().reshape(world, world)
+            seg_off = lambda src: int(allc[src, :rank].sum())
         ptrs, cnts = [], []
         for k in range(world):
             src = (rank + k) % world                                  # own segment first, then the peers in rotation
-            ptrs.append(self.peer_ptr[src] + int(allc[src, :rank].sum()) * 16)
+            ptrs.append(self.peer_ptr[src] + seg_off(src) * 16)
             cnts.append(int(allc[src, rank]))
         total = sum(cnts)
         self.bytes_pulled = (total - cnts[0]) * 16

@@ -329,6 +329,12 @@ int dge_route_count_slices_device(int device, const dge_record16 *in, size_t n, 
 int dge_route_scatter_slice_device(int device, const dge_record16 *in_slice, size_t n_slice, uint32_t n_ranks, uint64_t *slice_cursors_device,
                                    dge_record16 *out_slice, void *cuda_stream);
 
+/* Routing in ONE pass (no counting pass), for the peer-memory exchange: destination d owns the window out[d * seg_capacity, (d + 1) * seg_capacity);
+ * state_device (n_ranks + 1 uint64, DEVICE, zeroed by the call) receives the segment sizes and, in word n_ranks, an overflow flag.  When a
+ * window overflowed the routing is repeated with the exact two-pass scheme above: the result never depends on seg_capacity.  Asynchronous. */
+int dge_route_scatter_bounded_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, size_t seg_capacity, uint64_t *state_device,
+                                     dge_record16 *out, void *cuda_stream);
+
 /* Peer memory for the exchange (one process per GPU of one NVLink/NVSwitch node).  Instead of scatter -> all-to-all -> fill, the routed
  * records stay in the SOURCE rank's HBM (a dge_peer_alloc buffer, exported as a 64-byte CUDA IPC handle that the caller sends to the
  * peers by any transport) and every owner's fill kernel pulls its segment out of it over NVLink: dge_add_batch_device accepts pointers

@@ -63,12 +63,15 @@ def _worker_real(rank, world, port, n_total, out_dir, umi_len, n_genes, directio
     c = dg.Container(_real_config(dg, umi_len, n_genes, directional, device=rank, sharded=True))
     stream = torch.cuda.current_stream()
     c.set_stream(stream.cuda_stream)
-    if exchange == "peer":   # the fill kernel pulls the routed records out of the other rank's HBM (CUDA IPC peer memory over NVLink)
-        pipe = dgdist.PeerExchange(rank, per, world)
+    if exchange.startswith("peer"):   # the fill kernel pulls the routed records out of the other rank's HBM (CUDA IPC peer memory over NVLink)
+        # "peer_overflow": destination windows too small on purpose -> the single-pass routing reports it and the exact two-pass routing takes over
+        pipe = dgdist.PeerExchange(rank, per, world, slack=0.55 if exchange == "peer_overflow" else 1.25)
     else:                    # routing + sliced NCCL all-to-all overlapped with the fill
         pipe = dgdist.PipelinedExchange(rank, per, world, n_slices=5)
     cnt = pipe.run(c, raw.data_ptr(), stream)
     torch.cuda.synchronize()
+    if exchange.startswith("peer"):
+        assert pipe.n_fallbacks == (1 if exchange == "peer_overflow" else 0)
     dgdist.sync_umi_first_seen(c, f"cuda:{rank}")
     c.set_initialized()
     stats = dgdist.merge_across_ranks(c, f"cuda:{rank}")
@@ -86,12 +89,12 @@ def _worker_real(rank, world, port, n_total, out_dir, umi_len, n_genes, directio
     c.close()
     torch.cuda.synchronize()
     dist.barrier()
-    if exchange == "peer":
+    if exchange.startswith("peer"):
         pipe.close()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("umi_len,n_genes,directional,exchange", [(10, 150, False, "peer"), (10, 150, False, "nccl"), (5, 20, True, "peer")])
+@pytest.mark.parametrize("umi_len,n_genes,directional,exchange", [(10, 150, False, "peer"), (10, 150, False, "peer_overflow"), (10, 150, False, "nccl"), (5, 20, True, "peer")])
 def test_two_gpu_cross_rank_whitelist_merge_is_exact(tmp_path, umi_len, n_genes, directional, exchange):
     """Sharded run + cross-rank merge (dge_dist_*): the union of the per-rank results equals the single-GPU result.
     With the directional UMI merge the per-UMI first-seen table is min-reduced across ranks first."""
