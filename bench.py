@@ -308,6 +308,7 @@ def main():
     ap.add_argument("--slices", type=int, default=8, help="N > 1, --exchange nccl: slices of the pipelined route / all-to-all / fill")
     ap.add_argument("--chr", type=int, default=0, metavar="N_CHR",
                     help="N = 1: also feed Stats' per-chromosome counters (a 1-byte chromosome id per read, N_CHR chromosomes; dge_add_batch_chr_device)")
+    ap.add_argument("--no-chr-probe", action="store_true", help="skip the two extra steps that measure the optional per-chromosome counters")
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
                     help="N > 1: 'peer' = the owners' fill kernels pull the routed records out of the sources' HBM over NVLink (no all-to-all pass); "
                          "'nccl' = scatter -> NCCL all-to-all -> fill in slices")
@@ -414,16 +415,20 @@ def main():
 
     owned_reads = n
     chr_ids = None
-    if args.chr and world == 1:
-        # a chromosome per read (genes live on one chromosome each, reads without a gene fall anywhere), made on the device outside the timed region
-        chr_ids = torch.empty(n, dtype=torch.uint8, device=f"cuda:{dev}")
+
+    def make_chr_ids(n_chr):
+        """a chromosome per read (genes live on one chromosome each, reads without a gene fall anywhere), made on the device outside the timed region"""
+        ids = torch.empty(n, dtype=torch.uint8, device=f"cuda:{dev}")
         rec64 = raw.view(torch.int64).view(-1, 2)
         for a in range(0, n, 1 << 26):
             w = rec64[a:a + (1 << 26), 1]
             gene = w & 0xFFFFFF
             idx = (w >> 32) & 0xFFFFFFFF
-            chr_ids[a:a + (1 << 26)] = torch.where(gene == 0xFFFFFF, (idx * 40503 >> 3) % args.chr, (gene * 2654435761 >> 13) % max(1, args.chr - 1)).to(torch.uint8)
-        del rec64
+            ids[a:a + (1 << 26)] = torch.where(gene == 0xFFFFFF, (idx * 40503 >> 3) % n_chr, (gene * 2654435761 >> 13) % max(1, n_chr - 1)).to(torch.uint8)
+        return ids
+
+    if args.chr and world == 1:
+        chr_ids = make_chr_ids(args.chr)
         config["chromosomes"] = args.chr
 
     def step(k=None):
@@ -494,6 +499,25 @@ def main():
     total_reads = n * world * args.steps
     value = total_reads / (ms / 1000.0)
 
+    # ---- the optional per-chromosome Stats counters (1-byte chromosome id per read, SURVEY 8a rows a-R / a4): not part of `value` unless --chr
+    # is given; their cost is measured here so that the line says what including them would mean
+    chr_extra = None
+    if world == 1 and not args.chr and not args.no_chr_probe:
+        chr_ids = make_chr_ids(25)
+        step(); barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(2):
+            step()
+        c1.record(stream)
+        barrier()
+        ms_chr = c0.elapsed_time(c1) / 2
+        chr_extra = {"included_in_value": False, "chromosomes": 25, "ms_per_step_with_counters": ms_chr, "reads_per_s_with_counters": n / (ms_chr / 1e3),
+                     "note": "dge_add_batch_chr_device + k_chr_stats; the kernel runs at the random-L2-sector rate (profiles/r2_chr_stats_notes.txt)"}
+        chr_ids = None
+        del c0, c1
+    elif world == 1 and args.chr:
+        chr_extra = {"included_in_value": True, "chromosomes": args.chr}
     # ---- e2e: host (pinned) records -> C ABI -> count matrix back on the host
     e2e = None
     if not args.no_e2e:
@@ -632,6 +656,8 @@ def main():
                                       else "%d slices: route kernel -> NCCL all_to_all_single (async) -> fill, overlapped" % pipe.n_slices)
         line["step_breakdown_ms"] = breakdown
         line["verify"] = verify
+    if chr_extra is not None:
+        line["chromosome_stats"] = chr_extra
     if world == 1 and not args.no_cpu_baseline:
         try:
             cb = cpu_reference_run(wl_path, wl_parts, args.cpu_sample_reads, keep=True)
