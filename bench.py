@@ -184,10 +184,8 @@ def exchange_diagnostics(pipe, cont, raw, stream, torch, dist, n, world):
     torch.cuda.synchronize(); dist.barrier()
     if isinstance(pipe, dgdist.PeerExchange):
         # the routing kernel alone (single-pass scatter into the peer-mapped windows), then the fill alone pulling from the peers
-        import ctypes as C
         ev[0].record(stream)
-        dgdist.load_library().dge_route_scatter_bounded_device(pipe.device, C.c_void_p(raw.data_ptr()), n, world, pipe.cap, C.c_void_p(pipe.state.data_ptr()),
-                                                               C.c_void_p(pipe.routed_ptr), C.c_void_p(stream.cuda_stream))
+        pipe.scatter(raw.data_ptr(), stream.cuda_stream)
         ev[1].record(stream)
         torch.cuda.synchronize(); dist.barrier()
         cont.reset()
@@ -198,7 +196,7 @@ def exchange_diagnostics(pipe, cont, raw, stream, torch, dist, n, world):
         cont.reset()
         return {"diag_ms_route_kernels": ev[0].elapsed_time(ev[1]), "diag_ms_fill_kernels_pulling": ms_pull,
                 "diag_pulled_gbytes_per_gpu": pipe.bytes_pulled / 1e9, "diag_pull_gbs_per_gpu": pipe.bytes_pulled / 1e9 / max(ms_pull / 1e3, 1e-9),
-                "diag_routing_fallbacks": float(pipe.n_fallbacks)}
+                "diag_pushed_gbytes_per_gpu": pipe.bytes_pushed / 1e9, "diag_push16": float(pipe.push16), "diag_routing_fallbacks": float(pipe.n_fallbacks)}
     ev[0].record(stream)
     dgdist.route_count_slices(pipe.device, raw.data_ptr(), n, world, pipe.slice_len, pipe.n_slices, pipe.cursors.data_ptr(), stream.cuda_stream)
     for s in range(pipe.n_slices):
@@ -651,7 +649,7 @@ def main():
                                       "(BASELINE configs[3] '4B reads / 100k cells on 8 GPUs' at the per-GPU size of configs[1])"
                                       % (world, n // 1_000_000, args.cells, n * world // 1_000_000, args.cells * world, world))
         line["config"]["merge"] += "; exact cross-rank merge (dge_dist_step: all-gather of target summaries + 3 small all-to-alls), result.* are rank 0's shard"
-        line["config"]["exchange"] = ("peer: single-pass scatter by owner into per-destination windows of a CUDA-IPC buffer in the source's HBM -> all-gather of segment sizes -> "
+        line["config"]["exchange"] = ("peer: single-pass scatter by owner into per-destination windows of a CUDA-IPC buffer in the source's HBM, a share of the tiles pushed straight into the owners' HBM -> all-gather of segment sizes -> "
                                       "every owner's k_fill_pipe bulk-copies its segments over NVLink (no all-to-all pass)" if args.exchange == "peer"
                                       else "%d slices: route kernel -> NCCL all_to_all_single (async) -> fill, overlapped" % pipe.n_slices)
         line["step_breakdown_ms"] = breakdown

@@ -156,7 +156,8 @@ def load_library():
     lib.dge_add_batch_soa_chr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64]
     lib.dge_add_batch_chr_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.dge_get_chr_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.c_void_p]
-    lib.dge_route_scatter_bounded_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dge_route_scatter_bounded_device.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                     C.c_size_t, C.c_void_p, C.c_void_p]
     lib.dge_peer_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
     lib.dge_peer_free.argtypes = [C.c_int, C.c_void_p]
     lib.dge_peer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]

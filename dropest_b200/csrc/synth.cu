@@ -149,18 +149,24 @@ __global__ void __launch_bounds__(256) k_route_scatter_direct(const dge_record16
     }
 }
 
-// Single-pass variant: no counting pass.  Destination d owns the fixed window out[d * cap, (d + 1) * cap); tiles append to it through the global
-// cursor (which ends up holding the segment's size).  A tile that would run past the window writes nothing and raises *overflow: the caller
-// then repeats the routing with the exact two-pass scheme (counts first), so the result never depends on the window size.
-__global__ void __launch_bounds__(256) k_route_scatter_bounded(const dge_record16 *__restrict__ in, size_t n, uint32_t n_ranks, unsigned long long cap,
-                                                               unsigned long long *__restrict__ cursor, unsigned int *__restrict__ overflow,
-                                                               dge_record16 *__restrict__ out)
+// Single-pass variant: no counting pass.  Destination d owns the fixed window out[d * cap, (d + 1) * cap) of THIS rank's buffer (the owner's
+// fill kernel pulls it over NVLink later); tiles append to it through the global cursor (which ends up holding the segment's size).
+// PUSH: `push16` of every 16 tiles store their records for a remote destination d straight into d's HBM instead (push_base[d] = this
+// rank's receive window there, push_cursor[d] its fill level): NVLink is idle while the scatter streams through local HBM, so part of the
+// exchange rides along for free and the fill has less left to pull.  A tile that would run past a window writes nothing and raises
+// *overflow: the caller then repeats the routing with the exact two-pass scheme (counts first), so the result never depends on the window sizes.
+__global__ void __launch_bounds__(256) k_route_scatter_bounded(const dge_record16 *__restrict__ in, size_t n, uint32_t n_ranks, uint32_t me,
+                                                               unsigned long long cap, unsigned long long *__restrict__ cursor,
+                                                               unsigned int *__restrict__ overflow, dge_record16 *__restrict__ out,
+                                                               uint32_t push16, unsigned long long push_cap, unsigned long long *__restrict__ push_cursor,
+                                                               dge_record16 *const *__restrict__ push_base)
 {
     __shared__ uint32_t cnt[64];
-    __shared__ unsigned long long basep[64];
+    __shared__ dge_record16 *dst[64];
     if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
     __syncthreads();
     const size_t base = size_t(blockIdx.x) * 256 * ROUTE_ITEMS;
+    const bool pushing = push16 && (blockIdx.x & 15u) < push16;
     uint4 rec[ROUTE_ITEMS];
     uint32_t rk[ROUTE_ITEMS], pos[ROUTE_ITEMS];
 #pragma unroll
@@ -180,21 +186,31 @@ __global__ void __launch_bounds__(256) k_route_scatter_bounded(const dge_record1
     __syncthreads();
     if (threadIdx.x < n_ranks)
     {
-        unsigned long long b = 0;
-        if (cnt[threadIdx.x])
+        const uint32_t d = threadIdx.x;
+        dge_record16 *p = nullptr;
+        if (cnt[d])
         {
-            b = atomicAdd(&cursor[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
-            if (b + cnt[threadIdx.x] > cap) { atomicExch(overflow, 1u); b = ~0ull; }
-            else b += (unsigned long long)threadIdx.x * cap;
+            if (pushing && d != me)
+            {
+                const unsigned long long b = atomicAdd(&push_cursor[d], (unsigned long long)cnt[d]);
+                if (b + cnt[d] > push_cap) atomicExch(overflow, 1u);
+                else p = push_base[d] + b;
+            }
+            else
+            {
+                const unsigned long long b = atomicAdd(&cursor[d], (unsigned long long)cnt[d]);
+                if (b + cnt[d] > cap) atomicExch(overflow, 1u);
+                else p = out + (unsigned long long)d * cap + b;
+            }
         }
-        basep[threadIdx.x] = b;
+        dst[d] = p;
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ROUTE_ITEMS; ++j)
     {
         size_t i = base + size_t(j) * 256 + threadIdx.x;
-        if (i < n && basep[rk[j]] != ~0ull) reinterpret_cast<uint4 *>(out)[basep[rk[j]] + pos[j]] = rec[j];
+        if (i < n && dst[rk[j]]) reinterpret_cast<uint4 *>(dst[rk[j]])[pos[j]] = rec[j];
     }
 }
 
@@ -426,23 +442,29 @@ int dge_route_scatter_slice_device(int device, const dge_record16 *in_slice, siz
     catch (std::exception &e) { g_err = e.what(); fprintf(stderr, "dge_route_scatter_slice_device: %s\n", e.what()); return DGE_ERR_CUDA; }
 }
 
-/* Single-pass routing (no counting pass): destination d gets the window out[d * seg_capacity, (d + 1) * seg_capacity).  `state_device` = n_ranks + 1
- * uint64 words, zeroed by the call: [0, n_ranks) end up as the segment sizes, word n_ranks != 0 means a window overflowed -- the contents of
- * `out` are then unusable and the caller falls back to dge_route_count_slices_device + dge_route_scatter_slice_device.  Asynchronous. */
-int dge_route_scatter_bounded_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, size_t seg_capacity, uint64_t *state_device,
-                                     dge_record16 *out, void *cuda_stream)
+/* Single-pass routing (no counting pass).  Destination d gets the window out[d * seg_capacity, (d + 1) * seg_capacity) of this rank's buffer.
+ * push16 > 0: that many of every 16 tiles store their records for a remote destination d directly into d's memory at push_base_device[d]
+ * (room for push_capacity records; pointers from dge_peer_open).  `state_device` = 2 * n_ranks + 1 uint64 words, zeroed by the call:
+ * [0, n_ranks) the sizes of the local windows, [n_ranks, 2 n_ranks) the records pushed to each destination, word 2 n_ranks != 0 = a window
+ * overflowed -- the output is then unusable and the caller falls back to the exact two-pass routing.  Asynchronous. */
+int dge_route_scatter_bounded_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, uint32_t my_rank, size_t seg_capacity,
+                                     uint64_t *state_device, dge_record16 *out, uint32_t push16, size_t push_capacity,
+                                     dge_record16 *const *push_base_device, void *cuda_stream)
 {
-    if (n_ranks == 0 || n_ranks > 64 || !state_device || seg_capacity == 0 || (n && (!in || !out))) return DGE_ERR_INVALID;
+    if (n_ranks == 0 || n_ranks > 64 || my_rank >= n_ranks || !state_device || seg_capacity == 0 || (n && (!in || !out)) || push16 > 16 ||
+        (push16 && (!push_base_device || push_capacity == 0)))
+        return DGE_ERR_INVALID;
     try
     {
         DGE_CUDA(cudaSetDevice(device));
         cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-        DGE_CUDA(cudaMemsetAsync(state_device, 0, (size_t(n_ranks) + 1) * 8, st));
+        DGE_CUDA(cudaMemsetAsync(state_device, 0, (size_t(n_ranks) * 2 + 1) * 8, st));
         if (n)
         {
+            unsigned long long *state = reinterpret_cast<unsigned long long *>(state_device);
             k_route_scatter_bounded<<<unsigned(div_up(n, size_t(256 * ROUTE_ITEMS))), 256, 0, st>>>(
-                in, n, n_ranks, (unsigned long long)seg_capacity, reinterpret_cast<unsigned long long *>(state_device),
-                reinterpret_cast<unsigned int *>(state_device + n_ranks), out);
+                in, n, n_ranks, my_rank, (unsigned long long)seg_capacity, state, reinterpret_cast<unsigned int *>(state + 2 * n_ranks), out, push16,
+                (unsigned long long)push_capacity, state + n_ranks, push_base_device);
             DGE_LAUNCH_CHECK();
         }
         return DGE_OK;

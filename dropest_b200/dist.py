@@ -6,6 +6,7 @@ torch.distributed is only the transport here (NCCL on GPUs, gloo in the CPU test
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Tuple
 
 import numpy as np
@@ -103,27 +104,37 @@ class PipelinedExchange:
 
 
 class PeerExchange:
-    """Barcode-hash routing with the exchange fused into the fill (one process per GPU of one NVLink / NVSwitch node):
-        count pass -> scatter by owner into a buffer of THIS rank's HBM that every peer has mapped (CUDA IPC)
+    """Barcode-hash routing with the exchange fused into the kernels on both sides of it (one process per GPU of one NVLink / NVSwitch node):
+        single-pass scatter by owner: most tiles go into per-destination windows of THIS rank's HBM that every peer has mapped (CUDA IPC),
+            `push16` of every 16 tiles store their remote records straight into the owner's HBM (NVLink is idle during the scatter otherwise)
         -> all-gather of the segment sizes (doubles as the "scatter done" barrier)
-        -> the fill kernel of every owner pulls its segment out of each source's buffer over NVLink (bulk-async copies of the producer warp)
-    No all-to-all pass, no receive buffer: the records cross NVLink exactly once, inside the kernel that consumes them."""
+        -> ONE fill launch per owner over its own window, the windows the peers pushed into, and the peers' windows, which its bulk-async
+           copies pull over NVLink while local tiles are being processed
+    No all-to-all pass, no staging copy: every record crosses NVLink exactly once, inside a kernel that does other work at the same time."""
 
-    def __init__(self, device: int, n: int, world: int, group=None, fused: bool = True, slack: float = 1.25):
+    def __init__(self, device: int, n: int, world: int, group=None, fused: bool = True, slack: float = 1.25, push16=None):
         import torch
         import torch.distributed as dist
 
         self.device, self.n, self.world, self.group, self.fused = device, n, world, group, fused
         self.rank = dist.get_rank(group)
-        # every destination owns a window of `cap` records in the routed buffer (single-pass routing); a skewed batch that overflows a
-        # window is routed again with exact counts into the same buffer (dense layout: n records always fit)
+        # share of the remote records that travels during the scatter: about what NVLink can carry while the scatter streams 32 B per
+        # record through local HBM (measured: 2.6 ms for 400 M records)
+        if push16 is None:
+            push16 = int(os.environ.get("DGE_PUSH16", round(16 * min(0.5, 0.25 * world / max(1, world - 1))))) if world > 1 else 0
+        self.push16 = max(0, min(16, int(push16)))
+        # every destination owns a window of `cap` records in the routed buffer; the peers' pushes land in `world` more windows behind them.
+        # A skewed batch that overflows a window is routed again with exact counts (dense layout in the first part: n records always fit)
         self.cap = (int(max(n, 1) / world * slack) + 4096 + 15) // 16 * 16
+        self.push_cap = self.cap if self.push16 else 0
         lib = load_library()
         handle = C.create_string_buffer(64)
         p = C.c_void_p()
-        if lib.dge_peer_alloc(device, max(self.cap * world, max(n, 1)) * 16, C.byref(p), handle) != 0:
+        records = max(self.cap * world, max(n, 1)) + self.push_cap * world
+        if lib.dge_peer_alloc(device, records * 16, C.byref(p), handle) != 0:
             raise RuntimeError("dge_peer_alloc failed: " + lib.dge_last_error(None).decode())
         self.routed_ptr = p.value
+        self.recv_off = max(self.cap * world, max(n, 1))            # first record of the push windows (one per source rank)
         handles = [None] * world
         dist.all_gather_object(handles, bytes(handle.raw), group=group)
         self.peer_ptr = []
@@ -137,9 +148,11 @@ class PeerExchange:
             self.peer_ptr.append(q.value)
         dev = f"cuda:{device}"
         self.cursors = torch.empty(64, dtype=torch.int64, device=dev)
-        self.state = torch.empty(world + 1, dtype=torch.int64, device=dev)
+        self.state = torch.empty(2 * world + 1, dtype=torch.int64, device=dev)
+        # where this rank's pushes land in every peer: its window (index = source rank) behind the peer's pull windows
+        self.push_base = torch.tensor([self.peer_ptr[d] + (self.recv_off + self.rank * self.push_cap) * 16 for d in range(world)], dtype=torch.int64, device=dev)
         self.token = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.bytes_pulled = 0
+        self.bytes_pulled = self.bytes_pushed = 0
         self.n_fallbacks = 0
 
     def close(self):
@@ -152,6 +165,13 @@ class PeerExchange:
             lib.dge_peer_free(self.device, C.c_void_p(self.routed_ptr))
             self.routed_ptr = None
 
+    def scatter(self, raw_ptr: int, stream_ptr: int):
+        rc = load_library().dge_route_scatter_bounded_device(self.device, C.c_void_p(raw_ptr), self.n, self.world, self.rank, self.cap,
+                                                             C.c_void_p(self.state.data_ptr()), C.c_void_p(self.routed_ptr), self.push16, self.push_cap,
+                                                             C.c_void_p(self.push_base.data_ptr()), C.c_void_p(stream_ptr))
+        if rc != 0:
+            raise RuntimeError("dge_route_scatter_bounded_device failed")
+
     def run(self, cont, raw_ptr: int, stream) -> int:
         """Routes and fills; returns the number of records this rank owns.  The peers' buffers are read until this rank's
         set_initialized has run; the next run() starts with a barrier, so a source never overwrites records a peer still needs."""
@@ -160,37 +180,43 @@ class PeerExchange:
 
         world, rank = self.world, self.rank
         sp = stream.cuda_stream
-        lib = load_library()
         dist.all_reduce(self.token, group=self.group)                # every peer is done with the previous step's buffers
-        # single-pass routing into per-destination windows; sizes + overflow flag of every rank in one all-gather, which completes after
-        # every rank's scatter (stream order on each rank): the "scatter done" barrier
-        if lib.dge_route_scatter_bounded_device(self.device, C.c_void_p(raw_ptr), self.n, world, self.cap, C.c_void_p(self.state.data_ptr()),
-                                                C.c_void_p(self.routed_ptr), C.c_void_p(sp)) != 0:
-            raise RuntimeError("dge_route_scatter_bounded_device failed")
-        alls = torch.empty(world * (world + 1), dtype=torch.int64, device=self.token.device)
+        # single-pass routing; sizes + overflow flag of every rank in one all-gather, which completes after every rank's scatter
+        # (stream order on each rank): the "scatter done" barrier, for the local windows and for what was pushed into ours
+        self.scatter(raw_ptr, sp)
+        W = 2 * world + 1
+        alls = torch.empty(world * W, dtype=torch.int64, device=self.token.device)
         dist.all_gather_into_tensor(alls, self.state, group=self.group)
-        alls = alls.cpu().numpy().reshape(world, world + 1)
-        if not alls[:, world].any():
-            allc = alls[:, :world]                                    # [source, destination]
-            seg_off = lambda src: rank * self.cap
+        alls = alls.cpu().numpy().reshape(world, W)
+        ptrs, cnts = [], []
+        if not alls[:, 2 * world].any():
+            pull, push = alls[:, :world], alls[:, world:2 * world]   # [source, destination]
+            for k in range(world):
+                src = (rank + k) % world                              # own window first, then the peers in rotation
+                ptrs.append(self.peer_ptr[src] + rank * self.cap * 16)
+                cnts.append(int(pull[src, rank]))
+                if src != rank and push[src, rank]:
+                    ptrs.append(self.routed_ptr + (self.recv_off + src * self.push_cap) * 16)   # what `src` pushed: already in this rank's HBM
+                    cnts.append(int(push[src, rank]))
+            self.bytes_pulled = int(pull[:, rank].sum() - pull[rank, rank]) * 16
+            self.bytes_pushed = int(push[rank, :].sum()) * 16
         else:
             # a window overflowed somewhere (one barcode with a large share of the reads): every rank routes again with exact counts
             self.n_fallbacks += 1
-            dist.all_reduce(self.token, group=self.group)            # nobody still reads a window of the failed attempt (nobody started)
+            dist.all_reduce(self.token, group=self.group)
             counts = route_count_slices(self.device, raw_ptr, self.n, world, ((self.n + 2047) // 2048) * 2048 or 2048, 1, self.cursors.data_ptr(), sp)
             route_scatter_slice(self.device, raw_ptr, self.n, world, self.cursors.data_ptr(), self.routed_ptr, sp)
             mine = torch.from_numpy(counts.astype(np.int64).reshape(-1)).to(self.token.device)
             allc_t = torch.empty(world * world, dtype=torch.int64, device=self.token.device)
             dist.all_gather_into_tensor(allc_t, mine, group=self.group)
             allc = allc_t.cpu().numpy().reshape(world, world)
-            seg_off = lambda src: int(allc[src, :rank].sum())
-        ptrs, cnts = [], []
-        for k in range(world):
-            src = (rank + k) % world                                  # own segment first, then the peers in rotation
-            ptrs.append(self.peer_ptr[src] + seg_off(src) * 16)
-            cnts.append(int(allc[src, rank]))
+            for k in range(world):
+                src = (rank + k) % world
+                ptrs.append(self.peer_ptr[src] + int(allc[src, :rank].sum()) * 16)
+                cnts.append(int(allc[src, rank]))
+            self.bytes_pulled = int(allc[:, rank].sum() - allc[rank, rank]) * 16
+            self.bytes_pushed = 0
         total = sum(cnts)
-        self.bytes_pulled = (total - cnts[0]) * 16
         if self.fused:
             cont.add_batch_segments_device(ptrs, cnts)                # ONE launch: local and remote tiles alternate inside every block
         else:

@@ -329,11 +329,15 @@ int dge_route_count_slices_device(int device, const dge_record16 *in, size_t n, 
 int dge_route_scatter_slice_device(int device, const dge_record16 *in_slice, size_t n_slice, uint32_t n_ranks, uint64_t *slice_cursors_device,
                                    dge_record16 *out_slice, void *cuda_stream);
 
-/* Routing in ONE pass (no counting pass), for the peer-memory exchange: destination d owns the window out[d * seg_capacity, (d + 1) * seg_capacity);
- * state_device (n_ranks + 1 uint64, DEVICE, zeroed by the call) receives the segment sizes and, in word n_ranks, an overflow flag.  When a
- * window overflowed the routing is repeated with the exact two-pass scheme above: the result never depends on seg_capacity.  Asynchronous. */
-int dge_route_scatter_bounded_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, size_t seg_capacity, uint64_t *state_device,
-                                     dge_record16 *out, void *cuda_stream);
+/* Routing in ONE pass (no counting pass), for the peer-memory exchange: destination d owns the window out[d * seg_capacity, (d + 1) *
+ * seg_capacity) of this rank's buffer (pulled by d's fill kernel later).  push16 > 0: that many of every 16 tiles store their records for a
+ * remote destination d straight into d's HBM at push_base_device[d] (DEVICE array of n_ranks pointers obtained with dge_peer_open; room for
+ * push_capacity records each) -- NVLink is idle while the scatter streams through local HBM, so part of the exchange rides along.
+ * state_device (2 * n_ranks + 1 uint64, DEVICE, zeroed by the call): sizes of the local windows, records pushed per destination, overflow flag.
+ * When a window overflowed the routing is repeated with the exact two-pass scheme above: results never depend on the capacities.  Asynchronous. */
+int dge_route_scatter_bounded_device(int device, const dge_record16 *in, size_t n, uint32_t n_ranks, uint32_t my_rank, size_t seg_capacity,
+                                     uint64_t *state_device, dge_record16 *out, uint32_t push16, size_t push_capacity,
+                                     dge_record16 *const *push_base_device, void *cuda_stream);
 
 /* Peer memory for the exchange (one process per GPU of one NVLink/NVSwitch node).  Instead of scatter -> all-to-all -> fill, the routed
  * records stay in the SOURCE rank's HBM (a dge_peer_alloc buffer, exported as a 64-byte CUDA IPC handle that the caller sends to the
