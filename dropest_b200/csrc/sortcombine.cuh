@@ -17,6 +17,7 @@
 #include "sortdedup.cuh"
 #include <chrono>
 #include <cooperative_groups.h>
+#include <cub/device/device_segmented_radix_sort.cuh>
 #include <cstdlib>
 
 namespace dge
@@ -937,10 +938,70 @@ __global__ void __launch_bounds__(256) k_compact_uniques(const uint64_t *__restr
     }
 }
 
+// ---- oversized sub-buckets (more keys than the largest sort class: the sampling tail of a very long L1 bucket, or one heavily duplicated
+// key).  They used to stream through a shared-memory hash table, whose capacity made the whole run fail -- rarely, and depending on the
+// order in which the keys happened to arrive -- when such a sub-bucket held more than ~4 k distinct keys.  Now: no capacity anywhere.  The
+// listed sub-buckets are sorted as segments in global memory (cub::DeviceSegmentedRadixSort, library code, a few hundred k keys at most in
+// practice) and run-length encoded by k_tail_dedup.
+constexpr int SC_TAIL_MAX = 16384; // segments per launch; more raise the overflow flag (would need > 16 k oversized sub-buckets)
+
+__global__ void __launch_bounds__(256) k_tail_offsets(const uint32_t *__restrict__ list, const uint32_t *__restrict__ count, const uint32_t *__restrict__ sub_off,
+                                                      int *__restrict__ seg_begin, int *__restrict__ seg_end, int *__restrict__ overflow)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= uint32_t(SC_TAIL_MAX)) return;
+    const uint32_t n = *count;
+    if (i == 0 && n > uint32_t(SC_TAIL_MAX)) *overflow = 1;
+    int b = 0, e = 0;
+    if (i < n) { const uint32_t sb = list[i]; b = int(sub_off[sb]); e = int(sub_off[sb + 1]); }
+    seg_begin[i] = b; seg_end[i] = e;
+}
+
+// sorted[s..e) (full keys, ascending) -> distinct ukeys at keys[s..s+m), (count | mark << 29) at uvals[s..s+m), ucount[sb] = m
+__global__ void __launch_bounds__(256) k_tail_dedup(const uint64_t *__restrict__ sorted, uint64_t *__restrict__ keys, uint32_t *__restrict__ uvals,
+                                                    const uint32_t *__restrict__ sub_off, const uint32_t *__restrict__ list, const uint32_t *__restrict__ count,
+                                                    uint32_t *__restrict__ ucount)
+{
+    __shared__ uint32_t ws[33];
+    const uint32_t n_seg = min(*count, uint32_t(SC_TAIL_MAX));
+    for (uint32_t it = blockIdx.x; it < n_seg; it += gridDim.x)
+    {
+        const uint32_t sb = list[it], s = sub_off[sb], n = sub_off[sb + 1] - s;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) uvals[s + i] = 0;
+        __syncthreads();
+        uint32_t done = 0; // runs emitted by the chunks before this one
+        for (uint32_t c = 0; c < n; c += blockDim.x)
+        {
+            const uint32_t i = c + threadIdx.x;
+            uint64_t x = EMPTY64;
+            uint32_t head = 0;
+            if (i < n)
+            {
+                x = sorted[s + i];
+                head = i == 0 || (sorted[s + i - 1] >> 3) != (x >> 3);
+            }
+            uint32_t tot;
+            const uint32_t ex = block_exclusive_scan(head, ws, &tot);
+            if (i < n)
+            {
+                const uint32_t r = done + ex + head - 1; // index of the run this key belongs to
+                if (head) keys[s + r] = x >> 3;
+                atomicAdd(&uvals[s + r], 1u);
+                if (uint32_t(x) & 7u) atomicOr(&uvals[s + r], (uint32_t(x) & 7u) << VAL_MARK_SHIFT);
+            }
+            done += tot;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) ucount[sb] = done;
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 struct SortCombineWorkspace
 {
     DevBuf keysA, valsA, valsB, uvals_sparse, small, splitters, sub_cnt, sub_off, ucount, u_off, scan_scratch, cls_list, cls_count, ids, order;
+    DevBuf tail_begin, tail_end, tail_tmp; // oversized sub-buckets: segment offsets + cub temp storage
     // side stream of the long-bucket cluster kernel (runs beside the block-per-bucket kernel: disjoint buckets)
     cudaStream_t side = nullptr;
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
@@ -1262,10 +1323,18 @@ public:
 #undef DGE_MS
 #undef DGE_MS_NB
                 L += 5;
-                const int thr = sc_tuning().dedup_threads;
-                k_dedup_sort<false><<<148 * 2, thr, dedup_smem_bytes(SC_HT_MAX, SC_HT_MAX, thr), st>>>(keys_tmp, nullptr, uv, sub_off, n_sub_ptr, ucount, overflow_flag,
-                                                                                                        SC_HT_MAX, SC_HT_MAX, 0u, 0xFFFFFFFFu, cl + 4 * ls, cc + 4);
-                ++L;
+                {   // oversized sub-buckets: segmented sort in global memory (the L1 buffer is free by now) + run-length encoding; no capacity limit
+                    ws.tail_begin.reserve(size_t(SC_TAIL_MAX) * 4); ws.tail_end.reserve(size_t(SC_TAIL_MAX) * 4);
+                    int *tb = ws.tail_begin.as<int>(), *te = ws.tail_end.as<int>();
+                    k_tail_offsets<<<SC_TAIL_MAX / 256, 256, 0, st>>>(cl + 4 * ls, cc + 4, sub_off, tb, te, overflow_flag);
+                    if (n >= (size_t(1) << 31)) throw std::runtime_error("SortCombine: more than 2^31 keys in one run");
+                    size_t bytes = 0;
+                    DGE_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, bytes, keys_tmp, keysA, int(n), SC_TAIL_MAX, tb, te, 0, 64, st));
+                    ws.tail_tmp.reserve(bytes + 16);
+                    DGE_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(ws.tail_tmp.p, bytes, keys_tmp, keysA, int(n), SC_TAIL_MAX, tb, te, 0, 64, st));
+                    k_tail_dedup<<<148 * 2, 256, 0, st>>>(keysA, keys_tmp, uv, sub_off, cl + 4 * ls, cc + 4, ucount);
+                    L += 4;
+                }
             }
             else
             {

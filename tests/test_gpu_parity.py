@@ -399,6 +399,43 @@ def test_per_chromosome_stats(merge):
     assert presented[2, 6] and not presented[0, 6] and not presented[1, 6]   # the last chromosome only ever holds intergenic reads
 
 
+def test_oversized_sub_buckets_have_no_capacity_limit():
+    """One barcode with 9 M reads is ONE L1 bucket of ~9 M keys: with at most 2048 sub-buckets per bucket almost every sub-bucket is larger
+    than the biggest sort class (4096 keys) and holds thousands of distinct keys, plus one (gene, UMI) repeated 60 k times.  Such
+    sub-buckets are sorted as segments in global memory and run-length encoded (k_tail_offsets / cub segmented sort / k_tail_dedup);
+    they used to overflow a shared-memory hash table.  Checked against numpy: every distinct (cell, gene, UMI) with its read count and
+    accumulated mark."""
+    rng = np.random.default_rng(3)
+    n = 9_000_000
+    recs = np.zeros(n, dtype=dg.RECORD_DTYPE)
+    cb = np.where(rng.random(n) < 0.97, np.uint64(0x1234567), rng.integers(0, 1 << 20, size=n).astype(np.uint64))
+    umi = rng.integers(0, 1 << 20, size=n).astype(np.uint64)          # 10-base UMIs: ~3 M distinct values, so (gene, UMI) pairs repeat
+    gene = rng.integers(0, 40, size=n).astype(np.uint32)
+    mark = rng.choice(np.array([1, 2, 4, 6], dtype=np.uint32), size=n)
+    umi[:60_000] = 77; gene[:60_000] = 5; cb[:60_000] = np.uint64(0x1234567)
+    recs["key"] = (cb << np.uint64(24)) | umi
+    recs["gene"] = gene | (mark << np.uint32(24))
+    recs["read_idx"] = np.arange(n, dtype=np.uint32)
+    c = dg.Container(dg.Config(cb_len=16, umi_len=10, n_genes=40, merge_type=dg.MERGE_NONE, min_genes_before_merge=1, min_genes_after_merge=1,
+                               max_barcodes_hint=1 << 21))
+    c.add_batch(recs)
+    c.set_initialized()
+    c.merge_and_filter()
+    u = c.umigs(dg.CELLS_ALL)
+    cells = c.cells(dg.CELLS_ALL)
+    got_key = (cells["barcode"][u["cell"]].astype(np.uint64) << np.uint64(32)) | (u["gene"].astype(np.uint64) << np.uint64(24)) | u["umi"].astype(np.uint64)
+    exp_key = (cb << np.uint64(32)) | (gene.astype(np.uint64) << np.uint64(24)) | umi
+    uniq, inv, cnt = np.unique(exp_key, return_inverse=True, return_counts=True)
+    exp_mark = np.zeros(uniq.shape[0], dtype=np.uint32)
+    np.bitwise_or.at(exp_mark, inv, mark)
+    order = np.argsort(got_key)
+    np.testing.assert_array_equal(got_key[order], uniq)
+    np.testing.assert_array_equal(u["count"][order].astype(np.int64), cnt)
+    np.testing.assert_array_equal(u["mark"][order].astype(np.uint32), exp_mark)
+    assert cnt.max() >= 60_000
+    c.close()
+
+
 @pytest.mark.parametrize("giant", [1000, 50000])
 def test_long_l1_buckets_shared_by_clusters(monkeypatch, giant):
     """k_l2_bucket_cluster (8-CTA clusters, histograms combined through distributed shared memory) takes the L1 buckets longer than
