@@ -1210,7 +1210,6 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
     int *nb_count = h->pin_nbc.as<int>();
     uint32_t *nb_pc = h->pin_nbp.as<uint32_t>();
     std::vector<char> todo(n, 1);        // cells whose target the host still has to work out
-    bool have_nb_pc = false;
     const bool device_rows = h->rows_on_device && !h->cfg.sharded && h->wl_fast;
     if (h->wl_fast)
     {
@@ -1250,10 +1249,8 @@ void phase1_real(dge_handle *h, std::vector<long> &target)
         }
         DGE_CUDA(cudaMemcpyAsync(nb_pc, h->d_nb.p, n * WL_K * 4, cudaMemcpyDeviceToHost, st));
         DGE_CUDA(cudaStreamSynchronize(st));
-        have_nb_pc = true;
     }
     else std::fill(nb_count, nb_count + n, int(NB_SLOW));
-    (void)have_nb_pc;
     std::vector<uint32_t> &pc_to_real = h->h_pc_to_real;
     pc_to_real.assign(size_t(h->n_pc) + 1, NONE32);
     for (uint32_t i = 0; i < n; ++i) if (h->real[i].pc != NONE32) pc_to_real[h->real[i].pc] = i;

@@ -508,6 +508,16 @@ namespace Estimation
 		return res;
 	}
 
+	CellsDataContainer::s_ul_hash_t CellsDataContainer::umi_distribution() const
+	{
+		load_genes();
+		s_ul_hash_t umi_dist;
+		for (size_t cell_id : _filtered_cells)
+			for (auto const &gene : _cells[cell_id].genes())
+				for (auto const &umi : gene.second.umis()) umi_dist[_umi_indexer.get_value(umi.first)]++;
+		return umi_dist;
+	}
+
 	void CellsDataContainer::get_stat_by_real_cells(Stats::CellChrStatType stat, names_t &cell_barcodes, names_t &chromosome_names, counts_t &counts) const
 	{
 		if (_chr_overflow) throw std::runtime_error("per-chromosome statistics were dropped: more than 256 chromosome names");

@@ -517,6 +517,7 @@ namespace Estimation
 		using counts_t = std::vector<int>;
 		void get_stat_by_real_cells(Stats::CellChrStatType stat, names_t &cell_barcodes, names_t &chromosome_names, counts_t &counts) const;
 		bool chromosome_stats_available() const { return !_chr_overflow; }
+		s_ul_hash_t umi_distribution() const; // CellsDataContainer.cpp:182-197: occurrences of every UMI string over the (gene, UMI) entries of the filtered cells
 		const Cell &cell(size_t index) const;
 		size_t intergenic_reads_num() const;
 		size_t has_exon_reads_num() const;

@@ -166,7 +166,7 @@ typedef struct dge_timings {
     float ms_dedup_kernel; /* sub-bucket sort + dedup (k_sort_dedup size classes + hash tail), summed over its launches */
     uint32_t n_kernel_launches;
     uint32_t n_dedup_launches;
-    float ms_fill_kernel; /* k_fill_compact, summed over the batches of this run (CUDA events on the launching stream) */
+    float ms_fill_kernel; /* k_fill_pipe (the fill kernel), summed over the batches of this run (CUDA events on the launching stream) */
     uint32_t n_fill_launches;
 } dge_timings;
 

@@ -235,6 +235,16 @@ int main(int argc, char **argv)
 			CHECK_EQUAL(adjuster.estimate_adjusted_gene_expression(10), size_t(10));
 		}
 
+		// umi_distribution (CellsDataContainer.cpp:182-197) over the two filtered cells: AAATTAGGTCCA holds 6 (gene, UMI) entries, AAATTAGGTCCC 3
+		{
+			auto dist = container_full.umi_distribution();
+			size_t total_entries = 0;
+			for (auto const &kv : dist) total_entries += kv.second;
+			CHECK_EQUAL(total_entries, size_t(9));
+			CHECK_EQUAL(dist.at("CAACCT"), size_t(4));   // Gene1 of both cells, Gene10, Gene20
+			CHECK_EQUAL(dist.at("ACCCCT"), size_t(2));   // Gene3 and Gene4 of AAATTAGGTCCA
+		}
+
 		// get_stat_by_real_cells(CellChrStatType, ...), CellsDataContainer.cpp:292-307: Stats::merge has added the merged cells' counters
 		{
 			CellsDataContainer::names_t cells, chrs;

@@ -35,7 +35,7 @@ def cases():
         "real_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="real", seed=11),
         "none_7x9": pu.small_case(n_reads=20000, n_cells=25, n_genes=60, merge="none", seed=12),
         "simple_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="simple", seed=14),
-        # -M strategies: the oracle port is pinned against these; the CUDA path does not implement them yet
+        # -M strategies: oracle port and CUDA path are both pinned against these
         "poisson_simple_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="poisson_simple", seed=15),
         "poisson_real_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="poisson_real", seed=16),
         "all_7x9": pu.small_case(n_reads=30000, n_cells=30, n_genes=80, merge="all", seed=17),
