@@ -147,6 +147,112 @@ namespace Estimation
 			cfg.min_merge_fraction = _min_merge_fraction;
 		}
 
+		namespace
+		{
+			// Just enough XML for dropEst's configuration files: nested elements with text, comments, an optional declaration; attributes are
+			// skipped.  Yields "config.Estimation.Merge.barcodes_file" -> text (first occurrence wins, like ptree::get).
+			std::map<std::string, std::string> xml_leaves(const std::string &text, const std::string &fname)
+			{
+				std::map<std::string, std::string> out;
+				std::vector<std::string> path;
+				std::string value;
+				size_t i = 0;
+				auto fail = [&](const std::string &what) { throw std::runtime_error(fname + ": " + what); };
+				while (i < text.size())
+				{
+					if (text[i] != '<') { value += text[i++]; continue; }
+					if (text.compare(i, 4, "<!--") == 0)
+					{
+						const size_t e = text.find("-->", i + 4);
+						if (e == std::string::npos) fail("unterminated comment");
+						i = e + 3;
+						continue;
+					}
+					if (text.compare(i, 2, "<?") == 0)
+					{
+						const size_t e = text.find("?>", i + 2);
+						if (e == std::string::npos) fail("unterminated declaration");
+						i = e + 2;
+						continue;
+					}
+					const size_t e = text.find('>', i);
+					if (e == std::string::npos) fail("unterminated tag");
+					std::string tag = text.substr(i + 1, e - i - 1);
+					i = e + 1;
+					if (!tag.empty() && tag[0] == '/')
+					{
+						if (path.empty() || path.back() != tag.substr(1)) fail("mismatched closing tag </" + tag.substr(1) + ">");
+						std::string key;
+						for (auto const &p : path) key += (key.empty() ? "" : ".") + p;
+						const size_t a = value.find_first_not_of(" \t\r\n"), b = value.find_last_not_of(" \t\r\n");
+						out.emplace(key, a == std::string::npos ? std::string() : value.substr(a, b - a + 1));
+						path.pop_back();
+						value.clear();
+						continue;
+					}
+					const bool self_closing = !tag.empty() && tag.back() == '/';
+					if (self_closing) tag.pop_back();
+					const size_t sp = tag.find_first_of(" \t\r\n");
+					if (sp != std::string::npos) tag = tag.substr(0, sp);
+					if (tag.empty()) fail("empty tag");
+					value.clear();
+					if (!self_closing) path.push_back(tag);
+				}
+				if (!path.empty()) fail("unclosed element <" + path.back() + ">");
+				return out;
+			}
+		}
+
+		MergeStrategyFactory MergeStrategyFactory::from_xml(const std::string &config_file_name, int min_genes_after_merge_arg)
+		{
+			std::ifstream f(config_file_name);
+			if (!f) throw std::runtime_error("Can't open config file: '" + config_file_name + "'");
+			std::stringstream ss;
+			ss << f.rdbuf();
+			const auto leaves = xml_leaves(ss.str(), config_file_name);
+			auto get = [&](const std::string &block, const std::string &key) -> const std::string * {
+				auto it = leaves.find("config.Estimation." + block + "." + key);
+				return it == leaves.end() ? nullptr : &it->second;
+			};
+			auto number = [&](const std::string &key, const std::string &text) {
+				size_t used = 0;
+				double v = 0;
+				try { v = std::stod(text, &used); } catch (std::exception &) { used = 0; }
+				if (used != text.size() || text.empty()) throw std::runtime_error("conversion of data to type failed for '" + key + "': '" + text + "'");
+				return v;
+			};
+			MergeStrategyFactory fac;
+			if (auto v = get("Merge", "merge_type")) fac.merge_type = *v;
+			if (auto v = get("Merge", "min_genes_before_merge")) fac.min_genes_before_merge = size_t(number("min_genes_before_merge", *v));
+			if (min_genes_after_merge_arg > 0) fac.min_genes_after_merge = unsigned(min_genes_after_merge_arg);
+			else if (auto v = get("Merge", "min_genes_after_merge")) fac.min_genes_after_merge = size_t(number("min_genes_after_merge", *v));
+			auto ed = get("Merge", "max_cb_merge_edit_distance"); // no default in the reference: ptree::get throws
+			if (!ed) throw std::runtime_error("No such node (max_cb_merge_edit_distance)");
+			fac.max_merge_edit_distance = unsigned(number("max_cb_merge_edit_distance", *ed));
+			if (auto v = get("Merge", "min_merge_fraction")) fac.min_merge_fraction = number("min_merge_fraction", *v);
+			if (auto v = get("Merge", "barcodes_type")) fac.barcodes_type = *v;
+			if (auto v = get("Merge", "barcodes_file")) fac.barcodes_filename = *v;
+			// Tools::ltrim, expand_tilde_in_path, expand_relative_path (UtilFunctions.cpp:117-149)
+			std::string &bf = fac.barcodes_filename;
+			if (!bf.empty())
+			{
+				const size_t a = bf.find_first_not_of(" \t");
+				bf = a == std::string::npos ? std::string() : bf.substr(a);
+			}
+			if (bf.size() >= 2 && bf.compare(0, 2, "~/") == 0 && std::getenv("HOME")) bf = std::getenv("HOME") + bf.substr(1);
+			if (!bf.empty() && bf[0] != '/')
+			{
+				const size_t slash = config_file_name.find_last_of('/');
+				if (slash != std::string::npos) bf = config_file_name.substr(0, slash) + "/" + bf;
+			}
+			if (!bf.empty() && !std::ifstream(bf)) throw std::runtime_error("Can't open file with barcodes: '" + bf + "'");
+			if (auto v = get("PreciseMerge", "max_merge_prob")) fac.max_merge_prob = number("max_merge_prob", *v);
+			if (auto v = get("PreciseMerge", "max_real_merge_prob")) fac.max_real_cb_merge_prob = number("max_real_merge_prob", *v);
+			if (auto v = get("Merge", "max_umi_merge_edit_distance")) fac.max_umi_merge_edit_distance = unsigned(number("max_umi_merge_edit_distance", *v));
+			if (auto v = get("Merge", "umi_merge_multiplier")) fac.umi_merge_mult = number("umi_merge_multiplier", *v);
+			return fac;
+		}
+
 		std::shared_ptr<BarcodesParsing::BarcodesParser> MergeStrategyFactory::get_barcodes_parser() const
 		{
 			if (barcodes_type == "indrop") return std::make_shared<BarcodesParsing::InDropBarcodesParser>(barcodes_filename);

@@ -432,6 +432,13 @@ namespace Estimation
 			unsigned max_merge_edit_distance = 2, max_umi_merge_edit_distance = 1;
 			double min_merge_fraction = 0.2, max_merge_prob = 1e-4, max_real_cb_merge_prob = 1e-7, umi_merge_mult = 2;
 
+			MergeStrategyFactory() = default;
+			// MergeStrategyFactory(const ptree &config, const std::string &config_file_name, int min_genes_after_merge), MergeStrategyFactory.cpp:23-59:
+			// the <Estimation> block of a dropEst XML configuration (configs/*.xml).  Same keys, defaults and errors: max_cb_merge_edit_distance
+			// is mandatory, barcodes_file is resolved against the configuration file's directory (and ~/) and must exist, a positive
+			// min_genes_after_merge argument (the -G option) overrides the file.
+			static MergeStrategyFactory from_xml(const std::string &config_file_name, int min_genes_after_merge = -1);
+
 			std::shared_ptr<MergeStrategyAbstract> get_cb_strat(bool merge_tags, bool use_poisson) const;
 			std::shared_ptr<BarcodesParsing::BarcodesParser> get_barcodes_parser() const; // MergeStrategyFactory.cpp:113-126
 			std::shared_ptr<UMIs::MergeUMIsStrategyAbstract> get_umi(bool advanced) const;

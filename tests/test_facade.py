@@ -126,3 +126,12 @@ def test_reference_container_tests_through_the_cpp_facade(tmp_path):
     assert dict(zip(umis["attr"]["names"], umis["v"])) == {"AAATTAGGTCCA": 12, "AAATTAGGTCCC": 4}
     rreads = d["v"][9]
     assert dict(zip(rreads["attr"]["names"], rreads["v"])) == {"AAATTAGGTCCA": 12, "AAATTAGGTCCC": 4}
+
+
+def test_merge_strategy_factory_reads_the_xml_configuration():
+    """MergeStrategyFactory::from_xml (the <Estimation> block of configs/*.xml): keys, defaults, mandatory max_cb_merge_edit_distance,
+    barcodes_file resolved against the configuration file, -G override, strategy selection -- CPU only."""
+    exe = os.path.join(os.path.dirname(BIN), "test_factory_xml")
+    assert os.path.exists(exe), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    r = subprocess.run([exe, os.path.join(pu.GOLDEN, "configs")], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK (0 failures)" in r.stdout, r.stdout + r.stderr
