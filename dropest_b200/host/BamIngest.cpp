@@ -1,0 +1,317 @@
+// BamIngest.cpp -- see BamIngest.h.  BGZF: RFC 1952 members with a "BC" extra subfield holding the block size (SAM/BAM specification 4.1);
+// BAM records: specification 4.2.  Nothing here is taken from BamTools.
+#include "BamIngest.h"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+#include <thread>
+
+#include <zlib.h>
+
+namespace Estimation
+{
+namespace BamProcessing
+{
+	namespace
+	{
+		inline uint16_t le16(const uint8_t *p) { return uint16_t(p[0] | (p[1] << 8)); }
+		inline uint32_t le32(const uint8_t *p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24); }
+
+		struct Block { size_t in_off, in_len, out_off, out_len; };
+
+		// Length of the BGZF block starting at p (n bytes available), 0 when the header is not complete yet
+		size_t bgzf_block_size(const uint8_t *p, size_t n, const std::string &fname)
+		{
+			if (n < 18) return 0;
+			if (p[0] != 31 || p[1] != 139 || p[2] != 8 || !(p[3] & 4)) throw std::runtime_error("not a BGZF block in " + fname);
+			const size_t xlen = le16(p + 10);
+			if (n < 12 + xlen) return 0;
+			size_t off = 12;
+			while (off + 4 <= 12 + xlen)
+			{
+				const size_t slen = le16(p + off + 2);
+				if (p[off] == 'B' && p[off + 1] == 'C' && slen == 2) return size_t(le16(p + off + 4)) + 1;
+				off += 4 + slen;
+			}
+			throw std::runtime_error("BGZF block without a BC subfield in " + fname);
+		}
+
+		void inflate_block(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len, const std::string &fname)
+		{
+			const size_t xlen = le16(in + 10), hdr = 12 + xlen;
+			if (in_len < hdr + 8) throw std::runtime_error("truncated BGZF block in " + fname);
+			if (out_len == 0) return;
+			z_stream zs;
+			std::memset(&zs, 0, sizeof(zs));
+			if (inflateInit2(&zs, -15) != Z_OK) throw std::runtime_error("zlib: inflateInit2 failed");
+			zs.next_in = const_cast<Bytef *>(in + hdr);
+			zs.avail_in = uInt(in_len - hdr - 8);
+			zs.next_out = out;
+			zs.avail_out = uInt(out_len);
+			const int rc = inflate(&zs, Z_FINISH);
+			const bool ok = rc == Z_STREAM_END && zs.avail_out == 0;
+			inflateEnd(&zs);
+			if (!ok) throw std::runtime_error("corrupt BGZF block in " + fname);
+			if (uint32_t(crc32(crc32(0L, Z_NULL, 0), out, uInt(out_len))) != le32(in + in_len - 8)) throw std::runtime_error("BGZF CRC mismatch in " + fname);
+		}
+	}
+
+	BamReader::BamReader(const std::string &file_name, unsigned threads)
+		: _file_name(file_name), _f(std::fopen(file_name.c_str(), "rb")), _threads(threads ? threads : std::max(1u, std::thread::hardware_concurrency()))
+	{
+		if (!_f) throw std::runtime_error("Can't open BAM file: " + file_name); // BamController.cpp:77-78
+		read_header();
+	}
+
+	BamReader::~BamReader()
+	{
+		if (_f) std::fclose(_f);
+	}
+
+	bool BamReader::fill(size_t need)
+	{
+		while (_data.size() - _pos < need)
+		{
+			if (_pos > 0 && _pos == _data.size()) { _data.clear(); _pos = 0; }
+			// more compressed bytes
+			const size_t chunk = size_t(32) << 20;
+			if (!_eof)
+			{
+				const size_t old = _comp.size();
+				_comp.resize(old + chunk);
+				const size_t got = std::fread(_comp.data() + old, 1, chunk, _f);
+				_comp.resize(old + got);
+				if (got < chunk) _eof = true;
+			}
+			// the complete blocks in _comp
+			std::vector<Block> blocks;
+			size_t off = 0, out_total = 0;
+			while (off < _comp.size())
+			{
+				const size_t bs = bgzf_block_size(_comp.data() + off, _comp.size() - off, _file_name);
+				if (bs == 0 || off + bs > _comp.size()) break;
+				const size_t isize = le32(_comp.data() + off + bs - 4);
+				if (isize > 65536) throw std::runtime_error("BGZF block larger than 64 KiB in " + _file_name);
+				blocks.push_back(Block{off, bs, out_total, isize});
+				out_total += isize;
+				off += bs;
+			}
+			if (blocks.empty())
+			{
+				if (_eof)
+				{
+					if (off < _comp.size()) throw std::runtime_error("truncated BGZF block at the end of " + _file_name);
+					return _data.size() - _pos >= need && need > 0;
+				}
+				continue;
+			}
+			// drop what was consumed, make room, inflate every block into its place
+			if (_pos > 0) { _data.erase(_data.begin(), _data.begin() + long(_pos)); _pos = 0; }
+			const size_t base = _data.size();
+			_data.resize(base + out_total);
+			const unsigned nt = unsigned(std::min<size_t>(_threads, blocks.size()));
+			std::vector<std::string> errors(nt);
+			auto work = [&](unsigned t) {
+				try
+				{
+					for (size_t b = t; b < blocks.size(); b += nt)
+						inflate_block(_comp.data() + blocks[b].in_off, blocks[b].in_len, _data.data() + base + blocks[b].out_off, blocks[b].out_len, _file_name);
+				}
+				catch (std::exception &e) { errors[t] = e.what(); }
+			};
+			if (nt <= 1) work(0);
+			else
+			{
+				std::vector<std::thread> pool;
+				for (unsigned t = 0; t < nt; ++t) pool.emplace_back(work, t);
+				for (auto &th : pool) th.join();
+			}
+			for (auto const &e : errors) if (!e.empty()) throw std::runtime_error(e);
+			_comp.erase(_comp.begin(), _comp.begin() + long(off));
+		}
+		return true;
+	}
+
+	void BamReader::read_header()
+	{
+		if (!fill(12) || std::memcmp(_data.data() + _pos, "BAM\1", 4) != 0) throw std::runtime_error("not a BAM file: " + _file_name);
+		const size_t l_text = le32(_data.data() + _pos + 4);
+		_pos += 8;
+		if (!fill(l_text + 4)) throw std::runtime_error("truncated BAM header in " + _file_name);
+		_header_text.assign(reinterpret_cast<const char *>(_data.data() + _pos), l_text);
+		_pos += l_text;
+		const size_t n_ref = le32(_data.data() + _pos);
+		_pos += 4;
+		for (size_t r = 0; r < n_ref; ++r)
+		{
+			if (!fill(4)) throw std::runtime_error("truncated BAM header in " + _file_name);
+			const size_t l_name = le32(_data.data() + _pos);
+			_pos += 4;
+			if (l_name == 0 || !fill(l_name + 4)) throw std::runtime_error("truncated BAM header in " + _file_name);
+			_refs.emplace_back(reinterpret_cast<const char *>(_data.data() + _pos), l_name - 1);
+			_pos += l_name + 4;
+		}
+	}
+
+	bool BamReader::next(BamAlignment &al)
+	{
+		if (!fill(4)) return false;
+		const size_t block_size = le32(_data.data() + _pos);
+		if (block_size < 32) throw std::runtime_error("malformed alignment record in " + _file_name);
+		if (!fill(4 + block_size)) throw std::runtime_error("truncated alignment record in " + _file_name);
+		const uint8_t *p = _data.data() + _pos + 4, *end = p + block_size;
+		_pos += 4 + block_size;
+		al.ref_id = int32_t(le32(p));
+		al.position = int32_t(le32(p + 4));
+		const size_t l_read_name = p[8];
+		const size_t n_cigar = le16(p + 12);
+		al.flag = le16(p + 14);
+		const size_t l_seq = le32(p + 16);
+		const uint8_t *q = p + 32;
+		const size_t fixed = l_read_name + n_cigar * 4 + (l_seq + 1) / 2 + l_seq;
+		if (size_t(end - q) < fixed || l_read_name == 0) throw std::runtime_error("malformed alignment record in " + _file_name);
+		al.name.assign(reinterpret_cast<const char *>(q), l_read_name - 1);
+		al.tag_data = q + fixed;
+		al.tag_bytes = size_t(end - al.tag_data);
+		return true;
+	}
+
+	namespace
+	{
+		// walks the tag block; returns the value position of `tag` (type in *type) or nullptr
+		const uint8_t *find_tag(const uint8_t *p, size_t n, const std::string &tag, char *type, size_t *value_bytes)
+		{
+			if (tag.size() != 2) return nullptr;
+			const uint8_t *end = p + n;
+			auto bad = [] { throw std::runtime_error("malformed tag block in a BAM record"); };
+			while (p < end)
+			{
+				if (end - p < 3) bad();
+				const char t = char(p[2]);
+				const uint8_t *v = p + 3;
+				size_t len = 0;
+				switch (t)
+				{
+				case 'A': case 'c': case 'C': len = 1; break;
+				case 's': case 'S': len = 2; break;
+				case 'i': case 'I': case 'f': len = 4; break;
+				case 'Z': case 'H':
+				{
+					const void *z = std::memchr(v, 0, size_t(end - v));
+					if (!z) bad();
+					len = size_t(static_cast<const uint8_t *>(z) - v) + 1;
+					break;
+				}
+				case 'B':
+				{
+					if (end - v < 5) bad();
+					const char st = char(v[0]);
+					const size_t cnt = le32(v + 1);
+					const size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : (st == 'i' || st == 'I' || st == 'f') ? 4 : 0;
+					if (!es) bad();
+					len = 5 + cnt * es;
+					break;
+				}
+				default: bad();
+				}
+				if (size_t(end - v) < len) bad();
+				if (char(p[0]) == tag[0] && char(p[1]) == tag[1])
+				{
+					*type = t;
+					*value_bytes = len;
+					return v;
+				}
+				p = v + len;
+			}
+			return nullptr;
+		}
+	}
+
+	char BamAlignment::tag_type(const std::string &tag) const
+	{
+		char t = 0;
+		size_t n = 0;
+		return find_tag(tag_data, tag_bytes, tag, &t, &n) ? t : char(0);
+	}
+
+	bool BamAlignment::get_string_tag(const std::string &tag, std::string &value) const
+	{
+		char t = 0;
+		size_t n = 0;
+		const uint8_t *v = find_tag(tag_data, tag_bytes, tag, &t, &n);
+		if (!v) return false;
+		if (t == 'Z' || t == 'H') { value.assign(reinterpret_cast<const char *>(v), n - 1); return true; }
+		if (t == 'A') { value.assign(1, char(v[0])); return true; }
+		return false;
+	}
+
+	bool read_info_from_alignment(const BamAlignment &al, const std::string &chr_name, const IngestParams &params, IngestStats &stats,
+	                              Tools::ReadParameters &read_params, std::string &gene, UMI::Mark &mark)
+	{
+		// ---- barcode + UMI: FilledBamParamsParser::get_read_params (.cpp:12-40) / ReadParamsParser::get_read_params (.cpp:21-34)
+		bool pass_quality = true;
+		try
+		{
+			if (params.filled_bam)
+			{
+				std::string cb, umi, cbq, umiq;
+				if (!al.get_string_tag(params.tags.cell_barcode, cb) || !al.get_string_tag(params.tags.umi, umi)) { ++stats.cant_parse; return false; }
+				al.get_string_tag(params.tags.cell_barcode_quality, cbq);
+				al.get_string_tag(params.tags.umi_quality, umiq);
+				read_params = Tools::ReadParameters(cb, umi, cbq, umiq);
+				// ReadParameters::check_quality (Tools/ReadParameters.cpp:122-141): Phred+33 characters, every barcode and UMI base
+				const int min_phred = params.min_barcode_quality + 33;
+				if (min_phred > 33)
+				{
+					for (char c : cbq) if (c < min_phred) pass_quality = false;
+					for (char c : umiq) if (c < min_phred) pass_quality = false;
+				}
+			}
+			else read_params = Tools::ReadParameters::parse_encoded_id(al.name);
+		}
+		catch (std::runtime_error &)
+		{
+			++stats.cant_parse; // empty barcode / UMI, or a read name without "!CB#UMI"
+			return false;
+		}
+		if (!pass_quality) { ++stats.low_quality; return false; }
+
+		// ---- gene + mark: ReadParamsParser::get_gene / parse_read_type (.cpp:36-90)
+		mark = UMI::Mark();
+		gene.clear();
+		if (params.gene_in_chromosome_name)
+		{
+			gene = chr_name;
+			if (!chr_name.empty()) mark.add(UMI::Mark::HAS_EXONS);
+			return true;
+		}
+		if (!al.get_string_tag(params.tags.gene, gene))
+		{
+			gene.clear();
+			mark.add(UMI::Mark::HAS_NOT_ANNOTATED);
+			return true;
+		}
+		std::string read_type;
+		bool have_type = false;
+		if (!params.tags.read_type.empty())
+		{
+			const char t = al.tag_type(params.tags.read_type);
+			if (t && t != 'Z' && t != 'A') throw std::runtime_error(std::string("Expected string tag, but got ") + t); // get_bam_tag, .cpp:179-197
+			have_type = al.get_string_tag(params.tags.read_type, read_type);
+		}
+		if (!have_type) mark.add(UMI::Mark::HAS_EXONS);
+		else if (read_type == params.tags.intronic_read_value) mark.add(UMI::Mark::HAS_INTRONS);
+		else if (!params.tags.intergenic_read_value.empty() && read_type == params.tags.intergenic_read_value) mark.add(UMI::Mark::HAS_NOT_ANNOTATED);
+		else mark.add(UMI::Mark::HAS_EXONS);
+		return true;
+	}
+
+	void parse_bam_files(const std::vector<std::string> &bam_files, const IngestParams &params, CellsDataContainer &container, IngestStats &stats)
+	{
+		if (!params.tags.read_type.empty() && params.tags.intronic_read_value.empty()) // BamTags.cpp:22-23
+			throw std::runtime_error("You have to specify tag values to be able to parse info about read types");
+		for_each_read(bam_files, params, stats, [&](const ReadInfo &ri) { container.add_record(ri); });
+	}
+}
+}

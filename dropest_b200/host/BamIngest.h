@@ -1,0 +1,115 @@
+// BamIngest.h -- the caller of the count-matrix path: BAM alignments -> ReadInfo -> CellsDataContainer::add_record.
+// Replaces, for the tag-driven modes of `dropest`, the BamTools-based loop of the reference:
+//   Estimation/BamProcessing/BamController.cpp:70-172 (parse_bam_file / process_alignment), FilledBamParamsParser.cpp:12-40 (-f: barcode and
+//   UMI from tags, base-quality threshold), ReadParamsParser.cpp:21-90,179-197 (read-name codec, gene tag, read-type tag), BamTags.cpp:7-25.
+// Own BGZF / BAM reader (zlib is the only dependency): the compressed blocks of a chunk are inflated by a pool of threads straight into
+// their place of one contiguous buffer (block sizes are known from the headers and trailers without inflating), records are then parsed in
+// stream order -- the order is what defines cell / gene ids downstream.  GTF-based gene assignment (row f3) is not part of this file.
+#pragma once
+#include "Estimation.h"
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace Estimation
+{
+namespace BamProcessing
+{
+	struct BamTags // BamTags.cpp:7-25: names and defaults of the tags that are read
+	{
+		std::string cell_barcode = "CB", umi = "UB", gene = "GX", cell_barcode_quality = "CQ", umi_quality = "UQ";
+		std::string read_type, intronic_read_value, intergenic_read_value; // BamTags.Type.*: empty = every read with a gene is exonic
+	};
+
+	// One alignment, as a view into the reader's buffer (valid until the next call of BamReader::next)
+	struct BamAlignment
+	{
+		int32_t ref_id = -1, position = -1;
+		uint16_t flag = 0;
+		std::string name;
+		const uint8_t *tag_data = nullptr;
+		size_t tag_bytes = 0;
+
+		bool is_mapped() const { return !(flag & 0x4); }
+		bool is_primary_alignment() const { return !(flag & 0x100); }
+		// type of a tag ('Z', 'A', 'i', ...) or 0 when absent; throws std::runtime_error on a malformed tag block
+		char tag_type(const std::string &tag) const;
+		// string tags only (Z, H; A gives its one character): false when the tag is absent or of another type
+		bool get_string_tag(const std::string &tag, std::string &value) const;
+	};
+
+	class BamReader
+	{
+	public:
+		explicit BamReader(const std::string &file_name, unsigned threads = 0);
+		~BamReader();
+		BamReader(const BamReader &) = delete;
+		BamReader &operator=(const BamReader &) = delete;
+		const std::vector<std::string> &reference_names() const { return _refs; }
+		const std::string &header_text() const { return _header_text; }
+		bool next(BamAlignment &alignment); // false at the end of the file
+
+	private:
+		std::string _file_name;
+		std::FILE *_f = nullptr;
+		unsigned _threads;
+		std::vector<uint8_t> _comp;   // compressed bytes not yet inflated (whole blocks + a partial one at the end)
+		std::vector<uint8_t> _data;   // inflated bytes not yet consumed
+		size_t _pos = 0;              // read position in _data
+		bool _eof = false;
+		std::vector<std::string> _refs;
+		std::string _header_text;
+
+		bool fill(size_t need); // makes at least `need` bytes available at _pos; false at a clean end of file
+		void read_header();
+	};
+
+	struct IngestParams
+	{
+		bool filled_bam = true;               // -f: barcode / UMI from tags; false: from the read name "prefix!CB#UMI" (ReadParameters::parse_encoded_id)
+		BamTags tags;
+		bool gene_in_chromosome_name = false; // pseudo-aligner output: the reference name is the gene
+		int min_barcode_quality = 0;          // -f only: reads with a barcode / UMI base below this Phred quality are dropped (0 = off)
+		unsigned threads = 0;                 // BGZF inflate threads (0 = hardware concurrency)
+	};
+
+	struct IngestStats // the counters BamProcessorAbstract keeps (BamProcessorAbstract.cpp)
+	{
+		size_t total_reads = 0, cant_parse = 0, low_quality = 0, skipped_unmapped_or_secondary = 0;
+	};
+
+	// BamController::parse_bam_files + process_alignment for the tag / read-name modes: every primary mapped alignment of every file, in
+	// order, becomes one add_record call.
+	void parse_bam_files(const std::vector<std::string> &bam_files, const IngestParams &params, CellsDataContainer &container, IngestStats &stats);
+
+	// The same loop with the ReadInfo handed to a callback instead of a container (tests, other consumers)
+	template <class F> void for_each_read(const std::vector<std::string> &bam_files, const IngestParams &params, IngestStats &stats, F &&sink);
+
+	// one alignment -> ReadInfo; false = counted in `stats` and skipped (process_alignment, BamController.cpp:131-172)
+	bool read_info_from_alignment(const BamAlignment &alignment, const std::string &chr_name, const IngestParams &params, IngestStats &stats,
+	                              Tools::ReadParameters &read_params, std::string &gene, UMI::Mark &mark);
+
+	template <class F> void for_each_read(const std::vector<std::string> &bam_files, const IngestParams &params, IngestStats &stats, F &&sink)
+	{
+		for (auto const &file : bam_files)
+		{
+			BamReader reader(file, params.threads);
+			BamAlignment al;
+			while (reader.next(al))
+			{
+				if (!al.is_mapped() || !al.is_primary_alignment()) { ++stats.skipped_unmapped_or_secondary; continue; }
+				if (al.ref_id < 0 || size_t(al.ref_id) >= reader.reference_names().size()) { ++stats.cant_parse; continue; } // unknown chromosome: not counted as a read
+				++stats.total_reads;
+				const std::string &chr_name = reader.reference_names()[size_t(al.ref_id)];
+				Tools::ReadParameters rp;
+				std::string gene;
+				UMI::Mark mark;
+				if (!read_info_from_alignment(al, chr_name, params, stats, rp, gene, mark)) continue;
+				sink(ReadInfo(rp, gene, chr_name, mark));
+			}
+		}
+	}
+}
+}

@@ -25,6 +25,7 @@ namespace Tools
 		std::string _cell_barcode, _umi, _cell_barcode_quality, _umi_quality;
 
 	public:
+		ReadParameters() = default; // the reference's empty parameters (ReadParameters.cpp:34-41)
 		ReadParameters(const std::string &cell_barcode, const std::string &umi, const std::string &cell_barcode_quality,
 		               const std::string &umi_quality)
 			: _cell_barcode(cell_barcode), _umi(umi), _cell_barcode_quality(cell_barcode_quality), _umi_quality(umi_quality)

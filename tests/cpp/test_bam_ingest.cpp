@@ -1,0 +1,36 @@
+// CPU-only tool behind tests/test_bam_ingest.py: reads BAM files with dropest_b200/host/BamIngest and prints one line per accepted read
+// (barcode, UMI, gene, chromosome, mark bits, barcode quality) followed by the counters.  No container, no CUDA call.
+//   test_bam_ingest <filled 0|1> <min_barcode_quality> <gene_in_chr 0|1> <type tag or -> <intronic value or -> <intergenic value or -> <threads> file...
+#include "../../dropest_b200/host/BamIngest.h"
+
+#include <iostream>
+
+using namespace Estimation;
+
+int main(int argc, char **argv)
+{
+	if (argc < 9) { std::cerr << "usage: see the source\n"; return 2; }
+	try
+	{
+		BamProcessing::IngestParams p;
+		p.filled_bam = std::string(argv[1]) == "1";
+		p.min_barcode_quality = std::stoi(argv[2]);
+		p.gene_in_chromosome_name = std::string(argv[3]) == "1";
+		auto opt = [](const char *s) { return std::string(s) == "-" ? std::string() : std::string(s); };
+		p.tags.read_type = opt(argv[4]); p.tags.intronic_read_value = opt(argv[5]); p.tags.intergenic_read_value = opt(argv[6]);
+		p.threads = unsigned(std::stoi(argv[7]));
+		std::vector<std::string> files(argv + 8, argv + argc);
+		BamProcessing::IngestStats st;
+		BamProcessing::for_each_read(files, p, st, [](const ReadInfo &ri) {
+			std::cout << ri.params.cell_barcode() << '\t' << ri.params.umi() << '\t' << (ri.gene.empty() ? "-" : ri.gene) << '\t' << ri.chromosome_name << '\t'
+			          << ri.umi_mark.bits() << '\t' << (ri.params.cell_barcode_quality().empty() ? "-" : ri.params.cell_barcode_quality()) << '\n';
+		});
+		std::cout << "#stats\t" << st.total_reads << '\t' << st.cant_parse << '\t' << st.low_quality << '\t' << st.skipped_unmapped_or_secondary << '\n';
+	}
+	catch (std::exception &e)
+	{
+		std::cout << "#error\t" << e.what() << '\n';
+		return 1;
+	}
+	return 0;
+}

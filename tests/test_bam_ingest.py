@@ -1,0 +1,164 @@
+"""BAM ingest: dropest_b200/host/BamIngest against BAM files written by tests/bam_utils.py.  The parsing tests are CPU
+only; the end-to-end test (BAM -> container on the GPU -> count matrix vs the oracle on the same reads) needs a GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import parity_utils as pu
+from bam_utils import alignment, write_bam
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DUMP = os.path.join(ROOT, "dropest_b200", "lib", "test_bam_ingest")
+REFS = [("chr1", 1000000), ("chr2", 900000), ("chrM", 16000)]
+
+
+def _dump(files, filled=True, min_q=0, gene_in_chr=False, type_tag="-", intronic="-", intergenic="-", threads=3, expect_ok=True):
+    assert os.path.exists(DUMP), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    r = subprocess.run([DUMP, "1" if filled else "0", str(min_q), "1" if gene_in_chr else "0", type_tag, intronic, intergenic, str(threads)] + list(files),
+                       capture_output=True, text=True)
+    assert (r.returncode == 0) == expect_ok, r.stdout[-500:] + r.stderr[-500:]
+    lines = r.stdout.strip().split("\n")
+    return [tuple(l.split("\t")) for l in lines if not l.startswith("#")], [l.split("\t") for l in lines if l.startswith("#")]
+
+
+def _random_reads(n, seed):
+    rng = np.random.default_rng(seed)
+    acgt = np.array(list("ACGT"))
+    reads = []
+    for i in range(n):
+        cb = "".join(rng.choice(acgt, 16)) if rng.random() > 0.3 else "ACGTACGTACGTACGT"
+        umi = "".join(rng.choice(acgt, 10))
+        gene = f"G{int(rng.integers(0, 50))}" if rng.random() > 0.1 else None
+        reads.append((cb, umi, gene, int(rng.integers(0, 3)), int(rng.integers(0, 900000))))
+    return reads
+
+
+def test_filled_bam_tags_filters_and_counters(tmp_path):
+    """-f mode: CB / UB / GX tags; unmapped and secondary alignments, unknown reference ids, missing barcode tags and low base qualities
+    are skipped and counted as BamController::process_alignment does; records straddle many BGZF blocks; several inflate threads."""
+    reads = _random_reads(40000, 1)
+    als, exp = [], []
+    n_unmapped = n_noref = n_notag = n_lowq = 0
+    for i, (cb, umi, gene, ref, pos) in enumerate(reads):
+        tags = [("NH", ("i", 1)), ("CB", ("Z", cb)), ("UB", ("Z", umi)), ("CQ", ("Z", "I" * 16)), ("UQ", ("Z", "I" * 10)), ("xs", ("B", [1, 2, 3]))]
+        if gene:
+            tags.insert(1, ("GX", ("Z", gene)))
+        flag = 0
+        kind = i % 23
+        if kind == 3:
+            flag = 4; n_unmapped += 1
+        elif kind == 5:
+            flag = 0x100; n_unmapped += 1
+        elif kind == 7:
+            ref = 9; n_noref += 1
+        elif kind == 11:
+            tags = [t for t in tags if t[0] != "UB"]; n_notag += 1
+        elif kind == 13:
+            tags = [t if t[0] != "UQ" else ("UQ", ("Z", "IIII#IIIII")) for t in tags]; n_lowq += 1
+        als.append(alignment(f"r{i}", ref, pos, flag, tags))
+        if kind not in (3, 5, 7, 11, 13):
+            exp.append((cb, umi, gene or "-", REFS[ref][0], "2" if gene else "1", "I" * 16))
+    path = str(tmp_path / "a.bam")
+    write_bam(path, REFS, als, block_bytes=30000)
+    for threads in (1, 4):
+        got, meta = _dump([path], min_q=20, threads=threads)
+        assert got == exp
+        total = len(reads) - n_unmapped - n_noref
+        assert meta[-1] == ["#stats", str(total), str(n_noref + n_notag), str(n_lowq), str(n_unmapped)]
+    got, meta = _dump([path], min_q=0)   # quality filter off: the low-quality reads come through
+    assert len(got) == len(exp) + n_lowq and meta[-1][3] == "0"
+
+
+def test_read_name_mode_read_types_and_several_files(tmp_path):
+    """Without -f the barcode and UMI come from the read name ("...!CB#UMI", ReadParameters::parse_encoded_id); the read-type tag maps to
+    intron / not-annotated / exon marks (ReadParamsParser::parse_read_type); files are read one after the other."""
+    recs = [("x!AAAACCCCGGGGTTTT#ACGTACGTAC", [("GX", ("Z", "Gene1")), ("XF", ("Z", "INTRONIC"))], "4"),
+            ("y!AAAACCCCGGGGTTTT#TTTTTTTTTT", [("GX", ("Z", "Gene1")), ("XF", ("Z", "CODING"))], "2"),
+            ("z!CCCCCCCCGGGGTTTT#ACGTACGTAC", [("GX", ("Z", "Gene2")), ("XF", ("A", "I"))], "2"),
+            ("w!CCCCCCCCGGGGTTTT#ACGTACGTAA", [("GX", ("Z", "Gene2")), ("XF", ("Z", "INTERGENIC"))], "1"),
+            ("v!CCCCCCCCGGGGTTTT#ACGTACGTAG", [("XF", ("Z", "INTRONIC"))], "1"),          # no gene tag: not annotated, whatever the type
+            ("no_codec_here", [("GX", ("Z", "Gene2"))], None)]
+    a = [alignment(n, 0, 10, 0, t) for n, t, _ in recs[:3]]
+    b = [alignment(n, 1, 10, 16, t) for n, t, _ in recs[3:]]
+    pa, pb = str(tmp_path / "a.bam"), str(tmp_path / "b.bam")
+    write_bam(pa, REFS, a)
+    write_bam(pb, REFS, b)
+    got, meta = _dump([pa, pb], filled=False, type_tag="XF", intronic="INTRONIC", intergenic="INTERGENIC")
+    assert [(g[0], g[1], g[2], g[3], g[4]) for g in got] == [
+        ("AAAACCCCGGGGTTTT", "ACGTACGTAC", "Gene1", "chr1", "4"), ("AAAACCCCGGGGTTTT", "TTTTTTTTTT", "Gene1", "chr1", "2"),
+        ("CCCCCCCCGGGGTTTT", "ACGTACGTAC", "Gene2", "chr1", "2"), ("CCCCCCCCGGGGTTTT", "ACGTACGTAA", "Gene2", "chr2", "1"),
+        ("CCCCCCCCGGGGTTTT", "ACGTACGTAG", "-", "chr2", "1")]
+    assert meta[-1] == ["#stats", "6", "1", "0", "0"]
+    got, _ = _dump([pa], filled=False, gene_in_chr=True)
+    assert [g[2] for g in got] == ["chr1"] * 3 and [g[4] for g in got] == ["2"] * 3
+
+
+def test_corrupt_files_fail_loudly(tmp_path):
+    als = [alignment(f"r{i}", 0, i, 0, [("CB", ("Z", "ACGTACGTACGTACGT")), ("UB", ("Z", "ACGTACGTAC"))]) for i in range(5000)]
+    path = str(tmp_path / "a.bam")
+    write_bam(path, REFS, als, block_bytes=20000)
+    data = bytearray(open(path, "rb").read())
+    bad = str(tmp_path / "bad.bam")
+    data[len(data) // 2] ^= 0x55
+    open(bad, "wb").write(data)
+    _, meta = _dump([bad], expect_ok=False)
+    assert meta and meta[-1][0] == "#error"
+    trunc = str(tmp_path / "trunc.bam")
+    open(trunc, "wb").write(bytes(data[: len(data) // 3]))
+    _, meta = _dump([trunc], expect_ok=False)
+    assert meta and meta[-1][0] == "#error"
+    _, meta = _dump([str(tmp_path / "missing.bam")], expect_ok=False)
+    assert "Can't open BAM file" in meta[-1][1]
+
+
+@pytest.mark.gpu
+def test_bam_to_count_matrix_matches_the_reference(tmp_path):
+    """End to end: a BAM with CB / UB / GX / XF tags (two files, records straddling BGZF blocks) -> BamIngest -> the container on the GPU
+    -> filtered count matrix and per-chromosome exon table, against the oracle run on the same reads given as text."""
+    import oracle_io
+    from dropest_b200.capi import unpack_seq
+    from dropest_b200.synth import SynthTables
+
+    case = pu.small_case(n_reads=40000, n_cells=30, n_genes=80, merge="real", seed=23)
+    recs = SynthTables(case.spec).generate_host(0, case.spec.n_reads)
+    chr_ids = pu.synth_chr_ids(recs, 3)
+    type_of = {1: "INTERGENIC", 2: "CODING", 4: "INTRONIC", 6: "CODING"}   # a read-type tag carries one type
+    als, tsv = [], []
+    for r, c in zip(recs, chr_ids):
+        cb, umi = unpack_seq(int(r["key"]) >> 24, 16), unpack_seq(int(r["key"]) & 0xFFFFFF, case.umi_len)
+        gene_id, mark = int(r["gene"]) & 0xFFFFFF, (int(r["gene"]) >> 24) & 7
+        tags = [("CB", ("Z", cb)), ("UB", ("Z", umi))]
+        gene = None if gene_id == 0xFFFFFF else f"g{gene_id}"
+        if gene:
+            tags += [("GX", ("Z", gene)), ("XF", ("Z", type_of[mark]))]
+        eff_mark = 1 if gene is None else {"INTERGENIC": 1, "CODING": 2, "INTRONIC": 4}[type_of[mark]]
+        als.append(alignment(f"q{len(als)}", int(c), 100 + len(als), 0, tags))
+        tsv.append(f"{cb}\t{umi}\t{gene or '-'}\t{REFS[int(c)][0]}\t{eff_mark}")
+    half = len(als) // 2
+    pa, pb = str(tmp_path / "a.bam"), str(tmp_path / "b.bam")
+    write_bam(pa, REFS, als[:half], block_bytes=50000)
+    write_bam(pb, REFS, als[half:], block_bytes=33333)
+    exe = os.path.join(ROOT, "dropest_b200", "lib", "test_bam_pipeline")
+    out = subprocess.run([exe, case.barcodes, str(case.min_genes_before), str(case.min_genes_after), "XF", "INTRONIC", "INTERGENIC", pa, pb],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-800:] + out.stderr[-800:]
+    rows = [l.split("\t") for l in out.stdout.strip().split("\n")]
+    tsv_path = str(tmp_path / "reads.tsv")
+    open(tsv_path, "w").write("\n".join(tsv) + "\n")
+    ora = oracle_io.run_oracle(tsv_path, merge="real", barcodes=case.barcodes, barcodes_type="const", min_genes_before=case.min_genes_before,
+                               min_genes_after=case.min_genes_after)
+    o_bc = oracle_io.strings(ora["cell_barcodes"])
+    o_genes = oracle_io.strings(ora["gene_names"])
+    stats = [r for r in rows if r[0] == "stats"][0]
+    assert int(stats[1]) == len(als) and int(stats[2]) == 0 and int(stats[4]) == int(ora["n_cells"][0]) and int(stats[5]) == int(ora["real_cells_number"][0])
+    assert int(stats[6]) == int(ora["intergenic_reads"][0])
+    assert [r[1] for r in rows if r[0] == "cell"] == [o_bc[i] for i in ora["filtered_cells"]]
+    got = sorted((int(r[1]), r[2], int(r[3])) for r in rows if r[0] == "cm")
+    exp = sorted((int(c), o_genes[int(g)], int(v)) for c, g, v in zip(ora["cm_col"], ora["cm_gene"], ora["cm_val"]))
+    assert got == exp and len(got) > 500
+    o_cells, o_chrs = oracle_io.strings(ora["chr_exon_cells"]), oracle_io.strings(ora["chr_exon_chrs"])
+    o_counts = ora["chr_exon_counts"].reshape(len(o_cells), len(o_chrs))
+    exp_exon = sorted((o_cells[r], o_chrs[c], int(o_counts[r, c])) for r in range(len(o_cells)) for c in range(len(o_chrs)) if o_counts[r, c])
+    assert sorted((r[1], r[2], int(r[3])) for r in rows if r[0] == "exon") == exp_exon and exp_exon
