@@ -73,15 +73,13 @@ namespace BamProcessing
 	{
 		while (_data.size() - _pos < need)
 		{
-			if (_pos > 0 && _pos == _data.size()) { _data.clear(); _pos = 0; }
-			// more compressed bytes
-			const size_t chunk = size_t(32) << 20;
+			// more compressed bytes (a few MB at a time: the inflated chunk stays of the order of the last-level cache)
+			const size_t chunk = size_t(8) << 20;
 			if (!_eof)
 			{
-				const size_t old = _comp.size();
-				_comp.resize(old + chunk);
-				const size_t got = std::fread(_comp.data() + old, 1, chunk, _f);
-				_comp.resize(old + got);
+				_comp.grow_to(_comp.n + chunk);
+				const size_t got = std::fread(_comp.data() + _comp.n, 1, chunk, _f);
+				_comp.n += got;
 				if (got < chunk) _eof = true;
 			}
 			// the complete blocks in _comp
@@ -107,28 +105,31 @@ namespace BamProcessing
 				continue;
 			}
 			// drop what was consumed, make room, inflate every block into its place
-			if (_pos > 0) { _data.erase(_data.begin(), _data.begin() + long(_pos)); _pos = 0; }
+			_data.drop_front(_pos);
+			_pos = 0;
 			const size_t base = _data.size();
-			_data.resize(base + out_total);
-			const unsigned nt = unsigned(std::min<size_t>(_threads, blocks.size()));
-			std::vector<std::string> errors(nt);
-			auto work = [&](unsigned t) {
+			_data.grow_to(base + out_total);
+			_data.n = base + out_total;
+			const unsigned nt = unsigned(std::min<size_t>(_threads, (blocks.size() + 15) / 16));
+			std::vector<std::string> errors(std::max(1u, nt));
+			auto work = [&](unsigned t, size_t first, size_t last) { // contiguous runs of blocks per thread
 				try
 				{
-					for (size_t b = t; b < blocks.size(); b += nt)
+					for (size_t b = first; b < last; ++b)
 						inflate_block(_comp.data() + blocks[b].in_off, blocks[b].in_len, _data.data() + base + blocks[b].out_off, blocks[b].out_len, _file_name);
 				}
 				catch (std::exception &e) { errors[t] = e.what(); }
 			};
-			if (nt <= 1) work(0);
+			if (nt <= 1) work(0, 0, blocks.size());
 			else
 			{
 				std::vector<std::thread> pool;
-				for (unsigned t = 0; t < nt; ++t) pool.emplace_back(work, t);
+				const size_t per = (blocks.size() + nt - 1) / nt;
+				for (unsigned t = 0; t < nt; ++t) pool.emplace_back(work, t, std::min(blocks.size(), size_t(t) * per), std::min(blocks.size(), size_t(t + 1) * per));
 				for (auto &th : pool) th.join();
 			}
 			for (auto const &e : errors) if (!e.empty()) throw std::runtime_error(e);
-			_comp.erase(_comp.begin(), _comp.begin() + long(off));
+			_comp.drop_front(off);
 		}
 		return true;
 	}
@@ -154,35 +155,66 @@ namespace BamProcessing
 		}
 	}
 
+	bool BamReader::view_at(size_t pos, RecordView &v, size_t &next_pos) const
+	{
+		if (_data.size() - pos < 4) return false;
+		const size_t block_size = le32(_data.data() + pos);
+		if (block_size < 32) throw std::runtime_error("malformed alignment record in " + _file_name);
+		if (_data.size() - pos < 4 + block_size) return false;
+		const uint8_t *p = _data.data() + pos + 4, *end = p + block_size;
+		next_pos = pos + 4 + block_size;
+		v.al.ref_id = int32_t(le32(p));
+		v.al.position = int32_t(le32(p + 4));
+		const size_t l_read_name = p[8];
+		const size_t n_cigar = le16(p + 12);
+		v.al.flag = le16(p + 14);
+		const size_t l_seq = le32(p + 16);
+		const uint8_t *q = p + 32;
+		const size_t fixed = l_read_name + n_cigar * 4 + (l_seq + 1) / 2 + l_seq;
+		if (size_t(end - q) < fixed || l_read_name == 0) throw std::runtime_error("malformed alignment record in " + _file_name);
+		v.name_data = reinterpret_cast<const char *>(q);
+		v.name_len = l_read_name - 1;
+		v.al.tag_data = q + fixed;
+		v.al.tag_bytes = size_t(end - v.al.tag_data);
+		return true;
+	}
+
 	bool BamReader::next(BamAlignment &al)
 	{
 		if (!fill(4)) return false;
 		const size_t block_size = le32(_data.data() + _pos);
 		if (block_size < 32) throw std::runtime_error("malformed alignment record in " + _file_name);
 		if (!fill(4 + block_size)) throw std::runtime_error("truncated alignment record in " + _file_name);
-		const uint8_t *p = _data.data() + _pos + 4, *end = p + block_size;
-		_pos += 4 + block_size;
-		al.ref_id = int32_t(le32(p));
-		al.position = int32_t(le32(p + 4));
-		const size_t l_read_name = p[8];
-		const size_t n_cigar = le16(p + 12);
-		al.flag = le16(p + 14);
-		const size_t l_seq = le32(p + 16);
-		const uint8_t *q = p + 32;
-		const size_t fixed = l_read_name + n_cigar * 4 + (l_seq + 1) / 2 + l_seq;
-		if (size_t(end - q) < fixed || l_read_name == 0) throw std::runtime_error("malformed alignment record in " + _file_name);
-		al.name.assign(reinterpret_cast<const char *>(q), l_read_name - 1);
-		al.tag_data = q + fixed;
-		al.tag_bytes = size_t(end - al.tag_data);
+		RecordView v;
+		size_t np = 0;
+		view_at(_pos, v, np);
+		_pos = np;
+		al = v.al;
+		al.name.assign(v.name_data, v.name_len);
 		return true;
+	}
+
+	void BamReader::next_batch(std::vector<RecordView> &out, size_t max_records)
+	{
+		out.clear();
+		if (!fill(4)) return;
+		const size_t block_size = le32(_data.data() + _pos);
+		if (block_size < 32) throw std::runtime_error("malformed alignment record in " + _file_name);
+		if (!fill(4 + block_size)) throw std::runtime_error("truncated alignment record in " + _file_name);
+		RecordView v;
+		size_t np = 0;
+		while (out.size() < max_records && view_at(_pos, v, np)) // no fill() in here: the views stay valid
+		{
+			out.push_back(v);
+			_pos = np;
+		}
 	}
 
 	namespace
 	{
-		// walks the tag block; returns the value position of `tag` (type in *type) or nullptr
-		const uint8_t *find_tag(const uint8_t *p, size_t n, const std::string &tag, char *type, size_t *value_bytes)
+		// walks the tag block once; calls on_tag(two-character name, type, value, value bytes) for every tag
+		template <class F> void walk_tags(const uint8_t *p, size_t n, F &&on_tag)
 		{
-			if (tag.size() != 2) return nullptr;
 			const uint8_t *end = p + n;
 			auto bad = [] { throw std::runtime_error("malformed tag block in a BAM record"); };
 			while (p < end)
@@ -216,16 +248,39 @@ namespace BamProcessing
 				default: bad();
 				}
 				if (size_t(end - v) < len) bad();
-				if (char(p[0]) == tag[0] && char(p[1]) == tag[1])
-				{
-					*type = t;
-					*value_bytes = len;
-					return v;
-				}
+				on_tag(p, t, v, len);
 				p = v + len;
 			}
-			return nullptr;
 		}
+
+		const uint8_t *find_tag(const uint8_t *p, size_t n, const std::string &tag, char *type, size_t *value_bytes)
+		{
+			if (tag.size() != 2) return nullptr;
+			const uint8_t *hit = nullptr;
+			walk_tags(p, n, [&](const uint8_t *name, char t, const uint8_t *v, size_t len) {
+				if (!hit && char(name[0]) == tag[0] && char(name[1]) == tag[1]) { hit = v; *type = t; *value_bytes = len; }
+			});
+			return hit;
+		}
+	}
+
+	bool BamAlignment::TagValue::string(std::string &out) const
+	{
+		if (type == 'Z' || type == 'H') { out.assign(reinterpret_cast<const char *>(value), bytes - 1); return true; }
+		if (type == 'A') { out.assign(1, char(value[0])); return true; }
+		return false;
+	}
+
+	void BamAlignment::find_tags(const std::string *const *tags, size_t n_tags, TagValue *found) const
+	{
+		for (size_t k = 0; k < n_tags; ++k) found[k] = TagValue();
+		walk_tags(tag_data, tag_bytes, [&](const uint8_t *name, char t, const uint8_t *v, size_t len) {
+			for (size_t k = 0; k < n_tags; ++k)
+				if (!found[k].type && tags[k]->size() == 2 && char(name[0]) == (*tags[k])[0] && char(name[1]) == (*tags[k])[1])
+				{
+					found[k].type = t; found[k].value = v; found[k].bytes = len;
+				}
+		});
 	}
 
 	char BamAlignment::tag_type(const std::string &tag) const
@@ -249,6 +304,11 @@ namespace BamProcessing
 	bool read_info_from_alignment(const BamAlignment &al, const std::string &chr_name, const IngestParams &params, IngestStats &stats,
 	                              Tools::ReadParameters &read_params, std::string &gene, UMI::Mark &mark)
 	{
+		// every tag this read can need, found in ONE walk over its tag block
+		const std::string *wanted[6] = {&params.tags.cell_barcode, &params.tags.umi, &params.tags.cell_barcode_quality, &params.tags.umi_quality,
+		                                &params.tags.gene, &params.tags.read_type};
+		BamAlignment::TagValue tv[6];
+		al.find_tags(wanted, 6, tv);
 		// ---- barcode + UMI: FilledBamParamsParser::get_read_params (.cpp:12-40) / ReadParamsParser::get_read_params (.cpp:21-34)
 		bool pass_quality = true;
 		try
@@ -256,10 +316,9 @@ namespace BamProcessing
 			if (params.filled_bam)
 			{
 				std::string cb, umi, cbq, umiq;
-				if (!al.get_string_tag(params.tags.cell_barcode, cb) || !al.get_string_tag(params.tags.umi, umi)) { ++stats.cant_parse; return false; }
-				al.get_string_tag(params.tags.cell_barcode_quality, cbq);
-				al.get_string_tag(params.tags.umi_quality, umiq);
-				read_params = Tools::ReadParameters(cb, umi, cbq, umiq);
+				if (!tv[0].string(cb) || !tv[1].string(umi)) { ++stats.cant_parse; return false; }
+				tv[2].string(cbq);
+				tv[3].string(umiq);
 				// ReadParameters::check_quality (Tools/ReadParameters.cpp:122-141): Phred+33 characters, every barcode and UMI base
 				const int min_phred = params.min_barcode_quality + 33;
 				if (min_phred > 33)
@@ -267,6 +326,7 @@ namespace BamProcessing
 					for (char c : cbq) if (c < min_phred) pass_quality = false;
 					for (char c : umiq) if (c < min_phred) pass_quality = false;
 				}
+				read_params = Tools::ReadParameters(std::move(cb), std::move(umi), std::move(cbq), std::move(umiq));
 			}
 			else read_params = Tools::ReadParameters::parse_encoded_id(al.name);
 		}
@@ -286,7 +346,7 @@ namespace BamProcessing
 			if (!chr_name.empty()) mark.add(UMI::Mark::HAS_EXONS);
 			return true;
 		}
-		if (!al.get_string_tag(params.tags.gene, gene))
+		if (!tv[4].string(gene))
 		{
 			gene.clear();
 			mark.add(UMI::Mark::HAS_NOT_ANNOTATED);
@@ -296,15 +356,53 @@ namespace BamProcessing
 		bool have_type = false;
 		if (!params.tags.read_type.empty())
 		{
-			const char t = al.tag_type(params.tags.read_type);
+			const char t = tv[5].type;
 			if (t && t != 'Z' && t != 'A') throw std::runtime_error(std::string("Expected string tag, but got ") + t); // get_bam_tag, .cpp:179-197
-			have_type = al.get_string_tag(params.tags.read_type, read_type);
+			have_type = tv[5].string(read_type);
 		}
 		if (!have_type) mark.add(UMI::Mark::HAS_EXONS);
 		else if (read_type == params.tags.intronic_read_value) mark.add(UMI::Mark::HAS_INTRONS);
 		else if (!params.tags.intergenic_read_value.empty() && read_type == params.tags.intergenic_read_value) mark.add(UMI::Mark::HAS_NOT_ANNOTATED);
 		else mark.add(UMI::Mark::HAS_EXONS);
 		return true;
+	}
+
+	void parse_batch(const std::vector<BamReader::RecordView> &records, const std::vector<std::string> &refs, const IngestParams &params,
+	                 std::vector<ParsedRead> &out, unsigned threads)
+	{
+		const size_t n_refs = refs.size();
+		out.clear();
+		out.resize(records.size());
+		const unsigned nt = unsigned(std::min<size_t>(threads ? threads : std::max(1u, std::thread::hardware_concurrency()), (records.size() + 4095) / 4096));
+		std::vector<std::string> errors(std::max(1u, nt));
+		auto work = [&](unsigned t, size_t first, size_t last) {
+			try
+			{
+				BamAlignment al;
+				for (size_t k = first; k < last; ++k)
+				{
+					ParsedRead &r = out[k];
+					al = records[k].al;
+					r.ref_id = al.ref_id;
+					if (!al.is_mapped() || !al.is_primary_alignment()) { r.status = ParsedRead::SKIPPED; continue; }
+					if (al.ref_id < 0 || size_t(al.ref_id) >= n_refs) { r.status = ParsedRead::NO_CHROMOSOME; continue; }
+					if (!params.filled_bam) al.name.assign(records[k].name_data, records[k].name_len);
+					IngestStats st;
+					if (read_info_from_alignment(al, refs[size_t(al.ref_id)], params, st, r.params, r.gene, r.mark)) r.status = ParsedRead::OK;
+					else r.status = st.low_quality ? ParsedRead::LOW_QUALITY : ParsedRead::CANT_PARSE;
+				}
+			}
+			catch (std::exception &e) { errors[t] = e.what(); }
+		};
+		if (nt <= 1) work(0, 0, records.size());
+		else
+		{
+			std::vector<std::thread> pool;
+			const size_t per = (records.size() + nt - 1) / nt;
+			for (unsigned t = 0; t < nt; ++t) pool.emplace_back(work, t, std::min(records.size(), size_t(t) * per), std::min(records.size(), size_t(t + 1) * per));
+			for (auto &th : pool) th.join();
+		}
+		for (auto const &e : errors) if (!e.empty()) throw std::runtime_error(e);
 	}
 
 	void parse_bam_files(const std::vector<std::string> &bam_files, const IngestParams &params, CellsDataContainer &container, IngestStats &stats)

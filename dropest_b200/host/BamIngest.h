@@ -9,7 +9,10 @@
 #include "Estimation.h"
 
 #include <cstdint>
+#include <algorithm>
 #include <cstdio>
+#include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -38,6 +41,9 @@ namespace BamProcessing
 		char tag_type(const std::string &tag) const;
 		// string tags only (Z, H; A gives its one character): false when the tag is absent or of another type
 		bool get_string_tag(const std::string &tag, std::string &value) const;
+		// ONE walk over the tag block for several tags: found[k] = {type, value pointer, value bytes} of tags[k] (type 0 = absent)
+		struct TagValue { char type = 0; const uint8_t *value = nullptr; size_t bytes = 0; bool string(std::string &out) const; };
+		void find_tags(const std::string *const *tags, size_t n_tags, TagValue *found) const;
 	};
 
 	class BamReader
@@ -50,13 +56,35 @@ namespace BamProcessing
 		const std::vector<std::string> &reference_names() const { return _refs; }
 		const std::string &header_text() const { return _header_text; }
 		bool next(BamAlignment &alignment); // false at the end of the file
+		// Every complete record that is already inflated (at least one; up to `max_records`), as views into the reader's buffer that stay
+		// valid until the next call of next / next_batch.  Empty at the end of the file.  `name` is left empty (use `name_data`).
+		struct RecordView { BamAlignment al; const char *name_data = nullptr; size_t name_len = 0; };
+		void next_batch(std::vector<RecordView> &out, size_t max_records);
 
 	private:
 		std::string _file_name;
 		std::FILE *_f = nullptr;
 		unsigned _threads;
-		std::vector<uint8_t> _comp;   // compressed bytes not yet inflated (whole blocks + a partial one at the end)
-		std::vector<uint8_t> _data;   // inflated bytes not yet consumed
+		// byte buffers that grow without zero-filling (a vector's resize would touch every new byte once more)
+		struct Bytes
+		{
+			std::unique_ptr<uint8_t[]> p;
+			size_t n = 0, cap = 0;
+			uint8_t *data() { return p.get(); }
+			const uint8_t *data() const { return p.get(); }
+			size_t size() const { return n; }
+			void grow_to(size_t want) // keeps [0, n)
+			{
+				if (want <= cap) return;
+				size_t c = std::max(want, cap + cap / 2);
+				std::unique_ptr<uint8_t[]> q(new uint8_t[c]);
+				if (n) std::memcpy(q.get(), p.get(), n);
+				p = std::move(q); cap = c;
+			}
+			void drop_front(size_t k) { if (k) { std::memmove(p.get(), p.get() + k, n - k); n -= k; } }
+		};
+		Bytes _comp;                  // compressed bytes not yet inflated (whole blocks + a partial one at the end)
+		Bytes _data;                  // inflated bytes not yet consumed
 		size_t _pos = 0;              // read position in _data
 		bool _eof = false;
 		std::vector<std::string> _refs;
@@ -64,6 +92,7 @@ namespace BamProcessing
 
 		bool fill(size_t need); // makes at least `need` bytes available at _pos; false at a clean end of file
 		void read_header();
+		bool view_at(size_t pos, RecordView &v, size_t &next_pos) const; // the record at _data[pos], false when it is not complete yet
 	};
 
 	struct IngestParams
@@ -91,23 +120,45 @@ namespace BamProcessing
 	bool read_info_from_alignment(const BamAlignment &alignment, const std::string &chr_name, const IngestParams &params, IngestStats &stats,
 	                              Tools::ReadParameters &read_params, std::string &gene, UMI::Mark &mark);
 
+	// One parsed alignment of a batch (filled by several threads, consumed in order)
+	struct ParsedRead
+	{
+		enum Status : uint8_t { OK, SKIPPED, NO_CHROMOSOME, CANT_PARSE, LOW_QUALITY } status = SKIPPED;
+		int32_t ref_id = -1;
+		Tools::ReadParameters params;
+		std::string gene;
+		UMI::Mark mark;
+	};
+
+	// parses every record of the batch with `threads` threads (they share nothing); refs = the file's reference sequence names
+	void parse_batch(const std::vector<BamReader::RecordView> &records, const std::vector<std::string> &refs, const IngestParams &params,
+	                 std::vector<ParsedRead> &out, unsigned threads);
+
 	template <class F> void for_each_read(const std::vector<std::string> &bam_files, const IngestParams &params, IngestStats &stats, F &&sink)
 	{
+		std::vector<BamReader::RecordView> views;
+		std::vector<ParsedRead> parsed;
 		for (auto const &file : bam_files)
 		{
 			BamReader reader(file, params.threads);
-			BamAlignment al;
-			while (reader.next(al))
+			const auto &refs = reader.reference_names();
+			while (true)
 			{
-				if (!al.is_mapped() || !al.is_primary_alignment()) { ++stats.skipped_unmapped_or_secondary; continue; }
-				if (al.ref_id < 0 || size_t(al.ref_id) >= reader.reference_names().size()) { ++stats.cant_parse; continue; } // unknown chromosome: not counted as a read
-				++stats.total_reads;
-				const std::string &chr_name = reader.reference_names()[size_t(al.ref_id)];
-				Tools::ReadParameters rp;
-				std::string gene;
-				UMI::Mark mark;
-				if (!read_info_from_alignment(al, chr_name, params, stats, rp, gene, mark)) continue;
-				sink(ReadInfo(rp, gene, chr_name, mark));
+				reader.next_batch(views, size_t(1) << 18);
+				if (views.empty()) break;
+				parse_batch(views, refs, params, parsed, params.threads);
+				for (size_t k = 0; k < views.size(); ++k) // stream order: it defines cell / gene / chromosome ids downstream
+				{
+					ParsedRead &r = parsed[k];
+					switch (r.status)
+					{
+					case ParsedRead::SKIPPED: ++stats.skipped_unmapped_or_secondary; break;
+					case ParsedRead::NO_CHROMOSOME: ++stats.cant_parse; break; // unknown chromosome: not counted as a read (BamController.cpp:93-105)
+					case ParsedRead::CANT_PARSE: ++stats.total_reads; ++stats.cant_parse; break;
+					case ParsedRead::LOW_QUALITY: ++stats.total_reads; ++stats.low_quality; break;
+					case ParsedRead::OK: ++stats.total_reads; sink(ReadInfo(std::move(r.params), std::move(r.gene), refs[size_t(r.ref_id)], r.mark)); break;
+					}
+				}
 			}
 		}
 	}

@@ -33,6 +33,12 @@ namespace Tools
 			if (cell_barcode.empty() || umi.empty())
 				throw std::runtime_error("Wrong read parameters: '" + cell_barcode + "' '" + umi + "'");
 		}
+		ReadParameters(std::string &&cell_barcode, std::string &&umi, std::string &&cell_barcode_quality, std::string &&umi_quality)
+			: _cell_barcode(std::move(cell_barcode)), _umi(std::move(umi)), _cell_barcode_quality(std::move(cell_barcode_quality)), _umi_quality(std::move(umi_quality))
+		{
+			if (_cell_barcode.empty() || _umi.empty())
+				throw std::runtime_error("Wrong read parameters: '" + _cell_barcode + "' '" + _umi + "'");
+		}
 		// "prefix!CB#UMI" read-name codec (Tools/ReadParameters.cpp:42-56)
 		static ReadParameters parse_encoded_id(const std::string &encoded_id);
 		std::string encoded_id(const std::string &id_prefix) const { return id_prefix + '!' + _cell_barcode + '#' + _umi; }
@@ -140,6 +146,8 @@ namespace Estimation
 		const UMI::Mark umi_mark;
 		ReadInfo(const Tools::ReadParameters &params, const std::string &gene, const std::string &chromosome_name, const UMI::Mark &umi_mark)
 			: params(params), gene(gene), chromosome_name(chromosome_name), umi_mark(umi_mark) {}
+		ReadInfo(Tools::ReadParameters &&params, std::string &&gene, const std::string &chromosome_name, const UMI::Mark &umi_mark) // no string copies (BAM ingest)
+			: params(std::move(params)), gene(std::move(gene)), chromosome_name(chromosome_name), umi_mark(umi_mark) {}
 	};
 
 	class Stats // Stats.h (per-cell counters; the per-chromosome tables are read from the device by CellsDataContainer::get_stat_by_real_cells)

@@ -3,6 +3,8 @@
 //   test_bam_ingest <filled 0|1> <min_barcode_quality> <gene_in_chr 0|1> <type tag or -> <intronic value or -> <intergenic value or -> <threads> file...
 #include "../../dropest_b200/host/BamIngest.h"
 
+#include <chrono>
+#include <cstdlib>
 #include <iostream>
 
 using namespace Estimation;
@@ -21,7 +23,15 @@ int main(int argc, char **argv)
 		p.threads = unsigned(std::stoi(argv[7]));
 		std::vector<std::string> files(argv + 8, argv + argc);
 		BamProcessing::IngestStats st;
-		BamProcessing::for_each_read(files, p, st, [](const ReadInfo &ri) {
+		if (std::getenv("DGE_BAM_COUNT_ONLY"))
+		{   // parse rate without the printing
+			size_t n = 0, bytes = 0;
+			const auto t0 = std::chrono::steady_clock::now();
+			BamProcessing::for_each_read(files, p, st, [&](const ReadInfo &ri) { ++n; bytes += ri.gene.size() + ri.params.umi().size(); });
+			const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+			std::cout << "#count\t" << n << '\t' << bytes << '\t' << dt << " s\t" << double(n) / dt / 1e6 << " M reads/s\n";
+		}
+		else BamProcessing::for_each_read(files, p, st, [](const ReadInfo &ri) {
 			std::cout << ri.params.cell_barcode() << '\t' << ri.params.umi() << '\t' << (ri.gene.empty() ? "-" : ri.gene) << '\t' << ri.chromosome_name << '\t'
 			          << ri.umi_mark.bits() << '\t' << (ri.params.cell_barcode_quality().empty() ? "-" : ri.params.cell_barcode_quality()) << '\n';
 		});
