@@ -943,15 +943,11 @@ __global__ void __launch_bounds__(256) k_compact_uniques(const uint64_t *__restr
 // order in which the keys happened to arrive -- when such a sub-bucket held more than ~4 k distinct keys.  Now: no capacity anywhere.  The
 // listed sub-buckets are sorted as segments in global memory (cub::DeviceSegmentedRadixSort, library code, a few hundred k keys at most in
 // practice) and run-length encoded by k_tail_dedup.
-constexpr int SC_TAIL_MAX = 16384; // segments per launch; more raise the overflow flag (would need > 16 k oversized sub-buckets)
-
 __global__ void __launch_bounds__(256) k_tail_offsets(const uint32_t *__restrict__ list, const uint32_t *__restrict__ count, const uint32_t *__restrict__ sub_off,
-                                                      int *__restrict__ seg_begin, int *__restrict__ seg_end, int *__restrict__ overflow)
+                                                      int *__restrict__ seg_begin, int *__restrict__ seg_end)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= uint32_t(SC_TAIL_MAX)) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; // the grid covers the list rounded up to 256
     const uint32_t n = *count;
-    if (i == 0 && n > uint32_t(SC_TAIL_MAX)) *overflow = 1;
     int b = 0, e = 0;
     if (i < n) { const uint32_t sb = list[i]; b = int(sub_off[sb]); e = int(sub_off[sb + 1]); }
     seg_begin[i] = b; seg_end[i] = e;
@@ -963,7 +959,7 @@ __global__ void __launch_bounds__(256) k_tail_dedup(const uint64_t *__restrict__
                                                     uint32_t *__restrict__ ucount)
 {
     __shared__ uint32_t ws[33];
-    const uint32_t n_seg = min(*count, uint32_t(SC_TAIL_MAX));
+    const uint32_t n_seg = *count;
     for (uint32_t it = blockIdx.x; it < n_seg; it += gridDim.x)
     {
         const uint32_t sb = list[it], s = sub_off[sb], n = sub_off[sb + 1] - s;
@@ -1323,17 +1319,26 @@ public:
 #undef DGE_MS
 #undef DGE_MS_NB
                 L += 5;
-                {   // oversized sub-buckets: segmented sort in global memory (the L1 buffer is free by now) + run-length encoding; no capacity limit
-                    ws.tail_begin.reserve(size_t(SC_TAIL_MAX) * 4); ws.tail_end.reserve(size_t(SC_TAIL_MAX) * 4);
-                    int *tb = ws.tail_begin.as<int>(), *te = ws.tail_end.as<int>();
-                    k_tail_offsets<<<SC_TAIL_MAX / 256, 256, 0, st>>>(cl + 4 * ls, cc + 4, sub_off, tb, te, overflow_flag);
-                    if (n >= (size_t(1) << 31)) throw std::runtime_error("SortCombine: more than 2^31 keys in one run");
-                    size_t bytes = 0;
-                    DGE_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, bytes, keys_tmp, keysA, int(n), SC_TAIL_MAX, tb, te, 0, 64, st));
-                    ws.tail_tmp.reserve(bytes + 16);
-                    DGE_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(ws.tail_tmp.p, bytes, keys_tmp, keysA, int(n), SC_TAIL_MAX, tb, te, 0, 64, st));
-                    k_tail_dedup<<<148 * 2, 256, 0, st>>>(keysA, keys_tmp, uv, sub_off, cl + 4 * ls, cc + 4, ucount);
-                    L += 4;
+                {   // oversized sub-buckets: segmented sort in global memory (the L1 buffer is free by now) + run-length encoding; no capacity limit.
+                    // Their number comes back to the host here (one 4-byte read behind k_classify_sub, which finished long ago): the segmented
+                    // sort is sized exactly and skipped when there is nothing to do (8 passes over empty segments cost 0.4 ms per step).
+                    uint32_t n_tail = 0;
+                    DGE_CUDA(cudaMemcpyAsync(&n_tail, cc + 4, 4, cudaMemcpyDeviceToHost, st));
+                    DGE_CUDA(cudaStreamSynchronize(st));
+                    if (n_tail)
+                    {
+                        const size_t padded = div_up(size_t(n_tail), size_t(256)) * 256;
+                        ws.tail_begin.reserve(padded * 4); ws.tail_end.reserve(padded * 4);
+                        int *tb = ws.tail_begin.as<int>(), *te = ws.tail_end.as<int>();
+                        k_tail_offsets<<<unsigned(padded / 256), 256, 0, st>>>(cl + 4 * ls, cc + 4, sub_off, tb, te);
+                        if (n >= (size_t(1) << 31)) throw std::runtime_error("SortCombine: more than 2^31 keys in one run");
+                        size_t bytes = 0;
+                        DGE_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, bytes, keys_tmp, keysA, int(n), int(n_tail), tb, te, 0, 64, st));
+                        ws.tail_tmp.reserve(bytes + 16);
+                        DGE_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(ws.tail_tmp.p, bytes, keys_tmp, keysA, int(n), int(n_tail), tb, te, 0, 64, st));
+                        k_tail_dedup<<<unsigned(std::min<uint32_t>(n_tail, 148 * 4)), 256, 0, st>>>(keysA, keys_tmp, uv, sub_off, cl + 4 * ls, cc + 4, ucount);
+                        L += 4;
+                    }
                 }
             }
             else
