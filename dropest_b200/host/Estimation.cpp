@@ -387,6 +387,12 @@ namespace Estimation
 			const unsigned ub_n = std::max(2 * cfg.umi_len, 20u) + 1;
 			_allow_n = 61 >= gb + ub_n + 22;
 		}
+		// What the library refuses (explicit errors at merge_and_filter, never a silent difference): any N read with MergeUMIsStrategyDirectional
+		// (its random repair draws from the process-wide rand() stream in an order the device path does not replay yet), and a REAL cell whose
+		// barcode contains N with the strategies that compare barcodes on the device.  Rather than losing the whole run, the reads concerned
+		// are skipped and counted here, with a warning: all N reads under -u, N-barcode reads under the no-whitelist / Poisson strategies.
+		if (cfg.umi_merge_type == DGE_UMI_MERGE_DIRECTIONAL) _allow_n = false;
+		_allow_n_cb = _allow_n && (cfg.merge_type == DGE_MERGE_NONE || cfg.merge_type == DGE_MERGE_REAL);
 		cfg.allow_n = _allow_n ? 1 : 0;
 		int rc = dge_create(&cfg, &_h);
 		if (rc != DGE_OK) throw std::runtime_error(std::string("dropest_b200: ") + dge_last_error(nullptr));
@@ -460,10 +466,11 @@ namespace Estimation
 		// such reads: the barcode is a cell of its own, the UMI is repaired by MergeUMIsStrategySimple after the barcode merge)
 		uint64_t cbv, umiv;
 		uint32_t flags = 0;
-		if (!_allow_n && (cb.find('N') != std::string::npos || umi.find('N') != std::string::npos))
+		if ((!_allow_n && umi.find('N') != std::string::npos) || (!_allow_n_cb && cb.find('N') != std::string::npos))
 		{
 			if (_skipped_n_reads++ == 0)
-				std::cerr << "dropest_b200: reads whose barcode / UMI contains N are skipped (no room for the N flag in the grouping key: lower n_genes_hint)\n";
+				std::cerr << "dropest_b200: reads whose barcode / UMI contains N are skipped (directional UMI merge, a no-whitelist barcode merge, or no room "
+				             "for the N flag in the grouping key); skipped_n_reads() reports how many\n";
 			++_n_records;   // the skipped read keeps its position in the stream: the pending batch now has a gap (flush sends explicit read indices)
 			_batch_gaps = true;
 			return;

@@ -484,7 +484,7 @@ namespace Estimation
 		bool _chr_overflow = false;         // more than 256 chromosome names: the per-chromosome tables are dropped (1-byte side array)
 		bool _batch_gaps = false;
 		StringIndexer _n_umis, _n_cbs;      // UMIs / barcodes containing N, passed to the device as indices (DGE_FLAG_UMI_N / DGE_FLAG_CB_N)
-		bool _n_dirty = false, _allow_n = false;
+		bool _n_dirty = false, _allow_n = false, _allow_n_cb = false;
 		uint64_t _skipped_n_reads = 0, _skipped_length_reads = 0;
 		void upload_n_strings();
 		uint64_t _batch_first = 0;          // stream position of the first pending record
