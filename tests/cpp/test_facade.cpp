@@ -191,6 +191,20 @@ int main(int argc, char **argv)
 			CHECK_EQUAL(container.cell(1).at("Gene2").at("AAACCT").read_count(), size_t(1));
 		}
 
+		// -u with an N read: the library would refuse the run at merge_and_filter; the mirror skips and counts the read instead
+		{
+			auto directional = std::make_shared<Merge::UMIs::MergeUMIsStrategyDirectional>(2, 1);
+			CellsDataContainer container(real_cb_strat, directional, any_mark);
+			container.add_record(read_info("AAATTAGGTCCA", "AAACCT", "Gene1"));
+			container.add_record(read_info("AAATTAGGTCCA", "AAACNT", "Gene1"));
+			container.add_record(read_info("AAATTAGGTCCA", "AAACCT", "Gene1"));
+			container.set_initialized();
+			container.merge_and_filter();
+			CHECK_EQUAL(container.skipped_n_reads(), uint64_t(1));
+			CHECK_EQUAL(container.cell(0).at("Gene1").size(), size_t(1));
+			CHECK_EQUAL(container.cell(0).at("Gene1").at("AAACCT").read_count(), size_t(2));
+		}
+
 		// -M: MergeStrategyFactory::get_cb_poisson_strat (MergeStrategyFactory.cpp:91-103) + PoissonSimpleMergeStrategy through the container.
 		// Same reads as above: the small cell shares 3 UMI-genes with the big one 1 substitution away; with only 7 distinct UMIs in the whole
 		// container the expected random overlap is large (lambda ~ 0.6, P[X >= 3] ~ 0.02), so the thresholds are raised for this toy input;
