@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <future>
 #include <memory>
 #include <string>
 #include <vector>
@@ -137,28 +138,39 @@ namespace BamProcessing
 	template <class F> void for_each_read(const std::vector<std::string> &bam_files, const IngestParams &params, IngestStats &stats, F &&sink)
 	{
 		std::vector<BamReader::RecordView> views;
-		std::vector<ParsedRead> parsed;
+		std::vector<ParsedRead> parsed, parsed_next;
 		for (auto const &file : bam_files)
 		{
 			BamReader reader(file, params.threads);
 			const auto &refs = reader.reference_names();
-			while (true)
+			// the next batch is read, inflated and parsed (all on the pool) while this thread hands the current one to the sink
+			auto produce = [&]() -> bool {
+				reader.next_batch(views, size_t(1) << 17);
+				if (views.empty()) return false;
+				parse_batch(views, refs, params, parsed_next, params.threads);
+				return true;
+			};
+			bool have = produce();
+			while (have)
 			{
-				reader.next_batch(views, size_t(1) << 18);
-				if (views.empty()) break;
-				parse_batch(views, refs, params, parsed, params.threads);
-				for (size_t k = 0; k < views.size(); ++k) // stream order: it defines cell / gene / chromosome ids downstream
+				parsed.swap(parsed_next);
+				auto next = std::async(std::launch::async, produce);
+				try
 				{
-					ParsedRead &r = parsed[k];
-					switch (r.status)
+					for (ParsedRead &r : parsed) // stream order: it defines cell / gene / chromosome ids downstream
 					{
-					case ParsedRead::SKIPPED: ++stats.skipped_unmapped_or_secondary; break;
-					case ParsedRead::NO_CHROMOSOME: ++stats.cant_parse; break; // unknown chromosome: not counted as a read (BamController.cpp:93-105)
-					case ParsedRead::CANT_PARSE: ++stats.total_reads; ++stats.cant_parse; break;
-					case ParsedRead::LOW_QUALITY: ++stats.total_reads; ++stats.low_quality; break;
-					case ParsedRead::OK: ++stats.total_reads; sink(ReadInfo(std::move(r.params), std::move(r.gene), refs[size_t(r.ref_id)], r.mark)); break;
+						switch (r.status)
+						{
+						case ParsedRead::SKIPPED: ++stats.skipped_unmapped_or_secondary; break;
+						case ParsedRead::NO_CHROMOSOME: ++stats.cant_parse; break; // unknown chromosome: not counted as a read (BamController.cpp:93-105)
+						case ParsedRead::CANT_PARSE: ++stats.total_reads; ++stats.cant_parse; break;
+						case ParsedRead::LOW_QUALITY: ++stats.total_reads; ++stats.low_quality; break;
+						case ParsedRead::OK: ++stats.total_reads; sink(ReadInfo(std::move(r.params), std::move(r.gene), refs[size_t(r.ref_id)], r.mark)); break;
+						}
 					}
 				}
+				catch (...) { next.wait(); throw; }
+				have = next.get();
 			}
 		}
 	}

@@ -2,6 +2,7 @@
 //   test_bam_pipeline <whitelist (const type) or -> <min_genes_before> <min_genes_after> <type tag> <intronic> <intergenic> file...
 #include "../../dropest_b200/host/BamIngest.h"
 
+#include <chrono>
 #include <iostream>
 
 using namespace Estimation;
@@ -21,9 +22,14 @@ int main(int argc, char **argv)
 		std::vector<std::string> files(argv + 7, argv + argc);
 		CellsDataContainer container(factory.get_cb_strat(true, false), factory.get_umi(false), UMI::Mark::get_by_code(UMI::Mark::DEFAULT_CODE), false, -1, 0, 4096);
 		BamProcessing::IngestStats st;
+		const auto t0 = std::chrono::steady_clock::now();
 		BamProcessing::parse_bam_files(files, p, container, st);
+		const auto t1 = std::chrono::steady_clock::now();
 		container.set_initialized();
 		container.merge_and_filter();
+		const auto t2 = std::chrono::steady_clock::now();
+		std::cout << "timing\t" << std::chrono::duration<double>(t1 - t0).count() << "\t" << std::chrono::duration<double>(t2 - t1).count() << "\t"
+		          << double(st.total_reads) / std::chrono::duration<double>(t2 - t0).count() / 1e6 << " M reads/s BAM -> matrix\n";
 		std::cout << "stats\t" << st.total_reads << '\t' << st.cant_parse << '\t' << st.low_quality << '\t' << container.total_cells_number() << '\t'
 		          << container.real_cells_number() << '\t' << container.intergenic_reads_num() << '\n';
 		ResultsPrinter printer(false, false);
