@@ -90,8 +90,10 @@ namespace Estimation
 		index_t get_index(const std::string &value) const { return _indexes.at(value); }
 		index_t add(const std::string &value)
 		{
+			auto found = _indexes.find(value); // the common case allocates nothing (emplace builds a node before it looks)
+			if (found != _indexes.end()) return found->second;
 			auto it = _indexes.emplace(value, _indexes.size());
-			if (it.second) _values.push_back(value);
+			_values.push_back(value);
 			return it.first->second;
 		}
 	};

@@ -20,7 +20,7 @@ int main(int argc, char **argv)
 		BamProcessing::IngestParams p;
 		p.tags.read_type = argv[4]; p.tags.intronic_read_value = argv[5]; p.tags.intergenic_read_value = argv[6];
 		std::vector<std::string> files(argv + 7, argv + argc);
-		CellsDataContainer container(factory.get_cb_strat(true, false), factory.get_umi(false), UMI::Mark::get_by_code(UMI::Mark::DEFAULT_CODE), false, -1, 0, 4096);
+		CellsDataContainer container(factory.get_cb_strat(true, false), factory.get_umi(false), UMI::Mark::get_by_code(UMI::Mark::DEFAULT_CODE), false, -1, 0, 1u << 15);
 		BamProcessing::IngestStats st;
 		const auto t0 = std::chrono::steady_clock::now();
 		BamProcessing::parse_bam_files(files, p, container, st);
