@@ -174,6 +174,16 @@ namespace BamProcessing
 		if (size_t(end - q) < fixed || l_read_name == 0) throw std::runtime_error("malformed alignment record in " + _file_name);
 		v.name_data = reinterpret_cast<const char *>(q);
 		v.name_len = l_read_name - 1;
+		{
+			int32_t ref_len = 0;
+			const uint8_t *cg = q + l_read_name;
+			for (size_t k = 0; k < n_cigar; ++k)
+			{
+				const uint32_t op = le32(cg + 4 * k);
+				switch (op & 0xF) { case 0: case 2: case 3: case 7: case 8: ref_len += int32_t(op >> 4); break; default: break; } // M D N = X
+			}
+			v.al.end_position = v.al.position + ref_len;
+		}
 		v.al.tag_data = q + fixed;
 		v.al.tag_bytes = size_t(end - v.al.tag_data);
 		return true;
@@ -301,6 +311,70 @@ namespace BamProcessing
 		return false;
 	}
 
+	namespace
+	{
+		using Tools::GeneAnnotation::RefGenesContainer;
+
+		void add_type(UMI::Mark &mark, Tools::GeneAnnotation::RecordType type) // UMI::Mark::add(GtfRecord::RecordType), UMI.cpp:87-100
+		{
+			if (type == Tools::GeneAnnotation::EXON) mark.add(UMI::Mark::HAS_EXONS);
+			else if (type == Tools::GeneAnnotation::INTRON) mark.add(UMI::Mark::HAS_INTRONS);
+			else throw std::runtime_error("Unexpected GtfRecord type: " + std::to_string(int(type)));
+		}
+
+		// ReadParamsParser::find_exon (.cpp:152-172): the one gene whose exon is hit; false when exons of two genes are
+		bool find_exon(const RefGenesContainer::query_results_t &results, RefGenesContainer::QueryResult &exon)
+		{
+			for (auto const &r : results)
+			{
+				if (r.type != Tools::GeneAnnotation::EXON) continue;
+				if (exon.gene_name.empty()) { exon = r; continue; }
+				if (exon.gene_name != r.gene_name) return false;
+			}
+			return true;
+		}
+
+		// ReadParamsParser::get_gene_from_reference (.cpp:92-150): the annotation at the first and at the last aligned base decides
+		UMI::Mark gene_from_reference(const RefGenesContainer &genes, const std::string &chr_name, const BamAlignment &al, std::string &gene)
+		{
+			UMI::Mark mark;
+			const auto pos = RefGenesContainer::pos_t(al.position);
+			const int end_position = al.end_position;
+			auto set1 = genes.get_gene_info(chr_name, pos, pos + 1);
+			auto set2 = genes.get_gene_info(chr_name, RefGenesContainer::pos_t(end_position - 1), RefGenesContainer::pos_t(end_position));
+			if (set1.empty() && set2.empty()) return mark;
+			if (set1.size() == 1 && set2.size() == 1)
+			{
+				if (set1.begin()->gene_name == set2.begin()->gene_name)
+				{
+					add_type(mark, set1.begin()->type);
+					add_type(mark, set2.begin()->type);
+					gene = set1.begin()->gene_name;
+				}
+				return mark;
+			}
+			if (set1.size() <= 1 && set2.size() <= 1)
+			{   // one end in a gene, the other outside every gene
+				auto const &hit = set1.empty() ? *set2.begin() : *set1.begin();
+				gene = hit.gene_name;
+				add_type(mark, hit.type);
+				mark.add(UMI::Mark::HAS_NOT_ANNOTATED);
+				return mark;
+			}
+			if (set1.empty() || set2.empty()) return mark;
+			RefGenesContainer::QueryResult exon1, exon2;
+			if (!find_exon(set1, exon1) || !find_exon(set2, exon2)) return mark;
+			if (!exon1.gene_name.empty() && !exon2.gene_name.empty())
+			{
+				if (exon1.gene_name != exon2.gene_name) return mark;
+				gene = exon1.gene_name;
+				add_type(mark, exon1.type);
+				add_type(mark, exon2.type);
+			}
+			return mark;
+		}
+	}
+
 	bool read_info_from_alignment(const BamAlignment &al, const std::string &chr_name, const IngestParams &params, IngestStats &stats,
 	                              Tools::ReadParameters &read_params, std::string &gene, UMI::Mark &mark)
 	{
@@ -344,6 +418,12 @@ namespace BamProcessing
 		{
 			gene = chr_name;
 			if (!chr_name.empty()) mark.add(UMI::Mark::HAS_EXONS);
+			return true;
+		}
+		if (params.genes && !params.genes->is_empty())
+		{
+			try { mark = gene_from_reference(*params.genes, chr_name, al, gene); }
+			catch (Tools::GeneAnnotation::RefGenesContainer::ChrNotFoundException &) { ++stats.cant_parse; return false; } // BamController.cpp:158-166
 			return true;
 		}
 		if (!tv[4].string(gene))

@@ -7,6 +7,7 @@
 // stream order -- the order is what defines cell / gene ids downstream.  GTF-based gene assignment (row f3) is not part of this file.
 #pragma once
 #include "Estimation.h"
+#include "GeneAnnotation.h"
 
 #include <cstdint>
 #include <algorithm>
@@ -31,6 +32,7 @@ namespace BamProcessing
 	struct BamAlignment
 	{
 		int32_t ref_id = -1, position = -1;
+		int32_t end_position = -1; // position + reference bases consumed by the CIGAR (M, D, N, =, X): half-open end, like BamTools' GetEndPosition()
 		uint16_t flag = 0;
 		std::string name;
 		const uint8_t *tag_data = nullptr;
@@ -103,6 +105,11 @@ namespace BamProcessing
 		bool gene_in_chromosome_name = false; // pseudo-aligner output: the reference name is the gene
 		int min_barcode_quality = 0;          // -f only: reads with a barcode / UMI base below this Phred quality are dropped (0 = off)
 		unsigned threads = 0;                 // BGZF inflate threads (0 = hardware concurrency)
+		// -g: gene and mark from an annotation (GTF / BED, optionally .gz) instead of the gene tag: the positions of the first and the last
+		// aligned base are looked up (ReadParamsParser::get_gene_from_reference, ReadParamsParser.cpp:92-150).  Loaded by parse_bam_files /
+		// for_each_read when `genes` is not set yet.
+		std::string genes_filename;
+		std::shared_ptr<const Tools::GeneAnnotation::RefGenesContainer> genes;
 	};
 
 	struct IngestStats // the counters BamProcessorAbstract keeps (BamProcessorAbstract.cpp)
@@ -135,8 +142,11 @@ namespace BamProcessing
 	void parse_batch(const std::vector<BamReader::RecordView> &records, const std::vector<std::string> &refs, const IngestParams &params,
 	                 std::vector<ParsedRead> &out, unsigned threads);
 
-	template <class F> void for_each_read(const std::vector<std::string> &bam_files, const IngestParams &params, IngestStats &stats, F &&sink)
+	template <class F> void for_each_read(const std::vector<std::string> &bam_files, const IngestParams &params_in, IngestStats &stats, F &&sink)
 	{
+		IngestParams params(params_in);
+		if (!params.genes && !params.genes_filename.empty())
+			params.genes = std::make_shared<const Tools::GeneAnnotation::RefGenesContainer>(params.genes_filename);
 		std::vector<BamReader::RecordView> views;
 		std::vector<ParsedRead> parsed, parsed_next;
 		for (auto const &file : bam_files)

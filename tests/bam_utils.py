@@ -28,14 +28,20 @@ def _tag(name: str, value) -> bytes:
     raise ValueError(kind)
 
 
-def alignment(name: str, ref_id: int, pos: int, flag: int, tags, seq_len: int = 8) -> bytes:
-    """tags: list of (tag, (type, value)); sequence / qualities are filler (the ingest does not read them); one CIGAR op (seq_len M)"""
+CIGAR_OPS = "MIDNSHP=X"
+
+
+def alignment(name: str, ref_id: int, pos: int, flag: int, tags, seq_len: int = 8, cigar_ops=None) -> bytes:
+    """tags: list of (tag, (type, value)); sequence / qualities are filler (the ingest does not read them); cigar_ops: list of
+    (op letter, length), default one match of seq_len"""
     rn = name.encode() + b"\x00"
-    cigar = struct.pack("<I", (seq_len << 4) | 0)
+    if cigar_ops is None:
+        cigar_ops = [("M", seq_len)]
+    cigar = b"".join(struct.pack("<I", (length << 4) | CIGAR_OPS.index(op)) for op, length in cigar_ops)
     seq = b"\x11" * ((seq_len + 1) // 2)
     qual = b"\x1e" * seq_len
     tag_bytes = b"".join(_tag(t, v) for t, v in tags)
-    core = struct.pack("<iiBBHHHIiii", ref_id, pos, len(rn), 30, 4680, 1, flag, seq_len, -1, -1, 0)
+    core = struct.pack("<iiBBHHHIiii", ref_id, pos, len(rn), 30, 4680, len(cigar_ops), flag, seq_len, -1, -1, 0)
     rec = core + rn + cigar + seq + qual + tag_bytes
     return struct.pack("<I", len(rec)) + rec
 

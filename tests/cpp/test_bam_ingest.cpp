@@ -1,6 +1,7 @@
 // CPU-only tool behind tests/test_bam_ingest.py: reads BAM files with dropest_b200/host/BamIngest and prints one line per accepted read
 // (barcode, UMI, gene, chromosome, mark bits, barcode quality) followed by the counters.  No container, no CUDA call.
 //   test_bam_ingest <filled 0|1> <min_barcode_quality> <gene_in_chr 0|1> <type tag or -> <intronic value or -> <intergenic value or -> <threads> file...
+//   environment DGE_BAM_GENES=<annotation.gtf[.gz] | .bed[.gz]>: gene and mark from the annotation (-g) instead of the gene tag
 #include "../../dropest_b200/host/BamIngest.h"
 
 #include <chrono>
@@ -21,6 +22,7 @@ int main(int argc, char **argv)
 		auto opt = [](const char *s) { return std::string(s) == "-" ? std::string() : std::string(s); };
 		p.tags.read_type = opt(argv[4]); p.tags.intronic_read_value = opt(argv[5]); p.tags.intergenic_read_value = opt(argv[6]);
 		p.threads = unsigned(std::stoi(argv[7]));
+		if (const char *g = std::getenv("DGE_BAM_GENES")) p.genes_filename = g;
 		std::vector<std::string> files(argv + 8, argv + argc);
 		BamProcessing::IngestStats st;
 		if (std::getenv("DGE_BAM_COUNT_ONLY"))

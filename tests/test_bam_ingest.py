@@ -113,6 +113,65 @@ def test_corrupt_files_fail_loudly(tmp_path):
     assert "Can't open BAM file" in meta[-1][1]
 
 
+REF_RP = os.path.join(ROOT, "oracle", "_ref", "ref_readparams")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_RP), reason="compiled reference (oracle/_ref/ref_readparams) not built")
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_gene_assignment_from_annotation_matches_the_compiled_reference(tmp_path, seed):
+    """-g: gene and mark from the annotation at the first and the last aligned base (ReadParamsParser::get_gene_from_reference), CIGARs with
+    insertions / deletions / skips / clips, reads on chromosomes the annotation does not know; every alignment goes through the BAM file and
+    BamIngest on one side and, as text, through the reference's own ReadParamsParser (BamAlignment shimmed) on the other."""
+    import test_gene_annotation as tga
+
+    rng = np.random.default_rng(100 + seed)
+    if seed == 0:
+        genes_file = os.path.join(ROOT, "tests", "golden", "ref_gtf", "gtf_test.gtf.gz")
+        refs = [("chr1", 250000), ("chr2", 250000), ("chrX", 250000), ("chrNotInGtf", 1000)]
+        spans = [(0, 11800, 72100), (1, 11800, 72100), (2, 34000, 36100)]
+    else:
+        text, genes = tga._random_gtf(rng, with_introns=seed == 2, all_have_transcripts=True)
+        genes_file = str(tmp_path / "a.gtf")
+        open(genes_file, "w").write(text)
+        refs = [("chr1", 100000), ("chr2", 100000), ("chr3", 100000), ("chrNotInGtf", 1000)]
+        spans = [(int(c[3:]) - 1, max(0, a - 40), b + 40) for c, a, b in genes]
+    als, tsv = [], []
+    for i in range(6000):
+        ref, a, b = spans[int(rng.integers(0, len(spans)))] if rng.random() > 0.02 else (3, 0, 900)
+        pos = int(rng.integers(a, b))
+        ops = [("M", int(rng.integers(1, 60)))]
+        for _ in range(int(rng.integers(0, 3))):
+            ops.append((str(rng.choice(list("IDNS"))), int(rng.integers(1, 400 if seed == 0 else 40))))
+            ops.append(("M", int(rng.integers(1, 60))))
+        if rng.random() < 0.2:
+            ops.insert(0, ("S", 5))
+        name = f"r{i}!ACGTACGTACGTACGT#ACGTACGTAC"
+        tags = [("GX", ("Z", "IGNORED"))]   # the gene tag must not be looked at in this mode
+        als.append(alignment(name, ref, pos, 0, tags, seq_len=sum(l for o, l in ops if o in "MIS=X"), cigar_ops=ops))
+        tsv.append(f"{name}\t{refs[ref][0]}\t{pos}\t{''.join(f'{l}{o}' for o, l in ops)}\tGX:Z:IGNORED")
+    bam = str(tmp_path / "g.bam")
+    write_bam(bam, refs, als, block_bytes=40000)
+    tp = str(tmp_path / "g.tsv")
+    open(tp, "w").write("\n".join(tsv) + "\n")
+    ref_out = subprocess.run([REF_RP, genes_file, "0", "0", "0", "-", "-", "-", tp], capture_output=True, text=True)
+    assert ref_out.returncode == 0, ref_out.stdout[-300:]
+    exp, n_chr = [], 0
+    for line, (ref_name) in zip(ref_out.stdout.strip().split("\n"), [x.split("\t")[1] for x in tsv]):
+        if line == "!chr":
+            n_chr += 1
+            continue
+        cb, umi, gene, mark, _ = line.split(" ")
+        exp.append((cb, umi, gene, ref_name, mark))
+    r = subprocess.run([DUMP, "0", "0", "0", "-", "-", "-", "3", bam], capture_output=True, text=True, env=dict(os.environ, DGE_BAM_GENES=genes_file))
+    assert r.returncode == 0, r.stdout[-300:]
+    lines = r.stdout.strip().split("\n")
+    got = [tuple(l.split("\t")[:5]) for l in lines if not l.startswith("#")]
+    assert got == exp
+    assert lines[-1].split("\t")[:3] == ["#stats", str(len(als)), str(n_chr)]
+    marks = {g[4] for g in got}
+    assert {"0", "2"} <= marks and (marks & {"3", "4", "6"}) and n_chr > 50   # no gene, exonic, and mixed / intronic reads all occur
+
+
 @pytest.mark.gpu
 def test_bam_to_count_matrix_matches_the_reference(tmp_path):
     """End to end: a BAM with CB / UB / GX / XF tags (two files, records straddling BGZF blocks) -> BamIngest -> the container on the GPU
