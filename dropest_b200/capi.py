@@ -44,7 +44,7 @@ DIST_DONE, DIST_ALLGATHER, DIST_ALLTOALL = 0, 1, 2
 EXPORTS = [
     "dge_config_default", "dge_create", "dge_destroy", "dge_last_error", "dge_add_batch", "dge_add_batch_device", "dge_add_batch_segments_device", "dge_add_batch_soa",
     "dge_add_batch_chr", "dge_add_batch_soa_chr", "dge_add_batch_chr_device", "dge_get_chr_stats",
-    "dge_set_initialized", "dge_merge_and_filter", "dge_reset", "dge_set_stream", "dge_set_n_strings", "dge_get_summary", "dge_get_timings", "dge_get_cells",
+    "dge_set_initialized", "dge_merge_and_filter", "dge_reset", "dge_set_stream", "dge_set_n_strings", "dge_set_cb_strings", "dge_get_summary", "dge_get_timings", "dge_get_cells",
     "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
     "dge_route_by_barcode_device", "dge_route_count_slices_device", "dge_route_scatter_slice_device", "dge_dist_step",
@@ -163,6 +163,7 @@ def load_library():
     lib.dge_peer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
     lib.dge_peer_close.argtypes = [C.c_int, C.c_void_p]
     lib.dge_set_n_strings.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
+    lib.dge_set_cb_strings.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
     lib.dge_umi_first_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
     lib.dge_umi_first_export.argtypes = [C.c_void_p, C.c_void_p]
     lib.dge_umi_first_import.argtypes = [C.c_void_p, C.c_void_p]
@@ -352,7 +353,13 @@ class Container:
 
     # ---- cross-rank merge steps (sharded runs); the collectives live in dropest_b200/dist.py
     def set_n_strings(self, which: int, strings):
-        """The strings behind DGE_FLAG_UMI_N (which = 0) / DGE_FLAG_CB_N (which = 1) record indices (dge_set_n_strings)."""
+        """The strings behind DGE_FLAG_UMI_N (which = 0) / DGE_FLAG_CB_N (which = 1) record indices (dge_set_n_strings); barcode lists
+        with strings of several lengths go through dge_set_cb_strings."""
+        strings = list(strings)
+        if which == 1 and any(len(s) != int(self.cfg.cb_len) for s in strings):
+            lengths = np.array([len(s) for s in strings], dtype=np.uint32)
+            self._check(self._lib.dge_set_cb_strings(self._h, "".join(strings).encode(), lengths.ctypes.data, len(strings)))
+            return
         blob = "".join(strings).encode()
         self._check(self._lib.dge_set_n_strings(self._h, which, blob, len(strings)))
 

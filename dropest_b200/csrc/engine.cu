@@ -74,7 +74,8 @@ struct dge_handle
     dge_config cfg{};
     std::string barcodes_file;
     std::string err;
-    std::string n_umi_strings, n_cb_strings; // dge_set_n_strings: the strings behind DGE_FLAG_UMI_N / DGE_FLAG_CB_N indices
+    std::string n_umi_strings;                // dge_set_n_strings: the strings behind DGE_FLAG_UMI_N indices (umi_len characters each)
+    std::vector<std::string> n_cb_list;       // the strings behind DGE_FLAG_CB_N indices: barcodes with N and / or of another length than cb_len
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int state = 0; // 0 filling, 1 initialized, 2 merged
@@ -285,9 +286,9 @@ void reset_fill_state(dge_handle *h);
 std::string cb_string(const dge_handle *h, uint64_t cb)
 {
     if (!(cb & CB_N_BIT)) return unpack_seq(cb, h->cfg.cb_len);
-    const size_t idx = size_t(cb & (CB_N_BIT - 1)), len = h->cfg.cb_len;
-    if ((idx + 1) * len > h->n_cb_strings.size()) throw InvalidInput("barcode index beyond the N-barcode list (dge_set_n_strings)");
-    return h->n_cb_strings.substr(idx * len, len);
+    const size_t idx = size_t(cb & (CB_N_BIT - 1));
+    if (idx >= h->n_cb_list.size()) throw InvalidInput("barcode index beyond the escaped-barcode list (dge_set_n_strings / dge_set_cb_strings)");
+    return h->n_cb_list[idx];
 }
 
 bool umi_is_n(const dge_handle *h, uint32_t umi) { return h->kl.ne && ((umi >> (h->kl.ub - 1)) & 1u); }
@@ -2841,10 +2842,39 @@ int dge_set_n_strings(dge_handle *h, int which, const char *strings, size_t n)
     if (!h->cfg.allow_n) return fail(h, DGE_ERR_STATE, "dge_set_n_strings needs dge_config.allow_n = 1");
     return guarded(h, [&] {
         const size_t len = which == 0 ? h->cfg.umi_len : h->cfg.cb_len;
-        std::string &dst = which == 0 ? h->n_umi_strings : h->n_cb_strings;
-        dst.assign(strings ? strings : "", n * len);
-        for (char c : dst)
+        std::string all(strings ? strings : "", n * len);
+        for (char c : all)
             if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') throw InvalidInput("N-string lists hold A, C, G, T, N only");
+        if (which == 0) h->n_umi_strings = all;
+        else
+        {
+            h->n_cb_list.clear();
+            for (size_t k = 0; k < n; ++k) h->n_cb_list.push_back(all.substr(k * len, len));
+        }
+        return int(DGE_OK);
+    });
+}
+
+// The DGE_FLAG_CB_N list with strings of ANY length: barcodes whose length differs from dge_config.cb_len (variable-length inDrop v1 / v2
+// barcodes, InDropBarcodesParser.cpp:31-38) travel like barcodes with N -- as a cell of their own, identified by the list index on the
+// device, by their string wherever the reference looks at the string (whitelist walk, compare_cells ties, output).
+int dge_set_cb_strings(dge_handle *h, const char *strings, const uint32_t *lengths, size_t n)
+{
+    if (!h || (n && (!strings || !lengths))) return fail(h, DGE_ERR_INVALID, "bad argument");
+    if (!h->cfg.allow_n) return fail(h, DGE_ERR_STATE, "dge_set_cb_strings needs dge_config.allow_n = 1");
+    return guarded(h, [&] {
+        std::vector<std::string> list;
+        size_t off = 0;
+        for (size_t k = 0; k < n; ++k)
+        {
+            std::string s(strings + off, lengths[k]);
+            off += lengths[k];
+            if (s.empty()) throw InvalidInput("empty barcode in the escaped-barcode list");
+            for (char c : s)
+                if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') throw InvalidInput("barcode lists hold A, C, G, T, N only");
+            list.push_back(std::move(s));
+        }
+        h->n_cb_list.swap(list);
         return int(DGE_OK);
     });
 }

@@ -407,8 +407,9 @@ namespace Estimation
 		for (auto const &v : _n_umis.values()) blob += v;
 		check(dge_set_n_strings(_h, 0, blob.c_str(), _n_umis.values().size()));
 		blob.clear();
-		for (auto const &v : _n_cbs.values()) blob += v;
-		check(dge_set_n_strings(_h, 1, blob.c_str(), _n_cbs.values().size()));
+		std::vector<uint32_t> lengths;
+		for (auto const &v : _n_cbs.values()) { blob += v; lengths.push_back(uint32_t(v.size())); }
+		check(dge_set_cb_strings(_h, blob.c_str(), lengths.data(), lengths.size())); // any length: barcodes with N and variable-length barcodes
 		_n_dirty = false;
 	}
 
@@ -452,12 +453,16 @@ namespace Estimation
 			if (_cb_len > 20 || _umi_len > 12) throw std::runtime_error("barcode/UMI too long for the packed record (20/12 bp)");
 			ensure_handle();
 		}
-		if (cb.size() != _cb_len || umi.size() != _umi_len)
-		{   // the packed record has one barcode / UMI length per run (the first read's); reads of another length (variable-length inDrop v1/2
-			// barcodes) are counted and skipped, not fatal -- the skipped read keeps its stream position like a skipped N read
+		// The packed record has one barcode / UMI length per run (the first read's).  A barcode of another length (variable-length inDrop v1 / v2
+		// barcodes) travels like a barcode with N: through the escaped-barcode list, as a cell of its own (dge_set_cb_strings).  A UMI of another
+		// length -- or such a barcode under a strategy that cannot take escaped barcodes -- is counted and skipped, not fatal; the skipped read
+		// keeps its stream position like a skipped N read.
+		const bool odd_cb = cb.size() != _cb_len;
+		if (umi.size() != _umi_len || (odd_cb && (!_allow_n_cb || cb.empty() || cb.size() > 64)))
+		{
 			if (_skipped_length_reads++ == 0)
-				std::cerr << "dropest_b200: reads whose barcode / UMI length differs from the first read's (" << _cb_len << " / " << _umi_len
-				          << ") are skipped; skipped_length_reads() reports how many\n";
+				std::cerr << "dropest_b200: reads whose UMI length differs from the first read's (" << _umi_len << "), or whose barcode length does (" << _cb_len
+				          << ") under a strategy that cannot take such barcodes, are skipped; skipped_length_reads() reports how many\n";
 			++_n_records;
 			_batch_gaps = true;
 			return;
@@ -475,7 +480,7 @@ namespace Estimation
 			_batch_gaps = true;
 			return;
 		}
-		if (!pack2bit(cb, cbv))
+		if (odd_cb || !pack2bit(cb, cbv))
 		{
 			if (cb.find_first_not_of("ACGTN") != std::string::npos) throw std::runtime_error("unexpected character in the cell barcode: " + cb);
 			cbv = _n_cbs.add(cb); flags |= DGE_FLAG_CB_N; _n_dirty = true;

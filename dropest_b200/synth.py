@@ -250,8 +250,8 @@ class NLists:
         return self._c[s]
 
     def pack_cb(self, s: str) -> int:
-        """barcode string -> what dge_cell_info.barcode reports"""
-        return (CB_N_BIT | self._c[s]) if "N" in s else pack_seq(s)
+        """barcode string -> what dge_cell_info.barcode reports (escaped barcodes -- with N, or of another length -- report their list index)"""
+        return (CB_N_BIT | self._c[s]) if s in self._c else pack_seq(s)
 
     def pack_umi(self, s: str) -> int:
         """UMI string -> what dge_get_umigs reports"""
@@ -278,6 +278,27 @@ def inject_n(recs: np.ndarray, cb_len: int, umi_len: int, umi_ppm: int, cb_ppm: 
         c = list(unpack_seq(int(recs["key"][i]) >> 24, cb_len))
         c[int(rng.integers(0, cb_len))] = "N"
         idx = lists.cb_index("".join(c))
+        out["key"][i] = (idx << 24) | (int(out["key"][i]) & 0xFFFFFF)
+        out["gene"][i] = int(out["gene"][i]) | FLAG_CB_N
+    return out, lists
+
+
+def inject_odd_length_barcodes(recs: np.ndarray, cb_len: int, fraction: float, lists: "Optional[NLists]" = None, seed: int = 1):
+    """Variable-length barcodes (inDrop v1 / v2): a random subset of the BARCODES (all reads of the barcode alike) loses its first base or gains
+    one in front; those reads are re-encoded as indices into the escaped-barcode list (DGE_FLAG_CB_N), like barcodes with N."""
+    rng = np.random.default_rng(seed)
+    out = recs.copy()
+    lists = lists if lists is not None else NLists()
+    cbs = (recs["key"] >> np.uint64(24)).astype(np.uint64)
+    plain = (recs["gene"] & np.uint32(FLAG_CB_N)) == 0
+    uniq = np.unique(cbs[plain])
+    chosen = uniq[rng.random(uniq.shape[0]) < fraction]
+    new_of = {}
+    for v in chosen:
+        s = unpack_seq(int(v), cb_len)
+        new_of[int(v)] = s[1:] if rng.random() < 0.5 else "ACGT"[int(rng.integers(0, 4))] + s
+    for i in np.flatnonzero(plain & np.isin(cbs, chosen)):
+        idx = lists.cb_index(new_of[int(cbs[i])])
         out["key"][i] = (idx << 24) | (int(out["key"][i]) & 0xFFFFFF)
         out["gene"][i] = int(out["gene"][i]) | FLAG_CB_N
     return out, lists

@@ -227,6 +227,12 @@ int dge_reset(dge_handle *h);
  * walk of barcodes containing N): call any time before dge_merge_and_filter. */
 int dge_set_n_strings(dge_handle *h, int which, const char *strings, size_t n);
 
+/* The DGE_FLAG_CB_N list with strings of ANY length (concatenated, lengths[k] characters each; replaces the list): barcodes whose length
+ * differs from dge_config.cb_len -- variable-length inDrop v1 / v2 barcodes, InDropBarcodesParser.cpp:31-38 -- travel like barcodes with
+ * N: a cell of their own, identified by the list index on the device and by the string wherever the reference looks at the string
+ * (whitelist walk, compare_cells ties, output).  Same restrictions as barcodes with N (merge none / whitelist merge, one GPU). */
+int dge_set_cb_strings(dge_handle *h, const char *strings, const uint32_t *lengths, size_t n);
+
 /* Optional: run on this CUDA stream (a cudaStream_t passed as void*); default is a stream owned by the handle. */
 int dge_set_stream(dge_handle *h, void *cuda_stream);
 

@@ -177,18 +177,23 @@ int main(int argc, char **argv)
 				CHECK_EQUAL(container.umi_indexer().get_value(umi.first).find('N'), std::string::npos);
 		}
 
-		// reads whose barcode / UMI length differs from the run's are counted and skipped (never fatal), and keep their stream position
+		// variable-length barcodes (inDrop v1 / v2) are cells of their own, like barcodes with N; a UMI of another length is counted and skipped
+		// (never fatal) and keeps its stream position
 		{
 			CellsDataContainer container(real_cb_strat, umi_merge_strat, any_mark);
 			container.add_record(read_info("AAATTAGGTCCA", "AAACCT", "Gene1"));
-			container.add_record(read_info("AAATTAGGTCC", "AAACCT", "Gene1"));    // 11-base barcode
-			container.add_record(read_info("CCCTTAGGTCCA", "AAACC", "Gene2"));    // 5-base UMI
+			container.add_record(read_info("AAATTAGGTCC", "AAACCT", "Gene1"));    // 11-base barcode: kept
+			container.add_record(read_info("CCCTTAGGTCCA", "AAACC", "Gene2"));    // 5-base UMI: skipped
 			container.add_record(read_info("CCCTTAGGTCCA", "AAACCT", "Gene2"));
+			container.add_record(read_info("AAATTAGGTCC", "AAACCG", "Gene1"));
 			container.set_initialized();
-			CHECK_EQUAL(container.skipped_length_reads(), uint64_t(2));
-			CHECK_EQUAL(container.total_cells_number(), size_t(2));
-			CHECK_EQUAL(container.cell(1).barcode(), std::string("CCCTTAGGTCCA"));
-			CHECK_EQUAL(container.cell(1).at("Gene2").at("AAACCT").read_count(), size_t(1));
+			CHECK_EQUAL(container.skipped_length_reads(), uint64_t(1));
+			CHECK_EQUAL(container.total_cells_number(), size_t(3));
+			CHECK_EQUAL(container.cell(1).barcode(), std::string("AAATTAGGTCC"));
+			CHECK_EQUAL(container.cell(1).at("Gene1").size(), size_t(2));
+			CHECK_EQUAL(container.cell(2).barcode(), std::string("CCCTTAGGTCCA"));
+			CHECK_EQUAL(container.cell(2).at("Gene2").at("AAACCT").read_count(), size_t(1));
+			CHECK_EQUAL(container.cell_id_by_cb("AAATTAGGTCC"), size_t(1));
 		}
 
 		// -u with an N read: the library would refuse the run at merge_and_filter; the mirror skips and counts the read instead

@@ -55,6 +55,44 @@ def test_n_barcodes_are_cells_of_their_own_and_merge_through_the_whitelist_walk(
     assert np.any(is_n & ((allc["flags"] & 2) != 0)), "no barcode with N was merged: the test does not exercise the host walk"
 
 
+@pytest.mark.parametrize("wl,btype", [(pu.WL_SYNTH_8_8, "indrop"), (pu.WL_SYNTH_7_9, "const")])
+@pytest.mark.parametrize("merge", ["none", "real"])
+def test_variable_length_barcodes_travel_as_escaped_cells(merge, wl, btype):
+    """inDrop v1 / v2: barcodes of several lengths in one run (a9).  A quarter of the barcodes lose or gain a base; they are cells of their
+    own (dge_set_cb_strings), and with a whitelist their merge runs through the exact host walk on the strings (InDropBarcodesParser's
+    split takes the last len(part 2) characters, ConstLengthBarcodesParser fixed offsets) -- against the compiled reference."""
+    from dropest_b200.synth import inject_odd_length_barcodes
+
+    if not oracle_io.available("reference"):
+        pytest.skip("oracle/_ref (compiled reference) is not built")
+    parts = read_whitelist(wl, indrop=btype == "indrop")
+    spec = SynthSpec(n_reads=60000, n_cells=25, n_genes=80, cb_len=16, umi_len=10, whitelist_parts=parts, cb_error_ppm=40000, seed=61)
+    recs = SynthTables(spec).generate_host(0, spec.n_reads)
+    recs, lists = inject_n(recs, 16, 10, 3000, 3000, seed=5)
+    recs, lists = inject_odd_length_barcodes(recs, 16, 0.25, lists, seed=6)
+    case = pu.Case(name="varlen", recs=recs, cb_len=16, umi_len=10, n_genes=80, merge=merge, barcodes=wl if merge == "real" else None, barcodes_type=btype,
+                   min_genes_before=3, min_genes_after=6, n_lists=lists)
+    if merge == "real" and btype == "const":
+        # ConstLengthBarcodesParser::split_barcode (.cpp:34-48) refuses a barcode of another length: the reference run fails, and so does ours,
+        # with the same message
+        with pytest.raises(RuntimeError, match="oracle failed"):
+            pu.run_case(case, kind="reference")
+        with pytest.raises(dg.DgeError, match="has wrong length \\(16 expected\\)"):
+            pu.gpu_run(case, recs)
+        return
+    res = pu.run_case(case, kind="reference")
+    pu.assert_parity(res)
+    lens = {len(s) for s in lists.cbs}
+    assert {15, 16, 17} <= lens
+    allc = res["gpu"]["all"]
+    esc = (allc["barcode"] & np.uint64(dg.CB_N_BIT)) != 0
+    assert esc.sum() > 100
+    if merge == "real":
+        assert np.any(esc & ((allc["flags"] & 2) != 0)), "no variable-length barcode was merged"
+    else:
+        assert np.any(esc & ((allc["flags"] & 1) != 0)), "no variable-length barcode is a real cell"
+
+
 def test_flagged_records_need_allow_n():
     recs = np.zeros(1, dtype=dg.RECORD_DTYPE)
     recs["key"] = [(0x1234 << 24) | 3]
