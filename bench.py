@@ -671,3 +671,10 @@ def main():
 
 if __name__ == "__main__":
     main()
+    try:  # leave the process group cleanly (all ranks reach this point: rank 0 prints, the others return from main)
+        import torch.distributed as _dist
+
+        if _dist.is_available() and _dist.is_initialized():
+            _dist.destroy_process_group()
+    except Exception:
+        pass
