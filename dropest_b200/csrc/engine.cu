@@ -2044,6 +2044,93 @@ void umi_directional_replay(const dge_handle *h, std::vector<UmiItem> &items, st
     }
 }
 
+// A (cell, gene) segment that holds UMIs with N under MergeUMIsStrategyDirectional: the reference's own sequence of operations, literally,
+// on the strings (MergeUMIsStrategyDirectional.cpp:57-116: std::sort by reads, find_target with the N rules -- a source with N only stops at
+// distance 0 and, without any target, is renamed by fix_n_umi_with_random, i.e. the process-wide rand() --, one hop of path compression
+// through the unordered_map; Cell::merge_umis / Gene::merge, Cell.cpp:31-42, Gene.cpp:38-58: the map is walked in ITS order, a target that
+// does not exist is created, TOTAL_UMIS_PER_CB drops by one per entry).  Returns the segment's final content as (UMI code, count | mark) and
+// the number of applied entries.  `items` come with the first-seen read index of their UMI, which orders the UMI ids of the reference.
+void umi_directional_literal(const dge_handle *h, std::vector<UmiItem> &items, const std::unordered_map<std::string, uint32_t> &n_index,
+                             std::vector<std::pair<uint32_t, uint32_t>> &final_entries, uint32_t &n_applied)
+{
+    struct Wrap { std::string sequence; size_t n_reads; };
+    const unsigned max_ed = h->cfg.max_umi_merge_edit_distance;
+    const double mult = h->cfg.umi_merge_mult;
+    std::sort(items.begin(), items.end(), [](const UmiItem &a, const UmiItem &b) { return a.first < b.first; }); // Gene::umis(): map over UMI ids
+    std::map<std::string, std::pair<uint32_t, uint32_t>> content; // sequence -> (reads, mark)
+    std::vector<Wrap> umis;
+    for (auto const &it : items)
+    {
+        const std::string seq = umi_string(h, it.umi);
+        umis.push_back(Wrap{seq, size_t(it.reads & VAL_COUNT_MASK)});
+        content.emplace(seq, std::make_pair(it.reads & VAL_COUNT_MASK, it.reads >> VAL_MARK_SHIFT));
+    }
+    std::sort(umis.begin(), umis.end(), [](const Wrap &u1, const Wrap &u2) { return u1.n_reads < u2.n_reads; }); // the same call as the reference
+    std::unordered_map<std::string, std::string> merge_targets;
+    for (size_t src = 0; src < umis.size(); ++src)
+    {
+        const bool has_ns = umis[src].sequence.find('N') != std::string::npos;
+        std::string target;
+        unsigned min_ed = std::numeric_limits<unsigned>::max();
+        for (long dst = long(umis.size()) - 1; dst > long(src); --dst)
+        {
+            if (double(umis[src].n_reads) * mult > double(umis[size_t(dst)].n_reads)) break;
+            const unsigned ed = edit_distance_ref(umis[src].sequence.c_str(), umis[size_t(dst)].sequence.c_str(), true, max_ed);
+            if (ed > max_ed) continue;
+            if (ed < min_ed)
+            {
+                target = umis[size_t(dst)].sequence;
+                if ((!has_ns && ed <= 1) || ed == 0) break;
+                min_ed = ed;
+            }
+        }
+        if (has_ns && target.empty())
+        {   // MergeUMIsStrategyAbstract::fix_n_umi_with_random
+            target = umis[src].sequence;
+            for (char &c : target) if (c == 'N') c = "ACGT"[size_t(rand()) % 4];
+        }
+        if (!target.empty()) merge_targets[umis[src].sequence] = target;
+    }
+    for (long i = long(umis.size()) - 1; i >= 0; --i)
+    {
+        auto d = merge_targets.find(umis[size_t(i)].sequence);
+        if (d == merge_targets.end()) continue;
+        d = merge_targets.find(d->second);
+        if (d == merge_targets.end()) continue;
+        merge_targets[umis[size_t(i)].sequence] = d->second;
+    }
+    n_applied = 0;
+    for (auto const &t : merge_targets)
+    {
+        if (t.second == t.first) continue;
+        auto s = content.find(t.first);
+        if (s == content.end()) throw std::runtime_error("Source UMI doesn't belong to the gene: " + t.first); // Gene.cpp:45
+        auto ins = content.emplace(t.second, s->second);
+        if (!ins.second) { ins.first->second.first += s->second.first; ins.first->second.second |= s->second.second; }
+        content.erase(s);
+        ++n_applied;
+    }
+    final_entries.clear();
+    for (auto const &c : content)
+    {
+        uint32_t code;
+        if (c.first.find('N') != std::string::npos)
+        {
+            auto it = n_index.find(c.first);
+            if (it == n_index.end()) throw std::runtime_error("internal: a UMI with N that is not in the N-UMI list survived the directional merge");
+            code = (1u << (h->kl.ub - 1)) | it->second;
+        }
+        else
+        {
+            uint64_t packed = 0;
+            pack_seq(c.first, packed);
+            code = uint32_t(packed);
+        }
+        if (c.second.first > VAL_COUNT_MASK) throw std::runtime_error("UMI read count beyond the packed value");
+        final_entries.emplace_back(code, c.second.first | (c.second.second << VAL_MARK_SHIFT));
+    }
+}
+
 // MergeUMIsStrategyDirectional::merge over every (real cell, gene) segment.  Returns true when U changed.
 bool umi_merge_directional(dge_handle *h)
 {
@@ -2068,7 +2155,7 @@ bool umi_merge_directional(dge_handle *h)
     h->umi_pc_dec.reserve((size_t(n_pc) + 2) * 4);
     DGE_CUDA(cudaMemsetAsync(h->umi_ctr.p, 0, 32, st));
     DGE_CUDA(cudaMemsetAsync(h->umi_pc_dec.p, 0, (size_t(n_pc) + 2) * 4, st));
-    UmiDirParams p{h->kl.ub, int(h->cfg.umi_len), h->cfg.max_umi_merge_edit_distance, h->cfg.umi_merge_mult};
+    UmiDirParams p{h->kl.ub, int(h->cfg.umi_len), h->cfg.max_umi_merge_edit_distance, h->cfg.umi_merge_mult, h->kl.ne ? h->kl.ub - 1 : -1};
     UmiDirOut o{};
     o.big_list = h->umi_lists.as<uint32_t>(); o.big_cap = list_cap;
     o.host_list = h->umi_lists.as<uint32_t>() + list_cap; o.host_cap = list_cap;
@@ -2094,6 +2181,8 @@ bool umi_merge_directional(dge_handle *h)
     }
     const uint32_t n_host = d2h_scalar<uint32_t>(o.host_count, st);
     std::vector<uint32_t> host_dec_pc, host_dec_n;
+    std::vector<uint32_t> dir_kill, dir_new_vals; // N segments: every old entry is dropped, the final content comes back as new keys
+    std::vector<uint64_t> dir_new_keys;
     if (n_host)
     {   // exact replay of the segments whose outcome depends on how std::sort ordered equal read counts
         h->n_umi_segments_replayed = n_host;
@@ -2103,8 +2192,15 @@ bool umi_merge_directional(dge_handle *h)
         DGE_CUDA(cudaMemsetAsync(seg_n + n_host, 0, 4, st));
         const uint32_t *tot = device_exclusive_scan(seg_n, seg_off, size_t(n_host) + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
         (void)tot;
-        std::vector<uint32_t> hs_start, hs_off, hs_pc;
+        std::vector<uint32_t> hs_start, hs_off, hs_pc, hs_gene;
         d2h(hs_start, seg_start, n_host, st); d2h(hs_off, seg_off, size_t(n_host) + 1, st); d2h(hs_pc, seg_pc, n_host, st);
+        if (h->kl.ne)
+        {   // gene of every deferred segment: the N segments are replayed in the reference's traversal order and get new keys
+            h->misc.reserve(size_t(n_host + 1) * 4);
+            k_gather_u32<<<grid_for(n_host, 256), 256, 0, st>>>(h->cg_gene.as<uint32_t>(), o.host_list, n_host, h->misc.as<uint32_t>());
+            ++h->launches;
+            d2h(hs_gene, h->misc.as<uint32_t>(), n_host, st);
+        }
         DGE_CUDA(cudaStreamSynchronize(st));
         const size_t flat = hs_off[n_host];
         h->umi_flat.reserve(std::max<size_t>(flat, 1) * 3 * 4);
@@ -2119,9 +2215,11 @@ bool umi_merge_directional(dge_handle *h)
         std::vector<UmiItem> items;
         std::vector<uint32_t> root;
         uint64_t merged_host = 0;
+        std::vector<uint32_t> n_segments; // deferred segments that hold a UMI with N (they sort last: look at the last entry)
         for (uint32_t k = 0; k < n_host; ++k)
         {
             const uint32_t off = hs_off[k], n = hs_off[k + 1] - off;
+            if (h->kl.ne && n && umi_is_n(h, hf[off + n - 1])) { n_segments.push_back(k); continue; }
             items.resize(n);
             for (uint32_t i = 0; i < n; ++i) items[i] = UmiItem{hf[off + i], hf[flat + off + i] & VAL_COUNT_MASK, hf[2 * flat + off + i], i};
             umi_directional_replay(h, items, root);
@@ -2139,6 +2237,47 @@ bool umi_merge_directional(dge_handle *h)
             DGE_LAUNCH_CHECK();
             h->launches += 2;
             DGE_CUDA(cudaStreamSynchronize(st));
+        }
+        if (!n_segments.empty())
+        {   // literal replay, in the order in which the reference walks cells and genes (that order decides who gets which random number)
+            std::vector<uint32_t> pc_to_real(size_t(n_pc) + 2, NONE32);
+            for (uint32_t i = 0; i < h->real.size(); ++i) if (h->real[i].pc != NONE32) pc_to_real[h->real[i].pc] = i;
+            std::vector<uint32_t> gene_rank(h->cfg.n_genes, NONE32);
+            for (size_t r = 0; r < h->gene_order.size(); ++r) gene_rank[size_t(h->gene_order[r])] = uint32_t(r);
+            std::sort(n_segments.begin(), n_segments.end(), [&](uint32_t a, uint32_t b) {
+                const uint32_t ca = pc_to_real[hs_pc[a]], cb = pc_to_real[hs_pc[b]];
+                return ca != cb ? ca < cb : gene_rank[hs_gene[a]] < gene_rank[hs_gene[b]];
+            });
+            std::unordered_map<std::string, uint32_t> n_index;
+            for (size_t k = 0; (k + 1) * h->cfg.umi_len <= h->n_umi_strings.size(); ++k) n_index.emplace(h->n_umi_strings.substr(k * h->cfg.umi_len, h->cfg.umi_len), uint32_t(k));
+            srand(1); // the reference never seeds rand() on this path (only MergeUMIsStrategySimple's constructor does): the C default
+            std::vector<std::pair<uint32_t, uint32_t>> final_entries;
+            for (uint32_t k : n_segments)
+            {
+                const uint32_t off = hs_off[k], n = hs_off[k + 1] - off;
+                items.resize(n);
+                for (uint32_t i = 0; i < n; ++i) items[i] = UmiItem{hf[off + i], hf[flat + off + i], hf[2 * flat + off + i], i};
+                uint32_t applied = 0;
+                umi_directional_literal(h, items, n_index, final_entries, applied);
+                if (!applied) continue;
+                const HostCell &cell = h->real[pc_to_real[hs_pc[k]]];
+                for (uint32_t i = 0; i < n; ++i) dir_kill.push_back(hs_start[k] + i); // the segment is rewritten as a whole
+                for (auto const &fe : final_entries)
+                {
+                    dir_new_keys.push_back(((((uint64_t(cell.slot) << h->kl.gb) | hs_gene[k]) << h->kl.ub) | fe.first) << 3);
+                    dir_new_vals.push_back(fe.second);
+                }
+                host_dec_pc.push_back(hs_pc[k]); host_dec_n.push_back(applied); merged_host += applied;
+            }
+            if (!dir_kill.empty())
+            {
+                h->misc.reserve(dir_kill.size() * 4);
+                DGE_CUDA(cudaMemcpyAsync(h->misc.p, dir_kill.data(), dir_kill.size() * 4, cudaMemcpyHostToDevice, st));
+                k_zero_list<<<grid_for(dir_kill.size(), 256), 256, 0, st>>>(h->misc.as<uint32_t>(), uint32_t(dir_kill.size()), h->uval.as<uint32_t>());
+                DGE_LAUNCH_CHECK();
+                ++h->launches;
+                DGE_CUDA(cudaStreamSynchronize(st));
+            }
         }
         h->n_umis_merged += merged_host;
     }
@@ -2168,6 +2307,16 @@ bool umi_merge_directional(dge_handle *h)
     std::swap(h->uval.p, h->uval2.p); std::swap(h->uval.bytes, h->uval2.bytes);
     h->n_u = n_live;
     build_segments(h);
+    if (!dir_new_keys.empty())
+    {
+        build_slot_pc(h);
+        const uint64_t total = dir_new_keys.size();
+        h->mkeys.reserve(total * 8); h->mvals.reserve(total * 4);
+        DGE_CUDA(cudaMemcpyAsync(h->mkeys.p, dir_new_keys.data(), total * 8, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(cudaMemcpyAsync(h->mvals.p, dir_new_vals.data(), total * 4, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(cudaStreamSynchronize(st));
+        apply_moved(h, total);
+    }
     return true;
 }
 
@@ -2458,7 +2607,6 @@ void do_merge_and_filter(dge_handle *h)
     if (h->counters.n_flagged)
     {
         if (h->cfg.sharded) throw std::runtime_error("barcodes / UMIs with N are not supported on sharded (multi-GPU) handles yet");
-        if (h->cfg.umi_merge_type == DGE_UMI_MERGE_DIRECTIONAL) throw std::runtime_error("UMIs / barcodes with N are not supported with the directional UMI merge (-u) yet");
     }
     const bool dev_flow = !no_dev_flow && h->lazy_rows && !h->cfg.sharded && !h->dist_done && h->n_real_rows > 0 && !h->counters.n_flagged &&
                           (h->cfg.merge_type == DGE_MERGE_NONE || (h->cfg.merge_type == DGE_MERGE_REAL && h->wl_fast)) &&

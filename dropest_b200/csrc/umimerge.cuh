@@ -23,6 +23,7 @@ struct UmiDirParams
     int len;         // bases
     unsigned max_ed; // MergeUMIsStrategyDirectional::_max_edit_distance
     double mult;     // _mult
+    int n_bit;       // bit of the UMI field that marks an index into the N-UMI list (allow_n), -1 = no such UMIs
 };
 
 constexpr int UMI_WARP_CAP = 128;   // UMIs per segment handled by one warp
@@ -173,6 +174,14 @@ __global__ void __launch_bounds__(256) k_umi_dir_warp(const uint64_t *__restrict
             s = cg_start[cg];
             n = cg_start[cg + 1] - s;
             pc = cg_pc[cg];
+            // UMIs with N sort last in their segment (the marker bit is the top bit of the UMI field): such a segment -- even a single
+            // N-UMI, which the reference renames with random bases -- is decided on the host, where the strings and rand() are
+            if (p.n_bit >= 0 && n >= 1 && pc_real[pc] && ((uint32_t(ukey[s + n - 1]) >> p.n_bit) & 1u))
+            {
+                const uint32_t at = atomicAdd(o.host_count, 1u);
+                if (at < o.host_cap) o.host_list[at] = cg;
+                n = 0;
+            }
             if (n < 2 || !pc_real[pc]) n = 0;
         }
         unsigned todo = __ballot_sync(0xFFFFFFFFu, n >= 2);

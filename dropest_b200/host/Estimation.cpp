@@ -387,11 +387,9 @@ namespace Estimation
 			const unsigned ub_n = std::max(2 * cfg.umi_len, 20u) + 1;
 			_allow_n = 61 >= gb + ub_n + 22;
 		}
-		// What the library refuses (explicit errors at merge_and_filter, never a silent difference): any N read with MergeUMIsStrategyDirectional
-		// (its random repair draws from the process-wide rand() stream in an order the device path does not replay yet), and a REAL cell whose
-		// barcode contains N with the strategies that compare barcodes on the device.  Rather than losing the whole run, the reads concerned
-		// are skipped and counted here, with a warning: all N reads under -u, N-barcode reads under the no-whitelist / Poisson strategies.
-		if (cfg.umi_merge_type == DGE_UMI_MERGE_DIRECTIONAL) _allow_n = false;
+		// What the library refuses (an explicit error at merge_and_filter, never a silent difference): a REAL cell whose barcode is escaped (N,
+		// or another length) with the strategies that compare barcodes on the device.  Rather than losing the whole run, reads with such
+		// barcodes are skipped and counted here, with a warning, under the no-whitelist / Poisson strategies.
 		_allow_n_cb = _allow_n && (cfg.merge_type == DGE_MERGE_NONE || cfg.merge_type == DGE_MERGE_REAL);
 		cfg.allow_n = _allow_n ? 1 : 0;
 		int rc = dge_create(&cfg, &_h);
@@ -474,8 +472,8 @@ namespace Estimation
 		if ((!_allow_n && umi.find('N') != std::string::npos) || (!_allow_n_cb && cb.find('N') != std::string::npos))
 		{
 			if (_skipped_n_reads++ == 0)
-				std::cerr << "dropest_b200: reads whose barcode / UMI contains N are skipped (directional UMI merge, a no-whitelist barcode merge, or no room "
-				             "for the N flag in the grouping key); skipped_n_reads() reports how many\n";
+				std::cerr << "dropest_b200: reads whose barcode contains N (no-whitelist / Poisson barcode merge) or whose barcode / UMI contains N (no room "
+				             "for the N flag in the grouping key) are skipped; skipped_n_reads() reports how many\n";
 			++_n_records;   // the skipped read keeps its position in the stream: the pending batch now has a gap (flush sends explicit read indices)
 			_batch_gaps = true;
 			return;

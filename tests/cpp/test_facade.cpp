@@ -196,18 +196,22 @@ int main(int argc, char **argv)
 			CHECK_EQUAL(container.cell_id_by_cb("AAATTAGGTCC"), size_t(1));
 		}
 
-		// -u with an N read: the library would refuse the run at merge_and_filter; the mirror skips and counts the read instead
+		// -u with an N read (MergeUMIsStrategyDirectional.cpp:57-116): the N-UMI matches AAACCT at distance 0 (N is a wildcard) and merges into it
 		{
 			auto directional = std::make_shared<Merge::UMIs::MergeUMIsStrategyDirectional>(2, 1);
 			CellsDataContainer container(real_cb_strat, directional, any_mark);
 			container.add_record(read_info("AAATTAGGTCCA", "AAACCT", "Gene1"));
 			container.add_record(read_info("AAATTAGGTCCA", "AAACNT", "Gene1"));
 			container.add_record(read_info("AAATTAGGTCCA", "AAACCT", "Gene1"));
+			container.add_record(read_info("AAATTAGGTCCA", "TTNTTT", "Gene2"));   // alone in its gene: renamed with random bases
 			container.set_initialized();
 			container.merge_and_filter();
-			CHECK_EQUAL(container.skipped_n_reads(), uint64_t(1));
+			CHECK_EQUAL(container.skipped_n_reads(), uint64_t(0));
 			CHECK_EQUAL(container.cell(0).at("Gene1").size(), size_t(1));
-			CHECK_EQUAL(container.cell(0).at("Gene1").at("AAACCT").read_count(), size_t(2));
+			CHECK_EQUAL(container.cell(0).at("Gene1").at("AAACCT").read_count(), size_t(3));
+			CHECK_EQUAL(container.cell(0).at("Gene2").size(), size_t(1));
+			for (auto const &umi : container.cell(0).at("Gene2").umis())
+				CHECK_EQUAL(container.umi_indexer().get_value(umi.first).find('N'), std::string::npos);
 		}
 
 		// -M: MergeStrategyFactory::get_cb_poisson_strat (MergeStrategyFactory.cpp:91-103) + PoissonSimpleMergeStrategy through the container.

@@ -41,6 +41,21 @@ def test_n_umis_are_repaired_like_the_reference(merge, umi_len, n_genes, max_umi
     assert not np.any((u["umi"][np.isin(u["cell"], real_cells)] & dg.UMI_N_BIT) != 0), "an N-UMI survived in a real cell"
 
 
+@pytest.mark.parametrize("merge", ["none", "real"])
+@pytest.mark.parametrize("umi_len,n_genes,max_umi_ed,reads_per_umi", [(10, 120, 1, 3), (5, 15, 1, 6), (6, 30, 2, 5), (8, 25, 1, 8)])
+def test_n_umis_under_the_directional_umi_merge(merge, umi_len, n_genes, max_umi_ed, reads_per_umi):
+    """-u with N-UMIs (MergeUMIsStrategyDirectional.cpp:57-116): a source with N only stops at distance 0, and without any target is renamed by
+    fix_n_umi_with_random from the never-seeded rand(); targets travel through the unordered_map's one-hop compression and are applied in the
+    map's order (Cell::merge_umis).  Segments holding an N-UMI are replayed literally on the host, in the reference's traversal order."""
+    if not oracle_io.available("reference"):
+        pytest.skip("oracle/_ref (compiled reference) is not built")
+    case, lists = _case(merge, umi_len, n_genes, 60000, 30, seed=70 + umi_len, umi_ppm=30000, cb_ppm=0, max_umi_ed=max_umi_ed,
+                        umi_merge="directional", reads_per_umi=reads_per_umi)
+    res = pu.run_case(case, kind="reference")
+    pu.assert_parity(res)
+    assert res["gpu"]["summary"]["n_umis_merged"] > 100
+
+
 def test_n_barcodes_are_cells_of_their_own_and_merge_through_the_whitelist_walk():
     """1 % of the reads get an N in the barcode: those barcodes are cells of their own; the ones that become real take the exact host
     enumeration (N matches any base, BarcodesParser.cpp:21-74) and merge into their whitelist neighbour."""
