@@ -45,7 +45,7 @@ EXPORTS = [
     "dge_config_default", "dge_create", "dge_destroy", "dge_last_error", "dge_add_batch", "dge_add_batch_device", "dge_add_batch_segments_device", "dge_add_batch_soa",
     "dge_add_batch_chr", "dge_add_batch_soa_chr", "dge_add_batch_chr_device", "dge_get_chr_stats",
     "dge_set_initialized", "dge_merge_and_filter", "dge_reset", "dge_set_stream", "dge_set_n_strings", "dge_set_cb_strings", "dge_get_summary", "dge_get_timings", "dge_get_cells",
-    "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_edit_distance",
+    "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_get_umi_merge_targets", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
     "dge_route_by_barcode_device", "dge_route_count_slices_device", "dge_route_scatter_slice_device", "dge_dist_step",
     "dge_route_scatter_bounded_device", "dge_peer_alloc", "dge_peer_free", "dge_peer_open", "dge_peer_close",
@@ -68,7 +68,7 @@ class _Config(C.Structure):
         ("min_merge_fraction", C.c_double), ("max_merge_prob", C.c_double), ("max_real_merge_prob", C.c_double),
         ("umi_merge_mult", C.c_double), ("query_mark_mask", C.c_uint32), ("max_cells", C.c_int32),
         ("reads_output", C.c_uint32), ("sharded", C.c_uint32), ("barcodes_file", C.c_char_p),
-        ("max_barcodes_hint", C.c_uint64), ("allow_n", C.c_uint32), ("reserved0", C.c_uint32),
+        ("max_barcodes_hint", C.c_uint64), ("allow_n", C.c_uint32), ("save_umi_merge_targets", C.c_uint32),
     ]
 
 
@@ -138,6 +138,8 @@ def load_library():
     lib.dge_get_matrix.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.dge_get_gene_order.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.dge_get_merge_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.dge_get_umi_merge_targets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.dge_get_umi_merge_targets.restype = C.c_int
     lib.dge_get_umigs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.dge_edit_distance.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint]
     lib.dge_edit_distance.restype = C.c_uint
@@ -220,6 +222,7 @@ class Config:
     max_barcodes_hint: int = 0
     sharded: bool = False
     allow_n: bool = False
+    save_umi_merge_targets: bool = False
     _keep: list = field(default_factory=list, repr=False)
 
     def to_c(self) -> _Config:
@@ -235,6 +238,7 @@ class Config:
         c.reads_output = 1 if self.reads_output else 0
         c.sharded = 1 if self.sharded else 0
         c.allow_n = 1 if self.allow_n else 0
+        c.save_umi_merge_targets = 1 if self.save_umi_merge_targets else 0
         if self.barcodes_file:
             b = self.barcodes_file.encode()
             self._keep.append(b)
@@ -443,6 +447,17 @@ class Container:
         if n.value:
             self._check(self._lib.dge_get_merge_pairs(self._h, a.ctypes.data, b.ctypes.data, n.value, C.byref(n)))
         return a, b
+
+    def umi_merge_targets(self) -> dict:
+        """Gene::merge_targets() of every (cell, gene): rows (cell barcode code, gene, source UMI, target UMI)."""
+        n = C.c_size_t(0)
+        self._check(self._lib.dge_get_umi_merge_targets(self._h, None, None, None, None, 0, C.byref(n)))
+        m = n.value
+        out = {"cb": np.zeros(m, np.uint64), "gene": np.zeros(m, np.int32), "src": np.zeros(m, np.uint32), "dst": np.zeros(m, np.uint32)}
+        if m:
+            self._check(self._lib.dge_get_umi_merge_targets(self._h, out["cb"].ctypes.data, out["gene"].ctypes.data, out["src"].ctypes.data,
+                                                            out["dst"].ctypes.data, m, C.byref(n)))
+        return out
 
     def umigs(self, which: int) -> dict:
         n = C.c_size_t(0)

@@ -145,6 +145,11 @@ struct dge_handle
     DevBuf umi_lists, umi_ctr, umi_pc_dec, umi_seg, umi_flat, umi_pairs;
     PinnedBuf pin_umi;
     uint64_t n_umis_merged = 0, n_umi_segments_replayed = 0;
+    // Gene::_merge_targets (Gene.cpp:54-57, kept when the container is built with save_umi_merge_targets): one row per UMI that the UMI
+    // merge strategy moved into another one, codes as dge_get_umigs reports them
+    struct UmiMergeTarget { uint64_t cb; uint32_t gene, src, dst; };
+    std::vector<UmiMergeTarget> umi_mt;
+    DevBuf u_target, mt_keys, mt_dst;
     DevBuf dist_infos, dist_keys, dist_vals, dist_jobs, dist_cb, dist_umis, dist_eoff;
     std::vector<uint32_t> g_off;
     const uint64_t *g_keys = nullptr;
@@ -292,6 +297,8 @@ std::string cb_string(const dge_handle *h, uint64_t cb)
 }
 
 bool umi_is_n(const dge_handle *h, uint32_t umi) { return h->kl.ne && ((umi >> (h->kl.ub - 1)) & 1u); }
+// internal UMI field -> the code of the query surface (DGE_UMI_N_BIT | index into the N-UMI list)
+uint32_t umi_public_code(const dge_handle *h, uint32_t umi) { return umi_is_n(h, umi) ? (0x80000000u | (umi & ((1u << (h->kl.ub - 1)) - 1))) : umi; }
 
 std::string umi_string(const dge_handle *h, uint32_t umi)
 {
@@ -2051,8 +2058,20 @@ void umi_directional_replay(const dge_handle *h, std::vector<UmiItem> &items, st
 // does not exist is created, TOTAL_UMIS_PER_CB drops by one per entry).  Returns the segment's final content as (UMI code, count | mark) and
 // the number of applied entries.  `items` come with the first-seen read index of their UMI, which orders the UMI ids of the reference.
 void umi_directional_literal(const dge_handle *h, std::vector<UmiItem> &items, const std::unordered_map<std::string, uint32_t> &n_index,
-                             std::vector<std::pair<uint32_t, uint32_t>> &final_entries, uint32_t &n_applied)
+                             std::vector<std::pair<uint32_t, uint32_t>> &final_entries, uint32_t &n_applied,
+                             std::vector<std::pair<uint32_t, uint32_t>> *applied_targets = nullptr)
 {
+    auto code_of = [&](const std::string &seq) -> uint32_t { // internal UMI field of a string
+        if (seq.find('N') != std::string::npos)
+        {
+            auto it = n_index.find(seq);
+            if (it == n_index.end()) throw std::runtime_error("internal: a UMI with N that is not in the N-UMI list survived the directional merge");
+            return (1u << (h->kl.ub - 1)) | it->second;
+        }
+        uint64_t packed = 0;
+        pack_seq(seq, packed);
+        return uint32_t(packed);
+    };
     struct Wrap { std::string sequence; size_t n_reads; };
     const unsigned max_ed = h->cfg.max_umi_merge_edit_distance;
     const double mult = h->cfg.umi_merge_mult;
@@ -2109,23 +2128,12 @@ void umi_directional_literal(const dge_handle *h, std::vector<UmiItem> &items, c
         if (!ins.second) { ins.first->second.first += s->second.first; ins.first->second.second |= s->second.second; }
         content.erase(s);
         ++n_applied;
+        if (applied_targets) applied_targets->emplace_back(code_of(t.first), code_of(t.second)); // _merge_targets[source_umi] = target_umi
     }
     final_entries.clear();
     for (auto const &c : content)
     {
-        uint32_t code;
-        if (c.first.find('N') != std::string::npos)
-        {
-            auto it = n_index.find(c.first);
-            if (it == n_index.end()) throw std::runtime_error("internal: a UMI with N that is not in the N-UMI list survived the directional merge");
-            code = (1u << (h->kl.ub - 1)) | it->second;
-        }
-        else
-        {
-            uint64_t packed = 0;
-            pack_seq(c.first, packed);
-            code = uint32_t(packed);
-        }
+        const uint32_t code = code_of(c.first);
         if (c.second.first > VAL_COUNT_MASK) throw std::runtime_error("UMI read count beyond the packed value");
         final_entries.emplace_back(code, c.second.first | (c.second.second << VAL_MARK_SHIFT));
     }
@@ -2136,6 +2144,8 @@ bool umi_merge_directional(dge_handle *h)
 {
     cudaStream_t st = h->stream;
     h->n_umis_merged = 0; h->n_umi_segments_replayed = 0;
+    h->umi_mt.clear();
+    const bool save_targets = h->cfg.save_umi_merge_targets != 0;
     if (h->n_cg == 0 || h->n_u == 0) return false;
     const uint32_t n_cg = h->n_cg, n_pc = h->n_pc;
     // real flags per present cell
@@ -2162,6 +2172,13 @@ bool umi_merge_directional(dge_handle *h)
     o.big_count = h->umi_ctr.as<uint32_t>(); o.host_count = h->umi_ctr.as<uint32_t>() + 1;
     o.n_merged = reinterpret_cast<unsigned long long *>(h->umi_ctr.as<uint32_t>() + 2);
     o.pc_dec = h->umi_pc_dec.as<uint32_t>();
+    if (save_targets)
+    {
+        h->u_target.reserve((size_t(h->n_u) + 1) * 4);
+        DGE_CUDA(cudaMemsetAsync(h->u_target.p, 0xFF, (size_t(h->n_u) + 1) * 4, st));
+        o.u_target = h->u_target.as<uint32_t>();
+    }
+    size_t n_host_pairs = 0;
     k_umi_dir_warp<<<grid_for(div_up(size_t(n_cg), size_t(32)), 8, 148 * 8), 256, 0, st>>>(h->ukey.as<uint64_t>(), h->uval.as<uint32_t>(), h->cg_start.as<uint32_t>(),
                                                                                           h->cg_pc.as<uint32_t>(), n_cg, h->flags.as<uint32_t>(),
                                                                                           h->umi_first.as<uint32_t>(), p, o);
@@ -2233,10 +2250,11 @@ bool umi_merge_directional(dge_handle *h)
             h->umi_pairs.reserve(pairs.size() * sizeof(uint2));
             DGE_CUDA(cudaMemcpyAsync(h->umi_pairs.p, pairs.data(), pairs.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
             for (int phase = 0; phase < 2; ++phase)
-                k_umi_apply_pairs<<<grid_for(pairs.size(), 256, 1u << 30), 256, 0, st>>>(h->umi_pairs.as<uint2>(), uint32_t(pairs.size()), h->uval.as<uint32_t>(), phase);
+                k_umi_apply_pairs<<<grid_for(pairs.size(), 256, 1u << 30), 256, 0, st>>>(h->umi_pairs.as<uint2>(), uint32_t(pairs.size()), h->uval.as<uint32_t>(), phase, o.u_target);
             DGE_LAUNCH_CHECK();
             h->launches += 2;
             DGE_CUDA(cudaStreamSynchronize(st));
+            n_host_pairs = pairs.size();
         }
         if (!n_segments.empty())
         {   // literal replay, in the order in which the reference walks cells and genes (that order decides who gets which random number)
@@ -2251,16 +2269,19 @@ bool umi_merge_directional(dge_handle *h)
             std::unordered_map<std::string, uint32_t> n_index;
             for (size_t k = 0; (k + 1) * h->cfg.umi_len <= h->n_umi_strings.size(); ++k) n_index.emplace(h->n_umi_strings.substr(k * h->cfg.umi_len, h->cfg.umi_len), uint32_t(k));
             srand(1); // the reference never seeds rand() on this path (only MergeUMIsStrategySimple's constructor does): the C default
-            std::vector<std::pair<uint32_t, uint32_t>> final_entries;
+            std::vector<std::pair<uint32_t, uint32_t>> final_entries, applied_targets;
             for (uint32_t k : n_segments)
             {
                 const uint32_t off = hs_off[k], n = hs_off[k + 1] - off;
                 items.resize(n);
                 for (uint32_t i = 0; i < n; ++i) items[i] = UmiItem{hf[off + i], hf[flat + off + i], hf[2 * flat + off + i], i};
                 uint32_t applied = 0;
-                umi_directional_literal(h, items, n_index, final_entries, applied);
+                applied_targets.clear();
+                umi_directional_literal(h, items, n_index, final_entries, applied, save_targets ? &applied_targets : nullptr);
                 if (!applied) continue;
                 const HostCell &cell = h->real[pc_to_real[hs_pc[k]]];
+                for (auto const &t : applied_targets)
+                    h->umi_mt.push_back(dge_handle::UmiMergeTarget{cell.cb, hs_gene[k], umi_public_code(h, t.first), umi_public_code(h, t.second)});
                 for (uint32_t i = 0; i < n; ++i) dir_kill.push_back(hs_start[k] + i); // the segment is rewritten as a whole
                 for (auto const &fe : final_entries)
                 {
@@ -2284,6 +2305,32 @@ bool umi_merge_directional(dge_handle *h)
     const unsigned long long merged_dev = d2h_scalar<unsigned long long>(o.n_merged, st);
     h->n_umis_merged += merged_dev;
     if (h->n_umis_merged == 0) return false;
+    if (save_targets && merged_dev + n_host_pairs)
+    {   // the (source, root) decisions taken on the device and in the tie replays, before the sources leave U
+        const size_t cap = size_t(merged_dev) + n_host_pairs;
+        h->mt_keys.reserve(cap * 8); h->mt_dst.reserve(cap * 4);
+        uint32_t *cnt = h->umi_ctr.as<uint32_t>() + 4;
+        DGE_CUDA(cudaMemsetAsync(cnt, 0, 4, st));
+        k_umi_targets_collect<<<grid_for(h->n_u, 256), 256, 0, st>>>(h->ukey.as<uint64_t>(), h->u_target.as<uint32_t>(), h->n_u, h->kl.ub, h->mt_keys.as<uint64_t>(),
+                                                                      h->mt_dst.as<uint32_t>(), uint32_t(cap), cnt);
+        DGE_LAUNCH_CHECK();
+        ++h->launches;
+        const uint32_t got = d2h_scalar<uint32_t>(cnt, st);
+        if (got != cap) throw std::runtime_error("internal: UMI merge targets recorded on the device do not add up");
+        std::vector<uint64_t> keys;
+        std::vector<uint32_t> dsts;
+        d2h(keys, h->mt_keys.p, cap, st); d2h(dsts, h->mt_dst.p, cap, st);
+        DGE_CUDA(cudaStreamSynchronize(st));
+        std::unordered_map<uint32_t, uint64_t> slot_cb;
+        for (auto const &c : h->real) if (c.real && c.pc != NONE32) slot_cb.emplace(c.slot, c.cb);
+        const int gub = h->kl.gb + h->kl.ub;
+        const uint32_t umask = h->kl.ub >= 32 ? 0xFFFFFFFFu : ((1u << h->kl.ub) - 1);
+        for (size_t k = 0; k < cap; ++k)
+        {
+            const uint32_t slot = uint32_t(keys[k] >> gub), gene = uint32_t(keys[k] >> h->kl.ub) & ((1u << h->kl.gb) - 1);
+            h->umi_mt.push_back(dge_handle::UmiMergeTarget{slot_cb.at(slot), gene, umi_public_code(h, uint32_t(keys[k]) & umask), umi_public_code(h, dsts[k])});
+        }
+    }
 
     // TOTAL_UMIS_PER_CB decrements (Cell.cpp:39)
     {
@@ -2432,8 +2479,15 @@ bool umi_repair_n(dge_handle *h)
                 kill.push_back(src_u);
                 new_keys.push_back(((((uint64_t(cell.slot) << h->kl.gb) | hs_gene[k]) << h->kl.ub) | packed) << 3);
                 new_vals.push_back(items[src].val);
+                if (h->cfg.save_umi_merge_targets)
+                    h->umi_mt.push_back(dge_handle::UmiMergeTarget{cell.cb, hs_gene[k], umi_public_code(h, items[src].umi), uint32_t(packed)});
             }
-            else pairs.push_back(make_uint2(src_u, hs_start[k] + items[size_t(best)].idx));
+            else
+            {
+                pairs.push_back(make_uint2(src_u, hs_start[k] + items[size_t(best)].idx));
+                if (h->cfg.save_umi_merge_targets)
+                    h->umi_mt.push_back(dge_handle::UmiMergeTarget{cell.cb, hs_gene[k], umi_public_code(h, items[src].umi), umi_public_code(h, items[size_t(best)].umi)});
+            }
             dec_real.push_back(ridx);
         }
     }
@@ -2748,6 +2802,7 @@ void do_merge_and_filter(dge_handle *h)
     else if (h->kl.ne && h->counters.n_flagged)
     {   // MergeUMIsStrategySimple: UMIs with N of the real cells
         h->n_umis_merged = 0;
+        h->umi_mt.clear();
         if (umi_repair_n(h))
         {
             std::vector<uint32_t> owners;
@@ -3240,7 +3295,7 @@ int dge_reset(dge_handle *h)
         for (auto &c : h->chunks) h->chunk_pool.push_back(std::move(c));
         h->chunks.clear();
         h->n_chunk_counters = 0; h->n_fill_ev = 0; h->moves_ready = false; h->n_reads = 0; h->n_keys = 0; h->n_u = h->n_cg = h->n_pc = 0;
-        h->real.clear(); h->filtered.clear(); h->gene_order.clear(); h->merge_events.clear();
+        h->real.clear(); h->filtered.clear(); h->gene_order.clear(); h->merge_events.clear(); h->umi_mt.clear();
         h->n_merged = h->n_excluded = h->n_unresolved = 0; h->total_cells = 0;
         h->cm.built = h->cm_raw.built = false;
         h->host_stage = 0; h->lazy_rows = false; h->dev_merged = false; h->n_real_rows = 0; h->n_filtered_dev = 0;
@@ -3835,6 +3890,27 @@ int dge_get_merge_pairs(dge_handle *h, uint64_t *from, uint64_t *to, size_t capa
         }
     }
     return DGE_OK;
+}
+
+int dge_get_umi_merge_targets(dge_handle *h, uint64_t *cell_barcodes, int32_t *gene_ids, uint32_t *source_umis, uint32_t *target_umis, size_t capacity,
+                              size_t *n_out)
+{
+    if (!h || !n_out) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state != 2) return fail(h, DGE_ERR_STATE, "UMI merge targets exist after merge_and_filter");
+    if (!h->cfg.save_umi_merge_targets) return fail(h, DGE_ERR_STATE, "the handle was created without dge_config.save_umi_merge_targets");
+    return guarded(h, [&] {
+        *n_out = h->umi_mt.size();
+        if (capacity < h->umi_mt.size() || !cell_barcodes || !gene_ids || !source_umis || !target_umis) return int(DGE_OK);
+        std::sort(h->umi_mt.begin(), h->umi_mt.end(), [](const dge_handle::UmiMergeTarget &x, const dge_handle::UmiMergeTarget &y) {
+            return x.cb != y.cb ? x.cb < y.cb : x.gene != y.gene ? x.gene < y.gene : x.src < y.src;
+        });
+        for (size_t k = 0; k < h->umi_mt.size(); ++k)
+        {
+            cell_barcodes[k] = h->umi_mt[k].cb; gene_ids[k] = int32_t(h->umi_mt[k].gene);
+            source_umis[k] = h->umi_mt[k].src; target_umis[k] = h->umi_mt[k].dst;
+        }
+        return int(DGE_OK);
+    });
 }
 
 int dge_get_umigs(dge_handle *h, int which, uint32_t *cell_index, int32_t *gene_ids, uint32_t *umis, uint32_t *read_counts,

@@ -73,6 +73,7 @@ struct UmiDirOut
     uint32_t host_cap;
     uint32_t *pc_dec;                 // merged UMIs per present cell (TOTAL_UMIS_PER_CB decrement)
     unsigned long long *n_merged;
+    uint32_t *u_target;               // optional (save_umi_merge_targets): per U entry, the U index of the root it was merged into
 };
 
 // One group (a warp, or a whole block) resolves one segment held in shared memory.
@@ -142,6 +143,7 @@ __device__ __forceinline__ void umi_dir_segment(uint32_t *s_umi, uint32_t *s_cnt
         const uint32_t v = uval[s + i];
         atomicAdd(&uval[s + r], v & VAL_COUNT_MASK);
         atomicOr(&uval[s + r], v & ~VAL_COUNT_MASK);
+        if (o.u_target) o.u_target[s + i] = s + r;
     }
     sync(); // every read of a source value above happens before it is cleared below (roots are never sources)
     uint32_t m = 0;
@@ -260,7 +262,7 @@ __global__ void k_umi_seg_gather(const uint32_t *__restrict__ seg_start, const u
 }
 
 // (source index, root index) pairs in U decided on the host; two phases so that sources are read before they are cleared
-__global__ void k_umi_apply_pairs(const uint2 *__restrict__ pairs, uint32_t n, uint32_t *uval, int phase)
+__global__ void k_umi_apply_pairs(const uint2 *__restrict__ pairs, uint32_t n, uint32_t *uval, int phase, uint32_t *u_target = nullptr)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -270,8 +272,23 @@ __global__ void k_umi_apply_pairs(const uint2 *__restrict__ pairs, uint32_t n, u
         const uint32_t v = uval[pr.x];
         atomicAdd(&uval[pr.y], v & VAL_COUNT_MASK);
         atomicOr(&uval[pr.y], v & ~VAL_COUNT_MASK);
+        if (u_target) u_target[pr.x] = pr.y;
     }
     else uval[pr.x] = 0;
+}
+
+// Gene::_merge_targets (Gene.cpp:54-57) of the merges decided above: (key of the source entry, UMI of its root), in no particular order
+__global__ void k_umi_targets_collect(const uint64_t *__restrict__ ukey, const uint32_t *__restrict__ u_target, uint32_t n_u, int ub,
+                                      uint64_t *__restrict__ out_key, uint32_t *__restrict__ out_dst, uint32_t cap, uint32_t *__restrict__ count)
+{
+    const uint32_t umask = ub >= 32 ? 0xFFFFFFFFu : ((1u << ub) - 1);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_u; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t t = u_target[i];
+        if (t == NONE32) continue;
+        const uint32_t at = atomicAdd(count, 1u);
+        if (at < cap) { out_key[at] = ukey[i]; out_dst[at] = uint32_t(ukey[t]) & umask; }
+    }
 }
 
 // (cell, gene) segments of real cells that hold a UMI with N: inside a segment U is sorted by the UMI field and N-UMIs carry its top

@@ -1,6 +1,7 @@
 // BamIngest.cpp -- see BamIngest.h.  BGZF: RFC 1952 members with a "BC" extra subfield holding the block size (SAM/BAM specification 4.1);
 // BAM records: specification 4.2.  Nothing here is taken from BamTools.
 #include "BamIngest.h"
+#include "BamOutput.h"
 
 #include <algorithm>
 #include <cstring>
@@ -151,6 +152,7 @@ namespace BamProcessing
 			_pos += 4;
 			if (l_name == 0 || !fill(l_name + 4)) throw std::runtime_error("truncated BAM header in " + _file_name);
 			_refs.emplace_back(reinterpret_cast<const char *>(_data.data() + _pos), l_name - 1);
+			_ref_lengths.push_back(le32(_data.data() + _pos + l_name));
 			_pos += l_name + 4;
 		}
 	}
@@ -163,6 +165,8 @@ namespace BamProcessing
 		if (_data.size() - pos < 4 + block_size) return false;
 		const uint8_t *p = _data.data() + pos + 4, *end = p + block_size;
 		next_pos = pos + 4 + block_size;
+		v.raw = p;
+		v.raw_bytes = block_size;
 		v.al.ref_id = int32_t(le32(p));
 		v.al.position = int32_t(le32(p + 4));
 		const size_t l_read_name = p[8];
@@ -272,6 +276,12 @@ namespace BamProcessing
 			});
 			return hit;
 		}
+	}
+
+	void list_tags(const uint8_t *tag_data, size_t tag_bytes, std::vector<TagSpan> &out)
+	{
+		out.clear();
+		walk_tags(tag_data, tag_bytes, [&](const uint8_t *name, char, const uint8_t *v, size_t len) { out.push_back(TagSpan{name, size_t(v - name) + len}); });
 	}
 
 	bool BamAlignment::TagValue::string(std::string &out) const
@@ -485,11 +495,32 @@ namespace BamProcessing
 		for (auto const &e : errors) if (!e.empty()) throw std::runtime_error(e);
 	}
 
-	void parse_bam_files(const std::vector<std::string> &bam_files, const IngestParams &params, CellsDataContainer &container, IngestStats &stats)
+	void parse_bam_files(const std::vector<std::string> &bam_files, const IngestParams &params, CellsDataContainer &container, IngestStats &stats,
+	                     bool print_result_bams)
 	{
 		if (!params.tags.read_type.empty() && params.tags.intronic_read_value.empty()) // BamTags.cpp:22-23
 			throw std::runtime_error("You have to specify tag values to be able to parse info about read types");
-		for_each_read(bam_files, params, stats, [&](const ReadInfo &ri) { container.add_record(ri); });
+		if (!print_result_bams)
+		{
+			for_each_read(bam_files, params, stats, [&](const ReadInfo &ri) { container.add_record(ri); });
+			return;
+		}
+		// -b: BamProcessor::update_bam opens "<name>.tagged.bam" per input, write_alignment saves every accepted read before save_read
+		// (BamProcessor.cpp:50-72, BamController.cpp:169-171)
+		std::unique_ptr<BamWriter> writer;
+		std::vector<BamWriter::TagEdit> edits;
+		for_each_alignment(bam_files, params, stats, true,
+			[&](const std::string &file, const BamReader &reader) {
+				if (writer) writer->close();
+				writer.reset(new BamWriter(result_bam_name(file, ".tagged.bam", params.output_dir), reader.header_text(), reader.reference_names(),
+				                           reader.reference_lengths(), params.threads));
+			},
+			[&](const ReadInfo &ri, const BamReader::RecordView *view) {
+				tag_edits(params.tags, ri, std::string(), std::string(), edits);
+				writer->save_alignment(view->raw, view->raw_bytes, edits);
+				container.add_record(ri);
+			});
+		if (writer) writer->close();
 	}
 }
 }

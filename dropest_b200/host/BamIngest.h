@@ -26,6 +26,11 @@ namespace BamProcessing
 	{
 		std::string cell_barcode = "CB", umi = "UB", gene = "GX", cell_barcode_quality = "CQ", umi_quality = "UQ";
 		std::string read_type, intronic_read_value, intergenic_read_value; // BamTags.Type.*: empty = every read with a gene is exonic
+		// written only (BamOutput.h): the raw barcode / UMI tags and the read-type values of the output BAMs (BamTags.cpp:11-21)
+		std::string cell_barcode_raw = "CR", umi_raw = "UR", exonic_read_value;
+		std::string intronic_read_value_out() const { return intronic_read_value.empty() ? "INTRONIC" : intronic_read_value; }
+		std::string intergenic_read_value_out() const { return intergenic_read_value.empty() ? "INTERGENIC" : intergenic_read_value; }
+		std::string exonic_read_value_out() const { return exonic_read_value.empty() ? "EXONIC" : exonic_read_value; }
 	};
 
 	// One alignment, as a view into the reader's buffer (valid until the next call of BamReader::next)
@@ -49,6 +54,10 @@ namespace BamProcessing
 		void find_tags(const std::string *const *tags, size_t n_tags, TagValue *found) const;
 	};
 
+	// the tags of a record's tag block, each as the span [name(2) type(1) value...]; throws std::runtime_error on a malformed block
+	struct TagSpan { const uint8_t *begin; size_t bytes; };
+	void list_tags(const uint8_t *tag_data, size_t tag_bytes, std::vector<TagSpan> &out);
+
 	class BamReader
 	{
 	public:
@@ -57,11 +66,13 @@ namespace BamProcessing
 		BamReader(const BamReader &) = delete;
 		BamReader &operator=(const BamReader &) = delete;
 		const std::vector<std::string> &reference_names() const { return _refs; }
+		const std::vector<uint32_t> &reference_lengths() const { return _ref_lengths; }
 		const std::string &header_text() const { return _header_text; }
 		bool next(BamAlignment &alignment); // false at the end of the file
 		// Every complete record that is already inflated (at least one; up to `max_records`), as views into the reader's buffer that stay
 		// valid until the next call of next / next_batch.  Empty at the end of the file.  `name` is left empty (use `name_data`).
-		struct RecordView { BamAlignment al; const char *name_data = nullptr; size_t name_len = 0; };
+		// `raw` = the whole record after its 4-byte block_size field (what a writer copies), raw_bytes = block_size
+		struct RecordView { BamAlignment al; const char *name_data = nullptr; size_t name_len = 0; const uint8_t *raw = nullptr; size_t raw_bytes = 0; };
 		void next_batch(std::vector<RecordView> &out, size_t max_records);
 
 	private:
@@ -91,6 +102,7 @@ namespace BamProcessing
 		size_t _pos = 0;              // read position in _data
 		bool _eof = false;
 		std::vector<std::string> _refs;
+		std::vector<uint32_t> _ref_lengths;
 		std::string _header_text;
 
 		bool fill(size_t need); // makes at least `need` bytes available at _pos; false at a clean end of file
@@ -104,7 +116,8 @@ namespace BamProcessing
 		BamTags tags;
 		bool gene_in_chromosome_name = false; // pseudo-aligner output: the reference name is the gene
 		int min_barcode_quality = 0;          // -f only: reads with a barcode / UMI base below this Phred quality are dropped (0 = off)
-		unsigned threads = 0;                 // BGZF inflate threads (0 = hardware concurrency)
+		unsigned threads = 0;                 // BGZF inflate / deflate threads (0 = hardware concurrency)
+		std::string output_dir;               // where the tagged / filtered BAMs go; empty = the working directory, like the reference
 		// -g: gene and mark from an annotation (GTF / BED, optionally .gz) instead of the gene tag: the positions of the first and the last
 		// aligned base are looked up (ReadParamsParser::get_gene_from_reference, ReadParamsParser.cpp:92-150).  Loaded by parse_bam_files /
 		// for_each_read when `genes` is not set yet.
@@ -119,7 +132,9 @@ namespace BamProcessing
 
 	// BamController::parse_bam_files + process_alignment for the tag / read-name modes: every primary mapped alignment of every file, in
 	// order, becomes one add_record call.
-	void parse_bam_files(const std::vector<std::string> &bam_files, const IngestParams &params, CellsDataContainer &container, IngestStats &stats);
+	// With print_result_bams (-b) every accepted read is also written to "<bam name>.tagged.bam" (BamProcessor, see BamOutput.h).
+	void parse_bam_files(const std::vector<std::string> &bam_files, const IngestParams &params, CellsDataContainer &container, IngestStats &stats,
+	                     bool print_result_bams = false);
 
 	// The same loop with the ReadInfo handed to a callback instead of a container (tests, other consumers)
 	template <class F> void for_each_read(const std::vector<std::string> &bam_files, const IngestParams &params, IngestStats &stats, F &&sink);
@@ -142,7 +157,12 @@ namespace BamProcessing
 	void parse_batch(const std::vector<BamReader::RecordView> &records, const std::vector<std::string> &refs, const IngestParams &params,
 	                 std::vector<ParsedRead> &out, unsigned threads);
 
-	template <class F> void for_each_read(const std::vector<std::string> &bam_files, const IngestParams &params_in, IngestStats &stats, F &&sink)
+	// The loop of BamController::process_bam_files / parse_bam_file (BamController.cpp:49-116): on_open(file name, reader) once per file, then
+	// sink(read info, record view or nullptr) for every read that process_alignment accepts.  With keep_records the sink also gets the raw
+	// record (for the BAM writers, BamOutput.h); the next batch is then produced only after the current one was consumed, because the views
+	// point into the reader's buffer.  Without it the next batch is read, inflated and parsed while the current one is handed over.
+	template <class O, class F> void for_each_alignment(const std::vector<std::string> &bam_files, const IngestParams &params_in, IngestStats &stats,
+	                                                    bool keep_records, O &&on_open, F &&sink)
 	{
 		IngestParams params(params_in);
 		if (!params.genes && !params.genes_filename.empty())
@@ -152,8 +172,8 @@ namespace BamProcessing
 		for (auto const &file : bam_files)
 		{
 			BamReader reader(file, params.threads);
+			on_open(file, reader);
 			const auto &refs = reader.reference_names();
-			// the next batch is read, inflated and parsed (all on the pool) while this thread hands the current one to the sink
 			auto produce = [&]() -> bool {
 				reader.next_batch(views, size_t(1) << 17);
 				if (views.empty()) return false;
@@ -164,25 +184,36 @@ namespace BamProcessing
 			while (have)
 			{
 				parsed.swap(parsed_next);
-				auto next = std::async(std::launch::async, produce);
+				std::future<bool> next;
+				if (!keep_records) next = std::async(std::launch::async, produce);
 				try
 				{
-					for (ParsedRead &r : parsed) // stream order: it defines cell / gene / chromosome ids downstream
+					for (size_t k = 0; k < parsed.size(); ++k) // stream order: it defines cell / gene / chromosome ids downstream
 					{
+						ParsedRead &r = parsed[k];
 						switch (r.status)
 						{
 						case ParsedRead::SKIPPED: ++stats.skipped_unmapped_or_secondary; break;
 						case ParsedRead::NO_CHROMOSOME: ++stats.cant_parse; break; // unknown chromosome: not counted as a read (BamController.cpp:93-105)
 						case ParsedRead::CANT_PARSE: ++stats.total_reads; ++stats.cant_parse; break;
 						case ParsedRead::LOW_QUALITY: ++stats.total_reads; ++stats.low_quality; break;
-						case ParsedRead::OK: ++stats.total_reads; sink(ReadInfo(std::move(r.params), std::move(r.gene), refs[size_t(r.ref_id)], r.mark)); break;
+						case ParsedRead::OK:
+							++stats.total_reads;
+							sink(ReadInfo(std::move(r.params), std::move(r.gene), refs[size_t(r.ref_id)], r.mark), keep_records ? &views[k] : nullptr);
+							break;
 						}
 					}
 				}
-				catch (...) { next.wait(); throw; }
-				have = next.get();
+				catch (...) { if (next.valid()) next.wait(); throw; }
+				have = keep_records ? produce() : next.get();
 			}
 		}
+	}
+
+	template <class F> void for_each_read(const std::vector<std::string> &bam_files, const IngestParams &params, IngestStats &stats, F &&sink)
+	{
+		for_each_alignment(bam_files, params, stats, false, [](const std::string &, const BamReader &) {},
+		                   [&](const ReadInfo &ri, const BamReader::RecordView *) { sink(ri); });
 	}
 }
 }

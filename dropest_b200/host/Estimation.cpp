@@ -342,10 +342,11 @@ namespace Estimation
 
 	CellsDataContainer::CellsDataContainer(const std::shared_ptr<Merge::MergeStrategyAbstract> &merge_strategy,
 	                                       const std::shared_ptr<Merge::UMIs::MergeUMIsStrategyAbstract> &umi_merge_strategy,
-	                                       const std::vector<UMI::Mark> &gene_match_levels, bool, int max_cells_num, int device,
+	                                       const std::vector<UMI::Mark> &gene_match_levels, bool save_umi_merge_targets, int max_cells_num, int device,
 	                                       size_t n_genes_hint, bool reads_output)
 		: _merge_strategy(merge_strategy), _umi_merge_strategy(umi_merge_strategy), _max_cells_num(max_cells_num)
-		, _query_marks(gene_match_levels), _device(device), _reads_output(reads_output), _batch_capacity(n_genes_hint)
+		, _query_marks(gene_match_levels), _device(device), _reads_output(reads_output), _save_umi_merge_targets(save_umi_merge_targets)
+		, _batch_capacity(n_genes_hint)
 	{
 		// _batch_capacity temporarily carries the gene-space hint until the handle exists
 		std::memset(&_summary, 0, sizeof(_summary));
@@ -374,6 +375,7 @@ namespace Estimation
 		cfg.min_genes_after_merge = uint32_t(_merge_strategy->min_genes_after_merge());
 		cfg.max_cells = _max_cells_num;
 		cfg.reads_output = _reads_output ? 1 : 0;
+		cfg.save_umi_merge_targets = _save_umi_merge_targets ? 1 : 0;
 		cfg.query_mark_mask = 0;
 		for (auto const &m : _query_marks) cfg.query_mark_mask |= 1u << m.bits();
 		_merge_strategy->configure(cfg);
@@ -599,6 +601,24 @@ namespace Estimation
 			if (mark[k] & 2) m.add(UMI::Mark::HAS_EXONS);
 			if (mark[k] & 4) m.add(UMI::Mark::HAS_INTRONS);
 			git->second._umis.emplace(_umi_indexer.add(umi_string(umi[k])), UMI(reads[k], m));
+		}
+		if (_save_umi_merge_targets && _is_merged)
+		{   // Gene::_merge_targets: the source UMIs are gone from the gene, their strings still belong to the UMI indexer (Gene.cpp:38-58)
+			size_t nt = 0;
+			check(dge_get_umi_merge_targets(_h, nullptr, nullptr, nullptr, nullptr, 0, &nt));
+			std::vector<uint64_t> t_cb(nt);
+			std::vector<int32_t> t_gene(nt);
+			std::vector<uint32_t> t_src(nt), t_dst(nt);
+			if (nt) check(dge_get_umi_merge_targets(_h, t_cb.data(), t_gene.data(), t_src.data(), t_dst.data(), nt, &nt));
+			for (size_t k = 0; k < nt; ++k)
+			{
+				Cell &c = _cells.at(_cell_ids_by_cb.at(barcode_string(t_cb[k])));
+				auto git = c._genes.emplace(size_t(t_gene[k]), Gene(&_umi_indexer)).first;
+				const std::string src(umi_string(t_src[k])), dst(umi_string(t_dst[k]));
+				_umi_indexer.add(src);
+				_umi_indexer.add(dst);
+				git->second._merge_targets[src] = dst;
+			}
 		}
 		_genes_loaded = true;
 	}

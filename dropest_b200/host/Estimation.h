@@ -172,9 +172,11 @@ namespace Estimation
 	{
 	public:
 		using umis_t = std::map<StringIndexer::index_t, UMI>;
+		using s_s_hash_t = std::unordered_map<std::string, std::string>;
 
 	private:
 		umis_t _umis;
+		s_s_hash_t _merge_targets; // Gene.h:27, filled by Gene::merge(source_umi, target_umi) when the container keeps them (Gene.cpp:54-57)
 		const StringIndexer *_umi_indexer;
 		friend class CellsDataContainer;
 
@@ -184,6 +186,8 @@ namespace Estimation
 		const umis_t &umis() const { return _umis; }
 		size_t size() const { return _umis.size(); }
 		bool has(const std::string &umi) const;
+		// the UMIs the UMI merge strategy moved away from this gene and where they went (empty unless save_umi_merge_targets; Gene.cpp:125-128)
+		const s_s_hash_t &merge_targets() const { return _merge_targets; }
 		size_t number_of_requested_umis(const UMI::Mark::query_t &query, bool return_reads) const; // Gene.cpp:60-79
 		size_t number_of_umis(bool return_reads) const;                                             // Gene.cpp:81-93
 		using s_ul_hash_t = std::unordered_map<std::string, size_t>;
@@ -472,6 +476,7 @@ namespace Estimation
 		bool _is_initialized = false, _is_merged = false;
 		int _device;
 		bool _reads_output;
+		bool _save_umi_merge_targets;
 
 		dge_handle *_h = nullptr;
 		unsigned _cb_len = 0, _umi_len = 0;

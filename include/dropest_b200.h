@@ -106,7 +106,9 @@ typedef struct dge_config {
     uint64_t max_barcodes_hint; /* upper bound on distinct barcodes, 0 = automatic */
     uint32_t allow_n;           /* 1 = records may carry DGE_FLAG_UMI_N / DGE_FLAG_CB_N.  The grouping key then spends one more bit on the UMI field
                                    (and at least 21): with 12-base UMIs and > 16 k genes the barcode table halves (2^21 slots) */
-    uint32_t reserved0;
+    uint32_t save_umi_merge_targets; /* 1 = keep, per (cell, gene), which UMI every UMI merged by the UMI merge strategy went to: the
+                                   `save_umi_merge_targets` constructor argument (CellsDataContainer.h:83, Gene.cpp:54-57); read back with
+                                   dge_get_umi_merge_targets.  Was reserved0 (0 = off): the layout of ABI version 2 is unchanged */
 } dge_config;
 
 typedef struct dge_handle dge_handle;
@@ -273,6 +275,14 @@ int dge_get_merge_pairs(dge_handle *h, uint64_t *from, uint64_t *to, size_t capa
  * list dge_get_cells(which) returns. Any output pointer may be NULL. */
 int dge_get_umigs(dge_handle *h, int which, uint32_t *cell_index, int32_t *gene_ids, uint32_t *umis,
                   uint32_t *read_counts, uint8_t *marks, size_t capacity, size_t *n_out);
+
+/* Gene::merge_targets() (Gene.h:41, filled by Gene::merge(source_umi, target_umi), Gene.cpp:38-58) of every (cell, gene): one row per UMI
+ * that MergeUMIsStrategySimple (N repair) or MergeUMIsStrategyDirectional moved into another UMI -- the cell that owns the gene after the
+ * barcode merge, the gene, the source UMI and the UMI it went to (codes as in dge_get_umigs; a target created by the N repair is a new,
+ * N-free UMI).  Sorted by (barcode code, gene, source).  The only consumer in the reference is the filtered-BAM writer,
+ * FilteringBamProcessor::write_alignment (BamProcessing/FilteringBamProcessor.cpp:73-88).  Needs dge_config.save_umi_merge_targets. */
+int dge_get_umi_merge_targets(dge_handle *h, uint64_t *cell_barcodes, int32_t *gene_ids, uint32_t *source_umis, uint32_t *target_umis,
+                              size_t capacity, size_t *n_out);
 
 /* ---- helpers that mirror reference utilities on the path (host-side, exact restatements used by the facade and tests) -- */
 
