@@ -2,7 +2,7 @@
 //   test_bam_output cpu <out dir> <threads> <type tag or -> <intronic or -> <intergenic or -> file...
 //       CPU only: every accepted read of every file is written to "<out dir>/<name>.tagged.bam" with the tags of
 //       BamProcessorAbstract::save_alignment and made-up corrections (barcode reversed; the UMI itself when it starts with 'A', else none).
-//   test_bam_output gpu <out dir> <whitelist (const type) or -> <min_genes_before> <min_genes_after> <simple|directional> <type tag or -> <intronic or ->
+//   test_bam_output gpu <out dir> <whitelist (const type; '-' = no barcode merge)> <min_genes_before> <min_genes_after> <simple|directional> <type tag or -> <intronic or ->
 //                       <intergenic or -> <bam output 0|1> file...
 //       the whole flow on the GPU: parse_bam_files (-b) -> set_initialized -> merge_and_filter -> write_filtered_bam_files (-F)
 #include "../../dropest_b200/host/BamOutput.h"
@@ -56,7 +56,7 @@ int main(int argc, char **argv)
 			p.tags.read_type = opt(argv[7]); p.tags.intronic_read_value = opt(argv[8]); p.tags.intergenic_read_value = opt(argv[9]);
 			const bool bam_output = std::string(argv[10]) == "1";
 			std::vector<std::string> files(argv + 11, argv + argc);
-			CellsDataContainer container(factory.get_cb_strat(true, false), factory.get_umi(directional), UMI::Mark::get_by_code(UMI::Mark::DEFAULT_CODE),
+			CellsDataContainer container(factory.get_cb_strat(!factory.barcodes_filename.empty(), false), factory.get_umi(directional), UMI::Mark::get_by_code(UMI::Mark::DEFAULT_CODE),
 			                             true, -1, 0, 1u << 12);
 			BamProcessing::IngestStats st;
 			BamProcessing::parse_bam_files(files, p, container, st, bam_output);
