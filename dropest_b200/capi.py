@@ -45,7 +45,7 @@ EXPORTS = [
     "dge_config_default", "dge_create", "dge_destroy", "dge_last_error", "dge_add_batch", "dge_add_batch_device", "dge_add_batch_segments_device", "dge_add_batch_soa",
     "dge_add_batch_chr", "dge_add_batch_soa_chr", "dge_add_batch_chr_device", "dge_get_chr_stats",
     "dge_set_initialized", "dge_merge_and_filter", "dge_reset", "dge_set_stream", "dge_set_n_strings", "dge_set_cb_strings", "dge_get_summary", "dge_get_timings", "dge_get_cells",
-    "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_get_umi_merge_targets", "dge_edit_distance",
+    "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_get_umi_merge_targets", "dge_get_matrix_marks", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
     "dge_route_by_barcode_device", "dge_route_count_slices_device", "dge_route_scatter_slice_device", "dge_dist_step",
     "dge_route_scatter_bounded_device", "dge_peer_alloc", "dge_peer_free", "dge_peer_open", "dge_peer_close",
@@ -136,6 +136,8 @@ def load_library():
     lib.dge_get_timings.argtypes = [C.c_void_p, C.POINTER(_Timings)]
     lib.dge_get_cells.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.dge_get_matrix.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.dge_get_matrix_marks.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.dge_get_matrix_marks.restype = C.c_int
     lib.dge_get_gene_order.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.dge_get_merge_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.dge_get_umi_merge_targets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -416,6 +418,17 @@ class Container:
         vals = np.zeros(nnz.value, dtype=np.int32)
         self._check(self._lib.dge_get_matrix(self._h, which, indptr.ctypes.data, genes.ctypes.data, vals.ctypes.data,
                                              C.byref(nc), C.byref(nnz)))
+        return indptr, genes, vals
+
+    def matrix_marks(self, marks: str):
+        """The filtered matrix for another query-mark code (e.g. "e", "i", "BA": the -V matrices); same layout as matrix()"""
+        mask = marks_to_mask(marks)
+        nc, nnz = C.c_size_t(0), C.c_size_t(0)
+        self._check(self._lib.dge_get_matrix_marks(self._h, mask, None, None, None, C.byref(nc), C.byref(nnz)))
+        indptr = np.zeros(nc.value + 1, dtype=np.int64)
+        genes = np.zeros(nnz.value, dtype=np.int32)
+        vals = np.zeros(nnz.value, dtype=np.int32)
+        self._check(self._lib.dge_get_matrix_marks(self._h, mask, indptr.ctypes.data, genes.ctypes.data, vals.ctypes.data, C.byref(nc), C.byref(nnz)))
         return indptr, genes, vals
 
     def matrix_shape(self, which: int):

@@ -66,6 +66,7 @@ struct MatrixDev
     DevBuf indptr, gene, val, cols;
     size_t n_cols = 0, nnz = 0;
     bool built = false;
+    const uint32_t *cols_used = nullptr; // the column list the matrix was built from (device memory owned by the handle)
 };
 } // namespace
 
@@ -202,7 +203,9 @@ struct dge_handle
     std::vector<SelfRec> hx_all;
     std::vector<CellRow> hx_rows;
 
-    MatrixDev cm, cm_raw;
+    MatrixDev cm, cm_raw, cm_marks; // cm_marks: the filtered matrix for another set of query marks (dge_get_matrix_marks), built on request
+    uint32_t cm_marks_mask = 0;
+    DevBuf cg_marks;
     dge_timings timings{};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     unsigned launches = 0;
@@ -1971,7 +1974,7 @@ void apply_moved(dge_handle *h, uint64_t total)
 }
 
 // columns = present-cell indices in DEVICE memory
-void build_matrix_cols(dge_handle *h, MatrixDev &m, const uint32_t *d_cols, size_t n_cols, bool filtered);
+void build_matrix_cols(dge_handle *h, MatrixDev &m, const uint32_t *d_cols, size_t n_cols, bool filtered, const uint32_t *values_override = nullptr);
 
 void build_matrix(dge_handle *h, MatrixDev &m, const std::vector<uint32_t> &col_pcs, bool filtered)
 {
@@ -1980,17 +1983,18 @@ void build_matrix(dge_handle *h, MatrixDev &m, const std::vector<uint32_t> &col_
     build_matrix_cols(h, m, m.cols.as<uint32_t>(), col_pcs.size(), filtered);
 }
 
-void build_matrix_cols(dge_handle *h, MatrixDev &m, const uint32_t *d_cols, size_t n_cols, bool filtered)
+void build_matrix_cols(dge_handle *h, MatrixDev &m, const uint32_t *d_cols, size_t n_cols, bool filtered, const uint32_t *values_override)
 {
     cudaStream_t st = h->stream;
     m.n_cols = n_cols;
     m.nnz = 0;
     m.built = true;
+    m.cols_used = d_cols;
     m.indptr.reserve((m.n_cols + 2) * 4);
     if (m.n_cols == 0) { DGE_CUDA(cudaMemsetAsync(m.indptr.p, 0, 8, st)); return; }
     h->mat_nnz.reserve((m.n_cols + 2) * 4);
     k_matrix_col_nnz<<<grid_for(m.n_cols * 32, 256), 256, 0, st>>>(d_cols, uint32_t(m.n_cols), h->pc_cg_start.as<uint32_t>(),
-                                                                   h->cg_req.as<uint32_t>(), filtered ? 1 : 0, h->mat_nnz.as<uint32_t>());
+                                                                   values_override ? values_override : h->cg_req.as<uint32_t>(), filtered ? 1 : 0, h->mat_nnz.as<uint32_t>());
     ++h->launches;
     DGE_CUDA(cudaMemsetAsync(h->mat_nnz.as<uint32_t>() + m.n_cols, 0, 4, st));
     device_exclusive_scan(h->mat_nnz.as<uint32_t>(), m.indptr.as<uint32_t>(), m.n_cols + 1, h->scan_scratch.as<uint32_t>(), st, &h->launches);
@@ -1998,7 +2002,8 @@ void build_matrix_cols(dge_handle *h, MatrixDev &m, const uint32_t *d_cols, size
     m.gene.reserve(std::max<size_t>(m.nnz, 1) * 4); m.val.reserve(std::max<size_t>(m.nnz, 1) * 4);
     const uint32_t *values;
     int mode;
-    if (filtered) { values = h->cfg.reads_output ? h->cg_req_reads.as<uint32_t>() : h->cg_req.as<uint32_t>(); mode = 0; }
+    if (values_override) { values = values_override; mode = 0; }
+    else if (filtered) { values = h->cfg.reads_output ? h->cg_req_reads.as<uint32_t>() : h->cg_req.as<uint32_t>(); mode = 0; }
     else if (h->cfg.reads_output) { values = h->cg_reads.as<uint32_t>(); mode = 2; }
     else { values = nullptr; mode = 1; }
     k_matrix_fill<<<unsigned(m.n_cols), 256, 0, st>>>(d_cols, uint32_t(m.n_cols), m.indptr.as<uint32_t>(), h->pc_cg_start.as<uint32_t>(),
@@ -3297,7 +3302,7 @@ int dge_reset(dge_handle *h)
         h->n_chunk_counters = 0; h->n_fill_ev = 0; h->moves_ready = false; h->n_reads = 0; h->n_keys = 0; h->n_u = h->n_cg = h->n_pc = 0;
         h->real.clear(); h->filtered.clear(); h->gene_order.clear(); h->merge_events.clear(); h->umi_mt.clear();
         h->n_merged = h->n_excluded = h->n_unresolved = 0; h->total_cells = 0;
-        h->cm.built = h->cm_raw.built = false;
+        h->cm.built = h->cm_raw.built = h->cm_marks.built = false;
         h->host_stage = 0; h->lazy_rows = false; h->dev_merged = false; h->n_real_rows = 0; h->n_filtered_dev = 0;
         h->sum_real = h->sum_filtered = h->sum_genes_seen = 0; h->n_host_fallback = 0; h->pp_ready = false; h->n_poisson_replayed = 0;
         h->dist_done = false; h->slot_pc_built = false; h->dist_targets.clear(); h->n_order_ties = 0; h->dist_stage = 0;
@@ -3855,6 +3860,44 @@ int dge_get_matrix(dge_handle *h, int which, int64_t *indptr, int32_t *gene_ids,
         if (gene_ids && m.nnz) DGE_CUDA(cudaMemcpyAsync(gene_ids, m.gene.p, m.nnz * 4, cudaMemcpyDeviceToHost, h->stream));
         if (values && m.nnz) DGE_CUDA(cudaMemcpyAsync(values, m.val.p, m.nnz * 4, cudaMemcpyDeviceToHost, h->stream));
         DGE_CUDA(cudaStreamSynchronize(h->stream));
+        return int(DGE_OK);
+    });
+}
+
+int dge_get_matrix_marks(dge_handle *h, uint32_t query_mark_mask, int64_t *indptr, int32_t *gene_ids, int32_t *values, size_t *n_cols, size_t *nnz)
+{
+    if (!h || !n_cols || !nnz) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state != 2) return fail(h, DGE_ERR_STATE, "matrices exist after merge_and_filter");
+    if (query_mark_mask & ~0xFEu) return fail(h, DGE_ERR_INVALID, "query_mark_mask: bits 1..7 only");
+    return guarded(h, [&] {
+        DGE_CUDA(cudaSetDevice(h->cfg.device));
+        cudaStream_t st = h->stream;
+        MatrixDev &m = h->cm_marks;
+        if (!m.built || h->cm_marks_mask != query_mark_mask)
+        {
+            if (!h->cm.built) throw std::runtime_error("internal: the filtered matrix was not built");
+            h->cg_marks.reserve((size_t(h->n_cg) + 2) * 4);
+            // one more row than n_cg: the empty sentinel cell of barcodes without UMIs points at [n_cg, n_cg)
+            DGE_CUDA(cudaMemsetAsync(h->cg_marks.p, 0, (size_t(h->n_cg) + 2) * 4, st));
+            if (h->n_cg)
+                k_cg_mark_values<<<grid_for(size_t(h->n_cg) * 8, 256), 256, 0, st>>>(h->uval.as<uint32_t>(), h->cg_start.as<uint32_t>(), h->n_cg, query_mark_mask,
+                                                                                   h->cfg.reads_output ? 1 : 0, h->cg_marks.as<uint32_t>());
+            DGE_LAUNCH_CHECK();
+            ++h->launches;
+            build_matrix_cols(h, m, h->cm.cols_used, h->cm.n_cols, true, h->cg_marks.as<uint32_t>());
+            h->cm_marks_mask = query_mark_mask;
+        }
+        *n_cols = m.n_cols; *nnz = m.nnz;
+        std::vector<uint32_t> ip;
+        if (indptr)
+        {
+            d2h(ip, m.indptr.p, m.n_cols + 1, st);
+            DGE_CUDA(cudaStreamSynchronize(st));
+            for (size_t i = 0; i <= m.n_cols; ++i) indptr[i] = int64_t(ip[i]);
+        }
+        if (gene_ids && m.nnz) DGE_CUDA(cudaMemcpyAsync(gene_ids, m.gene.p, m.nnz * 4, cudaMemcpyDeviceToHost, st));
+        if (values && m.nnz) DGE_CUDA(cudaMemcpyAsync(values, m.val.p, m.nnz * 4, cudaMemcpyDeviceToHost, st));
+        DGE_CUDA(cudaStreamSynchronize(st));
         return int(DGE_OK);
     });
 }

@@ -629,6 +629,33 @@ __global__ void __launch_bounds__(256) k_matrix_fill(const uint32_t *__restrict_
     }
 }
 
+// Gene::number_of_requested_umis (Gene.cpp:60-79) for ANOTHER set of query marks than the container's: per (cell, gene) row, the UMIs (or
+// their reads) whose accumulated mark is one of `mark_mask`'s.  Eight lanes share a row.  Feeds the matrices of `-V`
+// (ResultsPrinter::save_intron_exon_matrices, ResultsPrinter.cpp:455-474).
+__global__ void __launch_bounds__(256) k_cg_mark_values(const uint32_t *__restrict__ uval, const uint32_t *__restrict__ cg_start, uint32_t n_cg,
+                                                         uint32_t mark_mask, int reads, uint32_t *__restrict__ out)
+{
+    const uint32_t sub = threadIdx.x & 7u;
+    const uint32_t groups = (gridDim.x * blockDim.x) >> 3;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; base < ((n_cg + groups - 1) / groups) * groups; base += groups)
+    {   // every lane of a warp runs the same number of rounds: the shuffles below need the whole warp
+        uint32_t v = 0;
+        if (base < n_cg)
+        {
+            const uint32_t s = cg_start[base], e = cg_start[base + 1];
+            for (uint32_t i = s + sub; i < e; i += 8)
+            {
+                const uint32_t u = uval[i];
+                if ((mark_mask >> (u >> VAL_MARK_SHIFT)) & 1u) v += reads ? (u & VAL_COUNT_MASK) : 1u;
+            }
+        }
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+        if (sub == 0 && base < n_cg) out[base] = v;
+    }
+}
+
 // ---- device-resident merge flow (RealBarcodesMergeStrategy without host cell rows) ------------------------------------------------
 // Per real cell (cell-id order, parallel to the CellRow table): the Stats counters that are counters and not set sizes
 // (TOTAL_UMIS_PER_CB / TOTAL_READS_PER_CB are ADDED on merges, Stats.cpp:29-43), the merge target and the Cell flags.

@@ -682,7 +682,6 @@ namespace Estimation
 	// ---- ResultsPrinter ---------------------------------------------------------------------------------------------------
 	ResultsPrinter::SparseMatrix ResultsPrinter::get_count_matrix(const CellsDataContainer &container, bool filtered) const
 	{
-		SparseMatrix m;
 		dge_handle *h = container.handle();
 		size_t n_cols = 0, nnz = 0;
 		const int which = filtered ? DGE_MATRIX_CM : DGE_MATRIX_CM_RAW;
@@ -690,6 +689,29 @@ namespace Estimation
 		std::vector<int64_t> indptr(n_cols + 1);
 		std::vector<int32_t> genes(nnz), vals(nnz);
 		if (dge_get_matrix(h, which, indptr.data(), genes.data(), vals.data(), &n_cols, &nnz) != DGE_OK) throw std::runtime_error(dge_last_error(h));
+		return assemble(container, filtered, indptr, genes, vals);
+	}
+
+	ResultsPrinter::SparseMatrix ResultsPrinter::get_count_matrix_filtered(const CellsDataContainer &container, const UMI::Mark::query_t &query_marks) const
+	{
+		dge_handle *h = container.handle();
+		uint32_t mask = 0;
+		for (auto const &m : query_marks) mask |= 1u << m.bits();
+		size_t n_cols = 0, nnz = 0;
+		if (dge_get_matrix_marks(h, mask, nullptr, nullptr, nullptr, &n_cols, &nnz) != DGE_OK) throw std::runtime_error(dge_last_error(h));
+		std::vector<int64_t> indptr(n_cols + 1);
+		std::vector<int32_t> genes(nnz), vals(nnz);
+		if (dge_get_matrix_marks(h, mask, indptr.data(), genes.data(), vals.data(), &n_cols, &nnz) != DGE_OK) throw std::runtime_error(dge_last_error(h));
+		return assemble(container, true, indptr, genes, vals);
+	}
+
+	// device CSC (columns = cells in the reference's order, gene ids ascending) -> the reference's matrix: its row numbering and names
+	ResultsPrinter::SparseMatrix ResultsPrinter::assemble(const CellsDataContainer &container, bool filtered, const std::vector<int64_t> &indptr,
+	                                                      const std::vector<int32_t> &genes, const std::vector<int32_t> &vals) const
+	{
+		SparseMatrix m;
+		dge_handle *h = container.handle();
+		const size_t n_cols = indptr.size() - 1, nnz = genes.size();
 		size_t n_cells = 0;
 		const int cls = filtered ? DGE_CELLS_FILTERED : DGE_CELLS_REAL;
 		dge_get_cells(h, cls, nullptr, 0, &n_cells);
@@ -913,5 +935,20 @@ namespace Estimation
 		SparseMatrix cm = get_count_matrix(container, true), cm_raw = get_count_matrix(container, false);
 		save_rds(container, cm, cm_raw, base);
 		if (write_matrix) save_mtx(cm, base);
+	}
+
+	void ResultsPrinter::save_intron_exon_matrices(const CellsDataContainer &container, const std::string &filename) const
+	{
+		// -V: matrices <- list(exon, intron, spanning); saveRDS(matrices, base.matrices.rds)  (ResultsPrinter.cpp:455-474)
+		std::string base = filename;
+		auto pos = filename.find_last_of('.');
+		if (pos != std::string::npos && filename.substr(pos + 1) == "rds") base = filename.substr(0, pos);
+		const SparseMatrix exon = get_count_matrix_filtered(container, UMI::Mark::get_by_code("e"));
+		const SparseMatrix intron = get_count_matrix_filtered(container, UMI::Mark::get_by_code("i"));
+		const SparseMatrix spanning = get_count_matrix_filtered(container, UMI::Mark::get_by_code("BA"));
+		RdsWriter w(base + ".matrices.rds");
+		w.list_header(3);
+		w.dgcmatrix(exon); w.dgcmatrix(intron); w.dgcmatrix(spanning);
+		w.list_names({"exon", "intron", "spanning"});
 	}
 }

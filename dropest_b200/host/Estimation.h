@@ -577,7 +577,14 @@ namespace Estimation
 			std::vector<std::string> row_names, col_names;
 		};
 		SparseMatrix get_count_matrix(const CellsDataContainer &container, bool filtered) const; // :334-396 incl. the first-met row order
+		// the filtered matrix for another set of query marks (:334-361), and the three matrices of -V written to "<base>.matrices.rds" (:455-474)
+		SparseMatrix get_count_matrix_filtered(const CellsDataContainer &container, const UMI::Mark::query_t &query_marks) const;
+		void save_intron_exon_matrices(const CellsDataContainer &container, const std::string &filename) const;
 		static void save_mtx(const SparseMatrix &m, const std::string &filename_base);            // :81-91
 		void save_rds(const CellsDataContainer &container, const SparseMatrix &cm, const SparseMatrix &cm_raw, const std::string &filename_base) const;
+
+	private:
+		SparseMatrix assemble(const CellsDataContainer &container, bool filtered, const std::vector<int64_t> &indptr, const std::vector<int32_t> &genes,
+		                      const std::vector<int32_t> &vals) const;
 	};
 }

@@ -255,6 +255,14 @@ int dge_get_cells(dge_handle *h, int which, dge_cell_info *out, size_t capacity,
 int dge_get_matrix(dge_handle *h, int which, int64_t *indptr, int32_t *gene_ids, int32_t *values,
                    size_t *n_cols, size_t *nnz);
 
+/* The filtered count matrix for ANOTHER set of query marks than dge_config.query_mark_mask, over the same columns as DGE_MATRIX_CM
+ * (filtered_cells() in order): ResultsPrinter::get_count_matrix_filtered(container, query_marks), ResultsPrinter.cpp:334-361, which `-V`
+ * (save_intron_exon_matrices, :455-474) calls with "e" (mask 0x04), "i" (0x10) and "BA" (0xC0).  Values are UMIs -- reads with
+ * reads_output -- whose accumulated mark is one of the mask's; zero entries are dropped.  Built on the device on request; the last mask is
+ * kept, so the size query and the fetch cost one build.  Same output convention as dge_get_matrix. */
+int dge_get_matrix_marks(dge_handle *h, uint32_t query_mark_mask, int64_t *indptr, int32_t *gene_ids, int32_t *values,
+                         size_t *n_cols, size_t *nnz);
+
 /* Per-chromosome read counters of the real cells (CellsDataContainer::get_stat_by_real_cells(CellChrStatType, ...), reference
  * CellsDataContainer.cpp:292-307 + Stats::get, Stats.cpp:50-63), after merge_and_filter, with Stats::merge applied (the counters of a merged
  * cell belong to its merge target, Stats.cpp:36-42).  counts[(cell * n_chr + chr) * 3 + t], t = 0 exon, 1 intron, 2 intergenic; cells in

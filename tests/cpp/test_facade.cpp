@@ -301,6 +301,14 @@ int main(int argc, char **argv)
 		double total = 0;
 		for (double v : cm.x) total += v;
 		CHECK_EQUAL(total, 3.0 + 6.0); // cell 1: 3 genes x 1 UMI ; merged cell 0: Gene1 2, Gene2 1, Gene3 2, Gene4 1
+		// -V: ResultsPrinter::save_intron_exon_matrices (ResultsPrinter.cpp:455-474); every read of the fixture is exonic
+		printer.save_intron_exon_matrices(container_full, out_dir + "/cell.counts.rds");
+		auto exon = printer.get_count_matrix_filtered(container_full, UMI::Mark::get_by_code("e"));
+		auto intron = printer.get_count_matrix_filtered(container_full, UMI::Mark::get_by_code("i"));
+		CHECK_EQUAL(exon.x.size(), cm.x.size());
+		CHECK_EQUAL(exon.row_names.size(), cm.row_names.size());
+		CHECK_EQUAL(intron.x.size(), size_t(0));
+		CHECK_EQUAL(intron.col_names.size(), size_t(2));
 	}
 	catch (std::exception &e)
 	{

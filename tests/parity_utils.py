@@ -138,6 +138,8 @@ def gpu_run(case: Case, recs: Optional[np.ndarray], device_generate: bool = Fals
         out["chr_stats"] = c.chr_stats()
     if case.dump_umis:
         out["umigs"] = c.umigs(dg.CELLS_ALL)
+    if case.extra.get("matrix_marks"):   # the filtered matrix for other query marks (the -V matrices)
+        out["cm_marks"] = {code: c.matrix_marks(code) for code in case.extra["matrix_marks"]}
     c.close()
     return out
 

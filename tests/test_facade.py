@@ -126,6 +126,18 @@ def test_reference_container_tests_through_the_cpp_facade(tmp_path):
     assert dict(zip(umis["attr"]["names"], umis["v"])) == {"AAATTAGGTCCA": 12, "AAATTAGGTCCC": 4}
     rreads = d["v"][9]
     assert dict(zip(rreads["attr"]["names"], rreads["v"])) == {"AAATTAGGTCCA": 12, "AAATTAGGTCCC": 4}
+    # ---- -V: list(exon, intron, spanning) of dgCMatrix over the filtered cells (ResultsPrinter.cpp:455-474); the fixture's reads are all exonic
+    raw = gzip.open(tmp_path / "cell.counts.matrices.rds").read()
+    rd = Rds(raw)
+    rd.o = 2
+    assert rd.i32() == 2
+    rd.i32(); rd.i32()
+    m = rd.item()
+    assert m["attr"]["names"] == ["exon", "intron", "spanning"]
+    ex, intr, span = (x["S4"] for x in m["v"])
+    assert ex["Dim"] == [6, 2] and ex["p"] == cm["p"] and ex["i"] == cm["i"] and ex["x"] == cm["x"] and ex["Dimnames"] == cm["Dimnames"]
+    for e in (intr, span):
+        assert e["Dim"] == [0, 2] and e["p"] == [0, 0, 0] and e["i"] == [] and e["Dimnames"][1] == cells
 
 
 def test_merge_strategy_factory_reads_the_xml_configuration():

@@ -5,6 +5,7 @@ import pytest
 import dropest_b200 as dg
 from dropest_b200.synth import SynthSpec, SynthTables, read_whitelist, records_from_strings
 
+import oracle_io
 import parity_utils as pu
 
 pytestmark = pytest.mark.gpu
@@ -127,6 +128,34 @@ def test_reads_output_max_cells_and_marks():
     res = pu.run_case(pu.small_case(n_reads=40000, n_cells=30, n_genes=90, merge="real", reads_output=True, max_cells=12, marks="eB"))
     pu.assert_parity(res)
     assert res["gpu"]["filtered"].shape[0] == 12
+
+
+@pytest.mark.parametrize("reads_output,merge", [(False, "real"), (True, "none")])
+def test_velocyto_matrices_for_other_query_marks(reads_output, merge):
+    """-V (ResultsPrinter::save_intron_exon_matrices, ResultsPrinter.cpp:455-474): the filtered matrix over the SAME filtered cells for the
+    query marks "e", "i" and "BA".  Expected values come from the reference's own (cell, gene, UMI, reads, mark) dump after merge_and_filter:
+    Gene::number_of_requested_umis (Gene.cpp:60-79) counts the UMIs -- or sums their reads -- whose accumulated mark equals one of the query's."""
+    case = pu.small_case(n_reads=60000, n_cells=30, n_genes=90, merge=merge, reads_output=reads_output, seed=41)
+    case.extra["matrix_marks"] = ["e", "i", "BA", "eEBA"]
+    res = pu.run_case(case)
+    pu.assert_parity(res)
+    ora, gpu = res["oracle"], res["gpu"]
+    o_gene_ids = pu._gene_id_of_name(case, oracle_io.strings(ora["gene_names"]))
+    col_of_cell = {int(c): k for k, c in enumerate(ora["filtered_cells"])}
+    marks_of = {"e": {2}, "i": {4}, "BA": {6, 7}, "eEBA": {2, 3, 6, 7}}
+    for code, (indptr, genes, vals) in gpu["cm_marks"].items():
+        exp = {}
+        for cell, gene, count, mark in zip(ora["umi_cell"], ora["umi_gene"], ora["umi_count"], ora["umi_mark"]):
+            if int(cell) in col_of_cell and int(mark) in marks_of[code]:
+                key = (col_of_cell[int(cell)], int(o_gene_ids[int(gene)]))
+                exp[key] = exp.get(key, 0) + (int(count) if reads_output else 1)
+        col = np.repeat(np.arange(indptr.shape[0] - 1), np.diff(indptr))
+        got = {(int(c), int(g)): int(v) for c, g, v in zip(col, genes, vals)}
+        assert indptr.shape[0] - 1 == len(col_of_cell) and got == exp and (len(exp) > 50 or code == "i"), code
+        assert all(np.all(np.diff(genes[indptr[k]:indptr[k + 1]]) > 0) for k in range(indptr.shape[0] - 1))   # genes ascending inside a column
+    # the container's own marks give the container's own matrix
+    np.testing.assert_array_equal(gpu["cm_marks"]["eEBA"][2], gpu["cm"][2])
+    assert sum(len(v[1]) for k, v in gpu["cm_marks"].items() if k != "eEBA") > 500
 
 
 def test_intergenic_only_and_empty_inputs():
