@@ -45,7 +45,7 @@ EXPORTS = [
     "dge_config_default", "dge_create", "dge_destroy", "dge_last_error", "dge_add_batch", "dge_add_batch_device", "dge_add_batch_segments_device", "dge_add_batch_soa",
     "dge_add_batch_chr", "dge_add_batch_soa_chr", "dge_add_batch_chr_device", "dge_get_chr_stats",
     "dge_set_initialized", "dge_merge_and_filter", "dge_reset", "dge_set_stream", "dge_set_n_strings", "dge_set_cb_strings", "dge_get_summary", "dge_get_timings", "dge_get_cells",
-    "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_get_umi_merge_targets", "dge_get_matrix_marks", "dge_edit_distance",
+    "dge_get_matrix", "dge_get_gene_order", "dge_get_merge_pairs", "dge_get_umigs", "dge_get_umi_merge_targets", "dge_get_matrix_marks", "dge_get_merge_events", "dge_edit_distance",
     "dge_hamming_distance", "dge_whitelist_shape", "dge_whitelist_token", "dge_synth_generate_device",
     "dge_route_by_barcode_device", "dge_route_count_slices_device", "dge_route_scatter_slice_device", "dge_dist_step",
     "dge_route_scatter_bounded_device", "dge_peer_alloc", "dge_peer_free", "dge_peer_open", "dge_peer_close",
@@ -140,7 +140,9 @@ def load_library():
     lib.dge_get_matrix_marks.restype = C.c_int
     lib.dge_get_gene_order.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.dge_get_merge_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
-    lib.dge_get_umi_merge_targets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.dge_get_umi_merge_targets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.dge_get_merge_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.dge_get_merge_events.restype = C.c_int
     lib.dge_get_umi_merge_targets.restype = C.c_int
     lib.dge_get_umigs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.dge_edit_distance.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint]
@@ -464,13 +466,24 @@ class Container:
     def umi_merge_targets(self) -> dict:
         """Gene::merge_targets() of every (cell, gene): rows (cell barcode code, gene, source UMI, target UMI)."""
         n = C.c_size_t(0)
-        self._check(self._lib.dge_get_umi_merge_targets(self._h, None, None, None, None, 0, C.byref(n)))
+        self._check(self._lib.dge_get_umi_merge_targets(self._h, None, None, None, None, None, 0, C.byref(n)))
         m = n.value
-        out = {"cb": np.zeros(m, np.uint64), "gene": np.zeros(m, np.int32), "src": np.zeros(m, np.uint32), "dst": np.zeros(m, np.uint32)}
+        out = {"cb": np.zeros(m, np.uint64), "gene": np.zeros(m, np.int32), "src": np.zeros(m, np.uint32), "dst": np.zeros(m, np.uint32),
+               "created": np.zeros(m, np.uint8)}
         if m:
             self._check(self._lib.dge_get_umi_merge_targets(self._h, out["cb"].ctypes.data, out["gene"].ctypes.data, out["src"].ctypes.data,
-                                                            out["dst"].ctypes.data, m, C.byref(n)))
+                                                            out["dst"].ctypes.data, out["created"].ctypes.data, m, C.byref(n)))
         return out
+
+    def merge_events(self):
+        """(from, to) barcode codes of the merge_cells calls in application order"""
+        n = C.c_size_t(0)
+        self._check(self._lib.dge_get_merge_events(self._h, None, None, 0, C.byref(n)))
+        a = np.zeros(n.value, dtype=np.uint64)
+        b = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            self._check(self._lib.dge_get_merge_events(self._h, a.ctypes.data, b.ctypes.data, n.value, C.byref(n)))
+        return a, b
 
     def umigs(self, which: int) -> dict:
         n = C.c_size_t(0)

@@ -24,6 +24,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -148,7 +149,7 @@ struct dge_handle
     uint64_t n_umis_merged = 0, n_umi_segments_replayed = 0;
     // Gene::_merge_targets (Gene.cpp:54-57, kept when the container is built with save_umi_merge_targets): one row per UMI that the UMI
     // merge strategy moved into another one, codes as dge_get_umigs reports them
-    struct UmiMergeTarget { uint64_t cb; uint32_t gene, src, dst; };
+    struct UmiMergeTarget { uint64_t cb; uint32_t gene, src, dst; uint32_t created; }; // created: the target did not exist, the source's UMI object became it (Gene.cpp:48)
     std::vector<UmiMergeTarget> umi_mt;
     DevBuf u_target, mt_keys, mt_dst;
     DevBuf dist_infos, dist_keys, dist_vals, dist_jobs, dist_cb, dist_umis, dist_eoff;
@@ -859,6 +860,11 @@ void materialize_host(dge_handle *h)
             DGE_CUDA(cudaStreamSynchronize(st));
             for (size_t i = 0; i < n; ++i) h->real[i].merged_to_cb = mcb[i];
         }
+        // merge_cells calls in application order: the walk of MergeStrategyBase::merge_inited over filtered_cells() as set_initialized left them
+        // (MergeStrategyBase.cpp:29-51); the device flow has no chains, so every merged cell went straight to its final target
+        h->merge_events.clear();
+        for (uint32_t base : h->filtered)
+            if (h->real[base].merged && uint32_t(h->real[base].target) != base) h->merge_events.emplace_back(base, uint32_t(h->real[base].target));
         const uint32_t nf = h->n_filtered_dev;
         const uint32_t skip = (h->cfg.max_cells > 0 && uint32_t(h->cfg.max_cells) < nf) ? nf - uint32_t(h->cfg.max_cells) : 0u;
         h->filtered.assign(fl + skip, fl + nf);
@@ -2064,7 +2070,7 @@ void umi_directional_replay(const dge_handle *h, std::vector<UmiItem> &items, st
 // the number of applied entries.  `items` come with the first-seen read index of their UMI, which orders the UMI ids of the reference.
 void umi_directional_literal(const dge_handle *h, std::vector<UmiItem> &items, const std::unordered_map<std::string, uint32_t> &n_index,
                              std::vector<std::pair<uint32_t, uint32_t>> &final_entries, uint32_t &n_applied,
-                             std::vector<std::pair<uint32_t, uint32_t>> *applied_targets = nullptr)
+                             std::vector<std::array<uint32_t, 3>> *applied_targets = nullptr)
 {
     auto code_of = [&](const std::string &seq) -> uint32_t { // internal UMI field of a string
         if (seq.find('N') != std::string::npos)
@@ -2133,7 +2139,7 @@ void umi_directional_literal(const dge_handle *h, std::vector<UmiItem> &items, c
         if (!ins.second) { ins.first->second.first += s->second.first; ins.first->second.second |= s->second.second; }
         content.erase(s);
         ++n_applied;
-        if (applied_targets) applied_targets->emplace_back(code_of(t.first), code_of(t.second)); // _merge_targets[source_umi] = target_umi
+        if (applied_targets) applied_targets->push_back({code_of(t.first), code_of(t.second), ins.second ? 1u : 0u}); // _merge_targets[source_umi] = target_umi
     }
     final_entries.clear();
     for (auto const &c : content)
@@ -2274,7 +2280,8 @@ bool umi_merge_directional(dge_handle *h)
             std::unordered_map<std::string, uint32_t> n_index;
             for (size_t k = 0; (k + 1) * h->cfg.umi_len <= h->n_umi_strings.size(); ++k) n_index.emplace(h->n_umi_strings.substr(k * h->cfg.umi_len, h->cfg.umi_len), uint32_t(k));
             srand(1); // the reference never seeds rand() on this path (only MergeUMIsStrategySimple's constructor does): the C default
-            std::vector<std::pair<uint32_t, uint32_t>> final_entries, applied_targets;
+            std::vector<std::pair<uint32_t, uint32_t>> final_entries;
+            std::vector<std::array<uint32_t, 3>> applied_targets;
             for (uint32_t k : n_segments)
             {
                 const uint32_t off = hs_off[k], n = hs_off[k + 1] - off;
@@ -2286,7 +2293,7 @@ bool umi_merge_directional(dge_handle *h)
                 if (!applied) continue;
                 const HostCell &cell = h->real[pc_to_real[hs_pc[k]]];
                 for (auto const &t : applied_targets)
-                    h->umi_mt.push_back(dge_handle::UmiMergeTarget{cell.cb, hs_gene[k], umi_public_code(h, t.first), umi_public_code(h, t.second)});
+                    h->umi_mt.push_back(dge_handle::UmiMergeTarget{cell.cb, hs_gene[k], umi_public_code(h, t[0]), umi_public_code(h, t[1]), t[2]});
                 for (uint32_t i = 0; i < n; ++i) dir_kill.push_back(hs_start[k] + i); // the segment is rewritten as a whole
                 for (auto const &fe : final_entries)
                 {
@@ -2333,7 +2340,7 @@ bool umi_merge_directional(dge_handle *h)
         for (size_t k = 0; k < cap; ++k)
         {
             const uint32_t slot = uint32_t(keys[k] >> gub), gene = uint32_t(keys[k] >> h->kl.ub) & ((1u << h->kl.gb) - 1);
-            h->umi_mt.push_back(dge_handle::UmiMergeTarget{slot_cb.at(slot), gene, umi_public_code(h, uint32_t(keys[k]) & umask), umi_public_code(h, dsts[k])});
+            h->umi_mt.push_back(dge_handle::UmiMergeTarget{slot_cb.at(slot), gene, umi_public_code(h, uint32_t(keys[k]) & umask), umi_public_code(h, dsts[k]), 0u}); // roots exist
         }
     }
 
@@ -2461,6 +2468,8 @@ bool umi_repair_n(dge_handle *h)
         for (auto const &it : items) if (it.seq.find('N') != std::string::npos) bad_umis.insert(it.seq);
         const uint32_t ridx = pc_to_real[hs_pc[k]];
         const HostCell &cell = h->real[ridx];
+        std::unordered_map<std::string, std::string> seg_targets; // find_targets' result, filled in the same order (its iteration order decides below)
+        const size_t mt_first = h->umi_mt.size();
         for (auto const &bad : bad_umis)
         {
             unsigned min_ed = std::numeric_limits<unsigned>::max();
@@ -2485,15 +2494,37 @@ bool umi_repair_n(dge_handle *h)
                 new_keys.push_back(((((uint64_t(cell.slot) << h->kl.gb) | hs_gene[k]) << h->kl.ub) | packed) << 3);
                 new_vals.push_back(items[src].val);
                 if (h->cfg.save_umi_merge_targets)
-                    h->umi_mt.push_back(dge_handle::UmiMergeTarget{cell.cb, hs_gene[k], umi_public_code(h, items[src].umi), uint32_t(packed)});
+                {
+                    h->umi_mt.push_back(dge_handle::UmiMergeTarget{cell.cb, hs_gene[k], umi_public_code(h, items[src].umi), uint32_t(packed), 0u});
+                    seg_targets[bad] = fixed;
+                }
             }
             else
             {
                 pairs.push_back(make_uint2(src_u, hs_start[k] + items[size_t(best)].idx));
                 if (h->cfg.save_umi_merge_targets)
-                    h->umi_mt.push_back(dge_handle::UmiMergeTarget{cell.cb, hs_gene[k], umi_public_code(h, items[src].umi), umi_public_code(h, items[size_t(best)].umi)});
+                {
+                    h->umi_mt.push_back(dge_handle::UmiMergeTarget{cell.cb, hs_gene[k], umi_public_code(h, items[src].umi), umi_public_code(h, items[size_t(best)].umi), 0u});
+                    seg_targets[bad] = items[size_t(best)].seq;
+                }
             }
             dec_real.push_back(ridx);
+        }
+        if (h->umi_mt.size() > mt_first)
+        {   // which source's UMI object BECAME its target (Gene::merge emplaces the target when it does not exist, Gene.cpp:48): Cell::merge_umis
+            // walks the map in its own order (Cell.cpp:34), the first source that reaches a missing target creates it
+            std::unordered_set<std::string> present;
+            for (auto const &it : items) present.insert(it.seq);
+            std::unordered_map<uint32_t, size_t> row_of_src;
+            for (size_t r = mt_first; r < h->umi_mt.size(); ++r) row_of_src.emplace(h->umi_mt[r].src, r);
+            for (auto const &t : seg_targets)
+            {
+                if (t.first == t.second) continue;
+                size_t si = 0;
+                while (items[si].seq != t.first) ++si;
+                if (present.insert(t.second).second) h->umi_mt[row_of_src.at(umi_public_code(h, items[si].umi))].created = 1u;
+                present.erase(t.first);
+            }
         }
     }
     (void)gub;
@@ -3935,8 +3966,8 @@ int dge_get_merge_pairs(dge_handle *h, uint64_t *from, uint64_t *to, size_t capa
     return DGE_OK;
 }
 
-int dge_get_umi_merge_targets(dge_handle *h, uint64_t *cell_barcodes, int32_t *gene_ids, uint32_t *source_umis, uint32_t *target_umis, size_t capacity,
-                              size_t *n_out)
+int dge_get_umi_merge_targets(dge_handle *h, uint64_t *cell_barcodes, int32_t *gene_ids, uint32_t *source_umis, uint32_t *target_umis, uint8_t *created,
+                              size_t capacity, size_t *n_out)
 {
     if (!h || !n_out) return fail(h, DGE_ERR_INVALID, "null argument");
     if (h->state != 2) return fail(h, DGE_ERR_STATE, "UMI merge targets exist after merge_and_filter");
@@ -3951,6 +3982,25 @@ int dge_get_umi_merge_targets(dge_handle *h, uint64_t *cell_barcodes, int32_t *g
         {
             cell_barcodes[k] = h->umi_mt[k].cb; gene_ids[k] = int32_t(h->umi_mt[k].gene);
             source_umis[k] = h->umi_mt[k].src; target_umis[k] = h->umi_mt[k].dst;
+            if (created) created[k] = uint8_t(h->umi_mt[k].created);
+        }
+        return int(DGE_OK);
+    });
+}
+
+int dge_get_merge_events(dge_handle *h, uint64_t *from, uint64_t *to, size_t capacity, size_t *n_out)
+{
+    if (!h || !n_out) return fail(h, DGE_ERR_INVALID, "null argument");
+    if (h->state != 2) return fail(h, DGE_ERR_STATE, "merge events exist after merge_and_filter");
+    if (h->cfg.sharded) return fail(h, DGE_ERR_STATE, "merge events are not kept on sharded handles");
+    return guarded(h, [&] {
+        materialize_host(h);
+        *n_out = h->merge_events.size();
+        if (!from || !to || capacity < h->merge_events.size()) return int(DGE_OK);
+        for (size_t k = 0; k < h->merge_events.size(); ++k)
+        {
+            from[k] = h->real[h->merge_events[k].first].cb;
+            to[k] = h->real[h->merge_events[k].second].cb;
         }
         return int(DGE_OK);
     });

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <sstream>
 
@@ -340,16 +341,81 @@ namespace Estimation
 		return s;
 	}
 
+	// (barcode code, gene id, UMI code) -> per-base sums of the quality characters of the reads add_record saw for it.  Open addressing, grows by
+	// doubling; the sums live in one flat array (`len` entries from `off`).
+	struct CellsDataContainer::QualityTable
+	{
+		struct Slot { uint64_t cb, gu; uint32_t off; uint16_t len; uint16_t used; };
+		std::vector<Slot> slots;
+		std::vector<unsigned> sums;
+		size_t n = 0;
+		QualityTable() : slots(size_t(1) << 16, Slot{0, 0, 0, 0, 0}) {}
+		static size_t hash(uint64_t cb, uint64_t gu)
+		{
+			uint64_t x = cb * 0x9E3779B97F4A7C15ull ^ (gu + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+			x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+			return size_t(x);
+		}
+		Slot *find(uint64_t cb, uint64_t gu)
+		{
+			const size_t mask = slots.size() - 1;
+			for (size_t i = hash(cb, gu) & mask;; i = (i + 1) & mask)
+			{
+				Slot &s = slots[i];
+				if (!s.used) return nullptr;
+				if (s.cb == cb && s.gu == gu) return &s;
+			}
+		}
+		void grow()
+		{
+			std::vector<Slot> old(slots.size() * 2, Slot{0, 0, 0, 0, 0});
+			old.swap(slots);
+			const size_t mask = slots.size() - 1;
+			for (auto const &s : old)
+			{
+				if (!s.used) continue;
+				size_t i = hash(s.cb, s.gu) & mask;
+				while (slots[i].used) i = (i + 1) & mask;
+				slots[i] = s;
+			}
+		}
+		// UMI::add_read (UMI.cpp:21-34): the first read of a UMI fixes the length of its quality vector
+		void add(uint64_t cb, uint64_t gu, const std::string &quality)
+		{
+			if ((n + 1) * 10 > slots.size() * 6) grow();
+			const size_t mask = slots.size() - 1;
+			size_t i = hash(cb, gu) & mask;
+			while (slots[i].used && !(slots[i].cb == cb && slots[i].gu == gu)) i = (i + 1) & mask;
+			Slot &s = slots[i];
+			if (!s.used)
+			{
+				if (quality.size() > 0xFFFF || sums.size() + quality.size() > 0xFFFFFFFFull) throw std::runtime_error("UMI quality table is full");
+				s = Slot{cb, gu, uint32_t(sums.size()), uint16_t(quality.size()), 1};
+				sums.resize(sums.size() + quality.size(), 0u);
+				++n;
+			}
+			if (quality.size() != s.len)
+				throw std::runtime_error("Wrong quality length: " + std::to_string(quality.size()) + ", expected: " + std::to_string(s.len));
+			unsigned *p = sums.data() + s.off;
+			for (size_t k = 0; k < quality.size(); ++k) p[k] += unsigned(quality[k]); // a char, sign-extended like the reference's `+=`
+		}
+	};
+
 	CellsDataContainer::CellsDataContainer(const std::shared_ptr<Merge::MergeStrategyAbstract> &merge_strategy,
 	                                       const std::shared_ptr<Merge::UMIs::MergeUMIsStrategyAbstract> &umi_merge_strategy,
 	                                       const std::vector<UMI::Mark> &gene_match_levels, bool save_umi_merge_targets, int max_cells_num, int device,
-	                                       size_t n_genes_hint, bool reads_output)
+	                                       size_t n_genes_hint, bool reads_output, bool save_umi_qualities)
 		: _merge_strategy(merge_strategy), _umi_merge_strategy(umi_merge_strategy), _max_cells_num(max_cells_num)
 		, _query_marks(gene_match_levels), _device(device), _reads_output(reads_output), _save_umi_merge_targets(save_umi_merge_targets)
 		, _batch_capacity(n_genes_hint)
 	{
 		// _batch_capacity temporarily carries the gene-space hint until the handle exists
 		std::memset(&_summary, 0, sizeof(_summary));
+		if (save_umi_qualities)
+		{   // where a UMI object ends up after the merges decides whose quality sums it shows: the UMI merge targets are needed too
+			_qualities.reset(new QualityTable());
+			_save_umi_merge_targets = true;
+		}
 	}
 
 	CellsDataContainer::~CellsDataContainer() { if (_h) dge_destroy(_h); }
@@ -520,6 +586,9 @@ namespace Estimation
 				}
 			}
 		}
+		if (_qualities && gene != DGE_NO_GENE)
+			_qualities->add((flags & DGE_FLAG_CB_N) ? (DGE_CB_N_BIT | cbv) : cbv, (uint64_t(gene) << 32) | ((flags & DGE_FLAG_UMI_N) ? (DGE_UMI_N_BIT | uint32_t(umiv)) : uint32_t(umiv)),
+			                read_info.params.umi_quality());
 		_batch_chr.push_back(chr_id);
 		_batch_keys.push_back((cbv << 24) | umiv);
 		_batch_genes.push_back(gene | (uint32_t(read_info.umi_mark.bits()) << 24) | flags);
@@ -558,10 +627,12 @@ namespace Estimation
 		_cells.assign(n, Cell());
 		_cell_ids_by_cb.clear();
 		_merge_targets.resize(n);
+		_cell_codes.resize(n);
 		for (size_t i = 0; i < n; ++i)
 		{
 			Cell &c = _cells[i];
 			c._barcode = barcode_string(info[i].barcode);
+			_cell_codes[i] = info[i].barcode;
 			c._is_real = info[i].flags & DGE_CELL_REAL; c._is_merged = info[i].flags & DGE_CELL_MERGED; c._is_excluded = info[i].flags & DGE_CELL_EXCLUDED;
 			c._n_genes = size_t(info[i].n_genes);
 			c._requested_genes_num = size_t(info[i].requested_genes_num); c._requested_umis_num = size_t(info[i].requested_umis_num);
@@ -605,11 +676,12 @@ namespace Estimation
 		if (_save_umi_merge_targets && _is_merged)
 		{   // Gene::_merge_targets: the source UMIs are gone from the gene, their strings still belong to the UMI indexer (Gene.cpp:38-58)
 			size_t nt = 0;
-			check(dge_get_umi_merge_targets(_h, nullptr, nullptr, nullptr, nullptr, 0, &nt));
+			check(dge_get_umi_merge_targets(_h, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &nt));
 			std::vector<uint64_t> t_cb(nt);
 			std::vector<int32_t> t_gene(nt);
 			std::vector<uint32_t> t_src(nt), t_dst(nt);
-			if (nt) check(dge_get_umi_merge_targets(_h, t_cb.data(), t_gene.data(), t_src.data(), t_dst.data(), nt, &nt));
+			std::vector<uint8_t> t_created(nt);
+			if (nt) check(dge_get_umi_merge_targets(_h, t_cb.data(), t_gene.data(), t_src.data(), t_dst.data(), t_created.data(), nt, &nt));
 			for (size_t k = 0; k < nt; ++k)
 			{
 				Cell &c = _cells.at(_cell_ids_by_cb.at(barcode_string(t_cb[k])));
@@ -619,8 +691,69 @@ namespace Estimation
 				_umi_indexer.add(dst);
 				git->second._merge_targets[src] = dst;
 			}
+			if (_qualities)
+			{
+				_created.clear();
+				for (size_t k = 0; k < nt; ++k)
+					if (t_created[k]) _created[std::make_pair(_cell_ids_by_cb.at(barcode_string(t_cb[k])), (uint64_t(uint32_t(t_gene[k])) << 32) | t_dst[k])] = t_src[k];
+			}
+		}
+		if (_qualities)
+		{
+			_loaded_cell = std::move(cell); _loaded_gene = std::move(gene); _loaded_umi = std::move(umi);
+			load_qualities();
 		}
 		_genes_loaded = true;
+	}
+
+	// UMI::_sum_quality of every held UMI.  A UMI object keeps the quality sums of the reads that were ADDED to it; merges move or drop objects:
+	//   * merge_cells -> Cell::merge -> Gene::merge(const Gene &) (Gene.cpp:26-36): the target keeps its own object, and takes a copy of the
+	//     source's only when it has none.  So a merged cell's UMI shows the sums of the first holder along the merge_cells calls, in the order
+	//     they were applied (dge_get_merge_events), the target itself first;
+	//   * Gene::merge(source_umi, target_umi) (Gene.cpp:38-58) of the UMI merge strategies: the source's object becomes the target when the
+	//     target does not exist (`created`), otherwise it is dropped.
+	void CellsDataContainer::load_qualities() const
+	{
+		QualityTable &qt = *_qualities;
+		// merge_cells calls into every cell, in time order
+		std::unordered_map<size_t, std::vector<std::pair<size_t, size_t>>> incoming; // target cell id -> (time, source cell id)
+		if (_is_merged)
+		{
+			size_t ne = 0;
+			check(dge_get_merge_events(_h, nullptr, nullptr, 0, &ne));
+			std::vector<uint64_t> from(ne), to(ne);
+			if (ne) check(dge_get_merge_events(_h, from.data(), to.data(), ne, &ne));
+			for (size_t t = 0; t < ne; ++t)
+				incoming[_cell_ids_by_cb.at(barcode_string(to[t]))].emplace_back(t, _cell_ids_by_cb.at(barcode_string(from[t])));
+		}
+		// the object (cell, gene, umi) held just before time `limit` of the barcode merge: its own, else the first one merged in
+		std::function<const QualityTable::Slot *(size_t, uint64_t, size_t)> held = [&](size_t cell_id, uint64_t gu, size_t limit) -> const QualityTable::Slot * {
+			if (const QualityTable::Slot *own = qt.find(_cell_codes[cell_id], gu)) return own;
+			auto in = incoming.find(cell_id);
+			if (in == incoming.end()) return nullptr;
+			for (auto const &e : in->second)
+			{
+				if (e.first >= limit) break;
+				if (const QualityTable::Slot *s = held(e.second, gu, e.first)) return s;
+			}
+			return nullptr;
+		};
+		const size_t forever = ~size_t(0);
+		for (size_t k = 0; k < _loaded_cell.size(); ++k)
+		{
+			const size_t cell_id = _loaded_cell[k];
+			uint64_t gu = (uint64_t(uint32_t(_loaded_gene[k])) << 32) | _loaded_umi[k];
+			for (int hop = 0; hop < 8; ++hop)
+			{   // an object that the UMI merge moved under another name
+				auto c = _created.find(std::make_pair(cell_id, gu));
+				if (c == _created.end()) break;
+				gu = (gu & 0xFFFFFFFF00000000ull) | c->second;
+			}
+			const QualityTable::Slot *s = held(cell_id, gu, forever);
+			if (!s) throw std::runtime_error("internal: no base-quality record for a held UMI");
+			UMI &u = _cells[cell_id]._genes.at(size_t(_loaded_gene[k]))._umis.at(_umi_indexer.get_index(umi_string(_loaded_umi[k])));
+			u._sum_quality.assign(qt.sums.begin() + s->off, qt.sums.begin() + s->off + s->len);
+		}
 	}
 
 	size_t CellsDataContainer::total_cells_number() const { load_cells(); return _cells.size(); }
@@ -839,6 +972,7 @@ namespace Estimation
 				tagged("names"); strvec(names); nil();
 			}
 			void list_header(size_t n) { flags(19, false, true); i32(int32_t(n)); }
+			void plain_list_header(size_t n) { flags(19); i32(int32_t(n)); } // a list without attributes (List::create without names)
 			void list_names(const std::vector<std::string> &names) { tagged("names"); strvec(names); nil(); }
 			void dgcmatrix(const ResultsPrinter::SparseMatrix &m)
 			{
@@ -854,6 +988,36 @@ namespace Estimation
 				nil();
 			}
 		};
+	}
+
+	ResultsPrinter::ReadsPerUmiPerCell ResultsPrinter::get_reads_per_umi_per_cell(const CellsDataContainer &container) const
+	{
+		if (!container.umi_qualities_saved())
+			throw std::runtime_error("dropest_b200: reads_per_umi_per_cell needs a CellsDataContainer built with save_umi_qualities = true");
+		ReadsPerUmiPerCell res;
+		StringIndexer cell_indexer, gene_indexer;
+		for (size_t container_cell_id : container.filtered_cells())
+		{
+			const Cell &cur_cell = container.cell(container_cell_id);
+			const unsigned cell_id = unsigned(cell_indexer.add(cur_cell.barcode()));
+			for (auto const &gene_rpus : cur_cell.requested_reads_per_umi_per_gene(container.gene_match_level()))
+			{
+				const unsigned gene_id = unsigned(gene_indexer.add(gene_rpus.first));
+				ReadsPerUmiPerCell::Entry e;
+				for (auto const &umi_reads : gene_rpus.second)
+				{
+					e.umis.push_back(umi_reads.first);
+					e.reads.push_back(unsigned(umi_reads.second));
+					e.mean_quality.push_back(cur_cell.at(gene_rpus.first).at(umi_reads.first).mean_quality());
+				}
+				res.reads_per_umi.push_back(std::move(e));
+				res.cell_indexes.push_back(cell_id);
+				res.gene_indexes.push_back(gene_id);
+			}
+		}
+		res.cells = cell_indexer.values();
+		res.genes = gene_indexer.values();
+		return res;
 	}
 
 	void ResultsPrinter::save_rds(const CellsDataContainer &container, const SparseMatrix &cm, const SparseMatrix &cm_raw,
@@ -894,8 +1058,10 @@ namespace Estimation
 				}
 		}
 		const bool chr_tables = container.chromosome_stats_available();
+		ReadsPerUmiPerCell rpupc;
+		if (umi_correction_info) rpupc = get_reads_per_umi_per_cell(container);
 		RdsWriter w(filename_base + ".rds");
-		w.list_header(chr_tables ? 10 : 9);
+		w.list_header((chr_tables ? 10 : 9) + (umi_correction_info ? 1 : 0));
 		w.dgcmatrix(cm);
 		w.dgcmatrix(cm_raw);
 		if (chr_tables)
@@ -920,10 +1086,33 @@ namespace Estimation
 		w.intvec(umis, &real_names);
 		w.intvec(req_umis, &real_names);
 		w.intvec(req_reads, &real_names);
+		if (umi_correction_info)
+		{   // d$reads_per_umi_per_cell <- list(cells, genes, cell_indexes, gene_indexes, reads_per_umi) (ResultsPrinter.cpp:59-64, 308-313); Rcpp wraps
+			// unsigned values as numeric
+			w.list_header(5);
+			w.strvec(rpupc.cells);
+			w.strvec(rpupc.genes);
+			w.realvec(std::vector<double>(rpupc.cell_indexes.begin(), rpupc.cell_indexes.end()));
+			w.realvec(std::vector<double>(rpupc.gene_indexes.begin(), rpupc.gene_indexes.end()));
+			w.plain_list_header(rpupc.reads_per_umi.size());
+			for (auto const &e : rpupc.reads_per_umi)
+			{
+				w.list_header(e.umis.size());
+				for (size_t k = 0; k < e.umis.size(); ++k)
+				{
+					w.plain_list_header(2);
+					w.realvec({double(e.reads[k])});
+					w.realvec(e.mean_quality[k]);
+				}
+				w.list_names(e.umis);
+			}
+			w.list_names({"cells", "genes", "cell_indexes", "gene_indexes", "reads_per_umi"});
+		}
 		std::vector<std::string> fields = {"cm", "cm_raw"};
 		if (chr_tables) fields.push_back("reads_per_chr_per_cells");
 		for (const char *f : {"mean_reads_per_umi", "saturation_info", "merge_targets", "aligned_reads_per_cell", "aligned_umis_per_cell",
 		                      "requested_umis_per_cb", "requested_reads_per_cb"}) fields.push_back(f);
+		if (umi_correction_info) fields.push_back("reads_per_umi_per_cell");
 		w.list_names(fields);
 	}
 
@@ -932,6 +1121,7 @@ namespace Estimation
 		std::string base = filename;
 		auto pos = filename.find_last_of('.');
 		if (pos != std::string::npos && filename.substr(pos + 1) == "rds") base = filename.substr(0, pos); // extract_filename_base, :93-100
+		if (validation_stats) throw std::runtime_error("dropest_b200: the merge validation statistics (-S, MergeProbabilityValidator) are not available");
 		SparseMatrix cm = get_count_matrix(container, true), cm_raw = get_count_matrix(container, false);
 		save_rds(container, cm, cm_raw, base);
 		if (write_matrix) save_mtx(cm, base);

@@ -132,11 +132,22 @@ namespace Estimation
 	private:
 		size_t _read_count;
 		Mark _mark;
+		std::vector<unsigned> _sum_quality; // UMI.h:51; filled only by a container built with save_umi_qualities
+		friend class CellsDataContainer;
 
 	public:
 		explicit UMI(size_t read_count = 0, Mark mark = Mark()) : _read_count(read_count), _mark(mark) {}
 		size_t read_count() const { return _read_count; }
 		const Mark &mark() const { return _mark; }
+		// UMI.cpp:46-55, literally: the Phred offset is subtracted ONCE from the per-base sum of quality characters and the difference is
+		// divided by the read count in unsigned integer arithmetic.  The sum covers the reads added to THIS object (UMI::add_read): UMI::merge
+		// (:15-19) adds read counts and marks but not qualities, so after barcode / UMI merges it is the first holder's sum over the merged count.
+		std::vector<double> mean_quality() const
+		{
+			std::vector<double> res(_sum_quality.size());
+			for (size_t i = 0; i < res.size(); ++i) res[i] = double(size_t(unsigned(_sum_quality[i] - unsigned(33))) / _read_count);
+			return res;
+		}
 	};
 
 	class ReadInfo // ReadInfo.h:9-24
@@ -507,7 +518,16 @@ namespace Estimation
 		mutable std::vector<Cell> _cells;
 		mutable std::unordered_map<std::string, size_t> _cell_ids_by_cb;
 		mutable ids_t _filtered_cells, _merge_targets;
+		mutable std::vector<uint64_t> _cell_codes; // barcode codes of the cells (dge_cell_info.barcode), cell-id order
 		mutable dge_summary _summary;
+		// per-base sums of the UMI quality characters of every (barcode, gene, UMI) as add_record saw it (UMI::add_read, UMI.cpp:21-34); host side
+		struct QualityTable;
+		std::unique_ptr<QualityTable> _qualities;
+		void load_qualities() const;
+		struct PairHash { size_t operator()(const std::pair<size_t, uint64_t> &p) const { return std::hash<uint64_t>()(p.second * 0x9E3779B97F4A7C15ull ^ p.first); } };
+		mutable std::unordered_map<std::pair<size_t, uint64_t>, uint32_t, PairHash> _created; // (cell id, gene << 32 | UMI) created by the UMI merge -> source UMI
+		mutable std::vector<uint32_t> _loaded_cell, _loaded_umi;                            // the rows of the last dge_get_umigs (load_genes)
+		mutable std::vector<int32_t> _loaded_gene;
 
 		void ensure_handle();
 		void flush();
@@ -520,7 +540,7 @@ namespace Estimation
 		CellsDataContainer(const std::shared_ptr<Merge::MergeStrategyAbstract> &merge_strategy,
 		                   const std::shared_ptr<Merge::UMIs::MergeUMIsStrategyAbstract> &umi_merge_strategy,
 		                   const std::vector<UMI::Mark> &gene_match_levels, bool save_umi_merge_targets = false, int max_cells_num = -1,
-		                   int device = 0, size_t n_genes_hint = 1u << 17, bool reads_output = false);
+		                   int device = 0, size_t n_genes_hint = 1u << 17, bool reads_output = false, bool save_umi_qualities = false);
 		~CellsDataContainer();
 		CellsDataContainer(const CellsDataContainer &) = delete;
 		CellsDataContainer &operator=(const CellsDataContainer &) = delete;
@@ -540,6 +560,7 @@ namespace Estimation
 		using counts_t = std::vector<int>;
 		void get_stat_by_real_cells(Stats::CellChrStatType stat, names_t &cell_barcodes, names_t &chromosome_names, counts_t &counts) const;
 		bool chromosome_stats_available() const { return !_chr_overflow; }
+		bool umi_qualities_saved() const { return bool(_qualities); } // built with save_umi_qualities: UMI::mean_quality is meaningful
 		s_ul_hash_t umi_distribution() const; // CellsDataContainer.cpp:182-197: occurrences of every UMI string over the (gene, UMI) entries of the filtered cells
 		const Cell &cell(size_t index) const;
 		size_t intergenic_reads_num() const;
@@ -564,10 +585,24 @@ namespace Estimation
 	// ResultsPrinter (ResultsPrinter.cpp:23-91,334-453): count matrices -> MatrixMarket + cells/genes tsv and an R-readable .rds
 	class ResultsPrinter
 	{
-		bool write_matrix, reads_output;
+		bool write_matrix, reads_output, validation_stats, umi_correction_info;
 
 	public:
-		ResultsPrinter(bool write_matrix, bool reads_output) : write_matrix(write_matrix), reads_output(reads_output) {}
+		// ResultsPrinter.cpp:16-21.  umi_correction_info (dropest passes !umi_merge, dropest.cpp:311) adds `reads_per_umi_per_cell` to the .rds and
+		// needs a container built with save_umi_qualities; validation_stats (-S, MergeProbabilityValidator) is not mirrored: save_results throws.
+		ResultsPrinter(bool write_matrix, bool reads_output, bool validation_stats = false, bool umi_correction_info = false)
+			: write_matrix(write_matrix), reads_output(reads_output), validation_stats(validation_stats), umi_correction_info(umi_correction_info) {}
+		// get_reads_per_umi_per_cell (ResultsPrinter.cpp:261-314): filtered cells, requested UMIs.  Entry k belongs to cells[cell_indexes[k]] and
+		// genes[gene_indexes[k]] and lists, per UMI, its read count and UMI::mean_quality.  Cells, genes and entries come in the reference's
+		// order; the UMIs inside an entry are an R named list whose order follows an unordered_map over UMI-indexer ids and is not reproduced.
+		struct ReadsPerUmiPerCell
+		{
+			std::vector<std::string> cells, genes;
+			std::vector<unsigned> cell_indexes, gene_indexes;
+			struct Entry { std::vector<std::string> umis; std::vector<unsigned> reads; std::vector<std::vector<double>> mean_quality; };
+			std::vector<Entry> reads_per_umi;
+		};
+		ReadsPerUmiPerCell get_reads_per_umi_per_cell(const CellsDataContainer &container) const;
 		void save_results(const CellsDataContainer &container, const std::string &filename) const;
 
 		struct SparseMatrix // dgCMatrix layout: column-compressed, rows ascending inside a column

@@ -287,10 +287,20 @@ int dge_get_umigs(dge_handle *h, int which, uint32_t *cell_index, int32_t *gene_
 /* Gene::merge_targets() (Gene.h:41, filled by Gene::merge(source_umi, target_umi), Gene.cpp:38-58) of every (cell, gene): one row per UMI
  * that MergeUMIsStrategySimple (N repair) or MergeUMIsStrategyDirectional moved into another UMI -- the cell that owns the gene after the
  * barcode merge, the gene, the source UMI and the UMI it went to (codes as in dge_get_umigs; a target created by the N repair is a new,
- * N-free UMI).  Sorted by (barcode code, gene, source).  The only consumer in the reference is the filtered-BAM writer,
- * FilteringBamProcessor::write_alignment (BamProcessing/FilteringBamProcessor.cpp:73-88).  Needs dge_config.save_umi_merge_targets. */
+ * N-free UMI).  Sorted by (barcode code, gene, source).  created[k] (optional, may be NULL) = 1 when the target did not exist in the gene
+ * and the source's UMI object BECAME it (Gene.cpp:48: emplace(target, source object) -- the target then carries the source's base-quality sums,
+ * which is all that distinguishes the two cases).  Consumers in the reference: the filtered-BAM writer, FilteringBamProcessor::write_alignment
+ * (BamProcessing/FilteringBamProcessor.cpp:73-88), and through UMI::mean_quality the `reads_per_umi_per_cell` table.  Needs
+ * dge_config.save_umi_merge_targets. */
 int dge_get_umi_merge_targets(dge_handle *h, uint64_t *cell_barcodes, int32_t *gene_ids, uint32_t *source_umis, uint32_t *target_umis,
-                              size_t capacity, size_t *n_out);
+                              uint8_t *created, size_t capacity, size_t *n_out);
+
+/* The merge_cells(source, target) calls of the barcode merge in the order they were applied (MergeStrategyBase::merge_inited,
+ * MergeStrategyBase.cpp:29-51 -> merge_force, :84-89): `to` is the cell the source's content went into AT THAT TIME, which with merge chains
+ * is not the final target dge_get_merge_pairs reports.  Needed where the order shows: Gene::merge keeps the target's own UMI object and only
+ * copies a source's when the target has none (Gene.cpp:26-36), so per-UMI base-quality sums (UMI::mean_quality) belong to the first holder.
+ * Single-GPU handles only. */
+int dge_get_merge_events(dge_handle *h, uint64_t *from, uint64_t *to, size_t capacity, size_t *n_out);
 
 /* ---- helpers that mirror reference utilities on the path (host-side, exact restatements used by the facade and tests) -- */
 

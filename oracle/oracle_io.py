@@ -64,7 +64,7 @@ def run_oracle(in_path: str, kind: str = "any", merge: str = "none", barcodes: O
                min_frac: float = 0.2, marks: str = "eEBA", max_cells: int = -1, reads_output: bool = False,
                dump_umis: bool = False, umi_merge: str = "simple", max_umi_ed: int = 1, umi_mult: float = 2.0, limit: int = 0,
                max_merge_prob: float = 1e-4, max_real_merge_prob: float = 1e-7, init_only: bool = False,
-               timeout: Optional[float] = None) -> Dict[str, np.ndarray]:
+               timeout: Optional[float] = None, dump_rpupc: bool = False) -> Dict[str, np.ndarray]:
     exe = oracle_binary(kind)
     with tempfile.TemporaryDirectory() as td:
         out = os.path.join(td, "out.dgeo")
@@ -78,6 +78,8 @@ def run_oracle(in_path: str, kind: str = "any", merge: str = "none", barcodes: O
             cmd.append("--reads-output")
         if dump_umis:
             cmd.append("--dump-umis")
+        if dump_rpupc:   # the compiled reference only (reads_per_umi_per_cell with UMI::mean_quality)
+            cmd.append("--dump-rpupc")
         if init_only:
             cmd.append("--init-only")
         if limit:

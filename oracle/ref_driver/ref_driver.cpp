@@ -40,7 +40,7 @@ struct Args
 	unsigned max_cb_ed = 2, max_umi_ed = 1;
 	double min_frac = 0.2, max_merge_prob = 1e-4, max_real_merge_prob = 1e-7, umi_mult = 2;
 	int max_cells = -1;
-	bool reads_output = false, dump_umis = false, stream = false, init_only = false;
+	bool reads_output = false, dump_umis = false, dump_rpupc = false, stream = false, init_only = false;
 	size_t limit = 0;
 };
 
@@ -73,6 +73,7 @@ static Args parse_args(int argc, char **argv)
 		else if (k == "--limit") a.limit = std::stoul(next());
 		else if (k == "--reads-output") a.reads_output = true;
 		else if (k == "--dump-umis") a.dump_umis = true;
+		else if (k == "--dump-rpupc") a.dump_rpupc = true;
 		else if (k == "--stream") a.stream = true;
 		else if (k == "--init-only") a.init_only = true;
 		else throw std::runtime_error("unknown argument " + k);
@@ -335,6 +336,42 @@ int main(int argc, char **argv)
 			w.add("umi_cell", dge_io::I64, ucell); w.add("umi_gene", dge_io::I64, ugene); w.add("umi_count", dge_io::I64, ucount);
 			w.add("umi_mark", dge_io::U8, umark);
 			w.add_strings("umi_seq", useq);
+		}
+
+		if (a.dump_rpupc)
+		{
+			// reads_per_umi_per_cell: the walk of ResultsPrinter::get_reads_per_umi_per_cell (ResultsPrinter.cpp:261-314; that file needs Rcpp) with
+			// the container's own accessors -- filtered cells, requested_reads_per_umi_per_gene, UMI::mean_quality
+			StringIndexer cell_indexer, gene_indexer;
+			std::vector<int64_t> e_cell, e_gene, u_entry, u_reads, u_qlen;
+			std::vector<std::string> u_seq;
+			std::vector<double> u_q;
+			for (auto container_cell_id : container.filtered_cells())
+			{
+				auto const &cur_cell = container.cell(container_cell_id);
+				unsigned cell_id = cell_indexer.add(cur_cell.barcode());
+				for (auto const &gene_rpus : cur_cell.requested_reads_per_umi_per_gene(container.gene_match_level()))
+				{
+					unsigned gene_id = gene_indexer.add(gene_rpus.first);
+					for (auto const &umi_reads : gene_rpus.second)
+					{
+						auto mean_quality = cur_cell.at(gene_rpus.first).at(umi_reads.first).mean_quality();
+						u_entry.push_back(int64_t(e_cell.size()));
+						u_seq.push_back(umi_reads.first);
+						u_reads.push_back(int64_t((unsigned) umi_reads.second));
+						u_qlen.push_back(int64_t(mean_quality.size()));
+						u_q.insert(u_q.end(), mean_quality.begin(), mean_quality.end());
+					}
+					e_cell.push_back(cell_id);
+					e_gene.push_back(gene_id);
+				}
+			}
+			w.add_strings("rp_cells", cell_indexer.values());
+			w.add_strings("rp_genes", gene_indexer.values());
+			w.add("rp_cell_indexes", dge_io::I64, e_cell); w.add("rp_gene_indexes", dge_io::I64, e_gene);
+			w.add("rp_umi_entry", dge_io::I64, u_entry); w.add("rp_umi_reads", dge_io::I64, u_reads); w.add("rp_umi_qlen", dge_io::I64, u_qlen);
+			w.add_strings("rp_umi_seq", u_seq);
+			w.add("rp_umi_quality", dge_io::F64, u_q);
 		}
 
 		w.add_scalar_i64("n_reads", int64_t(n_reads));
