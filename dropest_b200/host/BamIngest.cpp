@@ -4,6 +4,7 @@
 #include "BamOutput.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <thread>
@@ -385,9 +386,69 @@ namespace BamProcessing
 		}
 	}
 
-	bool read_info_from_alignment(const BamAlignment &al, const std::string &chr_name, const IngestParams &params, IngestStats &stats,
-	                              Tools::ReadParameters &read_params, std::string &gene, UMI::Mark &mark)
+	ReadParamsMap::ReadParamsMap(const std::string &read_param_filenames, int min_barcode_quality)
 	{
+		const int min_phred = min_barcode_quality + 33; // ReadParameters::quality_to_phred
+		size_t start = 0;
+		while (start <= read_param_filenames.size())
+		{
+			size_t end = read_param_filenames.find_first_of(" \t", start);
+			if (end == std::string::npos) end = read_param_filenames.size();
+			std::string name = read_param_filenames.substr(start, end - start);
+			start = end + 1;
+			if (name.empty()) continue;
+			if (name[0] == '~')
+				if (const char *home = std::getenv("HOME")) name = std::string(home) + name.substr(1); // Tools::expand_tilde_in_path
+			gzFile f = gzopen(name.c_str(), "rb");
+			if (!f) throw std::runtime_error("Can't open file with read parameters'" + name + "'");
+			std::string row;
+			char buf[1 << 16];
+			auto take_row = [&]() {
+				if (row.empty()) return;
+				// parse_from_string: four blanks split off name, barcode, UMI, barcode quality; the rest is the UMI quality
+				size_t pos[4], p0 = 0;
+				bool ok = true;
+				for (int k = 0; k < 4 && ok; ++k)
+				{
+					pos[k] = row.find(' ', p0);
+					if (pos[k] == std::string::npos) ok = false; else p0 = pos[k] + 1;
+				}
+				if (!ok) return; // "can't parse read parameters from string": logged and skipped
+				std::string read_name = row.substr(0, pos[0]);
+				if (!read_name.empty() && read_name[0] == '@') read_name.erase(0, 1);
+				const std::string cb = row.substr(pos[0] + 1, pos[1] - pos[0] - 1), umi = row.substr(pos[1] + 1, pos[2] - pos[1] - 1),
+				                  cbq = row.substr(pos[2] + 1, pos[3] - pos[2] - 1), umiq = row.substr(pos[3] + 1);
+				if (cb.empty() || umi.empty()) return; // "Wrong read parameters"
+				bool pass = true;
+				if (min_phred > 33)
+				{
+					for (char c : cbq) if (c < min_phred) pass = false;
+					for (char c : umiq) if (c < min_phred) pass = false;
+				}
+				// the indexers grow even when the name turns out to be a repeat, as the reference's do; only the first row of a name counts
+				const Entry e{uint32_t(_barcodes.add(cb)), uint32_t(_umis.add(umi)), uint32_t(_umi_qualities.add(umiq)), pass, false};
+				_reads.emplace(read_name, e);
+			};
+			while (gzgets(f, buf, int(sizeof(buf))))
+			{
+				const size_t n = std::strlen(buf);
+				if (n && buf[n - 1] == '\n') { row.append(buf, n - 1); take_row(); row.clear(); }
+				else row.append(buf, n);
+			}
+			take_row();
+			gzclose(f);
+		}
+	}
+
+	Tools::ReadParameters ReadParamsMap::parameters(const Entry &e) const
+	{
+		return Tools::ReadParameters(_barcodes.get_value(e.barcode), _umis.get_value(e.umi), "", _umi_qualities.get_value(e.umi_quality));
+	}
+
+	bool read_info_from_alignment(const BamAlignment &al, const std::string &chr_name, const IngestParams &params, IngestStats &stats,
+	                              Tools::ReadParameters &read_params, std::string &gene, UMI::Mark &mark, MapLookup *map)
+	{
+		if (map) *map = MapLookup();
 		// every tag this read can need, found in ONE walk over its tag block
 		const std::string *wanted[6] = {&params.tags.cell_barcode, &params.tags.umi, &params.tags.cell_barcode_quality, &params.tags.umi_quality,
 		                                &params.tags.gene, &params.tags.read_type};
@@ -412,6 +473,19 @@ namespace BamProcessing
 				}
 				read_params = Tools::ReadParameters(std::move(cb), std::move(umi), std::move(cbq), std::move(umiq));
 			}
+			else if (params.read_params)
+			{   // ReadMapParamsParser::get_read_params (.cpp:22-48)
+				ReadParamsMap::Entry *e = params.read_params->find(!al.name.empty() && al.name[0] == '@' ? al.name.substr(1) : al.name);
+				if (!e) { ++stats.cant_parse; return false; }
+				read_params = params.read_params->parameters(*e);
+				if (map) map->entry = e;
+				else
+				{   // a caller that walks the reads itself, in order
+					if (e->taken) { ++stats.cant_parse; return false; }
+					e->taken = true;
+					pass_quality = e->pass_quality;
+				}
+			}
 			else read_params = Tools::ReadParameters::parse_encoded_id(al.name);
 		}
 		catch (std::runtime_error &)
@@ -433,7 +507,12 @@ namespace BamProcessing
 		if (params.genes && !params.genes->is_empty())
 		{
 			try { mark = gene_from_reference(*params.genes, chr_name, al, gene); }
-			catch (Tools::GeneAnnotation::RefGenesContainer::ChrNotFoundException &) { ++stats.cant_parse; return false; } // BamController.cpp:158-166
+			catch (Tools::GeneAnnotation::RefGenesContainer::ChrNotFoundException &)
+			{   // BamController.cpp:158-166
+				if (map && map->entry) { map->chr_not_found = true; return true; }
+				++stats.cant_parse;
+				return false;
+			}
 			return true;
 		}
 		if (!tv[4].string(gene))
@@ -478,7 +557,7 @@ namespace BamProcessing
 					if (al.ref_id < 0 || size_t(al.ref_id) >= n_refs) { r.status = ParsedRead::NO_CHROMOSOME; continue; }
 					if (!params.filled_bam) al.name.assign(records[k].name_data, records[k].name_len);
 					IngestStats st;
-					if (read_info_from_alignment(al, refs[size_t(al.ref_id)], params, st, r.params, r.gene, r.mark)) r.status = ParsedRead::OK;
+					if (read_info_from_alignment(al, refs[size_t(al.ref_id)], params, st, r.params, r.gene, r.mark, &r.map)) r.status = ParsedRead::OK;
 					else r.status = st.low_quality ? ParsedRead::LOW_QUALITY : ParsedRead::CANT_PARSE;
 				}
 			}

@@ -16,6 +16,7 @@
 #include <future>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace Estimation
@@ -110,9 +111,35 @@ namespace BamProcessing
 		bool view_at(size_t pos, RecordView &v, size_t &next_pos) const; // the record at _data[pos], false when it is not complete yet
 	};
 
+	// -r: barcode, UMI and UMI quality of every read from separate (gzipped) text files written by droptag, one row per read:
+	// "name barcode UMI barcode_quality UMI_quality" (ReadMapParamsParser.cpp:50-109, ReadParameters::parse_from_string, ReadParameters.cpp:59-81).
+	// Rows that cannot be parsed and repeated names are skipped like the reference does; a read is handed out ONCE (get_read_params erases
+	// it, :22-48), a second alignment of the same name cannot be parsed.
+	class ReadParamsMap
+	{
+	public:
+		ReadParamsMap(const std::string &read_param_filenames, int min_barcode_quality); // file names separated by blanks / tabs
+		struct Entry { uint32_t barcode, umi, umi_quality; bool pass_quality; bool taken; };
+		Entry *find(const std::string &read_name) { auto it = _reads.find(read_name); return it == _reads.end() ? nullptr : &it->second; }
+		Tools::ReadParameters parameters(const Entry &e) const; // barcode quality is not kept (ReadParametersEfficient.cpp:15-23)
+		size_t size() const { return _reads.size(); }
+
+	private:
+		std::unordered_map<std::string, Entry> _reads;
+		StringIndexer _barcodes, _umis, _umi_qualities;
+	};
+
+	// -r bookkeeping of one read that is settled by whoever sees the reads in stream order: the row it found, and whether the annotation did
+	// not know its chromosome (which the reference only finds out after the row was taken and the quality checked, BamController.cpp:139-166)
+	struct MapLookup { ReadParamsMap::Entry *entry = nullptr; bool chr_not_found = false; };
+
 	struct IngestParams
 	{
 		bool filled_bam = true;               // -f: barcode / UMI from tags; false: from the read name "prefix!CB#UMI" (ReadParameters::parse_encoded_id)
+		// not -f and non-empty: -r, barcode / UMI looked up by read name in these files (BamController::get_parser, BamController.cpp:118-129).
+		// Loaded by parse_bam_files / for_each_alignment when `read_params` is not set yet.
+		std::string read_param_filenames;
+		std::shared_ptr<ReadParamsMap> read_params;
 		BamTags tags;
 		bool gene_in_chromosome_name = false; // pseudo-aligner output: the reference name is the gene
 		int min_barcode_quality = 0;          // -f only: reads with a barcode / UMI base below this Phred quality are dropped (0 = off)
@@ -140,13 +167,16 @@ namespace BamProcessing
 	template <class F> void for_each_read(const std::vector<std::string> &bam_files, const IngestParams &params, IngestStats &stats, F &&sink);
 
 	// one alignment -> ReadInfo; false = counted in `stats` and skipped (process_alignment, BamController.cpp:131-172)
+	// In -r mode `map` (when given) receives the row the parameters came from; its quality flag, its "taken" state and an unknown chromosome
+	// are left to the caller, which sees the reads in stream order.
 	bool read_info_from_alignment(const BamAlignment &alignment, const std::string &chr_name, const IngestParams &params, IngestStats &stats,
-	                              Tools::ReadParameters &read_params, std::string &gene, UMI::Mark &mark);
+	                              Tools::ReadParameters &read_params, std::string &gene, UMI::Mark &mark, MapLookup *map = nullptr);
 
 	// One parsed alignment of a batch (filled by several threads, consumed in order)
 	struct ParsedRead
 	{
 		enum Status : uint8_t { OK, SKIPPED, NO_CHROMOSOME, CANT_PARSE, LOW_QUALITY } status = SKIPPED;
+		MapLookup map; // -r: the row this read took its parameters from (claimed in stream order by the consumer)
 		int32_t ref_id = -1;
 		Tools::ReadParameters params;
 		std::string gene;
@@ -167,6 +197,8 @@ namespace BamProcessing
 		IngestParams params(params_in);
 		if (!params.genes && !params.genes_filename.empty())
 			params.genes = std::make_shared<const Tools::GeneAnnotation::RefGenesContainer>(params.genes_filename);
+		if (!params.filled_bam && !params.read_params && !params.read_param_filenames.empty())
+			params.read_params = std::make_shared<ReadParamsMap>(params.read_param_filenames, params.min_barcode_quality);
 		std::vector<BamReader::RecordView> views;
 		std::vector<ParsedRead> parsed, parsed_next;
 		for (auto const &file : bam_files)
@@ -199,6 +231,13 @@ namespace BamProcessing
 						case ParsedRead::LOW_QUALITY: ++stats.total_reads; ++stats.low_quality; break;
 						case ParsedRead::OK:
 							++stats.total_reads;
+							if (r.map.entry)
+							{   // -r: a row serves one alignment; the next one of that name is "can't find read name" (ReadMapParamsParser.cpp:27-42)
+								if (r.map.entry->taken) { ++stats.cant_parse; break; }
+								r.map.entry->taken = true;
+								if (!r.map.entry->pass_quality) { ++stats.low_quality; break; }
+								if (r.map.chr_not_found) { ++stats.cant_parse; break; }
+							}
 							sink(ReadInfo(std::move(r.params), std::move(r.gene), refs[size_t(r.ref_id)], r.mark), keep_records ? &views[k] : nullptr);
 							break;
 						}

@@ -7,7 +7,7 @@
 // driver reads and writes are TEXT (oracle/shim/api/BamReader.h, BamWriter.h); a test writes the same alignments as a real BAM for the
 // product and compares the tags of what comes out.  Output files land in the working directory, as the reference does.
 //   ref_bam_flow [--merge none|real|simple ...] [--barcodes F --barcodes-type const|indrop] [--min-genes-before N] [--min-genes-after N]
-//                [--umi-merge simple|directional] [--filled 0|1] [--type-tag T --intronic V --intergenic V --exonic V]
+//                [--umi-merge simple|directional] [--filled 0|1] [--read-params "F F ..."] [--min-quality Q] [--type-tag T --intronic V --intergenic V --exonic V]
 //                [--bam-output 0|1] [--filtered 0|1] alignments.txt ...
 #include <Estimation/BamProcessing/BamController.h>
 #include <Estimation/CellsDataContainer.h>
@@ -37,7 +37,8 @@ int main(int argc, char **argv)
 {
 	try
 	{
-		std::string merge = "none", barcodes, barcodes_type = "const", umi_merge = "simple", marks = "eEBA";
+		std::string merge = "none", barcodes, barcodes_type = "const", umi_merge = "simple", marks = "eEBA", read_params;
+		int min_quality = 0;
 		size_t min_before = 10, min_after = 10;
 		unsigned max_cb_ed = 2, max_umi_ed = 1;
 		double min_frac = 0.2, umi_mult = 2;
@@ -63,6 +64,8 @@ int main(int argc, char **argv)
 			else if (k == "--min-frac") min_frac = std::stod(next());
 			else if (k == "--umi-mult") umi_mult = std::stod(next());
 			else if (k == "--filled") filled = next() == "1";
+			else if (k == "--read-params") read_params = next();   // -r: file names separated by blanks
+			else if (k == "--min-quality") min_quality = std::stoi(next());
 			else if (k == "--bam-output") bam_output = next() == "1";
 			else if (k == "--filtered") filtered = next() == "1";
 			else if (k == "--type-tag") cfg.put("BamTags.Type.tag", next());
@@ -88,7 +91,7 @@ int main(int argc, char **argv)
 		if (umi_merge == "directional") umi_strat = std::make_shared<Merge::UMIs::MergeUMIsStrategyDirectional>(umi_mult, max_umi_ed);
 		else umi_strat = std::make_shared<Merge::UMIs::MergeUMIsStrategySimple>(max_umi_ed);
 
-		BamProcessing::BamController bam_controller(BamProcessing::BamTags(cfg), filled, "", "", false, Tools::ReadParameters::quality_to_phred(0));
+		BamProcessing::BamController bam_controller(BamProcessing::BamTags(cfg), filled, read_params, "", false, Tools::ReadParameters::quality_to_phred(min_quality));
 		// get_cells_container, dropest.cpp:239-254
 		CellsDataContainer container(cb_strat, umi_strat, UMI::Mark::get_by_code(marks), filtered, -1);
 		bam_controller.parse_bam_files(files, bam_output, container);

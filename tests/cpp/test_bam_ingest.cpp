@@ -2,6 +2,7 @@
 // (barcode, UMI, gene, chromosome, mark bits, barcode quality) followed by the counters.  No container, no CUDA call.
 //   test_bam_ingest <filled 0|1> <min_barcode_quality> <gene_in_chr 0|1> <type tag or -> <intronic value or -> <intergenic value or -> <threads> file...
 //   environment DGE_BAM_GENES=<annotation.gtf[.gz] | .bed[.gz]>: gene and mark from the annotation (-g) instead of the gene tag
+//   environment DGE_BAM_READ_PARAMS="<file> <file> ...": barcode / UMI by read name from droptag's read-parameter files (-r)
 #include "../../dropest_b200/host/BamIngest.h"
 
 #include <chrono>
@@ -23,6 +24,7 @@ int main(int argc, char **argv)
 		p.tags.read_type = opt(argv[4]); p.tags.intronic_read_value = opt(argv[5]); p.tags.intergenic_read_value = opt(argv[6]);
 		p.threads = unsigned(std::stoi(argv[7]));
 		if (const char *g = std::getenv("DGE_BAM_GENES")) p.genes_filename = g;
+		if (const char *r = std::getenv("DGE_BAM_READ_PARAMS")) p.read_param_filenames = r; // -r (with filled = 0)
 		std::vector<std::string> files(argv + 8, argv + argc);
 		BamProcessing::IngestStats st;
 		if (std::getenv("DGE_BAM_COUNT_ONLY"))
@@ -35,7 +37,8 @@ int main(int argc, char **argv)
 		}
 		else BamProcessing::for_each_read(files, p, st, [](const ReadInfo &ri) {
 			std::cout << ri.params.cell_barcode() << '\t' << ri.params.umi() << '\t' << (ri.gene.empty() ? "-" : ri.gene) << '\t' << ri.chromosome_name << '\t'
-			          << ri.umi_mark.bits() << '\t' << (ri.params.cell_barcode_quality().empty() ? "-" : ri.params.cell_barcode_quality()) << '\n';
+			          << ri.umi_mark.bits() << '\t' << (ri.params.cell_barcode_quality().empty() ? "-" : ri.params.cell_barcode_quality()) << '\t'
+			          << (ri.params.umi_quality().empty() ? "-" : ri.params.umi_quality()) << '\n';
 		});
 		std::cout << "#stats\t" << st.total_reads << '\t' << st.cant_parse << '\t' << st.low_quality << '\t' << st.skipped_unmapped_or_secondary << '\n';
 	}

@@ -14,13 +14,13 @@ DUMP = os.path.join(ROOT, "dropest_b200", "lib", "test_bam_ingest")
 REFS = [("chr1", 1000000), ("chr2", 900000), ("chrM", 16000)]
 
 
-def _dump(files, filled=True, min_q=0, gene_in_chr=False, type_tag="-", intronic="-", intergenic="-", threads=3, expect_ok=True):
+def _dump(files, filled=True, min_q=0, gene_in_chr=False, type_tag="-", intronic="-", intergenic="-", threads=3, expect_ok=True, n_columns=6, env=None):
     assert os.path.exists(DUMP), "build first: python -c 'import __graft_entry__ as g; g.build()'"
     r = subprocess.run([DUMP, "1" if filled else "0", str(min_q), "1" if gene_in_chr else "0", type_tag, intronic, intergenic, str(threads)] + list(files),
-                       capture_output=True, text=True)
+                       capture_output=True, text=True, env=dict(os.environ, **(env or {})))
     assert (r.returncode == 0) == expect_ok, r.stdout[-500:] + r.stderr[-500:]
     lines = r.stdout.strip().split("\n")
-    return [tuple(l.split("\t")) for l in lines if not l.startswith("#")], [l.split("\t") for l in lines if l.startswith("#")]
+    return [tuple(l.split("\t"))[:n_columns] for l in lines if not l.startswith("#")], [l.split("\t") for l in lines if l.startswith("#")]
 
 
 def _random_reads(n, seed):
@@ -93,6 +93,71 @@ def test_read_name_mode_read_types_and_several_files(tmp_path):
     assert meta[-1] == ["#stats", "6", "1", "0", "0"]
     got, _ = _dump([pa], filled=False, gene_in_chr=True)
     assert [g[2] for g in got] == ["chr1"] * 3 and [g[4] for g in got] == ["2"] * 3
+
+
+REF_FLOW = os.path.join(ROOT, "oracle", "_ref", "ref_bam_flow")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FLOW), reason="compiled reference (oracle/_ref/ref_bam_flow) not built")
+def test_read_parameter_files_mode_matches_the_compiled_reference(tmp_path):
+    """-r: barcode / UMI / UMI quality by read name from droptag's gzipped read-parameter files (ReadMapParamsParser.cpp:22-109): rows that
+    cannot be parsed, empty barcodes, repeated names (first row wins), names with '@', reads missing from the files, a second alignment of
+    a name (the row is handed out once), the base-quality threshold evaluated when the row is loaded -- the accepted reads, in order, are
+    those of the reference's own BamController + ReadMapParamsParser."""
+    import gzip
+
+    rng = np.random.default_rng(9)
+    acgt = np.array(list("ACGT"))
+    rows_a, rows_b, als, text = [], [], [], [f"@SQ\t{n}\t{l}" for n, l in REFS]
+    for i in range(6000):
+        name = f"read{i}"
+        cb, umi = "".join(rng.choice(acgt, 12)), "".join(rng.choice(acgt, 8))
+        cbq = "".join(chr(33 + int(q)) for q in rng.integers(12, 41, 12))
+        umiq = "".join(chr(33 + int(q)) for q in rng.integers(12, 41, 8))
+        kind = i % 37
+        row = f"{'@' if i % 2 else ''}{name} {cb} {umi} {cbq} {umiq}"
+        if kind == 3:
+            row = f"{name} {cb} {umi}"                       # too few fields
+        elif kind == 5:
+            row = f"{name}  {umi} {cbq} {umiq}"              # empty barcode
+        elif kind == 7:
+            row = None                                        # not in the files at all
+        elif kind == 11:
+            umiq = umiq[:3] + "#" + umiq[4:]                  # below the threshold
+            row = f"{name} {cb} {umi} {cbq} {umiq}"
+        if row is not None:
+            (rows_a if i % 3 else rows_b).append(row)
+            if kind == 13:
+                rows_b.append(f"{name} {cb[::-1]} {umi} {cbq} {umiq}")   # a second row of the same name: ignored
+        tags = [("NH", ("i", 1))] + ([("GX", ("Z", f"g{i % 40}"))] if i % 5 else [])
+        flag = 4 if kind == 17 else 0
+        ref = int(rng.integers(0, 3))
+        n_copies = 2 if kind == 19 else 1                     # the same read name aligned twice
+        for c in range(n_copies):
+            als.append(alignment(("@" if kind == 23 else "") + name, ref, 10 + i + c, flag, tags))
+            text.append("\t".join([("@" if kind == 23 else "") + name, str(ref), str(10 + i + c), "8M", str(flag)] + [f"{t}:{k}:{v}" for t, (k, v) in tags]))
+    fa, fb = str(tmp_path / "params_a.gz"), str(tmp_path / "params_b.gz")
+    gzip.open(fa, "wt").write("\n".join(rows_a) + "\n\n")
+    gzip.open(fb, "wt").write("\n".join(rows_b))            # no newline at the end
+    bam = str(tmp_path / "in.bam")
+    write_bam(bam, REFS, als, block_bytes=45000)
+    ref_dir = tmp_path / "ref"
+    ref_dir.mkdir()
+    open(str(ref_dir / "in.bam"), "w").write("\n".join(text) + "\n")
+    r = subprocess.run([REF_FLOW, "--filled", "0", "--read-params", f"{fa} {fb}", "--min-quality", "10", "--bam-output", "1", "--filtered", "0",
+                        "--min-genes-before", "1", "--min-genes-after", "1", "in.bam"], cwd=str(ref_dir), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    exp = []
+    for line in open(str(ref_dir / "in.tagged.bam")).read().strip().split("\n"):
+        f = line.split("\t")
+        tag = {x[:2]: x[5:] for x in f[1:]}
+        exp.append((tag["CR"], tag["UR"], tag.get("GX", "-"), tag["UQ"]))
+    for threads in (1, 4):
+        got, meta = _dump([bam], filled=False, min_q=10, threads=threads, n_columns=7, env={"DGE_BAM_READ_PARAMS": f"{fa}\t{fb}"})
+        assert [(g[0], g[1], g[2], g[6]) for g in got] == exp and len(exp) > 4500
+        assert all(g[5] == "-" for g in got)                  # the barcode quality is not kept (ReadParametersEfficient)
+        n_mapped = sum(1 for i in range(6000) if i % 37 != 17) + sum(1 for i in range(6000) if i % 37 == 19)
+        assert int(meta[-1][1]) == n_mapped and int(meta[-1][1]) - int(meta[-1][2]) - int(meta[-1][3]) == len(exp) and int(meta[-1][3]) > 100
 
 
 def test_corrupt_files_fail_loudly(tmp_path):
