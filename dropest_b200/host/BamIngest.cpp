@@ -574,11 +574,194 @@ namespace BamProcessing
 		for (auto const &e : errors) if (!e.empty()) throw std::runtime_error(e);
 	}
 
+	bool packed_path_applies(const IngestParams &params)
+	{
+		return params.filled_bam && !params.genes && params.genes_filename.empty();
+	}
+
+	namespace
+	{
+		inline bool pack_bases(const char *p, size_t n, uint64_t &out)
+		{
+			if (n > 32) return false;
+			uint64_t v = 0;
+			for (size_t i = 0; i < n; ++i)
+			{
+				unsigned b;
+				switch (p[i]) { case 'A': b = 0; break; case 'C': b = 1; break; case 'G': b = 2; break; case 'T': b = 3; break; default: return false; }
+				v = (v << 2) | b;
+			}
+			out = v;
+			return true;
+		}
+
+		// TagValue::string as a view
+		inline bool tag_view(const BamAlignment::TagValue &t, const char *&p, size_t &n)
+		{
+			if (t.type == 'Z' || t.type == 'H') { p = reinterpret_cast<const char *>(t.value); n = t.bytes - 1; return true; }
+			if (t.type == 'A') { p = reinterpret_cast<const char *>(t.value); n = 1; return true; }
+			p = nullptr; n = 0;
+			return false;
+		}
+	}
+
+	// read_info_from_alignment for the -f mode, producing a PackedRead: same decisions, same counters, same exception
+	void parse_batch_packed(const std::vector<BamReader::RecordView> &records, const std::vector<std::string> &refs, const IngestParams &params,
+	                        PackedBatch &out, unsigned threads)
+	{
+		const size_t n_refs = refs.size(), n = records.size();
+		out.status.assign(n, uint8_t(ParsedRead::SKIPPED));
+		out.reads.resize(n);
+		const unsigned nt = std::max(1u, unsigned(std::min<size_t>(threads ? threads : std::max(1u, std::thread::hardware_concurrency()), (n + 4095) / 4096)));
+		if (out.arenas.size() < nt) out.arenas.resize(nt);
+		std::vector<std::string> errors(nt);
+		const int min_phred = params.min_barcode_quality + 33;
+		const std::string *wanted[6] = {&params.tags.cell_barcode, &params.tags.umi, &params.tags.cell_barcode_quality, &params.tags.umi_quality,
+		                                &params.tags.gene, &params.tags.read_type};
+		auto work = [&](unsigned t, size_t first, size_t last) {
+			try
+			{
+				std::vector<char> &arena = out.arenas[t];
+				size_t cap = 0;
+				for (size_t k = first; k < last; ++k) cap += records[k].al.tag_bytes;
+				arena.clear();
+				arena.reserve(cap + 1); // every copied string is part of a tag block: the views below never move
+				auto keep = [&](const char *p, size_t len) -> const char * {
+					const size_t at = arena.size();
+					arena.insert(arena.end(), p, p + len);
+					return arena.data() + at;
+				};
+				BamAlignment::TagValue tv[6];
+				for (size_t k = first; k < last; ++k)
+				{
+					const BamAlignment &al = records[k].al;
+					if (!al.is_mapped() || !al.is_primary_alignment()) continue;
+					if (al.ref_id < 0 || size_t(al.ref_id) >= n_refs) { out.status[k] = ParsedRead::NO_CHROMOSOME; continue; }
+					al.find_tags(wanted, 6, tv);
+					const char *cb, *umi, *cbq, *umiq, *gene;
+					size_t cb_n, umi_n, cbq_n, umiq_n, gene_n;
+					if (!tag_view(tv[0], cb, cb_n) || !tag_view(tv[1], umi, umi_n) || cb_n == 0 || umi_n == 0) { out.status[k] = ParsedRead::CANT_PARSE; continue; }
+					tag_view(tv[2], cbq, cbq_n);
+					tag_view(tv[3], umiq, umiq_n);
+					bool pass_quality = true;
+					if (min_phred > 33)
+					{
+						for (size_t i = 0; i < cbq_n; ++i) if (cbq[i] < min_phred) pass_quality = false;
+						for (size_t i = 0; i < umiq_n; ++i) if (umiq[i] < min_phred) pass_quality = false;
+					}
+					if (!pass_quality) { out.status[k] = ParsedRead::LOW_QUALITY; continue; }
+					unsigned mark = 0;
+					if (params.gene_in_chromosome_name)
+					{
+						const std::string &chr = refs[size_t(al.ref_id)];
+						gene = chr.data(); gene_n = chr.size();
+						if (gene_n) mark = UMI::Mark::HAS_EXONS;
+					}
+					else if (!tag_view(tv[4], gene, gene_n)) mark = UMI::Mark::HAS_NOT_ANNOTATED;
+					else
+					{
+						const char *rt = nullptr;
+						size_t rt_n = 0;
+						bool have_type = false;
+						if (!params.tags.read_type.empty())
+						{
+							const char t5 = tv[5].type;
+							if (t5 && t5 != 'Z' && t5 != 'A') throw std::runtime_error(std::string("Expected string tag, but got ") + t5); // get_bam_tag
+							have_type = tag_view(tv[5], rt, rt_n);
+						}
+						auto equals = [&](const std::string &v) { return v.size() == rt_n && std::memcmp(v.data(), rt, rt_n) == 0; };
+						if (!have_type) mark = UMI::Mark::HAS_EXONS;
+						else if (equals(params.tags.intronic_read_value)) mark = UMI::Mark::HAS_INTRONS;
+						else if (!params.tags.intergenic_read_value.empty() && equals(params.tags.intergenic_read_value)) mark = UMI::Mark::HAS_NOT_ANNOTATED;
+						else mark = UMI::Mark::HAS_EXONS;
+					}
+					if (cb_n > 0xFFFF || umi_n > 0xFFFF || gene_n > 0xFFFF || cbq_n > 0xFFFF || umiq_n > 0xFFFF) { out.status[k] = ParsedRead::CANT_PARSE; continue; }
+					PackedRead &r = out.reads[k];
+					r.packable = 0;
+					uint64_t v = 0;
+					if (pack_bases(cb, cb_n, v)) { r.cb_packed = v; r.packable |= 1; }
+					if (umi_n <= 16 && pack_bases(umi, umi_n, v)) { r.umi_packed = uint32_t(v); r.packable |= 2; }
+					r.cb = keep(cb, cb_n); r.cb_len = uint16_t(cb_n);
+					r.umi = keep(umi, umi_n); r.umi_len = uint16_t(umi_n);
+					r.cb_quality = keep(cbq, cbq_n); r.cb_quality_len = uint16_t(cbq_n);
+					r.umi_quality = keep(umiq, umiq_n); r.umi_quality_len = uint16_t(umiq_n);
+					r.gene = params.gene_in_chromosome_name ? gene : keep(gene, gene_n); r.gene_len = uint16_t(gene_n);
+					r.mark_bits = uint8_t(mark);
+					r.chromosome = al.ref_id;
+					out.status[k] = ParsedRead::OK;
+				}
+			}
+			catch (std::exception &e) { errors[t] = e.what(); }
+		};
+		if (nt <= 1) work(0, 0, n);
+		else
+		{
+			std::vector<std::thread> pool;
+			const size_t per = (n + nt - 1) / nt;
+			for (unsigned t = 0; t < nt; ++t) pool.emplace_back(work, t, std::min(n, size_t(t) * per), std::min(n, size_t(t + 1) * per));
+			for (auto &th : pool) th.join();
+		}
+		for (auto const &e : errors) if (!e.empty()) throw std::runtime_error(e);
+	}
+
+	namespace
+	{
+		// parse_bam_files over PackedBatch: the next batch is read, inflated and parsed while the current one goes to the container
+		void parse_bam_files_packed(const std::vector<std::string> &bam_files, const IngestParams &params, CellsDataContainer &container, IngestStats &stats)
+		{
+			std::vector<BamReader::RecordView> views;
+			PackedBatch batches[2];
+			std::vector<PackedRead> accepted;
+			for (auto const &file : bam_files)
+			{
+				BamReader reader(file, params.threads);
+				const auto &refs = reader.reference_names();
+				int turn = 0;
+				auto produce = [&](int into) -> bool {
+					reader.next_batch(views, size_t(1) << 17);
+					if (views.empty()) return false;
+					parse_batch_packed(views, refs, params, batches[into], params.threads);
+					return true;
+				};
+				bool have = produce(turn);
+				while (have)
+				{
+					PackedBatch &cur = batches[turn];
+					auto next = std::async(std::launch::async, produce, turn ^ 1);
+					try
+					{
+						accepted.clear();
+						for (size_t k = 0; k < cur.status.size(); ++k)
+						{
+							switch (ParsedRead::Status(cur.status[k]))
+							{
+							case ParsedRead::SKIPPED: ++stats.skipped_unmapped_or_secondary; break;
+							case ParsedRead::NO_CHROMOSOME: ++stats.cant_parse; break;
+							case ParsedRead::CANT_PARSE: ++stats.total_reads; ++stats.cant_parse; break;
+							case ParsedRead::LOW_QUALITY: ++stats.total_reads; ++stats.low_quality; break;
+							case ParsedRead::OK: ++stats.total_reads; accepted.push_back(cur.reads[k]); break;
+							}
+						}
+						container.add_records(accepted.data(), accepted.size(), refs); // stream order: it defines cell / gene / chromosome ids
+					}
+					catch (...) { next.wait(); throw; }
+					have = next.get();
+					turn ^= 1;
+				}
+			}
+		}
+	}
+
 	void parse_bam_files(const std::vector<std::string> &bam_files, const IngestParams &params, CellsDataContainer &container, IngestStats &stats,
 	                     bool print_result_bams)
 	{
 		if (!params.tags.read_type.empty() && params.tags.intronic_read_value.empty()) // BamTags.cpp:22-23
 			throw std::runtime_error("You have to specify tag values to be able to parse info about read types");
+		if (!print_result_bams && packed_path_applies(params) && !std::getenv("DGE_BAM_ONE_BY_ONE"))
+		{
+			parse_bam_files_packed(bam_files, params, container, stats);
+			return;
+		}
 		if (!print_result_bams)
 		{
 			for_each_read(bam_files, params, stats, [&](const ReadInfo &ri) { container.add_record(ri); });

@@ -249,6 +249,19 @@ namespace BamProcessing
 		}
 	}
 
+	// The bulk form of a parsed batch for CellsDataContainer::add_records (-f mode without an annotation): no std::string per read, barcode
+	// and UMI 2-bit packed by the parsing threads; the strings a read may still need are copied into per-thread arenas that live as long
+	// as the batch.
+	struct PackedBatch
+	{
+		std::vector<uint8_t> status;            // ParsedRead::Status per record
+		std::vector<PackedRead> reads;          // per record; meaningful where status == OK
+		std::vector<std::vector<char>> arenas;  // what the views of `reads` point into
+	};
+	bool packed_path_applies(const IngestParams &params); // -f, gene from the gene tag or the chromosome name
+	void parse_batch_packed(const std::vector<BamReader::RecordView> &records, const std::vector<std::string> &refs, const IngestParams &params,
+	                        PackedBatch &out, unsigned threads);
+
 	template <class F> void for_each_read(const std::vector<std::string> &bam_files, const IngestParams &params, IngestStats &stats, F &&sink)
 	{
 		for_each_alignment(bam_files, params, stats, false, [](const std::string &, const BamReader &) {},

@@ -597,6 +597,69 @@ namespace Estimation
 		if (_batch_keys.size() >= _batch_capacity) flush();
 	}
 
+	void CellsDataContainer::add_records(const PackedRead *reads, size_t n, const std::vector<std::string> &chromosome_names)
+	{
+		if (_is_initialized) throw std::runtime_error("Container is already initialized");
+		if (_bulk_chr_names != chromosome_names)
+		{   // another file: its chromosome list maps afresh (ids come from the names, so this only resets the cache)
+			_bulk_chr_names = chromosome_names;
+			_bulk_chr_id.assign(chromosome_names.size(), -1);
+			_bulk_chr_presented.assign(chromosome_names.size(), 0);
+		}
+		for (size_t k = 0; k < n; ++k)
+		{
+			const PackedRead &r = reads[k];
+			const bool common = _h && !_qualities && r.packable == 3 && r.cb_len == _cb_len && r.umi_len == _umi_len && r.chromosome >= 0 &&
+			                    size_t(r.chromosome) < chromosome_names.size();
+			if (!common)
+			{   // the first read (it fixes the lengths and creates the handle), N, other lengths, quality bookkeeping: the one-read path
+				add_record(ReadInfo(Tools::ReadParameters(std::string(r.cb, r.cb_len), std::string(r.umi, r.umi_len), std::string(r.cb_quality, r.cb_quality_len),
+				                                          std::string(r.umi_quality, r.umi_quality_len)),
+				                    std::string(r.gene, r.gene_len), chromosome_names.at(size_t(r.chromosome)), UMI::Mark(UMI::Mark::MarkType(r.mark_bits))));
+				continue;
+			}
+			// ---- exactly what add_record does for such a read
+			uint32_t gene = DGE_NO_GENE;
+			if (r.gene_len) gene = uint32_t(_gene_indexer.add(r.gene, r.gene_len));
+			uint8_t chr_id = 0;
+			if (!_chr_overflow)
+			{
+				const unsigned m = r.mark_bits;
+				const bool inter = r.gene_len == 0;
+				if (inter || (m & 6u))
+				{
+					int32_t &cached = _bulk_chr_id[size_t(r.chromosome)];
+					if (cached < 0) cached = int32_t(_chromosome_indexer.add(chromosome_names[size_t(r.chromosome)]));
+					const size_t id = size_t(cached);
+					if (id > 255)
+					{
+						_chr_overflow = true;
+						std::cerr << "dropest_b200: more than 256 chromosome names; reads_per_chr_per_cells is not produced\n";
+					}
+					else
+					{
+						chr_id = uint8_t(id);
+						const uint8_t want = inter ? 1u : uint8_t(((m & 2u) ? 2u : 0u) | ((m & 4u) ? 4u : 0u));
+						uint8_t &have = _bulk_chr_presented[size_t(r.chromosome)];
+						if ((have & want) != want)
+						{
+							if (want & 1u) _presented_chromosomes[Stats::INTERGENIC_READS_PER_CHR_PER_CELL].insert(id);
+							if (want & 2u) _presented_chromosomes[Stats::EXON_READS_PER_CHR_PER_CELL].insert(id);
+							if (want & 4u) _presented_chromosomes[Stats::INTRON_READS_PER_CHR_PER_CELL].insert(id);
+							have |= want;
+						}
+					}
+				}
+			}
+			_batch_chr.push_back(chr_id);
+			_batch_keys.push_back((r.cb_packed << 24) | r.umi_packed);
+			_batch_genes.push_back(gene | (uint32_t(r.mark_bits) << 24));
+			_batch_idx.push_back(uint32_t(_n_records));
+			++_n_records;
+			if (_batch_keys.size() >= _batch_capacity) flush();
+		}
+	}
+
 	void CellsDataContainer::set_initialized()
 	{
 		if (_is_initialized) throw std::runtime_error("Container is already initialized");

@@ -12,6 +12,7 @@
 #include <map>
 #include <memory>
 #include <stdexcept>
+#include <cstring>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -74,7 +75,7 @@ namespace Tools
 
 namespace Estimation
 {
-	class StringIndexer // StringIndexer.h
+	class StringIndexer // StringIndexer.h: strings <-> ids in first-seen order
 	{
 	public:
 		using index_t = size_t;
@@ -82,20 +83,54 @@ namespace Estimation
 
 	private:
 		values_t _values;
-		std::unordered_map<std::string, index_t> _indexes;
+		// open addressing over _values (index + 1, 0 = empty): a lookup by (pointer, length) builds no std::string, which is what the per-read
+		// paths need (gene names of BAM records)
+		std::vector<uint32_t> _slots;
+
+		static uint64_t hash(const char *p, size_t n)
+		{
+			uint64_t h = 0xCBF29CE484222325ull;
+			for (size_t i = 0; i < n; ++i) { h ^= uint8_t(p[i]); h *= 0x100000001B3ull; }
+			return h ^ (h >> 29);
+		}
+		// slot of the string, or the empty slot where it would go
+		size_t probe(const char *p, size_t n) const
+		{
+			const size_t mask = _slots.size() - 1;
+			for (size_t i = size_t(hash(p, n)) & mask;; i = (i + 1) & mask)
+			{
+				const uint32_t v = _slots[i];
+				if (!v) return i;
+				const std::string &s = _values[v - 1];
+				if (s.size() == n && std::memcmp(s.data(), p, n) == 0) return i;
+			}
+		}
+		void grow()
+		{
+			std::vector<uint32_t> fresh(std::max<size_t>(64, _slots.size() * 2), 0u);
+			_slots.swap(fresh);
+			for (size_t k = 0; k < _values.size(); ++k) _slots[probe(_values[k].data(), _values[k].size())] = uint32_t(k + 1);
+		}
 
 	public:
 		const values_t &values() const { return _values; }
 		const std::string &get_value(index_t index) const { return _values.at(index); }
-		index_t get_index(const std::string &value) const { return _indexes.at(value); }
-		index_t add(const std::string &value)
+		index_t get_index(const std::string &value) const
 		{
-			auto found = _indexes.find(value); // the common case allocates nothing (emplace builds a node before it looks)
-			if (found != _indexes.end()) return found->second;
-			auto it = _indexes.emplace(value, _indexes.size());
-			_values.push_back(value);
-			return it.first->second;
+			if (!_slots.empty()) { const uint32_t v = _slots[probe(value.data(), value.size())]; if (v) return v - 1; }
+			throw std::out_of_range("StringIndexer::get_index: unknown value '" + value + "'"); // the reference's unordered_map::at
 		}
+		index_t add(const char *p, size_t n)
+		{
+			if ((_values.size() + 1) * 2 > _slots.size()) grow();
+			const size_t i = probe(p, n);
+			if (_slots[i]) return _slots[i] - 1;
+			if (_values.size() >= 0xFFFFFFFEull) throw std::runtime_error("StringIndexer: too many values");
+			_values.emplace_back(p, n);
+			_slots[i] = uint32_t(_values.size());
+			return _values.size() - 1;
+		}
+		index_t add(const std::string &value) { return add(value.data(), value.size()); }
 	};
 
 	class UMI // UMI.h
@@ -161,6 +196,19 @@ namespace Estimation
 			: params(params), gene(gene), chromosome_name(chromosome_name), umi_mark(umi_mark) {}
 		ReadInfo(Tools::ReadParameters &&params, std::string &&gene, const std::string &chromosome_name, const UMI::Mark &umi_mark) // no string copies (BAM ingest)
 			: params(std::move(params)), gene(std::move(gene)), chromosome_name(chromosome_name), umi_mark(umi_mark) {}
+	};
+
+	// One accepted read as the BAM ingest hands it over in bulk (CellsDataContainer::add_records): views into the ingest's buffers instead of
+	// the five std::strings of a ReadInfo, and the barcode / UMI already 2-bit packed when they consist of A, C, G, T only.
+	struct PackedRead
+	{
+		const char *cb, *umi, *gene, *cb_quality, *umi_quality;
+		uint16_t cb_len, umi_len, gene_len, cb_quality_len, umi_quality_len;
+		uint8_t mark_bits;     // UMI::Mark bits of the read
+		uint8_t packable;      // bit 0: `cb_packed` is valid, bit 1: `umi_packed` is valid
+		uint64_t cb_packed;
+		uint32_t umi_packed;
+		int32_t chromosome;    // index into the chromosome-name list passed with the batch
 	};
 
 	class Stats // Stats.h (per-cell counters; the per-chromosome tables are read from the device by CellsDataContainer::get_stat_by_real_cells)
@@ -501,6 +549,10 @@ namespace Estimation
 		std::unordered_set<size_t> _presented_chromosomes[Stats::CHROMOSOME_STAT_SIZE];
 		bool _chr_overflow = false;         // more than 256 chromosome names: the per-chromosome tables are dropped (1-byte side array)
 		bool _batch_gaps = false;
+		// add_records: per chromosome-list entry, the id Stats assigned (or -1) and which statistics already list it
+		std::vector<int32_t> _bulk_chr_id;
+		std::vector<uint8_t> _bulk_chr_presented;
+		std::vector<std::string> _bulk_chr_names;
 		StringIndexer _n_umis, _n_cbs;      // UMIs / barcodes containing N, passed to the device as indices (DGE_FLAG_UMI_N / DGE_FLAG_CB_N)
 		bool _n_dirty = false, _allow_n = false, _allow_n_cb = false;
 		uint64_t _skipped_n_reads = 0, _skipped_length_reads = 0;
@@ -546,6 +598,9 @@ namespace Estimation
 		CellsDataContainer &operator=(const CellsDataContainer &) = delete;
 
 		void add_record(const ReadInfo &read_info);   // throws std::runtime_error("Container is already initialized") after set_initialized
+		// n x add_record in order, for reads given as views: the common read (nominal lengths, no N, no base-quality bookkeeping) is packed
+		// without building a string; every other read goes through add_record itself.  chromosome_names[read.chromosome] is its chromosome.
+		void add_records(const PackedRead *reads, size_t n, const std::vector<std::string> &chromosome_names);
 		void set_initialized();                        // throws if called twice
 		void merge_and_filter();                       // throws std::runtime_error("You must initialize container")
 

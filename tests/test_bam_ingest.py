@@ -95,6 +95,66 @@ def test_read_name_mode_read_types_and_several_files(tmp_path):
     assert [g[2] for g in got] == ["chr1"] * 3 and [g[4] for g in got] == ["2"] * 3
 
 
+def test_bulk_packed_path_equals_the_one_read_path(tmp_path):
+    """parse_batch_packed (what parse_bam_files uses for -f input: views + 2-bit packed barcode / UMI, no string per read) takes the same
+    decisions as read_info_from_alignment on every kind of record: missing / non-string / character-typed tags, empty values, N and
+    lower-case bases (not packable), odd lengths, low base qualities, read-type values, unmapped / secondary / unknown-reference records."""
+    rng = np.random.default_rng(21)
+    acgt = np.array(list("ACGT"))
+    als = []
+    for i in range(30000):
+        cb, umi = "".join(rng.choice(acgt, 16)), "".join(rng.choice(acgt, 10))
+        kind = i % 47
+        if kind == 2:
+            umi = umi[:4] + "N" + umi[5:]
+        elif kind == 4:
+            cb = cb[:3] + "n" + cb[4:]
+        elif kind == 6:
+            cb = cb[:11]
+        elif kind == 8:
+            umi = umi + "ACGTACGT"          # 18 bases: not packable into 32 bits
+        tags = [("NH", ("i", int(rng.integers(1, 5)))), ("CB", ("Z", cb)), ("UB", ("Z", umi))]
+        if kind == 10:
+            tags[1] = ("CB", ("A", "G"))
+        elif kind == 12:
+            tags[2] = ("UB", ("i", 7))
+        elif kind == 14:
+            tags[1] = ("CB", ("Z", ""))
+        if i % 3:
+            q = ["I"] * 10
+            if kind == 16:
+                q[int(rng.integers(0, 10))] = "$"
+            tags += [("CQ", ("Z", "I" * 16)), ("UQ", ("Z", "".join(q)))]
+        if i % 7:
+            tags.append(("GX", ("Z", f"ENSG{int(rng.integers(0, 300)):09d}" if kind != 18 else "")))
+            if i % 2:
+                tags.append(("XF", ("Z", str(rng.choice(["CODING", "INTRONIC", "INTERGENIC", "UTR"])))) if kind != 20 else ("XF", ("A", "I")))
+        flag = 4 if kind == 22 else 0x100 if kind == 24 else 0
+        ref = 7 if kind == 26 else int(rng.integers(0, 3))
+        als.append(alignment(f"r{i}", ref, i, flag, tags))
+    path = str(tmp_path / "a.bam")
+    write_bam(path, REFS, als, block_bytes=40000)
+    for kw in (dict(min_q=20, type_tag="XF", intronic="INTRONIC", intergenic="INTERGENIC"), dict(min_q=0), dict(gene_in_chr=True)):
+        one, meta_one = _dump([path], n_columns=7, threads=1, **kw)
+        for threads in (1, 4):
+            bulk, meta_bulk = _dump([path], n_columns=10, threads=threads, env={"DGE_BAM_PACKED": "1"}, **kw)
+            assert [b[:7] for b in bulk] == one and meta_bulk[-1] == meta_one[-1] and len(one) > 20000
+        code = {"A": 0, "C": 1, "G": 2, "T": 3}
+        for b in bulk:
+            cb_ok, umi_ok = set(b[0]) <= set("ACGT"), set(b[1]) <= set("ACGT") and len(b[1]) <= 16
+            assert int(b[7]) == (1 if cb_ok else 0) | (2 if umi_ok else 0)
+            if cb_ok:
+                v = 0
+                for ch in b[0]:
+                    v = v * 4 + code[ch]
+                assert int(b[8]) == v
+            if umi_ok:
+                v = 0
+                for ch in b[1]:
+                    v = v * 4 + code[ch]
+                assert int(b[9]) == v
+
+
 REF_FLOW = os.path.join(ROOT, "oracle", "_ref", "ref_bam_flow")
 
 
