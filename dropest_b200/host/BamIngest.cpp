@@ -63,20 +63,29 @@ namespace BamProcessing
 		: _file_name(file_name), _f(std::fopen(file_name.c_str(), "rb")), _threads(threads ? threads : std::max(1u, std::thread::hardware_concurrency()))
 	{
 		if (!_f) throw std::runtime_error("Can't open BAM file: " + file_name); // BamController.cpp:77-78
+		// test hooks: small chunks / no headroom put records across every chunk boundary
+		if (const char *e = std::getenv("DGE_BAM_CHUNK_BYTES")) _chunk_bytes = std::max<size_t>(1, std::strtoull(e, nullptr, 10));
+		if (const char *e = std::getenv("DGE_BAM_HEADROOM_BYTES")) _headroom = std::strtoull(e, nullptr, 10);
 		read_header();
 	}
 
 	BamReader::~BamReader()
 	{
+		if (_ahead.valid()) { try { _ahead.get(); } catch (...) {} } // the loader reads from _f
 		if (_f) std::fclose(_f);
 	}
 
-	bool BamReader::fill(size_t need)
+	// One step of the background loader: reads compressed bytes until at least one whole BGZF block is there, inflates every whole block
+	// (thread pool, straight into place) behind `headroom` free bytes of the buffer it was given.  Only the loader touches _f, _comp, _eof.
+	BamReader::Chunk BamReader::load_chunk(Bytes buffer)
 	{
-		while (_data.size() - _pos < need)
+		Chunk c;
+		c.bytes = std::move(buffer);
+		c.bytes.n = 0;
+		while (true)
 		{
 			// more compressed bytes (a few MB at a time: the inflated chunk stays of the order of the last-level cache)
-			const size_t chunk = size_t(8) << 20;
+			const size_t chunk = _chunk_bytes;
 			if (!_eof)
 			{
 				_comp.grow_to(_comp.n + chunk);
@@ -102,23 +111,22 @@ namespace BamProcessing
 				if (_eof)
 				{
 					if (off < _comp.size()) throw std::runtime_error("truncated BGZF block at the end of " + _file_name);
-					return _data.size() - _pos >= need && need > 0;
+					c.end_of_file = true;
+					return c;
 				}
 				continue;
 			}
-			// drop what was consumed, make room, inflate every block into its place
-			_data.drop_front(_pos);
-			_pos = 0;
-			const size_t base = _data.size();
-			_data.grow_to(base + out_total);
-			_data.n = base + out_total;
+			const size_t base = _headroom;
+			c.bytes.grow_to(base + out_total);
+			c.bytes.n = base + out_total;
+			c.begin = base;
 			const unsigned nt = unsigned(std::min<size_t>(_threads, (blocks.size() + 15) / 16));
 			std::vector<std::string> errors(std::max(1u, nt));
 			auto work = [&](unsigned t, size_t first, size_t last) { // contiguous runs of blocks per thread
 				try
 				{
 					for (size_t b = first; b < last; ++b)
-						inflate_block(_comp.data() + blocks[b].in_off, blocks[b].in_len, _data.data() + base + blocks[b].out_off, blocks[b].out_len, _file_name);
+						inflate_block(_comp.data() + blocks[b].in_off, blocks[b].in_len, c.bytes.data() + base + blocks[b].out_off, blocks[b].out_len, _file_name);
 				}
 				catch (std::exception &e) { errors[t] = e.what(); }
 			};
@@ -132,6 +140,46 @@ namespace BamProcessing
 			}
 			for (auto const &e : errors) if (!e.empty()) throw std::runtime_error(e);
 			_comp.drop_front(off);
+			return c;
+		}
+	}
+
+	void BamReader::start_loading()
+	{
+		_ahead = std::async(std::launch::async, [this](Bytes buffer) { return load_chunk(std::move(buffer)); }, std::move(_spare));
+		_spare = Bytes();
+	}
+
+	// The chunk after the current one is read and inflated in the background while the caller frames and parses the current one; the
+	// bytes of a record cut by the chunk boundary are copied in front of the new chunk (into its headroom).
+	bool BamReader::fill(size_t need)
+	{
+		while (_data.size() - _pos < need)
+		{
+			if (_finished) return false;
+			if (!_ahead.valid()) start_loading();
+			Chunk c = _ahead.get(); // rethrows what the loader threw
+			if (c.end_of_file)
+			{
+				_finished = true;
+				return false;
+			}
+			const size_t tail = _data.size() - _pos;
+			if (tail > c.begin)
+			{   // more left over than the headroom takes (a record of megabytes): a buffer of the exact size
+				Bytes whole;
+				const size_t len = c.bytes.n - c.begin;
+				whole.grow_to(tail + len);
+				std::memcpy(whole.data() + tail, c.bytes.data() + c.begin, len);
+				whole.n = tail + len;
+				c.bytes = std::move(whole);
+				c.begin = tail;
+			}
+			if (tail) std::memcpy(c.bytes.data() + c.begin - tail, _data.data() + _pos, tail);
+			_pos = c.begin - tail;
+			_spare = std::move(_data);
+			_data = std::move(c.bytes);
+			start_loading();
 		}
 		return true;
 	}
@@ -581,16 +629,26 @@ namespace BamProcessing
 
 	namespace
 	{
+		// 2-bit code per base (A C G T), 0xFF for every other character
+		struct BaseCodes
+		{
+			uint8_t code[256];
+			BaseCodes() { std::memset(code, 0xFF, sizeof(code)); code[uint8_t('A')] = 0; code[uint8_t('C')] = 1; code[uint8_t('G')] = 2; code[uint8_t('T')] = 3; }
+		};
+		const BaseCodes base_codes;
+
 		inline bool pack_bases(const char *p, size_t n, uint64_t &out)
 		{
 			if (n > 32) return false;
 			uint64_t v = 0;
-			for (size_t i = 0; i < n; ++i)
+			unsigned bad = 0;
+			for (size_t i = 0; i < n; ++i) // no branch per base: random bases defeat the predictor
 			{
-				unsigned b;
-				switch (p[i]) { case 'A': b = 0; break; case 'C': b = 1; break; case 'G': b = 2; break; case 'T': b = 3; break; default: return false; }
-				v = (v << 2) | b;
+				const unsigned b = base_codes.code[uint8_t(p[i])];
+				bad |= b;
+				v = (v << 2) | (b & 3u);
 			}
+			if (bad & 0x80u) return false;
 			out = v;
 			return true;
 		}
@@ -621,20 +679,28 @@ namespace BamProcessing
 		auto work = [&](unsigned t, size_t first, size_t last) {
 			try
 			{
+				// every copied string is part of a tag block: an arena of their total size never moves.  The write position is a local of the
+				// thread (the headers of out.arenas[] share cache lines: bumping them per string makes the threads fight over those lines)
 				std::vector<char> &arena = out.arenas[t];
 				size_t cap = 0;
 				for (size_t k = first; k < last; ++k) cap += records[k].al.tag_bytes;
-				arena.clear();
-				arena.reserve(cap + 1); // every copied string is part of a tag block: the views below never move
+				if (arena.size() < cap + 1) arena.resize(cap + 1);
+				char *top = arena.data();
 				auto keep = [&](const char *p, size_t len) -> const char * {
-					const size_t at = arena.size();
-					arena.insert(arena.end(), p, p + len);
-					return arena.data() + at;
+					char *at = top;
+					std::memcpy(at, p, len);
+					top += len;
+					return at;
 				};
 				BamAlignment::TagValue tv[6];
 				for (size_t k = first; k < last; ++k)
 				{
 					const BamAlignment &al = records[k].al;
+					if (k + 8 < last)
+					{   // the tag blocks were written by the inflating threads: fetch the one needed a few records from now
+						const uint8_t *ahead = records[k + 8].al.tag_data;
+						__builtin_prefetch(ahead); __builtin_prefetch(ahead + 64);
+					}
 					if (!al.is_mapped() || !al.is_primary_alignment()) continue;
 					if (al.ref_id < 0 || size_t(al.ref_id) >= n_refs) { out.status[k] = ParsedRead::NO_CHROMOSOME; continue; }
 					al.find_tags(wanted, 6, tv);

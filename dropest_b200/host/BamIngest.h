@@ -98,15 +98,29 @@ namespace BamProcessing
 			}
 			void drop_front(size_t k) { if (k) { std::memmove(p.get(), p.get() + k, n - k); n -= k; } }
 		};
-		Bytes _comp;                  // compressed bytes not yet inflated (whole blocks + a partial one at the end)
-		Bytes _data;                  // inflated bytes not yet consumed
+		// what the background loader hands over: inflated bytes at [begin, bytes.n) of a buffer whose first `begin` bytes are free
+		struct Chunk
+		{
+			Bytes bytes;
+			size_t begin = 0;
+			bool end_of_file = false; // nothing left (bytes holds no data)
+		};
+		Bytes _comp;                  // loader: compressed bytes not yet inflated (whole blocks + a partial one at the end)
+		bool _eof = false;            // loader: the file has been read to its end
+		Bytes _data;                  // inflated bytes; [_pos, _data.n) not yet consumed
 		size_t _pos = 0;              // read position in _data
-		bool _eof = false;
+		Bytes _spare;                 // the buffer the next load may reuse
+		bool _finished = false;       // the loader reported the end of the file
+		std::future<Chunk> _ahead;    // the load in flight (at most one)
+		size_t _chunk_bytes = size_t(4) << 20; // compressed bytes read per load (the inflated chunk stays of the order of the last-level cache)
+		size_t _headroom = size_t(1) << 20;    // free bytes in front of a chunk for the record cut by the previous chunk's end
 		std::vector<std::string> _refs;
 		std::vector<uint32_t> _ref_lengths;
 		std::string _header_text;
 
 		bool fill(size_t need); // makes at least `need` bytes available at _pos; false at a clean end of file
+		Chunk load_chunk(Bytes buffer);
+		void start_loading();
 		void read_header();
 		bool view_at(size_t pos, RecordView &v, size_t &next_pos) const; // the record at _data[pos], false when it is not complete yet
 	};

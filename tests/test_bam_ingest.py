@@ -71,6 +71,37 @@ def test_filled_bam_tags_filters_and_counters(tmp_path):
     assert len(got) == len(exp) + n_lowq and meta[-1][3] == "0"
 
 
+def test_records_across_chunk_boundaries_and_loader_errors(tmp_path):
+    """The reader inflates the next chunk in the background while the current one is framed and parsed: a record cut by a chunk boundary is
+    completed in the new chunk's headroom (or, when it is longer than the headroom, in a buffer of its own).  Tiny chunks and no headroom put
+    a cut into nearly every chunk; the output must not depend on either.  What the loader throws (truncated file, corrupt block, CRC)
+    reaches the caller."""
+    reads = _random_reads(20000, 5)
+    als = [alignment(f"read{i}", ref, pos, 0, [("CB", ("Z", cb)), ("UB", ("Z", umi))] + ([("GX", ("Z", gene))] if gene else []) +
+                     ([("xl", ("Z", "x" * 70000))] if i % 4001 == 7 else []))   # a few records longer than a BGZF block
+           for i, (cb, umi, gene, ref, pos) in enumerate(reads)]
+    path = str(tmp_path / "a.bam")
+    write_bam(path, REFS, als, block_bytes=9000)
+    want, meta = _dump([path], threads=2)
+    assert len(want) == len(reads)
+    for chunk, headroom in ((20000, 1 << 20), (20000, 0), (1, 64), (300000, 100)):
+        env = {"DGE_BAM_CHUNK_BYTES": str(chunk), "DGE_BAM_HEADROOM_BYTES": str(headroom)}
+        for packed in (False, True):
+            got, m = _dump([path], threads=3, env=dict(env, **({"DGE_BAM_PACKED": "1"} if packed else {})))
+            assert got == want and m[-1] == meta[-1]
+    raw = open(path, "rb").read()
+    cut = str(tmp_path / "cut.bam")
+    open(cut, "wb").write(raw[:len(raw) * 2 // 3])
+    _, m = _dump([cut], env={"DGE_BAM_CHUNK_BYTES": "20000"}, expect_ok=False)
+    assert m[-1][0] == "#error" and "truncated" in m[-1][1]
+    bad = bytearray(raw)
+    bad[len(raw) // 2] ^= 0x55
+    flipped = str(tmp_path / "flipped.bam")
+    open(flipped, "wb").write(bytes(bad))
+    _, m = _dump([flipped], env={"DGE_BAM_CHUNK_BYTES": "20000"}, expect_ok=False)
+    assert m[-1][0] == "#error"
+
+
 def test_read_name_mode_read_types_and_several_files(tmp_path):
     """Without -f the barcode and UMI come from the read name ("...!CB#UMI", ReadParameters::parse_encoded_id); the read-type tag maps to
     intron / not-annotated / exon marks (ReadParamsParser::parse_read_type); files are read one after the other."""
