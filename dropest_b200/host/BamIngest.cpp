@@ -752,6 +752,7 @@ namespace BamProcessing
 					r.cb_quality = keep(cbq, cbq_n); r.cb_quality_len = uint16_t(cbq_n);
 					r.umi_quality = keep(umiq, umiq_n); r.umi_quality_len = uint16_t(umiq_n);
 					r.gene = params.gene_in_chromosome_name ? gene : keep(gene, gene_n); r.gene_len = uint16_t(gene_n);
+					r.gene_hash = StringIndexer::hash_of(gene, gene_n);
 					r.mark_bits = uint8_t(mark);
 					r.chromosome = al.ref_id;
 					out.status[k] = ParsedRead::OK;
@@ -777,7 +778,6 @@ namespace BamProcessing
 		{
 			std::vector<BamReader::RecordView> views;
 			PackedBatch batches[2];
-			std::vector<PackedRead> accepted;
 			for (auto const &file : bam_files)
 			{
 				BamReader reader(file, params.threads);
@@ -796,7 +796,9 @@ namespace BamProcessing
 					auto next = std::async(std::launch::async, produce, turn ^ 1);
 					try
 					{
-						accepted.clear();
+						// the accepted reads, in stream order (it defines cell / gene / chromosome ids): compacted in place, so a batch
+						// without a rejected record is handed over as it is
+						size_t n_ok = 0;
 						for (size_t k = 0; k < cur.status.size(); ++k)
 						{
 							switch (ParsedRead::Status(cur.status[k]))
@@ -805,10 +807,14 @@ namespace BamProcessing
 							case ParsedRead::NO_CHROMOSOME: ++stats.cant_parse; break;
 							case ParsedRead::CANT_PARSE: ++stats.total_reads; ++stats.cant_parse; break;
 							case ParsedRead::LOW_QUALITY: ++stats.total_reads; ++stats.low_quality; break;
-							case ParsedRead::OK: ++stats.total_reads; accepted.push_back(cur.reads[k]); break;
+							case ParsedRead::OK:
+								++stats.total_reads;
+								if (n_ok != k) cur.reads[n_ok] = cur.reads[k];
+								++n_ok;
+								break;
 							}
 						}
-						container.add_records(accepted.data(), accepted.size(), refs); // stream order: it defines cell / gene / chromosome ids
+						container.add_records(cur.reads.data(), n_ok, refs);
 					}
 					catch (...) { next.wait(); throw; }
 					have = next.get();

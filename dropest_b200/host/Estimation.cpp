@@ -609,6 +609,12 @@ namespace Estimation
 		for (size_t k = 0; k < n; ++k)
 		{
 			const PackedRead &r = reads[k];
+			if (k + 8 < n)
+			{   // the gene name lies in a parsing thread's arena, its slot in the indexer's table: both are fetched a few reads ahead
+				const PackedRead &ahead = reads[k + 8];
+				__builtin_prefetch(ahead.gene);
+				if (ahead.gene_len) _gene_indexer.prefetch(ahead.gene_hash);
+			}
 			const bool common = _h && !_qualities && r.packable == 3 && r.cb_len == _cb_len && r.umi_len == _umi_len && r.chromosome >= 0 &&
 			                    size_t(r.chromosome) < chromosome_names.size();
 			if (!common)
@@ -620,7 +626,7 @@ namespace Estimation
 			}
 			// ---- exactly what add_record does for such a read
 			uint32_t gene = DGE_NO_GENE;
-			if (r.gene_len) gene = uint32_t(_gene_indexer.add(r.gene, r.gene_len));
+			if (r.gene_len) gene = uint32_t(_gene_indexer.add(r.gene, r.gene_len, r.gene_hash));
 			uint8_t chr_id = 0;
 			if (!_chr_overflow)
 			{

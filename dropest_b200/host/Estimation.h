@@ -94,10 +94,11 @@ namespace Estimation
 			return h ^ (h >> 29);
 		}
 		// slot of the string, or the empty slot where it would go
-		size_t probe(const char *p, size_t n) const
+		size_t probe(const char *p, size_t n) const { return probe(p, n, hash(p, n)); }
+		size_t probe(const char *p, size_t n, uint64_t h) const
 		{
 			const size_t mask = _slots.size() - 1;
-			for (size_t i = size_t(hash(p, n)) & mask;; i = (i + 1) & mask)
+			for (size_t i = size_t(h) & mask;; i = (i + 1) & mask)
 			{
 				const uint32_t v = _slots[i];
 				if (!v) return i;
@@ -120,10 +121,14 @@ namespace Estimation
 			if (!_slots.empty()) { const uint32_t v = _slots[probe(value.data(), value.size())]; if (v) return v - 1; }
 			throw std::out_of_range("StringIndexer::get_index: unknown value '" + value + "'"); // the reference's unordered_map::at
 		}
-		index_t add(const char *p, size_t n)
+		index_t add(const char *p, size_t n) { return add(p, n, hash(p, n)); }
+		// the same with the hash computed by the caller (the BAM parsing threads hash the gene names; the thread that owns the indexer only probes)
+		static uint64_t hash_of(const char *p, size_t n) { return hash(p, n); }
+		void prefetch(uint64_t h) const { if (!_slots.empty()) __builtin_prefetch(&_slots[size_t(h) & (_slots.size() - 1)]); }
+		index_t add(const char *p, size_t n, uint64_t h)
 		{
 			if ((_values.size() + 1) * 2 > _slots.size()) grow();
-			const size_t i = probe(p, n);
+			const size_t i = probe(p, n, h);
 			if (_slots[i]) return _slots[i] - 1;
 			if (_values.size() >= 0xFFFFFFFEull) throw std::runtime_error("StringIndexer: too many values");
 			_values.emplace_back(p, n);
@@ -209,6 +214,7 @@ namespace Estimation
 		uint64_t cb_packed;
 		uint32_t umi_packed;
 		int32_t chromosome;    // index into the chromosome-name list passed with the batch
+		uint64_t gene_hash;    // StringIndexer::hash_of(gene, gene_len)
 	};
 
 	class Stats // Stats.h (per-cell counters; the per-chromosome tables are read from the device by CellsDataContainer::get_stat_by_real_cells)
