@@ -2,6 +2,7 @@
 // BAM records: specification 4.2.  Nothing here is taken from BamTools.
 #include "BamIngest.h"
 #include "BamOutput.h"
+#include "FastInflate.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -44,6 +45,11 @@ namespace BamProcessing
 			const size_t xlen = le16(in + 10), hdr = 12 + xlen;
 			if (in_len < hdr + 8) throw std::runtime_error("truncated BGZF block in " + fname);
 			if (out_len == 0) return;
+			const uint32_t want_crc = le32(in + in_len - 8);
+			auto crc_ok = [&] { return uint32_t(crc32(crc32(0L, Z_NULL, 0), out, uInt(out_len))) == want_crc; };
+			// our own decoder first (FastInflate.h); whatever it does not accept -- or gets wrong by the CRC -- is zlib's to judge
+			static const bool use_zlib_only = std::getenv("DGE_BAM_ZLIB_INFLATE") != nullptr;
+			if (!use_zlib_only && FastInflate::inflate_raw(in + hdr, in_len - hdr - 8, out, out_len) && crc_ok()) return;
 			z_stream zs;
 			std::memset(&zs, 0, sizeof(zs));
 			if (inflateInit2(&zs, -15) != Z_OK) throw std::runtime_error("zlib: inflateInit2 failed");
@@ -55,7 +61,7 @@ namespace BamProcessing
 			const bool ok = rc == Z_STREAM_END && zs.avail_out == 0;
 			inflateEnd(&zs);
 			if (!ok) throw std::runtime_error("corrupt BGZF block in " + fname);
-			if (uint32_t(crc32(crc32(0L, Z_NULL, 0), out, uInt(out_len))) != le32(in + in_len - 8)) throw std::runtime_error("BGZF CRC mismatch in " + fname);
+			if (!crc_ok()) throw std::runtime_error("BGZF CRC mismatch in " + fname);
 		}
 	}
 
@@ -88,9 +94,10 @@ namespace BamProcessing
 			const size_t chunk = _chunk_bytes;
 			if (!_eof)
 			{
-				_comp.grow_to(_comp.n + chunk);
+				_comp.grow_to(_comp.n + chunk + 16);
 				const size_t got = std::fread(_comp.data() + _comp.n, 1, chunk, _f);
 				_comp.n += got;
+				std::memset(_comp.data() + _comp.n, 0, 16); // FastInflate may look (not depend) on up to 15 bytes behind a block
 				if (got < chunk) _eof = true;
 			}
 			// the complete blocks in _comp

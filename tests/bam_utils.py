@@ -4,8 +4,8 @@ import struct
 import zlib
 
 
-def _bgzf_block(data: bytes) -> bytes:
-    comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+def _bgzf_block(data: bytes, level: int = 6) -> bytes:
+    comp = zlib.compressobj(level, zlib.DEFLATED, -15)
     body = comp.compress(data) + comp.flush()
     bsize = len(body) + 25  # header 18 + trailer 8 - 1
     assert bsize < 65536
@@ -46,7 +46,7 @@ def alignment(name: str, ref_id: int, pos: int, flag: int, tags, seq_len: int = 
     return struct.pack("<I", len(rec)) + rec
 
 
-def write_bam(path: str, references, alignments, block_bytes: int = 60000, header_text: str = "@HD\tVN:1.6\n"):
+def write_bam(path: str, references, alignments, block_bytes: int = 60000, header_text: str = "@HD\tVN:1.6\n", level: int = 6):
     """references: list of (name, length); alignments: iterable of bytes from alignment()"""
     head = b"BAM\x01" + struct.pack("<I", len(header_text)) + header_text.encode() + struct.pack("<I", len(references))
     for name, length in references:
@@ -54,7 +54,7 @@ def write_bam(path: str, references, alignments, block_bytes: int = 60000, heade
     payload = head + b"".join(alignments)
     with open(path, "wb") as f:
         for off in range(0, len(payload), block_bytes):   # records freely straddle blocks, as in real files
-            f.write(_bgzf_block(payload[off:off + block_bytes]))
+            f.write(_bgzf_block(payload[off:off + block_bytes], level))
         f.write(_bgzf_block(b""))
 
 

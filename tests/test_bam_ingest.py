@@ -71,6 +71,30 @@ def test_filled_bam_tags_filters_and_counters(tmp_path):
     assert len(got) == len(exp) + n_lowq and meta[-1][3] == "0"
 
 
+def test_fast_inflate_equals_zlib():
+    """host/FastInflate.h (the reader's own DEFLATE decoder) on ~3000 streams written by zlib at every level / strategy -- stored, fixed and
+    dynamic blocks, codes long enough for subtables, sizes around every boundary --, refusal of wrong output sizes, and ~3000 damaged
+    streams that must fail or decode without touching a byte outside the output (tests/cpp/test_fast_inflate.cpp)."""
+    exe = os.path.join(ROOT, "dropest_b200", "lib", "test_fast_inflate")
+    assert os.path.exists(exe), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok\t"), r.stdout[-500:] + r.stderr[-500:]
+
+
+def test_fast_inflate_and_zlib_paths_read_the_same(tmp_path):
+    """The reader with its own decoder and with zlib only (DGE_BAM_ZLIB_INFLATE) returns the same reads; BAMs deflated at level 0 (stored
+    blocks), 1 and 9."""
+    reads = _random_reads(12000, 9)
+    als = [alignment(f"q{i}", ref, pos, 0, [("CB", ("Z", cb)), ("UB", ("Z", umi))] + ([("GX", ("Z", gene))] if gene else []))
+           for i, (cb, umi, gene, ref, pos) in enumerate(reads)]
+    for level in (0, 1, 9):
+        path = str(tmp_path / f"l{level}.bam")
+        write_bam(path, REFS, als, block_bytes=60000, level=level)
+        ours, m1 = _dump([path], threads=2)
+        zl, m2 = _dump([path], threads=2, env={"DGE_BAM_ZLIB_INFLATE": "1"})
+        assert ours == zl and m1 == m2 and len(ours) == len(reads)
+
+
 def test_records_across_chunk_boundaries_and_loader_errors(tmp_path):
     """The reader inflates the next chunk in the background while the current one is framed and parsed: a record cut by a chunk boundary is
     completed in the new chunk's headroom (or, when it is longer than the headroom, in a buffer of its own).  Tiny chunks and no headroom put
