@@ -6,7 +6,10 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <exception>
+#include <mutex>
 #include <stdexcept>
 #include <thread>
 
@@ -273,8 +276,12 @@ namespace BamProcessing
 		if (!fill(4 + block_size)) throw std::runtime_error("truncated alignment record in " + _file_name);
 		RecordView v;
 		size_t np = 0;
+		const uint8_t *const base = _data.data(), *const limit = base + _data.size();
 		while (out.size() < max_records && view_at(_pos, v, np)) // no fill() in here: the views stay valid
 		{
+			// the bytes were written by the inflating threads; where the next record starts is known only after this one's length was read,
+			// so the walk is a chain of cache misses unless the lines a kilobyte ahead are already on their way
+			for (const uint8_t *q = base + ((_pos + 1024) & ~size_t(63)); q < base + np + 1024 && q < limit; q += 64) __builtin_prefetch(q);
 			out.push_back(v);
 			_pos = np;
 		}
@@ -783,26 +790,59 @@ namespace BamProcessing
 		// parse_bam_files over PackedBatch: the next batch is read, inflated and parsed while the current one goes to the container
 		void parse_bam_files_packed(const std::vector<std::string> &bam_files, const IngestParams &params, CellsDataContainer &container, IngestStats &stats)
 		{
-			std::vector<BamReader::RecordView> views;
-			PackedBatch batches[2];
+			// Three stages run side by side: the reader's loader inflates chunk k + 1, a producer thread frames and parses the records of
+			// chunk k batch by batch into a small ring, this thread hands the batches to the container in stream order.
+			constexpr size_t RING = 4;
+			struct Slot { PackedBatch batch; bool full = false; };
 			for (auto const &file : bam_files)
 			{
 				BamReader reader(file, params.threads);
 				const auto &refs = reader.reference_names();
-				int turn = 0;
-				auto produce = [&](int into) -> bool {
-					reader.next_batch(views, size_t(1) << 17);
-					if (views.empty()) return false;
-					parse_batch_packed(views, refs, params, batches[into], params.threads);
-					return true;
-				};
-				bool have = produce(turn);
-				while (have)
-				{
-					PackedBatch &cur = batches[turn];
-					auto next = std::async(std::launch::async, produce, turn ^ 1);
+				Slot ring[RING];
+				std::mutex m;
+				std::condition_variable cv;
+				bool done = false, stop = false;
+				std::exception_ptr failure;
+				std::thread producer([&] {
+					std::vector<BamReader::RecordView> views;
 					try
 					{
+						for (size_t head = 0;; ++head)
+						{
+							Slot &slot = ring[head % RING];
+							{
+								std::unique_lock<std::mutex> lock(m);
+								cv.wait(lock, [&] { return !slot.full || stop; });
+								if (stop) break;
+							}
+							reader.next_batch(views, size_t(1) << 15); // a few batches per inflated chunk
+							if (views.empty()) break;
+							parse_batch_packed(views, refs, params, slot.batch, params.threads);
+							{
+								std::lock_guard<std::mutex> lock(m);
+								slot.full = true;
+							}
+							cv.notify_all();
+						}
+					}
+					catch (...) { failure = std::current_exception(); }
+					{
+						std::lock_guard<std::mutex> lock(m);
+						done = true;
+					}
+					cv.notify_all();
+				});
+				try
+				{
+					for (size_t tail = 0;; ++tail)
+					{
+						Slot &slot = ring[tail % RING];
+						{
+							std::unique_lock<std::mutex> lock(m);
+							cv.wait(lock, [&] { return slot.full || done; });
+							if (!slot.full) break; // done, and every batch before it was taken
+						}
+						PackedBatch &cur = slot.batch;
 						// the accepted reads, in stream order (it defines cell / gene / chromosome ids): compacted in place, so a batch
 						// without a rejected record is handed over as it is
 						size_t n_ok = 0;
@@ -822,11 +862,25 @@ namespace BamProcessing
 							}
 						}
 						container.add_records(cur.reads.data(), n_ok, refs);
+						{
+							std::lock_guard<std::mutex> lock(m);
+							slot.full = false;
+						}
+						cv.notify_all();
 					}
-					catch (...) { next.wait(); throw; }
-					have = next.get();
-					turn ^= 1;
 				}
+				catch (...)
+				{
+					{
+						std::lock_guard<std::mutex> lock(m);
+						stop = true;
+					}
+					cv.notify_all();
+					producer.join();
+					throw;
+				}
+				producer.join();
+				if (failure) std::rethrow_exception(failure); // after the batches parsed before it went to the container, like the one-read path
 			}
 		}
 	}
