@@ -638,7 +638,9 @@ namespace BamProcessing
 
 	bool packed_path_applies(const IngestParams &params)
 	{
-		return params.filled_bam && !params.genes && params.genes_filename.empty();
+		// every mode but -r (the rows of the read-parameter files are claimed in stream order): barcode / UMI from the tags (-f) or from the
+		// read name, gene from the gene tag, the chromosome name or the annotation (-g)
+		return params.filled_bam || (!params.read_params && params.read_param_filenames.empty());
 	}
 
 	namespace
@@ -677,7 +679,8 @@ namespace BamProcessing
 		}
 	}
 
-	// read_info_from_alignment for the -f mode, producing a PackedRead: same decisions, same counters, same exception
+	// read_info_from_alignment for every mode but -r, producing a PackedRead: same decisions, same counters, same exception.
+	// params.genes must be loaded already when an annotation is used (parse_bam_files does that).
 	void parse_batch_packed(const std::vector<BamReader::RecordView> &records, const std::vector<std::string> &refs, const IngestParams &params,
 	                        PackedBatch &out, unsigned threads)
 	{
@@ -690,6 +693,7 @@ namespace BamProcessing
 		const int min_phred = params.min_barcode_quality + 33;
 		const std::string *wanted[6] = {&params.tags.cell_barcode, &params.tags.umi, &params.tags.cell_barcode_quality, &params.tags.umi_quality,
 		                                &params.tags.gene, &params.tags.read_type};
+		const size_t max_gene_name = params.genes ? params.genes->max_gene_name_length() : 0; // arena room per read for a name from the annotation
 		auto work = [&](unsigned t, size_t first, size_t last) {
 			try
 			{
@@ -697,16 +701,17 @@ namespace BamProcessing
 				// thread (the headers of out.arenas[] share cache lines: bumping them per string makes the threads fight over those lines)
 				std::vector<char> &arena = out.arenas[t];
 				size_t cap = 0;
-				for (size_t k = first; k < last; ++k) cap += records[k].al.tag_bytes;
+				for (size_t k = first; k < last; ++k) cap += records[k].al.tag_bytes + records[k].name_len + max_gene_name;
 				if (arena.size() < cap + 1) arena.resize(cap + 1);
 				char *top = arena.data();
 				auto keep = [&](const char *p, size_t len) -> const char * {
 					char *at = top;
-					std::memcpy(at, p, len);
+					if (len) std::memcpy(at, p, len);
 					top += len;
 					return at;
 				};
 				BamAlignment::TagValue tv[6];
+				std::string from_reference;
 				for (size_t k = first; k < last; ++k)
 				{
 					const BamAlignment &al = records[k].al;
@@ -718,11 +723,24 @@ namespace BamProcessing
 					if (!al.is_mapped() || !al.is_primary_alignment()) continue;
 					if (al.ref_id < 0 || size_t(al.ref_id) >= n_refs) { out.status[k] = ParsedRead::NO_CHROMOSOME; continue; }
 					al.find_tags(wanted, 6, tv);
-					const char *cb, *umi, *cbq, *umiq, *gene;
-					size_t cb_n, umi_n, cbq_n, umiq_n, gene_n;
-					if (!tag_view(tv[0], cb, cb_n) || !tag_view(tv[1], umi, umi_n) || cb_n == 0 || umi_n == 0) { out.status[k] = ParsedRead::CANT_PARSE; continue; }
-					tag_view(tv[2], cbq, cbq_n);
-					tag_view(tv[3], umiq, umiq_n);
+					const char *cb, *umi, *cbq = nullptr, *umiq = nullptr, *gene;
+					size_t cb_n, umi_n, cbq_n = 0, umiq_n = 0, gene_n;
+					if (params.filled_bam)
+					{
+						if (!tag_view(tv[0], cb, cb_n) || !tag_view(tv[1], umi, umi_n) || cb_n == 0 || umi_n == 0) { out.status[k] = ParsedRead::CANT_PARSE; continue; }
+						tag_view(tv[2], cbq, cbq_n);
+						tag_view(tv[3], umiq, umiq_n);
+					}
+					else
+					{   // ReadParameters::parse_encoded_id on the name, as views: "...!<barcode>#<UMI>", the last '#', the last '!' before it
+						const char *const begin = records[k].name_data, *const end = begin + records[k].name_len;
+						const char *hash = nullptr, *bang = nullptr;
+						for (const char *c = end; c != begin && !hash;) if (*--c == '#') hash = c;
+						if (hash) for (const char *c = hash + 1; c != begin && !bang;) if (*--c == '!') bang = c;
+						if (!hash || !bang || bang + 1 == hash || hash + 1 == end) { out.status[k] = ParsedRead::CANT_PARSE; continue; }
+						cb = bang + 1; cb_n = size_t(hash - cb);
+						umi = hash + 1; umi_n = size_t(end - umi);
+					}
 					bool pass_quality = true;
 					if (min_phred > 33)
 					{
@@ -736,6 +754,13 @@ namespace BamProcessing
 						const std::string &chr = refs[size_t(al.ref_id)];
 						gene = chr.data(); gene_n = chr.size();
 						if (gene_n) mark = UMI::Mark::HAS_EXONS;
+					}
+					else if (params.genes && !params.genes->is_empty())
+					{   // -g: the annotation decides (ReadParamsParser::get_gene_from_reference)
+						from_reference.clear();
+						try { mark = gene_from_reference(*params.genes, refs[size_t(al.ref_id)], al, from_reference).bits(); }
+						catch (Tools::GeneAnnotation::RefGenesContainer::ChrNotFoundException &) { out.status[k] = ParsedRead::CANT_PARSE; continue; }
+						gene = from_reference.data(); gene_n = from_reference.size();
 					}
 					else if (!tag_view(tv[4], gene, gene_n)) mark = UMI::Mark::HAS_NOT_ANNOTATED;
 					else
@@ -892,7 +917,10 @@ namespace BamProcessing
 			throw std::runtime_error("You have to specify tag values to be able to parse info about read types");
 		if (!print_result_bams && packed_path_applies(params) && !std::getenv("DGE_BAM_ONE_BY_ONE"))
 		{
-			parse_bam_files_packed(bam_files, params, container, stats);
+			IngestParams loaded(params);
+			if (!loaded.genes && !loaded.genes_filename.empty())
+				loaded.genes = std::make_shared<const Tools::GeneAnnotation::RefGenesContainer>(loaded.genes_filename);
+			parse_bam_files_packed(bam_files, loaded, container, stats);
 			return;
 		}
 		if (!print_result_bams)

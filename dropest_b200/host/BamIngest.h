@@ -221,7 +221,7 @@ namespace BamProcessing
 			on_open(file, reader);
 			const auto &refs = reader.reference_names();
 			auto produce = [&]() -> bool {
-				reader.next_batch(views, size_t(1) << 17);
+				reader.next_batch(views, size_t(1) << 15); // a few similar batches per inflated chunk: parsing one overlaps with consuming the previous one
 				if (views.empty()) return false;
 				parse_batch(views, refs, params, parsed_next, params.threads);
 				return true;

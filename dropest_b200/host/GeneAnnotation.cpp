@@ -99,6 +99,7 @@ namespace GeneAnnotation
 		span.second = std::max(span.second, rec.end);
 		_exons[rec.chr].emplace(rec.transcript_id(), IntervalIndex<RecordType>(false)).first->second.add(rec.start, rec.end, rec.type);
 		auto gene = _gene_of_transcript.emplace(rec.transcript_id(), rec.gene_name());
+		_max_gene_name = std::max(_max_gene_name, rec.gene_name().size());
 		if (!gene.second && gene.first->second != rec.gene_name())
 			throw std::runtime_error("Different gene names (" + rec.gene_name() + ", " + gene.first->second + ") for the same transcript (" +
 			                         rec.transcript_id() + ")");

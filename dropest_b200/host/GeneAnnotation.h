@@ -121,6 +121,7 @@ namespace GeneAnnotation
 		query_results_t get_gene_info(const std::string &chr_name, pos_t start_pos, pos_t end_pos) const;
 		bool is_empty() const { return _is_empty; }
 		bool has_introns() const { return _gtf_has_transcripts || _use_introns_from_gtf; }
+		size_t max_gene_name_length() const { return _max_gene_name; } // of every name a query can return
 
 	private:
 		struct Record // GtfRecord
@@ -133,6 +134,7 @@ namespace GeneAnnotation
 			const std::string &transcript_id() const { return transcript_raw.empty() ? gene_id : transcript_raw; }
 		};
 		bool _is_empty = true, _use_introns_from_gtf = false, _gtf_has_transcripts = true;
+		size_t _max_gene_name = 0;
 		std::string _file_format;
 		std::unordered_map<std::string, IntervalIndex<std::string>> _transcripts;                                   // chr -> transcripts
 		std::unordered_map<std::string, std::unordered_map<std::string, IntervalIndex<RecordType>>> _exons;          // chr -> transcript -> exon / intron spans

@@ -39,6 +39,7 @@ int main(int argc, char **argv)
 		else if (std::getenv("DGE_BAM_PACKED"))
 		{   // the bulk path (parse_batch_packed), printed like the one-read path prints its ReadInfo
 			if (!BamProcessing::packed_path_applies(p)) throw std::runtime_error("the packed path does not apply to these parameters");
+			if (!p.genes && !p.genes_filename.empty()) p.genes = std::make_shared<const Tools::GeneAnnotation::RefGenesContainer>(p.genes_filename);
 			for (auto const &file : files)
 			{
 				BamProcessing::BamReader reader(file, p.threads);

@@ -19,6 +19,8 @@ int main(int argc, char **argv)
 		factory.min_genes_after_merge = size_t(std::stoul(argv[3]));
 		BamProcessing::IngestParams p;
 		p.tags.read_type = argv[4]; p.tags.intronic_read_value = argv[5]; p.tags.intergenic_read_value = argv[6];
+		if (std::getenv("DGE_BAM_NAME_MODE")) p.filled_bam = false;                        // barcode / UMI from the read names
+		if (const char *g = std::getenv("DGE_BAM_GENES")) p.genes_filename = g;             // -g
 		std::vector<std::string> files(argv + 7, argv + argc);
 		CellsDataContainer container(factory.get_cb_strat(true, false), factory.get_umi(false), UMI::Mark::get_by_code(UMI::Mark::DEFAULT_CODE), false, -1, 0, 1u << 15);
 		BamProcessing::IngestStats st;

@@ -210,6 +210,37 @@ def test_bulk_packed_path_equals_the_one_read_path(tmp_path):
                 assert int(b[9]) == v
 
 
+def test_bulk_packed_path_read_name_mode(tmp_path):
+    """Without -f the bulk path takes barcode and UMI from the read name like ReadParameters::parse_encoded_id: the last '#', the last '!'
+    before it, empty parts and names without the codec cannot be parsed; N bases and odd lengths are kept (not packable)."""
+    rng = np.random.default_rng(33)
+    acgt = np.array(list("ACGT"))
+    names = []
+    for i in range(20000):
+        cb, umi = "".join(rng.choice(acgt, 12)), "".join(rng.choice(acgt, 8))
+        kind = i % 31
+        name = f"read{i}:x!{cb}#{umi}"
+        if kind == 1: name = f"read{i}"                        # no codec
+        elif kind == 3: name = f"read{i}#{umi}"                # no '!'
+        elif kind == 5: name = f"read{i}!#{umi}"               # empty barcode
+        elif kind == 7: name = f"read{i}!{cb}#"                # empty UMI
+        elif kind == 9: name = f"a!b#c!{cb}#{umi}"             # several separators: the last ones count
+        elif kind == 11: name = f"r!{cb}#{umi[:3]}N{umi[4:]}"  # N in the UMI
+        elif kind == 13: name = f"r#1!{cb[:7]}#{umi}"          # '#' before the '!': still the last '#'
+        elif kind == 15: name = f"r!{cb}!{cb}#{umi}"           # two '!': the last one before the '#'
+        tags = [("GX", ("Z", f"G{int(rng.integers(0, 99))}"))] if i % 5 else []
+        if i % 3 == 0:
+            tags.append(("XF", ("Z", str(rng.choice(["INTRONIC", "CODING", "INTERGENIC"])))))
+        names.append(alignment(name, int(rng.integers(0, 3)), i, 0, tags))
+    path = str(tmp_path / "n.bam")
+    write_bam(path, REFS, names, block_bytes=50000)
+    for kw in (dict(type_tag="XF", intronic="INTRONIC", intergenic="INTERGENIC"), dict(), dict(gene_in_chr=True)):
+        one, meta_one = _dump([path], filled=False, n_columns=7, threads=1, **kw)
+        bulk, meta_bulk = _dump([path], filled=False, n_columns=7, threads=4, env={"DGE_BAM_PACKED": "1"}, **kw)
+        assert bulk == one and meta_bulk[-1] == meta_one[-1] and 15000 < len(one) < 20000
+        assert int(meta_one[-1][2]) > 2000   # the names that cannot be parsed are counted
+
+
 REF_FLOW = os.path.join(ROOT, "oracle", "_ref", "ref_bam_flow")
 
 
@@ -350,6 +381,12 @@ def test_gene_assignment_from_annotation_matches_the_compiled_reference(tmp_path
     assert lines[-1].split("\t")[:3] == ["#stats", str(len(als)), str(n_chr)]
     marks = {g[4] for g in got}
     assert {"0", "2"} <= marks and (marks & {"3", "4", "6"}) and n_chr > 50   # no gene, exonic, and mixed / intronic reads all occur
+    # the bulk path (parse_batch_packed: read-name codec + annotation lookups on the parsing threads) takes the same decisions
+    rp = subprocess.run([DUMP, "0", "0", "0", "-", "-", "-", "3", bam], capture_output=True, text=True,
+                        env=dict(os.environ, DGE_BAM_GENES=genes_file, DGE_BAM_PACKED="1"))
+    assert rp.returncode == 0, rp.stdout[-300:]
+    plines = rp.stdout.strip().split("\n")
+    assert [tuple(l.split("\t")[:5]) for l in plines if not l.startswith("#")] == exp and plines[-1] == lines[-1]
 
 
 @pytest.mark.gpu
