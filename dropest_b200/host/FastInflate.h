@@ -3,8 +3,8 @@
 // machine that can stop after any byte.  This one cannot stop: 64-bit bit buffer refilled without a branch, one table lookup per symbol
 // (11-bit litlen / 8-bit offset primary tables with subtables for longer codes), up to two literals per refill, word-wise match copies.
 // Contract: returns true iff the stream is well formed, ends with its final block and produced EXACTLY out_len bytes.  On false the
-// output is unspecified and the caller falls back to zlib (which then decides whether the block is corrupt), so an unusual but legal
-// stream (incomplete code sets) costs time, never correctness.  It may read up to 15 bytes beyond in + in_len (their values do not matter:
+// output is unspecified and the caller falls back to zlib (which then decides whether the block is corrupt).  It accepts nothing zlib
+// refuses (same rules for the code-length sets; fuzzed against zlib with damaged streams) and produces the same bytes for what both accept.  It may read up to 15 bytes beyond in + in_len (their values do not matter:
 // a BGZF block has its 8-byte footer there, then the next block or the reader's spare bytes) and never writes outside [out, out + out_len).
 #pragma once
 #include <cstddef>
@@ -31,19 +31,24 @@ namespace FastInflate
 		return r;
 	}
 
-	// Canonical Huffman decode table for code lengths lens[0, n): false when the lengths over-subscribe the code space or the subtables do
-	// not fit.  An incomplete set leaves INVALID entries (decoding one fails the block).
-	inline bool build_table(const uint8_t *lens, unsigned n, unsigned table_bits, uint32_t *table, unsigned cap, const uint32_t *symbol_entry)
+	// Canonical Huffman decode table for code lengths lens[0, n): false when zlib would refuse the lengths (inftrees.c: over-subscribed, or
+	// incomplete unless the set is empty or -- literal/length and distance codes only -- one single code of length 1) or the subtables do not
+	// fit.  The entries an accepted incomplete set leaves open are INVALID (decoding one fails the block).
+	inline bool build_table(const uint8_t *lens, unsigned n, unsigned table_bits, uint32_t *table, unsigned cap, const uint32_t *symbol_entry,
+	                        bool is_precode = false)
 	{
 		unsigned count[16] = {0};
 		for (unsigned s = 0; s < n; ++s) ++count[lens[s]];
 		count[0] = 0;
 		int left = 1;
+		unsigned max_len = 0;
 		for (unsigned len = 1; len <= 15; ++len)
 		{
 			left = left * 2 - int(count[len]);
 			if (left < 0) return false;
+			if (count[len]) max_len = len;
 		}
+		if (left > 0 && max_len != 0 && (is_precode || max_len != 1)) return false;
 		unsigned next_code[16];
 		for (unsigned len = 1, code = 0; len <= 15; ++len)
 		{
@@ -198,7 +203,7 @@ namespace FastInflate
 					DGE_TAKE(3);
 				}
 				uint32_t precode[PRECODE_CAP];
-				if (!build_table(pre_lens, 19, PRECODE_BITS, precode, PRECODE_CAP, entries.precode)) return false;
+				if (!build_table(pre_lens, 19, PRECODE_BITS, precode, PRECODE_CAP, entries.precode, true)) return false;
 				uint8_t lens[288 + 32 + 138];
 				unsigned i = 0;
 				const unsigned total = hlit + hdist;

@@ -96,6 +96,44 @@ int main()
 							for (int k = 0; k < 16; ++k) if (o2[k] != 0xEE || o2[16 + n + k] != 0xEE) { std::puts("wrote outside the output"); return 1; }
 						}
 				}
-	std::printf("ok\t%zu streams equal to zlib's input\t%zu damaged streams survived (%zu decoded to something)\n", n_cases, n_damaged, n_damaged_ok);
+	// fuzz against zlib's verdict: valid streams with 0-3 damages (bit flips, byte overwrites, truncation), random bytes, wrong output
+	// sizes.  Whatever the decoder accepts, zlib accepts too, with the same bytes (the reverse need not hold); nothing is written outside.
+	size_t n_fuzz = 0, n_accepted = 0;
+	for (int iter = 0; iter < 40000; ++iter)
+	{
+		const size_t len = 1 + rng() % 3000;
+		std::vector<uint8_t> src(len);
+		const int kind = int(rng() % 4);
+		for (auto &b : src) b = kind == 0 ? uint8_t(rng()) : kind == 1 ? uint8_t("ACGT"[rng() & 3]) : kind == 2 ? uint8_t('a' + rng() % 3) : uint8_t(rng() % 7 ? 'I' : rng());
+		auto comp = deflate_raw(src, int(rng() % 10), int(rng() % 5), 1 + int(rng() % 9));
+		int damages = int(rng() % 4);
+		if (rng() % 50 == 0) { for (auto &b : comp) b = uint8_t(rng()); damages = 1; }
+		for (int d = 0; d < damages; ++d)
+			switch (rng() % 3)
+			{
+			case 0: comp[rng() % comp.size()] ^= uint8_t(1u << (rng() % 8)); break;
+			case 1: comp[rng() % comp.size()] = uint8_t(rng()); break;
+			default: if (comp.size() > 1) comp.resize(1 + rng() % (comp.size() - 1)); break;
+			}
+		const size_t clen = comp.size();
+		std::vector<uint8_t> padded(comp);
+		padded.resize(clen + 16, uint8_t(rng()));
+		const size_t out_len = rng() % 8 ? len : rng() % (2 * len + 1);
+		std::vector<uint8_t> out(out_len + 64, 0xEE), ref(out_len + 64, 0xEE);
+		const bool ok = inflate_raw(padded.data(), clen, out.data() + 32, out_len);
+		for (int k = 0; k < 32; ++k) if (out[k] != 0xEE || out[32 + out_len + k] != 0xEE) { std::puts("fuzz: wrote outside the output"); return 1; }
+		++n_fuzz;
+		if (!ok) continue;
+		++n_accepted;
+		z_stream is{};
+		inflateInit2(&is, -15);
+		is.next_in = comp.data(); is.avail_in = uInt(clen); is.next_out = ref.data() + 32; is.avail_out = uInt(out_len);
+		const int rc = inflate(&is, Z_FINISH);
+		const bool zok = rc == Z_STREAM_END && is.avail_out == 0;
+		inflateEnd(&is);
+		if (!zok || out != ref) { std::printf("fuzz: accepted what zlib refuses or decodes differently (iteration %d)\n", iter); return 1; }
+	}
+	std::printf("ok\t%zu streams equal to zlib's input\t%zu damaged streams survived (%zu decoded to something)\t%zu fuzz cases, %zu accepted, all as zlib decodes them\n",
+	            n_cases, n_damaged, n_damaged_ok, n_fuzz, n_accepted);
 	return 0;
 }
