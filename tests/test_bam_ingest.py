@@ -243,6 +243,53 @@ def test_bulk_packed_path_read_name_mode(tmp_path):
         assert int(meta_one[-1][2]) > 2000   # the names that cannot be parsed are counted
 
 
+HOST_PIPE = os.path.join(ROOT, "dropest_b200", "lib", "test_ingest_pipeline_host")
+
+
+def _host_pipeline(files, threads=4, name_mode=False, min_q=0, env=None, expect_ok=True):
+    assert os.path.exists(HOST_PIPE), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    r = subprocess.run([HOST_PIPE, str(threads), "1" if name_mode else "0", str(min_q)] + list(files), capture_output=True, text=True,
+                       env=dict(os.environ, **(env or {})))
+    assert (r.returncode == 0) == expect_ok, r.stdout[-500:] + r.stderr[-500:]
+    return r.stdout.strip().split("\n")[-1].split("\t")
+
+
+def test_host_side_of_parse_bam_files_threads_counters_and_errors(tmp_path):
+    """BamProcessing::parse_bam_files itself (background loader + producer thread + hand-over thread) with the device entry points replaced
+    by a no-op stand-in (tests/cpp/stub_device.c: test infrastructure, computes nothing): the counters, the number of reads that reach
+    dge_add_batch*, bulk path == one-read path, two files, tiny chunks (many hand-overs between the three threads), and an error raised on
+    the loader thread (truncated file) arriving at the caller after the earlier batches were handed over."""
+    rng = np.random.default_rng(77)
+    acgt = np.array(list("ACGT"))
+    als, n_ok = [], 0
+    for i in range(60000):
+        cb, umi = "".join(rng.choice(acgt, 16)), "".join(rng.choice(acgt, 10))
+        tags = [("CB", ("Z", cb)), ("UB", ("Z", umi)), ("CQ", ("Z", "I" * 16)), ("UQ", ("Z", "I" * 9 + ("#" if i % 13 == 0 else "I")))]
+        if i % 5:
+            tags.append(("GX", ("Z", f"G{int(rng.integers(0, 700))}")))
+        if i % 17 == 0:
+            tags = tags[1:]                   # no barcode tag: cannot be parsed
+        flag = 4 if i % 19 == 0 else 0
+        als.append(alignment(f"r{i}", int(rng.integers(0, 3)), i, flag, tags))
+    a, b = str(tmp_path / "a.bam"), str(tmp_path / "b.bam")
+    write_bam(a, REFS, als[:35000], block_bytes=20000)
+    write_bam(b, REFS, als[35000:], block_bytes=20000)
+    skipped = sum(1 for i in range(60000) if i % 19 == 0)
+    cant = sum(1 for i in range(60000) if i % 19 and i % 17 == 0)
+    lowq = sum(1 for i in range(60000) if i % 19 and i % 17 and i % 13 == 0)
+    total = 60000 - skipped
+    want = ["stats", str(total), str(cant), str(lowq), str(skipped), str(total - cant - lowq), "0", "0"]
+    for env in ({}, {"DGE_BAM_CHUNK_BYTES": "30000"}, {"DGE_BAM_ONE_BY_ONE": "1"}):
+        for threads in (1, 5):
+            assert _host_pipeline([a, b], threads=threads, min_q=10, env=env) == want
+    raw = open(b, "rb").read()
+    cut = str(tmp_path / "cut.bam")
+    open(cut, "wb").write(raw[:len(raw) // 2])
+    for env in ({"DGE_BAM_CHUNK_BYTES": "30000"}, {"DGE_BAM_ONE_BY_ONE": "1"}):
+        got = _host_pipeline([a, cut], env=env, expect_ok=False)
+        assert got[0] == "error" and "truncated" in got[1]
+
+
 REF_FLOW = os.path.join(ROOT, "oracle", "_ref", "ref_bam_flow")
 
 
