@@ -2,9 +2,11 @@
 // Replaces, for the tag-driven modes of `dropest`, the BamTools-based loop of the reference:
 //   Estimation/BamProcessing/BamController.cpp:70-172 (parse_bam_file / process_alignment), FilledBamParamsParser.cpp:12-40 (-f: barcode and
 //   UMI from tags, base-quality threshold), ReadParamsParser.cpp:21-90,179-197 (read-name codec, gene tag, read-type tag), BamTags.cpp:7-25.
-// Own BGZF / BAM reader (zlib is the only dependency): the compressed blocks of a chunk are inflated by a pool of threads straight into
-// their place of one contiguous buffer (block sizes are known from the headers and trailers without inflating), records are then parsed in
-// stream order -- the order is what defines cell / gene ids downstream.  GTF-based gene assignment (row f3) is not part of this file.
+// Own BGZF / BAM reader (zlib is the only dependency; the blocks are inflated by FastInflate.h, zlib checks the CRC and judges what that
+// decoder refuses): the compressed blocks of a chunk are inflated by a pool of threads straight into their place of one contiguous buffer
+// (block sizes are known from the headers and trailers without inflating) -- in the background, while the previous chunk is framed and
+// parsed --, records are handed to the container in stream order: the order is what defines cell / gene ids downstream.  The gene lookup in
+// an annotation (-g, row f3) lives in GeneAnnotation.h; this file calls it for the first and last aligned base of a read.
 #pragma once
 #include "Estimation.h"
 #include "GeneAnnotation.h"
