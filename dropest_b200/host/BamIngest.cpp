@@ -694,6 +694,12 @@ namespace BamProcessing
 		const std::string *wanted[6] = {&params.tags.cell_barcode, &params.tags.umi, &params.tags.cell_barcode_quality, &params.tags.umi_quality,
 		                                &params.tags.gene, &params.tags.read_type};
 		const size_t max_gene_name = params.genes ? params.genes->max_gene_name_length() : 0; // arena room per read for a name from the annotation
+		// the five strings kept per read are values of different tags, together shorter than the tag block -- unless one tag name was
+		// configured for several of them, in which case the same value is kept several times
+		size_t tag_copies = 1;
+		for (int a = 0; a < 5; ++a)
+			for (int b = a + 1; b < 5; ++b)
+				if (*wanted[a] == *wanted[b]) tag_copies = 5;
 		auto work = [&](unsigned t, size_t first, size_t last) {
 			try
 			{
@@ -701,7 +707,7 @@ namespace BamProcessing
 				// thread (the headers of out.arenas[] share cache lines: bumping them per string makes the threads fight over those lines)
 				std::vector<char> &arena = out.arenas[t];
 				size_t cap = 0;
-				for (size_t k = first; k < last; ++k) cap += records[k].al.tag_bytes + records[k].name_len + max_gene_name;
+				for (size_t k = first; k < last; ++k) cap += tag_copies * records[k].al.tag_bytes + records[k].name_len + max_gene_name;
 				if (arena.size() < cap + 1) arena.resize(cap + 1);
 				char *top = arena.data();
 				auto keep = [&](const char *p, size_t len) -> const char * {
