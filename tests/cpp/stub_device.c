@@ -9,10 +9,34 @@ int dge_create(const void *cfg, void **out) { (void)cfg; *out = &dummy_handle; r
 extern const unsigned long stub_dge_config_size; /* stub_device_sizes.c: sizeof(dge_config) from the real header */
 void dge_config_default(void *cfg) { memset(cfg, 0, stub_dge_config_size); }
 const char *dge_last_error(const void *h) { (void)h; return "stub device: nothing is computed"; }
-int dge_add_batch(void *h, const void *recs, unsigned long n) { (void)h; (void)recs; n_reads_seen += n; return 0; }
-int dge_add_batch_chr(void *h, const void *recs, const void *chr, unsigned long n) { (void)h; (void)recs; (void)chr; n_reads_seen += n; return 0; }
-int dge_add_batch_soa(void *h, const void *k, const void *g, unsigned long n, unsigned long long first) { (void)h; (void)k; (void)g; (void)first; n_reads_seen += n; return 0; }
-int dge_add_batch_soa_chr(void *h, const void *k, const void *g, const void *c, unsigned long n, unsigned long long first) { (void)h; (void)k; (void)g; (void)c; (void)first; n_reads_seen += n; return 0; }
+/* what reaches the device, read by read in arrival order: (key, gene word, read index, chromosome id) folded into one digest, so that two
+ * host paths can be compared on everything the device would see (packing, gene ids, marks, stream positions, chromosome ids) */
+static unsigned long long digest = 0xCBF29CE484222325ull;
+static void fold(const void *p, unsigned long n) { const unsigned char *b = (const unsigned char *)p; for (unsigned long i = 0; i < n; ++i) { digest ^= b[i]; digest *= 0x100000001B3ull; } }
+static void fold_read(unsigned long long key, unsigned gene, unsigned idx, unsigned char chr) { fold(&key, 8); fold(&gene, 4); fold(&idx, 4); fold(&chr, 1); }
+struct rec16 { unsigned long long key; unsigned gene, read_idx; };
+int dge_add_batch_chr(void *h, const void *recs, const void *chr, unsigned long n)
+{
+	(void)h;
+	const struct rec16 *r = (const struct rec16 *)recs;
+	const unsigned char *c = (const unsigned char *)chr;
+	for (unsigned long i = 0; i < n; ++i) fold_read(r[i].key, r[i].gene, r[i].read_idx, c ? c[i] : 0);
+	n_reads_seen += n;
+	return 0;
+}
+int dge_add_batch(void *h, const void *recs, unsigned long n) { return dge_add_batch_chr(h, recs, 0, n); }
+int dge_add_batch_soa_chr(void *h, const void *k, const void *g, const void *c, unsigned long n, unsigned long long first)
+{
+	(void)h;
+	const unsigned long long *keys = (const unsigned long long *)k;
+	const unsigned *genes = (const unsigned *)g;
+	const unsigned char *chr = (const unsigned char *)c;
+	for (unsigned long i = 0; i < n; ++i) fold_read(keys[i], genes[i], (unsigned)(first + i), chr ? chr[i] : 0);
+	n_reads_seen += n;
+	return 0;
+}
+int dge_add_batch_soa(void *h, const void *k, const void *g, unsigned long n, unsigned long long first) { return dge_add_batch_soa_chr(h, k, g, 0, n, first); }
+unsigned long long stub_digest(void) { return digest; }
 unsigned long long stub_reads_seen(void) { return n_reads_seen; }
 #define STUB(name) int name(void) { return 1; } /* DGE_ERR_*: anything past the fill is refused */
 STUB(dge_collisions_adjusted_sizes) STUB(dge_edit_distance) STUB(dge_get_cells) STUB(dge_get_chr_stats) STUB(dge_get_matrix) STUB(dge_get_matrix_marks)

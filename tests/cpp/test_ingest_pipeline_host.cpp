@@ -1,5 +1,6 @@
 // The HOST side of BAM -> container (BamProcessing::parse_bam_files: background loader, producer thread, hand-over thread) against the no-op
-// device stand-in tests/cpp/stub_device.c: counters, the number of reads that reach the device entry points, bulk path == one-read path,
+// device stand-in tests/cpp/stub_device.c: counters, the number of reads that reach the device entry points and a digest of everything they
+// carry (packed key, gene word, stream position, chromosome id per read), bulk path == one-read path,
 // errors thrown on the loader / producer threads arriving at the caller.  CPU only; nothing is computed (see stub_device.c).
 // usage: test_ingest_pipeline_host <threads> <name_mode 0|1> <min_quality> <bam>...
 #include "../../dropest_b200/host/BamIngest.h"
@@ -7,6 +8,7 @@
 #include <iostream>
 
 extern "C" unsigned long long stub_reads_seen(void);
+extern "C" unsigned long long stub_digest(void);
 
 using namespace Estimation;
 
@@ -29,7 +31,7 @@ int main(int argc, char **argv)
 		BamProcessing::parse_bam_files(files, p, container, st);
 		container.set_initialized(); // hands over the last batch
 		std::cout << "stats\t" << st.total_reads << '\t' << st.cant_parse << '\t' << st.low_quality << '\t' << st.skipped_unmapped_or_secondary << '\t'
-		          << stub_reads_seen() << '\t' << container.skipped_n_reads() << '\t' << container.skipped_length_reads() << std::endl;
+		          << stub_reads_seen() << '\t' << container.skipped_n_reads() << '\t' << container.skipped_length_reads() << '\t' << stub_digest() << std::endl;
 	}
 	catch (std::exception &e)
 	{

@@ -279,9 +279,32 @@ def test_host_side_of_parse_bam_files_threads_counters_and_errors(tmp_path):
     lowq = sum(1 for i in range(60000) if i % 19 and i % 17 and i % 13 == 0)
     total = 60000 - skipped
     want = ["stats", str(total), str(cant), str(lowq), str(skipped), str(total - cant - lowq), "0", "0"]
+    digests = set()
     for env in ({}, {"DGE_BAM_CHUNK_BYTES": "30000"}, {"DGE_BAM_ONE_BY_ONE": "1"}):
         for threads in (1, 5):
-            assert _host_pipeline([a, b], threads=threads, min_q=10, env=env) == want
+            got = _host_pipeline([a, b], threads=threads, min_q=10, env=env)
+            assert got[:8] == want
+            digests.add(got[8])
+    assert len(digests) == 1   # packed keys, gene ids + marks, stream positions, chromosome ids: the same read by read on every path
+    # read-name mode with N bases, barcodes of another length and names without the codec: the reads the packed record cannot carry take
+    # the one-read path inside add_records, and the device still sees the same stream
+    names = []
+    for i in range(30000):
+        cb, umi = "".join(rng.choice(acgt, 12)), "".join(rng.choice(acgt, 8))
+        if i % 41 == 2: umi = umi[:3] + "N" + umi[4:]
+        if i % 43 == 3: cb = cb[:5] + "N" + cb[6:]
+        if i % 47 == 4: cb = cb[:9]
+        if i % 53 == 5: umi = umi + "AC"
+        name = f"x{i}!{cb}#{umi}" if i % 59 else f"x{i}"
+        tags = [("GX", ("Z", f"G{int(rng.integers(0, 300))}"))] if i % 4 else []
+        if i % 3 == 0:
+            tags.append(("XF", ("Z", str(rng.choice(["INTRONIC", "CODING", "INTERGENIC"])))))
+        names.append(alignment(name, int(rng.integers(0, 3)), i, 0, tags))
+    c = str(tmp_path / "c.bam")
+    write_bam(c, REFS, names, block_bytes=30000)
+    bulk = _host_pipeline([c], name_mode=True)
+    one = _host_pipeline([c], name_mode=True, env={"DGE_BAM_ONE_BY_ONE": "1"})
+    assert bulk == one and int(bulk[5]) > 27000 and int(bulk[7]) > 0   # reads arrived; UMIs of another length were skipped and counted
     raw = open(b, "rb").read()
     cut = str(tmp_path / "cut.bam")
     open(cut, "wb").write(raw[:len(raw) // 2])
