@@ -160,6 +160,20 @@ namespace GeneAnnotation
 		auto chr = _transcripts.find(chr_name);
 		if (chr == _transcripts.end()) throw ChrNotFoundException(chr_name);
 		query_results_t results;
+		if (end_pos == start_pos + 1)
+		{   // one nucleotide (what the BAM ingest asks, twice per read): the covering label sets are read in place, same iteration order
+			const std::set<std::string> *transcripts = chr->second.query_point(start_pos);
+			if (!transcripts) return results;
+			auto const &exons_of = _exons.at(chr_name);
+			for (const std::string &transcript : *transcripts)
+			{
+				const std::set<RecordType> *types = exons_of.at(transcript).query_point(start_pos);
+				const std::string &gene = _gene_of_transcript.at(transcript);
+				if (!types) { if (!_use_introns_from_gtf) results.emplace(gene, INTRON); continue; }
+				for (RecordType t : *types) results.emplace(gene, t);
+			}
+			return results;
+		}
 		for (const std::string &transcript : chr->second.query(start_pos, end_pos))
 		{
 			auto types = _exons.at(chr_name).at(transcript).query(start_pos, end_pos);

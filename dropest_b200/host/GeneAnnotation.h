@@ -91,6 +91,14 @@ namespace GeneAnnotation
 			return out;
 		}
 
+		// query(pos, pos + 1) without the copy: the segments are disjoint, so at most one holds pos (nullptr: none)
+		const std::set<Label> *query_point(size_t pos) const
+		{
+			if (!_sealed) throw std::runtime_error("Interval must be initialized");
+			auto it = std::lower_bound(_segments.begin(), _segments.end(), pos, [](const Segment &s, size_t p) { return s.end <= p; });
+			return it != _segments.end() && it->start <= pos ? &it->labels : nullptr;
+		}
+
 		size_t n_segments() const { return _segments.size(); }
 	};
 
